@@ -1,0 +1,49 @@
+"""Create random-init TorchScript nets with the REFERENCE's own network code.
+
+Imports /root/reference/minizero/network/py (only possible in the build container) and writes
+`.pt` files the compiled reference (oracle/_ref/ref_*) and this repo's worker both load.
+Outputs go to oracle/_ref/nets/ (git-ignored, shipped to the GPU box by gpurun).
+TEST INFRASTRUCTURE ONLY.
+"""
+import os
+import sys
+
+import torch
+
+REF = os.environ.get("MZ_REFERENCE", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "nets")
+
+# name: (game_name, C, H, W, hidden, hH, hW, action_feat_ch, blocks, A, value_hidden, discrete, type)
+NETS = {
+    "ttt_az_2bx32": ("tictactoe", 4, 3, 3, 32, 3, 3, 1, 2, 9, 256, 1, "alphazero"),
+    "go9_az_1bx16": ("go_9x9", 18, 9, 9, 16, 9, 9, 1, 1, 82, 64, 1, "alphazero"),
+    "go9_az_2bx64": ("go_9x9", 18, 9, 9, 64, 9, 9, 1, 2, 82, 256, 1, "alphazero"),
+    "go9_az_6bx256": ("go_9x9", 18, 9, 9, 256, 9, 9, 1, 6, 82, 256, 1, "alphazero"),
+    "othello_mz_3bx128": ("othello_8x8", 4, 8, 8, 128, 8, 8, 1, 3, 65, 256, 1, "muzero"),
+}
+
+
+def main(names):
+    sys.path.insert(0, REF)
+    from minizero.network.py.create_network import create_network  # noqa: E402
+
+    os.makedirs(OUT, exist_ok=True)
+    for name in names:
+        path = os.path.join(OUT, name + ".pt")
+        torch.manual_seed(0)
+        net = create_network(*NETS[name])
+        # perturb BatchNorm statistics so that BN folding is actually exercised by parity tests
+        g = torch.Generator().manual_seed(1234)
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+                m.running_var.copy_(1.0 + 0.2 * torch.rand(m.running_var.shape, generator=g))
+                m.weight.data.copy_(1.0 + 0.1 * torch.randn(m.weight.shape, generator=g))
+                m.bias.data.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+        net.eval()
+        torch.jit.script(net).save(path)
+        print(path, sum(p.numel() for p in net.parameters()))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or list(NETS))
