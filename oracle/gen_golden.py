@@ -1,0 +1,72 @@
+"""Generate golden vectors for tests/golden/ by running the UNMODIFIED reference (oracle/_ref/ref_stepper_*).
+
+Only runs in the build container (needs oracle/_ref built from /root/reference and the nets from
+oracle/gen_nets.py). Output: tests/golden/<case>.npz with, per leaf evaluation, the game index,
+rotation, path length, bit-packed feature planes and the network outputs the reference consumed;
+and per move the root child table at the moment the move was decided.
+TEST INFRASTRUCTURE ONLY.
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "..", "tests", "golden")
+
+COMMON = "zero_num_threads=1:program_seed=%d:program_auto_seed=false:program_quiet=true:nn_type_name=alphazero"
+CASES = {
+    # name: (binary, net, conf, max_moves)
+    "ttt_s50_b2": ("tictactoe", "ttt_az_2bx32", "actor_num_simulation=50:zero_num_parallel_games=2:" + COMMON % 1, 40),
+    "ttt_s50_b1_det": ("tictactoe", "ttt_az_2bx32", "actor_num_simulation=50:zero_num_parallel_games=1:actor_use_dirichlet_noise=false:actor_use_random_rotation_features=false:actor_select_action_by_count=true:actor_select_action_by_softmax_count=false:" + COMMON % 1, 12),
+    "go5_s24_b2": ("go", "go5_az_1bx16", "env_board_size=5:actor_num_simulation=24:zero_num_parallel_games=2:" + COMMON % 3, 140),
+    "go9_s32_b2": ("go", "go9_az_1bx16", "env_board_size=9:actor_num_simulation=32:zero_num_parallel_games=2:" + COMMON % 5, 30),
+}
+
+
+def read_case(d, a_size, f_size):
+    ev = np.fromfile(os.path.join(d, "evals.bin"), dtype=np.uint8)
+    rec = 16 + f_size + 4 * (2 * a_size + 1)
+    assert ev.size % rec == 0
+    ev = ev.reshape(-1, rec)
+    hdr = ev[:, :16].copy().view(np.int32)
+    feats = ev[:, 16:16 + f_size]
+    fl = ev[:, 16 + f_size:].copy().view(np.float32)
+    mv = np.fromfile(os.path.join(d, "moves.bin"), dtype=np.uint8)
+    mrec = 4 * 9 + a_size * 28
+    assert mv.size % mrec == 0
+    mv = mv.reshape(-1, mrec)
+    mh_i = mv[:, :24].copy().view(np.int32)
+    mh_f = mv[:, 24:36].copy().view(np.float32)
+    ch = mv[:, 36:].copy().reshape(-1, a_size, 28)
+    return dict(
+        eval_cycle=hdr[:, 0], eval_game=hdr[:, 1], eval_rotation=hdr[:, 2].astype(np.uint8), eval_path_len=hdr[:, 3],
+        eval_features=np.packbits(feats, axis=1), eval_policy=fl[:, :a_size], eval_logits=fl[:, a_size:2 * a_size], eval_value=fl[:, 2 * a_size],
+        move_game=mh_i[:, 0], move_number=mh_i[:, 1], move_action=mh_i[:, 2], move_player=mh_i[:, 3], move_num_children=mh_i[:, 4], move_resign=mh_i[:, 5],
+        root_count=mh_f[:, 0], root_mean=mh_f[:, 1], root_value=mh_f[:, 2],
+        child_action=ch[:, :, 0:4].copy().view(np.int32)[..., 0],
+        child_count=ch[:, :, 4:8].copy().view(np.float32)[..., 0], child_mean=ch[:, :, 8:12].copy().view(np.float32)[..., 0],
+        child_policy=ch[:, :, 12:16].copy().view(np.float32)[..., 0], child_logit=ch[:, :, 16:20].copy().view(np.float32)[..., 0],
+        child_noise=ch[:, :, 20:24].copy().view(np.float32)[..., 0], child_value=ch[:, :, 24:28].copy().view(np.float32)[..., 0],
+    )
+
+
+def main(names):
+    os.makedirs(OUT, exist_ok=True)
+    for name in names:
+        binary, net, conf, max_moves = CASES[name]
+        with tempfile.TemporaryDirectory() as d:
+            conf_full = conf + ":nn_file_name=" + os.path.join(HERE, "_ref", "nets", net + ".pt")
+            res = subprocess.run([os.path.join(HERE, "_ref", "ref_stepper_" + binary), conf_full, d, str(max_moves)], check=True, capture_output=True, text=True)
+            meta = dict(line.split() for line in open(os.path.join(d, "meta.txt")))
+            data = read_case(d, int(meta["A"]), int(meta["F"]))
+            data.update(A=int(meta["A"]), F=int(meta["F"]), S=int(meta["S"]), B=int(meta["B"]), conf=conf, selfplay_lines=np.array(res.stdout.splitlines()))
+            np.savez_compressed(os.path.join(OUT, name + ".npz"), **data)
+            print(name, "evals", data["eval_game"].size, "moves", data["move_game"].size, "selfplay lines", len(res.stdout.splitlines()),
+                  os.path.getsize(os.path.join(OUT, name + ".npz")) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or list(CASES))

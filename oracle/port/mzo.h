@@ -1,0 +1,111 @@
+/*
+ * mzo — CPU restatement ("port") of MiniZero's batched-MCTS self-play hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY. This is the parity oracle for the CUDA path in minizero_b200/csrc.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load it; the product
+ * path never links, imports or executes anything under oracle/.
+ *
+ * Every function cites the reference file:line (relative to /root/reference/minizero) whose
+ * behaviour it restates. Pinned against outputs of the compiled reference itself
+ * (oracle/_ref/ref_stepper_*, fixtures under tests/golden/, generator oracle/gen_golden.py).
+ */
+#ifndef MZO_H
+#define MZO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MZO_GAME_TICTACTOE 0
+#define MZO_GAME_GO 1
+
+#define MZO_MAX_N 19
+#define MZO_MAX_CELLS (MZO_MAX_N * MZO_MAX_N)
+#define MZO_MAX_ACTIONS (MZO_MAX_CELLS + 1)
+#define MZO_MAX_MOVES (2 * MZO_MAX_CELLS + 2)
+#define MZO_HIST 8
+
+typedef struct {
+    int32_t game;           /* MZO_GAME_* */
+    int32_t board_size;     /* 3 for tictactoe, 2..19 for go */
+    int32_t num_games;      /* B */
+    int32_t num_simulation; /* actor_num_simulation (S); a search is S+1 evaluations */
+    float puct_base;        /* actor_mcts_puct_base */
+    float puct_init;        /* actor_mcts_puct_init */
+    float reward_discount;  /* actor_mcts_reward_discount */
+    float komi;             /* env_go_komi */
+    int32_t ko_situational; /* env_go_ko_rule == "situational" */
+    int32_t value_rescale;  /* actor_mcts_value_rescale */
+    float dirichlet_epsilon; /* actor_dirichlet_noise_epsilon (used when noise is supplied) */
+} mzo_config;
+
+/* ---- environment (environment/go/go.cpp, environment/tictactoe/tictactoe.cpp) ---- */
+typedef struct {
+    int32_t game, n, turn, num_moves;
+    float komi;
+    uint64_t turn_key, hash;
+    uint8_t board[MZO_MAX_CELLS];
+    uint8_t hist[MZO_HIST][MZO_MAX_CELLS]; /* ring: position after move i lives in hist[i % 8] */
+    int16_t actions[MZO_MAX_MOVES];
+    uint64_t hashes[MZO_MAX_MOVES];
+} mzo_env;
+
+void mzo_env_init(mzo_env* e, int game, int n, float komi, int ko_situational);
+int mzo_env_num_actions(const mzo_env* e);
+int mzo_env_input_channels(const mzo_env* e);
+int mzo_env_is_legal(const mzo_env* e, int action, int player);
+int mzo_env_act(mzo_env* e, int action, int player);
+int mzo_env_is_terminal(const mzo_env* e);
+float mzo_env_eval_score(const mzo_env* e, int is_resign);
+void mzo_env_features(const mzo_env* e, int rotation, float* out);
+int mzo_rotate_position(int rotation, int pos, int n);
+int mzo_reversed_rotation(int rotation);
+uint64_t mzo_go_key(int pos, int player);
+uint64_t mzo_mt19937_64_nth(uint64_t seed, int nth);
+
+/* ---- batched search (actor/mcts.cpp, actor/zero_actor.cpp) ---- */
+typedef struct mzo_batch mzo_batch;
+
+typedef struct {
+    int32_t num_children;
+    float count, mean, value;
+    int32_t action[MZO_MAX_ACTIONS];
+    float c_count[MZO_MAX_ACTIONS];
+    float c_mean[MZO_MAX_ACTIONS];
+    float c_policy[MZO_MAX_ACTIONS];
+    float c_logit[MZO_MAX_ACTIONS];
+    float c_noise[MZO_MAX_ACTIONS];
+    float c_value[MZO_MAX_ACTIONS];
+} mzo_root_out;
+
+mzo_batch* mzo_create(const mzo_config* cfg);
+void mzo_destroy(mzo_batch* b);
+void mzo_reset_game(mzo_batch* b, int g);
+/* ZeroActor::resetSearch for every game */
+void mzo_reset_search(mzo_batch* b, int g);
+/* ZeroActor::beforeNNEvaluation for every game: features [B][C*H*W], rotations [B] (NULL = none) */
+void mzo_select(mzo_batch* b, const uint8_t* rotations, float* features);
+/* ZeroActor::afterNNEvaluation for every game; noise [B][A] by child index (NULL = no noise) */
+void mzo_apply(mzo_batch* b, const float* policy, const float* logits, const float* value, const float* noise);
+int mzo_num_simulation_done(const mzo_batch* b, int g);
+int mzo_path_len(const mzo_batch* b, int g);
+void mzo_root(const mzo_batch* b, int g, mzo_root_out* out);
+const mzo_env* mzo_root_env(const mzo_batch* b, int g);
+/* BaseActor::act on the root environment; returns 1 if the move was legal and applied */
+int mzo_play(mzo_batch* b, int g, int action);
+int mzo_select_by_max_count(const mzo_batch* b, int g);
+
+/* ---- network forward, fp32 (network/py/alphazero_network.py, network_unit.py) ---- */
+typedef struct mzo_net mzo_net;
+mzo_net* mzo_net_create(int c, int h, int w, int hidden, int blocks, int actions, int value_hidden);
+void mzo_net_destroy(mzo_net* n);
+/* name = state_dict key; returns 0 on success */
+int mzo_net_set(mzo_net* n, const char* name, const float* data, int64_t numel);
+void mzo_net_forward(const mzo_net* n, const float* features, int batch, float* policy, float* logits, float* value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

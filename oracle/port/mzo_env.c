@@ -1,0 +1,404 @@
+/*
+ * Oracle port — environments (TicTacToe, Go). TEST INFRASTRUCTURE ONLY (see mzo.h).
+ *
+ * Restates, with plain arrays and flood fill instead of the reference's incremental
+ * block/area/Benson bookkeeping (which is not observable through legality, terminal test,
+ * score or features in plain Go):
+ *   environment/go/go.cpp:19-43     Zobrist keys from std::mt19937_64(0)
+ *   environment/go/go.cpp:132-190   act
+ *   environment/go/go.cpp:208-244   isLegalAction (suicide + positional/situational superko)
+ *   environment/go/go.cpp:246-257   isTerminal
+ *   environment/go/go.cpp:259-278,703-723  getEvalScore / Tromp-Taylor territory
+ *   environment/go/go.cpp:280-308   getFeatures (18 planes)
+ *   environment/tictactoe/tictactoe.cpp:11-146
+ *   utils/rotation.h:22-93          rotation tables
+ */
+#include "mzo.h"
+#include <string.h>
+
+/* ---- std::mt19937_64 (ISO C++ [rand.predef]; parameters of the 64-bit Mersenne twister) ---- */
+typedef struct {
+    uint64_t mt[312];
+    int idx;
+} mt64;
+
+static void mt64_seed(mt64* g, uint64_t seed)
+{
+    g->mt[0] = seed;
+    for (int i = 1; i < 312; ++i) { g->mt[i] = 6364136223846793005ULL * (g->mt[i - 1] ^ (g->mt[i - 1] >> 62)) + (uint64_t)i; }
+    g->idx = 312;
+}
+
+static uint64_t mt64_next(mt64* g)
+{
+    if (g->idx >= 312) {
+        for (int i = 0; i < 312; ++i) {
+            uint64_t x = (g->mt[i] & 0xFFFFFFFF80000000ULL) | (g->mt[(i + 1) % 312] & 0x7FFFFFFFULL);
+            uint64_t xa = x >> 1;
+            if (x & 1ULL) { xa ^= 0xB5026F5AA96619E9ULL; }
+            g->mt[i] = g->mt[(i + 156) % 312] ^ xa;
+        }
+        g->idx = 0;
+    }
+    uint64_t x = g->mt[g->idx++];
+    x ^= (x >> 29) & 0x5555555555555555ULL;
+    x ^= (x << 17) & 0x71D67FFFEDA60000ULL;
+    x ^= (x << 37) & 0xFFF7EEE000000000ULL;
+    x ^= (x >> 43);
+    return x;
+}
+
+uint64_t mzo_mt19937_64_nth(uint64_t seed, int nth)
+{
+    mt64 g;
+    mt64_seed(&g, seed);
+    uint64_t v = 0;
+    for (int i = 0; i <= nth; ++i) { v = mt64_next(&g); }
+    return v;
+}
+
+/* go.cpp:19-32: turn key, then for each of the 361 positions: empty, black, white */
+static uint64_t g_turn_key;
+static uint64_t g_grid_key[MZO_MAX_CELLS][3];
+static int g_keys_ready = 0;
+
+static void go_init_keys(void)
+{
+    if (g_keys_ready) { return; }
+    mt64 g;
+    mt64_seed(&g, 0);
+    g_turn_key = mt64_next(&g);
+    for (int pos = 0; pos < MZO_MAX_CELLS; ++pos) {
+        g_grid_key[pos][0] = mt64_next(&g);
+        g_grid_key[pos][1] = mt64_next(&g);
+        g_grid_key[pos][2] = mt64_next(&g);
+    }
+    g_keys_ready = 1;
+}
+
+uint64_t mzo_go_key(int pos, int player)
+{
+    go_init_keys();
+    return (pos < 0 ? g_turn_key : g_grid_key[pos][player]);
+}
+
+/* ---- rotation (utils/rotation.h:22-31 reversed table, :51-93 getPositionByRotating) ---- */
+int mzo_reversed_rotation(int r)
+{
+    static const int rev[8] = {0, 3, 2, 1, 4, 5, 6, 7};
+    return rev[r];
+}
+
+int mzo_rotate_position(int rotation, int pos, int n)
+{
+    if (pos == n * n) { return pos; }
+    /* doubled coordinates relative to the centre keep everything in integers */
+    int x = 2 * (pos % n) - (n - 1), y = 2 * (pos / n) - (n - 1), rx = x, ry = y;
+    switch (rotation) {
+        case 0: rx = x, ry = y; break;
+        case 1: rx = y, ry = -x; break;
+        case 2: rx = -x, ry = -y; break;
+        case 3: rx = -y, ry = x; break;
+        case 4: rx = x, ry = -y; break;
+        case 5: rx = -y, ry = -x; break;
+        case 6: rx = -x, ry = y; break;
+        case 7: rx = y, ry = x; break;
+    }
+    return ((ry + (n - 1)) / 2) * n + (rx + (n - 1)) / 2;
+}
+
+/* ---- common ---- */
+static int other(int p) { return p == 1 ? 2 : 1; }
+
+void mzo_env_init(mzo_env* e, int game, int n, float komi, int ko_situational)
+{
+    go_init_keys();
+    memset(e, 0, sizeof(*e));
+    e->game = game;
+    e->n = (game == MZO_GAME_TICTACTOE ? 3 : n);
+    e->turn = 1; /* go.cpp:105, tictactoe.cpp:13 */
+    e->komi = komi;
+    e->turn_key = (ko_situational ? g_turn_key : 0); /* go.cpp:45-49 */
+}
+
+int mzo_env_num_actions(const mzo_env* e) { return e->game == MZO_GAME_GO ? e->n * e->n + 1 : 9; }
+int mzo_env_input_channels(const mzo_env* e) { return e->game == MZO_GAME_GO ? 18 : 4; }
+
+/* neighbour order of go_grid.h:43-54: up(+n), right(+1), down(-n), left(-1) */
+static int neighbours(int n, int pos, int* out)
+{
+    int x = pos % n, y = pos / n, k = 0;
+    if (y + 1 < n) { out[k++] = pos + n; }
+    if (x + 1 < n) { out[k++] = pos + 1; }
+    if (y - 1 >= 0) { out[k++] = pos - n; }
+    if (x - 1 >= 0) { out[k++] = pos - 1; }
+    return k;
+}
+
+/* flood the block containing `start`; mark cells with `tag`; return #liberties and block hash */
+static int go_block(const mzo_env* e, int start, int* mark, int tag, int* cells, int* ncells, uint64_t* hash)
+{
+    int n = e->n, colour = e->board[start], top = 0, libs = 0, count = 0;
+    int stack[MZO_MAX_CELLS];
+    uint8_t libmark[MZO_MAX_CELLS];
+    memset(libmark, 0, (size_t)(n * n));
+    uint64_t h = 0;
+    stack[top++] = start;
+    mark[start] = tag;
+    while (top > 0) {
+        int p = stack[--top];
+        cells[count++] = p;
+        h ^= g_grid_key[p][colour];
+        int nb[4], k = neighbours(n, p, nb);
+        for (int i = 0; i < k; ++i) {
+            int q = nb[i];
+            if (e->board[q] == 0) {
+                if (!libmark[q]) {
+                    libmark[q] = 1;
+                    ++libs;
+                }
+            } else if (e->board[q] == colour && mark[q] != tag) {
+                mark[q] = tag;
+                stack[top++] = q;
+            }
+        }
+    }
+    *ncells = count;
+    *hash = h;
+    return libs;
+}
+
+static int hash_seen(const mzo_env* e, uint64_t h)
+{
+    for (int i = 0; i < e->num_moves; ++i) {
+        if (e->hashes[i] == h) { return 1; }
+    }
+    return 0;
+}
+
+static int go_is_legal(const mzo_env* e, int action, int player)
+{
+    int n = e->n;
+    if (action == n * n) { return 1; }                  /* go.cpp:213 */
+    if (action < 0 || action > n * n) { return 0; }
+    if (e->board[action] != 0) { return 0; }            /* go.cpp:218 */
+    int legal = 0;
+    uint64_t new_hash = e->hash ^ e->turn_key ^ g_grid_key[action][player]; /* go.cpp:222 */
+    int mark[MZO_MAX_CELLS];
+    memset(mark, 0, sizeof(int) * (size_t)(n * n));
+    int nb[4], k = neighbours(n, action, nb), cells[MZO_MAX_CELLS], nc;
+    for (int i = 0; i < k; ++i) {
+        int q = nb[i];
+        if (e->board[q] == 0) {
+            legal = 1; /* go.cpp:225-226 */
+            continue;
+        }
+        if (mark[q]) { continue; } /* block already examined, go.cpp:229 */
+        uint64_t bh;
+        int libs = go_block(e, q, mark, i + 1, cells, &nc, &bh);
+        if (e->board[q] == player) {
+            if (libs > 1) { legal = 1; } /* go.cpp:232-233 */
+        } else if (libs == 1) {          /* capture, go.cpp:235-238 */
+            new_hash ^= bh;
+            legal = 1;
+        }
+    }
+    return legal && !hash_seen(e, new_hash); /* go.cpp:243 */
+}
+
+static void push_history(mzo_env* e)
+{
+    memcpy(e->hist[e->num_moves % MZO_HIST], e->board, (size_t)(e->n * e->n));
+    e->hashes[e->num_moves] = e->hash;
+}
+
+static int go_act(mzo_env* e, int action, int player)
+{
+    if (!go_is_legal(e, action, player)) { return 0; } /* go.cpp:134 */
+    int n = e->n;
+    e->turn = other(player);   /* go.cpp:140 */
+    e->hash ^= e->turn_key;    /* go.cpp:141 */
+    e->actions[e->num_moves] = (int16_t)action;
+    if (action != n * n) {
+        e->board[action] = (uint8_t)player;
+        e->hash ^= g_grid_key[action][player]; /* go.cpp:154 */
+        int nb[4], k = neighbours(n, action, nb), cells[MZO_MAX_CELLS], nc;
+        int mark[MZO_MAX_CELLS];
+        memset(mark, 0, sizeof(int) * (size_t)(n * n));
+        for (int i = 0; i < k; ++i) {
+            int q = nb[i];
+            if (e->board[q] != other(player) || mark[q]) { continue; }
+            uint64_t bh;
+            int libs = go_block(e, q, mark, i + 1, cells, &nc, &bh);
+            if (libs == 0) { /* go.cpp:174, removeBlockFromBoard go.cpp:388-433 */
+                for (int c = 0; c < nc; ++c) { e->board[cells[c]] = 0; }
+                e->hash ^= bh;
+                /* cells are now empty: marks of removed stones must not suppress later blocks */
+            }
+        }
+    }
+    push_history(e); /* go.cpp:145-147,180-182 */
+    e->num_moves++;
+    return 1;
+}
+
+static int go_is_terminal(const mzo_env* e)
+{
+    int n2 = e->n * e->n, m = e->num_moves;
+    if (m >= 2 && e->actions[m - 1] == n2 && e->actions[m - 2] == n2) { return 1; } /* go.cpp:249-251 */
+    return m > 2 * n2;                                                                /* go.cpp:254 */
+}
+
+/* go.cpp:703-723 */
+static float go_eval_score(const mzo_env* e, int is_resign)
+{
+    int n = e->n, n2 = n * n, winner;
+    if (is_resign) {
+        winner = other(e->turn); /* go.cpp:262-263 */
+    } else {
+        float terr_b = 0.0f, terr_w = 0.0f;
+        int cb = 0, cw = 0;
+        for (int p = 0; p < n2; ++p) {
+            cb += (e->board[p] == 1);
+            cw += (e->board[p] == 2);
+        }
+        terr_b = (float)cb;
+        terr_w = (float)cw + e->komi; /* GamePair<float>(count, count + komi_) */
+        uint8_t seen[MZO_MAX_CELLS];
+        memset(seen, 0, (size_t)n2);
+        for (int s = 0; s < n2; ++s) {
+            if (e->board[s] != 0 || seen[s]) { continue; }
+            int stack[MZO_MAX_CELLS], top = 0, size = 0, touch_b = 0, touch_w = 0;
+            stack[top++] = s;
+            seen[s] = 1;
+            while (top > 0) {
+                int p = stack[--top];
+                ++size;
+                int nb[4], k = neighbours(n, p, nb);
+                for (int i = 0; i < k; ++i) {
+                    int q = nb[i];
+                    if (e->board[q] == 1) {
+                        touch_b = 1;
+                    } else if (e->board[q] == 2) {
+                        touch_w = 1;
+                    } else if (!seen[q]) {
+                        seen[q] = 1;
+                        stack[top++] = q;
+                    }
+                }
+            }
+            /* go.cpp:713-717: "surrounded only by black" is tested first and is also true for
+             * a region with no surrounding stones at all (empty board) */
+            if (!touch_w) {
+                terr_b += (float)size;
+            } else if (!touch_b) {
+                terr_w += (float)size;
+            }
+        }
+        winner = (terr_b > terr_w ? 1 : (terr_b < terr_w ? 2 : 0)); /* go.cpp:266-270 */
+    }
+    return winner == 1 ? 1.0f : (winner == 2 ? -1.0f : 0.0f);
+}
+
+/* go.cpp:280-308 */
+static void go_features(const mzo_env* e, int rotation, float* out)
+{
+    int n = e->n, n2 = n * n, rev = mzo_reversed_rotation(rotation);
+    for (int c = 0; c < 18; ++c) {
+        for (int pos = 0; pos < n2; ++pos) {
+            int rp = mzo_rotate_position(rev, pos, n);
+            float v = 0.0f;
+            if (c < 16) {
+                int idx = e->num_moves - 1 - c / 2;
+                if (idx >= 0) {
+                    int player = (c % 2 == 0 ? e->turn : other(e->turn));
+                    v = (e->hist[idx % MZO_HIST][rp] == player ? 1.0f : 0.0f);
+                }
+            } else if (c == 16) {
+                v = (e->turn == 1 ? 1.0f : 0.0f);
+            } else {
+                v = (e->turn == 2 ? 1.0f : 0.0f);
+            }
+            out[c * n2 + pos] = v;
+        }
+    }
+}
+
+/* ---- tictactoe (tictactoe.cpp:124-146 eval) ---- */
+static int ttt_eval(const mzo_env* e)
+{
+    const uint8_t* b = e->board;
+    int c;
+    for (int i = 0; i < 3; ++i) {
+        c = 3;
+        for (int j = 0; j < 3; ++j) { c &= b[i * 3 + j]; }
+        if (c) { return c; }
+        c = 3;
+        for (int j = 0; j < 3; ++j) { c &= b[j * 3 + i]; }
+        if (c) { return c; }
+    }
+    c = 3;
+    for (int i = 0; i < 3; ++i) { c &= b[i * 3 + i]; }
+    if (c) { return c; }
+    c = 3;
+    for (int i = 0; i < 3; ++i) { c &= b[i * 3 + (2 - i)]; }
+    return c;
+}
+
+int mzo_env_is_legal(const mzo_env* e, int action, int player)
+{
+    if (e->game == MZO_GAME_GO) { return go_is_legal(e, action, player); }
+    return action >= 0 && action < 9 && e->board[action] == 0; /* tictactoe.cpp:44-49 */
+}
+
+int mzo_env_act(mzo_env* e, int action, int player)
+{
+    if (e->game == MZO_GAME_GO) { return go_act(e, action, player); }
+    if (!mzo_env_is_legal(e, action, player)) { return 0; } /* tictactoe.cpp:19-26 */
+    e->actions[e->num_moves++] = (int16_t)action;
+    e->board[action] = (uint8_t)player;
+    e->turn = other(player);
+    return 1;
+}
+
+int mzo_env_is_terminal(const mzo_env* e)
+{
+    if (e->game == MZO_GAME_GO) { return go_is_terminal(e); }
+    if (ttt_eval(e) != 0) { return 1; } /* tictactoe.cpp:51-55 */
+    for (int i = 0; i < 9; ++i) {
+        if (e->board[i] == 0) { return 0; }
+    }
+    return 1;
+}
+
+float mzo_env_eval_score(const mzo_env* e, int is_resign)
+{
+    if (e->game == MZO_GAME_GO) { return go_eval_score(e, is_resign); }
+    int r = (is_resign ? other(e->turn) : ttt_eval(e)); /* tictactoe.cpp:57-65 */
+    return r == 1 ? 1.0f : (r == 2 ? -1.0f : 0.0f);
+}
+
+void mzo_env_features(const mzo_env* e, int rotation, float* out)
+{
+    if (e->game == MZO_GAME_GO) {
+        go_features(e, rotation, out);
+        return;
+    }
+    int rev = mzo_reversed_rotation(rotation); /* tictactoe.cpp:67-90 */
+    for (int c = 0; c < 4; ++c) {
+        for (int pos = 0; pos < 9; ++pos) {
+            int rp = mzo_rotate_position(rev, pos, 3);
+            float v;
+            if (c == 0) {
+                v = (e->board[rp] == e->turn);
+            } else if (c == 1) {
+                v = (e->board[rp] == other(e->turn));
+            } else if (c == 2) {
+                v = (e->turn == 1);
+            } else {
+                v = (e->turn == 2);
+            }
+            out[c * 9 + pos] = v;
+        }
+    }
+}

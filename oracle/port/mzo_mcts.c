@@ -1,0 +1,325 @@
+/*
+ * Oracle port — batched AlphaZero MCTS (PUCT select, expand, backup). TEST INFRASTRUCTURE ONLY
+ * (see mzo.h). Plain serial C, one game after another; arithmetic restated operation by
+ * operation, in the precision the compiled reference uses:
+ *
+ *   actor/mcts.cpp:20-28     MCTSNode::add                 -> node_add
+ *   actor/mcts.cpp:40-53     MCTSNode::getNormalizedMean   -> normalized_mean
+ *   actor/mcts.cpp:55-61     getNormalizedPUCTScore        -> puct_score
+ *   actor/mcts.cpp:91-104    selectChildByMaxCount         -> mzo_select_by_max_count
+ *   actor/mcts.cpp:139-148   selectFromNode                -> select_path
+ *   actor/mcts.cpp:151-164   expand                        -> expand
+ *   actor/mcts.cpp:166-179   backup                        -> backup
+ *   actor/mcts.cpp:181-198   selectChildByPUCTScore        -> select_child
+ *   actor/mcts.cpp:200-217   calculateInitQValue           -> init_q
+ *   actor/tree.h:64-77       Tree::reset / allocateNodes   -> tree_reset / cursor
+ *   actor/zero_actor.cpp:29-34   resetSearch (root action = (-1, previous player))
+ *   actor/zero_actor.cpp:51-72   beforeNNEvaluation        -> mzo_select
+ *   actor/zero_actor.cpp:74-98   afterNNEvaluation         -> mzo_apply
+ *   actor/zero_actor.cpp:194-204 addNoiseToNodeChildren (Dirichlet mix) -> in mzo_apply
+ *   actor/zero_actor.cpp:215-229 calculateAlphaZeroActionPolicy -> candidates
+ *   actor/zero_actor.cpp:247-252 getEnvironmentTransition  -> transition
+ *
+ * Build with -ffp-contract=off (oracle/Makefile): the reference is compiled for baseline
+ * x86-64 and therefore never fuses a multiply with an add.
+ *
+ * Candidate order: the reference sorts with std::sort (introsort, unstable). For distinct policy
+ * values every correct sort agrees; for exact ties this port is *stable* (ties keep ascending
+ * action id). Tests assert tie-freeness of every vector they compare (see tests/test_oracle_*.py).
+ */
+#include "mzo.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+    int32_t cursor; /* Tree::current_node_size_ */
+    int32_t* first_child;
+    int32_t* num_children;
+    int16_t* action;
+    uint8_t* player;
+    float *count, *mean, *policy, *logit, *noise, *value, *reward;
+} tree;
+
+struct mzo_batch {
+    mzo_config cfg;
+    int A, F, NP;
+    mzo_env* root_env;
+    mzo_env* leaf_env;
+    tree* trees;
+    int32_t* path;     /* [B][S+2] */
+    int32_t* path_len; /* [B] */
+    uint8_t* rotation; /* [B] */
+};
+
+static int other(int p) { return p == 1 ? 2 : 1; }
+
+static void node_reset(tree* t, int i)
+{
+    t->num_children[i] = 0;
+    t->first_child[i] = -1;
+    t->mean[i] = t->count[i] = t->policy[i] = t->logit[i] = t->noise[i] = t->value[i] = t->reward[i] = 0.0f;
+}
+
+static void tree_reset(tree* t)
+{
+    t->cursor = 1;
+    node_reset(t, 0);
+}
+
+mzo_batch* mzo_create(const mzo_config* cfg)
+{
+    mzo_batch* b = (mzo_batch*)calloc(1, sizeof(mzo_batch));
+    b->cfg = *cfg;
+    mzo_env tmp;
+    mzo_env_init(&tmp, cfg->game, cfg->board_size, cfg->komi, cfg->ko_situational);
+    b->A = mzo_env_num_actions(&tmp);
+    b->F = mzo_env_input_channels(&tmp) * tmp.n * tmp.n;
+    b->NP = 1 + (cfg->num_simulation + 1) * b->A; /* actor_group.cpp:183, tree.h:66 */
+    int B = cfg->num_games;
+    b->root_env = (mzo_env*)calloc((size_t)B, sizeof(mzo_env));
+    b->leaf_env = (mzo_env*)calloc((size_t)B, sizeof(mzo_env));
+    b->trees = (tree*)calloc((size_t)B, sizeof(tree));
+    b->path = (int32_t*)calloc((size_t)B * (size_t)(cfg->num_simulation + 2), sizeof(int32_t));
+    b->path_len = (int32_t*)calloc((size_t)B, sizeof(int32_t));
+    b->rotation = (uint8_t*)calloc((size_t)B, 1);
+    for (int g = 0; g < B; ++g) {
+        tree* t = &b->trees[g];
+        size_t n = (size_t)b->NP;
+        t->first_child = (int32_t*)malloc(n * 4);
+        t->num_children = (int32_t*)malloc(n * 4);
+        t->action = (int16_t*)malloc(n * 2);
+        t->player = (uint8_t*)malloc(n);
+        t->count = (float*)malloc(n * 4);
+        t->mean = (float*)malloc(n * 4);
+        t->policy = (float*)malloc(n * 4);
+        t->logit = (float*)malloc(n * 4);
+        t->noise = (float*)malloc(n * 4);
+        t->value = (float*)malloc(n * 4);
+        t->reward = (float*)malloc(n * 4);
+        mzo_reset_game(b, g);
+    }
+    return b;
+}
+
+void mzo_destroy(mzo_batch* b)
+{
+    if (!b) { return; }
+    for (int g = 0; g < b->cfg.num_games; ++g) {
+        tree* t = &b->trees[g];
+        free(t->first_child), free(t->num_children), free(t->action), free(t->player);
+        free(t->count), free(t->mean), free(t->policy), free(t->logit), free(t->noise), free(t->value), free(t->reward);
+    }
+    free(b->root_env), free(b->leaf_env), free(b->trees), free(b->path), free(b->path_len), free(b->rotation);
+    free(b);
+}
+
+/* ZeroActor::resetSearch, zero_actor.cpp:29-34 */
+void mzo_reset_search(mzo_batch* b, int g)
+{
+    tree* t = &b->trees[g];
+    tree_reset(t);
+    t->action[0] = -1;
+    t->player[0] = (uint8_t)other(b->root_env[g].turn); /* previous player of a 2-player game */
+    b->path_len[g] = 0;
+}
+
+/* BaseActor::reset, base_actor.cpp:8-13 */
+void mzo_reset_game(mzo_batch* b, int g)
+{
+    mzo_env_init(&b->root_env[g], b->cfg.game, b->cfg.board_size, b->cfg.komi, b->cfg.ko_situational);
+    mzo_reset_search(b, g);
+}
+
+/* mcts.cpp:40-53 with virtual_loss_ == 0 kept as an explicit term (self-play never sets it) */
+static float normalized_mean(const mzo_batch* b, const tree* t, int i)
+{
+    float value = t->reward[i] + b->cfg.reward_discount * t->mean[i];
+    /* actor_mcts_value_rescale is only used by Atari (mcts.cpp:43-49); not in this port's games */
+    if (t->player[i] == 2) { value = -value; } /* actor_mcts_value_flipping_player == 'W' */
+    const float vloss = 0.0f;
+    value = (value * t->count[i] - vloss) / (t->count[i] + vloss);
+    return value;
+}
+
+/* mcts.cpp:55-61 */
+static float puct_score(const mzo_batch* b, const tree* t, int i, int total_simulation, float init_q_value)
+{
+    float tt = (float)(1 + total_simulation) + b->cfg.puct_base;
+    tt = tt / b->cfg.puct_base;
+    float puct_bias = (float)((double)b->cfg.puct_init + log((double)tt));
+    float bp = puct_bias * t->policy[i];
+    float value_u = (float)(((double)bp * sqrt((double)total_simulation)) / (double)(1.0f + t->count[i]));
+    float value_q = (t->count[i] == 0.0f ? init_q_value : normalized_mean(b, t, i));
+    return value_u + value_q;
+}
+
+/* mcts.cpp:200-217 (board-game branch) */
+static float init_q(const mzo_batch* b, const tree* t, int node)
+{
+    float sum_of_win = 0.0f, sum = 0.0f;
+    for (int k = 0; k < t->num_children[node]; ++k) {
+        int c = t->first_child[node] + k;
+        if (t->count[c] == 0.0f) { continue; }
+        sum_of_win += normalized_mean(b, t, c);
+        sum += 1;
+    }
+    return (sum_of_win - 1) / (sum + 1);
+}
+
+/* mcts.cpp:181-198 */
+static int select_child(const mzo_batch* b, const tree* t, int node)
+{
+    int total_simulation = (int)(t->count[node] - 1);
+    float iq = init_q(b, t, node);
+    float best_score = -3.402823466e+38f, best_policy = -3.402823466e+38f;
+    int selected = -1;
+    for (int k = 0; k < t->num_children[node]; ++k) {
+        int c = t->first_child[node] + k;
+        float score = puct_score(b, t, c, total_simulation, iq);
+        if (score < best_score || (score == best_score && t->policy[c] <= best_policy)) { continue; }
+        best_score = score;
+        best_policy = t->policy[c];
+        selected = c;
+    }
+    return selected;
+}
+
+/* ZeroActor::beforeNNEvaluation, zero_actor.cpp:51-58 */
+void mzo_select(mzo_batch* b, const uint8_t* rotations, float* features)
+{
+    int S2 = b->cfg.num_simulation + 2;
+    for (int g = 0; g < b->cfg.num_games; ++g) {
+        tree* t = &b->trees[g];
+        int32_t* path = b->path + (size_t)g * S2;
+        int len = 0, node = 0;
+        path[len++] = 0;
+        while (t->num_children[node] > 0) { /* mcts.cpp:139-148 */
+            node = select_child(b, t, node);
+            path[len++] = node;
+        }
+        b->path_len[g] = len;
+        /* getEnvironmentTransition, zero_actor.cpp:247-252 */
+        mzo_env* e = &b->leaf_env[g];
+        *e = b->root_env[g];
+        for (int i = 1; i < len; ++i) { mzo_env_act(e, t->action[path[i]], t->player[path[i]]); }
+        b->rotation[g] = (rotations ? rotations[g] : 0);
+        if (features) { mzo_env_features(e, b->rotation[g], features + (size_t)g * b->F); }
+    }
+}
+
+/* mcts.cpp:20-28 with weight 1 */
+static void node_add(tree* t, int i, float value)
+{
+    t->count[i] += 1.0f;
+    t->mean[i] += 1.0f * (value - t->mean[i]) / t->count[i];
+}
+
+/* ZeroActor::afterNNEvaluation, zero_actor.cpp:74-98 (AlphaZero branch) */
+void mzo_apply(mzo_batch* b, const float* policy, const float* logits, const float* value, const float* noise)
+{
+    int S2 = b->cfg.num_simulation + 2, A = b->A;
+    for (int g = 0; g < b->cfg.num_games; ++g) {
+        tree* t = &b->trees[g];
+        const int32_t* path = b->path + (size_t)g * S2;
+        int len = b->path_len[g];
+        if (len == 0) { continue; }
+        int leaf = path[len - 1];
+        const mzo_env* e = &b->leaf_env[g];
+        float v;
+        if (!mzo_env_is_terminal(e)) {
+            /* calculateAlphaZeroActionPolicy, zero_actor.cpp:215-229 */
+            int cand_a[MZO_MAX_ACTIONS], k = 0;
+            float cand_p[MZO_MAX_ACTIONS], cand_l[MZO_MAX_ACTIONS];
+            for (int a = 0; a < A; ++a) {
+                if (!mzo_env_is_legal(e, a, e->turn)) { continue; }
+                int ra = (e->game == MZO_GAME_GO || e->game == MZO_GAME_TICTACTOE ? mzo_rotate_position(b->rotation[g], a, e->n) : a);
+                float p = policy[(size_t)g * A + ra], l = logits[(size_t)g * A + ra];
+                int j = k++; /* stable insertion: descending policy, ties keep action order */
+                while (j > 0 && cand_p[j - 1] < p) {
+                    cand_a[j] = cand_a[j - 1], cand_p[j] = cand_p[j - 1], cand_l[j] = cand_l[j - 1];
+                    --j;
+                }
+                cand_a[j] = a, cand_p[j] = p, cand_l[j] = l;
+            }
+            /* expand, mcts.cpp:151-164 */
+            t->first_child[leaf] = t->cursor;
+            t->num_children[leaf] = k;
+            for (int i = 0; i < k; ++i) {
+                int c = t->cursor + i;
+                node_reset(t, c);
+                t->action[c] = (int16_t)cand_a[i];
+                t->player[c] = (uint8_t)e->turn;
+                t->policy[c] = cand_p[i];
+                t->logit[c] = cand_l[i];
+            }
+            t->cursor += k;
+            v = value[g];
+        } else {
+            v = mzo_env_eval_score(e, 0);
+        }
+        /* backup, mcts.cpp:166-179; env reward is 0 for these games (go.h:50, tictactoe.h:25) */
+        float updated = v;
+        t->value[leaf] = v;
+        t->reward[leaf] = 0.0f;
+        for (int i = len - 1; i >= 0; --i) {
+            int n = path[i];
+            node_add(t, n, updated);
+            updated = t->reward[n] + b->cfg.reward_discount * updated;
+        }
+        /* addNoiseToNodeChildren, zero_actor.cpp:194-204: only when the evaluated leaf is the root */
+        if (leaf == 0 && noise && t->num_children[0] > 0) {
+            const float eps = b->cfg.dirichlet_epsilon;
+            for (int i = 0; i < t->num_children[0]; ++i) {
+                int c = t->first_child[0] + i;
+                float nz = noise[(size_t)g * A + i];
+                t->noise[c] = nz;
+                t->policy[c] = (1 - eps) * t->policy[c] + eps * nz;
+            }
+        }
+        b->path_len[g] = 0;
+    }
+}
+
+int mzo_num_simulation_done(const mzo_batch* b, int g) { return (int)b->trees[g].count[0]; }
+int mzo_path_len(const mzo_batch* b, int g) { return b->path_len[g]; }
+const mzo_env* mzo_root_env(const mzo_batch* b, int g) { return &b->root_env[g]; }
+
+void mzo_root(const mzo_batch* b, int g, mzo_root_out* out)
+{
+    const tree* t = &b->trees[g];
+    memset(out, 0, sizeof(*out));
+    out->num_children = t->num_children[0];
+    out->count = t->count[0], out->mean = t->mean[0], out->value = t->value[0];
+    for (int i = 0; i < b->A; ++i) { out->action[i] = -1; }
+    for (int i = 0; i < t->num_children[0]; ++i) {
+        int c = t->first_child[0] + i;
+        out->action[i] = t->action[c];
+        out->c_count[i] = t->count[c], out->c_mean[i] = t->mean[c], out->c_policy[i] = t->policy[c];
+        out->c_logit[i] = t->logit[c], out->c_noise[i] = t->noise[c], out->c_value[i] = t->value[c];
+    }
+}
+
+/* mcts.cpp:91-104: first child with the strictly largest count */
+int mzo_select_by_max_count(const mzo_batch* b, int g)
+{
+    const tree* t = &b->trees[g];
+    float max_count = 0.0f;
+    int selected = -1;
+    for (int i = 0; i < t->num_children[0]; ++i) {
+        int c = t->first_child[0] + i;
+        if (t->count[c] <= max_count) { continue; }
+        max_count = t->count[c];
+        selected = t->action[c];
+    }
+    return selected;
+}
+
+/* BaseActor::act (base_actor.cpp:22-30) + SlaveThread::handleSearchDone's resetSearch (actor_group.cpp:116-134) */
+int mzo_play(mzo_batch* b, int g, int action)
+{
+    mzo_env* e = &b->root_env[g];
+    int ok = mzo_env_act(e, action, e->turn);
+    if (ok) { mzo_reset_search(b, g); }
+    return ok;
+}

@@ -1,0 +1,72 @@
+"""Replays a golden case (tests/golden/*.npz, recorded from the compiled reference) through any
+search engine exposing select/apply/root/play — the CPU oracle or the CUDA path — and checks, bit
+for bit, the feature planes of every leaf evaluation and the root child table of every move."""
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def assert_tie_free(case):
+    """std::sort is unstable; child order is only implementation-independent without exact policy ties."""
+    for m in range(case["move_game"].size):
+        k = int(case["move_num_children"][m])
+        noise = case["child_noise"][m, :k]
+        if np.any(noise != 0):
+            continue  # policies were mixed with noise after sorting; order not checkable from the table
+        p = case["child_policy"][m, :k]
+        assert np.all(p[:-1] > p[1:]), "exact policy tie in golden vector"
+
+
+def replay(engine, case, check_features=True):
+    A, F, S, B = (int(case[k]) for k in "AFSB")
+    n_evals = case["eval_game"].size
+    n_cycles = n_evals // B
+    next_move = 0
+    moves_of_game = {g: [m for m in range(case["move_game"].size) if case["move_game"][m] == g] for g in range(B)}
+    move_ptr = {g: 0 for g in range(B)}
+    checked_moves = 0
+    for c in range(n_cycles):
+        sl = slice(c * B, (c + 1) * B)
+        assert np.all(case["eval_game"][sl] == np.arange(B))
+        feats = engine.select(case["eval_rotation"][sl])
+        if check_features:
+            want = np.unpackbits(case["eval_features"][sl], axis=1)[:, :F].astype(np.float32)
+            assert np.array_equal(feats, want), f"feature mismatch at cycle {c}"
+        for g in range(B):
+            assert engine.path_len(g) == case["eval_path_len"][sl][g], f"path length mismatch cycle {c} game {g}"
+        use_noise = bool(np.any(case["child_noise"] != 0))  # actor_use_dirichlet_noise in the recording
+        noise = np.zeros((B, A), np.float32) if use_noise else None
+        for g in range(B if use_noise else 0):
+            if engine.sims_done(g) == 0 and move_ptr[g] < len(moves_of_game[g]):
+                noise[g] = case["child_noise"][moves_of_game[g][move_ptr[g]]]
+        engine.apply(case["eval_policy"][sl], case["eval_logits"][sl], case["eval_value"][sl], noise)
+        for g in range(B):
+            if engine.sims_done(g) != S + 1:
+                continue
+            if move_ptr[g] >= len(moves_of_game[g]):
+                return checked_moves  # recording stopped here
+            m = moves_of_game[g][move_ptr[g]]
+            move_ptr[g] += 1
+            r = engine.root(g)
+            k = int(case["move_num_children"][m])
+            assert r["num_children"] == k
+            assert r["root_count"] == case["root_count"][m] and r["root_mean"] == case["root_mean"][m] and r["root_value"] == case["root_value"][m]
+            assert np.array_equal(r["action"][:k], case["child_action"][m, :k])
+            for name in ("count", "mean", "policy", "logit", "noise", "value"):
+                got, want = r[name][:k], case["child_" + name][m, :k]
+                assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"root child {name} mismatch at move {m}"
+            checked_moves += 1
+            if case["move_resign"][m]:
+                engine.reset_game(g)
+            else:
+                assert engine.play(g, int(case["move_action"][m])) == 1
+                if engine.root_terminal(g):
+                    engine.reset_game(g)
+    return checked_moves

@@ -1,0 +1,120 @@
+"""ctypes binding of the CPU oracle (oracle/port/*.c -> oracle/liboracle.so). TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MAX_ACTIONS = 19 * 19 + 1
+GAME_TICTACTOE, GAME_GO = 0, 1
+
+
+class Config(C.Structure):
+    _fields_ = [("game", C.c_int32), ("board_size", C.c_int32), ("num_games", C.c_int32), ("num_simulation", C.c_int32),
+                ("puct_base", C.c_float), ("puct_init", C.c_float), ("reward_discount", C.c_float), ("komi", C.c_float),
+                ("ko_situational", C.c_int32), ("value_rescale", C.c_int32), ("dirichlet_epsilon", C.c_float)]
+
+
+class RootOut(C.Structure):
+    _fields_ = [("num_children", C.c_int32), ("count", C.c_float), ("mean", C.c_float), ("value", C.c_float),
+                ("action", C.c_int32 * MAX_ACTIONS)] + [(n, C.c_float * MAX_ACTIONS) for n in ("c_count", "c_mean", "c_policy", "c_logit", "c_noise", "c_value")]
+
+
+def default_config(game, board_size, num_games, num_simulation):
+    # defaults of config/configuration.cpp:13-28,80
+    return Config(game, board_size, num_games, num_simulation, 19652.0, 1.25, 1.0, 7.5, 0, 0, 0.25)
+
+
+def load():
+    so = os.path.join(ROOT, "oracle", "liboracle.so")
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"], check=True)
+    lib = C.CDLL(so)
+    vp, i32, f32p, u8p = C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_uint8)
+    lib.mzo_create.restype = vp
+    lib.mzo_create.argtypes = [C.POINTER(Config)]
+    lib.mzo_destroy.argtypes = [vp]
+    lib.mzo_reset_game.argtypes = [vp, i32]
+    lib.mzo_reset_search.argtypes = [vp, i32]
+    lib.mzo_select.argtypes = [vp, u8p, f32p]
+    lib.mzo_apply.argtypes = [vp, f32p, f32p, f32p, f32p]
+    lib.mzo_num_simulation_done.argtypes = [vp, i32]
+    lib.mzo_path_len.argtypes = [vp, i32]
+    lib.mzo_root.argtypes = [vp, i32, C.POINTER(RootOut)]
+    lib.mzo_root_env.restype = vp
+    lib.mzo_root_env.argtypes = [vp, i32]
+    lib.mzo_play.argtypes = [vp, i32, i32]
+    lib.mzo_select_by_max_count.argtypes = [vp, i32]
+    lib.mzo_env_is_terminal.argtypes = [vp]
+    lib.mzo_env_is_legal.argtypes = [vp, i32, i32]
+    lib.mzo_env_eval_score.restype = C.c_float
+    lib.mzo_env_eval_score.argtypes = [vp, i32]
+    lib.mzo_net_create.restype = vp
+    lib.mzo_net_create.argtypes = [i32] * 7
+    lib.mzo_net_destroy.argtypes = [vp]
+    lib.mzo_net_set.argtypes = [vp, C.c_char_p, f32p, C.c_int64]
+    lib.mzo_net_forward.argtypes = [vp, f32p, i32, f32p, f32p, f32p]
+    return lib
+
+
+def fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def u8ptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+class OracleSearch:
+    """Thin numpy front-end over mzo_batch."""
+
+    def __init__(self, lib, game, board_size, num_games, num_simulation, **overrides):
+        self.lib = lib
+        self.cfg = default_config(game, board_size, num_games, num_simulation)
+        for k, v in overrides.items():
+            setattr(self.cfg, k, v)
+        self.h = lib.mzo_create(C.byref(self.cfg))
+        n = 3 if game == GAME_TICTACTOE else board_size
+        self.A = 9 if game == GAME_TICTACTOE else n * n + 1
+        self.F = (4 if game == GAME_TICTACTOE else 18) * n * n
+        self.B, self.S = num_games, num_simulation
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.mzo_destroy(self.h)
+            self.h = None
+
+    def select(self, rotations=None):
+        feats = np.zeros((self.B, self.F), np.float32)
+        rot = None if rotations is None else np.ascontiguousarray(rotations, np.uint8)
+        self.lib.mzo_select(self.h, None if rot is None else u8ptr(rot), fptr(feats))
+        return feats
+
+    def apply(self, policy, logits, value, noise=None):
+        p, l, v = (np.ascontiguousarray(x, np.float32) for x in (policy, logits, value))
+        nz = None if noise is None else np.ascontiguousarray(noise, np.float32)
+        self.lib.mzo_apply(self.h, fptr(p), fptr(l), fptr(v), None if nz is None else fptr(nz))
+
+    def sims_done(self, g):
+        return self.lib.mzo_num_simulation_done(self.h, g)
+
+    def path_len(self, g):
+        return self.lib.mzo_path_len(self.h, g)
+
+    def root(self, g):
+        out = RootOut()
+        self.lib.mzo_root(self.h, g, C.byref(out))
+        k = out.num_children
+        d = dict(num_children=k, root_count=out.count, root_mean=out.mean, root_value=out.value, action=np.array(out.action[:self.A], np.int32))
+        for n in ("c_count", "c_mean", "c_policy", "c_logit", "c_noise", "c_value"):
+            d[n[2:]] = np.array(getattr(out, n)[:self.A], np.float32)
+        return d
+
+    def play(self, g, action):
+        return self.lib.mzo_play(self.h, g, action)
+
+    def root_terminal(self, g):
+        return bool(self.lib.mzo_env_is_terminal(self.lib.mzo_root_env(self.h, g)))
+
+    def reset_game(self, g):
+        self.lib.mzo_reset_game(self.h, g)

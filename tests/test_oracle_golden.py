@@ -1,0 +1,52 @@
+"""The CPU oracle restatement (oracle/port) against vectors recorded from the compiled reference."""
+import numpy as np
+import pytest
+
+import golden_replay
+import oracle_lib
+
+CASES = {
+    "ttt_s50_b2": (oracle_lib.GAME_TICTACTOE, 3),
+    "ttt_s50_b1_det": (oracle_lib.GAME_TICTACTOE, 3),
+    "go5_s24_b2": (oracle_lib.GAME_GO, 5),
+    "go9_s32_b2": (oracle_lib.GAME_GO, 9),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_matches_reference_recording(oracle, name):
+    game, n = CASES[name]
+    case = golden_replay.load_case(name)
+    golden_replay.assert_tie_free(case)
+    eng = oracle_lib.OracleSearch(oracle, game, n, int(case["B"]), int(case["S"]))
+    checked = golden_replay.replay(eng, case)
+    assert checked >= case["move_game"].size - int(case["B"])
+
+
+@pytest.mark.parametrize("name,net,dims", [
+    ("ttt_s50_b2", "ttt_az_2bx32", (4, 3, 3, 32, 2, 9, 256)),
+    ("go5_s24_b2", "go5_az_1bx16", (18, 5, 5, 16, 1, 26, 64)),
+])
+def test_oracle_net_matches_reference_outputs(oracle, name, net, dims):
+    """fp32 restatement of the network vs the outputs the reference's TorchScript forward produced."""
+    import os
+    torch = pytest.importorskip("torch")
+    path = os.path.join(oracle_lib.ROOT, "oracle", "_ref", "nets", net + ".pt")
+    if not os.path.exists(path):
+        pytest.skip("net fixture not generated (oracle/gen_nets.py needs /root/reference)")
+    case = golden_replay.load_case(name)
+    sd = torch.jit.load(path).state_dict()
+    h = oracle.mzo_net_create(*dims)
+    for k, v in sd.items():
+        if k.endswith("num_batches_tracked"):
+            continue
+        a = np.ascontiguousarray(v.float().numpy())
+        assert oracle.mzo_net_set(h, k.encode(), oracle_lib.fptr(a), a.size) == 0
+    n, A, F = 64, int(case["A"]), int(case["F"])
+    feats = np.unpackbits(case["eval_features"][:n], axis=1)[:, :F].astype(np.float32)
+    pol, lg, val = np.zeros((n, A), np.float32), np.zeros((n, A), np.float32), np.zeros(n, np.float32)
+    oracle.mzo_net_forward(h, oracle_lib.fptr(feats), n, oracle_lib.fptr(pol), oracle_lib.fptr(lg), oracle_lib.fptr(val))
+    oracle.mzo_net_destroy(h)
+    assert np.abs(lg - case["eval_logits"][:n]).max() < 1e-5
+    assert np.abs(pol - case["eval_policy"][:n]).max() < 1e-6
+    assert np.abs(val - case["eval_value"][:n]).max() < 1e-5
