@@ -1,0 +1,782 @@
+// Warp-per-tree search core: PUCT selection, leaf environment transition (Go / TicTacToe rules on
+// row bitboards), feature packing, expansion and backup over a flat node pool.
+//
+// One warp owns one game (tree + environment). All functions are written against a tiny warp
+// abstraction (MZ_W lanes, ballot / any / butterfly reductions, lane-strided loops, flood fills
+// iterated to their unique fixpoint) so that the same source also compiles as plain C++ with
+// MZ_W == 1. That second build (tests/hostsim) exists ONLY so the CPU test-suite can check this
+// file's logic against the recordings of the reference before GPU time is spent; it is never
+// linked into libmzb200.so, whose entry points fail loudly without a CUDA device.
+//
+// Reference behaviour restated here (paths relative to /root/reference/minizero):
+//   actor/mcts.cpp:20-28,40-61,139-217   node update, normalised mean, PUCT score, selection, init-Q
+//   actor/mcts.cpp:151-179               expand, backup
+//   actor/zero_actor.cpp:51-98           beforeNNEvaluation / afterNNEvaluation (AlphaZero branch)
+//   actor/zero_actor.cpp:194-229,247-252 root noise mix, legal-filtered sorted candidates, env transition
+//   environment/go/go.cpp:132-308,690-723  act, isLegalAction (superko), isTerminal, Tromp-Taylor, features
+//   environment/tictactoe/tictactoe.cpp:19-146
+//   utils/rotation.h:22-93
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(MZ_HOSTSIM)
+#define MZ_DEV __device__ __forceinline__
+#define MZ_W 32
+#define MZ_FULL 0xffffffffu
+MZ_DEV unsigned mz_ballot(int p) { return __ballot_sync(MZ_FULL, p); }
+MZ_DEV int mz_any(int p) { return __any_sync(MZ_FULL, p); }
+MZ_DEV void mz_sync() { __syncwarp(); }
+MZ_DEV float mz_fmul(float a, float b) { return __fmul_rn(a, b); }
+MZ_DEV float mz_fadd(float a, float b) { return __fadd_rn(a, b); }
+MZ_DEV float mz_fsub(float a, float b) { return __fsub_rn(a, b); }
+MZ_DEV float mz_fdiv(float a, float b) { return __fdiv_rn(a, b); }
+MZ_DEV double mz_dmul(double a, double b) { return __dmul_rn(a, b); }
+MZ_DEV double mz_ddiv(double a, double b) { return __ddiv_rn(a, b); }
+MZ_DEV double mz_dsqrt(double a) { return __dsqrt_rn(a); }
+MZ_DEV int mz_popc(uint32_t x) { return __popc(x); }
+MZ_DEV int mz_ffs0(uint32_t x) { return __ffs(x) - 1; }
+MZ_DEV int mz_reduce_add(int v)
+{
+    for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(MZ_FULL, v, o); }
+    return v;
+}
+MZ_DEV uint32_t mz_reduce_or(uint32_t v)
+{
+    for (int o = 16; o > 0; o >>= 1) { v |= __shfl_xor_sync(MZ_FULL, v, o); }
+    return v;
+}
+MZ_DEV int mz_reduce_min(int v)
+{
+    for (int o = 16; o > 0; o >>= 1) { v = min(v, __shfl_xor_sync(MZ_FULL, v, o)); }
+    return v;
+}
+MZ_DEV uint64_t mz_reduce_xor64(uint64_t v)
+{
+    for (int o = 16; o > 0; o >>= 1) { v ^= __shfl_xor_sync(MZ_FULL, v, o); }
+    return v;
+}
+// lexicographic arg-max over (score desc, policy desc, index asc): the order-independent form of
+// the serial scan in mcts.cpp:187-194 (replace when score > best, or score == best and policy > best)
+MZ_DEV void mz_reduce_best(float& s, float& p, int& i)
+{
+    for (int o = 16; o > 0; o >>= 1) {
+        float s2 = __shfl_xor_sync(MZ_FULL, s, o), p2 = __shfl_xor_sync(MZ_FULL, p, o);
+        int i2 = __shfl_xor_sync(MZ_FULL, i, o);
+        bool take = (i2 >= 0) && (i < 0 || s2 > s || (s2 == s && (p2 > p || (p2 == p && i2 < i))));
+        if (take) { s = s2, p = p2, i = i2; }
+    }
+}
+struct __align__(16) mz_hot {
+    float count, mean, policy;
+    uint32_t link;
+};
+MZ_DEV mz_hot mz_load_hot(const mz_hot* p)
+{
+    float4 v = *reinterpret_cast<const float4*>(p);
+    mz_hot h;
+    h.count = v.x, h.mean = v.y, h.policy = v.z, h.link = __float_as_uint(v.w);
+    return h;
+}
+MZ_DEV void mz_store_hot(mz_hot* p, float count, float mean, float policy, uint32_t link)
+{
+    *reinterpret_cast<float4*>(p) = make_float4(count, mean, policy, __uint_as_float(link));
+}
+#else
+#include <math.h>
+#define MZ_DEV static inline
+#define MZ_W 1
+static inline unsigned mz_ballot(int p) { return p ? 1u : 0u; }
+static inline int mz_any(int p) { return p; }
+static inline void mz_sync() {}
+static inline float mz_fmul(float a, float b) { return a * b; }
+static inline float mz_fadd(float a, float b) { return a + b; }
+static inline float mz_fsub(float a, float b) { return a - b; }
+static inline float mz_fdiv(float a, float b) { return a / b; }
+static inline double mz_dmul(double a, double b) { return a * b; }
+static inline double mz_ddiv(double a, double b) { return a / b; }
+static inline double mz_dsqrt(double a) { return sqrt(a); }
+static inline int mz_popc(uint32_t x) { return __builtin_popcount(x); }
+static inline int mz_ffs0(uint32_t x) { return __builtin_ffs((int)x) - 1; }
+static inline int mz_reduce_add(int v) { return v; }
+static inline uint32_t mz_reduce_or(uint32_t v) { return v; }
+static inline int mz_reduce_min(int v) { return v; }
+static inline uint64_t mz_reduce_xor64(uint64_t v) { return v; }
+static inline void mz_reduce_best(float&, float&, int&) {}
+struct alignas(16) mz_hot {
+    float count, mean, policy;
+    uint32_t link;
+};
+static inline mz_hot mz_load_hot(const mz_hot* p) { return *p; }
+static inline void mz_store_hot(mz_hot* p, float count, float mean, float policy, uint32_t link)
+{
+    p->count = count, p->mean = mean, p->policy = policy, p->link = link;
+}
+#endif
+
+#define MZ_GAME_TICTACTOE 0
+#define MZ_GAME_GO 1
+#define MZ_MAXN 19
+#define MZ_MAXA (MZ_MAXN * MZ_MAXN + 1)
+#define MZ_ROWS 32           // row slots per bitboard (N <= 19 used)
+#define MZ_HIST 8            // positions kept for the feature planes (go.cpp:291-299)
+#define MZ_LEGAL_WORDS 12    // ceil(362 / 32)
+#define MZ_LINK_SHIFT 20     // link = first_child | num_children << 20
+#define MZ_NN_CPAD 64        // input channels of the first conv, padded to one K block
+#define MZ_HALF_ONE 0x3C00   // fp16 1.0
+
+struct mz_dims {
+    int game, N, A, C, S, NP, B;
+    int slots;      // NN rows per board: (N + 1) * (N + 1)   (one shared zero column / row, see nn_conv.cu)
+    int max_hashes; // per game: 2 * N * N + 4
+    float puct_init, puct_base, discount, komi, eps;
+    uint64_t turn_key; // go.cpp:45-49 (0 unless situational superko)
+};
+
+struct mz_state {
+    // node pool, per game NP entries
+    mz_hot* hot;
+    int16_t* action;
+    float* logit;
+    float* value;
+    float* root_noise; // [B][A] policy_noise_ of the root children
+    int32_t* cursor;   // [B]
+    // root environment
+    uint32_t* root_st;   // [B][2][MZ_ROWS]
+    uint32_t* root_hist; // [B][MZ_HIST][2][MZ_ROWS]
+    uint64_t* root_hash; // [B]
+    int32_t* root_meta;  // [B][4] turn, num_moves, last action, action before last
+    uint64_t* hashes;    // [B][max_hashes] position hashes of the game so far, then of the current path
+    // leaf of the current simulation
+    int32_t* path;        // [B][S + 2]
+    int32_t* path_len;    // [B]
+    uint32_t* leaf_legal; // [B][MZ_LEGAL_WORDS]
+    int32_t* leaf_meta;   // [B][4] terminal, turn, rotation, num_legal
+    float* leaf_score;    // [B]
+    // network io
+    uint16_t* nn_in; // [B * slots][MZ_NN_CPAD] fp16 bits, NHWC rows; only 0 / 1.0 are ever written
+    float* policy;   // [B][A]
+    float* logits;   // [B][A]
+    float* nn_value; // [B]
+    // per-search inputs
+    const uint8_t* rotations; // [B] for this cycle (may be null = identity)
+    const float* noise_in;    // [B][A] by root child index (may be null)
+    const float* puct_bias;   // [S + 2] host-computed: (float)(init + log((1 + n + base) / base)), mcts.cpp:57
+    const uint64_t* keys;     // [2][361] Zobrist stone keys, go.cpp:19-32
+};
+
+// per-warp scratch (shared memory on the device)
+struct mz_scratch {
+    uint32_t st[2][MZ_ROWS];
+    uint32_t hist[MZ_HIST][2][MZ_ROWS];
+    uint32_t fill[MZ_ROWS], checked[MZ_ROWS], tmp[MZ_ROWS], legal_rows[MZ_ROWS];
+    uint64_t cap_hash[MZ_MAXA];
+    float pol[MZ_MAXA], lg[MZ_MAXA], q[MZ_MAXA];
+    uint32_t legal[MZ_LEGAL_WORDS];
+    uint64_t hash;
+    int turn, num_moves, last, last2;
+};
+
+MZ_DEV uint32_t mz_rowmask(int N) { return (N >= 32 ? 0xffffffffu : ((1u << N) - 1u)); }
+
+// utils/rotation.h:51-93 in doubled integer coordinates
+MZ_DEV int mz_rotate(int rotation, int pos, int N)
+{
+    if (pos == N * N) { return pos; }
+    int x = 2 * (pos % N) - (N - 1), y = 2 * (pos / N) - (N - 1), rx = x, ry = y;
+    switch (rotation) {
+        case 1: rx = y, ry = -x; break;
+        case 2: rx = -x, ry = -y; break;
+        case 3: rx = -y, ry = x; break;
+        case 4: rx = x, ry = -y; break;
+        case 5: rx = -y, ry = -x; break;
+        case 6: rx = -x, ry = y; break;
+        case 7: rx = y, ry = x; break;
+        default: break;
+    }
+    return ((ry + (N - 1)) / 2) * N + (rx + (N - 1)) / 2;
+}
+MZ_DEV int mz_reversed_rotation(int r) { return (r == 1 ? 3 : (r == 3 ? 1 : r)); } // rotation.h:22-31
+
+// ---------------------------------------------------------------------------------------------
+// row-bitboard helpers: rows[r] bit x = cell (x, y = r); every routine is a warp collective
+// ---------------------------------------------------------------------------------------------
+
+// grow `f` through `mask` along the row until it stops changing
+MZ_DEV uint32_t mz_hfill(uint32_t f, uint32_t mask)
+{
+    uint32_t prev;
+    do {
+        prev = f;
+        f |= ((f << 1) | (f >> 1)) & mask;
+    } while (f != prev);
+    return f;
+}
+
+// flood `fill` (seeded by the caller, seeds inside `mask`) to the connected component(s) within mask
+MZ_DEV void mz_flood(uint32_t* fill, const uint32_t* mask, int N, int lane)
+{
+    int changed;
+    do {
+        changed = 0;
+        uint32_t g[(MZ_ROWS + MZ_W - 1) / MZ_W];
+        int k = 0;
+        for (int r = lane; r < N; r += MZ_W, ++k) {
+            uint32_t f = fill[r];
+            uint32_t v = f | (r > 0 ? fill[r - 1] : 0u) | (r + 1 < N ? fill[r + 1] : 0u);
+            v = mz_hfill(v & mask[r], mask[r]);
+            g[k] = v;
+            changed |= (v != f);
+        }
+        mz_sync();
+        k = 0;
+        for (int r = lane; r < N; r += MZ_W, ++k) { fill[r] = g[k]; }
+        mz_sync();
+        changed = mz_any(changed);
+    } while (changed);
+}
+
+// 4-neighbourhood dilation of rows `f` (including f itself), clipped to the board
+MZ_DEV uint32_t mz_dilate_row(const uint32_t* f, int r, int N)
+{
+    uint32_t v = f[r] | (f[r] << 1) | (f[r] >> 1) | (r > 0 ? f[r - 1] : 0u) | (r + 1 < N ? f[r + 1] : 0u);
+    return v & mz_rowmask(N);
+}
+
+MZ_DEV uint64_t mz_block_hash(const uint32_t* fill, int colour_idx, const uint64_t* keys, int N, int lane)
+{
+    uint64_t h = 0;
+    for (int r = lane; r < N; r += MZ_W) {
+        uint32_t m = fill[r];
+        while (m) {
+            int x = mz_ffs0(m);
+            m &= m - 1;
+            h ^= keys[colour_idx * 361 + r * N + x];
+        }
+    }
+    return mz_reduce_xor64(h);
+}
+
+// ---------------------------------------------------------------------------------------------
+// environment
+// ---------------------------------------------------------------------------------------------
+
+MZ_DEV void mz_env_load_root(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int lane)
+{
+    const uint32_t* st = s.root_st + (size_t)g * 2 * MZ_ROWS;
+    const uint32_t* hist = s.root_hist + (size_t)g * MZ_HIST * 2 * MZ_ROWS;
+    for (int i = lane; i < 2 * MZ_ROWS; i += MZ_W) { (&w->st[0][0])[i] = st[i]; }
+    for (int i = lane; i < MZ_HIST * 2 * MZ_ROWS; i += MZ_W) { (&w->hist[0][0][0])[i] = hist[i]; }
+    if (lane == 0) {
+        w->hash = s.root_hash[g];
+        w->turn = s.root_meta[g * 4 + 0];
+        w->num_moves = s.root_meta[g * 4 + 1];
+        w->last = s.root_meta[g * 4 + 2];
+        w->last2 = s.root_meta[g * 4 + 3];
+    }
+    mz_sync();
+}
+
+MZ_DEV void mz_env_store_root(const mz_dims& d, const mz_state& s, int g, const mz_scratch* w, int lane)
+{
+    uint32_t* st = s.root_st + (size_t)g * 2 * MZ_ROWS;
+    uint32_t* hist = s.root_hist + (size_t)g * MZ_HIST * 2 * MZ_ROWS;
+    for (int i = lane; i < 2 * MZ_ROWS; i += MZ_W) { st[i] = (&w->st[0][0])[i]; }
+    for (int i = lane; i < MZ_HIST * 2 * MZ_ROWS; i += MZ_W) { hist[i] = (&w->hist[0][0][0])[i]; }
+    if (lane == 0) {
+        s.root_hash[g] = w->hash;
+        s.root_meta[g * 4 + 0] = w->turn;
+        s.root_meta[g * 4 + 1] = w->num_moves;
+        s.root_meta[g * 4 + 2] = w->last;
+        s.root_meta[g * 4 + 3] = w->last2;
+    }
+}
+
+MZ_DEV void mz_env_reset(const mz_dims& d, mz_scratch* w, int lane)
+{
+    for (int i = lane; i < 2 * MZ_ROWS; i += MZ_W) { (&w->st[0][0])[i] = 0u; }
+    for (int i = lane; i < MZ_HIST * 2 * MZ_ROWS; i += MZ_W) { (&w->hist[0][0][0])[i] = 0u; }
+    if (lane == 0) {
+        w->hash = 0; // go.cpp:106
+        w->turn = 1; // go.cpp:105, tictactoe.cpp:13
+        w->num_moves = 0;
+        w->last = -1;
+        w->last2 = -1;
+    }
+    mz_sync();
+}
+
+// GoEnv::act (go.cpp:132-190) / TicTacToeEnv::act (tictactoe.cpp:19-26) for a move already known to
+// be legal. `hash_list` receives the new position hash at index num_moves (go.cpp:145-147,180-182).
+MZ_DEV void mz_env_act(const mz_dims& d, const mz_state& s, mz_scratch* w, int a, int player, uint64_t* hash_list, int lane)
+{
+    const int N = d.N, me = player - 1, opp = 1 - me;
+    uint64_t hash = w->hash ^ d.turn_key; // go.cpp:141
+    const int num_moves = w->num_moves;
+    if (d.game == MZ_GAME_GO) {
+        if (a != N * N) {
+            const int r = a / N, x = a % N;
+            if (lane == 0) { w->st[me][r] |= (1u << x); }
+            hash ^= s.keys[me * 361 + a]; // go.cpp:154
+            for (int i = lane; i < N; i += MZ_W) { w->checked[i] = 0u; }
+            mz_sync();
+            // neighbours in the order of go_grid.h:43-54 (up, right, down, left); the final position
+            // does not depend on the order
+            for (int k = 0; k < 4; ++k) {
+                int nr = r + (k == 0) - (k == 2), nx = x + (k == 1) - (k == 3);
+                if (nr < 0 || nr >= N || nx < 0 || nx >= N) { continue; }
+                const uint32_t bit = 1u << nx;
+                if (!(w->st[opp][nr] & bit) || (w->checked[nr] & bit)) { continue; } // warp-uniform
+                for (int i = lane; i < N; i += MZ_W) { w->fill[i] = (i == nr ? bit : 0u); }
+                mz_sync();
+                mz_flood(w->fill, w->st[opp], N, lane);
+                int has_lib = 0;
+                for (int i = lane; i < N; i += MZ_W) {
+                    uint32_t empty = ~(w->st[0][i] | w->st[1][i]) & mz_rowmask(N);
+                    has_lib |= ((mz_dilate_row(w->fill, i, N) & empty) != 0u);
+                }
+                has_lib = mz_any(has_lib);
+                if (!has_lib) { // removeBlockFromBoard, go.cpp:388-433
+                    hash ^= mz_block_hash(w->fill, opp, s.keys, N, lane);
+                    for (int i = lane; i < N; i += MZ_W) { w->st[opp][i] &= ~w->fill[i]; }
+                } else {
+                    for (int i = lane; i < N; i += MZ_W) { w->checked[i] |= w->fill[i]; }
+                }
+                mz_sync();
+            }
+        }
+        if (lane == 0) { hash_list[num_moves] = hash; }
+    } else {
+        if (lane == 0) { w->st[me][a / N] |= (1u << (a % N)); }
+        mz_sync();
+    }
+    const int slot = num_moves % MZ_HIST;
+    for (int i = lane; i < N; i += MZ_W) {
+        w->hist[slot][0][i] = w->st[0][i];
+        w->hist[slot][1][i] = w->st[1][i];
+    }
+    mz_sync();
+    if (lane == 0) {
+        w->hash = hash;
+        w->turn = 3 - player; // go.cpp:140
+        w->num_moves = num_moves + 1;
+        w->last2 = w->last;
+        w->last = a;
+    }
+    mz_sync();
+}
+
+// TicTacToeEnv::eval (tictactoe.cpp:124-146): 1 / 2 if that player owns a line, else 0
+MZ_DEV int mz_ttt_eval(const mz_scratch* w)
+{
+    for (int p = 0; p < 2; ++p) {
+        const uint32_t r0 = w->st[p][0], r1 = w->st[p][1], r2 = w->st[p][2];
+        bool win = (r0 == 7u) || (r1 == 7u) || (r2 == 7u) || ((r0 & r1 & r2) != 0u) ||
+                   ((r0 & 1u) && (r1 & 2u) && (r2 & 4u)) || ((r0 & 4u) && (r1 & 2u) && (r2 & 1u));
+        if (win) { return p + 1; }
+    }
+    return 0;
+}
+
+MZ_DEV int mz_env_is_terminal(const mz_dims& d, const mz_scratch* w)
+{
+    const int N = d.N;
+    if (d.game == MZ_GAME_GO) {
+        if (w->num_moves >= 2 && w->last == N * N && w->last2 == N * N) { return 1; } // go.cpp:249-251
+        return w->num_moves > 2 * N * N;                                              // go.cpp:254
+    }
+    if (mz_ttt_eval(w) != 0) { return 1; } // tictactoe.cpp:51-55
+    uint32_t occ = (w->st[0][0] | w->st[1][0]) & (w->st[0][1] | w->st[1][1]) & (w->st[0][2] | w->st[1][2]);
+    return occ == 7u;
+}
+
+// getEvalScore(false): Tromp-Taylor area (go.cpp:259-278,703-723) / line owner (tictactoe.cpp:57-65).
+// An empty region counts for Black unless it touches a White stone, else for White unless it touches a
+// Black stone — which two multi-seed floods through the empty cells decide for all regions at once.
+MZ_DEV float mz_env_eval_score(const mz_dims& d, mz_scratch* w, int lane)
+{
+    const int N = d.N;
+    int winner;
+    if (d.game == MZ_GAME_GO) {
+        int cnt_b = 0, cnt_w = 0;
+        for (int i = lane; i < N; i += MZ_W) {
+            uint32_t empty = ~(w->st[0][i] | w->st[1][i]) & mz_rowmask(N);
+            w->tmp[i] = empty;
+            cnt_b += mz_popc(w->st[0][i]);
+            cnt_w += mz_popc(w->st[1][i]);
+        }
+        mz_sync();
+        for (int c = 0; c < 2; ++c) { // c = 0: cells reaching Black -> checked[], c = 1: reaching White -> fill[]
+            uint32_t* out = (c == 0 ? w->checked : w->fill);
+            for (int i = lane; i < N; i += MZ_W) { out[i] = mz_dilate_row(w->st[c], i, N) & w->tmp[i]; }
+            mz_sync();
+            mz_flood(out, w->tmp, N, lane);
+        }
+        for (int i = lane; i < N; i += MZ_W) {
+            cnt_b += mz_popc(w->tmp[i] & ~w->fill[i]);
+            cnt_w += mz_popc(w->tmp[i] & w->fill[i] & ~w->checked[i]);
+        }
+        cnt_b = mz_reduce_add(cnt_b);
+        cnt_w = mz_reduce_add(cnt_w);
+        mz_sync();
+        const float tb = (float)cnt_b, tw = mz_fadd((float)cnt_w, d.komi);
+        winner = (tb > tw ? 1 : (tb < tw ? 2 : 0));
+    } else {
+        winner = mz_ttt_eval(w);
+    }
+    return winner == 1 ? 1.0f : (winner == 2 ? -1.0f : 0.0f);
+}
+
+// Legal action set of the side to move (go.cpp:208-244 for every action at once): writes w->legal (bit per
+// action id) and returns the number of legal actions. `hash_list[0..num_moves)` is the superko history.
+MZ_DEV int mz_env_legal(const mz_dims& d, const mz_state& s, mz_scratch* w, const uint64_t* hash_list, int lane)
+{
+    const int N = d.N, A = d.A, me = w->turn - 1;
+    for (int i = lane; i < MZ_LEGAL_WORDS; i += MZ_W) { w->legal[i] = 0u; }
+    if (d.game != MZ_GAME_GO) {
+        mz_sync();
+        if (lane == 0) {
+            uint32_t bits = 0;
+            for (int r = 0; r < N; ++r) { bits |= (~(w->st[0][r] | w->st[1][r]) & mz_rowmask(N)) << (r * N); }
+            w->legal[0] = bits; // tictactoe.cpp:44-49
+        }
+        mz_sync();
+        return mz_popc(w->legal[0]);
+    }
+    // (1) empty points with an empty neighbour (go.cpp:225-226)
+    for (int i = lane; i < N; i += MZ_W) { w->tmp[i] = ~(w->st[0][i] | w->st[1][i]) & mz_rowmask(N); }
+    for (int i = lane; i < N * N; i += MZ_W) { w->cap_hash[i] = 0; }
+    mz_sync();
+    for (int i = lane; i < N; i += MZ_W) {
+        uint32_t e = w->tmp[i];
+        uint32_t nb = (e << 1) | (e >> 1) | (i > 0 ? w->tmp[i - 1] : 0u) | (i + 1 < N ? w->tmp[i + 1] : 0u);
+        w->legal_rows[i] = e & nb;
+        w->checked[i] = 0u;
+    }
+    mz_sync();
+    // (2) every block once: own blocks with > 1 liberty make their liberties playable (go.cpp:232-233);
+    //     opponent blocks with exactly 1 liberty are captured by playing it (go.cpp:235-238)
+    for (;;) {
+        int first = 1 << 30;
+        for (int i = lane; i < N; i += MZ_W) {
+            uint32_t rem = (w->st[0][i] | w->st[1][i]) & ~w->checked[i];
+            if (rem) { const int cand = i * 32 + mz_ffs0(rem); first = (cand < first ? cand : first); }
+        }
+        first = mz_reduce_min(first);
+        if (first == (1 << 30)) { break; }
+        const int br = first >> 5, bx = first & 31;
+        const int c = ((w->st[0][br] >> bx) & 1u) ? 0 : 1;
+        for (int i = lane; i < N; i += MZ_W) { w->fill[i] = (i == br ? (1u << bx) : 0u); }
+        mz_sync();
+        mz_flood(w->fill, w->st[c], N, lane);
+        int nlib = 0;
+        uint32_t libs[(MZ_ROWS + MZ_W - 1) / MZ_W];
+        int k = 0;
+        for (int i = lane; i < N; i += MZ_W, ++k) {
+            libs[k] = mz_dilate_row(w->fill, i, N) & w->tmp[i];
+            nlib += mz_popc(libs[k]);
+        }
+        nlib = mz_reduce_add(nlib);
+        if (c == me) {
+            if (nlib > 1) {
+                k = 0;
+                for (int i = lane; i < N; i += MZ_W, ++k) { w->legal_rows[i] |= libs[k]; }
+            }
+        } else if (nlib == 1) {
+            uint64_t bh = mz_block_hash(w->fill, c, s.keys, N, lane);
+            k = 0;
+            for (int i = lane; i < N; i += MZ_W, ++k) {
+                if (libs[k]) {
+                    w->legal_rows[i] |= libs[k];
+                    w->cap_hash[i * N + mz_ffs0(libs[k])] ^= bh; // several blocks may share the liberty
+                }
+            }
+        }
+        for (int i = lane; i < N; i += MZ_W) { w->checked[i] |= w->fill[i]; }
+        mz_sync();
+    }
+    // (3) positional superko (go.cpp:222,237,243)
+    const uint64_t base = w->hash ^ d.turn_key;
+    const int H = w->num_moves;
+    for (int a = lane; a < N * N; a += MZ_W) {
+        const int r = a / N, x = a % N;
+        if (!((w->legal_rows[r] >> x) & 1u)) { continue; }
+        const uint64_t nh = base ^ s.keys[me * 361 + a] ^ w->cap_hash[a];
+        int seen = 0;
+        for (int i = 0; i < H; ++i) { seen |= (hash_list[i] == nh); }
+        if (!seen) {
+#if MZ_W == 1
+            w->legal[a >> 5] |= (1u << (a & 31));
+#else
+            atomicOr(&w->legal[a >> 5], 1u << (a & 31));
+#endif
+        }
+    }
+    mz_sync();
+    if (lane == 0) { w->legal[(N * N) >> 5] |= (1u << ((N * N) & 31)); } // pass, go.cpp:213
+    mz_sync();
+    int n = 0;
+    for (int i = lane; i < MZ_LEGAL_WORDS; i += MZ_W) { n += mz_popc(w->legal[i]); }
+    (void)A;
+    return mz_reduce_add(n);
+}
+
+// getFeatures (go.cpp:280-308, tictactoe.cpp:67-90) written as fp16 NHWC rows of the first conv's input:
+// board cell (x, y) of game g lives at row g * slots + (y + 1) * (N + 1) + x, channel c at column c.
+MZ_DEV void mz_env_features(const mz_dims& d, const mz_state& s, int g, const mz_scratch* w, int rotation, int lane)
+{
+    const int N = d.N, rev = mz_reversed_rotation(rotation);
+    const int turn = w->turn, me = turn - 1, opp = 1 - me;
+    uint16_t* base = s.nn_in + (size_t)g * d.slots * MZ_NN_CPAD;
+    for (int pos = lane; pos < N * N; pos += MZ_W) {
+        const int rp = mz_rotate(rev, pos, N), rr = rp / N, rx = rp % N;
+        uint16_t* out = base + (size_t)((pos / N + 1) * (N + 1) + pos % N) * MZ_NN_CPAD;
+        if (d.game == MZ_GAME_GO) {
+            for (int c = 0; c < 16; ++c) {
+                const int idx = w->num_moves - 1 - c / 2;
+                uint16_t v = 0;
+                if (idx >= 0) { v = ((w->hist[idx % MZ_HIST][(c & 1) ? opp : me][rr] >> rx) & 1u) ? MZ_HALF_ONE : 0; }
+                out[c] = v;
+            }
+            out[16] = (turn == 1 ? MZ_HALF_ONE : 0);
+            out[17] = (turn == 2 ? MZ_HALF_ONE : 0);
+        } else {
+            out[0] = ((w->st[me][rr] >> rx) & 1u) ? MZ_HALF_ONE : 0;
+            out[1] = ((w->st[opp][rr] >> rx) & 1u) ? MZ_HALF_ONE : 0;
+            out[2] = (turn == 1 ? MZ_HALF_ONE : 0);
+            out[3] = (turn == 2 ? MZ_HALF_ONE : 0);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tree
+// ---------------------------------------------------------------------------------------------
+
+// MCTSNode::getNormalizedMean (mcts.cpp:40-53) for board games: reward 0, no value rescale, no virtual loss
+MZ_DEV float mz_normalized_mean(const mz_dims& d, float mean, float count, int player)
+{
+    float v = mz_fadd(0.0f, mz_fmul(d.discount, mean));
+    if (player == 2) { v = -v; } // actor_mcts_value_flipping_player == 'W'
+    return mz_fdiv(mz_fsub(mz_fmul(v, count), 0.0f), mz_fadd(count, 0.0f));
+}
+
+// MCTS::select (mcts.cpp:139-148,181-217): returns the path length; path[] holds node indices from the root
+MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int root_turn, int lane)
+{
+    const mz_hot* hot = s.hot + (size_t)g * d.NP;
+    int32_t* path = s.path + (size_t)g * (d.S + 2);
+    int node = 0, len = 1, child_player = root_turn;
+    if (lane == 0) { path[0] = 0; }
+    for (;;) {
+        const mz_hot h = mz_load_hot(hot + node);
+        const int nc = (int)(h.link >> MZ_LINK_SHIFT), fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
+        if (nc == 0) { break; }
+        const int total = (int)mz_fsub(h.count, 1.0f); // mcts.cpp:185
+        // init-Q: ordered f32 sum over the visited children (mcts.cpp:200-217)
+        float sum_win = 0.0f, sum_n = 0.0f;
+        for (int base = 0; base < nc; base += MZ_W) {
+            const int i = base + lane;
+            int visited = 0;
+            if (i < nc) {
+                const mz_hot c = mz_load_hot(hot + fc + i);
+                visited = (c.count != 0.0f);
+                if (visited) { w->q[i] = mz_normalized_mean(d, c.mean, c.count, child_player); }
+            }
+            unsigned m = mz_ballot(visited);
+            mz_sync();
+            while (m) {
+                const int b = mz_ffs0(m);
+                m &= m - 1;
+                sum_win = mz_fadd(sum_win, w->q[base + b]);
+                sum_n = mz_fadd(sum_n, 1.0f);
+            }
+        }
+        const float init_q = mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
+        const float bias = s.puct_bias[total];
+        const double sqrt_n = mz_dsqrt((double)total);
+        float best_s = 0.0f, best_p = 0.0f;
+        int best_i = -1;
+        for (int i = lane; i < nc; i += MZ_W) {
+            const mz_hot c = mz_load_hot(hot + fc + i);
+            const float u = (float)mz_ddiv(mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n), (double)mz_fadd(1.0f, c.count));
+            const float qv = (c.count == 0.0f ? init_q : w->q[i]);
+            const float score = mz_fadd(u, qv);
+            if (best_i < 0 || score > best_s || (score == best_s && c.policy > best_p)) { best_s = score, best_p = c.policy, best_i = i; }
+        }
+        mz_reduce_best(best_s, best_p, best_i);
+        mz_sync();
+        node = fc + best_i;
+        if (lane == 0) { path[len] = node; }
+        ++len;
+        child_player = 3 - child_player;
+    }
+    return len;
+}
+
+// One "before NN evaluation" step of game g (zero_actor.cpp:51-58): select, transition, analyse the leaf
+// (terminal / score / legal set) and emit its feature planes.
+MZ_DEV void mz_before_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int lane)
+{
+    mz_env_load_root(d, s, g, w, lane);
+    const int root_turn = w->turn;
+    const int len = mz_select(d, s, g, w, root_turn, lane);
+    mz_sync();
+    const int32_t* path = s.path + (size_t)g * (d.S + 2);
+    uint64_t* hash_list = s.hashes + (size_t)g * d.max_hashes;
+    int player = root_turn;
+    for (int i = 1; i < len; ++i) { // getEnvironmentTransition, zero_actor.cpp:247-252
+        const int a = s.action[(size_t)g * d.NP + path[i]];
+        mz_env_act(d, s, w, a, player, hash_list, lane);
+        player = 3 - player;
+    }
+    const int rotation = (s.rotations ? s.rotations[g] : 0);
+    const int terminal = mz_env_is_terminal(d, w);
+    float score = 0.0f;
+    int num_legal = 0;
+    if (terminal) {
+        score = mz_env_eval_score(d, w, lane);
+    } else {
+        num_legal = mz_env_legal(d, s, w, hash_list, lane);
+    }
+    mz_env_features(d, s, g, w, rotation, lane);
+    for (int i = lane; i < MZ_LEGAL_WORDS; i += MZ_W) { s.leaf_legal[g * MZ_LEGAL_WORDS + i] = w->legal[i]; }
+    if (lane == 0) {
+        s.path_len[g] = len;
+        s.leaf_meta[g * 4 + 0] = terminal;
+        s.leaf_meta[g * 4 + 1] = w->turn;
+        s.leaf_meta[g * 4 + 2] = rotation;
+        s.leaf_meta[g * 4 + 3] = num_legal;
+        s.leaf_score[g] = score;
+    }
+}
+
+// One "after NN evaluation" step of game g (zero_actor.cpp:74-98): expand the leaf with the legal actions in
+// descending policy order (zero_actor.cpp:215-229, mcts.cpp:151-164), back the value up (mcts.cpp:166-179)
+// and mix the root noise in (zero_actor.cpp:194-204).
+MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int lane)
+{
+    const int len = s.path_len[g];
+    if (len <= 0) { return; }
+    const int A = d.A, N = d.N;
+    mz_hot* hot = s.hot + (size_t)g * d.NP;
+    const int32_t* path = s.path + (size_t)g * (d.S + 2);
+    const int leaf = path[len - 1];
+    const int terminal = s.leaf_meta[g * 4 + 0], rotation = s.leaf_meta[g * 4 + 2];
+    float v;
+    if (!terminal) {
+        for (int i = lane; i < MZ_LEGAL_WORDS; i += MZ_W) { w->legal[i] = s.leaf_legal[g * MZ_LEGAL_WORDS + i]; }
+        for (int a = lane; a < A; a += MZ_W) {
+            const int ra = mz_rotate(rotation, a, N); // getRotateAction, zero_actor.cpp:222
+            w->pol[a] = s.policy[(size_t)g * A + ra];
+            w->lg[a] = s.logits[(size_t)g * A + ra];
+        }
+        mz_sync();
+        const int first = s.cursor[g];
+        int k = 0;
+        for (int i = lane; i < MZ_LEGAL_WORDS; i += MZ_W) { k += mz_popc(w->legal[i]); }
+        k = mz_reduce_add(k);
+        // rank sort: descending policy, exact ties by ascending action id (std::sort is unstable there;
+        // see the note in oracle/port/mzo_mcts.c)
+        for (int a = lane; a < A; a += MZ_W) {
+            if (!((w->legal[a >> 5] >> (a & 31)) & 1u)) { continue; }
+            const float p = w->pol[a];
+            int rank = 0;
+            for (int b = 0; b < A; ++b) {
+                if (!((w->legal[b >> 5] >> (b & 31)) & 1u)) { continue; }
+                const float pb = w->pol[b];
+                rank += (pb > p) || (pb == p && b < a);
+            }
+            const int c = first + rank;
+            mz_store_hot(hot + c, 0.0f, 0.0f, p, 0u);
+            s.action[(size_t)g * d.NP + c] = (int16_t)a;
+            s.logit[(size_t)g * d.NP + c] = w->lg[a];
+            s.value[(size_t)g * d.NP + c] = 0.0f;
+        }
+        mz_sync();
+        if (lane == 0) {
+            s.cursor[g] = first + k;
+            const mz_hot h = mz_load_hot(hot + leaf);
+            mz_store_hot(hot + leaf, h.count, h.mean, h.policy, (uint32_t)first | ((uint32_t)k << MZ_LINK_SHIFT));
+        }
+        v = s.nn_value[g];
+        if (leaf == 0) {
+            for (int i = lane; i < A; i += MZ_W) { s.root_noise[(size_t)g * A + i] = 0.0f; }
+            if (s.noise_in) {
+                mz_sync();
+                const float eps = d.eps, one_minus = mz_fsub(1.0f, eps);
+                for (int i = lane; i < k; i += MZ_W) {
+                    const mz_hot h = mz_load_hot(hot + first + i);
+                    const float nz = s.noise_in[(size_t)g * A + i];
+                    s.root_noise[(size_t)g * A + i] = nz;
+                    mz_store_hot(hot + first + i, h.count, h.mean, mz_fadd(mz_fmul(one_minus, h.policy), mz_fmul(eps, nz)), h.link);
+                }
+            }
+        }
+    } else {
+        v = s.leaf_score[g];
+    }
+    mz_sync();
+    // backup: every path node receives the same chain value discounted per level (reward is 0)
+    if (lane == 0) { s.value[(size_t)g * d.NP + leaf] = v; }
+    for (int i = lane; i < len; i += MZ_W) {
+        float x = v;
+        for (int j = len - 1; j > i; --j) { x = mz_fadd(0.0f, mz_fmul(d.discount, x)); }
+        const int n = path[i];
+        const mz_hot h = mz_load_hot(hot + n);
+        const float cnt = mz_fadd(h.count, 1.0f);
+        const float mean = mz_fadd(h.mean, mz_fdiv(mz_fmul(1.0f, mz_fsub(x, h.mean)), cnt));
+        mz_store_hot(hot + n, cnt, mean, h.policy, h.link);
+    }
+    mz_sync();
+    if (lane == 0) { s.path_len[g] = 0; }
+}
+
+// Tree::reset + ZeroActor::resetSearch (tree.h:64-69, zero_actor.cpp:29-34)
+MZ_DEV void mz_tree_reset(const mz_dims& d, const mz_state& s, int g, int lane)
+{
+    if (lane == 0) {
+        mz_store_hot(s.hot + (size_t)g * d.NP, 0.0f, 0.0f, 0.0f, 0u);
+        s.value[(size_t)g * d.NP] = 0.0f;
+        s.logit[(size_t)g * d.NP] = 0.0f;
+        s.action[(size_t)g * d.NP] = -1;
+        s.cursor[g] = 1;
+        s.path_len[g] = 0;
+    }
+}
+
+// BaseActor::reset (base_actor.cpp:8-13)
+MZ_DEV void mz_game_reset(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int lane)
+{
+    mz_env_reset(d, w, lane);
+    mz_env_store_root(d, s, g, w, lane);
+    mz_tree_reset(d, s, g, lane);
+}
+
+// BaseActor::act on the root environment + resetSearch (base_actor.cpp:22-30, actor_group.cpp:116-134).
+// out[0] = 1 if the action was legal and applied, out[1] = terminal, out[2] = number of legal actions of the
+// new position (what the host needs to draw the next root's Dirichlet noise), out[3] = side to move;
+// *score = getEvalScore(false) of the new position when terminal.
+MZ_DEV void mz_play(const mz_dims& d, const mz_state& s, int g, int action, mz_scratch* w, int32_t* out, float* score, int lane)
+{
+    mz_env_load_root(d, s, g, w, lane);
+    uint64_t* hash_list = s.hashes + (size_t)g * d.max_hashes;
+    mz_env_legal(d, s, w, hash_list, lane);
+    const int ok = (action >= 0 && action < d.A && ((w->legal[action >> 5] >> (action & 31)) & 1u)) ? 1 : 0;
+    int terminal = 0, num_legal = 0;
+    float sc = 0.0f;
+    if (ok) {
+        mz_env_act(d, s, w, action, w->turn, hash_list, lane);
+        mz_env_store_root(d, s, g, w, lane);
+        mz_tree_reset(d, s, g, lane);
+    }
+    terminal = mz_env_is_terminal(d, w);
+    if (terminal) {
+        sc = mz_env_eval_score(d, w, lane);
+    } else {
+        num_legal = mz_env_legal(d, s, w, hash_list, lane);
+    }
+    if (lane == 0) {
+        out[0] = ok, out[1] = terminal, out[2] = num_legal, out[3] = w->turn;
+        *score = sc;
+    }
+}

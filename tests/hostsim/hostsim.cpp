@@ -1,0 +1,130 @@
+// TEST-ONLY build of minizero_b200/csrc/search_core.cuh as plain C++ (MZ_W == 1): lets the CPU
+// test-suite replay the reference recordings through the exact source the CUDA kernels are
+// compiled from. Never linked into the product library (libmzb200.so has no CPU path).
+#define MZ_HOSTSIM 1
+#include "../../minizero_b200/csrc/search_core.cuh"
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <vector>
+
+struct sim {
+    mz_dims d;
+    mz_state s;
+    std::vector<float> bias;
+    std::vector<uint64_t> keys;
+    std::vector<uint8_t> rot;
+    std::vector<float> noise;
+    mz_scratch w;
+};
+
+template <class T>
+static T* zalloc(size_t n) { return (T*)calloc(n, sizeof(T)); }
+
+extern "C" {
+
+sim* hs_create(int game, int N, int B, int S, float puct_base, float puct_init, float discount, float komi, float eps)
+{
+    sim* h = new sim();
+    mz_dims& d = h->d;
+    d.game = game, d.N = N, d.A = (game == MZ_GAME_GO ? N * N + 1 : 9), d.C = (game == MZ_GAME_GO ? 18 : 4), d.S = S, d.B = B;
+    d.NP = 1 + (S + 1) * d.A;
+    d.slots = (N + 1) * (N + 1);
+    d.max_hashes = 2 * N * N + 4;
+    d.puct_init = puct_init, d.puct_base = puct_base, d.discount = discount, d.komi = komi, d.eps = eps, d.turn_key = 0;
+    mz_state& s = h->s;
+    size_t np = (size_t)B * d.NP;
+    s.hot = zalloc<mz_hot>(np), s.action = zalloc<int16_t>(np), s.logit = zalloc<float>(np), s.value = zalloc<float>(np);
+    s.root_noise = zalloc<float>((size_t)B * d.A), s.cursor = zalloc<int32_t>(B);
+    s.root_st = zalloc<uint32_t>((size_t)B * 2 * MZ_ROWS), s.root_hist = zalloc<uint32_t>((size_t)B * MZ_HIST * 2 * MZ_ROWS);
+    s.root_hash = zalloc<uint64_t>(B), s.root_meta = zalloc<int32_t>((size_t)B * 4), s.hashes = zalloc<uint64_t>((size_t)B * d.max_hashes);
+    s.path = zalloc<int32_t>((size_t)B * (S + 2)), s.path_len = zalloc<int32_t>(B), s.leaf_legal = zalloc<uint32_t>((size_t)B * MZ_LEGAL_WORDS);
+    s.leaf_meta = zalloc<int32_t>((size_t)B * 4), s.leaf_score = zalloc<float>(B);
+    s.nn_in = zalloc<uint16_t>((size_t)B * d.slots * MZ_NN_CPAD);
+    s.policy = zalloc<float>((size_t)B * d.A), s.logits = zalloc<float>((size_t)B * d.A), s.nn_value = zalloc<float>(B);
+    h->bias.resize(S + 2);
+    for (int n = 0; n < S + 2; ++n) {
+        float t = (float)(1 + n) + puct_base;
+        t = t / puct_base;
+        h->bias[n] = (float)((double)puct_init + log((double)t));
+    }
+    std::mt19937_64 gen(0);
+    h->keys.resize(2 * 361);
+    (void)gen(); // turn key
+    for (int pos = 0; pos < 361; ++pos) {
+        (void)gen();
+        h->keys[0 * 361 + pos] = gen();
+        h->keys[1 * 361 + pos] = gen();
+    }
+    s.puct_bias = h->bias.data(), s.keys = h->keys.data();
+    h->rot.assign(B, 0), h->noise.assign((size_t)B * d.A, 0.0f);
+    s.rotations = h->rot.data(), s.noise_in = nullptr;
+    for (int g = 0; g < B; ++g) { mz_game_reset(d, s, g, &h->w, 0); }
+    return h;
+}
+
+void hs_select(sim* h, const uint8_t* rotations, float* features)
+{
+    const mz_dims& d = h->d;
+    for (int g = 0; g < d.B; ++g) { h->rot[g] = (rotations ? rotations[g] : 0); }
+    for (int g = 0; g < d.B; ++g) { mz_before_nn(d, h->s, g, &h->w, 0); }
+    if (features) {
+        const int N = d.N;
+        for (int g = 0; g < d.B; ++g) {
+            for (int c = 0; c < d.C; ++c) {
+                for (int pos = 0; pos < N * N; ++pos) {
+                    uint16_t v = h->s.nn_in[((size_t)g * d.slots + (pos / N + 1) * (N + 1) + pos % N) * MZ_NN_CPAD + c];
+                    features[((size_t)g * d.C + c) * N * N + pos] = (v == MZ_HALF_ONE ? 1.0f : 0.0f);
+                }
+            }
+        }
+    }
+}
+
+void hs_apply(sim* h, const float* policy, const float* logits, const float* value, const float* noise)
+{
+    const mz_dims& d = h->d;
+    memcpy(h->s.policy, policy, sizeof(float) * (size_t)d.B * d.A);
+    memcpy(h->s.logits, logits, sizeof(float) * (size_t)d.B * d.A);
+    memcpy(h->s.nn_value, value, sizeof(float) * (size_t)d.B);
+    if (noise) { memcpy(h->noise.data(), noise, sizeof(float) * (size_t)d.B * d.A); }
+    h->s.noise_in = (noise ? h->noise.data() : nullptr);
+    for (int g = 0; g < d.B; ++g) { mz_after_nn(d, h->s, g, &h->w, 0); }
+}
+
+int hs_path_len(sim* h, int g) { return h->s.path_len[g]; }
+int hs_sims_done(sim* h, int g) { return (int)h->s.hot[(size_t)g * h->d.NP].count; }
+
+// out_i: [1 + A] num_children, actions; out_f: [3 + 6 * A] root count/mean/value then count, mean, policy, logit, noise, value per child
+void hs_root(sim* h, int g, int32_t* out_i, float* out_f)
+{
+    const mz_dims& d = h->d;
+    const mz_hot* hot = h->s.hot + (size_t)g * d.NP;
+    const int nc = (int)(hot[0].link >> MZ_LINK_SHIFT), fc = (int)(hot[0].link & ((1u << MZ_LINK_SHIFT) - 1u));
+    out_i[0] = nc;
+    out_f[0] = hot[0].count, out_f[1] = hot[0].mean, out_f[2] = h->s.value[(size_t)g * d.NP];
+    for (int i = 0; i < nc; ++i) {
+        out_i[1 + i] = h->s.action[(size_t)g * d.NP + fc + i];
+        out_f[3 + 0 * d.A + i] = hot[fc + i].count;
+        out_f[3 + 1 * d.A + i] = hot[fc + i].mean;
+        out_f[3 + 2 * d.A + i] = hot[fc + i].policy;
+        out_f[3 + 3 * d.A + i] = h->s.logit[(size_t)g * d.NP + fc + i];
+        out_f[3 + 4 * d.A + i] = h->s.root_noise[(size_t)g * d.A + i];
+        out_f[3 + 5 * d.A + i] = h->s.value[(size_t)g * d.NP + fc + i];
+    }
+}
+
+// returns ok | terminal << 1 ; num_legal and score through pointers
+int hs_play(sim* h, int g, int action, int* num_legal, float* score)
+{
+    int32_t out[4];
+    mz_play(h->d, h->s, g, action, &h->w, out, score, 0);
+    *num_legal = out[2];
+    return out[0] | (out[1] << 1);
+}
+
+void hs_reset_game(sim* h, int g) { mz_game_reset(h->d, h->s, g, &h->w, 0); }
+
+void hs_destroy(sim* h) { delete h; } // test helper: buffers are reclaimed at process exit
+}
