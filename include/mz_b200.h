@@ -1,0 +1,130 @@
+/*
+ * mz_b200 — C ABI of the B200-native MiniZero self-play engine (libmzb200.so).
+ *
+ * The reference (rlglab/minizero) has no FFI layer; its replaceable seams are the C++ classes
+ * ActorGroup / BaseActor / Network and the `-mode sp` process. This header is the thin
+ * boundary between a host that keeps those seams (minizero_b200/host: the ActorGroup-compatible worker;
+ * minizero_b200/*.py: the ctypes mirror used by tests and bench) and the CUDA library. Each entry point
+ * names the reference interface it replaces (paths relative to /root/reference/minizero).
+ *
+ * Conventions: plain pointers and sizes, caller-owned host buffers, `int` status returns (0 = ok, <0 =
+ * error, text via mz_last_error()), no exceptions and no stdout/stderr writes across the boundary, one
+ * engine per device context, entry points of one engine are not re-entrant. There is NO CPU path: every
+ * call fails with MZ_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef MZ_B200_H
+#define MZ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MZ_OK 0
+#define MZ_ERR_ARG (-1)
+#define MZ_ERR_CUDA (-2)
+#define MZ_ERR_STATE (-3)
+
+#define MZ_GAME_TICTACTOE 0 /* environment/tictactoe */
+#define MZ_GAME_GO 1        /* environment/go        */
+
+typedef struct mz_engine mz_engine;
+
+/* Search / environment configuration: the config keys the actor path reads (config/configuration.cpp:13-28,80-81). */
+typedef struct {
+    int32_t device;             /* CUDA device ordinal */
+    int32_t game;               /* MZ_GAME_* (compile-time GAME_TYPE in the reference, environment/environment.h:5-110) */
+    int32_t board_size;         /* env_board_size (ignored for tictactoe) */
+    int32_t num_games;          /* zero_num_parallel_games handled by this engine */
+    int32_t num_simulation;     /* actor_num_simulation */
+    float puct_base;            /* actor_mcts_puct_base */
+    float puct_init;            /* actor_mcts_puct_init */
+    float reward_discount;      /* actor_mcts_reward_discount */
+    float komi;                 /* env_go_komi */
+    int32_t ko_situational;     /* env_go_ko_rule == "situational" */
+    float dirichlet_epsilon;    /* actor_dirichlet_noise_epsilon */
+} mz_config;
+
+/* Hyper-parameters the reference reads from the TorchScript module (network/network.cpp:30-41). */
+typedef struct {
+    int32_t num_input_channels, input_height, input_width;
+    int32_t num_hidden_channels, num_blocks, action_size, num_value_hidden_channels, discrete_value_size;
+} mz_net_dims;
+
+typedef struct {
+    int32_t applied;   /* 1 = the action was legal and has been played (Environment::act return value) */
+    int32_t terminal;  /* Environment::isTerminal() of the new position */
+    int32_t num_legal; /* number of legal actions of the new position (= root children of the next search) */
+    int32_t turn;      /* side to move: 1 = Black / first player, 2 = White */
+    float eval_score;  /* Environment::getEvalScore(false) when terminal, else 0 */
+} mz_play_result;
+
+typedef struct {
+    int32_t num_children;
+    float count, mean, value; /* MCTSNode::getCount / getMean / getValue of the root */
+} mz_root_info;
+
+/* ---- lifetime -------------------------------------------------------------------------------------- */
+/* replaces ActorGroup::initialize / createActors (actor/actor_group.cpp:150-187): allocates the node pools
+ * (1 + (S+1)*A nodes per game, actor_group.cpp:183) and environments in HBM and resets every game. */
+int mz_create(const mz_config* cfg, mz_engine** out);
+void mz_destroy(mz_engine* e);
+const char* mz_last_error(void);
+int mz_action_size(const mz_engine* e);
+int mz_num_features(const mz_engine* e); /* C * H * W of one position */
+
+/* ---- network (replaces Network::loadModel + AlphaZeroNetwork, network/network.cpp:14-42,
+ *      network/alphazero_network.h:48-104). The host reads the .pt with libtorch / torch.jit and hands over
+ *      the hyper-parameters and every state_dict tensor by name (fp32, contiguous). ---------------------- */
+int mz_net_configure(mz_engine* e, const mz_net_dims* dims);
+int mz_net_set_tensor(mz_engine* e, const char* state_dict_name, const float* data, int64_t numel);
+/* folds BatchNorm (eval mode, eps 1e-5) into the convolutions, converts to the kernels' fp16 layout and
+ * uploads one packed blob. */
+int mz_net_finalize(mz_engine* e);
+/* the packed device blob, for an NCCL broadcast from the rank that read the .pt */
+int mz_net_blob(mz_engine* e, void** device_ptr, int64_t* bytes);
+/* ranks that did not read the .pt: allocate the blob from the dims alone, then receive it */
+int mz_net_finalize_empty(mz_engine* e);
+/* AlphaZeroNetwork::pushBack x n + forward(): features [n][C][H][W] fp32 (n <= num_games) ->
+ * policy [n][A], policy_logit [n][A], value [n] */
+int mz_eval_batch(mz_engine* e, const float* features, int32_t n, float* policy, float* logits, float* value);
+
+/* ---- games ----------------------------------------------------------------------------------------- */
+/* BaseActor::reset (actor/base_actor.cpp:8-13); g < 0 resets every game */
+int mz_reset_game(mz_engine* e, int32_t g);
+/* BaseActor::act + resetSearch for every game with actions[g] >= 0 (actor/base_actor.cpp:22-30,
+ * actor/actor_group.cpp:116-134); results [num_games] */
+int mz_play(mz_engine* e, const int32_t* actions, mz_play_result* results);
+/* root child tables, children in stored (policy-sorted) order; any array may be NULL.
+ * info [B]; the others [B][A] (MCTSNode getters, actor/mcts.h:44-52) */
+int mz_get_roots(mz_engine* e, mz_root_info* info, int32_t* action, float* count, float* mean, float* policy, float* logit, float* noise,
+                 float* value);
+
+/* ---- search, one phase at a time (parity hooks; NN outputs supplied by the caller) ------------------ */
+/* ZeroActor::beforeNNEvaluation for every game (actor/zero_actor.cpp:51-58). rotations [B] or NULL;
+ * features_out [B][C*H*W] or NULL; path_len_out [B] or NULL */
+int mz_search_select(mz_engine* e, const uint8_t* rotations, float* features_out, int32_t* path_len_out);
+/* ZeroActor::afterNNEvaluation for every game (actor/zero_actor.cpp:74-98). policy/logits [B][A], value [B],
+ * noise [B][A] by root child index or NULL (Dirichlet values drawn by the host, utils/random.h:15-24) */
+int mz_search_apply(mz_engine* e, const float* policy, const float* logits, const float* value, const float* noise);
+
+/* ---- search, whole move on the device --------------------------------------------------------------- */
+/* host-drawn randomness of one search: rotations [(S+1)][B] (cycle-major) or NULL, root noise [B][A] or NULL */
+int mz_search_set_inputs(mz_engine* e, const uint8_t* rotations, const float* noise);
+/* runs num_evals (<= S+1; 0 = S+1) cycles of select -> features -> network -> expand/backup for all games as
+ * one CUDA graph (the ActorGroup::run loop, actor/actor_group.cpp:136-148, without its host round trips).
+ * device_ms (may be NULL) receives the CUDA-event time of the graph on the engine's stream. */
+int mz_search_run(mz_engine* e, int32_t num_evals, float* device_ms);
+
+/* ---- measurement hooks ------------------------------------------------------------------------------ */
+/* average device time (CUDA events on the engine's stream) of `iters` back-to-back launches of: the tower
+ * conv kernel (hidden -> hidden layer), the tree step kernel, the heads kernel; any pointer may be NULL */
+int mz_profile_kernels(mz_engine* e, int32_t iters, float* conv_ms, float* tree_ms, float* heads_ms);
+/* kernels launched by this engine so far */
+int64_t mz_launch_count(const mz_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

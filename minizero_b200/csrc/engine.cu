@@ -1,0 +1,795 @@
+// libmzb200.so — engine state, kernels launch logic and the C ABI of include/mz_b200.h.
+// No CPU path: every entry point needs a CUDA device of compute capability 10.x.
+#include "../../include/mz_b200.h"
+#include "nn_kernels.cuh"
+#include "search_core.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <random>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg)
+{
+    g_error = msg;
+    return code;
+}
+
+#define CUDA_OK(expr)                                                                                                        \
+    do {                                                                                                                     \
+        cudaError_t err__ = (expr);                                                                                          \
+        if (err__ != cudaSuccess) { return fail(MZ_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__)); }       \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// kernels around search_core.cuh: one warp (= one block of 32 threads) per game
+// ---------------------------------------------------------------------------------------------------
+constexpr int STEP_AFTER = 1, STEP_BEFORE = 2;
+
+__global__ void __launch_bounds__(32) k_step(const mz_dims d, const mz_state s, const int flags)
+{
+    __shared__ mz_scratch w;
+    const int g = blockIdx.x, lane = threadIdx.x;
+    if (flags & STEP_AFTER) { mz_after_nn(d, s, g, &w, lane); }
+    if (flags & STEP_BEFORE) {
+        __syncwarp();
+        mz_before_nn(d, s, g, &w, lane);
+    }
+}
+
+__global__ void __launch_bounds__(32) k_reset(const mz_dims d, const mz_state s, const int only_game)
+{
+    __shared__ mz_scratch w;
+    const int g = blockIdx.x, lane = threadIdx.x;
+    if (only_game >= 0 && g != only_game) { return; }
+    mz_game_reset(d, s, g, &w, lane);
+}
+
+__global__ void __launch_bounds__(32) k_play(const mz_dims d, const mz_state s, const int32_t* __restrict__ actions, int32_t* __restrict__ out, float* __restrict__ score)
+{
+    __shared__ mz_scratch w;
+    const int g = blockIdx.x, lane = threadIdx.x;
+    const int a = actions[g];
+    if (a < 0) {
+        if (lane == 0) { out[g * 4 + 0] = 0, out[g * 4 + 1] = 0, out[g * 4 + 2] = 0, out[g * 4 + 3] = s.root_meta[g * 4 + 0], score[g] = 0.0f; }
+        return;
+    }
+    mz_play(d, s, g, a, &w, out + g * 4, score + g, lane);
+}
+
+// root child table of every game, children in stored order (MCTSNode getters, actor/mcts.h:44-52)
+__global__ void __launch_bounds__(32) k_gather_roots(const mz_dims d, const mz_state s, float* __restrict__ info, int32_t* __restrict__ action, float* __restrict__ count,
+                                                     float* __restrict__ mean, float* __restrict__ policy, float* __restrict__ logit, float* __restrict__ noise,
+                                                     float* __restrict__ value)
+{
+    const int g = blockIdx.x, lane = threadIdx.x;
+    const mz_hot* hot = s.hot + (size_t)g * d.NP;
+    const mz_hot root = mz_load_hot(hot);
+    const int nc = (int)(root.link >> MZ_LINK_SHIFT), fc = (int)(root.link & ((1u << MZ_LINK_SHIFT) - 1u));
+    if (lane == 0) {
+        info[g * 4 + 0] = __int_as_float(nc);
+        info[g * 4 + 1] = root.count, info[g * 4 + 2] = root.mean, info[g * 4 + 3] = s.value[(size_t)g * d.NP];
+    }
+    for (int i = lane; i < d.A; i += 32) {
+        const size_t o = (size_t)g * d.A + i;
+        if (i < nc) {
+            const mz_hot c = mz_load_hot(hot + fc + i);
+            const size_t n = (size_t)g * d.NP + fc + i;
+            action[o] = s.action[n], count[o] = c.count, mean[o] = c.mean, policy[o] = c.policy;
+            logit[o] = s.logit[n], noise[o] = s.root_noise[o], value[o] = s.value[n];
+        } else {
+            action[o] = -1, count[o] = 0.0f, mean[o] = 0.0f, policy[o] = 0.0f, logit[o] = 0.0f, noise[o] = 0.0f, value[o] = 0.0f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// engine
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct ConvLayer {
+    int cin = 0, cout = 0, relu = 1;
+    size_t w_off = 0, b_off = 0; // offsets into the blob
+    CUtensorMap map_w;
+};
+
+struct Blob {
+    size_t size = 0;
+    size_t take(size_t bytes)
+    {
+        const size_t off = size;
+        size += (bytes + 255) & ~static_cast<size_t>(255);
+        return off;
+    }
+};
+
+} // namespace
+
+struct mz_engine {
+    mz_config cfg{};
+    mz_dims d{};
+    mz_state s{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<void*> allocs;
+    int64_t launches = 0;
+
+    // per-search inputs / outputs
+    uint8_t* d_rot_all = nullptr; // [(S+1)][B]
+    float* d_noise = nullptr;     // [B][A]
+    float* d_bias_table = nullptr;
+    uint64_t* d_keys = nullptr;
+    int32_t* d_actions = nullptr;
+    int32_t* d_play_out = nullptr;
+    float* d_play_score = nullptr;
+    float* d_root_info = nullptr;
+    int32_t* d_root_action = nullptr;
+    float* d_root_f[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* d_feat_f32 = nullptr; // [B][C*H*W] staging for the NCHW parity hooks
+    bool noise_enabled = false, rot_enabled = false;
+
+    // network
+    bool dims_set = false, net_ready = false;
+    mz_net_dims nd{};
+    int cpad = 0, pol_ch = 0, rows_alloc = 0, bn_tile = 0;
+    std::map<std::string, std::vector<float>> tensors;
+    std::vector<ConvLayer> convs;
+    Blob blob;
+    uint8_t* d_blob = nullptr;
+    size_t off_head[10] = {0};
+    __half* act[3] = {nullptr, nullptr, nullptr};
+    CUtensorMap map_in0, map_act[3];
+    encode_tiled_fn encode = nullptr;
+
+    // graphs keyed by (num_evals, noise, rotations)
+    std::map<int, cudaGraphExec_t> graphs;
+
+    template <class T>
+    int dalloc(T** p, size_t n)
+    {
+        CUDA_OK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+        CUDA_OK(cudaMemsetAsync(*p, 0, n * sizeof(T), stream));
+        allocs.push_back(*p);
+        return MZ_OK;
+    }
+};
+
+namespace {
+
+int make_map_2d(mz_engine* e, CUtensorMap* map, void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows)
+{
+    const cuuint64_t dims[2] = {inner, rows};
+    const cuuint64_t strides[1] = {inner * sizeof(__half)};
+    const cuuint32_t box[2] = {box_inner, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = e->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { return fail(MZ_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r))); }
+    return MZ_OK;
+}
+
+template <int BN, int STAGES>
+int launch_conv(mz_engine* e, const CUtensorMap& in, const ConvLayer& L, __half* out, const __half* residual)
+{
+    using Smem = mznn::ConvSmem<BN, STAGES>;
+    mznn::ConvParams p;
+    p.out = out, p.residual = residual, p.bias = reinterpret_cast<const float*>(e->d_blob + L.b_off);
+    p.rows_valid = e->d.B * e->d.slots, p.n1 = e->d.N + 1, p.slots = e->d.slots, p.cin = L.cin, p.cout = L.cout, p.relu = L.relu;
+    dim3 grid(e->rows_alloc / mznn::BM, L.cout / BN);
+    mznn::conv3x3_tcgen05_kernel<BN, STAGES><<<grid, mznn::CONV_THREADS, Smem::TOTAL, e->stream>>>(in, L.map_w, p);
+    e->launches++;
+    return MZ_OK;
+}
+
+int configure_conv_kernels()
+{
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_tcgen05_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mznn::ConvSmem<64, 4>::TOTAL));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_tcgen05_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mznn::ConvSmem<128, 3>::TOTAL));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_tcgen05_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mznn::ConvSmem<256, 4>::TOTAL));
+    return MZ_OK;
+}
+
+int conv(mz_engine* e, const CUtensorMap& in, const ConvLayer& L, __half* out, const __half* residual)
+{
+    switch (e->bn_tile) {
+        case 64: return launch_conv<64, 4>(e, in, L, out, residual);
+        case 128: return launch_conv<128, 3>(e, in, L, out, residual);
+        default: return launch_conv<256, 4>(e, in, L, out, residual);
+    }
+}
+
+int launch_heads(mz_engine* e, const __half* act)
+{
+    mznn::HeadParams p;
+    const float* const* dummy = nullptr;
+    (void)dummy;
+    auto f = [&](int i) { return reinterpret_cast<const float*>(e->d_blob + e->off_head[i]); };
+    p.act = act;
+    p.w_pc = f(0), p.b_pc = f(1), p.w_pf = f(2), p.b_pf = f(3), p.w_vc = f(4), p.b_vc = f(5), p.w_v1 = f(6), p.b_v1 = f(7), p.w_v2 = f(8), p.b_v2 = f(9);
+    p.policy = e->s.policy, p.logits = e->s.logits, p.value = e->s.nn_value;
+    p.c = e->cpad, p.n = e->d.N, p.slots = e->d.slots, p.pol_ch = e->pol_ch, p.actions = e->d.A, p.vh = e->nd.num_value_hidden_channels;
+    const int hw = e->d.N * e->d.N;
+    const size_t smem = sizeof(float) * ((p.pol_ch + 1) * hw + p.vh + p.actions + 32);
+    mznn::heads_kernel<<<e->d.B, 256, smem, e->stream>>>(p);
+    e->launches++;
+    return MZ_OK;
+}
+
+// AlphaZeroNetwork.forward (network/py/alphazero_network.py:90-113) on the rows already in nn_in
+int forward(mz_engine* e)
+{
+    if (!e->net_ready) { return fail(MZ_ERR_STATE, "network not finalized"); }
+    int rc = conv(e, e->map_in0, e->convs[0], e->act[0], nullptr);
+    if (rc) { return rc; }
+    int cur = 0;
+    for (int b = 0; b < e->nd.num_blocks; ++b) {
+        const int t = (cur + 1) % 3, o = (cur + 2) % 3;
+        if ((rc = conv(e, e->map_act[cur], e->convs[1 + 2 * b], e->act[t], nullptr))) { return rc; }
+        if ((rc = conv(e, e->map_act[t], e->convs[2 + 2 * b], e->act[o], e->act[cur]))) { return rc; }
+        cur = o;
+    }
+    return launch_heads(e, e->act[cur]);
+}
+
+int step(mz_engine* e, int flags, const uint8_t* rotations)
+{
+    mz_state s = e->s;
+    s.rotations = rotations;
+    s.noise_in = (e->noise_enabled ? e->d_noise : nullptr);
+    k_step<<<e->d.B, 32, 0, e->stream>>>(e->d, s, flags);
+    e->launches++;
+    return MZ_OK;
+}
+
+std::vector<float> fold_conv(const mz_engine* e, const std::string& conv, const std::string& bn, int cout, int cin, int k, std::vector<float>& bias_out, std::string& err)
+{
+    auto get = [&](const std::string& name, size_t n) -> const float* {
+        auto it = e->tensors.find(name);
+        if (it == e->tensors.end()) {
+            err = "missing tensor " + name;
+            return nullptr;
+        }
+        if (it->second.size() != n) {
+            err = "tensor " + name + " has " + std::to_string(it->second.size()) + " elements, expected " + std::to_string(n);
+            return nullptr;
+        }
+        return it->second.data();
+    };
+    const size_t wn = static_cast<size_t>(cout) * cin * k * k;
+    const float *w = get(conv + ".weight", wn), *b = get(conv + ".bias", cout), *g = get(bn + ".weight", cout), *be = get(bn + ".bias", cout),
+                *mu = get(bn + ".running_mean", cout), *var = get(bn + ".running_var", cout);
+    std::vector<float> out;
+    if (!w || !b || !g || !be || !mu || !var) { return out; }
+    out.resize(wn);
+    bias_out.resize(cout);
+    for (int co = 0; co < cout; ++co) {
+        const float sc = g[co] / std::sqrt(var[co] + 1e-5f); // BatchNorm2d eval, eps default
+        for (size_t i = 0; i < static_cast<size_t>(cin) * k * k; ++i) { out[co * static_cast<size_t>(cin) * k * k + i] = w[co * static_cast<size_t>(cin) * k * k + i] * sc; }
+        bias_out[co] = (b[co] - mu[co]) * sc + be[co];
+    }
+    return out;
+}
+
+int plan_blob(mz_engine* e)
+{
+    const mz_net_dims& nd = e->nd;
+    e->cpad = ((nd.num_hidden_channels + 63) / 64) * 64;
+    e->pol_ch = (nd.action_size + nd.input_height * nd.input_width - 1) / (nd.input_height * nd.input_width);
+    // output-channel tile of the conv kernel: 128 keeps two CTAs resident per SM (epilogue of one overlaps the
+    // main loop of the other) and gives 2x the tiles for wave balance; MZ_CONV_BN overrides for experiments
+    e->bn_tile = (e->cpad % 128 == 0 ? 128 : 64);
+    if (const char* env = std::getenv("MZ_CONV_BN")) {
+        const int v = std::atoi(env);
+        if ((v == 64 || v == 128 || v == 256) && e->cpad % v == 0) { e->bn_tile = v; }
+    }
+    e->blob = Blob();
+    e->convs.assign(1 + 2 * nd.num_blocks, ConvLayer());
+    for (size_t i = 0; i < e->convs.size(); ++i) {
+        ConvLayer& L = e->convs[i];
+        L.cin = (i == 0 ? MZ_NN_CPAD : e->cpad), L.cout = e->cpad, L.relu = 1;
+        L.w_off = e->blob.take(sizeof(__half) * 9 * static_cast<size_t>(L.cout) * L.cin);
+        L.b_off = e->blob.take(sizeof(float) * L.cout);
+    }
+    const int hw = nd.input_height * nd.input_width;
+    const size_t head_sizes[10] = {static_cast<size_t>(e->pol_ch) * e->cpad, static_cast<size_t>(e->pol_ch), static_cast<size_t>(nd.action_size) * e->pol_ch * hw,
+                                   static_cast<size_t>(nd.action_size), static_cast<size_t>(e->cpad), 1, static_cast<size_t>(nd.num_value_hidden_channels) * hw,
+                                   static_cast<size_t>(nd.num_value_hidden_channels), static_cast<size_t>(nd.num_value_hidden_channels), 1};
+    for (int i = 0; i < 10; ++i) { e->off_head[i] = e->blob.take(sizeof(float) * head_sizes[i]); }
+    return MZ_OK;
+}
+
+int alloc_net(mz_engine* e)
+{
+    if (e->d_blob) { return MZ_OK; }
+    int rc;
+    if ((rc = configure_conv_kernels())) { return rc; }
+    if ((rc = e->dalloc(&e->d_blob, e->blob.size))) { return rc; }
+    const size_t rows = e->rows_alloc;
+    for (int i = 0; i < 3; ++i) {
+        if ((rc = e->dalloc(&e->act[i], rows * e->cpad))) { return rc; }
+        if ((rc = make_map_2d(e, &e->map_act[i], e->act[i], e->cpad, rows, mznn::BK, mznn::BM))) { return rc; }
+    }
+    if ((rc = make_map_2d(e, &e->map_in0, e->s.nn_in, MZ_NN_CPAD, rows, mznn::BK, mznn::BM))) { return rc; }
+    for (ConvLayer& L : e->convs) {
+        if ((rc = make_map_2d(e, &L.map_w, e->d_blob + L.w_off, L.cin, 9ull * L.cout, mznn::BK, e->bn_tile))) { return rc; }
+    }
+    return MZ_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* mz_last_error(void) { return g_error.c_str(); }
+
+int mz_create(const mz_config* cfg, mz_engine** out)
+{
+    if (!cfg || !out) { return fail(MZ_ERR_ARG, "null argument"); }
+    *out = nullptr;
+    if (cfg->game != MZ_GAME_GO && cfg->game != MZ_GAME_TICTACTOE) { return fail(MZ_ERR_ARG, "unsupported game"); }
+    const int N = (cfg->game == MZ_GAME_GO ? cfg->board_size : 3);
+    if (N < 2 || N > MZ_MAXN) { return fail(MZ_ERR_ARG, "board_size must be in [2, 19]"); }
+    if (cfg->num_games < 1 || cfg->num_simulation < 1) { return fail(MZ_ERR_ARG, "num_games and num_simulation must be positive"); }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { return fail(MZ_ERR_CUDA, "no CUDA device: libmzb200 has no CPU path"); }
+    if (cfg->device < 0 || cfg->device >= ndev) { return fail(MZ_ERR_ARG, "bad device ordinal"); }
+    CUDA_OK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) { return fail(MZ_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100: libmzb200 is built for sm_100a only"); }
+
+    mz_engine* e = new mz_engine();
+    e->cfg = *cfg;
+    mz_dims& d = e->d;
+    d.game = cfg->game, d.N = N, d.A = (cfg->game == MZ_GAME_GO ? N * N + 1 : 9), d.C = (cfg->game == MZ_GAME_GO ? 18 : 4);
+    d.S = cfg->num_simulation, d.B = cfg->num_games;
+    d.NP = 1 + (d.S + 1) * d.A; // actor_group.cpp:183, tree.h:66
+    if (d.NP >= (1 << MZ_LINK_SHIFT)) {
+        delete e;
+        return fail(MZ_ERR_ARG, "node pool per game exceeds 2^20 nodes");
+    }
+    d.slots = (N + 1) * (N + 1);
+    d.max_hashes = 2 * N * N + 4;
+    d.puct_init = cfg->puct_init, d.puct_base = cfg->puct_base, d.discount = cfg->reward_discount, d.komi = cfg->komi, d.eps = cfg->dirichlet_epsilon;
+
+    // Zobrist keys exactly as go.cpp:19-32 draws them: mt19937_64(0): turn key, then per position empty / black / white
+    std::mt19937_64 gen(0);
+    std::vector<uint64_t> keys(2 * 361);
+    const uint64_t turn_key = gen();
+    for (int pos = 0; pos < 361; ++pos) {
+        (void)gen();
+        keys[0 * 361 + pos] = gen();
+        keys[1 * 361 + pos] = gen();
+    }
+    d.turn_key = (cfg->ko_situational ? turn_key : 0);
+    // puct_bias[n] = (float)(init + log((1 + n + base) / base)) with the reference's float / double mix (mcts.cpp:57)
+    std::vector<float> bias(d.S + 2);
+    for (int n = 0; n < d.S + 2; ++n) {
+        float t = static_cast<float>(1 + n) + cfg->puct_base;
+        t = t / cfg->puct_base;
+        bias[n] = static_cast<float>(static_cast<double>(cfg->puct_init) + std::log(static_cast<double>(t)));
+    }
+
+    int rc = MZ_OK;
+    auto guard = [&](int r) {
+        if (r && !rc) { rc = r; }
+    };
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) {
+        delete e;
+        return fail(MZ_ERR_CUDA, "stream / event creation failed");
+    }
+    mz_state& s = e->s;
+    const size_t B = d.B, np = B * d.NP, BA = B * d.A;
+    e->rows_alloc = static_cast<int>((B * d.slots + mznn::BM - 1) / mznn::BM * mznn::BM);
+    guard(e->dalloc(&s.hot, np)), guard(e->dalloc(&s.action, np)), guard(e->dalloc(&s.logit, np)), guard(e->dalloc(&s.value, np));
+    guard(e->dalloc(&s.root_noise, BA)), guard(e->dalloc(&s.cursor, B));
+    guard(e->dalloc(&s.root_st, B * 2 * MZ_ROWS)), guard(e->dalloc(&s.root_hist, B * MZ_HIST * 2 * MZ_ROWS)), guard(e->dalloc(&s.root_hash, B));
+    guard(e->dalloc(&s.root_meta, B * 4)), guard(e->dalloc(&s.hashes, B * d.max_hashes));
+    guard(e->dalloc(&s.path, B * (d.S + 2))), guard(e->dalloc(&s.path_len, B)), guard(e->dalloc(&s.leaf_legal, B * MZ_LEGAL_WORDS));
+    guard(e->dalloc(&s.leaf_meta, B * 4)), guard(e->dalloc(&s.leaf_score, B));
+    guard(e->dalloc(&s.nn_in, static_cast<size_t>(e->rows_alloc) * MZ_NN_CPAD));
+    guard(e->dalloc(&s.policy, BA)), guard(e->dalloc(&s.logits, BA)), guard(e->dalloc(&s.nn_value, B));
+    guard(e->dalloc(&e->d_rot_all, B * (d.S + 1))), guard(e->dalloc(&e->d_noise, BA));
+    guard(e->dalloc(&e->d_bias_table, bias.size())), guard(e->dalloc(&e->d_keys, keys.size()));
+    guard(e->dalloc(&e->d_actions, B)), guard(e->dalloc(&e->d_play_out, B * 4)), guard(e->dalloc(&e->d_play_score, B));
+    guard(e->dalloc(&e->d_root_info, B * 4)), guard(e->dalloc(&e->d_root_action, BA));
+    for (int i = 0; i < 6; ++i) { guard(e->dalloc(&e->d_root_f[i], BA)); }
+    guard(e->dalloc(&e->d_feat_f32, B * d.C * N * N));
+    if (rc) {
+        mz_destroy(e);
+        return rc;
+    }
+    if (cudaMemcpyAsync(e->d_bias_table, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
+        cudaMemcpyAsync(e->d_keys, keys.data(), keys.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream) != cudaSuccess) {
+        mz_destroy(e);
+        return fail(MZ_ERR_CUDA, "table upload failed");
+    }
+    s.puct_bias = e->d_bias_table, s.keys = e->d_keys;
+    // driver entry point for tensor maps (no link-time dependency on libcuda)
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+        mz_destroy(e);
+        return fail(MZ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    }
+    e->encode = reinterpret_cast<encode_tiled_fn>(fn);
+    k_reset<<<d.B, 32, 0, e->stream>>>(d, s, -1);
+    e->launches++;
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
+        std::string msg = cudaGetErrorString(cudaGetLastError());
+        mz_destroy(e);
+        return fail(MZ_ERR_CUDA, "engine initialisation failed: " + msg);
+    }
+    *out = e;
+    return MZ_OK;
+}
+
+void mz_destroy(mz_engine* e)
+{
+    if (!e) { return; }
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) { cudaStreamSynchronize(e->stream); }
+    for (auto& kv : e->graphs) { cudaGraphExecDestroy(kv.second); }
+    for (void* p : e->allocs) { cudaFree(p); }
+    if (e->ev0) { cudaEventDestroy(e->ev0); }
+    if (e->ev1) { cudaEventDestroy(e->ev1); }
+    if (e->stream) { cudaStreamDestroy(e->stream); }
+    delete e;
+}
+
+int mz_action_size(const mz_engine* e) { return e ? e->d.A : MZ_ERR_ARG; }
+int mz_num_features(const mz_engine* e) { return e ? e->d.C * e->d.N * e->d.N : MZ_ERR_ARG; }
+int64_t mz_launch_count(const mz_engine* e) { return e ? e->launches : 0; }
+
+int mz_net_configure(mz_engine* e, const mz_net_dims* dims)
+{
+    if (!e || !dims) { return fail(MZ_ERR_ARG, "null argument"); }
+    if (dims->discrete_value_size != 1) { return fail(MZ_ERR_ARG, "discrete value heads are not implemented in this engine yet"); }
+    if (dims->num_input_channels != e->d.C || dims->input_height != e->d.N || dims->input_width != e->d.N || dims->action_size != e->d.A) {
+        return fail(MZ_ERR_ARG, "network dimensions do not match the game");
+    }
+    if (dims->num_input_channels > MZ_NN_CPAD || dims->num_hidden_channels < 1 || dims->num_blocks < 0) { return fail(MZ_ERR_ARG, "unsupported network size"); }
+    if (e->d_blob) { return fail(MZ_ERR_STATE, "network already allocated for this engine"); }
+    e->nd = *dims;
+    e->dims_set = true;
+    e->net_ready = false;
+    e->tensors.clear();
+    return plan_blob(e);
+}
+
+int mz_net_set_tensor(mz_engine* e, const char* name, const float* data, int64_t numel)
+{
+    if (!e || !name || !data || numel < 0) { return fail(MZ_ERR_ARG, "bad argument"); }
+    if (!e->dims_set) { return fail(MZ_ERR_STATE, "mz_net_configure first"); }
+    e->tensors[name].assign(data, data + numel);
+    return MZ_OK;
+}
+
+int mz_net_finalize_empty(mz_engine* e)
+{
+    if (!e || !e->dims_set) { return fail(MZ_ERR_STATE, "mz_net_configure first"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    int rc = alloc_net(e);
+    if (rc) { return rc; }
+    for (auto& kv : e->graphs) { cudaGraphExecDestroy(kv.second); }
+    e->graphs.clear();
+    e->net_ready = true;
+    return MZ_OK;
+}
+
+int mz_net_finalize(mz_engine* e)
+{
+    if (!e || !e->dims_set) { return fail(MZ_ERR_STATE, "mz_net_configure first"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    const mz_net_dims& nd = e->nd;
+    const int hw = nd.input_height * nd.input_width, Ch = nd.num_hidden_channels, cp = e->cpad;
+    std::vector<uint8_t> host(e->blob.size, 0);
+    std::string err;
+    // 3x3 convolutions: [tap][cout_pad][cin_pad] fp16, BN folded
+    for (size_t li = 0; li < e->convs.size(); ++li) {
+        const ConvLayer& L = e->convs[li];
+        std::string cname, bname;
+        int cin_real;
+        if (li == 0) {
+            cname = "conv", bname = "bn", cin_real = nd.num_input_channels;
+        } else {
+            const int blk = static_cast<int>(li - 1) / 2, which = static_cast<int>(li - 1) % 2 + 1;
+            cname = "residual_blocks." + std::to_string(blk) + ".conv" + std::to_string(which);
+            bname = "residual_blocks." + std::to_string(blk) + ".bn" + std::to_string(which);
+            cin_real = Ch;
+        }
+        std::vector<float> bias;
+        std::vector<float> w = fold_conv(e, cname, bname, Ch, cin_real, 3, bias, err);
+        if (w.empty()) { return fail(MZ_ERR_ARG, err); }
+        __half* wd = reinterpret_cast<__half*>(host.data() + L.w_off);
+        float* bd = reinterpret_cast<float*>(host.data() + L.b_off);
+        for (int co = 0; co < Ch; ++co) {
+            bd[co] = bias[co];
+            for (int ci = 0; ci < cin_real; ++ci) {
+                for (int tap = 0; tap < 9; ++tap) {
+                    wd[(static_cast<size_t>(tap) * L.cout + co) * L.cin + ci] = __float2half_rn(w[(static_cast<size_t>(co) * cin_real + ci) * 9 + tap]);
+                }
+            }
+        }
+    }
+    // heads, fp32
+    auto put = [&](int idx, const std::vector<float>& v) { std::memcpy(host.data() + e->off_head[idx], v.data(), v.size() * sizeof(float)); };
+    auto raw = [&](const std::string& name, size_t n, std::vector<float>& out) -> bool {
+        auto it = e->tensors.find(name);
+        if (it == e->tensors.end() || it->second.size() != n) {
+            err = "missing or mis-sized tensor " + name;
+            return false;
+        }
+        out = it->second;
+        return true;
+    };
+    {
+        std::vector<float> bias, w = fold_conv(e, "policy.conv", "policy.bn", e->pol_ch, Ch, 1, bias, err);
+        if (w.empty()) { return fail(MZ_ERR_ARG, err); }
+        std::vector<float> wp(static_cast<size_t>(e->pol_ch) * cp, 0.0f);
+        for (int o = 0; o < e->pol_ch; ++o) {
+            for (int c = 0; c < Ch; ++c) { wp[static_cast<size_t>(o) * cp + c] = w[static_cast<size_t>(o) * Ch + c]; }
+        }
+        put(0, wp), put(1, bias);
+        std::vector<float> t;
+        if (!raw("policy.fc.weight", static_cast<size_t>(nd.action_size) * e->pol_ch * hw, t)) { return fail(MZ_ERR_ARG, err); }
+        put(2, t);
+        if (!raw("policy.fc.bias", nd.action_size, t)) { return fail(MZ_ERR_ARG, err); }
+        put(3, t);
+    }
+    {
+        std::vector<float> bias, w = fold_conv(e, "value.conv", "value.bn", 1, Ch, 1, bias, err);
+        if (w.empty()) { return fail(MZ_ERR_ARG, err); }
+        std::vector<float> wp(cp, 0.0f);
+        for (int c = 0; c < Ch; ++c) { wp[c] = w[c]; }
+        put(4, wp), put(5, bias);
+        std::vector<float> t;
+        if (!raw("value.fc1.weight", static_cast<size_t>(nd.num_value_hidden_channels) * hw, t)) { return fail(MZ_ERR_ARG, err); }
+        put(6, t);
+        if (!raw("value.fc1.bias", nd.num_value_hidden_channels, t)) { return fail(MZ_ERR_ARG, err); }
+        put(7, t);
+        if (!raw("value.fc2.weight", nd.num_value_hidden_channels, t)) { return fail(MZ_ERR_ARG, err); }
+        put(8, t);
+        if (!raw("value.fc2.bias", 1, t)) { return fail(MZ_ERR_ARG, err); }
+        put(9, t);
+    }
+    int rc = alloc_net(e);
+    if (rc) { return rc; }
+    CUDA_OK(cudaMemcpyAsync(e->d_blob, host.data(), host.size(), cudaMemcpyHostToDevice, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    e->tensors.clear();
+    e->net_ready = true;
+    return MZ_OK;
+}
+
+int mz_net_blob(mz_engine* e, void** device_ptr, int64_t* bytes)
+{
+    if (!e || !device_ptr || !bytes) { return fail(MZ_ERR_ARG, "null argument"); }
+    if (!e->d_blob) { return fail(MZ_ERR_STATE, "network not allocated"); }
+    *device_ptr = e->d_blob;
+    *bytes = static_cast<int64_t>(e->blob.size);
+    return MZ_OK;
+}
+
+int mz_eval_batch(mz_engine* e, const float* features, int32_t n, float* policy, float* logits, float* value)
+{
+    if (!e || !features || n < 1 || n > e->d.B) { return fail(MZ_ERR_ARG, "bad argument"); }
+    if (!e->net_ready) { return fail(MZ_ERR_STATE, "network not finalized"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    const mz_dims& d = e->d;
+    const size_t F = static_cast<size_t>(d.C) * d.N * d.N;
+    CUDA_OK(cudaMemcpyAsync(e->d_feat_f32, features, n * F * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CUDA_OK(cudaMemsetAsync(e->s.nn_in, 0, static_cast<size_t>(e->rows_alloc) * MZ_NN_CPAD * sizeof(uint16_t), e->stream));
+    mznn::pack_features_kernel<<<148, 256, 0, e->stream>>>(e->d_feat_f32, reinterpret_cast<__half*>(e->s.nn_in), n, d.C, d.N, d.slots, MZ_NN_CPAD);
+    e->launches++;
+    int rc = forward(e);
+    if (rc) { return rc; }
+    if (policy) { CUDA_OK(cudaMemcpyAsync(policy, e->s.policy, sizeof(float) * n * d.A, cudaMemcpyDeviceToHost, e->stream)); }
+    if (logits) { CUDA_OK(cudaMemcpyAsync(logits, e->s.logits, sizeof(float) * n * d.A, cudaMemcpyDeviceToHost, e->stream)); }
+    if (value) { CUDA_OK(cudaMemcpyAsync(value, e->s.nn_value, sizeof(float) * n, cudaMemcpyDeviceToHost, e->stream)); }
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    CUDA_OK(cudaGetLastError());
+    return MZ_OK;
+}
+
+int mz_reset_game(mz_engine* e, int32_t g)
+{
+    if (!e || g >= e->d.B) { return fail(MZ_ERR_ARG, "bad argument"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    k_reset<<<e->d.B, 32, 0, e->stream>>>(e->d, e->s, g);
+    e->launches++;
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    CUDA_OK(cudaGetLastError());
+    return MZ_OK;
+}
+
+int mz_play(mz_engine* e, const int32_t* actions, mz_play_result* results)
+{
+    if (!e || !actions || !results) { return fail(MZ_ERR_ARG, "null argument"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    const int B = e->d.B;
+    CUDA_OK(cudaMemcpyAsync(e->d_actions, actions, sizeof(int32_t) * B, cudaMemcpyHostToDevice, e->stream));
+    k_play<<<B, 32, 0, e->stream>>>(e->d, e->s, e->d_actions, e->d_play_out, e->d_play_score);
+    e->launches++;
+    std::vector<int32_t> out(static_cast<size_t>(B) * 4);
+    std::vector<float> score(B);
+    CUDA_OK(cudaMemcpyAsync(out.data(), e->d_play_out, sizeof(int32_t) * B * 4, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaMemcpyAsync(score.data(), e->d_play_score, sizeof(float) * B, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    CUDA_OK(cudaGetLastError());
+    for (int g = 0; g < B; ++g) {
+        results[g].applied = out[g * 4 + 0], results[g].terminal = out[g * 4 + 1], results[g].num_legal = out[g * 4 + 2], results[g].turn = out[g * 4 + 3];
+        results[g].eval_score = score[g];
+    }
+    return MZ_OK;
+}
+
+int mz_get_roots(mz_engine* e, mz_root_info* info, int32_t* action, float* count, float* mean, float* policy, float* logit, float* noise, float* value)
+{
+    if (!e) { return fail(MZ_ERR_ARG, "null argument"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    const int B = e->d.B;
+    const size_t BA = static_cast<size_t>(B) * e->d.A;
+    k_gather_roots<<<B, 32, 0, e->stream>>>(e->d, e->s, e->d_root_info, e->d_root_action, e->d_root_f[0], e->d_root_f[1], e->d_root_f[2], e->d_root_f[3], e->d_root_f[4],
+                                            e->d_root_f[5]);
+    e->launches++;
+    std::vector<float> hinfo(static_cast<size_t>(B) * 4);
+    CUDA_OK(cudaMemcpyAsync(hinfo.data(), e->d_root_info, sizeof(float) * B * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (action) { CUDA_OK(cudaMemcpyAsync(action, e->d_root_action, sizeof(int32_t) * BA, cudaMemcpyDeviceToHost, e->stream)); }
+    float* outs[6] = {count, mean, policy, logit, noise, value};
+    for (int i = 0; i < 6; ++i) {
+        if (outs[i]) { CUDA_OK(cudaMemcpyAsync(outs[i], e->d_root_f[i], sizeof(float) * BA, cudaMemcpyDeviceToHost, e->stream)); }
+    }
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    CUDA_OK(cudaGetLastError());
+    if (info) {
+        for (int g = 0; g < B; ++g) {
+            int32_t nc;
+            std::memcpy(&nc, &hinfo[g * 4], 4);
+            info[g].num_children = nc, info[g].count = hinfo[g * 4 + 1], info[g].mean = hinfo[g * 4 + 2], info[g].value = hinfo[g * 4 + 3];
+        }
+    }
+    return MZ_OK;
+}
+
+int mz_search_select(mz_engine* e, const uint8_t* rotations, float* features_out, int32_t* path_len_out)
+{
+    if (!e) { return fail(MZ_ERR_ARG, "null argument"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    const mz_dims& d = e->d;
+    if (rotations) { CUDA_OK(cudaMemcpyAsync(e->d_rot_all, rotations, d.B, cudaMemcpyHostToDevice, e->stream)); }
+    step(e, STEP_BEFORE, rotations ? e->d_rot_all : nullptr);
+    if (features_out) {
+        const size_t F = static_cast<size_t>(d.C) * d.N * d.N;
+        mznn::unpack_features_kernel<<<148, 256, 0, e->stream>>>(reinterpret_cast<const __half*>(e->s.nn_in), e->d_feat_f32, d.B, d.C, d.N, d.slots, MZ_NN_CPAD);
+        e->launches++;
+        CUDA_OK(cudaMemcpyAsync(features_out, e->d_feat_f32, sizeof(float) * d.B * F, cudaMemcpyDeviceToHost, e->stream));
+    }
+    if (path_len_out) { CUDA_OK(cudaMemcpyAsync(path_len_out, e->s.path_len, sizeof(int32_t) * d.B, cudaMemcpyDeviceToHost, e->stream)); }
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    CUDA_OK(cudaGetLastError());
+    return MZ_OK;
+}
+
+int mz_search_apply(mz_engine* e, const float* policy, const float* logits, const float* value, const float* noise)
+{
+    if (!e || !policy || !logits || !value) { return fail(MZ_ERR_ARG, "null argument"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    const mz_dims& d = e->d;
+    const size_t BA = static_cast<size_t>(d.B) * d.A;
+    CUDA_OK(cudaMemcpyAsync(e->s.policy, policy, sizeof(float) * BA, cudaMemcpyHostToDevice, e->stream));
+    CUDA_OK(cudaMemcpyAsync(e->s.logits, logits, sizeof(float) * BA, cudaMemcpyHostToDevice, e->stream));
+    CUDA_OK(cudaMemcpyAsync(e->s.nn_value, value, sizeof(float) * d.B, cudaMemcpyHostToDevice, e->stream));
+    if (noise) { CUDA_OK(cudaMemcpyAsync(e->d_noise, noise, sizeof(float) * BA, cudaMemcpyHostToDevice, e->stream)); }
+    const bool saved = e->noise_enabled;
+    e->noise_enabled = (noise != nullptr);
+    step(e, STEP_AFTER, nullptr);
+    e->noise_enabled = saved;
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    CUDA_OK(cudaGetLastError());
+    return MZ_OK;
+}
+
+int mz_search_set_inputs(mz_engine* e, const uint8_t* rotations, const float* noise)
+{
+    if (!e) { return fail(MZ_ERR_ARG, "null argument"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    const mz_dims& d = e->d;
+    if (rotations) { CUDA_OK(cudaMemcpyAsync(e->d_rot_all, rotations, static_cast<size_t>(d.B) * (d.S + 1), cudaMemcpyHostToDevice, e->stream)); }
+    if (noise) { CUDA_OK(cudaMemcpyAsync(e->d_noise, noise, sizeof(float) * d.B * d.A, cudaMemcpyHostToDevice, e->stream)); }
+    e->rot_enabled = (rotations != nullptr);
+    e->noise_enabled = (noise != nullptr);
+    return MZ_OK;
+}
+
+int mz_search_run(mz_engine* e, int32_t num_evals, float* device_ms)
+{
+    if (!e) { return fail(MZ_ERR_ARG, "null argument"); }
+    if (!e->net_ready) { return fail(MZ_ERR_STATE, "network not finalized"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    const mz_dims& d = e->d;
+    if (num_evals <= 0) { num_evals = d.S + 1; }
+    if (num_evals > d.S + 1) { return fail(MZ_ERR_ARG, "num_evals exceeds actor_num_simulation + 1"); }
+    const int key = num_evals * 4 + (e->noise_enabled ? 2 : 0) + (e->rot_enabled ? 1 : 0);
+    auto it = e->graphs.find(key);
+    if (it == e->graphs.end()) {
+        // capture the whole search: before | (NN, after+before) x (n-1) | NN, after
+        cudaGraph_t graph = nullptr;
+        const int64_t launches_before = e->launches;
+        CUDA_OK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = MZ_OK;
+        for (int c = 0; c < num_evals && !rc; ++c) {
+            step(e, (c > 0 ? STEP_AFTER : 0) | STEP_BEFORE, e->rot_enabled ? e->d_rot_all + static_cast<size_t>(c) * d.B : nullptr);
+            rc = forward(e);
+        }
+        step(e, STEP_AFTER, nullptr);
+        cudaError_t cerr = cudaStreamEndCapture(e->stream, &graph);
+        e->launches = launches_before;
+        if (rc) { return rc; }
+        if (cerr != cudaSuccess) { return fail(MZ_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(cerr)); }
+        cudaGraphExec_t exec = nullptr;
+        cerr = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (cerr != cudaSuccess) { return fail(MZ_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(cerr)); }
+        it = e->graphs.emplace(key, exec).first;
+    }
+    CUDA_OK(cudaEventRecord(e->ev0, e->stream));
+    CUDA_OK(cudaGraphLaunch(it->second, e->stream));
+    CUDA_OK(cudaEventRecord(e->ev1, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    CUDA_OK(cudaGetLastError());
+    e->launches += 1 + static_cast<int64_t>(num_evals) * (2 + static_cast<int64_t>(e->convs.size()));
+    if (device_ms) { CUDA_OK(cudaEventElapsedTime(device_ms, e->ev0, e->ev1)); }
+    return MZ_OK;
+}
+
+int mz_profile_kernels(mz_engine* e, int32_t iters, float* conv_ms, float* tree_ms, float* heads_ms)
+{
+    if (!e || iters < 1) { return fail(MZ_ERR_ARG, "bad argument"); }
+    if (!e->net_ready) { return fail(MZ_ERR_STATE, "network not finalized"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    float ms = 0.0f;
+    if (conv_ms) {
+        const ConvLayer& L = e->convs.back();
+        for (int i = 0; i < 3; ++i) { conv(e, e->map_act[0], L, e->act[1], e->act[2]); }
+        CUDA_OK(cudaEventRecord(e->ev0, e->stream));
+        for (int i = 0; i < iters; ++i) { conv(e, e->map_act[0], L, e->act[1], e->act[2]); }
+        CUDA_OK(cudaEventRecord(e->ev1, e->stream));
+        CUDA_OK(cudaStreamSynchronize(e->stream));
+        CUDA_OK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+        *conv_ms = ms / iters;
+    }
+    if (heads_ms) {
+        for (int i = 0; i < 3; ++i) { launch_heads(e, e->act[0]); }
+        CUDA_OK(cudaEventRecord(e->ev0, e->stream));
+        for (int i = 0; i < iters; ++i) { launch_heads(e, e->act[0]); }
+        CUDA_OK(cudaEventRecord(e->ev1, e->stream));
+        CUDA_OK(cudaStreamSynchronize(e->stream));
+        CUDA_OK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+        *heads_ms = ms / iters;
+    }
+    if (tree_ms) {
+        // selection + transition + leaf analysis on the trees as they stand (STEP_BEFORE does not modify them)
+        for (int i = 0; i < 3; ++i) { step(e, STEP_BEFORE, nullptr); }
+        CUDA_OK(cudaEventRecord(e->ev0, e->stream));
+        for (int i = 0; i < iters; ++i) { step(e, STEP_BEFORE, nullptr); }
+        CUDA_OK(cudaEventRecord(e->ev1, e->stream));
+        CUDA_OK(cudaStreamSynchronize(e->stream));
+        CUDA_OK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+        *tree_ms = ms / iters;
+    }
+    CUDA_OK(cudaGetLastError());
+    return MZ_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,359 @@
+// Network kernels for sm_100a: BN-folded 3x3 convolution as an implicit GEMM on tcgen05 tensor cores
+// (TMA-staged operands, fp32 accumulators in TMEM, fused bias + residual + ReLU epilogue) and the fused
+// policy / value heads.
+//
+// Math restated (paths relative to /root/reference/minizero):
+//   network/py/alphazero_network.py:90-113  stem conv-BN-ReLU, residual tower, heads, softmax
+//   network/py/network_unit.py:6-23         ResidualBlock: conv3x3-BN-ReLU-conv3x3-BN-(+x)-ReLU
+//   network/py/network_unit.py:26-42        PolicyNetwork: conv1x1-BN-ReLU-fc
+//   network/py/network_unit.py:45-65        ValueNetwork: conv1x1-BN-ReLU-fc1-ReLU-fc2-tanh
+//
+// Activation layout ("shared-halo rows"): fp16 [rows][C], one row per board slot. A board of N x N cells owns
+// (N+1) x (N+1) consecutive rows: slot (yy, xx) = yy * (N+1) + xx holds cell (x = xx, y = yy - 1); slots with
+// yy == 0 or xx == N are zero and serve as the halo of the cells next to them — and, because boards are stored
+// back to back, as the halo of the neighbouring board too. A 3x3 tap (ky, kx) of EVERY output row is then the
+// input row at the constant offset (ky-1)*(N+1) + (kx-1), so the convolution is 9 accumulated GEMMs whose A
+// tiles are plain 2-D TMA boxes of the same matrix shifted by a row offset (rows outside the matrix are
+// zero-filled by TMA). Cost: the halo rows are computed and then zeroed, (N+1)^2 / N^2 of the useful FLOPs.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mznn {
+
+constexpr int BM = 128;      // rows (board slots) per tile = UMMA M
+constexpr int BK = 64;       // K per pipeline stage: 64 fp16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;   // K per tcgen05.mma for 16-bit inputs
+constexpr int CONV_THREADS = 192; // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile in shared memory, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart
+// (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+// layout [61,64) with SWIZZLE_128B = 2)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+// InstrDescriptor (same header): D = F32 [4,6) = 1, A/B = F16 (0), K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n)
+{
+    return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct ConvParams {
+    __half* out;            // [rows_alloc][cout]
+    const __half* residual; // [rows_alloc][cout] or null
+    const float* bias;      // [cout] BN-folded
+    int rows_valid;         // B * slots
+    int n1;                 // N + 1: slots per board row
+    int slots;              // (N + 1)^2
+    int cin;                // multiple of BK
+    int cout;               // multiple of BN
+    int relu;
+};
+
+template <int BN, int STAGES>
+struct ConvSmem {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024; // + alignment slack
+};
+
+// out[r][n0 + j] = act( bias[n0 + j] + sum_{tap, ci} in[r + off(tap)][ci] * w[tap][n0 + j][ci] (+ residual[r][n0 + j]) ),
+// halo rows forced to zero. grid = (row tiles, cout / BN).
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w, const ConvParams p)
+{
+    using L = ConvSmem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int kb_per_tap = p.cin / BK, num_k = 9 * kb_per_tap;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_in)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) { // TMEM accumulator: BN fp32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) { // ===== TMA producer =====
+            for (int k = 0; k < num_k; ++k) {
+                const int s = k % STAGES;
+                if (k >= STAGES) { mbar_wait(&empty_bar[s], ((k / STAGES) - 1) & 1); }
+                const int tap = k / kb_per_tap, kb = k - tap * kb_per_tap;
+                const int off = (tap / 3 - 1) * p.n1 + (tap % 3 - 1);
+                uint8_t* a_dst = smem + s * L::STAGE_BYTES;
+                uint8_t* b_dst = a_dst + L::A_BYTES;
+                mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+                tma_load_2d(a_dst, &map_in, &full_bar[s], kb * BK, m0 + off);
+                tma_load_2d(b_dst, &map_w, &full_bar[s], kb * BK, tap * p.cout + n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) { // ===== MMA issuer =====
+            constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+            for (int k = 0; k < num_k; ++k) {
+                const int s = k % STAGES;
+                mbar_wait(&full_bar[s], (k / STAGES) & 1);
+                tcgen05_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES), b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                    umma_f16(tmem_base, umma_desc_sw128(a_addr + kk * UMMA_K * 2), umma_desc_sw128(b_addr + kk * UMMA_K * 2), idesc, (k | kk) != 0);
+                }
+                tcgen05_commit(&empty_bar[s]); // frees the stage once these MMAs have read it
+            }
+            tcgen05_commit(accum_bar); // accumulator complete
+        }
+    } else { // ===== epilogue: TMEM -> registers -> bias (+ residual) (ReLU) -> fp16 rows =====
+        const int quarter = warp & 3; // TMEM lanes [32 * (warp % 4), +32) are the only ones this warp may read
+        const int r = m0 + quarter * 32 + lane;
+        const int rr = r % p.slots;
+        const bool live = (r < p.rows_valid) && (rr / p.n1 != 0) && (rr % p.n1 != p.n1 - 1);
+        mbar_wait(accum_bar, 0);
+        tcgen05_fence_after();
+        __half* out_row = p.out + static_cast<size_t>(r) * p.cout + n0;
+        const __half* res_row = (p.residual ? p.residual + static_cast<size_t>(r) * p.cout + n0 : nullptr);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c, v);
+            tmem_ld_wait();
+            uint4 packed[4];
+            uint32_t* pk = reinterpret_cast<uint32_t*>(packed);
+            uint4 res[4];
+            if (res_row && live) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { res[q] = *reinterpret_cast<const uint4*>(res_row + c + q * 8); }
+            }
+            const __half2* rh = reinterpret_cast<const __half2*>(res);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float x0 = __uint_as_float(v[2 * j]) + __ldg(p.bias + n0 + c + 2 * j);
+                float x1 = __uint_as_float(v[2 * j + 1]) + __ldg(p.bias + n0 + c + 2 * j + 1);
+                if (res_row && live) {
+                    const float2 rf = __half22float2(rh[j]);
+                    x0 += rf.x, x1 += rf.y;
+                }
+                if (p.relu) { x0 = fmaxf(x0, 0.0f), x1 = fmaxf(x1, 0.0f); }
+                if (!live) { x0 = 0.0f, x1 = 0.0f; }
+                const __half2 h = __floats2half2_rn(x0, x1);
+                pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { *reinterpret_cast<uint4*>(out_row + c + q * 8) = packed[q]; }
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// heads: one CTA per board. conv1x1 (+folded BN) + ReLU for the policy and value planes, then the
+// fully connected layers, softmax over the policy logits and tanh on the value. fp32 SIMT: 0.2 MFLOP / board.
+// ---------------------------------------------------------------------------------------------
+struct HeadParams {
+    const __half* act;  // [rows][c] final tower activations
+    const float* w_pc;  // [pol_ch][c] policy conv (BN folded)   b_pc [pol_ch]
+    const float* b_pc;
+    const float* w_pf;  // [A][pol_ch * hw] policy fc            b_pf [A]
+    const float* b_pf;
+    const float* w_vc;  // [c] value conv (BN folded)            b_vc [1]
+    const float* b_vc;
+    const float* w_v1;  // [vh][hw]   b_v1 [vh]
+    const float* b_v1;
+    const float* w_v2;  // [vh]       b_v2 [1]
+    const float* b_v2;
+    float* policy;      // [B][A]
+    float* logits;      // [B][A]
+    float* value;       // [B]
+    int c, n, slots, pol_ch, actions, vh;
+};
+
+__global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
+{
+    extern __shared__ float sm[];
+    const int hw = p.n * p.n, n1 = p.n + 1;
+    float* planes = sm;                          // [(pol_ch + 1)][hw]: policy planes then the value plane
+    float* vhid = planes + (p.pol_ch + 1) * hw;  // [vh]
+    float* lg = vhid + p.vh;                     // [A]
+    float* red = lg + p.actions;                 // [32]
+    const int g = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    const __half* act = p.act + static_cast<size_t>(g) * p.slots * p.c;
+    // 1x1 convolutions: one (plane, cell) dot product of length c per work item
+    for (int item = tid; item < (p.pol_ch + 1) * hw; item += nthr) {
+        const int plane = item / hw, cell = item % hw;
+        const __half2* row = reinterpret_cast<const __half2*>(act + static_cast<size_t>((cell / p.n + 1) * n1 + cell % p.n) * p.c);
+        const float* w = (plane < p.pol_ch ? p.w_pc + static_cast<size_t>(plane) * p.c : p.w_vc);
+        float acc = 0.0f;
+        for (int i = 0; i < p.c / 2; ++i) {
+            const float2 a = __half22float2(row[i]);
+            acc = fmaf(a.x, w[2 * i], acc);
+            acc = fmaf(a.y, w[2 * i + 1], acc);
+        }
+        acc += (plane < p.pol_ch ? p.b_pc[plane] : p.b_vc[0]);
+        planes[item] = fmaxf(acc, 0.0f);
+    }
+    __syncthreads();
+    // policy fc and value fc1
+    for (int o = tid; o < p.actions + p.vh; o += nthr) {
+        if (o < p.actions) {
+            const float* w = p.w_pf + static_cast<size_t>(o) * p.pol_ch * hw;
+            float acc = 0.0f;
+            for (int i = 0; i < p.pol_ch * hw; ++i) { acc = fmaf(planes[i], w[i], acc); }
+            lg[o] = acc + p.b_pf[o];
+        } else {
+            const int j = o - p.actions;
+            const float* w = p.w_v1 + static_cast<size_t>(j) * hw;
+            const float* vp = planes + p.pol_ch * hw;
+            float acc = 0.0f;
+            for (int i = 0; i < hw; ++i) { acc = fmaf(vp[i], w[i], acc); }
+            vhid[j] = fmaxf(acc + p.b_v1[j], 0.0f);
+        }
+    }
+    __syncthreads();
+    // softmax over the logits (block reduction), value fc2 + tanh
+    float mx = -3.402823466e+38f;
+    for (int a = tid; a < p.actions; a += nthr) { mx = fmaxf(mx, lg[a]); }
+    for (int o = 16; o > 0; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    if ((tid & 31) == 0) { red[tid >> 5] = mx; }
+    __syncthreads();
+    mx = red[0];
+    for (int i = 1; i < (nthr + 31) / 32; ++i) { mx = fmaxf(mx, red[i]); }
+    __syncthreads();
+    float sum = 0.0f;
+    for (int a = tid; a < p.actions; a += nthr) { sum += expf(lg[a] - mx); }
+    for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); }
+    if ((tid & 31) == 0) { red[tid >> 5] = sum; }
+    __syncthreads();
+    sum = 0.0f;
+    for (int i = 0; i < (nthr + 31) / 32; ++i) { sum += red[i]; }
+    for (int a = tid; a < p.actions; a += nthr) {
+        p.logits[static_cast<size_t>(g) * p.actions + a] = lg[a];
+        p.policy[static_cast<size_t>(g) * p.actions + a] = expf(lg[a] - mx) / sum;
+    }
+    if (tid < 32) {
+        float acc = 0.0f;
+        for (int j = tid; j < p.vh; j += 32) { acc = fmaf(vhid[j], p.w_v2[j], acc); }
+        for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); }
+        if (tid == 0) { p.value[g] = tanhf(acc + p.b_v2[0]); }
+    }
+}
+
+// float NCHW feature planes (host layout of the reference, alphazero_network.h:48-61) -> fp16 shared-halo rows
+__global__ void pack_features_kernel(const float* __restrict__ feats, __half* __restrict__ rows, int batch, int c, int n, int slots, int cpad)
+{
+    const int hw = n * n, total = batch * c * hw;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int g = i / (c * hw), ch = (i / hw) % c, cell = i % hw;
+        rows[(static_cast<size_t>(g) * slots + (cell / n + 1) * (n + 1) + cell % n) * cpad + ch] = __float2half_rn(feats[i]);
+    }
+}
+
+// fp16 shared-halo rows -> float NCHW planes (parity hook for the feature planes the search produced)
+__global__ void unpack_features_kernel(const __half* __restrict__ rows, float* __restrict__ feats, int batch, int c, int n, int slots, int cpad)
+{
+    const int hw = n * n, total = batch * c * hw;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int g = i / (c * hw), ch = (i / hw) % c, cell = i % hw;
+        feats[i] = __half2float(rows[(static_cast<size_t>(g) * slots + (cell / n + 1) * (n + 1) + cell % n) * cpad + ch]);
+    }
+}
+
+} // namespace mznn

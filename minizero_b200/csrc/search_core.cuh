@@ -676,7 +676,7 @@ MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* 
         for (int i = lane; i < MZ_LEGAL_WORDS; i += MZ_W) { k += mz_popc(w->legal[i]); }
         k = mz_reduce_add(k);
         // rank sort: descending policy, exact ties by ascending action id (std::sort is unstable there;
-        // see the note in oracle/port/mzo_mcts.c)
+        // DESIGN.md "candidate order")
         for (int a = lane; a < A; a += MZ_W) {
             if (!((w->legal[a >> 5] >> (a & 31)) & 1u)) { continue; }
             const float p = w->pol[a];

@@ -1,0 +1,282 @@
+"""ctypes binding of libmzb200.so + the host-side mirror of the reference's actor interface for the hot path.
+
+Reference interfaces mirrored (paths relative to /root/reference/minizero):
+  network/network.cpp:14-42, create_network.h:11-30  -> Engine.load_network (TorchScript .pt reader)
+  network/alphazero_network.h:48-104                 -> Engine.eval_batch
+  actor/zero_actor.cpp:51-98                         -> Engine.select / Engine.apply (per-phase parity hooks)
+  actor/actor_group.cpp:136-148                      -> Engine.search (whole move, one CUDA graph)
+  actor/base_actor.cpp:8-30                          -> Engine.reset_game / Engine.play
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+GAME_TICTACTOE, GAME_GO = 0, 1
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class _Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("game", C.c_int32), ("board_size", C.c_int32), ("num_games", C.c_int32), ("num_simulation", C.c_int32),
+                ("puct_base", C.c_float), ("puct_init", C.c_float), ("reward_discount", C.c_float), ("komi", C.c_float), ("ko_situational", C.c_int32),
+                ("dirichlet_epsilon", C.c_float)]
+
+
+class _NetDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("num_input_channels", "input_height", "input_width", "num_hidden_channels", "num_blocks", "action_size",
+                                        "num_value_hidden_channels", "discrete_value_size")]
+
+
+class _PlayResult(C.Structure):
+    _fields_ = [("applied", C.c_int32), ("terminal", C.c_int32), ("num_legal", C.c_int32), ("turn", C.c_int32), ("eval_score", C.c_float)]
+
+
+class _RootInfo(C.Structure):
+    _fields_ = [("num_children", C.c_int32), ("count", C.c_float), ("mean", C.c_float), ("value", C.c_float)]
+
+
+def library_path():
+    return os.path.join(_ROOT, "minizero_b200", "lib", "libmzb200.so")
+
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+
+
+def build_library(force=False, verbose=False):
+    """nvcc-compile minizero_b200/csrc/engine.cu for sm_100a into minizero_b200/lib/libmzb200.so (in-tree)."""
+    src_dir = os.path.join(_ROOT, "minizero_b200", "csrc")
+    srcs = [os.path.join(src_dir, f) for f in sorted(os.listdir(src_dir))] + [os.path.join(_ROOT, "include", "mz_b200.h")]
+    out = library_path()
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(s) for s in srcs):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, os.path.join(src_dir, "engine.cu")]
+    subprocess.run(cmd, check=True)
+    return out
+
+
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise EngineError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)")
+    lib = C.CDLL(path)
+    vp, i32, f32p, u8p, i32p = C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
+    lib.mz_last_error.restype = C.c_char_p
+    lib.mz_create.argtypes = [C.POINTER(_Config), C.POINTER(vp)]
+    lib.mz_destroy.argtypes = [vp]
+    lib.mz_destroy.restype = None
+    lib.mz_action_size.argtypes = [vp]
+    lib.mz_num_features.argtypes = [vp]
+    lib.mz_net_configure.argtypes = [vp, C.POINTER(_NetDims)]
+    lib.mz_net_set_tensor.argtypes = [vp, C.c_char_p, f32p, C.c_int64]
+    lib.mz_net_finalize.argtypes = [vp]
+    lib.mz_net_finalize_empty.argtypes = [vp]
+    lib.mz_net_blob.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int64)]
+    lib.mz_eval_batch.argtypes = [vp, f32p, i32, f32p, f32p, f32p]
+    lib.mz_reset_game.argtypes = [vp, i32]
+    lib.mz_play.argtypes = [vp, i32p, C.POINTER(_PlayResult)]
+    lib.mz_get_roots.argtypes = [vp, C.POINTER(_RootInfo), i32p] + [f32p] * 6
+    lib.mz_search_select.argtypes = [vp, u8p, f32p, i32p]
+    lib.mz_search_apply.argtypes = [vp, f32p, f32p, f32p, f32p]
+    lib.mz_search_set_inputs.argtypes = [vp, u8p, f32p]
+    lib.mz_search_run.argtypes = [vp, i32, f32p]
+    lib.mz_profile_kernels.argtypes = [vp, i32, f32p, f32p, f32p]
+    lib.mz_launch_count.argtypes = [vp]
+    lib.mz_launch_count.restype = C.c_int64
+    _lib = lib
+    return lib
+
+
+EXPORTS = ["mz_create", "mz_destroy", "mz_last_error", "mz_action_size", "mz_num_features", "mz_net_configure", "mz_net_set_tensor", "mz_net_finalize",
+           "mz_net_blob", "mz_net_finalize_empty", "mz_eval_batch", "mz_reset_game", "mz_play", "mz_get_roots", "mz_search_select", "mz_search_apply",
+           "mz_search_set_inputs", "mz_search_run", "mz_profile_kernels", "mz_launch_count"]
+
+
+def _fp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _u8(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def _i32(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class Engine:
+    """One GPU's share of the self-play games: node pools, environments and the network, all resident in HBM."""
+
+    def __init__(self, game, board_size, num_games, num_simulation, device=0, puct_base=19652.0, puct_init=1.25, reward_discount=1.0, komi=7.5,
+                 ko_situational=False, dirichlet_epsilon=0.25):
+        self.lib = _load()
+        cfg = _Config(device, game, board_size, num_games, num_simulation, puct_base, puct_init, reward_discount, komi, int(ko_situational), dirichlet_epsilon)
+        h = C.c_void_p()
+        self.h = None
+        self._check(self.lib.mz_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.B, self.S = num_games, num_simulation
+        self.A = self.lib.mz_action_size(self.h)
+        self.F = self.lib.mz_num_features(self.h)
+        self.terminal = [False] * num_games
+        self.last_play = None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(f"libmzb200 error {rc}: {self.lib.mz_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mz_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    # ---- network ------------------------------------------------------------------------------
+    def load_network(self, source):
+        """source: path of a TorchScript .pt written by the reference's learner (or oracle/gen_nets.py),
+        or a (dims dict, state_dict of numpy arrays) pair."""
+        if isinstance(source, str):
+            import torch  # host-side .pt reader only (the reference uses libtorch for the same, network.cpp:21)
+            m = torch.jit.load(source, map_location="cpu")
+            dims = dict(num_input_channels=m.get_num_input_channels(), input_height=m.get_input_channel_height(), input_width=m.get_input_channel_width(),
+                        num_hidden_channels=m.get_num_hidden_channels(), num_blocks=m.get_num_blocks(), action_size=m.get_action_size(),
+                        num_value_hidden_channels=m.get_num_value_hidden_channels(), discrete_value_size=m.get_discrete_value_size())
+            state = {k: v.detach().float().contiguous().numpy() for k, v in m.state_dict().items() if not k.endswith("num_batches_tracked")}
+        else:
+            dims, state = source
+        nd = _NetDims(*[int(dims[n]) for n, _ in _NetDims._fields_])
+        self._check(self.lib.mz_net_configure(self.h, C.byref(nd)))
+        for k, v in state.items():
+            a = np.ascontiguousarray(v, np.float32)
+            self._check(self.lib.mz_net_set_tensor(self.h, k.encode(), _fp(a), a.size))
+        self._check(self.lib.mz_net_finalize(self.h))
+        self.net_dims = dims
+
+    def configure_network_empty(self, dims):
+        nd = _NetDims(*[int(dims[n]) for n, _ in _NetDims._fields_])
+        self._check(self.lib.mz_net_configure(self.h, C.byref(nd)))
+        self._check(self.lib.mz_net_finalize_empty(self.h))
+        self.net_dims = dims
+
+    def weight_blob(self):
+        p, n = C.c_void_p(), C.c_int64()
+        self._check(self.lib.mz_net_blob(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def eval_batch(self, features):
+        f = np.ascontiguousarray(features, np.float32).reshape(-1, self.F)
+        n = f.shape[0]
+        pol, lg, val = np.zeros((n, self.A), np.float32), np.zeros((n, self.A), np.float32), np.zeros(n, np.float32)
+        self._check(self.lib.mz_eval_batch(self.h, _fp(f), n, _fp(pol), _fp(lg), _fp(val)))
+        return pol, lg, val
+
+    # ---- per-phase hooks (per-phase parity hooks) ------------------------
+    def select(self, rotations=None, want_features=True):
+        rot = None if rotations is None else np.ascontiguousarray(rotations, np.uint8)
+        feats = np.zeros((self.B, self.F), np.float32) if want_features else None
+        self._path_len = np.zeros(self.B, np.int32)
+        self._check(self.lib.mz_search_select(self.h, _u8(rot), _fp(feats), _i32(self._path_len)))
+        self._roots = None
+        return feats
+
+    def apply(self, policy, logits, value, noise=None):
+        p, l, v = (np.ascontiguousarray(x, np.float32) for x in (policy, logits, value))
+        nz = None if noise is None else np.ascontiguousarray(noise, np.float32)
+        self._check(self.lib.mz_search_apply(self.h, _fp(p), _fp(l), _fp(v), _fp(nz)))
+        self._roots = None
+
+    def path_len(self, g):
+        return int(self._path_len[g])
+
+    def get_roots(self):
+        B, A = self.B, self.A
+        info = (_RootInfo * B)()
+        out = dict(action=np.zeros((B, A), np.int32))
+        for n in ("count", "mean", "policy", "logit", "noise", "value"):
+            out[n] = np.zeros((B, A), np.float32)
+        self._check(self.lib.mz_get_roots(self.h, info, _i32(out["action"]), *[_fp(out[n]) for n in ("count", "mean", "policy", "logit", "noise", "value")]))
+        out["num_children"] = np.array([info[g].num_children for g in range(B)], np.int32)
+        out["root_count"] = np.array([info[g].count for g in range(B)], np.float32)
+        out["root_mean"] = np.array([info[g].mean for g in range(B)], np.float32)
+        out["root_value"] = np.array([info[g].value for g in range(B)], np.float32)
+        return out
+
+    def _cached_roots(self):
+        if getattr(self, "_roots", None) is None:
+            self._roots = self.get_roots()
+        return self._roots
+
+    def sims_done(self, g):
+        return int(self._cached_roots()["root_count"][g])
+
+    def root(self, g):
+        r = self._cached_roots()
+        d = dict(num_children=int(r["num_children"][g]), root_count=float(r["root_count"][g]), root_mean=float(r["root_mean"][g]), root_value=float(r["root_value"][g]))
+        for n in ("action", "count", "mean", "policy", "logit", "noise", "value"):
+            d[n] = r[n][g]
+        return d
+
+    # ---- games ----------------------------------------------------------------------------------
+    def play_all(self, actions):
+        a = np.ascontiguousarray(actions, np.int32)
+        res = (_PlayResult * self.B)()
+        self._check(self.lib.mz_play(self.h, _i32(a), res))
+        self._roots = None
+        out = dict(applied=np.array([r.applied for r in res], np.int32), terminal=np.array([r.terminal for r in res], np.int32),
+                   num_legal=np.array([r.num_legal for r in res], np.int32), turn=np.array([r.turn for r in res], np.int32),
+                   eval_score=np.array([r.eval_score for r in res], np.float32))
+        for g in range(self.B):
+            if a[g] >= 0:
+                self.terminal[g] = bool(out["terminal"][g])
+        self.last_play = out
+        return out
+
+    def play(self, g, action):
+        a = np.full(self.B, -1, np.int32)
+        a[g] = action
+        return int(self.play_all(a)["applied"][g])
+
+    def root_terminal(self, g):
+        return self.terminal[g]
+
+    def reset_game(self, g=-1):
+        self._check(self.lib.mz_reset_game(self.h, g))
+        self._roots = None
+        if g < 0:
+            self.terminal = [False] * self.B
+        else:
+            self.terminal[g] = False
+
+    # ---- whole-move search --------------------------------------------------------------------------
+    def set_search_inputs(self, rotations=None, noise=None):
+        rot = None if rotations is None else np.ascontiguousarray(rotations, np.uint8).reshape(self.S + 1, self.B)
+        nz = None if noise is None else np.ascontiguousarray(noise, np.float32).reshape(self.B, self.A)
+        self._keep = (rot, nz)
+        self._check(self.lib.mz_search_set_inputs(self.h, _u8(rot), _fp(nz)))
+
+    def search(self, num_evals=0):
+        ms = C.c_float(0)
+        self._check(self.lib.mz_search_run(self.h, num_evals, C.byref(ms)))
+        self._roots = None
+        return ms.value
+
+    def profile_kernels(self, iters=20):
+        c, t, h = C.c_float(0), C.c_float(0), C.c_float(0)
+        self._check(self.lib.mz_profile_kernels(self.h, iters, C.byref(c), C.byref(t), C.byref(h)))
+        return dict(conv_ms=c.value, tree_ms=t.value, heads_ms=h.value)
+
+    def launch_count(self):
+        return int(self.lib.mz_launch_count(self.h))

@@ -118,3 +118,22 @@ class OracleSearch:
 
     def reset_game(self, g):
         self.lib.mzo_reset_game(self.h, g)
+
+
+class OracleNet:
+    """fp32 network restatement (oracle/port/mzo_net.c) with a reference-named state_dict."""
+
+    def __init__(self, lib, dims, state):
+        self.lib, self.A = lib, dims["action_size"]
+        self.h = lib.mzo_net_create(dims["num_input_channels"], dims["input_height"], dims["input_width"], dims["num_hidden_channels"], dims["num_blocks"],
+                                    dims["action_size"], dims["num_value_hidden_channels"])
+        for k, v in state.items():
+            a = np.ascontiguousarray(v, np.float32)
+            assert lib.mzo_net_set(self.h, k.encode(), fptr(a), a.size) == 0
+
+    def forward(self, feats):
+        f = np.ascontiguousarray(feats, np.float32)
+        n = f.shape[0]
+        pol, lg, val = np.zeros((n, self.A), np.float32), np.zeros((n, self.A), np.float32), np.zeros(n, np.float32)
+        self.lib.mzo_net_forward(self.h, fptr(f), n, fptr(pol), fptr(lg), fptr(val))
+        return pol, lg, val
