@@ -96,6 +96,10 @@ int mz_reset_game(mz_engine* e, int32_t g);
 /* BaseActor::act + resetSearch for every game with actions[g] >= 0 (actor/base_actor.cpp:22-30,
  * actor/actor_group.cpp:116-134); results [num_games] */
 int mz_play(mz_engine* e, const int32_t* actions, mz_play_result* results);
+/* actor_select_action_by_count=true decided on the device: MCTS::selectChildByMaxCount at every root
+ * (actor/mcts.cpp:91-104) followed by mz_play of that action; auto_reset != 0 also restarts finished games in place.
+ * actions_out / results [num_games] may both be NULL, in which case the call is asynchronous (no host read-back). */
+int mz_play_max_count(mz_engine* e, int32_t auto_reset, int32_t* actions_out, mz_play_result* results);
 /* root child tables, children in stored (policy-sorted) order; any array may be NULL.
  * info [B]; the others [B][A] (MCTSNode getters, actor/mcts.h:44-52) */
 int mz_get_roots(mz_engine* e, mz_root_info* info, int32_t* action, float* count, float* mean, float* policy, float* logit, float* noise,
@@ -114,8 +118,15 @@ int mz_search_apply(mz_engine* e, const float* policy, const float* logits, cons
 int mz_search_set_inputs(mz_engine* e, const uint8_t* rotations, const float* noise);
 /* runs num_evals (<= S+1; 0 = S+1) cycles of select -> features -> network -> expand/backup for all games as
  * one CUDA graph (the ActorGroup::run loop, actor/actor_group.cpp:136-148, without its host round trips).
- * device_ms (may be NULL) receives the CUDA-event time of the graph on the engine's stream. */
+ * device_ms receives the CUDA-event time of the graph on the engine's stream (the call then waits for it);
+ * with device_ms == NULL the graph is only enqueued. */
 int mz_search_run(mz_engine* e, int32_t num_evals, float* device_ms);
+
+/* device_ms == NULL makes mz_search_run asynchronous; these bracket any sequence of calls with CUDA events on the
+ * engine's stream (mz_timer_end and mz_sync wait for the stream). */
+int mz_sync(mz_engine* e);
+int mz_timer_begin(mz_engine* e);
+int mz_timer_end(mz_engine* e, float* device_ms);
 
 /* ---- measurement hooks ------------------------------------------------------------------------------ */
 /* average device time (CUDA events on the engine's stream) of `iters` back-to-back launches of: the tower

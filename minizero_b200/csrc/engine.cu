@@ -65,6 +65,24 @@ __global__ void __launch_bounds__(32) k_play(const mz_dims d, const mz_state s, 
     mz_play(d, s, g, a, &w, out + g * 4, score + g, lane);
 }
 
+// actor_select_action_by_count decided on the device: play the most visited root child of every game; a game that
+// ends is reset in place when auto_reset is set (records are then the caller's loss: throughput runs only)
+__global__ void __launch_bounds__(32) k_play_max_count(const mz_dims d, const mz_state s, int32_t* __restrict__ actions_out, int32_t* __restrict__ out,
+                                                       float* __restrict__ score, const int auto_reset)
+{
+    __shared__ mz_scratch w;
+    const int g = blockIdx.x, lane = threadIdx.x;
+    const int a = mz_root_max_count_action(d, s, g, lane);
+    if (lane == 0) { actions_out[g] = a; }
+    if (a < 0) {
+        if (lane == 0) { out[g * 4 + 0] = 0, out[g * 4 + 1] = 0, out[g * 4 + 2] = 0, out[g * 4 + 3] = s.root_meta[g * 4 + 0], score[g] = 0.0f; }
+        return;
+    }
+    mz_play(d, s, g, a, &w, out + g * 4, score + g, lane);
+    __syncwarp();
+    if (auto_reset && out[g * 4 + 1]) { mz_game_reset(d, s, g, &w, lane); }
+}
+
 // root child table of every game, children in stored order (MCTSNode getters, actor/mcts.h:44-52)
 __global__ void __launch_bounds__(32) k_gather_roots(const mz_dims d, const mz_state s, float* __restrict__ info, int32_t* __restrict__ action, float* __restrict__ count,
                                                      float* __restrict__ mean, float* __restrict__ policy, float* __restrict__ logit, float* __restrict__ noise,
@@ -120,7 +138,7 @@ struct mz_engine {
     mz_dims d{};
     mz_state s{};
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     std::vector<void*> allocs;
     int64_t launches = 0;
 
@@ -211,8 +229,6 @@ int conv(mz_engine* e, const CUtensorMap& in, const ConvLayer& L, __half* out, c
 int launch_heads(mz_engine* e, const __half* act)
 {
     mznn::HeadParams p;
-    const float* const* dummy = nullptr;
-    (void)dummy;
     auto f = [&](int i) { return reinterpret_cast<const float*>(e->d_blob + e->off_head[i]); };
     p.act = act;
     p.w_pc = f(0), p.b_pc = f(1), p.w_pf = f(2), p.b_pf = f(3), p.w_vc = f(4), p.b_vc = f(5), p.w_v1 = f(6), p.b_v1 = f(7), p.w_v2 = f(8), p.b_v2 = f(9);
@@ -384,7 +400,8 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     auto guard = [&](int r) {
         if (r && !rc) { rc = r; }
     };
-    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
+        cudaEventCreate(&e->ev2) != cudaSuccess || cudaEventCreate(&e->ev3) != cudaSuccess) {
         delete e;
         return fail(MZ_ERR_CUDA, "stream / event creation failed");
     }
@@ -443,6 +460,8 @@ void mz_destroy(mz_engine* e)
     for (void* p : e->allocs) { cudaFree(p); }
     if (e->ev0) { cudaEventDestroy(e->ev0); }
     if (e->ev1) { cudaEventDestroy(e->ev1); }
+    if (e->ev2) { cudaEventDestroy(e->ev2); }
+    if (e->ev3) { cudaEventDestroy(e->ev3); }
     if (e->stream) { cudaStreamDestroy(e->stream); }
     delete e;
 }
@@ -634,6 +653,58 @@ int mz_play(mz_engine* e, const int32_t* actions, mz_play_result* results)
     return MZ_OK;
 }
 
+int mz_play_max_count(mz_engine* e, int32_t auto_reset, int32_t* actions_out, mz_play_result* results)
+{
+    if (!e) { return fail(MZ_ERR_ARG, "null argument"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    const int B = e->d.B;
+    k_play_max_count<<<B, 32, 0, e->stream>>>(e->d, e->s, e->d_actions, e->d_play_out, e->d_play_score, auto_reset);
+    e->launches++;
+    if (!actions_out && !results) { return MZ_OK; } // asynchronous: nothing read back
+    std::vector<int32_t> out(static_cast<size_t>(B) * 4);
+    std::vector<float> score(B);
+    if (actions_out) { CUDA_OK(cudaMemcpyAsync(actions_out, e->d_actions, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, e->stream)); }
+    CUDA_OK(cudaMemcpyAsync(out.data(), e->d_play_out, sizeof(int32_t) * B * 4, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaMemcpyAsync(score.data(), e->d_play_score, sizeof(float) * B, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    CUDA_OK(cudaGetLastError());
+    if (results) {
+        for (int g = 0; g < B; ++g) {
+            results[g].applied = out[g * 4 + 0], results[g].terminal = out[g * 4 + 1], results[g].num_legal = out[g * 4 + 2], results[g].turn = out[g * 4 + 3];
+            results[g].eval_score = score[g];
+        }
+    }
+    return MZ_OK;
+}
+
+int mz_sync(mz_engine* e)
+{
+    if (!e) { return fail(MZ_ERR_ARG, "null argument"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    CUDA_OK(cudaGetLastError());
+    return MZ_OK;
+}
+
+int mz_timer_begin(mz_engine* e)
+{
+    if (!e) { return fail(MZ_ERR_ARG, "null argument"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    CUDA_OK(cudaEventRecord(e->ev2, e->stream));
+    return MZ_OK;
+}
+
+int mz_timer_end(mz_engine* e, float* device_ms)
+{
+    if (!e || !device_ms) { return fail(MZ_ERR_ARG, "null argument"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    CUDA_OK(cudaEventRecord(e->ev3, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventElapsedTime(device_ms, e->ev2, e->ev3));
+    return MZ_OK;
+}
+
 int mz_get_roots(mz_engine* e, mz_root_info* info, int32_t* action, float* count, float* mean, float* policy, float* logit, float* noise, float* value)
 {
     if (!e) { return fail(MZ_ERR_ARG, "null argument"); }
@@ -743,13 +814,17 @@ int mz_search_run(mz_engine* e, int32_t num_evals, float* device_ms)
         if (cerr != cudaSuccess) { return fail(MZ_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(cerr)); }
         it = e->graphs.emplace(key, exec).first;
     }
+    e->launches += 1 + static_cast<int64_t>(num_evals) * (2 + static_cast<int64_t>(e->convs.size()));
+    if (!device_ms) { // asynchronous: the caller brackets several calls with mz_timer_begin / mz_timer_end or mz_sync
+        CUDA_OK(cudaGraphLaunch(it->second, e->stream));
+        return MZ_OK;
+    }
     CUDA_OK(cudaEventRecord(e->ev0, e->stream));
     CUDA_OK(cudaGraphLaunch(it->second, e->stream));
     CUDA_OK(cudaEventRecord(e->ev1, e->stream));
     CUDA_OK(cudaStreamSynchronize(e->stream));
     CUDA_OK(cudaGetLastError());
-    e->launches += 1 + static_cast<int64_t>(num_evals) * (2 + static_cast<int64_t>(e->convs.size()));
-    if (device_ms) { CUDA_OK(cudaEventElapsedTime(device_ms, e->ev0, e->ev1)); }
+    CUDA_OK(cudaEventElapsedTime(device_ms, e->ev0, e->ev1));
     return MZ_OK;
 }
 

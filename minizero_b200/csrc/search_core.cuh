@@ -780,3 +780,20 @@ MZ_DEV void mz_play(const mz_dims& d, const mz_state& s, int g, int action, mz_s
         *score = sc;
     }
 }
+
+// MCTS::selectChildByMaxCount at the root (mcts.cpp:91-104): first child with the strictly largest count.
+// Returns its action id (-1 if the root has no visited child).
+MZ_DEV int mz_root_max_count_action(const mz_dims& d, const mz_state& s, int g, int lane)
+{
+    const mz_hot* hot = s.hot + (size_t)g * d.NP;
+    const mz_hot root = mz_load_hot(hot);
+    const int nc = (int)(root.link >> MZ_LINK_SHIFT), fc = (int)(root.link & ((1u << MZ_LINK_SHIFT) - 1u));
+    float best_c = 0.0f, zero = 0.0f;
+    int best_i = -1;
+    for (int i = lane; i < nc; i += MZ_W) {
+        const mz_hot c = mz_load_hot(hot + fc + i);
+        if (c.count > best_c) { best_c = c.count, best_i = i; }
+    }
+    mz_reduce_best(best_c, zero, best_i); // (count desc, index asc)
+    return best_i < 0 ? -1 : (int)s.action[(size_t)g * d.NP + fc + best_i];
+}

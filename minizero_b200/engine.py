@@ -86,6 +86,10 @@ def _load():
     lib.mz_eval_batch.argtypes = [vp, f32p, i32, f32p, f32p, f32p]
     lib.mz_reset_game.argtypes = [vp, i32]
     lib.mz_play.argtypes = [vp, i32p, C.POINTER(_PlayResult)]
+    lib.mz_play_max_count.argtypes = [vp, i32, i32p, C.POINTER(_PlayResult)]
+    lib.mz_sync.argtypes = [vp]
+    lib.mz_timer_begin.argtypes = [vp]
+    lib.mz_timer_end.argtypes = [vp, f32p]
     lib.mz_get_roots.argtypes = [vp, C.POINTER(_RootInfo), i32p] + [f32p] * 6
     lib.mz_search_select.argtypes = [vp, u8p, f32p, i32p]
     lib.mz_search_apply.argtypes = [vp, f32p, f32p, f32p, f32p]
@@ -100,7 +104,7 @@ def _load():
 
 EXPORTS = ["mz_create", "mz_destroy", "mz_last_error", "mz_action_size", "mz_num_features", "mz_net_configure", "mz_net_set_tensor", "mz_net_finalize",
            "mz_net_blob", "mz_net_finalize_empty", "mz_eval_batch", "mz_reset_game", "mz_play", "mz_get_roots", "mz_search_select", "mz_search_apply",
-           "mz_search_set_inputs", "mz_search_run", "mz_profile_kernels", "mz_launch_count"]
+           "mz_search_set_inputs", "mz_search_run", "mz_profile_kernels", "mz_launch_count", "mz_play_max_count", "mz_sync", "mz_timer_begin", "mz_timer_end"]
 
 
 def _fp(a):
@@ -267,10 +271,33 @@ class Engine:
         self._keep = (rot, nz)
         self._check(self.lib.mz_search_set_inputs(self.h, _u8(rot), _fp(nz)))
 
-    def search(self, num_evals=0):
+    def search(self, num_evals=0, wait=True):
+        """one whole move search for every game; returns the CUDA-event milliseconds when wait is True"""
         ms = C.c_float(0)
-        self._check(self.lib.mz_search_run(self.h, num_evals, C.byref(ms)))
+        self._check(self.lib.mz_search_run(self.h, num_evals, C.byref(ms) if wait else None))
         self._roots = None
+        return ms.value if wait else None
+
+    def play_max_count(self, auto_reset=True, read_back=True):
+        self._roots = None
+        if not read_back:
+            self._check(self.lib.mz_play_max_count(self.h, int(auto_reset), None, None))
+            return None
+        acts = np.zeros(self.B, np.int32)
+        res = (_PlayResult * self.B)()
+        self._check(self.lib.mz_play_max_count(self.h, int(auto_reset), _i32(acts), res))
+        return dict(action=acts, applied=np.array([r.applied for r in res], np.int32), terminal=np.array([r.terminal for r in res], np.int32),
+                    num_legal=np.array([r.num_legal for r in res], np.int32), eval_score=np.array([r.eval_score for r in res], np.float32))
+
+    def sync(self):
+        self._check(self.lib.mz_sync(self.h))
+
+    def timer_begin(self):
+        self._check(self.lib.mz_timer_begin(self.h))
+
+    def timer_end(self):
+        ms = C.c_float(0)
+        self._check(self.lib.mz_timer_end(self.h, C.byref(ms)))
         return ms.value
 
     def profile_kernels(self, iters=20):
