@@ -37,6 +37,9 @@ constexpr int STEP_AFTER = 1, STEP_BEFORE = 2;
 __global__ void __launch_bounds__(32) k_step(const mz_dims d, const mz_state s, const int flags)
 {
     __shared__ mz_scratch w;
+    extern __shared__ uint64_t dyn_path_hashes[]; // [S + 2]
+    if (threadIdx.x == 0) { w.path_hashes = dyn_path_hashes; }
+    __syncwarp();
     const int g = blockIdx.x, lane = threadIdx.x;
     if (flags & STEP_AFTER) { mz_after_nn(d, s, g, &w, lane); }
     if (flags & STEP_BEFORE) {
@@ -167,6 +170,8 @@ struct mz_engine {
     size_t off_head[10] = {0};
     __half* act[3] = {nullptr, nullptr, nullptr};
     CUtensorMap map_in0, map_act[3];
+    CUtensorMap map_in0_ext, map_act_ext[3]; // same buffers, box = the resident block of conv3x3_resident_kernel
+    int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148;
     encode_tiled_fn encode = nullptr;
 
     // graphs keyed by (num_evals, noise, rotations)
@@ -209,16 +214,43 @@ int launch_conv(mz_engine* e, const CUtensorMap& in, const ConvLayer& L, __half*
     return MZ_OK;
 }
 
+template <int BN, int STAGES>
+size_t resident_smem(const mz_engine* e, int cin)
+{
+    return static_cast<size_t>(cin / mznn::BK) * e->rows_ext * 128 + static_cast<size_t>(STAGES) * BN * mznn::BK * 2 + (2 * STAGES + 6) * 8 + 16 + 1024;
+}
+
+template <int BN, int STAGES>
+int launch_conv_resident(mz_engine* e, const CUtensorMap& in_ext, const ConvLayer& L, __half* out, const __half* residual)
+{
+    mznn::ConvResParams rp;
+    mznn::ConvParams& p = rp.c;
+    p.out = out, p.residual = residual, p.bias = reinterpret_cast<const float*>(e->d_blob + L.b_off);
+    p.rows_valid = e->d.B * e->d.slots, p.n1 = e->d.N + 1, p.slots = e->d.slots, p.cin = L.cin, p.cout = L.cout, p.relu = L.relu;
+    rp.rows_ext = e->rows_ext, rp.halo = e->d.N + 2, rp.num_mtiles = e->rows_alloc / mznn::BM, rp.base_off_mode = e->base_off_mode;
+    const int units = rp.num_mtiles * (L.cout / BN);
+    const int grid = units < e->num_sms ? units : e->num_sms;
+    mznn::conv3x3_resident_kernel<BN, STAGES><<<grid, mznn::CONV_THREADS, resident_smem<BN, STAGES>(e, L.cin), e->stream>>>(in_ext, L.map_w, rp);
+    e->launches++;
+    return MZ_OK;
+}
+
 int configure_conv_kernels()
 {
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_tcgen05_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mznn::ConvSmem<64, 4>::TOTAL));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_tcgen05_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mznn::ConvSmem<128, 3>::TOTAL));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_tcgen05_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mznn::ConvSmem<256, 4>::TOTAL));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<64, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return MZ_OK;
 }
 
-int conv(mz_engine* e, const CUtensorMap& in, const ConvLayer& L, __half* out, const __half* residual)
+int conv(mz_engine* e, const CUtensorMap& in, const CUtensorMap& in_ext, const ConvLayer& L, __half* out, const __half* residual)
 {
+    if (e->conv_mode == 1) {
+        if (e->bn_tile == 64) { return launch_conv_resident<64, 6>(e, in_ext, L, out, residual); }
+        return launch_conv_resident<128, 6>(e, in_ext, L, out, residual);
+    }
     switch (e->bn_tile) {
         case 64: return launch_conv<64, 4>(e, in, L, out, residual);
         case 128: return launch_conv<128, 3>(e, in, L, out, residual);
@@ -235,7 +267,7 @@ int launch_heads(mz_engine* e, const __half* act)
     p.policy = e->s.policy, p.logits = e->s.logits, p.value = e->s.nn_value;
     p.c = e->cpad, p.n = e->d.N, p.slots = e->d.slots, p.pol_ch = e->pol_ch, p.actions = e->d.A, p.vh = e->nd.num_value_hidden_channels;
     const int hw = e->d.N * e->d.N;
-    const size_t smem = sizeof(float) * ((p.pol_ch + 1) * hw + p.vh + p.actions + 32);
+    const size_t smem = sizeof(float) * ((p.pol_ch + 1) * hw + p.vh + p.actions + 32 + (p.pol_ch + 1) * p.c);
     mznn::heads_kernel<<<e->d.B, 256, smem, e->stream>>>(p);
     e->launches++;
     return MZ_OK;
@@ -245,13 +277,13 @@ int launch_heads(mz_engine* e, const __half* act)
 int forward(mz_engine* e)
 {
     if (!e->net_ready) { return fail(MZ_ERR_STATE, "network not finalized"); }
-    int rc = conv(e, e->map_in0, e->convs[0], e->act[0], nullptr);
+    int rc = conv(e, e->map_in0, e->map_in0_ext, e->convs[0], e->act[0], nullptr);
     if (rc) { return rc; }
     int cur = 0;
     for (int b = 0; b < e->nd.num_blocks; ++b) {
         const int t = (cur + 1) % 3, o = (cur + 2) % 3;
-        if ((rc = conv(e, e->map_act[cur], e->convs[1 + 2 * b], e->act[t], nullptr))) { return rc; }
-        if ((rc = conv(e, e->map_act[t], e->convs[2 + 2 * b], e->act[o], e->act[cur]))) { return rc; }
+        if ((rc = conv(e, e->map_act[cur], e->map_act_ext[cur], e->convs[1 + 2 * b], e->act[t], nullptr))) { return rc; }
+        if ((rc = conv(e, e->map_act[t], e->map_act_ext[t], e->convs[2 + 2 * b], e->act[o], e->act[cur]))) { return rc; }
         cur = o;
     }
     return launch_heads(e, e->act[cur]);
@@ -262,7 +294,7 @@ int step(mz_engine* e, int flags, const uint8_t* rotations)
     mz_state s = e->s;
     s.rotations = rotations;
     s.noise_in = (e->noise_enabled ? e->d_noise : nullptr);
-    k_step<<<e->d.B, 32, 0, e->stream>>>(e->d, s, flags);
+    k_step<<<e->d.B, 32, sizeof(uint64_t) * (e->d.S + 2), e->stream>>>(e->d, s, flags);
     e->launches++;
     return MZ_OK;
 }
@@ -331,11 +363,22 @@ int alloc_net(mz_engine* e)
     if ((rc = configure_conv_kernels())) { return rc; }
     if ((rc = e->dalloc(&e->d_blob, e->blob.size))) { return rc; }
     const size_t rows = e->rows_alloc;
+    e->rows_ext = (mznn::BM + 2 * (e->d.N + 2) + 7) / 8 * 8;
+    // conv kernel variant: 1 = resident input block (default), 0 = every tap re-loads its shifted A tile
+    e->conv_mode = 1;
+    if (const char* env = std::getenv("MZ_CONV_MODE")) { e->conv_mode = std::atoi(env); }
+    if (const char* env = std::getenv("MZ_CONV_BASEOFF")) { e->base_off_mode = std::atoi(env); }
+    if (e->bn_tile == 256) { e->conv_mode = 0; }
+    const size_t need = (e->bn_tile == 64 ? resident_smem<64, 6>(e, e->cpad) : resident_smem<128, 6>(e, e->cpad));
+    if (need > 227 * 1024) { e->conv_mode = 0; }
+    cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->cfg.device);
     for (int i = 0; i < 3; ++i) {
         if ((rc = e->dalloc(&e->act[i], rows * e->cpad))) { return rc; }
         if ((rc = make_map_2d(e, &e->map_act[i], e->act[i], e->cpad, rows, mznn::BK, mznn::BM))) { return rc; }
+        if ((rc = make_map_2d(e, &e->map_act_ext[i], e->act[i], e->cpad, rows, mznn::BK, e->rows_ext))) { return rc; }
     }
     if ((rc = make_map_2d(e, &e->map_in0, e->s.nn_in, MZ_NN_CPAD, rows, mznn::BK, mznn::BM))) { return rc; }
+    if ((rc = make_map_2d(e, &e->map_in0_ext, e->s.nn_in, MZ_NN_CPAD, rows, mznn::BK, e->rows_ext))) { return rc; }
     for (ConvLayer& L : e->convs) {
         if ((rc = make_map_2d(e, &L.map_w, e->d_blob + L.w_off, L.cin, 9ull * L.cout, mznn::BK, e->bn_tile))) { return rc; }
     }
@@ -410,6 +453,8 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     e->rows_alloc = static_cast<int>((B * d.slots + mznn::BM - 1) / mznn::BM * mznn::BM);
     guard(e->dalloc(&s.hot, np)), guard(e->dalloc(&s.action, np)), guard(e->dalloc(&s.logit, np)), guard(e->dalloc(&s.value, np));
     guard(e->dalloc(&s.root_noise, BA)), guard(e->dalloc(&s.cursor, B));
+    guard(e->dalloc(&s.node_slot, np)), guard(e->dalloc(&s.slot_st, B * (d.S + 1) * 2 * N)), guard(e->dalloc(&s.slot_hash, B * (d.S + 1)));
+    guard(e->dalloc(&s.slot_meta, B * (d.S + 1) * 4));
     guard(e->dalloc(&s.root_st, B * 2 * MZ_ROWS)), guard(e->dalloc(&s.root_hist, B * MZ_HIST * 2 * MZ_ROWS)), guard(e->dalloc(&s.root_hash, B));
     guard(e->dalloc(&s.root_meta, B * 4)), guard(e->dalloc(&s.hashes, B * d.max_hashes));
     guard(e->dalloc(&s.path, B * (d.S + 2))), guard(e->dalloc(&s.path_len, B)), guard(e->dalloc(&s.leaf_legal, B * MZ_LEGAL_WORDS));
@@ -476,6 +521,9 @@ int mz_net_configure(mz_engine* e, const mz_net_dims* dims)
     if (dims->discrete_value_size != 1) { return fail(MZ_ERR_ARG, "discrete value heads are not implemented in this engine yet"); }
     if (dims->num_input_channels != e->d.C || dims->input_height != e->d.N || dims->input_width != e->d.N || dims->action_size != e->d.A) {
         return fail(MZ_ERR_ARG, "network dimensions do not match the game");
+    }
+    if ((dims->action_size + dims->input_height * dims->input_width - 1) / (dims->input_height * dims->input_width) > 7) {
+        return fail(MZ_ERR_ARG, "policy head with more than 7 planes is not supported");
     }
     if (dims->num_input_channels > MZ_NN_CPAD || dims->num_hidden_channels < 1 || dims->num_blocks < 0) { return fail(MZ_ERR_ARG, "unsupported network size"); }
     if (e->d_blob) { return fail(MZ_ERR_STATE, "network already allocated for this engine"); }
@@ -836,9 +884,9 @@ int mz_profile_kernels(mz_engine* e, int32_t iters, float* conv_ms, float* tree_
     float ms = 0.0f;
     if (conv_ms) {
         const ConvLayer& L = e->convs.back();
-        for (int i = 0; i < 3; ++i) { conv(e, e->map_act[0], L, e->act[1], e->act[2]); }
+        for (int i = 0; i < 3; ++i) { conv(e, e->map_act[0], e->map_act_ext[0], L, e->act[1], e->act[2]); }
         CUDA_OK(cudaEventRecord(e->ev0, e->stream));
-        for (int i = 0; i < iters; ++i) { conv(e, e->map_act[0], L, e->act[1], e->act[2]); }
+        for (int i = 0; i < iters; ++i) { conv(e, e->map_act[0], e->map_act_ext[0], L, e->act[1], e->act[2]); }
         CUDA_OK(cudaEventRecord(e->ev1, e->stream));
         CUDA_OK(cudaStreamSynchronize(e->stream));
         CUDA_OK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));

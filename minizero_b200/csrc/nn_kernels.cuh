@@ -245,6 +245,189 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Resident-A variant (the default): the 9 taps of one row tile read the SAME input rows shifted by at most
+// +-(N+2), so the tile's input block (128 + 2*(N+2) rows, all input channels) is brought into shared memory ONCE
+// and every tap's A operand is a descriptor into that block at a different start row; only the weight tiles
+// stream through the TMA ring. L2 -> SM traffic per tile drops from 9 x (A + B) to A + 9 x B, and a persistent
+// CTA that handles both output-channel halves of a row tile reuses the block again. Accumulators are double
+// buffered in TMEM so the epilogue of one unit overlaps the MMAs of the next.
+// ---------------------------------------------------------------------------------------------
+struct ConvResParams {
+    ConvParams c;
+    int rows_ext;   // rows of the resident block: 128 + 2 * halo, rounded up to 8
+    int halo;       // N + 2
+    int num_mtiles; // row tiles
+    int base_off_mode; // 1: descriptor base-offset field = (start address >> 7) & 7 for row-shifted starts
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w, const ConvResParams rp)
+{
+    const ConvParams& p = rp.c;
+    constexpr int B_BYTES = BN * BK * 2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const int a_kb = p.cin / BK;
+    const int a_kb_bytes = rp.rows_ext * 128;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + a_kb * a_kb_bytes;
+    uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_BYTES);
+    uint64_t* b_empty = b_full + STAGES;
+    uint64_t* a_full = b_empty + STAGES;
+    uint64_t* a_empty = a_full + 1;
+    uint64_t* acc_full = a_empty + 1;  // [2]
+    uint64_t* acc_empty = acc_full + 2; // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nh = p.cout / BN;
+    const int units = rp.num_mtiles * nh;
+    const int u_begin = static_cast<int>((static_cast<long long>(blockIdx.x) * units) / gridDim.x);
+    const int u_end = static_cast<int>((static_cast<long long>(blockIdx.x + 1) * units) / gridDim.x);
+    const int num_k = 9 * a_kb;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_in)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4); // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) { // ===== TMA producer =====
+            int cur_mt = -1, a_loads = 0, kcount = 0;
+            for (int u = u_begin; u < u_end; ++u) {
+                const int mt = u / nh, half = u - mt * nh;
+                if (mt != cur_mt) {
+                    if (a_loads > 0) { mbar_wait(a_empty, (a_loads - 1) & 1); } // every MMA on the previous block has completed
+                    mbar_arrive_expect_tx(a_full, a_kb * a_kb_bytes);
+                    for (int kb = 0; kb < a_kb; ++kb) { tma_load_2d(smem_a + kb * a_kb_bytes, &map_in, a_full, kb * BK, mt * BM - rp.halo); }
+                    cur_mt = mt;
+                    ++a_loads;
+                }
+                for (int k = 0; k < num_k; ++k, ++kcount) {
+                    const int s = kcount % STAGES;
+                    if (kcount >= STAGES) { mbar_wait(&b_empty[s], ((kcount / STAGES) - 1) & 1); }
+                    const int tap = k / a_kb, kb = k - tap * a_kb;
+                    mbar_arrive_expect_tx(&b_full[s], B_BYTES);
+                    tma_load_2d(smem_b + s * B_BYTES, &map_w, &b_full[s], kb * BK, tap * p.cout + half * BN);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) { // ===== MMA issuer =====
+            constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+            int cur_mt = -1, a_cnt = 0, kcount = 0, ucount = 0;
+            for (int u = u_begin; u < u_end; ++u, ++ucount) {
+                const int mt = u / nh;
+                if (mt != cur_mt) {
+                    mbar_wait(a_full, a_cnt & 1);
+                    ++a_cnt;
+                    cur_mt = mt;
+                }
+                const int buf = ucount & 1;
+                if (ucount >= 2) { mbar_wait(&acc_empty[buf], ((ucount >> 1) - 1) & 1); }
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * BN;
+                for (int k = 0; k < num_k; ++k, ++kcount) {
+                    const int s = kcount % STAGES;
+                    mbar_wait(&b_full[s], (kcount / STAGES) & 1);
+                    tcgen05_fence_after();
+                    const int tap = k / a_kb, kb = k - tap * a_kb;
+                    const int row0 = rp.halo + (tap / 3 - 1) * p.n1 + (tap % 3 - 1);
+                    const uint32_t a_addr = smem_u32(smem_a + kb * a_kb_bytes) + row0 * 128;
+                    const uint32_t b_addr = smem_u32(smem_b + s * B_BYTES);
+                    const uint64_t base_off = (rp.base_off_mode ? (static_cast<uint64_t>((a_addr >> 7) & 7u) << 49) : 0ull);
+#pragma unroll
+                    for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                        umma_f16(tmem_d, umma_desc_sw128(a_addr + kk * UMMA_K * 2) | base_off, umma_desc_sw128(b_addr + kk * UMMA_K * 2), idesc, (k | kk) != 0);
+                    }
+                    tcgen05_commit(&b_empty[s]);
+                }
+                tcgen05_commit(&acc_full[buf]);
+                const bool last_of_block = (u + 1 == u_end) || ((u + 1) / nh != mt);
+                if (last_of_block) { tcgen05_commit(a_empty); }
+            }
+        }
+    } else { // ===== epilogue =====
+        const int quarter = warp & 3;
+        int ucount = 0;
+        for (int u = u_begin; u < u_end; ++u, ++ucount) {
+            const int mt = u / nh, half = u - mt * nh, buf = ucount & 1;
+            const int n0 = half * BN;
+            const int r = mt * BM + quarter * 32 + lane;
+            const int rr = r % p.slots;
+            const bool live = (r < p.rows_valid) && (rr / p.n1 != 0) && (rr % p.n1 != p.n1 - 1);
+            mbar_wait(&acc_full[buf], (ucount >> 1) & 1);
+            tcgen05_fence_after();
+            __half* out_row = p.out + static_cast<size_t>(r) * p.cout + n0;
+            const __half* res_row = (p.residual ? p.residual + static_cast<size_t>(r) * p.cout + n0 : nullptr);
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + c, v);
+                tmem_ld_wait();
+                uint4 packed[4];
+                uint32_t* pk = reinterpret_cast<uint32_t*>(packed);
+                uint4 res[4];
+                if (res_row && live) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { res[q] = *reinterpret_cast<const uint4*>(res_row + c + q * 8); }
+                }
+                const __half2* rh = reinterpret_cast<const __half2*>(res);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float x0 = __uint_as_float(v[2 * j]) + __ldg(p.bias + n0 + c + 2 * j);
+                    float x1 = __uint_as_float(v[2 * j + 1]) + __ldg(p.bias + n0 + c + 2 * j + 1);
+                    if (res_row && live) {
+                        const float2 rf = __half22float2(rh[j]);
+                        x0 += rf.x, x1 += rf.y;
+                    }
+                    if (p.relu) { x0 = fmaxf(x0, 0.0f), x1 = fmaxf(x1, 0.0f); }
+                    if (!live) { x0 = 0.0f, x1 = 0.0f; }
+                    const __half2 h = __floats2half2_rn(x0, x1);
+                    pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { *reinterpret_cast<uint4*>(out_row + c + q * 8) = packed[q]; }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&acc_empty[buf]); }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // heads: one CTA per board. conv1x1 (+folded BN) + ReLU for the policy and value planes, then the
 // fully connected layers, softmax over the policy logits and tanh on the value. fp32 SIMT: 0.2 MFLOP / board.
 // ---------------------------------------------------------------------------------------------
@@ -269,42 +452,59 @@ struct HeadParams {
 __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
 {
     extern __shared__ float sm[];
-    const int hw = p.n * p.n, n1 = p.n + 1;
-    float* planes = sm;                          // [(pol_ch + 1)][hw]: policy planes then the value plane
-    float* vhid = planes + (p.pol_ch + 1) * hw;  // [vh]
-    float* lg = vhid + p.vh;                     // [A]
-    float* red = lg + p.actions;                 // [32]
-    const int g = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    const int hw = p.n * p.n, n1 = p.n + 1, np1 = p.pol_ch + 1;
+    float* planes = sm;                 // [(pol_ch + 1)][hw]: policy planes then the value plane
+    float* vhid = planes + np1 * hw;    // [vh]
+    float* lg = vhid + p.vh;            // [A]
+    float* red = lg + p.actions;        // [32]
+    float* wc = red + 32;               // [(pol_ch + 1)][c] 1x1 conv weights
+    const int g = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
     const __half* act = p.act + static_cast<size_t>(g) * p.slots * p.c;
-    // 1x1 convolutions: one (plane, cell) dot product of length c per work item
-    for (int item = tid; item < (p.pol_ch + 1) * hw; item += nthr) {
-        const int plane = item / hw, cell = item % hw;
-        const __half2* row = reinterpret_cast<const __half2*>(act + static_cast<size_t>((cell / p.n + 1) * n1 + cell % p.n) * p.c);
-        const float* w = (plane < p.pol_ch ? p.w_pc + static_cast<size_t>(plane) * p.c : p.w_vc);
-        float acc = 0.0f;
-        for (int i = 0; i < p.c / 2; ++i) {
+    for (int i = tid; i < np1 * p.c; i += nthr) { wc[i] = (i < p.pol_ch * p.c ? p.w_pc[i] : p.w_vc[i - p.pol_ch * p.c]); }
+    __syncthreads();
+    // 1x1 convolutions: one warp per cell; lanes own contiguous channel chunks so the row is one coalesced read
+    const int cpl = p.c / 32; // channels per lane (c is a multiple of 64)
+    for (int cell = warp; cell < hw; cell += nwarp) {
+        const __half2* row = reinterpret_cast<const __half2*>(act + static_cast<size_t>((cell / p.n + 1) * n1 + cell % p.n) * p.c + lane * cpl);
+        float acc[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) { acc[o] = 0.0f; }
+        for (int i = 0; i < cpl / 2; ++i) {
             const float2 a = __half22float2(row[i]);
-            acc = fmaf(a.x, w[2 * i], acc);
-            acc = fmaf(a.y, w[2 * i + 1], acc);
+            const int ch = lane * cpl + 2 * i;
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                if (o < np1) { acc[o] = fmaf(a.x, wc[o * p.c + ch], fmaf(a.y, wc[o * p.c + ch + 1], acc[o])); }
+            }
         }
-        acc += (plane < p.pol_ch ? p.b_pc[plane] : p.b_vc[0]);
-        planes[item] = fmaxf(acc, 0.0f);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            if (o < np1) {
+                float v = acc[o];
+                for (int sft = 16; sft > 0; sft >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, sft); }
+                if (lane == 0) { planes[o * hw + cell] = fmaxf(v + (o < p.pol_ch ? p.b_pc[o] : p.b_vc[0]), 0.0f); }
+            }
+        }
     }
     __syncthreads();
-    // policy fc and value fc1
-    for (int o = tid; o < p.actions + p.vh; o += nthr) {
+    // policy fc and value fc1: one warp per output, lanes stride over the inputs (coalesced weight rows)
+    for (int o = warp; o < p.actions + p.vh; o += nwarp) {
+        float acc = 0.0f;
         if (o < p.actions) {
             const float* w = p.w_pf + static_cast<size_t>(o) * p.pol_ch * hw;
-            float acc = 0.0f;
-            for (int i = 0; i < p.pol_ch * hw; ++i) { acc = fmaf(planes[i], w[i], acc); }
-            lg[o] = acc + p.b_pf[o];
+            for (int i = lane; i < p.pol_ch * hw; i += 32) { acc = fmaf(planes[i], w[i], acc); }
         } else {
-            const int j = o - p.actions;
-            const float* w = p.w_v1 + static_cast<size_t>(j) * hw;
+            const float* w = p.w_v1 + static_cast<size_t>(o - p.actions) * hw;
             const float* vp = planes + p.pol_ch * hw;
-            float acc = 0.0f;
-            for (int i = 0; i < hw; ++i) { acc = fmaf(vp[i], w[i], acc); }
-            vhid[j] = fmaxf(acc + p.b_v1[j], 0.0f);
+            for (int i = lane; i < hw; i += 32) { acc = fmaf(vp[i], w[i], acc); }
+        }
+        for (int sft = 16; sft > 0; sft >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, sft); }
+        if (lane == 0) {
+            if (o < p.actions) {
+                lg[o] = acc + p.b_pf[o];
+            } else {
+                vhid[o - p.actions] = fmaxf(acc + p.b_v1[o - p.actions], 0.0f);
+            }
         }
     }
     __syncthreads();
@@ -312,18 +512,18 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
     float mx = -3.402823466e+38f;
     for (int a = tid; a < p.actions; a += nthr) { mx = fmaxf(mx, lg[a]); }
     for (int o = 16; o > 0; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
-    if ((tid & 31) == 0) { red[tid >> 5] = mx; }
+    if (lane == 0) { red[warp] = mx; }
     __syncthreads();
     mx = red[0];
-    for (int i = 1; i < (nthr + 31) / 32; ++i) { mx = fmaxf(mx, red[i]); }
+    for (int i = 1; i < nwarp; ++i) { mx = fmaxf(mx, red[i]); }
     __syncthreads();
     float sum = 0.0f;
     for (int a = tid; a < p.actions; a += nthr) { sum += expf(lg[a] - mx); }
     for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); }
-    if ((tid & 31) == 0) { red[tid >> 5] = sum; }
+    if (lane == 0) { red[warp] = sum; }
     __syncthreads();
     sum = 0.0f;
-    for (int i = 0; i < (nthr + 31) / 32; ++i) { sum += red[i]; }
+    for (int i = 0; i < nwarp; ++i) { sum += red[i]; }
     for (int a = tid; a < p.actions; a += nthr) {
         p.logits[static_cast<size_t>(g) * p.actions + a] = lg[a];
         p.policy[static_cast<size_t>(g) * p.actions + a] = expf(lg[a] - mx) / sum;

@@ -140,12 +140,17 @@ struct mz_state {
     float* value;
     float* root_noise; // [B][A] policy_noise_ of the root children
     int32_t* cursor;   // [B]
+    int16_t* node_slot; // [B][NP] index of the cached environment of an evaluated node (-1: none)
+    // environment of every evaluated node of the current search, slot = simulation index (0 .. S)
+    uint32_t* slot_st;   // [B][S + 1][2][N] stone rows
+    uint64_t* slot_hash; // [B][S + 1]
+    int32_t* slot_meta;  // [B][S + 1][4] turn, num_moves, last action, action before last
     // root environment
     uint32_t* root_st;   // [B][2][MZ_ROWS]
     uint32_t* root_hist; // [B][MZ_HIST][2][MZ_ROWS]
     uint64_t* root_hash; // [B]
     int32_t* root_meta;  // [B][4] turn, num_moves, last action, action before last
-    uint64_t* hashes;    // [B][max_hashes] position hashes of the game so far, then of the current path
+    uint64_t* hashes;    // [B][max_hashes] position hashes of the game so far (superko history of the root)
     // leaf of the current simulation
     int32_t* path;        // [B][S + 2]
     int32_t* path_len;    // [B]
@@ -174,6 +179,7 @@ struct mz_scratch {
     uint32_t legal[MZ_LEGAL_WORDS];
     uint64_t hash;
     int turn, num_moves, last, last2;
+    uint64_t* path_hashes; // [S + 2] position hashes of the nodes on the current path (shared memory on the device)
 };
 
 MZ_DEV uint32_t mz_rowmask(int N) { return (N >= 32 ? 0xffffffffu : ((1u << N) - 1u)); }
@@ -306,8 +312,8 @@ MZ_DEV void mz_env_reset(const mz_dims& d, mz_scratch* w, int lane)
 }
 
 // GoEnv::act (go.cpp:132-190) / TicTacToeEnv::act (tictactoe.cpp:19-26) for a move already known to
-// be legal. `hash_list` receives the new position hash at index num_moves (go.cpp:145-147,180-182).
-MZ_DEV void mz_env_act(const mz_dims& d, const mz_state& s, mz_scratch* w, int a, int player, uint64_t* hash_list, int lane)
+// be legal. The caller appends the new w->hash to the superko history (go.cpp:145-147,180-182).
+MZ_DEV void mz_env_act(const mz_dims& d, const mz_state& s, mz_scratch* w, int a, int player, int lane)
 {
     const int N = d.N, me = player - 1, opp = 1 - me;
     uint64_t hash = w->hash ^ d.turn_key; // go.cpp:141
@@ -344,7 +350,6 @@ MZ_DEV void mz_env_act(const mz_dims& d, const mz_state& s, mz_scratch* w, int a
                 mz_sync();
             }
         }
-        if (lane == 0) { hash_list[num_moves] = hash; }
     } else {
         if (lane == 0) { w->st[me][a / N] |= (1u << (a % N)); }
         mz_sync();
@@ -427,8 +432,9 @@ MZ_DEV float mz_env_eval_score(const mz_dims& d, mz_scratch* w, int lane)
 }
 
 // Legal action set of the side to move (go.cpp:208-244 for every action at once): writes w->legal (bit per
-// action id) and returns the number of legal actions. `hash_list[0..num_moves)` is the superko history.
-MZ_DEV int mz_env_legal(const mz_dims& d, const mz_state& s, mz_scratch* w, const uint64_t* hash_list, int lane)
+// action id) and returns the number of legal actions. The superko history is root_list[0..root_n) (positions of the
+// game so far) followed by path_list[0..path_n) (positions along the current search path).
+MZ_DEV int mz_env_legal(const mz_dims& d, const mz_state& s, mz_scratch* w, const uint64_t* root_list, int root_n, const uint64_t* path_list, int path_n, int lane)
 {
     const int N = d.N, A = d.A, me = w->turn - 1;
     for (int i = lane; i < MZ_LEGAL_WORDS; i += MZ_W) { w->legal[i] = 0u; }
@@ -496,13 +502,13 @@ MZ_DEV int mz_env_legal(const mz_dims& d, const mz_state& s, mz_scratch* w, cons
     }
     // (3) positional superko (go.cpp:222,237,243)
     const uint64_t base = w->hash ^ d.turn_key;
-    const int H = w->num_moves;
     for (int a = lane; a < N * N; a += MZ_W) {
         const int r = a / N, x = a % N;
         if (!((w->legal_rows[r] >> x) & 1u)) { continue; }
         const uint64_t nh = base ^ s.keys[me * 361 + a] ^ w->cap_hash[a];
         int seen = 0;
-        for (int i = 0; i < H; ++i) { seen |= (hash_list[i] == nh); }
+        for (int i = 0; i < root_n; ++i) { seen |= (root_list[i] == nh); }
+        for (int i = 0; i < path_n; ++i) { seen |= (path_list[i] == nh); }
         if (!seen) {
 #if MZ_W == 1
             w->legal[a >> 5] |= (1u << (a & 31));
@@ -560,19 +566,23 @@ MZ_DEV float mz_normalized_mean(const mz_dims& d, float mean, float count, int p
     return mz_fdiv(mz_fsub(mz_fmul(v, count), 0.0f), mz_fadd(count, 0.0f));
 }
 
-// MCTS::select (mcts.cpp:139-148,181-217): returns the path length; path[] holds node indices from the root
+// MCTS::select (mcts.cpp:139-148,181-217): returns the path length; path[] holds node indices from the root.
+// One dependent memory round trip per level: the record of the chosen child (with its link) is taken from the lane
+// that scored it instead of being loaded again.
 MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int root_turn, int lane)
 {
     const mz_hot* hot = s.hot + (size_t)g * d.NP;
     int32_t* path = s.path + (size_t)g * (d.S + 2);
-    int node = 0, len = 1, child_player = root_turn;
+    int len = 1, child_player = root_turn;
     if (lane == 0) { path[0] = 0; }
+    mz_hot h = mz_load_hot(hot);
     for (;;) {
-        const mz_hot h = mz_load_hot(hot + node);
         const int nc = (int)(h.link >> MZ_LINK_SHIFT), fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
         if (nc == 0) { break; }
         const int total = (int)mz_fsub(h.count, 1.0f); // mcts.cpp:185
-        // init-Q: ordered f32 sum over the visited children (mcts.cpp:200-217)
+        const float bias = s.puct_bias[total];
+        const double sqrt_n = mz_dsqrt((double)total);
+        // pass 1: ordered f32 sum of the visited children's Q (init-Q, mcts.cpp:200-217)
         float sum_win = 0.0f, sum_n = 0.0f;
         for (int base = 0; base < nc; base += MZ_W) {
             const int i = base + lane;
@@ -592,43 +602,119 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
             }
         }
         const float init_q = mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
-        const float bias = s.puct_bias[total];
-        const double sqrt_n = mz_dsqrt((double)total);
+        // pass 2 (records come from L1): PUCT score, lexicographic arg-max (mcts.cpp:55-61,187-194)
         float best_s = 0.0f, best_p = 0.0f;
         int best_i = -1;
+        mz_hot best_h = h;
         for (int i = lane; i < nc; i += MZ_W) {
             const mz_hot c = mz_load_hot(hot + fc + i);
             const float u = (float)mz_ddiv(mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n), (double)mz_fadd(1.0f, c.count));
             const float qv = (c.count == 0.0f ? init_q : w->q[i]);
             const float score = mz_fadd(u, qv);
-            if (best_i < 0 || score > best_s || (score == best_s && c.policy > best_p)) { best_s = score, best_p = c.policy, best_i = i; }
+            if (best_i < 0 || score > best_s || (score == best_s && c.policy > best_p)) { best_s = score, best_p = c.policy, best_i = i, best_h = c; }
         }
+        const int mine = best_i;
         mz_reduce_best(best_s, best_p, best_i);
         mz_sync();
-        node = fc + best_i;
-        if (lane == 0) { path[len] = node; }
+        // broadcast the winner's record from the lane that holds it
+#if MZ_W == 1
+        h = best_h;
+#else
+        {
+            const unsigned owner_mask = mz_ballot(mine == best_i);
+            const int owner = mz_ffs0(owner_mask);
+            h.count = __shfl_sync(MZ_FULL, best_h.count, owner);
+            h.mean = __shfl_sync(MZ_FULL, best_h.mean, owner);
+            h.policy = __shfl_sync(MZ_FULL, best_h.policy, owner);
+            h.link = __shfl_sync(MZ_FULL, best_h.link, owner);
+        }
+#endif
+        if (lane == 0) { path[len] = fc + best_i; }
         ++len;
         child_player = 3 - child_player;
     }
     return len;
 }
 
+MZ_DEV void mz_slot_store(const mz_dims& d, const mz_state& s, int g, int slot, const mz_scratch* w, int lane)
+{
+    const size_t e = (size_t)g * (d.S + 1) + slot;
+    uint32_t* st = s.slot_st + e * 2 * d.N;
+    for (int i = lane; i < 2 * d.N; i += MZ_W) { st[i] = w->st[i / d.N][i % d.N]; }
+    if (lane == 0) {
+        s.slot_hash[e] = w->hash;
+        s.slot_meta[e * 4 + 0] = w->turn, s.slot_meta[e * 4 + 1] = w->num_moves, s.slot_meta[e * 4 + 2] = w->last, s.slot_meta[e * 4 + 3] = w->last2;
+    }
+}
+
+MZ_DEV void mz_slot_load(const mz_dims& d, const mz_state& s, int g, int slot, mz_scratch* w, int lane)
+{
+    const size_t e = (size_t)g * (d.S + 1) + slot;
+    const uint32_t* st = s.slot_st + e * 2 * d.N;
+    for (int i = lane; i < 2 * d.N; i += MZ_W) { w->st[i / d.N][i % d.N] = st[i]; }
+    if (lane == 0) {
+        w->hash = s.slot_hash[e];
+        w->turn = s.slot_meta[e * 4 + 0], w->num_moves = s.slot_meta[e * 4 + 1], w->last = s.slot_meta[e * 4 + 2], w->last2 = s.slot_meta[e * 4 + 3];
+    }
+    mz_sync();
+}
+
 // One "before NN evaluation" step of game g (zero_actor.cpp:51-58): select, transition, analyse the leaf
 // (terminal / score / legal set) and emit its feature planes.
+//
+// The reference rebuilds the leaf position by copying the root environment and replaying the whole path
+// (zero_actor.cpp:247-252). Here every evaluated node keeps its position (stone rows, hash, last two actions) in a
+// slot indexed by the simulation that evaluated it, so the transition is "parent's slot + one move"; the 8-position
+// feature history and the superko hash list are gathered from the slots of the nodes on the path (and from the root
+// environment for positions older than the root). Same positions, same results, cost independent of the depth.
 MZ_DEV void mz_before_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int lane)
 {
-    mz_env_load_root(d, s, g, w, lane);
-    const int root_turn = w->turn;
+    const int N = d.N;
+    const int root_turn = s.root_meta[g * 4 + 0], root_moves = s.root_meta[g * 4 + 1];
     const int len = mz_select(d, s, g, w, root_turn, lane);
     mz_sync();
     const int32_t* path = s.path + (size_t)g * (d.S + 2);
-    uint64_t* hash_list = s.hashes + (size_t)g * d.max_hashes;
-    int player = root_turn;
-    for (int i = 1; i < len; ++i) { // getEnvironmentTransition, zero_actor.cpp:247-252
-        const int a = s.action[(size_t)g * d.NP + path[i]];
-        mz_env_act(d, s, w, a, player, hash_list, lane);
-        player = 3 - player;
+    const int16_t* node_slot = s.node_slot + (size_t)g * d.NP;
+    const uint64_t* root_list = s.hashes + (size_t)g * d.max_hashes;
+    const int L = len - 1; // depth of the leaf
+    const int slot = (int)mz_load_hot(s.hot + (size_t)g * d.NP).count; // simulations finished so far
+    const int leaf = path[L];
+    // position hashes of the path nodes 1 .. L-1 (superko history beyond the root)
+    for (int j = 1 + lane; j < L; j += MZ_W) { w->path_hashes[j - 1] = s.slot_hash[(size_t)g * (d.S + 1) + node_slot[path[j]]]; }
+    if (L == 0) {
+        mz_env_load_root(d, s, g, w, lane);
+    } else {
+        // feature history: positions of the (up to 7) ancestors, newest first, then the root's own ring
+        for (int k = 1; k < MZ_HIST; ++k) {
+            const int pos = root_moves + L - 1 - k; // index of the position k moves before the leaf's
+            if (pos < 0) { break; }
+            const int ring = pos % MZ_HIST;
+            if (pos >= root_moves) {
+                const uint32_t* st = s.slot_st + ((size_t)g * (d.S + 1) + node_slot[path[L - k]]) * 2 * N;
+                for (int i = lane; i < 2 * N; i += MZ_W) { w->hist[ring][i / N][i % N] = st[i]; }
+            } else {
+                const uint32_t* hist = s.root_hist + ((size_t)g * MZ_HIST + ring) * 2 * MZ_ROWS;
+                for (int i = lane; i < 2 * N; i += MZ_W) { w->hist[ring][i / N][i % N] = hist[(i / N) * MZ_ROWS + i % N]; }
+            }
+        }
+        if (L == 1) {
+            const uint32_t* st = s.root_st + (size_t)g * 2 * MZ_ROWS;
+            for (int i = lane; i < 2 * N; i += MZ_W) { w->st[i / N][i % N] = st[(i / N) * MZ_ROWS + i % N]; }
+            if (lane == 0) {
+                w->hash = s.root_hash[g];
+                w->turn = root_turn, w->num_moves = root_moves, w->last = s.root_meta[g * 4 + 2], w->last2 = s.root_meta[g * 4 + 3];
+            }
+            mz_sync();
+        } else {
+            mz_slot_load(d, s, g, node_slot[path[L - 1]], w, lane);
+        }
+        const int a = s.action[(size_t)g * d.NP + leaf];
+        mz_env_act(d, s, w, a, w->turn, lane); // getEnvironmentTransition's last step, zero_actor.cpp:250
+        if (lane == 0) { w->path_hashes[L - 1] = w->hash; }
+        mz_sync();
     }
+    mz_slot_store(d, s, g, slot, w, lane);
+    if (lane == 0) { s.node_slot[(size_t)g * d.NP + leaf] = (int16_t)slot; }
     const int rotation = (s.rotations ? s.rotations[g] : 0);
     const int terminal = mz_env_is_terminal(d, w);
     float score = 0.0f;
@@ -636,7 +722,7 @@ MZ_DEV void mz_before_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch*
     if (terminal) {
         score = mz_env_eval_score(d, w, lane);
     } else {
-        num_legal = mz_env_legal(d, s, w, hash_list, lane);
+        num_legal = mz_env_legal(d, s, w, root_list, root_moves, w->path_hashes, L, lane);
     }
     mz_env_features(d, s, g, w, rotation, lane);
     for (int i = lane; i < MZ_LEGAL_WORDS; i += MZ_W) { s.leaf_legal[g * MZ_LEGAL_WORDS + i] = w->legal[i]; }
@@ -691,6 +777,7 @@ MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* 
             s.action[(size_t)g * d.NP + c] = (int16_t)a;
             s.logit[(size_t)g * d.NP + c] = w->lg[a];
             s.value[(size_t)g * d.NP + c] = 0.0f;
+            s.node_slot[(size_t)g * d.NP + c] = -1;
         }
         mz_sync();
         if (lane == 0) {
@@ -739,6 +826,7 @@ MZ_DEV void mz_tree_reset(const mz_dims& d, const mz_state& s, int g, int lane)
         s.value[(size_t)g * d.NP] = 0.0f;
         s.logit[(size_t)g * d.NP] = 0.0f;
         s.action[(size_t)g * d.NP] = -1;
+        s.node_slot[(size_t)g * d.NP] = -1;
         s.cursor[g] = 1;
         s.path_len[g] = 0;
     }
@@ -760,12 +848,14 @@ MZ_DEV void mz_play(const mz_dims& d, const mz_state& s, int g, int action, mz_s
 {
     mz_env_load_root(d, s, g, w, lane);
     uint64_t* hash_list = s.hashes + (size_t)g * d.max_hashes;
-    mz_env_legal(d, s, w, hash_list, lane);
+    mz_env_legal(d, s, w, hash_list, w->num_moves, hash_list, 0, lane);
     const int ok = (action >= 0 && action < d.A && ((w->legal[action >> 5] >> (action & 31)) & 1u)) ? 1 : 0;
     int terminal = 0, num_legal = 0;
     float sc = 0.0f;
     if (ok) {
-        mz_env_act(d, s, w, action, w->turn, hash_list, lane);
+        mz_env_act(d, s, w, action, w->turn, lane);
+        if (lane == 0) { hash_list[w->num_moves - 1] = w->hash; } // hashkey_history_ / hash_table_, go.cpp:145-147,180-182
+        mz_sync();
         mz_env_store_root(d, s, g, w, lane);
         mz_tree_reset(d, s, g, lane);
     }
@@ -773,7 +863,7 @@ MZ_DEV void mz_play(const mz_dims& d, const mz_state& s, int g, int action, mz_s
     if (terminal) {
         sc = mz_env_eval_score(d, w, lane);
     } else {
-        num_legal = mz_env_legal(d, s, w, hash_list, lane);
+        num_legal = mz_env_legal(d, s, w, hash_list, w->num_moves, hash_list, 0, lane);
     }
     if (lane == 0) {
         out[0] = ok, out[1] = terminal, out[2] = num_legal, out[3] = w->turn;

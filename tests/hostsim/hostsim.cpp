@@ -37,6 +37,9 @@ sim* hs_create(int game, int N, int B, int S, float puct_base, float puct_init, 
     size_t np = (size_t)B * d.NP;
     s.hot = zalloc<mz_hot>(np), s.action = zalloc<int16_t>(np), s.logit = zalloc<float>(np), s.value = zalloc<float>(np);
     s.root_noise = zalloc<float>((size_t)B * d.A), s.cursor = zalloc<int32_t>(B);
+    s.node_slot = zalloc<int16_t>(np);
+    s.slot_st = zalloc<uint32_t>((size_t)B * (S + 1) * 2 * N), s.slot_hash = zalloc<uint64_t>((size_t)B * (S + 1)), s.slot_meta = zalloc<int32_t>((size_t)B * (S + 1) * 4);
+    h->w.path_hashes = zalloc<uint64_t>(S + 2);
     s.root_st = zalloc<uint32_t>((size_t)B * 2 * MZ_ROWS), s.root_hist = zalloc<uint32_t>((size_t)B * MZ_HIST * 2 * MZ_ROWS);
     s.root_hash = zalloc<uint64_t>(B), s.root_meta = zalloc<int32_t>((size_t)B * 4), s.hashes = zalloc<uint64_t>((size_t)B * d.max_hashes);
     s.path = zalloc<int32_t>((size_t)B * (S + 2)), s.path_len = zalloc<int32_t>(B), s.leaf_legal = zalloc<uint32_t>((size_t)B * MZ_LEGAL_WORDS);
