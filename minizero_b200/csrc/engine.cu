@@ -171,7 +171,7 @@ struct mz_engine {
     __half* act[3] = {nullptr, nullptr, nullptr};
     CUtensorMap map_in0, map_act[3];
     CUtensorMap map_in0_ext, map_act_ext[3]; // same buffers, box = the resident block of conv3x3_resident_kernel
-    int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148;
+    int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148, krot = 0;
     encode_tiled_fn encode = nullptr;
 
     // graphs keyed by (num_evals, noise, rotations)
@@ -207,7 +207,7 @@ int launch_conv(mz_engine* e, const CUtensorMap& in, const ConvLayer& L, __half*
     using Smem = mznn::ConvSmem<BN, STAGES>;
     mznn::ConvParams p;
     p.out = out, p.residual = residual, p.bias = reinterpret_cast<const float*>(e->d_blob + L.b_off);
-    p.rows_valid = e->d.B * e->d.slots, p.n1 = e->d.N + 1, p.slots = e->d.slots, p.cin = L.cin, p.cout = L.cout, p.relu = L.relu;
+    p.rows_valid = e->d.B * e->d.slots, p.n1 = e->d.N + 1, p.slots = e->d.slots, p.cin = L.cin, p.cout = L.cout, p.relu = L.relu, p.krot = e->krot;
     dim3 grid(e->rows_alloc / mznn::BM, L.cout / BN);
     mznn::conv3x3_tcgen05_kernel<BN, STAGES><<<grid, mznn::CONV_THREADS, Smem::TOTAL, e->stream>>>(in, L.map_w, p);
     e->launches++;
@@ -226,7 +226,7 @@ int launch_conv_resident(mz_engine* e, const CUtensorMap& in_ext, const ConvLaye
     mznn::ConvResParams rp;
     mznn::ConvParams& p = rp.c;
     p.out = out, p.residual = residual, p.bias = reinterpret_cast<const float*>(e->d_blob + L.b_off);
-    p.rows_valid = e->d.B * e->d.slots, p.n1 = e->d.N + 1, p.slots = e->d.slots, p.cin = L.cin, p.cout = L.cout, p.relu = L.relu;
+    p.rows_valid = e->d.B * e->d.slots, p.n1 = e->d.N + 1, p.slots = e->d.slots, p.cin = L.cin, p.cout = L.cout, p.relu = L.relu, p.krot = e->krot;
     rp.rows_ext = e->rows_ext, rp.halo = e->d.N + 2, rp.num_mtiles = e->rows_alloc / mznn::BM, rp.base_off_mode = e->base_off_mode;
     const int units = rp.num_mtiles * (L.cout / BN);
     const int grid = units < e->num_sms ? units : e->num_sms;
@@ -241,7 +241,7 @@ int configure_conv_kernels()
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_tcgen05_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mznn::ConvSmem<128, 3>::TOTAL));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_tcgen05_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mznn::ConvSmem<256, 4>::TOTAL));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<64, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return MZ_OK;
 }
 
@@ -249,7 +249,7 @@ int conv(mz_engine* e, const CUtensorMap& in, const CUtensorMap& in_ext, const C
 {
     if (e->conv_mode == 1) {
         if (e->bn_tile == 64) { return launch_conv_resident<64, 6>(e, in_ext, L, out, residual); }
-        return launch_conv_resident<128, 6>(e, in_ext, L, out, residual);
+        return launch_conv_resident<128, 9>(e, in_ext, L, out, residual);
     }
     switch (e->bn_tile) {
         case 64: return launch_conv<64, 4>(e, in, L, out, residual);
@@ -368,8 +368,9 @@ int alloc_net(mz_engine* e)
     e->conv_mode = 1;
     if (const char* env = std::getenv("MZ_CONV_MODE")) { e->conv_mode = std::atoi(env); }
     if (const char* env = std::getenv("MZ_CONV_BASEOFF")) { e->base_off_mode = std::atoi(env); }
+    if (const char* env = std::getenv("MZ_CONV_ROT")) { e->krot = std::atoi(env); }
     if (e->bn_tile == 256) { e->conv_mode = 0; }
-    const size_t need = (e->bn_tile == 64 ? resident_smem<64, 6>(e, e->cpad) : resident_smem<128, 6>(e, e->cpad));
+    const size_t need = (e->bn_tile == 64 ? resident_smem<64, 6>(e, e->cpad) : resident_smem<128, 9>(e, e->cpad));
     if (need > 227 * 1024) { e->conv_mode = 0; }
     cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->cfg.device);
     for (int i = 0; i < 3; ++i) {
@@ -610,7 +611,14 @@ int mz_net_finalize(mz_engine* e)
         put(0, wp), put(1, bias);
         std::vector<float> t;
         if (!raw("policy.fc.weight", static_cast<size_t>(nd.action_size) * e->pol_ch * hw, t)) { return fail(MZ_ERR_ARG, err); }
-        put(2, t);
+        {
+            const int nin = e->pol_ch * hw;
+            std::vector<float> tt(t.size());
+            for (int o = 0; o < nd.action_size; ++o) {
+                for (int i = 0; i < nin; ++i) { tt[static_cast<size_t>(i) * nd.action_size + o] = t[static_cast<size_t>(o) * nin + i]; }
+            }
+            put(2, tt);
+        }
         if (!raw("policy.fc.bias", nd.action_size, t)) { return fail(MZ_ERR_ARG, err); }
         put(3, t);
     }
@@ -622,7 +630,14 @@ int mz_net_finalize(mz_engine* e)
         put(4, wp), put(5, bias);
         std::vector<float> t;
         if (!raw("value.fc1.weight", static_cast<size_t>(nd.num_value_hidden_channels) * hw, t)) { return fail(MZ_ERR_ARG, err); }
-        put(6, t);
+        {
+            const int vh = nd.num_value_hidden_channels;
+            std::vector<float> tt(t.size());
+            for (int j = 0; j < vh; ++j) {
+                for (int i = 0; i < hw; ++i) { tt[static_cast<size_t>(i) * vh + j] = t[static_cast<size_t>(j) * hw + i]; }
+            }
+            put(6, tt);
+        }
         if (!raw("value.fc1.bias", nd.num_value_hidden_channels, t)) { return fail(MZ_ERR_ARG, err); }
         put(7, t);
         if (!raw("value.fc2.weight", nd.num_value_hidden_channels, t)) { return fail(MZ_ERR_ARG, err); }

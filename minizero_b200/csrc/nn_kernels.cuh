@@ -118,6 +118,7 @@ struct ConvParams {
     int cin;                // multiple of BK
     int cout;               // multiple of BN
     int relu;
+    int krot;               // rotate each CTA's K-loop start so that CTAs do not stream the same weight tile at the same time
 };
 
 template <int BN, int STAGES>
@@ -146,6 +147,7 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     const int kb_per_tap = p.cin / BK, num_k = 9 * kb_per_tap;
+    const int rot = (p.krot ? static_cast<int>((blockIdx.x * 7u + blockIdx.y * 3u) % static_cast<unsigned>(num_k)) : 0);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_in)) : "memory");
@@ -172,7 +174,8 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_
             for (int k = 0; k < num_k; ++k) {
                 const int s = k % STAGES;
                 if (k >= STAGES) { mbar_wait(&empty_bar[s], ((k / STAGES) - 1) & 1); }
-                const int tap = k / kb_per_tap, kb = k - tap * kb_per_tap;
+                const int kr = (k + rot >= num_k ? k + rot - num_k : k + rot);
+                const int tap = kr / kb_per_tap, kb = kr - tap * kb_per_tap;
                 const int off = (tap / 3 - 1) * p.n1 + (tap % 3 - 1);
                 uint8_t* a_dst = smem + s * L::STAGE_BYTES;
                 uint8_t* b_dst = a_dst + L::A_BYTES;
@@ -291,6 +294,7 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
     const int u_begin = static_cast<int>((static_cast<long long>(blockIdx.x) * units) / gridDim.x);
     const int u_end = static_cast<int>((static_cast<long long>(blockIdx.x + 1) * units) / gridDim.x);
     const int num_k = 9 * a_kb;
+    const int rot = (p.krot ? static_cast<int>((blockIdx.x * 7u) % static_cast<unsigned>(num_k)) : 0);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_in)) : "memory");
@@ -332,7 +336,8 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
                 for (int k = 0; k < num_k; ++k, ++kcount) {
                     const int s = kcount % STAGES;
                     if (kcount >= STAGES) { mbar_wait(&b_empty[s], ((kcount / STAGES) - 1) & 1); }
-                    const int tap = k / a_kb, kb = k - tap * a_kb;
+                    const int kr = (k + rot >= num_k ? k + rot - num_k : k + rot);
+                    const int tap = kr / a_kb, kb = kr - tap * a_kb;
                     mbar_arrive_expect_tx(&b_full[s], B_BYTES);
                     tma_load_2d(smem_b + s * B_BYTES, &map_w, &b_full[s], kb * BK, tap * p.cout + half * BN);
                 }
@@ -357,7 +362,8 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
                     const int s = kcount % STAGES;
                     mbar_wait(&b_full[s], (kcount / STAGES) & 1);
                     tcgen05_fence_after();
-                    const int tap = k / a_kb, kb = k - tap * a_kb;
+                    const int kr = (k + rot >= num_k ? k + rot - num_k : k + rot);
+                    const int tap = kr / a_kb, kb = kr - tap * a_kb;
                     const int row0 = rp.halo + (tap / 3 - 1) * p.n1 + (tap % 3 - 1);
                     const uint32_t a_addr = smem_u32(smem_a + kb * a_kb_bytes) + row0 * 128;
                     const uint32_t b_addr = smem_u32(smem_b + s * B_BYTES);
@@ -435,11 +441,11 @@ struct HeadParams {
     const __half* act;  // [rows][c] final tower activations
     const float* w_pc;  // [pol_ch][c] policy conv (BN folded)   b_pc [pol_ch]
     const float* b_pc;
-    const float* w_pf;  // [A][pol_ch * hw] policy fc            b_pf [A]
+    const float* w_pf;  // [pol_ch * hw][A] policy fc, transposed  b_pf [A]
     const float* b_pf;
     const float* w_vc;  // [c] value conv (BN folded)            b_vc [1]
     const float* b_vc;
-    const float* w_v1;  // [vh][hw]   b_v1 [vh]
+    const float* w_v1;  // [hw][vh] transposed   b_v1 [vh]
     const float* b_v1;
     const float* w_v2;  // [vh]       b_v2 [1]
     const float* b_v2;
@@ -462,19 +468,23 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
     const __half* act = p.act + static_cast<size_t>(g) * p.slots * p.c;
     for (int i = tid; i < np1 * p.c; i += nthr) { wc[i] = (i < p.pol_ch * p.c ? p.w_pc[i] : p.w_vc[i - p.pol_ch * p.c]); }
     __syncthreads();
-    // 1x1 convolutions: one warp per cell; lanes own contiguous channel chunks so the row is one coalesced read
-    const int cpl = p.c / 32; // channels per lane (c is a multiple of 64)
+    // 1x1 convolutions: one warp per cell; lane l owns channel pairs {2l + 64i}: every load instruction is one
+    // contiguous 128-byte row segment and the weight reads from shared memory are conflict-free
+    const int npair = p.c / 64; // half2 loads per lane (c is a multiple of 64)
     for (int cell = warp; cell < hw; cell += nwarp) {
-        const __half2* row = reinterpret_cast<const __half2*>(act + static_cast<size_t>((cell / p.n + 1) * n1 + cell % p.n) * p.c + lane * cpl);
+        const __half2* row = reinterpret_cast<const __half2*>(act + static_cast<size_t>((cell / p.n + 1) * n1 + cell % p.n) * p.c);
         float acc[8];
 #pragma unroll
         for (int o = 0; o < 8; ++o) { acc[o] = 0.0f; }
-        for (int i = 0; i < cpl / 2; ++i) {
-            const float2 a = __half22float2(row[i]);
-            const int ch = lane * cpl + 2 * i;
+        for (int i = 0; i < npair; ++i) {
+            const float2 a = __half22float2(row[lane + 32 * i]);
+            const int ch = 2 * lane + 64 * i;
 #pragma unroll
             for (int o = 0; o < 8; ++o) {
-                if (o < np1) { acc[o] = fmaf(a.x, wc[o * p.c + ch], fmaf(a.y, wc[o * p.c + ch + 1], acc[o])); }
+                if (o < np1) {
+                    const float2 wv = *reinterpret_cast<const float2*>(wc + o * p.c + ch);
+                    acc[o] = fmaf(a.x, wv.x, fmaf(a.y, wv.y, acc[o]));
+                }
             }
         }
 #pragma unroll
@@ -487,24 +497,21 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
         }
     }
     __syncthreads();
-    // policy fc and value fc1: one warp per output, lanes stride over the inputs (coalesced weight rows)
-    for (int o = warp; o < p.actions + p.vh; o += nwarp) {
+    // policy fc and value fc1: one thread per output over TRANSPOSED weights [in][out] (coalesced across threads,
+    // independent loads the compiler can keep in flight)
+    for (int o = tid; o < p.actions + p.vh; o += nthr) {
         float acc = 0.0f;
         if (o < p.actions) {
-            const float* w = p.w_pf + static_cast<size_t>(o) * p.pol_ch * hw;
-            for (int i = lane; i < p.pol_ch * hw; i += 32) { acc = fmaf(planes[i], w[i], acc); }
+            const int nin = p.pol_ch * hw;
+#pragma unroll 8
+            for (int i = 0; i < nin; ++i) { acc = fmaf(planes[i], __ldg(p.w_pf + static_cast<size_t>(i) * p.actions + o), acc); }
+            lg[o] = acc + p.b_pf[o];
         } else {
-            const float* w = p.w_v1 + static_cast<size_t>(o - p.actions) * hw;
+            const int j = o - p.actions;
             const float* vp = planes + p.pol_ch * hw;
-            for (int i = lane; i < hw; i += 32) { acc = fmaf(vp[i], w[i], acc); }
-        }
-        for (int sft = 16; sft > 0; sft >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, sft); }
-        if (lane == 0) {
-            if (o < p.actions) {
-                lg[o] = acc + p.b_pf[o];
-            } else {
-                vhid[o - p.actions] = fmaxf(acc + p.b_v1[o - p.actions], 0.0f);
-            }
+#pragma unroll 8
+            for (int i = 0; i < hw; ++i) { acc = fmaf(vp[i], __ldg(p.w_v1 + static_cast<size_t>(i) * p.vh + j), acc); }
+            vhid[j] = fmaxf(acc + p.b_v1[j], 0.0f);
         }
     }
     __syncthreads();
