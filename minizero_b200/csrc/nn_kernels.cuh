@@ -268,6 +268,38 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// spin on an mbarrier phase with the minimum of instructions (labels are local to the PTX block)
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar_addr, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t}" ::"r"(bar_addr),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_u32(uint32_t bar_addr)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+
+// The producer and the MMA issuer are single threads: every instruction in their per-K-block loops is on the
+// critical path (measured: ~650 cycles of address arithmetic per K block starve a 256-cycle MMA), so the loops keep
+// stage / phase / descriptor words incrementally and contain no division.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w, const ConvResParams rp)
@@ -284,7 +316,7 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
     uint64_t* b_empty = b_full + STAGES;
     uint64_t* a_full = b_empty + STAGES;
     uint64_t* a_empty = a_full + 1;
-    uint64_t* acc_full = a_empty + 1;  // [2]
+    uint64_t* acc_full = a_empty + 1;   // [2]
     uint64_t* acc_empty = acc_full + 2; // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -293,8 +325,6 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
     const int units = rp.num_mtiles * nh;
     const int u_begin = static_cast<int>((static_cast<long long>(blockIdx.x) * units) / gridDim.x);
     const int u_end = static_cast<int>((static_cast<long long>(blockIdx.x + 1) * units) / gridDim.x);
-    const int num_k = 9 * a_kb;
-    const int rot = (p.krot ? static_cast<int>((blockIdx.x * 7u) % static_cast<unsigned>(num_k)) : 0);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_in)) : "memory");
@@ -320,63 +350,88 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t full0 = smem_u32(b_full), empty0 = smem_u32(b_empty);
 
     if (warp == 0) {
         if (lane == 0) { // ===== TMA producer =====
-            int cur_mt = -1, a_loads = 0, kcount = 0;
+            int s = 0, mt = u_begin / nh, half = u_begin - mt * nh, cur_mt = -1;
+            uint32_t ph = 1, a_ph = 1; // "empty" barriers: the first pass over the ring must not block
+            const uint32_t b_dst0 = smem_u32(smem_b), a_dst0 = smem_u32(smem_a);
+            const uint64_t map_w_ptr = reinterpret_cast<uint64_t>(&map_w), map_in_ptr = reinterpret_cast<uint64_t>(&map_in);
             for (int u = u_begin; u < u_end; ++u) {
-                const int mt = u / nh, half = u - mt * nh;
                 if (mt != cur_mt) {
-                    if (a_loads > 0) { mbar_wait(a_empty, (a_loads - 1) & 1); } // every MMA on the previous block has completed
+                    mbar_wait_u32(smem_u32(a_empty), a_ph); // every MMA on the previous input block has completed
+                    a_ph ^= 1;
                     mbar_arrive_expect_tx(a_full, a_kb * a_kb_bytes);
-                    for (int kb = 0; kb < a_kb; ++kb) { tma_load_2d(smem_a + kb * a_kb_bytes, &map_in, a_full, kb * BK, mt * BM - rp.halo); }
+                    for (int kb = 0; kb < a_kb; ++kb) {
+                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(a_dst0 + kb * a_kb_bytes),
+                                     "l"(map_in_ptr), "r"(smem_u32(a_full)), "r"(kb * BK), "r"(mt * BM - rp.halo)
+                                     : "memory");
+                    }
                     cur_mt = mt;
-                    ++a_loads;
                 }
-                for (int k = 0; k < num_k; ++k, ++kcount) {
-                    const int s = kcount % STAGES;
-                    if (kcount >= STAGES) { mbar_wait(&b_empty[s], ((kcount / STAGES) - 1) & 1); }
-                    const int kr = (k + rot >= num_k ? k + rot - num_k : k + rot);
-                    const int tap = kr / a_kb, kb = kr - tap * a_kb;
-                    mbar_arrive_expect_tx(&b_full[s], B_BYTES);
-                    tma_load_2d(smem_b + s * B_BYTES, &map_w, &b_full[s], kb * BK, tap * p.cout + half * BN);
+                int wrow = half * BN; // row of the weight matrix: tap * cout + half * BN
+                for (int tap = 0; tap < 9; ++tap, wrow += p.cout) {
+                    for (int kc = 0; kc < p.cin; kc += BK) {
+                        const uint32_t full = full0 + s * 8;
+                        mbar_wait_u32(empty0 + s * 8, ph);
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(B_BYTES) : "memory");
+                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(b_dst0 + s * B_BYTES),
+                                     "l"(map_w_ptr), "r"(full), "r"(kc), "r"(wrow)
+                                     : "memory");
+                        if (++s == STAGES) { s = 0, ph ^= 1; }
+                    }
                 }
+                if (++half == nh) { half = 0, ++mt; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) { // ===== MMA issuer =====
             constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
-            int cur_mt = -1, a_cnt = 0, kcount = 0, ucount = 0;
-            for (int u = u_begin; u < u_end; ++u, ++ucount) {
-                const int mt = u / nh;
+            // descriptor words (cute/arch/mma_sm100_desc.hpp): lo = start>>4 | LBO(1)<<16 ; hi = SBO(1024>>4) | version 1<<14 | SWIZZLE_128B 2<<29
+            constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFFu) >> 4) | (1u << 16), b_lo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t a_kb_step = static_cast<uint32_t>(a_kb_bytes) >> 4;
+            int s = 0, mt = u_begin / nh, half = u_begin - mt * nh, cur_mt = -1, buf = 0;
+            uint32_t ph = 0, a_ph = 0, acc_ph0 = 1, acc_ph1 = 1;
+            for (int u = u_begin; u < u_end; ++u) {
                 if (mt != cur_mt) {
-                    mbar_wait(a_full, a_cnt & 1);
-                    ++a_cnt;
+                    mbar_wait_u32(smem_u32(a_full), a_ph);
+                    a_ph ^= 1;
                     cur_mt = mt;
                 }
-                const int buf = ucount & 1;
-                if (ucount >= 2) { mbar_wait(&acc_empty[buf], ((ucount >> 1) - 1) & 1); }
+                if (buf == 0) {
+                    mbar_wait_u32(smem_u32(&acc_empty[0]), acc_ph0);
+                    acc_ph0 ^= 1;
+                } else {
+                    mbar_wait_u32(smem_u32(&acc_empty[1]), acc_ph1);
+                    acc_ph1 ^= 1;
+                }
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * BN;
-                for (int k = 0; k < num_k; ++k, ++kcount) {
-                    const int s = kcount % STAGES;
-                    mbar_wait(&b_full[s], (kcount / STAGES) & 1);
-                    tcgen05_fence_after();
-                    const int kr = (k + rot >= num_k ? k + rot - num_k : k + rot);
-                    const int tap = kr / a_kb, kb = kr - tap * a_kb;
-                    const int row0 = rp.halo + (tap / 3 - 1) * p.n1 + (tap % 3 - 1);
-                    const uint32_t a_addr = smem_u32(smem_a + kb * a_kb_bytes) + row0 * 128;
-                    const uint32_t b_addr = smem_u32(smem_b + s * B_BYTES);
-                    const uint64_t base_off = (rp.base_off_mode ? (static_cast<uint64_t>((a_addr >> 7) & 7u) << 49) : 0ull);
-#pragma unroll
-                    for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                        umma_f16(tmem_d, umma_desc_sw128(a_addr + kk * UMMA_K * 2) | base_off, umma_desc_sw128(b_addr + kk * UMMA_K * 2), idesc, (k | kk) != 0);
+                uint32_t accumulate = 0;
+                int row0 = rp.halo - p.n1 - 1; // first tap: (ky, kx) = (0, 0) -> offset -(N+1) - 1
+                for (int ty = 0; ty < 3; ++ty, row0 += p.n1 - 3) {
+                    for (int tx = 0; tx < 3; ++tx, ++row0) {
+                        uint32_t a_lo = a_lo0 + static_cast<uint32_t>(row0) * 8u; // + row0 * 128 bytes
+                        for (int kc = 0; kc < p.cin; kc += BK, a_lo += a_kb_step) {
+                            mbar_wait_u32(full0 + s * 8, ph);
+                            tcgen05_fence_after();
+                            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(s) * (B_BYTES >> 4);
+                            umma_f16_lohi(tmem_d, a_lo, b_lo, desc_hi, idesc, accumulate);
+                            umma_f16_lohi(tmem_d, a_lo + 2, b_lo + 2, desc_hi, idesc, 1u);
+                            umma_f16_lohi(tmem_d, a_lo + 4, b_lo + 4, desc_hi, idesc, 1u);
+                            umma_f16_lohi(tmem_d, a_lo + 6, b_lo + 6, desc_hi, idesc, 1u);
+                            accumulate = 1u;
+                            tcgen05_commit_u32(empty0 + s * 8);
+                            if (++s == STAGES) { s = 0, ph ^= 1; }
+                        }
                     }
-                    tcgen05_commit(&b_empty[s]);
                 }
-                tcgen05_commit(&acc_full[buf]);
-                const bool last_of_block = (u + 1 == u_end) || ((u + 1) / nh != mt);
-                if (last_of_block) { tcgen05_commit(a_empty); }
+                tcgen05_commit_u32(smem_u32(&acc_full[buf]));
+                buf ^= 1;
+                if (++half == nh) { half = 0, ++mt; }
+                if (mt != cur_mt || u + 1 == u_end) { tcgen05_commit_u32(smem_u32(a_empty)); } // input block no longer needed
             }
         }
     } else { // ===== epilogue =====
@@ -396,19 +451,23 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
             for (int c = 0; c < BN; c += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + c, v);
-                tmem_ld_wait();
-                uint4 packed[4];
-                uint32_t* pk = reinterpret_cast<uint32_t*>(packed);
                 uint4 res[4];
                 if (res_row && live) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) { res[q] = *reinterpret_cast<const uint4*>(res_row + c + q * 8); }
                 }
+                float4 bias4[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { bias4[q] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c) + q); }
+                const float* bias = reinterpret_cast<const float*>(bias4);
+                tmem_ld_wait();
+                uint4 packed[4];
+                uint32_t* pk = reinterpret_cast<uint32_t*>(packed);
                 const __half2* rh = reinterpret_cast<const __half2*>(res);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    float x0 = __uint_as_float(v[2 * j]) + __ldg(p.bias + n0 + c + 2 * j);
-                    float x1 = __uint_as_float(v[2 * j + 1]) + __ldg(p.bias + n0 + c + 2 * j + 1);
+                    float x0 = __uint_as_float(v[2 * j]) + bias[2 * j];
+                    float x1 = __uint_as_float(v[2 * j + 1]) + bias[2 * j + 1];
                     if (res_row && live) {
                         const float2 rf = __half22float2(rh[j]);
                         x0 += rf.x, x1 += rf.y;
@@ -459,11 +518,11 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
 {
     extern __shared__ float sm[];
     const int hw = p.n * p.n, n1 = p.n + 1, np1 = p.pol_ch + 1;
-    float* planes = sm;                 // [(pol_ch + 1)][hw]: policy planes then the value plane
+    float* wc = sm;                     // [(pol_ch + 1)][c] 1x1 conv weights (first: float2 reads need 8-byte alignment)
+    float* planes = wc + np1 * p.c;     // [(pol_ch + 1)][hw]: policy planes then the value plane
     float* vhid = planes + np1 * hw;    // [vh]
     float* lg = vhid + p.vh;            // [A]
     float* red = lg + p.actions;        // [32]
-    float* wc = red + 32;               // [(pol_ch + 1)][c] 1x1 conv weights
     const int g = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
     const __half* act = p.act + static_cast<size_t>(g) * p.slots * p.c;
     for (int i = tid; i < np1 * p.c; i += nthr) { wc[i] = (i < p.pol_ch * p.c ? p.w_pc[i] : p.w_vc[i - p.pol_ch * p.c]); }

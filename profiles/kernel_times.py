@@ -19,3 +19,4 @@ ms = eng.search()
 p = eng.profile_kernels(100)
 tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("MZ_"))
 print(f"[{tag}] search {ms:.1f} ms ({bench.GAMES * (bench.SIMS + 1) / ms * 1e3:.0f} evals/s)  conv {p['conv_ms'] * 1e3:.1f} us  tree {p['tree_ms'] * 1e3:.1f} us  heads {p['heads_ms'] * 1e3:.1f} us")
+
