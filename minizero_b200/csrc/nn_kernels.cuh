@@ -292,6 +292,16 @@ __device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, ui
         "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ uint32_t elect_one_sync()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xFFFFFFFF;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(pred));
+    return pred;
+}
 __device__ __forceinline__ void tcgen05_commit_u32(uint32_t bar_addr)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
@@ -353,7 +363,7 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
     const uint32_t full0 = smem_u32(b_full), empty0 = smem_u32(b_empty);
 
     if (warp == 0) {
-        if (lane == 0) { // ===== TMA producer =====
+        { // ===== TMA producer: the whole warp runs the loop (uniform control flow), one elected lane issues =====
             int s = 0, mt = u_begin / nh, half = u_begin - mt * nh, cur_mt = -1;
             uint32_t ph = 1, a_ph = 1; // "empty" barriers: the first pass over the ring must not block
             const uint32_t b_dst0 = smem_u32(smem_b), a_dst0 = smem_u32(smem_a);
@@ -362,12 +372,15 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
                 if (mt != cur_mt) {
                     mbar_wait_u32(smem_u32(a_empty), a_ph); // every MMA on the previous input block has completed
                     a_ph ^= 1;
-                    mbar_arrive_expect_tx(a_full, a_kb * a_kb_bytes);
-                    for (int kb = 0; kb < a_kb; ++kb) {
-                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(a_dst0 + kb * a_kb_bytes),
-                                     "l"(map_in_ptr), "r"(smem_u32(a_full)), "r"(kb * BK), "r"(mt * BM - rp.halo)
-                                     : "memory");
+                    if (elect_one_sync()) {
+                        mbar_arrive_expect_tx(a_full, a_kb * a_kb_bytes);
+                        for (int kb = 0; kb < a_kb; ++kb) {
+                            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(a_dst0 + kb * a_kb_bytes),
+                                         "l"(map_in_ptr), "r"(smem_u32(a_full)), "r"(kb * BK), "r"(mt * BM - rp.halo)
+                                         : "memory");
+                        }
                     }
+                    __syncwarp();
                     cur_mt = mt;
                 }
                 int wrow = half * BN; // row of the weight matrix: tap * cout + half * BN
@@ -375,10 +388,13 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
                     for (int kc = 0; kc < p.cin; kc += BK) {
                         const uint32_t full = full0 + s * 8;
                         mbar_wait_u32(empty0 + s * 8, ph);
-                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(B_BYTES) : "memory");
-                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(b_dst0 + s * B_BYTES),
-                                     "l"(map_w_ptr), "r"(full), "r"(kc), "r"(wrow)
-                                     : "memory");
+                        if (elect_one_sync()) {
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(B_BYTES) : "memory");
+                            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(b_dst0 + s * B_BYTES),
+                                         "l"(map_w_ptr), "r"(full), "r"(kc), "r"(wrow)
+                                         : "memory");
+                        }
+                        __syncwarp();
                         if (++s == STAGES) { s = 0, ph ^= 1; }
                     }
                 }
@@ -386,7 +402,7 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) { // ===== MMA issuer =====
+        { // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
             constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
             // descriptor words (cute/arch/mma_sm100_desc.hpp): lo = start>>4 | LBO(1)<<16 ; hi = SBO(1024>>4) | version 1<<14 | SWIZZLE_128B 2<<29
             constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -418,20 +434,26 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
                             mbar_wait_u32(full0 + s * 8, ph);
                             tcgen05_fence_after();
                             const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(s) * (B_BYTES >> 4);
-                            umma_f16_lohi(tmem_d, a_lo, b_lo, desc_hi, idesc, accumulate);
-                            umma_f16_lohi(tmem_d, a_lo + 2, b_lo + 2, desc_hi, idesc, 1u);
-                            umma_f16_lohi(tmem_d, a_lo + 4, b_lo + 4, desc_hi, idesc, 1u);
-                            umma_f16_lohi(tmem_d, a_lo + 6, b_lo + 6, desc_hi, idesc, 1u);
+                            if (elect_one_sync()) {
+                                umma_f16_lohi(tmem_d, a_lo, b_lo, desc_hi, idesc, accumulate);
+                                umma_f16_lohi(tmem_d, a_lo + 2, b_lo + 2, desc_hi, idesc, 1u);
+                                umma_f16_lohi(tmem_d, a_lo + 4, b_lo + 4, desc_hi, idesc, 1u);
+                                umma_f16_lohi(tmem_d, a_lo + 6, b_lo + 6, desc_hi, idesc, 1u);
+                                tcgen05_commit_u32(empty0 + s * 8);
+                            }
+                            __syncwarp();
                             accumulate = 1u;
-                            tcgen05_commit_u32(empty0 + s * 8);
                             if (++s == STAGES) { s = 0, ph ^= 1; }
                         }
                     }
                 }
-                tcgen05_commit_u32(smem_u32(&acc_full[buf]));
-                buf ^= 1;
                 if (++half == nh) { half = 0, ++mt; }
-                if (mt != cur_mt || u + 1 == u_end) { tcgen05_commit_u32(smem_u32(a_empty)); } // input block no longer needed
+                if (elect_one_sync()) {
+                    tcgen05_commit_u32(smem_u32(&acc_full[buf]));
+                    if (mt != cur_mt || u + 1 == u_end) { tcgen05_commit_u32(smem_u32(a_empty)); } // input block no longer needed
+                }
+                __syncwarp();
+                buf ^= 1;
             }
         }
     } else { // ===== epilogue =====
