@@ -55,6 +55,10 @@ MZ_DEV uint64_t mz_reduce_xor64(uint64_t v)
     for (int o = 16; o > 0; o >>= 1) { v ^= __shfl_xor_sync(MZ_FULL, v, o); }
     return v;
 }
+MZ_DEV uint32_t mz_redux_max(uint32_t v) { return __reduce_max_sync(MZ_FULL, v); }
+MZ_DEV uint32_t mz_redux_min(uint32_t v) { return __reduce_min_sync(MZ_FULL, v); }
+MZ_DEV void mz_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+MZ_DEV uint32_t mz_float_bits(float f) { return __float_as_uint(f); }
 // lexicographic arg-max over (score desc, policy desc, index asc): the order-independent form of
 // the serial scan in mcts.cpp:187-194 (replace when score > best, or score == best and policy > best)
 MZ_DEV void mz_reduce_best(float& s, float& p, int& i)
@@ -101,6 +105,15 @@ static inline int mz_reduce_add(int v) { return v; }
 static inline uint32_t mz_reduce_or(uint32_t v) { return v; }
 static inline int mz_reduce_min(int v) { return v; }
 static inline uint64_t mz_reduce_xor64(uint64_t v) { return v; }
+static inline uint32_t mz_redux_max(uint32_t v) { return v; }
+static inline uint32_t mz_redux_min(uint32_t v) { return v; }
+static inline void mz_prefetch(const void*) {}
+static inline uint32_t mz_float_bits(float f)
+{
+    uint32_t u;
+    __builtin_memcpy(&u, &f, 4);
+    return u;
+}
 static inline void mz_reduce_best(float&, float&, int&) {}
 struct alignas(16) mz_hot {
     float count, mean, policy;
@@ -566,9 +579,22 @@ MZ_DEV float mz_normalized_mean(const mz_dims& d, float mean, float count, int p
     return mz_fdiv(mz_fsub(mz_fmul(v, count), 0.0f), mz_fadd(count, 0.0f));
 }
 
+// order-preserving map float -> uint32 (for REDUX arg-max); +0.0 and -0.0 are made equal first
+MZ_DEV uint32_t mz_sortable(float f)
+{
+    uint32_t u = mz_float_bits(f == 0.0f ? 0.0f : f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
 // MCTS::select (mcts.cpp:139-148,181-217): returns the path length; path[] holds node indices from the root.
-// One dependent memory round trip per level: the record of the chosen child (with its link) is taken from the lane
-// that scored it instead of being loaded again.
+//
+// Per level: one coalesced read of the children's hot records (the only dependent memory round trip), the ordered f32
+// sum of the visited children's Q for init-Q, then the arg-max of the PUCT score. Below the root the children are
+// stored in non-increasing prior order and all unvisited children share the same Q (init-Q), so the best unvisited
+// child is the FIRST unvisited one (score is monotone in the prior; ties go to the higher prior, then to the lower
+// index — mcts.cpp:191): only the visited children and that one candidate are scored. The root's priors are mixed
+// with noise after sorting (zero_actor.cpp:194-204), so every root child is scored. As soon as a level's records
+// arrive, the children blocks of its visited children — the only nodes the search can descend into — are prefetched.
 MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int root_turn, int lane)
 {
     const mz_hot* hot = s.hot + (size_t)g * d.NP;
@@ -579,20 +605,27 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
     for (;;) {
         const int nc = (int)(h.link >> MZ_LINK_SHIFT), fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
         if (nc == 0) { break; }
+        const bool score_all = (len == 1);
         const int total = (int)mz_fsub(h.count, 1.0f); // mcts.cpp:185
-        const float bias = s.puct_bias[total];
-        const double sqrt_n = mz_dsqrt((double)total);
-        // pass 1: ordered f32 sum of the visited children's Q (init-Q, mcts.cpp:200-217)
+        // pass 1: visited set, ordered f32 sum of the visited children's Q (mcts.cpp:200-217), first unvisited child
         float sum_win = 0.0f, sum_n = 0.0f;
+        int first_unvisited = nc;
         for (int base = 0; base < nc; base += MZ_W) {
             const int i = base + lane;
             int visited = 0;
             if (i < nc) {
                 const mz_hot c = mz_load_hot(hot + fc + i);
                 visited = (c.count != 0.0f);
-                if (visited) { w->q[i] = mz_normalized_mean(d, c.mean, c.count, child_player); }
+                if (visited) {
+                    w->q[i] = mz_normalized_mean(d, c.mean, c.count, child_player);
+                    const int cnc = (int)(c.link >> MZ_LINK_SHIFT), cfc = (int)(c.link & ((1u << MZ_LINK_SHIFT) - 1u));
+                    for (int l = 0; l < cnc && l < 128; l += 8) { mz_prefetch(hot + cfc + l); } // 8 records per 128-byte line
+                }
             }
             unsigned m = mz_ballot(visited);
+            const unsigned valid = (nc - base >= MZ_W ? ~0u >> (32 - MZ_W) : ((1u << (nc - base)) - 1u));
+            const unsigned unv = ~m & valid;
+            if (first_unvisited == nc && unv) { first_unvisited = base + mz_ffs0(unv); }
             mz_sync();
             while (m) {
                 const int b = mz_ffs0(m);
@@ -602,33 +635,43 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
             }
         }
         const float init_q = mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
-        // pass 2 (records come from L1): PUCT score, lexicographic arg-max (mcts.cpp:55-61,187-194)
+        const float bias = s.puct_bias[total];
+        const double sqrt_n = mz_dsqrt((double)total);
+        // pass 2 (records come from L1): PUCT score of the candidates (mcts.cpp:55-61)
         float best_s = 0.0f, best_p = 0.0f;
         int best_i = -1;
         mz_hot best_h = h;
         for (int i = lane; i < nc; i += MZ_W) {
             const mz_hot c = mz_load_hot(hot + fc + i);
-            const float u = (float)mz_ddiv(mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n), (double)mz_fadd(1.0f, c.count));
-            const float qv = (c.count == 0.0f ? init_q : w->q[i]);
-            const float score = mz_fadd(u, qv);
+            const bool visited = (c.count != 0.0f);
+            if (!(score_all || visited || i == first_unvisited)) { continue; }
+            const double num = mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n);
+            const float u = (float)(visited ? mz_ddiv(num, (double)mz_fadd(1.0f, c.count)) : num); // x / 1.0 == x
+            const float score = mz_fadd(u, visited ? w->q[i] : init_q);
             if (best_i < 0 || score > best_s || (score == best_s && c.policy > best_p)) { best_s = score, best_p = c.policy, best_i = i, best_h = c; }
         }
+        // lexicographic arg-max (score desc, prior desc, index asc) over the lanes' candidates (mcts.cpp:187-194)
         const int mine = best_i;
-        mz_reduce_best(best_s, best_p, best_i);
-        mz_sync();
-        // broadcast the winner's record from the lane that holds it
-#if MZ_W == 1
-        h = best_h;
-#else
+#if MZ_W > 1
         {
-            const unsigned owner_mask = mz_ballot(mine == best_i);
-            const int owner = mz_ffs0(owner_mask);
+            const uint32_t ks = (mine >= 0 ? mz_sortable(best_s) : 0u);
+            const uint32_t top_s = mz_redux_max(ks);
+            const bool in_s = (mine >= 0 && ks == top_s);
+            const uint32_t kp = (in_s ? mz_sortable(best_p) : 0u);
+            const uint32_t top_p = mz_redux_max(kp);
+            const bool in_p = (in_s && kp == top_p);
+            best_i = (int)mz_redux_min(in_p ? (uint32_t)mine : 0xffffffffu);
+            const int owner = mz_ffs0(mz_ballot(in_p && mine == best_i));
             h.count = __shfl_sync(MZ_FULL, best_h.count, owner);
             h.mean = __shfl_sync(MZ_FULL, best_h.mean, owner);
             h.policy = __shfl_sync(MZ_FULL, best_h.policy, owner);
             h.link = __shfl_sync(MZ_FULL, best_h.link, owner);
         }
+#else
+        (void)mine;
+        h = best_h;
 #endif
+        mz_sync();
         if (lane == 0) { path[len] = fc + best_i; }
         ++len;
         child_player = 3 - child_player;
