@@ -34,17 +34,24 @@ int fail(int code, const std::string& msg)
 // ---------------------------------------------------------------------------------------------------
 constexpr int STEP_AFTER = 1, STEP_BEFORE = 2;
 
-__global__ void __launch_bounds__(32) k_step(const mz_dims d, const mz_state s, const int flags)
+constexpr int STEP_WARPS = 8; // warps per game in k_step: the previous path is re-evaluated level-parallel (search_core.cuh, mz_select)
+
+__global__ void __launch_bounds__(32 * STEP_WARPS) k_step(const mz_dims d, const mz_state s, const int flags)
 {
     __shared__ mz_scratch w;
-    extern __shared__ uint64_t dyn_path_hashes[]; // [S + 2]
-    if (threadIdx.x == 0) { w.path_hashes = dyn_path_hashes; }
-    __syncwarp();
-    const int g = blockIdx.x, lane = threadIdx.x;
-    if (flags & STEP_AFTER) { mz_after_nn(d, s, g, &w, lane); }
+    extern __shared__ uint64_t dyn_smem[]; // path_hashes [S + 2] u64 | sel [S + 2] i32 | q_warp [STEP_WARPS][MZ_MAXA] f32
+    const int g = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        w.path_hashes = dyn_smem;
+        w.sel = reinterpret_cast<int32_t*>(dyn_smem + (d.S + 2));
+        w.q_warp = reinterpret_cast<float*>(w.sel + (d.S + 2));
+    }
+    __syncthreads();
+    if ((flags & STEP_AFTER) && wid == 0) { mz_after_nn(d, s, g, &w, lane); }
     if (flags & STEP_BEFORE) {
-        __syncwarp();
-        mz_before_nn(d, s, g, &w, lane);
+        __threadfence_block();
+        __syncthreads();
+        mz_before_nn(d, s, g, &w, lane, wid, STEP_WARPS);
     }
 }
 
@@ -149,6 +156,7 @@ struct mz_engine {
     uint8_t* d_rot_all = nullptr; // [(S+1)][B]
     float* d_noise = nullptr;     // [B][A]
     float* d_bias_table = nullptr;
+    double* d_sqrt_table = nullptr;
     uint64_t* d_keys = nullptr;
     int32_t* d_actions = nullptr;
     int32_t* d_play_out = nullptr;
@@ -294,7 +302,7 @@ int step(mz_engine* e, int flags, const uint8_t* rotations)
     mz_state s = e->s;
     s.rotations = rotations;
     s.noise_in = (e->noise_enabled ? e->d_noise : nullptr);
-    k_step<<<e->d.B, 32, sizeof(uint64_t) * (e->d.S + 2), e->stream>>>(e->d, s, flags);
+    k_step<<<e->d.B, 32 * STEP_WARPS, sizeof(uint64_t) * (e->d.S + 2) + sizeof(int32_t) * (e->d.S + 2) + sizeof(float) * STEP_WARPS * MZ_MAXA, e->stream>>>(e->d, s, flags);
     e->launches++;
     return MZ_OK;
 }
@@ -458,12 +466,14 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     guard(e->dalloc(&s.slot_meta, B * (d.S + 1) * 4));
     guard(e->dalloc(&s.root_st, B * 2 * MZ_ROWS)), guard(e->dalloc(&s.root_hist, B * MZ_HIST * 2 * MZ_ROWS)), guard(e->dalloc(&s.root_hash, B));
     guard(e->dalloc(&s.root_meta, B * 4)), guard(e->dalloc(&s.hashes, B * d.max_hashes));
+    guard(e->dalloc(&s.spec_len, B));
     guard(e->dalloc(&s.path, B * (d.S + 2))), guard(e->dalloc(&s.path_len, B)), guard(e->dalloc(&s.leaf_legal, B * MZ_LEGAL_WORDS));
     guard(e->dalloc(&s.leaf_meta, B * 4)), guard(e->dalloc(&s.leaf_score, B));
     guard(e->dalloc(&s.nn_in, static_cast<size_t>(e->rows_alloc) * MZ_NN_CPAD));
     guard(e->dalloc(&s.policy, BA)), guard(e->dalloc(&s.logits, BA)), guard(e->dalloc(&s.nn_value, B));
     guard(e->dalloc(&e->d_rot_all, B * (d.S + 1))), guard(e->dalloc(&e->d_noise, BA));
     guard(e->dalloc(&e->d_bias_table, bias.size())), guard(e->dalloc(&e->d_keys, keys.size()));
+    guard(e->dalloc(&e->d_sqrt_table, bias.size()));
     guard(e->dalloc(&e->d_actions, B)), guard(e->dalloc(&e->d_play_out, B * 4)), guard(e->dalloc(&e->d_play_score, B));
     guard(e->dalloc(&e->d_root_info, B * 4)), guard(e->dalloc(&e->d_root_action, BA));
     for (int i = 0; i < 6; ++i) { guard(e->dalloc(&e->d_root_f[i], BA)); }
@@ -477,7 +487,16 @@ int mz_create(const mz_config* cfg, mz_engine** out)
         mz_destroy(e);
         return fail(MZ_ERR_CUDA, "table upload failed");
     }
-    s.puct_bias = e->d_bias_table, s.keys = e->d_keys;
+    {
+        std::vector<double> sq(bias.size());
+        for (size_t n = 0; n < sq.size(); ++n) { sq[n] = std::sqrt(static_cast<double>(n)); } // sqrt(total_simulation), mcts.cpp:58
+        if (cudaMemcpyAsync(e->d_sqrt_table, sq.data(), sq.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
+            cudaStreamSynchronize(e->stream) != cudaSuccess) {
+            mz_destroy(e);
+            return fail(MZ_ERR_CUDA, "table upload failed");
+        }
+    }
+    s.puct_bias = e->d_bias_table, s.keys = e->d_keys, s.sqrt_table = e->d_sqrt_table;
     // driver entry point for tensor maps (no link-time dependency on libcuda)
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -888,6 +907,24 @@ int mz_search_run(mz_engine* e, int32_t num_evals, float* device_ms)
     CUDA_OK(cudaStreamSynchronize(e->stream));
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventElapsedTime(device_ms, e->ev0, e->ev1));
+    return MZ_OK;
+}
+
+int mz_debug_tree_timing(mz_engine* e, uint64_t* out)
+{
+    if (!e || !out) { return fail(MZ_ERR_ARG, "bad argument"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    unsigned long long* buf = nullptr;
+    const size_t n = static_cast<size_t>(e->d.B) * 8;
+    CUDA_OK(cudaMalloc(&buf, sizeof(unsigned long long) * n));
+    CUDA_OK(cudaMemsetAsync(buf, 0, sizeof(unsigned long long) * n, e->stream));
+    e->s.dbg = buf;
+    step(e, STEP_BEFORE, nullptr);
+    e->s.dbg = nullptr;
+    cudaError_t err = cudaMemcpyAsync(out, buf, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) { err = cudaStreamSynchronize(e->stream); }
+    cudaFree(buf);
+    if (err != cudaSuccess) { return fail(MZ_ERR_CUDA, cudaGetErrorString(err)); }
     return MZ_OK;
 }
 

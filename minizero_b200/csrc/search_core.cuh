@@ -23,6 +23,9 @@
 #define MZ_DEV __device__ __forceinline__
 #define MZ_W 32
 #define MZ_FULL 0xffffffffu
+MZ_DEV long long mz_clock() { return clock64(); }
+MZ_DEV void mz_block_sync() { __syncthreads(); }
+MZ_DEV void mz_atomic_min(int* p, int v) { atomicMin(p, v); }
 MZ_DEV unsigned mz_ballot(int p) { return __ballot_sync(MZ_FULL, p); }
 MZ_DEV int mz_any(int p) { return __any_sync(MZ_FULL, p); }
 MZ_DEV void mz_sync() { __syncwarp(); }
@@ -89,6 +92,9 @@ MZ_DEV void mz_store_hot(mz_hot* p, float count, float mean, float policy, uint3
 #include <math.h>
 #define MZ_DEV static inline
 #define MZ_W 1
+static inline long long mz_clock() { return 0; }
+static inline void mz_block_sync() {}
+static inline void mz_atomic_min(int* p, int v) { *p = (v < *p ? v : *p); }
 static inline unsigned mz_ballot(int p) { return p ? 1u : 0u; }
 static inline int mz_any(int p) { return p; }
 static inline void mz_sync() {}
@@ -167,6 +173,7 @@ struct mz_state {
     // leaf of the current simulation
     int32_t* path;        // [B][S + 2]
     int32_t* path_len;    // [B]
+    int32_t* spec_len;    // [B] length of the previous simulation's path while it is still valid for speculation (0: none)
     uint32_t* leaf_legal; // [B][MZ_LEGAL_WORDS]
     int32_t* leaf_meta;   // [B][4] terminal, turn, rotation, num_legal
     float* leaf_score;    // [B]
@@ -179,7 +186,9 @@ struct mz_state {
     const uint8_t* rotations; // [B] for this cycle (may be null = identity)
     const float* noise_in;    // [B][A] by root child index (may be null)
     const float* puct_bias;   // [S + 2] host-computed: (float)(init + log((1 + n + base) / base)), mcts.cpp:57
+    const double* sqrt_table; // [S + 2] sqrt((double)n): IEEE-exact, identical to the host's sqrt (mcts.cpp:58)
     const uint64_t* keys;     // [2][361] Zobrist stone keys, go.cpp:19-32
+    unsigned long long* dbg;  // optional [B][8] per-phase cycle counters of the last before-NN step (profiling only)
 };
 
 // per-warp scratch (shared memory on the device)
@@ -193,6 +202,9 @@ struct mz_scratch {
     uint64_t hash;
     int turn, num_moves, last, last2;
     uint64_t* path_hashes; // [S + 2] position hashes of the nodes on the current path (shared memory on the device)
+    int32_t* sel;          // [S + 2] child chosen at every level of the previous path by the speculative re-evaluation
+    float* q_warp;         // [num_warps][MZ_MAXA] per-warp Q scratch of the level evaluation
+    int mismatch;          // first level whose re-evaluated choice differs from the previous path
 };
 
 MZ_DEV uint32_t mz_rowmask(int N) { return (N >= 32 ? 0xffffffffu : ((1u << N) - 1u)); }
@@ -586,97 +598,131 @@ MZ_DEV uint32_t mz_sortable(float f)
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-// MCTS::select (mcts.cpp:139-148,181-217): returns the path length; path[] holds node indices from the root.
+// One level of MCTS::select: MCTS::selectChildByPUCTScore (mcts.cpp:181-198) for the node whose hot record is `h`.
+// Returns the index (0 .. nc-1) of the chosen child and its hot record in `out`. Warp collective; `q` is this warp's
+// scratch of MZ_MAXA floats.
 //
-// Per level: one coalesced read of the children's hot records (the only dependent memory round trip), the ordered f32
-// sum of the visited children's Q for init-Q, then the arg-max of the PUCT score. Below the root the children are
-// stored in non-increasing prior order and all unvisited children share the same Q (init-Q), so the best unvisited
-// child is the FIRST unvisited one (score is monotone in the prior; ties go to the higher prior, then to the lower
-// index — mcts.cpp:191): only the visited children and that one candidate are scored. The root's priors are mixed
-// with noise after sorting (zero_actor.cpp:194-204), so every root child is scored. As soon as a level's records
-// arrive, the children blocks of its visited children — the only nodes the search can descend into — are prefetched.
-MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int root_turn, int lane)
+// One coalesced read of the children's hot records, the ordered f32 sum of the visited children's Q for init-Q
+// (mcts.cpp:200-217), then the arg-max of the PUCT score (mcts.cpp:55-61). Below the root the children are stored in
+// non-increasing prior order and all unvisited children share the same Q (init-Q), so the best unvisited child is the
+// FIRST unvisited one (score is monotone in the prior; ties go to the higher prior, then to the lower index —
+// mcts.cpp:191): only the visited children and that one candidate are scored. The root's priors are mixed with noise
+// after sorting (zero_actor.cpp:194-204), so every root child is scored.
+MZ_DEV int mz_select_level(const mz_dims& d, const mz_state& s, const mz_hot* hot, const mz_hot& h, bool score_all, int child_player, float* q, int lane,
+                           mz_hot& out)
+{
+    const int nc = (int)(h.link >> MZ_LINK_SHIFT), fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
+    const int total = (int)mz_fsub(h.count, 1.0f); // mcts.cpp:185
+    float sum_win = 0.0f, sum_n = 0.0f;
+    int first_unvisited = nc;
+    for (int base = 0; base < nc; base += MZ_W) {
+        const int i = base + lane;
+        int visited = 0;
+        if (i < nc) {
+            const mz_hot c = mz_load_hot(hot + fc + i);
+            visited = (c.count != 0.0f);
+            if (visited) { q[i] = mz_normalized_mean(d, c.mean, c.count, child_player); }
+        }
+        unsigned m = mz_ballot(visited);
+        const unsigned valid = (nc - base >= MZ_W ? ~0u >> (32 - MZ_W) : ((1u << (nc - base)) - 1u));
+        const unsigned unv = ~m & valid;
+        if (first_unvisited == nc && unv) { first_unvisited = base + mz_ffs0(unv); }
+        mz_sync();
+        while (m) {
+            const int b = mz_ffs0(m);
+            m &= m - 1;
+            sum_win = mz_fadd(sum_win, q[base + b]);
+            sum_n = mz_fadd(sum_n, 1.0f);
+        }
+    }
+    const float init_q = mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
+    const float bias = s.puct_bias[total];
+    const double sqrt_n = s.sqrt_table[total];
+    float best_s = 0.0f, best_p = 0.0f;
+    int best_i = -1;
+    mz_hot best_h = h;
+    for (int i = lane; i < nc; i += MZ_W) {
+        const mz_hot c = mz_load_hot(hot + fc + i); // second read comes from L1
+        const bool visited = (c.count != 0.0f);
+        if (!(score_all || visited || i == first_unvisited)) { continue; }
+        const double num = mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n);
+        const float u = (float)(visited ? mz_ddiv(num, (double)mz_fadd(1.0f, c.count)) : num); // x / 1.0 == x
+        const float score = mz_fadd(u, visited ? q[i] : init_q);
+        if (best_i < 0 || score > best_s || (score == best_s && c.policy > best_p)) { best_s = score, best_p = c.policy, best_i = i, best_h = c; }
+    }
+    // lexicographic arg-max (score desc, prior desc, index asc) over the lanes' candidates (mcts.cpp:187-194)
+#if MZ_W > 1
+    {
+        const int mine = best_i;
+        const uint32_t ks = (mine >= 0 ? mz_sortable(best_s) : 0u);
+        const uint32_t top_s = mz_redux_max(ks);
+        const bool in_s = (mine >= 0 && ks == top_s);
+        const uint32_t kp = (in_s ? mz_sortable(best_p) : 0u);
+        const uint32_t top_p = mz_redux_max(kp);
+        const bool in_p = (in_s && kp == top_p);
+        best_i = (int)mz_redux_min(in_p ? (uint32_t)mine : 0xffffffffu);
+        const int owner = mz_ffs0(mz_ballot(in_p && mine == best_i));
+        out.count = __shfl_sync(MZ_FULL, best_h.count, owner);
+        out.mean = __shfl_sync(MZ_FULL, best_h.mean, owner);
+        out.policy = __shfl_sync(MZ_FULL, best_h.policy, owner);
+        out.link = __shfl_sync(MZ_FULL, best_h.link, owner);
+    }
+#else
+    out = best_h;
+#endif
+    mz_sync();
+    return best_i;
+}
+
+// MCTS::select (mcts.cpp:139-148): returns the path length; path[] holds node indices from the root.
+//
+// The block has `nw` warps. Consecutive simulations of a game mostly retrace the previous path (with a random-init
+// network the tree is a few long chains), and every level's choice depends only on that level's node — so the warps
+// first RE-EVALUATE all levels of the previous path in parallel (level j by warp j mod nw) and find the first level
+// whose choice changed; warp 0 then continues serially from there. Every choice is still made by mz_select_level on
+// the current statistics: the path is exactly the serial one, found in (depth / nw) level-times instead of depth.
+MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int root_turn, int lane, int wid, int nw)
 {
     const mz_hot* hot = s.hot + (size_t)g * d.NP;
     int32_t* path = s.path + (size_t)g * (d.S + 2);
-    int len = 1, child_player = root_turn;
-    if (lane == 0) { path[0] = 0; }
-    mz_hot h = mz_load_hot(hot);
-    for (;;) {
-        const int nc = (int)(h.link >> MZ_LINK_SHIFT), fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
-        if (nc == 0) { break; }
-        const bool score_all = (len == 1);
-        const int total = (int)mz_fsub(h.count, 1.0f); // mcts.cpp:185
-        // pass 1: visited set, ordered f32 sum of the visited children's Q (mcts.cpp:200-217), first unvisited child
-        float sum_win = 0.0f, sum_n = 0.0f;
-        int first_unvisited = nc;
-        for (int base = 0; base < nc; base += MZ_W) {
-            const int i = base + lane;
-            int visited = 0;
-            if (i < nc) {
-                const mz_hot c = mz_load_hot(hot + fc + i);
-                visited = (c.count != 0.0f);
-                if (visited) {
-                    w->q[i] = mz_normalized_mean(d, c.mean, c.count, child_player);
-                    const int cnc = (int)(c.link >> MZ_LINK_SHIFT), cfc = (int)(c.link & ((1u << MZ_LINK_SHIFT) - 1u));
-                    for (int l = 0; l < cnc && l < 128; l += 8) { mz_prefetch(hot + cfc + l); } // 8 records per 128-byte line
-                }
-            }
-            unsigned m = mz_ballot(visited);
-            const unsigned valid = (nc - base >= MZ_W ? ~0u >> (32 - MZ_W) : ((1u << (nc - base)) - 1u));
-            const unsigned unv = ~m & valid;
-            if (first_unvisited == nc && unv) { first_unvisited = base + mz_ffs0(unv); }
-            mz_sync();
-            while (m) {
-                const int b = mz_ffs0(m);
-                m &= m - 1;
-                sum_win = mz_fadd(sum_win, w->q[base + b]);
-                sum_n = mz_fadd(sum_n, 1.0f);
-            }
+    float* q = w->q_warp + (size_t)wid * MZ_MAXA;
+    const int old_len = s.spec_len[g];
+    if (wid == 0 && lane == 0) { w->mismatch = (old_len > 0 ? old_len - 1 : 0); }
+    mz_block_sync();
+    for (int j = wid; j < old_len - 1; j += nw) {
+        const mz_hot h = mz_load_hot(hot + path[j]);
+        mz_hot c;
+        const int fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
+        const int best = mz_select_level(d, s, hot, h, j == 0, (j & 1) ? 3 - root_turn : root_turn, q, lane, c);
+        if (lane == 0) {
+            w->sel[j] = fc + best;
+            if (fc + best != path[j + 1]) { mz_atomic_min(&w->mismatch, j); }
         }
-        const float init_q = mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
-        const float bias = s.puct_bias[total];
-        const double sqrt_n = mz_dsqrt((double)total);
-        // pass 2 (records come from L1): PUCT score of the candidates (mcts.cpp:55-61)
-        float best_s = 0.0f, best_p = 0.0f;
-        int best_i = -1;
-        mz_hot best_h = h;
-        for (int i = lane; i < nc; i += MZ_W) {
-            const mz_hot c = mz_load_hot(hot + fc + i);
-            const bool visited = (c.count != 0.0f);
-            if (!(score_all || visited || i == first_unvisited)) { continue; }
-            const double num = mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n);
-            const float u = (float)(visited ? mz_ddiv(num, (double)mz_fadd(1.0f, c.count)) : num); // x / 1.0 == x
-            const float score = mz_fadd(u, visited ? w->q[i] : init_q);
-            if (best_i < 0 || score > best_s || (score == best_s && c.policy > best_p)) { best_s = score, best_p = c.policy, best_i = i, best_h = c; }
-        }
-        // lexicographic arg-max (score desc, prior desc, index asc) over the lanes' candidates (mcts.cpp:187-194)
-        const int mine = best_i;
-#if MZ_W > 1
-        {
-            const uint32_t ks = (mine >= 0 ? mz_sortable(best_s) : 0u);
-            const uint32_t top_s = mz_redux_max(ks);
-            const bool in_s = (mine >= 0 && ks == top_s);
-            const uint32_t kp = (in_s ? mz_sortable(best_p) : 0u);
-            const uint32_t top_p = mz_redux_max(kp);
-            const bool in_p = (in_s && kp == top_p);
-            best_i = (int)mz_redux_min(in_p ? (uint32_t)mine : 0xffffffffu);
-            const int owner = mz_ffs0(mz_ballot(in_p && mine == best_i));
-            h.count = __shfl_sync(MZ_FULL, best_h.count, owner);
-            h.mean = __shfl_sync(MZ_FULL, best_h.mean, owner);
-            h.policy = __shfl_sync(MZ_FULL, best_h.policy, owner);
-            h.link = __shfl_sync(MZ_FULL, best_h.link, owner);
-        }
-#else
-        (void)mine;
-        h = best_h;
-#endif
-        mz_sync();
-        if (lane == 0) { path[len] = fc + best_i; }
-        ++len;
-        child_player = 3 - child_player;
     }
-    return len;
+    mz_block_sync();
+    int len = 1;
+    if (wid == 0) { // serial continuation (the whole search when there is no previous path)
+        int level = w->mismatch; // levels 0 .. level of the previous path are still valid
+        int node = (old_len > 0 ? path[level] : 0);
+        if (old_len > 0 && level < old_len - 1) { // the choice at `level` changed: take the re-evaluated one
+            node = w->sel[level];
+            ++level;
+            if (lane == 0) { path[level] = node; }
+        } else if (lane == 0 && old_len == 0) {
+            path[0] = 0;
+        }
+        mz_hot h = mz_load_hot(hot + node);
+        while ((h.link >> MZ_LINK_SHIFT) != 0) {
+            const int fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
+            mz_hot c;
+            const int best = mz_select_level(d, s, hot, h, level == 0, (level & 1) ? 3 - root_turn : root_turn, q, lane, c);
+            h = c;
+            ++level;
+            if (lane == 0) { path[level] = fc + best; }
+        }
+        len = level + 1;
+    }
+    return len; // valid in warp 0
 }
 
 MZ_DEV void mz_slot_store(const mz_dims& d, const mz_state& s, int g, int slot, const mz_scratch* w, int lane)
@@ -710,12 +756,15 @@ MZ_DEV void mz_slot_load(const mz_dims& d, const mz_state& s, int g, int slot, m
 // slot indexed by the simulation that evaluated it, so the transition is "parent's slot + one move"; the 8-position
 // feature history and the superko hash list are gathered from the slots of the nodes on the path (and from the root
 // environment for positions older than the root). Same positions, same results, cost independent of the depth.
-MZ_DEV void mz_before_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int lane)
+MZ_DEV void mz_before_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int lane, int wid, int nw)
 {
     const int N = d.N;
     const int root_turn = s.root_meta[g * 4 + 0], root_moves = s.root_meta[g * 4 + 1];
-    const int len = mz_select(d, s, g, w, root_turn, lane);
+    const long long t0 = mz_clock();
+    const int len = mz_select(d, s, g, w, root_turn, lane, wid, nw);
+    if (wid != 0) { return; } // the rest of the step is done by warp 0
     mz_sync();
+    const long long t1 = mz_clock();
     const int32_t* path = s.path + (size_t)g * (d.S + 2);
     const int16_t* node_slot = s.node_slot + (size_t)g * d.NP;
     const uint64_t* root_list = s.hashes + (size_t)g * d.max_hashes;
@@ -758,6 +807,7 @@ MZ_DEV void mz_before_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch*
     }
     mz_slot_store(d, s, g, slot, w, lane);
     if (lane == 0) { s.node_slot[(size_t)g * d.NP + leaf] = (int16_t)slot; }
+    const long long t2 = mz_clock();
     const int rotation = (s.rotations ? s.rotations[g] : 0);
     const int terminal = mz_env_is_terminal(d, w);
     float score = 0.0f;
@@ -767,15 +817,23 @@ MZ_DEV void mz_before_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch*
     } else {
         num_legal = mz_env_legal(d, s, w, root_list, root_moves, w->path_hashes, L, lane);
     }
+    const long long t3 = mz_clock();
     mz_env_features(d, s, g, w, rotation, lane);
     for (int i = lane; i < MZ_LEGAL_WORDS; i += MZ_W) { s.leaf_legal[g * MZ_LEGAL_WORDS + i] = w->legal[i]; }
     if (lane == 0) {
         s.path_len[g] = len;
+        s.spec_len[g] = len;
         s.leaf_meta[g * 4 + 0] = terminal;
         s.leaf_meta[g * 4 + 1] = w->turn;
         s.leaf_meta[g * 4 + 2] = rotation;
         s.leaf_meta[g * 4 + 3] = num_legal;
         s.leaf_score[g] = score;
+        if (s.dbg) {
+            unsigned long long* o = s.dbg + (size_t)g * 8;
+            o[0] = (unsigned long long)(t1 - t0), o[1] = (unsigned long long)(t2 - t1), o[2] = (unsigned long long)(t3 - t2);
+            o[3] = (unsigned long long)(mz_clock() - t3), o[4] = (unsigned long long)len, o[5] = (unsigned long long)terminal, o[6] = (unsigned long long)w->num_moves;
+            o[7] = (unsigned long long)num_legal;
+        }
     }
 }
 
@@ -872,6 +930,7 @@ MZ_DEV void mz_tree_reset(const mz_dims& d, const mz_state& s, int g, int lane)
         s.node_slot[(size_t)g * d.NP] = -1;
         s.cursor[g] = 1;
         s.path_len[g] = 0;
+        s.spec_len[g] = 0;
     }
 }
 

@@ -96,6 +96,7 @@ def _load():
     lib.mz_search_set_inputs.argtypes = [vp, u8p, f32p]
     lib.mz_search_run.argtypes = [vp, i32, f32p]
     lib.mz_profile_kernels.argtypes = [vp, i32, f32p, f32p, f32p]
+    lib.mz_debug_tree_timing.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.mz_launch_count.argtypes = [vp]
     lib.mz_launch_count.restype = C.c_int64
     _lib = lib
@@ -104,7 +105,7 @@ def _load():
 
 EXPORTS = ["mz_create", "mz_destroy", "mz_last_error", "mz_action_size", "mz_num_features", "mz_net_configure", "mz_net_set_tensor", "mz_net_finalize",
            "mz_net_blob", "mz_net_finalize_empty", "mz_eval_batch", "mz_reset_game", "mz_play", "mz_get_roots", "mz_search_select", "mz_search_apply",
-           "mz_search_set_inputs", "mz_search_run", "mz_profile_kernels", "mz_launch_count", "mz_play_max_count", "mz_sync", "mz_timer_begin", "mz_timer_end"]
+           "mz_search_set_inputs", "mz_search_run", "mz_profile_kernels", "mz_launch_count", "mz_play_max_count", "mz_sync", "mz_timer_begin", "mz_timer_end", "mz_debug_tree_timing"]
 
 
 def _fp(a):
@@ -304,6 +305,11 @@ class Engine:
         c, t, h = C.c_float(0), C.c_float(0), C.c_float(0)
         self._check(self.lib.mz_profile_kernels(self.h, iters, C.byref(c), C.byref(t), C.byref(h)))
         return dict(conv_ms=c.value, tree_ms=t.value, heads_ms=h.value)
+
+    def tree_timing(self):
+        out = np.zeros((self.B, 8), np.uint64)
+        self._check(self.lib.mz_debug_tree_timing(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
 
     def launch_count(self):
         return int(self.lib.mz_launch_count(self.h))

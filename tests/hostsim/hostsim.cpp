@@ -13,6 +13,7 @@ struct sim {
     mz_dims d;
     mz_state s;
     std::vector<float> bias;
+    std::vector<double> sqrt_table;
     std::vector<uint64_t> keys;
     std::vector<uint8_t> rot;
     std::vector<float> noise;
@@ -40,6 +41,12 @@ sim* hs_create(int game, int N, int B, int S, float puct_base, float puct_init, 
     s.node_slot = zalloc<int16_t>(np);
     s.slot_st = zalloc<uint32_t>((size_t)B * (S + 1) * 2 * N), s.slot_hash = zalloc<uint64_t>((size_t)B * (S + 1)), s.slot_meta = zalloc<int32_t>((size_t)B * (S + 1) * 4);
     h->w.path_hashes = zalloc<uint64_t>(S + 2);
+    h->w.sel = zalloc<int32_t>(S + 2);
+    h->w.q_warp = zalloc<float>(MZ_MAXA);
+    s.spec_len = zalloc<int32_t>(B);
+    h->sqrt_table.resize(S + 2);
+    for (int n = 0; n < S + 2; ++n) { h->sqrt_table[n] = sqrt((double)n); }
+    s.sqrt_table = h->sqrt_table.data();
     s.root_st = zalloc<uint32_t>((size_t)B * 2 * MZ_ROWS), s.root_hist = zalloc<uint32_t>((size_t)B * MZ_HIST * 2 * MZ_ROWS);
     s.root_hash = zalloc<uint64_t>(B), s.root_meta = zalloc<int32_t>((size_t)B * 4), s.hashes = zalloc<uint64_t>((size_t)B * d.max_hashes);
     s.path = zalloc<int32_t>((size_t)B * (S + 2)), s.path_len = zalloc<int32_t>(B), s.leaf_legal = zalloc<uint32_t>((size_t)B * MZ_LEGAL_WORDS);
@@ -71,7 +78,7 @@ void hs_select(sim* h, const uint8_t* rotations, float* features)
 {
     const mz_dims& d = h->d;
     for (int g = 0; g < d.B; ++g) { h->rot[g] = (rotations ? rotations[g] : 0); }
-    for (int g = 0; g < d.B; ++g) { mz_before_nn(d, h->s, g, &h->w, 0); }
+    for (int g = 0; g < d.B; ++g) { mz_before_nn(d, h->s, g, &h->w, 0, 0, 1); }
     if (features) {
         const int N = d.N;
         for (int g = 0; g < d.B; ++g) {
