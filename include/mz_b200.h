@@ -4,7 +4,7 @@
  * The reference (rlglab/minizero) has no FFI layer; its replaceable seams are the C++ classes
  * ActorGroup / BaseActor / Network and the `-mode sp` process. This header is the thin
  * boundary between a host that keeps those seams (minizero_b200/host: the ActorGroup-compatible worker;
- * minizero_b200/*.py: the ctypes mirror used by tests and bench) and the CUDA library. Each entry point
+ * the minizero_b200 Python package: the ctypes mirror used by tests and bench) and the CUDA library. Each entry point
  * names the reference interface it replaces (paths relative to /root/reference/minizero).
  *
  * Conventions: plain pointers and sizes, caller-owned host buffers, `int` status returns (0 = ok, <0 =

@@ -546,7 +546,13 @@ int mz_net_configure(mz_engine* e, const mz_net_dims* dims)
         return fail(MZ_ERR_ARG, "policy head with more than 7 planes is not supported");
     }
     if (dims->num_input_channels > MZ_NN_CPAD || dims->num_hidden_channels < 1 || dims->num_blocks < 0) { return fail(MZ_ERR_ARG, "unsupported network size"); }
-    if (e->d_blob) { return fail(MZ_ERR_STATE, "network already allocated for this engine"); }
+    if (e->d_blob && std::memcmp(&e->nd, dims, sizeof(*dims)) != 0) {
+        return fail(MZ_ERR_STATE, "a network of a different shape is already allocated for this engine");
+    }
+    if (e->d_blob) { // load_model of the next iteration: same shape, new values; buffers, tensor maps and graphs stay valid
+        e->tensors.clear();
+        return MZ_OK;
+    }
     e->nd = *dims;
     e->dims_set = true;
     e->net_ready = false;

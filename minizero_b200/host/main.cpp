@@ -1,0 +1,102 @@
+// mz_sp — drop-in for the reference's `-mode sp` executable (console/mode_handler.cpp:29-74,145-149):
+//   mz_sp -conf_file <file> -conf_str "k=v:k=v" -mode sp
+// plus `-mode record_test` (CPU only): formats a game described on stdin into a SelfPlay line, used by the tests to pin
+// the wire format against lines recorded from the reference.
+#include "config.h"
+#include "record.h"
+#include "worker.h"
+#include <cstring>
+#include <iostream>
+#include <sstream>
+
+namespace {
+
+float hexFloat(const std::string& s)
+{
+    uint32_t bits = static_cast<uint32_t>(std::stoul(s, nullptr, 16));
+    float f;
+    std::memcpy(&f, &bits, 4);
+    return f;
+}
+
+// stdin: "header <game_name> <board> <has_komi> <komi> <model_file> <terminal> <eval_hex> <turn_to_move>"
+//        "move <player> <action> <root_mean_hex> <k> a:count_hex ..."   (one line per move), then EOF
+int recordTest()
+{
+    mzhost::GameHeader h;
+    std::vector<mzhost::MoveRecord> moves;
+    bool terminal = true;
+    float eval = 0.0f;
+    int turn = 1;
+    std::string line;
+    while (std::getline(std::cin, line)) {
+        std::istringstream iss(line);
+        std::string kind;
+        iss >> kind;
+        if (kind == "header") {
+            std::string eval_hex;
+            int has_komi, term;
+            iss >> h.game_name >> h.board_size >> has_komi >> h.komi >> h.model_file >> term >> eval_hex >> turn;
+            h.has_komi = has_komi != 0, terminal = term != 0, eval = hexFloat(eval_hex);
+        } else if (kind == "move") {
+            mzhost::MoveRecord m;
+            std::string mean_hex;
+            int k;
+            iss >> m.player >> m.action >> mean_hex >> k;
+            std::vector<int> acts(k);
+            std::vector<float> counts(k);
+            for (int i = 0; i < k; ++i) {
+                std::string tok;
+                iss >> tok;
+                acts[i] = std::stoi(tok.substr(0, tok.find(':')));
+                counts[i] = hexFloat(tok.substr(tok.find(':') + 1));
+            }
+            m.policy = mzhost::searchDistribution(acts.data(), counts.data(), k);
+            m.value = std::to_string(hexFloat(mean_hex));
+            m.reward = "0";
+            moves.push_back(m);
+        }
+    }
+    std::cout << mzhost::selfPlayLine(h, moves, terminal, eval, turn) << std::endl;
+    return 0;
+}
+
+} // namespace
+
+int main(int argc, char** argv)
+{
+    std::string mode, conf_file, conf_str;
+    for (int i = 1; i + 1 < argc; i += 2) {
+        const std::string flag = argv[i];
+        if (flag == "-mode") {
+            mode = argv[i + 1];
+        } else if (flag == "-conf_file") {
+            conf_file = argv[i + 1];
+        } else if (flag == "-conf_str") {
+            conf_str = argv[i + 1];
+        } else {
+            std::cerr << "unknown flag " << flag << std::endl;
+            return -1;
+        }
+    }
+    if (mode == "record_test") { return recordTest(); }
+    if (mode != "sp") {
+        std::cerr << "usage: mz_sp -mode sp [-conf_file F] [-conf_str \"k=v:...\"]   (other modes of the reference binary are out of scope)" << std::endl;
+        return -1;
+    }
+    mzhost::Config cfg;
+    if (!conf_file.empty() && !cfg.loadFromFile(conf_file)) {
+        std::cerr << "Failed to load configuration file." << std::endl;
+        return -1;
+    }
+    if (!conf_str.empty() && !cfg.loadFromString(conf_str)) {
+        std::cerr << "Failed to load configuration string." << std::endl;
+        return -1;
+    }
+    if (cfg.getBool("actor_use_gumbel") || cfg.getString("nn_type_name") != "alphazero") {
+        std::cerr << "this worker implements the AlphaZero self-play path only" << std::endl;
+        return -1;
+    }
+    mzhost::Worker worker(cfg);
+    return worker.run();
+}

@@ -1,0 +1,87 @@
+// Game record and `SelfPlay` line of the zero-server wire protocol, byte for byte as the reference writes them:
+//   actor/actor_group.cpp:24-50      ThreadSharedData::outputGame ("SelfPlay <terminal> <data len> <game len> <return> <record> #")
+//   actor/base_actor.cpp:42-66       BaseActor::getRecord / getActionInfo (tags EV, RE on resign, DLEN; P / V / R per move)
+//   environment/base/base_env.h:207-233,303-313   loadFromEnvironment / toString / escapeSGFString (tag order = insertion order)
+//   environment/go/go.h:129-133      KM tag; environment/base/base_env.h:363-367 SZ tag
+//   actor/mcts.cpp:126-137           getSearchDistributionString ("action:count" of the visited root children, child order)
+#pragma once
+#include <sstream>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace mzhost {
+
+struct MoveRecord {
+    int action = 0;
+    int player = 1; // 1 = 'B', 2 = 'W'
+    std::string policy, value, reward; // P, V, R
+};
+
+inline char playerToChar(int p) { return p == 1 ? 'B' : (p == 2 ? 'W' : 'N'); } // environment/base/base_env.cpp:5-13
+
+inline std::string escapeSGF(const std::string& str)
+{
+    static const std::string special = "()[]\\";
+    std::string escaped;
+    for (char c : str) {
+        if (special.find(c) != std::string::npos) { escaped += '\\'; }
+        escaped += c;
+    }
+    return escaped;
+}
+
+// MCTS::getSearchDistributionString: counts are floats streamed with operator<<
+inline std::string searchDistribution(const int* actions, const float* counts, int num_children)
+{
+    std::ostringstream oss;
+    bool first = true;
+    for (int i = 0; i < num_children; ++i) {
+        if (counts[i] == 0) { continue; }
+        oss << (first ? "" : ",") << actions[i] << ":" << counts[i];
+        first = false;
+    }
+    return oss.str();
+}
+
+struct GameHeader {
+    std::string game_name;  // Environment::name(): "go_9x9", "tictactoe"
+    int board_size = 0;
+    bool has_komi = false;
+    float komi = 0.0f;
+    std::string model_file; // config::nn_file_name
+};
+
+// eval_score: Environment::getEvalScore(false) of the final position; terminal: Environment::isTerminal().
+// When the game is not terminal (resign) the side to move loses (base_actor.cpp:48-54, go.cpp:262-263).
+inline std::string selfPlayLine(const GameHeader& h, const std::vector<MoveRecord>& moves, bool terminal, float eval_score, int turn_to_move)
+{
+    const float resign_score = (turn_to_move == 1 ? -1.0f : 1.0f); // the next player of `turn` wins
+    std::vector<std::pair<std::string, std::string>> tags;
+    tags.push_back({"GM", h.game_name});
+    tags.push_back({"RE", std::to_string(eval_score)}); // loadFromEnvironment: std::to_string(env.getEvalScore())
+    tags.push_back({"OBS", ""});
+    tags.push_back({"SZ", std::to_string(h.board_size)});
+    if (h.has_komi) { tags.push_back({"KM", std::to_string(h.komi)}); }
+    tags.push_back({"EV", h.model_file.substr(h.model_file.find_last_of('/') + 1)});
+    if (!terminal) {
+        std::ostringstream oss;
+        oss << resign_score;
+        tags[1].second = oss.str();
+    }
+    const int game_length = static_cast<int>(moves.size());
+    tags.push_back({"DLEN", "0-" + std::to_string(game_length - 1)}); // calculateTrainingDataRange with sequence length 0
+    std::ostringstream rec;
+    rec << "(;";
+    for (const auto& t : tags) { rec << t.first << "[" << escapeSGF(t.second) << "]"; }
+    for (const MoveRecord& m : moves) {
+        rec << ";" << playerToChar(m.player) << "[" << m.action << "]";
+        rec << "P[" << escapeSGF(m.policy) << "]V[" << escapeSGF(m.value) << "]R[" << escapeSGF(m.reward) << "]";
+    }
+    rec << ")";
+    std::ostringstream oss;
+    oss << "SelfPlay " << "true" << " " << game_length << " " << game_length << " " << (terminal ? eval_score : resign_score) << " " << rec.str() << " #";
+    return oss.str();
+}
+
+} // namespace mzhost

@@ -1,0 +1,419 @@
+#include "worker.h"
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include <iostream>
+#include <nccl.h>
+#include <random>
+#include <sstream>
+
+namespace mzhost {
+
+Worker::~Worker()
+{
+    for (mz_engine* e : engines_) { mz_destroy(e); }
+    if (io_thread_.joinable()) { io_thread_.detach(); }
+}
+
+// ---- start-up: createNeuralNetworks + createActors (actor_group.cpp:150-187) ---------------------------------
+bool Worker::initialize()
+{
+    const std::string model = cfg_.getString("nn_file_name");
+    std::string err;
+    if (!readNetInfo(model, net_, err)) {
+        std::cerr << "Failed to load model \"" << model << "\": " << err << std::endl;
+        return false;
+    }
+    if (net_.type_name != "alphazero") {
+        std::cerr << "nn_type_name \"" << net_.type_name << "\" is not implemented by this worker (AlphaZero only)" << std::endl;
+        return false;
+    }
+    // the reference binary is compiled per game (environment/environment.h:5-110); here the model names its game
+    if (net_.game_name == "tictactoe") {
+        game_type_ = MZ_GAME_TICTACTOE, board_ = 3;
+    } else if (net_.game_name.rfind("go_", 0) == 0) {
+        game_type_ = MZ_GAME_GO, board_ = net_.dims.input_height;
+        if (cfg_.getInt("env_board_size") != 0 && cfg_.getInt("env_board_size") != board_) {
+            std::cerr << "env_board_size does not match the model's board" << std::endl;
+            return false;
+        }
+    } else {
+        std::cerr << "game \"" << net_.game_name << "\" is not implemented by this worker" << std::endl;
+        return false;
+    }
+    actions_ = net_.dims.action_size;
+    sims_ = cfg_.getInt("actor_num_simulation");
+    num_games_ = cfg_.getInt("zero_num_parallel_games");
+    header_.game_name = net_.game_name, header_.board_size = board_, header_.has_komi = (game_type_ == MZ_GAME_GO), header_.komi = cfg_.getFloat("env_go_komi");
+    header_.model_file = model;
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        std::cerr << "No CUDA device: this worker has no CPU path" << std::endl;
+        return false;
+    }
+    ndev = std::min(ndev, num_games_);
+    engine_games_.assign(ndev, 0);
+    for (int g = 0; g < num_games_; ++g) { engine_games_[g % ndev]++; }
+    for (int dev = 0; dev < ndev; ++dev) {
+        mz_config c{};
+        c.device = dev, c.game = game_type_, c.board_size = board_, c.num_games = engine_games_[dev], c.num_simulation = sims_;
+        c.puct_base = cfg_.getFloat("actor_mcts_puct_base"), c.puct_init = cfg_.getFloat("actor_mcts_puct_init");
+        c.reward_discount = cfg_.getFloat("actor_mcts_reward_discount"), c.komi = cfg_.getFloat("env_go_komi");
+        c.ko_situational = (cfg_.getString("env_go_ko_rule") == "situational"), c.dirichlet_epsilon = cfg_.getFloat("actor_dirichlet_noise_epsilon");
+        mz_engine* e = nullptr;
+        if (mz_create(&c, &e) != MZ_OK) {
+            std::cerr << "mz_create failed on device " << dev << ": " << mz_last_error() << std::endl;
+            return false;
+        }
+        engines_.push_back(e);
+        rotations_.emplace_back(static_cast<size_t>(sims_ + 1) * engine_games_[dev], 0);
+        noise_.emplace_back(static_cast<size_t>(engine_games_[dev]) * actions_, 0.0f);
+    }
+    if (ndev > 1) { // one communicator per GPU in this process: the packed weights travel over NVLink
+        ncclComm_t* comms = new ncclComm_t[ndev];
+        std::vector<int> devs(ndev);
+        for (int i = 0; i < ndev; ++i) { devs[i] = i; }
+        if (ncclCommInitAll(comms, ndev, devs.data()) != ncclSuccess) {
+            std::cerr << "ncclCommInitAll failed" << std::endl;
+            return false;
+        }
+        nccl_comms_ = comms;
+    }
+    if (!loadModel(model)) { return false; }
+
+    // createActors: ZeroActor::reset draws the resign switch of every game on the main thread's generator,
+    // seeded with program_seed (console/mode_handler.cpp:62, create_actor.h:12-14, zero_actor.cpp:23-27)
+    games_.assign(num_games_, Game());
+    for (int g = 0; g < num_games_; ++g) { resetGameHost(g); }
+    // slave thread 0 re-seeds: program_seed + thread id, or a random device (actor_group.cpp:66-70)
+    rng_.seed(cfg_.getBool("program_auto_seed") ? static_cast<int>(std::random_device()()) : cfg_.getInt("program_seed") + 0);
+    // first beforeNNEvaluation of every game: rotation draw of cycle 0 (zero_actor.cpp:56)
+    const bool random_rotation = cfg_.getBool("actor_use_random_rotation_features");
+    for (int g = 0; g < num_games_; ++g) {
+        const int e = g % static_cast<int>(engines_.size()), slot = g / static_cast<int>(engines_.size());
+        rotations_[e][slot] = (random_rotation ? static_cast<uint8_t>(rng_.randInt() % 8) : 0);
+    }
+    io_thread_ = std::thread(&Worker::handleIO, this);
+    return true;
+}
+
+void Worker::resetGameHost(int g)
+{
+    Game& game = games_[g];
+    game.moves.clear();
+    game.turn = 1;
+    game.num_legal = (game_type_ == MZ_GAME_GO ? board_ * board_ + 1 : 9);
+    std::fill(game.ttt, game.ttt + 9, 0);
+    game.enable_resign = (rng_.randReal() < cfg_.getFloat("zero_disable_resign_ratio") ? false : true);
+}
+
+bool Worker::loadModel(const std::string& path)
+{
+    std::string err;
+    if (!loadNetwork(path, engines_[0], err)) {
+        std::cerr << "Failed to load model \"" << path << "\": " << err << std::endl;
+        return false;
+    }
+    const int n = static_cast<int>(engines_.size());
+    if (n > 1) {
+        for (int i = 1; i < n; ++i) {
+            if (!configureEmpty(net_, engines_[i], err)) {
+                std::cerr << "network allocation failed: " << err << std::endl;
+                return false;
+            }
+        }
+        ncclComm_t* comms = static_cast<ncclComm_t*>(nccl_comms_);
+        ncclGroupStart();
+        for (int i = 0; i < n; ++i) {
+            void* blob = nullptr;
+            int64_t bytes = 0;
+            mz_net_blob(engines_[i], &blob, &bytes);
+            cudaSetDevice(i);
+            ncclBroadcast(blob, blob, static_cast<size_t>(bytes), ncclUint8, 0, comms[i], nullptr);
+        }
+        ncclGroupEnd();
+        for (int i = 0; i < n; ++i) {
+            cudaSetDevice(i);
+            cudaDeviceSynchronize();
+        }
+    }
+    cfg_.set("nn_file_name", path);
+    header_.model_file = path;
+    return true;
+}
+
+// ---- commands (actor_group.cpp:189-252) --------------------------------------------------------------------------
+void Worker::handleIO()
+{
+    std::string command;
+    while (std::getline(std::cin, command)) {
+        std::lock_guard<std::mutex> lock(mutex_);
+        commands_.push_back(command);
+    }
+    std::lock_guard<std::mutex> lock(mutex_);
+    commands_.push_back("quit"); // stdin closed: the server is gone
+}
+
+void Worker::handleCommands()
+{
+    std::deque<std::string> todo;
+    {
+        std::lock_guard<std::mutex> lock(mutex_);
+        todo.swap(commands_);
+    }
+    const std::string ignored = cfg_.getString("zero_actor_ignored_command");
+    for (const std::string& command : todo) {
+        const std::string prefix = (command.find(" ") == std::string::npos ? command : command.substr(0, command.find(" ")));
+        {
+            std::istringstream iss(ignored);
+            std::string word;
+            bool skip = false;
+            while (iss >> word) { skip |= (word == prefix); }
+            if (skip) {
+                std::cerr << "[ignored command] " << command << std::endl;
+                continue;
+            }
+        }
+        if (prefix == "reset_actors") {
+            std::cerr << "[command] " << command << std::endl;
+            for (int g = 0; g < num_games_; ++g) { resetGameHost(g); }
+            for (mz_engine* e : engines_) { mz_reset_game(e, -1); }
+        } else if (prefix == "load_model") {
+            std::cerr << "[command] " << command << std::endl;
+            if (command.find(" ") != std::string::npos && !loadModel(command.substr(command.find(" ") + 1))) { std::exit(0); }
+        } else if (prefix == "update_config") {
+            std::cerr << "[command] " << command << std::endl;
+            if (command.find(" ") == std::string::npos || !cfg_.loadFromString(command.substr(command.find(" ") + 1))) {
+                std::cerr << "Failed to load configuration string." << std::endl;
+                std::exit(0);
+            }
+        } else if (prefix == "start") {
+            std::cerr << "[command] " << command << std::endl;
+            running_ = true;
+        } else if (prefix == "stop") {
+            std::cerr << "[command] " << command << std::endl;
+            running_ = false;
+        } else if (prefix == "quit") {
+            std::cerr << "[command] " << command << std::endl;
+            quit_ = true;
+        } // anything else (keep_alive ...) falls through silently, as in the reference
+    }
+}
+
+// ---- move decision (zero_actor.cpp:178-192, mcts.cpp:84-124) -----------------------------------------------------
+namespace {
+// MCTSNode::getNormalizedMean for board games (mcts.cpp:40-53): reward 0, no rescale, no virtual loss
+float normalizedMean(float mean, float count, int player, float discount)
+{
+    float value = 0.0f + discount * mean;
+    value = (player == 2 ? -value : value);
+    value = (value * count - 0.0f) / (count + 0.0f);
+    return value;
+}
+} // namespace
+
+int Worker::decideAction(int g, const int* actions, const float* counts, const float* means, int num_children, float root_mean, bool& resign, int& child_index)
+{
+    const Game& game = games_[g];
+    const float discount = cfg_.getFloat("actor_mcts_reward_discount");
+    const int child_player = game.turn; // children of the root carry the side to move (zero_actor.cpp:33,217)
+    // selectChildByMaxCount (mcts.cpp:91-104)
+    int best = -1;
+    float max_count = 0.0f;
+    for (int i = 0; i < num_children; ++i) {
+        if (counts[i] <= max_count) { continue; }
+        max_count = counts[i];
+        best = i;
+    }
+    int selected = best;
+    if (!cfg_.getBool("actor_select_action_by_count") && cfg_.getBool("actor_select_action_by_softmax_count")) {
+        // selectChildBySoftmaxCount (mcts.cpp:106-124)
+        const float temperature = cfg_.getFloat("actor_select_action_softmax_temperature"), value_threshold = 0.1f;
+        const float best_mean = normalizedMean(means[best], counts[best], child_player, discount);
+        float sum = 0.0f;
+        selected = -1;
+        for (int i = 0; i < num_children; ++i) {
+            float count = std::pow(counts[i], 1 / temperature);
+            float mean = (counts[i] == 0 ? 0.0f / 0.0f : normalizedMean(means[i], counts[i], child_player, discount));
+            if (count == 0 || (mean < best_mean - value_threshold)) { continue; }
+            sum += count;
+            float rand = rng_.randReal(sum);
+            if (selected == -1 || rand < count) { selected = i; }
+        }
+    }
+    child_index = selected;
+    // isResign (zero_actor.h:42, mcts.cpp:84-89); the root's action player is the previous player (zero_actor.cpp:33)
+    const float root_count = static_cast<float>(sims_ + 1);
+    const float root_win_rate = normalizedMean(root_mean, root_count, 3 - game.turn, discount);
+    const float action_win_rate = normalizedMean(means[selected], counts[selected], child_player, discount);
+    const float threshold = cfg_.getFloat("actor_resign_threshold");
+    resign = game.enable_resign && (-root_win_rate < threshold && action_win_rate < threshold);
+    return actions[selected];
+}
+
+bool Worker::hostTerminal(const Game& game) const
+{
+    const int n = static_cast<int>(game.moves.size());
+    if (game_type_ == MZ_GAME_GO) {
+        const int pass = board_ * board_;
+        if (n >= 2 && game.moves[n - 1].action == pass && game.moves[n - 2].action == pass) { return true; } // go.cpp:249-251
+        return n > 2 * board_ * board_;                                                                        // go.cpp:254
+    }
+    static const int lines[8][3] = {{0, 1, 2}, {3, 4, 5}, {6, 7, 8}, {0, 3, 6}, {1, 4, 7}, {2, 5, 8}, {0, 4, 8}, {2, 4, 6}};
+    for (const auto& l : lines) {
+        if (game.ttt[l[0]] != 0 && game.ttt[l[0]] == game.ttt[l[1]] && game.ttt[l[1]] == game.ttt[l[2]]) { return true; }
+    }
+    return n == 9; // tictactoe.cpp:51-55
+}
+
+void Worker::emitGame(int g, bool terminal, float eval_score)
+{
+    const std::string line = selfPlayLine(header_, games_[g].moves, terminal, eval_score, games_[g].turn);
+    std::cout << line << std::endl; // the only thing this process ever writes to stdout (zero_server.cpp:111-139)
+    ++games_finished_;
+}
+
+// ---- one move for every game ------------------------------------------------------------------------------------------
+bool Worker::playOneMove()
+{
+    const int ne = static_cast<int>(engines_.size()), S1 = sims_ + 1, A = actions_;
+    const bool use_noise = cfg_.getBool("actor_use_dirichlet_noise"), random_rotation = cfg_.getBool("actor_use_random_rotation_features");
+    const float alpha = cfg_.getFloat("actor_dirichlet_noise_alpha");
+    // (1) randomness of cycles 1 .. S in the reference's per-cycle, per-actor order: in cycle 1 every
+    //     actor first receives its root noise (afterNNEvaluation of the root) and then draws the rotation of its next leaf
+    for (int c = 1; c < S1; ++c) {
+        for (int g = 0; g < num_games_; ++g) {
+            const int e = g % ne, slot = g / ne;
+            if (c == 1 && use_noise) {
+                std::vector<float> dir = rng_.randDirichlet(alpha, games_[g].num_legal);
+                float* dst = noise_[e].data() + static_cast<size_t>(slot) * A;
+                std::fill(dst, dst + A, 0.0f);
+                std::copy(dir.begin(), dir.end(), dst);
+            }
+            rotations_[e][static_cast<size_t>(c) * engine_games_[e] + slot] = (random_rotation ? static_cast<uint8_t>(rng_.randInt() % 8) : 0);
+        }
+    }
+    // (2) the whole search on the devices, all engines in flight together
+    for (int e = 0; e < ne; ++e) {
+        if (mz_search_set_inputs(engines_[e], random_rotation ? rotations_[e].data() : nullptr, use_noise ? noise_[e].data() : nullptr) != MZ_OK ||
+            mz_search_run(engines_[e], 0, nullptr) != MZ_OK) {
+            std::cerr << "search failed: " << mz_last_error() << std::endl;
+            return false;
+        }
+    }
+    // (3) root tables
+    struct Roots {
+        std::vector<mz_root_info> info;
+        std::vector<int32_t> action;
+        std::vector<float> count, mean;
+    };
+    std::vector<Roots> roots(ne);
+    for (int e = 0; e < ne; ++e) {
+        const size_t n = engine_games_[e];
+        roots[e].info.resize(n), roots[e].action.resize(n * A), roots[e].count.resize(n * A), roots[e].mean.resize(n * A);
+        if (mz_get_roots(engines_[e], roots[e].info.data(), roots[e].action.data(), roots[e].count.data(), roots[e].mean.data(), nullptr, nullptr, nullptr, nullptr) != MZ_OK) {
+            std::cerr << "mz_get_roots failed: " << mz_last_error() << std::endl;
+            return false;
+        }
+    }
+    // (4) per actor, in order: decide, act or resign, restart finished games, draw the first rotation of the next search
+    std::vector<std::vector<int32_t>> play(ne);
+    for (int e = 0; e < ne; ++e) { play[e].assign(engine_games_[e], -1); }
+    std::vector<int> ended; // games to emit after the devices have applied the moves (the final score comes from there)
+    std::vector<char> ended_by_resign(num_games_, 0);
+    for (int g = 0; g < num_games_; ++g) {
+        const int e = g % ne, slot = g / ne;
+        Game& game = games_[g];
+        const mz_root_info& ri = roots[e].info[slot];
+        const int32_t* acts = roots[e].action.data() + static_cast<size_t>(slot) * A;
+        const float* cnt = roots[e].count.data() + static_cast<size_t>(slot) * A;
+        const float* mean = roots[e].mean.data() + static_cast<size_t>(slot) * A;
+        bool resign = false;
+        int child = -1;
+        const int action = decideAction(g, acts, cnt, mean, ri.num_children, ri.mean, resign, child);
+        bool end = resign;
+        if (!resign) { // BaseActor::act + getActionInfo (base_actor.cpp:22-30,59-66)
+            MoveRecord m;
+            m.action = action, m.player = game.turn;
+            m.policy = searchDistribution(acts, cnt, ri.num_children);
+            m.value = std::to_string(ri.mean); // zero_actor.h:49
+            m.reward = "0";                    // operator<< of Environment::getReward() == 0.0f (go.h:50, tictactoe.h:25)
+            game.moves.push_back(m);
+            if (game_type_ == MZ_GAME_TICTACTOE && action >= 0 && action < 9) { game.ttt[action] = static_cast<uint8_t>(game.turn); }
+            game.turn = 3 - game.turn;
+            play[e][slot] = action;
+            end = hostTerminal(game);
+        }
+        if (end) {
+            ended.push_back(g);
+            ended_by_resign[g] = resign ? 1 : 0;
+        }
+        if (g == 0 && !cfg_.getBool("program_quiet")) {
+            std::cerr << "[actor 0] move " << game.moves.size() << " action " << action << (resign ? " (resign)" : "") << " root mean " << ri.mean << std::endl;
+        }
+        // actor->reset() draws the resign switch of the next game (zero_actor.cpp:26); deferred state reset below must not
+        // consume randomness, so only the draw happens here, in order
+        if (end) { game.enable_resign = (rng_.randReal() < cfg_.getFloat("zero_disable_resign_ratio") ? false : true); }
+        rotations_[e][slot] = (random_rotation ? static_cast<uint8_t>(rng_.randInt() % 8) : 0); // cycle 0 of the next search
+    }
+    // (5) apply the moves on the devices; finished games are emitted with the device's score and restarted
+    std::vector<std::vector<mz_play_result>> res(ne);
+    for (int e = 0; e < ne; ++e) {
+        res[e].resize(engine_games_[e]);
+        if (mz_play(engines_[e], play[e].data(), res[e].data()) != MZ_OK) {
+            std::cerr << "mz_play failed: " << mz_last_error() << std::endl;
+            return false;
+        }
+    }
+    for (int g = 0; g < num_games_; ++g) {
+        const int e = g % ne, slot = g / ne;
+        if (play[e][slot] >= 0) {
+            if (!res[e][slot].applied) {
+                std::cerr << "device rejected action " << play[e][slot] << " of game " << g << std::endl;
+                return false;
+            }
+            games_[g].num_legal = res[e][slot].num_legal;
+        }
+    }
+    for (int g : ended) {
+        const int e = g % ne, slot = g / ne;
+        const bool terminal = !ended_by_resign[g];
+        if (terminal && !res[e][slot].terminal) {
+            std::cerr << "host / device disagree on the end of game " << g << std::endl;
+            return false;
+        }
+        const bool keep_resign = games_[g].enable_resign; // already drawn for the next game
+        emitGame(g, terminal, terminal ? res[e][slot].eval_score : 0.0f);
+        mz_reset_game(engines_[e], slot);
+        Game& game = games_[g];
+        game.moves.clear();
+        game.turn = 1;
+        game.num_legal = (game_type_ == MZ_GAME_GO ? board_ * board_ + 1 : 9);
+        std::fill(game.ttt, game.ttt + 9, 0);
+        game.enable_resign = keep_resign;
+    }
+    ++moves_played_;
+    return true;
+}
+
+int Worker::run()
+{
+    // main thread generator: program_seed (console/mode_handler.cpp:62)
+    rng_.seed(cfg_.getInt("program_seed"));
+    if (!initialize()) { return -1; }
+    while (!quit_) {
+        handleCommands();
+        if (quit_) { break; }
+        if (!running_) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(1));
+            continue;
+        }
+        if (!playOneMove()) { return -1; }
+    }
+    return 0;
+}
+
+} // namespace mzhost

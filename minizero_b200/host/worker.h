@@ -1,0 +1,62 @@
+// The self-play worker: same outside behaviour as the reference's ActorGroup (actor/actor_group.{h,cpp}) — stdin
+// commands, one `SelfPlay ... #` line per finished game on stdout, diagnostics on stderr — with every simulation of
+// every game executed on the GPU(s) through the C ABI of include/mz_b200.h. The host is touched once per MOVE: it draws
+// the search's randomness in the reference's order, decides the moves from the root tables, keeps the records.
+#pragma once
+#include "../../include/mz_b200.h"
+#include "config.h"
+#include "net_loader.h"
+#include "record.h"
+#include "rng.h"
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace mzhost {
+
+struct Game {                    // what BaseActor / ZeroActor keep per game on the host
+    std::vector<MoveRecord> moves; // action_info_history_ + action history
+    bool enable_resign = true;     // zero_actor.cpp:23-27
+    int turn = 1;
+    int num_legal = 0;             // root children of the next search (= Dirichlet draws)
+    uint8_t ttt[9] = {0};          // tictactoe board, only to know the end of the game in RNG order
+};
+
+class Worker {
+public:
+    explicit Worker(Config& cfg) : cfg_(cfg) {}
+    ~Worker();
+    int run(); // ActorGroup::run (actor_group.cpp:136-148)
+
+private:
+    bool initialize();                       // actor_group.cpp:150-187
+    bool loadModel(const std::string& path); // load_model command (actor_group.cpp:227-232): rank-0 GPU reads, NCCL broadcast
+    void handleIO();                         // actor_group.cpp:189-198
+    void handleCommands();                   // actor_group.cpp:200-252
+    bool playOneMove();                      // S + 1 cycles of actor_group.cpp:81-134 for every game
+    int decideAction(int g, const int* actions, const float* counts, const float* means, int num_children, float root_mean, bool& resign, int& child_index);
+    bool hostTerminal(const Game& game) const;
+    void emitGame(int g, bool terminal, float eval_score);
+    void resetGameHost(int g);
+
+    Config& cfg_;
+    Random rng_;
+    NetInfo net_;
+    GameHeader header_;
+    int game_type_ = MZ_GAME_GO, board_ = 9, actions_ = 82, sims_ = 0, num_games_ = 0;
+    std::vector<mz_engine*> engines_;  // one per visible GPU (actor_group.cpp:168-177)
+    std::vector<int> engine_games_;    // games handled by each engine: game g -> engine g % n, slot g / n (actor_group.cpp:184-186)
+    std::vector<Game> games_;
+    std::vector<std::vector<uint8_t>> rotations_; // per engine [(S+1)][games]
+    std::vector<std::vector<float>> noise_;       // per engine [games][A]
+    void* nccl_comms_ = nullptr;
+    bool running_ = false, quit_ = false;
+    std::deque<std::string> commands_;
+    std::mutex mutex_;
+    std::thread io_thread_;
+    long long moves_played_ = 0, games_finished_ = 0;
+};
+
+} // namespace mzhost

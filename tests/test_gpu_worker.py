@@ -1,0 +1,73 @@
+"""The drop-in worker executable (minizero_b200/bin/mz_sp) end to end on a B200: it is driven over stdin exactly as the zero
+server drives the reference's `-mode sp` process, and every `SelfPlay` line it prints is handed to the REFERENCE's own record
+loader and rules (oracle/_ref/ref_record_check_*), which must parse it, replay every move as legal and agree on result,
+lengths and return."""
+import os
+import subprocess
+import time
+
+import pytest
+
+import oracle_lib
+
+pytestmark = pytest.mark.gpu
+ROOT = oracle_lib.ROOT
+BIN = os.path.join(ROOT, "minizero_b200", "bin", "mz_sp")
+NETS = os.path.join(ROOT, "oracle", "_ref", "nets")
+
+
+def run_worker(conf, want_lines, timeout=240):
+    p = subprocess.Popen([BIN, "-mode", "sp", "-conf_str", conf], stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    p.stdin.write("keep_alive\nstart\n")
+    p.stdin.flush()
+    lines, t0 = [], time.time()
+    while len(lines) < want_lines and time.time() - t0 < timeout:
+        line = p.stdout.readline()
+        if not line:
+            break
+        lines.append(line.rstrip("\n"))
+    p.stdin.write("quit\n")
+    p.stdin.flush()
+    try:
+        out, err = p.communicate(timeout=60)
+    except subprocess.TimeoutExpired:
+        p.kill()
+        out, err = p.communicate()
+    lines += [l for l in out.splitlines() if l]
+    return lines, err, p.returncode
+
+
+@pytest.mark.parametrize("game,net,conf,checker_conf", [
+    ("tictactoe", "ttt_az_2bx32", "actor_num_simulation=50:zero_num_parallel_games=16", ""),
+    ("go", "go5_az_1bx16", "env_board_size=5:actor_num_simulation=24:zero_num_parallel_games=16", "env_board_size=5"),
+    ("go", "go9_az_2bx64", "env_board_size=9:actor_num_simulation=32:zero_num_parallel_games=32", "env_board_size=9"),
+])
+def test_worker_speaks_the_wire_protocol_and_reference_accepts_its_records(game, net, conf, checker_conf):
+    checker = os.path.join(ROOT, "oracle", "_ref", "ref_record_check_" + game)
+    model = os.path.join(NETS, net + ".pt")
+    if not (os.path.exists(BIN) and os.path.exists(checker) and os.path.exists(model)):
+        pytest.skip("worker binary / oracle/_ref not built")
+    conf = conf + f":nn_file_name={model}:program_seed=3:program_auto_seed=false:program_quiet=true:zero_num_threads=1"
+    lines, err, rc = run_worker(conf, want_lines=24)
+    assert rc == 0, err[-500:]
+    assert len(lines) >= 24, err[-500:]
+    assert all(l.startswith("SelfPlay ") and l.endswith(" #") for l in lines), "stdout must carry nothing but SelfPlay lines (zero_server.cpp:130-139)"
+    r = subprocess.run([checker, checker_conf], input="\n".join(lines) + "\n", capture_output=True, text=True)
+    assert r.stdout.strip() == f"RECORDS_OK {len(lines)}", r.stdout + r.stderr[-300:]
+    assert f"EV[{net}.pt]" in lines[0]
+
+
+def test_worker_reloads_model_and_updates_config():
+    model = os.path.join(NETS, "ttt_az_2bx32.pt")
+    if not (os.path.exists(BIN) and os.path.exists(model)):
+        pytest.skip("worker binary / nets not built")
+    conf = f"actor_num_simulation=20:zero_num_parallel_games=8:nn_file_name={model}:program_quiet=true"
+    p = subprocess.Popen([BIN, "-mode", "sp", "-conf_str", conf], stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    p.stdin.write(f"load_model {model}\nupdate_config actor_num_simulation=20:actor_select_action_by_count=true:actor_select_action_by_softmax_count=false\nreset_actors\nstart\n")
+    p.stdin.flush()
+    first = p.stdout.readline()
+    p.stdin.write("stop\nquit\n")
+    p.stdin.flush()
+    out, err = p.communicate(timeout=120)
+    assert first.startswith("SelfPlay ") and p.returncode == 0, err[-400:]
+    assert "[ignored command] reset_actors" in err  # zero_actor_ignored_command default (configuration.cpp:47)

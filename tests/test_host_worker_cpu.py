@@ -1,0 +1,77 @@
+"""Host side of the drop-in worker (minizero_b200/host), CPU-only checks:
+  * the SelfPlay line / game record formatter reproduces, byte for byte, every line the compiled reference printed in the
+    golden recordings (terminal and resigned games);
+  * the configuration loader accepts the reference's keys and refuses unknown ones."""
+import os
+import re
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_replay
+import oracle_lib
+
+ROOT = oracle_lib.ROOT
+BIN = os.path.join(ROOT, "minizero_b200", "bin", "mz_sp")
+
+
+def hexf(x):
+    return "%08x" % struct.unpack("<I", struct.pack("<f", float(x)))[0]
+
+
+@pytest.fixture(scope="module")
+def worker_binary():
+    if not os.path.exists(BIN):
+        import __graft_entry__ as ge
+        ge.build()
+    return BIN
+
+
+@pytest.mark.parametrize("name,gname,board,komi", [("ttt_s50_b2", "tictactoe", 3, None), ("ttt_s50_b1_det", "tictactoe", 3, None), ("go5_s24_b2", "go_5x5", 5, 7.5)])
+def test_selfplay_lines_match_reference_bytes(worker_binary, name, gname, board, komi):
+    z = golden_replay.load_case(name)
+    lines = [str(l) for l in z["selfplay_lines"]]
+    games = []
+    for g in range(int(z["B"])):
+        cur = []
+        for m in [m for m in range(z["move_game"].size) if z["move_game"][m] == g]:
+            if cur and int(z["move_number"][m]) == 0:
+                games.append(cur)
+                cur = []
+            cur.append(m)
+            if z["move_resign"][m]:
+                games.append(cur)
+                cur = []
+        if cur:
+            games.append(cur)
+    produced = set()
+    for gm in games:
+        resigned = bool(z["move_resign"][gm[-1]])
+        moves = gm[:-1] if resigned else gm
+        turn = 1 if len(moves) % 2 == 0 else 2
+        for eval_score in (1.0, -1.0, 0.0):
+            inp = [f"header {gname} {board} {0 if komi is None else 1} {komi or 0} /some/dir/{name_of_model(lines)} {0 if resigned else 1} {hexf(eval_score)} {turn}"]
+            for m in moves:
+                k = int(z["move_num_children"][m])
+                pairs = " ".join(f"{int(z['child_action'][m, i])}:{hexf(z['child_count'][m, i])}" for i in range(k))
+                inp.append(f"move {int(z['move_player'][m])} {int(z['move_action'][m])} {hexf(z['root_mean'][m])} {k} {pairs}")
+            r = subprocess.run([worker_binary, "-mode", "record_test"], input="\n".join(inp) + "\n", capture_output=True, text=True, check=True)
+            produced.add(r.stdout.strip())
+    for l in lines:
+        assert l.strip() in produced, l[:120]
+
+
+def name_of_model(lines):
+    return re.search(r"EV\[([^\]]*)\]", lines[0]).group(1)
+
+
+def test_config_accepts_reference_keys_and_refuses_unknown(worker_binary):
+    ok = subprocess.run([worker_binary, "-mode", "record_test", "-conf_str", "actor_num_simulation=5"], input="", capture_output=True, text=True)
+    assert ok.returncode == 0
+    bad = subprocess.run([worker_binary, "-mode", "sp", "-conf_str", "no_such_key=1"], input="", capture_output=True, text=True)
+    assert bad.returncode != 0 and "Invalid key" in bad.stderr
+    # without a GPU (or a model) the worker must fail loudly and write nothing to stdout
+    nogpu = subprocess.run([worker_binary, "-mode", "sp", "-conf_str", "nn_file_name=/nonexistent.pt:zero_num_parallel_games=2"], input="quit\n", capture_output=True, text=True)
+    assert nogpu.returncode != 0 and nogpu.stdout == ""
