@@ -189,13 +189,10 @@ def main():
     else:
         eng.configure_network_empty(dims)
     if dist is not None:
+        from minizero_b200 import dist as mzdist
         ptr, nbytes = eng.weight_blob()
-
-        class _Blob:
-            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
-
-        blob = torch.as_tensor(_Blob(), device=torch.device("cuda", local_rank))
-        dist.broadcast(blob, src=0)
+        blob = torch.as_tensor(mzdist.DeviceBlob(ptr, nbytes), device=torch.device("cuda", local_rank))
+        mzdist.broadcast_blob(dist, blob, src=0)
         torch.cuda.synchronize()
 
     rng = np.random.default_rng(1234 + rank)
@@ -262,12 +259,9 @@ def main():
     prof = eng.profile_kernels(50)
 
     if dist is not None:
-        t = torch.tensor([dev_ms, e2e_s, float(launches)], device=torch.device("cuda", local_rank), dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s = float(t[0]), float(t[1])
-        tl = torch.tensor([float(launches)], device=torch.device("cuda", local_rank), dtype=torch.float64)
-        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
-        launches = int(tl[0])
+        dev = torch.device("cuda", local_rank)
+        dev_ms, e2e_s = mzdist.max_over_ranks(dist, [dev_ms, e2e_s], device=dev)
+        launches = int(mzdist.sum_over_ranks(dist, [float(launches)], device=dev)[0])
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
