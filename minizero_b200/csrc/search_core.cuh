@@ -26,6 +26,9 @@
 MZ_DEV long long mz_clock() { return clock64(); }
 MZ_DEV void mz_block_sync() { __syncthreads(); }
 MZ_DEV void mz_atomic_min(int* p, int v) { atomicMin(p, v); }
+MZ_DEV void mz_atomic_or(uint32_t* p, uint32_t v) { atomicOr(p, v); }
+MZ_DEV void mz_atomic_inc(int* p) { atomicAdd(p, 1); }
+MZ_DEV void mz_atomic_xor64(uint64_t* p, uint64_t v) { atomicXor(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(v)); }
 MZ_DEV unsigned mz_ballot(int p) { return __ballot_sync(MZ_FULL, p); }
 MZ_DEV int mz_any(int p) { return __any_sync(MZ_FULL, p); }
 MZ_DEV void mz_sync() { __syncwarp(); }
@@ -95,6 +98,9 @@ MZ_DEV void mz_store_hot(mz_hot* p, float count, float mean, float policy, uint3
 static inline long long mz_clock() { return 0; }
 static inline void mz_block_sync() {}
 static inline void mz_atomic_min(int* p, int v) { *p = (v < *p ? v : *p); }
+static inline void mz_atomic_or(uint32_t* p, uint32_t v) { *p |= v; }
+static inline void mz_atomic_inc(int* p) { ++*p; }
+static inline void mz_atomic_xor64(uint64_t* p, uint64_t v) { *p ^= v; }
 static inline unsigned mz_ballot(int p) { return p ? 1u : 0u; }
 static inline int mz_any(int p) { return p; }
 static inline void mz_sync() {}
@@ -205,6 +211,11 @@ struct mz_scratch {
     int32_t* sel;          // [S + 2] child chosen at every level of the previous path by the speculative re-evaluation
     float* q_warp;         // [num_warps][MZ_MAXA] per-warp Q scratch of the level evaluation
     int mismatch;          // first level whose re-evaluated choice differs from the previous path
+    // block-wide leaf analysis (mz_env_legal_block)
+    int label[MZ_MAXN * MZ_MAXN];  // block id of a stone = smallest cell index of its block
+    int libcnt[MZ_MAXN * MZ_MAXN]; // liberties per block id
+    uint32_t bloom[64];            // 2048-bit filter over the superko history
+    int flag, shared_len, shared_count;
 };
 
 MZ_DEV uint32_t mz_rowmask(int N) { return (N >= 32 ? 0xffffffffu : ((1u << N) - 1u)); }
@@ -551,14 +562,146 @@ MZ_DEV int mz_env_legal(const mz_dims& d, const mz_state& s, mz_scratch* w, cons
     return mz_reduce_add(n);
 }
 
+MZ_DEV int mz_cell_colour(const mz_scratch* w, int c, int N)
+{
+    const int r = c / N, x = c % N;
+    return ((w->st[0][r] >> x) & 1u) ? 1 : (((w->st[1][r] >> x) & 1u) ? 2 : 0);
+}
+
+// Same result as mz_env_legal, computed by ALL threads of the block (tid / nthreads), one cell per thread:
+// blocks are labelled by min-propagation with pointer jumping (label = smallest cell index of the block, the unique
+// fixpoint whatever the update order), liberties are counted per label with shared-memory atomics, block hashes are
+// XOR-folded per label, and every empty cell then tests its <= 4 neighbouring blocks (go.cpp:208-244). The superko
+// lookup goes through a 2048-bit filter of the history first; only filter hits scan the list.
+MZ_DEV int mz_env_legal_block(const mz_dims& d, const mz_state& s, mz_scratch* w, const uint64_t* root_list, int root_n, const uint64_t* path_list, int path_n,
+                              int tid, int nthreads)
+{
+    const int N = d.N, NN = N * N, me = w->turn - 1;
+    for (int i = tid; i < MZ_LEGAL_WORDS; i += nthreads) { w->legal[i] = 0u; }
+    if (d.game != MZ_GAME_GO) {
+        mz_block_sync();
+        if (tid == 0) {
+            uint32_t bits = 0;
+            for (int r = 0; r < N; ++r) { bits |= (~(w->st[0][r] | w->st[1][r]) & mz_rowmask(N)) << (r * N); }
+            w->legal[0] = bits; // tictactoe.cpp:44-49
+        }
+        mz_block_sync();
+        return mz_popc(w->legal[0]);
+    }
+    uint64_t* bhash = w->cap_hash; // per-label block hash
+    for (int c = tid; c < NN; c += nthreads) {
+        w->label[c] = (mz_cell_colour(w, c, N) != 0 ? c : -1);
+        w->libcnt[c] = 0;
+        bhash[c] = 0;
+    }
+    for (int i = tid; i < 64; i += nthreads) { w->bloom[i] = 0u; }
+    mz_block_sync();
+    // superko filter
+    for (int i = tid; i < root_n + path_n; i += nthreads) {
+        const uint64_t h = (i < root_n ? root_list[i] : path_list[i - root_n]);
+        mz_atomic_or(&w->bloom[(h >> 5) & 63], 1u << (h & 31));
+    }
+    // block labels
+    for (;;) {
+        if (tid == 0) { w->flag = 0; }
+        mz_block_sync();
+        int changed = 0;
+        for (int c = tid; c < NN; c += nthreads) {
+            int l = w->label[c];
+            if (l < 0) { continue; }
+            const int r = c / N, x = c % N, col = mz_cell_colour(w, c, N);
+            int m = l;
+            if (r + 1 < N && mz_cell_colour(w, c + N, N) == col) { m = (w->label[c + N] < m ? w->label[c + N] : m); }
+            if (x + 1 < N && mz_cell_colour(w, c + 1, N) == col) { m = (w->label[c + 1] < m ? w->label[c + 1] : m); }
+            if (r > 0 && mz_cell_colour(w, c - N, N) == col) { m = (w->label[c - N] < m ? w->label[c - N] : m); }
+            if (x > 0 && mz_cell_colour(w, c - 1, N) == col) { m = (w->label[c - 1] < m ? w->label[c - 1] : m); }
+            const int mm = w->label[m]; // pointer jumping: the label of my label's cell
+            m = (mm < m ? mm : m);
+            if (m < l) {
+                w->label[c] = m;
+                changed = 1;
+            }
+        }
+        if (changed) { w->flag = 1; }
+        mz_block_sync();
+        if (!w->flag) { break; }
+        mz_block_sync();
+    }
+    // liberties and hashes per label
+    for (int c = tid; c < NN; c += nthreads) {
+        const int col = mz_cell_colour(w, c, N);
+        if (col != 0) {
+            mz_atomic_xor64(&bhash[w->label[c]], s.keys[(col - 1) * 361 + c]);
+            continue;
+        }
+        const int r = c / N, x = c % N;
+        int nb[4], k = 0;
+        if (r + 1 < N && w->label[c + N] >= 0) { nb[k++] = w->label[c + N]; }
+        if (x + 1 < N && w->label[c + 1] >= 0) { nb[k++] = w->label[c + 1]; }
+        if (r > 0 && w->label[c - N] >= 0) { nb[k++] = w->label[c - N]; }
+        if (x > 0 && w->label[c - 1] >= 0) { nb[k++] = w->label[c - 1]; }
+        for (int i = 0; i < k; ++i) {
+            bool dup = false;
+            for (int j = 0; j < i; ++j) { dup |= (nb[j] == nb[i]); }
+            if (!dup) { mz_atomic_inc(&w->libcnt[nb[i]]); }
+        }
+    }
+    mz_block_sync();
+    // legality of every empty cell (go.cpp:208-244)
+    const uint64_t base = w->hash ^ d.turn_key;
+    for (int c = tid; c < NN; c += nthreads) {
+        if (mz_cell_colour(w, c, N) != 0) { continue; }
+        const int r = c / N, x = c % N;
+        int nbc[4], k = 0;
+        if (r + 1 < N) { nbc[k++] = c + N; }
+        if (x + 1 < N) { nbc[k++] = c + 1; }
+        if (r > 0) { nbc[k++] = c - N; }
+        if (x > 0) { nbc[k++] = c - 1; }
+        bool legal = false;
+        uint64_t nh = base ^ s.keys[me * 361 + c];
+        int seen_lab[4], ns = 0;
+        for (int i = 0; i < k; ++i) {
+            const int l = w->label[nbc[i]];
+            if (l < 0) { // empty neighbour (go.cpp:225-226)
+                legal = true;
+                continue;
+            }
+            bool dup = false;
+            for (int j = 0; j < ns; ++j) { dup |= (seen_lab[j] == l); }
+            if (dup) { continue; } // block already examined (go.cpp:229)
+            seen_lab[ns++] = l;
+            const int lc = w->libcnt[l];
+            if (mz_cell_colour(w, l, N) - 1 == me) {
+                if (lc > 1) { legal = true; } // go.cpp:232-233
+            } else if (lc == 1) {             // capture (go.cpp:235-238)
+                nh ^= bhash[l];
+                legal = true;
+            }
+        }
+        if (!legal) { continue; }
+        bool seen = false;
+        if ((w->bloom[(nh >> 5) & 63] >> (nh & 31)) & 1u) {
+            for (int i = 0; i < root_n; ++i) { seen |= (root_list[i] == nh); }
+            for (int i = 0; i < path_n; ++i) { seen |= (path_list[i] == nh); }
+        }
+        if (!seen) { mz_atomic_or(&w->legal[c >> 5], 1u << (c & 31)); }
+    }
+    mz_block_sync();
+    if (tid == 0) { w->legal[NN >> 5] |= (1u << (NN & 31)); } // pass, go.cpp:213
+    mz_block_sync();
+    int n = 0;
+    for (int i = 0; i < MZ_LEGAL_WORDS; ++i) { n += mz_popc(w->legal[i]); }
+    return n;
+}
+
 // getFeatures (go.cpp:280-308, tictactoe.cpp:67-90) written as fp16 NHWC rows of the first conv's input:
 // board cell (x, y) of game g lives at row g * slots + (y + 1) * (N + 1) + x, channel c at column c.
-MZ_DEV void mz_env_features(const mz_dims& d, const mz_state& s, int g, const mz_scratch* w, int rotation, int lane)
+MZ_DEV void mz_env_features(const mz_dims& d, const mz_state& s, int g, const mz_scratch* w, int rotation, int lane, int stride = MZ_W)
 {
     const int N = d.N, rev = mz_reversed_rotation(rotation);
     const int turn = w->turn, me = turn - 1, opp = 1 - me;
     uint16_t* base = s.nn_in + (size_t)g * d.slots * MZ_NN_CPAD;
-    for (int pos = lane; pos < N * N; pos += MZ_W) {
+    for (int pos = lane; pos < N * N; pos += stride) {
         const int rp = mz_rotate(rev, pos, N), rr = rp / N, rx = rp % N;
         uint16_t* out = base + (size_t)((pos / N + 1) * (N + 1) + pos % N) * MZ_NN_CPAD;
         if (d.game == MZ_GAME_GO) {
@@ -758,69 +901,93 @@ MZ_DEV void mz_slot_load(const mz_dims& d, const mz_state& s, int g, int slot, m
 // environment for positions older than the root). Same positions, same results, cost independent of the depth.
 MZ_DEV void mz_before_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int lane, int wid, int nw)
 {
-    const int N = d.N;
+    const int N = d.N, tid = wid * MZ_W + lane, nthreads = nw * MZ_W;
     const int root_turn = s.root_meta[g * 4 + 0], root_moves = s.root_meta[g * 4 + 1];
     const long long t0 = mz_clock();
-    const int len = mz_select(d, s, g, w, root_turn, lane, wid, nw);
-    if (wid != 0) { return; } // the rest of the step is done by warp 0
-    mz_sync();
+    {
+        const int len0 = mz_select(d, s, g, w, root_turn, lane, wid, nw);
+        if (wid == 0 && lane == 0) {
+            w->shared_len = len0;
+            w->shared_count = (int)mz_load_hot(s.hot + (size_t)g * d.NP).count; // simulations finished so far
+        }
+    }
+    mz_block_sync();
     const long long t1 = mz_clock();
+    const int len = w->shared_len, slot = w->shared_count;
     const int32_t* path = s.path + (size_t)g * (d.S + 2);
     const int16_t* node_slot = s.node_slot + (size_t)g * d.NP;
     const uint64_t* root_list = s.hashes + (size_t)g * d.max_hashes;
     const int L = len - 1; // depth of the leaf
-    const int slot = (int)mz_load_hot(s.hot + (size_t)g * d.NP).count; // simulations finished so far
     const int leaf = path[L];
-    // position hashes of the path nodes 1 .. L-1 (superko history beyond the root)
-    for (int j = 1 + lane; j < L; j += MZ_W) { w->path_hashes[j - 1] = s.slot_hash[(size_t)g * (d.S + 1) + node_slot[path[j]]]; }
+    // ---- gather (all threads): hashes of the path nodes 1 .. L-1, the ancestors' positions for the feature history,
+    //      and the parent's position
+    for (int j = 1 + tid; j < L; j += nthreads) { w->path_hashes[j - 1] = s.slot_hash[(size_t)g * (d.S + 1) + node_slot[path[j]]]; }
     if (L == 0) {
-        mz_env_load_root(d, s, g, w, lane);
+        if (wid == 0) { mz_env_load_root(d, s, g, w, lane); }
     } else {
-        // feature history: positions of the (up to 7) ancestors, newest first, then the root's own ring
-        for (int k = 1; k < MZ_HIST; ++k) {
+        for (int i = tid; i < (MZ_HIST - 1) * 2 * N; i += nthreads) {
+            const int k = 1 + i / (2 * N), e = i % (2 * N);
             const int pos = root_moves + L - 1 - k; // index of the position k moves before the leaf's
-            if (pos < 0) { break; }
+            if (pos < 0) { continue; }
             const int ring = pos % MZ_HIST;
+            uint32_t v;
             if (pos >= root_moves) {
-                const uint32_t* st = s.slot_st + ((size_t)g * (d.S + 1) + node_slot[path[L - k]]) * 2 * N;
-                for (int i = lane; i < 2 * N; i += MZ_W) { w->hist[ring][i / N][i % N] = st[i]; }
+                v = s.slot_st[((size_t)g * (d.S + 1) + node_slot[path[L - k]]) * 2 * N + e];
             } else {
-                const uint32_t* hist = s.root_hist + ((size_t)g * MZ_HIST + ring) * 2 * MZ_ROWS;
-                for (int i = lane; i < 2 * N; i += MZ_W) { w->hist[ring][i / N][i % N] = hist[(i / N) * MZ_ROWS + i % N]; }
+                v = s.root_hist[((size_t)g * MZ_HIST + ring) * 2 * MZ_ROWS + (e / N) * MZ_ROWS + e % N];
             }
+            w->hist[ring][e / N][e % N] = v;
         }
         if (L == 1) {
             const uint32_t* st = s.root_st + (size_t)g * 2 * MZ_ROWS;
-            for (int i = lane; i < 2 * N; i += MZ_W) { w->st[i / N][i % N] = st[(i / N) * MZ_ROWS + i % N]; }
-            if (lane == 0) {
+            for (int i = tid; i < 2 * N; i += nthreads) { w->st[i / N][i % N] = st[(i / N) * MZ_ROWS + i % N]; }
+            if (tid == 0) {
                 w->hash = s.root_hash[g];
                 w->turn = root_turn, w->num_moves = root_moves, w->last = s.root_meta[g * 4 + 2], w->last2 = s.root_meta[g * 4 + 3];
             }
-            mz_sync();
         } else {
-            mz_slot_load(d, s, g, node_slot[path[L - 1]], w, lane);
+            const size_t e = (size_t)g * (d.S + 1) + node_slot[path[L - 1]];
+            for (int i = tid; i < 2 * N; i += nthreads) { w->st[i / N][i % N] = s.slot_st[e * 2 * N + i]; }
+            if (tid == 0) {
+                w->hash = s.slot_hash[e];
+                w->turn = s.slot_meta[e * 4 + 0], w->num_moves = s.slot_meta[e * 4 + 1], w->last = s.slot_meta[e * 4 + 2], w->last2 = s.slot_meta[e * 4 + 3];
+            }
         }
-        const int a = s.action[(size_t)g * d.NP + leaf];
-        mz_env_act(d, s, w, a, w->turn, lane); // getEnvironmentTransition's last step, zero_actor.cpp:250
-        if (lane == 0) { w->path_hashes[L - 1] = w->hash; }
-        mz_sync();
     }
-    mz_slot_store(d, s, g, slot, w, lane);
-    if (lane == 0) { s.node_slot[(size_t)g * d.NP + leaf] = (int16_t)slot; }
+    mz_block_sync();
+    // ---- transition (warp 0): getEnvironmentTransition's last step, zero_actor.cpp:250
+    if (wid == 0 && L > 0) {
+        const int a = s.action[(size_t)g * d.NP + leaf];
+        mz_env_act(d, s, w, a, w->turn, lane);
+        if (lane == 0) { w->path_hashes[L - 1] = w->hash; }
+    }
+    mz_block_sync();
+    {
+        const size_t e = (size_t)g * (d.S + 1) + slot;
+        for (int i = tid; i < 2 * N; i += nthreads) { s.slot_st[e * 2 * N + i] = w->st[i / N][i % N]; }
+        if (tid == 0) {
+            s.slot_hash[e] = w->hash;
+            s.slot_meta[e * 4 + 0] = w->turn, s.slot_meta[e * 4 + 1] = w->num_moves, s.slot_meta[e * 4 + 2] = w->last, s.slot_meta[e * 4 + 3] = w->last2;
+            s.node_slot[(size_t)g * d.NP + leaf] = (int16_t)slot;
+        }
+    }
     const long long t2 = mz_clock();
+    // ---- leaf analysis and feature planes (all threads)
     const int rotation = (s.rotations ? s.rotations[g] : 0);
     const int terminal = mz_env_is_terminal(d, w);
     float score = 0.0f;
     int num_legal = 0;
     if (terminal) {
-        score = mz_env_eval_score(d, w, lane);
+        if (wid == 0) { score = mz_env_eval_score(d, w, lane); }
+        for (int i = tid; i < MZ_LEGAL_WORDS; i += nthreads) { w->legal[i] = 0u; }
+        mz_block_sync();
     } else {
-        num_legal = mz_env_legal(d, s, w, root_list, root_moves, w->path_hashes, L, lane);
+        num_legal = mz_env_legal_block(d, s, w, root_list, root_moves, w->path_hashes, L, tid, nthreads);
     }
     const long long t3 = mz_clock();
-    mz_env_features(d, s, g, w, rotation, lane);
-    for (int i = lane; i < MZ_LEGAL_WORDS; i += MZ_W) { s.leaf_legal[g * MZ_LEGAL_WORDS + i] = w->legal[i]; }
-    if (lane == 0) {
+    mz_env_features(d, s, g, w, rotation, tid, nthreads);
+    for (int i = tid; i < MZ_LEGAL_WORDS; i += nthreads) { s.leaf_legal[g * MZ_LEGAL_WORDS + i] = w->legal[i]; }
+    if (tid == 0) {
         s.path_len[g] = len;
         s.spec_len[g] = len;
         s.leaf_meta[g * 4 + 0] = terminal;
@@ -908,7 +1075,11 @@ MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* 
     if (lane == 0) { s.value[(size_t)g * d.NP + leaf] = v; }
     for (int i = lane; i < len; i += MZ_W) {
         float x = v;
-        for (int j = len - 1; j > i; --j) { x = mz_fadd(0.0f, mz_fmul(d.discount, x)); }
+        if (d.discount == 1.0f) {
+            if (i < len - 1 && x == 0.0f) { x = 0.0f; } // 0 + 1 * x: only -0 changes (to +0)
+        } else {
+            for (int j = len - 1; j > i; --j) { x = mz_fadd(0.0f, mz_fmul(d.discount, x)); }
+        }
         const int n = path[i];
         const mz_hot h = mz_load_hot(hot + n);
         const float cnt = mz_fadd(h.count, 1.0f);
@@ -950,7 +1121,7 @@ MZ_DEV void mz_play(const mz_dims& d, const mz_state& s, int g, int action, mz_s
 {
     mz_env_load_root(d, s, g, w, lane);
     uint64_t* hash_list = s.hashes + (size_t)g * d.max_hashes;
-    mz_env_legal(d, s, w, hash_list, w->num_moves, hash_list, 0, lane);
+    mz_env_legal_block(d, s, w, hash_list, w->num_moves, hash_list, 0, lane, MZ_W);
     const int ok = (action >= 0 && action < d.A && ((w->legal[action >> 5] >> (action & 31)) & 1u)) ? 1 : 0;
     int terminal = 0, num_legal = 0;
     float sc = 0.0f;
@@ -965,7 +1136,7 @@ MZ_DEV void mz_play(const mz_dims& d, const mz_state& s, int g, int action, mz_s
     if (terminal) {
         sc = mz_env_eval_score(d, w, lane);
     } else {
-        num_legal = mz_env_legal(d, s, w, hash_list, w->num_moves, hash_list, 0, lane);
+        num_legal = mz_env_legal_block(d, s, w, hash_list, w->num_moves, hash_list, 0, lane, MZ_W);
     }
     if (lane == 0) {
         out[0] = ok, out[1] = terminal, out[2] = num_legal, out[3] = w->turn;
