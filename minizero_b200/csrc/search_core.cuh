@@ -589,8 +589,11 @@ MZ_DEV int mz_env_legal_block(const mz_dims& d, const mz_state& s, mz_scratch* w
         return mz_popc(w->legal[0]);
     }
     uint64_t* bhash = w->cap_hash; // per-label block hash
+    uint8_t* cinfo = reinterpret_cast<uint8_t*>(w->pol); // per cell: colour | up << 2 | right << 3 | down << 4 | left << 5 (pol[] is free here)
     for (int c = tid; c < NN; c += nthreads) {
-        w->label[c] = (mz_cell_colour(w, c, N) != 0 ? c : -1);
+        const int r = c / N, x = c % N, col = mz_cell_colour(w, c, N);
+        cinfo[c] = (uint8_t)(col | ((r + 1 < N) << 2) | ((x + 1 < N) << 3) | ((r > 0) << 4) | ((x > 0) << 5));
+        w->label[c] = (col != 0 ? c : -1);
         w->libcnt[c] = 0;
         bhash[c] = 0;
     }
@@ -607,14 +610,14 @@ MZ_DEV int mz_env_legal_block(const mz_dims& d, const mz_state& s, mz_scratch* w
         mz_block_sync();
         int changed = 0;
         for (int c = tid; c < NN; c += nthreads) {
-            int l = w->label[c];
+            const int l = w->label[c];
             if (l < 0) { continue; }
-            const int r = c / N, x = c % N, col = mz_cell_colour(w, c, N);
+            const int info = cinfo[c], col = info & 3;
             int m = l;
-            if (r + 1 < N && mz_cell_colour(w, c + N, N) == col) { m = (w->label[c + N] < m ? w->label[c + N] : m); }
-            if (x + 1 < N && mz_cell_colour(w, c + 1, N) == col) { m = (w->label[c + 1] < m ? w->label[c + 1] : m); }
-            if (r > 0 && mz_cell_colour(w, c - N, N) == col) { m = (w->label[c - N] < m ? w->label[c - N] : m); }
-            if (x > 0 && mz_cell_colour(w, c - 1, N) == col) { m = (w->label[c - 1] < m ? w->label[c - 1] : m); }
+            if ((info & 4) && (cinfo[c + N] & 3) == col) { m = (w->label[c + N] < m ? w->label[c + N] : m); }
+            if ((info & 8) && (cinfo[c + 1] & 3) == col) { m = (w->label[c + 1] < m ? w->label[c + 1] : m); }
+            if ((info & 16) && (cinfo[c - N] & 3) == col) { m = (w->label[c - N] < m ? w->label[c - N] : m); }
+            if ((info & 32) && (cinfo[c - 1] & 3) == col) { m = (w->label[c - 1] < m ? w->label[c - 1] : m); }
             const int mm = w->label[m]; // pointer jumping: the label of my label's cell
             m = (mm < m ? mm : m);
             if (m < l) {
@@ -629,17 +632,16 @@ MZ_DEV int mz_env_legal_block(const mz_dims& d, const mz_state& s, mz_scratch* w
     }
     // liberties and hashes per label
     for (int c = tid; c < NN; c += nthreads) {
-        const int col = mz_cell_colour(w, c, N);
+        const int info = cinfo[c], col = info & 3;
         if (col != 0) {
             mz_atomic_xor64(&bhash[w->label[c]], s.keys[(col - 1) * 361 + c]);
             continue;
         }
-        const int r = c / N, x = c % N;
         int nb[4], k = 0;
-        if (r + 1 < N && w->label[c + N] >= 0) { nb[k++] = w->label[c + N]; }
-        if (x + 1 < N && w->label[c + 1] >= 0) { nb[k++] = w->label[c + 1]; }
-        if (r > 0 && w->label[c - N] >= 0) { nb[k++] = w->label[c - N]; }
-        if (x > 0 && w->label[c - 1] >= 0) { nb[k++] = w->label[c - 1]; }
+        if ((info & 4) && w->label[c + N] >= 0) { nb[k++] = w->label[c + N]; }
+        if ((info & 8) && w->label[c + 1] >= 0) { nb[k++] = w->label[c + 1]; }
+        if ((info & 16) && w->label[c - N] >= 0) { nb[k++] = w->label[c - N]; }
+        if ((info & 32) && w->label[c - 1] >= 0) { nb[k++] = w->label[c - 1]; }
         for (int i = 0; i < k; ++i) {
             bool dup = false;
             for (int j = 0; j < i; ++j) { dup |= (nb[j] == nb[i]); }
@@ -650,13 +652,13 @@ MZ_DEV int mz_env_legal_block(const mz_dims& d, const mz_state& s, mz_scratch* w
     // legality of every empty cell (go.cpp:208-244)
     const uint64_t base = w->hash ^ d.turn_key;
     for (int c = tid; c < NN; c += nthreads) {
-        if (mz_cell_colour(w, c, N) != 0) { continue; }
-        const int r = c / N, x = c % N;
+        const int info = cinfo[c];
+        if ((info & 3) != 0) { continue; }
         int nbc[4], k = 0;
-        if (r + 1 < N) { nbc[k++] = c + N; }
-        if (x + 1 < N) { nbc[k++] = c + 1; }
-        if (r > 0) { nbc[k++] = c - N; }
-        if (x > 0) { nbc[k++] = c - 1; }
+        if (info & 4) { nbc[k++] = c + N; }
+        if (info & 8) { nbc[k++] = c + 1; }
+        if (info & 16) { nbc[k++] = c - N; }
+        if (info & 32) { nbc[k++] = c - 1; }
         bool legal = false;
         uint64_t nh = base ^ s.keys[me * 361 + c];
         int seen_lab[4], ns = 0;
@@ -671,7 +673,7 @@ MZ_DEV int mz_env_legal_block(const mz_dims& d, const mz_state& s, mz_scratch* w
             if (dup) { continue; } // block already examined (go.cpp:229)
             seen_lab[ns++] = l;
             const int lc = w->libcnt[l];
-            if (mz_cell_colour(w, l, N) - 1 == me) {
+            if ((cinfo[l] & 3) - 1 == me) {
                 if (lc > 1) { legal = true; } // go.cpp:232-233
             } else if (lc == 1) {             // capture (go.cpp:235-238)
                 nh ^= bhash[l];
@@ -817,13 +819,51 @@ MZ_DEV int mz_select_level(const mz_dims& d, const mz_state& s, const mz_hot* ho
     return best_i;
 }
 
+// The same choice made by ONE thread scanning the children in order, exactly like the loops of mcts.cpp:181-217
+// (ordered f32 sum for init-Q, then first-best arg-max), with the unvisited children below the root reduced to the
+// first one as explained above. Used by the level-parallel re-evaluation: one thread per level of the previous path.
+MZ_DEV int mz_select_level_serial(const mz_dims& d, const mz_state& s, const mz_hot* hot, const mz_hot& h, bool score_all, int child_player)
+{
+    const int nc = (int)(h.link >> MZ_LINK_SHIFT), fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
+    const int total = (int)mz_fsub(h.count, 1.0f);
+    float sum_win = 0.0f, sum_n = 0.0f;
+    int first_unvisited = nc;
+#pragma unroll 4
+    for (int i = 0; i < nc; ++i) {
+        const mz_hot c = mz_load_hot(hot + fc + i);
+        if (c.count != 0.0f) {
+            sum_win = mz_fadd(sum_win, mz_normalized_mean(d, c.mean, c.count, child_player));
+            sum_n = mz_fadd(sum_n, 1.0f);
+        } else if (first_unvisited == nc) {
+            first_unvisited = i;
+        }
+    }
+    const float init_q = mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
+    const float bias = s.puct_bias[total];
+    const double sqrt_n = s.sqrt_table[total];
+    float best_s = 0.0f, best_p = 0.0f;
+    int best_i = -1;
+#pragma unroll 4
+    for (int i = 0; i < nc; ++i) {
+        const mz_hot c = mz_load_hot(hot + fc + i); // L1
+        const bool visited = (c.count != 0.0f);
+        if (!(score_all || visited || i == first_unvisited)) { continue; }
+        const double num = mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n);
+        const float u = (float)(visited ? mz_ddiv(num, (double)mz_fadd(1.0f, c.count)) : num);
+        const float score = mz_fadd(u, visited ? mz_normalized_mean(d, c.mean, c.count, child_player) : init_q);
+        if (best_i < 0 || score > best_s || (score == best_s && c.policy > best_p)) { best_s = score, best_p = c.policy, best_i = i; }
+    }
+    return fc + best_i;
+}
+
 // MCTS::select (mcts.cpp:139-148): returns the path length; path[] holds node indices from the root.
 //
-// The block has `nw` warps. Consecutive simulations of a game mostly retrace the previous path (with a random-init
-// network the tree is a few long chains), and every level's choice depends only on that level's node — so the warps
-// first RE-EVALUATE all levels of the previous path in parallel (level j by warp j mod nw) and find the first level
-// whose choice changed; warp 0 then continues serially from there. Every choice is still made by mz_select_level on
-// the current statistics: the path is exactly the serial one, found in (depth / nw) level-times instead of depth.
+// Consecutive simulations of a game mostly retrace the previous path (with a random-init network the tree is a few
+// chains as deep as the game), and every level's choice depends only on that level's node — so the block first
+// RE-EVALUATES all levels of the previous path in parallel, one thread per level (mz_select_level_serial), and finds the
+// first level whose choice changed; warp 0 then continues from there with the coalesced warp-per-level evaluation.
+// Every choice is still made on the current statistics: the path is exactly the serial one, found in about one
+// level-time instead of depth level-times.
 MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int root_turn, int lane, int wid, int nw)
 {
     const mz_hot* hot = s.hot + (size_t)g * d.NP;
@@ -832,15 +872,11 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
     const int old_len = s.spec_len[g];
     if (wid == 0 && lane == 0) { w->mismatch = (old_len > 0 ? old_len - 1 : 0); }
     mz_block_sync();
-    for (int j = wid; j < old_len - 1; j += nw) {
+    for (int j = wid * MZ_W + lane; j < old_len - 1; j += nw * MZ_W) { // one THREAD per level of the previous path
         const mz_hot h = mz_load_hot(hot + path[j]);
-        mz_hot c;
-        const int fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
-        const int best = mz_select_level(d, s, hot, h, j == 0, (j & 1) ? 3 - root_turn : root_turn, q, lane, c);
-        if (lane == 0) {
-            w->sel[j] = fc + best;
-            if (fc + best != path[j + 1]) { mz_atomic_min(&w->mismatch, j); }
-        }
+        const int chosen = mz_select_level_serial(d, s, hot, h, j == 0, (j & 1) ? 3 - root_turn : root_turn);
+        w->sel[j] = chosen;
+        if (chosen != path[j + 1]) { mz_atomic_min(&w->mismatch, j); }
     }
     mz_block_sync();
     int len = 1;
