@@ -872,11 +872,27 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
     const int old_len = s.spec_len[g];
     if (wid == 0 && lane == 0) { w->mismatch = (old_len > 0 ? old_len - 1 : 0); }
     mz_block_sync();
-    for (int j = wid * MZ_W + lane; j < old_len - 1; j += nw * MZ_W) { // one THREAD per level of the previous path
-        const mz_hot h = mz_load_hot(hot + path[j]);
-        const int chosen = mz_select_level_serial(d, s, hot, h, j == 0, (j & 1) ? 3 - root_turn : root_turn);
-        w->sel[j] = chosen;
-        if (chosen != path[j + 1]) { mz_atomic_min(&w->mismatch, j); }
+    // level 0 (the root: every child is scored, most are visited) by one whole warp, coalesced; the deeper levels (few
+    // visited children each) by one THREAD per level
+    const int root_warp = nw - 1;
+    if (wid == root_warp && old_len > 1) {
+        const mz_hot h = mz_load_hot(hot + path[0]);
+        mz_hot c;
+        const int fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
+        const int best = mz_select_level(d, s, hot, h, true, root_turn, q, lane, c);
+        if (lane == 0) {
+            w->sel[0] = fc + best;
+            if (fc + best != path[1]) { mz_atomic_min(&w->mismatch, 0); }
+        }
+    }
+    if (wid != root_warp || nw == 1) {
+        const int workers = (nw == 1 ? MZ_W : (nw - 1) * MZ_W);
+        for (int j = 1 + wid * MZ_W + lane; j < old_len - 1; j += workers) {
+            const mz_hot h = mz_load_hot(hot + path[j]);
+            const int chosen = mz_select_level_serial(d, s, hot, h, false, (j & 1) ? 3 - root_turn : root_turn);
+            w->sel[j] = chosen;
+            if (chosen != path[j + 1]) { mz_atomic_min(&w->mismatch, j); }
+        }
     }
     mz_block_sync();
     int len = 1;
