@@ -47,7 +47,11 @@ __global__ void __launch_bounds__(32 * STEP_WARPS) k_step(const mz_dims d, const
         w.q_warp = reinterpret_cast<float*>(w.sel + (d.S + 2));
     }
     __syncthreads();
-    if ((flags & STEP_AFTER) && wid == 0) { mz_after_nn(d, s, g, &w, lane); }
+    if ((flags & STEP_AFTER) && wid == 0) {
+        const long long ta = clock64();
+        mz_after_nn(d, s, g, &w, lane);
+        if (s.dbg && lane == 0) { s.dbg[(size_t)g * 8 + 4] += (unsigned long long)(clock64() - ta); }
+    }
     if (flags & STEP_BEFORE) {
         __threadfence_block();
         __syncthreads();
@@ -129,6 +133,7 @@ struct ConvLayer {
     int cin = 0, cout = 0, relu = 1;
     size_t w_off = 0, b_off = 0; // offsets into the blob
     CUtensorMap map_w;
+    CUtensorMap map_w_mc; // box = 1 / conv_cluster of the weight tile (multicast slices)
 };
 
 struct Blob {
@@ -179,7 +184,7 @@ struct mz_engine {
     __half* act[3] = {nullptr, nullptr, nullptr};
     CUtensorMap map_in0, map_act[3];
     CUtensorMap map_in0_ext, map_act_ext[3]; // same buffers, box = the resident block of conv3x3_resident_kernel
-    int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148, krot = 0;
+    int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148, krot = 0, conv_cluster = 1;
     encode_tiled_fn encode = nullptr;
 
     // graphs keyed by (num_evals, noise, rotations)
@@ -228,7 +233,7 @@ size_t resident_smem(const mz_engine* e, int cin)
     return static_cast<size_t>(cin / mznn::BK) * e->rows_ext * 128 + static_cast<size_t>(STAGES) * BN * mznn::BK * 2 + (2 * STAGES + 6) * 8 + 16 + 1024;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CL>
 int launch_conv_resident(mz_engine* e, const CUtensorMap& in_ext, const ConvLayer& L, __half* out, const __half* residual)
 {
     mznn::ConvResParams rp;
@@ -236,9 +241,17 @@ int launch_conv_resident(mz_engine* e, const CUtensorMap& in_ext, const ConvLaye
     p.out = out, p.residual = residual, p.bias = reinterpret_cast<const float*>(e->d_blob + L.b_off);
     p.rows_valid = e->d.B * e->d.slots, p.n1 = e->d.N + 1, p.slots = e->d.slots, p.cin = L.cin, p.cout = L.cout, p.relu = L.relu, p.krot = e->krot;
     rp.rows_ext = e->rows_ext, rp.halo = e->d.N + 2, rp.num_mtiles = e->rows_alloc / mznn::BM, rp.base_off_mode = e->base_off_mode;
-    const int units = rp.num_mtiles * (L.cout / BN);
-    const int grid = units < e->num_sms ? units : e->num_sms;
-    mznn::conv3x3_resident_kernel<BN, STAGES><<<grid, mznn::CONV_THREADS, resident_smem<BN, STAGES>(e, L.cin), e->stream>>>(in_ext, L.map_w, rp);
+    const int units = ((rp.num_mtiles + CL - 1) / CL) * (L.cout / BN);
+    int clusters = e->num_sms / CL;
+    if (units < clusters) { clusters = units; }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * CL), cfg.blockDim = dim3(mznn::CONV_THREADS), cfg.dynamicSmemBytes = resident_smem<BN, STAGES>(e, L.cin), cfg.stream = e->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    const CUtensorMap& wmap = (CL == 1 ? L.map_w : L.map_w_mc);
+    CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv3x3_resident_kernel<BN, STAGES, CL>, in_ext, wmap, rp));
     e->launches++;
     return MZ_OK;
 }
@@ -248,16 +261,20 @@ int configure_conv_kernels()
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_tcgen05_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mznn::ConvSmem<64, 4>::TOTAL));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_tcgen05_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mznn::ConvSmem<128, 3>::TOTAL));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_tcgen05_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mznn::ConvSmem<256, 4>::TOTAL));
-    CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<64, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<64, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return MZ_OK;
 }
 
 int conv(mz_engine* e, const CUtensorMap& in, const CUtensorMap& in_ext, const ConvLayer& L, __half* out, const __half* residual)
 {
     if (e->conv_mode == 1) {
-        if (e->bn_tile == 64) { return launch_conv_resident<64, 6>(e, in_ext, L, out, residual); }
-        return launch_conv_resident<128, 9>(e, in_ext, L, out, residual);
+        if (e->bn_tile == 64) { return launch_conv_resident<64, 6, 1>(e, in_ext, L, out, residual); }
+        if (e->conv_cluster == 2) { return launch_conv_resident<128, 9, 2>(e, in_ext, L, out, residual); }
+        if (e->conv_cluster == 4) { return launch_conv_resident<128, 9, 4>(e, in_ext, L, out, residual); }
+        return launch_conv_resident<128, 9, 1>(e, in_ext, L, out, residual);
     }
     switch (e->bn_tile) {
         case 64: return launch_conv<64, 4>(e, in, L, out, residual);
@@ -377,8 +394,14 @@ int alloc_net(mz_engine* e)
     if (const char* env = std::getenv("MZ_CONV_MODE")) { e->conv_mode = std::atoi(env); }
     if (const char* env = std::getenv("MZ_CONV_BASEOFF")) { e->base_off_mode = std::atoi(env); }
     if (const char* env = std::getenv("MZ_CONV_ROT")) { e->krot = std::atoi(env); }
+    e->conv_cluster = 1; // CTAs per cluster sharing every weight tile by TMA multicast (1, 2 or 4)
+    if (const char* env = std::getenv("MZ_CONV_CLUSTER")) {
+        const int v = std::atoi(env);
+        if (v == 1 || v == 2 || v == 4) { e->conv_cluster = v; }
+    }
     if (e->bn_tile == 256) { e->conv_mode = 0; }
     const size_t need = (e->bn_tile == 64 ? resident_smem<64, 6>(e, e->cpad) : resident_smem<128, 9>(e, e->cpad));
+    if (e->bn_tile == 64) { e->conv_cluster = 1; }
     if (need > 227 * 1024) { e->conv_mode = 0; }
     cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->cfg.device);
     for (int i = 0; i < 3; ++i) {
@@ -390,6 +413,7 @@ int alloc_net(mz_engine* e)
     if ((rc = make_map_2d(e, &e->map_in0_ext, e->s.nn_in, MZ_NN_CPAD, rows, mznn::BK, e->rows_ext))) { return rc; }
     for (ConvLayer& L : e->convs) {
         if ((rc = make_map_2d(e, &L.map_w, e->d_blob + L.w_off, L.cin, 9ull * L.cout, mznn::BK, e->bn_tile))) { return rc; }
+        if ((rc = make_map_2d(e, &L.map_w_mc, e->d_blob + L.w_off, L.cin, 9ull * L.cout, mznn::BK, e->bn_tile / e->conv_cluster))) { return rc; }
     }
     return MZ_OK;
 }
@@ -478,6 +502,9 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     guard(e->dalloc(&e->d_root_info, B * 4)), guard(e->dalloc(&e->d_root_action, BA));
     for (int i = 0; i < 6; ++i) { guard(e->dalloc(&e->d_root_f[i], BA)); }
     guard(e->dalloc(&e->d_feat_f32, B * d.C * N * N));
+    if (const char* env = std::getenv("MZ_DEBUG_TREE")) {
+        if (std::atoi(env) != 0) { guard(e->dalloc(&s.dbg, B * 8)); }
+    }
     if (rc) {
         mz_destroy(e);
         return rc;
@@ -887,11 +914,14 @@ int mz_search_run(mz_engine* e, int32_t num_evals, float* device_ms)
         const int64_t launches_before = e->launches;
         CUDA_OK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
         int rc = MZ_OK;
+        // MZ_DEBUG_SKIP=tree|nn leaves one half of the cycle out of the captured graph: timing experiments only (results are wrong)
+        const char* skip = std::getenv("MZ_DEBUG_SKIP");
+        const bool skip_tree = (skip && std::string(skip) == "tree"), skip_nn = (skip && std::string(skip) == "nn");
         for (int c = 0; c < num_evals && !rc; ++c) {
-            step(e, (c > 0 ? STEP_AFTER : 0) | STEP_BEFORE, e->rot_enabled ? e->d_rot_all + static_cast<size_t>(c) * d.B : nullptr);
-            rc = forward(e);
+            if (!skip_tree) { step(e, (c > 0 ? STEP_AFTER : 0) | STEP_BEFORE, e->rot_enabled ? e->d_rot_all + static_cast<size_t>(c) * d.B : nullptr); }
+            if (!skip_nn) { rc = forward(e); }
         }
-        step(e, STEP_AFTER, nullptr);
+        if (!skip_tree) { step(e, STEP_AFTER, nullptr); }
         cudaError_t cerr = cudaStreamEndCapture(e->stream, &graph);
         e->launches = launches_before;
         if (rc) { return rc; }
@@ -918,19 +948,15 @@ int mz_search_run(mz_engine* e, int32_t num_evals, float* device_ms)
 
 int mz_debug_tree_timing(mz_engine* e, uint64_t* out)
 {
+    // counters accumulated by every tree step since mz_create when MZ_DEBUG_TREE=1 was set (profiling runs only):
+    // out [num_games][8] = cycles in {selection, transition, leaf analysis, features, expand+backup}, steps, max path, sum of paths
     if (!e || !out) { return fail(MZ_ERR_ARG, "bad argument"); }
+    if (!e->s.dbg) { return fail(MZ_ERR_STATE, "set MZ_DEBUG_TREE=1 before creating the engine"); }
     CUDA_OK(cudaSetDevice(e->cfg.device));
-    unsigned long long* buf = nullptr;
     const size_t n = static_cast<size_t>(e->d.B) * 8;
-    CUDA_OK(cudaMalloc(&buf, sizeof(unsigned long long) * n));
-    CUDA_OK(cudaMemsetAsync(buf, 0, sizeof(unsigned long long) * n, e->stream));
-    e->s.dbg = buf;
-    step(e, STEP_BEFORE, nullptr);
-    e->s.dbg = nullptr;
-    cudaError_t err = cudaMemcpyAsync(out, buf, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, e->stream);
-    if (err == cudaSuccess) { err = cudaStreamSynchronize(e->stream); }
-    cudaFree(buf);
-    if (err != cudaSuccess) { return fail(MZ_ERR_CUDA, cudaGetErrorString(err)); }
+    CUDA_OK(cudaMemcpyAsync(out, e->s.dbg, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    CUDA_OK(cudaMemsetAsync(e->s.dbg, 0, sizeof(unsigned long long) * n, e->stream));
     return MZ_OK;
 }
 

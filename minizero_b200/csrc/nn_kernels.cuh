@@ -310,7 +310,27 @@ __device__ __forceinline__ void tcgen05_commit_u32(uint32_t bar_addr)
 // The producer and the MMA issuer are single threads: every instruction in their per-K-block loops is on the
 // critical path (measured: ~650 cycles of address arithmetic per K block starve a 256-cycle MMA), so the loops keep
 // stage / phase / descriptor words incrementally and contain no division.
-template <int BN, int STAGES>
+// CL > 1: thread-block clusters of CL CTAs work on CL different row tiles with the SAME sequence of weight tiles; each CTA
+// fetches 1/CL of every weight tile and TMA-multicasts it into the shared memory of all CTAs of the cluster, so the
+// L2 -> SM weight traffic (the dominant stream once the input block is resident) drops by CL. A stage may be overwritten
+// only after every CTA of the cluster has consumed it: the MMA warps commit their "stage free" arrival to all CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_mc_u32(uint32_t bar_addr, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_addr), "h"(mask) : "memory");
+}
+
+template <int BN, int STAGES, int CL>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w, const ConvResParams rp)
 {
@@ -332,16 +352,21 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nh = p.cout / BN;
-    const int units = rp.num_mtiles * nh;
-    const int u_begin = static_cast<int>((static_cast<long long>(blockIdx.x) * units) / gridDim.x);
-    const int u_end = static_cast<int>((static_cast<long long>(blockIdx.x + 1) * units) / gridDim.x);
+    // work units: (group of CL consecutive row tiles, output-channel half); contiguous ranges of units per cluster;
+    // CTA `crank` of the cluster takes row tile group * CL + crank
+    const int crank = (CL > 1 ? static_cast<int>(cluster_ctarank()) : 0);
+    const int cid = blockIdx.x / CL, num_clusters = gridDim.x / CL;
+    const int units = ((rp.num_mtiles + CL - 1) / CL) * nh;
+    const int u_begin = static_cast<int>((static_cast<long long>(cid) * units) / num_clusters);
+    const int u_end = static_cast<int>((static_cast<long long>(cid + 1) * units) / num_clusters);
+    constexpr uint16_t mc_mask = static_cast<uint16_t>((1u << CL) - 1u);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_in)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&b_full[s], 1);
-            mbar_init(&b_empty[s], 1);
+            mbar_init(&b_empty[s], CL); // one "stage consumed" arrival from the MMA warp of every CTA of the cluster
         }
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
@@ -358,13 +383,15 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
     }
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) { cluster_sync_all(); } // every CTA's barriers exist before any peer signals them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t full0 = smem_u32(b_full), empty0 = smem_u32(b_empty);
 
     if (warp == 0) {
         { // ===== TMA producer: the whole warp runs the loop (uniform control flow), one elected lane issues =====
-            int s = 0, mt = u_begin / nh, half = u_begin - mt * nh, cur_mt = -1;
+            int s = 0, grp = u_begin / nh, half = u_begin - grp * nh, cur_mt = -1;
+            int mt = grp * CL + crank;
             uint32_t ph = 1, a_ph = 1; // "empty" barriers: the first pass over the ring must not block
             const uint32_t b_dst0 = smem_u32(smem_b), a_dst0 = smem_u32(smem_a);
             const uint64_t map_w_ptr = reinterpret_cast<uint64_t>(&map_w), map_in_ptr = reinterpret_cast<uint64_t>(&map_in);
@@ -390,15 +417,23 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
                         mbar_wait_u32(empty0 + s * 8, ph);
                         if (elect_one_sync()) {
                             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(B_BYTES) : "memory");
-                            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(b_dst0 + s * B_BYTES),
-                                         "l"(map_w_ptr), "r"(full), "r"(kc), "r"(wrow)
-                                         : "memory");
+                            if constexpr (CL == 1) {
+                                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(b_dst0 + s * B_BYTES),
+                                             "l"(map_w_ptr), "r"(full), "r"(kc), "r"(wrow)
+                                             : "memory");
+                            } else { // this CTA's 1/CL slice of the tile, delivered to every CTA of the cluster
+                                asm volatile(
+                                    "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+                                        b_dst0 + s * B_BYTES + crank * (B_BYTES / CL)),
+                                    "l"(map_w_ptr), "r"(full), "r"(kc), "r"(wrow + crank * (BN / CL)), "h"(mc_mask)
+                                    : "memory");
+                            }
                         }
                         __syncwarp();
                         if (++s == STAGES) { s = 0, ph ^= 1; }
                     }
                 }
-                if (++half == nh) { half = 0, ++mt; }
+                if (++half == nh) { half = 0, mt += CL; }
             }
         }
     } else if (warp == 1) {
@@ -408,7 +443,8 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
             constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
             const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFFu) >> 4) | (1u << 16), b_lo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | (1u << 16);
             const uint32_t a_kb_step = static_cast<uint32_t>(a_kb_bytes) >> 4;
-            int s = 0, mt = u_begin / nh, half = u_begin - mt * nh, cur_mt = -1, buf = 0;
+            int s = 0, grp = u_begin / nh, half = u_begin - grp * nh, cur_mt = -1, buf = 0;
+            int mt = grp * CL + crank;
             uint32_t ph = 0, a_ph = 0, acc_ph0 = 1, acc_ph1 = 1;
             for (int u = u_begin; u < u_end; ++u) {
                 if (mt != cur_mt) {
@@ -439,7 +475,11 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
                                 umma_f16_lohi(tmem_d, a_lo + 2, b_lo + 2, desc_hi, idesc, 1u);
                                 umma_f16_lohi(tmem_d, a_lo + 4, b_lo + 4, desc_hi, idesc, 1u);
                                 umma_f16_lohi(tmem_d, a_lo + 6, b_lo + 6, desc_hi, idesc, 1u);
-                                tcgen05_commit_u32(empty0 + s * 8);
+                                if constexpr (CL == 1) {
+                                    tcgen05_commit_u32(empty0 + s * 8);
+                                } else {
+                                    tcgen05_commit_mc_u32(empty0 + s * 8, mc_mask);
+                                }
                             }
                             __syncwarp();
                             accumulate = 1u;
@@ -447,7 +487,7 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
                         }
                     }
                 }
-                if (++half == nh) { half = 0, ++mt; }
+                if (++half == nh) { half = 0, mt += CL; }
                 if (elect_one_sync()) {
                     tcgen05_commit_u32(smem_u32(&acc_full[buf]));
                     if (mt != cur_mt || u + 1 == u_end) { tcgen05_commit_u32(smem_u32(a_empty)); } // input block no longer needed
@@ -460,17 +500,19 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
         const int quarter = warp & 3;
         int ucount = 0;
         for (int u = u_begin; u < u_end; ++u, ++ucount) {
-            const int mt = u / nh, half = u - mt * nh, buf = ucount & 1;
+            const int grp = u / nh, half = u - grp * nh, buf = ucount & 1;
+            const int mt = grp * CL + crank;
             const int n0 = half * BN;
             const int r = mt * BM + quarter * 32 + lane;
             const int rr = r % p.slots;
             const bool live = (r < p.rows_valid) && (rr / p.n1 != 0) && (rr % p.n1 != p.n1 - 1);
+            const bool in_range = (mt < rp.num_mtiles); // padding tile of an incomplete group: computed (lockstep), not stored
             mbar_wait(&acc_full[buf], (ucount >> 1) & 1);
             tcgen05_fence_after();
             __half* out_row = p.out + static_cast<size_t>(r) * p.cout + n0;
             const __half* res_row = (p.residual ? p.residual + static_cast<size_t>(r) * p.cout + n0 : nullptr);
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
+            for (int c = 0; c < BN && in_range; c += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + c, v);
                 uint4 res[4];
@@ -508,6 +550,7 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
         }
     }
     __syncthreads();
+    if constexpr (CL > 1) { cluster_sync_all(); } // no CTA leaves while a peer may still multicast into it or signal its barriers
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");

@@ -1049,9 +1049,9 @@ MZ_DEV void mz_before_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch*
         s.leaf_score[g] = score;
         if (s.dbg) {
             unsigned long long* o = s.dbg + (size_t)g * 8;
-            o[0] = (unsigned long long)(t1 - t0), o[1] = (unsigned long long)(t2 - t1), o[2] = (unsigned long long)(t3 - t2);
-            o[3] = (unsigned long long)(mz_clock() - t3), o[4] = (unsigned long long)len, o[5] = (unsigned long long)terminal, o[6] = (unsigned long long)w->num_moves;
-            o[7] = (unsigned long long)num_legal;
+            o[0] += (unsigned long long)(t1 - t0), o[1] += (unsigned long long)(t2 - t1), o[2] += (unsigned long long)(t3 - t2);
+            o[3] += (unsigned long long)(mz_clock() - t3), o[5] += 1ull, o[6] = ((unsigned long long)len > o[6] ? (unsigned long long)len : o[6]);
+            o[7] += (unsigned long long)len;
         }
     }
 }

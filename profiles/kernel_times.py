@@ -21,12 +21,16 @@ tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("MZ_"))
 print(f"[{tag}] search {ms:.1f} ms ({bench.GAMES * (bench.SIMS + 1) / ms * 1e3:.0f} evals/s)  conv {p['conv_ms'] * 1e3:.1f} us  tree {p['tree_ms'] * 1e3:.1f} us  heads {p['heads_ms'] * 1e3:.1f} us")
 
 
-if os.environ.get("MZ_DBG"):
+if os.environ.get("MZ_DEBUG_TREE"):
+    eng.tree_timing()  # reset the counters
+    eng.play_max_count(auto_reset=True, read_back=True)
+    eng.set_search_inputs(rot, noise)
+    ms = eng.search()
     t = eng.tree_timing().astype(np.float64)
-    tot = t[:, :4].sum(axis=1)
-    order = np.argsort(-tot)
-    print("tree step per-game cycles: mean total %.0f, max %.0f" % (tot.mean(), tot.max()))
-    print("phase means (select, transition, leaf analysis, features):", t[:, :4].mean(axis=0).round(0))
-    print("path len: mean %.1f max %d; leaf move number mean %.1f max %d; terminal leaves %d" % (t[:, 4].mean(), t[:, 4].max(), t[:, 6].mean(), t[:, 6].max(), int(t[:, 5].sum())))
-    for g in order[:6]:
-        print("  game %3d: select %7d transition %6d analysis %7d features %6d | path %3d terminal %d move %3d legal %2d" % ((g,) + tuple(int(x) for x in t[g])))
+    steps = t[:, 5].max()
+    names = ["select", "transition", "analysis", "features", "expand+backup"]
+    per_step = t[:, :5] / np.maximum(t[:, 5:6], 1)
+    print("in-situ search %.1f ms; tree cycles per step per game (mean over games | max over games):" % ms)
+    for i, n in enumerate(names):
+        print("  %-14s %8.0f | %8.0f" % (n, per_step[:, i].mean(), per_step[:, i].max()))
+    print("  path length mean %.1f, longest %d" % ((t[:, 7] / np.maximum(t[:, 5], 1)).mean(), t[:, 6].max()))
