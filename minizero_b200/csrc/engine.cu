@@ -486,6 +486,7 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     e->rows_alloc = static_cast<int>((B * d.slots + mznn::BM - 1) / mznn::BM * mznn::BM);
     guard(e->dalloc(&s.hot, np)), guard(e->dalloc(&s.action, np)), guard(e->dalloc(&s.logit, np)), guard(e->dalloc(&s.value, np));
     guard(e->dalloc(&s.root_noise, BA)), guard(e->dalloc(&s.cursor, B));
+    guard(e->dalloc(&s.last_child, np));
     guard(e->dalloc(&s.node_slot, np)), guard(e->dalloc(&s.slot_st, B * (d.S + 1) * 2 * N)), guard(e->dalloc(&s.slot_hash, B * (d.S + 1)));
     guard(e->dalloc(&s.slot_meta, B * (d.S + 1) * 4));
     guard(e->dalloc(&s.root_st, B * 2 * MZ_ROWS)), guard(e->dalloc(&s.root_hist, B * MZ_HIST * 2 * MZ_ROWS)), guard(e->dalloc(&s.root_hash, B));

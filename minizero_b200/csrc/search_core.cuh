@@ -166,6 +166,7 @@ struct mz_state {
     float* root_noise; // [B][A] policy_noise_ of the root children
     int32_t* cursor;   // [B]
     int16_t* node_slot; // [B][NP] index of the cached environment of an evaluated node (-1: none)
+    int32_t* last_child; // [B][NP] child chosen the last time selection passed through the node (-1: never): speculation hint only
     // environment of every evaluated node of the current search, slot = simulation index (0 .. S)
     uint32_t* slot_st;   // [B][S + 1][2][N] stone rows
     uint64_t* slot_hash; // [B][S + 1]
@@ -758,22 +759,44 @@ MZ_DEV int mz_select_level(const mz_dims& d, const mz_state& s, const mz_hot* ho
 {
     const int nc = (int)(h.link >> MZ_LINK_SHIFT), fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
     const int total = (int)mz_fsub(h.count, 1.0f); // mcts.cpp:185
+    const float bias = s.puct_bias[total];
+    const double sqrt_n = s.sqrt_table[total];
     float sum_win = 0.0f, sum_n = 0.0f;
     int first_unvisited = nc;
+    // candidates of this lane among the VISITED children (their score does not depend on init-Q)
+    float best_s = 0.0f, best_p = 0.0f;
+    int best_i = -1;
+    mz_hot best_h = h, h_fu = h;
     for (int base = 0; base < nc; base += MZ_W) {
         const int i = base + lane;
         int visited = 0;
+        mz_hot c = h;
         if (i < nc) {
-            const mz_hot c = mz_load_hot(hot + fc + i);
+            c = mz_load_hot(hot + fc + i);
             visited = (c.count != 0.0f);
-            if (visited) { q[i] = mz_normalized_mean(d, c.mean, c.count, child_player); }
+            if (visited) {
+                const float qv = mz_normalized_mean(d, c.mean, c.count, child_player);
+                q[i] = qv;
+                const double num = mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n);
+                const float score = mz_fadd((float)mz_ddiv(num, (double)mz_fadd(1.0f, c.count)), qv);
+                if (best_i < 0 || score > best_s || (score == best_s && c.policy > best_p)) { best_s = score, best_p = c.policy, best_i = i, best_h = c; }
+            }
         }
         unsigned m = mz_ballot(visited);
         const unsigned valid = (nc - base >= MZ_W ? ~0u >> (32 - MZ_W) : ((1u << (nc - base)) - 1u));
         const unsigned unv = ~m & valid;
-        if (first_unvisited == nc && unv) { first_unvisited = base + mz_ffs0(unv); }
+        if (first_unvisited == nc && unv) {
+            const int fl = mz_ffs0(unv);
+            first_unvisited = base + fl;
+#if MZ_W > 1
+            h_fu.count = __shfl_sync(MZ_FULL, c.count, fl), h_fu.mean = __shfl_sync(MZ_FULL, c.mean, fl);
+            h_fu.policy = __shfl_sync(MZ_FULL, c.policy, fl), h_fu.link = __shfl_sync(MZ_FULL, c.link, fl);
+#else
+            h_fu = c;
+#endif
+        }
         mz_sync();
-        while (m) {
+        while (m) { // ordered f32 sum of the visited children's Q (mcts.cpp:200-217)
             const int b = mz_ffs0(m);
             m &= m - 1;
             sum_win = mz_fadd(sum_win, q[base + b]);
@@ -781,19 +804,21 @@ MZ_DEV int mz_select_level(const mz_dims& d, const mz_state& s, const mz_hot* ho
         }
     }
     const float init_q = mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
-    const float bias = s.puct_bias[total];
-    const double sqrt_n = s.sqrt_table[total];
-    float best_s = 0.0f, best_p = 0.0f;
-    int best_i = -1;
-    mz_hot best_h = h;
-    for (int i = lane; i < nc; i += MZ_W) {
-        const mz_hot c = mz_load_hot(hot + fc + i); // second read comes from L1
-        const bool visited = (c.count != 0.0f);
-        if (!(score_all || visited || i == first_unvisited)) { continue; }
-        const double num = mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n);
-        const float u = (float)(visited ? mz_ddiv(num, (double)mz_fadd(1.0f, c.count)) : num); // x / 1.0 == x
-        const float score = mz_fadd(u, visited ? q[i] : init_q);
-        if (best_i < 0 || score > best_s || (score == best_s && c.policy > best_p)) { best_s = score, best_p = c.policy, best_i = i, best_h = c; }
+    if (score_all) { // root: the unvisited children's priors are not sorted (noise), score every one of them
+        for (int i = lane; i < nc; i += MZ_W) {
+            const mz_hot c = mz_load_hot(hot + fc + i); // L1
+            if (c.count != 0.0f) { continue; }
+            const float score = mz_fadd((float)mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n), init_q); // n = 0: division by 1.0
+            if (best_i < 0 || score > best_s || (score == best_s && (c.policy > best_p || (c.policy == best_p && i < best_i)))) {
+                best_s = score, best_p = c.policy, best_i = i, best_h = c;
+            }
+        }
+    } else if (first_unvisited < nc && (lane == first_unvisited % MZ_W)) { // the one unvisited candidate, held by its own lane
+        const float score = mz_fadd((float)mz_dmul((double)mz_fmul(bias, h_fu.policy), sqrt_n), init_q);
+        const int i = first_unvisited;
+        if (best_i < 0 || score > best_s || (score == best_s && (h_fu.policy > best_p || (h_fu.policy == best_p && i < best_i)))) {
+            best_s = score, best_p = h_fu.policy, best_i = i, best_h = h_fu;
+        }
     }
     // lexicographic arg-max (score desc, prior desc, index asc) over the lanes' candidates (mcts.cpp:187-194)
 #if MZ_W > 1
@@ -820,104 +845,151 @@ MZ_DEV int mz_select_level(const mz_dims& d, const mz_state& s, const mz_hot* ho
 }
 
 // The same choice made by ONE thread scanning the children in order, exactly like the loops of mcts.cpp:181-217
-// (ordered f32 sum for init-Q, then first-best arg-max), with the unvisited children below the root reduced to the
-// first one as explained above. Used by the level-parallel re-evaluation: one thread per level of the previous path.
-MZ_DEV int mz_select_level_serial(const mz_dims& d, const mz_state& s, const mz_hot* hot, const mz_hot& h, bool score_all, int child_player)
+// (ordered f32 sum for init-Q, first-best arg-max), with the unvisited children below the root reduced to the first
+// one as explained above. Used by the level-parallel re-evaluation of deep paths: one thread per level.
+MZ_DEV int mz_select_level_serial(const mz_dims& d, const mz_state& s, const mz_hot* hot, const mz_hot& h, int child_player)
 {
     const int nc = (int)(h.link >> MZ_LINK_SHIFT), fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
     const int total = (int)mz_fsub(h.count, 1.0f);
-    float sum_win = 0.0f, sum_n = 0.0f;
-    int first_unvisited = nc;
+    const float bias = s.puct_bias[total];
+    const double sqrt_n = s.sqrt_table[total];
+    float sum_win = 0.0f, sum_n = 0.0f, best_s = 0.0f, best_p = 0.0f, p_fu = 0.0f;
+    int first_unvisited = nc, best_i = -1;
 #pragma unroll 4
     for (int i = 0; i < nc; ++i) {
         const mz_hot c = mz_load_hot(hot + fc + i);
         if (c.count != 0.0f) {
-            sum_win = mz_fadd(sum_win, mz_normalized_mean(d, c.mean, c.count, child_player));
+            const float qv = mz_normalized_mean(d, c.mean, c.count, child_player);
+            sum_win = mz_fadd(sum_win, qv);
             sum_n = mz_fadd(sum_n, 1.0f);
+            const double num = mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n);
+            const float score = mz_fadd((float)mz_ddiv(num, (double)mz_fadd(1.0f, c.count)), qv);
+            if (best_i < 0 || score > best_s || (score == best_s && c.policy > best_p)) { best_s = score, best_p = c.policy, best_i = i; }
         } else if (first_unvisited == nc) {
             first_unvisited = i;
+            p_fu = c.policy;
         }
     }
-    const float init_q = mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
-    const float bias = s.puct_bias[total];
-    const double sqrt_n = s.sqrt_table[total];
-    float best_s = 0.0f, best_p = 0.0f;
-    int best_i = -1;
-#pragma unroll 4
-    for (int i = 0; i < nc; ++i) {
-        const mz_hot c = mz_load_hot(hot + fc + i); // L1
-        const bool visited = (c.count != 0.0f);
-        if (!(score_all || visited || i == first_unvisited)) { continue; }
-        const double num = mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n);
-        const float u = (float)(visited ? mz_ddiv(num, (double)mz_fadd(1.0f, c.count)) : num);
-        const float score = mz_fadd(u, visited ? mz_normalized_mean(d, c.mean, c.count, child_player) : init_q);
-        if (best_i < 0 || score > best_s || (score == best_s && c.policy > best_p)) { best_s = score, best_p = c.policy, best_i = i; }
+    if (first_unvisited < nc) {
+        const float init_q = mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
+        const float score = mz_fadd((float)mz_dmul((double)mz_fmul(bias, p_fu), sqrt_n), init_q);
+        if (best_i < 0 || score > best_s || (score == best_s && (p_fu > best_p || (p_fu == best_p && first_unvisited < best_i)))) { best_i = first_unvisited; }
     }
     return fc + best_i;
 }
 
-// MCTS::select (mcts.cpp:139-148): returns the path length; path[] holds node indices from the root.
+// MCTS::select (mcts.cpp:139-148): returns the path length (valid in warp 0); path[] holds node indices from the root.
 //
-// Consecutive simulations of a game mostly retrace the previous path (with a random-init network the tree is a few
-// chains as deep as the game), and every level's choice depends only on that level's node — so the block first
-// RE-EVALUATES all levels of the previous path in parallel, one thread per level (mz_select_level_serial), and finds the
-// first level whose choice changed; warp 0 then continues from there with the coalesced warp-per-level evaluation.
-// Every choice is still made on the current statistics: the path is exactly the serial one, found in about one
-// level-time instead of depth level-times.
+// Every level's choice depends only on that level's node, so a GUESSED path can be checked level-parallel: the block
+// re-evaluates all levels of the guess at once (the root by a whole warp, the deeper levels warp-per-level when the
+// path is short and thread-per-level when it is long), finds the first level whose choice differs, takes the
+// re-evaluated child there and extends the guess below it along the `last_child` hints (the child chosen the last time
+// selection passed through a node). The loop ends when a guess is confirmed down to a node without hint, from where
+// warp 0 finishes serially (normally the one freshly expanded leaf). The first guess is the previous simulation's
+// path. Every choice is made by mz_select_level / _serial on the current statistics: the path is exactly the serial one.
 MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int root_turn, int lane, int wid, int nw)
 {
     const mz_hot* hot = s.hot + (size_t)g * d.NP;
     int32_t* path = s.path + (size_t)g * (d.S + 2);
+    int32_t* last_child = s.last_child + (size_t)g * d.NP;
     float* q = w->q_warp + (size_t)wid * MZ_MAXA;
-    const int old_len = s.spec_len[g];
-    if (wid == 0 && lane == 0) { w->mismatch = (old_len > 0 ? old_len - 1 : 0); }
-    mz_block_sync();
-    // level 0 (the root: every child is scored, most are visited) by one whole warp, coalesced; the deeper levels (few
-    // visited children each) by one THREAD per level
-    const int root_warp = nw - 1;
-    if (wid == root_warp && old_len > 1) {
-        const mz_hot h = mz_load_hot(hot + path[0]);
-        mz_hot c;
-        const int fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
-        const int best = mz_select_level(d, s, hot, h, true, root_turn, q, lane, c);
-        if (lane == 0) {
-            w->sel[0] = fc + best;
-            if (fc + best != path[1]) { mz_atomic_min(&w->mismatch, 0); }
-        }
+    const int tid = wid * MZ_W + lane;
+    int glen = s.spec_len[g]; // length of the guessed path (uniform across the block)
+    if (glen == 0) {
+        if (tid == 0) { path[0] = 0; }
+        glen = 1;
     }
-    if (wid != root_warp || nw == 1) {
-        const int workers = (nw == 1 ? MZ_W : (nw - 1) * MZ_W);
-        for (int j = 1 + wid * MZ_W + lane; j < old_len - 1; j += workers) {
-            const mz_hot h = mz_load_hot(hot + path[j]);
-            const int chosen = mz_select_level_serial(d, s, hot, h, false, (j & 1) ? 3 - root_turn : root_turn);
-            w->sel[j] = chosen;
-            if (chosen != path[j + 1]) { mz_atomic_min(&w->mismatch, j); }
+    int start = 0; // levels below `start` are confirmed
+    for (;;) {
+        if (tid == 0) { w->mismatch = glen - 1; }
+        mz_block_sync();
+        // ---- check levels start .. glen-2 of the guess
+        const int nlev = glen - 1 - start;
+        if (nlev > 0) {
+            const bool by_thread = (nw > 1 && nlev > 3 * nw);
+            if (by_thread) {
+                const int root_warp = nw - 1;
+                if (start == 0 && wid == root_warp) {
+                    const mz_hot h = mz_load_hot(hot + path[0]);
+                    mz_hot c;
+                    const int chosen = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u)) + mz_select_level(d, s, hot, h, true, root_turn, q, lane, c);
+                    if (lane == 0) {
+                        w->sel[0] = chosen;
+                        last_child[path[0]] = chosen;
+                        if (chosen != path[1]) { mz_atomic_min(&w->mismatch, 0); }
+                    }
+                }
+                if (wid != root_warp) {
+                    for (int j = (start == 0 ? 1 : start) + tid; j < glen - 1; j += (nw - 1) * MZ_W) {
+                        const int node = path[j];
+                        const int chosen = mz_select_level_serial(d, s, hot, mz_load_hot(hot + node), (j & 1) ? 3 - root_turn : root_turn);
+                        w->sel[j] = chosen;
+                        last_child[node] = chosen;
+                        if (chosen != path[j + 1]) { mz_atomic_min(&w->mismatch, j); }
+                    }
+                }
+            } else {
+                for (int j = start + wid; j < glen - 1; j += nw) {
+                    const int node = path[j];
+                    const mz_hot h = mz_load_hot(hot + node);
+                    mz_hot c;
+                    const int chosen = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u)) + mz_select_level(d, s, hot, h, j == 0, (j & 1) ? 3 - root_turn : root_turn, q, lane, c);
+                    if (lane == 0) {
+                        w->sel[j] = chosen;
+                        last_child[node] = chosen;
+                        if (chosen != path[j + 1]) { mz_atomic_min(&w->mismatch, j); }
+                    }
+                }
+            }
         }
+        mz_block_sync();
+        // ---- take the re-evaluated child at the first changed level, extend the guess along the hints (thread 0)
+        if (tid == 0) {
+            int level = w->mismatch;
+            if (level < glen - 1) {
+                ++level;
+                path[level] = w->sel[level - 1];
+            }
+            const int confirmed = level; // path[0 .. level] is now the true prefix
+            int node = path[level];
+            for (;;) {
+                const int lc = last_child[node];
+                if (lc < 0) { break; }
+                node = lc;
+                path[++level] = node;
+            }
+            w->shared_len = level + 1;
+            w->flag = confirmed;
+        }
+        mz_block_sync();
+        const int confirmed = w->flag, new_len = w->shared_len;
+        mz_block_sync();
+        if (new_len - 1 == confirmed) { // nothing left to check: finish serially from path[confirmed]
+            glen = new_len;
+            break;
+        }
+        start = confirmed;
+        glen = new_len;
     }
-    mz_block_sync();
-    int len = 1;
-    if (wid == 0) { // serial continuation (the whole search when there is no previous path)
-        int level = w->mismatch; // levels 0 .. level of the previous path are still valid
-        int node = (old_len > 0 ? path[level] : 0);
-        if (old_len > 0 && level < old_len - 1) { // the choice at `level` changed: take the re-evaluated one
-            node = w->sel[level];
-            ++level;
-            if (lane == 0) { path[level] = node; }
-        } else if (lane == 0 && old_len == 0) {
-            path[0] = 0;
-        }
-        mz_hot h = mz_load_hot(hot + node);
+    int len = glen;
+    if (wid == 0) {
+        int level = glen - 1;
+        mz_hot h = mz_load_hot(hot + path[level]);
         while ((h.link >> MZ_LINK_SHIFT) != 0) {
             const int fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
             mz_hot c;
             const int best = mz_select_level(d, s, hot, h, level == 0, (level & 1) ? 3 - root_turn : root_turn, q, lane, c);
+            if (lane == 0) {
+                last_child[path[level]] = fc + best;
+                path[level + 1] = fc + best;
+            }
             h = c;
             ++level;
-            if (lane == 0) { path[level] = fc + best; }
+            mz_sync();
         }
         len = level + 1;
     }
-    return len; // valid in warp 0
+    return len;
 }
 
 MZ_DEV void mz_slot_store(const mz_dims& d, const mz_state& s, int g, int slot, const mz_scratch* w, int lane)
@@ -1098,6 +1170,7 @@ MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* 
             s.logit[(size_t)g * d.NP + c] = w->lg[a];
             s.value[(size_t)g * d.NP + c] = 0.0f;
             s.node_slot[(size_t)g * d.NP + c] = -1;
+            s.last_child[(size_t)g * d.NP + c] = -1;
         }
         mz_sync();
         if (lane == 0) {
@@ -1151,6 +1224,7 @@ MZ_DEV void mz_tree_reset(const mz_dims& d, const mz_state& s, int g, int lane)
         s.logit[(size_t)g * d.NP] = 0.0f;
         s.action[(size_t)g * d.NP] = -1;
         s.node_slot[(size_t)g * d.NP] = -1;
+        s.last_child[(size_t)g * d.NP] = -1;
         s.cursor[g] = 1;
         s.path_len[g] = 0;
         s.spec_len[g] = 0;

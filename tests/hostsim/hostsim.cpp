@@ -39,6 +39,7 @@ sim* hs_create(int game, int N, int B, int S, float puct_base, float puct_init, 
     s.hot = zalloc<mz_hot>(np), s.action = zalloc<int16_t>(np), s.logit = zalloc<float>(np), s.value = zalloc<float>(np);
     s.root_noise = zalloc<float>((size_t)B * d.A), s.cursor = zalloc<int32_t>(B);
     s.node_slot = zalloc<int16_t>(np);
+    s.last_child = zalloc<int32_t>(np);
     s.slot_st = zalloc<uint32_t>((size_t)B * (S + 1) * 2 * N), s.slot_hash = zalloc<uint64_t>((size_t)B * (S + 1)), s.slot_meta = zalloc<int32_t>((size_t)B * (S + 1) * 4);
     h->w.path_hashes = zalloc<uint64_t>(S + 2);
     h->w.sel = zalloc<int32_t>(S + 2);
