@@ -133,8 +133,9 @@ int mz_timer_end(mz_engine* e, float* device_ms);
  * conv kernel (hidden -> hidden layer), the tree step kernel, the heads kernel; any pointer may be NULL */
 int mz_profile_kernels(mz_engine* e, int32_t iters, float* conv_ms, float* tree_ms, float* heads_ms);
 /* per-game cycle counters accumulated by every tree step since the last call, when the engine was created with the
- * environment variable MZ_DEBUG_TREE=1 (profiling only): out [num_games][8] = cycles in {selection, transition, leaf
- * analysis, feature planes, expand + backup}, number of steps, longest path, sum of path lengths */
+ * environment variable MZ_DEBUG_TREE=1 (profiling only): out [num_games][16] = cycles in {selection, transition, leaf
+ * analysis, feature planes, expand + backup}, number of steps, longest path, sum of path lengths, then selection detail:
+ * cycles in {guess checking, hint chasing, serial finish}, check rounds, levels checked, levels finished serially, 2 unused */
 int mz_debug_tree_timing(mz_engine* e, uint64_t* out);
 /* kernels launched by this engine so far */
 int64_t mz_launch_count(const mz_engine* e);

@@ -34,23 +34,24 @@ int fail(int code, const std::string& msg)
 // ---------------------------------------------------------------------------------------------------
 constexpr int STEP_AFTER = 1, STEP_BEFORE = 2;
 
-constexpr int STEP_WARPS = 8; // warps per game in k_step: the previous path is re-evaluated level-parallel (search_core.cuh, mz_select)
+constexpr int STEP_WARPS = 16; // warps per game in k_step: the previous path is re-evaluated level-parallel (search_core.cuh, mz_select)
 
 __global__ void __launch_bounds__(32 * STEP_WARPS) k_step(const mz_dims d, const mz_state s, const int flags)
 {
     __shared__ mz_scratch w;
-    extern __shared__ uint64_t dyn_smem[]; // path_hashes [S + 2] u64 | sel [S + 2] i32 | q_warp [STEP_WARPS][MZ_MAXA] f32
+    extern __shared__ uint64_t dyn_smem[]; // lvl_h [S + 2] 16 B | path_hashes [S + 2] u64 | sel [S + 2] i32 | q_warp [STEP_WARPS][A] f32
     const int g = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
-        w.path_hashes = dyn_smem;
-        w.sel = reinterpret_cast<int32_t*>(dyn_smem + (d.S + 2));
+        w.lvl_h = reinterpret_cast<mz_hot*>(dyn_smem);
+        w.path_hashes = dyn_smem + 2 * (d.S + 2);
+        w.sel = reinterpret_cast<int32_t*>(w.path_hashes + (d.S + 2));
         w.q_warp = reinterpret_cast<float*>(w.sel + (d.S + 2));
     }
     __syncthreads();
-    if ((flags & STEP_AFTER) && wid == 0) {
+    if (flags & STEP_AFTER) {
         const long long ta = clock64();
-        mz_after_nn(d, s, g, &w, lane);
-        if (s.dbg && lane == 0) { s.dbg[(size_t)g * 8 + 4] += (unsigned long long)(clock64() - ta); }
+        mz_after_nn(d, s, g, &w, threadIdx.x, blockDim.x);
+        if (s.dbg && threadIdx.x == 0) { s.dbg[(size_t)g * 16 + 4] += (unsigned long long)(clock64() - ta); }
     }
     if (flags & STEP_BEFORE) {
         __threadfence_block();
@@ -314,12 +315,17 @@ int forward(mz_engine* e)
     return launch_heads(e, e->act[cur]);
 }
 
+size_t step_smem_bytes(const mz_dims& d)
+{
+    return (16 + sizeof(uint64_t) + sizeof(int32_t)) * static_cast<size_t>(d.S + 2) + sizeof(float) * STEP_WARPS * d.A;
+}
+
 int step(mz_engine* e, int flags, const uint8_t* rotations)
 {
     mz_state s = e->s;
     s.rotations = rotations;
     s.noise_in = (e->noise_enabled ? e->d_noise : nullptr);
-    k_step<<<e->d.B, 32 * STEP_WARPS, sizeof(uint64_t) * (e->d.S + 2) + sizeof(int32_t) * (e->d.S + 2) + sizeof(float) * STEP_WARPS * MZ_MAXA, e->stream>>>(e->d, s, flags);
+    k_step<<<e->d.B, 32 * STEP_WARPS, step_smem_bytes(e->d), e->stream>>>(e->d, s, flags);
     e->launches++;
     return MZ_OK;
 }
@@ -504,7 +510,7 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     for (int i = 0; i < 6; ++i) { guard(e->dalloc(&e->d_root_f[i], BA)); }
     guard(e->dalloc(&e->d_feat_f32, B * d.C * N * N));
     if (const char* env = std::getenv("MZ_DEBUG_TREE")) {
-        if (std::atoi(env) != 0) { guard(e->dalloc(&s.dbg, B * 8)); }
+        if (std::atoi(env) != 0) { guard(e->dalloc(&s.dbg, B * 16)); }
     }
     if (rc) {
         mz_destroy(e);
@@ -533,6 +539,10 @@ int mz_create(const mz_config* cfg, mz_engine** out)
         return fail(MZ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     }
     e->encode = reinterpret_cast<encode_tiled_fn>(fn);
+    if (cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(step_smem_bytes(d))) != cudaSuccess) {
+        mz_destroy(e);
+        return fail(MZ_ERR_CUDA, "k_step shared memory request refused");
+    }
     k_reset<<<d.B, 32, 0, e->stream>>>(d, s, -1);
     e->launches++;
     if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
@@ -954,7 +964,7 @@ int mz_debug_tree_timing(mz_engine* e, uint64_t* out)
     if (!e || !out) { return fail(MZ_ERR_ARG, "bad argument"); }
     if (!e->s.dbg) { return fail(MZ_ERR_STATE, "set MZ_DEBUG_TREE=1 before creating the engine"); }
     CUDA_OK(cudaSetDevice(e->cfg.device));
-    const size_t n = static_cast<size_t>(e->d.B) * 8;
+    const size_t n = static_cast<size_t>(e->d.B) * 16;
     CUDA_OK(cudaMemcpyAsync(out, e->s.dbg, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, e->stream));
     CUDA_OK(cudaStreamSynchronize(e->stream));
     CUDA_OK(cudaMemsetAsync(e->s.dbg, 0, sizeof(unsigned long long) * n, e->stream));

@@ -195,7 +195,7 @@ struct mz_state {
     const float* puct_bias;   // [S + 2] host-computed: (float)(init + log((1 + n + base) / base)), mcts.cpp:57
     const double* sqrt_table; // [S + 2] sqrt((double)n): IEEE-exact, identical to the host's sqrt (mcts.cpp:58)
     const uint64_t* keys;     // [2][361] Zobrist stone keys, go.cpp:19-32
-    unsigned long long* dbg;  // optional [B][8] per-phase cycle counters of the last before-NN step (profiling only)
+    unsigned long long* dbg;  // optional [B][16] per-phase cycle counters (profiling only)
 };
 
 // per-warp scratch (shared memory on the device)
@@ -210,7 +210,8 @@ struct mz_scratch {
     int turn, num_moves, last, last2;
     uint64_t* path_hashes; // [S + 2] position hashes of the nodes on the current path (shared memory on the device)
     int32_t* sel;          // [S + 2] child chosen at every level of the previous path by the speculative re-evaluation
-    float* q_warp;         // [num_warps][MZ_MAXA] per-warp Q scratch of the level evaluation
+    mz_hot* lvl_h;         // [S + 2] hot record of the node at every level of the guessed path
+    float* q_warp;         // [num_warps][A] per-warp Q scratch of the level evaluation
     int mismatch;          // first level whose re-evaluated choice differs from the previous path
     // block-wide leaf analysis (mz_env_legal_block)
     int label[MZ_MAXN * MZ_MAXN];  // block id of a stone = smallest cell index of its block
@@ -892,7 +893,7 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
     const mz_hot* hot = s.hot + (size_t)g * d.NP;
     int32_t* path = s.path + (size_t)g * (d.S + 2);
     int32_t* last_child = s.last_child + (size_t)g * d.NP;
-    float* q = w->q_warp + (size_t)wid * MZ_MAXA;
+    float* q = w->q_warp + (size_t)wid * d.A;
     const int tid = wid * MZ_W + lane;
     int glen = s.spec_len[g]; // length of the guessed path (uniform across the block)
     if (glen == 0) {
@@ -900,17 +901,30 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
         glen = 1;
     }
     int start = 0; // levels below `start` are confirmed
+    long long t_verify = 0, t_chase = 0, n_rounds = 0, n_checked = 0;
     for (;;) {
         if (tid == 0) { w->mismatch = glen - 1; }
         mz_block_sync();
+        const long long tv0 = mz_clock();
+        ++n_rounds;
+        n_checked += (glen - 1 - start > 0 ? glen - 1 - start : 0);
         // ---- check levels start .. glen-2 of the guess
         const int nlev = glen - 1 - start;
+        // all node records of the guess at once, and their children blocks on their way into L2, so that the per-level
+        // evaluations below do not each pay two dependent misses
+        for (int j = start + tid; j < glen - 1; j += nw * MZ_W) {
+            const mz_hot h = mz_load_hot(hot + path[j]);
+            w->lvl_h[j] = h;
+            const int cnc = (int)(h.link >> MZ_LINK_SHIFT), cfc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
+            for (int l = 0; l < cnc; l += 8) { mz_prefetch(hot + cfc + l); }
+        }
+        mz_block_sync();
         if (nlev > 0) {
             const bool by_thread = (nw > 1 && nlev > 3 * nw);
             if (by_thread) {
                 const int root_warp = nw - 1;
                 if (start == 0 && wid == root_warp) {
-                    const mz_hot h = mz_load_hot(hot + path[0]);
+                    const mz_hot h = w->lvl_h[0];
                     mz_hot c;
                     const int chosen = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u)) + mz_select_level(d, s, hot, h, true, root_turn, q, lane, c);
                     if (lane == 0) {
@@ -922,7 +936,7 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
                 if (wid != root_warp) {
                     for (int j = (start == 0 ? 1 : start) + tid; j < glen - 1; j += (nw - 1) * MZ_W) {
                         const int node = path[j];
-                        const int chosen = mz_select_level_serial(d, s, hot, mz_load_hot(hot + node), (j & 1) ? 3 - root_turn : root_turn);
+                        const int chosen = mz_select_level_serial(d, s, hot, w->lvl_h[j], (j & 1) ? 3 - root_turn : root_turn);
                         w->sel[j] = chosen;
                         last_child[node] = chosen;
                         if (chosen != path[j + 1]) { mz_atomic_min(&w->mismatch, j); }
@@ -931,7 +945,7 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
             } else {
                 for (int j = start + wid; j < glen - 1; j += nw) {
                     const int node = path[j];
-                    const mz_hot h = mz_load_hot(hot + node);
+                    const mz_hot h = w->lvl_h[j];
                     mz_hot c;
                     const int chosen = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u)) + mz_select_level(d, s, hot, h, j == 0, (j & 1) ? 3 - root_turn : root_turn, q, lane, c);
                     if (lane == 0) {
@@ -943,6 +957,8 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
             }
         }
         mz_block_sync();
+        const long long tv1 = mz_clock();
+        t_verify += tv1 - tv0;
         // ---- take the re-evaluated child at the first changed level, extend the guess along the hints (thread 0)
         if (tid == 0) {
             int level = w->mismatch;
@@ -964,6 +980,7 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
         mz_block_sync();
         const int confirmed = w->flag, new_len = w->shared_len;
         mz_block_sync();
+        t_chase += mz_clock() - tv1;
         if (new_len - 1 == confirmed) { // nothing left to check: finish serially from path[confirmed]
             glen = new_len;
             break;
@@ -972,6 +989,7 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
         glen = new_len;
     }
     int len = glen;
+    const long long ts0 = mz_clock();
     if (wid == 0) {
         int level = glen - 1;
         mz_hot h = mz_load_hot(hot + path[level]);
@@ -988,6 +1006,11 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
             mz_sync();
         }
         len = level + 1;
+        if (s.dbg && lane == 0) {
+            unsigned long long* o = s.dbg + (size_t)g * 16;
+            o[8] += (unsigned long long)t_verify, o[9] += (unsigned long long)t_chase, o[10] += (unsigned long long)(mz_clock() - ts0);
+            o[11] += (unsigned long long)n_rounds, o[12] += (unsigned long long)n_checked, o[13] += (unsigned long long)(len - glen);
+        }
     }
     return len;
 }
@@ -1120,7 +1143,7 @@ MZ_DEV void mz_before_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch*
         s.leaf_meta[g * 4 + 3] = num_legal;
         s.leaf_score[g] = score;
         if (s.dbg) {
-            unsigned long long* o = s.dbg + (size_t)g * 8;
+            unsigned long long* o = s.dbg + (size_t)g * 16;
             o[0] += (unsigned long long)(t1 - t0), o[1] += (unsigned long long)(t2 - t1), o[2] += (unsigned long long)(t3 - t2);
             o[3] += (unsigned long long)(mz_clock() - t3), o[5] += 1ull, o[6] = ((unsigned long long)len > o[6] ? (unsigned long long)len : o[6]);
             o[7] += (unsigned long long)len;
@@ -1131,10 +1154,10 @@ MZ_DEV void mz_before_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch*
 // One "after NN evaluation" step of game g (zero_actor.cpp:74-98): expand the leaf with the legal actions in
 // descending policy order (zero_actor.cpp:215-229, mcts.cpp:151-164), back the value up (mcts.cpp:166-179)
 // and mix the root noise in (zero_actor.cpp:194-204).
-MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int lane)
+MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int tid, int nthreads)
 {
     const int len = s.path_len[g];
-    if (len <= 0) { return; }
+    if (len <= 0) { return; } // uniform for the block
     const int A = d.A, N = d.N;
     mz_hot* hot = s.hot + (size_t)g * d.NP;
     const int32_t* path = s.path + (size_t)g * (d.S + 2);
@@ -1142,27 +1165,26 @@ MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* 
     const int terminal = s.leaf_meta[g * 4 + 0], rotation = s.leaf_meta[g * 4 + 2];
     float v;
     if (!terminal) {
-        for (int i = lane; i < MZ_LEGAL_WORDS; i += MZ_W) { w->legal[i] = s.leaf_legal[g * MZ_LEGAL_WORDS + i]; }
-        for (int a = lane; a < A; a += MZ_W) {
+        for (int i = tid; i < MZ_LEGAL_WORDS; i += nthreads) { w->legal[i] = s.leaf_legal[g * MZ_LEGAL_WORDS + i]; }
+        for (int a = tid; a < A; a += nthreads) {
             const int ra = mz_rotate(rotation, a, N); // getRotateAction, zero_actor.cpp:222
             w->pol[a] = s.policy[(size_t)g * A + ra];
             w->lg[a] = s.logits[(size_t)g * A + ra];
         }
-        mz_sync();
         const int first = s.cursor[g];
+        mz_block_sync();
         int k = 0;
-        for (int i = lane; i < MZ_LEGAL_WORDS; i += MZ_W) { k += mz_popc(w->legal[i]); }
-        k = mz_reduce_add(k);
-        // rank sort: descending policy, exact ties by ascending action id (std::sort is unstable there;
-        // DESIGN.md "candidate order")
-        for (int a = lane; a < A; a += MZ_W) {
+        for (int i = 0; i < MZ_LEGAL_WORDS; ++i) { k += mz_popc(w->legal[i]); }
+        // rank sort, one candidate per thread: descending policy, exact ties by ascending action id (std::sort is
+        // unstable there; DESIGN.md "candidate order")
+        for (int a = tid; a < A; a += nthreads) {
             if (!((w->legal[a >> 5] >> (a & 31)) & 1u)) { continue; }
             const float p = w->pol[a];
             int rank = 0;
             for (int b = 0; b < A; ++b) {
-                if (!((w->legal[b >> 5] >> (b & 31)) & 1u)) { continue; }
                 const float pb = w->pol[b];
-                rank += (pb > p) || (pb == p && b < a);
+                const bool legal_b = ((w->legal[b >> 5] >> (b & 31)) & 1u) != 0u;
+                rank += (legal_b && ((pb > p) || (pb == p && b < a))) ? 1 : 0;
             }
             const int c = first + rank;
             mz_store_hot(hot + c, 0.0f, 0.0f, p, 0u);
@@ -1172,33 +1194,32 @@ MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* 
             s.node_slot[(size_t)g * d.NP + c] = -1;
             s.last_child[(size_t)g * d.NP + c] = -1;
         }
-        mz_sync();
-        if (lane == 0) {
+        mz_block_sync();
+        if (tid == 0) {
             s.cursor[g] = first + k;
             const mz_hot h = mz_load_hot(hot + leaf);
             mz_store_hot(hot + leaf, h.count, h.mean, h.policy, (uint32_t)first | ((uint32_t)k << MZ_LINK_SHIFT));
         }
         v = s.nn_value[g];
         if (leaf == 0) {
-            for (int i = lane; i < A; i += MZ_W) { s.root_noise[(size_t)g * A + i] = 0.0f; }
-            if (s.noise_in) {
-                mz_sync();
-                const float eps = d.eps, one_minus = mz_fsub(1.0f, eps);
-                for (int i = lane; i < k; i += MZ_W) {
+            const float eps = d.eps, one_minus = mz_fsub(1.0f, eps);
+            for (int i = tid; i < A; i += nthreads) {
+                float nz = 0.0f;
+                if (s.noise_in && i < k) {
                     const mz_hot h = mz_load_hot(hot + first + i);
-                    const float nz = s.noise_in[(size_t)g * A + i];
-                    s.root_noise[(size_t)g * A + i] = nz;
+                    nz = s.noise_in[(size_t)g * A + i];
                     mz_store_hot(hot + first + i, h.count, h.mean, mz_fadd(mz_fmul(one_minus, h.policy), mz_fmul(eps, nz)), h.link);
                 }
+                s.root_noise[(size_t)g * A + i] = nz;
             }
         }
     } else {
         v = s.leaf_score[g];
     }
-    mz_sync();
+    mz_block_sync();
     // backup: every path node receives the same chain value discounted per level (reward is 0)
-    if (lane == 0) { s.value[(size_t)g * d.NP + leaf] = v; }
-    for (int i = lane; i < len; i += MZ_W) {
+    if (tid == 0) { s.value[(size_t)g * d.NP + leaf] = v; }
+    for (int i = tid; i < len; i += nthreads) {
         float x = v;
         if (d.discount == 1.0f) {
             if (i < len - 1 && x == 0.0f) { x = 0.0f; } // 0 + 1 * x: only -0 changes (to +0)
@@ -1211,8 +1232,8 @@ MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* 
         const float mean = mz_fadd(h.mean, mz_fdiv(mz_fmul(1.0f, mz_fsub(x, h.mean)), cnt));
         mz_store_hot(hot + n, cnt, mean, h.policy, h.link);
     }
-    mz_sync();
-    if (lane == 0) { s.path_len[g] = 0; }
+    mz_block_sync();
+    if (tid == 0) { s.path_len[g] = 0; }
 }
 
 // Tree::reset + ZeroActor::resetSearch (tree.h:64-69, zero_actor.cpp:29-34)

@@ -307,7 +307,7 @@ class Engine:
         return dict(conv_ms=c.value, tree_ms=t.value, heads_ms=h.value)
 
     def tree_timing(self):
-        out = np.zeros((self.B, 8), np.uint64)
+        out = np.zeros((self.B, 16), np.uint64)
         self._check(self.lib.mz_debug_tree_timing(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
         return out
 

@@ -34,3 +34,6 @@ if os.environ.get("MZ_DEBUG_TREE"):
     for i, n in enumerate(names):
         print("  %-14s %8.0f | %8.0f" % (n, per_step[:, i].mean(), per_step[:, i].max()))
     print("  path length mean %.1f, longest %d" % ((t[:, 7] / np.maximum(t[:, 5], 1)).mean(), t[:, 6].max()))
+    st = np.maximum(t[:, 5:6], 1)
+    d = t[:, 8:14] / st
+    print("  select detail per step (mean over games): check %.0f cyc, chase %.0f cyc, serial finish %.0f cyc; rounds %.2f, levels checked %.1f, serial levels %.2f" % tuple(d.mean(axis=0)))

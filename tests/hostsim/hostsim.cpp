@@ -43,6 +43,7 @@ sim* hs_create(int game, int N, int B, int S, float puct_base, float puct_init, 
     s.slot_st = zalloc<uint32_t>((size_t)B * (S + 1) * 2 * N), s.slot_hash = zalloc<uint64_t>((size_t)B * (S + 1)), s.slot_meta = zalloc<int32_t>((size_t)B * (S + 1) * 4);
     h->w.path_hashes = zalloc<uint64_t>(S + 2);
     h->w.sel = zalloc<int32_t>(S + 2);
+    h->w.lvl_h = zalloc<mz_hot>(S + 2);
     h->w.q_warp = zalloc<float>(MZ_MAXA);
     s.spec_len = zalloc<int32_t>(B);
     h->sqrt_table.resize(S + 2);
@@ -101,7 +102,7 @@ void hs_apply(sim* h, const float* policy, const float* logits, const float* val
     memcpy(h->s.nn_value, value, sizeof(float) * (size_t)d.B);
     if (noise) { memcpy(h->noise.data(), noise, sizeof(float) * (size_t)d.B * d.A); }
     h->s.noise_in = (noise ? h->noise.data() : nullptr);
-    for (int g = 0; g < d.B; ++g) { mz_after_nn(d, h->s, g, &h->w, 0); }
+    for (int g = 0; g < d.B; ++g) { mz_after_nn(d, h->s, g, &h->w, 0, 1); }
 }
 
 int hs_path_len(sim* h, int g) { return h->s.path_len[g]; }
