@@ -539,7 +539,10 @@ int mz_create(const mz_config* cfg, mz_engine** out)
         return fail(MZ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     }
     e->encode = reinterpret_cast<encode_tiled_fn>(fn);
-    if (cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(step_smem_bytes(d))) != cudaSuccess) {
+    // the attribute belongs to the function, not to the engine: only ever raise it (several engines may coexist)
+    static size_t step_smem_max = 0;
+    if (step_smem_bytes(d) > step_smem_max) { step_smem_max = step_smem_bytes(d); }
+    if (cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(step_smem_max)) != cudaSuccess) {
         mz_destroy(e);
         return fail(MZ_ERR_CUDA, "k_step shared memory request refused");
     }
