@@ -257,6 +257,29 @@ int launch_conv_resident(mz_engine* e, const CUtensorMap& in_ext, const ConvLaye
     return MZ_OK;
 }
 
+template <int BN, int STAGES>
+int launch_conv_pair(mz_engine* e, const CUtensorMap& in_ext, const ConvLayer& L, __half* out, const __half* residual)
+{
+    mznn::ConvResParams rp;
+    mznn::ConvParams& p = rp.c;
+    p.out = out, p.residual = residual, p.bias = reinterpret_cast<const float*>(e->d_blob + L.b_off);
+    p.rows_valid = e->d.B * e->d.slots, p.n1 = e->d.N + 1, p.slots = e->d.slots, p.cin = L.cin, p.cout = L.cout, p.relu = L.relu, p.krot = 0;
+    rp.rows_ext = e->rows_ext, rp.halo = e->d.N + 2, rp.num_mtiles = e->rows_alloc / mznn::BM, rp.base_off_mode = 0;
+    const int units = ((rp.num_mtiles + 1) / 2) * (L.cout / BN);
+    int clusters = e->num_sms / 2;
+    if (units < clusters) { clusters = units; }
+    const size_t smem = static_cast<size_t>(L.cin / mznn::BK) * e->rows_ext * 128 + static_cast<size_t>(STAGES) * (BN / 2) * mznn::BK * 2 + (2 * STAGES + 6) * 8 + 16 + 1024;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * 2), cfg.blockDim = dim3(mznn::CONV_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = e->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv3x3_pair_kernel<BN, STAGES>, in_ext, L.map_w_mc, rp));
+    e->launches++;
+    return MZ_OK;
+}
+
 int configure_conv_kernels()
 {
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_tcgen05_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mznn::ConvSmem<64, 4>::TOTAL));
@@ -266,11 +289,13 @@ int configure_conv_kernels()
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_pair_kernel<128, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return MZ_OK;
 }
 
 int conv(mz_engine* e, const CUtensorMap& in, const CUtensorMap& in_ext, const ConvLayer& L, __half* out, const __half* residual)
 {
+    if (e->conv_mode == 2) { return launch_conv_pair<128, 9>(e, in_ext, L, out, residual); }
     if (e->conv_mode == 1) {
         if (e->bn_tile == 64) { return launch_conv_resident<64, 6, 1>(e, in_ext, L, out, residual); }
         if (e->conv_cluster == 2) { return launch_conv_resident<128, 9, 2>(e, in_ext, L, out, residual); }
@@ -408,6 +433,13 @@ int alloc_net(mz_engine* e)
     if (e->bn_tile == 256) { e->conv_mode = 0; }
     const size_t need = (e->bn_tile == 64 ? resident_smem<64, 6>(e, e->cpad) : resident_smem<128, 9>(e, e->cpad));
     if (e->bn_tile == 64) { e->conv_cluster = 1; }
+    if (e->conv_mode == 2) { // CTA pairs: needs the 128-wide tile and half-tile weight boxes
+        if (e->bn_tile == 128 && need <= 227 * 1024) {
+            e->conv_cluster = 2;
+        } else {
+            e->conv_mode = 1;
+        }
+    }
     if (need > 227 * 1024) { e->conv_mode = 0; }
     cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->cfg.device);
     for (int i = 0; i < 3; ++i) {

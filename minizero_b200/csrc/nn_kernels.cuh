@@ -558,6 +558,251 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): two CTAs of a cluster issue ONE M=256 MMA over their two row tiles. Each CTA
+// keeps its own resident input block and only HALF of every weight tile (the tensor cores of both SMs read both halves),
+// so per SM the shared-memory traffic per MMA drops from A + B (at N = 128 exactly the 128 B/clk the SM can deliver,
+// before the TMA writes are added) to A + B/2, and the weight bytes arriving per SM halve. The leader CTA (cluster rank 0)
+// issues all MMAs; both CTAs run a producer warp (their loads signal the LEADER's barriers) and epilogue warps (each
+// drains its own TMEM half); stage / block / accumulator releases are committed to both CTAs at once.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void umma_f16_lohi_2sm(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_2sm_u32(uint32_t bar_addr)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_addr), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, uint64_t map_ptr, uint32_t leader_bar, int32_t c0, int32_t c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst), "l"(map_ptr),
+                 "r"(leader_bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar_addr, uint32_t cta_rank)
+{
+    asm volatile(
+        "{\n\t.reg .b32 remote;\n\t"
+        "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t}" ::"r"(local_bar_addr),
+        "r"(cta_rank)
+        : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w_half, const ConvResParams rp)
+{
+    const ConvParams& p = rp.c;
+    constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
+    constexpr uint32_t kPeerMask = 0xFEFFFFFFu; // cute/arch/copy_sm100_tma.hpp Sm100MmaPeerBitMask: address the leader CTA's barrier
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const int a_kb = p.cin / BK;
+    const int a_kb_bytes = rp.rows_ext * 128;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + a_kb * a_kb_bytes;
+    uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_HALF_BYTES);
+    uint64_t* b_empty = b_full + STAGES;
+    uint64_t* a_full = b_empty + STAGES;
+    uint64_t* a_empty = a_full + 1;
+    uint64_t* acc_full = a_empty + 1;   // [2]
+    uint64_t* acc_empty = acc_full + 2; // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nh = p.cout / BN;
+    const int crank = static_cast<int>(cluster_ctarank());
+    const bool leader = (crank == 0);
+    const int cid = blockIdx.x / 2, num_clusters = gridDim.x / 2;
+    const int units = ((rp.num_mtiles + 1) / 2) * nh;
+    const int u_begin = static_cast<int>((static_cast<long long>(cid) * units) / num_clusters);
+    const int u_end = static_cast<int>((static_cast<long long>(cid + 1) * units) / num_clusters);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_in)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w_half)) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 8); // the 4 epilogue warps of both CTAs
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) { // the same warp of both CTAs allocates the pair's TMEM columns
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t full0 = smem_u32(b_full), empty0 = smem_u32(b_empty);
+
+    if (warp == 0) {
+        { // ===== TMA producer (both CTAs): own input block, own half of every weight tile; completion goes to the leader =====
+            int s = 0, grp = u_begin / nh, half = u_begin - grp * nh, cur_mt = -1;
+            int mt = grp * 2 + crank;
+            uint32_t ph = 1, a_ph = 1;
+            const uint32_t b_dst0 = smem_u32(smem_b), a_dst0 = smem_u32(smem_a);
+            const uint64_t map_w_ptr = reinterpret_cast<uint64_t>(&map_w_half), map_in_ptr = reinterpret_cast<uint64_t>(&map_in);
+            const uint32_t a_full_leader = smem_u32(a_full) & kPeerMask;
+            for (int u = u_begin; u < u_end; ++u) {
+                if (mt != cur_mt) {
+                    mbar_wait_u32(smem_u32(a_empty), a_ph);
+                    a_ph ^= 1;
+                    if (elect_one_sync()) {
+                        if (leader) { mbar_arrive_expect_tx(a_full, 2 * a_kb * a_kb_bytes); }
+                        for (int kb = 0; kb < a_kb; ++kb) { tma_load_2d_2sm(a_dst0 + kb * a_kb_bytes, map_in_ptr, a_full_leader, kb * BK, mt * BM - rp.halo); }
+                    }
+                    __syncwarp();
+                    cur_mt = mt;
+                }
+                int wrow = half * BN + crank * (BN / 2);
+                for (int tap = 0; tap < 9; ++tap, wrow += p.cout) {
+                    for (int kc = 0; kc < p.cin; kc += BK) {
+                        mbar_wait_u32(empty0 + s * 8, ph);
+                        if (elect_one_sync()) {
+                            if (leader) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + s * 8), "r"(2 * B_HALF_BYTES) : "memory"); }
+                            tma_load_2d_2sm(b_dst0 + s * B_HALF_BYTES, map_w_ptr, (full0 + s * 8) & kPeerMask, kc, wrow);
+                        }
+                        __syncwarp();
+                        if (++s == STAGES) { s = 0, ph ^= 1; }
+                    }
+                }
+                if (++half == nh) { half = 0, mt += 2; }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader) { // ===== MMA issuer (leader CTA only): M = 256 over both CTAs' row tiles =====
+            constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN);
+            constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFFu) >> 4) | (1u << 16), b_lo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t a_kb_step = static_cast<uint32_t>(a_kb_bytes) >> 4;
+            int s = 0, grp = u_begin / nh, half = u_begin - grp * nh, cur_grp = -1, buf = 0;
+            uint32_t ph = 0, a_ph = 0, acc_ph0 = 1, acc_ph1 = 1;
+            for (int u = u_begin; u < u_end; ++u) {
+                if (grp != cur_grp) {
+                    mbar_wait_u32(smem_u32(a_full), a_ph);
+                    a_ph ^= 1;
+                    cur_grp = grp;
+                }
+                if (buf == 0) {
+                    mbar_wait_u32(smem_u32(&acc_empty[0]), acc_ph0);
+                    acc_ph0 ^= 1;
+                } else {
+                    mbar_wait_u32(smem_u32(&acc_empty[1]), acc_ph1);
+                    acc_ph1 ^= 1;
+                }
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * BN;
+                uint32_t accumulate = 0;
+                int row0 = rp.halo - p.n1 - 1;
+                for (int ty = 0; ty < 3; ++ty, row0 += p.n1 - 3) {
+                    for (int tx = 0; tx < 3; ++tx, ++row0) {
+                        uint32_t a_lo = a_lo0 + static_cast<uint32_t>(row0) * 8u;
+                        for (int kc = 0; kc < p.cin; kc += BK, a_lo += a_kb_step) {
+                            mbar_wait_u32(full0 + s * 8, ph);
+                            tcgen05_fence_after();
+                            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(s) * (B_HALF_BYTES >> 4);
+                            if (elect_one_sync()) {
+                                umma_f16_lohi_2sm(tmem_d, a_lo, b_lo, desc_hi, idesc, accumulate);
+                                umma_f16_lohi_2sm(tmem_d, a_lo + 2, b_lo + 2, desc_hi, idesc, 1u);
+                                umma_f16_lohi_2sm(tmem_d, a_lo + 4, b_lo + 4, desc_hi, idesc, 1u);
+                                umma_f16_lohi_2sm(tmem_d, a_lo + 6, b_lo + 6, desc_hi, idesc, 1u);
+                                tcgen05_commit_2sm_u32(empty0 + s * 8); // frees the stage in BOTH CTAs
+                            }
+                            __syncwarp();
+                            accumulate = 1u;
+                            if (++s == STAGES) { s = 0, ph ^= 1; }
+                        }
+                    }
+                }
+                if (++half == nh) { half = 0, ++grp; }
+                if (elect_one_sync()) {
+                    tcgen05_commit_2sm_u32(smem_u32(&acc_full[buf]));
+                    if (grp != cur_grp || u + 1 == u_end) { tcgen05_commit_2sm_u32(smem_u32(a_empty)); }
+                }
+                __syncwarp();
+                buf ^= 1;
+            }
+        }
+    } else { // ===== epilogue (both CTAs): own 128 rows of the pair's accumulator =====
+        const int quarter = warp & 3;
+        int ucount = 0;
+        for (int u = u_begin; u < u_end; ++u, ++ucount) {
+            const int grp = u / nh, half = u - grp * nh, buf = ucount & 1;
+            const int mt = grp * 2 + crank;
+            const int n0 = half * BN;
+            const int r = mt * BM + quarter * 32 + lane;
+            const int rr = r % p.slots;
+            const bool live = (r < p.rows_valid) && (rr / p.n1 != 0) && (rr % p.n1 != p.n1 - 1);
+            const bool in_range = (mt < rp.num_mtiles);
+            mbar_wait(&acc_full[buf], (ucount >> 1) & 1);
+            tcgen05_fence_after();
+            __half* out_row = p.out + static_cast<size_t>(r) * p.cout + n0;
+            const __half* res_row = (p.residual ? p.residual + static_cast<size_t>(r) * p.cout + n0 : nullptr);
+#pragma unroll 1
+            for (int c = 0; c < BN && in_range; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + c, v);
+                uint4 res[4];
+                if (res_row && live) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { res[q] = *reinterpret_cast<const uint4*>(res_row + c + q * 8); }
+                }
+                float4 bias4[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { bias4[q] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c) + q); }
+                const float* bias = reinterpret_cast<const float*>(bias4);
+                tmem_ld_wait();
+                uint4 packed[4];
+                uint32_t* pk = reinterpret_cast<uint32_t*>(packed);
+                const __half2* rh = reinterpret_cast<const __half2*>(res);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float x0 = __uint_as_float(v[2 * j]) + bias[2 * j];
+                    float x1 = __uint_as_float(v[2 * j + 1]) + bias[2 * j + 1];
+                    if (res_row && live) {
+                        const float2 rf = __half22float2(rh[j]);
+                        x0 += rf.x, x1 += rf.y;
+                    }
+                    if (p.relu) { x0 = fmaxf(x0, 0.0f), x1 = fmaxf(x1, 0.0f); }
+                    if (!live) { x0 = 0.0f, x1 = 0.0f; }
+                    const __half2 h = __floats2half2_rn(x0, x1);
+                    pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { *reinterpret_cast<uint4*>(out_row + c + q * 8) = packed[q]; }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u); } // the leader's barrier counts both CTAs
+        }
+    }
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // heads: one CTA per board. conv1x1 (+folded BN) + ReLU for the policy and value planes, then the
 // fully connected layers, softmax over the policy logits and tanh on the value. fp32 SIMT: 0.2 MFLOP / board.
 // ---------------------------------------------------------------------------------------------
