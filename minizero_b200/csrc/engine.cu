@@ -290,6 +290,7 @@ int configure_conv_kernels()
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_pair_kernel<128, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return MZ_OK;
 }
 
@@ -318,8 +319,13 @@ int launch_heads(mz_engine* e, const __half* act)
     p.policy = e->s.policy, p.logits = e->s.logits, p.value = e->s.nn_value;
     p.c = e->cpad, p.n = e->d.N, p.slots = e->d.slots, p.pol_ch = e->pol_ch, p.actions = e->d.A, p.vh = e->nd.num_value_hidden_channels;
     const int hw = e->d.N * e->d.N;
-    const size_t smem = sizeof(float) * ((p.pol_ch + 1) * hw + p.vh + p.actions + 32 + (p.pol_ch + 1) * p.c);
-    mznn::heads_kernel<<<e->d.B, 256, smem, e->stream>>>(p);
+    const size_t base = sizeof(float) * ((p.pol_ch + 1) * hw + p.vh + p.actions + 32 + (p.pol_ch + 1) * p.c);
+    const size_t fc = sizeof(float) * (static_cast<size_t>((p.pol_ch * hw * p.actions + 3) / 4) * 4 + static_cast<size_t>((hw * p.vh + 3) / 4) * 4);
+    p.batch = e->d.B;
+    p.fc_in_smem = (base + fc <= 200 * 1024 && e->d.B > e->num_sms / 2) ? 1 : 0; // staging pays off once CTAs serve >= 1 board each with reuse
+    const size_t smem = base + 16 + (p.fc_in_smem ? fc : 0);
+    const int grid = (p.fc_in_smem ? (e->d.B < e->num_sms ? e->d.B : e->num_sms) : e->d.B);
+    mznn::heads_kernel<<<grid, 256, smem, e->stream>>>(p);
     e->launches++;
     return MZ_OK;
 }

@@ -822,6 +822,8 @@ struct HeadParams {
     float* logits;      // [B][A]
     float* value;       // [B]
     int c, n, slots, pol_ch, actions, vh;
+    int batch;          // boards; CTAs loop over them
+    int fc_in_smem;     // 1: the transposed FC weights are staged in shared memory once per CTA
 };
 
 __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
@@ -833,10 +835,21 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
     float* vhid = planes + np1 * hw;    // [vh]
     float* lg = vhid + p.vh;            // [A]
     float* red = lg + p.actions;        // [32]
-    const int g = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
-    const __half* act = p.act + static_cast<size_t>(g) * p.slots * p.c;
+    const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
+    float* wfc = sm + (((np1 * p.c + np1 * hw + p.vh + p.actions + 32) + 3) & ~3); // 16-byte aligned: transposed FC weights when fc_in_smem
     for (int i = tid; i < np1 * p.c; i += nthr) { wc[i] = (i < p.pol_ch * p.c ? p.w_pc[i] : p.w_vc[i - p.pol_ch * p.c]); }
+    const int n_pf = p.pol_ch * hw * p.actions, n_v1 = hw * p.vh;
+    if (p.fc_in_smem) { // 16-byte vector copy: both arrays start 256-byte aligned and n_pf is padded to a multiple of 4 by the host
+        const int n_pf4 = (n_pf + 3) / 4, n_v14 = (n_v1 + 3) / 4;
+        float4* dst = reinterpret_cast<float4*>(wfc);
+        for (int i = tid; i < n_pf4; i += nthr) { dst[i] = __ldg(reinterpret_cast<const float4*>(p.w_pf) + i); }
+        for (int i = tid; i < n_v14; i += nthr) { dst[n_pf4 + i] = __ldg(reinterpret_cast<const float4*>(p.w_v1) + i); }
+    }
+    const float* w_pf = (p.fc_in_smem ? wfc : p.w_pf);
+    const float* w_v1 = (p.fc_in_smem ? wfc + ((n_pf + 3) / 4) * 4 : p.w_v1);
     __syncthreads();
+    for (int g = blockIdx.x; g < p.batch; g += gridDim.x) {
+    const __half* act = p.act + static_cast<size_t>(g) * p.slots * p.c;
     // 1x1 convolutions: one warp per cell; lane l owns channel pairs {2l + 64i}: every load instruction is one
     // contiguous 128-byte row segment and the weight reads from shared memory are conflict-free
     const int npair = p.c / 64; // half2 loads per lane (c is a multiple of 64)
@@ -873,13 +886,13 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
         if (o < p.actions) {
             const int nin = p.pol_ch * hw;
 #pragma unroll 8
-            for (int i = 0; i < nin; ++i) { acc = fmaf(planes[i], __ldg(p.w_pf + static_cast<size_t>(i) * p.actions + o), acc); }
+            for (int i = 0; i < nin; ++i) { acc = fmaf(planes[i], w_pf[static_cast<size_t>(i) * p.actions + o], acc); }
             lg[o] = acc + p.b_pf[o];
         } else {
             const int j = o - p.actions;
             const float* vp = planes + p.pol_ch * hw;
 #pragma unroll 8
-            for (int i = 0; i < hw; ++i) { acc = fmaf(vp[i], __ldg(p.w_v1 + static_cast<size_t>(i) * p.vh + j), acc); }
+            for (int i = 0; i < hw; ++i) { acc = fmaf(vp[i], w_v1[static_cast<size_t>(i) * p.vh + j], acc); }
             vhid[j] = fmaxf(acc + p.b_v1[j], 0.0f);
         }
     }
@@ -909,6 +922,8 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
         for (int j = tid; j < p.vh; j += 32) { acc = fmaf(vhid[j], p.w_v2[j], acc); }
         for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); }
         if (tid == 0) { p.value[g] = tanhf(acc + p.b_v2[0]); }
+    }
+    __syncthreads(); // planes / lg / vhid are reused by the next board
     }
 }
 
