@@ -322,10 +322,11 @@ int launch_heads(mz_engine* e, const __half* act)
     const size_t base = sizeof(float) * ((p.pol_ch + 1) * hw + p.vh + p.actions + 32 + (p.pol_ch + 1) * p.c);
     const size_t fc = sizeof(float) * (static_cast<size_t>((p.pol_ch * hw * p.actions + 3) / 4) * 4 + static_cast<size_t>((hw * p.vh + 3) / 4) * 4);
     p.batch = e->d.B;
-    p.fc_in_smem = (base + fc <= 200 * 1024 && e->d.B > e->num_sms / 2) ? 1 : 0; // staging pays off once CTAs serve >= 1 board each with reuse
-    const size_t smem = base + 16 + (p.fc_in_smem ? fc : 0);
-    const int grid = (p.fc_in_smem ? (e->d.B < e->num_sms ? e->d.B : e->num_sms) : e->d.B);
-    mznn::heads_kernel<<<grid, 256, smem, e->stream>>>(p);
+    p.fc_in_smem = 0; // staging the FC weights per CTA was measured slower than reading them from L2 with enough loads in flight
+    (void)fc;
+    const int threads = 1024;
+    const size_t smem = base + 16 + sizeof(float) * 4 * (p.actions + p.vh);
+    mznn::heads_kernel<<<e->d.B, threads, smem, e->stream>>>(p);
     e->launches++;
     return MZ_OK;
 }

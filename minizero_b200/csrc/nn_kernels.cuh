@@ -826,7 +826,7 @@ struct HeadParams {
     int fc_in_smem;     // 1: the transposed FC weights are staged in shared memory once per CTA
 };
 
-__global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
+__global__ void __launch_bounds__(1024) heads_kernel(const HeadParams p)
 {
     extern __shared__ float sm[];
     const int hw = p.n * p.n, n1 = p.n + 1, np1 = p.pol_ch + 1;
@@ -879,21 +879,36 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
         }
     }
     __syncthreads();
-    // policy fc and value fc1: one thread per output over TRANSPOSED weights [in][out] (coalesced across threads,
-    // independent loads the compiler can keep in flight)
-    for (int o = tid; o < p.actions + p.vh; o += nthr) {
-        float acc = 0.0f;
-        if (o < p.actions) {
-            const int nin = p.pol_ch * hw;
+    // policy fc and value fc1 over TRANSPOSED weights [in][out] (coalesced across threads). The input range of every output
+    // is split over `parts` threads so that enough independent loads are in flight; partial sums meet in shared memory.
+    {
+        const int nout = p.actions + p.vh;
+        const int parts = (nthr / nout >= 1 ? (nthr / nout > 4 ? 4 : nthr / nout) : 1);
+        float* partial = wfc; // [parts][nout] (the FC staging area is free when fc_in_smem == 0; sized by the host either way)
+        for (int t = tid; t < parts * nout; t += nthr) {
+            const int part = t / nout, o = t - part * nout;
+            float acc = 0.0f;
+            if (o < p.actions) {
+                const int nin = p.pol_ch * hw, i0 = (nin * part) / parts, i1 = (nin * (part + 1)) / parts;
 #pragma unroll 8
-            for (int i = 0; i < nin; ++i) { acc = fmaf(planes[i], w_pf[static_cast<size_t>(i) * p.actions + o], acc); }
-            lg[o] = acc + p.b_pf[o];
-        } else {
-            const int j = o - p.actions;
-            const float* vp = planes + p.pol_ch * hw;
+                for (int i = i0; i < i1; ++i) { acc = fmaf(planes[i], w_pf[static_cast<size_t>(i) * p.actions + o], acc); }
+            } else {
+                const int j = o - p.actions, i0 = (hw * part) / parts, i1 = (hw * (part + 1)) / parts;
+                const float* vp = planes + p.pol_ch * hw;
 #pragma unroll 8
-            for (int i = 0; i < hw; ++i) { acc = fmaf(vp[i], w_v1[static_cast<size_t>(i) * p.vh + j], acc); }
-            vhid[j] = fmaxf(acc + p.b_v1[j], 0.0f);
+                for (int i = i0; i < i1; ++i) { acc = fmaf(vp[i], w_v1[static_cast<size_t>(i) * p.vh + j], acc); }
+            }
+            partial[t] = acc;
+        }
+        __syncthreads();
+        for (int o = tid; o < nout; o += nthr) {
+            float acc = 0.0f;
+            for (int part = 0; part < parts; ++part) { acc += partial[part * nout + o]; }
+            if (o < p.actions) {
+                lg[o] = acc + p.b_pf[o];
+            } else {
+                vhid[o - p.actions] = fmaxf(acc + p.b_v1[o - p.actions], 0.0f);
+            }
         }
     }
     __syncthreads();
