@@ -290,7 +290,6 @@ int configure_conv_kernels()
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_pair_kernel<128, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(mznn::heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return MZ_OK;
 }
 
@@ -318,15 +317,15 @@ int launch_heads(mz_engine* e, const __half* act)
     p.w_pc = f(0), p.b_pc = f(1), p.w_pf = f(2), p.b_pf = f(3), p.w_vc = f(4), p.b_vc = f(5), p.w_v1 = f(6), p.b_v1 = f(7), p.w_v2 = f(8), p.b_v2 = f(9);
     p.policy = e->s.policy, p.logits = e->s.logits, p.value = e->s.nn_value;
     p.c = e->cpad, p.n = e->d.N, p.slots = e->d.slots, p.pol_ch = e->pol_ch, p.actions = e->d.A, p.vh = e->nd.num_value_hidden_channels;
-    const int hw = e->d.N * e->d.N;
-    const size_t base = sizeof(float) * ((p.pol_ch + 1) * hw + p.vh + p.actions + 32 + (p.pol_ch + 1) * p.c);
-    const size_t fc = sizeof(float) * (static_cast<size_t>((p.pol_ch * hw * p.actions + 3) / 4) * 4 + static_cast<size_t>((hw * p.vh + 3) / 4) * 4);
-    p.batch = e->d.B;
-    p.fc_in_smem = 0; // staging the FC weights per CTA was measured slower than reading them from L2 with enough loads in flight
-    (void)fc;
-    const int threads = 1024;
-    const size_t smem = base + 16 + sizeof(float) * 4 * (p.actions + p.vh);
-    mznn::heads_kernel<<<e->d.B, threads, smem, e->stream>>>(p);
+    const int hw = e->d.N * e->d.N, np1 = p.pol_ch + 1;
+    p.batch = e->d.B, p.fc_in_smem = 0;
+    const size_t smem = sizeof(float) * (np1 * p.c + np1 * hw + p.vh + p.actions + 32 + hw + 4 * (p.actions + p.vh));
+    switch (np1) {
+        case 2: mznn::heads_kernel<2><<<e->d.B, 256, smem, e->stream>>>(p); break;
+        case 3: mznn::heads_kernel<3><<<e->d.B, 256, smem, e->stream>>>(p); break;
+        case 4: mznn::heads_kernel<4><<<e->d.B, 256, smem, e->stream>>>(p); break;
+        default: return fail(MZ_ERR_ARG, "policy head with more than 3 planes is not supported");
+    }
     e->launches++;
     return MZ_OK;
 }
@@ -622,8 +621,8 @@ int mz_net_configure(mz_engine* e, const mz_net_dims* dims)
     if (dims->num_input_channels != e->d.C || dims->input_height != e->d.N || dims->input_width != e->d.N || dims->action_size != e->d.A) {
         return fail(MZ_ERR_ARG, "network dimensions do not match the game");
     }
-    if ((dims->action_size + dims->input_height * dims->input_width - 1) / (dims->input_height * dims->input_width) > 7) {
-        return fail(MZ_ERR_ARG, "policy head with more than 7 planes is not supported");
+    if ((dims->action_size + dims->input_height * dims->input_width - 1) / (dims->input_height * dims->input_width) > 3) {
+        return fail(MZ_ERR_ARG, "policy head with more than 3 planes is not supported");
     }
     if (dims->num_input_channels > MZ_NN_CPAD || dims->num_hidden_channels < 1 || dims->num_blocks < 0) { return fail(MZ_ERR_ARG, "unsupported network size"); }
     if (e->d_blob && std::memcmp(&e->nd, dims, sizeof(*dims)) != 0) {

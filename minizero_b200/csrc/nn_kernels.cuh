@@ -826,119 +826,111 @@ struct HeadParams {
     int fc_in_smem;     // 1: the transposed FC weights are staged in shared memory once per CTA
 };
 
-__global__ void __launch_bounds__(1024) heads_kernel(const HeadParams p)
+template <int NP1> // NP1 = policy planes + 1 value plane, a compile-time constant so that the plane loops carry no predicates
+__global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
 {
     extern __shared__ float sm[];
-    const int hw = p.n * p.n, n1 = p.n + 1, np1 = p.pol_ch + 1;
-    float* wc = sm;                     // [(pol_ch + 1)][c] 1x1 conv weights (first: float2 reads need 8-byte alignment)
-    float* planes = wc + np1 * p.c;     // [(pol_ch + 1)][hw]: policy planes then the value plane
-    float* vhid = planes + np1 * hw;    // [vh]
-    float* lg = vhid + p.vh;            // [A]
-    float* red = lg + p.actions;        // [32]
+    const int hw = p.n * p.n, n1 = p.n + 1;
+    float* wc = sm;                      // [NP1][c] 1x1 conv weights (first: float2 reads need 8-byte alignment)
+    float* planes = wc + NP1 * p.c;      // [NP1][hw]: policy planes then the value plane
+    float* vhid = planes + NP1 * hw;     // [vh]
+    float* lg = vhid + p.vh;             // [A]
+    float* red = lg + p.actions;         // [32]
+    int* rowoff = reinterpret_cast<int*>(red + 32); // [hw] element offset of every cell's activation row
+    float* partial = reinterpret_cast<float*>(rowoff + hw); // [parts][A + vh]
     const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
-    float* wfc = sm + (((np1 * p.c + np1 * hw + p.vh + p.actions + 32) + 3) & ~3); // 16-byte aligned: transposed FC weights when fc_in_smem
-    for (int i = tid; i < np1 * p.c; i += nthr) { wc[i] = (i < p.pol_ch * p.c ? p.w_pc[i] : p.w_vc[i - p.pol_ch * p.c]); }
-    const int n_pf = p.pol_ch * hw * p.actions, n_v1 = hw * p.vh;
-    if (p.fc_in_smem) { // 16-byte vector copy: both arrays start 256-byte aligned and n_pf is padded to a multiple of 4 by the host
-        const int n_pf4 = (n_pf + 3) / 4, n_v14 = (n_v1 + 3) / 4;
-        float4* dst = reinterpret_cast<float4*>(wfc);
-        for (int i = tid; i < n_pf4; i += nthr) { dst[i] = __ldg(reinterpret_cast<const float4*>(p.w_pf) + i); }
-        for (int i = tid; i < n_v14; i += nthr) { dst[n_pf4 + i] = __ldg(reinterpret_cast<const float4*>(p.w_v1) + i); }
-    }
-    const float* w_pf = (p.fc_in_smem ? wfc : p.w_pf);
-    const float* w_v1 = (p.fc_in_smem ? wfc + ((n_pf + 3) / 4) * 4 : p.w_v1);
-    __syncthreads();
-    for (int g = blockIdx.x; g < p.batch; g += gridDim.x) {
+    const int g = blockIdx.x;
     const __half* act = p.act + static_cast<size_t>(g) * p.slots * p.c;
-    // 1x1 convolutions: one warp per cell; lane l owns channel pairs {2l + 64i}: every load instruction is one
-    // contiguous 128-byte row segment and the weight reads from shared memory are conflict-free
-    const int npair = p.c / 64; // half2 loads per lane (c is a multiple of 64)
+    for (int i = tid; i < NP1 * p.c; i += nthr) { wc[i] = (i < p.pol_ch * p.c ? p.w_pc[i] : p.w_vc[i - p.pol_ch * p.c]); }
+    for (int cell = tid; cell < hw; cell += nthr) { rowoff[cell] = ((cell / p.n + 1) * n1 + cell % p.n) * p.c; }
+    __syncthreads();
+    // 1x1 convolutions: one warp per cell; lane l owns channel pairs {2l + 64i}: every load instruction is one contiguous
+    // 128-byte row segment and the weight reads from shared memory are conflict-free
+    const int npair = p.c / 64;
     for (int cell = warp; cell < hw; cell += nwarp) {
-        const __half2* row = reinterpret_cast<const __half2*>(act + static_cast<size_t>((cell / p.n + 1) * n1 + cell % p.n) * p.c);
-        float acc[8];
+        const __half2* row = reinterpret_cast<const __half2*>(act + rowoff[cell]);
+        float acc[NP1];
 #pragma unroll
-        for (int o = 0; o < 8; ++o) { acc[o] = 0.0f; }
+        for (int o = 0; o < NP1; ++o) { acc[o] = 0.0f; }
         for (int i = 0; i < npair; ++i) {
             const float2 a = __half22float2(row[lane + 32 * i]);
-            const int ch = 2 * lane + 64 * i;
+            const float* wp = wc + 2 * lane + 64 * i;
 #pragma unroll
-            for (int o = 0; o < 8; ++o) {
-                if (o < np1) {
-                    const float2 wv = *reinterpret_cast<const float2*>(wc + o * p.c + ch);
-                    acc[o] = fmaf(a.x, wv.x, fmaf(a.y, wv.y, acc[o]));
-                }
+            for (int o = 0; o < NP1; ++o) {
+                const float2 wv = *reinterpret_cast<const float2*>(wp + o * p.c);
+                acc[o] = fmaf(a.x, wv.x, fmaf(a.y, wv.y, acc[o]));
             }
         }
 #pragma unroll
-        for (int o = 0; o < 8; ++o) {
-            if (o < np1) {
-                float v = acc[o];
-                for (int sft = 16; sft > 0; sft >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, sft); }
-                if (lane == 0) { planes[o * hw + cell] = fmaxf(v + (o < p.pol_ch ? p.b_pc[o] : p.b_vc[0]), 0.0f); }
-            }
+        for (int o = 0; o < NP1; ++o) {
+            float v = acc[o];
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, sft); }
+            acc[o] = v;
+        }
+        if (lane < NP1) {
+            float v = acc[0];
+#pragma unroll
+            for (int o = 1; o < NP1; ++o) { v = (lane == o ? acc[o] : v); }
+            planes[lane * hw + cell] = fmaxf(v + (lane < p.pol_ch ? p.b_pc[lane] : p.b_vc[0]), 0.0f);
         }
     }
     __syncthreads();
-    // policy fc and value fc1 over TRANSPOSED weights [in][out] (coalesced across threads). The input range of every output
-    // is split over `parts` threads so that enough independent loads are in flight; partial sums meet in shared memory.
-    {
-        const int nout = p.actions + p.vh;
-        const int parts = (nthr / nout >= 1 ? (nthr / nout > 4 ? 4 : nthr / nout) : 1);
-        float* partial = wfc; // [parts][nout] (the FC staging area is free when fc_in_smem == 0; sized by the host either way)
-        for (int t = tid; t < parts * nout; t += nthr) {
-            const int part = t / nout, o = t - part * nout;
-            float acc = 0.0f;
-            if (o < p.actions) {
-                const int nin = p.pol_ch * hw, i0 = (nin * part) / parts, i1 = (nin * (part + 1)) / parts;
+    // policy fc and value fc1 over TRANSPOSED weights [in][out] (coalesced across threads); every output's input range is
+    // split over `parts` threads so that enough independent loads are in flight; partial sums meet in shared memory
+    const int nout = p.actions + p.vh;
+    const int parts = (nthr >= 4 * nout ? 4 : (nthr >= 2 * nout ? 2 : 1));
+    for (int t = tid; t < parts * nout; t += nthr) {
+        const int part = t / nout, o = t - part * nout;
+        float acc = 0.0f;
+        if (o < p.actions) {
+            const int nin = p.pol_ch * hw, i0 = (nin * part) / parts, i1 = (nin * (part + 1)) / parts;
+            const float* wp = p.w_pf + o;
 #pragma unroll 8
-                for (int i = i0; i < i1; ++i) { acc = fmaf(planes[i], w_pf[static_cast<size_t>(i) * p.actions + o], acc); }
-            } else {
-                const int j = o - p.actions, i0 = (hw * part) / parts, i1 = (hw * (part + 1)) / parts;
-                const float* vp = planes + p.pol_ch * hw;
+            for (int i = i0; i < i1; ++i) { acc = fmaf(planes[i], __ldg(wp + static_cast<size_t>(i) * p.actions), acc); }
+        } else {
+            const int i0 = (hw * part) / parts, i1 = (hw * (part + 1)) / parts;
+            const float* vp = planes + p.pol_ch * hw;
+            const float* wp = p.w_v1 + (o - p.actions);
 #pragma unroll 8
-                for (int i = i0; i < i1; ++i) { acc = fmaf(vp[i], w_v1[static_cast<size_t>(i) * p.vh + j], acc); }
-            }
-            partial[t] = acc;
+            for (int i = i0; i < i1; ++i) { acc = fmaf(vp[i], __ldg(wp + static_cast<size_t>(i) * p.vh), acc); }
         }
-        __syncthreads();
-        for (int o = tid; o < nout; o += nthr) {
-            float acc = 0.0f;
-            for (int part = 0; part < parts; ++part) { acc += partial[part * nout + o]; }
-            if (o < p.actions) {
-                lg[o] = acc + p.b_pf[o];
-            } else {
-                vhid[o - p.actions] = fmaxf(acc + p.b_v1[o - p.actions], 0.0f);
-            }
+        partial[t] = acc;
+    }
+    __syncthreads();
+    for (int o = tid; o < nout; o += nthr) {
+        float acc = 0.0f;
+        for (int part = 0; part < parts; ++part) { acc += partial[part * nout + o]; }
+        if (o < p.actions) {
+            lg[o] = acc + p.b_pf[o];
+        } else {
+            vhid[o - p.actions] = fmaxf(acc + p.b_v1[o - p.actions], 0.0f);
         }
     }
     __syncthreads();
-    // softmax over the logits (block reduction), value fc2 + tanh
-    float mx = -3.402823466e+38f;
-    for (int a = tid; a < p.actions; a += nthr) { mx = fmaxf(mx, lg[a]); }
-    for (int o = 16; o > 0; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
-    if (lane == 0) { red[warp] = mx; }
+    // softmax over the logits and value fc2 + tanh: warp 0 reduces, everybody normalises
+    if (warp == 0) {
+        float mx = -3.402823466e+38f;
+        for (int a = lane; a < p.actions; a += 32) { mx = fmaxf(mx, lg[a]); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+        float sum = 0.0f;
+        for (int a = lane; a < p.actions; a += 32) { sum += expf(lg[a] - mx); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); }
+        if (lane == 0) { red[0] = mx, red[1] = sum; }
+    } else if (warp == 1) {
+        float acc = 0.0f;
+        for (int j = lane; j < p.vh; j += 32) { acc = fmaf(vhid[j], p.w_v2[j], acc); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); }
+        if (lane == 0) { p.value[g] = tanhf(acc + p.b_v2[0]); }
+    }
     __syncthreads();
-    mx = red[0];
-    for (int i = 1; i < nwarp; ++i) { mx = fmaxf(mx, red[i]); }
-    __syncthreads();
-    float sum = 0.0f;
-    for (int a = tid; a < p.actions; a += nthr) { sum += expf(lg[a] - mx); }
-    for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); }
-    if (lane == 0) { red[warp] = sum; }
-    __syncthreads();
-    sum = 0.0f;
-    for (int i = 0; i < nwarp; ++i) { sum += red[i]; }
+    const float mx = red[0], inv = 1.0f / red[1];
     for (int a = tid; a < p.actions; a += nthr) {
         p.logits[static_cast<size_t>(g) * p.actions + a] = lg[a];
-        p.policy[static_cast<size_t>(g) * p.actions + a] = expf(lg[a] - mx) / sum;
-    }
-    if (tid < 32) {
-        float acc = 0.0f;
-        for (int j = tid; j < p.vh; j += 32) { acc = fmaf(vhid[j], p.w_v2[j], acc); }
-        for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); }
-        if (tid == 0) { p.value[g] = tanhf(acc + p.b_v2[0]); }
-    }
-    __syncthreads(); // planes / lg / vhid are reused by the next board
+        p.policy[static_cast<size_t>(g) * p.actions + a] = expf(lg[a] - mx) * inv;
     }
 }
 
