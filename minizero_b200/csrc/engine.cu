@@ -426,8 +426,9 @@ int alloc_net(mz_engine* e)
     if ((rc = e->dalloc(&e->d_blob, e->blob.size))) { return rc; }
     const size_t rows = e->rows_alloc;
     e->rows_ext = (mznn::BM + 2 * (e->d.N + 2) + 7) / 8 * 8;
-    // conv kernel variant: 1 = resident input block (default), 0 = every tap re-loads its shifted A tile
-    e->conv_mode = 1;
+    // conv kernel variant: 2 = CTA pairs (cta_group::2) over resident input blocks (default where the shape allows),
+    // 1 = one CTA per tile with a resident input block, 0 = every tap re-loads its shifted A tile
+    e->conv_mode = 2;
     if (const char* env = std::getenv("MZ_CONV_MODE")) { e->conv_mode = std::atoi(env); }
     if (const char* env = std::getenv("MZ_CONV_BASEOFF")) { e->base_off_mode = std::atoi(env); }
     if (const char* env = std::getenv("MZ_CONV_ROT")) { e->krot = std::atoi(env); }
