@@ -268,7 +268,7 @@ int launch_conv_pair(mz_engine* e, const CUtensorMap& in_ext, const ConvLayer& L
     const int units = ((rp.num_mtiles + 1) / 2) * (L.cout / BN);
     int clusters = e->num_sms / 2;
     if (units < clusters) { clusters = units; }
-    const size_t smem = static_cast<size_t>(L.cin / mznn::BK) * e->rows_ext * 128 + static_cast<size_t>(STAGES) * (BN / 2) * mznn::BK * 2 + (2 * STAGES + 6) * 8 + 16 + 1024;
+    const size_t smem = 2 * static_cast<size_t>(L.cin / mznn::BK) * e->rows_ext * 128 + static_cast<size_t>(STAGES) * (BN / 2) * mznn::BK * 2 + (2 * STAGES + 8) * 8 + 16 + 1024;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * 2), cfg.blockDim = dim3(mznn::CONV_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = e->stream;
     cudaLaunchAttribute attr[1];
@@ -289,13 +289,13 @@ int configure_conv_kernels()
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_pair_kernel<128, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_pair_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return MZ_OK;
 }
 
 int conv(mz_engine* e, const CUtensorMap& in, const CUtensorMap& in_ext, const ConvLayer& L, __half* out, const __half* residual)
 {
-    if (e->conv_mode == 2) { return launch_conv_pair<128, 9>(e, in_ext, L, out, residual); }
+    if (e->conv_mode == 2) { return launch_conv_pair<128, 8>(e, in_ext, L, out, residual); }
     if (e->conv_mode == 1) {
         if (e->bn_tile == 64) { return launch_conv_resident<64, 6, 1>(e, in_ext, L, out, residual); }
         if (e->conv_cluster == 2) { return launch_conv_resident<128, 9, 2>(e, in_ext, L, out, residual); }
@@ -441,7 +441,8 @@ int alloc_net(mz_engine* e)
     const size_t need = (e->bn_tile == 64 ? resident_smem<64, 6>(e, e->cpad) : resident_smem<128, 9>(e, e->cpad));
     if (e->bn_tile == 64) { e->conv_cluster = 1; }
     if (e->conv_mode == 2) { // CTA pairs: needs the 128-wide tile and half-tile weight boxes
-        if (e->bn_tile == 128 && need <= 227 * 1024) {
+        const size_t pair_need = 2 * static_cast<size_t>(e->cpad / mznn::BK) * e->rows_ext * 128 + 8 * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
+        if (e->bn_tile == 128 && pair_need <= 227 * 1024) {
             e->conv_cluster = 2;
         } else {
             e->conv_mode = 1;

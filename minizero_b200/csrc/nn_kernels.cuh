@@ -607,14 +607,15 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     const int a_kb = p.cin / BK;
     const int a_kb_bytes = rp.rows_ext * 128;
+    const int a_bytes = a_kb * a_kb_bytes; // one input block; two of them: the next row-tile group is prefetched during the current one
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + a_kb * a_kb_bytes;
+    uint8_t* smem_b = smem + 2 * a_bytes;
     uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_HALF_BYTES);
     uint64_t* b_empty = b_full + STAGES;
-    uint64_t* a_full = b_empty + STAGES;
-    uint64_t* a_empty = a_full + 1;
-    uint64_t* acc_full = a_empty + 1;   // [2]
-    uint64_t* acc_empty = acc_full + 2; // [2]
+    uint64_t* a_full = b_empty + STAGES; // [2]
+    uint64_t* a_empty = a_full + 2;      // [2]
+    uint64_t* acc_full = a_empty + 2;    // [2]
+    uint64_t* acc_empty = acc_full + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -633,9 +634,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
             mbar_init(&b_full[s], 1);
             mbar_init(&b_empty[s], 1);
         }
-        mbar_init(a_full, 1);
-        mbar_init(a_empty, 1);
         for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], 8); // the 4 epilogue warps of both CTAs
         }
@@ -652,26 +653,27 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t full0 = smem_u32(b_full), empty0 = smem_u32(b_empty);
+    const int g_first = u_begin / nh, g_last = (u_end - 1) / nh; // row-tile groups this cluster touches
 
     if (warp == 0) {
-        { // ===== TMA producer (both CTAs): own input block, own half of every weight tile; completion goes to the leader =====
-            int s = 0, grp = u_begin / nh, half = u_begin - grp * nh, cur_mt = -1;
-            int mt = grp * 2 + crank;
-            uint32_t ph = 1, a_ph = 1;
+        { // ===== TMA producer (both CTAs): own input blocks, own half of every weight tile; completion goes to the leader =====
+            int s = 0, grp = g_first, half = u_begin - g_first * nh;
+            uint32_t ph = 1;
             const uint32_t b_dst0 = smem_u32(smem_b), a_dst0 = smem_u32(smem_a);
             const uint64_t map_w_ptr = reinterpret_cast<uint64_t>(&map_w_half), map_in_ptr = reinterpret_cast<uint64_t>(&map_in);
-            const uint32_t a_full_leader = smem_u32(a_full) & kPeerMask;
-            for (int u = u_begin; u < u_end; ++u) {
-                if (mt != cur_mt) {
-                    mbar_wait_u32(smem_u32(a_empty), a_ph);
-                    a_ph ^= 1;
-                    if (elect_one_sync()) {
-                        if (leader) { mbar_arrive_expect_tx(a_full, 2 * a_kb * a_kb_bytes); }
-                        for (int kb = 0; kb < a_kb; ++kb) { tma_load_2d_2sm(a_dst0 + kb * a_kb_bytes, map_in_ptr, a_full_leader, kb * BK, mt * BM - rp.halo); }
-                    }
-                    __syncwarp();
-                    cur_mt = mt;
+            auto load_block = [&](int g) { // input block of group g into buffer (g - g_first) & 1
+                const int gi = g - g_first, buf = gi & 1;
+                mbar_wait_u32(smem_u32(&a_empty[buf]), ((gi >> 1) & 1) ^ 1); // the MMAs that read this buffer two groups ago are done
+                if (elect_one_sync()) {
+                    if (leader) { mbar_arrive_expect_tx(&a_full[buf], 2 * a_bytes); }
+                    const uint32_t bar = smem_u32(&a_full[buf]) & kPeerMask;
+                    for (int kb = 0; kb < a_kb; ++kb) { tma_load_2d_2sm(a_dst0 + buf * a_bytes + kb * a_kb_bytes, map_in_ptr, bar, kb * BK, (g * 2 + crank) * BM - rp.halo); }
                 }
+                __syncwarp();
+            };
+            if (u_begin < u_end) { load_block(g_first); }
+            int prefetched = g_first;
+            for (int u = u_begin; u < u_end; ++u) {
                 int wrow = half * BN + crank * (BN / 2);
                 for (int tap = 0; tap < 9; ++tap, wrow += p.cout) {
                     for (int kc = 0; kc < p.cin; kc += BK) {
@@ -684,7 +686,13 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
                         if (++s == STAGES) { s = 0, ph ^= 1; }
                     }
                 }
-                if (++half == nh) { half = 0, mt += 2; }
+                // the weights of this unit are on their way: now (the MMAs are at most STAGES K-blocks behind, far past the
+                // previous group) fetch the NEXT group's input block into the other buffer
+                if (prefetched == grp && grp < g_last) {
+                    load_block(grp + 1);
+                    prefetched = grp + 1;
+                }
+                if (++half == nh) { half = 0, ++grp; }
             }
         }
     } else if (warp == 1) {
@@ -692,13 +700,13 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
             constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN);
             constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
             const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFFu) >> 4) | (1u << 16), b_lo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | (1u << 16);
-            const uint32_t a_kb_step = static_cast<uint32_t>(a_kb_bytes) >> 4;
-            int s = 0, grp = u_begin / nh, half = u_begin - grp * nh, cur_grp = -1, buf = 0;
-            uint32_t ph = 0, a_ph = 0, acc_ph0 = 1, acc_ph1 = 1;
+            const uint32_t a_kb_step = static_cast<uint32_t>(a_kb_bytes) >> 4, a_buf_step = static_cast<uint32_t>(a_bytes) >> 4;
+            int s = 0, grp = g_first, half = u_begin - g_first * nh, cur_grp = -1, buf = 0;
+            uint32_t ph = 0, acc_ph0 = 1, acc_ph1 = 1;
             for (int u = u_begin; u < u_end; ++u) {
+                const int gi = grp - g_first, abuf = gi & 1;
                 if (grp != cur_grp) {
-                    mbar_wait_u32(smem_u32(a_full), a_ph);
-                    a_ph ^= 1;
+                    mbar_wait_u32(smem_u32(&a_full[abuf]), (gi >> 1) & 1);
                     cur_grp = grp;
                 }
                 if (buf == 0) {
@@ -714,7 +722,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
                 int row0 = rp.halo - p.n1 - 1;
                 for (int ty = 0; ty < 3; ++ty, row0 += p.n1 - 3) {
                     for (int tx = 0; tx < 3; ++tx, ++row0) {
-                        uint32_t a_lo = a_lo0 + static_cast<uint32_t>(row0) * 8u;
+                        uint32_t a_lo = a_lo0 + static_cast<uint32_t>(abuf) * a_buf_step + static_cast<uint32_t>(row0) * 8u;
                         for (int kc = 0; kc < p.cin; kc += BK, a_lo += a_kb_step) {
                             mbar_wait_u32(full0 + s * 8, ph);
                             tcgen05_fence_after();
@@ -735,7 +743,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
                 if (++half == nh) { half = 0, ++grp; }
                 if (elect_one_sync()) {
                     tcgen05_commit_2sm_u32(smem_u32(&acc_full[buf]));
-                    if (grp != cur_grp || u + 1 == u_end) { tcgen05_commit_2sm_u32(smem_u32(a_empty)); }
+                    if (grp != cur_grp || u + 1 == u_end) { tcgen05_commit_2sm_u32(smem_u32(&a_empty[abuf])); } // this input block is free again
                 }
                 __syncwarp();
                 buf ^= 1;

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <iostream>
 #include <sstream>
+#include <unistd.h>
 
 namespace {
 
@@ -97,6 +98,14 @@ int main(int argc, char** argv)
         std::cerr << "this worker implements the AlphaZero self-play path only" << std::endl;
         return -1;
     }
-    mzhost::Worker worker(cfg);
+    // stdout belongs to the wire protocol: the server drops the connection on anything but `SelfPlay` lines
+    // (zero/zero_server.cpp:130-139). Libraries in this process (NCCL prints its version banner to stdout) must not be able
+    // to write there, so the real stdout is kept on a private descriptor and fd 1 is pointed at stderr.
+    const int wire_fd = dup(1);
+    if (wire_fd < 0 || dup2(2, 1) < 0) {
+        std::cerr << "cannot set up the output descriptors" << std::endl;
+        return -1;
+    }
+    mzhost::Worker worker(cfg, wire_fd);
     return worker.run();
 }

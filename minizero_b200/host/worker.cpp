@@ -8,6 +8,7 @@
 #include <nccl.h>
 #include <random>
 #include <sstream>
+#include <unistd.h>
 
 namespace mzhost {
 
@@ -272,7 +273,16 @@ bool Worker::hostTerminal(const Game& game) const
 void Worker::emitGame(int g, bool terminal, float eval_score)
 {
     const std::string line = selfPlayLine(header_, games_[g].moves, terminal, eval_score, games_[g].turn);
-    std::cout << line << std::endl; // the only thing this process ever writes to stdout (zero_server.cpp:111-139)
+    const std::string out = line + "\n"; // the only thing this process ever writes to the server (zero_server.cpp:111-139)
+    size_t done = 0;
+    while (done < out.size()) {
+        const ssize_t n = write(wire_fd_, out.data() + done, out.size() - done);
+        if (n <= 0) {
+            std::cerr << "server connection closed" << std::endl;
+            std::exit(0);
+        }
+        done += static_cast<size_t>(n);
+    }
     ++games_finished_;
 }
 

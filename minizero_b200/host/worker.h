@@ -26,7 +26,7 @@ struct Game {                    // what BaseActor / ZeroActor keep per game on 
 
 class Worker {
 public:
-    explicit Worker(Config& cfg) : cfg_(cfg) {}
+    Worker(Config& cfg, int wire_fd) : cfg_(cfg), wire_fd_(wire_fd) {}
     ~Worker();
     int run(); // ActorGroup::run (actor_group.cpp:136-148)
 
@@ -42,6 +42,7 @@ private:
     void resetGameHost(int g);
 
     Config& cfg_;
+    int wire_fd_; // the zero server's end of the pipe (the process's original stdout)
     Random rng_;
     NetInfo net_;
     GameHeader header_;
