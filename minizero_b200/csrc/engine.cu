@@ -185,6 +185,8 @@ struct mz_engine {
     __half* act[3] = {nullptr, nullptr, nullptr};
     CUtensorMap map_in0, map_act[3];
     CUtensorMap map_in0_ext, map_act_ext[3]; // same buffers, box = the resident block of conv3x3_resident_kernel
+    mznn::TowerParams* tower = nullptr; // host copy of the fused-tower launch parameters (conv_mode 3)
+    int* d_tower_done = nullptr;
     int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148, krot = 0, conv_cluster = 1;
     encode_tiled_fn encode = nullptr;
 
@@ -290,6 +292,7 @@ int configure_conv_kernels()
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_pair_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return MZ_OK;
 }
 
@@ -334,6 +337,24 @@ int launch_heads(mz_engine* e, const __half* act)
 int forward(mz_engine* e)
 {
     if (!e->net_ready) { return fail(MZ_ERR_STATE, "network not finalized"); }
+    if (e->conv_mode == 3) {
+        const int num_groups = (e->tower->num_mtiles + 1) / 2;
+        CUDA_OK(cudaMemsetAsync(e->d_tower_done, 0, sizeof(int) * e->tower->num_layers * num_groups, e->stream));
+        const int units = num_groups * (e->cpad / 128);
+        int clusters = e->num_sms / 2;
+        if (units < clusters) { clusters = units; }
+        const size_t smem = 2 * static_cast<size_t>(e->cpad / mznn::BK) * e->rows_ext * 128 + 8 * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(clusters * 2), cfg.blockDim = dim3(mznn::CONV_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = e->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr, cfg.numAttrs = 1;
+        CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8>, *e->tower));
+        e->launches++;
+        const int last = static_cast<int>(e->convs.size()) - 1;
+        return launch_heads(e, e->tower->layer[last].out);
+    }
     int rc = conv(e, e->map_in0, e->map_in0_ext, e->convs[0], e->act[0], nullptr);
     if (rc) { return rc; }
     int cur = 0;
@@ -428,8 +449,10 @@ int alloc_net(mz_engine* e)
     e->rows_ext = (mznn::BM + 2 * (e->d.N + 2) + 7) / 8 * 8;
     // conv kernel variant: 2 = CTA pairs (cta_group::2) over resident input blocks (default where the shape allows),
     // 1 = one CTA per tile with a resident input block, 0 = every tap re-loads its shifted A tile
-    e->conv_mode = 2;
+    e->conv_mode = 3;
     if (const char* env = std::getenv("MZ_CONV_MODE")) { e->conv_mode = std::atoi(env); }
+    const bool want_tower = (e->conv_mode == 3);
+    if (want_tower) { e->conv_mode = 2; } // the tower needs everything the pair kernel needs
     if (const char* env = std::getenv("MZ_CONV_BASEOFF")) { e->base_off_mode = std::atoi(env); }
     if (const char* env = std::getenv("MZ_CONV_ROT")) { e->krot = std::atoi(env); }
     e->conv_cluster = 1; // CTAs per cluster sharing every weight tile by TMA multicast (1, 2 or 4)
@@ -460,6 +483,32 @@ int alloc_net(mz_engine* e)
     for (ConvLayer& L : e->convs) {
         if ((rc = make_map_2d(e, &L.map_w, e->d_blob + L.w_off, L.cin, 9ull * L.cout, mznn::BK, e->bn_tile))) { return rc; }
         if ((rc = make_map_2d(e, &L.map_w_mc, e->d_blob + L.w_off, L.cin, 9ull * L.cout, mznn::BK, e->bn_tile / e->conv_cluster))) { return rc; }
+    }
+    if (want_tower && e->conv_mode == 2 && static_cast<int>(e->convs.size()) <= mznn::TOWER_MAX_LAYERS) {
+        // whole-tower launch: same buffer rotation as forward() (cur -> t -> o per residual block)
+        e->tower = new mznn::TowerParams();
+        mznn::TowerParams& T = *e->tower;
+        T.num_layers = static_cast<int>(e->convs.size());
+        T.rows_valid = e->d.B * e->d.slots, T.n1 = e->d.N + 1, T.slots = e->d.slots, T.cout = e->cpad, T.rows_ext = e->rows_ext, T.halo = e->d.N + 2;
+        T.num_mtiles = e->rows_alloc / mznn::BM;
+        T.rotate = 27;
+        auto set = [&](int li, const CUtensorMap& in, __half* out, const __half* residual) {
+            mznn::TowerLayer& L = T.layer[li];
+            L.map_in = in, L.map_w = e->convs[li].map_w_mc, L.out = out, L.residual = residual;
+            L.bias = reinterpret_cast<const float*>(e->d_blob + e->convs[li].b_off), L.cin = e->convs[li].cin, L.relu = e->convs[li].relu;
+        };
+        set(0, e->map_in0_ext, e->act[0], nullptr);
+        int cur = 0;
+        for (int b = 0; b < e->nd.num_blocks; ++b) {
+            const int t = (cur + 1) % 3, o = (cur + 2) % 3;
+            set(1 + 2 * b, e->map_act_ext[cur], e->act[t], nullptr);
+            set(2 + 2 * b, e->map_act_ext[t], e->act[o], e->act[cur]);
+            cur = o;
+        }
+        const int num_groups = (T.num_mtiles + 1) / 2;
+        if ((rc = e->dalloc(&e->d_tower_done, static_cast<size_t>(T.num_layers) * num_groups))) { return rc; }
+        T.done = e->d_tower_done;
+        e->conv_mode = 3;
     }
     return MZ_OK;
 }
@@ -604,6 +653,7 @@ void mz_destroy(mz_engine* e)
     if (e->stream) { cudaStreamSynchronize(e->stream); }
     for (auto& kv : e->graphs) { cudaGraphExecDestroy(kv.second); }
     for (void* p : e->allocs) { cudaFree(p); }
+    delete e->tower;
     if (e->ev0) { cudaEventDestroy(e->ev0); }
     if (e->ev1) { cudaEventDestroy(e->ev1); }
     if (e->ev2) { cudaEventDestroy(e->ev2); }

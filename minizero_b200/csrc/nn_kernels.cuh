@@ -811,6 +811,311 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
+// Whole-tower variant: ALL 3x3 conv layers of the network (stem + 2 per residual block) in ONE persistent launch of CTA
+// pairs. Per launch the separate-kernel version pays launch gap + barrier / TMEM set-up + pipeline fill + a tail where the
+// CTAs with fewer units idle (measured: the tensor pipe is busy 45 % of a layer's wall time); here the set-up happens once,
+// the per-layer unit ranges rotate over the clusters so that nobody is systematically short of work, and a cluster moves on
+// to the next layer as soon as ITS inputs are complete: a unit (layer l, row-tile group g) only needs groups g-1, g, g+1 of
+// layer l-1 (the 3x3 halo), which it learns from per-(layer, group) completion counters in global memory
+// (release: epilogue stores -> __threadfence -> atomicAdd; acquire: producer polls with ld.acquire.gpu, then a
+// generic->async proxy fence before the TMA loads). All CTAs are co-resident (one per SM), and every wait points at a
+// strictly earlier layer, so the waits cannot cycle.
+// ---------------------------------------------------------------------------------------------
+constexpr int TOWER_MAX_LAYERS = 48;
+
+struct alignas(64) TowerLayer {
+    CUtensorMap map_in;     // input activations, box = resident block
+    CUtensorMap map_w;      // weights [9 * cout][cin], box = half tile
+    __half* out;
+    const __half* residual; // or null
+    const float* bias;
+    int cin;
+    int relu;
+};
+
+struct TowerParams {
+    TowerLayer layer[TOWER_MAX_LAYERS];
+    int num_layers;
+    int rows_valid, n1, slots, cout, rows_ext, halo, num_mtiles;
+    int rotate;   // cluster offset per layer for the unit ranges
+    int* done;    // [num_layers][num_groups] completion counters, zeroed before every launch
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_tower_kernel(const __grid_constant__ TowerParams tp)
+{
+    constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
+    constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const int a_kb_bytes = tp.rows_ext * 128;
+    const int a_bytes_max = (tp.cout / BK) * a_kb_bytes; // hidden layers have cin == cout; the stem is smaller
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + 2 * a_bytes_max;
+    uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_HALF_BYTES);
+    uint64_t* b_empty = b_full + STAGES;
+    uint64_t* a_full = b_empty + STAGES; // [2]
+    uint64_t* a_empty = a_full + 2;      // [2]
+    uint64_t* acc_full = a_empty + 2;    // [2]
+    uint64_t* acc_empty = acc_full + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nh = tp.cout / BN;
+    const int crank = static_cast<int>(cluster_ctarank());
+    const bool leader = (crank == 0);
+    const int cid = blockIdx.x / 2, nc = gridDim.x / 2;
+    const int num_groups = (tp.num_mtiles + 1) / 2;
+    const int units = num_groups * nh;
+    const int need = 8 * nh; // arrivals per (layer, group): 4 epilogue warps x 2 CTAs x nh halves
+
+    if (warp == 0 && lane == 0) {
+        for (int l = 0; l < tp.num_layers; ++l) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tp.layer[l].map_in)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tp.layer[l].map_w)) : "memory");
+        }
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t full0 = smem_u32(b_full), empty0 = smem_u32(b_empty);
+
+    // unit range of this cluster in layer l (rotated so that the uneven split does not always hit the same clusters)
+    auto range = [&](int l, int& ub, int& ue) {
+        const int cl = (cid + l * tp.rotate) % nc;
+        ub = static_cast<int>((static_cast<long long>(cl) * units) / nc);
+        ue = static_cast<int>((static_cast<long long>(cl + 1) * units) / nc);
+    };
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs) =====
+        int s = 0, gcount = 0; // gcount: input blocks loaded so far by this cluster (buffer = gcount & 1)
+        uint32_t ph = 1;
+        const uint32_t b_dst0 = smem_u32(smem_b), a_dst0 = smem_u32(smem_a);
+        auto load_block = [&](int l, int g) {
+            const TowerLayer& L = tp.layer[l];
+            const int buf = gcount & 1, a_kb = L.cin / BK;
+            if (l > 0) { // the 3x3 halo reaches into the neighbouring groups of the previous layer
+                if (lane == 0) {
+                    const int* d = tp.done + (l - 1) * num_groups;
+                    const int g0 = (g > 0 ? g - 1 : 0), g1 = (g + 1 < num_groups ? g + 1 : num_groups - 1);
+                    for (int gg = g0; gg <= g1; ++gg) {
+                        while (ld_acquire_gpu(d + gg) < need) { __nanosleep(64); }
+                    }
+                }
+                __syncwarp();
+                asm volatile("fence.proxy.async;" ::: "memory"); // generic-proxy writes of other SMs -> this warp's TMA (async proxy) reads
+            }
+            mbar_wait_u32(smem_u32(&a_empty[buf]), ((gcount >> 1) & 1) ^ 1);
+            if (elect_one_sync()) {
+                if (leader) { mbar_arrive_expect_tx(&a_full[buf], 2 * a_kb * a_kb_bytes); }
+                const uint32_t bar = smem_u32(&a_full[buf]) & kPeerMask;
+                const uint64_t map_in_ptr = reinterpret_cast<uint64_t>(&L.map_in);
+                for (int kb = 0; kb < a_kb; ++kb) { tma_load_2d_2sm(a_dst0 + buf * a_bytes_max + kb * a_kb_bytes, map_in_ptr, bar, kb * BK, (g * 2 + crank) * BM - tp.halo); }
+            }
+            __syncwarp();
+            ++gcount;
+        };
+        int next_l = 0, next_g = -1; // the block to load next (lookahead of one group)
+        {
+            int ub, ue;
+            range(0, ub, ue);
+            next_g = ub / nh;
+            load_block(0, next_g);
+        }
+        for (int l = 0; l < tp.num_layers; ++l) {
+            const TowerLayer& L = tp.layer[l];
+            const uint64_t map_w_ptr = reinterpret_cast<uint64_t>(&L.map_w);
+            int ub, ue;
+            range(l, ub, ue);
+            const int g_last = (ue - 1) / nh;
+            for (int u = ub; u < ue; ++u) {
+                const int grp = u / nh, half = u - grp * nh;
+                int wrow = half * BN + crank * (BN / 2);
+                for (int tap = 0; tap < 9; ++tap, wrow += tp.cout) {
+                    for (int kc = 0; kc < L.cin; kc += BK) {
+                        mbar_wait_u32(empty0 + s * 8, ph);
+                        if (elect_one_sync()) {
+                            if (leader) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + s * 8), "r"(2 * B_HALF_BYTES) : "memory"); }
+                            tma_load_2d_2sm(b_dst0 + s * B_HALF_BYTES, map_w_ptr, (full0 + s * 8) & kPeerMask, kc, wrow);
+                        }
+                        __syncwarp();
+                        if (++s == STAGES) { s = 0, ph ^= 1; }
+                    }
+                }
+                // this unit's weights are in flight: fetch the input block of the NEXT group (possibly of the next layer)
+                if (next_l == l && next_g == grp) {
+                    if (grp < g_last) {
+                        next_g = grp + 1;
+                        load_block(l, next_g);
+                    } else if (l + 1 < tp.num_layers) {
+                        int nb, ne;
+                        range(l + 1, nb, ne);
+                        next_l = l + 1, next_g = nb / nh;
+                        load_block(next_l, next_g);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader) { // ===== MMA issuer =====
+            constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN);
+            constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFFu) >> 4) | (1u << 16), b_lo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t a_kb_step = static_cast<uint32_t>(a_kb_bytes) >> 4, a_buf_step = static_cast<uint32_t>(a_bytes_max) >> 4;
+            int s = 0, buf = 0, gcount = -1, cur_key = -1;
+            uint32_t ph = 0, acc_ph0 = 1, acc_ph1 = 1;
+            for (int l = 0; l < tp.num_layers; ++l) {
+                const int cin = tp.layer[l].cin;
+                int ub, ue;
+                range(l, ub, ue);
+                for (int u = ub; u < ue; ++u) {
+                    const int grp = u / nh;
+                    const int key = l * 65536 + grp;
+                    if (key != cur_key) {
+                        ++gcount;
+                        mbar_wait_u32(smem_u32(&a_full[gcount & 1]), (gcount >> 1) & 1);
+                        cur_key = key;
+                    }
+                    const int abuf = gcount & 1;
+                    if (buf == 0) {
+                        mbar_wait_u32(smem_u32(&acc_empty[0]), acc_ph0);
+                        acc_ph0 ^= 1;
+                    } else {
+                        mbar_wait_u32(smem_u32(&acc_empty[1]), acc_ph1);
+                        acc_ph1 ^= 1;
+                    }
+                    tcgen05_fence_after();
+                    const uint32_t tmem_d = tmem_base + buf * BN;
+                    uint32_t accumulate = 0;
+                    int row0 = tp.halo - tp.n1 - 1;
+                    for (int ty = 0; ty < 3; ++ty, row0 += tp.n1 - 3) {
+                        for (int tx = 0; tx < 3; ++tx, ++row0) {
+                            uint32_t a_lo = a_lo0 + static_cast<uint32_t>(abuf) * a_buf_step + static_cast<uint32_t>(row0) * 8u;
+                            for (int kc = 0; kc < cin; kc += BK, a_lo += a_kb_step) {
+                                mbar_wait_u32(full0 + s * 8, ph);
+                                tcgen05_fence_after();
+                                const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(s) * (B_HALF_BYTES >> 4);
+                                if (elect_one_sync()) {
+                                    umma_f16_lohi_2sm(tmem_d, a_lo, b_lo, desc_hi, idesc, accumulate);
+                                    umma_f16_lohi_2sm(tmem_d, a_lo + 2, b_lo + 2, desc_hi, idesc, 1u);
+                                    umma_f16_lohi_2sm(tmem_d, a_lo + 4, b_lo + 4, desc_hi, idesc, 1u);
+                                    umma_f16_lohi_2sm(tmem_d, a_lo + 6, b_lo + 6, desc_hi, idesc, 1u);
+                                    tcgen05_commit_2sm_u32(empty0 + s * 8);
+                                }
+                                __syncwarp();
+                                accumulate = 1u;
+                                if (++s == STAGES) { s = 0, ph ^= 1; }
+                            }
+                        }
+                    }
+                    const bool last_of_group = (u + 1 == ue) || ((u + 1) / nh != grp);
+                    if (elect_one_sync()) {
+                        tcgen05_commit_2sm_u32(smem_u32(&acc_full[buf]));
+                        if (last_of_group) { tcgen05_commit_2sm_u32(smem_u32(&a_empty[abuf])); }
+                    }
+                    __syncwarp();
+                    buf ^= 1;
+                }
+            }
+        }
+    } else { // ===== epilogue (both CTAs) =====
+        const int quarter = warp & 3;
+        int ucount = 0;
+        for (int l = 0; l < tp.num_layers; ++l) {
+            const TowerLayer& L = tp.layer[l];
+            int ub, ue;
+            range(l, ub, ue);
+            for (int u = ub; u < ue; ++u, ++ucount) {
+                const int grp = u / nh, half = u - grp * nh, buf = ucount & 1;
+                const int mt = grp * 2 + crank;
+                const int n0 = half * BN;
+                const int r = mt * BM + quarter * 32 + lane;
+                const int rr = r % tp.slots;
+                const bool live = (r < tp.rows_valid) && (rr / tp.n1 != 0) && (rr % tp.n1 != tp.n1 - 1);
+                const bool in_range = (mt < tp.num_mtiles);
+                mbar_wait(&acc_full[buf], (ucount >> 1) & 1);
+                tcgen05_fence_after();
+                __half* out_row = L.out + static_cast<size_t>(r) * tp.cout + n0;
+                const __half* res_row = (L.residual ? L.residual + static_cast<size_t>(r) * tp.cout + n0 : nullptr);
+#pragma unroll 1
+                for (int c = 0; c < BN && in_range; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + c, v);
+                    uint4 res[4];
+                    if (res_row && live) { // written by other SMs earlier in this launch: read through L2, never through this SM's L1
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { res[q] = __ldcg(reinterpret_cast<const uint4*>(res_row + c + q * 8)); }
+                    }
+                    float4 bias4[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { bias4[q] = __ldg(reinterpret_cast<const float4*>(L.bias + n0 + c) + q); }
+                    const float* bias = reinterpret_cast<const float*>(bias4);
+                    tmem_ld_wait();
+                    uint4 packed[4];
+                    uint32_t* pk = reinterpret_cast<uint32_t*>(packed);
+                    const __half2* rh = reinterpret_cast<const __half2*>(res);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float x0 = __uint_as_float(v[2 * j]) + bias[2 * j];
+                        float x1 = __uint_as_float(v[2 * j + 1]) + bias[2 * j + 1];
+                        if (res_row && live) {
+                            const float2 rf = __half22float2(rh[j]);
+                            x0 += rf.x, x1 += rf.y;
+                        }
+                        if (L.relu) { x0 = fmaxf(x0, 0.0f), x1 = fmaxf(x1, 0.0f); }
+                        if (!live) { x0 = 0.0f, x1 = 0.0f; }
+                        const __half2 h = __floats2half2_rn(x0, x1);
+                        pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { *reinterpret_cast<uint4*>(out_row + c + q * 8) = packed[q]; }
+                }
+                tcgen05_fence_before();
+                __threadfence(); // this warp's rows of (layer l, group grp) are visible device-wide before the counter moves
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u);
+                    atomicAdd(tp.done + l * num_groups + grp, 1);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // heads: one CTA per board. conv1x1 (+folded BN) + ReLU for the policy and value planes, then the
 // fully connected layers, softmax over the policy logits and tanh on the value. fp32 SIMT: 0.2 MFLOP / board.
 // ---------------------------------------------------------------------------------------------
