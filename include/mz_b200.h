@@ -137,6 +137,10 @@ int mz_profile_kernels(mz_engine* e, int32_t iters, float* conv_ms, float* tree_
  * analysis, feature planes, expand + backup}, number of steps, longest path, sum of path lengths, then selection detail:
  * cycles in {guess checking, hint chasing, serial finish}, check rounds, levels checked, levels finished serially, 2 unused */
 int mz_debug_tree_timing(mz_engine* e, uint64_t* out);
+/* per-CTA cycle counters of one launch of the fused tower kernel (engine created with MZ_DEBUG_TOWER=1): out [max_ctas][8] =
+ * {producer total, producer waiting for the previous layer's groups, producer waiting for a free weight stage,
+ *  MMA total, MMA waiting for the input block, for a free accumulator, for weights, epilogue busy}; returns the CTAs written */
+int mz_debug_tower_timing(mz_engine* e, uint64_t* out, int32_t max_ctas);
 /* kernels launched by this engine so far */
 int64_t mz_launch_count(const mz_engine* e);
 

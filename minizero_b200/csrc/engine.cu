@@ -292,7 +292,8 @@ int configure_conv_kernels()
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_resident_kernel<128, 9, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_pair_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return MZ_OK;
 }
 
@@ -350,7 +351,11 @@ int forward(mz_engine* e)
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr, cfg.numAttrs = 1;
-        CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8>, *e->tower));
+        if (e->tower->dbg) {
+            CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8, true>, *e->tower));
+        } else {
+            CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8, false>, *e->tower));
+        }
         e->launches++;
         const int last = static_cast<int>(e->convs.size()) - 1;
         return launch_heads(e, e->tower->layer[last].out);
@@ -491,7 +496,9 @@ int alloc_net(mz_engine* e)
         T.num_layers = static_cast<int>(e->convs.size());
         T.rows_valid = e->d.B * e->d.slots, T.n1 = e->d.N + 1, T.slots = e->d.slots, T.cout = e->cpad, T.rows_ext = e->rows_ext, T.halo = e->d.N + 2;
         T.num_mtiles = e->rows_alloc / mznn::BM;
-        T.rotate = 27;
+        T.rotate = 0, T.shift = 1;
+        if (const char* env = std::getenv("MZ_TOWER_ROT")) { T.rotate = std::atoi(env); }
+        if (const char* env = std::getenv("MZ_TOWER_SHIFT")) { T.shift = std::atoi(env); }
         auto set = [&](int li, const CUtensorMap& in, __half* out, const __half* residual) {
             mznn::TowerLayer& L = T.layer[li];
             L.map_in = in, L.map_w = e->convs[li].map_w_mc, L.out = out, L.residual = residual;
@@ -508,6 +515,14 @@ int alloc_net(mz_engine* e)
         const int num_groups = (T.num_mtiles + 1) / 2;
         if ((rc = e->dalloc(&e->d_tower_done, static_cast<size_t>(T.num_layers) * num_groups))) { return rc; }
         T.done = e->d_tower_done;
+        T.dbg = nullptr;
+        if (const char* env = std::getenv("MZ_DEBUG_TOWER")) {
+            if (std::atoi(env) != 0) {
+                unsigned long long* buf = nullptr;
+                if ((rc = e->dalloc(&buf, static_cast<size_t>(e->num_sms) * 8))) { return rc; }
+                T.dbg = buf;
+            }
+        }
         e->conv_mode = 3;
     }
     return MZ_OK;
@@ -1062,6 +1077,19 @@ int mz_debug_tree_timing(mz_engine* e, uint64_t* out)
     CUDA_OK(cudaStreamSynchronize(e->stream));
     CUDA_OK(cudaMemsetAsync(e->s.dbg, 0, sizeof(unsigned long long) * n, e->stream));
     return MZ_OK;
+}
+
+int mz_debug_tower_timing(mz_engine* e, uint64_t* out, int32_t max_ctas)
+{
+    if (!e || !out) { return fail(MZ_ERR_ARG, "bad argument"); }
+    if (!e->tower || !e->tower->dbg) { return fail(MZ_ERR_STATE, "set MZ_DEBUG_TOWER=1 before loading the network"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    int rc = forward(e);
+    if (rc) { return rc; }
+    const int n = (max_ctas < e->num_sms ? max_ctas : e->num_sms);
+    CUDA_OK(cudaMemcpyAsync(out, e->tower->dbg, sizeof(unsigned long long) * 8 * n, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    return n;
 }
 
 int mz_profile_kernels(mz_engine* e, int32_t iters, float* conv_ms, float* tree_ms, float* heads_ms)

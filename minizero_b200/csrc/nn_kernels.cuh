@@ -838,7 +838,9 @@ struct TowerParams {
     int num_layers;
     int rows_valid, n1, slots, cout, rows_ext, halo, num_mtiles;
     int rotate;   // cluster offset per layer for the unit ranges
+    int shift;    // unit offset per layer: position q of layer l is unit (q + l * shift) mod units
     int* done;    // [num_layers][num_groups] completion counters, zeroed before every launch
+    unsigned long long* dbg; // optional [grid][8] cycle counters (profiling)
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p)
@@ -848,7 +850,7 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p)
     return v;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool DBG>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tower_kernel(const __grid_constant__ TowerParams tp)
 {
@@ -907,29 +909,46 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
     const uint32_t full0 = smem_u32(b_full), empty0 = smem_u32(b_empty);
 
     // unit range of this cluster in layer l (rotated so that the uneven split does not always hit the same clusters)
+    // (ub .. ue are positions in the layer's unit order; position q is unit (q + l * shift) mod units, so the range borders
+    //  slide from layer to layer and a range that is long in one layer leans on shorter ones in the next)
     auto range = [&](int l, int& ub, int& ue) {
         const int cl = (cid + l * tp.rotate) % nc;
         ub = static_cast<int>((static_cast<long long>(cl) * units) / nc);
         ue = static_cast<int>((static_cast<long long>(cl + 1) * units) / nc);
     };
+    auto unit_of = [&](int l, int q) { return (q + l * tp.shift) % units; };
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs) =====
         int s = 0, gcount = 0; // gcount: input blocks loaded so far by this cluster (buffer = gcount & 1)
         uint32_t ph = 1;
+        long long t_dep = 0, t_bempty = 0;
+        const long long t_start = (DBG ? clock64() : 0ll);
         const uint32_t b_dst0 = smem_u32(smem_b), a_dst0 = smem_u32(smem_a);
-        auto load_block = [&](int l, int g) {
+        // input block of (layer l, group g) into buffer gcount & 1. blocking == false: give up (return false) when the previous
+        // layer's groups g-1 .. g+1 are not complete yet — a prefetch must never hold back the weight loads of the current unit
+        auto load_block = [&](int l, int g, bool blocking) -> bool {
             const TowerLayer& L = tp.layer[l];
             const int buf = gcount & 1, a_kb = L.cin / BK;
             if (l > 0) { // the 3x3 halo reaches into the neighbouring groups of the previous layer
+                const long long td = (DBG ? clock64() : 0ll);
+                int ready = 1;
                 if (lane == 0) {
                     const int* d = tp.done + (l - 1) * num_groups;
                     const int g0 = (g > 0 ? g - 1 : 0), g1 = (g + 1 < num_groups ? g + 1 : num_groups - 1);
-                    for (int gg = g0; gg <= g1; ++gg) {
-                        while (ld_acquire_gpu(d + gg) < need) { __nanosleep(64); }
+                    for (int gg = g0; gg <= g1 && ready; ++gg) {
+                        while (ld_acquire_gpu(d + gg) < need) {
+                            if (!blocking) {
+                                ready = 0;
+                                break;
+                            }
+                            __nanosleep(32);
+                        }
                     }
                 }
-                __syncwarp();
+                ready = __shfl_sync(0xffffffffu, ready, 0);
+                t_dep += (DBG ? clock64() : 0ll) - td;
+                if (!ready) { return false; }
                 asm volatile("fence.proxy.async;" ::: "memory"); // generic-proxy writes of other SMs -> this warp's TMA (async proxy) reads
             }
             mbar_wait_u32(smem_u32(&a_empty[buf]), ((gcount >> 1) & 1) ^ 1);
@@ -941,26 +960,56 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
             }
             __syncwarp();
             ++gcount;
+            return true;
         };
-        int next_l = 0, next_g = -1; // the block to load next (lookahead of one group)
+        // the block sequence of this cluster: groups in unit order, layer after layer
+        int next_l = 0, next_q = 0; // position (in layer next_l's unit order) of the first unit of the next block to load
+        bool next_valid = true;
         {
             int ub, ue;
             range(0, ub, ue);
-            next_g = ub / nh;
-            load_block(0, next_g);
+            next_q = ub;
         }
+        auto advance_next = [&]() { // step to the first unit of the following group of this cluster
+            int ub, ue;
+            range(next_l, ub, ue);
+            const int g = unit_of(next_l, next_q) / nh;
+            int q = next_q + 1;
+            while (q < ue && unit_of(next_l, q) / nh == g) { ++q; }
+            if (q < ue) {
+                next_q = q;
+            } else if (next_l + 1 < tp.num_layers) {
+                ++next_l;
+                range(next_l, ub, ue);
+                next_q = ub;
+            } else {
+                next_valid = false;
+            }
+        };
+        int used = 0; // blocks consumed by the units issued so far (the MMA warp counts the same way)
+        int cur_key = -1;
         for (int l = 0; l < tp.num_layers; ++l) {
             const TowerLayer& L = tp.layer[l];
             const uint64_t map_w_ptr = reinterpret_cast<uint64_t>(&L.map_w);
             int ub, ue;
             range(l, ub, ue);
-            const int g_last = (ue - 1) / nh;
-            for (int u = ub; u < ue; ++u) {
+            for (int q = ub; q < ue; ++q) {
+                const int u = unit_of(l, q);
                 const int grp = u / nh, half = u - grp * nh;
+                if (l * 65536 + grp != cur_key) {
+                    cur_key = l * 65536 + grp;
+                    ++used;
+                    if (gcount < used) { // not prefetched: now it is needed, wait for it
+                        load_block(next_l, unit_of(next_l, next_q) / nh, true);
+                        advance_next();
+                    }
+                }
                 int wrow = half * BN + crank * (BN / 2);
                 for (int tap = 0; tap < 9; ++tap, wrow += tp.cout) {
                     for (int kc = 0; kc < L.cin; kc += BK) {
+                        const long long te = (DBG ? clock64() : 0ll);
                         mbar_wait_u32(empty0 + s * 8, ph);
+                        t_bempty += (DBG ? clock64() : 0ll) - te;
                         if (elect_one_sync()) {
                             if (leader) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + s * 8), "r"(2 * B_HALF_BYTES) : "memory"); }
                             tma_load_2d_2sm(b_dst0 + s * B_HALF_BYTES, map_w_ptr, (full0 + s * 8) & kPeerMask, kc, wrow);
@@ -969,19 +1018,16 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                         if (++s == STAGES) { s = 0, ph ^= 1; }
                     }
                 }
-                // this unit's weights are in flight: fetch the input block of the NEXT group (possibly of the next layer)
-                if (next_l == l && next_g == grp) {
-                    if (grp < g_last) {
-                        next_g = grp + 1;
-                        load_block(l, next_g);
-                    } else if (l + 1 < tp.num_layers) {
-                        int nb, ne;
-                        range(l + 1, nb, ne);
-                        next_l = l + 1, next_g = nb / nh;
-                        load_block(next_l, next_g);
-                    }
+                // this unit's weights are in flight: try to fetch the next group's input block into the other buffer
+                if (next_valid && gcount == used) {
+                    if (load_block(next_l, unit_of(next_l, next_q) / nh, false)) { advance_next(); }
                 }
             }
+        }
+        if (DBG && tp.dbg && lane == 0) {
+            tp.dbg[blockIdx.x * 8 + 0] = (DBG ? clock64() : 0ll) - t_start;
+            tp.dbg[blockIdx.x * 8 + 1] = t_dep;
+            tp.dbg[blockIdx.x * 8 + 2] = t_bempty;
         }
     } else if (warp == 1) {
         if (leader) { // ===== MMA issuer =====
@@ -991,19 +1037,24 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
             const uint32_t a_kb_step = static_cast<uint32_t>(a_kb_bytes) >> 4, a_buf_step = static_cast<uint32_t>(a_bytes_max) >> 4;
             int s = 0, buf = 0, gcount = -1, cur_key = -1;
             uint32_t ph = 0, acc_ph0 = 1, acc_ph1 = 1;
+            long long t_afull = 0, t_acc = 0, t_bfull = 0;
+            const long long t_start = (DBG ? clock64() : 0ll);
             for (int l = 0; l < tp.num_layers; ++l) {
                 const int cin = tp.layer[l].cin;
                 int ub, ue;
                 range(l, ub, ue);
-                for (int u = ub; u < ue; ++u) {
-                    const int grp = u / nh;
+                for (int q = ub; q < ue; ++q) {
+                    const int grp = unit_of(l, q) / nh;
                     const int key = l * 65536 + grp;
                     if (key != cur_key) {
                         ++gcount;
+                        const long long ta = (DBG ? clock64() : 0ll);
                         mbar_wait_u32(smem_u32(&a_full[gcount & 1]), (gcount >> 1) & 1);
+                        t_afull += (DBG ? clock64() : 0ll) - ta;
                         cur_key = key;
                     }
                     const int abuf = gcount & 1;
+                    const long long tc = (DBG ? clock64() : 0ll);
                     if (buf == 0) {
                         mbar_wait_u32(smem_u32(&acc_empty[0]), acc_ph0);
                         acc_ph0 ^= 1;
@@ -1011,6 +1062,7 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                         mbar_wait_u32(smem_u32(&acc_empty[1]), acc_ph1);
                         acc_ph1 ^= 1;
                     }
+                    t_acc += (DBG ? clock64() : 0ll) - tc;
                     tcgen05_fence_after();
                     const uint32_t tmem_d = tmem_base + buf * BN;
                     uint32_t accumulate = 0;
@@ -1019,7 +1071,9 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                         for (int tx = 0; tx < 3; ++tx, ++row0) {
                             uint32_t a_lo = a_lo0 + static_cast<uint32_t>(abuf) * a_buf_step + static_cast<uint32_t>(row0) * 8u;
                             for (int kc = 0; kc < cin; kc += BK, a_lo += a_kb_step) {
+                                const long long tf = (DBG ? clock64() : 0ll);
                                 mbar_wait_u32(full0 + s * 8, ph);
+                                t_bfull += (DBG ? clock64() : 0ll) - tf;
                                 tcgen05_fence_after();
                                 const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(s) * (B_HALF_BYTES >> 4);
                                 if (elect_one_sync()) {
@@ -1035,7 +1089,7 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                             }
                         }
                     }
-                    const bool last_of_group = (u + 1 == ue) || ((u + 1) / nh != grp);
+                    const bool last_of_group = (q + 1 == ue) || (unit_of(l, q + 1) / nh != grp);
                     if (elect_one_sync()) {
                         tcgen05_commit_2sm_u32(smem_u32(&acc_full[buf]));
                         if (last_of_group) { tcgen05_commit_2sm_u32(smem_u32(&a_empty[abuf])); }
@@ -1044,15 +1098,23 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                     buf ^= 1;
                 }
             }
+            if (DBG && tp.dbg && lane == 0) {
+                tp.dbg[blockIdx.x * 8 + 3] = (DBG ? clock64() : 0ll) - t_start;
+                tp.dbg[blockIdx.x * 8 + 4] = t_afull;
+                tp.dbg[blockIdx.x * 8 + 5] = t_acc;
+                tp.dbg[blockIdx.x * 8 + 6] = t_bfull;
+            }
         }
     } else { // ===== epilogue (both CTAs) =====
         const int quarter = warp & 3;
         int ucount = 0;
+        long long t_epi_work = 0;
         for (int l = 0; l < tp.num_layers; ++l) {
             const TowerLayer& L = tp.layer[l];
             int ub, ue;
             range(l, ub, ue);
-            for (int u = ub; u < ue; ++u, ++ucount) {
+            for (int q = ub; q < ue; ++q, ++ucount) {
+                const int u = unit_of(l, q);
                 const int grp = u / nh, half = u - grp * nh, buf = ucount & 1;
                 const int mt = grp * 2 + crank;
                 const int n0 = half * BN;
@@ -1061,6 +1123,7 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                 const bool live = (r < tp.rows_valid) && (rr / tp.n1 != 0) && (rr % tp.n1 != tp.n1 - 1);
                 const bool in_range = (mt < tp.num_mtiles);
                 mbar_wait(&acc_full[buf], (ucount >> 1) & 1);
+                const long long tw = (DBG ? clock64() : 0ll);
                 tcgen05_fence_after();
                 __half* out_row = L.out + static_cast<size_t>(r) * tp.cout + n0;
                 const __half* res_row = (L.residual ? L.residual + static_cast<size_t>(r) * tp.cout + n0 : nullptr);
@@ -1104,8 +1167,10 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                     mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u);
                     atomicAdd(tp.done + l * num_groups + grp, 1);
                 }
+                t_epi_work += (DBG ? clock64() : 0ll) - tw;
             }
         }
+        if (DBG && tp.dbg && warp == 2 && lane == 0) { tp.dbg[blockIdx.x * 8 + 7] = t_epi_work; }
     }
     __syncthreads();
     cluster_sync_all();

@@ -37,3 +37,12 @@ if os.environ.get("MZ_DEBUG_TREE"):
     st = np.maximum(t[:, 5:6], 1)
     d = t[:, 8:14] / st
     print("  select detail per step (mean over games): check %.0f cyc, chase %.0f cyc, serial finish %.0f cyc; rounds %.2f, levels checked %.1f, serial levels %.2f" % tuple(d.mean(axis=0)))
+
+if os.environ.get("MZ_DEBUG_TOWER"):
+    eng.tower_timing()
+    t = eng.tower_timing().astype(np.float64)
+    names = ["prod_total", "prod_wait_deps", "prod_wait_stage", "mma_total", "mma_wait_block", "mma_wait_acc", "mma_wait_weights", "epi_busy"]
+    lead = t[0::2]
+    print("tower per-CTA cycles, leaders (mean / max):", ", ".join(f"{n}={lead[:, i].mean():.0f}/{lead[:, i].max():.0f}" for i, n in enumerate(names)))
+    peer = t[1::2]
+    print("tower per-CTA cycles, peers   (mean / max):", ", ".join(f"{n}={peer[:, i].mean():.0f}/{peer[:, i].max():.0f}" for i, n in enumerate(names)))
