@@ -187,7 +187,7 @@ struct mz_engine {
     CUtensorMap map_in0_ext, map_act_ext[3]; // same buffers, box = the resident block of conv3x3_resident_kernel
     mznn::TowerParams* tower = nullptr; // host copy of the fused-tower launch parameters (conv_mode 3)
     int* d_tower_done = nullptr;
-    int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148, krot = 0, conv_cluster = 1;
+    int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148, krot = 0, conv_cluster = 1, conv_pdl = 1;
     encode_tiled_fn encode = nullptr;
 
     // graphs keyed by (num_evals, noise, rotations)
@@ -273,10 +273,12 @@ int launch_conv_pair(mz_engine* e, const CUtensorMap& in_ext, const ConvLayer& L
     const size_t smem = 2 * static_cast<size_t>(L.cin / mznn::BK) * e->rows_ext * 128 + static_cast<size_t>(STAGES) * (BN / 2) * mznn::BK * 2 + (2 * STAGES + 8) * 8 + 16 + 1024;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * 2), cfg.blockDim = dim3(mznn::CONV_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = e->stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; // the kernel orders itself with griddepcontrol.wait
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = (e->conv_pdl ? 2 : 1);
     CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv3x3_pair_kernel<BN, STAGES>, in_ext, L.map_w_mc, rp));
     e->launches++;
     return MZ_OK;
@@ -452,10 +454,13 @@ int alloc_net(mz_engine* e)
     if ((rc = e->dalloc(&e->d_blob, e->blob.size))) { return rc; }
     const size_t rows = e->rows_alloc;
     e->rows_ext = (mznn::BM + 2 * (e->d.N + 2) + 7) / 8 * 8;
-    // conv kernel variant: 2 = CTA pairs (cta_group::2) over resident input blocks (default where the shape allows),
-    // 1 = one CTA per tile with a resident input block, 0 = every tap re-loads its shifted A tile
-    e->conv_mode = 3;
+    // conv kernel variant: 2 = CTA pairs (cta_group::2) over resident input blocks, one launch per layer chained by
+    // programmatic dependent launch (default where the shape allows); 3 = all layers in one persistent launch with
+    // completion counters (measured slower: the per-layer halo dependency stalls replace the launch overheads);
+    // 1 = one CTA per tile with a resident input block; 0 = every tap re-loads its shifted A tile
+    e->conv_mode = 2;
     if (const char* env = std::getenv("MZ_CONV_MODE")) { e->conv_mode = std::atoi(env); }
+    if (const char* env = std::getenv("MZ_CONV_PDL")) { e->conv_pdl = std::atoi(env); }
     const bool want_tower = (e->conv_mode == 3);
     if (want_tower) { e->conv_mode = 2; } // the tower needs everything the pair kernel needs
     if (const char* env = std::getenv("MZ_CONV_BASEOFF")) { e->base_off_mode = std::atoi(env); }
