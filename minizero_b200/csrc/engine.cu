@@ -187,7 +187,7 @@ struct mz_engine {
     CUtensorMap map_in0_ext, map_act_ext[3]; // same buffers, box = the resident block of conv3x3_resident_kernel
     mznn::TowerParams* tower = nullptr; // host copy of the fused-tower launch parameters (conv_mode 3)
     int* d_tower_done = nullptr;
-    int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148, krot = 0, conv_cluster = 1, conv_pdl = 1;
+    int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148, krot = 0, conv_cluster = 1, conv_pdl = 0;
     encode_tiled_fn encode = nullptr;
 
     // graphs keyed by (num_evals, noise, rotations)
@@ -454,8 +454,8 @@ int alloc_net(mz_engine* e)
     if ((rc = e->dalloc(&e->d_blob, e->blob.size))) { return rc; }
     const size_t rows = e->rows_alloc;
     e->rows_ext = (mznn::BM + 2 * (e->d.N + 2) + 7) / 8 * 8;
-    // conv kernel variant: 2 = CTA pairs (cta_group::2) over resident input blocks, one launch per layer chained by
-    // programmatic dependent launch (default where the shape allows); 3 = all layers in one persistent launch with
+    // conv kernel variant: 2 = CTA pairs (cta_group::2) over resident input blocks, one launch per layer
+    // (default where the shape allows); 3 = all layers in one persistent launch with
     // completion counters (measured slower: the per-layer halo dependency stalls replace the launch overheads);
     // 1 = one CTA per tile with a resident input block; 0 = every tap re-loads its shifted A tile
     e->conv_mode = 2;

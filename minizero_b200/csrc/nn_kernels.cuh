@@ -657,9 +657,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t full0 = smem_u32(b_full), empty0 = smem_u32(b_empty);
     const int g_first = u_begin / nh, g_last = (u_end - 1) / nh; // row-tile groups this cluster touches
-    // everything above touched no global data of the previous layer; the weight tiles (warp 0 below) do not either. Only the
-    // activation reads / writes have to wait for the previous grid.
-    if (warp != 0) { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+    // everything above touched no global data of the previous layer (with programmatic dependent launch — MZ_CONV_PDL=1,
+    // measured no faster than plain stream order on this path — the set-up overlaps the previous grid's tail)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         { // ===== TMA producer (both CTAs): own input blocks, own half of every weight tile; completion goes to the leader =====
@@ -677,19 +677,12 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
                 }
                 __syncwarp();
             };
+            if (u_begin < u_end) { load_block(g_first); }
             int prefetched = g_first;
-            bool waited = false;
             for (int u = u_begin; u < u_end; ++u) {
                 int wrow = half * BN + crank * (BN / 2);
-                int issued = 0;
                 for (int tap = 0; tap < 9; ++tap, wrow += p.cout) {
-                    for (int kc = 0; kc < p.cin; kc += BK, ++issued) {
-                        if (!waited && (issued == STAGES || (tap == 8 && kc + BK >= p.cin))) {
-                            // the ring is full of this unit's first weight tiles: now wait for the previous layer and fetch the input block
-                            asm volatile("griddepcontrol.wait;" ::: "memory");
-                            waited = true;
-                            load_block(g_first);
-                        }
+                    for (int kc = 0; kc < p.cin; kc += BK) {
                         mbar_wait_u32(empty0 + s * 8, ph);
                         if (elect_one_sync()) {
                             if (leader) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + s * 8), "r"(2 * B_HALF_BYTES) : "memory"); }
