@@ -845,6 +845,7 @@ struct TowerParams {
     int rows_valid, n1, slots, cout, rows_ext, halo, num_mtiles;
     int rotate;   // cluster offset per layer for the unit ranges
     int shift;    // unit offset per layer: position q of layer l is unit (q + l * shift) mod units
+    int zigzag;   // odd layers process the cluster's range in reverse order
     int* done;    // [num_layers][num_groups] completion counters, zeroed before every launch
     unsigned long long* dbg; // optional [grid][8] cycle counters (profiling)
 };
@@ -922,7 +923,17 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
         ub = static_cast<int>((static_cast<long long>(cl) * units) / nc);
         ue = static_cast<int>((static_cast<long long>(cl + 1) * units) / nc);
     };
-    auto unit_of = [&](int l, int q) { return (q + l * tp.shift) % units; };
+    // zigzag: odd layers walk the cluster's range backwards. With fixed ownership (rotate == 0, shift == 0) a cluster then
+    // starts every layer with the group it finished last, and the neighbours' edge groups it needs were the FIRST ones they
+    // computed in the previous layer: the halo dependency stops acting as a per-layer barrier.
+    auto unit_of = [&](int l, int q) {
+        if (tp.zigzag && (l & 1)) {
+            int ub, ue;
+            range(l, ub, ue);
+            q = ub + ue - 1 - q;
+        }
+        return (q + l * tp.shift) % units;
+    };
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs) =====
