@@ -501,7 +501,8 @@ int alloc_net(mz_engine* e)
         T.num_layers = static_cast<int>(e->convs.size());
         T.rows_valid = e->d.B * e->d.slots, T.n1 = e->d.N + 1, T.slots = e->d.slots, T.cout = e->cpad, T.rows_ext = e->rows_ext, T.halo = e->d.N + 2;
         T.num_mtiles = e->rows_alloc / mznn::BM;
-        T.rotate = 0, T.shift = 0, T.zigzag = 1;
+        T.rotate = 0, T.shift = 0, T.zigzag = 0, T.strided = 1;
+        if (const char* env = std::getenv("MZ_TOWER_STRIDED")) { T.strided = std::atoi(env); }
         if (const char* env = std::getenv("MZ_TOWER_ZIGZAG")) { T.zigzag = std::atoi(env); }
         if (const char* env = std::getenv("MZ_TOWER_ROT")) { T.rotate = std::atoi(env); }
         if (const char* env = std::getenv("MZ_TOWER_SHIFT")) { T.shift = std::atoi(env); }

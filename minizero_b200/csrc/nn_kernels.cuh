@@ -846,6 +846,7 @@ struct TowerParams {
     int rotate;   // cluster offset per layer for the unit ranges
     int shift;    // unit offset per layer: position q of layer l is unit (q + l * shift) mod units
     int zigzag;   // odd layers process the cluster's range in reverse order
+    int strided;  // units dealt round-robin to the clusters instead of in contiguous ranges
     int* done;    // [num_layers][num_groups] completion counters, zeroed before every launch
     unsigned long long* dbg; // optional [grid][8] cycle counters (profiling)
 };
@@ -918,7 +919,16 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
     // unit range of this cluster in layer l (rotated so that the uneven split does not always hit the same clusters)
     // (ub .. ue are positions in the layer's unit order; position q is unit (q + l * shift) mod units, so the range borders
     //  slide from layer to layer and a range that is long in one layer leans on shorter ones in the next)
+    // strided ownership (tp.strided): cluster c owns units c, c + nc, c + 2 nc, ... of every layer. The six units a unit's
+    // halo needs (groups g-1 .. g+1, both halves) then belong to six neighbouring clusters in the SAME pass of the previous
+    // layer, finished a whole layer-time ago — the epilogue -> counter -> TMA round trip never sits on the critical path.
+    // (Cost: the two halves of a group go to different clusters, so every unit loads its own input block.)
     auto range = [&](int l, int& ub, int& ue) {
+        if (tp.strided) {
+            ub = 0;
+            ue = (units - cid + nc - 1) / nc;
+            return;
+        }
         const int cl = (cid + l * tp.rotate) % nc;
         ub = static_cast<int>((static_cast<long long>(cl) * units) / nc);
         ue = static_cast<int>((static_cast<long long>(cl + 1) * units) / nc);
@@ -927,6 +937,7 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
     // starts every layer with the group it finished last, and the neighbours' edge groups it needs were the FIRST ones they
     // computed in the previous layer: the halo dependency stops acting as a per-layer barrier.
     auto unit_of = [&](int l, int q) {
+        if (tp.strided) { return cid + q * nc; }
         if (tp.zigzag && (l & 1)) {
             int ub, ue;
             range(l, ub, ue);
