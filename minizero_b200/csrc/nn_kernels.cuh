@@ -1033,14 +1033,8 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                     }
                 }
                 int wrow = half * BN + crank * (BN / 2);
-                int issued = 0;
                 for (int tap = 0; tap < 9; ++tap, wrow += tp.cout) {
-                    for (int kc = 0; kc < L.cin; kc += BK, ++issued) {
-                        // once more than a ring of this unit's weight tiles has been issued the MMAs have certainly left the
-                        // previous unit (its input buffer is free): fetch the next unit's input block now, a whole unit ahead
-                        if (issued == STAGES + 2 && next_valid && gcount == used) {
-                            if (load_block(next_l, unit_of(next_l, next_q) / nh, false)) { advance_next(); }
-                        }
+                    for (int kc = 0; kc < L.cin; kc += BK) {
                         const long long te = (DBG ? clock64() : 0ll);
                         mbar_wait_u32(empty0 + s * 8, ph);
                         t_bempty += (DBG ? clock64() : 0ll) - te;
