@@ -348,7 +348,7 @@ int forward(mz_engine* e)
         if (units < clusters) { clusters = units; }
         const size_t smem = 2 * static_cast<size_t>(e->cpad / mznn::BK) * e->rows_ext * 128 + 8 * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(clusters * 2), cfg.blockDim = dim3(mznn::CONV_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = e->stream;
+        cfg.gridDim = dim3(clusters * 2), cfg.blockDim = dim3(mznn::TOWER_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = e->stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
@@ -501,7 +501,7 @@ int alloc_net(mz_engine* e)
         T.num_layers = static_cast<int>(e->convs.size());
         T.rows_valid = e->d.B * e->d.slots, T.n1 = e->d.N + 1, T.slots = e->d.slots, T.cout = e->cpad, T.rows_ext = e->rows_ext, T.halo = e->d.N + 2;
         T.num_mtiles = e->rows_alloc / mznn::BM;
-        T.rotate = 0, T.shift = 0, T.zigzag = 0, T.strided = 1;
+        T.rotate = 22, T.shift = 0, T.zigzag = 0, T.strided = 1;
         if (const char* env = std::getenv("MZ_TOWER_STRIDED")) { T.strided = std::atoi(env); }
         if (const char* env = std::getenv("MZ_TOWER_ZIGZAG")) { T.zigzag = std::atoi(env); }
         if (const char* env = std::getenv("MZ_TOWER_ROT")) { T.rotate = std::atoi(env); }

@@ -828,6 +828,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
 // strictly earlier layer, so the waits cannot cycle.
 // ---------------------------------------------------------------------------------------------
 constexpr int TOWER_MAX_LAYERS = 48;
+constexpr int TOWER_THREADS = 224; // warp 0: weight TMA, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue, warp 6: input-block TMA + dependency waits
 
 struct alignas(64) TowerLayer {
     CUtensorMap map_in;     // input activations, box = resident block
@@ -859,7 +860,7 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p)
 }
 
 template <int BN, int STAGES, bool DBG>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(TOWER_THREADS, 1)
 conv_tower_kernel(const __grid_constant__ TowerParams tp)
 {
     constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
@@ -926,7 +927,7 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
     auto range = [&](int l, int& ub, int& ue) {
         if (tp.strided) {
             ub = 0;
-            ue = (units - cid + nc - 1) / nc;
+            ue = (units - (cid + l * tp.rotate) % nc + nc - 1) / nc;
             return;
         }
         const int cl = (cid + l * tp.rotate) % nc;
@@ -937,7 +938,7 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
     // starts every layer with the group it finished last, and the neighbours' edge groups it needs were the FIRST ones they
     // computed in the previous layer: the halo dependency stops acting as a per-layer barrier.
     auto unit_of = [&](int l, int q) {
-        if (tp.strided) { return cid + q * nc; }
+        if (tp.strided) { return (cid + l * tp.rotate) % nc + q * nc; } // ownership rotates so that the clusters take turns at the short lists
         if (tp.zigzag && (l & 1)) {
             int ub, ue;
             range(l, ub, ue);
@@ -947,75 +948,12 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
     };
 
     if (warp == 0) {
-        // ===== TMA producer (both CTAs) =====
-        int s = 0, gcount = 0; // gcount: input blocks loaded so far by this cluster (buffer = gcount & 1)
+        // ===== weight producer (both CTAs): streams this CTA's half of every weight tile, never waits for anything but a free stage =====
+        int s = 0;
         uint32_t ph = 1;
-        long long t_dep = 0, t_bempty = 0;
+        long long t_bempty = 0;
         const long long t_start = (DBG ? clock64() : 0ll);
-        const uint32_t b_dst0 = smem_u32(smem_b), a_dst0 = smem_u32(smem_a);
-        // input block of (layer l, group g) into buffer gcount & 1. blocking == false: give up (return false) when the previous
-        // layer's groups g-1 .. g+1 are not complete yet — a prefetch must never hold back the weight loads of the current unit
-        auto load_block = [&](int l, int g, bool blocking) -> bool {
-            const TowerLayer& L = tp.layer[l];
-            const int buf = gcount & 1, a_kb = L.cin / BK;
-            if (l > 0) { // the 3x3 halo reaches into the neighbouring groups of the previous layer
-                const long long td = (DBG ? clock64() : 0ll);
-                int ready = 1;
-                if (lane == 0) {
-                    const int* d = tp.done + (l - 1) * num_groups;
-                    const int g0 = (g > 0 ? g - 1 : 0), g1 = (g + 1 < num_groups ? g + 1 : num_groups - 1);
-                    for (int gg = g0; gg <= g1 && ready; ++gg) {
-                        while (ld_acquire_gpu(d + gg) < need) {
-                            if (!blocking) {
-                                ready = 0;
-                                break;
-                            }
-                            __nanosleep(32);
-                        }
-                    }
-                }
-                ready = __shfl_sync(0xffffffffu, ready, 0);
-                t_dep += (DBG ? clock64() : 0ll) - td;
-                if (!ready) { return false; }
-                asm volatile("fence.proxy.async;" ::: "memory"); // generic-proxy writes of other SMs -> this warp's TMA (async proxy) reads
-            }
-            mbar_wait_u32(smem_u32(&a_empty[buf]), ((gcount >> 1) & 1) ^ 1);
-            if (elect_one_sync()) {
-                if (leader) { mbar_arrive_expect_tx(&a_full[buf], 2 * a_kb * a_kb_bytes); }
-                const uint32_t bar = smem_u32(&a_full[buf]) & kPeerMask;
-                const uint64_t map_in_ptr = reinterpret_cast<uint64_t>(&L.map_in);
-                for (int kb = 0; kb < a_kb; ++kb) { tma_load_2d_2sm(a_dst0 + buf * a_bytes_max + kb * a_kb_bytes, map_in_ptr, bar, kb * BK, (g * 2 + crank) * BM - tp.halo); }
-            }
-            __syncwarp();
-            ++gcount;
-            return true;
-        };
-        // the block sequence of this cluster: groups in unit order, layer after layer
-        int next_l = 0, next_q = 0; // position (in layer next_l's unit order) of the first unit of the next block to load
-        bool next_valid = true;
-        {
-            int ub, ue;
-            range(0, ub, ue);
-            next_q = ub;
-        }
-        auto advance_next = [&]() { // step to the first unit of the following group of this cluster
-            int ub, ue;
-            range(next_l, ub, ue);
-            const int g = unit_of(next_l, next_q) / nh;
-            int q = next_q + 1;
-            while (q < ue && unit_of(next_l, q) / nh == g) { ++q; }
-            if (q < ue) {
-                next_q = q;
-            } else if (next_l + 1 < tp.num_layers) {
-                ++next_l;
-                range(next_l, ub, ue);
-                next_q = ub;
-            } else {
-                next_valid = false;
-            }
-        };
-        int used = 0; // blocks consumed by the units issued so far (the MMA warp counts the same way)
-        int cur_key = -1;
+        const uint32_t b_dst0 = smem_u32(smem_b);
         for (int l = 0; l < tp.num_layers; ++l) {
             const TowerLayer& L = tp.layer[l];
             const uint64_t map_w_ptr = reinterpret_cast<uint64_t>(&L.map_w);
@@ -1023,15 +961,7 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
             range(l, ub, ue);
             for (int q = ub; q < ue; ++q) {
                 const int u = unit_of(l, q);
-                const int grp = u / nh, half = u - grp * nh;
-                if (l * 65536 + grp != cur_key) {
-                    cur_key = l * 65536 + grp;
-                    ++used;
-                    if (gcount < used) { // not prefetched: now it is needed, wait for it
-                        load_block(next_l, unit_of(next_l, next_q) / nh, true);
-                        advance_next();
-                    }
-                }
+                const int half = u % nh;
                 int wrow = half * BN + crank * (BN / 2);
                 for (int tap = 0; tap < 9; ++tap, wrow += tp.cout) {
                     for (int kc = 0; kc < L.cin; kc += BK) {
@@ -1046,17 +976,53 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                         if (++s == STAGES) { s = 0, ph ^= 1; }
                     }
                 }
-                // this unit's weights are in flight: try to fetch the next group's input block into the other buffer
-                if (next_valid && gcount == used) {
-                    if (load_block(next_l, unit_of(next_l, next_q) / nh, false)) { advance_next(); }
-                }
             }
         }
         if (DBG && tp.dbg && lane == 0) {
             tp.dbg[blockIdx.x * 8 + 0] = (DBG ? clock64() : 0ll) - t_start;
-            tp.dbg[blockIdx.x * 8 + 1] = t_dep;
             tp.dbg[blockIdx.x * 8 + 2] = t_bempty;
         }
+    } else if (warp == 6) {
+        // ===== input-block producer (both CTAs): one block per group of consecutive units, as far ahead as the two buffers allow;
+        //       it alone waits for the previous layer's completion counters =====
+        int gcount = 0, cur_key = -1;
+        long long t_dep = 0;
+        const uint32_t a_dst0 = smem_u32(smem_a);
+        for (int l = 0; l < tp.num_layers; ++l) {
+            const TowerLayer& L = tp.layer[l];
+            const int a_kb = L.cin / BK;
+            int ub, ue;
+            range(l, ub, ue);
+            for (int q = ub; q < ue; ++q) {
+                const int g = unit_of(l, q) / nh;
+                if (l * 65536 + g == cur_key) { continue; }
+                cur_key = l * 65536 + g;
+                const int buf = gcount & 1;
+                mbar_wait_u32(smem_u32(&a_empty[buf]), ((gcount >> 1) & 1) ^ 1); // the MMAs that read this buffer two blocks ago are done
+                if (l > 0) { // the 3x3 halo reaches into the neighbouring groups of the previous layer
+                    const long long td = (DBG ? clock64() : 0ll);
+                    if (lane == 0) {
+                        const int* d = tp.done + (l - 1) * num_groups;
+                        const int g0 = (g > 0 ? g - 1 : 0), g1 = (g + 1 < num_groups ? g + 1 : num_groups - 1);
+                        for (int gg = g0; gg <= g1; ++gg) {
+                            while (ld_acquire_gpu(d + gg) < need) { __nanosleep(32); }
+                        }
+                    }
+                    __syncwarp();
+                    asm volatile("fence.proxy.async;" ::: "memory"); // generic-proxy writes of other SMs -> this warp's TMA (async proxy) reads
+                    t_dep += (DBG ? clock64() : 0ll) - td;
+                }
+                if (elect_one_sync()) {
+                    if (leader) { mbar_arrive_expect_tx(&a_full[buf], 2 * a_kb * a_kb_bytes); }
+                    const uint32_t bar = smem_u32(&a_full[buf]) & kPeerMask;
+                    const uint64_t map_in_ptr = reinterpret_cast<uint64_t>(&L.map_in);
+                    for (int kb = 0; kb < a_kb; ++kb) { tma_load_2d_2sm(a_dst0 + buf * a_bytes_max + kb * a_kb_bytes, map_in_ptr, bar, kb * BK, (g * 2 + crank) * BM - tp.halo); }
+                }
+                __syncwarp();
+                ++gcount;
+            }
+        }
+        if (DBG && tp.dbg && lane == 0) { tp.dbg[blockIdx.x * 8 + 1] = t_dep; }
     } else if (warp == 1) {
         if (leader) { // ===== MMA issuer =====
             constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN);
@@ -1133,7 +1099,7 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                 tp.dbg[blockIdx.x * 8 + 6] = t_bfull;
             }
         }
-    } else { // ===== epilogue (both CTAs) =====
+    } else if (warp >= 2 && warp <= 5) { // ===== epilogue (both CTAs) =====
         const int quarter = warp & 3;
         int ucount = 0;
         long long t_epi_work = 0;
