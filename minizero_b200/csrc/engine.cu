@@ -454,11 +454,10 @@ int alloc_net(mz_engine* e)
     if ((rc = e->dalloc(&e->d_blob, e->blob.size))) { return rc; }
     const size_t rows = e->rows_alloc;
     e->rows_ext = (mznn::BM + 2 * (e->d.N + 2) + 7) / 8 * 8;
-    // conv kernel variant: 2 = CTA pairs (cta_group::2) over resident input blocks, one launch per layer
-    // (default where the shape allows); 3 = all layers in one persistent launch with
-    // completion counters (measured slower: the per-layer halo dependency stalls replace the launch overheads);
+    // conv kernel variant: 3 = all layers in one persistent launch of CTA pairs, chained by completion counters (default
+    // where the shape allows); 2 = CTA pairs (cta_group::2) over resident input blocks, one launch per layer;
     // 1 = one CTA per tile with a resident input block; 0 = every tap re-loads its shifted A tile
-    e->conv_mode = 2;
+    e->conv_mode = 3;
     if (const char* env = std::getenv("MZ_CONV_MODE")) { e->conv_mode = std::atoi(env); }
     if (const char* env = std::getenv("MZ_CONV_PDL")) { e->conv_pdl = std::atoi(env); }
     const bool want_tower = (e->conv_mode == 3);
