@@ -271,7 +271,14 @@ def main():
     evals = world * GAMES * S1 * args.steps
     value = evals / (dev_ms * 1e-3)
     e2e_value = world * GAMES * S1 * args.steps / e2e_s
-    conv_tflops = FLOPS_PER_CONV_LAUNCH / (prof["conv_ms"] * 1e-3) / 1e12
+    layers = eng.conv_layers_per_launch()
+    if layers > 1:  # fused tower: stem (18 real input channels) + 2 convs per block in one launch
+        conv_kernel = f"conv_tower_kernel (all {layers} 3x3 conv layers of the 6bx256 tower, 256 positions, one launch)"
+        flops_per_launch = GAMES * (2.0 * 81 * 9 * IN_CH * HIDDEN + (layers - 1) * 95551488.0)
+    else:
+        conv_kernel = "conv3x3 kernel (one hidden->hidden 3x3 conv layer, 256 positions)"
+        flops_per_launch = FLOPS_PER_CONV_LAUNCH
+    conv_tflops = flops_per_launch / (prof["conv_ms"] * 1e-3) / 1e12
     line = {
         "metric": "selfplay_leaf_evals_per_sec", "value": value, "unit": "leaf-evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate; tree work f32/f64/int)",
@@ -282,7 +289,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "leaf-evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "conv3x3_tcgen05_kernel (hidden->hidden 3x3 conv, 256 positions)", "bound": "tensor", "achieved": conv_tflops, "peak": pk["bf16_tflops"],
+        "roofline": {"kernel": conv_kernel, "flops_per_launch": flops_per_launch, "bound": "tensor", "achieved": conv_tflops, "peak": pk["bf16_tflops"],
                      "unit": "TFLOP/s", "frac": conv_tflops / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " burst (kernel timed alone, 50 launches)",
                      "launch_ms": prof["conv_ms"]},
         "kernels_ms": {"conv3x3": prof["conv_ms"], "tree_select_transition": prof["tree_ms"], "heads": prof["heads_ms"]},

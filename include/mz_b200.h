@@ -130,7 +130,7 @@ int mz_timer_end(mz_engine* e, float* device_ms);
 
 /* ---- measurement hooks ------------------------------------------------------------------------------ */
 /* average device time (CUDA events on the engine's stream) of `iters` back-to-back launches of: the tower
- * conv kernel (hidden -> hidden layer), the tree step kernel, the heads kernel; any pointer may be NULL */
+ * conv kernel (one launch = mz_conv_layers_per_launch layers), the tree step kernel, the heads kernel; any pointer may be NULL */
 int mz_profile_kernels(mz_engine* e, int32_t iters, float* conv_ms, float* tree_ms, float* heads_ms);
 /* per-game cycle counters accumulated by every tree step since the last call, when the engine was created with the
  * environment variable MZ_DEBUG_TREE=1 (profiling only): out [num_games][16] = cycles in {selection, transition, leaf
@@ -141,6 +141,9 @@ int mz_debug_tree_timing(mz_engine* e, uint64_t* out);
  * {producer total, producer waiting for the previous layer's groups, producer waiting for a free weight stage,
  *  MMA total, MMA waiting for the input block, for a free accumulator, for weights, epilogue busy}; returns the CTAs written */
 int mz_debug_tower_timing(mz_engine* e, uint64_t* out, int32_t max_ctas);
+/* how many 3x3 conv layers one launch of the conv kernel covers: all of them for the fused tower (then the conv time of
+ * mz_profile_kernels is the whole tower), else 1 */
+int mz_conv_layers_per_launch(const mz_engine* e);
 /* kernels launched by this engine so far */
 int64_t mz_launch_count(const mz_engine* e);
 

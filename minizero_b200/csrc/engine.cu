@@ -336,11 +336,33 @@ int launch_heads(mz_engine* e, const __half* act)
     return MZ_OK;
 }
 
+int launch_tower(mz_engine* e);
+
 // AlphaZeroNetwork.forward (network/py/alphazero_network.py:90-113) on the rows already in nn_in
 int forward(mz_engine* e)
 {
     if (!e->net_ready) { return fail(MZ_ERR_STATE, "network not finalized"); }
     if (e->conv_mode == 3) {
+        int rc = launch_tower(e);
+        if (rc) { return rc; }
+        const int last = static_cast<int>(e->convs.size()) - 1;
+        return launch_heads(e, e->tower->layer[last].out);
+    }
+    int rc = conv(e, e->map_in0, e->map_in0_ext, e->convs[0], e->act[0], nullptr);
+    if (rc) { return rc; }
+    int cur = 0;
+    for (int b = 0; b < e->nd.num_blocks; ++b) {
+        const int t = (cur + 1) % 3, o = (cur + 2) % 3;
+        if ((rc = conv(e, e->map_act[cur], e->map_act_ext[cur], e->convs[1 + 2 * b], e->act[t], nullptr))) { return rc; }
+        if ((rc = conv(e, e->map_act[t], e->map_act_ext[t], e->convs[2 + 2 * b], e->act[o], e->act[cur]))) { return rc; }
+        cur = o;
+    }
+    return launch_heads(e, e->act[cur]);
+}
+
+int launch_tower(mz_engine* e)
+{
+    {
         const int num_groups = (e->tower->num_mtiles + 1) / 2;
         CUDA_OK(cudaMemsetAsync(e->d_tower_done, 0, sizeof(int) * e->tower->num_layers * num_groups, e->stream));
         const int units = num_groups * (e->cpad / 128);
@@ -359,19 +381,8 @@ int forward(mz_engine* e)
             CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8, false>, *e->tower));
         }
         e->launches++;
-        const int last = static_cast<int>(e->convs.size()) - 1;
-        return launch_heads(e, e->tower->layer[last].out);
     }
-    int rc = conv(e, e->map_in0, e->map_in0_ext, e->convs[0], e->act[0], nullptr);
-    if (rc) { return rc; }
-    int cur = 0;
-    for (int b = 0; b < e->nd.num_blocks; ++b) {
-        const int t = (cur + 1) % 3, o = (cur + 2) % 3;
-        if ((rc = conv(e, e->map_act[cur], e->map_act_ext[cur], e->convs[1 + 2 * b], e->act[t], nullptr))) { return rc; }
-        if ((rc = conv(e, e->map_act[t], e->map_act_ext[t], e->convs[2 + 2 * b], e->act[o], e->act[cur]))) { return rc; }
-        cur = o;
-    }
-    return launch_heads(e, e->act[cur]);
+    return MZ_OK;
 }
 
 size_t step_smem_bytes(const mz_dims& d)
@@ -686,6 +697,7 @@ void mz_destroy(mz_engine* e)
 int mz_action_size(const mz_engine* e) { return e ? e->d.A : MZ_ERR_ARG; }
 int mz_num_features(const mz_engine* e) { return e ? e->d.C * e->d.N * e->d.N : MZ_ERR_ARG; }
 int64_t mz_launch_count(const mz_engine* e) { return e ? e->launches : 0; }
+int mz_conv_layers_per_launch(const mz_engine* e) { return (e && e->net_ready) ? (e->conv_mode == 3 ? static_cast<int>(e->convs.size()) : 1) : MZ_ERR_STATE; }
 
 int mz_net_configure(mz_engine* e, const mz_net_dims* dims)
 {
@@ -1057,7 +1069,7 @@ int mz_search_run(mz_engine* e, int32_t num_evals, float* device_ms)
         if (cerr != cudaSuccess) { return fail(MZ_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(cerr)); }
         it = e->graphs.emplace(key, exec).first;
     }
-    e->launches += 1 + static_cast<int64_t>(num_evals) * (2 + static_cast<int64_t>(e->convs.size()));
+    e->launches += 1 + static_cast<int64_t>(num_evals) * (2 + (e->conv_mode == 3 ? 1 : static_cast<int64_t>(e->convs.size())));
     if (!device_ms) { // asynchronous: the caller brackets several calls with mz_timer_begin / mz_timer_end or mz_sync
         CUDA_OK(cudaGraphLaunch(it->second, e->stream));
         return MZ_OK;
@@ -1104,7 +1116,15 @@ int mz_profile_kernels(mz_engine* e, int32_t iters, float* conv_ms, float* tree_
     if (!e->net_ready) { return fail(MZ_ERR_STATE, "network not finalized"); }
     CUDA_OK(cudaSetDevice(e->cfg.device));
     float ms = 0.0f;
-    if (conv_ms) {
+    if (conv_ms && e->conv_mode == 3) { // the whole tower is one launch
+        for (int i = 0; i < 3; ++i) { launch_tower(e); }
+        CUDA_OK(cudaEventRecord(e->ev0, e->stream));
+        for (int i = 0; i < iters; ++i) { launch_tower(e); }
+        CUDA_OK(cudaEventRecord(e->ev1, e->stream));
+        CUDA_OK(cudaStreamSynchronize(e->stream));
+        CUDA_OK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+        *conv_ms = ms / iters;
+    } else if (conv_ms) {
         const ConvLayer& L = e->convs.back();
         for (int i = 0; i < 3; ++i) { conv(e, e->map_act[0], e->map_act_ext[0], L, e->act[1], e->act[2]); }
         CUDA_OK(cudaEventRecord(e->ev0, e->stream));

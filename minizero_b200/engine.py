@@ -98,6 +98,7 @@ def _load():
     lib.mz_profile_kernels.argtypes = [vp, i32, f32p, f32p, f32p]
     lib.mz_debug_tree_timing.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.mz_debug_tower_timing.argtypes = [vp, C.POINTER(C.c_uint64), i32]
+    lib.mz_conv_layers_per_launch.argtypes = [vp]
     lib.mz_launch_count.argtypes = [vp]
     lib.mz_launch_count.restype = C.c_int64
     _lib = lib
@@ -106,7 +107,7 @@ def _load():
 
 EXPORTS = ["mz_create", "mz_destroy", "mz_last_error", "mz_action_size", "mz_num_features", "mz_net_configure", "mz_net_set_tensor", "mz_net_finalize",
            "mz_net_blob", "mz_net_finalize_empty", "mz_eval_batch", "mz_reset_game", "mz_play", "mz_get_roots", "mz_search_select", "mz_search_apply",
-           "mz_search_set_inputs", "mz_search_run", "mz_profile_kernels", "mz_launch_count", "mz_play_max_count", "mz_sync", "mz_timer_begin", "mz_timer_end", "mz_debug_tree_timing", "mz_debug_tower_timing"]
+           "mz_search_set_inputs", "mz_search_run", "mz_profile_kernels", "mz_launch_count", "mz_play_max_count", "mz_sync", "mz_timer_begin", "mz_timer_end", "mz_debug_tree_timing", "mz_debug_tower_timing", "mz_conv_layers_per_launch"]
 
 
 def _fp(a):
@@ -318,6 +319,9 @@ class Engine:
         if n < 0:
             self._check(n)
         return out[:n]
+
+    def conv_layers_per_launch(self):
+        return int(self.lib.mz_conv_layers_per_launch(self.h))
 
     def launch_count(self):
         return int(self.lib.mz_launch_count(self.h))
