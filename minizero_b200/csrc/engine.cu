@@ -187,7 +187,7 @@ struct mz_engine {
     CUtensorMap map_in0_ext, map_act_ext[3]; // same buffers, box = the resident block of conv3x3_resident_kernel
     mznn::TowerParams* tower = nullptr; // host copy of the fused-tower launch parameters (conv_mode 3)
     int* d_tower_done = nullptr;
-    int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148, krot = 0, conv_cluster = 1, conv_pdl = 0;
+    int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148, krot = 0, conv_cluster = 1, conv_pdl = 0, tower_sms = 148;
     encode_tiled_fn encode = nullptr;
 
     // graphs keyed by (num_evals, noise, rotations)
@@ -366,7 +366,7 @@ int launch_tower(mz_engine* e)
         const int num_groups = (e->tower->num_mtiles + 1) / 2;
         CUDA_OK(cudaMemsetAsync(e->d_tower_done, 0, sizeof(int) * e->tower->num_layers * num_groups, e->stream));
         const int units = num_groups * (e->cpad / 128);
-        int clusters = e->num_sms / 2;
+        int clusters = e->tower_sms / 2;
         if (units < clusters) { clusters = units; }
         const size_t smem = 2 * static_cast<size_t>(e->cpad / mznn::BK) * e->rows_ext * 128 + 8 * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
         cudaLaunchConfig_t cfg{};
@@ -532,6 +532,12 @@ int alloc_net(mz_engine* e)
         const int num_groups = (T.num_mtiles + 1) / 2;
         if ((rc = e->dalloc(&e->d_tower_done, static_cast<size_t>(T.num_layers) * num_groups))) { return rc; }
         T.done = e->d_tower_done;
+        // SMs the persistent tower may occupy: leaving a few free lets another engine's tree / heads kernels run beside it
+        e->tower_sms = e->num_sms;
+        if (const char* env = std::getenv("MZ_TOWER_SMS")) {
+            const int v = std::atoi(env);
+            if (v >= 2 && v <= e->num_sms) { e->tower_sms = v & ~1; }
+        }
         T.dbg = nullptr;
         if (const char* env = std::getenv("MZ_DEBUG_TOWER")) {
             if (std::atoi(env) != 0) {
