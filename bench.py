@@ -34,6 +34,19 @@ CONFIG = {"workload": "go9x9_alphazero_400sims_256games_6bx256 (BASELINE configs
           "l2": "per-step working set (node pools 219 MB + activations) exceeds the 126 MB L2; no explicit flush"}
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one tower launch from the committed `ncu --set full` capture (profiles/)."""
+    best = None
+    for name in sorted(os.listdir(os.path.join(ROOT, "profiles"))):
+        if name.endswith("_ncu_full_summary.json"):
+            best = os.path.join(ROOT, "profiles", name)
+    try:
+        with open(best) as f:
+            return json.load(f)["tower"]["dram_traffic_bytes_per_launch"], os.path.basename(best)
+    except Exception:
+        return None, None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -279,6 +292,7 @@ def main():
         conv_kernel = "conv3x3 kernel (one hidden->hidden 3x3 conv layer, 256 positions)"
         flops_per_launch = FLOPS_PER_CONV_LAUNCH
     conv_tflops = flops_per_launch / (prof["conv_ms"] * 1e-3) / 1e12
+    traffic, traffic_src = ncu_traffic() if layers > 1 else (None, None)
     line = {
         "metric": "selfplay_leaf_evals_per_sec", "value": value, "unit": "leaf-evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate; tree work f32/f64/int)",
@@ -290,7 +304,7 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": conv_kernel, "flops_per_launch": flops_per_launch, "bound": "tensor", "achieved": conv_tflops, "peak": pk["bf16_tflops"],
-                     "unit": "TFLOP/s", "frac": conv_tflops / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " burst (kernel timed alone, 50 launches)",
+                     "unit": "TFLOP/s", "frac": conv_tflops / pk["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk["source"] + " burst (kernel timed alone, 50 launches)",
                      "launch_ms": prof["conv_ms"]},
         "kernels_ms": {"conv3x3": prof["conv_ms"], "tree_select_transition": prof["tree_ms"], "heads": prof["heads_ms"]},
     }
