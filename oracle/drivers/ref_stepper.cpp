@@ -129,13 +129,21 @@ int main(int argc, char** argv)
             actor->beforeNNEvaluation();
             // what was pushed: recompute the same features the actor just handed to the network
             const auto& path = actor->nodePath();
-            cycle_hdr[i] = {static_cast<int32_t>(cycle), static_cast<int32_t>(i), actor->rotation(), static_cast<int32_t>(path.size())};
+            cycle_hdr[i] = {static_cast<int32_t>(cycle), static_cast<int32_t>(i), is_az ? actor->rotation() : 0, static_cast<int32_t>(path.size())};
+            if (!is_az) {
+                // MuZero: the leaf is identified by its action and the path by a hash of its action ids (records of the
+                // muzero type carry a 6-int header; alphazero records keep the 4-int header of the committed fixtures)
+                uint32_t h = 2166136261u;
+                for (size_t k = 1; k < path.size(); ++k) { h = (h ^ static_cast<uint32_t>(path[k]->getAction().getActionID())) * 16777619u; }
+                cycle_hdr[i].push_back(path.back()->getAction().getActionID());
+                cycle_hdr[i].push_back(static_cast<int32_t>(h & 0x7fffffffu));
+            }
             if (is_az) {
                 Environment t = actor->transition();
                 cycle_feats[i] = t.getFeatures(static_cast<utils::Rotation>(actor->rotation()));
             } else {
                 cycle_feats[i].assign(F, 0.0f);
-                if (actor->getMCTS()->getNumSimulation() == 0) { cycle_feats[i] = actor->getEnvironment().getFeatures(); }
+                if (path.size() == 1) { cycle_feats[i] = actor->getEnvironment().getFeatures(); }
             }
         }
         if (stop) { break; }
@@ -147,7 +155,7 @@ int main(int argc, char** argv)
         }
         for (size_t i = 0; i < actors.size(); ++i) {
             int idx = actors[i]->getNNEvaluationBatchIndex();
-            fwrite(cycle_hdr[i].data(), 4, 4, f_eval);
+            fwrite(cycle_hdr[i].data(), 4, cycle_hdr[i].size(), f_eval);
             std::vector<uint8_t> fb(F);
             for (int k = 0; k < F; ++k) { fb[k] = (cycle_feats[i][k] != 0.0f); }
             fwrite(fb.data(), 1, F, f_eval);

@@ -17,23 +17,32 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "..", "tests", "golden")
 
 COMMON = "zero_num_threads=1:program_seed=%d:program_auto_seed=false:program_quiet=true:nn_type_name=alphazero"
+COMMON_MZ = "zero_num_threads=1:program_seed=%d:program_auto_seed=false:program_quiet=true:nn_type_name=muzero"
+# BASELINE configs[2] search settings (tools/quick-run.sh:333-346 "gmz"), small net
+GUMBEL = "actor_use_gumbel=true:actor_use_gumbel_noise=true:actor_gumbel_sample_size=%d:actor_gumbel_sigma_visit_c=50:actor_gumbel_sigma_scale_c=1:actor_use_dirichlet_noise=false:"
 CASES = {
     # name: (binary, net, conf, max_moves)
     "ttt_s50_b2": ("tictactoe", "ttt_az_2bx32", "actor_num_simulation=50:zero_num_parallel_games=2:" + COMMON % 1, 40),
     "ttt_s50_b1_det": ("tictactoe", "ttt_az_2bx32", "actor_num_simulation=50:zero_num_parallel_games=1:actor_use_dirichlet_noise=false:actor_use_random_rotation_features=false:actor_select_action_by_count=true:actor_select_action_by_softmax_count=false:" + COMMON % 1, 12),
     "go5_s24_b2": ("go", "go5_az_1bx16", "env_board_size=5:actor_num_simulation=24:zero_num_parallel_games=2:" + COMMON % 3, 140),
     "go9_s32_b2": ("go", "go9_az_1bx16", "env_board_size=9:actor_num_simulation=32:zero_num_parallel_games=2:" + COMMON % 5, 30),
+    # Othello 8x8 MuZero: Gumbel (configs[2] settings: n=16, m=16), Gumbel with real halving (n=32, m=8), plain PUCT MuZero with Dirichlet noise
+    "othello_gmz_s16_b2": ("othello", "othello_mz_1bx32", "actor_num_simulation=16:zero_num_parallel_games=2:" + GUMBEL % 16 + COMMON_MZ % 7, 130),
+    "othello_gmz_s32_m8_b2": ("othello", "othello_mz_1bx32", "actor_num_simulation=32:zero_num_parallel_games=2:" + GUMBEL % 8 + COMMON_MZ % 8, 70),
+    "othello_mz_s24_b2": ("othello", "othello_mz_1bx32", "actor_num_simulation=24:zero_num_parallel_games=2:" + COMMON_MZ % 9, 70),
 }
 
 
-def read_case(d, a_size, f_size):
+def read_case(d, a_size, f_size, hdr_ints=4):
     ev = np.fromfile(os.path.join(d, "evals.bin"), dtype=np.uint8)
-    rec = 16 + f_size + 4 * (2 * a_size + 1)
+    hb = 4 * hdr_ints
+    rec = hb + f_size + 4 * (2 * a_size + 1)
     assert ev.size % rec == 0
     ev = ev.reshape(-1, rec)
-    hdr = ev[:, :16].copy().view(np.int32)
-    feats = ev[:, 16:16 + f_size]
-    fl = ev[:, 16 + f_size:].copy().view(np.float32)
+    hdr = ev[:, :hb].copy().view(np.int32)
+    feats = ev[:, hb:hb + f_size]
+    fl = ev[:, hb + f_size:].copy().view(np.float32)
+    extra = dict(eval_leaf_action=hdr[:, 4], eval_path_hash=hdr[:, 5]) if hdr_ints == 6 else {}
     mv = np.fromfile(os.path.join(d, "moves.bin"), dtype=np.uint8)
     mrec = 4 * 9 + a_size * 28
     assert mv.size % mrec == 0
@@ -42,6 +51,7 @@ def read_case(d, a_size, f_size):
     mh_f = mv[:, 24:36].copy().view(np.float32)
     ch = mv[:, 36:].copy().reshape(-1, a_size, 28)
     return dict(
+        **extra,
         eval_cycle=hdr[:, 0], eval_game=hdr[:, 1], eval_rotation=hdr[:, 2].astype(np.uint8), eval_path_len=hdr[:, 3],
         eval_features=np.packbits(feats, axis=1), eval_policy=fl[:, :a_size], eval_logits=fl[:, a_size:2 * a_size], eval_value=fl[:, 2 * a_size],
         move_game=mh_i[:, 0], move_number=mh_i[:, 1], move_action=mh_i[:, 2], move_player=mh_i[:, 3], move_num_children=mh_i[:, 4], move_resign=mh_i[:, 5],
@@ -61,8 +71,8 @@ def main(names):
             conf_full = conf + ":nn_file_name=" + os.path.join(HERE, "_ref", "nets", net + ".pt")
             res = subprocess.run([os.path.join(HERE, "_ref", "ref_stepper_" + binary), conf_full, d, str(max_moves)], check=True, capture_output=True, text=True)
             meta = dict(line.split() for line in open(os.path.join(d, "meta.txt")))
-            data = read_case(d, int(meta["A"]), int(meta["F"]))
-            data.update(A=int(meta["A"]), F=int(meta["F"]), S=int(meta["S"]), B=int(meta["B"]), conf=conf, selfplay_lines=np.array(res.stdout.splitlines()))
+            data = read_case(d, int(meta["A"]), int(meta["F"]), 4 if meta["type"] == "alphazero" else 6)
+            data.update(A=int(meta["A"]), F=int(meta["F"]), S=int(meta["S"]), B=int(meta["B"]), conf=conf, net_type=meta["type"], selfplay_lines=np.array(res.stdout.splitlines()))
             np.savez_compressed(os.path.join(OUT, name + ".npz"), **data)
             print(name, "evals", data["eval_game"].size, "moves", data["move_game"].size, "selfplay lines", len(res.stdout.splitlines()),
                   os.path.getsize(os.path.join(OUT, name + ".npz")) // 1024, "KiB")

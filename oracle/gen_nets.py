@@ -20,6 +20,7 @@ NETS = {
     "go9_az_1bx16": ("go_9x9", 18, 9, 9, 16, 9, 9, 1, 1, 82, 64, 1, "alphazero"),
     "go9_az_2bx64": ("go_9x9", 18, 9, 9, 64, 9, 9, 1, 2, 82, 256, 1, "alphazero"),
     "go9_az_6bx256": ("go_9x9", 18, 9, 9, 256, 9, 9, 1, 6, 82, 256, 1, "alphazero"),
+    "othello_mz_1bx32": ("othello_8x8", 4, 8, 8, 32, 8, 8, 1, 1, 65, 64, 1, "muzero"),
     "othello_mz_3bx128": ("othello_8x8", 4, 8, 8, 128, 8, 8, 1, 3, 65, 256, 1, "muzero"),
 }
 

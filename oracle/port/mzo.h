@@ -20,6 +20,7 @@ extern "C" {
 
 #define MZO_GAME_TICTACTOE 0
 #define MZO_GAME_GO 1
+#define MZO_GAME_OTHELLO 2
 
 #define MZO_MAX_N 19
 #define MZO_MAX_CELLS (MZO_MAX_N * MZO_MAX_N)
@@ -39,6 +40,12 @@ typedef struct {
     int32_t ko_situational; /* env_go_ko_rule == "situational" */
     int32_t value_rescale;  /* actor_mcts_value_rescale */
     float dirichlet_epsilon; /* actor_dirichlet_noise_epsilon (used when noise is supplied) */
+    int32_t muzero;          /* nn_type_name == "muzero": no environment below the root (zero_actor.cpp:59-67,86-90) */
+    int32_t use_gumbel;      /* actor_use_gumbel */
+    int32_t gumbel_noise;    /* actor_use_gumbel_noise: supplied noise is added to the root children's logits (zero_actor.cpp:205-211) */
+    int32_t gumbel_sample_size; /* actor_gumbel_sample_size */
+    float gumbel_sigma_visit_c; /* actor_gumbel_sigma_visit_c */
+    float gumbel_sigma_scale_c; /* actor_gumbel_sigma_scale_c */
 } mzo_config;
 
 /* ---- environment (environment/go/go.cpp, environment/tictactoe/tictactoe.cpp) ---- */
@@ -60,6 +67,7 @@ int mzo_env_act(mzo_env* e, int action, int player);
 int mzo_env_is_terminal(const mzo_env* e);
 float mzo_env_eval_score(const mzo_env* e, int is_resign);
 void mzo_env_features(const mzo_env* e, int rotation, float* out);
+void mzo_env_action_features(const mzo_env* e, int action, float* out);
 int mzo_rotate_position(int rotation, int pos, int n);
 int mzo_reversed_rotation(int rotation);
 uint64_t mzo_go_key(int pos, int player);
@@ -96,6 +104,17 @@ const mzo_env* mzo_root_env(const mzo_batch* b, int g);
 /* BaseActor::act on the root environment; returns 1 if the move was legal and applied */
 int mzo_play(mzo_batch* b, int g, int action);
 int mzo_select_by_max_count(const mzo_batch* b, int g);
+/* MuZero: action id of the leaf chosen by the last mzo_select (-1 for the root) and of its parent's evaluation slot
+ * (the simulation index whose hidden state feeds the dynamics network, zero_actor.cpp:62-66) */
+int mzo_leaf_action(const mzo_batch* b, int g);
+int mzo_leaf_parent_slot(const mzo_batch* b, int g);
+/* FNV-1a over the action ids of the selected path (same formula as oracle/drivers/ref_stepper.cpp) */
+int mzo_path_hash(const mzo_batch* b, int g);
+/* GumbelZero::decideActionNode with actor_select_action_by_count (gumbel_zero.cpp:61-66): action id */
+int mzo_gumbel_best_action(mzo_batch* b, int g);
+/* GumbelZero::getMCTSPolicy (gumbel_zero.cpp:9-59): fills action ids / probabilities of the entries the reference prints
+ * (completed-Q softmax, entries below -38 dropped) in ascending action id; returns how many */
+int mzo_gumbel_policy(const mzo_batch* b, int g, int32_t* actions, float* probs);
 
 /* ---- network forward, fp32 (network/py/alphazero_network.py, network_unit.py) ---- */
 typedef struct mzo_net mzo_net;

@@ -119,9 +119,14 @@ void mzo_env_init(mzo_env* e, int game, int n, float komi, int ko_situational)
     e->turn = 1; /* go.cpp:105, tictactoe.cpp:13 */
     e->komi = komi;
     e->turn_key = (ko_situational ? g_turn_key : 0); /* go.cpp:45-49 */
+    if (game == MZO_GAME_OTHELLO) { /* othello.cpp:13-31: initial four stones; Black (kPlayer1) to move */
+        const int bs = e->n, init_place = bs * (bs / 2 - (1 - bs % 2)) + (bs / 2 - 1);
+        e->board[init_place + 1] = 2, e->board[init_place + bs] = 2;
+        e->board[init_place] = 1, e->board[init_place + bs + 1] = 1;
+    }
 }
 
-int mzo_env_num_actions(const mzo_env* e) { return e->game == MZO_GAME_GO ? e->n * e->n + 1 : 9; }
+int mzo_env_num_actions(const mzo_env* e) { return e->game == MZO_GAME_TICTACTOE ? 9 : e->n * e->n + 1; }
 int mzo_env_input_channels(const mzo_env* e) { return e->game == MZO_GAME_GO ? 18 : 4; }
 
 /* neighbour order of go_grid.h:43-54: up(+n), right(+1), down(-n), left(-1) */
@@ -324,6 +329,95 @@ static void go_features(const mzo_env* e, int rotation, float* out)
     }
 }
 
+
+/* ---- othello (environment/othello/othello.cpp) ----
+ * The reference keeps per-player "legal boards" refreshed by every non-pass act() with shift-and-mask
+ * bitboard sweeps (othello.cpp:63-99,125-137). Those sweeps compute exactly the standard rule — a point is
+ * playable when, in at least one of the 8 directions, a run of one or more opposing stones is followed by
+ * an own stone — so legality here is that rule evaluated on the current board. legal_pass_ is "the legal
+ * board is empty" (othello.cpp:135-136); it starts false (othello.cpp:17) and the initial position has
+ * moves for both sides, so it too is a function of the board alone. */
+static const int oth_dx[8] = {0, 0, -1, 1, -1, 1, 1, -1};
+static const int oth_dy[8] = {1, -1, 0, 0, 1, 1, -1, -1};
+
+/* stones flipped by `player` playing the empty point pos (othello.cpp:63-82); flips may be NULL */
+static int othello_flips(const mzo_env* e, int pos, int player, int* flips)
+{
+    const int n = e->n, x0 = pos % n, y0 = pos / n, opp = other(player);
+    int total = 0;
+    for (int d = 0; d < 8; ++d) {
+        int x = x0 + oth_dx[d], y = y0 + oth_dy[d], run = 0;
+        while (x >= 0 && x < n && y >= 0 && y < n && e->board[y * n + x] == opp) { x += oth_dx[d], y += oth_dy[d], ++run; }
+        if (run == 0 || x < 0 || x >= n || y < 0 || y >= n || e->board[y * n + x] != player) { continue; }
+        for (int k = 1; k <= run; ++k) {
+            if (flips) { flips[total] = (y0 + k * oth_dy[d]) * n + x0 + k * oth_dx[d]; }
+            ++total;
+        }
+    }
+    return total;
+}
+
+static int othello_can_put(const mzo_env* e, int pos, int player) { return e->board[pos] == 0 && othello_flips(e, pos, player, 0) > 0; }
+
+static int othello_has_move(const mzo_env* e, int player)
+{
+    for (int pos = 0; pos < e->n * e->n; ++pos) {
+        if (othello_can_put(e, pos, player)) { return 1; }
+    }
+    return 0;
+}
+
+/* othello.cpp:192-199 */
+static int othello_is_legal(const mzo_env* e, int action, int player)
+{
+    if (action < 0 || action > e->n * e->n) { return 0; }
+    if (action == e->n * e->n) { return !othello_has_move(e, player); }
+    return othello_can_put(e, action, player);
+}
+
+/* othello.cpp:102-139 */
+static int othello_act(mzo_env* e, int action, int player)
+{
+    if (!othello_is_legal(e, action, player)) { return 0; }
+    e->actions[e->num_moves++] = (int16_t)action;
+    e->turn = other(player);
+    if (action == e->n * e->n) { return 1; }
+    int flips[MZO_MAX_CELLS];
+    const int k = othello_flips(e, action, player, flips);
+    e->board[action] = (uint8_t)player;
+    for (int i = 0; i < k; ++i) { e->board[flips[i]] = (uint8_t)player; }
+    return 1;
+}
+
+/* othello.cpp:201-207 */
+static int othello_is_terminal(const mzo_env* e)
+{
+    const int pass = e->n * e->n;
+    return e->num_moves >= 2 && e->actions[e->num_moves - 1] == pass && e->actions[e->num_moves - 2] == pass;
+}
+
+/* othello.cpp:209-236 */
+static float othello_eval_score(const mzo_env* e, int is_resign)
+{
+    int r = 0;
+    if (is_resign) {
+        r = other(e->turn);
+    } else if (!othello_has_move(e, 1) && !othello_has_move(e, 2)) {
+        int c1 = 0, c2 = 0;
+        for (int i = 0; i < e->n * e->n; ++i) { c1 += (e->board[i] == 1), c2 += (e->board[i] == 2); }
+        r = (c1 > c2 ? 1 : (c1 < c2 ? 2 : 0));
+    }
+    return r == 1 ? 1.0f : (r == 2 ? -1.0f : 0.0f);
+}
+
+/* getActionFeatures (othello.cpp:257-262): one-hot plane of the action, all zero for a pass */
+void mzo_env_action_features(const mzo_env* e, int action, float* out)
+{
+    const int cells = e->n * e->n;
+    for (int i = 0; i < cells; ++i) { out[i] = 0.0f; }
+    if (action >= 0 && action < cells) { out[action] = 1.0f; }
+}
+
 /* ---- tictactoe (tictactoe.cpp:124-146 eval) ---- */
 static int ttt_eval(const mzo_env* e)
 {
@@ -348,12 +442,14 @@ static int ttt_eval(const mzo_env* e)
 int mzo_env_is_legal(const mzo_env* e, int action, int player)
 {
     if (e->game == MZO_GAME_GO) { return go_is_legal(e, action, player); }
+    if (e->game == MZO_GAME_OTHELLO) { return othello_is_legal(e, action, player); }
     return action >= 0 && action < 9 && e->board[action] == 0; /* tictactoe.cpp:44-49 */
 }
 
 int mzo_env_act(mzo_env* e, int action, int player)
 {
     if (e->game == MZO_GAME_GO) { return go_act(e, action, player); }
+    if (e->game == MZO_GAME_OTHELLO) { return othello_act(e, action, player); }
     if (!mzo_env_is_legal(e, action, player)) { return 0; } /* tictactoe.cpp:19-26 */
     e->actions[e->num_moves++] = (int16_t)action;
     e->board[action] = (uint8_t)player;
@@ -364,6 +460,7 @@ int mzo_env_act(mzo_env* e, int action, int player)
 int mzo_env_is_terminal(const mzo_env* e)
 {
     if (e->game == MZO_GAME_GO) { return go_is_terminal(e); }
+    if (e->game == MZO_GAME_OTHELLO) { return othello_is_terminal(e); }
     if (ttt_eval(e) != 0) { return 1; } /* tictactoe.cpp:51-55 */
     for (int i = 0; i < 9; ++i) {
         if (e->board[i] == 0) { return 0; }
@@ -374,6 +471,7 @@ int mzo_env_is_terminal(const mzo_env* e)
 float mzo_env_eval_score(const mzo_env* e, int is_resign)
 {
     if (e->game == MZO_GAME_GO) { return go_eval_score(e, is_resign); }
+    if (e->game == MZO_GAME_OTHELLO) { return othello_eval_score(e, is_resign); }
     int r = (is_resign ? other(e->turn) : ttt_eval(e)); /* tictactoe.cpp:57-65 */
     return r == 1 ? 1.0f : (r == 2 ? -1.0f : 0.0f);
 }
@@ -384,10 +482,11 @@ void mzo_env_features(const mzo_env* e, int rotation, float* out)
         go_features(e, rotation, out);
         return;
     }
-    int rev = mzo_reversed_rotation(rotation); /* tictactoe.cpp:67-90 */
+    int rev = mzo_reversed_rotation(rotation); /* tictactoe.cpp:67-90, othello.cpp:237-255: same four planes */
+    const int cells = e->n * e->n;
     for (int c = 0; c < 4; ++c) {
-        for (int pos = 0; pos < 9; ++pos) {
-            int rp = mzo_rotate_position(rev, pos, 3);
+        for (int pos = 0; pos < cells; ++pos) {
+            int rp = mzo_rotate_position(rev, pos, e->n);
             float v;
             if (c == 0) {
                 v = (e->board[rp] == e->turn);
@@ -398,7 +497,7 @@ void mzo_env_features(const mzo_env* e, int rotation, float* out)
             } else {
                 v = (e->turn == 2);
             }
-            out[c * 9 + pos] = v;
+            out[c * cells + pos] = v;
         }
     }
 }

@@ -39,6 +39,10 @@ typedef struct {
     int16_t* action;
     uint8_t* player;
     float *count, *mean, *policy, *logit, *noise, *value, *reward;
+    int16_t* slot; /* MuZero: simulation index that evaluated the node = index of its hidden state (tree.h hidden_state_data_index_) */
+    /* GumbelZero state (gumbel_zero.h:20-23) */
+    int32_t cand[MZO_MAX_ACTIONS];
+    int32_t num_cand, sample_size, budget;
 } tree;
 
 struct mzo_batch {
@@ -59,6 +63,7 @@ static void node_reset(tree* t, int i)
     t->num_children[i] = 0;
     t->first_child[i] = -1;
     t->mean[i] = t->count[i] = t->policy[i] = t->logit[i] = t->noise[i] = t->value[i] = t->reward[i] = 0.0f;
+    t->slot[i] = -1;
 }
 
 static void tree_reset(tree* t)
@@ -97,6 +102,7 @@ mzo_batch* mzo_create(const mzo_config* cfg)
         t->noise = (float*)malloc(n * 4);
         t->value = (float*)malloc(n * 4);
         t->reward = (float*)malloc(n * 4);
+        t->slot = (int16_t*)malloc(n * 2);
         mzo_reset_game(b, g);
     }
     return b;
@@ -108,7 +114,7 @@ void mzo_destroy(mzo_batch* b)
     for (int g = 0; g < b->cfg.num_games; ++g) {
         tree* t = &b->trees[g];
         free(t->first_child), free(t->num_children), free(t->action), free(t->player);
-        free(t->count), free(t->mean), free(t->policy), free(t->logit), free(t->noise), free(t->value), free(t->reward);
+        free(t->count), free(t->mean), free(t->policy), free(t->logit), free(t->noise), free(t->value), free(t->reward), free(t->slot);
     }
     free(b->root_env), free(b->leaf_env), free(b->trees), free(b->path), free(b->path_len), free(b->rotation);
     free(b);
@@ -185,6 +191,116 @@ static int select_child(const mzo_batch* b, const tree* t, int node)
     return selected;
 }
 
+
+/* ---- Gumbel (actor/gumbel_zero.cpp) ---- */
+static float gumbel_max_child_count(const tree* t)
+{
+    float m = 0;
+    for (int i = 0; i < t->num_children[0]; ++i) { m = (float)fmax(m, t->count[t->first_child[0] + i]); }
+    return m;
+}
+
+/* gumbel_zero.cpp:120-137: candidates by descending logit + (c_visit + max_count) * c_scale * q; unvisited ones last */
+static void sort_candidates_by_score(const mzo_batch* b, tree* t)
+{
+    const float max_child_count = gumbel_max_child_count(t);
+    float score[MZO_MAX_ACTIONS];
+    for (int i = 0; i < t->num_cand; ++i) {
+        int c = t->cand[i];
+        float v = normalized_mean(b, t, c);
+        float s = t->logit[c] + (b->cfg.gumbel_sigma_visit_c + max_child_count) * b->cfg.gumbel_sigma_scale_c * v;
+        score[i] = (t->count[c] > 0 ? s : -3.402823466e+38f);
+    }
+    for (int i = 1; i < t->num_cand; ++i) { /* stable insertion sort, descending */
+        int c = t->cand[i];
+        float s = score[i];
+        int j = i;
+        while (j > 0 && score[j - 1] < s) {
+            t->cand[j] = t->cand[j - 1], score[j] = score[j - 1];
+            --j;
+        }
+        t->cand[j] = c, score[j] = s;
+    }
+}
+
+/* gumbel_zero.cpp:87-118 */
+static void sequential_halving(const mzo_batch* b, tree* t)
+{
+    const int S = b->cfg.num_simulation, m = b->cfg.gumbel_sample_size;
+    if ((int)t->count[0] == 1) {
+        t->num_cand = 0;
+        for (int i = 0; i < t->num_children[0]; ++i) { /* descending logit (noise already added), stable */
+            int c = t->first_child[0] + i, j = t->num_cand++;
+            while (j > 0 && t->logit[t->cand[j - 1]] < t->logit[c]) {
+                t->cand[j] = t->cand[j - 1];
+                --j;
+            }
+            t->cand[j] = c;
+        }
+        if (t->num_cand > m) { t->num_cand = m; }
+        t->sample_size = m;
+        t->budget = (int)fmax(1.0, floor(S / (log2((double)m) * t->sample_size)));
+    } else {
+        for (int i = 0; i < t->num_cand; ++i) {
+            if (!(t->count[t->cand[i]] >= (float)t->budget)) { return; }
+        }
+        int next_budget = (int)floor(S / (log2((double)m) * (t->sample_size / 2)));
+        if (next_budget > 0 && t->sample_size > 2) {
+            t->sample_size /= 2;
+            sort_candidates_by_score(b, t);
+            if (t->num_cand > t->sample_size) { t->num_cand = t->sample_size; }
+            t->budget = (int)(t->count[t->cand[0]] + next_budget);
+        }
+    }
+}
+
+int mzo_gumbel_best_action(mzo_batch* b, int g)
+{
+    tree* t = &b->trees[g];
+    if (t->num_cand <= 0) { return -1; }
+    sort_candidates_by_score(b, t);
+    return t->action[t->cand[0]];
+}
+
+/* gumbel_zero.cpp:9-59 */
+int mzo_gumbel_policy(const mzo_batch* b, int g, int32_t* actions, float* probs)
+{
+    const tree* t = &b->trees[g];
+    const int nc = t->num_children[0], fc = t->first_child[0];
+    float pi_sum = 0.0f, q_sum = 0.0f;
+    for (int i = 0; i < nc; ++i) {
+        int c = fc + i;
+        if (t->count[c] == 0) { continue; }
+        float value = normalized_mean(b, t, c);
+        pi_sum += t->policy[c];
+        q_sum += t->policy[c] * value;
+    }
+    float value_pi = t->value[0];
+    value_pi = (t->player[fc] == 2 ? -value_pi : value_pi);
+    const int S = b->cfg.num_simulation;
+    float non_visited = (float)(1.0 / (1 + S) * (value_pi + (S / pi_sum) * q_sum));
+    float max_logit = -3.402823466e+38f, max_child_count = gumbel_max_child_count(t);
+    float score[MZO_MAX_ACTIONS];
+    for (int i = 0; i < nc; ++i) {
+        int c = fc + i;
+        float value = (t->count[c] == 0 ? non_visited : normalized_mean(b, t, c));
+        float lw = t->logit[c] - t->noise[c];
+        score[i] = lw + (b->cfg.gumbel_sigma_visit_c + max_child_count) * b->cfg.gumbel_sigma_scale_c * value;
+        max_logit = (float)fmax(max_logit, score[i]);
+    }
+    int n = 0;
+    for (int a = 0; a < b->A; ++a) { /* ascending action id (the reference prints in unordered_map order) */
+        for (int i = 0; i < nc; ++i) {
+            if (t->action[fc + i] != a) { continue; }
+            float l = score[i] - max_logit;
+            if (l < -38) { continue; }
+            actions[n] = a;
+            probs[n++] = (float)exp(l);
+        }
+    }
+    return n;
+}
+
 /* ZeroActor::beforeNNEvaluation, zero_actor.cpp:51-58 */
 void mzo_select(mzo_batch* b, const uint8_t* rotations, float* features)
 {
@@ -194,11 +310,32 @@ void mzo_select(mzo_batch* b, const uint8_t* rotations, float* features)
         int32_t* path = b->path + (size_t)g * S2;
         int len = 0, node = 0;
         path[len++] = 0;
+        if (b->cfg.use_gumbel && t->count[0] != 0.0f) {
+            /* GumbelZero::selection, gumbel_zero.cpp:70-85: the least visited candidate (ties: larger logit), PUCT below it */
+            int best = 0;
+            for (int i = 1; i < t->num_cand; ++i) {
+                int c = t->cand[i], d = t->cand[best];
+                if (t->count[c] < t->count[d] || (t->count[c] == t->count[d] && t->logit[c] > t->logit[d])) { best = i; }
+            }
+            node = t->cand[best];
+            path[len++] = node;
+        }
         while (t->num_children[node] > 0) { /* mcts.cpp:139-148 */
             node = select_child(b, t, node);
             path[len++] = node;
         }
         b->path_len[g] = len;
+        if (b->cfg.muzero) { /* zero_actor.cpp:59-67: root features for the initial inference, nothing else touches the environment */
+            b->rotation[g] = 0;
+            if (features) {
+                if (len == 1) {
+                    mzo_env_features(&b->root_env[g], 0, features + (size_t)g * b->F);
+                } else {
+                    memset(features + (size_t)g * b->F, 0, sizeof(float) * (size_t)b->F);
+                }
+            }
+            continue;
+        }
         /* getEnvironmentTransition, zero_actor.cpp:247-252 */
         mzo_env* e = &b->leaf_env[g];
         *e = b->root_env[g];
@@ -227,7 +364,36 @@ void mzo_apply(mzo_batch* b, const float* policy, const float* logits, const flo
         int leaf = path[len - 1];
         const mzo_env* e = &b->leaf_env[g];
         float v;
-        if (!mzo_env_is_terminal(e)) {
+        if (b->cfg.muzero) {
+            /* calculateMuZeroActionPolicy, zero_actor.cpp:231-245: every action below the root, the legal ones at the root */
+            const mzo_env* re = &b->root_env[g];
+            const int turn = (t->player[leaf] == 1 ? 2 : 1); /* leaf_node->getAction().nextPlayer() */
+            int cand_a[MZO_MAX_ACTIONS], k = 0;
+            float cand_p[MZO_MAX_ACTIONS], cand_l[MZO_MAX_ACTIONS];
+            for (int a = 0; a < A; ++a) {
+                if (leaf == 0 && !mzo_env_is_legal(re, a, turn)) { continue; }
+                float p = policy[(size_t)g * A + a], l = logits[(size_t)g * A + a];
+                int j = k++;
+                while (j > 0 && cand_p[j - 1] < p) {
+                    cand_a[j] = cand_a[j - 1], cand_p[j] = cand_p[j - 1], cand_l[j] = cand_l[j - 1];
+                    --j;
+                }
+                cand_a[j] = a, cand_p[j] = p, cand_l[j] = l;
+            }
+            t->first_child[leaf] = t->cursor;
+            t->num_children[leaf] = k;
+            for (int i = 0; i < k; ++i) {
+                int c = t->cursor + i;
+                node_reset(t, c);
+                t->action[c] = (int16_t)cand_a[i];
+                t->player[c] = (uint8_t)turn;
+                t->policy[c] = cand_p[i];
+                t->logit[c] = cand_l[i];
+            }
+            t->cursor += k;
+            v = value[g];
+            t->slot[leaf] = (int16_t)t->count[0]; /* hidden states are stored in evaluation order (zero_actor.cpp:90) */
+        } else if (!mzo_env_is_terminal(e)) {
             /* calculateAlphaZeroActionPolicy, zero_actor.cpp:215-229 */
             int cand_a[MZO_MAX_ACTIONS], k = 0;
             float cand_p[MZO_MAX_ACTIONS], cand_l[MZO_MAX_ACTIONS];
@@ -274,15 +440,37 @@ void mzo_apply(mzo_batch* b, const float* policy, const float* logits, const flo
                 int c = t->first_child[0] + i;
                 float nz = noise[(size_t)g * A + i];
                 t->noise[c] = nz;
-                t->policy[c] = (1 - eps) * t->policy[c] + eps * nz;
+                if (b->cfg.gumbel_noise) { /* zero_actor.cpp:205-211 */
+                    t->logit[c] = t->logit[c] + nz;
+                } else {
+                    t->policy[c] = (1 - eps) * t->policy[c] + eps * nz;
+                }
             }
         }
+        if (b->cfg.use_gumbel) { sequential_halving(b, t); } /* zero_actor.cpp:97 */
         b->path_len[g] = 0;
     }
 }
 
 int mzo_num_simulation_done(const mzo_batch* b, int g) { return (int)b->trees[g].count[0]; }
 int mzo_path_len(const mzo_batch* b, int g) { return b->path_len[g]; }
+int mzo_leaf_action(const mzo_batch* b, int g)
+{
+    const int32_t* path = b->path + (size_t)g * (b->cfg.num_simulation + 2);
+    return b->path_len[g] > 0 ? b->trees[g].action[path[b->path_len[g] - 1]] : -1;
+}
+int mzo_leaf_parent_slot(const mzo_batch* b, int g)
+{
+    const int32_t* path = b->path + (size_t)g * (b->cfg.num_simulation + 2);
+    return b->path_len[g] > 1 ? b->trees[g].slot[path[b->path_len[g] - 2]] : -1;
+}
+int mzo_path_hash(const mzo_batch* b, int g)
+{
+    const int32_t* path = b->path + (size_t)g * (b->cfg.num_simulation + 2);
+    uint32_t h = 2166136261u;
+    for (int k = 1; k < b->path_len[g]; ++k) { h = (h ^ (uint32_t)(int32_t)b->trees[g].action[path[k]]) * 16777619u; }
+    return (int)(h & 0x7fffffffu);
+}
 const mzo_env* mzo_root_env(const mzo_batch* b, int g) { return &b->root_env[g]; }
 
 void mzo_root(const mzo_batch* b, int g, mzo_root_out* out)

@@ -15,16 +15,21 @@ def load_case(name):
 
 def assert_tie_free(case):
     """std::sort is unstable; child order is only implementation-independent without exact policy ties."""
+    gumbel = "actor_use_gumbel_noise=true" in str(case.get("conf", ""))
     for m in range(case["move_game"].size):
         k = int(case["move_num_children"][m])
         noise = case["child_noise"][m, :k]
+        if gumbel:  # Gumbel noise goes to the logits; the priors stay sorted
+            p = case["child_policy"][m, :k]
+            assert np.all(p[:-1] > p[1:]), "exact policy tie in golden vector"
+            continue
         if np.any(noise != 0):
             continue  # policies were mixed with noise after sorting; order not checkable from the table
         p = case["child_policy"][m, :k]
         assert np.all(p[:-1] > p[1:]), "exact policy tie in golden vector"
 
 
-def replay(engine, case, check_features=True):
+def replay(engine, case, check_features=True, on_move=None):
     A, F, S, B = (int(case[k]) for k in "AFSB")
     n_evals = case["eval_game"].size
     n_cycles = n_evals // B
@@ -36,11 +41,19 @@ def replay(engine, case, check_features=True):
         sl = slice(c * B, (c + 1) * B)
         assert np.all(case["eval_game"][sl] == np.arange(B))
         feats = engine.select(case["eval_rotation"][sl])
+        muzero = "eval_leaf_action" in case
         if check_features:
             want = np.unpackbits(case["eval_features"][sl], axis=1)[:, :F].astype(np.float32)
-            assert np.array_equal(feats, want), f"feature mismatch at cycle {c}"
+            if muzero:  # only the initial inference consumes feature planes (zero_actor.cpp:59-61)
+                root = case["eval_path_len"][sl] == 1
+                assert np.array_equal(feats[root], want[root]), f"feature mismatch at cycle {c}"
+            else:
+                assert np.array_equal(feats, want), f"feature mismatch at cycle {c}"
         for g in range(B):
             assert engine.path_len(g) == case["eval_path_len"][sl][g], f"path length mismatch cycle {c} game {g}"
+            if muzero:
+                assert engine.leaf_action(g) == case["eval_leaf_action"][sl][g], f"leaf action mismatch cycle {c} game {g}"
+                assert engine.path_hash(g) == case["eval_path_hash"][sl][g], f"path mismatch cycle {c} game {g}"
         use_noise = bool(np.any(case["child_noise"] != 0))  # actor_use_dirichlet_noise in the recording
         noise = np.zeros((B, A), np.float32) if use_noise else None
         for g in range(B if use_noise else 0):
@@ -63,6 +76,8 @@ def replay(engine, case, check_features=True):
                 got, want = r[name][:k], case["child_" + name][m, :k]
                 assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"root child {name} mismatch at move {m}"
             checked_moves += 1
+            if on_move is not None:
+                on_move(g, m, engine)
             if case["move_resign"][m]:
                 engine.reset_game(g)
             else:

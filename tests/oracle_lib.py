@@ -7,13 +7,15 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MAX_ACTIONS = 19 * 19 + 1
-GAME_TICTACTOE, GAME_GO = 0, 1
+GAME_TICTACTOE, GAME_GO, GAME_OTHELLO = 0, 1, 2
 
 
 class Config(C.Structure):
     _fields_ = [("game", C.c_int32), ("board_size", C.c_int32), ("num_games", C.c_int32), ("num_simulation", C.c_int32),
                 ("puct_base", C.c_float), ("puct_init", C.c_float), ("reward_discount", C.c_float), ("komi", C.c_float),
-                ("ko_situational", C.c_int32), ("value_rescale", C.c_int32), ("dirichlet_epsilon", C.c_float)]
+                ("ko_situational", C.c_int32), ("value_rescale", C.c_int32), ("dirichlet_epsilon", C.c_float),
+                ("muzero", C.c_int32), ("use_gumbel", C.c_int32), ("gumbel_noise", C.c_int32), ("gumbel_sample_size", C.c_int32),
+                ("gumbel_sigma_visit_c", C.c_float), ("gumbel_sigma_scale_c", C.c_float)]
 
 
 class RootOut(C.Structure):
@@ -23,7 +25,17 @@ class RootOut(C.Structure):
 
 def default_config(game, board_size, num_games, num_simulation):
     # defaults of config/configuration.cpp:13-28,80
-    return Config(game, board_size, num_games, num_simulation, 19652.0, 1.25, 1.0, 7.5, 0, 0, 0.25)
+    return Config(game, board_size, num_games, num_simulation, 19652.0, 1.25, 1.0, 7.5, 0, 0, 0.25, 0, 0, 0, 16, 50.0, 1.0)
+
+
+def conf_overrides(conf):
+    """search settings of a golden case's conf string -> Config / Engine keyword overrides (config/configuration.cpp:95-195)"""
+    kv = dict(item.split("=", 1) for item in str(conf).split(":") if "=" in item)
+    true = lambda k, default: kv.get(k, default) == "true"
+    return dict(muzero=int(kv.get("nn_type_name", "alphazero") == "muzero"), use_gumbel=int(true("actor_use_gumbel", "false")),
+                gumbel_noise=int(true("actor_use_gumbel_noise", "false") and not true("actor_use_dirichlet_noise", "true")),
+                gumbel_sample_size=int(kv.get("actor_gumbel_sample_size", 16)), gumbel_sigma_visit_c=float(kv.get("actor_gumbel_sigma_visit_c", 50)),
+                gumbel_sigma_scale_c=float(kv.get("actor_gumbel_sigma_scale_c", 1)))
 
 
 def load():
@@ -45,6 +57,9 @@ def load():
     lib.mzo_root_env.argtypes = [vp, i32]
     lib.mzo_play.argtypes = [vp, i32, i32]
     lib.mzo_select_by_max_count.argtypes = [vp, i32]
+    for fn in ("mzo_leaf_action", "mzo_leaf_parent_slot", "mzo_path_hash", "mzo_gumbel_best_action"):
+        getattr(lib, fn).argtypes = [vp, i32]
+    lib.mzo_gumbel_policy.argtypes = [vp, i32, C.POINTER(C.c_int32), f32p]
     lib.mzo_env_is_terminal.argtypes = [vp]
     lib.mzo_env_is_legal.argtypes = [vp, i32, i32]
     lib.mzo_env_eval_score.restype = C.c_float
@@ -76,7 +91,7 @@ class OracleSearch:
         self.h = lib.mzo_create(C.byref(self.cfg))
         n = 3 if game == GAME_TICTACTOE else board_size
         self.A = 9 if game == GAME_TICTACTOE else n * n + 1
-        self.F = (4 if game == GAME_TICTACTOE else 18) * n * n
+        self.F = (18 if game == GAME_GO else 4) * n * n
         self.B, self.S = num_games, num_simulation
 
     def __del__(self):
@@ -100,6 +115,23 @@ class OracleSearch:
 
     def path_len(self, g):
         return self.lib.mzo_path_len(self.h, g)
+
+    def leaf_action(self, g):
+        return self.lib.mzo_leaf_action(self.h, g)
+
+    def leaf_parent_slot(self, g):
+        return self.lib.mzo_leaf_parent_slot(self.h, g)
+
+    def path_hash(self, g):
+        return self.lib.mzo_path_hash(self.h, g)
+
+    def gumbel_best_action(self, g):
+        return self.lib.mzo_gumbel_best_action(self.h, g)
+
+    def gumbel_policy(self, g):
+        a, p = np.zeros(self.A, np.int32), np.zeros(self.A, np.float32)
+        n = self.lib.mzo_gumbel_policy(self.h, g, a.ctypes.data_as(C.POINTER(C.c_int32)), fptr(p))
+        return a[:n], p[:n]
 
     def root(self, g):
         out = RootOut()

@@ -10,6 +10,9 @@ CASES = {
     "ttt_s50_b1_det": (oracle_lib.GAME_TICTACTOE, 3),
     "go5_s24_b2": (oracle_lib.GAME_GO, 5),
     "go9_s32_b2": (oracle_lib.GAME_GO, 9),
+    "othello_gmz_s16_b2": (oracle_lib.GAME_OTHELLO, 8),
+    "othello_gmz_s32_m8_b2": (oracle_lib.GAME_OTHELLO, 8),
+    "othello_mz_s24_b2": (oracle_lib.GAME_OTHELLO, 8),
 }
 
 
@@ -18,7 +21,7 @@ def test_oracle_matches_reference_recording(oracle, name):
     game, n = CASES[name]
     case = golden_replay.load_case(name)
     golden_replay.assert_tie_free(case)
-    eng = oracle_lib.OracleSearch(oracle, game, n, int(case["B"]), int(case["S"]))
+    eng = oracle_lib.OracleSearch(oracle, game, n, int(case["B"]), int(case["S"]), **oracle_lib.conf_overrides(case["conf"]))
     checked = golden_replay.replay(eng, case)
     assert checked >= case["move_game"].size - int(case["B"])
 
@@ -50,3 +53,31 @@ def test_oracle_net_matches_reference_outputs(oracle, name, net, dims):
     assert np.abs(lg - case["eval_logits"][:n]).max() < 1e-5
     assert np.abs(pol - case["eval_policy"][:n]).max() < 1e-6
     assert np.abs(val - case["eval_value"][:n]).max() < 1e-5
+
+
+def test_oracle_gumbel_policy_matches_reference_records(oracle):
+    """GumbelZero::getMCTSPolicy (gumbel_zero.cpp:9-59): the P[...] tags of the records the compiled reference printed."""
+    import re
+    case = golden_replay.load_case("othello_gmz_s16_b2")
+    eng = oracle_lib.OracleSearch(oracle, oracle_lib.GAME_OTHELLO, 8, int(case["B"]), int(case["S"]), **oracle_lib.conf_overrides(case["conf"]))
+    got = {g: [] for g in range(int(case["B"]))}
+
+    def on_move(g, m, engine):
+        a, p = engine.gumbel_policy(g)
+        got[g].append((int(case["move_action"][m]), dict(zip(a.tolist(), p.tolist()))))
+
+    golden_replay.replay(eng, case, on_move=on_move)
+    lines = [str(x) for x in case["selfplay_lines"]]
+    assert lines
+    compared = 0
+    for line in lines:
+        moves = re.findall(r";[BW]\[(\d+)\]P\[([^\]]*)\]", line)
+        acts = [int(a) for a, _ in moves]
+        g = next(g for g in got if [a for a, _ in got[g][:len(acts)]] == acts)
+        for (a, ptag), (a2, dist) in zip(moves, got[g]):
+            want = {int(k): float(v) for k, v in (kv.split(":") for kv in ptag.split(","))}
+            assert set(want) == set(dist), (want, dist)
+            for k in want:
+                assert abs(want[k] - dist[k]) <= 1e-5 * max(1.0, abs(want[k])) + 5e-7, (k, want[k], dist[k])
+            compared += 1
+    assert compared > 100
