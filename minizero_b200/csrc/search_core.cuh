@@ -15,6 +15,9 @@
 //   actor/zero_actor.cpp:194-229,247-252 root noise mix, legal-filtered sorted candidates, env transition
 //   environment/go/go.cpp:132-308,690-723  act, isLegalAction (superko), isTerminal, Tromp-Taylor, features
 //   environment/tictactoe/tictactoe.cpp:19-146
+//   environment/othello/othello.cpp:13-262 act (flips), legal boards, pass, terminal, score, features
+//   actor/zero_actor.cpp:59-67,86-90,231-245  MuZero branch (no environment below the root, all actions expanded)
+//   actor/gumbel_zero.cpp:61-137           Gumbel: candidate selection, sequential halving, score order
 //   utils/rotation.h:22-93
 #pragma once
 #include <stdint.h>
@@ -140,6 +143,8 @@ static inline void mz_store_hot(mz_hot* p, float count, float mean, float policy
 
 #define MZ_GAME_TICTACTOE 0
 #define MZ_GAME_GO 1
+#define MZ_GAME_OTHELLO 2
+#define MZ_GUMBEL_LEVELS 12  // halvings of actor_gumbel_sample_size that can ever happen (m <= 362)
 #define MZ_MAXN 19
 #define MZ_MAXA (MZ_MAXN * MZ_MAXN + 1)
 #define MZ_ROWS 32           // row slots per bitboard (N <= 19 used)
@@ -155,6 +160,16 @@ struct mz_dims {
     int max_hashes; // per game: 2 * N * N + 4
     float puct_init, puct_base, discount, komi, eps;
     uint64_t turn_key; // go.cpp:45-49 (0 unless situational superko)
+    // MuZero (nn_type_name == "muzero"): no environment below the root; every evaluated node keeps its hidden state
+    int muzero;
+    int hid_c;   // channels per cell of a stored hidden state (the network's padded hidden width)
+    int dyn_c;   // channels per row of the dynamics network's input: hidden state, then the action planes, zero padded
+    int act_col; // column of the (single) action plane in a dynamics input row = num_hidden_channels
+    // Gumbel (actor_use_gumbel, gumbel_zero.cpp)
+    int gumbel, gumbel_noise, gumbel_m;
+    float sigma_visit_c, sigma_scale_c;
+    int gumbel_budget0;                   // max(1, floor(S / (log2(m) * m))), gumbel_zero.cpp:99 (host-computed in double)
+    int gumbel_next[MZ_GUMBEL_LEVELS];    // floor(S / (log2(m) * ((m >> level) / 2))), gumbel_zero.cpp:109
 };
 
 struct mz_state {
@@ -196,6 +211,14 @@ struct mz_state {
     const double* sqrt_table; // [S + 2] sqrt((double)n): IEEE-exact, identical to the host's sqrt (mcts.cpp:58)
     const uint64_t* keys;     // [2][361] Zobrist stone keys, go.cpp:19-32
     unsigned long long* dbg;  // optional [B][16] per-phase cycle counters (profiling only)
+    // MuZero: hidden states of the evaluated nodes of the current search, slot = simulation index (TreeData<HiddenStateData>, tree.h)
+    uint16_t* hid;       // [B][S + 1][N * N][hid_c] fp16, written by the hidden-state scaling kernel (null when not MuZero / host build)
+    uint16_t* dyn_in;    // [B * slots][dyn_c] fp16 rows of the dynamics network's input (parent hidden state + action plane)
+    int32_t* eval_slot;  // [B] slot the hidden state of this cycle's evaluation goes to
+    int32_t* leaf_parent; // [B][2] parent's slot (-1 for the root), leaf action: what the recurrent inference consumes (parity hook)
+    // Gumbel: GumbelZero::candidates_ / sample_size_ / simulation_budget_ (gumbel_zero.h:20-23)
+    int32_t* gum_cand;   // [B][A] node indices
+    int32_t* gum_meta;   // [B][4] number of candidates, sample size, budget, halving level
 };
 
 // per-warp scratch (shared memory on the device)
@@ -339,9 +362,15 @@ MZ_DEV void mz_env_reset(const mz_dims& d, mz_scratch* w, int lane)
 {
     for (int i = lane; i < 2 * MZ_ROWS; i += MZ_W) { (&w->st[0][0])[i] = 0u; }
     for (int i = lane; i < MZ_HIST * 2 * MZ_ROWS; i += MZ_W) { (&w->hist[0][0][0])[i] = 0u; }
+    mz_sync();
+    if (lane == 0 && d.game == MZ_GAME_OTHELLO) { // othello.cpp:22-27: Black (player 1) on init_place and its diagonal
+        const int bs = d.N, ip = bs * (bs / 2 - (1 - bs % 2)) + (bs / 2 - 1);
+        w->st[1][(ip + 1) / bs] |= 1u << ((ip + 1) % bs), w->st[1][(ip + bs) / bs] |= 1u << ((ip + bs) % bs);
+        w->st[0][ip / bs] |= 1u << (ip % bs), w->st[0][(ip + bs + 1) / bs] |= 1u << ((ip + bs + 1) % bs);
+    }
     if (lane == 0) {
         w->hash = 0; // go.cpp:106
-        w->turn = 1; // go.cpp:105, tictactoe.cpp:13
+        w->turn = 1; // go.cpp:105, tictactoe.cpp:13, othello.cpp:15
         w->num_moves = 0;
         w->last = -1;
         w->last2 = -1;
@@ -349,7 +378,39 @@ MZ_DEV void mz_env_reset(const mz_dims& d, mz_scratch* w, int lane)
     mz_sync();
 }
 
-// GoEnv::act (go.cpp:132-190) / TicTacToeEnv::act (tictactoe.cpp:19-26) for a move already known to
+
+// Othello: stones `player` (1 / 2) would flip by playing the EMPTY cell (x0, y0), as row masks OR-ed into flips[] when it
+// is not null; returns their number (OthelloEnv::getFlipPoint over the 8 directions, othello.cpp:63-82,119-121). The
+// reference's shift-and-mask sweeps implement the standard rule: a run of opposing stones closed by an own stone.
+MZ_DEV int mz_othello_flips(const mz_scratch* w, int N, int x0, int y0, int player, uint32_t* flips)
+{
+    const int me = player - 1, opp = 1 - me;
+    int total = 0;
+    for (int dir = 0; dir < 8; ++dir) {
+        const int dx = (dir == 2 || dir == 4 || dir == 7) ? -1 : ((dir == 3 || dir == 5 || dir == 6) ? 1 : 0);
+        const int dy = (dir == 0 || dir == 4 || dir == 5) ? 1 : ((dir == 1 || dir == 6 || dir == 7) ? -1 : 0);
+        int x = x0 + dx, y = y0 + dy, run = 0;
+        while (x >= 0 && x < N && y >= 0 && y < N && ((w->st[opp][y] >> x) & 1u)) { x += dx, y += dy, ++run; }
+        if (run == 0 || x < 0 || x >= N || y < 0 || y >= N || !((w->st[me][y] >> x) & 1u)) { continue; }
+        total += run;
+        if (flips) {
+            for (int k = 1; k <= run; ++k) { flips[y0 + k * dy] |= 1u << (x0 + k * dx); }
+        }
+    }
+    return total;
+}
+
+MZ_DEV int mz_othello_has_move(const mz_scratch* w, int N, int player)
+{
+    for (int c = 0; c < N * N; ++c) {
+        const int x = c % N, y = c / N;
+        if (((w->st[0][y] | w->st[1][y]) >> x) & 1u) { continue; }
+        if (mz_othello_flips(w, N, x, y, player, nullptr) > 0) { return 1; }
+    }
+    return 0;
+}
+
+// GoEnv::act (go.cpp:132-190) / TicTacToeEnv::act (tictactoe.cpp:19-26) / OthelloEnv::act (othello.cpp:102-139) for a move already known to
 // be legal. The caller appends the new w->hash to the superko history (go.cpp:145-147,180-182).
 MZ_DEV void mz_env_act(const mz_dims& d, const mz_state& s, mz_scratch* w, int a, int player, int lane)
 {
@@ -388,6 +449,14 @@ MZ_DEV void mz_env_act(const mz_dims& d, const mz_state& s, mz_scratch* w, int a
                 mz_sync();
             }
         }
+    } else if (d.game == MZ_GAME_OTHELLO) {
+        if (lane == 0 && a != N * N) { // a pass only hands the turn over (othello.cpp:111)
+            for (int i = 0; i < N; ++i) { w->tmp[i] = 0u; }
+            mz_othello_flips(w, N, a % N, a / N, player, w->tmp);
+            w->st[me][a / N] |= (1u << (a % N));
+            for (int i = 0; i < N; ++i) { w->st[me][i] |= w->tmp[i], w->st[opp][i] &= ~w->tmp[i]; }
+        }
+        mz_sync();
     } else {
         if (lane == 0) { w->st[me][a / N] |= (1u << (a % N)); }
         mz_sync();
@@ -427,6 +496,7 @@ MZ_DEV int mz_env_is_terminal(const mz_dims& d, const mz_scratch* w)
         if (w->num_moves >= 2 && w->last == N * N && w->last2 == N * N) { return 1; } // go.cpp:249-251
         return w->num_moves > 2 * N * N;                                              // go.cpp:254
     }
+    if (d.game == MZ_GAME_OTHELLO) { return w->num_moves >= 2 && w->last == N * N && w->last2 == N * N; } // othello.cpp:201-207
     if (mz_ttt_eval(w) != 0) { return 1; } // tictactoe.cpp:51-55
     uint32_t occ = (w->st[0][0] | w->st[1][0]) & (w->st[0][1] | w->st[1][1]) & (w->st[0][2] | w->st[1][2]);
     return occ == 7u;
@@ -463,105 +533,17 @@ MZ_DEV float mz_env_eval_score(const mz_dims& d, mz_scratch* w, int lane)
         mz_sync();
         const float tb = (float)cnt_b, tw = mz_fadd((float)cnt_w, d.komi);
         winner = (tb > tw ? 1 : (tb < tw ? 2 : 0));
+    } else if (d.game == MZ_GAME_OTHELLO) { // OthelloEnv::eval, othello.cpp:219-236
+        winner = 0;
+        if (!mz_othello_has_move(w, N, 1) && !mz_othello_has_move(w, N, 2)) {
+            int c1 = 0, c2 = 0;
+            for (int i = 0; i < N; ++i) { c1 += mz_popc(w->st[0][i]), c2 += mz_popc(w->st[1][i]); }
+            winner = (c1 > c2 ? 1 : (c1 < c2 ? 2 : 0));
+        }
     } else {
         winner = mz_ttt_eval(w);
     }
     return winner == 1 ? 1.0f : (winner == 2 ? -1.0f : 0.0f);
-}
-
-// Legal action set of the side to move (go.cpp:208-244 for every action at once): writes w->legal (bit per
-// action id) and returns the number of legal actions. The superko history is root_list[0..root_n) (positions of the
-// game so far) followed by path_list[0..path_n) (positions along the current search path).
-MZ_DEV int mz_env_legal(const mz_dims& d, const mz_state& s, mz_scratch* w, const uint64_t* root_list, int root_n, const uint64_t* path_list, int path_n, int lane)
-{
-    const int N = d.N, A = d.A, me = w->turn - 1;
-    for (int i = lane; i < MZ_LEGAL_WORDS; i += MZ_W) { w->legal[i] = 0u; }
-    if (d.game != MZ_GAME_GO) {
-        mz_sync();
-        if (lane == 0) {
-            uint32_t bits = 0;
-            for (int r = 0; r < N; ++r) { bits |= (~(w->st[0][r] | w->st[1][r]) & mz_rowmask(N)) << (r * N); }
-            w->legal[0] = bits; // tictactoe.cpp:44-49
-        }
-        mz_sync();
-        return mz_popc(w->legal[0]);
-    }
-    // (1) empty points with an empty neighbour (go.cpp:225-226)
-    for (int i = lane; i < N; i += MZ_W) { w->tmp[i] = ~(w->st[0][i] | w->st[1][i]) & mz_rowmask(N); }
-    for (int i = lane; i < N * N; i += MZ_W) { w->cap_hash[i] = 0; }
-    mz_sync();
-    for (int i = lane; i < N; i += MZ_W) {
-        uint32_t e = w->tmp[i];
-        uint32_t nb = (e << 1) | (e >> 1) | (i > 0 ? w->tmp[i - 1] : 0u) | (i + 1 < N ? w->tmp[i + 1] : 0u);
-        w->legal_rows[i] = e & nb;
-        w->checked[i] = 0u;
-    }
-    mz_sync();
-    // (2) every block once: own blocks with > 1 liberty make their liberties playable (go.cpp:232-233);
-    //     opponent blocks with exactly 1 liberty are captured by playing it (go.cpp:235-238)
-    for (;;) {
-        int first = 1 << 30;
-        for (int i = lane; i < N; i += MZ_W) {
-            uint32_t rem = (w->st[0][i] | w->st[1][i]) & ~w->checked[i];
-            if (rem) { const int cand = i * 32 + mz_ffs0(rem); first = (cand < first ? cand : first); }
-        }
-        first = mz_reduce_min(first);
-        if (first == (1 << 30)) { break; }
-        const int br = first >> 5, bx = first & 31;
-        const int c = ((w->st[0][br] >> bx) & 1u) ? 0 : 1;
-        for (int i = lane; i < N; i += MZ_W) { w->fill[i] = (i == br ? (1u << bx) : 0u); }
-        mz_sync();
-        mz_flood(w->fill, w->st[c], N, lane);
-        int nlib = 0;
-        uint32_t libs[(MZ_ROWS + MZ_W - 1) / MZ_W];
-        int k = 0;
-        for (int i = lane; i < N; i += MZ_W, ++k) {
-            libs[k] = mz_dilate_row(w->fill, i, N) & w->tmp[i];
-            nlib += mz_popc(libs[k]);
-        }
-        nlib = mz_reduce_add(nlib);
-        if (c == me) {
-            if (nlib > 1) {
-                k = 0;
-                for (int i = lane; i < N; i += MZ_W, ++k) { w->legal_rows[i] |= libs[k]; }
-            }
-        } else if (nlib == 1) {
-            uint64_t bh = mz_block_hash(w->fill, c, s.keys, N, lane);
-            k = 0;
-            for (int i = lane; i < N; i += MZ_W, ++k) {
-                if (libs[k]) {
-                    w->legal_rows[i] |= libs[k];
-                    w->cap_hash[i * N + mz_ffs0(libs[k])] ^= bh; // several blocks may share the liberty
-                }
-            }
-        }
-        for (int i = lane; i < N; i += MZ_W) { w->checked[i] |= w->fill[i]; }
-        mz_sync();
-    }
-    // (3) positional superko (go.cpp:222,237,243)
-    const uint64_t base = w->hash ^ d.turn_key;
-    for (int a = lane; a < N * N; a += MZ_W) {
-        const int r = a / N, x = a % N;
-        if (!((w->legal_rows[r] >> x) & 1u)) { continue; }
-        const uint64_t nh = base ^ s.keys[me * 361 + a] ^ w->cap_hash[a];
-        int seen = 0;
-        for (int i = 0; i < root_n; ++i) { seen |= (root_list[i] == nh); }
-        for (int i = 0; i < path_n; ++i) { seen |= (path_list[i] == nh); }
-        if (!seen) {
-#if MZ_W == 1
-            w->legal[a >> 5] |= (1u << (a & 31));
-#else
-            atomicOr(&w->legal[a >> 5], 1u << (a & 31));
-#endif
-        }
-    }
-    mz_sync();
-    if (lane == 0) { w->legal[(N * N) >> 5] |= (1u << ((N * N) & 31)); } // pass, go.cpp:213
-    mz_sync();
-    int n = 0;
-    for (int i = lane; i < MZ_LEGAL_WORDS; i += MZ_W) { n += mz_popc(w->legal[i]); }
-    (void)A;
-    return mz_reduce_add(n);
 }
 
 MZ_DEV int mz_cell_colour(const mz_scratch* w, int c, int N)
@@ -580,6 +562,24 @@ MZ_DEV int mz_env_legal_block(const mz_dims& d, const mz_state& s, mz_scratch* w
 {
     const int N = d.N, NN = N * N, me = w->turn - 1;
     for (int i = tid; i < MZ_LEGAL_WORDS; i += nthreads) { w->legal[i] = 0u; }
+    if (d.game == MZ_GAME_OTHELLO) { // legal_board_ of the side to move (othello.cpp:125-134), pass iff it is empty (:135-136,194-196)
+        mz_block_sync();
+        for (int c = tid; c < NN; c += nthreads) {
+            const int x = c % N, y = c / N;
+            if (((w->st[0][y] | w->st[1][y]) >> x) & 1u) { continue; }
+            if (mz_othello_flips(w, N, x, y, w->turn, nullptr) > 0) { mz_atomic_or(&w->legal[c >> 5], 1u << (c & 31)); }
+        }
+        mz_block_sync();
+        int n = 0;
+        for (int i = 0; i < MZ_LEGAL_WORDS; ++i) { n += mz_popc(w->legal[i]); }
+        mz_block_sync();
+        if (n == 0) {
+            if (tid == 0) { w->legal[NN >> 5] |= (1u << (NN & 31)); }
+            mz_block_sync();
+            n = 1;
+        }
+        return n;
+    }
     if (d.game != MZ_GAME_GO) {
         mz_block_sync();
         if (tid == 0) {
@@ -1038,6 +1038,177 @@ MZ_DEV void mz_slot_load(const mz_dims& d, const mz_state& s, int g, int slot, m
     mz_sync();
 }
 
+
+// GumbelZero::sortCandidatesByScore (gumbel_zero.cpp:120-137): candidates by descending
+// logit + (c_visit + max child count) * c_scale * q, unvisited ones last. One thread; the lists are short
+// (actor_gumbel_sample_size) and this runs only at a halving and at the move decision.
+MZ_DEV void mz_gumbel_sort_by_score(const mz_dims& d, const mz_state& s, int g, int root_turn)
+{
+    const mz_hot* hot = s.hot + (size_t)g * d.NP;
+    int32_t* cand = s.gum_cand + (size_t)g * d.A;
+    const int n = s.gum_meta[g * 4 + 0];
+    const mz_hot root = mz_load_hot(hot);
+    const int nc = (int)(root.link >> MZ_LINK_SHIFT), fc = (int)(root.link & ((1u << MZ_LINK_SHIFT) - 1u));
+    float max_count = 0.0f;
+    for (int i = 0; i < nc; ++i) {
+        const float c = mz_load_hot(hot + fc + i).count;
+        max_count = (c > max_count ? c : max_count);
+    }
+    const float scale = mz_fmul(mz_fadd(d.sigma_visit_c, max_count), d.sigma_scale_c);
+    for (int i = 1; i < n; ++i) { // stable insertion sort, descending score
+        const int c = cand[i];
+        const mz_hot hc = mz_load_hot(hot + c);
+        const float sc = (hc.count > 0.0f ? mz_fadd(s.logit[(size_t)g * d.NP + c], mz_fmul(scale, mz_normalized_mean(d, hc.mean, hc.count, root_turn))) : -3.402823466e+38f);
+        int j = i;
+        while (j > 0) {
+            const int p = cand[j - 1];
+            const mz_hot hp = mz_load_hot(hot + p);
+            const float sp = (hp.count > 0.0f ? mz_fadd(s.logit[(size_t)g * d.NP + p], mz_fmul(scale, mz_normalized_mean(d, hp.mean, hp.count, root_turn))) : -3.402823466e+38f);
+            if (!(sp < sc)) { break; }
+            cand[j] = p;
+            --j;
+        }
+        cand[j] = c;
+    }
+}
+
+// GumbelZero::sequentialHalving (gumbel_zero.cpp:87-118), after every backup. Block collective.
+MZ_DEV void mz_gumbel_halving(const mz_dims& d, const mz_state& s, int g, int root_turn, int tid, int nthreads)
+{
+    const mz_hot* hot = s.hot + (size_t)g * d.NP;
+    int32_t* cand = s.gum_cand + (size_t)g * d.A;
+    int32_t* meta = s.gum_meta + g * 4;
+    const mz_hot root = mz_load_hot(hot);
+    const int nc = (int)(root.link >> MZ_LINK_SHIFT), fc = (int)(root.link & ((1u << MZ_LINK_SHIFT) - 1u));
+    if ((int)root.count == 1) { // first call of a search: the m root children with the largest (noisy) logits
+        const float* lg = s.logit + (size_t)g * d.NP + fc;
+        for (int i = tid; i < nc; i += nthreads) {
+            const float l = lg[i];
+            int rank = 0;
+            for (int j = 0; j < nc; ++j) { rank += (lg[j] > l || (lg[j] == l && j < i)) ? 1 : 0; }
+            if (rank < d.gumbel_m) { cand[rank] = fc + i; }
+        }
+        if (tid == 0) { meta[0] = (nc < d.gumbel_m ? nc : d.gumbel_m), meta[1] = d.gumbel_m, meta[2] = d.gumbel_budget0, meta[3] = 0; }
+        mz_block_sync();
+        return;
+    }
+    if (tid == 0) {
+        const int n = meta[0];
+        bool all = true;
+        for (int i = 0; i < n && all; ++i) { all = (mz_load_hot(hot + cand[i]).count >= (float)meta[2]); }
+        if (all) {
+            const int level = meta[3];
+            const int next_budget = (level < MZ_GUMBEL_LEVELS ? d.gumbel_next[level] : 0);
+            if (next_budget > 0 && meta[1] > 2) {
+                meta[1] /= 2;
+                meta[3] = level + 1;
+                mz_gumbel_sort_by_score(d, s, g, root_turn);
+                if (n > meta[1]) { meta[0] = meta[1]; }
+                meta[2] = (int)mz_fadd(mz_load_hot(hot + cand[0]).count, (float)next_budget);
+            }
+        }
+    }
+    mz_block_sync();
+}
+
+// GumbelZero::selection's root-level choice (gumbel_zero.cpp:76-81): least visited candidate, ties to the larger logit
+MZ_DEV int mz_gumbel_pick(const mz_dims& d, const mz_state& s, int g)
+{
+    const mz_hot* hot = s.hot + (size_t)g * d.NP;
+    const int32_t* cand = s.gum_cand + (size_t)g * d.A;
+    const int n = s.gum_meta[g * 4 + 0];
+    int best = cand[0];
+    float bc = mz_load_hot(hot + best).count, bl = s.logit[(size_t)g * d.NP + best];
+    for (int i = 1; i < n; ++i) {
+        const int c = cand[i];
+        const float cc = mz_load_hot(hot + c).count, cl = s.logit[(size_t)g * d.NP + c];
+        if (cc < bc || (cc == bc && cl > bl)) { best = c, bc = cc, bl = cl; }
+    }
+    return best;
+}
+
+// ZeroActor::beforeNNEvaluation, MuZero branch (zero_actor.cpp:51-72): selection (PUCT, or Gumbel at the root level), then
+// either the root position's feature planes (initial inference) or the parent's hidden state + the leaf's action plane
+// (recurrent inference) are laid out as the network's input rows. No environment exists below the root.
+MZ_DEV void mz_before_nn_muzero(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int lane, int wid, int nw)
+{
+    const int N = d.N, tid = wid * MZ_W + lane, nthreads = nw * MZ_W;
+    const int root_turn = s.root_meta[g * 4 + 0];
+    const mz_hot* hot = s.hot + (size_t)g * d.NP;
+    int32_t* path = s.path + (size_t)g * (d.S + 2);
+    const int sims = (int)mz_load_hot(hot).count; // MCTS::getNumSimulation, mcts.h:100
+    if (d.gumbel && sims > 0) {
+        if (wid == 0) {
+            int level = 1;
+            if (lane == 0) {
+                path[0] = 0;
+                path[1] = mz_gumbel_pick(d, s, g);
+            }
+            mz_sync();
+            mz_hot h = mz_load_hot(hot + path[1]);
+            while ((h.link >> MZ_LINK_SHIFT) != 0) { // MCTS::selectFromNode below the candidate, mcts.cpp:139-148
+                const int fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
+                mz_hot c;
+                const int best = mz_select_level(d, s, hot, h, false, (level & 1) ? 3 - root_turn : root_turn, w->q_warp, lane, c);
+                if (lane == 0) { path[level + 1] = fc + best; }
+                h = c;
+                ++level;
+                mz_sync();
+            }
+            if (lane == 0) { w->shared_len = level + 1; }
+        }
+    } else {
+        const int len0 = mz_select(d, s, g, w, root_turn, lane, wid, nw);
+        if (wid == 0 && lane == 0) { w->shared_len = len0; }
+    }
+    mz_block_sync();
+    const int len = w->shared_len, L = len - 1, leaf = path[L];
+    int num_legal = d.A;
+    if (L == 0) { // initial inference: env_.getFeatures() and the root's legal set (zero_actor.cpp:60,238)
+        if (wid == 0) { mz_env_load_root(d, s, g, w, lane); }
+        mz_block_sync();
+        const uint64_t* root_list = s.hashes + (size_t)g * d.max_hashes;
+        num_legal = mz_env_legal_block(d, s, w, root_list, s.root_meta[g * 4 + 1], root_list, 0, tid, nthreads);
+        mz_env_features(d, s, g, w, 0, tid, nthreads);
+    } else {
+        for (int i = tid; i < MZ_LEGAL_WORDS; i += nthreads) { // every action is expanded below the root (zero_actor.cpp:238)
+            const int lo = i * 32;
+            w->legal[i] = (d.A >= lo + 32 ? 0xffffffffu : (d.A > lo ? ((1u << (d.A - lo)) - 1u) : 0u));
+        }
+        const int pslot = s.node_slot[(size_t)g * d.NP + path[L - 1]];
+        const int a = s.action[(size_t)g * d.NP + leaf];
+#if MZ_W > 1
+        if (s.hid) { // recurrent inference input: parent's hidden state (zero_actor.cpp:65) + getActionFeatures(leaf action) (:66)
+            const uint4* src = reinterpret_cast<const uint4*>(s.hid + ((size_t)g * (d.S + 1) + pslot) * N * N * d.hid_c);
+            uint16_t* dst = s.dyn_in + (size_t)g * d.slots * d.dyn_c;
+            const int per_cell = d.hid_c / 8; // 16-byte chunks
+            for (int i = tid; i < N * N * per_cell; i += nthreads) {
+                const int cell = i / per_cell, k = i - cell * per_cell;
+                *reinterpret_cast<uint4*>(dst + (size_t)((cell / N + 1) * (N + 1) + cell % N) * d.dyn_c + k * 8) = src[i];
+            }
+            for (int cell = tid; cell < N * N; cell += nthreads) { // one-hot plane; all zero for a pass (othello.cpp:257-262)
+                dst[(size_t)((cell / N + 1) * (N + 1) + cell % N) * d.dyn_c + d.act_col] = (cell == a ? MZ_HALF_ONE : 0);
+            }
+        }
+#endif
+        if (tid == 0 && s.leaf_parent) { s.leaf_parent[g * 2 + 0] = pslot, s.leaf_parent[g * 2 + 1] = a; }
+    }
+    mz_block_sync();
+    for (int i = tid; i < MZ_LEGAL_WORDS; i += nthreads) { s.leaf_legal[g * MZ_LEGAL_WORDS + i] = w->legal[i]; }
+    if (tid == 0) {
+        s.node_slot[(size_t)g * d.NP + leaf] = (int16_t)sims; // hidden states are stored in evaluation order (zero_actor.cpp:90)
+        if (s.eval_slot) { s.eval_slot[g] = sims; }
+        if (L == 0 && s.leaf_parent) { s.leaf_parent[g * 2 + 0] = -1, s.leaf_parent[g * 2 + 1] = -1; }
+        s.path_len[g] = len;
+        s.spec_len[g] = (d.gumbel ? 0 : len);
+        s.leaf_meta[g * 4 + 0] = 0;
+        s.leaf_meta[g * 4 + 1] = (L & 1) ? 3 - root_turn : root_turn;
+        s.leaf_meta[g * 4 + 2] = 0;
+        s.leaf_meta[g * 4 + 3] = num_legal;
+        s.leaf_score[g] = 0.0f;
+    }
+}
+
 // One "before NN evaluation" step of game g (zero_actor.cpp:51-58): select, transition, analyse the leaf
 // (terminal / score / legal set) and emit its feature planes.
 //
@@ -1048,6 +1219,10 @@ MZ_DEV void mz_slot_load(const mz_dims& d, const mz_state& s, int g, int slot, m
 // environment for positions older than the root). Same positions, same results, cost independent of the depth.
 MZ_DEV void mz_before_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int lane, int wid, int nw)
 {
+    if (d.muzero) {
+        mz_before_nn_muzero(d, s, g, w, lane, wid, nw);
+        return;
+    }
     const int N = d.N, tid = wid * MZ_W + lane, nthreads = nw * MZ_W;
     const int root_turn = s.root_meta[g * 4 + 0], root_moves = s.root_meta[g * 4 + 1];
     const long long t0 = mz_clock();
@@ -1206,9 +1381,13 @@ MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* 
             for (int i = tid; i < A; i += nthreads) {
                 float nz = 0.0f;
                 if (s.noise_in && i < k) {
-                    const mz_hot h = mz_load_hot(hot + first + i);
                     nz = s.noise_in[(size_t)g * A + i];
-                    mz_store_hot(hot + first + i, h.count, h.mean, mz_fadd(mz_fmul(one_minus, h.policy), mz_fmul(eps, nz)), h.link);
+                    if (d.gumbel_noise) { // Gumbel noise goes to the logit (zero_actor.cpp:205-211)
+                        s.logit[(size_t)g * d.NP + first + i] = mz_fadd(s.logit[(size_t)g * d.NP + first + i], nz);
+                    } else {
+                        const mz_hot h = mz_load_hot(hot + first + i);
+                        mz_store_hot(hot + first + i, h.count, h.mean, mz_fadd(mz_fmul(one_minus, h.policy), mz_fmul(eps, nz)), h.link);
+                    }
                 }
                 s.root_noise[(size_t)g * A + i] = nz;
             }
@@ -1233,6 +1412,7 @@ MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* 
         mz_store_hot(hot + n, cnt, mean, h.policy, h.link);
     }
     mz_block_sync();
+    if (d.gumbel) { mz_gumbel_halving(d, s, g, s.root_meta[g * 4 + 0], tid, nthreads); } // zero_actor.cpp:97
     if (tid == 0) { s.path_len[g] = 0; }
 }
 
@@ -1249,6 +1429,7 @@ MZ_DEV void mz_tree_reset(const mz_dims& d, const mz_state& s, int g, int lane)
         s.cursor[g] = 1;
         s.path_len[g] = 0;
         s.spec_len[g] = 0;
+        if (s.gum_meta) { s.gum_meta[g * 4 + 0] = 0, s.gum_meta[g * 4 + 1] = 0, s.gum_meta[g * 4 + 2] = 0, s.gum_meta[g * 4 + 3] = 0; }
     }
 }
 
@@ -1274,7 +1455,7 @@ MZ_DEV void mz_play(const mz_dims& d, const mz_state& s, int g, int action, mz_s
     float sc = 0.0f;
     if (ok) {
         mz_env_act(d, s, w, action, w->turn, lane);
-        if (lane == 0) { hash_list[w->num_moves - 1] = w->hash; } // hashkey_history_ / hash_table_, go.cpp:145-147,180-182
+        if (lane == 0 && w->num_moves - 1 < d.max_hashes) { hash_list[w->num_moves - 1] = w->hash; } // hashkey_history_ / hash_table_, go.cpp:145-147,180-182
         mz_sync();
         mz_env_store_root(d, s, g, w, lane);
         mz_tree_reset(d, s, g, lane);
@@ -1306,4 +1487,16 @@ MZ_DEV int mz_root_max_count_action(const mz_dims& d, const mz_state& s, int g, 
     }
     mz_reduce_best(best_c, zero, best_i); // (count desc, index asc)
     return best_i < 0 ? -1 : (int)s.action[(size_t)g * d.NP + fc + best_i];
+}
+
+// GumbelZero::decideActionNode with actor_select_action_by_count (gumbel_zero.cpp:61-66): the best-scoring candidate.
+// Returns its action id (-1 without candidates). Result valid in lane 0.
+MZ_DEV int mz_root_gumbel_action(const mz_dims& d, const mz_state& s, int g, int lane)
+{
+    int a = -1;
+    if (lane == 0 && s.gum_meta[g * 4 + 0] > 0) {
+        mz_gumbel_sort_by_score(d, s, g, s.root_meta[g * 4 + 0]);
+        a = (int)s.action[(size_t)g * d.NP + s.gum_cand[(size_t)g * d.A]];
+    }
+    return a;
 }

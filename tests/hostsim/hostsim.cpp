@@ -3,6 +3,7 @@
 // compiled from. Never linked into the product library (libmzb200.so has no CPU path).
 #define MZ_HOSTSIM 1
 #include "../../minizero_b200/csrc/search_core.cuh"
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -25,11 +26,32 @@ static T* zalloc(size_t n) { return (T*)calloc(n, sizeof(T)); }
 
 extern "C" {
 
+// search options beyond the AlphaZero defaults: muzero, use_gumbel, gumbel_noise, gumbel_sample_size, sigma_visit_c, sigma_scale_c
+static int g_opt_i[4] = {0, 0, 0, 16};
+static float g_opt_f[2] = {50.0f, 1.0f};
+void hs_set_options(int muzero, int use_gumbel, int gumbel_noise, int m, float visit_c, float scale_c)
+{
+    g_opt_i[0] = muzero, g_opt_i[1] = use_gumbel, g_opt_i[2] = gumbel_noise, g_opt_i[3] = m;
+    g_opt_f[0] = visit_c, g_opt_f[1] = scale_c;
+}
+
 sim* hs_create(int game, int N, int B, int S, float puct_base, float puct_init, float discount, float komi, float eps)
 {
     sim* h = new sim();
     mz_dims& d = h->d;
-    d.game = game, d.N = N, d.A = (game == MZ_GAME_GO ? N * N + 1 : 9), d.C = (game == MZ_GAME_GO ? 18 : 4), d.S = S, d.B = B;
+    memset(&d, 0, sizeof(d));
+    memset(&h->s, 0, sizeof(h->s));
+    d.game = game, d.N = N, d.A = (game == MZ_GAME_TICTACTOE ? 9 : N * N + 1), d.C = (game == MZ_GAME_GO ? 18 : 4), d.S = S, d.B = B;
+    d.muzero = g_opt_i[0], d.gumbel = g_opt_i[1], d.gumbel_noise = g_opt_i[2], d.gumbel_m = g_opt_i[3];
+    d.sigma_visit_c = g_opt_f[0], d.sigma_scale_c = g_opt_f[1];
+    if (d.gumbel) { // gumbel_zero.cpp:99,109 in the reference's double arithmetic
+        const double lg = std::log2((double)d.gumbel_m);
+        d.gumbel_budget0 = (int)std::max(1.0, std::floor(S / (lg * d.gumbel_m)));
+        for (int l = 0; l < MZ_GUMBEL_LEVELS; ++l) {
+            const int half = (d.gumbel_m >> l) / 2;
+            d.gumbel_next[l] = (half > 0 ? (int)std::floor(S / (lg * half)) : 0);
+        }
+    }
     d.NP = 1 + (S + 1) * d.A;
     d.slots = (N + 1) * (N + 1);
     d.max_hashes = 2 * N * N + 4;
@@ -46,6 +68,8 @@ sim* hs_create(int game, int N, int B, int S, float puct_base, float puct_init, 
     h->w.lvl_h = zalloc<mz_hot>(S + 2);
     h->w.q_warp = zalloc<float>(MZ_MAXA);
     s.spec_len = zalloc<int32_t>(B);
+    s.gum_cand = zalloc<int32_t>((size_t)B * d.A), s.gum_meta = zalloc<int32_t>((size_t)B * 4);
+    s.leaf_parent = zalloc<int32_t>((size_t)B * 2);
     h->sqrt_table.resize(S + 2);
     for (int n = 0; n < S + 2; ++n) { h->sqrt_table[n] = sqrt((double)n); }
     s.sqrt_table = h->sqrt_table.data();
@@ -106,6 +130,16 @@ void hs_apply(sim* h, const float* policy, const float* logits, const float* val
 }
 
 int hs_path_len(sim* h, int g) { return h->s.path_len[g]; }
+int hs_leaf_action(sim* h, int g) { return h->s.leaf_parent[g * 2 + 1]; }
+int hs_leaf_parent_slot(sim* h, int g) { return h->s.leaf_parent[g * 2 + 0]; }
+int hs_path_hash(sim* h, int g)
+{
+    const int32_t* path = h->s.path + (size_t)g * (h->d.S + 2);
+    uint32_t x = 2166136261u;
+    for (int k = 1; k < h->s.path_len[g]; ++k) { x = (x ^ (uint32_t)(int32_t)h->s.action[(size_t)g * h->d.NP + path[k]]) * 16777619u; }
+    return (int)(x & 0x7fffffffu);
+}
+int hs_gumbel_best_action(sim* h, int g) { return mz_root_gumbel_action(h->d, h->s, g, 0); }
 int hs_sims_done(sim* h, int g) { return (int)h->s.hot[(size_t)g * h->d.NP].count; }
 
 // out_i: [1 + A] num_children, actions; out_f: [3 + 6 * A] root count/mean/value then count, mean, policy, logit, noise, value per child

@@ -26,6 +26,9 @@ def load():
     lib.hs_play.argtypes = [vp, i32, i32, i32p, f32p]
     lib.hs_reset_game.argtypes = [vp, i32]
     lib.hs_destroy.argtypes = [vp]
+    lib.hs_set_options.argtypes = [i32, i32, i32, i32, f32, f32]
+    for fn in ("hs_leaf_action", "hs_leaf_parent_slot", "hs_path_hash", "hs_gumbel_best_action"):
+        getattr(lib, fn).argtypes = [vp, i32]
     return lib
 
 
@@ -38,12 +41,14 @@ def root_dict(A, out_i, out_f):
 
 
 class HostSimSearch:
-    def __init__(self, lib, game, board_size, num_games, num_simulation):
+    def __init__(self, lib, game, board_size, num_games, num_simulation, muzero=0, use_gumbel=0, gumbel_noise=0, gumbel_sample_size=16,
+                 gumbel_sigma_visit_c=50.0, gumbel_sigma_scale_c=1.0):
         self.lib = lib
         n = 3 if game == 0 else board_size
         self.A = 9 if game == 0 else n * n + 1
-        self.F = (4 if game == 0 else 18) * n * n
+        self.F = (18 if game == 1 else 4) * n * n
         self.B, self.S = num_games, num_simulation
+        lib.hs_set_options(muzero, use_gumbel, gumbel_noise, gumbel_sample_size, gumbel_sigma_visit_c, gumbel_sigma_scale_c)
         self.h = lib.hs_create(game, n, num_games, num_simulation, 19652.0, 1.25, 1.0, 7.5, 0.25)
         self.terminal = [False] * num_games
 
@@ -64,6 +69,18 @@ class HostSimSearch:
 
     def path_len(self, g):
         return self.lib.hs_path_len(self.h, g)
+
+    def leaf_action(self, g):
+        return self.lib.hs_leaf_action(self.h, g)
+
+    def leaf_parent_slot(self, g):
+        return self.lib.hs_leaf_parent_slot(self.h, g)
+
+    def path_hash(self, g):
+        return self.lib.hs_path_hash(self.h, g)
+
+    def gumbel_best_action(self, g):
+        return self.lib.hs_gumbel_best_action(self.h, g)
 
     def root(self, g):
         out_i = np.zeros(1 + self.A, np.int32)
