@@ -28,6 +28,7 @@ extern "C" {
 
 #define MZ_GAME_TICTACTOE 0 /* environment/tictactoe */
 #define MZ_GAME_GO 1        /* environment/go        */
+#define MZ_GAME_OTHELLO 2   /* environment/othello   */
 
 typedef struct mz_engine mz_engine;
 
@@ -44,12 +45,20 @@ typedef struct {
     float komi;                 /* env_go_komi */
     int32_t ko_situational;     /* env_go_ko_rule == "situational" */
     float dirichlet_epsilon;    /* actor_dirichlet_noise_epsilon */
+    int32_t muzero;             /* nn_type_name == "muzero" (actor/zero_actor.cpp:59-67,86-90): hidden-state search, no environment below the root */
+    int32_t use_gumbel;         /* actor_use_gumbel (actor/gumbel_zero.cpp) */
+    int32_t gumbel_noise;       /* actor_use_gumbel_noise && !actor_use_dirichlet_noise: supplied root noise is added to the logits (zero_actor.cpp:205-211) */
+    int32_t gumbel_sample_size; /* actor_gumbel_sample_size */
+    float gumbel_sigma_visit_c; /* actor_gumbel_sigma_visit_c */
+    float gumbel_sigma_scale_c; /* actor_gumbel_sigma_scale_c */
 } mz_config;
 
 /* Hyper-parameters the reference reads from the TorchScript module (network/network.cpp:30-41). */
 typedef struct {
     int32_t num_input_channels, input_height, input_width;
     int32_t num_hidden_channels, num_blocks, action_size, num_value_hidden_channels, discrete_value_size;
+    int32_t num_action_feature_channels; /* MuZero only (network/muzero_network.h:51); board games: 1 */
+    int32_t is_muzero;                   /* get_type_name() == "muzero"; must match mz_config.muzero */
 } mz_net_dims;
 
 typedef struct {
@@ -89,6 +98,14 @@ int mz_net_finalize_empty(mz_engine* e);
 /* AlphaZeroNetwork::pushBack x n + forward(): features [n][C][H][W] fp32 (n <= num_games) ->
  * policy [n][A], policy_logit [n][A], value [n] */
 int mz_eval_batch(mz_engine* e, const float* features, int32_t n, float* policy, float* logits, float* value);
+/* MuZeroNetwork::pushBackInitialData x n + initialInference() (network/muzero_network.h:64-76,95-103; module
+ * network/py/muzero_network.py:136-142): features [n][C][H][W] -> policy, policy_logit [n][A], value [n],
+ * hidden_state [n][Ch][H][W] fp32 (scaled to [0, 1]); any output may be NULL */
+int mz_eval_initial(mz_engine* e, const float* features, int32_t n, float* policy, float* logits, float* value, float* hidden_out);
+/* MuZeroNetwork::pushBackRecurrentData x n + recurrentInference() (network/muzero_network.h:78-93,105-116; module
+ * muzero_network.py:144-150): hidden [n][Ch][H][W] fp32 and the action ids whose planes Environment::getActionFeatures
+ * would produce (one-hot cell, all zero for a pass; environment/othello/othello.cpp:257-262) */
+int mz_eval_recurrent(mz_engine* e, const float* hidden, const int32_t* actions, int32_t n, float* policy, float* logits, float* value, float* hidden_out);
 
 /* ---- games ----------------------------------------------------------------------------------------- */
 /* BaseActor::reset (actor/base_actor.cpp:8-13); g < 0 resets every game */
@@ -112,6 +129,13 @@ int mz_search_select(mz_engine* e, const uint8_t* rotations, float* features_out
 /* ZeroActor::afterNNEvaluation for every game (actor/zero_actor.cpp:74-98). policy/logits [B][A], value [B],
  * noise [B][A] by root child index or NULL (Dirichlet values drawn by the host, utils/random.h:15-24) */
 int mz_search_apply(mz_engine* e, const float* policy, const float* logits, const float* value, const float* noise);
+
+/* MuZero / Gumbel parity hooks after mz_search_select: for every game the evaluation slot of the leaf's parent (-1 at the root;
+ * the hidden state the recurrent inference reads, zero_actor.cpp:62-66), the leaf's action id (-1 at the root) and the action ids
+ * along the selected path ([B][S + 2], -1 padded; path_actions may be NULL) */
+int mz_search_leaf(mz_engine* e, int32_t* parent_slot, int32_t* leaf_action, int32_t* path_actions);
+/* GumbelZero::decideActionNode with actor_select_action_by_count (gumbel_zero.cpp:61-66) for every game: action ids [B] */
+int mz_gumbel_best_actions(mz_engine* e, int32_t* actions_out);
 
 /* ---- search, whole move on the device --------------------------------------------------------------- */
 /* host-drawn randomness of one search: rotations [(S+1)][B] (cycle-major) or NULL, root noise [B][A] or NULL */

@@ -87,7 +87,13 @@ __global__ void __launch_bounds__(32) k_play_max_count(const mz_dims d, const mz
 {
     __shared__ mz_scratch w;
     const int g = blockIdx.x, lane = threadIdx.x;
-    const int a = mz_root_max_count_action(d, s, g, lane);
+    int a;
+    if (d.gumbel) { // GumbelZero::decideActionNode, gumbel_zero.cpp:61-66
+        a = mz_root_gumbel_action(d, s, g, lane);
+        a = __shfl_sync(MZ_FULL, a, 0);
+    } else {
+        a = mz_root_max_count_action(d, s, g, lane);
+    }
     if (lane == 0) { actions_out[g] = a; }
     if (a < 0) {
         if (lane == 0) { out[g * 4 + 0] = 0, out[g * 4 + 1] = 0, out[g * 4 + 2] = 0, out[g * 4 + 3] = s.root_meta[g * 4 + 0], score[g] = 0.0f; }
@@ -124,6 +130,21 @@ __global__ void __launch_bounds__(32) k_gather_roots(const mz_dims d, const mz_s
     }
 }
 
+// action ids along the selected path of every game (-1 padded): parity hook for the MuZero / Gumbel selection
+__global__ void k_path_actions(const mz_dims d, const mz_state s, int32_t* __restrict__ out)
+{
+    const int g = blockIdx.x;
+    const int len = s.path_len[g];
+    const int32_t* path = s.path + (size_t)g * (d.S + 2);
+    for (int i = threadIdx.x; i < d.S + 2; i += blockDim.x) { out[(size_t)g * (d.S + 2) + i] = (i < len ? (int32_t)s.action[(size_t)g * d.NP + path[i]] : -1); }
+}
+
+__global__ void __launch_bounds__(32) k_gumbel_best(const mz_dims d, const mz_state s, int32_t* __restrict__ out)
+{
+    const int a = mz_root_gumbel_action(d, s, blockIdx.x, threadIdx.x);
+    if (threadIdx.x == 0) { out[blockIdx.x] = a; }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // engine
 // ---------------------------------------------------------------------------------------------------
@@ -135,6 +156,18 @@ struct ConvLayer {
     size_t w_off = 0, b_off = 0; // offsets into the blob
     CUtensorMap map_w;
     CUtensorMap map_w_mc; // box = 1 / conv_cluster of the weight tile (multicast slices)
+};
+
+// one residual tower: AlphaZero's, or MuZero's representation (0) / dynamics (1) network
+struct NetTower {
+    std::vector<ConvLayer> convs;
+    std::string prefix;                  // state_dict prefix of its modules
+    int cin0_real = 0, cin0 = 0;         // real / padded input channels of its first conv
+    void* in = nullptr;                  // fp16 input rows [rows_alloc][cin0]
+    CUtensorMap map_in, map_in_ext;      // box = one row tile / the resident block
+    mznn::TowerParams* params = nullptr; // host copy of the fused-tower launch parameters (conv_mode 3)
+    int* d_done = nullptr;
+    int out_buf = 0;                     // index of the activation buffer holding its output
 };
 
 struct Blob {
@@ -178,15 +211,18 @@ struct mz_engine {
     mz_net_dims nd{};
     int cpad = 0, pol_ch = 0, rows_alloc = 0, bn_tile = 0;
     std::map<std::string, std::vector<float>> tensors;
-    std::vector<ConvLayer> convs;
+    NetTower tw[2];
+    int num_towers = 1;
     Blob blob;
     uint8_t* d_blob = nullptr;
     size_t off_head[10] = {0};
     __half* act[3] = {nullptr, nullptr, nullptr};
-    CUtensorMap map_in0, map_act[3];
-    CUtensorMap map_in0_ext, map_act_ext[3]; // same buffers, box = the resident block of conv3x3_resident_kernel
-    mznn::TowerParams* tower = nullptr; // host copy of the fused-tower launch parameters (conv_mode 3)
-    int* d_tower_done = nullptr;
+    CUtensorMap map_act[3];
+    CUtensorMap map_act_ext[3]; // same buffers, box = the resident block of conv3x3_resident_kernel
+    // MuZero
+    float* d_hidden_f32 = nullptr;   // [B][Ch * H * W] staging of the parity hooks
+    int32_t* d_path_actions = nullptr; // [B][S + 2]
+    int cin_max = 0;
     int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148, krot = 0, conv_cluster = 1, conv_pdl = 0, tower_sms = 148;
     encode_tiled_fn encode = nullptr;
 
@@ -336,49 +372,57 @@ int launch_heads(mz_engine* e, const __half* act)
     return MZ_OK;
 }
 
-int launch_tower(mz_engine* e);
+int launch_tower(mz_engine* e, int which);
 
-// AlphaZeroNetwork.forward (network/py/alphazero_network.py:90-113) on the rows already in nn_in
-int forward(mz_engine* e)
+// AlphaZeroNetwork.forward (network/py/alphazero_network.py:90-113) on the rows already in nn_in; for a MuZero network
+// `which` selects initial_inference (0: representation, rows in nn_in) or recurrent_inference (1: dynamics, rows in dyn_in),
+// each followed by scale_hidden_state and the prediction heads (network/py/muzero_network.py:136-160)
+int forward(mz_engine* e, int which = 0)
 {
     if (!e->net_ready) { return fail(MZ_ERR_STATE, "network not finalized"); }
+    NetTower& T = e->tw[which];
+    int rc;
     if (e->conv_mode == 3) {
-        int rc = launch_tower(e);
-        if (rc) { return rc; }
-        const int last = static_cast<int>(e->convs.size()) - 1;
-        return launch_heads(e, e->tower->layer[last].out);
+        if ((rc = launch_tower(e, which))) { return rc; }
+    } else {
+        if ((rc = conv(e, T.map_in, T.map_in_ext, T.convs[0], e->act[0], nullptr))) { return rc; }
+        int cur = 0;
+        for (int b = 0; b < e->nd.num_blocks; ++b) {
+            const int t = (cur + 1) % 3, o = (cur + 2) % 3;
+            if ((rc = conv(e, e->map_act[cur], e->map_act_ext[cur], T.convs[1 + 2 * b], e->act[t], nullptr))) { return rc; }
+            if ((rc = conv(e, e->map_act[t], e->map_act_ext[t], T.convs[2 + 2 * b], e->act[o], e->act[cur]))) { return rc; }
+            cur = o;
+        }
     }
-    int rc = conv(e, e->map_in0, e->map_in0_ext, e->convs[0], e->act[0], nullptr);
-    if (rc) { return rc; }
-    int cur = 0;
-    for (int b = 0; b < e->nd.num_blocks; ++b) {
-        const int t = (cur + 1) % 3, o = (cur + 2) % 3;
-        if ((rc = conv(e, e->map_act[cur], e->map_act_ext[cur], e->convs[1 + 2 * b], e->act[t], nullptr))) { return rc; }
-        if ((rc = conv(e, e->map_act[t], e->map_act_ext[t], e->convs[2 + 2 * b], e->act[o], e->act[cur]))) { return rc; }
-        cur = o;
+    __half* out = e->act[T.out_buf];
+    if (e->cfg.muzero) {
+        mznn::scale_hidden_kernel<<<e->d.B, 256, 0, e->stream>>>(out, reinterpret_cast<__half*>(e->s.hid), e->s.eval_slot, e->d.N, e->d.slots, e->cpad,
+                                                                  e->nd.num_hidden_channels, e->d.S + 1);
+        e->launches++;
     }
-    return launch_heads(e, e->act[cur]);
+    return launch_heads(e, out);
 }
 
-int launch_tower(mz_engine* e)
+int launch_tower(mz_engine* e, int which)
 {
     {
-        const int num_groups = (e->tower->num_mtiles + 1) / 2;
-        CUDA_OK(cudaMemsetAsync(e->d_tower_done, 0, sizeof(int) * e->tower->num_layers * num_groups, e->stream));
+        NetTower& T = e->tw[which];
+        const int num_groups = (T.params->num_mtiles + 1) / 2;
+        CUDA_OK(cudaMemsetAsync(T.d_done, 0, sizeof(int) * T.params->num_layers * num_groups, e->stream));
         const int units = num_groups * (e->cpad / 128);
         int clusters = e->tower_sms / 2;
         if (units < clusters) { clusters = units; }
-        const size_t smem = 2 * static_cast<size_t>(e->cpad / mznn::BK) * e->rows_ext * 128 + 8 * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
+        const size_t smem = 2 * static_cast<size_t>(e->cin_max / mznn::BK) * e->rows_ext * 128 + 8 * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(clusters * 2), cfg.blockDim = dim3(mznn::TOWER_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = e->stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr, cfg.numAttrs = 1;
-        if (e->tower->dbg) {
-            CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8, true>, *e->tower));
+        if (T.params->dbg) {
+            CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8, true>, *T.params));
         } else {
-            CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8, false>, *e->tower));
+            CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8, false>, *T.params));
         }
         e->launches++;
     }
@@ -442,12 +486,23 @@ int plan_blob(mz_engine* e)
         if ((v == 64 || v == 128 || v == 256) && e->cpad % v == 0) { e->bn_tile = v; }
     }
     e->blob = Blob();
-    e->convs.assign(1 + 2 * nd.num_blocks, ConvLayer());
-    for (size_t i = 0; i < e->convs.size(); ++i) {
-        ConvLayer& L = e->convs[i];
-        L.cin = (i == 0 ? MZ_NN_CPAD : e->cpad), L.cout = e->cpad, L.relu = 1;
-        L.w_off = e->blob.take(sizeof(__half) * 9 * static_cast<size_t>(L.cout) * L.cin);
-        L.b_off = e->blob.take(sizeof(float) * L.cout);
+    e->num_towers = (e->cfg.muzero ? 2 : 1);
+    e->tw[0].prefix = (e->cfg.muzero ? "representation_network." : "");
+    e->tw[0].cin0_real = nd.num_input_channels, e->tw[0].cin0 = MZ_NN_CPAD;
+    e->tw[1].prefix = "dynamics_network.";
+    e->tw[1].cin0_real = nd.num_hidden_channels + nd.num_action_feature_channels; // torch.cat((hidden_state, action_plane), dim=1), muzero_network.py:31
+    e->tw[1].cin0 = ((e->tw[1].cin0_real + 63) / 64) * 64;
+    e->cin_max = e->cpad;
+    for (int t = 0; t < e->num_towers; ++t) {
+        NetTower& T = e->tw[t];
+        T.convs.assign(1 + 2 * nd.num_blocks, ConvLayer());
+        if (T.cin0 > e->cin_max) { e->cin_max = T.cin0; }
+        for (size_t i = 0; i < T.convs.size(); ++i) {
+            ConvLayer& L = T.convs[i];
+            L.cin = (i == 0 ? T.cin0 : e->cpad), L.cout = e->cpad, L.relu = 1;
+            L.w_off = e->blob.take(sizeof(__half) * 9 * static_cast<size_t>(L.cout) * L.cin);
+            L.b_off = e->blob.take(sizeof(float) * L.cout);
+        }
     }
     const int hw = nd.input_height * nd.input_width;
     const size_t head_sizes[10] = {static_cast<size_t>(e->pol_ch) * e->cpad, static_cast<size_t>(e->pol_ch), static_cast<size_t>(nd.action_size) * e->pol_ch * hw,
@@ -481,10 +536,10 @@ int alloc_net(mz_engine* e)
         if (v == 1 || v == 2 || v == 4) { e->conv_cluster = v; }
     }
     if (e->bn_tile == 256) { e->conv_mode = 0; }
-    const size_t need = (e->bn_tile == 64 ? resident_smem<64, 6>(e, e->cpad) : resident_smem<128, 9>(e, e->cpad));
+    const size_t need = (e->bn_tile == 64 ? resident_smem<64, 6>(e, e->cin_max) : resident_smem<128, 9>(e, e->cin_max));
     if (e->bn_tile == 64) { e->conv_cluster = 1; }
     if (e->conv_mode == 2) { // CTA pairs: needs the 128-wide tile and half-tile weight boxes
-        const size_t pair_need = 2 * static_cast<size_t>(e->cpad / mznn::BK) * e->rows_ext * 128 + 8 * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
+        const size_t pair_need = 2 * static_cast<size_t>(e->cin_max / mznn::BK) * e->rows_ext * 128 + 8 * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
         if (e->bn_tile == 128 && pair_need <= 227 * 1024) {
             e->conv_cluster = 2;
         } else {
@@ -498,19 +553,38 @@ int alloc_net(mz_engine* e)
         if ((rc = make_map_2d(e, &e->map_act[i], e->act[i], e->cpad, rows, mznn::BK, mznn::BM))) { return rc; }
         if ((rc = make_map_2d(e, &e->map_act_ext[i], e->act[i], e->cpad, rows, mznn::BK, e->rows_ext))) { return rc; }
     }
-    if ((rc = make_map_2d(e, &e->map_in0, e->s.nn_in, MZ_NN_CPAD, rows, mznn::BK, mznn::BM))) { return rc; }
-    if ((rc = make_map_2d(e, &e->map_in0_ext, e->s.nn_in, MZ_NN_CPAD, rows, mznn::BK, e->rows_ext))) { return rc; }
-    for (ConvLayer& L : e->convs) {
-        if ((rc = make_map_2d(e, &L.map_w, e->d_blob + L.w_off, L.cin, 9ull * L.cout, mznn::BK, e->bn_tile))) { return rc; }
-        if ((rc = make_map_2d(e, &L.map_w_mc, e->d_blob + L.w_off, L.cin, 9ull * L.cout, mznn::BK, e->bn_tile / e->conv_cluster))) { return rc; }
+    if (e->cfg.muzero) {
+        // hidden states of the evaluated nodes (slot = simulation index) and the dynamics network's input rows
+        const size_t hw = static_cast<size_t>(e->d.N) * e->d.N;
+        if ((rc = e->dalloc(&e->s.hid, static_cast<size_t>(e->d.B) * (e->d.S + 1) * hw * e->cpad))) { return rc; }
+        if ((rc = e->dalloc(&e->s.dyn_in, rows * e->tw[1].cin0))) { return rc; }
+        if ((rc = e->dalloc(&e->d_hidden_f32, static_cast<size_t>(e->d.B) * e->nd.num_hidden_channels * hw))) { return rc; }
+        e->d.hid_c = e->cpad, e->d.dyn_c = e->tw[1].cin0, e->d.act_col = e->nd.num_hidden_channels;
     }
-    if (want_tower && e->conv_mode == 2 && static_cast<int>(e->convs.size()) <= mznn::TOWER_MAX_LAYERS) {
-        // whole-tower launch: same buffer rotation as forward() (cur -> t -> o per residual block)
-        e->tower = new mznn::TowerParams();
-        mznn::TowerParams& T = *e->tower;
-        T.num_layers = static_cast<int>(e->convs.size());
+    e->tw[0].in = e->s.nn_in, e->tw[1].in = e->s.dyn_in;
+    e->tower_sms = e->num_sms; // SMs the persistent tower may occupy (MZ_TOWER_SMS: experiments with a second engine beside it)
+    if (const char* env = std::getenv("MZ_TOWER_SMS")) {
+        const int v = std::atoi(env);
+        if (v >= 2 && v <= e->num_sms) { e->tower_sms = v & ~1; }
+    }
+    const bool tower_ok = (want_tower && e->conv_mode == 2 && 1 + 2 * e->nd.num_blocks <= mznn::TOWER_MAX_LAYERS);
+    for (int t = 0; t < e->num_towers; ++t) {
+        NetTower& NT = e->tw[t];
+        if ((rc = make_map_2d(e, &NT.map_in, NT.in, NT.cin0, rows, mznn::BK, mznn::BM))) { return rc; }
+        if ((rc = make_map_2d(e, &NT.map_in_ext, NT.in, NT.cin0, rows, mznn::BK, e->rows_ext))) { return rc; }
+        for (ConvLayer& L : NT.convs) {
+            if ((rc = make_map_2d(e, &L.map_w, e->d_blob + L.w_off, L.cin, 9ull * L.cout, mznn::BK, e->bn_tile))) { return rc; }
+            if ((rc = make_map_2d(e, &L.map_w_mc, e->d_blob + L.w_off, L.cin, 9ull * L.cout, mznn::BK, e->bn_tile / e->conv_cluster))) { return rc; }
+        }
+        NT.out_buf = (2 * e->nd.num_blocks) % 3; // forward()'s buffer rotation: cur -> t -> o per residual block, o = cur + 2
+        if (!tower_ok) { continue; }
+        // whole-tower launch: same buffer rotation as forward()
+        NT.params = new mznn::TowerParams();
+        mznn::TowerParams& T = *NT.params;
+        T.num_layers = static_cast<int>(NT.convs.size());
         T.rows_valid = e->d.B * e->d.slots, T.n1 = e->d.N + 1, T.slots = e->d.slots, T.cout = e->cpad, T.rows_ext = e->rows_ext, T.halo = e->d.N + 2;
         T.num_mtiles = e->rows_alloc / mznn::BM;
+        T.cin_max = e->cin_max;
         T.rotate = 22, T.shift = 0, T.zigzag = 0, T.strided = 1;
         if (const char* env = std::getenv("MZ_TOWER_STRIDED")) { T.strided = std::atoi(env); }
         if (const char* env = std::getenv("MZ_TOWER_ZIGZAG")) { T.zigzag = std::atoi(env); }
@@ -518,26 +592,20 @@ int alloc_net(mz_engine* e)
         if (const char* env = std::getenv("MZ_TOWER_SHIFT")) { T.shift = std::atoi(env); }
         auto set = [&](int li, const CUtensorMap& in, __half* out, const __half* residual) {
             mznn::TowerLayer& L = T.layer[li];
-            L.map_in = in, L.map_w = e->convs[li].map_w_mc, L.out = out, L.residual = residual;
-            L.bias = reinterpret_cast<const float*>(e->d_blob + e->convs[li].b_off), L.cin = e->convs[li].cin, L.relu = e->convs[li].relu;
+            L.map_in = in, L.map_w = NT.convs[li].map_w_mc, L.out = out, L.residual = residual;
+            L.bias = reinterpret_cast<const float*>(e->d_blob + NT.convs[li].b_off), L.cin = NT.convs[li].cin, L.relu = NT.convs[li].relu;
         };
-        set(0, e->map_in0_ext, e->act[0], nullptr);
+        set(0, NT.map_in_ext, e->act[0], nullptr);
         int cur = 0;
         for (int b = 0; b < e->nd.num_blocks; ++b) {
-            const int t = (cur + 1) % 3, o = (cur + 2) % 3;
-            set(1 + 2 * b, e->map_act_ext[cur], e->act[t], nullptr);
-            set(2 + 2 * b, e->map_act_ext[t], e->act[o], e->act[cur]);
+            const int tt = (cur + 1) % 3, o = (cur + 2) % 3;
+            set(1 + 2 * b, e->map_act_ext[cur], e->act[tt], nullptr);
+            set(2 + 2 * b, e->map_act_ext[tt], e->act[o], e->act[cur]);
             cur = o;
         }
         const int num_groups = (T.num_mtiles + 1) / 2;
-        if ((rc = e->dalloc(&e->d_tower_done, static_cast<size_t>(T.num_layers) * num_groups))) { return rc; }
-        T.done = e->d_tower_done;
-        // SMs the persistent tower may occupy: leaving a few free lets another engine's tree / heads kernels run beside it
-        e->tower_sms = e->num_sms;
-        if (const char* env = std::getenv("MZ_TOWER_SMS")) {
-            const int v = std::atoi(env);
-            if (v >= 2 && v <= e->num_sms) { e->tower_sms = v & ~1; }
-        }
+        if ((rc = e->dalloc(&NT.d_done, static_cast<size_t>(T.num_layers) * num_groups))) { return rc; }
+        T.done = NT.d_done;
         T.dbg = nullptr;
         if (const char* env = std::getenv("MZ_DEBUG_TOWER")) {
             if (std::atoi(env) != 0) {
@@ -546,8 +614,8 @@ int alloc_net(mz_engine* e)
                 T.dbg = buf;
             }
         }
-        e->conv_mode = 3;
     }
+    if (tower_ok) { e->conv_mode = 3; }
     return MZ_OK;
 }
 
@@ -561,9 +629,11 @@ int mz_create(const mz_config* cfg, mz_engine** out)
 {
     if (!cfg || !out) { return fail(MZ_ERR_ARG, "null argument"); }
     *out = nullptr;
-    if (cfg->game != MZ_GAME_GO && cfg->game != MZ_GAME_TICTACTOE) { return fail(MZ_ERR_ARG, "unsupported game"); }
-    const int N = (cfg->game == MZ_GAME_GO ? cfg->board_size : 3);
+    if (cfg->game != MZ_GAME_GO && cfg->game != MZ_GAME_TICTACTOE && cfg->game != MZ_GAME_OTHELLO) { return fail(MZ_ERR_ARG, "unsupported game"); }
+    const int N = (cfg->game == MZ_GAME_TICTACTOE ? 3 : cfg->board_size);
     if (N < 2 || N > MZ_MAXN) { return fail(MZ_ERR_ARG, "board_size must be in [2, 19]"); }
+    if (cfg->game == MZ_GAME_OTHELLO && (N < 4 || N > 16 || (N & 1))) { return fail(MZ_ERR_ARG, "othello board_size must be even and in [4, 16]"); }
+    if (cfg->use_gumbel && cfg->gumbel_sample_size < 2) { return fail(MZ_ERR_ARG, "actor_gumbel_sample_size must be at least 2"); }
     if (cfg->num_games < 1 || cfg->num_simulation < 1) { return fail(MZ_ERR_ARG, "num_games and num_simulation must be positive"); }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { return fail(MZ_ERR_CUDA, "no CUDA device: libmzb200 has no CPU path"); }
@@ -576,7 +646,17 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     mz_engine* e = new mz_engine();
     e->cfg = *cfg;
     mz_dims& d = e->d;
-    d.game = cfg->game, d.N = N, d.A = (cfg->game == MZ_GAME_GO ? N * N + 1 : 9), d.C = (cfg->game == MZ_GAME_GO ? 18 : 4);
+    d.game = cfg->game, d.N = N, d.A = (cfg->game == MZ_GAME_TICTACTOE ? 9 : N * N + 1), d.C = (cfg->game == MZ_GAME_GO ? 18 : 4);
+    d.muzero = (cfg->muzero != 0), d.gumbel = (cfg->use_gumbel != 0), d.gumbel_noise = (cfg->gumbel_noise != 0), d.gumbel_m = cfg->gumbel_sample_size;
+    d.sigma_visit_c = cfg->gumbel_sigma_visit_c, d.sigma_scale_c = cfg->gumbel_sigma_scale_c;
+    if (d.gumbel) { // simulation budgets in the reference's double arithmetic (gumbel_zero.cpp:99,109)
+        const double lg = std::log2(static_cast<double>(d.gumbel_m));
+        d.gumbel_budget0 = static_cast<int>(std::max(1.0, std::floor(cfg->num_simulation / (lg * d.gumbel_m))));
+        for (int l = 0; l < MZ_GUMBEL_LEVELS; ++l) {
+            const int half = (d.gumbel_m >> l) / 2;
+            d.gumbel_next[l] = (half > 0 ? static_cast<int>(std::floor(cfg->num_simulation / (lg * half))) : 0);
+        }
+    }
     d.S = cfg->num_simulation, d.B = cfg->num_games;
     d.NP = 1 + (d.S + 1) * d.A; // actor_group.cpp:183, tree.h:66
     if (d.NP >= (1 << MZ_LINK_SHIFT)) {
@@ -625,6 +705,8 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     guard(e->dalloc(&s.root_st, B * 2 * MZ_ROWS)), guard(e->dalloc(&s.root_hist, B * MZ_HIST * 2 * MZ_ROWS)), guard(e->dalloc(&s.root_hash, B));
     guard(e->dalloc(&s.root_meta, B * 4)), guard(e->dalloc(&s.hashes, B * d.max_hashes));
     guard(e->dalloc(&s.spec_len, B));
+    guard(e->dalloc(&s.eval_slot, B)), guard(e->dalloc(&s.leaf_parent, B * 2)), guard(e->dalloc(&s.gum_cand, BA)), guard(e->dalloc(&s.gum_meta, B * 4));
+    guard(e->dalloc(&e->d_path_actions, B * (d.S + 2)));
     guard(e->dalloc(&s.path, B * (d.S + 2))), guard(e->dalloc(&s.path_len, B)), guard(e->dalloc(&s.leaf_legal, B * MZ_LEGAL_WORDS));
     guard(e->dalloc(&s.leaf_meta, B * 4)), guard(e->dalloc(&s.leaf_score, B));
     guard(e->dalloc(&s.nn_in, static_cast<size_t>(e->rows_alloc) * MZ_NN_CPAD));
@@ -691,7 +773,8 @@ void mz_destroy(mz_engine* e)
     if (e->stream) { cudaStreamSynchronize(e->stream); }
     for (auto& kv : e->graphs) { cudaGraphExecDestroy(kv.second); }
     for (void* p : e->allocs) { cudaFree(p); }
-    delete e->tower;
+    delete e->tw[0].params;
+    delete e->tw[1].params;
     if (e->ev0) { cudaEventDestroy(e->ev0); }
     if (e->ev1) { cudaEventDestroy(e->ev1); }
     if (e->ev2) { cudaEventDestroy(e->ev2); }
@@ -703,7 +786,7 @@ void mz_destroy(mz_engine* e)
 int mz_action_size(const mz_engine* e) { return e ? e->d.A : MZ_ERR_ARG; }
 int mz_num_features(const mz_engine* e) { return e ? e->d.C * e->d.N * e->d.N : MZ_ERR_ARG; }
 int64_t mz_launch_count(const mz_engine* e) { return e ? e->launches : 0; }
-int mz_conv_layers_per_launch(const mz_engine* e) { return (e && e->net_ready) ? (e->conv_mode == 3 ? static_cast<int>(e->convs.size()) : 1) : MZ_ERR_STATE; }
+int mz_conv_layers_per_launch(const mz_engine* e) { return (e && e->net_ready) ? (e->conv_mode == 3 ? static_cast<int>(e->tw[0].convs.size()) : 1) : MZ_ERR_STATE; }
 
 int mz_net_configure(mz_engine* e, const mz_net_dims* dims)
 {
@@ -716,6 +799,8 @@ int mz_net_configure(mz_engine* e, const mz_net_dims* dims)
         return fail(MZ_ERR_ARG, "policy head with more than 3 planes is not supported");
     }
     if (dims->num_input_channels > MZ_NN_CPAD || dims->num_hidden_channels < 1 || dims->num_blocks < 0) { return fail(MZ_ERR_ARG, "unsupported network size"); }
+    if ((dims->is_muzero != 0) != (e->cfg.muzero != 0)) { return fail(MZ_ERR_ARG, "network type (alphazero / muzero) does not match the engine's nn_type_name"); }
+    if (dims->is_muzero && dims->num_action_feature_channels != 1) { return fail(MZ_ERR_ARG, "only board-game MuZero networks (one action plane) are supported"); }
     if (e->d_blob && std::memcmp(&e->nd, dims, sizeof(*dims)) != 0) {
         return fail(MZ_ERR_STATE, "a network of a different shape is already allocated for this engine");
     }
@@ -759,16 +844,18 @@ int mz_net_finalize(mz_engine* e)
     std::vector<uint8_t> host(e->blob.size, 0);
     std::string err;
     // 3x3 convolutions: [tap][cout_pad][cin_pad] fp16, BN folded
-    for (size_t li = 0; li < e->convs.size(); ++li) {
-        const ConvLayer& L = e->convs[li];
+    for (int t = 0; t < e->num_towers; ++t) {
+    const NetTower& T = e->tw[t];
+    for (size_t li = 0; li < T.convs.size(); ++li) {
+        const ConvLayer& L = T.convs[li];
         std::string cname, bname;
         int cin_real;
         if (li == 0) {
-            cname = "conv", bname = "bn", cin_real = nd.num_input_channels;
+            cname = T.prefix + "conv", bname = T.prefix + "bn", cin_real = T.cin0_real;
         } else {
             const int blk = static_cast<int>(li - 1) / 2, which = static_cast<int>(li - 1) % 2 + 1;
-            cname = "residual_blocks." + std::to_string(blk) + ".conv" + std::to_string(which);
-            bname = "residual_blocks." + std::to_string(blk) + ".bn" + std::to_string(which);
+            cname = T.prefix + "residual_blocks." + std::to_string(blk) + ".conv" + std::to_string(which);
+            bname = T.prefix + "residual_blocks." + std::to_string(blk) + ".bn" + std::to_string(which);
             cin_real = Ch;
         }
         std::vector<float> bias;
@@ -785,6 +872,8 @@ int mz_net_finalize(mz_engine* e)
             }
         }
     }
+    }
+    const std::string hp = (e->cfg.muzero ? "prediction_network." : ""); // muzero_network.py:44-45
     // heads, fp32
     auto put = [&](int idx, const std::vector<float>& v) { std::memcpy(host.data() + e->off_head[idx], v.data(), v.size() * sizeof(float)); };
     auto raw = [&](const std::string& name, size_t n, std::vector<float>& out) -> bool {
@@ -797,7 +886,7 @@ int mz_net_finalize(mz_engine* e)
         return true;
     };
     {
-        std::vector<float> bias, w = fold_conv(e, "policy.conv", "policy.bn", e->pol_ch, Ch, 1, bias, err);
+        std::vector<float> bias, w = fold_conv(e, hp + "policy.conv", hp + "policy.bn", e->pol_ch, Ch, 1, bias, err);
         if (w.empty()) { return fail(MZ_ERR_ARG, err); }
         std::vector<float> wp(static_cast<size_t>(e->pol_ch) * cp, 0.0f);
         for (int o = 0; o < e->pol_ch; ++o) {
@@ -805,7 +894,7 @@ int mz_net_finalize(mz_engine* e)
         }
         put(0, wp), put(1, bias);
         std::vector<float> t;
-        if (!raw("policy.fc.weight", static_cast<size_t>(nd.action_size) * e->pol_ch * hw, t)) { return fail(MZ_ERR_ARG, err); }
+        if (!raw(hp + "policy.fc.weight", static_cast<size_t>(nd.action_size) * e->pol_ch * hw, t)) { return fail(MZ_ERR_ARG, err); }
         {
             const int nin = e->pol_ch * hw;
             std::vector<float> tt(t.size());
@@ -814,17 +903,17 @@ int mz_net_finalize(mz_engine* e)
             }
             put(2, tt);
         }
-        if (!raw("policy.fc.bias", nd.action_size, t)) { return fail(MZ_ERR_ARG, err); }
+        if (!raw(hp + "policy.fc.bias", nd.action_size, t)) { return fail(MZ_ERR_ARG, err); }
         put(3, t);
     }
     {
-        std::vector<float> bias, w = fold_conv(e, "value.conv", "value.bn", 1, Ch, 1, bias, err);
+        std::vector<float> bias, w = fold_conv(e, hp + "value.conv", hp + "value.bn", 1, Ch, 1, bias, err);
         if (w.empty()) { return fail(MZ_ERR_ARG, err); }
         std::vector<float> wp(cp, 0.0f);
         for (int c = 0; c < Ch; ++c) { wp[c] = w[c]; }
         put(4, wp), put(5, bias);
         std::vector<float> t;
-        if (!raw("value.fc1.weight", static_cast<size_t>(nd.num_value_hidden_channels) * hw, t)) { return fail(MZ_ERR_ARG, err); }
+        if (!raw(hp + "value.fc1.weight", static_cast<size_t>(nd.num_value_hidden_channels) * hw, t)) { return fail(MZ_ERR_ARG, err); }
         {
             const int vh = nd.num_value_hidden_channels;
             std::vector<float> tt(t.size());
@@ -833,11 +922,11 @@ int mz_net_finalize(mz_engine* e)
             }
             put(6, tt);
         }
-        if (!raw("value.fc1.bias", nd.num_value_hidden_channels, t)) { return fail(MZ_ERR_ARG, err); }
+        if (!raw(hp + "value.fc1.bias", nd.num_value_hidden_channels, t)) { return fail(MZ_ERR_ARG, err); }
         put(7, t);
-        if (!raw("value.fc2.weight", nd.num_value_hidden_channels, t)) { return fail(MZ_ERR_ARG, err); }
+        if (!raw(hp + "value.fc2.weight", nd.num_value_hidden_channels, t)) { return fail(MZ_ERR_ARG, err); }
         put(8, t);
-        if (!raw("value.fc2.bias", 1, t)) { return fail(MZ_ERR_ARG, err); }
+        if (!raw(hp + "value.fc2.bias", 1, t)) { return fail(MZ_ERR_ARG, err); }
         put(9, t);
     }
     int rc = alloc_net(e);
@@ -858,10 +947,33 @@ int mz_net_blob(mz_engine* e, void** device_ptr, int64_t* bytes)
     return MZ_OK;
 }
 
-int mz_eval_batch(mz_engine* e, const float* features, int32_t n, float* policy, float* logits, float* value)
+namespace {
+
+// outputs of the last forward() back to the host; MuZero: also the scaled hidden state (stored in slot 0 by the hooks)
+int read_outputs(mz_engine* e, int32_t n, float* policy, float* logits, float* value, float* hidden_out)
+{
+    const mz_dims& d = e->d;
+    if (policy) { CUDA_OK(cudaMemcpyAsync(policy, e->s.policy, sizeof(float) * n * d.A, cudaMemcpyDeviceToHost, e->stream)); }
+    if (logits) { CUDA_OK(cudaMemcpyAsync(logits, e->s.logits, sizeof(float) * n * d.A, cudaMemcpyDeviceToHost, e->stream)); }
+    if (value) { CUDA_OK(cudaMemcpyAsync(value, e->s.nn_value, sizeof(float) * n, cudaMemcpyDeviceToHost, e->stream)); }
+    if (hidden_out) {
+        const int ch = e->nd.num_hidden_channels;
+        mznn::unpack_hidden_kernel<<<148, 256, 0, e->stream>>>(reinterpret_cast<const __half*>(e->s.hid), e->d_hidden_f32, n, ch, d.N, e->cpad, d.S + 1, 0);
+        e->launches++;
+        CUDA_OK(cudaMemcpyAsync(hidden_out, e->d_hidden_f32, sizeof(float) * n * ch * d.N * d.N, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    CUDA_OK(cudaGetLastError());
+    return MZ_OK;
+}
+
+} // namespace
+
+int mz_eval_initial(mz_engine* e, const float* features, int32_t n, float* policy, float* logits, float* value, float* hidden_out)
 {
     if (!e || !features || n < 1 || n > e->d.B) { return fail(MZ_ERR_ARG, "bad argument"); }
     if (!e->net_ready) { return fail(MZ_ERR_STATE, "network not finalized"); }
+    if (hidden_out && !e->cfg.muzero) { return fail(MZ_ERR_STATE, "hidden states exist only for a muzero network"); }
     CUDA_OK(cudaSetDevice(e->cfg.device));
     const mz_dims& d = e->d;
     const size_t F = static_cast<size_t>(d.C) * d.N * d.N;
@@ -869,11 +981,65 @@ int mz_eval_batch(mz_engine* e, const float* features, int32_t n, float* policy,
     CUDA_OK(cudaMemsetAsync(e->s.nn_in, 0, static_cast<size_t>(e->rows_alloc) * MZ_NN_CPAD * sizeof(uint16_t), e->stream));
     mznn::pack_features_kernel<<<148, 256, 0, e->stream>>>(e->d_feat_f32, reinterpret_cast<__half*>(e->s.nn_in), n, d.C, d.N, d.slots, MZ_NN_CPAD);
     e->launches++;
-    int rc = forward(e);
+    if (e->cfg.muzero) { CUDA_OK(cudaMemsetAsync(e->s.eval_slot, 0, sizeof(int32_t) * d.B, e->stream)); } // the hooks keep their hidden states in slot 0
+    int rc = forward(e, 0);
     if (rc) { return rc; }
-    if (policy) { CUDA_OK(cudaMemcpyAsync(policy, e->s.policy, sizeof(float) * n * d.A, cudaMemcpyDeviceToHost, e->stream)); }
-    if (logits) { CUDA_OK(cudaMemcpyAsync(logits, e->s.logits, sizeof(float) * n * d.A, cudaMemcpyDeviceToHost, e->stream)); }
-    if (value) { CUDA_OK(cudaMemcpyAsync(value, e->s.nn_value, sizeof(float) * n, cudaMemcpyDeviceToHost, e->stream)); }
+    return read_outputs(e, n, policy, logits, value, hidden_out);
+}
+
+int mz_eval_batch(mz_engine* e, const float* features, int32_t n, float* policy, float* logits, float* value)
+{
+    return mz_eval_initial(e, features, n, policy, logits, value, nullptr);
+}
+
+int mz_eval_recurrent(mz_engine* e, const float* hidden, const int32_t* actions, int32_t n, float* policy, float* logits, float* value, float* hidden_out)
+{
+    if (!e || !hidden || !actions || n < 1 || n > e->d.B) { return fail(MZ_ERR_ARG, "bad argument"); }
+    if (!e->net_ready) { return fail(MZ_ERR_STATE, "network not finalized"); }
+    if (!e->cfg.muzero) { return fail(MZ_ERR_STATE, "recurrent inference needs a muzero network"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    const mz_dims& d = e->d;
+    const int ch = e->nd.num_hidden_channels;
+    CUDA_OK(cudaMemcpyAsync(e->d_hidden_f32, hidden, sizeof(float) * n * ch * d.N * d.N, cudaMemcpyHostToDevice, e->stream));
+    CUDA_OK(cudaMemcpyAsync(e->d_actions, actions, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    CUDA_OK(cudaMemsetAsync(e->s.dyn_in, 0, static_cast<size_t>(e->rows_alloc) * d.dyn_c * sizeof(uint16_t), e->stream));
+    mznn::pack_hidden_kernel<<<148, 256, 0, e->stream>>>(e->d_hidden_f32, e->d_actions, reinterpret_cast<__half*>(e->s.dyn_in), n, ch, d.N, d.slots, d.dyn_c, d.act_col);
+    e->launches++;
+    CUDA_OK(cudaMemsetAsync(e->s.eval_slot, 0, sizeof(int32_t) * d.B, e->stream));
+    int rc = forward(e, 1);
+    if (rc) { return rc; }
+    return read_outputs(e, n, policy, logits, value, hidden_out);
+}
+
+int mz_search_leaf(mz_engine* e, int32_t* parent_slot, int32_t* leaf_action, int32_t* path_actions)
+{
+    if (!e) { return fail(MZ_ERR_ARG, "null argument"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    const mz_dims& d = e->d;
+    std::vector<int32_t> lp(static_cast<size_t>(d.B) * 2);
+    CUDA_OK(cudaMemcpyAsync(lp.data(), e->s.leaf_parent, sizeof(int32_t) * d.B * 2, cudaMemcpyDeviceToHost, e->stream));
+    if (path_actions) {
+        k_path_actions<<<d.B, 64, 0, e->stream>>>(d, e->s, e->d_path_actions);
+        e->launches++;
+        CUDA_OK(cudaMemcpyAsync(path_actions, e->d_path_actions, sizeof(int32_t) * d.B * (d.S + 2), cudaMemcpyDeviceToHost, e->stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    CUDA_OK(cudaGetLastError());
+    for (int g = 0; g < d.B; ++g) {
+        if (parent_slot) { parent_slot[g] = lp[g * 2]; }
+        if (leaf_action) { leaf_action[g] = lp[g * 2 + 1]; }
+    }
+    return MZ_OK;
+}
+
+int mz_gumbel_best_actions(mz_engine* e, int32_t* actions_out)
+{
+    if (!e || !actions_out) { return fail(MZ_ERR_ARG, "null argument"); }
+    if (!e->cfg.use_gumbel) { return fail(MZ_ERR_STATE, "engine created without actor_use_gumbel"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    k_gumbel_best<<<e->d.B, 32, 0, e->stream>>>(e->d, e->s, e->d_actions);
+    e->launches++;
+    CUDA_OK(cudaMemcpyAsync(actions_out, e->d_actions, sizeof(int32_t) * e->d.B, cudaMemcpyDeviceToHost, e->stream));
     CUDA_OK(cudaStreamSynchronize(e->stream));
     CUDA_OK(cudaGetLastError());
     return MZ_OK;
@@ -1062,7 +1228,7 @@ int mz_search_run(mz_engine* e, int32_t num_evals, float* device_ms)
         const bool skip_tree = (skip && std::string(skip) == "tree"), skip_nn = (skip && std::string(skip) == "nn");
         for (int c = 0; c < num_evals && !rc; ++c) {
             if (!skip_tree) { step(e, (c > 0 ? STEP_AFTER : 0) | STEP_BEFORE, e->rot_enabled ? e->d_rot_all + static_cast<size_t>(c) * d.B : nullptr); }
-            if (!skip_nn) { rc = forward(e); }
+            if (!skip_nn) { rc = forward(e, (e->cfg.muzero && c > 0) ? 1 : 0); } // MuZero: initial inference for the root, recurrent below
         }
         if (!skip_tree) { step(e, STEP_AFTER, nullptr); }
         cudaError_t cerr = cudaStreamEndCapture(e->stream, &graph);
@@ -1075,7 +1241,7 @@ int mz_search_run(mz_engine* e, int32_t num_evals, float* device_ms)
         if (cerr != cudaSuccess) { return fail(MZ_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(cerr)); }
         it = e->graphs.emplace(key, exec).first;
     }
-    e->launches += 1 + static_cast<int64_t>(num_evals) * (2 + (e->conv_mode == 3 ? 1 : static_cast<int64_t>(e->convs.size())));
+    e->launches += 1 + static_cast<int64_t>(num_evals) * (2 + (e->cfg.muzero ? 1 : 0) + (e->conv_mode == 3 ? 1 : static_cast<int64_t>(e->tw[0].convs.size())));
     if (!device_ms) { // asynchronous: the caller brackets several calls with mz_timer_begin / mz_timer_end or mz_sync
         CUDA_OK(cudaGraphLaunch(it->second, e->stream));
         return MZ_OK;
@@ -1106,12 +1272,12 @@ int mz_debug_tree_timing(mz_engine* e, uint64_t* out)
 int mz_debug_tower_timing(mz_engine* e, uint64_t* out, int32_t max_ctas)
 {
     if (!e || !out) { return fail(MZ_ERR_ARG, "bad argument"); }
-    if (!e->tower || !e->tower->dbg) { return fail(MZ_ERR_STATE, "set MZ_DEBUG_TOWER=1 before loading the network"); }
+    if (!e->tw[0].params || !e->tw[0].params->dbg) { return fail(MZ_ERR_STATE, "set MZ_DEBUG_TOWER=1 before loading the network"); }
     CUDA_OK(cudaSetDevice(e->cfg.device));
     int rc = forward(e);
     if (rc) { return rc; }
     const int n = (max_ctas < e->num_sms ? max_ctas : e->num_sms);
-    CUDA_OK(cudaMemcpyAsync(out, e->tower->dbg, sizeof(unsigned long long) * 8 * n, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaMemcpyAsync(out, e->tw[0].params->dbg, sizeof(unsigned long long) * 8 * n, cudaMemcpyDeviceToHost, e->stream));
     CUDA_OK(cudaStreamSynchronize(e->stream));
     return n;
 }
@@ -1123,15 +1289,16 @@ int mz_profile_kernels(mz_engine* e, int32_t iters, float* conv_ms, float* tree_
     CUDA_OK(cudaSetDevice(e->cfg.device));
     float ms = 0.0f;
     if (conv_ms && e->conv_mode == 3) { // the whole tower is one launch
-        for (int i = 0; i < 3; ++i) { launch_tower(e); }
+        const int which = e->num_towers - 1; // MuZero: the dynamics tower (S of the S + 1 evaluations of a move)
+        for (int i = 0; i < 3; ++i) { launch_tower(e, which); }
         CUDA_OK(cudaEventRecord(e->ev0, e->stream));
-        for (int i = 0; i < iters; ++i) { launch_tower(e); }
+        for (int i = 0; i < iters; ++i) { launch_tower(e, which); }
         CUDA_OK(cudaEventRecord(e->ev1, e->stream));
         CUDA_OK(cudaStreamSynchronize(e->stream));
         CUDA_OK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
         *conv_ms = ms / iters;
     } else if (conv_ms) {
-        const ConvLayer& L = e->convs.back();
+        const ConvLayer& L = e->tw[0].convs.back();
         for (int i = 0; i < 3; ++i) { conv(e, e->map_act[0], e->map_act_ext[0], L, e->act[1], e->act[2]); }
         CUDA_OK(cudaEventRecord(e->ev0, e->stream));
         for (int i = 0; i < iters; ++i) { conv(e, e->map_act[0], e->map_act_ext[0], L, e->act[1], e->act[2]); }

@@ -844,6 +844,7 @@ struct TowerParams {
     TowerLayer layer[TOWER_MAX_LAYERS];
     int num_layers;
     int rows_valid, n1, slots, cout, rows_ext, halo, num_mtiles;
+    int cin_max;  // widest layer input (the dynamics stem of a MuZero network reads hidden + action planes): sizes the input-block buffers
     int rotate;   // cluster offset per layer for the unit ranges
     int shift;    // unit offset per layer: position q of layer l is unit (q + l * shift) mod units
     int zigzag;   // odd layers process the cluster's range in reverse order
@@ -868,7 +869,7 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     const int a_kb_bytes = tp.rows_ext * 128;
-    const int a_bytes_max = (tp.cout / BK) * a_kb_bytes; // hidden layers have cin == cout; the stem is smaller
+    const int a_bytes_max = (tp.cin_max / BK) * a_kb_bytes; // hidden layers have cin == cout; an AlphaZero stem is narrower, a MuZero dynamics stem wider
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + 2 * a_bytes_max;
     uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_HALF_BYTES);
@@ -1303,6 +1304,81 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
     for (int a = tid; a < p.actions; a += nthr) {
         p.logits[static_cast<size_t>(g) * p.actions + a] = lg[a];
         p.policy[static_cast<size_t>(g) * p.actions + a] = expf(lg[a] - mx) * inv;
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// MuZero: MuZeroNetwork.scale_hidden_state (network/py/muzero_network.py:150-160) on the tower's output rows, one CTA per
+// board: min / max over the board's real channels and cells, x <- (x - min) / scale with scale = max - min (+1e-5 when
+// below 1e-5). The scaled state is written back in place (the prediction heads read it there) and into the hidden-state
+// slot of the node being evaluated (hid[g][slot[g]], compact [cell][c] rows; padded channels stay zero).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) scale_hidden_kernel(__half* __restrict__ act, __half* __restrict__ hid, const int32_t* __restrict__ slot, int n, int slots, int c,
+                                                          int c_real, int num_slots)
+{
+    __shared__ float red_mn[8], red_mx[8];
+    const int g = blockIdx.x, tid = threadIdx.x, hw = n * n, n1 = n + 1;
+    __half* rows = act + static_cast<size_t>(g) * slots * c;
+    const int pairs = c_real / 2; // channels are handled two at a time (c_real is even for every supported width)
+    float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
+    for (int i = tid; i < hw * pairs; i += blockDim.x) {
+        const int cell = i / pairs, k = i - cell * pairs;
+        const float2 v = __half22float2(*reinterpret_cast<const __half2*>(rows + static_cast<size_t>((cell / n + 1) * n1 + cell % n) * c + 2 * k));
+        mn = fminf(mn, fminf(v.x, v.y)), mx = fmaxf(mx, fmaxf(v.x, v.y));
+    }
+    if (c_real & 1) {
+        for (int cell = tid; cell < hw; cell += blockDim.x) {
+            const float v = __half2float(rows[static_cast<size_t>((cell / n + 1) * n1 + cell % n) * c + c_real - 1]);
+            mn = fminf(mn, v), mx = fmaxf(mx, v);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)), mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    if ((tid & 31) == 0) { red_mn[tid >> 5] = mn, red_mx[tid >> 5] = mx; }
+    __syncthreads();
+    mn = red_mn[0], mx = red_mx[0];
+    for (int i = 1; i < (blockDim.x >> 5); ++i) { mn = fminf(mn, red_mn[i]), mx = fmaxf(mx, red_mx[i]); }
+    float scale = mx - mn;
+    if (scale < 1e-5f) { scale += 1e-5f; }
+    __half* dst = hid + (static_cast<size_t>(g) * num_slots + slot[g]) * hw * c;
+    for (int i = tid; i < hw * c; i += blockDim.x) {
+        const int cell = i / c, ch = i - cell * c;
+        __half* p = rows + static_cast<size_t>((cell / n + 1) * n1 + cell % n) * c + ch;
+        __half out = __float2half_rn(0.0f);
+        if (ch < c_real) {
+            out = __float2half_rn((__half2float(*p) - mn) / scale);
+            *p = out;
+        }
+        dst[i] = out;
+    }
+}
+
+// MuZeroNetwork::pushBackRecurrentData layout (network/muzero_network.h:78-93) -> rows of the dynamics network's input:
+// hidden [n][c_real][H][W] fp32 + action ids -> [rows][dyn_c] fp16 with the one-hot action plane at column act_col (parity hook)
+__global__ void pack_hidden_kernel(const float* __restrict__ hidden, const int32_t* __restrict__ actions, __half* __restrict__ rows, int batch, int c_real, int n,
+                                   int slots, int dyn_c, int act_col)
+{
+    const int hw = n * n, total = batch * hw * dyn_c;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int g = i / (hw * dyn_c), cell = (i / dyn_c) % hw, ch = i % dyn_c;
+        float v = 0.0f;
+        if (ch < c_real) {
+            v = hidden[(static_cast<size_t>(g) * c_real + ch) * hw + cell];
+        } else if (ch == act_col) {
+            v = (actions[g] == cell ? 1.0f : 0.0f);
+        }
+        rows[(static_cast<size_t>(g) * slots + (cell / n + 1) * (n + 1) + cell % n) * dyn_c + ch] = __float2half_rn(v);
+    }
+}
+
+// stored hidden state (slot `which` of every game, compact [cell][c] fp16) -> [n][c_real][H][W] fp32 (parity hook)
+__global__ void unpack_hidden_kernel(const __half* __restrict__ hid, float* __restrict__ hidden, int batch, int c_real, int n, int c, int num_slots, int which)
+{
+    const int hw = n * n, total = batch * c_real * hw;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int g = i / (c_real * hw), ch = (i / hw) % c_real, cell = i % hw;
+        hidden[i] = __half2float(hid[((static_cast<size_t>(g) * num_slots + which) * hw + cell) * c + ch]);
     }
 }
 

@@ -13,7 +13,7 @@ import subprocess
 
 import numpy as np
 
-GAME_TICTACTOE, GAME_GO = 0, 1
+GAME_TICTACTOE, GAME_GO, GAME_OTHELLO = 0, 1, 2
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -24,12 +24,13 @@ class EngineError(RuntimeError):
 class _Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("game", C.c_int32), ("board_size", C.c_int32), ("num_games", C.c_int32), ("num_simulation", C.c_int32),
                 ("puct_base", C.c_float), ("puct_init", C.c_float), ("reward_discount", C.c_float), ("komi", C.c_float), ("ko_situational", C.c_int32),
-                ("dirichlet_epsilon", C.c_float)]
+                ("dirichlet_epsilon", C.c_float), ("muzero", C.c_int32), ("use_gumbel", C.c_int32), ("gumbel_noise", C.c_int32),
+                ("gumbel_sample_size", C.c_int32), ("gumbel_sigma_visit_c", C.c_float), ("gumbel_sigma_scale_c", C.c_float)]
 
 
 class _NetDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("num_input_channels", "input_height", "input_width", "num_hidden_channels", "num_blocks", "action_size",
-                                        "num_value_hidden_channels", "discrete_value_size")]
+                                        "num_value_hidden_channels", "discrete_value_size", "num_action_feature_channels", "is_muzero")]
 
 
 class _PlayResult(C.Structure):
@@ -84,6 +85,10 @@ def _load():
     lib.mz_net_finalize_empty.argtypes = [vp]
     lib.mz_net_blob.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int64)]
     lib.mz_eval_batch.argtypes = [vp, f32p, i32, f32p, f32p, f32p]
+    lib.mz_eval_initial.argtypes = [vp, f32p, i32, f32p, f32p, f32p, f32p]
+    lib.mz_eval_recurrent.argtypes = [vp, f32p, i32p, i32, f32p, f32p, f32p, f32p]
+    lib.mz_search_leaf.argtypes = [vp, i32p, i32p, i32p]
+    lib.mz_gumbel_best_actions.argtypes = [vp, i32p]
     lib.mz_reset_game.argtypes = [vp, i32]
     lib.mz_play.argtypes = [vp, i32p, C.POINTER(_PlayResult)]
     lib.mz_play_max_count.argtypes = [vp, i32, i32p, C.POINTER(_PlayResult)]
@@ -107,7 +112,8 @@ def _load():
 
 EXPORTS = ["mz_create", "mz_destroy", "mz_last_error", "mz_action_size", "mz_num_features", "mz_net_configure", "mz_net_set_tensor", "mz_net_finalize",
            "mz_net_blob", "mz_net_finalize_empty", "mz_eval_batch", "mz_reset_game", "mz_play", "mz_get_roots", "mz_search_select", "mz_search_apply",
-           "mz_search_set_inputs", "mz_search_run", "mz_profile_kernels", "mz_launch_count", "mz_play_max_count", "mz_sync", "mz_timer_begin", "mz_timer_end", "mz_debug_tree_timing", "mz_debug_tower_timing", "mz_conv_layers_per_launch"]
+           "mz_search_set_inputs", "mz_search_run", "mz_profile_kernels", "mz_launch_count", "mz_play_max_count", "mz_sync", "mz_timer_begin", "mz_timer_end", "mz_debug_tree_timing", "mz_debug_tower_timing", "mz_conv_layers_per_launch",
+           "mz_eval_initial", "mz_eval_recurrent", "mz_search_leaf", "mz_gumbel_best_actions"]
 
 
 def _fp(a):
@@ -126,9 +132,12 @@ class Engine:
     """One GPU's share of the self-play games: node pools, environments and the network, all resident in HBM."""
 
     def __init__(self, game, board_size, num_games, num_simulation, device=0, puct_base=19652.0, puct_init=1.25, reward_discount=1.0, komi=7.5,
-                 ko_situational=False, dirichlet_epsilon=0.25):
+                 ko_situational=False, dirichlet_epsilon=0.25, muzero=0, use_gumbel=0, gumbel_noise=0, gumbel_sample_size=16, gumbel_sigma_visit_c=50.0,
+                 gumbel_sigma_scale_c=1.0):
         self.lib = _load()
-        cfg = _Config(device, game, board_size, num_games, num_simulation, puct_base, puct_init, reward_discount, komi, int(ko_situational), dirichlet_epsilon)
+        cfg = _Config(device, game, board_size, num_games, num_simulation, puct_base, puct_init, reward_discount, komi, int(ko_situational), dirichlet_epsilon,
+                      int(muzero), int(use_gumbel), int(gumbel_noise), int(gumbel_sample_size), gumbel_sigma_visit_c, gumbel_sigma_scale_c)
+        self.muzero = bool(muzero)
         h = C.c_void_p()
         self.h = None
         self._check(self.lib.mz_create(C.byref(cfg), C.byref(h)))
@@ -161,10 +170,12 @@ class Engine:
             dims = dict(num_input_channels=m.get_num_input_channels(), input_height=m.get_input_channel_height(), input_width=m.get_input_channel_width(),
                         num_hidden_channels=m.get_num_hidden_channels(), num_blocks=m.get_num_blocks(), action_size=m.get_action_size(),
                         num_value_hidden_channels=m.get_num_value_hidden_channels(), discrete_value_size=m.get_discrete_value_size())
+            if m.get_type_name() == "muzero":  # network/muzero_network.h:46-52
+                dims.update(num_action_feature_channels=m.get_num_action_feature_channels(), is_muzero=1)
             state = {k: v.detach().float().contiguous().numpy() for k, v in m.state_dict().items() if not k.endswith("num_batches_tracked")}
         else:
             dims, state = source
-        nd = _NetDims(*[int(dims[n]) for n, _ in _NetDims._fields_])
+        nd = _NetDims(*[int(dims.get(n, 0)) for n, _ in _NetDims._fields_])
         self._check(self.lib.mz_net_configure(self.h, C.byref(nd)))
         for k, v in state.items():
             a = np.ascontiguousarray(v, np.float32)
@@ -173,7 +184,7 @@ class Engine:
         self.net_dims = dims
 
     def configure_network_empty(self, dims):
-        nd = _NetDims(*[int(dims[n]) for n, _ in _NetDims._fields_])
+        nd = _NetDims(*[int(dims.get(n, 0)) for n, _ in _NetDims._fields_])
         self._check(self.lib.mz_net_configure(self.h, C.byref(nd)))
         self._check(self.lib.mz_net_finalize_empty(self.h))
         self.net_dims = dims
@@ -190,6 +201,24 @@ class Engine:
         self._check(self.lib.mz_eval_batch(self.h, _fp(f), n, _fp(pol), _fp(lg), _fp(val)))
         return pol, lg, val
 
+    def eval_initial(self, features):
+        """MuZeroNetwork initial inference: policy, logits, value, scaled hidden state [n][Ch*H*W]"""
+        f = np.ascontiguousarray(features, np.float32).reshape(-1, self.F)
+        n = f.shape[0]
+        hsz = int(self.net_dims["num_hidden_channels"]) * int(self.net_dims["input_height"]) * int(self.net_dims["input_width"])
+        pol, lg, val, hid = np.zeros((n, self.A), np.float32), np.zeros((n, self.A), np.float32), np.zeros(n, np.float32), np.zeros((n, hsz), np.float32)
+        self._check(self.lib.mz_eval_initial(self.h, _fp(f), n, _fp(pol), _fp(lg), _fp(val), _fp(hid)))
+        return pol, lg, val, hid
+
+    def eval_recurrent(self, hidden, actions):
+        """MuZeroNetwork recurrent inference on (hidden state, action id) pairs"""
+        h = np.ascontiguousarray(hidden, np.float32)
+        n = h.shape[0]
+        a = np.ascontiguousarray(actions, np.int32)
+        pol, lg, val, hid = np.zeros((n, self.A), np.float32), np.zeros((n, self.A), np.float32), np.zeros(n, np.float32), np.zeros_like(h)
+        self._check(self.lib.mz_eval_recurrent(self.h, _fp(h), _i32(a), n, _fp(pol), _fp(lg), _fp(val), _fp(hid)))
+        return pol, lg, val, hid
+
     # ---- per-phase hooks (per-phase parity hooks) ------------------------
     def select(self, rotations=None, want_features=True):
         rot = None if rotations is None else np.ascontiguousarray(rotations, np.uint8)
@@ -197,7 +226,33 @@ class Engine:
         self._path_len = np.zeros(self.B, np.int32)
         self._check(self.lib.mz_search_select(self.h, _u8(rot), _fp(feats), _i32(self._path_len)))
         self._roots = None
+        self._leaf = None
         return feats
+
+    def _leaf_info(self):
+        if getattr(self, "_leaf", None) is None:
+            ps, la, pa = np.zeros(self.B, np.int32), np.zeros(self.B, np.int32), np.zeros((self.B, self.S + 2), np.int32)
+            self._check(self.lib.mz_search_leaf(self.h, _i32(ps), _i32(la), _i32(pa)))
+            self._leaf = (ps, la, pa)
+        return self._leaf
+
+    def leaf_action(self, g):
+        return int(self._leaf_info()[1][g])
+
+    def leaf_parent_slot(self, g):
+        return int(self._leaf_info()[0][g])
+
+    def path_hash(self, g):
+        """FNV-1a over the action ids of the selected path (same formula as oracle/drivers/ref_stepper.cpp)"""
+        h = 2166136261
+        for a in self._leaf_info()[2][g][1:self.path_len(g)]:
+            h = ((h ^ (int(a) & 0xffffffff)) * 16777619) & 0xffffffff
+        return h & 0x7fffffff
+
+    def gumbel_best_actions(self):
+        out = np.zeros(self.B, np.int32)
+        self._check(self.lib.mz_gumbel_best_actions(self.h, _i32(out)))
+        return out
 
     def apply(self, policy, logits, value, noise=None):
         p, l, v = (np.ascontiguousarray(x, np.float32) for x in (policy, logits, value))

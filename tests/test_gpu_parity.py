@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 
 ROOT = oracle_lib.ROOT
 NETS = os.path.join(ROOT, "oracle", "_ref", "nets")
-CASES = {"ttt_s50_b2": (0, 3), "ttt_s50_b1_det": (0, 3), "go5_s24_b2": (1, 5), "go9_s32_b2": (1, 9)}
+CASES = {"ttt_s50_b2": (0, 3), "ttt_s50_b1_det": (0, 3), "go5_s24_b2": (1, 5), "go9_s32_b2": (1, 9),
+         "othello_gmz_s16_b2": (2, 8), "othello_gmz_s32_m8_b2": (2, 8), "othello_mz_s24_b2": (2, 8)}
 
 
 def engine(*args, **kw):
@@ -27,7 +28,7 @@ def test_tree_and_env_kernels_replay_reference_recording(name):
     game, n = CASES[name]
     case = golden_replay.load_case(name)
     golden_replay.assert_tie_free(case)
-    eng = engine(game, n, int(case["B"]), int(case["S"]))
+    eng = engine(game, n, int(case["B"]), int(case["S"]), **oracle_lib.conf_overrides(case["conf"]))
     checked = golden_replay.replay(eng, case)
     assert checked >= case["move_game"].size - int(case["B"])
     eng.close()
@@ -181,4 +182,147 @@ def test_full_size_search_invariants():
     r2 = eng.get_roots()
     assert np.array_equal(r["count"], r2["count"]) and np.array_equal(r["mean"].view(np.uint32), r2["mean"].view(np.uint32))
     print("full-size search: %.1f ms, %.0f evals/s" % (ms, B * (S + 1) / ms * 1e3))
+    eng.close()
+
+
+# ---- MuZero / Gumbel (BASELINE configs[2]: Othello 8x8 Gumbel MuZero) ------------------------------------------------
+
+@pytest.mark.parametrize("net,batch", [("othello_mz_1bx32", 32), ("othello_mz_3bx128", 64)])
+def test_muzero_network_matches_torchscript_fp32(net, batch):
+    """initial_inference and recurrent_inference (network/py/muzero_network.py:136-150) against the reference TorchScript
+    module in fp32 on the CPU: logits / value / policy within 1e-3; the scaled hidden state (values in [0, 1], kept in fp16
+    here) within 2e-3"""
+    torch, m, path = torchscript(net)
+    n = 8
+    eng = engine(2, n, batch, 8, muzero=1)
+    eng.load_network(path)
+    rng = np.random.default_rng(11)
+    feats = np.zeros((batch, 4, n, n), np.float32)
+    stones = rng.integers(0, 3, size=(batch, n, n))
+    feats[:, 0] = stones == 1
+    feats[:, 1] = stones == 2
+    turn = rng.integers(0, 2, size=batch)
+    feats[:, 2] = (turn == 0)[:, None, None]
+    feats[:, 3] = (turn == 1)[:, None, None]
+    with torch.no_grad():
+        ref = m.initial_inference(torch.from_numpy(feats))
+    pol, lg, val, hid = eng.eval_initial(feats)
+    assert np.abs(lg - ref["policy_logit"].numpy()).max() < 1e-3
+    assert np.abs(val - ref["value"].numpy().reshape(-1)).max() < 1e-3
+    assert np.abs(pol - ref["policy"].numpy()).max() < 1e-3
+    ref_hid = ref["hidden_state"].numpy().reshape(batch, -1)
+    assert hid.min() >= 0.0 and hid.max() <= 1.0 and np.abs(hid - ref_hid).max() < 2e-3
+    # recurrent inference from the REFERENCE's hidden states; actions include the pass (all-zero plane, othello.cpp:257-262)
+    actions = rng.integers(0, n * n + 1, size=batch).astype(np.int32)
+    actions[:2] = n * n
+    planes = np.zeros((batch, 1, n * n), np.float32)
+    for g in range(batch):
+        if actions[g] < n * n:
+            planes[g, 0, actions[g]] = 1.0
+    with torch.no_grad():
+        ref2 = m.recurrent_inference(ref["hidden_state"], torch.from_numpy(planes.reshape(batch, 1, n, n)))
+    pol2, lg2, val2, hid2 = eng.eval_recurrent(ref_hid, actions)
+    assert np.abs(lg2 - ref2["policy_logit"].numpy()).max() < 1e-3
+    assert np.abs(val2 - ref2["value"].numpy().reshape(-1)).max() < 1e-3
+    assert np.abs(pol2 - ref2["policy"].numpy()).max() < 1e-3
+    assert np.abs(hid2 - ref2["hidden_state"].numpy().reshape(batch, -1)).max() < 2e-3
+    eng.close()
+
+
+def run_muzero_search_vs_oracle(B, S, net_path, moves, seed, **opts):
+    """whole-move on-device MuZero searches (CUDA graph: tree kernels, hidden-state gather, representation / dynamics towers,
+    hidden-state scaling, heads) against the oracle fed with the engine's own network outputs, move after move"""
+    lib = oracle_lib.load()
+    n = 8
+    eng = engine(2, n, B, S, muzero=1, **opts)
+    eng.load_network(net_path)
+    ev = engine(2, n, B, 2, muzero=1)  # network-only engine
+    ev.load_network(net_path)
+    orc = oracle_lib.OracleSearch(lib, oracle_lib.GAME_OTHELLO, n, B, S, muzero=1, **opts)
+    rng = np.random.default_rng(seed)
+    A = eng.A
+    gumbel = bool(opts.get("use_gumbel"))
+    for move in range(moves):
+        noise = (rng.gumbel(size=(B, A)) if opts.get("gumbel_noise") else rng.dirichlet([0.3] * A, size=B)).astype(np.float32)
+        eng.set_search_inputs(None, noise)
+        eng.search()
+        store = None
+        for c in range(S + 1):
+            feats = orc.select(None)
+            lens = np.array([orc.path_len(g) for g in range(B)])
+            if c == 0:
+                assert np.all(lens == 1)
+                pol, lg, val, hid = ev.eval_initial(feats)
+                store = np.zeros((B, S + 1) + hid.shape[1:], np.float32)
+            else:
+                assert np.all(lens > 1)
+                parent = np.array([orc.leaf_parent_slot(g) for g in range(B)])
+                acts = np.array([orc.leaf_action(g) for g in range(B)], np.int32)
+                pol, lg, val, hid = ev.eval_recurrent(store[np.arange(B), parent], acts)
+            store[:, c] = hid
+            orc.apply(pol, lg, val, noise)
+        best = eng.gumbel_best_actions() if gumbel else None
+        actions = np.zeros(B, np.int32)
+        for g in range(B):
+            a, b = eng.root(g), orc.root(g)
+            assert a["num_children"] == b["num_children"], (move, g)
+            k = a["num_children"]
+            assert np.array_equal(a["action"][:k], b["action"][:k]), (move, g)
+            assert np.array_equal(a["count"][:k], b["count"][:k]), (move, g, a["count"][:k], b["count"][:k])
+            assert np.array_equal(a["mean"][:k].view(np.uint32), b["mean"][:k].view(np.uint32)), (move, g)
+            assert np.array_equal(a["logit"][:k].view(np.uint32), b["logit"][:k].view(np.uint32)), (move, g)
+            assert a["root_count"] == S + 1 and a["count"][:k].sum() == S
+            if gumbel:
+                assert best[g] == orc.gumbel_best_action(g), (move, g)
+                actions[g] = best[g]
+            else:
+                actions[g] = a["action"][int(np.argmax(a["count"][:k]))]
+        res = eng.play_all(actions)
+        for g in range(B):
+            assert res["applied"][g] == 1 and orc.play(g, int(actions[g])) == 1
+            assert bool(res["terminal"][g]) == orc.root_terminal(g)
+            if res["terminal"][g]:
+                eng.reset_game(g)
+                orc.reset_game(g)
+    eng.close()
+    ev.close()
+
+
+def test_on_device_gumbel_muzero_search_matches_oracle_othello():
+    torch, m, path = torchscript("othello_mz_1bx32")
+    run_muzero_search_vs_oracle(8, 16, path, moves=66, seed=4, use_gumbel=1, gumbel_noise=1, gumbel_sample_size=16)
+
+
+def test_on_device_gumbel_muzero_search_with_halving_matches_oracle_othello():
+    torch, m, path = torchscript("othello_mz_3bx128")
+    run_muzero_search_vs_oracle(8, 32, path, moves=12, seed=5, use_gumbel=1, gumbel_noise=1, gumbel_sample_size=8)
+
+
+def test_on_device_puct_muzero_search_matches_oracle_othello():
+    torch, m, path = torchscript("othello_mz_1bx32")
+    run_muzero_search_vs_oracle(8, 24, path, moves=10, seed=6)
+
+
+def test_full_size_gumbel_muzero_invariants():
+    """BASELINE config 3 at full size (512 games, Gumbel n=16 m=16, 3b x 128 MuZero): size-independent properties"""
+    torch, m, path = torchscript("othello_mz_3bx128")
+    B, S = 512, 16
+    eng = engine(2, 8, B, S, muzero=1, use_gumbel=1, gumbel_noise=1, gumbel_sample_size=16)
+    eng.load_network(path)
+    rng = np.random.default_rng(9)
+    noise = rng.gumbel(size=(B, eng.A)).astype(np.float32)
+    eng.set_search_inputs(None, noise)
+    ms = eng.search()
+    r = eng.get_roots()
+    assert np.all(r["root_count"] == S + 1)
+    assert np.all(r["num_children"] == 4)  # the four opening moves of Othello
+    assert np.all(np.sort(r["action"][:, :4], axis=1) == np.array([20, 29, 34, 43]))
+    assert np.all(r["count"][:, :4] == 4)  # budget 1 per candidate, no halving (gumbel_zero.cpp:99,109): 16 simulations over 4 candidates
+    assert np.all(np.isfinite(r["mean"])) and np.all(np.abs(r["root_mean"]) <= 1.0)
+    eng.reset_game(-1)
+    eng.set_search_inputs(None, noise)
+    eng.search()
+    r2 = eng.get_roots()
+    assert np.array_equal(r["count"], r2["count"]) and np.array_equal(r["mean"].view(np.uint32), r2["mean"].view(np.uint32))
+    print("config-3 search: %.2f ms, %.0f evals/s" % (ms, B * (S + 1) / ms * 1e3))
     eng.close()
