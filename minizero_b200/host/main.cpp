@@ -56,6 +56,31 @@ int recordTest()
             m.value = std::to_string(hexFloat(mean_hex));
             m.reward = "0";
             moves.push_back(m);
+        } else if (kind == "gmove") { // Gumbel: "gmove <player> <action> <root_mean_hex> <root_value_hex> <S> <visit_c> <scale_c> <k> a:count:mean:policy:logit:noise ..."
+            mzhost::MoveRecord m;
+            std::string mean_hex, value_hex;
+            int k, sims;
+            float visit_c, scale_c;
+            iss >> m.player >> m.action >> mean_hex >> value_hex >> sims >> visit_c >> scale_c >> k;
+            std::vector<int> acts(k);
+            std::vector<float> f[5];
+            for (auto& v : f) { v.resize(k); }
+            for (int i = 0; i < k; ++i) {
+                std::string tok, part;
+                iss >> tok;
+                std::istringstream ts(tok);
+                std::getline(ts, part, ':');
+                acts[i] = std::stoi(part);
+                for (auto& v : f) {
+                    std::getline(ts, part, ':');
+                    v[i] = hexFloat(part);
+                }
+            }
+            m.policy = mzhost::gumbelPolicy(acts.data(), f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), k, hexFloat(value_hex), m.player, 1.0f, sims,
+                                            visit_c, scale_c);
+            m.value = std::to_string(hexFloat(mean_hex));
+            m.reward = "0";
+            moves.push_back(m);
         }
     }
     std::cout << mzhost::selfPlayLine(h, moves, terminal, eval, turn) << std::endl;
@@ -94,8 +119,8 @@ int main(int argc, char** argv)
         std::cerr << "Failed to load configuration string." << std::endl;
         return -1;
     }
-    if (cfg.getBool("actor_use_gumbel") || cfg.getString("nn_type_name") != "alphazero") {
-        std::cerr << "this worker implements the AlphaZero self-play path only" << std::endl;
+    if (cfg.getString("nn_type_name") != "alphazero" && cfg.getString("nn_type_name") != "muzero") {
+        std::cerr << "this worker implements the alphazero and (board-game) muzero self-play paths" << std::endl;
         return -1;
     }
     // stdout belongs to the wire protocol: the server drops the connection on anything but `SelfPlay` lines

@@ -5,8 +5,11 @@
 //   environment/go/go.h:129-133      KM tag; environment/base/base_env.h:363-367 SZ tag
 //   actor/mcts.cpp:126-137           getSearchDistributionString ("action:count" of the visited root children, child order)
 #pragma once
+#include <cmath>
+#include <limits>
 #include <sstream>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -40,6 +43,47 @@ inline std::string searchDistribution(const int* actions, const float* counts, i
         if (counts[i] == 0) { continue; }
         oss << (first ? "" : ",") << actions[i] << ":" << counts[i];
         first = false;
+    }
+    return oss.str();
+}
+
+// GumbelZero::getMCTSPolicy (actor/gumbel_zero.cpp:9-59) from the root child table: softmax of the completed-Q logits,
+// entries below -38 dropped, printed in the iteration order of the same std::unordered_map<int, float> the reference fills
+// (same libstdc++, same insertion sequence => same order). Board games: no value rescale. child_player = side to move.
+inline std::string gumbelPolicy(const int* actions, const float* counts, const float* means, const float* policy, const float* logit, const float* noise,
+                                int num_children, float root_value, int child_player, float discount, int num_simulation, float sigma_visit_c, float sigma_scale_c)
+{
+    auto normalized = [&](int i) { // MCTSNode::getNormalizedMean, mcts.cpp:40-53 (reward 0, no rescale, no virtual loss)
+        float value = 0.0f + discount * means[i];
+        value = (child_player == 2 ? -value : value);
+        return (value * counts[i] - 0.0f) / (counts[i] + 0.0f);
+    };
+    float pi_sum = 0.0f, q_sum = 0.0f;
+    for (int i = 0; i < num_children; ++i) {
+        if (counts[i] == 0) { continue; }
+        float value = normalized(i);
+        pi_sum += policy[i];
+        q_sum += policy[i] * value;
+    }
+    float value_pi = root_value;
+    value_pi = (child_player == 2 ? -value_pi : value_pi);
+    float non_visited_node_value = 1.0 / (1 + num_simulation) * (value_pi + (num_simulation / pi_sum) * q_sum);
+    std::unordered_map<int, float> new_logits;
+    float max_logit = -std::numeric_limits<float>::max();
+    float max_child_count = 0;
+    for (int i = 0; i < num_children; ++i) { max_child_count = fmax(max_child_count, counts[i]); }
+    for (int i = 0; i < num_children; ++i) {
+        float value = (counts[i] == 0 ? non_visited_node_value : normalized(i));
+        float logit_without_noise = logit[i] - noise[i];
+        float score = logit_without_noise + (sigma_visit_c + max_child_count) * sigma_scale_c * value;
+        new_logits.insert({actions[i], score});
+        max_logit = fmax(max_logit, score);
+    }
+    std::ostringstream oss;
+    for (auto& l : new_logits) {
+        l.second = l.second - max_logit;
+        if (l.second < -38) { continue; }
+        oss << (oss.str().empty() ? "" : ",") << l.first << ":" << exp(l.second);
     }
     return oss.str();
 }

@@ -29,6 +29,19 @@ public:
         return dirichlet;
     }
 
+    // utils/random.h:26-36
+    std::vector<float> randGumbel(int size)
+    {
+        std::extreme_value_distribution<float> gumbel_distribution(0.0, 1.0);
+        std::vector<float> gumbel;
+        for (int i = 0; i < size; ++i) {
+            float value = gumbel_distribution(generator_);
+            while (std::isinf(value)) { value = gumbel_distribution(generator_); }
+            gumbel.emplace_back(value);
+        }
+        return gumbel;
+    }
+
 private:
     std::mt19937 generator_;
     std::uniform_int_distribution<int> int_distribution_;

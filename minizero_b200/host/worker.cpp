@@ -27,10 +27,12 @@ bool Worker::initialize()
         std::cerr << "Failed to load model \"" << model << "\": " << err << std::endl;
         return false;
     }
-    if (net_.type_name != "alphazero") {
-        std::cerr << "nn_type_name \"" << net_.type_name << "\" is not implemented by this worker (AlphaZero only)" << std::endl;
+    if (net_.type_name != "alphazero" && net_.type_name != "muzero") {
+        std::cerr << "nn_type_name \"" << net_.type_name << "\" is not implemented by this worker (alphazero and board-game muzero)" << std::endl;
         return false;
     }
+    muzero_ = (net_.type_name == "muzero"); // the actor follows the loaded network's type (zero_actor.cpp:100-114)
+    gumbel_ = cfg_.getBool("actor_use_gumbel");
     // the reference binary is compiled per game (environment/environment.h:5-110); here the model names its game
     if (net_.game_name == "tictactoe") {
         game_type_ = MZ_GAME_TICTACTOE, board_ = 3;
@@ -40,6 +42,8 @@ bool Worker::initialize()
             std::cerr << "env_board_size does not match the model's board" << std::endl;
             return false;
         }
+    } else if (net_.game_name.rfind("othello_", 0) == 0) {
+        game_type_ = MZ_GAME_OTHELLO, board_ = net_.dims.input_height;
     } else {
         std::cerr << "game \"" << net_.game_name << "\" is not implemented by this worker" << std::endl;
         return false;
@@ -64,6 +68,10 @@ bool Worker::initialize()
         c.puct_base = cfg_.getFloat("actor_mcts_puct_base"), c.puct_init = cfg_.getFloat("actor_mcts_puct_init");
         c.reward_discount = cfg_.getFloat("actor_mcts_reward_discount"), c.komi = cfg_.getFloat("env_go_komi");
         c.ko_situational = (cfg_.getString("env_go_ko_rule") == "situational"), c.dirichlet_epsilon = cfg_.getFloat("actor_dirichlet_noise_epsilon");
+        c.muzero = muzero_, c.use_gumbel = gumbel_;
+        c.gumbel_noise = (!cfg_.getBool("actor_use_dirichlet_noise") && cfg_.getBool("actor_use_gumbel_noise")); // zero_actor.cpp:197,205
+        c.gumbel_sample_size = cfg_.getInt("actor_gumbel_sample_size");
+        c.gumbel_sigma_visit_c = cfg_.getFloat("actor_gumbel_sigma_visit_c"), c.gumbel_sigma_scale_c = cfg_.getFloat("actor_gumbel_sigma_scale_c");
         mz_engine* e = nullptr;
         if (mz_create(&c, &e) != MZ_OK) {
             std::cerr << "mz_create failed on device " << dev << ": " << mz_last_error() << std::endl;
@@ -92,7 +100,7 @@ bool Worker::initialize()
     // slave thread 0 re-seeds: program_seed + thread id, or a random device (actor_group.cpp:66-70)
     rng_.seed(cfg_.getBool("program_auto_seed") ? static_cast<int>(std::random_device()()) : cfg_.getInt("program_seed") + 0);
     // first beforeNNEvaluation of every game: rotation draw of cycle 0 (zero_actor.cpp:56)
-    const bool random_rotation = cfg_.getBool("actor_use_random_rotation_features");
+    const bool random_rotation = cfg_.getBool("actor_use_random_rotation_features") && !muzero_; // only the AlphaZero branch draws one (zero_actor.cpp:54-57)
     for (int g = 0; g < num_games_; ++g) {
         const int e = g % static_cast<int>(engines_.size()), slot = g / static_cast<int>(engines_.size());
         rotations_[e][slot] = (random_rotation ? static_cast<uint8_t>(rng_.randInt() % 8) : 0);
@@ -106,7 +114,7 @@ void Worker::resetGameHost(int g)
     Game& game = games_[g];
     game.moves.clear();
     game.turn = 1;
-    game.num_legal = (game_type_ == MZ_GAME_GO ? board_ * board_ + 1 : 9);
+    game.num_legal = initialNumLegal();
     std::fill(game.ttt, game.ttt + 9, 0);
     game.enable_resign = (rng_.randReal() < cfg_.getFloat("zero_disable_resign_ratio") ? false : true);
 }
@@ -263,6 +271,10 @@ bool Worker::hostTerminal(const Game& game) const
         if (n >= 2 && game.moves[n - 1].action == pass && game.moves[n - 2].action == pass) { return true; } // go.cpp:249-251
         return n > 2 * board_ * board_;                                                                        // go.cpp:254
     }
+    if (game_type_ == MZ_GAME_OTHELLO) { // othello.cpp:201-207
+        const int pass = board_ * board_;
+        return n >= 2 && game.moves[n - 1].action == pass && game.moves[n - 2].action == pass;
+    }
     static const int lines[8][3] = {{0, 1, 2}, {3, 4, 5}, {6, 7, 8}, {0, 3, 6}, {1, 4, 7}, {2, 5, 8}, {0, 4, 8}, {2, 4, 6}};
     for (const auto& l : lines) {
         if (game.ttt[l[0]] != 0 && game.ttt[l[0]] == game.ttt[l[1]] && game.ttt[l[1]] == game.ttt[l[2]]) { return true; }
@@ -290,7 +302,8 @@ void Worker::emitGame(int g, bool terminal, float eval_score)
 bool Worker::playOneMove()
 {
     const int ne = static_cast<int>(engines_.size()), S1 = sims_ + 1, A = actions_;
-    const bool use_noise = cfg_.getBool("actor_use_dirichlet_noise"), random_rotation = cfg_.getBool("actor_use_random_rotation_features");
+    const bool use_dirichlet = cfg_.getBool("actor_use_dirichlet_noise"), use_gumbel_noise = (!use_dirichlet && cfg_.getBool("actor_use_gumbel_noise"));
+    const bool use_noise = use_dirichlet || use_gumbel_noise, random_rotation = cfg_.getBool("actor_use_random_rotation_features") && !muzero_;
     const float alpha = cfg_.getFloat("actor_dirichlet_noise_alpha");
     // (1) randomness of cycles 1 .. S in the reference's per-cycle, per-actor order: in cycle 1 every
     //     actor first receives its root noise (afterNNEvaluation of the root) and then draws the rotation of its next leaf
@@ -298,7 +311,7 @@ bool Worker::playOneMove()
         for (int g = 0; g < num_games_; ++g) {
             const int e = g % ne, slot = g / ne;
             if (c == 1 && use_noise) {
-                std::vector<float> dir = rng_.randDirichlet(alpha, games_[g].num_legal);
+                std::vector<float> dir = (use_dirichlet ? rng_.randDirichlet(alpha, games_[g].num_legal) : rng_.randGumbel(games_[g].num_legal)); // zero_actor.cpp:194-213
                 float* dst = noise_[e].data() + static_cast<size_t>(slot) * A;
                 std::fill(dst, dst + A, 0.0f);
                 std::copy(dir.begin(), dir.end(), dst);
@@ -318,14 +331,21 @@ bool Worker::playOneMove()
     struct Roots {
         std::vector<mz_root_info> info;
         std::vector<int32_t> action;
-        std::vector<float> count, mean;
+        std::vector<float> count, mean, policy, logit, noise;
+        std::vector<int32_t> gumbel_best;
     };
     std::vector<Roots> roots(ne);
     for (int e = 0; e < ne; ++e) {
         const size_t n = engine_games_[e];
         roots[e].info.resize(n), roots[e].action.resize(n * A), roots[e].count.resize(n * A), roots[e].mean.resize(n * A);
-        if (mz_get_roots(engines_[e], roots[e].info.data(), roots[e].action.data(), roots[e].count.data(), roots[e].mean.data(), nullptr, nullptr, nullptr, nullptr) != MZ_OK) {
+        if (gumbel_) { roots[e].policy.resize(n * A), roots[e].logit.resize(n * A), roots[e].noise.resize(n * A), roots[e].gumbel_best.resize(n); }
+        if (mz_get_roots(engines_[e], roots[e].info.data(), roots[e].action.data(), roots[e].count.data(), roots[e].mean.data(), gumbel_ ? roots[e].policy.data() : nullptr,
+                         gumbel_ ? roots[e].logit.data() : nullptr, gumbel_ ? roots[e].noise.data() : nullptr, nullptr) != MZ_OK) {
             std::cerr << "mz_get_roots failed: " << mz_last_error() << std::endl;
+            return false;
+        }
+        if (gumbel_ && mz_gumbel_best_actions(engines_[e], roots[e].gumbel_best.data()) != MZ_OK) {
+            std::cerr << "mz_gumbel_best_actions failed: " << mz_last_error() << std::endl;
             return false;
         }
     }
@@ -343,12 +363,26 @@ bool Worker::playOneMove()
         const float* mean = roots[e].mean.data() + static_cast<size_t>(slot) * A;
         bool resign = false;
         int child = -1;
-        const int action = decideAction(g, acts, cnt, mean, ri.num_children, ri.mean, resign, child);
+        int action = decideAction(g, acts, cnt, mean, ri.num_children, ri.mean, resign, child);
+        if (gumbel_ && cfg_.getBool("actor_select_action_by_count")) { // GumbelZero::decideActionNode: best-scoring candidate (gumbel_zero.cpp:61-66)
+            action = roots[e].gumbel_best[slot];
+            for (int i = 0; i < ri.num_children; ++i) {
+                if (acts[i] == action) { child = i; }
+            }
+            const float discount = cfg_.getFloat("actor_mcts_reward_discount"), threshold = cfg_.getFloat("actor_resign_threshold");
+            const float root_win_rate = normalizedMean(ri.mean, static_cast<float>(sims_ + 1), 3 - game.turn, discount);
+            const float action_win_rate = normalizedMean(mean[child], cnt[child], game.turn, discount);
+            resign = game.enable_resign && (-root_win_rate < threshold && action_win_rate < threshold); // mcts.cpp:84-89
+        }
         bool end = resign;
         if (!resign) { // BaseActor::act + getActionInfo (base_actor.cpp:22-30,59-66)
             MoveRecord m;
             m.action = action, m.player = game.turn;
-            m.policy = searchDistribution(acts, cnt, ri.num_children);
+            m.policy = (gumbel_ ? gumbelPolicy(acts, cnt, mean, roots[e].policy.data() + static_cast<size_t>(slot) * A, roots[e].logit.data() + static_cast<size_t>(slot) * A,
+                                               roots[e].noise.data() + static_cast<size_t>(slot) * A, ri.num_children, ri.value, game.turn,
+                                               cfg_.getFloat("actor_mcts_reward_discount"), sims_, cfg_.getFloat("actor_gumbel_sigma_visit_c"),
+                                               cfg_.getFloat("actor_gumbel_sigma_scale_c"))
+                                : searchDistribution(acts, cnt, ri.num_children)); // zero_actor.h:48
             m.value = std::to_string(ri.mean); // zero_actor.h:49
             m.reward = "0";                    // operator<< of Environment::getReward() == 0.0f (go.h:50, tictactoe.h:25)
             game.moves.push_back(m);
@@ -401,7 +435,7 @@ bool Worker::playOneMove()
         Game& game = games_[g];
         game.moves.clear();
         game.turn = 1;
-        game.num_legal = (game_type_ == MZ_GAME_GO ? board_ * board_ + 1 : 9);
+        game.num_legal = initialNumLegal();
         std::fill(game.ttt, game.ttt + 9, 0);
         game.enable_resign = keep_resign;
     }

@@ -47,6 +47,8 @@ private:
     NetInfo net_;
     GameHeader header_;
     int game_type_ = MZ_GAME_GO, board_ = 9, actions_ = 82, sims_ = 0, num_games_ = 0;
+    bool muzero_ = false, gumbel_ = false;
+    int initialNumLegal() const { return game_type_ == MZ_GAME_GO ? board_ * board_ + 1 : (game_type_ == MZ_GAME_OTHELLO ? 4 : 9); }
     std::vector<mz_engine*> engines_;  // one per visible GPU (actor_group.cpp:168-177)
     std::vector<int> engine_games_;    // games handled by each engine: game g -> engine g % n, slot g / n (actor_group.cpp:184-186)
     std::vector<Game> games_;

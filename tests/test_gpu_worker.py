@@ -41,6 +41,10 @@ def run_worker(conf, want_lines, timeout=240):
     ("tictactoe", "ttt_az_2bx32", "actor_num_simulation=50:zero_num_parallel_games=16", ""),
     ("go", "go5_az_1bx16", "env_board_size=5:actor_num_simulation=24:zero_num_parallel_games=16", "env_board_size=5"),
     ("go", "go9_az_2bx64", "env_board_size=9:actor_num_simulation=32:zero_num_parallel_games=32", "env_board_size=9"),
+    # BASELINE configs[2] search settings (tools/quick-run.sh "gmz"): Gumbel MuZero on Othello
+    ("othello", "othello_mz_1bx32", "actor_num_simulation=16:zero_num_parallel_games=16:nn_type_name=muzero:actor_use_gumbel=true:actor_use_gumbel_noise=true:"
+     "actor_gumbel_sample_size=16:actor_use_dirichlet_noise=false", ""),
+    ("othello", "othello_mz_1bx32", "actor_num_simulation=24:zero_num_parallel_games=16:nn_type_name=muzero", ""),
 ])
 def test_worker_speaks_the_wire_protocol_and_reference_accepts_its_records(game, net, conf, checker_conf):
     checker = os.path.join(ROOT, "oracle", "_ref", "ref_record_check_" + game)

@@ -75,3 +75,33 @@ def test_config_accepts_reference_keys_and_refuses_unknown(worker_binary):
     # without a GPU (or a model) the worker must fail loudly and write nothing to stdout
     nogpu = subprocess.run([worker_binary, "-mode", "sp", "-conf_str", "nn_file_name=/nonexistent.pt:zero_num_parallel_games=2"], input="quit\n", capture_output=True, text=True)
     assert nogpu.returncode != 0 and nogpu.stdout == ""
+
+
+def test_gumbel_selfplay_lines_match_reference_bytes(worker_binary):
+    """Othello Gumbel MuZero records: the completed-Q policy tags (gumbel_zero.cpp:9-59, unordered_map order included) and the rest
+    of the line, byte for byte as the compiled reference printed them"""
+    z = golden_replay.load_case("othello_gmz_s16_b2")
+    lines = [str(l) for l in z["selfplay_lines"]]
+    assert lines
+    produced = set()
+    for g in range(int(z["B"])):
+        ms = [m for m in range(z["move_game"].size) if z["move_game"][m] == g]
+        games, cur = [], []
+        for m in ms:
+            if cur and int(z["move_number"][m]) == 0:
+                games.append(cur)
+                cur = []
+            cur.append(m)
+        games.append(cur)
+        for gm in games:
+            for eval_score in (1.0, -1.0, 0.0):
+                inp = [f"header othello_8x8 8 0 0 /some/dir/{name_of_model(lines)} 1 {hexf(eval_score)} 1"]
+                for m in gm:
+                    k = int(z["move_num_children"][m])
+                    toks = " ".join(":".join([str(int(z["child_action"][m, i]))] + [hexf(z["child_" + n][m, i]) for n in ("count", "mean", "policy", "logit", "noise")])
+                                    for i in range(k))
+                    inp.append(f"gmove {int(z['move_player'][m])} {int(z['move_action'][m])} {hexf(z['root_mean'][m])} {hexf(z['root_value'][m])} {int(z['S'])} 50 1 {k} {toks}")
+                r = subprocess.run([worker_binary, "-mode", "record_test"], input="\n".join(inp) + "\n", capture_output=True, text=True, check=True)
+                produced.add(r.stdout.strip())
+    for l in lines:
+        assert l.strip() in produced, l[:200]
