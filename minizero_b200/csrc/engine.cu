@@ -223,7 +223,7 @@ struct mz_engine {
     float* d_hidden_f32 = nullptr;   // [B][Ch * H * W] staging of the parity hooks
     int32_t* d_path_actions = nullptr; // [B][S + 2]
     int cin_max = 0;
-    int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148, krot = 0, conv_cluster = 1, conv_pdl = 0, tower_sms = 148;
+    int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148, krot = 0, conv_cluster = 1, conv_pdl = 0, tower_sms = 148, tower_stages = 8;
     encode_tiled_fn encode = nullptr;
 
     // graphs keyed by (num_evals, noise, rotations)
@@ -332,6 +332,8 @@ int configure_conv_kernels()
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_pair_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return MZ_OK;
 }
 
@@ -412,15 +414,20 @@ int launch_tower(mz_engine* e, int which)
         const int units = num_groups * (e->cpad / 128);
         int clusters = e->tower_sms / 2;
         if (units < clusters) { clusters = units; }
-        const size_t smem = 2 * static_cast<size_t>(e->cin_max / mznn::BK) * e->rows_ext * 128 + 8 * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
+        const int stages = e->tower_stages;
+        const size_t smem = 2 * static_cast<size_t>(e->cin_max / mznn::BK) * e->rows_ext * 128 + static_cast<size_t>(stages) * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(clusters * 2), cfg.blockDim = dim3(mznn::TOWER_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = e->stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr, cfg.numAttrs = 1;
-        if (T.params->dbg) {
+        if (T.params->dbg && stages == 8) {
             CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8, true>, *T.params));
+        } else if (stages == 4) { // 185 KB of shared memory: a tree-step block (30 KB) of another engine fits on the same SM
+            CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 4, false>, *T.params));
+        } else if (stages == 5) {
+            CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 5, false>, *T.params));
         } else {
             CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8, false>, *T.params));
         }
@@ -539,14 +546,23 @@ int alloc_net(mz_engine* e)
     const size_t need = (e->bn_tile == 64 ? resident_smem<64, 6>(e, e->cin_max) : resident_smem<128, 9>(e, e->cin_max));
     if (e->bn_tile == 64) { e->conv_cluster = 1; }
     if (e->conv_mode == 2) { // CTA pairs: needs the 128-wide tile and half-tile weight boxes
-        const size_t pair_need = 2 * static_cast<size_t>(e->cin_max / mznn::BK) * e->rows_ext * 128 + 8 * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
-        if (e->bn_tile == 128 && pair_need <= 227 * 1024) {
+        // the fused tower runs as fast with 4 or 5 weight stages as with 8 (measured), so a larger resident block (19x19: 176 rows)
+        // simply takes fewer stages; the per-layer pair kernel is instantiated for 8 only
+        auto pair_need = [&](int stages) {
+            return 2 * static_cast<size_t>(e->cin_max / mznn::BK) * e->rows_ext * 128 + static_cast<size_t>(stages) * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
+        };
+        int stages = 0;
+        for (int cand : {8, 5, 4}) {
+            if (stages == 0 && pair_need(cand) <= 227 * 1024 && (want_tower || cand == 8)) { stages = cand; }
+        }
+        if (e->bn_tile == 128 && stages != 0) {
             e->conv_cluster = 2;
+            if (!std::getenv("MZ_TOWER_STAGES")) { e->tower_stages = stages; }
         } else {
             e->conv_mode = 1;
         }
     }
-    if (need > 227 * 1024) { e->conv_mode = 0; }
+    if (e->conv_mode == 1 && need > 227 * 1024) { e->conv_mode = 0; }
     cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->cfg.device);
     for (int i = 0; i < 3; ++i) {
         if ((rc = e->dalloc(&e->act[i], rows * e->cpad))) { return rc; }
@@ -562,6 +578,10 @@ int alloc_net(mz_engine* e)
         e->d.hid_c = e->cpad, e->d.dyn_c = e->tw[1].cin0, e->d.act_col = e->nd.num_hidden_channels;
     }
     e->tw[0].in = e->s.nn_in, e->tw[1].in = e->s.dyn_in;
+    if (const char* env = std::getenv("MZ_TOWER_STAGES")) {
+        const int v = std::atoi(env);
+        if (v == 4 || v == 5 || v == 8) { e->tower_stages = v; }
+    }
     e->tower_sms = e->num_sms; // SMs the persistent tower may occupy (MZ_TOWER_SMS: experiments with a second engine beside it)
     if (const char* env = std::getenv("MZ_TOWER_SMS")) {
         const int v = std::atoi(env);
@@ -751,6 +771,16 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     // the attribute belongs to the function, not to the engine: only ever raise it (several engines may coexist)
     static size_t step_smem_max = 0;
     if (step_smem_bytes(d) > step_smem_max) { step_smem_max = step_smem_bytes(d); }
+    if (const char* env = std::getenv("MZ_CARVEOUT")) {
+        // same shared-memory carve-out as the tower kernel, so that tree-step / heads blocks of one engine can be co-resident
+        // with the tower CTAs of another engine on the same SM (an SM runs one carve-out configuration at a time)
+        if (std::atoi(env) != 0) {
+            cudaFuncSetAttribute(k_step, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(mznn::heads_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(mznn::heads_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(mznn::heads_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
+    }
     if (cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(step_smem_max)) != cudaSuccess) {
         mz_destroy(e);
         return fail(MZ_ERR_CUDA, "k_step shared memory request refused");

@@ -1326,6 +1326,148 @@ MZ_DEV void mz_before_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch*
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// std::sort(candidates, lhs.policy_ > rhs.policy_) (zero_actor.cpp:225-227,241-243) EXACTLY as libstdc++ orders them.
+// std::sort is unstable: where candidates with equal priors end up is decided by the library's algorithm, and the child
+// order is observable (PUCT ties, the record's P[...] tag). libstdc++'s std::__sort (bits/stl_algo.h, unchanged since
+// GCC 4.9): introsort — median-of-three quicksort down to ranges of 16 with a depth limit of 2 * floor(log2 n) and heapsort
+// beyond it — then one insertion-sort pass. Restated here for ONE thread over elements packed as
+// (float bits of the prior) << 32 | action id, given in ascending action id (the order the reference pushes them). Only
+// used when the parallel rank sort found an exact tie; without ties every correct sort agrees.
+// ---------------------------------------------------------------------------------------------
+MZ_DEV float mz_key_policy(uint64_t e)
+{
+#if MZ_W > 1
+    return __uint_as_float((uint32_t)(e >> 32));
+#else
+    uint32_t u = (uint32_t)(e >> 32);
+    float f;
+    __builtin_memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+MZ_DEV bool mz_cand_gt(uint64_t x, uint64_t y) { return mz_key_policy(x) > mz_key_policy(y); }
+MZ_DEV void mz_cand_swap(uint64_t* e, int i, int j)
+{
+    const uint64_t t = e[i];
+    e[i] = e[j];
+    e[j] = t;
+}
+MZ_DEV void mz_cand_adjust_heap(uint64_t* f, int hole, int len, uint64_t value) // stl_heap.h:224-249 + __push_heap :135-148
+{
+    const int top = hole;
+    int second = hole;
+    while (second < (len - 1) / 2) {
+        second = 2 * (second + 1);
+        if (mz_cand_gt(f[second], f[second - 1])) { second--; }
+        f[hole] = f[second];
+        hole = second;
+    }
+    if ((len & 1) == 0 && second == (len - 2) / 2) {
+        second = 2 * (second + 1);
+        f[hole] = f[second - 1];
+        hole = second - 1;
+    }
+    int parent = (hole - 1) / 2;
+    while (hole > top && mz_cand_gt(f[parent], value)) {
+        f[hole] = f[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    f[hole] = value;
+}
+MZ_DEV void mz_cand_unguarded_linear_insert(uint64_t* e, int last) // stl_algo.h:1792-1807
+{
+    const uint64_t val = e[last];
+    int next = last - 1;
+    while (mz_cand_gt(val, e[next])) {
+        e[last] = e[next];
+        last = next;
+        --next;
+    }
+    e[last] = val;
+}
+MZ_DEV void mz_cand_insertion_sort(uint64_t* e, int first, int last) // stl_algo.h:1812-1831
+{
+    if (first == last) { return; }
+    for (int i = first + 1; i != last; ++i) {
+        if (mz_cand_gt(e[i], e[first])) {
+            const uint64_t val = e[i];
+            for (int j = i; j != first; --j) { e[j] = e[j - 1]; }
+            e[first] = val;
+        } else {
+            mz_cand_unguarded_linear_insert(e, i);
+        }
+    }
+}
+MZ_DEV void mz_std_sort_candidates(uint64_t* e, int n)
+{
+    if (n <= 0) { return; }
+    int lg = 0;
+    for (int m = n; m > 1; m >>= 1) { ++lg; }
+    // __introsort_loop (stl_algo.h:1918-1935); the recursion on the right part becomes a stack (the two parts are disjoint,
+    // so the order in which they are finished does not matter)
+    int st_first[40], st_last[40], st_depth[40], sp = 0;
+    st_first[0] = 0, st_last[0] = n, st_depth[0] = lg * 2, sp = 1;
+    while (sp > 0) {
+        --sp;
+        const int first = st_first[sp];
+        int last = st_last[sp], depth = st_depth[sp];
+        while (last - first > 16) {
+            if (depth == 0) { // __partial_sort(first, last, last): make_heap + sort_heap (stl_heap.h:340-362,415-427)
+                uint64_t* f = e + first;
+                const int len = last - first;
+                for (int parent = (len - 2) / 2;; --parent) {
+                    mz_cand_adjust_heap(f, parent, len, f[parent]);
+                    if (parent == 0) { break; }
+                }
+                for (int l = len - 1; l >= 1; --l) {
+                    const uint64_t value = f[l];
+                    f[l] = f[0];
+                    mz_cand_adjust_heap(f, 0, l, value);
+                }
+                break;
+            }
+            --depth;
+            // __unguarded_partition_pivot (stl_algo.h:1893-1900): median of (first + 1, mid, last - 1) to first
+            const int mid = first + (last - first) / 2, a = first + 1, b = mid, c = last - 1;
+            if (mz_cand_gt(e[a], e[b])) {
+                if (mz_cand_gt(e[b], e[c])) {
+                    mz_cand_swap(e, first, b);
+                } else if (mz_cand_gt(e[a], e[c])) {
+                    mz_cand_swap(e, first, c);
+                } else {
+                    mz_cand_swap(e, first, a);
+                }
+            } else if (mz_cand_gt(e[a], e[c])) {
+                mz_cand_swap(e, first, a);
+            } else if (mz_cand_gt(e[b], e[c])) {
+                mz_cand_swap(e, first, c);
+            } else {
+                mz_cand_swap(e, first, b);
+            }
+            int lo = first + 1, hi = last; // __unguarded_partition (stl_algo.h:1871-1888)
+            for (;;) {
+                while (mz_cand_gt(e[lo], e[first])) { ++lo; }
+                --hi;
+                while (mz_cand_gt(e[first], e[hi])) { --hi; }
+                if (!(lo < hi)) { break; }
+                mz_cand_swap(e, lo, hi);
+                ++lo;
+            }
+            st_first[sp] = lo, st_last[sp] = last, st_depth[sp] = depth, ++sp; // __introsort_loop(cut, last, depth)
+            last = lo;
+        }
+    }
+    if (n > 16) { // __final_insertion_sort (stl_algo.h:1854-1865)
+        mz_cand_insertion_sort(e, 0, 16);
+        for (int i = 16; i != n; ++i) { mz_cand_unguarded_linear_insert(e, i); }
+    } else {
+        mz_cand_insertion_sort(e, 0, n);
+    }
+}
+
 // One "after NN evaluation" step of game g (zero_actor.cpp:74-98): expand the leaf with the legal actions in
 // descending policy order (zero_actor.cpp:215-229, mcts.cpp:151-164), back the value up (mcts.cpp:166-179)
 // and mix the root noise in (zero_actor.cpp:194-204).
@@ -1347,20 +1489,23 @@ MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* 
             w->lg[a] = s.logits[(size_t)g * A + ra];
         }
         const int first = s.cursor[g];
+        if (tid == 0) { w->flag = 0; }
         mz_block_sync();
         int k = 0;
         for (int i = 0; i < MZ_LEGAL_WORDS; ++i) { k += mz_popc(w->legal[i]); }
-        // rank sort, one candidate per thread: descending policy, exact ties by ascending action id (std::sort is
-        // unstable there; DESIGN.md "candidate order")
+        // rank sort, one candidate per thread: descending policy. Exact ties are ranked by ascending action id here and
+        // re-ordered below the way std::sort leaves them (mz_std_sort_candidates)
         for (int a = tid; a < A; a += nthreads) {
             if (!((w->legal[a >> 5] >> (a & 31)) & 1u)) { continue; }
             const float p = w->pol[a];
-            int rank = 0;
+            int rank = 0, tie = 0;
             for (int b = 0; b < A; ++b) {
                 const float pb = w->pol[b];
                 const bool legal_b = ((w->legal[b >> 5] >> (b & 31)) & 1u) != 0u;
                 rank += (legal_b && ((pb > p) || (pb == p && b < a))) ? 1 : 0;
+                tie |= (legal_b && pb == p && b != a) ? 1 : 0;
             }
+            if (tie) { w->flag = 1; }
             const int c = first + rank;
             mz_store_hot(hot + c, 0.0f, 0.0f, p, 0u);
             s.action[(size_t)g * d.NP + c] = (int16_t)a;
@@ -1370,6 +1515,23 @@ MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* 
             s.last_child[(size_t)g * d.NP + c] = -1;
         }
         mz_block_sync();
+        if (w->flag) { // rare: candidates with exactly equal priors
+            if (tid == 0) {
+                uint64_t* e = w->cap_hash;
+                int n = 0;
+                for (int a = 0; a < A; ++a) {
+                    if ((w->legal[a >> 5] >> (a & 31)) & 1u) { e[n++] = ((uint64_t)mz_float_bits(w->pol[a]) << 32) | (uint32_t)a; }
+                }
+                mz_std_sort_candidates(e, n);
+                for (int i = 0; i < n; ++i) {
+                    const int a = (int)(e[i] & 0xffffffffu);
+                    mz_store_hot(hot + first + i, 0.0f, 0.0f, w->pol[a], 0u);
+                    s.action[(size_t)g * d.NP + first + i] = (int16_t)a;
+                    s.logit[(size_t)g * d.NP + first + i] = w->lg[a];
+                }
+            }
+            mz_block_sync();
+        }
         if (tid == 0) {
             s.cursor[g] = first + k;
             const mz_hot h = mz_load_hot(hot + leaf);

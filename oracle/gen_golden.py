@@ -26,6 +26,8 @@ CASES = {
     "ttt_s50_b1_det": ("tictactoe", "ttt_az_2bx32", "actor_num_simulation=50:zero_num_parallel_games=1:actor_use_dirichlet_noise=false:actor_use_random_rotation_features=false:actor_select_action_by_count=true:actor_select_action_by_softmax_count=false:" + COMMON % 1, 12),
     "go5_s24_b2": ("go", "go5_az_1bx16", "env_board_size=5:actor_num_simulation=24:zero_num_parallel_games=2:" + COMMON % 3, 140),
     "go9_s32_b2": ("go", "go9_az_1bx16", "env_board_size=9:actor_num_simulation=32:zero_num_parallel_games=2:" + COMMON % 5, 30),
+    # 19x19 (BASELINE configs[3] board): two-plane policy head, 362 actions, row bitboards at full width
+    "go19_s8_b2": ("go", "go19_az_1bx16", "env_board_size=19:actor_num_simulation=8:zero_num_parallel_games=2:" + COMMON % 13, 30),
     # Othello 8x8 MuZero: Gumbel (configs[2] settings: n=16, m=16), Gumbel with real halving (n=32, m=8), plain PUCT MuZero with Dirichlet noise
     "othello_gmz_s16_b2": ("othello", "othello_mz_1bx32", "actor_num_simulation=16:zero_num_parallel_games=2:" + GUMBEL % 16 + COMMON_MZ % 7, 130),
     "othello_gmz_s32_m8_b2": ("othello", "othello_mz_1bx32", "actor_num_simulation=32:zero_num_parallel_games=2:" + GUMBEL % 8 + COMMON_MZ % 8, 70),

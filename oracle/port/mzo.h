@@ -116,6 +116,9 @@ int mzo_gumbel_best_action(mzo_batch* b, int g);
  * (completed-Q softmax, entries below -38 dropped) in ascending action id; returns how many */
 int mzo_gumbel_policy(const mzo_batch* b, int g, int32_t* actions, float* probs);
 
+/* std::sort(candidates, policy descending) exactly as libstdc++ orders them, ties included (mzo_sort.c) */
+void mzo_std_sort_candidates(int n, int32_t* action, float* policy, float* logit);
+
 /* ---- network forward, fp32 (network/py/alphazero_network.py, network_unit.py) ---- */
 typedef struct mzo_net mzo_net;
 mzo_net* mzo_net_create(int c, int h, int w, int hidden, int blocks, int actions, int value_hidden);

@@ -23,9 +23,8 @@
  * Build with -ffp-contract=off (oracle/Makefile): the reference is compiled for baseline
  * x86-64 and therefore never fuses a multiply with an add.
  *
- * Candidate order: the reference sorts with std::sort (introsort, unstable). For distinct policy
- * values every correct sort agrees; for exact ties this port is *stable* (ties keep ascending
- * action id). Tests assert tie-freeness of every vector they compare (see tests/test_oracle_*.py).
+ * Candidate order: the reference sorts with std::sort (introsort, unstable); mzo_sort.c restates
+ * libstdc++'s algorithm so that candidates with exactly equal priors land where the reference puts them.
  */
 #include "mzo.h"
 #include <math.h>
@@ -368,18 +367,15 @@ void mzo_apply(mzo_batch* b, const float* policy, const float* logits, const flo
             /* calculateMuZeroActionPolicy, zero_actor.cpp:231-245: every action below the root, the legal ones at the root */
             const mzo_env* re = &b->root_env[g];
             const int turn = (t->player[leaf] == 1 ? 2 : 1); /* leaf_node->getAction().nextPlayer() */
-            int cand_a[MZO_MAX_ACTIONS], k = 0;
+            int32_t cand_a[MZO_MAX_ACTIONS];
+            int k = 0;
             float cand_p[MZO_MAX_ACTIONS], cand_l[MZO_MAX_ACTIONS];
             for (int a = 0; a < A; ++a) {
                 if (leaf == 0 && !mzo_env_is_legal(re, a, turn)) { continue; }
-                float p = policy[(size_t)g * A + a], l = logits[(size_t)g * A + a];
-                int j = k++;
-                while (j > 0 && cand_p[j - 1] < p) {
-                    cand_a[j] = cand_a[j - 1], cand_p[j] = cand_p[j - 1], cand_l[j] = cand_l[j - 1];
-                    --j;
-                }
-                cand_a[j] = a, cand_p[j] = p, cand_l[j] = l;
+                cand_a[k] = a, cand_p[k] = policy[(size_t)g * A + a], cand_l[k] = logits[(size_t)g * A + a];
+                ++k;
             }
+            mzo_std_sort_candidates(k, cand_a, cand_p, cand_l); /* zero_actor.cpp:241-243 */
             t->first_child[leaf] = t->cursor;
             t->num_children[leaf] = k;
             for (int i = 0; i < k; ++i) {
@@ -395,19 +391,16 @@ void mzo_apply(mzo_batch* b, const float* policy, const float* logits, const flo
             t->slot[leaf] = (int16_t)t->count[0]; /* hidden states are stored in evaluation order (zero_actor.cpp:90) */
         } else if (!mzo_env_is_terminal(e)) {
             /* calculateAlphaZeroActionPolicy, zero_actor.cpp:215-229 */
-            int cand_a[MZO_MAX_ACTIONS], k = 0;
+            int32_t cand_a[MZO_MAX_ACTIONS];
+            int k = 0;
             float cand_p[MZO_MAX_ACTIONS], cand_l[MZO_MAX_ACTIONS];
             for (int a = 0; a < A; ++a) {
                 if (!mzo_env_is_legal(e, a, e->turn)) { continue; }
                 int ra = (e->game == MZO_GAME_GO || e->game == MZO_GAME_TICTACTOE ? mzo_rotate_position(b->rotation[g], a, e->n) : a);
-                float p = policy[(size_t)g * A + ra], l = logits[(size_t)g * A + ra];
-                int j = k++; /* stable insertion: descending policy, ties keep action order */
-                while (j > 0 && cand_p[j - 1] < p) {
-                    cand_a[j] = cand_a[j - 1], cand_p[j] = cand_p[j - 1], cand_l[j] = cand_l[j - 1];
-                    --j;
-                }
-                cand_a[j] = a, cand_p[j] = p, cand_l[j] = l;
+                cand_a[k] = a, cand_p[k] = policy[(size_t)g * A + ra], cand_l[k] = logits[(size_t)g * A + ra];
+                ++k;
             }
+            mzo_std_sort_candidates(k, cand_a, cand_p, cand_l); /* zero_actor.cpp:225-227 */
             /* expand, mcts.cpp:151-164 */
             t->first_child[leaf] = t->cursor;
             t->num_children[leaf] = k;

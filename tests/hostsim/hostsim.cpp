@@ -172,5 +172,29 @@ int hs_play(sim* h, int g, int action, int* num_legal, float* score)
 
 void hs_reset_game(sim* h, int g) { mz_game_reset(h->d, h->s, g, &h->w, 0); }
 
+// property-test hook: policies[n] (candidates in ascending action id) -> action order left by (a) the restatement in
+// search_core.cuh and (b) the real std::sort with the reference's comparator (zero_actor.cpp:225-227); returns 1 if equal
+int hs_sort_matches_std(int n, const float* policy, int32_t* order_out)
+{
+    struct Cand {
+        int a;
+        float p;
+    };
+    std::vector<Cand> ref(n);
+    std::vector<uint64_t> e(n);
+    for (int i = 0; i < n; ++i) {
+        ref[i] = {i, policy[i]};
+        e[i] = ((uint64_t)mz_float_bits(policy[i]) << 32) | (uint32_t)i;
+    }
+    std::sort(ref.begin(), ref.end(), [](const Cand& lhs, const Cand& rhs) { return lhs.p > rhs.p; });
+    mz_std_sort_candidates(e.data(), n);
+    int same = 1;
+    for (int i = 0; i < n; ++i) {
+        order_out[i] = (int)(e[i] & 0xffffffffu);
+        same &= (order_out[i] == ref[i].a);
+    }
+    return same;
+}
+
 void hs_destroy(sim* h) { delete h; } // test helper: buffers are reclaimed at process exit
 }

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 ROOT = oracle_lib.ROOT
 NETS = os.path.join(ROOT, "oracle", "_ref", "nets")
-CASES = {"ttt_s50_b2": (0, 3), "ttt_s50_b1_det": (0, 3), "go5_s24_b2": (1, 5), "go9_s32_b2": (1, 9),
+CASES = {"ttt_s50_b2": (0, 3), "ttt_s50_b1_det": (0, 3), "go5_s24_b2": (1, 5), "go9_s32_b2": (1, 9), "go19_s8_b2": (1, 19),
          "othello_gmz_s16_b2": (2, 8), "othello_gmz_s32_m8_b2": (2, 8), "othello_mz_s24_b2": (2, 8)}
 
 
@@ -325,4 +325,52 @@ def test_full_size_gumbel_muzero_invariants():
     r2 = eng.get_roots()
     assert np.array_equal(r["count"], r2["count"]) and np.array_equal(r["mean"].view(np.uint32), r2["mean"].view(np.uint32))
     print("config-3 search: %.2f ms, %.0f evals/s" % (ms, B * (S + 1) / ms * 1e3))
+    eng.close()
+
+
+# ---- 19x19 (BASELINE configs[3]: Go 19x19 AlphaZero, 800 simulations, 128 games, 20b x 256) ------------------------------
+
+def test_network_19x19_matches_oracle_port_random_weights():
+    import __graft_entry__ as ge
+    rng = np.random.default_rng(13)
+    dims = dict(num_input_channels=18, input_height=19, input_width=19, num_hidden_channels=128, num_blocks=2, action_size=362, num_value_hidden_channels=64,
+                discrete_value_size=1)
+    state = ge.make_random_state(dims, rng)
+    net = oracle_lib.OracleNet(oracle_lib.load(), dims, state)
+    eng = engine(1, 19, 8, 4)
+    eng.load_network((dims, state))
+    assert eng.conv_layers_per_launch() == 5  # the fused tower also covers the 19x19 resident block (fewer weight stages)
+    feats = (rng.random((8, 18, 19, 19)) < 0.3).astype(np.float32)
+    pol, lg, val = eng.eval_batch(feats)
+    p2, l2, v2 = net.forward(feats.reshape(8, -1))
+    assert np.abs(lg - l2).max() < 1e-3 and np.abs(val - v2).max() < 1e-3 and np.abs(pol - p2).max() < 1e-3
+    eng.close()
+
+
+def test_full_size_19x19_search_invariants():
+    """BASELINE config 4 at full size (128 games, 800 simulations, 20b x 256 random-init): size-independent properties"""
+    import __graft_entry__ as ge
+    B, S = 128, 800
+    dims = dict(num_input_channels=18, input_height=19, input_width=19, num_hidden_channels=256, num_blocks=20, action_size=362, num_value_hidden_channels=256,
+                discrete_value_size=1)
+    eng = engine(1, 19, B, S)
+    eng.load_network((dims, ge.make_random_state(dims, np.random.default_rng(17))))
+    assert eng.conv_layers_per_launch() == 41
+    rng = np.random.default_rng(5)
+    rot = rng.integers(0, 8, size=(S + 1, B)).astype(np.uint8)
+    noise = rng.dirichlet([0.03] * eng.A, size=B).astype(np.float32)
+    eng.set_search_inputs(rot, noise)
+    ms = eng.search()
+    r = eng.get_roots()
+    assert np.all(r["root_count"] == S + 1)
+    assert np.all(r["num_children"] == 362)
+    assert np.all(r["count"].sum(axis=1) == S)
+    assert np.all(np.sort(r["action"], axis=1) == np.arange(362))
+    assert np.all(np.abs(r["root_mean"]) <= 1.0) and np.all(np.isfinite(r["mean"]))
+    eng.reset_game(-1)
+    eng.set_search_inputs(rot, noise)
+    eng.search()
+    r2 = eng.get_roots()
+    assert np.array_equal(r["count"], r2["count"]) and np.array_equal(r["mean"].view(np.uint32), r2["mean"].view(np.uint32))
+    print("config-4 search: %.1f ms, %.0f evals/s, %.1f TFLOP/s algorithmic" % (ms, B * (S + 1) / ms * 1e3, B * (S + 1) * 17.07e9 / ms * 1e3 / 1e12))
     eng.close()

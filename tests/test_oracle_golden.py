@@ -10,6 +10,7 @@ CASES = {
     "ttt_s50_b1_det": (oracle_lib.GAME_TICTACTOE, 3),
     "go5_s24_b2": (oracle_lib.GAME_GO, 5),
     "go9_s32_b2": (oracle_lib.GAME_GO, 9),
+    "go19_s8_b2": (oracle_lib.GAME_GO, 19),
     "othello_gmz_s16_b2": (oracle_lib.GAME_OTHELLO, 8),
     "othello_gmz_s32_m8_b2": (oracle_lib.GAME_OTHELLO, 8),
     "othello_mz_s24_b2": (oracle_lib.GAME_OTHELLO, 8),

@@ -8,7 +8,7 @@ import hostsim_lib
 
 import oracle_lib
 
-CASES = {"ttt_s50_b2": (0, 3), "ttt_s50_b1_det": (0, 3), "go5_s24_b2": (1, 5), "go9_s32_b2": (1, 9),
+CASES = {"ttt_s50_b2": (0, 3), "ttt_s50_b1_det": (0, 3), "go5_s24_b2": (1, 5), "go9_s32_b2": (1, 9), "go19_s8_b2": (1, 19),
          "othello_gmz_s16_b2": (2, 8), "othello_gmz_s32_m8_b2": (2, 8), "othello_mz_s24_b2": (2, 8)}
 
 
@@ -19,3 +19,34 @@ def test_search_core_matches_reference_recording(name):
     eng = hostsim_lib.HostSimSearch(hostsim_lib.load(), game, n, int(case["B"]), int(case["S"]), **oracle_lib.conf_overrides(case["conf"]))
     checked = golden_replay.replay(eng, case)
     assert checked >= case["move_game"].size - int(case["B"])
+
+
+def test_candidate_sort_is_libstdcxx_std_sort():
+    """mz_std_sort_candidates (search_core.cuh) and mzo_std_sort_candidates (oracle) against the real std::sort with the
+    reference's comparator, on inputs full of exact ties (where an unstable sort's result is algorithm-defined)"""
+    import ctypes as C
+
+    import numpy as np
+    lib = hostsim_lib.load()
+    orc = oracle_lib.load()
+    orc.mzo_std_sort_candidates.argtypes = [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    rng = np.random.default_rng(0)
+    cases = []
+    for n in list(range(0, 40)) + [64, 65, 82, 100, 200, 362]:
+        for levels in (1, 2, 3, 7, 50, 10 ** 6):
+            for _ in range(6):
+                cases.append(rng.integers(0, levels, size=n).astype(np.float32) / np.float32(levels))
+    for n in (82, 362):  # shapes that push the quicksort towards its depth limit
+        cases.append(np.arange(n, dtype=np.float32))
+        cases.append(np.arange(n, dtype=np.float32)[::-1].copy())
+        cases.append(np.concatenate([np.arange(n // 2), np.arange(n - n // 2)[::-1]]).astype(np.float32))
+        cases.append(np.zeros(n, np.float32))
+        k = np.arange(n)
+        cases.append(np.where(k % 2 == 0, k, n - k).astype(np.float32))
+    for pol in cases:
+        n = pol.size
+        order = np.zeros(max(n, 1), np.int32)
+        assert lib.hs_sort_matches_std(n, pol.ctypes.data_as(C.POINTER(C.c_float)), order.ctypes.data_as(C.POINTER(C.c_int32))) == 1, (n, pol[:20])
+        a, p, l = np.arange(n, dtype=np.int32), pol.copy(), np.zeros(n, np.float32)
+        orc.mzo_std_sort_candidates(n, a.ctypes.data_as(C.POINTER(C.c_int32)), p.ctypes.data_as(C.POINTER(C.c_float)), l.ctypes.data_as(C.POINTER(C.c_float)))
+        assert np.array_equal(a, order[:n]), (n, pol[:20])
