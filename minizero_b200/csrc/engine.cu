@@ -36,7 +36,7 @@ constexpr int STEP_AFTER = 1, STEP_BEFORE = 2;
 
 constexpr int STEP_WARPS = 16; // warps per game in k_step: the previous path is re-evaluated level-parallel (search_core.cuh, mz_select)
 
-__global__ void __launch_bounds__(32 * STEP_WARPS) k_step(const mz_dims d, const mz_state s, const int flags)
+__global__ void __launch_bounds__(32 * STEP_WARPS, 2) k_step(const mz_dims d, const mz_state s, const int flags)
 {
     __shared__ mz_scratch w;
     extern __shared__ uint64_t dyn_smem[]; // lvl_h [S + 2] 16 B | path_hashes [S + 2] u64 | sel [S + 2] i32 | q_warp [STEP_WARPS][A] f32
@@ -364,10 +364,17 @@ int launch_heads(mz_engine* e, const __half* act)
     const int hw = e->d.N * e->d.N, np1 = p.pol_ch + 1;
     p.batch = e->d.B, p.fc_in_smem = 0;
     const size_t smem = sizeof(float) * (np1 * p.c + np1 * hw + p.vh + p.actions + 32 + hw + 4 * (p.actions + p.vh));
+    static const int threads_env = [] {
+        const char* env = std::getenv("MZ_HEADS_THREADS");
+        const int v = (env ? std::atoi(env) : 0);
+        return (v == 256 || v == 512 || v == 1024) ? v : 0;
+    }();
+    // measured (profiles/): 256 hidden channels 31.0 / 22.6 / 18.5 us at 256 / 512 / 1024 threads; 128 channels are fastest at 512
+    const int threads = (threads_env ? threads_env : (e->cpad >= 256 ? 1024 : 512));
     switch (np1) {
-        case 2: mznn::heads_kernel<2><<<e->d.B, 256, smem, e->stream>>>(p); break;
-        case 3: mznn::heads_kernel<3><<<e->d.B, 256, smem, e->stream>>>(p); break;
-        case 4: mznn::heads_kernel<4><<<e->d.B, 256, smem, e->stream>>>(p); break;
+        case 2: mznn::heads_kernel<2><<<e->d.B, threads, smem, e->stream>>>(p); break;
+        case 3: mznn::heads_kernel<3><<<e->d.B, threads, smem, e->stream>>>(p); break;
+        case 4: mznn::heads_kernel<4><<<e->d.B, threads, smem, e->stream>>>(p); break;
         default: return fail(MZ_ERR_ARG, "policy head with more than 3 planes is not supported");
     }
     e->launches++;

@@ -1200,7 +1200,7 @@ struct HeadParams {
 };
 
 template <int NP1> // NP1 = policy planes + 1 value plane, a compile-time constant so that the plane loops carry no predicates
-__global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
+__global__ void __launch_bounds__(1024) heads_kernel(const HeadParams p)
 {
     extern __shared__ float sm[];
     const int hw = p.n * p.n, n1 = p.n + 1;
@@ -1259,13 +1259,13 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
         if (o < p.actions) {
             const int nin = p.pol_ch * hw, i0 = (nin * part) / parts, i1 = (nin * (part + 1)) / parts;
             const float* wp = p.w_pf + o;
-#pragma unroll 8
+#pragma unroll 16
             for (int i = i0; i < i1; ++i) { acc = fmaf(planes[i], __ldg(wp + static_cast<size_t>(i) * p.actions), acc); }
         } else {
             const int i0 = (hw * part) / parts, i1 = (hw * (part + 1)) / parts;
             const float* vp = planes + p.pol_ch * hw;
             const float* wp = p.w_v1 + (o - p.actions);
-#pragma unroll 8
+#pragma unroll 16
             for (int i = i0; i < i1; ++i) { acc = fmaf(vp[i], __ldg(wp + static_cast<size_t>(i) * p.vh), acc); }
         }
         partial[t] = acc;
@@ -1320,16 +1320,25 @@ __global__ void __launch_bounds__(256) scale_hidden_kernel(__half* __restrict__ 
     __shared__ float red_mn[8], red_mx[8];
     const int g = blockIdx.x, tid = threadIdx.x, hw = n * n, n1 = n + 1;
     __half* rows = act + static_cast<size_t>(g) * slots * c;
-    const int pairs = c_real / 2; // channels are handled two at a time (c_real is even for every supported width)
+    __half* dst = hid + (static_cast<size_t>(g) * num_slots + slot[g]) * hw * c;
+    const bool vec = (c_real % 8 == 0); // 16-byte accesses: 8 channels per thread and step
+    const int per_cell = c / 8, real_per_cell = c_real / 8;
     float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
-    for (int i = tid; i < hw * pairs; i += blockDim.x) {
-        const int cell = i / pairs, k = i - cell * pairs;
-        const float2 v = __half22float2(*reinterpret_cast<const __half2*>(rows + static_cast<size_t>((cell / n + 1) * n1 + cell % n) * c + 2 * k));
-        mn = fminf(mn, fminf(v.x, v.y)), mx = fmaxf(mx, fmaxf(v.x, v.y));
-    }
-    if (c_real & 1) {
-        for (int cell = tid; cell < hw; cell += blockDim.x) {
-            const float v = __half2float(rows[static_cast<size_t>((cell / n + 1) * n1 + cell % n) * c + c_real - 1]);
+    if (vec) {
+        for (int i = tid; i < hw * real_per_cell; i += blockDim.x) {
+            const int cell = i / real_per_cell, k = i - cell * real_per_cell;
+            const uint4 v = *reinterpret_cast<const uint4*>(rows + static_cast<size_t>((cell / n + 1) * n1 + cell % n) * c + 8 * k);
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h[j]);
+                mn = fminf(mn, fminf(f.x, f.y)), mx = fmaxf(mx, fmaxf(f.x, f.y));
+            }
+        }
+    } else {
+        for (int i = tid; i < hw * c_real; i += blockDim.x) {
+            const int cell = i / c_real, ch = i - cell * c_real;
+            const float v = __half2float(rows[static_cast<size_t>((cell / n + 1) * n1 + cell % n) * c + ch]);
             mn = fminf(mn, v), mx = fmaxf(mx, v);
         }
     }
@@ -1341,16 +1350,35 @@ __global__ void __launch_bounds__(256) scale_hidden_kernel(__half* __restrict__ 
     for (int i = 1; i < (blockDim.x >> 5); ++i) { mn = fminf(mn, red_mn[i]), mx = fmaxf(mx, red_mx[i]); }
     float scale = mx - mn;
     if (scale < 1e-5f) { scale += 1e-5f; }
-    __half* dst = hid + (static_cast<size_t>(g) * num_slots + slot[g]) * hw * c;
-    for (int i = tid; i < hw * c; i += blockDim.x) {
-        const int cell = i / c, ch = i - cell * c;
-        __half* p = rows + static_cast<size_t>((cell / n + 1) * n1 + cell % n) * c + ch;
-        __half out = __float2half_rn(0.0f);
-        if (ch < c_real) {
-            out = __float2half_rn((__half2float(*p) - mn) / scale);
-            *p = out;
+    if (vec) {
+        for (int i = tid; i < hw * per_cell; i += blockDim.x) {
+            const int cell = i / per_cell, k = i - cell * per_cell;
+            uint4 out = make_uint4(0u, 0u, 0u, 0u); // padded channels stay zero
+            if (k < real_per_cell) {
+                uint4* p = reinterpret_cast<uint4*>(rows + static_cast<size_t>((cell / n + 1) * n1 + cell % n) * c + 8 * k);
+                const uint4 v = *p;
+                const __half2* h = reinterpret_cast<const __half2*>(&v);
+                __half2* o = reinterpret_cast<__half2*>(&out);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h[j]);
+                    o[j] = __floats2half2_rn((f.x - mn) / scale, (f.y - mn) / scale);
+                }
+                *p = out;
+            }
+            *reinterpret_cast<uint4*>(dst + static_cast<size_t>(i) * 8) = out;
         }
-        dst[i] = out;
+    } else {
+        for (int i = tid; i < hw * c; i += blockDim.x) {
+            const int cell = i / c, ch = i - cell * c;
+            __half* p = rows + static_cast<size_t>((cell / n + 1) * n1 + cell % n) * c + ch;
+            __half out = __float2half_rn(0.0f);
+            if (ch < c_real) {
+                out = __float2half_rn((__half2float(*p) - mn) / scale);
+                *p = out;
+            }
+            dst[i] = out;
+        }
     }
 }
 

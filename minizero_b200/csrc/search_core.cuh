@@ -153,6 +153,7 @@ static inline void mz_store_hot(mz_hot* p, float count, float mean, float policy
 #define MZ_LINK_SHIFT 20     // link = first_child | num_children << 20
 #define MZ_NN_CPAD 64        // input channels of the first conv, padded to one K block
 #define MZ_HALF_ONE 0x3C00   // fp16 1.0
+#define MZ_SEL_AHEAD 3       // chunks of 32 children fetched together by a selection level (3 covers the 82 actions of 9x9 Go)
 
 struct mz_dims {
     int game, N, A, C, S, NP, B;
@@ -768,40 +769,53 @@ MZ_DEV int mz_select_level(const mz_dims& d, const mz_state& s, const mz_hot* ho
     float best_s = 0.0f, best_p = 0.0f;
     int best_i = -1;
     mz_hot best_h = h, h_fu = h;
-    for (int base = 0; base < nc; base += MZ_W) {
-        const int i = base + lane;
-        int visited = 0;
-        mz_hot c = h;
-        if (i < nc) {
-            c = mz_load_hot(hot + fc + i);
-            visited = (c.count != 0.0f);
-            if (visited) {
-                const float qv = mz_normalized_mean(d, c.mean, c.count, child_player);
-                q[i] = qv;
-                const double num = mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n);
-                const float score = mz_fadd((float)mz_ddiv(num, (double)mz_fadd(1.0f, c.count)), qv);
-                if (best_i < 0 || score > best_s || (score == best_s && c.policy > best_p)) { best_s = score, best_p = c.policy, best_i = i, best_h = c; }
+    // the children's records are fetched MZ_SEL_AHEAD chunks at a time, so that a node with up to MZ_SEL_AHEAD * 32 children costs
+    // one memory round trip instead of one per chunk (the ordered init-Q sum below serialises the chunks)
+    for (int base0 = 0; base0 < nc; base0 += MZ_SEL_AHEAD * MZ_W) {
+        mz_hot cbuf[MZ_SEL_AHEAD];
+#pragma unroll
+        for (int u = 0; u < MZ_SEL_AHEAD; ++u) {
+            const int i = base0 + u * MZ_W + lane;
+            cbuf[u] = h;
+            if (i < nc) { cbuf[u] = mz_load_hot(hot + fc + i); }
+        }
+#pragma unroll
+        for (int u = 0; u < MZ_SEL_AHEAD; ++u) {
+            const int base = base0 + u * MZ_W;
+            if (base >= nc) { break; } // warp-uniform
+            const int i = base + lane;
+            int visited = 0;
+            const mz_hot c = cbuf[u];
+            if (i < nc) {
+                visited = (c.count != 0.0f);
+                if (visited) {
+                    const float qv = mz_normalized_mean(d, c.mean, c.count, child_player);
+                    q[i] = qv;
+                    const double num = mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n);
+                    const float score = mz_fadd((float)mz_ddiv(num, (double)mz_fadd(1.0f, c.count)), qv);
+                    if (best_i < 0 || score > best_s || (score == best_s && c.policy > best_p)) { best_s = score, best_p = c.policy, best_i = i, best_h = c; }
+                }
             }
-        }
-        unsigned m = mz_ballot(visited);
-        const unsigned valid = (nc - base >= MZ_W ? ~0u >> (32 - MZ_W) : ((1u << (nc - base)) - 1u));
-        const unsigned unv = ~m & valid;
-        if (first_unvisited == nc && unv) {
-            const int fl = mz_ffs0(unv);
-            first_unvisited = base + fl;
+            unsigned m = mz_ballot(visited);
+            const unsigned valid = (nc - base >= MZ_W ? ~0u >> (32 - MZ_W) : ((1u << (nc - base)) - 1u));
+            const unsigned unv = ~m & valid;
+            if (first_unvisited == nc && unv) {
+                const int fl = mz_ffs0(unv);
+                first_unvisited = base + fl;
 #if MZ_W > 1
-            h_fu.count = __shfl_sync(MZ_FULL, c.count, fl), h_fu.mean = __shfl_sync(MZ_FULL, c.mean, fl);
-            h_fu.policy = __shfl_sync(MZ_FULL, c.policy, fl), h_fu.link = __shfl_sync(MZ_FULL, c.link, fl);
+                h_fu.count = __shfl_sync(MZ_FULL, c.count, fl), h_fu.mean = __shfl_sync(MZ_FULL, c.mean, fl);
+                h_fu.policy = __shfl_sync(MZ_FULL, c.policy, fl), h_fu.link = __shfl_sync(MZ_FULL, c.link, fl);
 #else
-            h_fu = c;
+                h_fu = c;
 #endif
-        }
-        mz_sync();
-        while (m) { // ordered f32 sum of the visited children's Q (mcts.cpp:200-217)
-            const int b = mz_ffs0(m);
-            m &= m - 1;
-            sum_win = mz_fadd(sum_win, q[base + b]);
-            sum_n = mz_fadd(sum_n, 1.0f);
+            }
+            mz_sync();
+            while (m) { // ordered f32 sum of the visited children's Q (mcts.cpp:200-217)
+                const int b = mz_ffs0(m);
+                m &= m - 1;
+                sum_win = mz_fadd(sum_win, q[base + b]);
+                sum_n = mz_fadd(sum_n, 1.0f);
+            }
         }
     }
     const float init_q = mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
