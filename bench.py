@@ -155,6 +155,11 @@ def main():
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL prints its version banner there) are pointed at
+    # stderr, the line goes to a private copy of the original descriptor
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         if rank != 0:
@@ -169,7 +174,7 @@ def main():
                 "games_per_sec_at_163_moves": ref["value"] / (SIMS + 1) / 163.0,
                 "cpu_baseline": {k: ref[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": ref["value"], "unit": "leaf-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
         return 0
 
     import torch
@@ -314,7 +319,7 @@ def main():
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:  # the baseline is a report, never a reason to lose the measurement
             line["cpu_baseline"] = {"value": None, "unit": "leaf-evals/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: " + str(ex)[:200]}
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0

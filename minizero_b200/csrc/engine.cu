@@ -1252,6 +1252,7 @@ int mz_search_run(mz_engine* e, int32_t num_evals, float* device_ms)
     const mz_dims& d = e->d;
     if (num_evals <= 0) { num_evals = d.S + 1; }
     if (num_evals > d.S + 1) { return fail(MZ_ERR_ARG, "num_evals exceeds actor_num_simulation + 1"); }
+    if (e->cfg.muzero && num_evals != d.S + 1) { return fail(MZ_ERR_ARG, "a muzero search runs whole (the first evaluation is the initial inference): num_evals must be 0 or S + 1"); }
     const int key = num_evals * 4 + (e->noise_enabled ? 2 : 0) + (e->rot_enabled ? 1 : 0);
     auto it = e->graphs.find(key);
     if (it == e->graphs.end()) {
