@@ -39,11 +39,12 @@ constexpr int STEP_WARPS = 16; // warps per game in k_step: the previous path is
 __global__ void __launch_bounds__(32 * STEP_WARPS, 2) k_step(const mz_dims d, const mz_state s, const int flags)
 {
     __shared__ mz_scratch w;
-    extern __shared__ uint64_t dyn_smem[]; // lvl_h [S + 2] 16 B | path_hashes [S + 2] u64 | sel [S + 2] i32 | q_warp [STEP_WARPS][A] f32
+    extern __shared__ uint64_t dyn_smem[]; // lvl_h [S + 2] 16 B | lvl_v [S + 2] 16 B | path_hashes [S + 2] u64 | sel [S + 2] i32 | q_warp [STEP_WARPS][A] f32
     const int g = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         w.lvl_h = reinterpret_cast<mz_hot*>(dyn_smem);
-        w.path_hashes = dyn_smem + 2 * (d.S + 2);
+        w.lvl_v = reinterpret_cast<mz_vis*>(dyn_smem + 2 * (d.S + 2));
+        w.path_hashes = dyn_smem + 4 * (d.S + 2);
         w.sel = reinterpret_cast<int32_t*>(w.path_hashes + (d.S + 2));
         w.q_warp = reinterpret_cast<float*>(w.sel + (d.S + 2));
     }
@@ -445,7 +446,7 @@ int launch_tower(mz_engine* e, int which)
 
 size_t step_smem_bytes(const mz_dims& d)
 {
-    return (16 + sizeof(uint64_t) + sizeof(int32_t)) * static_cast<size_t>(d.S + 2) + sizeof(float) * STEP_WARPS * d.A;
+    return (16 + 16 + sizeof(uint64_t) + sizeof(int32_t)) * static_cast<size_t>(d.S + 2) + sizeof(float) * STEP_WARPS * d.A;
 }
 
 int step(mz_engine* e, int flags, const uint8_t* rotations)
@@ -727,6 +728,7 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     guard(e->dalloc(&s.hot, np)), guard(e->dalloc(&s.action, np)), guard(e->dalloc(&s.logit, np)), guard(e->dalloc(&s.value, np));
     guard(e->dalloc(&s.root_noise, BA)), guard(e->dalloc(&s.cursor, B));
     guard(e->dalloc(&s.last_child, np));
+    if (!std::getenv("MZ_NO_VIS")) { guard(e->dalloc(&s.vis, np)); } // MZ_NO_VIS=1: selection always scans (A/B timing of the visited lists)
     guard(e->dalloc(&s.node_slot, np)), guard(e->dalloc(&s.slot_st, B * (d.S + 1) * 2 * N)), guard(e->dalloc(&s.slot_hash, B * (d.S + 1)));
     guard(e->dalloc(&s.slot_meta, B * (d.S + 1) * 4));
     guard(e->dalloc(&s.root_st, B * 2 * MZ_ROWS)), guard(e->dalloc(&s.root_hist, B * MZ_HIST * 2 * MZ_ROWS)), guard(e->dalloc(&s.root_hash, B));

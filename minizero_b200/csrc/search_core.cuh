@@ -141,6 +141,38 @@ static inline void mz_store_hot(mz_hot* p, float count, float mean, float policy
 }
 #endif
 
+// visited children of a node, in child order: what selection below the root has to look at (the unvisited children are
+// represented by the first of them, see mz_select_level). n > MZ_VIS_MAX: list overflowed, scan the children instead.
+#define MZ_VIS_MAX 6
+struct alignas(16) mz_vis {
+    uint16_t idx[MZ_VIS_MAX]; // child indices (relative to first_child), ascending
+    uint16_t n;               // number of visited children
+    uint16_t fu;              // index of the first unvisited child (== num_children when all are visited)
+};
+#if defined(__CUDACC__) && !defined(MZ_HOSTSIM)
+MZ_DEV mz_vis mz_load_vis(const mz_vis* p)
+{
+    union {
+        uint4 u;
+        mz_vis v;
+    } x;
+    x.u = *reinterpret_cast<const uint4*>(p);
+    return x.v;
+}
+MZ_DEV void mz_store_vis(mz_vis* p, const mz_vis& v)
+{
+    union {
+        uint4 u;
+        mz_vis v;
+    } x;
+    x.v = v;
+    *reinterpret_cast<uint4*>(p) = x.u;
+}
+#else
+static inline mz_vis mz_load_vis(const mz_vis* p) { return *p; }
+static inline void mz_store_vis(mz_vis* p, const mz_vis& v) { *p = v; }
+#endif
+
 #define MZ_GAME_TICTACTOE 0
 #define MZ_GAME_GO 1
 #define MZ_GAME_OTHELLO 2
@@ -183,6 +215,7 @@ struct mz_state {
     int32_t* cursor;   // [B]
     int16_t* node_slot; // [B][NP] index of the cached environment of an evaluated node (-1: none)
     int32_t* last_child; // [B][NP] child chosen the last time selection passed through the node (-1: never): speculation hint only
+    mz_vis* vis;         // [B][NP] visited-children list of every expanded node (selection accelerator; null = always scan)
     // environment of every evaluated node of the current search, slot = simulation index (0 .. S)
     uint32_t* slot_st;   // [B][S + 1][2][N] stone rows
     uint64_t* slot_hash; // [B][S + 1]
@@ -235,6 +268,7 @@ struct mz_scratch {
     uint64_t* path_hashes; // [S + 2] position hashes of the nodes on the current path (shared memory on the device)
     int32_t* sel;          // [S + 2] child chosen at every level of the previous path by the speculative re-evaluation
     mz_hot* lvl_h;         // [S + 2] hot record of the node at every level of the guessed path
+    mz_vis* lvl_v;         // [S + 2] its visited-children list
     float* q_warp;         // [num_warps][A] per-warp Q scratch of the level evaluation
     int mismatch;          // first level whose re-evaluated choice differs from the previous path
     // block-wide leaf analysis (mz_env_legal_block)
@@ -893,6 +927,128 @@ MZ_DEV int mz_select_level_serial(const mz_dims& d, const mz_state& s, const mz_
     return fc + best_i;
 }
 
+
+// mz_select_level for a node below the root whose visited children are listed in `v` (v.n <= MZ_VIS_MAX): the same choice
+// from the same arithmetic in the same child order — the listed children and the first unvisited one are the only candidates
+// (see mz_select_level) — but one gather of <= 7 records instead of a scan of all children. Warp collective.
+MZ_DEV int mz_select_level_vis(const mz_dims& d, const mz_state& s, const mz_hot* hot, const mz_hot& h, const mz_vis& v, int child_player, int lane)
+{
+    const int nc = (int)(h.link >> MZ_LINK_SHIFT), fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
+    const int total = (int)mz_fsub(h.count, 1.0f); // mcts.cpp:185
+    const float bias = s.puct_bias[total];
+    const double sqrt_n = s.sqrt_table[total];
+    const int n = v.n;
+#if MZ_W > 1
+    const int my = (lane < n ? (int)v.idx[lane] : (lane == n && v.fu < nc ? (int)v.fu : -1));
+    mz_hot c = h;
+    if (my >= 0) { c = mz_load_hot(hot + fc + my); }
+    float qv = 0.0f, score = 0.0f;
+    if (lane < n) {
+        qv = mz_normalized_mean(d, c.mean, c.count, child_player);
+        const double num = mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n);
+        score = mz_fadd((float)mz_ddiv(num, (double)mz_fadd(1.0f, c.count)), qv);
+    }
+    float sum_win = 0.0f, sum_n = 0.0f;
+    for (int i = 0; i < n; ++i) { // ordered f32 sum of the visited children's Q (mcts.cpp:200-217)
+        sum_win = mz_fadd(sum_win, __shfl_sync(MZ_FULL, qv, i));
+        sum_n = mz_fadd(sum_n, 1.0f);
+    }
+    if (lane == n && my >= 0) {
+        const float init_q = mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
+        score = mz_fadd((float)mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n), init_q);
+    }
+    const uint32_t ks = (my >= 0 ? mz_sortable(score) : 0u);
+    const uint32_t top_s = mz_redux_max(ks);
+    const bool in_s = (my >= 0 && ks == top_s);
+    const uint32_t kp = (in_s ? mz_sortable(c.policy) : 0u);
+    const uint32_t top_p = mz_redux_max(kp);
+    const bool in_p = (in_s && kp == top_p);
+    return fc + (int)mz_redux_min(in_p ? (uint32_t)my : 0xffffffffu);
+#else
+    float sum_win = 0.0f, sum_n = 0.0f, best_s = 0.0f, best_p = 0.0f;
+    int best_i = -1;
+    for (int k = 0; k < n; ++k) {
+        const int i = v.idx[k];
+        const mz_hot c = mz_load_hot(hot + fc + i);
+        const float qv = mz_normalized_mean(d, c.mean, c.count, child_player);
+        sum_win = mz_fadd(sum_win, qv);
+        sum_n = mz_fadd(sum_n, 1.0f);
+        const double num = mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n);
+        const float score = mz_fadd((float)mz_ddiv(num, (double)mz_fadd(1.0f, c.count)), qv);
+        if (best_i < 0 || score > best_s || (score == best_s && c.policy > best_p)) { best_s = score, best_p = c.policy, best_i = i; }
+    }
+    if (v.fu < nc) {
+        const mz_hot c = mz_load_hot(hot + fc + v.fu);
+        const float init_q = mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
+        const float score = mz_fadd((float)mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n), init_q);
+        if (best_i < 0 || score > best_s || (score == best_s && (c.policy > best_p || (c.policy == best_p && (int)v.fu < best_i)))) { best_i = v.fu; }
+    }
+    return fc + best_i;
+#endif
+}
+
+// the same by ONE thread (level-parallel re-evaluation of deep paths): all records are requested before the first is used
+MZ_DEV int mz_select_level_vis_serial(const mz_dims& d, const mz_state& s, const mz_hot* hot, const mz_hot& h, const mz_vis& v, int child_player)
+{
+    const int nc = (int)(h.link >> MZ_LINK_SHIFT), fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
+    const int total = (int)mz_fsub(h.count, 1.0f);
+    const float bias = s.puct_bias[total];
+    const double sqrt_n = s.sqrt_table[total];
+    const int n = v.n;
+    mz_hot c[MZ_VIS_MAX + 1];
+#pragma unroll
+    for (int k = 0; k < MZ_VIS_MAX; ++k) {
+        c[k] = h;
+        if (k < n) { c[k] = mz_load_hot(hot + fc + v.idx[k]); }
+    }
+    c[MZ_VIS_MAX] = h;
+    if (v.fu < nc) { c[MZ_VIS_MAX] = mz_load_hot(hot + fc + v.fu); }
+    float sum_win = 0.0f, sum_n = 0.0f, best_s = 0.0f, best_p = 0.0f;
+    int best_i = -1;
+#pragma unroll
+    for (int k = 0; k < MZ_VIS_MAX; ++k) {
+        if (k < n) {
+            const float qv = mz_normalized_mean(d, c[k].mean, c[k].count, child_player);
+            sum_win = mz_fadd(sum_win, qv);
+            sum_n = mz_fadd(sum_n, 1.0f);
+            const double num = mz_dmul((double)mz_fmul(bias, c[k].policy), sqrt_n);
+            const float score = mz_fadd((float)mz_ddiv(num, (double)mz_fadd(1.0f, c[k].count)), qv);
+            if (best_i < 0 || score > best_s || (score == best_s && c[k].policy > best_p)) { best_s = score, best_p = c[k].policy, best_i = v.idx[k]; }
+        }
+    }
+    if (v.fu < nc) {
+        const float p_fu = c[MZ_VIS_MAX].policy;
+        const float init_q = mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
+        const float score = mz_fadd((float)mz_dmul((double)mz_fmul(bias, p_fu), sqrt_n), init_q);
+        if (best_i < 0 || score > best_s || (score == best_s && (p_fu > best_p || (p_fu == best_p && (int)v.fu < best_i)))) { best_i = v.fu; }
+    }
+    return fc + best_i;
+}
+
+// a child of `parent` received its first visit: keep the parent's list in child order, move first-unvisited on
+MZ_DEV void mz_vis_insert(const mz_state& s, size_t base, int parent, int child_index, int num_children)
+{
+    mz_vis v = mz_load_vis(s.vis + base + parent);
+    if (v.n < MZ_VIS_MAX) {
+        int k = v.n;
+        while (k > 0 && v.idx[k - 1] > child_index) {
+            v.idx[k] = v.idx[k - 1];
+            --k;
+        }
+        v.idx[k] = (uint16_t)child_index;
+    }
+    if (v.n <= MZ_VIS_MAX) { ++v.n; } // MZ_VIS_MAX + 1 = overflowed: selection scans this node's children from now on
+    if (v.n <= MZ_VIS_MAX) {
+        int fu = v.fu;
+        for (int k = 0; k < v.n; ++k) { // idx[] ascending: one pass finds the first index not in the list at or after fu
+            if (v.idx[k] == fu) { ++fu; }
+        }
+        v.fu = (uint16_t)fu;
+    }
+    (void)num_children;
+    mz_store_vis(s.vis + base + parent, v);
+}
+
 // MCTS::select (mcts.cpp:139-148): returns the path length (valid in warp 0); path[] holds node indices from the root.
 //
 // Every level's choice depends only on that level's node, so a GUESSED path can be checked level-parallel: the block
@@ -930,7 +1086,19 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
             const mz_hot h = mz_load_hot(hot + path[j]);
             w->lvl_h[j] = h;
             const int cnc = (int)(h.link >> MZ_LINK_SHIFT), cfc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
-            for (int l = 0; l < cnc; l += 8) { mz_prefetch(hot + cfc + l); }
+            bool listed = false;
+            if (s.vis && j > 0) {
+                const mz_vis v = mz_load_vis(s.vis + (size_t)g * d.NP + path[j]);
+                w->lvl_v[j] = v;
+                listed = (v.n <= MZ_VIS_MAX);
+                if (listed) { // only these records will be read
+                    for (int l = 0; l < v.n; ++l) { mz_prefetch(hot + cfc + v.idx[l]); }
+                    if (v.fu < cnc) { mz_prefetch(hot + cfc + v.fu); }
+                }
+            }
+            if (!listed) {
+                for (int l = 0; l < cnc; l += 8) { mz_prefetch(hot + cfc + l); }
+            }
         }
         mz_block_sync();
         if (nlev > 0) {
@@ -950,7 +1118,9 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
                 if (wid != root_warp) {
                     for (int j = (start == 0 ? 1 : start) + tid; j < glen - 1; j += (nw - 1) * MZ_W) {
                         const int node = path[j];
-                        const int chosen = mz_select_level_serial(d, s, hot, w->lvl_h[j], (j & 1) ? 3 - root_turn : root_turn);
+                        const int cp = (j & 1) ? 3 - root_turn : root_turn;
+                        const int chosen = (s.vis && w->lvl_v[j].n <= MZ_VIS_MAX ? mz_select_level_vis_serial(d, s, hot, w->lvl_h[j], w->lvl_v[j], cp)
+                                                                                  : mz_select_level_serial(d, s, hot, w->lvl_h[j], cp));
                         w->sel[j] = chosen;
                         last_child[node] = chosen;
                         if (chosen != path[j + 1]) { mz_atomic_min(&w->mismatch, j); }
@@ -961,7 +1131,10 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
                     const int node = path[j];
                     const mz_hot h = w->lvl_h[j];
                     mz_hot c;
-                    const int chosen = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u)) + mz_select_level(d, s, hot, h, j == 0, (j & 1) ? 3 - root_turn : root_turn, q, lane, c);
+                    const int cp = (j & 1) ? 3 - root_turn : root_turn;
+                    const int chosen = (s.vis && j > 0 && w->lvl_v[j].n <= MZ_VIS_MAX)
+                                           ? mz_select_level_vis(d, s, hot, h, w->lvl_v[j], cp, lane)
+                                           : (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u)) + mz_select_level(d, s, hot, h, j == 0, cp, q, lane, c);
                     if (lane == 0) {
                         w->sel[j] = chosen;
                         last_child[node] = chosen;
@@ -1550,6 +1723,12 @@ MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* 
             s.cursor[g] = first + k;
             const mz_hot h = mz_load_hot(hot + leaf);
             mz_store_hot(hot + leaf, h.count, h.mean, h.policy, (uint32_t)first | ((uint32_t)k << MZ_LINK_SHIFT));
+            if (s.vis) {
+                mz_vis v;
+                for (int i = 0; i < MZ_VIS_MAX; ++i) { v.idx[i] = 0xffffu; }
+                v.n = 0, v.fu = 0;
+                mz_store_vis(s.vis + (size_t)g * d.NP + leaf, v);
+            }
         }
         v = s.nn_value[g];
         if (leaf == 0) {
@@ -1588,6 +1767,12 @@ MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* 
         mz_store_hot(hot + n, cnt, mean, h.policy, h.link);
     }
     mz_block_sync();
+    // a simulation gives exactly one node its first visit: the leaf, unless it is a terminal node seen before (count now > 1)
+    if (tid == 0 && s.vis && len >= 2 && mz_load_hot(hot + leaf).count == 1.0f) {
+        const int parent = path[len - 2];
+        const mz_hot ph = mz_load_hot(hot + parent);
+        mz_vis_insert(s, (size_t)g * d.NP, parent, leaf - (int)(ph.link & ((1u << MZ_LINK_SHIFT) - 1u)), (int)(ph.link >> MZ_LINK_SHIFT));
+    }
     if (d.gumbel) { mz_gumbel_halving(d, s, g, s.root_meta[g * 4 + 0], tid, nthreads); } // zero_actor.cpp:97
     if (tid == 0) { s.path_len[g] = 0; }
 }

@@ -66,6 +66,8 @@ sim* hs_create(int game, int N, int B, int S, float puct_base, float puct_init, 
     h->w.path_hashes = zalloc<uint64_t>(S + 2);
     h->w.sel = zalloc<int32_t>(S + 2);
     h->w.lvl_h = zalloc<mz_hot>(S + 2);
+    h->w.lvl_v = zalloc<mz_vis>(S + 2);
+    if (!getenv("HS_NO_VIS")) { s.vis = zalloc<mz_vis>(np); }
     h->w.q_warp = zalloc<float>(MZ_MAXA);
     s.spec_len = zalloc<int32_t>(B);
     s.gum_cand = zalloc<int32_t>((size_t)B * d.A), s.gum_meta = zalloc<int32_t>((size_t)B * 4);
@@ -194,6 +196,36 @@ int hs_sort_matches_std(int n, const float* policy, int32_t* order_out)
         same &= (order_out[i] == ref[i].a);
     }
     return same;
+}
+
+// differential check of the four per-level selection routines on every expanded node below the root of game g's current
+// tree: the full scans (warp-collective and single-thread forms) and the visited-list forms must choose the same child.
+// Returns the number of nodes compared, or -(node index) - 1 of the first disagreement.
+int hs_check_level_variants(sim* h, int g)
+{
+    const mz_dims& d = h->d;
+    const mz_state& s = h->s;
+    const mz_hot* hot = s.hot + (size_t)g * d.NP;
+    if (!s.vis) { return 0; }
+    int compared = 0;
+    const int used = s.cursor[g];
+    for (int node = 1; node < used; ++node) {
+        const mz_hot hn = hot[node];
+        if ((hn.link >> MZ_LINK_SHIFT) == 0 || hn.count < 1.0f) { continue; }
+        const mz_vis v = s.vis[(size_t)g * d.NP + node];
+        for (int player = 1; player <= 2; ++player) {
+            mz_hot c;
+            const int fc = (int)(hn.link & ((1u << MZ_LINK_SHIFT) - 1u));
+            const int a = fc + mz_select_level(d, s, hot, hn, false, player, h->w.q_warp, 0, c);
+            const int b = mz_select_level_serial(d, s, hot, hn, player);
+            if (a != b) { return -node - 1; }
+            if (v.n <= MZ_VIS_MAX) {
+                if (mz_select_level_vis(d, s, hot, hn, v, player, 0) != a || mz_select_level_vis_serial(d, s, hot, hn, v, player) != a) { return -node - 1; }
+                ++compared;
+            }
+        }
+    }
+    return compared;
 }
 
 void hs_destroy(sim* h) { delete h; } // test helper: buffers are reclaimed at process exit

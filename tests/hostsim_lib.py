@@ -26,6 +26,7 @@ def load():
     lib.hs_play.argtypes = [vp, i32, i32, i32p, f32p]
     lib.hs_reset_game.argtypes = [vp, i32]
     lib.hs_destroy.argtypes = [vp]
+    lib.hs_check_level_variants.argtypes = [vp, i32]
     lib.hs_sort_matches_std.argtypes = [i32, f32p, i32p]
     lib.hs_set_options.argtypes = [i32, i32, i32, i32, f32, f32]
     for fn in ("hs_leaf_action", "hs_leaf_parent_slot", "hs_path_hash", "hs_gumbel_best_action"):
@@ -82,6 +83,9 @@ class HostSimSearch:
 
     def gumbel_best_action(self, g):
         return self.lib.hs_gumbel_best_action(self.h, g)
+
+    def check_level_variants(self, g):
+        return self.lib.hs_check_level_variants(self.h, g)
 
     def root(self, g):
         out_i = np.zeros(1 + self.A, np.int32)

@@ -136,6 +136,13 @@ def test_on_device_search_matches_oracle_go9():
     run_search_vs_oracle(1, 9, 8, 32, path, moves=20, seed=3)
 
 
+def test_on_device_search_matches_oracle_go9_deep_paths():
+    """240 simulations with a random 1-block net: the tree degenerates into chains deeper than 48 levels, which the device
+    re-evaluates one THREAD per level (visited-list and scan forms) instead of one warp per level"""
+    torch, m, path = torchscript("go9_az_1bx16")
+    run_search_vs_oracle(1, 9, 4, 240, path, moves=3, seed=8)
+
+
 def test_live_reference_stepper_replay_go9():
     """run the compiled reference itself (oracle/_ref, shipped with the snapshot) on this box and replay it"""
     binary = os.path.join(ROOT, "oracle", "_ref", "ref_stepper_go")

@@ -17,8 +17,16 @@ def test_search_core_matches_reference_recording(name):
     game, n = CASES[name]
     case = golden_replay.load_case(name)
     eng = hostsim_lib.HostSimSearch(hostsim_lib.load(), game, n, int(case["B"]), int(case["S"]), **oracle_lib.conf_overrides(case["conf"]))
-    checked = golden_replay.replay(eng, case)
+    compared = []
+
+    def on_move(g, m, engine):  # the finished tree of every move: all per-level selection routines must agree on every node
+        r = engine.check_level_variants(g)
+        assert r >= 0, f"selection variants disagree on node {-r - 1} (move {m})"
+        compared.append(r)
+
+    checked = golden_replay.replay(eng, case, on_move=on_move)
     assert checked >= case["move_game"].size - int(case["B"])
+    assert sum(compared) > 0
 
 
 def test_candidate_sort_is_libstdcxx_std_sort():
