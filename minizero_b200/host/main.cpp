@@ -20,7 +20,8 @@ float hexFloat(const std::string& s)
     return f;
 }
 
-// stdin: "header <game_name> <board> <has_komi> <komi> <model_file> <terminal> <eval_hex> <turn_to_move>"
+// stdin: "header <game_name> <board> <has_komi> <komi> <model_file> <terminal> <eval_hex> <turn_to_move> [<sequence_length> <unrolling_step> <n_step_return>]"
+//        (with a sequence length, intermediate lines are printed after the moves where actor_group.cpp:129-131 sends them)
 //        "move <player> <action> <root_mean_hex> <k> a:count_hex ..."   (one line per move), then EOF
 int recordTest()
 {
@@ -29,6 +30,12 @@ int recordTest()
     bool terminal = true;
     float eval = 0.0f;
     int turn = 1;
+    mzhost::SequenceConfig seq;
+    auto maybe_intermediate = [&]() {
+        if (!mzhost::intermediateSequenceDue(static_cast<int>(moves.size()), seq)) { return; }
+        std::cout << mzhost::selfPlayLine(h, moves, false, 0.0f, moves.size() % 2 == 0 ? 1 : 2, seq) << std::endl;
+        mzhost::clearSentActionInfo(moves, false, seq);
+    };
     std::string line;
     while (std::getline(std::cin, line)) {
         std::istringstream iss(line);
@@ -39,6 +46,7 @@ int recordTest()
             int has_komi, term;
             iss >> h.game_name >> h.board_size >> has_komi >> h.komi >> h.model_file >> term >> eval_hex >> turn;
             h.has_komi = has_komi != 0, terminal = term != 0, eval = hexFloat(eval_hex);
+            if (!(iss >> seq.sequence_length >> seq.unrolling_step >> seq.n_step_return)) { seq = mzhost::SequenceConfig(); }
         } else if (kind == "move") {
             mzhost::MoveRecord m;
             std::string mean_hex;
@@ -56,6 +64,7 @@ int recordTest()
             m.value = std::to_string(hexFloat(mean_hex));
             m.reward = "0";
             moves.push_back(m);
+            maybe_intermediate();
         } else if (kind == "gmove") { // Gumbel: "gmove <player> <action> <root_mean_hex> <root_value_hex> <S> <visit_c> <scale_c> <k> a:count:mean:policy:logit:noise ..."
             mzhost::MoveRecord m;
             std::string mean_hex, value_hex;
@@ -83,7 +92,7 @@ int recordTest()
             moves.push_back(m);
         }
     }
-    std::cout << mzhost::selfPlayLine(h, moves, terminal, eval, turn) << std::endl;
+    std::cout << mzhost::selfPlayLine(h, moves, terminal, eval, turn, seq) << std::endl;
     return 0;
 }
 

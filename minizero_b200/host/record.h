@@ -5,6 +5,7 @@
 //   environment/go/go.h:129-133      KM tag; environment/base/base_env.h:363-367 SZ tag
 //   actor/mcts.cpp:126-137           getSearchDistributionString ("action:count" of the visited root children, child order)
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <limits>
 #include <sstream>
@@ -19,7 +20,33 @@ struct MoveRecord {
     int action = 0;
     int player = 1; // 1 = 'B', 2 = 'W'
     std::string policy, value, reward; // P, V, R
+    bool cleared = false; // action info dropped after an intermediate sequence was sent (actor_group.cpp:40-47)
 };
+
+// zero_actor_intermediate_sequence_length > 0: long games are sent in pieces (actor_group.cpp:24-64,129-131)
+struct SequenceConfig {
+    int sequence_length = 0; // zero_actor_intermediate_sequence_length
+    int unrolling_step = 5;  // learner_muzero_unrolling_step
+    int n_step_return = 0;   // learner_n_step_return
+};
+
+// ThreadSharedData::calculateTrainingDataRange (actor_group.cpp:52-64)
+inline std::pair<int, int> trainingDataRange(int game_length, bool env_terminal, const SequenceConfig& c)
+{
+    int data_start = 0, data_end = game_length - 1;
+    if (c.sequence_length > 0) {
+        data_end = std::max(0, (env_terminal ? data_end : data_end - c.unrolling_step - c.n_step_return));
+        data_start = std::max(0, (env_terminal ? data_end - data_end % c.sequence_length : data_end + 1 - c.sequence_length));
+        if (env_terminal && (data_end % c.sequence_length < c.unrolling_step + c.n_step_return)) { data_start = std::max(0, data_start - c.sequence_length); }
+    }
+    return {data_start, data_end};
+}
+
+// SlaveThread::handleSearchDone (actor_group.cpp:129-131): is an intermediate sequence due after a move that did not end the game?
+inline bool intermediateSequenceDue(int game_length, const SequenceConfig& c)
+{
+    return c.sequence_length > 0 && game_length >= c.sequence_length && (game_length - c.n_step_return - c.unrolling_step) % c.sequence_length == 0;
+}
 
 inline char playerToChar(int p) { return p == 1 ? 'B' : (p == 2 ? 'W' : 'N'); } // environment/base/base_env.cpp:5-13
 
@@ -98,7 +125,8 @@ struct GameHeader {
 
 // eval_score: Environment::getEvalScore(false) of the final position; terminal: Environment::isTerminal().
 // When the game is not terminal (resign) the side to move loses (base_actor.cpp:48-54, go.cpp:262-263).
-inline std::string selfPlayLine(const GameHeader& h, const std::vector<MoveRecord>& moves, bool terminal, float eval_score, int turn_to_move)
+inline std::string selfPlayLine(const GameHeader& h, const std::vector<MoveRecord>& moves, bool terminal, float eval_score, int turn_to_move,
+                                const SequenceConfig& seq = SequenceConfig())
 {
     const float resign_score = (turn_to_move == 1 ? -1.0f : 1.0f); // the next player of `turn` wins
     std::vector<std::pair<std::string, std::string>> tags;
@@ -114,18 +142,30 @@ inline std::string selfPlayLine(const GameHeader& h, const std::vector<MoveRecor
         tags[1].second = oss.str();
     }
     const int game_length = static_cast<int>(moves.size());
-    tags.push_back({"DLEN", "0-" + std::to_string(game_length - 1)}); // calculateTrainingDataRange with sequence length 0
+    const std::pair<int, int> range = trainingDataRange(game_length, terminal, seq);
+    tags.push_back({"DLEN", std::to_string(range.first) + "-" + std::to_string(range.second)});
     std::ostringstream rec;
     rec << "(;";
     for (const auto& t : tags) { rec << t.first << "[" << escapeSGF(t.second) << "]"; }
     for (const MoveRecord& m : moves) {
         rec << ";" << playerToChar(m.player) << "[" << m.action << "]";
+        if (m.cleared) { continue; }
         rec << "P[" << escapeSGF(m.policy) << "]V[" << escapeSGF(m.value) << "]R[" << escapeSGF(m.reward) << "]";
     }
     rec << ")";
     std::ostringstream oss;
-    oss << "SelfPlay " << "true" << " " << game_length << " " << game_length << " " << (terminal ? eval_score : resign_score) << " " << rec.str() << " #";
+    const bool is_terminal = (seq.sequence_length == 0 || terminal); // actor_group.cpp:30
+    oss << "SelfPlay " << (is_terminal ? "true" : "false") << " " << (range.second - range.first + 1) << " " << game_length << " "
+        << (terminal ? eval_score : resign_score) << " " << rec.str() << " #";
     return oss.str();
+}
+
+// after a non-terminal record was sent: "delete action info history if not complete record to save memory" (actor_group.cpp:40-47)
+inline void clearSentActionInfo(std::vector<MoveRecord>& moves, bool terminal, const SequenceConfig& seq)
+{
+    if (seq.sequence_length == 0 || terminal) { return; }
+    const std::pair<int, int> range = trainingDataRange(static_cast<int>(moves.size()), terminal, seq);
+    for (int i = range.first; i <= range.second && i < static_cast<int>(moves.size()); ++i) { moves[i].cleared = true; }
 }
 
 } // namespace mzhost

@@ -284,7 +284,7 @@ bool Worker::hostTerminal(const Game& game) const
 
 void Worker::emitGame(int g, bool terminal, float eval_score)
 {
-    const std::string line = selfPlayLine(header_, games_[g].moves, terminal, eval_score, games_[g].turn);
+    const std::string line = selfPlayLine(header_, games_[g].moves, terminal, eval_score, games_[g].turn, sequenceConfig());
     const std::string out = line + "\n"; // the only thing this process ever writes to the server (zero_server.cpp:111-139)
     size_t done = 0;
     while (done < out.size()) {
@@ -420,6 +420,18 @@ bool Worker::playOneMove()
                 return false;
             }
             games_[g].num_legal = res[e][slot].num_legal;
+        }
+    }
+    // games that go on: an intermediate sequence may be due (actor_group.cpp:126-132)
+    {
+        const SequenceConfig seq = sequenceConfig();
+        for (int g = 0; g < num_games_ && seq.sequence_length > 0; ++g) {
+            const int e = g % ne, slot = g / ne;
+            if (play[e][slot] < 0 || std::find(ended.begin(), ended.end(), g) != ended.end()) { continue; }
+            if (!intermediateSequenceDue(static_cast<int>(games_[g].moves.size()), seq)) { continue; }
+            emitGame(g, false, 0.0f);
+            --games_finished_;
+            clearSentActionInfo(games_[g].moves, false, seq);
         }
     }
     for (int g : ended) {

@@ -48,6 +48,13 @@ private:
     GameHeader header_;
     int game_type_ = MZ_GAME_GO, board_ = 9, actions_ = 82, sims_ = 0, num_games_ = 0;
     bool muzero_ = false, gumbel_ = false;
+    SequenceConfig sequenceConfig() const
+    {
+        SequenceConfig c;
+        c.sequence_length = cfg_.getInt("zero_actor_intermediate_sequence_length"), c.unrolling_step = cfg_.getInt("learner_muzero_unrolling_step");
+        c.n_step_return = cfg_.getInt("learner_n_step_return");
+        return c;
+    }
     int initialNumLegal() const { return game_type_ == MZ_GAME_GO ? board_ * board_ + 1 : (game_type_ == MZ_GAME_OTHELLO ? 4 : 9); }
     std::vector<mz_engine*> engines_;  // one per visible GPU (actor_group.cpp:168-177)
     std::vector<int> engine_games_;    // games handled by each engine: game g -> engine g % n, slot g / n (actor_group.cpp:184-186)

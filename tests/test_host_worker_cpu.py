@@ -105,3 +105,34 @@ def test_gumbel_selfplay_lines_match_reference_bytes(worker_binary):
                 produced.add(r.stdout.strip())
     for l in lines:
         assert l.strip() in produced, l[:200]
+
+
+def test_intermediate_sequence_lines_match_reference_bytes(worker_binary):
+    """zero_actor_intermediate_sequence_length > 0 (actor_group.cpp:24-64,129-131): when a piece is due, its data range, the
+    `false` terminal flag, the resign-style return, and the action info dropped from moves already sent"""
+    z = golden_replay.load_case("go5_seq_s8_b2")
+    lines = [str(l) for l in z["selfplay_lines"]]
+    assert len(lines) >= 8 and any(l.startswith("SelfPlay false") for l in lines)
+    produced = set()
+    for g in range(int(z["B"])):
+        games, cur = [], []
+        for m in [m for m in range(z["move_game"].size) if z["move_game"][m] == g]:
+            if cur and int(z["move_number"][m]) == 0:
+                games.append(cur)
+                cur = []
+            cur.append(m)
+        games.append(cur)
+        for gm in games:
+            resigned = bool(z["move_resign"][gm[-1]])  # the resigning search's move is not played; the game is sent as a non-terminal piece
+            gm = gm[:-1] if resigned else gm
+            turn = 1 if len(gm) % 2 == 0 else 2
+            for eval_score in (1.0, -1.0, 0.0):
+                inp = [f"header go_5x5 5 1 7.5 /some/dir/{name_of_model(lines)} {0 if resigned else 1} {hexf(eval_score)} {turn} 8 2 3"]
+                for m in gm:
+                    k = int(z["move_num_children"][m])
+                    pairs = " ".join(f"{int(z['child_action'][m, i])}:{hexf(z['child_count'][m, i])}" for i in range(k))
+                    inp.append(f"move {int(z['move_player'][m])} {int(z['move_action'][m])} {hexf(z['root_mean'][m])} {k} {pairs}")
+                r = subprocess.run([worker_binary, "-mode", "record_test"], input="\n".join(inp) + "\n", capture_output=True, text=True, check=True)
+                produced.update(x.strip() for x in r.stdout.splitlines())
+    for l in lines:
+        assert l.strip() in produced, l[:160]
