@@ -60,8 +60,10 @@ def test_state_errors_are_reported():
     # a network of another game / type is refused and the engine stays usable
     with pytest.raises(m.EngineError, match="do not match|does not match"):
         eng.load_network(net("go9_az_1bx16"))
+    oth = m.Engine(m.GAME_OTHELLO, 8, 2, 4)  # an AlphaZero-type engine must refuse a muzero network of the right shape
     with pytest.raises(m.EngineError, match="does not match"):
-        eng.load_network(net("othello_mz_1bx32"))
+        oth.load_network(net("othello_mz_1bx32"))
+    oth.close()
     eng.load_network(net("ttt_az_2bx32"))
     eng.search()
     assert np.all(eng.get_roots()["root_count"] == 5)
