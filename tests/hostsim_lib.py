@@ -97,6 +97,7 @@ class HostSimSearch:
         nl, sc = C.c_int32(0), C.c_float(0)
         r = self.lib.hs_play(self.h, g, action, C.byref(nl), C.byref(sc))
         self.terminal[g] = bool(r & 2)
+        self.last_score = sc.value
         return r & 1
 
     def root_terminal(self, g):

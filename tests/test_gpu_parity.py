@@ -381,3 +381,15 @@ def test_full_size_19x19_search_invariants():
     assert np.array_equal(r["count"], r2["count"]) and np.array_equal(r["mean"].view(np.uint32), r2["mean"].view(np.uint32))
     print("config-4 search: %.1f ms, %.0f evals/s, %.1f TFLOP/s algorithmic" % (ms, B * (S + 1) / ms * 1e3, B * (S + 1) * 17.07e9 / ms * 1e3 / 1e12))
     eng.close()
+
+
+@pytest.mark.parametrize("name,game,n", [("env_ttt", 0, 3), ("env_go5", 1, 5), ("env_go9", 1, 9), ("env_go9_situational", 1, 9), ("env_go19", 1, 19),
+                                         ("env_othello8", 2, 8)])
+def test_device_env_matches_reference_playouts(name, game, n):
+    """the device rule / feature kernels against random playouts of the reference's own environments (captures, ko and superko,
+    suicide, passes, Othello flips and forced passes): legal sets, rotated planes, terminal flags, final scores"""
+    import env_replay
+    case = env_replay.load(name)
+    eng = engine(game, n, 1, 1, ko_situational="situational" in str(case["conf"]))
+    assert env_replay.replay(eng, case, check_score=lambda e: float(e.last_play["eval_score"][0])) == case["game"].size
+    eng.close()

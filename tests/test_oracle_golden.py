@@ -82,3 +82,30 @@ def test_oracle_gumbel_policy_matches_reference_records(oracle):
                 assert abs(want[k] - dist[k]) <= 1e-5 * max(1.0, abs(want[k])) + 5e-7, (k, want[k], dist[k])
             compared += 1
     assert compared > 100
+
+
+ENV_CASES = {"env_ttt": (oracle_lib.GAME_TICTACTOE, 3), "env_go5": (oracle_lib.GAME_GO, 5), "env_go9": (oracle_lib.GAME_GO, 9),
+             "env_go9_situational": (oracle_lib.GAME_GO, 9), "env_go19": (oracle_lib.GAME_GO, 19), "env_othello8": (oracle_lib.GAME_OTHELLO, 8)}
+
+
+@pytest.mark.parametrize("name", list(ENV_CASES))
+def test_oracle_env_matches_reference_playouts(oracle, name):
+    """random legal playouts of the reference's own environments (the reference's `-mode env_test` idea): legal sets, rotated
+    feature planes, terminal flags and the evaluation score after EVERY move (Tromp-Taylor on hundreds of mid-game positions)"""
+    import env_replay
+    game, n = ENV_CASES[name]
+    case = env_replay.load(name)
+    eng = oracle_lib.OracleSearch(oracle, game, n, 1, 1, ko_situational=int("situational" in str(case["conf"])))
+    state = {"i": 0}
+
+    def score(e):
+        return oracle.mzo_env_eval_score(oracle.mzo_root_env(e.h, 0), 0)
+
+    assert env_replay.replay(eng, case, check_score=score) == case["game"].size
+    # the score of every intermediate position as well
+    eng.reset_game(0)
+    for i in range(case["game"].size):
+        if case["step"][i] == 0:
+            eng.reset_game(0)
+        assert eng.play(0, int(case["action"][i])) == 1
+        assert score(eng) == case["score_after"][i], i

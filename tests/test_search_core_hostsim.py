@@ -58,3 +58,11 @@ def test_candidate_sort_is_libstdcxx_std_sort():
         a, p, l = np.arange(n, dtype=np.int32), pol.copy(), np.zeros(n, np.float32)
         orc.mzo_std_sort_candidates(n, a.ctypes.data_as(C.POINTER(C.c_int32)), p.ctypes.data_as(C.POINTER(C.c_float)), l.ctypes.data_as(C.POINTER(C.c_float)))
         assert np.array_equal(a, order[:n]), (n, pol[:20])
+
+
+@pytest.mark.parametrize("name,game,n", [("env_ttt", 0, 3), ("env_go5", 1, 5), ("env_go9", 1, 9), ("env_go19", 1, 19), ("env_othello8", 2, 8)])
+def test_search_core_env_matches_reference_playouts(name, game, n):
+    import env_replay
+    case = env_replay.load(name)
+    eng = hostsim_lib.HostSimSearch(hostsim_lib.load(), game, n, 1, 1)
+    assert env_replay.replay(eng, case, check_score=lambda e: e.last_score) == case["game"].size
