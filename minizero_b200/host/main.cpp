@@ -140,6 +140,13 @@ int main(int argc, char** argv)
         std::cerr << "cannot set up the output descriptors" << std::endl;
         return -1;
     }
-    mzhost::Worker worker(cfg, wire_fd);
-    return worker.run();
+    int rc;
+    {
+        mzhost::Worker worker(cfg, wire_fd);
+        rc = worker.run();
+    } // engines destroyed here
+    // the stdin reader thread may still sit inside std::getline holding std::cin's lock: leave without running the iostream
+    // destructors, which would wait for it (the reference's `quit` ends the process with exit(0), actor_group.cpp:250)
+    std::cerr.flush();
+    _exit(rc);
 }

@@ -305,6 +305,8 @@ bool Worker::playOneMove()
     const bool use_dirichlet = cfg_.getBool("actor_use_dirichlet_noise"), use_gumbel_noise = (!use_dirichlet && cfg_.getBool("actor_use_gumbel_noise"));
     const bool use_noise = use_dirichlet || use_gumbel_noise, random_rotation = cfg_.getBool("actor_use_random_rotation_features") && !muzero_;
     const float alpha = cfg_.getFloat("actor_dirichlet_noise_alpha");
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     // (1) randomness of cycles 1 .. S in the reference's per-cycle, per-actor order: in cycle 1 every
     //     actor first receives its root noise (afterNNEvaluation of the root) and then draws the rotation of its next leaf
     for (int c = 1; c < S1; ++c) {
@@ -319,6 +321,7 @@ bool Worker::playOneMove()
             rotations_[e][static_cast<size_t>(c) * engine_games_[e] + slot] = (random_rotation ? static_cast<uint8_t>(rng_.randInt() % 8) : 0);
         }
     }
+    const double t1 = now();
     // (2) the whole search on the devices, all engines in flight together
     for (int e = 0; e < ne; ++e) {
         if (mz_search_set_inputs(engines_[e], random_rotation ? rotations_[e].data() : nullptr, use_noise ? noise_[e].data() : nullptr) != MZ_OK ||
@@ -349,6 +352,7 @@ bool Worker::playOneMove()
             return false;
         }
     }
+    const double t2 = now();
     // (4) per actor, in order: decide, act or resign, restart finished games, draw the first rotation of the next search
     std::vector<std::vector<int32_t>> play(ne);
     for (int e = 0; e < ne; ++e) { play[e].assign(engine_games_[e], -1); }
@@ -403,6 +407,7 @@ bool Worker::playOneMove()
         if (end) { game.enable_resign = (rng_.randReal() < cfg_.getFloat("zero_disable_resign_ratio") ? false : true); }
         rotations_[e][slot] = (random_rotation ? static_cast<uint8_t>(rng_.randInt() % 8) : 0); // cycle 0 of the next search
     }
+    const double t3 = now();
     // (5) apply the moves on the devices; finished games are emitted with the device's score and restarted
     std::vector<std::vector<mz_play_result>> res(ne);
     for (int e = 0; e < ne; ++e) {
@@ -422,6 +427,7 @@ bool Worker::playOneMove()
             games_[g].num_legal = res[e][slot].num_legal;
         }
     }
+    const double t4 = now();
     // games that go on: an intermediate sequence may be due (actor_group.cpp:126-132)
     {
         const SequenceConfig seq = sequenceConfig();
@@ -452,6 +458,7 @@ bool Worker::playOneMove()
         game.enable_resign = keep_resign;
     }
     ++moves_played_;
+    t_draw_ += t1 - t0, t_search_ += t2 - t1, t_decide_ += t3 - t2, t_play_ += t4 - t3, t_emit_ += now() - t4;
     return true;
 }
 
@@ -468,6 +475,11 @@ int Worker::run()
             continue;
         }
         if (!playOneMove()) { return -1; }
+    }
+    if (moves_played_ > 0) {
+        const double k = 1e3 / static_cast<double>(moves_played_);
+        std::cerr << "[timing] " << moves_played_ << " moves, " << games_finished_ << " games; ms per move: draw " << t_draw_ * k << ", search + root tables " << t_search_ * k
+                  << ", decide + records " << t_decide_ * k << ", play " << t_play_ * k << ", emit + restart " << t_emit_ * k << std::endl;
     }
     return 0;
 }

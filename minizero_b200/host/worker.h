@@ -67,6 +67,7 @@ private:
     std::mutex mutex_;
     std::thread io_thread_;
     long long moves_played_ = 0, games_finished_ = 0;
+    double t_draw_ = 0, t_search_ = 0, t_decide_ = 0, t_play_ = 0, t_emit_ = 0; // host wall seconds per phase (diagnostics on stderr at exit)
 };
 
 } // namespace mzhost
