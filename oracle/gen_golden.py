@@ -31,6 +31,9 @@ CASES = {
     # intermediate sequences (actor_group.cpp:24-64,129-131): long games sent in pieces, action info of sent moves dropped
     "go5_seq_s8_b2": ("go", "go5_az_1bx16", "env_board_size=5:actor_num_simulation=8:zero_num_parallel_games=2:zero_actor_intermediate_sequence_length=8:"
                       "learner_n_step_return=3:learner_muzero_unrolling_step=2:" + COMMON % 21, 110),
+    # MuZero on the other board games (their action planes are the same one-hot cell: go.cpp:310-315, tictactoe.cpp:92-97)
+    "go5_mz_s16_b2": ("go", "go5_mz_1bx16", "env_board_size=5:actor_num_simulation=16:zero_num_parallel_games=2:" + COMMON_MZ % 31, 90),
+    "ttt_gmz_s16_b2": ("tictactoe", "ttt_mz_1bx16", "actor_num_simulation=16:zero_num_parallel_games=2:" + GUMBEL % 4 + COMMON_MZ % 32, 40),
     # Othello 8x8 MuZero: Gumbel (configs[2] settings: n=16, m=16), Gumbel with real halving (n=32, m=8), plain PUCT MuZero with Dirichlet noise
     "othello_gmz_s16_b2": ("othello", "othello_mz_1bx32", "actor_num_simulation=16:zero_num_parallel_games=2:" + GUMBEL % 16 + COMMON_MZ % 7, 130),
     "othello_gmz_s32_m8_b2": ("othello", "othello_mz_1bx32", "actor_num_simulation=32:zero_num_parallel_games=2:" + GUMBEL % 8 + COMMON_MZ % 8, 70),

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 ROOT = oracle_lib.ROOT
 NETS = os.path.join(ROOT, "oracle", "_ref", "nets")
 CASES = {"ttt_s50_b2": (0, 3), "ttt_s50_b1_det": (0, 3), "go5_s24_b2": (1, 5), "go9_s32_b2": (1, 9), "go19_s8_b2": (1, 19),
-         "othello_gmz_s16_b2": (2, 8), "othello_gmz_s32_m8_b2": (2, 8), "othello_mz_s24_b2": (2, 8)}
+         "go5_mz_s16_b2": (1, 5), "ttt_gmz_s16_b2": (0, 3), "othello_gmz_s16_b2": (2, 8), "othello_gmz_s32_m8_b2": (2, 8), "othello_mz_s24_b2": (2, 8)}
 
 
 def engine(*args, **kw):
@@ -194,23 +194,20 @@ def test_full_size_search_invariants():
 
 # ---- MuZero / Gumbel (BASELINE configs[2]: Othello 8x8 Gumbel MuZero) ------------------------------------------------
 
-@pytest.mark.parametrize("net,batch", [("othello_mz_1bx32", 32), ("othello_mz_3bx128", 64)])
-def test_muzero_network_matches_torchscript_fp32(net, batch):
+@pytest.mark.parametrize("net,batch,game,n", [("othello_mz_1bx32", 32, 2, 8), ("othello_mz_3bx128", 64, 2, 8), ("go5_mz_1bx16", 16, 1, 5), ("ttt_mz_1bx16", 16, 0, 3)])
+def test_muzero_network_matches_torchscript_fp32(net, batch, game, n):
     """initial_inference and recurrent_inference (network/py/muzero_network.py:136-150) against the reference TorchScript
     module in fp32 on the CPU: logits / value / policy within 1e-3; the scaled hidden state (values in [0, 1], kept in fp16
     here) within 2e-3"""
     torch, m, path = torchscript(net)
-    n = 8
-    eng = engine(2, n, batch, 8, muzero=1)
+    eng = engine(game, n, batch, 8, muzero=1)
     eng.load_network(path)
     rng = np.random.default_rng(11)
-    feats = np.zeros((batch, 4, n, n), np.float32)
-    stones = rng.integers(0, 3, size=(batch, n, n))
-    feats[:, 0] = stones == 1
-    feats[:, 1] = stones == 2
+    C = m.get_num_input_channels()
+    feats = (rng.random((batch, C, n, n)) < 0.3).astype(np.float32)
     turn = rng.integers(0, 2, size=batch)
-    feats[:, 2] = (turn == 0)[:, None, None]
-    feats[:, 3] = (turn == 1)[:, None, None]
+    feats[:, C - 2] = (turn == 0)[:, None, None]
+    feats[:, C - 1] = (turn == 1)[:, None, None]
     with torch.no_grad():
         ref = m.initial_inference(torch.from_numpy(feats))
     pol, lg, val, hid = eng.eval_initial(feats)
@@ -220,8 +217,9 @@ def test_muzero_network_matches_torchscript_fp32(net, batch):
     ref_hid = ref["hidden_state"].numpy().reshape(batch, -1)
     assert hid.min() >= 0.0 and hid.max() <= 1.0 and np.abs(hid - ref_hid).max() < 2e-3
     # recurrent inference from the REFERENCE's hidden states; actions include the pass (all-zero plane, othello.cpp:257-262)
-    actions = rng.integers(0, n * n + 1, size=batch).astype(np.int32)
-    actions[:2] = n * n
+    actions = rng.integers(0, eng.A, size=batch).astype(np.int32)
+    if eng.A > n * n:
+        actions[:2] = n * n
     planes = np.zeros((batch, 1, n * n), np.float32)
     for g in range(batch):
         if actions[g] < n * n:
@@ -236,16 +234,15 @@ def test_muzero_network_matches_torchscript_fp32(net, batch):
     eng.close()
 
 
-def run_muzero_search_vs_oracle(B, S, net_path, moves, seed, **opts):
+def run_muzero_search_vs_oracle(B, S, net_path, moves, seed, game=2, n=8, **opts):
     """whole-move on-device MuZero searches (CUDA graph: tree kernels, hidden-state gather, representation / dynamics towers,
     hidden-state scaling, heads) against the oracle fed with the engine's own network outputs, move after move"""
     lib = oracle_lib.load()
-    n = 8
-    eng = engine(2, n, B, S, muzero=1, **opts)
+    eng = engine(game, n, B, S, muzero=1, **opts)
     eng.load_network(net_path)
-    ev = engine(2, n, B, 2, muzero=1)  # network-only engine
+    ev = engine(game, n, B, 2, muzero=1)  # network-only engine
     ev.load_network(net_path)
-    orc = oracle_lib.OracleSearch(lib, oracle_lib.GAME_OTHELLO, n, B, S, muzero=1, **opts)
+    orc = oracle_lib.OracleSearch(lib, game, n, B, S, muzero=1, **opts)
     rng = np.random.default_rng(seed)
     A = eng.A
     gumbel = bool(opts.get("use_gumbel"))
@@ -308,6 +305,16 @@ def test_on_device_gumbel_muzero_search_with_halving_matches_oracle_othello():
 def test_on_device_puct_muzero_search_matches_oracle_othello():
     torch, m, path = torchscript("othello_mz_1bx32")
     run_muzero_search_vs_oracle(8, 24, path, moves=10, seed=6)
+
+
+def test_on_device_muzero_search_matches_oracle_go5():
+    torch, m, path = torchscript("go5_mz_1bx16")
+    run_muzero_search_vs_oracle(8, 16, path, moves=30, seed=7, game=1, n=5)
+
+
+def test_on_device_gumbel_muzero_search_matches_oracle_tictactoe():
+    torch, m, path = torchscript("ttt_mz_1bx16")
+    run_muzero_search_vs_oracle(8, 16, path, moves=9, seed=8, game=0, n=3, use_gumbel=1, gumbel_noise=1, gumbel_sample_size=4)
 
 
 def test_full_size_gumbel_muzero_invariants():

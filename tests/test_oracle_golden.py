@@ -11,6 +11,8 @@ CASES = {
     "go5_s24_b2": (oracle_lib.GAME_GO, 5),
     "go9_s32_b2": (oracle_lib.GAME_GO, 9),
     "go19_s8_b2": (oracle_lib.GAME_GO, 19),
+    "go5_mz_s16_b2": (oracle_lib.GAME_GO, 5),
+    "ttt_gmz_s16_b2": (oracle_lib.GAME_TICTACTOE, 3),
     "othello_gmz_s16_b2": (oracle_lib.GAME_OTHELLO, 8),
     "othello_gmz_s32_m8_b2": (oracle_lib.GAME_OTHELLO, 8),
     "othello_mz_s24_b2": (oracle_lib.GAME_OTHELLO, 8),

@@ -9,7 +9,7 @@ import hostsim_lib
 import oracle_lib
 
 CASES = {"ttt_s50_b2": (0, 3), "ttt_s50_b1_det": (0, 3), "go5_s24_b2": (1, 5), "go9_s32_b2": (1, 9), "go19_s8_b2": (1, 19),
-         "othello_gmz_s16_b2": (2, 8), "othello_gmz_s32_m8_b2": (2, 8), "othello_mz_s24_b2": (2, 8)}
+         "go5_mz_s16_b2": (1, 5), "ttt_gmz_s16_b2": (0, 3), "othello_gmz_s16_b2": (2, 8), "othello_gmz_s32_m8_b2": (2, 8), "othello_mz_s24_b2": (2, 8)}
 
 
 @pytest.mark.parametrize("name", list(CASES))
