@@ -1,0 +1,40 @@
+"""Small driver for compute-sanitizer (memcheck / racecheck / initcheck / synccheck): one short on-device search of every kind
+(AlphaZero Go with captures and rotations + noise, Gumbel MuZero Othello) plus the per-phase hooks, all through the C ABI."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import minizero_b200 as mz  # noqa: E402
+
+NETS = os.path.join(ROOT, "oracle", "_ref", "nets")
+rng = np.random.default_rng(0)
+
+eng = mz.Engine(mz.GAME_GO, 5, 4, 24)
+eng.load_network(os.path.join(NETS, "go5_az_1bx16.pt"))
+for move in range(6):
+    eng.set_search_inputs(rng.integers(0, 8, size=(25, 4)).astype(np.uint8), rng.dirichlet([0.3] * 26, size=4).astype(np.float32))
+    eng.search()
+    r = eng.get_roots()
+    assert np.all(r["root_count"] == 25)
+    eng.play_max_count(auto_reset=True, read_back=True)
+eng.close()
+
+eng = mz.Engine(mz.GAME_OTHELLO, 8, 4, 16, muzero=1, use_gumbel=1, gumbel_noise=1, gumbel_sample_size=16)
+eng.load_network(os.path.join(NETS, "othello_mz_1bx32.pt"))
+for move in range(6):
+    eng.set_search_inputs(None, rng.gumbel(size=(4, 65)).astype(np.float32))
+    eng.search()
+    assert np.all(eng.get_roots()["root_count"] == 17)
+    eng.play_max_count(auto_reset=True, read_back=True)
+eng.close()
+
+import golden_replay  # noqa: E402
+case = golden_replay.load_case("ttt_s50_b2")
+eng = mz.Engine(mz.GAME_TICTACTOE, 3, 2, 50)
+print("replayed", golden_replay.replay(eng, case), "moves")
+eng.close()
+print("sanitizer driver done")
