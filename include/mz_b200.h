@@ -29,6 +29,7 @@ extern "C" {
 #define MZ_GAME_TICTACTOE 0 /* environment/tictactoe */
 #define MZ_GAME_GO 1        /* environment/go        */
 #define MZ_GAME_OTHELLO 2   /* environment/othello   */
+#define MZ_GAME_NOGO 3      /* environment/nogo (GoEnv with its own legality / end / result; 9x9 in the reference) */
 
 typedef struct mz_engine mz_engine;
 

@@ -657,7 +657,9 @@ int mz_create(const mz_config* cfg, mz_engine** out)
 {
     if (!cfg || !out) { return fail(MZ_ERR_ARG, "null argument"); }
     *out = nullptr;
-    if (cfg->game != MZ_GAME_GO && cfg->game != MZ_GAME_TICTACTOE && cfg->game != MZ_GAME_OTHELLO) { return fail(MZ_ERR_ARG, "unsupported game"); }
+    if (cfg->game != MZ_GAME_GO && cfg->game != MZ_GAME_TICTACTOE && cfg->game != MZ_GAME_OTHELLO && cfg->game != MZ_GAME_NOGO) {
+        return fail(MZ_ERR_ARG, "unsupported game");
+    }
     const int N = (cfg->game == MZ_GAME_TICTACTOE ? 3 : cfg->board_size);
     if (N < 2 || N > MZ_MAXN) { return fail(MZ_ERR_ARG, "board_size must be in [2, 19]"); }
     if (cfg->game == MZ_GAME_OTHELLO && (N < 4 || N > 16 || (N & 1))) { return fail(MZ_ERR_ARG, "othello board_size must be even and in [4, 16]"); }
@@ -674,7 +676,7 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     mz_engine* e = new mz_engine();
     e->cfg = *cfg;
     mz_dims& d = e->d;
-    d.game = cfg->game, d.N = N, d.A = (cfg->game == MZ_GAME_TICTACTOE ? 9 : N * N + 1), d.C = (cfg->game == MZ_GAME_GO ? 18 : 4);
+    d.game = cfg->game, d.N = N, d.A = (cfg->game == MZ_GAME_TICTACTOE ? 9 : N * N + 1), d.C = (MZ_GO_FAMILY(cfg->game) ? 18 : 4);
     d.muzero = (cfg->muzero != 0), d.gumbel = (cfg->use_gumbel != 0), d.gumbel_noise = (cfg->gumbel_noise != 0), d.gumbel_m = cfg->gumbel_sample_size;
     d.sigma_visit_c = cfg->gumbel_sigma_visit_c, d.sigma_scale_c = cfg->gumbel_sigma_scale_c;
     if (d.gumbel) { // simulation budgets in the reference's double arithmetic (gumbel_zero.cpp:99,109)

@@ -176,6 +176,8 @@ static inline void mz_store_vis(mz_vis* p, const mz_vis& v) { *p = v; }
 #define MZ_GAME_TICTACTOE 0
 #define MZ_GAME_GO 1
 #define MZ_GAME_OTHELLO 2
+#define MZ_GAME_NOGO 3       // environment/nogo/nogo.h: GoEnv with its own legality, terminal test and result
+#define MZ_GO_FAMILY(game) ((game) == MZ_GAME_GO || (game) == MZ_GAME_NOGO)
 #define MZ_GUMBEL_LEVELS 12  // halvings of actor_gumbel_sample_size that can ever happen (m <= 362)
 #define MZ_MAXN 19
 #define MZ_MAXA (MZ_MAXN * MZ_MAXN + 1)
@@ -452,7 +454,7 @@ MZ_DEV void mz_env_act(const mz_dims& d, const mz_state& s, mz_scratch* w, int a
     const int N = d.N, me = player - 1, opp = 1 - me;
     uint64_t hash = w->hash ^ d.turn_key; // go.cpp:141
     const int num_moves = w->num_moves;
-    if (d.game == MZ_GAME_GO) {
+    if (MZ_GO_FAMILY(d.game)) { // NoGoEnv inherits GoEnv::act; its legality rules out every capture
         if (a != N * N) {
             const int r = a / N, x = a % N;
             if (lane == 0) { w->st[me][r] |= (1u << x); }
@@ -532,6 +534,7 @@ MZ_DEV int mz_env_is_terminal(const mz_dims& d, const mz_scratch* w)
         return w->num_moves > 2 * N * N;                                              // go.cpp:254
     }
     if (d.game == MZ_GAME_OTHELLO) { return w->num_moves >= 2 && w->last == N * N && w->last2 == N * N; } // othello.cpp:201-207
+    if (d.game == MZ_GAME_NOGO) { return 0; } // "no legal move left" (nogo.h:61-68): decided by the callers from the legal set
     if (mz_ttt_eval(w) != 0) { return 1; } // tictactoe.cpp:51-55
     uint32_t occ = (w->st[0][0] | w->st[1][0]) & (w->st[0][1] | w->st[1][1]) & (w->st[0][2] | w->st[1][2]);
     return occ == 7u;
@@ -544,7 +547,9 @@ MZ_DEV float mz_env_eval_score(const mz_dims& d, mz_scratch* w, int lane)
 {
     const int N = d.N;
     int winner;
-    if (d.game == MZ_GAME_GO) {
+    if (d.game == MZ_GAME_NOGO) { // the side to move has lost (nogo.h:70-78)
+        winner = 3 - w->turn;
+    } else if (d.game == MZ_GAME_GO) {
         int cnt_b = 0, cnt_w = 0;
         for (int i = lane; i < N; i += MZ_W) {
             uint32_t empty = ~(w->st[0][i] | w->st[1][i]) & mz_rowmask(N);
@@ -615,7 +620,7 @@ MZ_DEV int mz_env_legal_block(const mz_dims& d, const mz_state& s, mz_scratch* w
         }
         return n;
     }
-    if (d.game != MZ_GAME_GO) {
+    if (!MZ_GO_FAMILY(d.game)) {
         mz_block_sync();
         if (tid == 0) {
             uint32_t bits = 0;
@@ -696,7 +701,7 @@ MZ_DEV int mz_env_legal_block(const mz_dims& d, const mz_state& s, mz_scratch* w
         if (info & 8) { nbc[k++] = c + 1; }
         if (info & 16) { nbc[k++] = c - N; }
         if (info & 32) { nbc[k++] = c - 1; }
-        bool legal = false;
+        bool legal = false, forbidden = false;
         uint64_t nh = base ^ s.keys[me * 361 + c];
         int seen_lab[4], ns = 0;
         for (int i = 0; i < k; ++i) {
@@ -715,18 +720,19 @@ MZ_DEV int mz_env_legal_block(const mz_dims& d, const mz_state& s, mz_scratch* w
             } else if (lc == 1) {             // capture (go.cpp:235-238)
                 nh ^= bhash[l];
                 legal = true;
+                forbidden = (d.game == MZ_GAME_NOGO); // "illegal when suicide or capture opponent's stones", nogo.h:40-56
             }
         }
-        if (!legal) { continue; }
+        if (!legal || forbidden) { continue; }
         bool seen = false;
-        if ((w->bloom[(nh >> 5) & 63] >> (nh & 31)) & 1u) {
+        if (d.game == MZ_GAME_GO && ((w->bloom[(nh >> 5) & 63] >> (nh & 31)) & 1u)) { // NoGo has no repetition rule
             for (int i = 0; i < root_n; ++i) { seen |= (root_list[i] == nh); }
             for (int i = 0; i < path_n; ++i) { seen |= (path_list[i] == nh); }
         }
         if (!seen) { mz_atomic_or(&w->legal[c >> 5], 1u << (c & 31)); }
     }
     mz_block_sync();
-    if (tid == 0) { w->legal[NN >> 5] |= (1u << (NN & 31)); } // pass, go.cpp:213
+    if (tid == 0 && d.game == MZ_GAME_GO) { w->legal[NN >> 5] |= (1u << (NN & 31)); } // pass, go.cpp:213 (never legal in NoGo, nogo.h:32)
     mz_block_sync();
     int n = 0;
     for (int i = 0; i < MZ_LEGAL_WORDS; ++i) { n += mz_popc(w->legal[i]); }
@@ -743,7 +749,7 @@ MZ_DEV void mz_env_features(const mz_dims& d, const mz_state& s, int g, const mz
     for (int pos = lane; pos < N * N; pos += stride) {
         const int rp = mz_rotate(rev, pos, N), rr = rp / N, rx = rp % N;
         uint16_t* out = base + (size_t)((pos / N + 1) * (N + 1) + pos % N) * MZ_NN_CPAD;
-        if (d.game == MZ_GAME_GO) {
+        if (MZ_GO_FAMILY(d.game)) {
             for (int c = 0; c < 16; ++c) {
                 const int idx = w->num_moves - 1 - c / 2;
                 uint16_t v = 0;
@@ -1483,7 +1489,7 @@ MZ_DEV void mz_before_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch*
     const long long t2 = mz_clock();
     // ---- leaf analysis and feature planes (all threads)
     const int rotation = (s.rotations ? s.rotations[g] : 0);
-    const int terminal = mz_env_is_terminal(d, w);
+    int terminal = mz_env_is_terminal(d, w);
     float score = 0.0f;
     int num_legal = 0;
     if (terminal) {
@@ -1492,6 +1498,10 @@ MZ_DEV void mz_before_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch*
         mz_block_sync();
     } else {
         num_legal = mz_env_legal_block(d, s, w, root_list, root_moves, w->path_hashes, L, tid, nthreads);
+        if (d.game == MZ_GAME_NOGO && num_legal == 0) { // nogo.h:61-68: the game is over when the side to move has no legal move
+            terminal = 1;
+            score = mz_env_eval_score(d, w, lane);
+        }
     }
     const long long t3 = mz_clock();
     mz_env_features(d, s, g, w, rotation, tid, nthreads);
@@ -1826,6 +1836,10 @@ MZ_DEV void mz_play(const mz_dims& d, const mz_state& s, int g, int action, mz_s
         sc = mz_env_eval_score(d, w, lane);
     } else {
         num_legal = mz_env_legal_block(d, s, w, hash_list, w->num_moves, hash_list, 0, lane, MZ_W);
+        if (d.game == MZ_GAME_NOGO && num_legal == 0) {
+            terminal = 1;
+            sc = mz_env_eval_score(d, w, lane);
+        }
     }
     if (lane == 0) {
         out[0] = ok, out[1] = terminal, out[2] = num_legal, out[3] = w->turn;

@@ -13,7 +13,7 @@ import subprocess
 
 import numpy as np
 
-GAME_TICTACTOE, GAME_GO, GAME_OTHELLO = 0, 1, 2
+GAME_TICTACTOE, GAME_GO, GAME_OTHELLO, GAME_NOGO = 0, 1, 2, 3
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 

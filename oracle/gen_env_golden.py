@@ -17,6 +17,7 @@ CASES = {
     "env_go9": ("go", "env_board_size=9:program_quiet=true", 3, 4, 400),
     "env_go9_situational": ("go", "env_board_size=9:env_go_ko_rule=situational:program_quiet=true", 4, 2, 400),
     "env_go19": ("go", "env_board_size=19:program_quiet=true", 5, 1, 420),
+    "env_nogo9": ("nogo", "program_quiet=true", 7, 6, 200),
     "env_othello8": ("othello", "program_quiet=true", 6, 8, 200),
 }
 

@@ -34,6 +34,8 @@ CASES = {
     # MuZero on the other board games (their action planes are the same one-hot cell: go.cpp:310-315, tictactoe.cpp:92-97)
     "go5_mz_s16_b2": ("go", "go5_mz_1bx16", "env_board_size=5:actor_num_simulation=16:zero_num_parallel_games=2:" + COMMON_MZ % 31, 90),
     "ttt_gmz_s16_b2": ("tictactoe", "ttt_mz_1bx16", "actor_num_simulation=16:zero_num_parallel_games=2:" + GUMBEL % 4 + COMMON_MZ % 32, 40),
+    # NoGo 9x9 (environment/nogo/nogo.h): GoEnv with its own legality (no capture, no suicide, no pass), end and result
+    "nogo9_s8_b2": ("nogo", "nogo9_az_1bx16", "actor_num_simulation=8:zero_num_parallel_games=2:" + COMMON % 41, 100),
     # Othello 8x8 MuZero: Gumbel (configs[2] settings: n=16, m=16), Gumbel with real halving (n=32, m=8), plain PUCT MuZero with Dirichlet noise
     "othello_gmz_s16_b2": ("othello", "othello_mz_1bx32", "actor_num_simulation=16:zero_num_parallel_games=2:" + GUMBEL % 16 + COMMON_MZ % 7, 130),
     "othello_gmz_s32_m8_b2": ("othello", "othello_mz_1bx32", "actor_num_simulation=32:zero_num_parallel_games=2:" + GUMBEL % 8 + COMMON_MZ % 8, 70),

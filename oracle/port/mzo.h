@@ -21,6 +21,7 @@ extern "C" {
 #define MZO_GAME_TICTACTOE 0
 #define MZO_GAME_GO 1
 #define MZO_GAME_OTHELLO 2
+#define MZO_GAME_NOGO 3
 
 #define MZO_MAX_N 19
 #define MZO_MAX_CELLS (MZO_MAX_N * MZO_MAX_N)

@@ -127,7 +127,7 @@ void mzo_env_init(mzo_env* e, int game, int n, float komi, int ko_situational)
 }
 
 int mzo_env_num_actions(const mzo_env* e) { return e->game == MZO_GAME_TICTACTOE ? 9 : e->n * e->n + 1; }
-int mzo_env_input_channels(const mzo_env* e) { return e->game == MZO_GAME_GO ? 18 : 4; }
+int mzo_env_input_channels(const mzo_env* e) { return (e->game == MZO_GAME_GO || e->game == MZO_GAME_NOGO) ? 18 : 4; }
 
 /* neighbour order of go_grid.h:43-54: up(+n), right(+1), down(-n), left(-1) */
 static int neighbours(int n, int pos, int* out)
@@ -211,6 +211,34 @@ static int go_is_legal(const mzo_env* e, int action, int player)
     return legal && !hash_seen(e, new_hash); /* go.cpp:243 */
 }
 
+/* NoGoEnv::isLegalAction (nogo.h:27-59): no pass, no suicide, no capture, no repetition rule */
+static int nogo_is_legal(const mzo_env* e, int action, int player)
+{
+    int n = e->n;
+    if (action < 0 || action >= n * n) { return 0; } /* the pass is never legal, nogo.h:32 */
+    if (e->board[action] != 0) { return 0; }
+    int legal = 0;
+    int mark[MZO_MAX_CELLS];
+    memset(mark, 0, sizeof(int) * (size_t)(n * n));
+    int nb[4], k = neighbours(n, action, nb), cells[MZO_MAX_CELLS], nc;
+    for (int i = 0; i < k; ++i) {
+        int q = nb[i];
+        if (e->board[q] == 0) {
+            legal = 1;
+            continue;
+        }
+        if (mark[q]) { continue; }
+        uint64_t bh;
+        int libs = go_block(e, q, mark, i + 1, cells, &nc, &bh);
+        if (e->board[q] == player) {
+            if (libs > 1) { legal = 1; }
+        } else if (libs == 1) {
+            return 0; /* would capture */
+        }
+    }
+    return legal;
+}
+
 static void push_history(mzo_env* e)
 {
     memcpy(e->hist[e->num_moves % MZO_HIST], e->board, (size_t)(e->n * e->n));
@@ -219,7 +247,7 @@ static void push_history(mzo_env* e)
 
 static int go_act(mzo_env* e, int action, int player)
 {
-    if (!go_is_legal(e, action, player)) { return 0; } /* go.cpp:134 */
+    if (!(e->game == MZO_GAME_NOGO ? nogo_is_legal(e, action, player) : go_is_legal(e, action, player))) { return 0; } /* go.cpp:134 (virtual call) */
     int n = e->n;
     e->turn = other(player);   /* go.cpp:140 */
     e->hash ^= e->turn_key;    /* go.cpp:141 */
@@ -442,13 +470,14 @@ static int ttt_eval(const mzo_env* e)
 int mzo_env_is_legal(const mzo_env* e, int action, int player)
 {
     if (e->game == MZO_GAME_GO) { return go_is_legal(e, action, player); }
+    if (e->game == MZO_GAME_NOGO) { return nogo_is_legal(e, action, player); }
     if (e->game == MZO_GAME_OTHELLO) { return othello_is_legal(e, action, player); }
     return action >= 0 && action < 9 && e->board[action] == 0; /* tictactoe.cpp:44-49 */
 }
 
 int mzo_env_act(mzo_env* e, int action, int player)
 {
-    if (e->game == MZO_GAME_GO) { return go_act(e, action, player); }
+    if (e->game == MZO_GAME_GO || e->game == MZO_GAME_NOGO) { return go_act(e, action, player); }
     if (e->game == MZO_GAME_OTHELLO) { return othello_act(e, action, player); }
     if (!mzo_env_is_legal(e, action, player)) { return 0; } /* tictactoe.cpp:19-26 */
     e->actions[e->num_moves++] = (int16_t)action;
@@ -460,6 +489,12 @@ int mzo_env_act(mzo_env* e, int action, int player)
 int mzo_env_is_terminal(const mzo_env* e)
 {
     if (e->game == MZO_GAME_GO) { return go_is_terminal(e); }
+    if (e->game == MZO_GAME_NOGO) { /* nogo.h:61-68 */
+        for (int pos = 0; pos < e->n * e->n; ++pos) {
+            if (nogo_is_legal(e, pos, e->turn)) { return 0; }
+        }
+        return 1;
+    }
     if (e->game == MZO_GAME_OTHELLO) { return othello_is_terminal(e); }
     if (ttt_eval(e) != 0) { return 1; } /* tictactoe.cpp:51-55 */
     for (int i = 0; i < 9; ++i) {
@@ -471,6 +506,7 @@ int mzo_env_is_terminal(const mzo_env* e)
 float mzo_env_eval_score(const mzo_env* e, int is_resign)
 {
     if (e->game == MZO_GAME_GO) { return go_eval_score(e, is_resign); }
+    if (e->game == MZO_GAME_NOGO) { return other(e->turn) == 1 ? 1.0f : -1.0f; } /* nogo.h:70-78: whoever is to move has lost */
     if (e->game == MZO_GAME_OTHELLO) { return othello_eval_score(e, is_resign); }
     int r = (is_resign ? other(e->turn) : ttt_eval(e)); /* tictactoe.cpp:57-65 */
     return r == 1 ? 1.0f : (r == 2 ? -1.0f : 0.0f);
@@ -478,7 +514,7 @@ float mzo_env_eval_score(const mzo_env* e, int is_resign)
 
 void mzo_env_features(const mzo_env* e, int rotation, float* out)
 {
-    if (e->game == MZO_GAME_GO) {
+    if (e->game == MZO_GAME_GO || e->game == MZO_GAME_NOGO) {
         go_features(e, rotation, out);
         return;
     }

@@ -48,7 +48,7 @@ class HostSimSearch:
         self.lib = lib
         n = 3 if game == 0 else board_size
         self.A = 9 if game == 0 else n * n + 1
-        self.F = (18 if game == 1 else 4) * n * n
+        self.F = (18 if game in (1, 3) else 4) * n * n
         self.B, self.S = num_games, num_simulation
         lib.hs_set_options(muzero, use_gumbel, gumbel_noise, gumbel_sample_size, gumbel_sigma_visit_c, gumbel_sigma_scale_c)
         self.h = lib.hs_create(game, n, num_games, num_simulation, 19652.0, 1.25, 1.0, 7.5, 0.25)

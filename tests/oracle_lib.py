@@ -7,7 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MAX_ACTIONS = 19 * 19 + 1
-GAME_TICTACTOE, GAME_GO, GAME_OTHELLO = 0, 1, 2
+GAME_TICTACTOE, GAME_GO, GAME_OTHELLO, GAME_NOGO = 0, 1, 2, 3
 
 
 class Config(C.Structure):
@@ -91,7 +91,7 @@ class OracleSearch:
         self.h = lib.mzo_create(C.byref(self.cfg))
         n = 3 if game == GAME_TICTACTOE else board_size
         self.A = 9 if game == GAME_TICTACTOE else n * n + 1
-        self.F = (18 if game == GAME_GO else 4) * n * n
+        self.F = (18 if game in (GAME_GO, GAME_NOGO) else 4) * n * n
         self.B, self.S = num_games, num_simulation
 
     def __del__(self):

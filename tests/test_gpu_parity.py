@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 ROOT = oracle_lib.ROOT
 NETS = os.path.join(ROOT, "oracle", "_ref", "nets")
-CASES = {"ttt_s50_b2": (0, 3), "ttt_s50_b1_det": (0, 3), "go5_s24_b2": (1, 5), "go9_s32_b2": (1, 9), "go19_s8_b2": (1, 19),
+CASES = {"ttt_s50_b2": (0, 3), "ttt_s50_b1_det": (0, 3), "go5_s24_b2": (1, 5), "go9_s32_b2": (1, 9), "go19_s8_b2": (1, 19), "nogo9_s8_b2": (3, 9),
          "go5_mz_s16_b2": (1, 5), "ttt_gmz_s16_b2": (0, 3), "othello_gmz_s16_b2": (2, 8), "othello_gmz_s32_m8_b2": (2, 8), "othello_mz_s24_b2": (2, 8)}
 
 
@@ -134,6 +134,12 @@ def test_on_device_search_matches_oracle_go5():
 def test_on_device_search_matches_oracle_go9():
     torch, m, path = torchscript("go9_az_2bx64")
     run_search_vs_oracle(1, 9, 8, 32, path, moves=20, seed=3)
+
+
+def test_on_device_search_matches_oracle_nogo9():
+    """NoGo (GoEnv with its own legality, end and result): random moves carry the games to their end several times"""
+    torch, m, path = torchscript("nogo9_az_1bx16")
+    run_search_vs_oracle(3, 9, 4, 16, path, moves=90, seed=9)
 
 
 def test_on_device_search_matches_oracle_go9_deep_paths():
@@ -391,7 +397,7 @@ def test_full_size_19x19_search_invariants():
 
 
 @pytest.mark.parametrize("name,game,n", [("env_ttt", 0, 3), ("env_go5", 1, 5), ("env_go9", 1, 9), ("env_go9_situational", 1, 9), ("env_go19", 1, 19),
-                                         ("env_othello8", 2, 8)])
+                                         ("env_othello8", 2, 8), ("env_nogo9", 3, 9)])
 def test_device_env_matches_reference_playouts(name, game, n):
     """the device rule / feature kernels against random playouts of the reference's own environments (captures, ko and superko,
     suicide, passes, Othello flips and forced passes): legal sets, rotated planes, terminal flags, final scores"""

@@ -11,6 +11,7 @@ CASES = {
     "go5_s24_b2": (oracle_lib.GAME_GO, 5),
     "go9_s32_b2": (oracle_lib.GAME_GO, 9),
     "go19_s8_b2": (oracle_lib.GAME_GO, 19),
+    "nogo9_s8_b2": (oracle_lib.GAME_NOGO, 9),
     "go5_mz_s16_b2": (oracle_lib.GAME_GO, 5),
     "ttt_gmz_s16_b2": (oracle_lib.GAME_TICTACTOE, 3),
     "othello_gmz_s16_b2": (oracle_lib.GAME_OTHELLO, 8),
@@ -87,7 +88,7 @@ def test_oracle_gumbel_policy_matches_reference_records(oracle):
 
 
 ENV_CASES = {"env_ttt": (oracle_lib.GAME_TICTACTOE, 3), "env_go5": (oracle_lib.GAME_GO, 5), "env_go9": (oracle_lib.GAME_GO, 9),
-             "env_go9_situational": (oracle_lib.GAME_GO, 9), "env_go19": (oracle_lib.GAME_GO, 19), "env_othello8": (oracle_lib.GAME_OTHELLO, 8)}
+             "env_go9_situational": (oracle_lib.GAME_GO, 9), "env_go19": (oracle_lib.GAME_GO, 19), "env_othello8": (oracle_lib.GAME_OTHELLO, 8), "env_nogo9": (oracle_lib.GAME_NOGO, 9)}
 
 
 @pytest.mark.parametrize("name", list(ENV_CASES))
