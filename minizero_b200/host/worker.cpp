@@ -42,6 +42,8 @@ bool Worker::initialize()
             std::cerr << "env_board_size does not match the model's board" << std::endl;
             return false;
         }
+    } else if (net_.game_name.rfind("nogo_", 0) == 0) {
+        game_type_ = MZ_GAME_NOGO, board_ = net_.dims.input_height;
     } else if (net_.game_name.rfind("othello_", 0) == 0) {
         game_type_ = MZ_GAME_OTHELLO, board_ = net_.dims.input_height;
     } else {
@@ -51,7 +53,7 @@ bool Worker::initialize()
     actions_ = net_.dims.action_size;
     sims_ = cfg_.getInt("actor_num_simulation");
     num_games_ = cfg_.getInt("zero_num_parallel_games");
-    header_.game_name = net_.game_name, header_.board_size = board_, header_.has_komi = (game_type_ == MZ_GAME_GO), header_.komi = cfg_.getFloat("env_go_komi");
+    header_.game_name = net_.game_name, header_.board_size = board_, header_.has_komi = (game_type_ == MZ_GAME_GO || game_type_ == MZ_GAME_NOGO), header_.komi = cfg_.getFloat("env_go_komi");
     header_.model_file = model;
 
     int ndev = 0;
@@ -116,6 +118,7 @@ void Worker::resetGameHost(int g)
     game.turn = 1;
     game.num_legal = initialNumLegal();
     std::fill(game.ttt, game.ttt + 9, 0);
+    game.stones.assign(game_type_ == MZ_GAME_NOGO ? board_ * board_ : 0, 0);
     game.enable_resign = (rng_.randReal() < cfg_.getFloat("zero_disable_resign_ratio") ? false : true);
 }
 
@@ -271,6 +274,7 @@ bool Worker::hostTerminal(const Game& game) const
         if (n >= 2 && game.moves[n - 1].action == pass && game.moves[n - 2].action == pass) { return true; } // go.cpp:249-251
         return n > 2 * board_ * board_;                                                                        // go.cpp:254
     }
+    if (game_type_ == MZ_GAME_NOGO) { return !nogoHasLegalMove(game); } // nogo.h:61-68
     if (game_type_ == MZ_GAME_OTHELLO) { // othello.cpp:201-207
         const int pass = board_ * board_;
         return n >= 2 && game.moves[n - 1].action == pass && game.moves[n - 2].action == pass;
@@ -280,6 +284,54 @@ bool Worker::hostTerminal(const Game& game) const
         if (game.ttt[l[0]] != 0 && game.ttt[l[0]] == game.ttt[l[1]] && game.ttt[l[1]] == game.ttt[l[2]]) { return true; }
     }
     return n == 9; // tictactoe.cpp:51-55
+}
+
+// NoGoEnv::isLegalAction for the side to move (nogo.h:27-59): an empty point with an empty neighbour or an own neighbouring block
+// with more than one liberty, and no opposing neighbouring block in atari. Stones never leave the board in NoGo.
+bool Worker::nogoHasLegalMove(const Game& game) const
+{
+    const int n = board_, nn = n * n, me = game.turn, opp = 3 - me;
+    const std::vector<uint8_t>& b = game.stones;
+    auto liberties = [&](int start) {
+        std::vector<int> stack{start};
+        std::vector<uint8_t> seen(nn, 0), lib(nn, 0);
+        seen[start] = 1;
+        int libs = 0;
+        while (!stack.empty()) {
+            const int p = stack.back();
+            stack.pop_back();
+            const int x = p % n, y = p / n;
+            const int nb[4] = {y + 1 < n ? p + n : -1, x + 1 < n ? p + 1 : -1, y > 0 ? p - n : -1, x > 0 ? p - 1 : -1};
+            for (int q : nb) {
+                if (q < 0) { continue; }
+                if (b[q] == 0) {
+                    if (!lib[q]) { lib[q] = 1, ++libs; }
+                } else if (b[q] == b[start] && !seen[q]) {
+                    seen[q] = 1;
+                    stack.push_back(q);
+                }
+            }
+        }
+        return libs;
+    };
+    for (int pos = 0; pos < nn; ++pos) {
+        if (b[pos] != 0) { continue; }
+        const int x = pos % n, y = pos / n;
+        const int nb[4] = {y + 1 < n ? pos + n : -1, x + 1 < n ? pos + 1 : -1, y > 0 ? pos - n : -1, x > 0 ? pos - 1 : -1};
+        bool legal = false, captures = false;
+        for (int q : nb) {
+            if (q < 0) { continue; }
+            if (b[q] == 0) {
+                legal = true;
+            } else if (b[q] == me) {
+                if (liberties(q) > 1) { legal = true; }
+            } else if (b[q] == opp && liberties(q) == 1) {
+                captures = true;
+            }
+        }
+        if (legal && !captures) { return true; }
+    }
+    return false;
 }
 
 void Worker::emitGame(int g, bool terminal, float eval_score)
@@ -391,6 +443,7 @@ bool Worker::playOneMove()
             m.reward = "0";                    // operator<< of Environment::getReward() == 0.0f (go.h:50, tictactoe.h:25)
             game.moves.push_back(m);
             if (game_type_ == MZ_GAME_TICTACTOE && action >= 0 && action < 9) { game.ttt[action] = static_cast<uint8_t>(game.turn); }
+            if (game_type_ == MZ_GAME_NOGO && action >= 0 && action < board_ * board_) { game.stones[action] = static_cast<uint8_t>(game.turn); }
             game.turn = 3 - game.turn;
             play[e][slot] = action;
             end = hostTerminal(game);
@@ -455,6 +508,7 @@ bool Worker::playOneMove()
         game.turn = 1;
         game.num_legal = initialNumLegal();
         std::fill(game.ttt, game.ttt + 9, 0);
+        std::fill(game.stones.begin(), game.stones.end(), 0);
         game.enable_resign = keep_resign;
     }
     ++moves_played_;

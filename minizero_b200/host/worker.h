@@ -22,6 +22,7 @@ struct Game {                    // what BaseActor / ZeroActor keep per game on 
     int turn = 1;
     int num_legal = 0;             // root children of the next search (= Dirichlet draws)
     uint8_t ttt[9] = {0};          // tictactoe board, only to know the end of the game in RNG order
+    std::vector<uint8_t> stones;   // NoGo board (stones are never removed), for the same purpose
 };
 
 class Worker {
@@ -38,6 +39,7 @@ private:
     bool playOneMove();                      // S + 1 cycles of actor_group.cpp:81-134 for every game
     int decideAction(int g, const int* actions, const float* counts, const float* means, int num_children, float root_mean, bool& resign, int& child_index);
     bool hostTerminal(const Game& game) const;
+    bool nogoHasLegalMove(const Game& game) const; // NoGoEnv::isTerminal needs the legal set (environment/nogo/nogo.h:27-68)
     void emitGame(int g, bool terminal, float eval_score);
     void resetGameHost(int g);
 
@@ -55,7 +57,10 @@ private:
         c.n_step_return = cfg_.getInt("learner_n_step_return");
         return c;
     }
-    int initialNumLegal() const { return game_type_ == MZ_GAME_GO ? board_ * board_ + 1 : (game_type_ == MZ_GAME_OTHELLO ? 4 : 9); }
+    int initialNumLegal() const
+    {
+        return game_type_ == MZ_GAME_GO ? board_ * board_ + 1 : (game_type_ == MZ_GAME_NOGO ? board_ * board_ : (game_type_ == MZ_GAME_OTHELLO ? 4 : 9));
+    }
     std::vector<mz_engine*> engines_;  // one per visible GPU (actor_group.cpp:168-177)
     std::vector<int> engine_games_;    // games handled by each engine: game g -> engine g % n, slot g / n (actor_group.cpp:184-186)
     std::vector<Game> games_;
