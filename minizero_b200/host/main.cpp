@@ -115,7 +115,7 @@ int main(int argc, char** argv)
         }
     }
     if (mode == "record_test") { return recordTest(); }
-    if (mode != "sp") {
+    if (mode != "sp" && mode != "rng_test") {
         std::cerr << "usage: mz_sp -mode sp [-conf_file F] [-conf_str \"k=v:...\"]   (other modes of the reference binary are out of scope)" << std::endl;
         return -1;
     }
@@ -131,6 +131,10 @@ int main(int argc, char** argv)
     if (cfg.getString("nn_type_name") != "alphazero" && cfg.getString("nn_type_name") != "muzero") {
         std::cerr << "this worker implements the alphazero and (board-game) muzero self-play paths" << std::endl;
         return -1;
+    }
+    if (mode == "rng_test") { // CPU only: prints the host's draw sequence for root tables given on stdin
+        mzhost::Worker worker(cfg, 1);
+        return worker.rngTest(std::cin);
     }
     // stdout belongs to the wire protocol: the server drops the connection on anything but `SelfPlay` lines
     // (zero/zero_server.cpp:130-139). Libraries in this process (NCCL prints its version banner to stdout) must not be able

@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstring>
 #include <cstdlib>
 #include <cuda_runtime.h>
 #include <iostream>
@@ -95,6 +96,14 @@ bool Worker::initialize()
     }
     if (!loadModel(model)) { return false; }
 
+    startGames();
+    io_thread_ = std::thread(&Worker::handleIO, this);
+    return true;
+}
+
+// the host-side start of a run, in the reference's draw order
+void Worker::startGames()
+{
     // createActors: ZeroActor::reset draws the resign switch of every game on the main thread's generator,
     // seeded with program_seed (console/mode_handler.cpp:62, create_actor.h:12-14, zero_actor.cpp:23-27)
     games_.assign(num_games_, Game());
@@ -103,12 +112,11 @@ bool Worker::initialize()
     rng_.seed(cfg_.getBool("program_auto_seed") ? static_cast<int>(std::random_device()()) : cfg_.getInt("program_seed") + 0);
     // first beforeNNEvaluation of every game: rotation draw of cycle 0 (zero_actor.cpp:56)
     const bool random_rotation = cfg_.getBool("actor_use_random_rotation_features") && !muzero_; // only the AlphaZero branch draws one (zero_actor.cpp:54-57)
+    const int ne = static_cast<int>(engine_games_.size());
     for (int g = 0; g < num_games_; ++g) {
-        const int e = g % static_cast<int>(engines_.size()), slot = g / static_cast<int>(engines_.size());
+        const int e = g % ne, slot = g / ne;
         rotations_[e][slot] = (random_rotation ? static_cast<uint8_t>(rng_.randInt() % 8) : 0);
     }
-    io_thread_ = std::thread(&Worker::handleIO, this);
-    return true;
 }
 
 void Worker::resetGameHost(int g)
@@ -350,17 +358,14 @@ void Worker::emitGame(int g, bool terminal, float eval_score)
     ++games_finished_;
 }
 
-// ---- one move for every game ------------------------------------------------------------------------------------------
-bool Worker::playOneMove()
+// (1) randomness of cycles 1 .. S of one search in the reference's per-cycle, per-actor order: in cycle 1
+//     every actor first receives its root noise (afterNNEvaluation of the root) and then draws the rotation of its next leaf
+void Worker::drawSearchRandomness()
 {
-    const int ne = static_cast<int>(engines_.size()), S1 = sims_ + 1, A = actions_;
+    const int ne = static_cast<int>(engine_games_.size()), S1 = sims_ + 1, A = actions_;
     const bool use_dirichlet = cfg_.getBool("actor_use_dirichlet_noise"), use_gumbel_noise = (!use_dirichlet && cfg_.getBool("actor_use_gumbel_noise"));
     const bool use_noise = use_dirichlet || use_gumbel_noise, random_rotation = cfg_.getBool("actor_use_random_rotation_features") && !muzero_;
     const float alpha = cfg_.getFloat("actor_dirichlet_noise_alpha");
-    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double t0 = now();
-    // (1) randomness of cycles 1 .. S in the reference's per-cycle, per-actor order: in cycle 1 every
-    //     actor first receives its root noise (afterNNEvaluation of the root) and then draws the rotation of its next leaf
     for (int c = 1; c < S1; ++c) {
         for (int g = 0; g < num_games_; ++g) {
             const int e = g % ne, slot = g / ne;
@@ -373,6 +378,75 @@ bool Worker::playOneMove()
             rotations_[e][static_cast<size_t>(c) * engine_games_[e] + slot] = (random_rotation ? static_cast<uint8_t>(rng_.randInt() % 8) : 0);
         }
     }
+}
+
+// (4) for one actor, in the reference's order: decide the move (softmax-count draws), act or resign, detect the end of the game, draw the
+//     resign switch of the next game if it ended, draw the first rotation of the next search. Returns the action to play (-1: resigned).
+int Worker::advanceGame(int g, const RootView& r, bool& resign, bool& end)
+{
+    const int ne = static_cast<int>(engine_games_.size()), e = g % ne, slot = g / ne;
+    const bool random_rotation = cfg_.getBool("actor_use_random_rotation_features") && !muzero_;
+    Game& game = games_[g];
+    resign = false;
+    int child = -1;
+    int action = decideAction(g, r.acts, r.cnt, r.mean, r.num_children, r.root_mean, resign, child);
+    if (gumbel_ && cfg_.getBool("actor_select_action_by_count")) { // GumbelZero::decideActionNode: best-scoring candidate (gumbel_zero.cpp:61-66)
+        action = r.gumbel_best;
+        for (int i = 0; i < r.num_children; ++i) {
+            if (r.acts[i] == action) { child = i; }
+        }
+        const float discount = cfg_.getFloat("actor_mcts_reward_discount"), threshold = cfg_.getFloat("actor_resign_threshold");
+        const float root_win_rate = normalizedMean(r.root_mean, static_cast<float>(sims_ + 1), 3 - game.turn, discount);
+        const float action_win_rate = normalizedMean(r.mean[child], r.cnt[child], game.turn, discount);
+        resign = game.enable_resign && (-root_win_rate < threshold && action_win_rate < threshold); // mcts.cpp:84-89
+    }
+    end = resign;
+    int play = -1;
+    if (!resign) { // BaseActor::act + getActionInfo (base_actor.cpp:22-30,59-66)
+        MoveRecord m;
+        m.action = action, m.player = game.turn;
+        m.policy = (gumbel_ ? gumbelPolicy(r.acts, r.cnt, r.mean, r.policy, r.logit, r.noise, r.num_children, r.root_value, game.turn, cfg_.getFloat("actor_mcts_reward_discount"),
+                                           sims_, cfg_.getFloat("actor_gumbel_sigma_visit_c"), cfg_.getFloat("actor_gumbel_sigma_scale_c"))
+                            : searchDistribution(r.acts, r.cnt, r.num_children)); // zero_actor.h:48
+        m.value = std::to_string(r.root_mean); // zero_actor.h:49
+        m.reward = "0";                        // operator<< of Environment::getReward() == 0.0f (go.h:50, tictactoe.h:25)
+        game.moves.push_back(m);
+        if (game_type_ == MZ_GAME_TICTACTOE && action >= 0 && action < 9) { game.ttt[action] = static_cast<uint8_t>(game.turn); }
+        if (game_type_ == MZ_GAME_NOGO && action >= 0 && action < board_ * board_) { game.stones[action] = static_cast<uint8_t>(game.turn); }
+        game.turn = 3 - game.turn;
+        play = action;
+        end = hostTerminal(game);
+    }
+    if (g == 0 && !cfg_.getBool("program_quiet")) {
+        std::cerr << "[actor 0] move " << game.moves.size() << " action " << action << (resign ? " (resign)" : "") << " root mean " << r.root_mean << std::endl;
+    }
+    // actor->reset() draws the resign switch of the next game (zero_actor.cpp:26); the deferred state reset must not consume
+    // randomness, so only the draw happens here, in order
+    if (end) { game.enable_resign = (rng_.randReal() < cfg_.getFloat("zero_disable_resign_ratio") ? false : true); }
+    rotations_[e][slot] = (random_rotation ? static_cast<uint8_t>(rng_.randInt() % 8) : 0); // cycle 0 of the next search
+    return play;
+}
+
+// BaseActor::reset of a finished game on the host (the resign switch of the next game was already drawn, in order)
+void Worker::restartGameHost(int g)
+{
+    Game& game = games_[g];
+    game.moves.clear();
+    game.turn = 1;
+    game.num_legal = initialNumLegal();
+    std::fill(game.ttt, game.ttt + 9, 0);
+    std::fill(game.stones.begin(), game.stones.end(), 0);
+}
+
+// ---- one move for every game ------------------------------------------------------------------------------------------
+bool Worker::playOneMove()
+{
+    const int ne = static_cast<int>(engines_.size()), A = actions_;
+    const bool use_dirichlet = cfg_.getBool("actor_use_dirichlet_noise"), use_gumbel_noise = (!use_dirichlet && cfg_.getBool("actor_use_gumbel_noise"));
+    const bool use_noise = use_dirichlet || use_gumbel_noise, random_rotation = cfg_.getBool("actor_use_random_rotation_features") && !muzero_;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    drawSearchRandomness(); // (1)
     const double t1 = now();
     // (2) the whole search on the devices, all engines in flight together
     for (int e = 0; e < ne; ++e) {
@@ -412,53 +486,21 @@ bool Worker::playOneMove()
     std::vector<char> ended_by_resign(num_games_, 0);
     for (int g = 0; g < num_games_; ++g) {
         const int e = g % ne, slot = g / ne;
-        Game& game = games_[g];
         const mz_root_info& ri = roots[e].info[slot];
-        const int32_t* acts = roots[e].action.data() + static_cast<size_t>(slot) * A;
-        const float* cnt = roots[e].count.data() + static_cast<size_t>(slot) * A;
-        const float* mean = roots[e].mean.data() + static_cast<size_t>(slot) * A;
-        bool resign = false;
-        int child = -1;
-        int action = decideAction(g, acts, cnt, mean, ri.num_children, ri.mean, resign, child);
-        if (gumbel_ && cfg_.getBool("actor_select_action_by_count")) { // GumbelZero::decideActionNode: best-scoring candidate (gumbel_zero.cpp:61-66)
-            action = roots[e].gumbel_best[slot];
-            for (int i = 0; i < ri.num_children; ++i) {
-                if (acts[i] == action) { child = i; }
-            }
-            const float discount = cfg_.getFloat("actor_mcts_reward_discount"), threshold = cfg_.getFloat("actor_resign_threshold");
-            const float root_win_rate = normalizedMean(ri.mean, static_cast<float>(sims_ + 1), 3 - game.turn, discount);
-            const float action_win_rate = normalizedMean(mean[child], cnt[child], game.turn, discount);
-            resign = game.enable_resign && (-root_win_rate < threshold && action_win_rate < threshold); // mcts.cpp:84-89
+        RootView r;
+        r.num_children = ri.num_children, r.root_mean = ri.mean, r.root_value = ri.value;
+        r.acts = roots[e].action.data() + static_cast<size_t>(slot) * A;
+        r.cnt = roots[e].count.data() + static_cast<size_t>(slot) * A, r.mean = roots[e].mean.data() + static_cast<size_t>(slot) * A;
+        if (gumbel_) {
+            r.policy = roots[e].policy.data() + static_cast<size_t>(slot) * A, r.logit = roots[e].logit.data() + static_cast<size_t>(slot) * A;
+            r.noise = roots[e].noise.data() + static_cast<size_t>(slot) * A, r.gumbel_best = roots[e].gumbel_best[slot];
         }
-        bool end = resign;
-        if (!resign) { // BaseActor::act + getActionInfo (base_actor.cpp:22-30,59-66)
-            MoveRecord m;
-            m.action = action, m.player = game.turn;
-            m.policy = (gumbel_ ? gumbelPolicy(acts, cnt, mean, roots[e].policy.data() + static_cast<size_t>(slot) * A, roots[e].logit.data() + static_cast<size_t>(slot) * A,
-                                               roots[e].noise.data() + static_cast<size_t>(slot) * A, ri.num_children, ri.value, game.turn,
-                                               cfg_.getFloat("actor_mcts_reward_discount"), sims_, cfg_.getFloat("actor_gumbel_sigma_visit_c"),
-                                               cfg_.getFloat("actor_gumbel_sigma_scale_c"))
-                                : searchDistribution(acts, cnt, ri.num_children)); // zero_actor.h:48
-            m.value = std::to_string(ri.mean); // zero_actor.h:49
-            m.reward = "0";                    // operator<< of Environment::getReward() == 0.0f (go.h:50, tictactoe.h:25)
-            game.moves.push_back(m);
-            if (game_type_ == MZ_GAME_TICTACTOE && action >= 0 && action < 9) { game.ttt[action] = static_cast<uint8_t>(game.turn); }
-            if (game_type_ == MZ_GAME_NOGO && action >= 0 && action < board_ * board_) { game.stones[action] = static_cast<uint8_t>(game.turn); }
-            game.turn = 3 - game.turn;
-            play[e][slot] = action;
-            end = hostTerminal(game);
-        }
+        bool resign = false, end = false;
+        play[e][slot] = advanceGame(g, r, resign, end);
         if (end) {
             ended.push_back(g);
             ended_by_resign[g] = resign ? 1 : 0;
         }
-        if (g == 0 && !cfg_.getBool("program_quiet")) {
-            std::cerr << "[actor 0] move " << game.moves.size() << " action " << action << (resign ? " (resign)" : "") << " root mean " << ri.mean << std::endl;
-        }
-        // actor->reset() draws the resign switch of the next game (zero_actor.cpp:26); deferred state reset below must not
-        // consume randomness, so only the draw happens here, in order
-        if (end) { game.enable_resign = (rng_.randReal() < cfg_.getFloat("zero_disable_resign_ratio") ? false : true); }
-        rotations_[e][slot] = (random_rotation ? static_cast<uint8_t>(rng_.randInt() % 8) : 0); // cycle 0 of the next search
     }
     const double t3 = now();
     // (5) apply the moves on the devices; finished games are emitted with the device's score and restarted
@@ -503,17 +545,99 @@ bool Worker::playOneMove()
         const bool keep_resign = games_[g].enable_resign; // already drawn for the next game
         emitGame(g, terminal, terminal ? res[e][slot].eval_score : 0.0f);
         mz_reset_game(engines_[e], slot);
-        Game& game = games_[g];
-        game.moves.clear();
-        game.turn = 1;
-        game.num_legal = initialNumLegal();
-        std::fill(game.ttt, game.ttt + 9, 0);
-        std::fill(game.stones.begin(), game.stones.end(), 0);
-        game.enable_resign = keep_resign;
+        restartGameHost(g);
+        games_[g].enable_resign = keep_resign;
     }
     ++moves_played_;
     t_draw_ += t1 - t0, t_search_ += t2 - t1, t_decide_ += t3 - t2, t_play_ += t4 - t3, t_emit_ += now() - t4;
     return true;
+}
+
+// `-mode rng_test` (CPU only): the host's draw sequence of a run, driven by root tables read from stdin instead of the devices, so that
+// it can be compared with what the reference drew for the same seed (rotations, Dirichlet / Gumbel noise, moves, resignations).
+// stdin: "setup <game_type> <board> <actions>", then per move and game "root <g> <k> <root_mean_hex> <root_value_hex> a:count_hex:mean_hex ..."
+// (B lines per move). stdout: "rot <cycle> <g> <r>", "noise <g> <hex ...>", "act <g> <action> <resign> <ended>".
+int Worker::rngTest(std::istream& in)
+{
+    auto hexf = [](const std::string& t) {
+        const uint32_t bits = static_cast<uint32_t>(std::stoul(t, nullptr, 16));
+        float f;
+        std::memcpy(&f, &bits, 4);
+        return f;
+    };
+    std::string word;
+    in >> word >> game_type_ >> board_ >> actions_;
+    sims_ = cfg_.getInt("actor_num_simulation"), num_games_ = cfg_.getInt("zero_num_parallel_games");
+    muzero_ = (cfg_.getString("nn_type_name") == "muzero"), gumbel_ = cfg_.getBool("actor_use_gumbel");
+    engine_games_.assign(1, num_games_);
+    rotations_.assign(1, std::vector<uint8_t>(static_cast<size_t>(sims_ + 1) * num_games_, 0));
+    noise_.assign(1, std::vector<float>(static_cast<size_t>(num_games_) * actions_, 0.0f));
+    rng_.seed(cfg_.getInt("program_seed")); // main thread generator (console/mode_handler.cpp:62)
+    startGames();
+    const int A = actions_;
+    long cycle = 0;
+    std::vector<std::vector<int32_t>> acts(num_games_);
+    std::vector<std::vector<float>> cnt(num_games_), mean(num_games_), pol(num_games_), lgt(num_games_), nse(num_games_);
+    std::vector<RootView> views(num_games_);
+    for (;;) {
+        bool ok = true;
+        for (int i = 0; i < num_games_ && ok; ++i) {
+            int g, k;
+            std::string mean_hex, value_hex;
+            if (!(in >> word >> g >> k >> mean_hex >> value_hex)) {
+                ok = false;
+                break;
+            }
+            acts[g].assign(A, -1), cnt[g].assign(A, 0.0f), mean[g].assign(A, 0.0f), pol[g].assign(A, 0.0f), lgt[g].assign(A, 0.0f), nse[g].assign(A, 0.0f);
+            for (int j = 0; j < k; ++j) {
+                std::string tok, part;
+                in >> tok;
+                std::istringstream ts(tok);
+                std::getline(ts, part, ':');
+                acts[g][j] = std::stoi(part);
+                std::getline(ts, part, ':');
+                cnt[g][j] = hexf(part);
+                std::getline(ts, part, ':');
+                mean[g][j] = hexf(part);
+                if (std::getline(ts, part, ':')) { pol[g][j] = hexf(part); } // optional: policy, logit, noise (Gumbel records)
+                if (std::getline(ts, part, ':')) { lgt[g][j] = hexf(part); }
+                if (std::getline(ts, part, ':')) { nse[g][j] = hexf(part); }
+            }
+            RootView& r = views[g];
+            r.num_children = k, r.root_mean = hexf(mean_hex), r.root_value = hexf(value_hex);
+            r.acts = acts[g].data(), r.cnt = cnt[g].data(), r.mean = mean[g].data();
+            r.policy = pol[g].data(), r.logit = lgt[g].data(), r.noise = nse[g].data();
+            games_[g].num_legal = k; // the root's children are its legal actions (Dirichlet / Gumbel draws, zero_actor.cpp:197,206)
+        }
+        if (!ok) { break; }
+        for (int g = 0; g < num_games_; ++g) { std::cout << "rot " << cycle << " " << g << " " << static_cast<int>(rotations_[0][g]) << "\n"; }
+        drawSearchRandomness();
+        for (int c = 1; c <= sims_; ++c) {
+            for (int g = 0; g < num_games_; ++g) { std::cout << "rot " << cycle + c << " " << g << " " << static_cast<int>(rotations_[0][static_cast<size_t>(c) * num_games_ + g]) << "\n"; }
+        }
+        cycle += sims_ + 1;
+        for (int g = 0; g < num_games_; ++g) {
+            std::cout << "noise " << g;
+            for (int j = 0; j < views[g].num_children; ++j) {
+                uint32_t bits;
+                std::memcpy(&bits, &noise_[0][static_cast<size_t>(g) * A + j], 4);
+                std::cout << " " << std::hex << bits << std::dec;
+            }
+            std::cout << "\n";
+        }
+        for (int g = 0; g < num_games_; ++g) {
+            bool resign = false, end = false;
+            const int action = advanceGame(g, views[g], resign, end);
+            std::cout << "act " << g << " " << action << " " << (resign ? 1 : 0) << " " << (end ? 1 : 0) << "\n";
+            if (end) {
+                const bool keep = games_[g].enable_resign;
+                restartGameHost(g);
+                games_[g].enable_resign = keep;
+            }
+        }
+    }
+    std::cout.flush();
+    return 0;
 }
 
 int Worker::run()

@@ -9,6 +9,7 @@
 #include "record.h"
 #include "rng.h"
 #include <deque>
+#include <istream>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -25,11 +26,20 @@ struct Game {                    // what BaseActor / ZeroActor keep per game on 
     std::vector<uint8_t> stones;   // NoGo board (stones are never removed), for the same purpose
 };
 
+struct RootView { // one game's root child table, children in stored order (what MCTS hands to the move decision and the record)
+    int num_children = 0;
+    float root_mean = 0.0f, root_value = 0.0f;
+    const int32_t* acts = nullptr;
+    const float *cnt = nullptr, *mean = nullptr, *policy = nullptr, *logit = nullptr, *noise = nullptr;
+    int gumbel_best = -1;
+};
+
 class Worker {
 public:
     Worker(Config& cfg, int wire_fd) : cfg_(cfg), wire_fd_(wire_fd) {}
     ~Worker();
     int run(); // ActorGroup::run (actor_group.cpp:136-148)
+    int rngTest(std::istream& in); // `-mode rng_test`: the host's draw sequence without devices (CPU test hook)
 
 private:
     bool initialize();                       // actor_group.cpp:150-187
@@ -37,6 +47,10 @@ private:
     void handleIO();                         // actor_group.cpp:189-198
     void handleCommands();                   // actor_group.cpp:200-252
     bool playOneMove();                      // S + 1 cycles of actor_group.cpp:81-134 for every game
+    void startGames();                       // createActors + first rotation draws, in the reference's draw order
+    void drawSearchRandomness();             // root noise + rotations of cycles 1 .. S of one search
+    int advanceGame(int g, const RootView& r, bool& resign, bool& end); // decide / act / end / next-game draws of one actor
+    void restartGameHost(int g);
     int decideAction(int g, const int* actions, const float* counts, const float* means, int num_children, float root_mean, bool& resign, int& child_index);
     bool hostTerminal(const Game& game) const;
     bool nogoHasLegalMove(const Game& game) const; // NoGoEnv::isTerminal needs the legal set (environment/nogo/nogo.h:27-68)

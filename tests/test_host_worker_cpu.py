@@ -136,3 +136,51 @@ def test_intermediate_sequence_lines_match_reference_bytes(worker_binary):
                 produced.update(x.strip() for x in r.stdout.splitlines())
     for l in lines:
         assert l.strip() in produced, l[:160]
+
+
+@pytest.mark.parametrize("name,game_type,board", [("go5_s24_b2", 1, 5), ("ttt_s50_b2", 0, 3), ("go9_s32_b2", 1, 9), ("othello_gmz_s16_b2", 2, 8),
+                                                  ("othello_mz_s24_b2", 2, 8)])
+def test_host_draw_sequence_matches_reference_seed(worker_binary, name, game_type, board):
+    """Seed-exact randomness: fed with the root tables the reference saw, the worker's host logic — the same
+    member functions the GPU path uses, libstdc++'s mt19937 and distributions in the reference's order — reproduces every rotation
+    the reference drew, its Dirichlet noise bit for bit, its softmax-count move choices and its resignations"""
+    z = golden_replay.load_case(name)
+    B, S, A = int(z["B"]), int(z["S"]), int(z["A"])
+    conf = str(z["conf"])
+    per_game = {g: [m for m in range(z["move_game"].size) if z["move_game"][m] == g] for g in range(B)}
+    rounds = min(len(v) for v in per_game.values())
+    inp = [f"setup {game_type} {board} {A}"]
+    for r in range(rounds):
+        for g in range(B):
+            m = per_game[g][r]
+            k = int(z["move_num_children"][m])
+            toks = " ".join(":".join([str(int(z["child_action"][m, i]))] + [hexf(z["child_" + n][m, i]) for n in ("count", "mean", "policy", "logit", "noise")])
+                            for i in range(k))
+            inp.append(f"root {g} {k} {hexf(z['root_mean'][m])} {hexf(z['root_value'][m])} {toks}")
+    out = subprocess.run([worker_binary, "-mode", "rng_test", "-conf_str", conf], input="\n".join(inp) + "\n", capture_output=True, text=True, check=True).stdout
+    rot, noise, acts = {}, [], []
+    for line in out.splitlines():
+        f = line.split()
+        if f[0] == "rot":
+            rot[(int(f[1]), int(f[2]))] = int(f[3])
+        elif f[0] == "noise":
+            noise.append((int(f[1]), [int(x, 16) for x in f[2:]]))
+        elif f[0] == "act":
+            acts.append((int(f[1]), int(f[2]), int(f[3])))
+    n_cycles = z["eval_game"].size // B
+    checked = 0
+    for c in range(min(n_cycles, rounds * (S + 1))):
+        for g in range(B):
+            assert rot[(c, g)] == int(z["eval_rotation"][c * B + g]), (c, g)
+            checked += 1
+    assert checked >= rounds * (S + 1) * B - B
+    assert len(noise) == rounds * B and len(acts) == rounds * B
+    for r in range(rounds):
+        for g in range(B):
+            m = per_game[g][r]
+            k = int(z["move_num_children"][m])
+            gg, bits = noise[r * B + g]
+            assert gg == g and bits == z["child_noise"][m, :k].view(np.uint32).tolist(), (r, g)
+            gg, action, resign = acts[r * B + g]
+            assert gg == g and resign == int(z["move_resign"][m]), (r, g)
+            assert action == (-1 if resign else int(z["move_action"][m])), (r, g, action, int(z["move_action"][m]))  # a resigning search plays nothing
