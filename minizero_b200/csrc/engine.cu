@@ -354,9 +354,10 @@ int conv(mz_engine* e, const CUtensorMap& in, const CUtensorMap& in_ext, const C
     }
 }
 
-int launch_heads(mz_engine* e, const __half* act)
+int launch_heads(mz_engine* e, const __half* act, int* clear = nullptr, int clear_count = 0)
 {
     mznn::HeadParams p;
+    p.clear = clear, p.clear_count = clear_count;
     auto f = [&](int i) { return reinterpret_cast<const float*>(e->d_blob + e->off_head[i]); };
     p.act = act;
     p.w_pc = f(0), p.b_pc = f(1), p.w_pf = f(2), p.b_pf = f(3), p.w_vc = f(4), p.b_vc = f(5), p.w_v1 = f(6), p.b_v1 = f(7), p.w_v2 = f(8), p.b_v2 = f(9);
@@ -382,7 +383,7 @@ int launch_heads(mz_engine* e, const __half* act)
     return MZ_OK;
 }
 
-int launch_tower(mz_engine* e, int which);
+int launch_tower(mz_engine* e, int which, bool clear_counters = true);
 
 // AlphaZeroNetwork.forward (network/py/alphazero_network.py:90-113) on the rows already in nn_in; for a MuZero network
 // `which` selects initial_inference (0: representation, rows in nn_in) or recurrent_inference (1: dynamics, rows in dyn_in),
@@ -393,7 +394,7 @@ int forward(mz_engine* e, int which = 0)
     NetTower& T = e->tw[which];
     int rc;
     if (e->conv_mode == 3) {
-        if ((rc = launch_tower(e, which))) { return rc; }
+        if ((rc = launch_tower(e, which, false))) { return rc; } // counters: zero from allocation, then re-zeroed by every heads launch below
     } else {
         if ((rc = conv(e, T.map_in, T.map_in_ext, T.convs[0], e->act[0], nullptr))) { return rc; }
         int cur = 0;
@@ -410,15 +411,16 @@ int forward(mz_engine* e, int which = 0)
                                                                   e->nd.num_hidden_channels, e->d.S + 1);
         e->launches++;
     }
+    if (e->conv_mode == 3) { return launch_heads(e, out, T.d_done, T.params->num_layers * ((T.params->num_mtiles + 1) / 2)); }
     return launch_heads(e, out);
 }
 
-int launch_tower(mz_engine* e, int which)
+int launch_tower(mz_engine* e, int which, bool clear_counters)
 {
     {
         NetTower& T = e->tw[which];
         const int num_groups = (T.params->num_mtiles + 1) / 2;
-        CUDA_OK(cudaMemsetAsync(T.d_done, 0, sizeof(int) * T.params->num_layers * num_groups, e->stream));
+        if (clear_counters) { CUDA_OK(cudaMemsetAsync(T.d_done, 0, sizeof(int) * T.params->num_layers * num_groups, e->stream)); }
         const int units = num_groups * (e->cpad / 128);
         int clusters = e->tower_sms / 2;
         if (units < clusters) { clusters = units; }
@@ -1336,6 +1338,10 @@ int mz_profile_kernels(mz_engine* e, int32_t iters, float* conv_ms, float* tree_
         CUDA_OK(cudaEventRecord(e->ev0, e->stream));
         for (int i = 0; i < iters; ++i) { launch_tower(e, which); }
         CUDA_OK(cudaEventRecord(e->ev1, e->stream));
+        {   // leave the completion counters as a network forward expects them (zero; normally the heads kernel re-zeroes them)
+            const NetTower& T = e->tw[which];
+            CUDA_OK(cudaMemsetAsync(T.d_done, 0, sizeof(int) * T.params->num_layers * ((T.params->num_mtiles + 1) / 2), e->stream));
+        }
         CUDA_OK(cudaStreamSynchronize(e->stream));
         CUDA_OK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
         *conv_ms = ms / iters;

@@ -1197,6 +1197,8 @@ struct HeadParams {
     int c, n, slots, pol_ch, actions, vh;
     int batch;          // boards; CTAs loop over them
     int fc_in_smem;     // 1: the transposed FC weights are staged in shared memory once per CTA
+    int* clear;         // completion counters of the tower launch that produced `act` (or null): zeroed here for its next launch,
+    int clear_count;    // which saves a memset node between every two kernels of the search graph
 };
 
 template <int NP1> // NP1 = policy planes + 1 value plane, a compile-time constant so that the plane loops carry no predicates
@@ -1214,6 +1216,9 @@ __global__ void __launch_bounds__(1024) heads_kernel(const HeadParams p)
     const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
     const int g = blockIdx.x;
     const __half* act = p.act + static_cast<size_t>(g) * p.slots * p.c;
+    if (p.clear) { // the tower has finished (stream order); its next launch comes after this kernel
+        for (int i = g * nthr + tid; i < p.clear_count; i += gridDim.x * nthr) { p.clear[i] = 0; }
+    }
     for (int i = tid; i < NP1 * p.c; i += nthr) { wc[i] = (i < p.pol_ch * p.c ? p.w_pc[i] : p.w_vc[i - p.pol_ch * p.c]); }
     for (int cell = tid; cell < hw; cell += nthr) { rowoff[cell] = ((cell / p.n + 1) * n1 + cell % p.n) * p.c; }
     __syncthreads();
