@@ -49,6 +49,9 @@ __global__ void __launch_bounds__(32 * STEP_WARPS, 2) k_step(const mz_dims d, co
         w.q_warp = reinterpret_cast<float*>(w.sel + (d.S + 2));
     }
     __syncthreads();
+    // the network kernel that follows may be launched while this grid is still running (programmatic dependent launch): it only sets
+    // itself up and prefetches weights until griddepcontrol.wait lets it read this kernel's output
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (flags & STEP_AFTER) {
         const long long ta = clock64();
         mz_after_nn(d, s, g, &w, threadIdx.x, blockDim.x);
@@ -224,7 +227,7 @@ struct mz_engine {
     float* d_hidden_f32 = nullptr;   // [B][Ch * H * W] staging of the parity hooks
     int32_t* d_path_actions = nullptr; // [B][S + 2]
     int cin_max = 0;
-    int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148, krot = 0, conv_cluster = 1, conv_pdl = 0, tower_sms = 148, tower_stages = 8;
+    int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148, krot = 0, conv_cluster = 1, conv_pdl = 0, tower_sms = 148, tower_stages = 8, tower_pdl = 0;
     encode_tiled_fn encode = nullptr;
 
     // graphs keyed by (num_evals, noise, rotations)
@@ -383,18 +386,18 @@ int launch_heads(mz_engine* e, const __half* act, int* clear = nullptr, int clea
     return MZ_OK;
 }
 
-int launch_tower(mz_engine* e, int which, bool clear_counters = true);
+int launch_tower(mz_engine* e, int which, bool clear_counters = true, bool pdl = false);
 
 // AlphaZeroNetwork.forward (network/py/alphazero_network.py:90-113) on the rows already in nn_in; for a MuZero network
 // `which` selects initial_inference (0: representation, rows in nn_in) or recurrent_inference (1: dynamics, rows in dyn_in),
 // each followed by scale_hidden_state and the prediction heads (network/py/muzero_network.py:136-160)
-int forward(mz_engine* e, int which = 0)
+int forward(mz_engine* e, int which = 0, bool after_tree_step = false)
 {
     if (!e->net_ready) { return fail(MZ_ERR_STATE, "network not finalized"); }
     NetTower& T = e->tw[which];
     int rc;
     if (e->conv_mode == 3) {
-        if ((rc = launch_tower(e, which, false))) { return rc; } // counters: zero from allocation, then re-zeroed by every heads launch below
+        if ((rc = launch_tower(e, which, false, after_tree_step && e->tower_pdl))) { return rc; } // counters: zero from allocation, then re-zeroed by every heads launch below
     } else {
         if ((rc = conv(e, T.map_in, T.map_in_ext, T.convs[0], e->act[0], nullptr))) { return rc; }
         int cur = 0;
@@ -415,7 +418,7 @@ int forward(mz_engine* e, int which = 0)
     return launch_heads(e, out);
 }
 
-int launch_tower(mz_engine* e, int which, bool clear_counters)
+int launch_tower(mz_engine* e, int which, bool clear_counters, bool pdl)
 {
     {
         NetTower& T = e->tw[which];
@@ -428,10 +431,13 @@ int launch_tower(mz_engine* e, int which, bool clear_counters)
         const size_t smem = 2 * static_cast<size_t>(e->cin_max / mznn::BK) * e->rows_ext * 128 + static_cast<size_t>(stages) * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(clusters * 2), cfg.blockDim = dim3(mznn::TOWER_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = e->stream;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr, cfg.numAttrs = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        T.params->pdl = (pdl ? 1 : 0);
+        cfg.attrs = attr, cfg.numAttrs = (pdl ? 2 : 1);
         if (T.params->dbg && stages == 8) {
             CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8, true>, *T.params));
         } else if (stages == 4) { // 185 KB of shared memory: a tree-step block (30 KB) of another engine fits on the same SM
@@ -588,6 +594,7 @@ int alloc_net(mz_engine* e)
         e->d.hid_c = e->cpad, e->d.dyn_c = e->tw[1].cin0, e->d.act_col = e->nd.num_hidden_channels;
     }
     e->tw[0].in = e->s.nn_in, e->tw[1].in = e->s.dyn_in;
+    if (const char* env = std::getenv("MZ_PDL")) { e->tower_pdl = std::atoi(env); }
     if (const char* env = std::getenv("MZ_TOWER_STAGES")) {
         const int v = std::atoi(env);
         if (v == 4 || v == 5 || v == 8) { e->tower_stages = v; }
@@ -1272,7 +1279,7 @@ int mz_search_run(mz_engine* e, int32_t num_evals, float* device_ms)
         const bool skip_tree = (skip && std::string(skip) == "tree"), skip_nn = (skip && std::string(skip) == "nn");
         for (int c = 0; c < num_evals && !rc; ++c) {
             if (!skip_tree) { step(e, (c > 0 ? STEP_AFTER : 0) | STEP_BEFORE, e->rot_enabled ? e->d_rot_all + static_cast<size_t>(c) * d.B : nullptr); }
-            if (!skip_nn) { rc = forward(e, (e->cfg.muzero && c > 0) ? 1 : 0); } // MuZero: initial inference for the root, recurrent below
+            if (!skip_nn) { rc = forward(e, (e->cfg.muzero && c > 0) ? 1 : 0, !skip_tree); } // MuZero: initial inference for the root, recurrent below
         }
         if (!skip_tree) { step(e, STEP_AFTER, nullptr); }
         cudaError_t cerr = cudaStreamEndCapture(e->stream, &graph);

@@ -849,6 +849,8 @@ struct TowerParams {
     int shift;    // unit offset per layer: position q of layer l is unit (q + l * shift) mod units
     int zigzag;   // odd layers process the cluster's range in reverse order
     int strided;  // units dealt round-robin to the clusters instead of in contiguous ranges
+    int pdl;      // launched with programmatic stream serialization: the grid may start while the tree step before it is still running;
+                  // only the first layer's input rows depend on that kernel, and the input producer waits for it (griddepcontrol.wait)
     int* done;    // [num_layers][num_groups] completion counters, zeroed before every launch
     unsigned long long* dbg; // optional [grid][8] cycle counters (profiling)
 };
@@ -1000,6 +1002,10 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                 cur_key = l * 65536 + g;
                 const int buf = gcount & 1;
                 mbar_wait_u32(smem_u32(&a_empty[buf]), ((gcount >> 1) & 1) ^ 1); // the MMAs that read this buffer two blocks ago are done
+                if (l == 0 && gcount == 0 && tp.pdl) { // everything before this point (barriers, TMEM, weight prefetch) overlapped the previous kernel
+                    asm volatile("griddepcontrol.wait;" ::: "memory");
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
                 if (l > 0) { // the 3x3 halo reaches into the neighbouring groups of the previous layer
                     const long long td = (DBG ? clock64() : 0ll);
                     if (lane == 0) {
