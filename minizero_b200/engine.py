@@ -249,6 +249,9 @@ class Engine:
             h = ((h ^ (int(a) & 0xffffffff)) * 16777619) & 0xffffffff
         return h & 0x7fffffff
 
+    def gumbel_best_action(self, g):
+        return int(self.gumbel_best_actions()[g])
+
     def gumbel_best_actions(self):
         out = np.zeros(self.B, np.int32)
         self._check(self.lib.mz_gumbel_best_actions(self.h, _i32(out)))

@@ -406,3 +406,23 @@ def test_device_env_matches_reference_playouts(name, game, n):
     eng = engine(game, n, 1, 1, ko_situational="situational" in str(case["conf"]))
     assert env_replay.replay(eng, case, check_score=lambda e: float(e.last_play["eval_score"][0])) == case["game"].size
     eng.close()
+
+
+@pytest.mark.parametrize("name,game,board,A,sims,games,moves,opts", [
+    ("go5_az", 1, 5, 26, 200, 4, 30, {}),
+    ("go9_az", 1, 9, 82, 120, 4, 16, {}),
+    ("nogo9_az", 3, 9, 82, 40, 4, 80, {}),
+    ("othello_gumbel_muzero_m8", 2, 8, 65, 32, 4, 66, dict(muzero=1, use_gumbel=1, gumbel_noise=1, gumbel_sample_size=8)),
+    ("othello_muzero", 2, 8, 65, 64, 4, 20, dict(muzero=1)),
+], ids=["go5_az", "go9_az", "nogo9_az", "othello_gumbel_muzero_m8", "othello_muzero"])
+def test_device_and_oracle_agree_on_synthetic_searches(name, game, board, A, sims, games, moves, opts):
+    """differential fuzzing through the per-phase hooks of the C ABI: random priors (with exact ties), values, noise and rotations"""
+    import zlib
+
+    import fuzz_differential
+    orc = oracle_lib.OracleSearch(oracle_lib.load(), game, board, games, sims, **opts)
+    eng = engine(game, board, games, sims, **opts)
+    n = fuzz_differential.run(eng, orc, num_actions=A, sims=sims, games=games, moves=moves, seed=zlib.crc32(name.encode()) % 1000,
+                              noise=("gumbel" if opts.get("gumbel_noise") else "dirichlet"), muzero=bool(opts.get("muzero")), gumbel=bool(opts.get("use_gumbel")))
+    assert n == games * moves
+    eng.close()
