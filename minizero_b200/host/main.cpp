@@ -132,6 +132,10 @@ int main(int argc, char** argv)
         std::cerr << "this worker implements the alphazero and (board-game) muzero self-play paths" << std::endl;
         return -1;
     }
+    if (cfg.getBool("actor_mcts_value_rescale")) { // MCTS::updateTreeValueBound / min-max Q rescaling (mcts.cpp:43-49,219-228): Atari setting, not built
+        std::cerr << "actor_mcts_value_rescale=true is not implemented by this worker" << std::endl;
+        return -1;
+    }
     if (mode == "rng_test") { // CPU only: prints the host's draw sequence for root tables given on stdin
         mzhost::Worker worker(cfg, 1);
         return worker.rngTest(std::cin);

@@ -72,6 +72,9 @@ def test_config_accepts_reference_keys_and_refuses_unknown(worker_binary):
     assert ok.returncode == 0
     bad = subprocess.run([worker_binary, "-mode", "sp", "-conf_str", "no_such_key=1"], input="", capture_output=True, text=True)
     assert bad.returncode != 0 and "Invalid key" in bad.stderr
+    # settings the engine does not implement are refused, not ignored
+    resc = subprocess.run([worker_binary, "-mode", "sp", "-conf_str", "actor_mcts_value_rescale=true"], input="", capture_output=True, text=True)
+    assert resc.returncode != 0 and "not implemented" in resc.stderr and resc.stdout == ""
     # without a GPU (or a model) the worker must fail loudly and write nothing to stdout
     nogpu = subprocess.run([worker_binary, "-mode", "sp", "-conf_str", "nn_file_name=/nonexistent.pt:zero_num_parallel_games=2"], input="quit\n", capture_output=True, text=True)
     assert nogpu.returncode != 0 and nogpu.stdout == ""
