@@ -30,6 +30,7 @@ extern "C" {
 #define MZ_GAME_GO 1        /* environment/go        */
 #define MZ_GAME_OTHELLO 2   /* environment/othello   */
 #define MZ_GAME_NOGO 3      /* environment/nogo (GoEnv with its own legality / end / result; 9x9 in the reference) */
+#define MZ_GAME_GOMOKU 4    /* environment/gomoku (N x N, no pass, five in a row through the last move) */
 
 typedef struct mz_engine mz_engine;
 
@@ -52,6 +53,8 @@ typedef struct {
     int32_t gumbel_sample_size; /* actor_gumbel_sample_size */
     float gumbel_sigma_visit_c; /* actor_gumbel_sigma_visit_c */
     float gumbel_sigma_scale_c; /* actor_gumbel_sigma_scale_c */
+    int32_t gomoku_exactly_five; /* env_gomoku_exactly_five_stones (reference default: true) */
+    int32_t gomoku_outer_open;   /* env_gomoku_rule == "outer_open" */
 } mz_config;
 
 /* Hyper-parameters the reference reads from the TorchScript module (network/network.cpp:30-41). */

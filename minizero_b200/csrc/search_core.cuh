@@ -177,6 +177,7 @@ static inline void mz_store_vis(mz_vis* p, const mz_vis& v) { *p = v; }
 #define MZ_GAME_GO 1
 #define MZ_GAME_OTHELLO 2
 #define MZ_GAME_NOGO 3       // environment/nogo/nogo.h: GoEnv with its own legality, terminal test and result
+#define MZ_GAME_GOMOKU 4     // environment/gomoku: N x N, no pass, five in a row through the last move
 #define MZ_GO_FAMILY(game) ((game) == MZ_GAME_GO || (game) == MZ_GAME_NOGO)
 #define MZ_GUMBEL_LEVELS 12  // halvings of actor_gumbel_sample_size that can ever happen (m <= 362)
 #define MZ_MAXN 19
@@ -201,6 +202,7 @@ struct mz_dims {
     int dyn_c;   // channels per row of the dynamics network's input: hidden state, then the action planes, zero padded
     int act_col; // column of the (single) action plane in a dynamics input row = num_hidden_channels
     // Gumbel (actor_use_gumbel, gumbel_zero.cpp)
+    int gomoku_exactly_five, gomoku_outer_open; // env_gomoku_exactly_five_stones, env_gomoku_rule == "outer_open"
     int gumbel, gumbel_noise, gumbel_m;
     float sigma_visit_c, sigma_scale_c;
     int gumbel_budget0;                   // max(1, floor(S / (log2(m) * m))), gumbel_zero.cpp:99 (host-computed in double)
@@ -526,9 +528,35 @@ MZ_DEV int mz_ttt_eval(const mz_scratch* w)
     return 0;
 }
 
+// GomokuEnv::updateWinner for the last move (gomoku.cpp:140-164): winner_ is a function of the board and the last action
+MZ_DEV int mz_gomoku_winner(const mz_dims& d, const mz_scratch* w)
+{
+    const int N = d.N;
+    if (w->num_moves == 0 || w->last < 0) { return 0; }
+    const int x0 = w->last % N, y0 = w->last / N;
+    const int p = ((w->st[0][y0] >> x0) & 1u) ? 0 : 1; // the mover's colour index
+    for (int dir = 0; dir < 4; ++dir) {
+        const int dx = (dir == 1 ? 0 : 1), dy = (dir == 0 ? 0 : (dir == 3 ? -1 : 1));
+        int c = 1;
+        for (int sgn = -1; sgn <= 1; sgn += 2) {
+            int x = x0 + sgn * dx, y = y0 + sgn * dy;
+            while (x >= 0 && x < N && y >= 0 && y < N && ((w->st[p][y] >> x) & 1u)) { ++c, x += sgn * dx, y += sgn * dy; }
+        }
+        if (d.gomoku_exactly_five ? (c == 5) : (c >= 5)) { return p + 1; } // gomoku.h:46
+    }
+    return 0;
+}
+
 MZ_DEV int mz_env_is_terminal(const mz_dims& d, const mz_scratch* w)
 {
     const int N = d.N;
+    if (d.game == MZ_GAME_GOMOKU) { // gomoku.cpp:60-63
+        if (mz_gomoku_winner(d, w) != 0) { return 1; }
+        for (int r = 0; r < N; ++r) {
+            if (((w->st[0][r] | w->st[1][r]) & mz_rowmask(N)) != mz_rowmask(N)) { return 0; }
+        }
+        return 1;
+    }
     if (d.game == MZ_GAME_GO) {
         if (w->num_moves >= 2 && w->last == N * N && w->last2 == N * N) { return 1; } // go.cpp:249-251
         return w->num_moves > 2 * N * N;                                              // go.cpp:254
@@ -549,6 +577,8 @@ MZ_DEV float mz_env_eval_score(const mz_dims& d, mz_scratch* w, int lane)
     int winner;
     if (d.game == MZ_GAME_NOGO) { // the side to move has lost (nogo.h:70-78)
         winner = 3 - w->turn;
+    } else if (d.game == MZ_GAME_GOMOKU) { // gomoku.cpp:65-73
+        winner = mz_gomoku_winner(d, w);
     } else if (d.game == MZ_GAME_GO) {
         int cnt_b = 0, cnt_w = 0;
         for (int i = lane; i < N; i += MZ_W) {
@@ -618,6 +648,20 @@ MZ_DEV int mz_env_legal_block(const mz_dims& d, const mz_state& s, mz_scratch* w
             mz_block_sync();
             n = 1;
         }
+        return n;
+    }
+    if (d.game == MZ_GAME_GOMOKU) { // gomoku.cpp:49-58: empty points; "outer_open": Black's first stone within two lines of an edge
+        mz_block_sync();
+        for (int c = tid; c < NN; c += nthreads) {
+            const int x = c % N, y = c / N;
+            bool ok = !(((w->st[0][y] | w->st[1][y]) >> x) & 1u);
+            if (w->num_moves == 0 && d.gomoku_outer_open) { ok = (y < 2 || y >= N - 2) || (x < 2 || x >= N - 2); }
+            if (ok) { mz_atomic_or(&w->legal[c >> 5], 1u << (c & 31)); }
+        }
+        mz_block_sync();
+        int n = 0;
+        for (int i = 0; i < MZ_LEGAL_WORDS; ++i) { n += mz_popc(w->legal[i]); }
+        mz_block_sync();
         return n;
     }
     if (!MZ_GO_FAMILY(d.game)) {

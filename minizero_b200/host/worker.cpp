@@ -43,6 +43,8 @@ bool Worker::initialize()
             std::cerr << "env_board_size does not match the model's board" << std::endl;
             return false;
         }
+    } else if (net_.game_name.rfind("gomoku_", 0) == 0) { // "gomoku_15x15" or, with env_gomoku_rule=outer_open, "gomoku_oo_15x15" (gomoku.h:36)
+        game_type_ = MZ_GAME_GOMOKU, board_ = net_.dims.input_height;
     } else if (net_.game_name.rfind("nogo_", 0) == 0) {
         game_type_ = MZ_GAME_NOGO, board_ = net_.dims.input_height;
     } else if (net_.game_name.rfind("othello_", 0) == 0) {
@@ -72,6 +74,7 @@ bool Worker::initialize()
         c.reward_discount = cfg_.getFloat("actor_mcts_reward_discount"), c.komi = cfg_.getFloat("env_go_komi");
         c.ko_situational = (cfg_.getString("env_go_ko_rule") == "situational"), c.dirichlet_epsilon = cfg_.getFloat("actor_dirichlet_noise_epsilon");
         c.muzero = muzero_, c.use_gumbel = gumbel_;
+        c.gomoku_exactly_five = cfg_.getBool("env_gomoku_exactly_five_stones"), c.gomoku_outer_open = (cfg_.getString("env_gomoku_rule") == "outer_open");
         c.gumbel_noise = (!cfg_.getBool("actor_use_dirichlet_noise") && cfg_.getBool("actor_use_gumbel_noise")); // zero_actor.cpp:197,205
         c.gumbel_sample_size = cfg_.getInt("actor_gumbel_sample_size");
         c.gumbel_sigma_visit_c = cfg_.getFloat("actor_gumbel_sigma_visit_c"), c.gumbel_sigma_scale_c = cfg_.getFloat("actor_gumbel_sigma_scale_c");
@@ -126,7 +129,7 @@ void Worker::resetGameHost(int g)
     game.turn = 1;
     game.num_legal = initialNumLegal();
     std::fill(game.ttt, game.ttt + 9, 0);
-    game.stones.assign(game_type_ == MZ_GAME_NOGO ? board_ * board_ : 0, 0);
+    game.stones.assign((game_type_ == MZ_GAME_NOGO || game_type_ == MZ_GAME_GOMOKU) ? board_ * board_ : 0, 0);
     game.enable_resign = (rng_.randReal() < cfg_.getFloat("zero_disable_resign_ratio") ? false : true);
 }
 
@@ -283,6 +286,20 @@ bool Worker::hostTerminal(const Game& game) const
         return n > 2 * board_ * board_;                                                                        // go.cpp:254
     }
     if (game_type_ == MZ_GAME_NOGO) { return !nogoHasLegalMove(game); } // nogo.h:61-68
+    if (game_type_ == MZ_GAME_GOMOKU) { // gomoku.cpp:60-63,140-164: five in a row through the last move, or a full board
+        if (n == 0) { return false; }
+        const int pos = game.moves[n - 1].action, who = game.stones[pos], N = board_;
+        static const int dirs[4][2] = {{1, 0}, {0, 1}, {1, 1}, {1, -1}};
+        for (const auto& d : dirs) {
+            int count = 1;
+            for (int sgn = -1; sgn <= 1; sgn += 2) {
+                int x = pos % N + sgn * d[0], y = pos / N + sgn * d[1];
+                while (x >= 0 && x < N && y >= 0 && y < N && game.stones[y * N + x] == who) { ++count, x += sgn * d[0], y += sgn * d[1]; }
+            }
+            if (cfg_.getBool("env_gomoku_exactly_five_stones") ? (count == 5) : (count >= 5)) { return true; }
+        }
+        return n == N * N;
+    }
     if (game_type_ == MZ_GAME_OTHELLO) { // othello.cpp:201-207
         const int pass = board_ * board_;
         return n >= 2 && game.moves[n - 1].action == pass && game.moves[n - 2].action == pass;
@@ -412,7 +429,9 @@ int Worker::advanceGame(int g, const RootView& r, bool& resign, bool& end)
         m.reward = "0";                        // operator<< of Environment::getReward() == 0.0f (go.h:50, tictactoe.h:25)
         game.moves.push_back(m);
         if (game_type_ == MZ_GAME_TICTACTOE && action >= 0 && action < 9) { game.ttt[action] = static_cast<uint8_t>(game.turn); }
-        if (game_type_ == MZ_GAME_NOGO && action >= 0 && action < board_ * board_) { game.stones[action] = static_cast<uint8_t>(game.turn); }
+        if ((game_type_ == MZ_GAME_NOGO || game_type_ == MZ_GAME_GOMOKU) && action >= 0 && action < board_ * board_) {
+            game.stones[action] = static_cast<uint8_t>(game.turn);
+        }
         game.turn = 3 - game.turn;
         play = action;
         end = hostTerminal(game);

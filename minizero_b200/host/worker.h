@@ -73,6 +73,10 @@ private:
     }
     int initialNumLegal() const
     {
+        if (game_type_ == MZ_GAME_GOMOKU) { // every point, or the two outer lines under env_gomoku_rule=outer_open (gomoku.cpp:53-56)
+            const int inner = (board_ > 4 ? board_ - 4 : 0);
+            return cfg_.getString("env_gomoku_rule") == "outer_open" ? board_ * board_ - inner * inner : board_ * board_;
+        }
         return game_type_ == MZ_GAME_GO ? board_ * board_ + 1 : (game_type_ == MZ_GAME_NOGO ? board_ * board_ : (game_type_ == MZ_GAME_OTHELLO ? 4 : 9));
     }
     std::vector<mz_engine*> engines_;  // one per visible GPU (actor_group.cpp:168-177)

@@ -18,6 +18,8 @@ CASES = {
     "env_go9_situational": ("go", "env_board_size=9:env_go_ko_rule=situational:program_quiet=true", 4, 2, 400),
     "env_go19": ("go", "env_board_size=19:program_quiet=true", 5, 1, 420),
     "env_nogo9": ("nogo", "program_quiet=true", 7, 6, 200),
+    "env_gomoku15": ("gomoku", "program_quiet=true", 8, 5, 230),
+    "env_gomoku15_freestyle": ("gomoku", "env_gomoku_exactly_five_stones=false:env_gomoku_rule=outer_open:program_quiet=true", 9, 3, 230),
     "env_othello8": ("othello", "program_quiet=true", 6, 8, 200),
 }
 

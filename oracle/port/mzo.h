@@ -22,6 +22,9 @@ extern "C" {
 #define MZO_GAME_GO 1
 #define MZO_GAME_OTHELLO 2
 #define MZO_GAME_NOGO 3
+#define MZO_GAME_GOMOKU 4
+#define MZO_GOMOKU_EXACTLY_FIVE 1 /* env_gomoku_exactly_five_stones (default true) */
+#define MZO_GOMOKU_OUTER_OPEN 2   /* env_gomoku_rule == "outer_open" */
 
 #define MZO_MAX_N 19
 #define MZO_MAX_CELLS (MZO_MAX_N * MZO_MAX_N)
@@ -47,11 +50,13 @@ typedef struct {
     int32_t gumbel_sample_size; /* actor_gumbel_sample_size */
     float gumbel_sigma_visit_c; /* actor_gumbel_sigma_visit_c */
     float gumbel_sigma_scale_c; /* actor_gumbel_sigma_scale_c */
+    int32_t gomoku_flags;       /* MZO_GOMOKU_* */
 } mzo_config;
 
 /* ---- environment (environment/go/go.cpp, environment/tictactoe/tictactoe.cpp) ---- */
 typedef struct {
     int32_t game, n, turn, num_moves;
+    int32_t flags; /* MZO_GOMOKU_* */
     float komi;
     uint64_t turn_key, hash;
     uint8_t board[MZO_MAX_CELLS];
@@ -61,6 +66,7 @@ typedef struct {
 } mzo_env;
 
 void mzo_env_init(mzo_env* e, int game, int n, float komi, int ko_situational);
+void mzo_env_set_flags(mzo_env* e, int flags);
 int mzo_env_num_actions(const mzo_env* e);
 int mzo_env_input_channels(const mzo_env* e);
 int mzo_env_is_legal(const mzo_env* e, int action, int player);

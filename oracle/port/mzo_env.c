@@ -126,7 +126,12 @@ void mzo_env_init(mzo_env* e, int game, int n, float komi, int ko_situational)
     }
 }
 
-int mzo_env_num_actions(const mzo_env* e) { return e->game == MZO_GAME_TICTACTOE ? 9 : e->n * e->n + 1; }
+void mzo_env_set_flags(mzo_env* e, int flags) { e->flags = flags; }
+int mzo_env_num_actions(const mzo_env* e)
+{
+    if (e->game == MZO_GAME_TICTACTOE) { return 9; }
+    return e->game == MZO_GAME_GOMOKU ? e->n * e->n : e->n * e->n + 1; /* gomoku.h:32: no pass */
+}
 int mzo_env_input_channels(const mzo_env* e) { return (e->game == MZO_GAME_GO || e->game == MZO_GAME_NOGO) ? 18 : 4; }
 
 /* neighbour order of go_grid.h:43-54: up(+n), right(+1), down(-n), left(-1) */
@@ -446,6 +451,41 @@ void mzo_env_action_features(const mzo_env* e, int action, float* out)
     if (action >= 0 && action < cells) { out[action] = 1.0f; }
 }
 
+/* ---- gomoku (environment/gomoku/gomoku.cpp) ---- */
+/* calculateNumberOfConnection, gomoku.cpp:150-164 */
+static int gomoku_run(const mzo_env* e, int start, int dx, int dy)
+{
+    int n = e->n, x = start % n, y = start / n, count = 0, who = e->board[start];
+    while (x >= 0 && x < n && y >= 0 && y < n && e->board[y * n + x] == who) { ++count, x += dx, y += dy; }
+    return count;
+}
+
+/* updateWinner for the last move (gomoku.cpp:140-148); winner_ is a function of the board and the last action */
+static int gomoku_winner(const mzo_env* e)
+{
+    if (e->num_moves == 0) { return 0; }
+    const int pos = e->actions[e->num_moves - 1];
+    static const int dirs[4][2] = {{1, 0}, {0, 1}, {1, 1}, {1, -1}};
+    for (int d = 0; d < 4; ++d) {
+        int c = gomoku_run(e, pos, dirs[d][0], dirs[d][1]) + gomoku_run(e, pos, -dirs[d][0], -dirs[d][1]) - 1;
+        if ((e->flags & MZO_GOMOKU_EXACTLY_FIVE) ? (c == 5) : (c >= 5)) { return e->board[pos]; } /* gomoku.h:46 */
+    }
+    return 0;
+}
+
+/* gomoku.cpp:49-58 */
+static int gomoku_is_legal(const mzo_env* e, int action, int player)
+{
+    (void)player;
+    int n = e->n;
+    if (action < 0 || action >= n * n) { return 0; }
+    if (e->num_moves == 0 && (e->flags & MZO_GOMOKU_OUTER_OPEN)) {
+        int i = action / n, j = action % n;
+        return (i < 2 || i >= n - 2) || (j < 2 || j >= n - 2);
+    }
+    return e->board[action] == 0;
+}
+
 /* ---- tictactoe (tictactoe.cpp:124-146 eval) ---- */
 static int ttt_eval(const mzo_env* e)
 {
@@ -471,6 +511,7 @@ int mzo_env_is_legal(const mzo_env* e, int action, int player)
 {
     if (e->game == MZO_GAME_GO) { return go_is_legal(e, action, player); }
     if (e->game == MZO_GAME_NOGO) { return nogo_is_legal(e, action, player); }
+    if (e->game == MZO_GAME_GOMOKU) { return gomoku_is_legal(e, action, player); }
     if (e->game == MZO_GAME_OTHELLO) { return othello_is_legal(e, action, player); }
     return action >= 0 && action < 9 && e->board[action] == 0; /* tictactoe.cpp:44-49 */
 }
@@ -479,6 +520,13 @@ int mzo_env_act(mzo_env* e, int action, int player)
 {
     if (e->game == MZO_GAME_GO || e->game == MZO_GAME_NOGO) { return go_act(e, action, player); }
     if (e->game == MZO_GAME_OTHELLO) { return othello_act(e, action, player); }
+    if (e->game == MZO_GAME_GOMOKU) { /* gomoku.cpp:23-31 */
+        if (!gomoku_is_legal(e, action, player)) { return 0; }
+        e->actions[e->num_moves++] = (int16_t)action;
+        e->board[action] = (uint8_t)player;
+        e->turn = other(player);
+        return 1;
+    }
     if (!mzo_env_is_legal(e, action, player)) { return 0; } /* tictactoe.cpp:19-26 */
     e->actions[e->num_moves++] = (int16_t)action;
     e->board[action] = (uint8_t)player;
@@ -496,6 +544,13 @@ int mzo_env_is_terminal(const mzo_env* e)
         return 1;
     }
     if (e->game == MZO_GAME_OTHELLO) { return othello_is_terminal(e); }
+    if (e->game == MZO_GAME_GOMOKU) { /* gomoku.cpp:60-63 */
+        if (gomoku_winner(e) != 0) { return 1; }
+        for (int i = 0; i < e->n * e->n; ++i) {
+            if (e->board[i] == 0) { return 0; }
+        }
+        return 1;
+    }
     if (ttt_eval(e) != 0) { return 1; } /* tictactoe.cpp:51-55 */
     for (int i = 0; i < 9; ++i) {
         if (e->board[i] == 0) { return 0; }
@@ -508,6 +563,10 @@ float mzo_env_eval_score(const mzo_env* e, int is_resign)
     if (e->game == MZO_GAME_GO) { return go_eval_score(e, is_resign); }
     if (e->game == MZO_GAME_NOGO) { return other(e->turn) == 1 ? 1.0f : -1.0f; } /* nogo.h:70-78: whoever is to move has lost */
     if (e->game == MZO_GAME_OTHELLO) { return othello_eval_score(e, is_resign); }
+    if (e->game == MZO_GAME_GOMOKU) { /* gomoku.cpp:65-73 */
+        int w = (is_resign ? other(e->turn) : gomoku_winner(e));
+        return w == 1 ? 1.0f : (w == 2 ? -1.0f : 0.0f);
+    }
     int r = (is_resign ? other(e->turn) : ttt_eval(e)); /* tictactoe.cpp:57-65 */
     return r == 1 ? 1.0f : (r == 2 ? -1.0f : 0.0f);
 }

@@ -77,6 +77,7 @@ mzo_batch* mzo_create(const mzo_config* cfg)
     b->cfg = *cfg;
     mzo_env tmp;
     mzo_env_init(&tmp, cfg->game, cfg->board_size, cfg->komi, cfg->ko_situational);
+    mzo_env_set_flags(&tmp, cfg->gomoku_flags);
     b->A = mzo_env_num_actions(&tmp);
     b->F = mzo_env_input_channels(&tmp) * tmp.n * tmp.n;
     b->NP = 1 + (cfg->num_simulation + 1) * b->A; /* actor_group.cpp:183, tree.h:66 */
@@ -133,6 +134,7 @@ void mzo_reset_search(mzo_batch* b, int g)
 void mzo_reset_game(mzo_batch* b, int g)
 {
     mzo_env_init(&b->root_env[g], b->cfg.game, b->cfg.board_size, b->cfg.komi, b->cfg.ko_situational);
+    mzo_env_set_flags(&b->root_env[g], b->cfg.gomoku_flags);
     mzo_reset_search(b, g);
 }
 

@@ -7,7 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MAX_ACTIONS = 19 * 19 + 1
-GAME_TICTACTOE, GAME_GO, GAME_OTHELLO, GAME_NOGO = 0, 1, 2, 3
+GAME_TICTACTOE, GAME_GO, GAME_OTHELLO, GAME_NOGO, GAME_GOMOKU = 0, 1, 2, 3, 4
 
 
 class Config(C.Structure):
@@ -15,7 +15,7 @@ class Config(C.Structure):
                 ("puct_base", C.c_float), ("puct_init", C.c_float), ("reward_discount", C.c_float), ("komi", C.c_float),
                 ("ko_situational", C.c_int32), ("value_rescale", C.c_int32), ("dirichlet_epsilon", C.c_float),
                 ("muzero", C.c_int32), ("use_gumbel", C.c_int32), ("gumbel_noise", C.c_int32), ("gumbel_sample_size", C.c_int32),
-                ("gumbel_sigma_visit_c", C.c_float), ("gumbel_sigma_scale_c", C.c_float)]
+                ("gumbel_sigma_visit_c", C.c_float), ("gumbel_sigma_scale_c", C.c_float), ("gomoku_flags", C.c_int32)]
 
 
 class RootOut(C.Structure):
@@ -25,7 +25,7 @@ class RootOut(C.Structure):
 
 def default_config(game, board_size, num_games, num_simulation):
     # defaults of config/configuration.cpp:13-28,80
-    return Config(game, board_size, num_games, num_simulation, 19652.0, 1.25, 1.0, 7.5, 0, 0, 0.25, 0, 0, 0, 16, 50.0, 1.0)
+    return Config(game, board_size, num_games, num_simulation, 19652.0, 1.25, 1.0, 7.5, 0, 0, 0.25, 0, 0, 0, 16, 50.0, 1.0, 1)
 
 
 def conf_overrides(conf):
@@ -90,7 +90,7 @@ class OracleSearch:
             setattr(self.cfg, k, v)
         self.h = lib.mzo_create(C.byref(self.cfg))
         n = 3 if game == GAME_TICTACTOE else board_size
-        self.A = 9 if game == GAME_TICTACTOE else n * n + 1
+        self.A = 9 if game == GAME_TICTACTOE else (n * n if game == GAME_GOMOKU else n * n + 1)
         self.F = (18 if game in (GAME_GO, GAME_NOGO) else 4) * n * n
         self.B, self.S = num_games, num_simulation
 

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 ROOT = oracle_lib.ROOT
 NETS = os.path.join(ROOT, "oracle", "_ref", "nets")
-CASES = {"ttt_s50_b2": (0, 3), "ttt_s50_b1_det": (0, 3), "go5_s24_b2": (1, 5), "go9_s32_b2": (1, 9), "go19_s8_b2": (1, 19), "nogo9_s8_b2": (3, 9),
+CASES = {"ttt_s50_b2": (0, 3), "ttt_s50_b1_det": (0, 3), "go5_s24_b2": (1, 5), "go9_s32_b2": (1, 9), "go19_s8_b2": (1, 19), "nogo9_s8_b2": (3, 9), "gomoku15_s8_b2": (4, 15),
          "go5_mz_s16_b2": (1, 5), "ttt_gmz_s16_b2": (0, 3), "othello_gmz_s16_b2": (2, 8), "othello_gmz_s32_m8_b2": (2, 8), "othello_mz_s24_b2": (2, 8)}
 
 
@@ -397,13 +397,15 @@ def test_full_size_19x19_search_invariants():
 
 
 @pytest.mark.parametrize("name,game,n", [("env_ttt", 0, 3), ("env_go5", 1, 5), ("env_go9", 1, 9), ("env_go9_situational", 1, 9), ("env_go19", 1, 19),
-                                         ("env_othello8", 2, 8), ("env_nogo9", 3, 9)])
+                                         ("env_othello8", 2, 8), ("env_nogo9", 3, 9), ("env_gomoku15", 4, 15),
+                                         ("env_gomoku15_freestyle", 4, 15)])
 def test_device_env_matches_reference_playouts(name, game, n):
     """the device rule / feature kernels against random playouts of the reference's own environments (captures, ko and superko,
     suicide, passes, Othello flips and forced passes): legal sets, rotated planes, terminal flags, final scores"""
     import env_replay
     case = env_replay.load(name)
-    eng = engine(game, n, 1, 1, ko_situational="situational" in str(case["conf"]))
+    eng = engine(game, n, 1, 1, ko_situational="situational" in str(case["conf"]), gomoku_exactly_five="exactly_five_stones=false" not in str(case["conf"]),
+                 gomoku_outer_open="outer_open" in str(case["conf"]))
     assert env_replay.replay(eng, case, check_score=lambda e: float(e.last_play["eval_score"][0])) == case["game"].size
     eng.close()
 
