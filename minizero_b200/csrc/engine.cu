@@ -30,7 +30,7 @@ int fail(int code, const std::string& msg)
     } while (0)
 
 // ---------------------------------------------------------------------------------------------------
-// kernels around search_core.cuh: one warp (= one block of 32 threads) per game
+// kernels around search_core.cuh: one block per game (16 warps for the per-cycle tree step, one warp for the per-move kernels)
 // ---------------------------------------------------------------------------------------------------
 constexpr int STEP_AFTER = 1, STEP_BEFORE = 2;
 

@@ -1,7 +1,8 @@
-// Warp-per-tree search core: PUCT selection, leaf environment transition (Go / TicTacToe rules on
-// row bitboards), feature packing, expansion and backup over a flat node pool.
+// Search core: PUCT / Gumbel selection, leaf environment transition (Go, NoGo, Othello, Gomoku, TicTacToe rules on
+// row bitboards), feature packing, expansion and backup over a flat node pool; AlphaZero and MuZero branches.
 //
-// One warp owns one game (tree + environment). All functions are written against a tiny warp
+// One thread block owns one game (tree + environment): warp-collective routines for one level / one flood fill, block-wide
+// ones for the leaf analysis and the level-parallel re-evaluation of a path. All functions are written against a tiny warp
 // abstraction (MZ_W lanes, ballot / any / butterfly reductions, lane-strided loops, flood fills
 // iterated to their unique fixpoint) so that the same source also compiles as plain C++ with
 // MZ_W == 1. That second build (tests/hostsim) exists ONLY so the CPU test-suite can check this
