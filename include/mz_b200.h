@@ -31,6 +31,7 @@ extern "C" {
 #define MZ_GAME_OTHELLO 2   /* environment/othello   */
 #define MZ_GAME_NOGO 3      /* environment/nogo (GoEnv with its own legality / end / result; 9x9 in the reference) */
 #define MZ_GAME_GOMOKU 4    /* environment/gomoku (N x N, no pass, five in a row through the last move) */
+#define MZ_GAME_HEX 5       /* environment/hex (N x N, no pass, swap rule, connect the two own edges; features and policy are never rotated) */
 
 typedef struct mz_engine mz_engine;
 
@@ -55,6 +56,7 @@ typedef struct {
     float gumbel_sigma_scale_c; /* actor_gumbel_sigma_scale_c */
     int32_t gomoku_exactly_five; /* env_gomoku_exactly_five_stones (reference default: true) */
     int32_t gomoku_outer_open;   /* env_gomoku_rule == "outer_open" */
+    int32_t hex_swap_rule;       /* env_hex_use_swap_rule (reference default: true) */
 } mz_config;
 
 /* Hyper-parameters the reference reads from the TorchScript module (network/network.cpp:30-41). */

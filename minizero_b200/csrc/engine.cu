@@ -666,7 +666,7 @@ int mz_create(const mz_config* cfg, mz_engine** out)
 {
     if (!cfg || !out) { return fail(MZ_ERR_ARG, "null argument"); }
     *out = nullptr;
-    if (cfg->game != MZ_GAME_GO && cfg->game != MZ_GAME_TICTACTOE && cfg->game != MZ_GAME_OTHELLO && cfg->game != MZ_GAME_NOGO && cfg->game != MZ_GAME_GOMOKU) {
+    if (cfg->game != MZ_GAME_GO && cfg->game != MZ_GAME_TICTACTOE && cfg->game != MZ_GAME_OTHELLO && cfg->game != MZ_GAME_NOGO && cfg->game != MZ_GAME_GOMOKU && cfg->game != MZ_GAME_HEX) {
         return fail(MZ_ERR_ARG, "unsupported game");
     }
     const int N = (cfg->game == MZ_GAME_TICTACTOE ? 3 : cfg->board_size);
@@ -685,7 +685,8 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     mz_engine* e = new mz_engine();
     e->cfg = *cfg;
     mz_dims& d = e->d;
-    d.game = cfg->game, d.N = N, d.A = (cfg->game == MZ_GAME_TICTACTOE ? 9 : (cfg->game == MZ_GAME_GOMOKU ? N * N : N * N + 1)), d.C = (MZ_GO_FAMILY(cfg->game) ? 18 : 4);
+    d.game = cfg->game, d.N = N, d.A = (cfg->game == MZ_GAME_TICTACTOE ? 9 : ((cfg->game == MZ_GAME_GOMOKU || cfg->game == MZ_GAME_HEX) ? N * N : N * N + 1)), d.C = (MZ_GO_FAMILY(cfg->game) ? 18 : 4);
+    d.hex_swap_rule = (cfg->hex_swap_rule != 0);
     d.gomoku_exactly_five = (cfg->gomoku_exactly_five != 0), d.gomoku_outer_open = (cfg->gomoku_outer_open != 0);
     d.muzero = (cfg->muzero != 0), d.gumbel = (cfg->use_gumbel != 0), d.gumbel_noise = (cfg->gumbel_noise != 0), d.gumbel_m = cfg->gumbel_sample_size;
     d.sigma_visit_c = cfg->gumbel_sigma_visit_c, d.sigma_scale_c = cfg->gumbel_sigma_scale_c;

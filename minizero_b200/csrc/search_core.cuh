@@ -179,6 +179,7 @@ static inline void mz_store_vis(mz_vis* p, const mz_vis& v) { *p = v; }
 #define MZ_GAME_OTHELLO 2
 #define MZ_GAME_NOGO 3       // environment/nogo/nogo.h: GoEnv with its own legality, terminal test and result
 #define MZ_GAME_GOMOKU 4     // environment/gomoku: N x N, no pass, five in a row through the last move
+#define MZ_GAME_HEX 5        // environment/hex: N x N, no pass, swap rule, connect the two own edges; never rotated
 #define MZ_GO_FAMILY(game) ((game) == MZ_GAME_GO || (game) == MZ_GAME_NOGO)
 #define MZ_GUMBEL_LEVELS 12  // halvings of actor_gumbel_sample_size that can ever happen (m <= 362)
 #define MZ_MAXN 19
@@ -203,6 +204,7 @@ struct mz_dims {
     int dyn_c;   // channels per row of the dynamics network's input: hidden state, then the action planes, zero padded
     int act_col; // column of the (single) action plane in a dynamics input row = num_hidden_channels
     // Gumbel (actor_use_gumbel, gumbel_zero.cpp)
+    int hex_swap_rule; // env_hex_use_swap_rule
     int gomoku_exactly_five, gomoku_outer_open; // env_gomoku_exactly_five_stones, env_gomoku_rule == "outer_open"
     int gumbel, gumbel_noise, gumbel_m;
     float sigma_visit_c, sigma_scale_c;
@@ -489,6 +491,18 @@ MZ_DEV void mz_env_act(const mz_dims& d, const mz_state& s, mz_scratch* w, int a
                 mz_sync();
             }
         }
+    } else if (d.game == MZ_GAME_HEX) { // hex.cpp:21-66
+        if (lane == 0) {
+            int id = a;
+            if (d.hex_swap_rule && num_moves == 1 && a == w->last) { // swap: the first stone changes sides, mirrored over the other diagonal
+                const int row = a / N, col = a % N;
+                id = (N - 1 - col) * N + (N - 1 - row);
+                w->st[0][row] &= ~(1u << col);
+                w->st[1][row] &= ~(1u << col);
+            }
+            w->st[me][id / N] |= (1u << (id % N));
+        }
+        mz_sync();
     } else if (d.game == MZ_GAME_OTHELLO) {
         if (lane == 0 && a != N * N) { // a pass only hands the turn over (othello.cpp:111)
             for (int i = 0; i < N; ++i) { w->tmp[i] = 0u; }
@@ -529,6 +543,39 @@ MZ_DEV int mz_ttt_eval(const mz_scratch* w)
     return 0;
 }
 
+// Hex: does `player` connect its two edges (Black: columns 0 and N-1, White: rows 0 and N-1; hex.cpp:47-58)? The reference merges
+// per-cell edge flags through the six neighbours of every new stone (hex.cpp:305-347); the same relation as a flood fill from
+// edge 1 through the player's stones, dilated over the six hex neighbours (x-1,y-1) (x,y-1) (x-1,y) (x+1,y) (x,y+1) (x+1,y+1).
+// Single thread; rows of at most 19 bits.
+MZ_DEV int mz_hex_connected(const mz_scratch* w, int N, int player)
+{
+    const uint32_t* st = w->st[player - 1];
+    uint32_t f[MZ_MAXN];
+    for (int y = 0; y < N; ++y) { f[y] = (player == 1 ? (st[y] & 1u) : (y == 0 ? st[y] : 0u)); }
+    bool changed = true;
+    while (changed) {
+        changed = false;
+        for (int y = 0; y < N; ++y) {
+            uint32_t v = f[y] | (f[y] << 1) | (f[y] >> 1);
+            if (y > 0) { v |= f[y - 1] | (f[y - 1] << 1); }
+            if (y + 1 < N) { v |= f[y + 1] | (f[y + 1] >> 1); }
+            v &= st[y];
+            if (v != f[y]) {
+                f[y] = v;
+                changed = true;
+            }
+        }
+    }
+    if (player == 1) {
+        for (int y = 0; y < N; ++y) {
+            if ((f[y] >> (N - 1)) & 1u) { return 1; }
+        }
+        return 0;
+    }
+    return f[N - 1] != 0u;
+}
+MZ_DEV int mz_hex_winner(const mz_dims& d, const mz_scratch* w) { return mz_hex_connected(w, d.N, 1) ? 1 : (mz_hex_connected(w, d.N, 2) ? 2 : 0); }
+
 // GomokuEnv::updateWinner for the last move (gomoku.cpp:140-164): winner_ is a function of the board and the last action
 MZ_DEV int mz_gomoku_winner(const mz_dims& d, const mz_scratch* w)
 {
@@ -551,6 +598,7 @@ MZ_DEV int mz_gomoku_winner(const mz_dims& d, const mz_scratch* w)
 MZ_DEV int mz_env_is_terminal(const mz_dims& d, const mz_scratch* w)
 {
     const int N = d.N;
+    if (d.game == MZ_GAME_HEX) { return mz_hex_winner(d, w) != 0; } // hex.cpp:96-99
     if (d.game == MZ_GAME_GOMOKU) { // gomoku.cpp:60-63
         if (mz_gomoku_winner(d, w) != 0) { return 1; }
         for (int r = 0; r < N; ++r) {
@@ -580,6 +628,8 @@ MZ_DEV float mz_env_eval_score(const mz_dims& d, mz_scratch* w, int lane)
         winner = 3 - w->turn;
     } else if (d.game == MZ_GAME_GOMOKU) { // gomoku.cpp:65-73
         winner = mz_gomoku_winner(d, w);
+    } else if (d.game == MZ_GAME_HEX) { // hex.cpp:101-111
+        winner = mz_hex_winner(d, w);
     } else if (d.game == MZ_GAME_GO) {
         int cnt_b = 0, cnt_w = 0;
         for (int i = lane; i < N; i += MZ_W) {
@@ -651,12 +701,15 @@ MZ_DEV int mz_env_legal_block(const mz_dims& d, const mz_state& s, mz_scratch* w
         }
         return n;
     }
-    if (d.game == MZ_GAME_GOMOKU) { // gomoku.cpp:49-58: empty points; "outer_open": Black's first stone within two lines of an edge
+    if (d.game == MZ_GAME_GOMOKU || d.game == MZ_GAME_HEX) {
+        // gomoku.cpp:49-58: empty points; "outer_open": Black's first stone within two lines of an edge
+        // hex.cpp:83-94: empty points; with the swap rule every point on the second move (playing the first stone's point swaps)
         mz_block_sync();
         for (int c = tid; c < NN; c += nthreads) {
             const int x = c % N, y = c / N;
             bool ok = !(((w->st[0][y] | w->st[1][y]) >> x) & 1u);
-            if (w->num_moves == 0 && d.gomoku_outer_open) { ok = (y < 2 || y >= N - 2) || (x < 2 || x >= N - 2); }
+            if (d.game == MZ_GAME_GOMOKU && w->num_moves == 0 && d.gomoku_outer_open) { ok = (y < 2 || y >= N - 2) || (x < 2 || x >= N - 2); }
+            if (d.game == MZ_GAME_HEX && w->num_moves == 1 && d.hex_swap_rule) { ok = true; }
             if (ok) { mz_atomic_or(&w->legal[c >> 5], 1u << (c & 31)); }
         }
         mz_block_sync();
@@ -788,7 +841,7 @@ MZ_DEV int mz_env_legal_block(const mz_dims& d, const mz_state& s, mz_scratch* w
 // board cell (x, y) of game g lives at row g * slots + (y + 1) * (N + 1) + x, channel c at column c.
 MZ_DEV void mz_env_features(const mz_dims& d, const mz_state& s, int g, const mz_scratch* w, int rotation, int lane, int stride = MZ_W)
 {
-    const int N = d.N, rev = mz_reversed_rotation(rotation);
+    const int N = d.N, rev = (d.game == MZ_GAME_HEX ? 0 : mz_reversed_rotation(rotation)); // HexEnv::getFeatures ignores it (hex.cpp:123-124)
     const int turn = w->turn, me = turn - 1, opp = 1 - me;
     uint16_t* base = s.nn_in + (size_t)g * d.slots * MZ_NN_CPAD;
     for (int pos = lane; pos < N * N; pos += stride) {
@@ -1726,7 +1779,7 @@ MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* 
     if (!terminal) {
         for (int i = tid; i < MZ_LEGAL_WORDS; i += nthreads) { w->legal[i] = s.leaf_legal[g * MZ_LEGAL_WORDS + i]; }
         for (int a = tid; a < A; a += nthreads) {
-            const int ra = mz_rotate(rotation, a, N); // getRotateAction, zero_actor.cpp:222
+            const int ra = (d.game == MZ_GAME_HEX ? a : mz_rotate(rotation, a, N)); // getRotateAction, zero_actor.cpp:222 (identity for Hex, hex.h:65)
             w->pol[a] = s.policy[(size_t)g * A + ra];
             w->lg[a] = s.logits[(size_t)g * A + ra];
         }

@@ -13,7 +13,7 @@ import subprocess
 
 import numpy as np
 
-GAME_TICTACTOE, GAME_GO, GAME_OTHELLO, GAME_NOGO, GAME_GOMOKU = 0, 1, 2, 3, 4
+GAME_TICTACTOE, GAME_GO, GAME_OTHELLO, GAME_NOGO, GAME_GOMOKU, GAME_HEX = 0, 1, 2, 3, 4, 5
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -26,7 +26,7 @@ class _Config(C.Structure):
                 ("puct_base", C.c_float), ("puct_init", C.c_float), ("reward_discount", C.c_float), ("komi", C.c_float), ("ko_situational", C.c_int32),
                 ("dirichlet_epsilon", C.c_float), ("muzero", C.c_int32), ("use_gumbel", C.c_int32), ("gumbel_noise", C.c_int32),
                 ("gumbel_sample_size", C.c_int32), ("gumbel_sigma_visit_c", C.c_float), ("gumbel_sigma_scale_c", C.c_float),
-                ("gomoku_exactly_five", C.c_int32), ("gomoku_outer_open", C.c_int32)]
+                ("gomoku_exactly_five", C.c_int32), ("gomoku_outer_open", C.c_int32), ("hex_swap_rule", C.c_int32)]
 
 
 class _NetDims(C.Structure):
@@ -134,11 +134,11 @@ class Engine:
 
     def __init__(self, game, board_size, num_games, num_simulation, device=0, puct_base=19652.0, puct_init=1.25, reward_discount=1.0, komi=7.5,
                  ko_situational=False, dirichlet_epsilon=0.25, muzero=0, use_gumbel=0, gumbel_noise=0, gumbel_sample_size=16, gumbel_sigma_visit_c=50.0,
-                 gumbel_sigma_scale_c=1.0, gomoku_exactly_five=True, gomoku_outer_open=False):
+                 gumbel_sigma_scale_c=1.0, gomoku_exactly_five=True, gomoku_outer_open=False, hex_swap_rule=True):
         self.lib = _load()
         cfg = _Config(device, game, board_size, num_games, num_simulation, puct_base, puct_init, reward_discount, komi, int(ko_situational), dirichlet_epsilon,
                       int(muzero), int(use_gumbel), int(gumbel_noise), int(gumbel_sample_size), gumbel_sigma_visit_c, gumbel_sigma_scale_c,
-                      int(gomoku_exactly_five), int(gomoku_outer_open))
+                      int(gomoku_exactly_five), int(gomoku_outer_open), int(hex_swap_rule))
         self.muzero = bool(muzero)
         h = C.c_void_p()
         self.h = None

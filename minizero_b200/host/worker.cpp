@@ -43,6 +43,8 @@ bool Worker::initialize()
             std::cerr << "env_board_size does not match the model's board" << std::endl;
             return false;
         }
+    } else if (net_.game_name.rfind("hex_", 0) == 0) {
+        game_type_ = MZ_GAME_HEX, board_ = net_.dims.input_height;
     } else if (net_.game_name.rfind("gomoku_", 0) == 0) { // "gomoku_15x15" or, with env_gomoku_rule=outer_open, "gomoku_oo_15x15" (gomoku.h:36)
         game_type_ = MZ_GAME_GOMOKU, board_ = net_.dims.input_height;
     } else if (net_.game_name.rfind("nogo_", 0) == 0) {
@@ -74,6 +76,7 @@ bool Worker::initialize()
         c.reward_discount = cfg_.getFloat("actor_mcts_reward_discount"), c.komi = cfg_.getFloat("env_go_komi");
         c.ko_situational = (cfg_.getString("env_go_ko_rule") == "situational"), c.dirichlet_epsilon = cfg_.getFloat("actor_dirichlet_noise_epsilon");
         c.muzero = muzero_, c.use_gumbel = gumbel_;
+        c.hex_swap_rule = cfg_.getBool("env_hex_use_swap_rule");
         c.gomoku_exactly_five = cfg_.getBool("env_gomoku_exactly_five_stones"), c.gomoku_outer_open = (cfg_.getString("env_gomoku_rule") == "outer_open");
         c.gumbel_noise = (!cfg_.getBool("actor_use_dirichlet_noise") && cfg_.getBool("actor_use_gumbel_noise")); // zero_actor.cpp:197,205
         c.gumbel_sample_size = cfg_.getInt("actor_gumbel_sample_size");
@@ -129,7 +132,7 @@ void Worker::resetGameHost(int g)
     game.turn = 1;
     game.num_legal = initialNumLegal();
     std::fill(game.ttt, game.ttt + 9, 0);
-    game.stones.assign((game_type_ == MZ_GAME_NOGO || game_type_ == MZ_GAME_GOMOKU) ? board_ * board_ : 0, 0);
+    game.stones.assign((game_type_ == MZ_GAME_NOGO || game_type_ == MZ_GAME_GOMOKU || game_type_ == MZ_GAME_HEX) ? board_ * board_ : 0, 0);
     game.enable_resign = (rng_.randReal() < cfg_.getFloat("zero_disable_resign_ratio") ? false : true);
 }
 
@@ -286,6 +289,30 @@ bool Worker::hostTerminal(const Game& game) const
         return n > 2 * board_ * board_;                                                                        // go.cpp:254
     }
     if (game_type_ == MZ_GAME_NOGO) { return !nogoHasLegalMove(game); } // nogo.h:61-68
+    if (game_type_ == MZ_GAME_HEX) { // hex.cpp:96-99: a player connects its two edges (Black columns 0 / N-1, White rows 0 / N-1; hex.cpp:47-58,305-347)
+        const int N = board_;
+        for (int player = 1; player <= 2; ++player) {
+            std::vector<int> stack;
+            std::vector<uint8_t> seen(N * N, 0);
+            for (int i = 0; i < N; ++i) {
+                const int p = (player == 1 ? i * N : i);
+                if (game.stones[p] == player) { seen[p] = 1, stack.push_back(p); }
+            }
+            static const int dx[6] = {-1, 0, -1, 1, 0, 1}, dy[6] = {-1, -1, 0, 0, 1, 1};
+            while (!stack.empty()) {
+                const int p = stack.back(), x = p % N, y = p / N;
+                stack.pop_back();
+                if (player == 1 ? (x == N - 1) : (y == N - 1)) { return true; }
+                for (int k = 0; k < 6; ++k) {
+                    const int qx = x + dx[k], qy = y + dy[k];
+                    if (qx < 0 || qx >= N || qy < 0 || qy >= N) { continue; }
+                    const int q = qy * N + qx;
+                    if (game.stones[q] == player && !seen[q]) { seen[q] = 1, stack.push_back(q); }
+                }
+            }
+        }
+        return false;
+    }
     if (game_type_ == MZ_GAME_GOMOKU) { // gomoku.cpp:60-63,140-164: five in a row through the last move, or a full board
         if (n == 0) { return false; }
         const int pos = game.moves[n - 1].action, who = game.stones[pos], N = board_;
@@ -431,6 +458,14 @@ int Worker::advanceGame(int g, const RootView& r, bool& resign, bool& end)
         if (game_type_ == MZ_GAME_TICTACTOE && action >= 0 && action < 9) { game.ttt[action] = static_cast<uint8_t>(game.turn); }
         if ((game_type_ == MZ_GAME_NOGO || game_type_ == MZ_GAME_GOMOKU) && action >= 0 && action < board_ * board_) {
             game.stones[action] = static_cast<uint8_t>(game.turn);
+        }
+        if (game_type_ == MZ_GAME_HEX && action >= 0 && action < board_ * board_) { // hex.cpp:21-66 (game.moves already holds this move)
+            int id = action;
+            if (cfg_.getBool("env_hex_use_swap_rule") && game.moves.size() == 2 && action == game.moves[0].action) { // swap: mirrored, first stone removed
+                id = (board_ - 1 - action % board_) * board_ + (board_ - 1 - action / board_);
+                game.stones[action] = 0;
+            }
+            game.stones[id] = static_cast<uint8_t>(game.turn);
         }
         game.turn = 3 - game.turn;
         play = action;

@@ -73,6 +73,7 @@ private:
     }
     int initialNumLegal() const
     {
+        if (game_type_ == MZ_GAME_HEX) { return board_ * board_; }
         if (game_type_ == MZ_GAME_GOMOKU) { // every point, or the two outer lines under env_gomoku_rule=outer_open (gomoku.cpp:53-56)
             const int inner = (board_ > 4 ? board_ - 4 : 0);
             return cfg_.getString("env_gomoku_rule") == "outer_open" ? board_ * board_ - inner * inner : board_ * board_;

@@ -33,6 +33,7 @@ int main(int argc, char** argv)
     Environment env;
     const int A = env.getPolicySize();
     int F = 0;
+    int first_action = 0;
     for (int g = 0; g < num_games; ++g) {
         env.reset();
         for (int step = 0; step < max_moves && !env.isTerminal(); ++step) {
@@ -51,6 +52,9 @@ int main(int argc, char** argv)
             // mostly board moves: a uniformly random choice would pass far too early in Go
             int action = ids[rng() % ids.size()];
             if (ids.size() > 1 && action == A - 1 && (rng() % 8) != 0) { action = ids[rng() % (ids.size() - 1)]; }
+            // Hex swap rule: the second move may repeat the first one (every other game refuses that, and then no coin is drawn)
+            if (step == 1 && legal[first_action] && (rng() % 2) == 0) { action = first_action; }
+            if (step == 0) { first_action = action; }
             const int turn = static_cast<int>(env.getTurn());
             if (!env.act(Action(action, env.getTurn()))) {
                 std::cerr << "reference refused a move it reported legal" << std::endl;

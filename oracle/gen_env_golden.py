@@ -20,6 +20,8 @@ CASES = {
     "env_nogo9": ("nogo", "program_quiet=true", 7, 6, 200),
     "env_gomoku15": ("gomoku", "program_quiet=true", 8, 5, 230),
     "env_gomoku15_freestyle": ("gomoku", "env_gomoku_exactly_five_stones=false:env_gomoku_rule=outer_open:program_quiet=true", 9, 3, 230),
+    "env_hex11": ("hex", "program_quiet=true", 10, 10, 130),
+    "env_hex11_noswap": ("hex", "env_hex_use_swap_rule=false:program_quiet=true", 11, 4, 130),
     "env_othello8": ("othello", "program_quiet=true", 6, 8, 200),
 }
 

@@ -38,6 +38,8 @@ CASES = {
     "nogo9_s8_b2": ("nogo", "nogo9_az_1bx16", "actor_num_simulation=8:zero_num_parallel_games=2:" + COMMON % 41, 100),
     # Gomoku 15x15 (environment/gomoku): no pass, exactly five in a row through the last move wins
     "gomoku15_s8_b2": ("gomoku", "gomoku15_az_1bx16", "actor_num_simulation=8:zero_num_parallel_games=2:" + COMMON % 51, 80),
+    # Hex 11x11 (environment/hex): swap rule, connect the two own edges; features / policy are not rotated although a rotation is drawn
+    "hex11_s8_b2": ("hex", "hex11_az_1bx16", "actor_num_simulation=8:zero_num_parallel_games=2:" + COMMON % 61, 110),
     # Othello 8x8 MuZero: Gumbel (configs[2] settings: n=16, m=16), Gumbel with real halving (n=32, m=8), plain PUCT MuZero with Dirichlet noise
     "othello_gmz_s16_b2": ("othello", "othello_mz_1bx32", "actor_num_simulation=16:zero_num_parallel_games=2:" + GUMBEL % 16 + COMMON_MZ % 7, 130),
     "othello_gmz_s32_m8_b2": ("othello", "othello_mz_1bx32", "actor_num_simulation=32:zero_num_parallel_games=2:" + GUMBEL % 8 + COMMON_MZ % 8, 70),

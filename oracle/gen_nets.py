@@ -21,6 +21,7 @@ NETS = {
     "go19_az_1bx16": ("go_19x19", 18, 19, 19, 16, 19, 19, 1, 1, 362, 64, 1, "alphazero"),
     "nogo9_az_1bx16": ("nogo_9x9", 18, 9, 9, 16, 9, 9, 1, 1, 82, 64, 1, "alphazero"),
     "gomoku15_az_1bx16": ("gomoku_15x15", 4, 15, 15, 16, 15, 15, 1, 1, 225, 64, 1, "alphazero"),
+    "hex11_az_1bx16": ("hex_11x11", 4, 11, 11, 16, 11, 11, 1, 1, 121, 64, 1, "alphazero"),
     "go9_az_2bx64": ("go_9x9", 18, 9, 9, 64, 9, 9, 1, 2, 82, 256, 1, "alphazero"),
     "go9_az_6bx256": ("go_9x9", 18, 9, 9, 256, 9, 9, 1, 6, 82, 256, 1, "alphazero"),
     "go5_mz_1bx16": ("go_5x5", 18, 5, 5, 16, 5, 5, 1, 1, 26, 64, 1, "muzero"),

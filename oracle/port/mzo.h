@@ -23,6 +23,8 @@ extern "C" {
 #define MZO_GAME_OTHELLO 2
 #define MZO_GAME_NOGO 3
 #define MZO_GAME_GOMOKU 4
+#define MZO_GAME_HEX 5
+#define MZO_HEX_SWAP_RULE 4       /* env_hex_use_swap_rule (default true); shares the flags word with the Gomoku options */
 #define MZO_GOMOKU_EXACTLY_FIVE 1 /* env_gomoku_exactly_five_stones (default true) */
 #define MZO_GOMOKU_OUTER_OPEN 2   /* env_gomoku_rule == "outer_open" */
 

@@ -130,7 +130,7 @@ void mzo_env_set_flags(mzo_env* e, int flags) { e->flags = flags; }
 int mzo_env_num_actions(const mzo_env* e)
 {
     if (e->game == MZO_GAME_TICTACTOE) { return 9; }
-    return e->game == MZO_GAME_GOMOKU ? e->n * e->n : e->n * e->n + 1; /* gomoku.h:32: no pass */
+    return (e->game == MZO_GAME_GOMOKU || e->game == MZO_GAME_HEX) ? e->n * e->n : e->n * e->n + 1; /* gomoku.h:32, hex.h:56: no pass */
 }
 int mzo_env_input_channels(const mzo_env* e) { return (e->game == MZO_GAME_GO || e->game == MZO_GAME_NOGO) ? 18 : 4; }
 
@@ -486,6 +486,65 @@ static int gomoku_is_legal(const mzo_env* e, int action, int player)
     return e->board[action] == 0;
 }
 
+/* ---- hex (environment/hex/hex.cpp) ---- */
+/* The reference keeps per-cell edge-connection flags, merged through the six neighbours of every new stone (hex.cpp:305-347);
+ * a group's cells all carry the union of the edges the group touches, so "winner_" is: the group of the stone just placed
+ * touches both of its owner's edges — Black (player 1) the columns x = 0 and x = n-1, White the rows y = 0 and y = n-1
+ * (hex.cpp:47-58). Restated as a flood fill over the same neighbourhood. */
+static int hex_connected(const mzo_env* e, int player)
+{
+    int n = e->n, top = 0, stack[MZO_MAX_CELLS];
+    uint8_t seen[MZO_MAX_CELLS];
+    memset(seen, 0, (size_t)(n * n));
+    for (int i = 0; i < n; ++i) {
+        int p = (player == 1 ? i * n : i); /* edge 1: x == 0 for Black, y == 0 for White */
+        if (e->board[p] == player) {
+            seen[p] = 1;
+            stack[top++] = p;
+        }
+    }
+    static const int dx[6] = {-1, 0, -1, 1, 0, 1}, dy[6] = {-1, -1, 0, 0, 1, 1}; /* hex.cpp:313-316 */
+    while (top > 0) {
+        int p = stack[--top], x = p % n, y = p / n;
+        if (player == 1 ? (x == n - 1) : (y == n - 1)) { return 1; }
+        for (int k = 0; k < 6; ++k) {
+            int qx = x + dx[k], qy = y + dy[k];
+            if (qx < 0 || qx >= n || qy < 0 || qy >= n) { continue; }
+            int q = qy * n + qx;
+            if (e->board[q] == player && !seen[q]) {
+                seen[q] = 1;
+                stack[top++] = q;
+            }
+        }
+    }
+    return 0;
+}
+
+static int hex_winner(const mzo_env* e) { return hex_connected(e, 1) ? 1 : (hex_connected(e, 2) ? 2 : 0); }
+
+/* hex.cpp:83-94 */
+static int hex_is_legal(const mzo_env* e, int action, int player)
+{
+    if (action < 0 || action >= e->n * e->n) { return 0; }
+    return player == e->turn && (((e->flags & MZO_HEX_SWAP_RULE) && e->num_moves == 1) || e->board[action] == 0);
+}
+
+/* hex.cpp:21-66 */
+static int hex_act(mzo_env* e, int action, int player)
+{
+    if (!hex_is_legal(e, action, player)) { return 0; }
+    int n = e->n, id = action;
+    if ((e->flags & MZO_HEX_SWAP_RULE) && e->num_moves == 1 && action == e->actions[0]) { /* swap: the first stone changes sides, mirrored */
+        int row = e->actions[0] / n, col = e->actions[0] % n;
+        id = (n - 1 - col) * n + (n - 1 - row);
+        e->board[e->actions[0]] = 0;
+    }
+    e->board[id] = (uint8_t)player;
+    e->actions[e->num_moves++] = (int16_t)action;
+    e->turn = other(player);
+    return 1;
+}
+
 /* ---- tictactoe (tictactoe.cpp:124-146 eval) ---- */
 static int ttt_eval(const mzo_env* e)
 {
@@ -512,6 +571,7 @@ int mzo_env_is_legal(const mzo_env* e, int action, int player)
     if (e->game == MZO_GAME_GO) { return go_is_legal(e, action, player); }
     if (e->game == MZO_GAME_NOGO) { return nogo_is_legal(e, action, player); }
     if (e->game == MZO_GAME_GOMOKU) { return gomoku_is_legal(e, action, player); }
+    if (e->game == MZO_GAME_HEX) { return hex_is_legal(e, action, player); }
     if (e->game == MZO_GAME_OTHELLO) { return othello_is_legal(e, action, player); }
     return action >= 0 && action < 9 && e->board[action] == 0; /* tictactoe.cpp:44-49 */
 }
@@ -520,6 +580,7 @@ int mzo_env_act(mzo_env* e, int action, int player)
 {
     if (e->game == MZO_GAME_GO || e->game == MZO_GAME_NOGO) { return go_act(e, action, player); }
     if (e->game == MZO_GAME_OTHELLO) { return othello_act(e, action, player); }
+    if (e->game == MZO_GAME_HEX) { return hex_act(e, action, player); }
     if (e->game == MZO_GAME_GOMOKU) { /* gomoku.cpp:23-31 */
         if (!gomoku_is_legal(e, action, player)) { return 0; }
         e->actions[e->num_moves++] = (int16_t)action;
@@ -544,6 +605,7 @@ int mzo_env_is_terminal(const mzo_env* e)
         return 1;
     }
     if (e->game == MZO_GAME_OTHELLO) { return othello_is_terminal(e); }
+    if (e->game == MZO_GAME_HEX) { return hex_winner(e) != 0; } /* hex.cpp:96-99 */
     if (e->game == MZO_GAME_GOMOKU) { /* gomoku.cpp:60-63 */
         if (gomoku_winner(e) != 0) { return 1; }
         for (int i = 0; i < e->n * e->n; ++i) {
@@ -563,6 +625,10 @@ float mzo_env_eval_score(const mzo_env* e, int is_resign)
     if (e->game == MZO_GAME_GO) { return go_eval_score(e, is_resign); }
     if (e->game == MZO_GAME_NOGO) { return other(e->turn) == 1 ? 1.0f : -1.0f; } /* nogo.h:70-78: whoever is to move has lost */
     if (e->game == MZO_GAME_OTHELLO) { return othello_eval_score(e, is_resign); }
+    if (e->game == MZO_GAME_HEX) { /* hex.cpp:101-111 */
+        int w = (is_resign ? other(e->turn) : hex_winner(e));
+        return w == 1 ? 1.0f : (w == 2 ? -1.0f : 0.0f);
+    }
     if (e->game == MZO_GAME_GOMOKU) { /* gomoku.cpp:65-73 */
         int w = (is_resign ? other(e->turn) : gomoku_winner(e));
         return w == 1 ? 1.0f : (w == 2 ? -1.0f : 0.0f);
@@ -578,6 +644,7 @@ void mzo_env_features(const mzo_env* e, int rotation, float* out)
         return;
     }
     int rev = mzo_reversed_rotation(rotation); /* tictactoe.cpp:67-90, othello.cpp:237-255: same four planes */
+    if (e->game == MZO_GAME_HEX) { rev = 0; }  /* HexEnv::getFeatures ignores the rotation (hex.cpp:123-124) */
     const int cells = e->n * e->n;
     for (int c = 0; c < 4; ++c) {
         for (int pos = 0; pos < cells; ++pos) {

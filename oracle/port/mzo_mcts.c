@@ -398,7 +398,7 @@ void mzo_apply(mzo_batch* b, const float* policy, const float* logits, const flo
             float cand_p[MZO_MAX_ACTIONS], cand_l[MZO_MAX_ACTIONS];
             for (int a = 0; a < A; ++a) {
                 if (!mzo_env_is_legal(e, a, e->turn)) { continue; }
-                int ra = mzo_rotate_position(b->rotation[g], a, e->n); /* getRotateAction, zero_actor.cpp:222; the pass does not rotate (rotation.h:54) */
+                int ra = (e->game == MZO_GAME_HEX ? a : mzo_rotate_position(b->rotation[g], a, e->n)); /* getRotateAction, zero_actor.cpp:222 (identity for Hex, hex.h:65); the pass does not rotate (rotation.h:54) */
                 cand_a[k] = a, cand_p[k] = policy[(size_t)g * A + ra], cand_l[k] = logits[(size_t)g * A + ra];
                 ++k;
             }

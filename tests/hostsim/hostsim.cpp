@@ -41,8 +41,8 @@ sim* hs_create(int game, int N, int B, int S, float puct_base, float puct_init, 
     mz_dims& d = h->d;
     memset(&d, 0, sizeof(d));
     memset(&h->s, 0, sizeof(h->s));
-    d.game = game, d.N = N, d.A = (game == MZ_GAME_TICTACTOE ? 9 : (game == MZ_GAME_GOMOKU ? N * N : N * N + 1)), d.C = (MZ_GO_FAMILY(game) ? 18 : 4), d.S = S, d.B = B;
-    d.gomoku_exactly_five = 1, d.gomoku_outer_open = 0; // reference defaults (configuration.cpp:82-83)
+    d.game = game, d.N = N, d.A = (game == MZ_GAME_TICTACTOE ? 9 : ((game == MZ_GAME_GOMOKU || game == MZ_GAME_HEX) ? N * N : N * N + 1)), d.C = (MZ_GO_FAMILY(game) ? 18 : 4), d.S = S, d.B = B;
+    d.gomoku_exactly_five = 1, d.gomoku_outer_open = 0, d.hex_swap_rule = 1; // reference defaults (configuration.cpp:82-85)
     d.muzero = g_opt_i[0], d.gumbel = g_opt_i[1], d.gumbel_noise = g_opt_i[2], d.gumbel_m = g_opt_i[3];
     d.sigma_visit_c = g_opt_f[0], d.sigma_scale_c = g_opt_f[1];
     if (d.gumbel) { // gumbel_zero.cpp:99,109 in the reference's double arithmetic

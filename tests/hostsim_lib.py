@@ -47,7 +47,7 @@ class HostSimSearch:
                  gumbel_sigma_visit_c=50.0, gumbel_sigma_scale_c=1.0):
         self.lib = lib
         n = 3 if game == 0 else board_size
-        self.A = 9 if game == 0 else (n * n if game == 4 else n * n + 1)
+        self.A = 9 if game == 0 else (n * n if game in (4, 5) else n * n + 1)
         self.F = (18 if game in (1, 3) else 4) * n * n
         self.B, self.S = num_games, num_simulation
         lib.hs_set_options(muzero, use_gumbel, gumbel_noise, gumbel_sample_size, gumbel_sigma_visit_c, gumbel_sigma_scale_c)

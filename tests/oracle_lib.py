@@ -7,7 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MAX_ACTIONS = 19 * 19 + 1
-GAME_TICTACTOE, GAME_GO, GAME_OTHELLO, GAME_NOGO, GAME_GOMOKU = 0, 1, 2, 3, 4
+GAME_TICTACTOE, GAME_GO, GAME_OTHELLO, GAME_NOGO, GAME_GOMOKU, GAME_HEX = 0, 1, 2, 3, 4, 5
 
 
 class Config(C.Structure):
@@ -25,7 +25,7 @@ class RootOut(C.Structure):
 
 def default_config(game, board_size, num_games, num_simulation):
     # defaults of config/configuration.cpp:13-28,80
-    return Config(game, board_size, num_games, num_simulation, 19652.0, 1.25, 1.0, 7.5, 0, 0, 0.25, 0, 0, 0, 16, 50.0, 1.0, 1)
+    return Config(game, board_size, num_games, num_simulation, 19652.0, 1.25, 1.0, 7.5, 0, 0, 0.25, 0, 0, 0, 16, 50.0, 1.0, 1 | 4)  # exactly five, hex swap rule
 
 
 def conf_overrides(conf):
@@ -90,7 +90,7 @@ class OracleSearch:
             setattr(self.cfg, k, v)
         self.h = lib.mzo_create(C.byref(self.cfg))
         n = 3 if game == GAME_TICTACTOE else board_size
-        self.A = 9 if game == GAME_TICTACTOE else (n * n if game == GAME_GOMOKU else n * n + 1)
+        self.A = 9 if game == GAME_TICTACTOE else (n * n if game in (GAME_GOMOKU, GAME_HEX) else n * n + 1)
         self.F = (18 if game in (GAME_GO, GAME_NOGO) else 4) * n * n
         self.B, self.S = num_games, num_simulation
 

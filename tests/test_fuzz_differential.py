@@ -16,6 +16,7 @@ CASES = [
     ("nogo9_az", 3, 9, 82, 60, 2, 90, {}),
     ("othello_az", 2, 8, 65, 80, 2, 70, {}),
     ("gomoku15_az", 4, 15, 225, 40, 2, 120, {}),
+    ("hex11_az", 5, 11, 121, 40, 2, 130, {}),
     ("othello_muzero", 2, 8, 65, 64, 2, 40, dict(muzero=1)),
     ("othello_gumbel_muzero_m8", 2, 8, 65, 32, 2, 66, dict(muzero=1, use_gumbel=1, gumbel_noise=1, gumbel_sample_size=8)),
     ("othello_gumbel_muzero_m16_s200", 2, 8, 65, 200, 2, 20, dict(muzero=1, use_gumbel=1, gumbel_noise=1, gumbel_sample_size=16)),

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 ROOT = oracle_lib.ROOT
 NETS = os.path.join(ROOT, "oracle", "_ref", "nets")
-CASES = {"ttt_s50_b2": (0, 3), "ttt_s50_b1_det": (0, 3), "go5_s24_b2": (1, 5), "go9_s32_b2": (1, 9), "go19_s8_b2": (1, 19), "nogo9_s8_b2": (3, 9), "gomoku15_s8_b2": (4, 15),
+CASES = {"ttt_s50_b2": (0, 3), "ttt_s50_b1_det": (0, 3), "go5_s24_b2": (1, 5), "go9_s32_b2": (1, 9), "go19_s8_b2": (1, 19), "nogo9_s8_b2": (3, 9), "gomoku15_s8_b2": (4, 15), "hex11_s8_b2": (5, 11),
          "go5_mz_s16_b2": (1, 5), "ttt_gmz_s16_b2": (0, 3), "othello_gmz_s16_b2": (2, 8), "othello_gmz_s32_m8_b2": (2, 8), "othello_mz_s24_b2": (2, 8)}
 
 
@@ -398,14 +398,14 @@ def test_full_size_19x19_search_invariants():
 
 @pytest.mark.parametrize("name,game,n", [("env_ttt", 0, 3), ("env_go5", 1, 5), ("env_go9", 1, 9), ("env_go9_situational", 1, 9), ("env_go19", 1, 19),
                                          ("env_othello8", 2, 8), ("env_nogo9", 3, 9), ("env_gomoku15", 4, 15),
-                                         ("env_gomoku15_freestyle", 4, 15)])
+                                         ("env_gomoku15_freestyle", 4, 15), ("env_hex11", 5, 11), ("env_hex11_noswap", 5, 11)])
 def test_device_env_matches_reference_playouts(name, game, n):
     """the device rule / feature kernels against random playouts of the reference's own environments (captures, ko and superko,
     suicide, passes, Othello flips and forced passes): legal sets, rotated planes, terminal flags, final scores"""
     import env_replay
     case = env_replay.load(name)
     eng = engine(game, n, 1, 1, ko_situational="situational" in str(case["conf"]), gomoku_exactly_five="exactly_five_stones=false" not in str(case["conf"]),
-                 gomoku_outer_open="outer_open" in str(case["conf"]))
+                 gomoku_outer_open="outer_open" in str(case["conf"]), hex_swap_rule="hex_use_swap_rule=false" not in str(case["conf"]))
     assert env_replay.replay(eng, case, check_score=lambda e: float(e.last_play["eval_score"][0])) == case["game"].size
     eng.close()
 
@@ -414,9 +414,10 @@ def test_device_env_matches_reference_playouts(name, game, n):
     ("go5_az", 1, 5, 26, 200, 4, 30, {}),
     ("go9_az", 1, 9, 82, 120, 4, 16, {}),
     ("nogo9_az", 3, 9, 82, 40, 4, 80, {}),
+    ("hex11_az", 5, 11, 121, 24, 4, 125, {}),
     ("othello_gumbel_muzero_m8", 2, 8, 65, 32, 4, 66, dict(muzero=1, use_gumbel=1, gumbel_noise=1, gumbel_sample_size=8)),
     ("othello_muzero", 2, 8, 65, 64, 4, 20, dict(muzero=1)),
-], ids=["go5_az", "go9_az", "nogo9_az", "othello_gumbel_muzero_m8", "othello_muzero"])
+], ids=["go5_az", "go9_az", "nogo9_az", "hex11_az", "othello_gumbel_muzero_m8", "othello_muzero"])
 def test_device_and_oracle_agree_on_synthetic_searches(name, game, board, A, sims, games, moves, opts):
     """differential fuzzing through the per-phase hooks of the C ABI: random priors (with exact ties), values, noise and rotations"""
     import zlib

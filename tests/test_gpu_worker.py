@@ -48,6 +48,7 @@ def run_worker(conf, want_lines, timeout=240):
     ("go", "go5_mz_1bx16", "env_board_size=5:actor_num_simulation=16:zero_num_parallel_games=16:nn_type_name=muzero", "env_board_size=5"),
     ("nogo", "nogo9_az_1bx16", "actor_num_simulation=16:zero_num_parallel_games=16", ""),
     ("gomoku", "gomoku15_az_1bx16", "actor_num_simulation=8:zero_num_parallel_games=24", ""),
+    ("hex", "hex11_az_1bx16", "actor_num_simulation=8:zero_num_parallel_games=24", ""),
 ])
 def test_worker_speaks_the_wire_protocol_and_reference_accepts_its_records(game, net, conf, checker_conf):
     checker = os.path.join(ROOT, "oracle", "_ref", "ref_record_check_" + game)

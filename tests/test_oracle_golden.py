@@ -13,6 +13,7 @@ CASES = {
     "go19_s8_b2": (oracle_lib.GAME_GO, 19),
     "nogo9_s8_b2": (oracle_lib.GAME_NOGO, 9),
     "gomoku15_s8_b2": (oracle_lib.GAME_GOMOKU, 15),
+    "hex11_s8_b2": (oracle_lib.GAME_HEX, 11),
     "go5_mz_s16_b2": (oracle_lib.GAME_GO, 5),
     "ttt_gmz_s16_b2": (oracle_lib.GAME_TICTACTOE, 3),
     "othello_gmz_s16_b2": (oracle_lib.GAME_OTHELLO, 8),
@@ -90,7 +91,8 @@ def test_oracle_gumbel_policy_matches_reference_records(oracle):
 
 ENV_CASES = {"env_ttt": (oracle_lib.GAME_TICTACTOE, 3), "env_go5": (oracle_lib.GAME_GO, 5), "env_go9": (oracle_lib.GAME_GO, 9),
              "env_go9_situational": (oracle_lib.GAME_GO, 9), "env_go19": (oracle_lib.GAME_GO, 19), "env_othello8": (oracle_lib.GAME_OTHELLO, 8), "env_nogo9": (oracle_lib.GAME_NOGO, 9),
-             "env_gomoku15": (oracle_lib.GAME_GOMOKU, 15), "env_gomoku15_freestyle": (oracle_lib.GAME_GOMOKU, 15)}
+             "env_gomoku15": (oracle_lib.GAME_GOMOKU, 15), "env_gomoku15_freestyle": (oracle_lib.GAME_GOMOKU, 15),
+             "env_hex11": (oracle_lib.GAME_HEX, 11), "env_hex11_noswap": (oracle_lib.GAME_HEX, 11)}
 
 
 @pytest.mark.parametrize("name", list(ENV_CASES))
@@ -101,6 +103,7 @@ def test_oracle_env_matches_reference_playouts(oracle, name):
     game, n = ENV_CASES[name]
     case = env_replay.load(name)
     flags = (0 if "exactly_five_stones=false" in str(case["conf"]) else 1) | (2 if "outer_open" in str(case["conf"]) else 0)
+    flags |= (0 if "hex_use_swap_rule=false" in str(case["conf"]) else 4)
     eng = oracle_lib.OracleSearch(oracle, game, n, 1, 1, ko_situational=int("situational" in str(case["conf"])), gomoku_flags=flags)
     state = {"i": 0}
 

@@ -8,7 +8,7 @@ import hostsim_lib
 
 import oracle_lib
 
-CASES = {"ttt_s50_b2": (0, 3), "ttt_s50_b1_det": (0, 3), "go5_s24_b2": (1, 5), "go9_s32_b2": (1, 9), "go19_s8_b2": (1, 19), "nogo9_s8_b2": (3, 9), "gomoku15_s8_b2": (4, 15),
+CASES = {"ttt_s50_b2": (0, 3), "ttt_s50_b1_det": (0, 3), "go5_s24_b2": (1, 5), "go9_s32_b2": (1, 9), "go19_s8_b2": (1, 19), "nogo9_s8_b2": (3, 9), "gomoku15_s8_b2": (4, 15), "hex11_s8_b2": (5, 11),
          "go5_mz_s16_b2": (1, 5), "ttt_gmz_s16_b2": (0, 3), "othello_gmz_s16_b2": (2, 8), "othello_gmz_s32_m8_b2": (2, 8), "othello_mz_s24_b2": (2, 8)}
 
 
@@ -60,7 +60,7 @@ def test_candidate_sort_is_libstdcxx_std_sort():
         assert np.array_equal(a, order[:n]), (n, pol[:20])
 
 
-@pytest.mark.parametrize("name,game,n", [("env_ttt", 0, 3), ("env_go5", 1, 5), ("env_go9", 1, 9), ("env_go19", 1, 19), ("env_othello8", 2, 8), ("env_nogo9", 3, 9), ("env_gomoku15", 4, 15)])
+@pytest.mark.parametrize("name,game,n", [("env_ttt", 0, 3), ("env_go5", 1, 5), ("env_go9", 1, 9), ("env_go19", 1, 19), ("env_othello8", 2, 8), ("env_nogo9", 3, 9), ("env_gomoku15", 4, 15), ("env_hex11", 5, 11)])
 def test_search_core_env_matches_reference_playouts(name, game, n):
     import env_replay
     case = env_replay.load(name)
