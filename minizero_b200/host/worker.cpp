@@ -212,9 +212,22 @@ void Worker::handleCommands()
             if (command.find(" ") != std::string::npos && !loadModel(command.substr(command.find(" ") + 1))) { std::exit(0); }
         } else if (prefix == "update_config") {
             std::cerr << "[command] " << command << std::endl;
+            // settings the engines captured when they were created: the reference reads most of them on every use, here they need a restart
+            static const char* const fixed[] = {"actor_num_simulation", "zero_num_parallel_games", "actor_mcts_puct_base", "actor_mcts_puct_init",
+                                                "actor_mcts_reward_discount", "actor_dirichlet_noise_epsilon", "actor_use_gumbel", "actor_use_gumbel_noise",
+                                                "actor_gumbel_sample_size", "actor_gumbel_sigma_visit_c", "actor_gumbel_sigma_scale_c", "env_board_size",
+                                                "env_go_komi", "env_go_ko_rule", "env_gomoku_rule", "env_gomoku_exactly_five_stones", "env_hex_use_swap_rule"};
+            std::vector<std::string> before;
+            for (const char* k : fixed) { before.push_back(cfg_.getString(k)); }
             if (command.find(" ") == std::string::npos || !cfg_.loadFromString(command.substr(command.find(" ") + 1))) {
                 std::cerr << "Failed to load configuration string." << std::endl;
                 std::exit(0);
+            }
+            for (size_t i = 0; i < before.size(); ++i) {
+                if (cfg_.getString(fixed[i]) != before[i]) {
+                    std::cerr << "[warning] " << fixed[i] << " is fixed when the worker starts; the running engines keep " << before[i] << std::endl;
+                    cfg_.set(fixed[i], before[i]); // keep the host's view consistent with the engines
+                }
             }
         } else if (prefix == "start") {
             std::cerr << "[command] " << command << std::endl;
