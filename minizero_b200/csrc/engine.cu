@@ -694,8 +694,9 @@ int mz_create(const mz_config* cfg, mz_engine** out)
         const double lg = std::log2(static_cast<double>(d.gumbel_m));
         d.gumbel_budget0 = static_cast<int>(std::max(1.0, std::floor(cfg->num_simulation / (lg * d.gumbel_m))));
         for (int l = 0; l < MZ_GUMBEL_LEVELS; ++l) {
-            const int half = (d.gumbel_m >> l) / 2;
-            d.gumbel_next[l] = (half > 0 ? static_cast<int>(std::floor(cfg->num_simulation / (lg * half))) : 0);
+            // divisor evaluated in double like the reference: log2(m) * sample_size_ / 2 (an odd sample size divides by x.5, gumbel_zero.cpp:109)
+            const int size = (d.gumbel_m >> l);
+            d.gumbel_next[l] = (size > 0 ? static_cast<int>(std::floor(cfg->num_simulation / (lg * size / 2))) : 0);
         }
     }
     d.S = cfg->num_simulation, d.B = cfg->num_games;

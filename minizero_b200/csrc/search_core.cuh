@@ -209,7 +209,7 @@ struct mz_dims {
     int gumbel, gumbel_noise, gumbel_m;
     float sigma_visit_c, sigma_scale_c;
     int gumbel_budget0;                   // max(1, floor(S / (log2(m) * m))), gumbel_zero.cpp:99 (host-computed in double)
-    int gumbel_next[MZ_GUMBEL_LEVELS];    // floor(S / (log2(m) * ((m >> level) / 2))), gumbel_zero.cpp:109
+    int gumbel_next[MZ_GUMBEL_LEVELS];    // floor(S / (log2(m) * (m >> level) / 2)) in double, gumbel_zero.cpp:109
 };
 
 struct mz_state {

@@ -44,6 +44,15 @@ CASES = {
     "othello_gmz_s16_b2": ("othello", "othello_mz_1bx32", "actor_num_simulation=16:zero_num_parallel_games=2:" + GUMBEL % 16 + COMMON_MZ % 7, 130),
     "othello_gmz_s32_m8_b2": ("othello", "othello_mz_1bx32", "actor_num_simulation=32:zero_num_parallel_games=2:" + GUMBEL % 8 + COMMON_MZ % 8, 70),
     "othello_mz_s24_b2": ("othello", "othello_mz_1bx32", "actor_num_simulation=24:zero_num_parallel_games=2:" + COMMON_MZ % 9, 70),
+    # Gumbel sample sizes that are not powers of two: the halving divisor log2(m) * sample_size / 2 is evaluated in double
+    # (gumbel_zero.cpp:109), so 12 -> 6 -> 3 -> 1 divides by 1.5 * log2(m) at sample size 3
+    "go5_gmz_s64_m12_b2": ("go", "go5_mz_1bx16", "env_board_size=5:actor_num_simulation=64:zero_num_parallel_games=2:" + GUMBEL % 12 + COMMON_MZ % 71, 24),
+    # 14 -> 7 -> 3 -> 1: the budget computed at sample size 7 (divisor 3.5 * log2(m), not 3) decides how many visits the last three get
+    "go5_gmz_s100_m14_b2": ("go", "go5_mz_1bx16", "env_board_size=5:actor_num_simulation=100:zero_num_parallel_games=2:" + GUMBEL % 14 + COMMON_MZ % 72, 24),
+    # BASELINE search lengths: configs[1] (400 simulations, the 6b x 256 net) and configs[3] (19x19, 800 simulations): f32 visit counts,
+    # chains deeper than 48 levels, nodes with more than 6 visited children
+    "go9_s400_b2": ("go", "go9_az_6bx256", "env_board_size=9:actor_num_simulation=400:zero_num_parallel_games=2:" + COMMON % 81, 6),
+    "go19_s800_b2": ("go", "go19_az_1bx16", "env_board_size=19:actor_num_simulation=800:zero_num_parallel_games=2:" + COMMON % 82, 2),
 }
 
 

@@ -245,7 +245,7 @@ static void sequential_halving(const mzo_batch* b, tree* t)
         for (int i = 0; i < t->num_cand; ++i) {
             if (!(t->count[t->cand[i]] >= (float)t->budget)) { return; }
         }
-        int next_budget = (int)floor(S / (log2((double)m) * (t->sample_size / 2)));
+        int next_budget = (int)floor(S / (log2((double)m) * t->sample_size / 2)); /* (double * int) / 2: odd sample sizes are not truncated */
         if (next_budget > 0 && t->sample_size > 2) {
             t->sample_size /= 2;
             sort_candidates_by_score(b, t);

@@ -49,8 +49,8 @@ sim* hs_create(int game, int N, int B, int S, float puct_base, float puct_init, 
         const double lg = std::log2((double)d.gumbel_m);
         d.gumbel_budget0 = (int)std::max(1.0, std::floor(S / (lg * d.gumbel_m)));
         for (int l = 0; l < MZ_GUMBEL_LEVELS; ++l) {
-            const int half = (d.gumbel_m >> l) / 2;
-            d.gumbel_next[l] = (half > 0 ? (int)std::floor(S / (lg * half)) : 0);
+            const int size = (d.gumbel_m >> l);
+            d.gumbel_next[l] = (size > 0 ? (int)std::floor(S / (lg * size / 2)) : 0);
         }
     }
     d.NP = 1 + (S + 1) * d.A;

@@ -19,6 +19,10 @@ CASES = {
     "othello_gmz_s16_b2": (oracle_lib.GAME_OTHELLO, 8),
     "othello_gmz_s32_m8_b2": (oracle_lib.GAME_OTHELLO, 8),
     "othello_mz_s24_b2": (oracle_lib.GAME_OTHELLO, 8),
+    "go5_gmz_s64_m12_b2": (oracle_lib.GAME_GO, 5),
+    "go5_gmz_s100_m14_b2": (oracle_lib.GAME_GO, 5),
+    "go9_s400_b2": (oracle_lib.GAME_GO, 9),
+    "go19_s800_b2": (oracle_lib.GAME_GO, 19),
 }
 
 
