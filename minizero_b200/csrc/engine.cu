@@ -17,6 +17,15 @@ namespace {
 
 thread_local std::string g_error;
 
+// Experiment switches (tile shapes, stage counts, debug counters ...) exist only in a library built with -DMZ_EXPERIMENT
+// (MZ_BUILD_EXPERIMENT=1 python -c "import minizero_b200; minizero_b200.build_library(force=True)"); in the release build no
+// environment variable can change what the library computes or how a benchmark runs.
+#ifdef MZ_EXPERIMENT
+const char* knob(const char* name) { return std::getenv(name); }
+#else
+const char* knob(const char*) { return nullptr; }
+#endif
+
 int fail(int code, const std::string& msg)
 {
     g_error = msg;
@@ -186,6 +195,11 @@ struct Blob {
 
 } // namespace
 
+struct SearchGraph {
+    cudaGraphExec_t exec;
+    int64_t kernels; // kernel nodes of the graph, counted at capture
+};
+
 struct mz_engine {
     mz_config cfg{};
     mz_dims d{};
@@ -231,7 +245,7 @@ struct mz_engine {
     encode_tiled_fn encode = nullptr;
 
     // graphs keyed by (num_evals, noise, rotations)
-    std::map<int, cudaGraphExec_t> graphs;
+    std::map<int, SearchGraph> graphs;
 
     template <class T>
     int dalloc(T** p, size_t n)
@@ -370,7 +384,7 @@ int launch_heads(mz_engine* e, const __half* act, int* clear = nullptr, int clea
     p.batch = e->d.B, p.fc_in_smem = 0;
     const size_t smem = sizeof(float) * (np1 * p.c + np1 * hw + p.vh + p.actions + 32 + hw + 4 * (p.actions + p.vh));
     static const int threads_env = [] {
-        const char* env = std::getenv("MZ_HEADS_THREADS");
+        const char* env = knob("MZ_HEADS_THREADS");
         const int v = (env ? std::atoi(env) : 0);
         return (v == 256 || v == 512 || v == 1024) ? v : 0;
     }();
@@ -504,7 +518,7 @@ int plan_blob(mz_engine* e)
     // output-channel tile of the conv kernel: 128 keeps two CTAs resident per SM (epilogue of one overlaps the
     // main loop of the other) and gives 2x the tiles for wave balance; MZ_CONV_BN overrides for experiments
     e->bn_tile = (e->cpad % 128 == 0 ? 128 : 64);
-    if (const char* env = std::getenv("MZ_CONV_BN")) {
+    if (const char* env = knob("MZ_CONV_BN")) {
         const int v = std::atoi(env);
         if ((v == 64 || v == 128 || v == 256) && e->cpad % v == 0) { e->bn_tile = v; }
     }
@@ -547,14 +561,14 @@ int alloc_net(mz_engine* e)
     // where the shape allows); 2 = CTA pairs (cta_group::2) over resident input blocks, one launch per layer;
     // 1 = one CTA per tile with a resident input block; 0 = every tap re-loads its shifted A tile
     e->conv_mode = 3;
-    if (const char* env = std::getenv("MZ_CONV_MODE")) { e->conv_mode = std::atoi(env); }
-    if (const char* env = std::getenv("MZ_CONV_PDL")) { e->conv_pdl = std::atoi(env); }
+    if (const char* env = knob("MZ_CONV_MODE")) { e->conv_mode = std::atoi(env); }
+    if (const char* env = knob("MZ_CONV_PDL")) { e->conv_pdl = std::atoi(env); }
     const bool want_tower = (e->conv_mode == 3);
     if (want_tower) { e->conv_mode = 2; } // the tower needs everything the pair kernel needs
-    if (const char* env = std::getenv("MZ_CONV_BASEOFF")) { e->base_off_mode = std::atoi(env); }
-    if (const char* env = std::getenv("MZ_CONV_ROT")) { e->krot = std::atoi(env); }
+    if (const char* env = knob("MZ_CONV_BASEOFF")) { e->base_off_mode = std::atoi(env); }
+    if (const char* env = knob("MZ_CONV_ROT")) { e->krot = std::atoi(env); }
     e->conv_cluster = 1; // CTAs per cluster sharing every weight tile by TMA multicast (1, 2 or 4)
-    if (const char* env = std::getenv("MZ_CONV_CLUSTER")) {
+    if (const char* env = knob("MZ_CONV_CLUSTER")) {
         const int v = std::atoi(env);
         if (v == 1 || v == 2 || v == 4) { e->conv_cluster = v; }
     }
@@ -573,7 +587,7 @@ int alloc_net(mz_engine* e)
         }
         if (e->bn_tile == 128 && stages != 0) {
             e->conv_cluster = 2;
-            if (!std::getenv("MZ_TOWER_STAGES")) { e->tower_stages = stages; }
+            if (!knob("MZ_TOWER_STAGES")) { e->tower_stages = stages; }
         } else {
             e->conv_mode = 1;
         }
@@ -594,13 +608,13 @@ int alloc_net(mz_engine* e)
         e->d.hid_c = e->cpad, e->d.dyn_c = e->tw[1].cin0, e->d.act_col = e->nd.num_hidden_channels;
     }
     e->tw[0].in = e->s.nn_in, e->tw[1].in = e->s.dyn_in;
-    if (const char* env = std::getenv("MZ_PDL")) { e->tower_pdl = std::atoi(env); }
-    if (const char* env = std::getenv("MZ_TOWER_STAGES")) {
+    if (const char* env = knob("MZ_PDL")) { e->tower_pdl = std::atoi(env); }
+    if (const char* env = knob("MZ_TOWER_STAGES")) {
         const int v = std::atoi(env);
         if (v == 4 || v == 5 || v == 8) { e->tower_stages = v; }
     }
     e->tower_sms = e->num_sms; // SMs the persistent tower may occupy (MZ_TOWER_SMS: experiments with a second engine beside it)
-    if (const char* env = std::getenv("MZ_TOWER_SMS")) {
+    if (const char* env = knob("MZ_TOWER_SMS")) {
         const int v = std::atoi(env);
         if (v >= 2 && v <= e->num_sms) { e->tower_sms = v & ~1; }
     }
@@ -623,10 +637,10 @@ int alloc_net(mz_engine* e)
         T.num_mtiles = e->rows_alloc / mznn::BM;
         T.cin_max = e->cin_max;
         T.rotate = 22, T.shift = 0, T.zigzag = 0, T.strided = 1;
-        if (const char* env = std::getenv("MZ_TOWER_STRIDED")) { T.strided = std::atoi(env); }
-        if (const char* env = std::getenv("MZ_TOWER_ZIGZAG")) { T.zigzag = std::atoi(env); }
-        if (const char* env = std::getenv("MZ_TOWER_ROT")) { T.rotate = std::atoi(env); }
-        if (const char* env = std::getenv("MZ_TOWER_SHIFT")) { T.shift = std::atoi(env); }
+        if (const char* env = knob("MZ_TOWER_STRIDED")) { T.strided = std::atoi(env); }
+        if (const char* env = knob("MZ_TOWER_ZIGZAG")) { T.zigzag = std::atoi(env); }
+        if (const char* env = knob("MZ_TOWER_ROT")) { T.rotate = std::atoi(env); }
+        if (const char* env = knob("MZ_TOWER_SHIFT")) { T.shift = std::atoi(env); }
         auto set = [&](int li, const CUtensorMap& in, __half* out, const __half* residual) {
             mznn::TowerLayer& L = T.layer[li];
             L.map_in = in, L.map_w = NT.convs[li].map_w_mc, L.out = out, L.residual = residual;
@@ -644,7 +658,7 @@ int alloc_net(mz_engine* e)
         if ((rc = e->dalloc(&NT.d_done, static_cast<size_t>(T.num_layers) * num_groups))) { return rc; }
         T.done = NT.d_done;
         T.dbg = nullptr;
-        if (const char* env = std::getenv("MZ_DEBUG_TOWER")) {
+        if (const char* env = knob("MZ_DEBUG_TOWER")) {
             if (std::atoi(env) != 0) {
                 unsigned long long* buf = nullptr;
                 if ((rc = e->dalloc(&buf, static_cast<size_t>(e->num_sms) * 8))) { return rc; }
@@ -742,7 +756,7 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     guard(e->dalloc(&s.hot, np)), guard(e->dalloc(&s.action, np)), guard(e->dalloc(&s.logit, np)), guard(e->dalloc(&s.value, np));
     guard(e->dalloc(&s.root_noise, BA)), guard(e->dalloc(&s.cursor, B));
     guard(e->dalloc(&s.last_child, np));
-    if (!std::getenv("MZ_NO_VIS")) { guard(e->dalloc(&s.vis, np)); } // MZ_NO_VIS=1: selection always scans (A/B timing of the visited lists)
+    if (!knob("MZ_NO_VIS")) { guard(e->dalloc(&s.vis, np)); } // MZ_NO_VIS=1: selection always scans (A/B timing of the visited lists)
     guard(e->dalloc(&s.node_slot, np)), guard(e->dalloc(&s.slot_st, B * (d.S + 1) * 2 * N)), guard(e->dalloc(&s.slot_hash, B * (d.S + 1)));
     guard(e->dalloc(&s.slot_meta, B * (d.S + 1) * 4));
     guard(e->dalloc(&s.root_st, B * 2 * MZ_ROWS)), guard(e->dalloc(&s.root_hist, B * MZ_HIST * 2 * MZ_ROWS)), guard(e->dalloc(&s.root_hash, B));
@@ -761,7 +775,7 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     guard(e->dalloc(&e->d_root_info, B * 4)), guard(e->dalloc(&e->d_root_action, BA));
     for (int i = 0; i < 6; ++i) { guard(e->dalloc(&e->d_root_f[i], BA)); }
     guard(e->dalloc(&e->d_feat_f32, B * d.C * N * N));
-    if (const char* env = std::getenv("MZ_DEBUG_TREE")) {
+    if (const char* env = knob("MZ_DEBUG_TREE")) {
         if (std::atoi(env) != 0) { guard(e->dalloc(&s.dbg, B * 16)); }
     }
     if (rc) {
@@ -794,7 +808,7 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     // the attribute belongs to the function, not to the engine: only ever raise it (several engines may coexist)
     static size_t step_smem_max = 0;
     if (step_smem_bytes(d) > step_smem_max) { step_smem_max = step_smem_bytes(d); }
-    if (const char* env = std::getenv("MZ_CARVEOUT")) {
+    if (const char* env = knob("MZ_CARVEOUT")) {
         // same shared-memory carve-out as the tower kernel, so that tree-step / heads blocks of one engine can be co-resident
         // with the tower CTAs of another engine on the same SM (an SM runs one carve-out configuration at a time)
         if (std::atoi(env) != 0) {
@@ -824,7 +838,7 @@ void mz_destroy(mz_engine* e)
     if (!e) { return; }
     cudaSetDevice(e->cfg.device);
     if (e->stream) { cudaStreamSynchronize(e->stream); }
-    for (auto& kv : e->graphs) { cudaGraphExecDestroy(kv.second); }
+    for (auto& kv : e->graphs) { cudaGraphExecDestroy(kv.second.exec); }
     for (void* p : e->allocs) { cudaFree(p); }
     delete e->tw[0].params;
     delete e->tw[1].params;
@@ -882,7 +896,7 @@ int mz_net_finalize_empty(mz_engine* e)
     CUDA_OK(cudaSetDevice(e->cfg.device));
     int rc = alloc_net(e);
     if (rc) { return rc; }
-    for (auto& kv : e->graphs) { cudaGraphExecDestroy(kv.second); }
+    for (auto& kv : e->graphs) { cudaGraphExecDestroy(kv.second.exec); }
     e->graphs.clear();
     e->net_ready = true;
     return MZ_OK;
@@ -1277,31 +1291,37 @@ int mz_search_run(mz_engine* e, int32_t num_evals, float* device_ms)
         const int64_t launches_before = e->launches;
         CUDA_OK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
         int rc = MZ_OK;
-        // MZ_DEBUG_SKIP=tree|nn leaves one half of the cycle out of the captured graph: timing experiments only (results are wrong)
-        const char* skip = std::getenv("MZ_DEBUG_SKIP");
-        const bool skip_tree = (skip && std::string(skip) == "tree"), skip_nn = (skip && std::string(skip) == "nn");
         for (int c = 0; c < num_evals && !rc; ++c) {
-            if (!skip_tree) { step(e, (c > 0 ? STEP_AFTER : 0) | STEP_BEFORE, e->rot_enabled ? e->d_rot_all + static_cast<size_t>(c) * d.B : nullptr); }
-            if (!skip_nn) { rc = forward(e, (e->cfg.muzero && c > 0) ? 1 : 0, !skip_tree); } // MuZero: initial inference for the root, recurrent below
+            step(e, (c > 0 ? STEP_AFTER : 0) | STEP_BEFORE, e->rot_enabled ? e->d_rot_all + static_cast<size_t>(c) * d.B : nullptr);
+            rc = forward(e, (e->cfg.muzero && c > 0) ? 1 : 0, true); // MuZero: initial inference for the root, recurrent below
         }
-        if (!skip_tree) { step(e, STEP_AFTER, nullptr); }
+        step(e, STEP_AFTER, nullptr);
         cudaError_t cerr = cudaStreamEndCapture(e->stream, &graph);
+        const int64_t captured = e->launches - launches_before; // kernel launches recorded into the graph: every launch site counts itself
         e->launches = launches_before;
-        if (rc) { return rc; }
-        if (cerr != cudaSuccess) { return fail(MZ_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(cerr)); }
+        if (rc || cerr != cudaSuccess) {
+            if (graph) { cudaGraphDestroy(graph); }
+            return rc ? rc : fail(MZ_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(cerr));
+        }
+        size_t num_nodes = 0;
+        cudaGraphGetNodes(graph, nullptr, &num_nodes);
+        if (static_cast<int64_t>(num_nodes) != captured) { // the graph holds kernel nodes only; a mismatch means a launch site does not count itself
+            cudaGraphDestroy(graph);
+            return fail(MZ_ERR_STATE, "captured graph has " + std::to_string(num_nodes) + " nodes but " + std::to_string(captured) + " launches were counted");
+        }
         cudaGraphExec_t exec = nullptr;
         cerr = cudaGraphInstantiate(&exec, graph, 0);
         cudaGraphDestroy(graph);
         if (cerr != cudaSuccess) { return fail(MZ_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(cerr)); }
-        it = e->graphs.emplace(key, exec).first;
+        it = e->graphs.emplace(key, SearchGraph{exec, captured}).first;
     }
-    e->launches += 1 + static_cast<int64_t>(num_evals) * (2 + (e->cfg.muzero ? 1 : 0) + (e->conv_mode == 3 ? 1 : static_cast<int64_t>(e->tw[0].convs.size())));
+    e->launches += it->second.kernels;
     if (!device_ms) { // asynchronous: the caller brackets several calls with mz_timer_begin / mz_timer_end or mz_sync
-        CUDA_OK(cudaGraphLaunch(it->second, e->stream));
+        CUDA_OK(cudaGraphLaunch(it->second.exec, e->stream));
         return MZ_OK;
     }
     CUDA_OK(cudaEventRecord(e->ev0, e->stream));
-    CUDA_OK(cudaGraphLaunch(it->second, e->stream));
+    CUDA_OK(cudaGraphLaunch(it->second.exec, e->stream));
     CUDA_OK(cudaEventRecord(e->ev1, e->stream));
     CUDA_OK(cudaStreamSynchronize(e->stream));
     CUDA_OK(cudaGetLastError());

@@ -25,6 +25,7 @@ namespace mznn {
 
 constexpr int BM = 128;      // rows (board slots) per tile = UMMA M
 constexpr int BK = 64;       // K per pipeline stage: 64 fp16 = one 128-byte swizzle row
+constexpr float MZ_HALF_MAX = 65504.0f; // activations are stored as fp16: the epilogues saturate instead of producing inf
 constexpr int UMMA_K = 16;   // K per tcgen05.mma for 16-bit inputs
 constexpr int CONV_THREADS = 192; // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 
@@ -230,7 +231,7 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_
                     const float2 rf = __half22float2(rh[j]);
                     x0 += rf.x, x1 += rf.y;
                 }
-                if (p.relu) { x0 = fmaxf(x0, 0.0f), x1 = fmaxf(x1, 0.0f); }
+                x0 = fminf(fmaxf(x0, p.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX), x1 = fminf(fmaxf(x1, p.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX); // ReLU + saturation at the fp16 range
                 if (!live) { x0 = 0.0f, x1 = 0.0f; }
                 const __half2 h = __floats2half2_rn(x0, x1);
                 pk[j] = *reinterpret_cast<const uint32_t*>(&h);
@@ -536,7 +537,7 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
                         const float2 rf = __half22float2(rh[j]);
                         x0 += rf.x, x1 += rf.y;
                     }
-                    if (p.relu) { x0 = fmaxf(x0, 0.0f), x1 = fmaxf(x1, 0.0f); }
+                    x0 = fminf(fmaxf(x0, p.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX), x1 = fminf(fmaxf(x1, p.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX); // ReLU + saturation at the fp16 range
                     if (!live) { x0 = 0.0f, x1 = 0.0f; }
                     const __half2 h = __floats2half2_rn(x0, x1);
                     pk[j] = *reinterpret_cast<const uint32_t*>(&h);
@@ -795,7 +796,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
                         const float2 rf = __half22float2(rh[j]);
                         x0 += rf.x, x1 += rf.y;
                     }
-                    if (p.relu) { x0 = fmaxf(x0, 0.0f), x1 = fmaxf(x1, 0.0f); }
+                    x0 = fminf(fmaxf(x0, p.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX), x1 = fminf(fmaxf(x1, p.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX); // ReLU + saturation at the fp16 range
                     if (!live) { x0 = 0.0f, x1 = 0.0f; }
                     const __half2 h = __floats2half2_rn(x0, x1);
                     pk[j] = *reinterpret_cast<const uint32_t*>(&h);
@@ -1153,7 +1154,7 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                             const float2 rf = __half22float2(rh[j]);
                             x0 += rf.x, x1 += rf.y;
                         }
-                        if (L.relu) { x0 = fmaxf(x0, 0.0f), x1 = fmaxf(x1, 0.0f); }
+                        x0 = fminf(fmaxf(x0, L.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX), x1 = fminf(fmaxf(x1, L.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX); // ReLU + saturation at the fp16 range
                         if (!live) { x0 = 0.0f, x1 = 0.0f; }
                         const __half2 h = __floats2half2_rn(x0, x1);
                         pk[j] = *reinterpret_cast<const uint32_t*>(&h);

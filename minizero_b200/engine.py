@@ -57,7 +57,9 @@ def build_library(force=False, verbose=False):
     if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(s) for s in srcs):
         return out
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, os.path.join(src_dir, "engine.cu")]
+    # MZ_BUILD_EXPERIMENT=1: compile the experiment switches in (tile / stage sweeps, per-phase cycle counters); the release library reads no environment variable
+    exp = ["-DMZ_EXPERIMENT"] if os.environ.get("MZ_BUILD_EXPERIMENT") == "1" else []
+    cmd = ["nvcc"] + NVCC_FLAGS + exp + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, os.path.join(src_dir, "engine.cu")]
     subprocess.run(cmd, check=True)
     return out
 

@@ -24,6 +24,8 @@ NETS = {
     "hex11_az_1bx16": ("hex_11x11", 4, 11, 11, 16, 11, 11, 1, 1, 121, 64, 1, "alphazero"),
     "go9_az_2bx64": ("go_9x9", 18, 9, 9, 64, 9, 9, 1, 2, 82, 256, 1, "alphazero"),
     "go9_az_6bx256": ("go_9x9", 18, 9, 9, 256, 9, 9, 1, 6, 82, 256, 1, "alphazero"),
+    "go19_az_2bx128": ("go_19x19", 18, 19, 19, 128, 19, 19, 1, 2, 362, 64, 1, "alphazero"),     # smallest 19x19 net the fused tower takes
+    "go19_az_20bx256": ("go_19x19", 18, 19, 19, 256, 19, 19, 1, 20, 362, 256, 1, "alphazero"),  # BASELINE configs[3]
     "go5_mz_1bx16": ("go_5x5", 18, 5, 5, 16, 5, 5, 1, 1, 26, 64, 1, "muzero"),
     "ttt_mz_1bx16": ("tictactoe", 4, 3, 3, 16, 3, 3, 1, 1, 9, 32, 1, "muzero"),
     "othello_mz_1bx32": ("othello_8x8", 4, 8, 8, 32, 8, 8, 1, 1, 65, 64, 1, "muzero"),
