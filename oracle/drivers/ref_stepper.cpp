@@ -12,6 +12,7 @@
 #include "environment.h"
 #include "random.h"
 #include "zero_actor.h"
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
@@ -53,6 +54,7 @@ int main(int argc, char** argv)
 
     std::shared_ptr<Network> network = createNetwork(config::nn_file_name, -1);
     const bool is_az = (network->getNetworkTypeName() == "alphazero");
+    const bool is_atari = (network->getNetworkTypeName() == "muzero_atari"); // discrete value / reward heads, value rescale, rewards in the tree
     const int A = network->getActionSize();
     const int F = network->getNumInputChannels() * network->getInputChannelHeight() * network->getInputChannelWidth();
     const uint64_t tree_node_size = static_cast<uint64_t>(config::actor_num_simulation + 1) * A;
@@ -69,6 +71,7 @@ int main(int argc, char** argv)
 
     FILE* f_eval = fopen((out_dir + "/evals.bin").c_str(), "wb");
     FILE* f_move = fopen((out_dir + "/moves.bin").c_str(), "wb");
+    FILE* f_root = (is_atari ? fopen((out_dir + "/roots.bin").c_str(), "wb") : nullptr);
     FILE* f_meta = fopen((out_dir + "/meta.txt").c_str(), "w");
     fprintf(f_meta, "A %d\nF %d\nS %d\nB %d\ntype %s\n", A, F, config::actor_num_simulation, config::zero_num_parallel_games, network->getNetworkTypeName().c_str());
     fclose(f_meta);
@@ -100,6 +103,12 @@ int main(int argc, char** argv)
                     put_f32(f_move, root->getCount());
                     put_f32(f_move, root->getMean());
                     put_f32(f_move, root->getValue());
+                    if (is_atari) { // the value bounds the search ended with (mcts.h:106, used by the move choice and the resign test)
+                        const auto& vb = mcts->getTreeValueBound();
+                        put_i32(f_move, static_cast<int32_t>(vb.size()));
+                        put_f32(f_move, vb.empty() ? 0.f : vb.begin()->first);
+                        put_f32(f_move, vb.empty() ? 0.f : vb.rbegin()->first);
+                    }
                     for (int c = 0; c < A; ++c) {
                         const MCTSNode* ch = (c < root->getNumChildren() ? root->getChild(c) : nullptr);
                         put_i32(f_move, ch ? ch->getAction().getActionID() : -1);
@@ -109,9 +118,21 @@ int main(int argc, char** argv)
                         put_f32(f_move, ch ? ch->getPolicyLogit() : 0.f);
                         put_f32(f_move, ch ? ch->getPolicyNoise() : 0.f);
                         put_f32(f_move, ch ? ch->getValue() : 0.f);
+                        if (is_atari) { put_f32(f_move, ch ? ch->getReward() : 0.f); }
                     }
                     // SlaveThread::handleSearchDone (actor_group.cpp:116-134)
                     if (!resign) { actor->act(action); }
+                    if (is_atari) { // what the environment answered: reward of the move, terminal flag (the frame itself is in the next root's planes)
+                        put_f32(f_move, actor->getEnvironment().getReward());
+                        put_f32(f_move, actor->getEnvironment().getEvalScore());
+                        put_i32(f_move, actor->isEnvTerminal() ? 1 : 0);
+#if ATARI
+                        put_i32(f_move, actor->getEnvironment().getSeed());
+                        put_i32(f_move, actor->getEnvironment().getLives());
+#else
+                        put_i32(f_move, 0), put_i32(f_move, 0);
+#endif
+                    }
                     bool is_endgame = (resign || actor->isEnvTerminal());
                     if (is_endgame) {
                         shared.outputGame(actor);
@@ -157,8 +178,19 @@ int main(int argc, char** argv)
             int idx = actors[i]->getNNEvaluationBatchIndex();
             fwrite(cycle_hdr[i].data(), 4, cycle_hdr[i].size(), f_eval);
             std::vector<uint8_t> fb(F);
-            for (int k = 0; k < F; ++k) { fb[k] = (cycle_feats[i][k] != 0.0f); }
-            fwrite(fb.data(), 1, F, f_eval);
+            if (is_atari) {
+                // planes are bytes / 255 (RGB) or action id / 18 (atari.cpp:82,156): recorded as those integers, the test rebuilds the floats.
+                // Only root evaluations push planes (zero_actor.cpp:59-61); they go to roots.bin as (cycle, game, F bytes)
+                if (cycle_hdr[i][3] == 1) {
+                    const int hw = network->getInputChannelHeight() * network->getInputChannelWidth();
+                    for (int k = 0; k < F; ++k) { fb[k] = static_cast<uint8_t>(std::lround(cycle_feats[i][k] * (((k / hw) % 4 == 0) ? 18.0f : 255.0f))); }
+                    fwrite(cycle_hdr[i].data(), 4, 2, f_root);
+                    fwrite(fb.data(), 1, F, f_root);
+                }
+            } else {
+                for (int k = 0; k < F; ++k) { fb[k] = (cycle_feats[i][k] != 0.0f); }
+                fwrite(fb.data(), 1, F, f_eval);
+            }
             if (is_az) {
                 auto o = std::static_pointer_cast<AlphaZeroNetworkOutput>(outputs[idx]);
                 fwrite(o->policy_.data(), 4, A, f_eval);
@@ -169,10 +201,12 @@ int main(int argc, char** argv)
                 fwrite(o->policy_.data(), 4, A, f_eval);
                 fwrite(o->policy_logits_.data(), 4, A, f_eval);
                 put_f32(f_eval, o->value_);
+                if (is_atari) { put_f32(f_eval, o->reward_); } // after the expectation over the 601 bins and invertValue (muzero_network.h:157-171)
             }
         }
     }
     fclose(f_eval);
     fclose(f_move);
+    if (f_root) { fclose(f_root); }
     return 0;
 }

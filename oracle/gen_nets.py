@@ -30,6 +30,10 @@ NETS = {
     "ttt_mz_1bx16": ("tictactoe", 4, 3, 3, 16, 3, 3, 1, 1, 9, 32, 1, "muzero"),
     "othello_mz_1bx32": ("othello_8x8", 4, 8, 8, 32, 8, 8, 1, 1, 65, 64, 1, "muzero"),
     "othello_mz_3bx128": ("othello_8x8", 4, 8, 8, 128, 8, 8, 1, 3, 65, 256, 1, "muzero"),
+    # Atari MuZero (muzero_atari_network.py): 32 x 96 x 96 planes, 6 x 6 hidden state, 18 action planes, 601-bin value / reward heads.
+    # BASELINE configs[4] does not pin the size; the reference's defaults are 1 block x 256 channels (configuration.cpp:70-71)
+    "atari_mz_1bx32": ("atari_ms_pacman", 32, 96, 96, 32, 6, 6, 18, 1, 18, 32, 601, "muzero"),
+    "atari_mz_1bx256": ("atari_ms_pacman", 32, 96, 96, 256, 6, 6, 18, 1, 18, 256, 601, "muzero"),
 }
 
 

@@ -24,6 +24,9 @@ extern "C" {
 #define MZO_GAME_NOGO 3
 #define MZO_GAME_GOMOKU 4
 #define MZO_GAME_HEX 5
+#define MZO_GAME_ATARI 6 /* environment/atari: one player, 18 actions, host-side emulator; MuZero only (6 x 6 hidden state) */
+#define MZO_ATARI_RES 96
+#define MZO_ATARI_HIST 8
 #define MZO_HEX_SWAP_RULE 4       /* env_hex_use_swap_rule (default true); shares the flags word with the Gomoku options */
 #define MZO_GOMOKU_EXACTLY_FIVE 1 /* env_gomoku_exactly_five_stones (default true) */
 #define MZO_GOMOKU_OUTER_OPEN 2   /* env_gomoku_rule == "outer_open" */
@@ -53,6 +56,7 @@ typedef struct {
     float gumbel_sigma_visit_c; /* actor_gumbel_sigma_visit_c */
     float gumbel_sigma_scale_c; /* actor_gumbel_sigma_scale_c */
     int32_t gomoku_flags;       /* MZO_GOMOKU_* */
+    uint32_t atari_legal_mask;  /* Atari: ALE minimal action set of the game as a bit mask over the 18 actions (atari.h:57) */
 } mzo_config;
 
 /* ---- environment (environment/go/go.cpp, environment/tictactoe/tictactoe.cpp) ---- */
@@ -124,6 +128,16 @@ int mzo_gumbel_best_action(mzo_batch* b, int g);
 /* GumbelZero::getMCTSPolicy (gumbel_zero.cpp:9-59): fills action ids / probabilities of the entries the reference prints
  * (completed-Q softmax, entries below -38 dropped) in ascending action id; returns how many */
 int mzo_gumbel_policy(const mzo_batch* b, int g, int32_t* actions, float* probs);
+
+/* ---- Atari MuZero (BASELINE configs[4]) ----
+ * mzo_apply with the reward head's output (muzero_network.h:165-171; zero_actor.cpp:88); reward may be NULL (= 0) */
+void mzo_apply_mz(mzo_batch* b, const float* policy, const float* logits, const float* value, const float* reward, const float* noise);
+/* rewards of the root children and the value bounds (mcts.h:106): what the move choice / resign test read beside mzo_root */
+void mzo_root_extra(const mzo_batch* b, int g, float* c_reward, int32_t* bound_size, float* bound_lo, float* bound_hi);
+/* MCTSNode::getNormalizedMean of root child i (i < 0: the root itself) with the tree's value bounds (mcts.cpp:40-53) */
+float mzo_root_normalized_mean(const mzo_batch* b, int g, int i);
+/* AtariEnv: reset() (action < 0: the initial screen) or act() (atari.cpp:47-93): frame = resized screen, RGB bytes [3][96][96] */
+void mzo_atari_observe(mzo_batch* b, int g, int action, const uint8_t* frame_chw, int terminal);
 
 /* std::sort(candidates, policy descending) exactly as libstdc++ orders them, ties included (mzo_sort.c) */
 void mzo_std_sort_candidates(int n, int32_t* action, float* policy, float* logit);

@@ -115,7 +115,7 @@ void mzo_env_init(mzo_env* e, int game, int n, float komi, int ko_situational)
     go_init_keys();
     memset(e, 0, sizeof(*e));
     e->game = game;
-    e->n = (game == MZO_GAME_TICTACTOE ? 3 : n);
+    e->n = (game == MZO_GAME_TICTACTOE ? 3 : (game == MZO_GAME_ATARI ? 6 : n)); /* Atari: n = side of the hidden state (atari.h:25-26) */
     e->turn = 1; /* go.cpp:105, tictactoe.cpp:13 */
     e->komi = komi;
     e->turn_key = (ko_situational ? g_turn_key : 0); /* go.cpp:45-49 */
@@ -129,6 +129,7 @@ void mzo_env_init(mzo_env* e, int game, int n, float komi, int ko_situational)
 void mzo_env_set_flags(mzo_env* e, int flags) { e->flags = flags; }
 int mzo_env_num_actions(const mzo_env* e)
 {
+    if (e->game == MZO_GAME_ATARI) { return 18; } /* atari.h:20 */
     if (e->game == MZO_GAME_TICTACTOE) { return 9; }
     return (e->game == MZO_GAME_GOMOKU || e->game == MZO_GAME_HEX) ? e->n * e->n : e->n * e->n + 1; /* gomoku.h:32, hex.h:56: no pass */
 }

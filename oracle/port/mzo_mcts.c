@@ -42,7 +42,19 @@ typedef struct {
     /* GumbelZero state (gumbel_zero.h:20-23) */
     int32_t cand[MZO_MAX_ACTIONS];
     int32_t num_cand, sample_size, budget;
+    /* MCTS::tree_value_bound_ (mcts.h:117): std::map<float, int>, kept as arrays sorted by key */
+    float* vb_key;
+    int32_t* vb_cnt;
+    int32_t vb_n;
 } tree;
+
+/* Atari root environment (atari.cpp:47-93): the last 8 screens and the actions that led to them; the emulator is the host's */
+typedef struct {
+    uint8_t frame[MZO_ATARI_HIST][3 * MZO_ATARI_RES * MZO_ATARI_RES];
+    int8_t has_frame[MZO_ATARI_HIST]; /* 0: the all-zero planes the history starts with (atari.cpp:52-54) */
+    int32_t action[MZO_ATARI_HIST];   /* action id whose plane is id / 18; -1: all-zero plane (atari.cpp:57-58) */
+    int32_t terminal;
+} atari_env;
 
 struct mzo_batch {
     mzo_config cfg;
@@ -53,6 +65,7 @@ struct mzo_batch {
     int32_t* path;     /* [B][S+2] */
     int32_t* path_len; /* [B] */
     uint8_t* rotation; /* [B] */
+    atari_env* atari;  /* [B] when cfg.game == MZO_GAME_ATARI */
 };
 
 static int other(int p) { return p == 1 ? 2 : 1; }
@@ -68,6 +81,7 @@ static void node_reset(tree* t, int i)
 static void tree_reset(tree* t)
 {
     t->cursor = 1;
+    t->vb_n = 0; /* MCTS::reset clears tree_value_bound_, mcts.cpp:78-83 */
     node_reset(t, 0);
 }
 
@@ -80,6 +94,10 @@ mzo_batch* mzo_create(const mzo_config* cfg)
     mzo_env_set_flags(&tmp, cfg->gomoku_flags);
     b->A = mzo_env_num_actions(&tmp);
     b->F = mzo_env_input_channels(&tmp) * tmp.n * tmp.n;
+    if (cfg->game == MZO_GAME_ATARI) { /* atari.h:68-74: 8 x (action plane + RGB) at 96 x 96 */
+        b->F = MZO_ATARI_HIST * 4 * MZO_ATARI_RES * MZO_ATARI_RES;
+        b->atari = (atari_env*)calloc((size_t)cfg->num_games, sizeof(atari_env));
+    }
     b->NP = 1 + (cfg->num_simulation + 1) * b->A; /* actor_group.cpp:183, tree.h:66 */
     int B = cfg->num_games;
     b->root_env = (mzo_env*)calloc((size_t)B, sizeof(mzo_env));
@@ -103,6 +121,8 @@ mzo_batch* mzo_create(const mzo_config* cfg)
         t->value = (float*)malloc(n * 4);
         t->reward = (float*)malloc(n * 4);
         t->slot = (int16_t*)malloc(n * 2);
+        t->vb_key = (float*)malloc(sizeof(float) * (size_t)(2 * cfg->num_simulation + 8));
+        t->vb_cnt = (int32_t*)malloc(sizeof(int32_t) * (size_t)(2 * cfg->num_simulation + 8));
         mzo_reset_game(b, g);
     }
     return b;
@@ -115,7 +135,9 @@ void mzo_destroy(mzo_batch* b)
         tree* t = &b->trees[g];
         free(t->first_child), free(t->num_children), free(t->action), free(t->player);
         free(t->count), free(t->mean), free(t->policy), free(t->logit), free(t->noise), free(t->value), free(t->reward), free(t->slot);
+        free(t->vb_key), free(t->vb_cnt);
     }
+    free(b->atari);
     free(b->root_env), free(b->leaf_env), free(b->trees), free(b->path), free(b->path_len), free(b->rotation);
     free(b);
 }
@@ -126,7 +148,7 @@ void mzo_reset_search(mzo_batch* b, int g)
     tree* t = &b->trees[g];
     tree_reset(t);
     t->action[0] = -1;
-    t->player[0] = (uint8_t)other(b->root_env[g].turn); /* previous player of a 2-player game */
+    t->player[0] = (uint8_t)(b->cfg.game == MZO_GAME_ATARI ? 1 : other(b->root_env[g].turn)); /* env::getPreviousPlayer: the other player of a 2-player game, player 1 of a 1-player game */
     b->path_len[g] = 0;
 }
 
@@ -135,6 +157,10 @@ void mzo_reset_game(mzo_batch* b, int g)
 {
     mzo_env_init(&b->root_env[g], b->cfg.game, b->cfg.board_size, b->cfg.komi, b->cfg.ko_situational);
     mzo_env_set_flags(&b->root_env[g], b->cfg.gomoku_flags);
+    if (b->atari) {
+        memset(&b->atari[g], 0, sizeof(atari_env));
+        for (int i = 0; i < MZO_ATARI_HIST; ++i) { b->atari[g].action[i] = -1; }
+    }
     mzo_reset_search(b, g);
 }
 
@@ -142,11 +168,41 @@ void mzo_reset_game(mzo_batch* b, int g)
 static float normalized_mean(const mzo_batch* b, const tree* t, int i)
 {
     float value = t->reward[i] + b->cfg.reward_discount * t->mean[i];
-    /* actor_mcts_value_rescale is only used by Atari (mcts.cpp:43-49); not in this port's games */
+    if (b->cfg.value_rescale) { /* mcts.cpp:43-49 */
+        if (t->vb_n < 2) { return 1.0f; }
+        const float lower = t->vb_key[0], upper = t->vb_key[t->vb_n - 1];
+        value = (value - lower) / (upper - lower);
+        value = (float)fmin(1, fmax(-1, 2 * value - 1)); /* the double overloads of fmin / fmax, as compiled (SURVEY a-3) */
+    }
     if (t->player[i] == 2) { value = -value; } /* actor_mcts_value_flipping_player == 'W' */
     const float vloss = 0.0f;
     value = (value * t->count[i] - vloss) / (t->count[i] + vloss);
     return value;
+}
+
+/* MCTS::updateTreeValueBound, mcts.cpp:219-228: decrement (and erase at zero) the old key when present, then count the new one */
+static void update_value_bound(const mzo_batch* b, tree* t, float old_value, float new_value)
+{
+    if (!b->cfg.value_rescale) { return; }
+    int i = 0;
+    while (i < t->vb_n && t->vb_key[i] < old_value) { ++i; }
+    if (i < t->vb_n && !(old_value < t->vb_key[i])) { /* map::count(old_value): neither key orders before the other */
+        if (--t->vb_cnt[i] == 0) {
+            memmove(t->vb_key + i, t->vb_key + i + 1, sizeof(float) * (size_t)(t->vb_n - i - 1));
+            memmove(t->vb_cnt + i, t->vb_cnt + i + 1, sizeof(int32_t) * (size_t)(t->vb_n - i - 1));
+            --t->vb_n;
+        }
+    }
+    i = 0;
+    while (i < t->vb_n && t->vb_key[i] < new_value) { ++i; }
+    if (i < t->vb_n && !(new_value < t->vb_key[i])) {
+        ++t->vb_cnt[i];
+    } else {
+        memmove(t->vb_key + i + 1, t->vb_key + i, sizeof(float) * (size_t)(t->vb_n - i));
+        memmove(t->vb_cnt + i + 1, t->vb_cnt + i, sizeof(int32_t) * (size_t)(t->vb_n - i));
+        t->vb_key[i] = new_value, t->vb_cnt[i] = 1;
+        ++t->vb_n;
+    }
 }
 
 /* mcts.cpp:55-61 */
@@ -171,6 +227,7 @@ static float init_q(const mzo_batch* b, const tree* t, int node)
         sum_of_win += normalized_mean(b, t, c);
         sum += 1;
     }
+    if (b->cfg.game == MZO_GAME_ATARI) { return (sum > 0 ? sum_of_win / sum : 1.0f); } /* the #if ATARI branch, mcts.cpp:211-213 */
     return (sum_of_win - 1) / (sum + 1);
 }
 
@@ -302,6 +359,37 @@ int mzo_gumbel_policy(const mzo_batch* b, int g, int32_t* actions, float* probs)
     return n;
 }
 
+/* AtariEnv::getFeatures, atari.cpp:106-116: for each of the 8 history entries the action plane (id / 18) then R, G, B (byte / 255) */
+static void atari_features(const atari_env* e, float* out)
+{
+    const int hw = MZO_ATARI_RES * MZO_ATARI_RES;
+    for (int i = 0; i < MZO_ATARI_HIST; ++i) {
+        const float a = (e->action[i] < 0 ? 0.0f : e->action[i] * 1.0f / 18); /* atari.cpp:82 */
+        for (int k = 0; k < hw; ++k) { out[(size_t)(4 * i) * hw + k] = a; }
+        for (int k = 0; k < 3 * hw; ++k) {
+            float v = (float)e->frame[i][k];
+            out[(size_t)(4 * i + 1) * hw + k] = (e->has_frame[i] ? v / 255.0f : 0.0f); /* atari.cpp:152-156 */
+        }
+    }
+}
+
+void mzo_atari_observe(mzo_batch* b, int g, int action, const uint8_t* frame_chw, int terminal)
+{
+    atari_env* e = &b->atari[g];
+    if (action < 0) { /* AtariEnv::reset, atari.cpp:47-59: seven zero screens + the initial one, eight zero action planes */
+        memset(e, 0, sizeof(*e));
+        for (int i = 0; i < MZO_ATARI_HIST; ++i) { e->action[i] = -1; }
+    } else { /* AtariEnv::act, atari.cpp:82-85: the action plane joins the history together with the screen it produced */
+        memmove(e->action, e->action + 1, sizeof(int32_t) * (MZO_ATARI_HIST - 1));
+        e->action[MZO_ATARI_HIST - 1] = action;
+    }
+    memmove(e->frame[0], e->frame[1], sizeof(e->frame[0]) * (MZO_ATARI_HIST - 1));
+    memmove(e->has_frame, e->has_frame + 1, MZO_ATARI_HIST - 1);
+    memcpy(e->frame[MZO_ATARI_HIST - 1], frame_chw, sizeof(e->frame[0]));
+    e->has_frame[MZO_ATARI_HIST - 1] = 1;
+    e->terminal = terminal;
+}
+
 /* ZeroActor::beforeNNEvaluation, zero_actor.cpp:51-58 */
 void mzo_select(mzo_batch* b, const uint8_t* rotations, float* features)
 {
@@ -329,7 +417,9 @@ void mzo_select(mzo_batch* b, const uint8_t* rotations, float* features)
         if (b->cfg.muzero) { /* zero_actor.cpp:59-67: root features for the initial inference, nothing else touches the environment */
             b->rotation[g] = 0;
             if (features) {
-                if (len == 1) {
+                if (len == 1 && b->atari) {
+                    atari_features(&b->atari[g], features + (size_t)g * b->F);
+                } else if (len == 1) {
                     mzo_env_features(&b->root_env[g], 0, features + (size_t)g * b->F);
                 } else {
                     memset(features + (size_t)g * b->F, 0, sizeof(float) * (size_t)b->F);
@@ -353,8 +443,13 @@ static void node_add(tree* t, int i, float value)
     t->mean[i] += 1.0f * (value - t->mean[i]) / t->count[i];
 }
 
-/* ZeroActor::afterNNEvaluation, zero_actor.cpp:74-98 (AlphaZero branch) */
 void mzo_apply(mzo_batch* b, const float* policy, const float* logits, const float* value, const float* noise)
+{
+    mzo_apply_mz(b, policy, logits, value, NULL, noise);
+}
+
+/* ZeroActor::afterNNEvaluation, zero_actor.cpp:74-98 */
+void mzo_apply_mz(mzo_batch* b, const float* policy, const float* logits, const float* value, const float* reward, const float* noise)
 {
     int S2 = b->cfg.num_simulation + 2, A = b->A;
     for (int g = 0; g < b->cfg.num_games; ++g) {
@@ -368,12 +463,12 @@ void mzo_apply(mzo_batch* b, const float* policy, const float* logits, const flo
         if (b->cfg.muzero) {
             /* calculateMuZeroActionPolicy, zero_actor.cpp:231-245: every action below the root, the legal ones at the root */
             const mzo_env* re = &b->root_env[g];
-            const int turn = (t->player[leaf] == 1 ? 2 : 1); /* leaf_node->getAction().nextPlayer() */
+            const int turn = (b->cfg.game == MZO_GAME_ATARI ? 1 : (t->player[leaf] == 1 ? 2 : 1)); /* leaf_node->getAction().nextPlayer() */
             int32_t cand_a[MZO_MAX_ACTIONS];
             int k = 0;
             float cand_p[MZO_MAX_ACTIONS], cand_l[MZO_MAX_ACTIONS];
             for (int a = 0; a < A; ++a) {
-                if (leaf == 0 && !mzo_env_is_legal(re, a, turn)) { continue; }
+                if (leaf == 0 && !(b->cfg.game == MZO_GAME_ATARI ? (int)((b->cfg.atari_legal_mask >> a) & 1u) : mzo_env_is_legal(re, a, turn))) { continue; }
                 cand_a[k] = a, cand_p[k] = policy[(size_t)g * A + a], cand_l[k] = logits[(size_t)g * A + a];
                 ++k;
             }
@@ -419,13 +514,16 @@ void mzo_apply(mzo_batch* b, const float* policy, const float* logits, const flo
         } else {
             v = mzo_env_eval_score(e, 0);
         }
-        /* backup, mcts.cpp:166-179; env reward is 0 for these games (go.h:50, tictactoe.h:25) */
+        /* backup, mcts.cpp:166-179. AlphaZero: env reward, 0 for the board games (go.h:50, tictactoe.h:25); MuZero: the reward head's
+         * output, 0 unless the network is muzero_atari (muzero_network.h:25,165-171) */
         float updated = v;
         t->value[leaf] = v;
-        t->reward[leaf] = 0.0f;
+        t->reward[leaf] = (b->cfg.muzero && reward ? reward[g] : 0.0f);
         for (int i = len - 1; i >= 0; --i) {
             int n = path[i];
+            float old_mean = t->reward[n] + b->cfg.reward_discount * t->mean[n];
             node_add(t, n, updated);
+            update_value_bound(b, t, old_mean, t->reward[n] + b->cfg.reward_discount * t->mean[n]);
             updated = t->reward[n] + b->cfg.reward_discount * updated;
         }
         /* addNoiseToNodeChildren, zero_actor.cpp:194-204: only when the evaluated leaf is the root */
@@ -483,6 +581,20 @@ void mzo_root(const mzo_batch* b, int g, mzo_root_out* out)
     }
 }
 
+void mzo_root_extra(const mzo_batch* b, int g, float* c_reward, int32_t* bound_size, float* bound_lo, float* bound_hi)
+{
+    const tree* t = &b->trees[g];
+    for (int i = 0; i < t->num_children[0]; ++i) { c_reward[i] = t->reward[t->first_child[0] + i]; }
+    *bound_size = t->vb_n;
+    *bound_lo = (t->vb_n ? t->vb_key[0] : 0.0f), *bound_hi = (t->vb_n ? t->vb_key[t->vb_n - 1] : 0.0f);
+}
+
+float mzo_root_normalized_mean(const mzo_batch* b, int g, int i)
+{
+    const tree* t = &b->trees[g];
+    return normalized_mean(b, t, i < 0 ? 0 : t->first_child[0] + i);
+}
+
 /* mcts.cpp:91-104: first child with the strictly largest count */
 int mzo_select_by_max_count(const mzo_batch* b, int g)
 {
@@ -502,6 +614,12 @@ int mzo_select_by_max_count(const mzo_batch* b, int g)
 int mzo_play(mzo_batch* b, int g, int action)
 {
     mzo_env* e = &b->root_env[g];
+    if (b->cfg.game == MZO_GAME_ATARI) { /* the emulator is the host's (mzo_atari_observe): only legality and the move count live here */
+        if (action < 0 || action >= 18 || !((b->cfg.atari_legal_mask >> action) & 1u)) { return 0; }
+        ++e->num_moves;
+        mzo_reset_search(b, g);
+        return 1;
+    }
     int ok = mzo_env_act(e, action, e->turn);
     if (ok) { mzo_reset_search(b, g); }
     return ok;

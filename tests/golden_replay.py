@@ -85,3 +85,81 @@ def replay(engine, case, check_features=True, on_move=None):
                 if engine.root_terminal(g):
                     engine.reset_game(g)
     return checked_moves
+
+
+def atari_planes(codes):
+    """integer codes of a root record (RGB bytes, action ids; oracle/drivers/ref_stepper.cpp) -> the float planes of
+    AtariEnv::getFeatures (atari.cpp:82,152-156): byte / 255.0f and id * 1.0f / 18, both single-precision divisions"""
+    c = codes.reshape(32, 96 * 96).astype(np.float32)
+    out = c / np.float32(255.0)
+    out[0::4] = c[0::4] * np.float32(1.0) / np.float32(18)
+    return out.reshape(-1)
+
+
+def replay_atari(engine, case, check_features=True):
+    """Atari MuZero recordings: the emulator's frames come from the recorded root planes (the newest history entry of the next root
+    evaluation of the game), rewards from the recorded network outputs; checks planes, paths, root tables incl. the children's
+    rewards and the value bounds the search ended with"""
+    A, S, B = (int(case[k]) for k in "ASB")
+    n_cycles = case["eval_game"].size // B
+    roots_of_game = {g: [r for r in range(case["root_game"].size) if case["root_game"][r] == g] for g in range(B)}
+    root_ptr = {g: 0 for g in range(B)}
+    moves_of_game = {g: [m for m in range(case["move_game"].size) if case["move_game"][m] == g] for g in range(B)}
+    move_ptr = {g: 0 for g in range(B)}
+    use_noise = bool(np.any(case["child_noise"] != 0))
+
+    def newest(r):  # (action id of the newest history entry, its frame)
+        planes = case["root_planes"][r].reshape(32, 96 * 96)
+        return int(planes[28, 0]), planes[29:32]
+
+    for g in range(B):
+        engine.observe(g, -1, newest(roots_of_game[g][0])[1])
+    checked = 0
+    for c in range(n_cycles):
+        sl = slice(c * B, (c + 1) * B)
+        feats = engine.select(None)
+        for g in range(B):
+            assert engine.path_len(g) == case["eval_path_len"][sl][g], f"path length mismatch cycle {c} game {g}"
+            assert engine.leaf_action(g) == case["eval_leaf_action"][sl][g], f"leaf action mismatch cycle {c} game {g}"
+            assert engine.path_hash(g) == case["eval_path_hash"][sl][g], f"path mismatch cycle {c} game {g}"
+            if case["eval_path_len"][sl][g] == 1:
+                r = roots_of_game[g][root_ptr[g]]
+                assert case["root_cycle"][r] == c
+                if check_features and feats is not None:
+                    want = atari_planes(case["root_planes"][r])
+                    assert np.array_equal(feats[g].view(np.uint32), want.view(np.uint32)), f"plane mismatch at cycle {c} game {g}"
+        noise = np.zeros((B, A), np.float32) if use_noise else None
+        for g in range(B if use_noise else 0):
+            if engine.sims_done(g) == 0 and move_ptr[g] < len(moves_of_game[g]):
+                noise[g] = case["child_noise"][moves_of_game[g][move_ptr[g]]]
+        engine.apply(case["eval_policy"][sl], case["eval_logits"][sl], case["eval_value"][sl], noise, reward=case["eval_reward"][sl])
+        for g in range(B):
+            if engine.sims_done(g) != S + 1:
+                continue
+            if move_ptr[g] >= len(moves_of_game[g]):
+                return checked
+            m = moves_of_game[g][move_ptr[g]]
+            move_ptr[g] += 1
+            r = engine.root(g)
+            k = int(case["move_num_children"][m])
+            assert r["num_children"] == k
+            assert r["root_count"] == case["root_count"][m] and r["root_mean"] == case["root_mean"][m] and r["root_value"] == case["root_value"][m]
+            assert np.array_equal(r["action"][:k], case["child_action"][m, :k])
+            for name in ("count", "mean", "policy", "logit", "noise", "value", "reward"):
+                got, want = r[name][:k], case["child_" + name][m, :k]
+                assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"root child {name} mismatch at move {m}: {got} {want}"
+            assert r["bound_size"] == case["bound_size"][m], (m, r["bound_size"], case["bound_size"][m])
+            assert np.float32(r["bound_lo"]) == case["bound_lo"][m] and np.float32(r["bound_hi"]) == case["bound_hi"][m], f"value bounds mismatch at move {m}"
+            checked += 1
+            root_ptr[g] += 1
+            if root_ptr[g] >= len(roots_of_game[g]):
+                return checked  # the recording holds no later frame of this game
+            action, frame = newest(roots_of_game[g][root_ptr[g]])
+            if case["move_resign"][m] or case["env_terminal"][m]:
+                engine.reset_game(g)
+                engine.observe(g, -1, frame)
+            else:
+                assert engine.play(g, int(case["move_action"][m])) == 1
+                assert action == case["move_action"][m]
+                engine.observe(g, action, frame)
+    return checked

@@ -36,6 +36,17 @@ def test_oracle_matches_reference_recording(oracle, name):
     assert checked >= case["move_game"].size - int(case["B"])
 
 
+@pytest.mark.parametrize("name", ["atari_mz_s20_b2", "atari_mz_s50_b2_det", "atari_mz_s18_gumbel_b2"])
+def test_oracle_matches_reference_recording_atari(oracle, name):
+    """Atari MuZero (-DATARI reference over the synthetic frame source): rewards in the tree, the value-bound multiset and its
+    rescaling, the #if ATARI init-Q, one-player value sign, AtariEnv::getFeatures planes"""
+    case = golden_replay.load_case(name)
+    eng = oracle_lib.OracleSearch(oracle, oracle_lib.GAME_ATARI, 6, int(case["B"]), int(case["S"]), **oracle_lib.conf_overrides(case["conf"]))
+    checked = golden_replay.replay_atari(eng, case)
+    assert checked >= case["move_game"].size - int(case["B"])
+    assert int(case["bound_size"].max()) > 2 and float(np.abs(case["child_reward"]).max()) > 0  # the recording exercises what it is here for
+
+
 @pytest.mark.parametrize("name,net,dims", [
     ("ttt_s50_b2", "ttt_az_2bx32", (4, 3, 3, 32, 2, 9, 256)),
     ("go5_s24_b2", "go5_az_1bx16", (18, 5, 5, 16, 1, 26, 64)),
