@@ -180,6 +180,9 @@ static inline void mz_store_vis(mz_vis* p, const mz_vis& v) { *p = v; }
 #define MZ_GAME_NOGO 3       // environment/nogo/nogo.h: GoEnv with its own legality, terminal test and result
 #define MZ_GAME_GOMOKU 4     // environment/gomoku: N x N, no pass, five in a row through the last move
 #define MZ_GAME_HEX 5        // environment/hex: N x N, no pass, swap rule, connect the two own edges; never rotated
+#define MZ_GAME_ATARI 6      // environment/atari: one player, 18 actions, the emulator is the host's; MuZero only (hidden state 6 x 6)
+#define MZ_ATARI_RES 96      // kAtariResolution, atari.h:24
+#define MZ_ATARI_FRAME (3 * MZ_ATARI_RES * MZ_ATARI_RES)
 #define MZ_GO_FAMILY(game) ((game) == MZ_GAME_GO || (game) == MZ_GAME_NOGO)
 #define MZ_GUMBEL_LEVELS 12  // halvings of actor_gumbel_sample_size that can ever happen (m <= 362)
 #define MZ_MAXN 19
@@ -209,7 +212,15 @@ struct mz_dims {
     int gumbel, gumbel_noise, gumbel_m;
     float sigma_visit_c, sigma_scale_c;
     int gumbel_budget0;                   // max(1, floor(S / (log2(m) * m))), gumbel_zero.cpp:99 (host-computed in double)
-    int gumbel_next[MZ_GUMBEL_LEVELS];    // floor(S / (log2(m) * (m >> level) / 2)) in double, gumbel_zero.cpp:109
+    int gumbel_next[MZ_GUMBEL_LEVELS];
+    // Atari MuZero (BASELINE configs[4])
+    int num_players;    // 1 for Atari: the value is never flipped, every node is player 1's (atari.h:18, base_env.h getNextPlayer)
+    int value_rescale;  // actor_mcts_value_rescale: Q is min-max normalised with the tree's value bounds (mcts.cpp:43-49)
+    int atari_init_q;   // the `#if ATARI` branch of MCTS::calculateInitQValue (mcts.cpp:211-213)
+    int has_reward;     // the network has a reward head (muzero_atari): nodes carry rewards, backup discounts through them
+    int act_planes;     // action planes of the dynamics input: 1 (one-hot cell) or 18 (one-hot channel block, atari.cpp:124-130)
+    uint32_t legal_mask; // Atari: minimal action set of the game (the root's legal actions, atari.h:57)
+    int vb_cap;         // capacity of the value-bound table per game    // floor(S / (log2(m) * (m >> level) / 2)) in double, gumbel_zero.cpp:109
 };
 
 struct mz_state {
@@ -260,6 +271,22 @@ struct mz_state {
     // Gumbel: GumbelZero::candidates_ / sample_size_ / simulation_budget_ (gumbel_zero.h:20-23)
     int32_t* gum_cand;   // [B][A] node indices
     int32_t* gum_meta;   // [B][4] number of candidates, sample size, budget, halving level
+    // rewards and value bounds (null unless has_reward / value_rescale)
+    float* reward;       // [B][NP] MCTSNode::reward_
+    float* nn_reward;    // [B] reward head output of this cycle's evaluation (after expectation + invertValue)
+    float* vb_key;       // [B][vb_cap] MCTS::tree_value_bound_ (std::map<float, int>, mcts.h:117): distinct keys, unordered
+    int32_t* vb_cnt;     // [B][vb_cap] their multiplicities
+    int32_t* vb_n;       // [B] number of keys
+    // Atari root environment: the last 8 screens and the actions that led to them (atari.cpp:47-93); ring, oldest entry at at_head
+    uint8_t* at_frames;  // [B][8][3][96][96]
+    int32_t* at_meta;    // [B][16]: [0] head, [1..8] action id per ring slot (-1: zero plane), [9] bit mask of slots holding a screen
+};
+
+// value bounds of the tree being searched + the game's reward column: what MCTSNode::getNormalizedMean reads beside the node
+struct mz_qb {
+    const float* reward; // game-local rewards (null: all zero)
+    float lo, hi;
+    int n;               // number of distinct keys (< 2: Q is 1, mcts.cpp:44)
 };
 
 // per-warp scratch (shared memory on the device)
@@ -283,6 +310,7 @@ struct mz_scratch {
     int libcnt[MZ_MAXN * MZ_MAXN]; // liberties per block id
     uint32_t bloom[64];            // 2048-bit filter over the superko history
     int flag, shared_len, shared_count;
+    mz_qb qb;                      // value bounds during selection (uniform for the block)
 };
 
 MZ_DEV uint32_t mz_rowmask(int N) { return (N >= 32 ? 0xffffffffu : ((1u << N) - 1u)); }
@@ -869,13 +897,30 @@ MZ_DEV void mz_env_features(const mz_dims& d, const mz_state& s, int g, const mz
 // tree
 // ---------------------------------------------------------------------------------------------
 
-// MCTSNode::getNormalizedMean (mcts.cpp:40-53) for board games: reward 0, no value rescale, no virtual loss
-MZ_DEV float mz_normalized_mean(const mz_dims& d, float mean, float count, int player)
+// MCTSNode::getNormalizedMean (mcts.cpp:40-53), no virtual loss: reward + discount * mean, min-max rescaled by the tree's value
+// bounds when actor_mcts_value_rescale (Atari), negated for White's nodes
+MZ_DEV float mz_normalized_mean(const mz_dims& d, const mz_qb& qb, int node, float mean, float count, int player)
 {
-    float v = mz_fadd(0.0f, mz_fmul(d.discount, mean));
+    float v = mz_fadd(qb.reward ? qb.reward[node] : 0.0f, mz_fmul(d.discount, mean));
+    if (d.value_rescale) {
+        if (qb.n < 2) { return 1.0f; }
+        v = mz_fdiv(mz_fsub(v, qb.lo), mz_fsub(qb.hi, qb.lo));
+        v = mz_fsub(mz_fmul(2.0f, v), 1.0f);
+        v = (v < -1.0f ? -1.0f : v), v = (v > 1.0f ? 1.0f : v); // fmin(1, fmax(-1, x)) on a non-NaN x
+    }
     if (player == 2) { v = -v; } // actor_mcts_value_flipping_player == 'W'
     return mz_fdiv(mz_fsub(mz_fmul(v, count), 0.0f), mz_fadd(count, 0.0f));
 }
+
+// MCTS::calculateInitQValue (mcts.cpp:200-217) from the ordered sum over the visited children
+MZ_DEV float mz_init_q(const mz_dims& d, float sum_win, float sum_n)
+{
+    if (d.atari_init_q) { return sum_n > 0.0f ? mz_fdiv(sum_win, sum_n) : 1.0f; } // #if ATARI
+    return mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
+}
+
+// player of the CHILDREN of a node at depth `level` below a root where `root_turn` is to move (a one-player game has only player 1)
+MZ_DEV int mz_child_player(const mz_dims& d, int root_turn, int level) { return d.num_players == 1 ? 1 : ((level & 1) ? 3 - root_turn : root_turn); }
 
 // order-preserving map float -> uint32 (for REDUX arg-max); +0.0 and -0.0 are made equal first
 MZ_DEV uint32_t mz_sortable(float f)
@@ -894,7 +939,7 @@ MZ_DEV uint32_t mz_sortable(float f)
 // FIRST unvisited one (score is monotone in the prior; ties go to the higher prior, then to the lower index —
 // mcts.cpp:191): only the visited children and that one candidate are scored. The root's priors are mixed with noise
 // after sorting (zero_actor.cpp:194-204), so every root child is scored.
-MZ_DEV int mz_select_level(const mz_dims& d, const mz_state& s, const mz_hot* hot, const mz_hot& h, bool score_all, int child_player, float* q, int lane,
+MZ_DEV int mz_select_level(const mz_dims& d, const mz_state& s, const mz_qb& qb, const mz_hot* hot, const mz_hot& h, bool score_all, int child_player, float* q, int lane,
                            mz_hot& out)
 {
     const int nc = (int)(h.link >> MZ_LINK_SHIFT), fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
@@ -927,7 +972,7 @@ MZ_DEV int mz_select_level(const mz_dims& d, const mz_state& s, const mz_hot* ho
             if (i < nc) {
                 visited = (c.count != 0.0f);
                 if (visited) {
-                    const float qv = mz_normalized_mean(d, c.mean, c.count, child_player);
+                    const float qv = mz_normalized_mean(d, qb, fc + i, c.mean, c.count, child_player);
                     q[i] = qv;
                     const double num = mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n);
                     const float score = mz_fadd((float)mz_ddiv(num, (double)mz_fadd(1.0f, c.count)), qv);
@@ -956,7 +1001,7 @@ MZ_DEV int mz_select_level(const mz_dims& d, const mz_state& s, const mz_hot* ho
             }
         }
     }
-    const float init_q = mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
+    const float init_q = mz_init_q(d, sum_win, sum_n);
     if (score_all) { // root: the unvisited children's priors are not sorted (noise), score every one of them
         for (int i = lane; i < nc; i += MZ_W) {
             const mz_hot c = mz_load_hot(hot + fc + i); // L1
@@ -1000,7 +1045,7 @@ MZ_DEV int mz_select_level(const mz_dims& d, const mz_state& s, const mz_hot* ho
 // The same choice made by ONE thread scanning the children in order, exactly like the loops of mcts.cpp:181-217
 // (ordered f32 sum for init-Q, first-best arg-max), with the unvisited children below the root reduced to the first
 // one as explained above. Used by the level-parallel re-evaluation of deep paths: one thread per level.
-MZ_DEV int mz_select_level_serial(const mz_dims& d, const mz_state& s, const mz_hot* hot, const mz_hot& h, int child_player)
+MZ_DEV int mz_select_level_serial(const mz_dims& d, const mz_state& s, const mz_qb& qb, const mz_hot* hot, const mz_hot& h, int child_player)
 {
     const int nc = (int)(h.link >> MZ_LINK_SHIFT), fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
     const int total = (int)mz_fsub(h.count, 1.0f);
@@ -1012,7 +1057,7 @@ MZ_DEV int mz_select_level_serial(const mz_dims& d, const mz_state& s, const mz_
     for (int i = 0; i < nc; ++i) {
         const mz_hot c = mz_load_hot(hot + fc + i);
         if (c.count != 0.0f) {
-            const float qv = mz_normalized_mean(d, c.mean, c.count, child_player);
+            const float qv = mz_normalized_mean(d, qb, fc + i, c.mean, c.count, child_player);
             sum_win = mz_fadd(sum_win, qv);
             sum_n = mz_fadd(sum_n, 1.0f);
             const double num = mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n);
@@ -1024,7 +1069,7 @@ MZ_DEV int mz_select_level_serial(const mz_dims& d, const mz_state& s, const mz_
         }
     }
     if (first_unvisited < nc) {
-        const float init_q = mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
+        const float init_q = mz_init_q(d, sum_win, sum_n);
         const float score = mz_fadd((float)mz_dmul((double)mz_fmul(bias, p_fu), sqrt_n), init_q);
         if (best_i < 0 || score > best_s || (score == best_s && (p_fu > best_p || (p_fu == best_p && first_unvisited < best_i)))) { best_i = first_unvisited; }
     }
@@ -1035,7 +1080,7 @@ MZ_DEV int mz_select_level_serial(const mz_dims& d, const mz_state& s, const mz_
 // mz_select_level for a node below the root whose visited children are listed in `v` (v.n <= MZ_VIS_MAX): the same choice
 // from the same arithmetic in the same child order — the listed children and the first unvisited one are the only candidates
 // (see mz_select_level) — but one gather of <= 7 records instead of a scan of all children. Warp collective.
-MZ_DEV int mz_select_level_vis(const mz_dims& d, const mz_state& s, const mz_hot* hot, const mz_hot& h, const mz_vis& v, int child_player, int lane)
+MZ_DEV int mz_select_level_vis(const mz_dims& d, const mz_state& s, const mz_qb& qb, const mz_hot* hot, const mz_hot& h, const mz_vis& v, int child_player, int lane)
 {
     const int nc = (int)(h.link >> MZ_LINK_SHIFT), fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
     const int total = (int)mz_fsub(h.count, 1.0f); // mcts.cpp:185
@@ -1048,7 +1093,7 @@ MZ_DEV int mz_select_level_vis(const mz_dims& d, const mz_state& s, const mz_hot
     if (my >= 0) { c = mz_load_hot(hot + fc + my); }
     float qv = 0.0f, score = 0.0f;
     if (lane < n) {
-        qv = mz_normalized_mean(d, c.mean, c.count, child_player);
+        qv = mz_normalized_mean(d, qb, fc + my, c.mean, c.count, child_player);
         const double num = mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n);
         score = mz_fadd((float)mz_ddiv(num, (double)mz_fadd(1.0f, c.count)), qv);
     }
@@ -1058,7 +1103,7 @@ MZ_DEV int mz_select_level_vis(const mz_dims& d, const mz_state& s, const mz_hot
         sum_n = mz_fadd(sum_n, 1.0f);
     }
     if (lane == n && my >= 0) {
-        const float init_q = mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
+        const float init_q = mz_init_q(d, sum_win, sum_n);
         score = mz_fadd((float)mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n), init_q);
     }
     const uint32_t ks = (my >= 0 ? mz_sortable(score) : 0u);
@@ -1074,7 +1119,7 @@ MZ_DEV int mz_select_level_vis(const mz_dims& d, const mz_state& s, const mz_hot
     for (int k = 0; k < n; ++k) {
         const int i = v.idx[k];
         const mz_hot c = mz_load_hot(hot + fc + i);
-        const float qv = mz_normalized_mean(d, c.mean, c.count, child_player);
+        const float qv = mz_normalized_mean(d, qb, fc + i, c.mean, c.count, child_player);
         sum_win = mz_fadd(sum_win, qv);
         sum_n = mz_fadd(sum_n, 1.0f);
         const double num = mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n);
@@ -1083,7 +1128,7 @@ MZ_DEV int mz_select_level_vis(const mz_dims& d, const mz_state& s, const mz_hot
     }
     if (v.fu < nc) {
         const mz_hot c = mz_load_hot(hot + fc + v.fu);
-        const float init_q = mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
+        const float init_q = mz_init_q(d, sum_win, sum_n);
         const float score = mz_fadd((float)mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n), init_q);
         if (best_i < 0 || score > best_s || (score == best_s && (c.policy > best_p || (c.policy == best_p && (int)v.fu < best_i)))) { best_i = v.fu; }
     }
@@ -1092,7 +1137,7 @@ MZ_DEV int mz_select_level_vis(const mz_dims& d, const mz_state& s, const mz_hot
 }
 
 // the same by ONE thread (level-parallel re-evaluation of deep paths): all records are requested before the first is used
-MZ_DEV int mz_select_level_vis_serial(const mz_dims& d, const mz_state& s, const mz_hot* hot, const mz_hot& h, const mz_vis& v, int child_player)
+MZ_DEV int mz_select_level_vis_serial(const mz_dims& d, const mz_state& s, const mz_qb& qb, const mz_hot* hot, const mz_hot& h, const mz_vis& v, int child_player)
 {
     const int nc = (int)(h.link >> MZ_LINK_SHIFT), fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
     const int total = (int)mz_fsub(h.count, 1.0f);
@@ -1112,7 +1157,7 @@ MZ_DEV int mz_select_level_vis_serial(const mz_dims& d, const mz_state& s, const
 #pragma unroll
     for (int k = 0; k < MZ_VIS_MAX; ++k) {
         if (k < n) {
-            const float qv = mz_normalized_mean(d, c[k].mean, c[k].count, child_player);
+            const float qv = mz_normalized_mean(d, qb, fc + v.idx[k], c[k].mean, c[k].count, child_player);
             sum_win = mz_fadd(sum_win, qv);
             sum_n = mz_fadd(sum_n, 1.0f);
             const double num = mz_dmul((double)mz_fmul(bias, c[k].policy), sqrt_n);
@@ -1122,7 +1167,7 @@ MZ_DEV int mz_select_level_vis_serial(const mz_dims& d, const mz_state& s, const
     }
     if (v.fu < nc) {
         const float p_fu = c[MZ_VIS_MAX].policy;
-        const float init_q = mz_fdiv(mz_fsub(sum_win, 1.0f), mz_fadd(sum_n, 1.0f));
+        const float init_q = mz_init_q(d, sum_win, sum_n);
         const float score = mz_fadd((float)mz_dmul((double)mz_fmul(bias, p_fu), sqrt_n), init_q);
         if (best_i < 0 || score > best_s || (score == best_s && (p_fu > best_p || (p_fu == best_p && (int)v.fu < best_i)))) { best_i = v.fu; }
     }
@@ -1153,6 +1198,74 @@ MZ_DEV void mz_vis_insert(const mz_state& s, size_t base, int parent, int child_
     mz_store_vis(s.vis + base + parent, v);
 }
 
+// ---- MCTS::tree_value_bound_ (mcts.h:117, mcts.cpp:219-228): a std::map<float, int> used as a multiset of the Q values of the
+// evaluated nodes. Kept per game as unordered (key, multiplicity) arrays; the map's only observable properties are its size,
+// its smallest / largest key and whether a key is present. Keys compare with == (what !(a < b) && !(b < a) is for non-NaN floats).
+
+// smallest / largest key and the number of keys of game g -> qb (warp collective; every lane returns the same)
+MZ_DEV mz_qb mz_vb_bounds(const mz_dims& d, const mz_state& s, int g, int lane)
+{
+    mz_qb qb;
+    qb.reward = (s.reward ? s.reward + (size_t)g * d.NP : nullptr);
+    qb.lo = 0.0f, qb.hi = 0.0f, qb.n = 0;
+    if (!d.value_rescale) { return qb; }
+    const float* key = s.vb_key + (size_t)g * d.vb_cap;
+    const int n = s.vb_n[g];
+    float lo = 3.402823466e+38f, hi = -3.402823466e+38f;
+    for (int i = lane; i < n; i += MZ_W) {
+        const float k = key[i];
+        lo = (k < lo ? k : lo), hi = (k > hi ? k : hi);
+    }
+#if MZ_W > 1
+    for (int o = 16; o > 0; o >>= 1) {
+        const float l2 = __shfl_xor_sync(MZ_FULL, lo, o), h2 = __shfl_xor_sync(MZ_FULL, hi, o);
+        lo = (l2 < lo ? l2 : lo), hi = (h2 > hi ? h2 : hi);
+    }
+#endif
+    qb.lo = lo, qb.hi = hi, qb.n = n;
+    return qb;
+}
+
+// index of `x` among the n keys, or -1 (warp collective)
+MZ_DEV int mz_vb_find(const float* key, int n, float x, int lane)
+{
+    for (int base = 0; base < n; base += MZ_W) {
+        const int i = base + lane;
+        const unsigned m = mz_ballot(i < n && key[i] == x);
+        if (m) { return base + mz_ffs0(m); }
+    }
+    return -1;
+}
+
+// MCTS::updateTreeValueBound (mcts.cpp:219-228): one less of the old value when it is present (erased at zero), one more of the new
+MZ_DEV void mz_vb_update(const mz_dims& d, const mz_state& s, int g, float old_value, float new_value, int lane)
+{
+    float* key = s.vb_key + (size_t)g * d.vb_cap;
+    int32_t* cnt = s.vb_cnt + (size_t)g * d.vb_cap;
+    int n = s.vb_n[g];
+    int pos = mz_vb_find(key, n, old_value, lane);
+    if (pos >= 0) {
+        const int left = cnt[pos] - 1;
+        mz_sync();
+        if (left == 0) {
+            if (lane == 0) { key[pos] = key[n - 1], cnt[pos] = cnt[n - 1]; }
+            --n;
+        } else if (lane == 0) {
+            cnt[pos] = left;
+        }
+        mz_sync();
+    }
+    pos = mz_vb_find(key, n, new_value, lane);
+    if (pos >= 0) {
+        if (lane == 0) { cnt[pos] += 1; }
+    } else if (n < d.vb_cap) { // cannot overflow: every evaluated node holds at most one key (S + 1 nodes)
+        if (lane == 0) { key[n] = new_value, cnt[n] = 1; }
+        ++n;
+    }
+    if (lane == 0) { s.vb_n[g] = n; }
+    mz_sync();
+}
+
 // MCTS::select (mcts.cpp:139-148): returns the path length (valid in warp 0); path[] holds node indices from the root.
 //
 // Every level's choice depends only on that level's node, so a GUESSED path can be checked level-parallel: the block
@@ -1169,6 +1282,10 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
     int32_t* last_child = s.last_child + (size_t)g * d.NP;
     float* q = w->q_warp + (size_t)wid * d.A;
     const int tid = wid * MZ_W + lane;
+    if (wid == 0) { // value bounds are fixed during a selection: read once (uniform for the block after the first sync below)
+        const mz_qb qb = mz_vb_bounds(d, s, g, lane);
+        if (lane == 0) { w->qb = qb; }
+    }
     int glen = s.spec_len[g]; // length of the guessed path (uniform across the block)
     if (glen == 0) {
         if (tid == 0) { path[0] = 0; }
@@ -1212,7 +1329,7 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
                 if (start == 0 && wid == root_warp) {
                     const mz_hot h = w->lvl_h[0];
                     mz_hot c;
-                    const int chosen = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u)) + mz_select_level(d, s, hot, h, true, root_turn, q, lane, c);
+                    const int chosen = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u)) + mz_select_level(d, s, w->qb, hot, h, true, mz_child_player(d, root_turn, 0), q, lane, c);
                     if (lane == 0) {
                         w->sel[0] = chosen;
                         last_child[path[0]] = chosen;
@@ -1222,9 +1339,9 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
                 if (wid != root_warp) {
                     for (int j = (start == 0 ? 1 : start) + tid; j < glen - 1; j += (nw - 1) * MZ_W) {
                         const int node = path[j];
-                        const int cp = (j & 1) ? 3 - root_turn : root_turn;
-                        const int chosen = (s.vis && w->lvl_v[j].n <= MZ_VIS_MAX ? mz_select_level_vis_serial(d, s, hot, w->lvl_h[j], w->lvl_v[j], cp)
-                                                                                  : mz_select_level_serial(d, s, hot, w->lvl_h[j], cp));
+                        const int cp = mz_child_player(d, root_turn, j);
+                        const int chosen = (s.vis && w->lvl_v[j].n <= MZ_VIS_MAX ? mz_select_level_vis_serial(d, s, w->qb, hot, w->lvl_h[j], w->lvl_v[j], cp)
+                                                                                  : mz_select_level_serial(d, s, w->qb, hot, w->lvl_h[j], cp));
                         w->sel[j] = chosen;
                         last_child[node] = chosen;
                         if (chosen != path[j + 1]) { mz_atomic_min(&w->mismatch, j); }
@@ -1235,10 +1352,10 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
                     const int node = path[j];
                     const mz_hot h = w->lvl_h[j];
                     mz_hot c;
-                    const int cp = (j & 1) ? 3 - root_turn : root_turn;
+                    const int cp = mz_child_player(d, root_turn, j);
                     const int chosen = (s.vis && j > 0 && w->lvl_v[j].n <= MZ_VIS_MAX)
-                                           ? mz_select_level_vis(d, s, hot, h, w->lvl_v[j], cp, lane)
-                                           : (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u)) + mz_select_level(d, s, hot, h, j == 0, cp, q, lane, c);
+                                           ? mz_select_level_vis(d, s, w->qb, hot, h, w->lvl_v[j], cp, lane)
+                                           : (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u)) + mz_select_level(d, s, w->qb, hot, h, j == 0, cp, q, lane, c);
                     if (lane == 0) {
                         w->sel[j] = chosen;
                         last_child[node] = chosen;
@@ -1287,7 +1404,7 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
         while ((h.link >> MZ_LINK_SHIFT) != 0) {
             const int fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
             mz_hot c;
-            const int best = mz_select_level(d, s, hot, h, level == 0, (level & 1) ? 3 - root_turn : root_turn, q, lane, c);
+            const int best = mz_select_level(d, s, w->qb, hot, h, level == 0, mz_child_player(d, root_turn, level), q, lane, c);
             if (lane == 0) {
                 last_child[path[level]] = fc + best;
                 path[level + 1] = fc + best;
@@ -1346,15 +1463,23 @@ MZ_DEV void mz_gumbel_sort_by_score(const mz_dims& d, const mz_state& s, int g, 
         max_count = (c > max_count ? c : max_count);
     }
     const float scale = mz_fmul(mz_fadd(d.sigma_visit_c, max_count), d.sigma_scale_c);
+    mz_qb qb; // one thread: the bounds are read serially (getNormalizedMean(tree_value_bound), gumbel_zero.cpp:128)
+    qb.reward = (s.reward ? s.reward + (size_t)g * d.NP : nullptr), qb.lo = 0.0f, qb.hi = 0.0f, qb.n = 0;
+    if (d.value_rescale) {
+        const float* key = s.vb_key + (size_t)g * d.vb_cap;
+        qb.n = s.vb_n[g];
+        for (int i = 0; i < qb.n; ++i) { qb.lo = (i == 0 || key[i] < qb.lo ? key[i] : qb.lo), qb.hi = (i == 0 || key[i] > qb.hi ? key[i] : qb.hi); }
+    }
+    root_turn = mz_child_player(d, root_turn, 0);
     for (int i = 1; i < n; ++i) { // stable insertion sort, descending score
         const int c = cand[i];
         const mz_hot hc = mz_load_hot(hot + c);
-        const float sc = (hc.count > 0.0f ? mz_fadd(s.logit[(size_t)g * d.NP + c], mz_fmul(scale, mz_normalized_mean(d, hc.mean, hc.count, root_turn))) : -3.402823466e+38f);
+        const float sc = (hc.count > 0.0f ? mz_fadd(s.logit[(size_t)g * d.NP + c], mz_fmul(scale, mz_normalized_mean(d, qb, c, hc.mean, hc.count, root_turn))) : -3.402823466e+38f);
         int j = i;
         while (j > 0) {
             const int p = cand[j - 1];
             const mz_hot hp = mz_load_hot(hot + p);
-            const float sp = (hp.count > 0.0f ? mz_fadd(s.logit[(size_t)g * d.NP + p], mz_fmul(scale, mz_normalized_mean(d, hp.mean, hp.count, root_turn))) : -3.402823466e+38f);
+            const float sp = (hp.count > 0.0f ? mz_fadd(s.logit[(size_t)g * d.NP + p], mz_fmul(scale, mz_normalized_mean(d, qb, p, hp.mean, hp.count, root_turn))) : -3.402823466e+38f);
             if (!(sp < sc)) { break; }
             cand[j] = p;
             --j;
@@ -1431,7 +1556,9 @@ MZ_DEV void mz_before_nn_muzero(const mz_dims& d, const mz_state& s, int g, mz_s
     if (d.gumbel && sims > 0) {
         if (wid == 0) {
             int level = 1;
+            const mz_qb qb = mz_vb_bounds(d, s, g, lane);
             if (lane == 0) {
+                w->qb = qb;
                 path[0] = 0;
                 path[1] = mz_gumbel_pick(d, s, g);
             }
@@ -1440,7 +1567,7 @@ MZ_DEV void mz_before_nn_muzero(const mz_dims& d, const mz_state& s, int g, mz_s
             while ((h.link >> MZ_LINK_SHIFT) != 0) { // MCTS::selectFromNode below the candidate, mcts.cpp:139-148
                 const int fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
                 mz_hot c;
-                const int best = mz_select_level(d, s, hot, h, false, (level & 1) ? 3 - root_turn : root_turn, w->q_warp, lane, c);
+                const int best = mz_select_level(d, s, w->qb, hot, h, false, mz_child_player(d, root_turn, level), w->q_warp, lane, c);
                 if (lane == 0) { path[level + 1] = fc + best; }
                 h = c;
                 ++level;
@@ -1455,7 +1582,11 @@ MZ_DEV void mz_before_nn_muzero(const mz_dims& d, const mz_state& s, int g, mz_s
     mz_block_sync();
     const int len = w->shared_len, L = len - 1, leaf = path[L];
     int num_legal = d.A;
-    if (L == 0) { // initial inference: env_.getFeatures() and the root's legal set (zero_actor.cpp:60,238)
+    if (L == 0 && d.game == MZ_GAME_ATARI) {
+        // the planes come from the screen ring (packed by its own kernel, engine.cu); legal actions = the game's minimal action set
+        for (int i = tid; i < MZ_LEGAL_WORDS; i += nthreads) { w->legal[i] = (i == 0 ? d.legal_mask : 0u); }
+        num_legal = mz_popc(d.legal_mask);
+    } else if (L == 0) { // initial inference: env_.getFeatures() and the root's legal set (zero_actor.cpp:60,238)
         if (wid == 0) { mz_env_load_root(d, s, g, w, lane); }
         mz_block_sync();
         const uint64_t* root_list = s.hashes + (size_t)g * d.max_hashes;
@@ -1477,8 +1608,15 @@ MZ_DEV void mz_before_nn_muzero(const mz_dims& d, const mz_state& s, int g, mz_s
                 const int cell = i / per_cell, k = i - cell * per_cell;
                 *reinterpret_cast<uint4*>(dst + (size_t)((cell / N + 1) * (N + 1) + cell % N) * d.dyn_c + k * 8) = src[i];
             }
-            for (int cell = tid; cell < N * N; cell += nthreads) { // one-hot plane; all zero for a pass (othello.cpp:257-262)
-                dst[(size_t)((cell / N + 1) * (N + 1) + cell % N) * d.dyn_c + d.act_col] = (cell == a ? MZ_HALF_ONE : 0);
+            if (d.act_planes > 1) { // Atari: plane `a` of the 18 action planes is all ones (atari.cpp:124-130)
+                for (int i = tid; i < N * N * d.act_planes; i += nthreads) {
+                    const int cell = i / d.act_planes, k = i - cell * d.act_planes;
+                    dst[(size_t)((cell / N + 1) * (N + 1) + cell % N) * d.dyn_c + d.act_col + k] = (k == a ? MZ_HALF_ONE : 0);
+                }
+            } else {
+                for (int cell = tid; cell < N * N; cell += nthreads) { // one-hot plane; all zero for a pass (othello.cpp:257-262)
+                    dst[(size_t)((cell / N + 1) * (N + 1) + cell % N) * d.dyn_c + d.act_col] = (cell == a ? MZ_HALF_ONE : 0);
+                }
             }
         }
 #endif
@@ -1493,7 +1631,7 @@ MZ_DEV void mz_before_nn_muzero(const mz_dims& d, const mz_state& s, int g, mz_s
         s.path_len[g] = len;
         s.spec_len[g] = (d.gumbel ? 0 : len);
         s.leaf_meta[g * 4 + 0] = 0;
-        s.leaf_meta[g * 4 + 1] = (L & 1) ? 3 - root_turn : root_turn;
+        s.leaf_meta[g * 4 + 1] = (d.num_players == 1 ? 1 : ((L & 1) ? 3 - root_turn : root_turn));
         s.leaf_meta[g * 4 + 2] = 0;
         s.leaf_meta[g * 4 + 3] = num_legal;
         s.leaf_score[g] = 0.0f;
@@ -1806,6 +1944,7 @@ MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* 
             s.action[(size_t)g * d.NP + c] = (int16_t)a;
             s.logit[(size_t)g * d.NP + c] = w->lg[a];
             s.value[(size_t)g * d.NP + c] = 0.0f;
+            if (s.reward) { s.reward[(size_t)g * d.NP + c] = 0.0f; }
             s.node_slot[(size_t)g * d.NP + c] = -1;
             s.last_child[(size_t)g * d.NP + c] = -1;
         }
@@ -1859,11 +1998,19 @@ MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* 
         v = s.leaf_score[g];
     }
     mz_block_sync();
-    // backup: every path node receives the same chain value discounted per level (reward is 0)
-    if (tid == 0) { s.value[(size_t)g * d.NP + leaf] = v; }
+    // backup (mcts.cpp:166-179): node i of the path receives the leaf value carried up through the rewards and the discount of the
+    // nodes below it; every thread folds the chain for its own node (paths are short where rewards exist)
+    float* rew = (s.reward ? s.reward + (size_t)g * d.NP : nullptr);
+    if (tid == 0) {
+        s.value[(size_t)g * d.NP + leaf] = v;
+        if (rew) { rew[leaf] = (d.has_reward && s.nn_reward ? s.nn_reward[g] : 0.0f); } // muzero_output->reward_, zero_actor.cpp:88
+    }
+    if (rew) { mz_block_sync(); }
     for (int i = tid; i < len; i += nthreads) {
         float x = v;
-        if (d.discount == 1.0f) {
+        if (rew) {
+            for (int j = len - 1; j > i; --j) { x = mz_fadd(rew[path[j]], mz_fmul(d.discount, x)); }
+        } else if (d.discount == 1.0f) {
             if (i < len - 1 && x == 0.0f) { x = 0.0f; } // 0 + 1 * x: only -0 changes (to +0)
         } else {
             for (int j = len - 1; j > i; --j) { x = mz_fadd(0.0f, mz_fmul(d.discount, x)); }
@@ -1873,8 +2020,20 @@ MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* 
         const float cnt = mz_fadd(h.count, 1.0f);
         const float mean = mz_fadd(h.mean, mz_fdiv(mz_fmul(1.0f, mz_fsub(x, h.mean)), cnt));
         mz_store_hot(hot + n, cnt, mean, h.policy, h.link);
+        if (d.value_rescale) { // Q of the node before / after this visit, for the value bounds below (path_hashes is free here)
+            const float r = (rew ? rew[n] : 0.0f);
+            float* qq = reinterpret_cast<float*>(w->path_hashes + i);
+            qq[0] = mz_fadd(r, mz_fmul(d.discount, h.mean)), qq[1] = mz_fadd(r, mz_fmul(d.discount, mean));
+        }
     }
     mz_block_sync();
+    if (d.value_rescale && tid < MZ_W) { // updateTreeValueBound leaf -> root, in that order (the map's state is order dependent)
+        for (int i = len - 1; i >= 0; --i) {
+            const float* qq = reinterpret_cast<const float*>(w->path_hashes + i);
+            mz_vb_update(d, s, g, qq[0], qq[1], tid);
+        }
+    }
+    if (d.value_rescale) { mz_block_sync(); }
     // a simulation gives exactly one node its first visit: the leaf, unless it is a terminal node seen before (count now > 1)
     if (tid == 0 && s.vis && len >= 2 && mz_load_hot(hot + leaf).count == 1.0f) {
         const int parent = path[len - 2];
@@ -1898,6 +2057,8 @@ MZ_DEV void mz_tree_reset(const mz_dims& d, const mz_state& s, int g, int lane)
         s.cursor[g] = 1;
         s.path_len[g] = 0;
         s.spec_len[g] = 0;
+        if (s.reward) { s.reward[(size_t)g * d.NP] = 0.0f; }
+        if (s.vb_n) { s.vb_n[g] = 0; } // MCTS::reset clears tree_value_bound_ (mcts.cpp:78-83)
         if (s.gum_meta) { s.gum_meta[g * 4 + 0] = 0, s.gum_meta[g * 4 + 1] = 0, s.gum_meta[g * 4 + 2] = 0, s.gum_meta[g * 4 + 3] = 0; }
     }
 }
@@ -1908,6 +2069,27 @@ MZ_DEV void mz_game_reset(const mz_dims& d, const mz_state& s, int g, mz_scratch
     mz_env_reset(d, w, lane);
     mz_env_store_root(d, s, g, w, lane);
     mz_tree_reset(d, s, g, lane);
+    if (d.game == MZ_GAME_ATARI && s.at_meta && lane == 0) { // AtariEnv::reset, atari.cpp:52-58: empty screen and action histories
+        int32_t* m = s.at_meta + (size_t)g * 16;
+        m[0] = 0, m[9] = 0;
+        for (int i = 0; i < MZ_HIST; ++i) { m[1 + i] = -1; }
+    }
+}
+
+// AtariEnv::reset's first screen (action < 0) or AtariEnv::act (atari.cpp:82-85): the screen the emulator answered with joins the
+// 8-entry history together with the action that produced it; the oldest entry leaves. Block collective (any number of threads);
+// the frame bytes are copied by the caller's threads, the bookkeeping by thread 0. Returns the ring slot the frame belongs in.
+MZ_DEV int mz_atari_push(const mz_state& s, int g, int action, int tid)
+{
+    int32_t* m = s.at_meta + (size_t)g * 16;
+    const int slot = m[0];
+    mz_block_sync();
+    if (tid == 0) {
+        m[0] = (slot + 1) % MZ_HIST;
+        m[1 + slot] = action; // -1 after a reset: the all-zero action plane (atari.cpp:57-58)
+        m[9] |= 1 << slot;
+    }
+    return slot;
 }
 
 // BaseActor::act on the root environment + resetSearch (base_actor.cpp:22-30, actor_group.cpp:116-134).
@@ -1916,6 +2098,18 @@ MZ_DEV void mz_game_reset(const mz_dims& d, const mz_state& s, int g, mz_scratch
 // *score = getEvalScore(false) of the new position when terminal.
 MZ_DEV void mz_play(const mz_dims& d, const mz_state& s, int g, int action, mz_scratch* w, int32_t* out, float* score, int lane)
 {
+    if (d.game == MZ_GAME_ATARI) { // the emulator is the host's: legality against the minimal action set, move count, new search
+        const int ok = (action >= 0 && action < d.A && ((d.legal_mask >> action) & 1u)) ? 1 : 0;
+        if (ok) {
+            if (lane == 0) { s.root_meta[g * 4 + 1] += 1, s.root_meta[g * 4 + 3] = s.root_meta[g * 4 + 2], s.root_meta[g * 4 + 2] = action; }
+            mz_tree_reset(d, s, g, lane);
+        }
+        if (lane == 0) {
+            out[0] = ok, out[1] = 0, out[2] = mz_popc(d.legal_mask), out[3] = 1;
+            *score = 0.0f;
+        }
+        return;
+    }
     mz_env_load_root(d, s, g, w, lane);
     uint64_t* hash_list = s.hashes + (size_t)g * d.max_hashes;
     mz_env_legal_block(d, s, w, hash_list, w->num_moves, hash_list, 0, lane, MZ_W);

@@ -29,6 +29,8 @@ extern "C" {
 // search options beyond the AlphaZero defaults: muzero, use_gumbel, gumbel_noise, gumbel_sample_size, sigma_visit_c, sigma_scale_c
 static int g_opt_i[4] = {0, 0, 0, 16};
 static float g_opt_f[2] = {50.0f, 1.0f};
+static int g_opt_atari[2] = {0, 0}; // value_rescale, legal mask (Atari MuZero)
+void hs_set_atari_options(int value_rescale, int legal_mask) { g_opt_atari[0] = value_rescale, g_opt_atari[1] = legal_mask; }
 void hs_set_options(int muzero, int use_gumbel, int gumbel_noise, int m, float visit_c, float scale_c)
 {
     g_opt_i[0] = muzero, g_opt_i[1] = use_gumbel, g_opt_i[2] = gumbel_noise, g_opt_i[3] = m;
@@ -43,6 +45,12 @@ sim* hs_create(int game, int N, int B, int S, float puct_base, float puct_init, 
     memset(&h->s, 0, sizeof(h->s));
     d.game = game, d.N = N, d.A = (game == MZ_GAME_TICTACTOE ? 9 : ((game == MZ_GAME_GOMOKU || game == MZ_GAME_HEX) ? N * N : N * N + 1)), d.C = (MZ_GO_FAMILY(game) ? 18 : 4), d.S = S, d.B = B;
     d.gomoku_exactly_five = 1, d.gomoku_outer_open = 0, d.hex_swap_rule = 1; // reference defaults (configuration.cpp:82-85)
+    d.num_players = 2, d.act_planes = 1;
+    if (game == MZ_GAME_ATARI) { // atari.h:18-26
+        d.A = 18, d.C = 32, d.num_players = 1, d.atari_init_q = 1, d.has_reward = 1, d.act_planes = 18;
+        d.value_rescale = g_opt_atari[0], d.legal_mask = (uint32_t)g_opt_atari[1];
+    }
+    d.vb_cap = S + 2;
     d.muzero = g_opt_i[0], d.gumbel = g_opt_i[1], d.gumbel_noise = g_opt_i[2], d.gumbel_m = g_opt_i[3];
     d.sigma_visit_c = g_opt_f[0], d.sigma_scale_c = g_opt_f[1];
     if (d.gumbel) { // gumbel_zero.cpp:99,109 in the reference's double arithmetic
@@ -73,6 +81,9 @@ sim* hs_create(int game, int N, int B, int S, float puct_base, float puct_init, 
     s.spec_len = zalloc<int32_t>(B);
     s.gum_cand = zalloc<int32_t>((size_t)B * d.A), s.gum_meta = zalloc<int32_t>((size_t)B * 4);
     s.leaf_parent = zalloc<int32_t>((size_t)B * 2);
+    if (d.has_reward) { s.reward = zalloc<float>(np), s.nn_reward = zalloc<float>(B); }
+    if (d.value_rescale) { s.vb_key = zalloc<float>((size_t)B * d.vb_cap), s.vb_cnt = zalloc<int32_t>((size_t)B * d.vb_cap), s.vb_n = zalloc<int32_t>(B); }
+    if (game == MZ_GAME_ATARI) { s.at_meta = zalloc<int32_t>((size_t)B * 16); }
     h->sqrt_table.resize(S + 2);
     for (int n = 0; n < S + 2; ++n) { h->sqrt_table[n] = sqrt((double)n); }
     s.sqrt_table = h->sqrt_table.data();
@@ -108,7 +119,7 @@ void hs_select(sim* h, const uint8_t* rotations, float* features)
     const mz_dims& d = h->d;
     for (int g = 0; g < d.B; ++g) { h->rot[g] = (rotations ? rotations[g] : 0); }
     for (int g = 0; g < d.B; ++g) { mz_before_nn(d, h->s, g, &h->w, 0, 0, 1); }
-    if (features) {
+    if (features && d.game != MZ_GAME_ATARI) { // Atari planes are produced by the device's screen-ring kernel, not by search_core.cuh
         const int N = d.N;
         for (int g = 0; g < d.B; ++g) {
             for (int c = 0; c < d.C; ++c) {
@@ -121,9 +132,15 @@ void hs_select(sim* h, const uint8_t* rotations, float* features)
     }
 }
 
-void hs_apply(sim* h, const float* policy, const float* logits, const float* value, const float* noise)
+void hs_apply_mz(sim* h, const float* policy, const float* logits, const float* value, const float* reward, const float* noise);
+void hs_apply(sim* h, const float* policy, const float* logits, const float* value, const float* noise) { hs_apply_mz(h, policy, logits, value, nullptr, noise); }
+
+void hs_apply_mz(sim* h, const float* policy, const float* logits, const float* value, const float* reward, const float* noise)
 {
     const mz_dims& d = h->d;
+    if (h->s.nn_reward) {
+        for (int g = 0; g < d.B; ++g) { h->s.nn_reward[g] = (reward ? reward[g] : 0.0f); }
+    }
     memcpy(h->s.policy, policy, sizeof(float) * (size_t)d.B * d.A);
     memcpy(h->s.logits, logits, sizeof(float) * (size_t)d.B * d.A);
     memcpy(h->s.nn_value, value, sizeof(float) * (size_t)d.B);
@@ -175,6 +192,21 @@ int hs_play(sim* h, int g, int action, int* num_legal, float* score)
 
 void hs_reset_game(sim* h, int g) { mz_game_reset(h->d, h->s, g, &h->w, 0); }
 
+// Atari: the history bookkeeping of a new screen (the bytes themselves only matter to the device's plane kernel)
+void hs_atari_observe(sim* h, int g, int action) { mz_atari_push(h->s, g, action, 0); }
+
+// rewards of the root children, number of value-bound keys, smallest / largest key
+void hs_root_extra(sim* h, int g, float* c_reward, int32_t* bound)
+{
+    const mz_dims& d = h->d;
+    const mz_hot* hot = h->s.hot + (size_t)g * d.NP;
+    const int nc = (int)(hot[0].link >> MZ_LINK_SHIFT), fc = (int)(hot[0].link & ((1u << MZ_LINK_SHIFT) - 1u));
+    for (int i = 0; i < nc; ++i) { c_reward[i] = (h->s.reward ? h->s.reward[(size_t)g * d.NP + fc + i] : 0.0f); }
+    const mz_qb qb = mz_vb_bounds(d, h->s, g, 0);
+    bound[0] = qb.n;
+    memcpy(&bound[1], &qb.lo, 4), memcpy(&bound[2], &qb.hi, 4);
+}
+
 // property-test hook: policies[n] (candidates in ascending action id) -> action order left by (a) the restatement in
 // search_core.cuh and (b) the real std::sort with the reference's comparator (zero_actor.cpp:225-227); returns 1 if equal
 int hs_sort_matches_std(int n, const float* policy, int32_t* order_out)
@@ -214,14 +246,15 @@ int hs_check_level_variants(sim* h, int g)
         const mz_hot hn = hot[node];
         if ((hn.link >> MZ_LINK_SHIFT) == 0 || hn.count < 1.0f) { continue; }
         const mz_vis v = s.vis[(size_t)g * d.NP + node];
-        for (int player = 1; player <= 2; ++player) {
+        for (int player = 1; player <= d.num_players; ++player) {
             mz_hot c;
             const int fc = (int)(hn.link & ((1u << MZ_LINK_SHIFT) - 1u));
-            const int a = fc + mz_select_level(d, s, hot, hn, false, player, h->w.q_warp, 0, c);
-            const int b = mz_select_level_serial(d, s, hot, hn, player);
+            const mz_qb qb = mz_vb_bounds(d, s, g, 0);
+            const int a = fc + mz_select_level(d, s, qb, hot, hn, false, player, h->w.q_warp, 0, c);
+            const int b = mz_select_level_serial(d, s, qb, hot, hn, player);
             if (a != b) { return -node - 1; }
             if (v.n <= MZ_VIS_MAX) {
-                if (mz_select_level_vis(d, s, hot, hn, v, player, 0) != a || mz_select_level_vis_serial(d, s, hot, hn, v, player) != a) { return -node - 1; }
+                if (mz_select_level_vis(d, s, qb, hot, hn, v, player, 0) != a || mz_select_level_vis_serial(d, s, qb, hot, hn, v, player) != a) { return -node - 1; }
                 ++compared;
             }
         }

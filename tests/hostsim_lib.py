@@ -29,6 +29,10 @@ def load():
     lib.hs_check_level_variants.argtypes = [vp, i32]
     lib.hs_sort_matches_std.argtypes = [i32, f32p, i32p]
     lib.hs_set_options.argtypes = [i32, i32, i32, i32, f32, f32]
+    lib.hs_set_atari_options.argtypes = [i32, i32]
+    lib.hs_apply_mz.argtypes = [vp, f32p, f32p, f32p, f32p, f32p]
+    lib.hs_atari_observe.argtypes = [vp, i32, i32]
+    lib.hs_root_extra.argtypes = [vp, i32, f32p, i32p]
     for fn in ("hs_leaf_action", "hs_leaf_parent_slot", "hs_path_hash", "hs_gumbel_best_action"):
         getattr(lib, fn).argtypes = [vp, i32]
     return lib
@@ -44,14 +48,17 @@ def root_dict(A, out_i, out_f):
 
 class HostSimSearch:
     def __init__(self, lib, game, board_size, num_games, num_simulation, muzero=0, use_gumbel=0, gumbel_noise=0, gumbel_sample_size=16,
-                 gumbel_sigma_visit_c=50.0, gumbel_sigma_scale_c=1.0):
+                 gumbel_sigma_visit_c=50.0, gumbel_sigma_scale_c=1.0, value_rescale=0, reward_discount=1.0, atari_legal_mask=0b1111111101):
         self.lib = lib
         n = 3 if game == 0 else board_size
         self.A = 9 if game == 0 else (n * n if game in (4, 5) else n * n + 1)
         self.F = (18 if game in (1, 3) else 4) * n * n
+        if game == 6:  # Atari MuZero: 18 actions, planes from the device's screen ring (not produced by the host build)
+            self.A, self.F = 18, 0
         self.B, self.S = num_games, num_simulation
         lib.hs_set_options(muzero, use_gumbel, gumbel_noise, gumbel_sample_size, gumbel_sigma_visit_c, gumbel_sigma_scale_c)
-        self.h = lib.hs_create(game, n, num_games, num_simulation, 19652.0, 1.25, 1.0, 7.5, 0.25)
+        lib.hs_set_atari_options(value_rescale, atari_legal_mask)
+        self.h = lib.hs_create(game, n, num_games, num_simulation, 19652.0, 1.25, reward_discount, 7.5, 0.25)
         self.terminal = [False] * num_games
 
     def select(self, rotations=None):
@@ -60,11 +67,16 @@ class HostSimSearch:
         self.lib.hs_select(self.h, None if rot is None else rot.ctypes.data_as(C.POINTER(C.c_uint8)), feats.ctypes.data_as(C.POINTER(C.c_float)))
         return feats
 
-    def apply(self, policy, logits, value, noise=None):
+    def apply(self, policy, logits, value, noise=None, reward=None):
         fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
         p, l, v = (np.ascontiguousarray(x, np.float32) for x in (policy, logits, value))
         nz = None if noise is None else np.ascontiguousarray(noise, np.float32)
-        self.lib.hs_apply(self.h, fp(p), fp(l), fp(v), None if nz is None else fp(nz))
+        rw = None if reward is None else np.ascontiguousarray(reward, np.float32)
+        self.lib.hs_apply_mz(self.h, fp(p), fp(l), fp(v), None if rw is None else fp(rw), None if nz is None else fp(nz))
+
+    def observe(self, g, action, frame, terminal=False):
+        self.lib.hs_atari_observe(self.h, g, int(action))
+        self.terminal[g] = bool(terminal)
 
     def sims_done(self, g):
         return self.lib.hs_sims_done(self.h, g)
@@ -91,7 +103,11 @@ class HostSimSearch:
         out_i = np.zeros(1 + self.A, np.int32)
         out_f = np.zeros(3 + 6 * self.A, np.float32)
         self.lib.hs_root(self.h, g, out_i.ctypes.data_as(C.POINTER(C.c_int32)), out_f.ctypes.data_as(C.POINTER(C.c_float)))
-        return root_dict(self.A, out_i, out_f)
+        d = root_dict(self.A, out_i, out_f)
+        rw, bound = np.zeros(self.A, np.float32), np.zeros(3, np.int32)
+        self.lib.hs_root_extra(self.h, g, rw.ctypes.data_as(C.POINTER(C.c_float)), bound.ctypes.data_as(C.POINTER(C.c_int32)))
+        d.update(reward=rw, bound_size=int(bound[0]), bound_lo=float(bound[1:2].view(np.float32)[0]), bound_hi=float(bound[2:3].view(np.float32)[0]))
+        return d
 
     def play(self, g, action):
         nl, sc = C.c_int32(0), C.c_float(0)

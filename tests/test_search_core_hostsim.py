@@ -31,6 +31,17 @@ def test_search_core_matches_reference_recording(name):
     assert sum(compared) > 0
 
 
+@pytest.mark.parametrize("name", ["atari_mz_s20_b2", "atari_mz_s50_b2_det", "atari_mz_s18_gumbel_b2"])
+def test_search_core_matches_reference_recording_atari(name):
+    """Atari MuZero tree semantics of search_core.cuh (rewards, value-bound table, rescaled Q, ATARI init-Q) against the -DATARI reference"""
+    case = golden_replay.load_case(name)
+    eng = hostsim_lib.HostSimSearch(hostsim_lib.load(), 6, 6, int(case["B"]), int(case["S"]), **oracle_lib.conf_overrides(case["conf"]))
+    checked = golden_replay.replay_atari(eng, case, check_features=False)
+    assert checked >= case["move_game"].size - int(case["B"])
+    for g in range(int(case["B"])):
+        assert eng.check_level_variants(g) >= 0
+
+
 def test_candidate_sort_is_libstdcxx_std_sort():
     """mz_std_sort_candidates (search_core.cuh) and mzo_std_sort_candidates (oracle) against the real std::sort with the
     reference's comparator, on inputs full of exact ties (where an unstable sort's result is algorithm-defined)"""
