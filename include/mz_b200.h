@@ -33,6 +33,8 @@ extern "C" {
 #define MZ_GAME_GOMOKU 4    /* environment/gomoku (N x N, no pass, five in a row through the last move) */
 #define MZ_GAME_HEX 5       /* environment/hex (N x N, no pass, swap rule, connect the two own edges; features and policy are never rotated) */
 
+#define MZ_GAME_ATARI 6     /* environment/atari: one player, 18 actions, 32 x 96 x 96 planes; the emulator stays with the host (mz_atari_observe); MuZero only */
+
 typedef struct mz_engine mz_engine;
 
 /* Search / environment configuration: the config keys the actor path reads (config/configuration.cpp:13-28,80-81). */
@@ -57,6 +59,8 @@ typedef struct {
     int32_t gomoku_exactly_five; /* env_gomoku_exactly_five_stones (reference default: true) */
     int32_t gomoku_outer_open;   /* env_gomoku_rule == "outer_open" */
     int32_t hex_swap_rule;       /* env_hex_use_swap_rule (reference default: true) */
+    int32_t value_rescale;       /* actor_mcts_value_rescale: min-max normalised Q from the tree's value bounds (actor/mcts.cpp:43-49,219-228) */
+    uint32_t atari_legal_mask;   /* MZ_GAME_ATARI: the game's minimal action set as a bit mask over the 18 actions (AtariEnv::isLegalAction, atari.h:57) */
 } mz_config;
 
 /* Hyper-parameters the reference reads from the TorchScript module (network/network.cpp:30-41). */
@@ -113,6 +117,10 @@ int mz_eval_initial(mz_engine* e, const float* features, int32_t n, float* polic
  * would produce (one-hot cell, all zero for a pass; environment/othello/othello.cpp:257-262) */
 int mz_eval_recurrent(mz_engine* e, const float* hidden, const int32_t* actions, int32_t n, float* policy, float* logits, float* value, float* hidden_out);
 
+/* reward head output of the last mz_eval_recurrent / mz_eval_initial (muzero_atari networks; after the expectation over the
+ * bins and utils::invertValue, network/muzero_network.h:165-171): reward [n] */
+int mz_eval_rewards(mz_engine* e, int32_t n, float* reward);
+
 /* ---- games ----------------------------------------------------------------------------------------- */
 /* BaseActor::reset (actor/base_actor.cpp:8-13); g < 0 resets every game */
 int mz_reset_game(mz_engine* e, int32_t g);
@@ -123,6 +131,15 @@ int mz_play(mz_engine* e, const int32_t* actions, mz_play_result* results);
  * (actor/mcts.cpp:91-104) followed by mz_play of that action; auto_reset != 0 also restarts finished games in place.
  * actions_out / results [num_games] may both be NULL, in which case the call is asynchronous (no host read-back). */
 int mz_play_max_count(mz_engine* e, int32_t auto_reset, int32_t* actions_out, mz_play_result* results);
+/* MZ_GAME_ATARI: what the host's emulator answered. For every game, actions[g] >= 0: AtariEnv::act's history update (the screen
+ * joins the 8-entry observation history with the action that produced it, environment/atari/atari.cpp:82-85; call after mz_play);
+ * -1: the initial screen after a reset (atari.cpp:52-56); -2: nothing for this game. frames [num_games][3][96][96]: the screen
+ * resized to 96 x 96, RGB bytes, channel-major (AtariEnv::getObservation, atari.cpp:136-160) */
+int mz_atari_observe(mz_engine* e, const int32_t* actions, const uint8_t* frames);
+/* beside mz_get_roots: MCTSNode::getReward of the root children [B][A] and the tree's value bounds (number of distinct values,
+ * smallest, largest: MCTS::getTreeValueBound, actor/mcts.h:106) [B]; what the move choice and the resign test of a rescaled search
+ * read (actor/mcts.cpp:40-53,85-124). Any pointer may be NULL */
+int mz_get_root_rewards(mz_engine* e, float* reward, int32_t* bound_size, float* bound_lo, float* bound_hi);
 /* root child tables, children in stored (policy-sorted) order; any array may be NULL.
  * info [B]; the others [B][A] (MCTSNode getters, actor/mcts.h:44-52) */
 int mz_get_roots(mz_engine* e, mz_root_info* info, int32_t* action, float* count, float* mean, float* policy, float* logit, float* noise,
@@ -135,6 +152,8 @@ int mz_search_select(mz_engine* e, const uint8_t* rotations, float* features_out
 /* ZeroActor::afterNNEvaluation for every game (actor/zero_actor.cpp:74-98). policy/logits [B][A], value [B],
  * noise [B][A] by root child index or NULL (Dirichlet values drawn by the host, utils/random.h:15-24) */
 int mz_search_apply(mz_engine* e, const float* policy, const float* logits, const float* value, const float* noise);
+/* the same with the reward head's outputs [B] (MuZeroNetworkOutput::reward_, zero_actor.cpp:88); reward may be NULL (= 0) */
+int mz_search_apply_reward(mz_engine* e, const float* policy, const float* logits, const float* value, const float* reward, const float* noise);
 
 /* MuZero / Gumbel parity hooks after mz_search_select: for every game the evaluation slot of the leaf's parent (-1 at the root;
  * the hidden state the recurrent inference reads, zero_actor.cpp:62-66), the leaf's action id (-1 at the root) and the action ids

@@ -2,8 +2,10 @@
 // No CPU path: every entry point needs a CUDA device of compute capability 10.x.
 #include "../../include/mz_b200.h"
 #include "nn_kernels.cuh"
+#include "atari_kernels.cuh"
 #include "search_core.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -143,6 +145,30 @@ __global__ void __launch_bounds__(32) k_gather_roots(const mz_dims d, const mz_s
     }
 }
 
+// rewards of the root children and the tree's value bounds (MCTSNode::getReward, MCTS::getTreeValueBound)
+__global__ void __launch_bounds__(32) k_gather_root_rewards(const mz_dims d, const mz_state s, float* __restrict__ reward, int32_t* __restrict__ bsize, float* __restrict__ blo,
+                                                            float* __restrict__ bhi)
+{
+    const int g = blockIdx.x, lane = threadIdx.x;
+    const mz_hot root = mz_load_hot(s.hot + (size_t)g * d.NP);
+    const int nc = (int)(root.link >> MZ_LINK_SHIFT), fc = (int)(root.link & ((1u << MZ_LINK_SHIFT) - 1u));
+    for (int i = lane; i < d.A; i += 32) { reward[(size_t)g * d.A + i] = (i < nc && s.reward ? s.reward[(size_t)g * d.NP + fc + i] : 0.0f); }
+    const mz_qb qb = mz_vb_bounds(d, s, g, lane);
+    if (lane == 0) { bsize[g] = qb.n, blo[g] = (qb.n ? qb.lo : 0.0f), bhi[g] = (qb.n ? qb.hi : 0.0f); }
+}
+
+// AtariEnv::reset's first screen / AtariEnv::act's history update for every game with actions[g] > -2 (atari.cpp:52-56,82-85)
+__global__ void __launch_bounds__(256) k_atari_observe(const mz_dims d, const mz_state s, const int32_t* __restrict__ actions, const uint8_t* __restrict__ frames_in)
+{
+    const int g = blockIdx.x;
+    const int a = actions[g];
+    if (a < -1) { return; } // uniform for the block
+    const int slot = mz_atari_push(s, g, a, threadIdx.x);
+    const uint4* src = reinterpret_cast<const uint4*>(frames_in + (size_t)g * MZ_ATARI_FRAME);
+    uint4* dst = reinterpret_cast<uint4*>(s.at_frames + ((size_t)g * MZ_HIST + slot) * MZ_ATARI_FRAME);
+    for (int i = threadIdx.x; i < MZ_ATARI_FRAME / 16; i += blockDim.x) { dst[i] = src[i]; }
+}
+
 // action ids along the selected path of every game (-1 padded): parity hook for the MuZero / Gumbel selection
 __global__ void k_path_actions(const mz_dims d, const mz_state s, int32_t* __restrict__ out)
 {
@@ -169,6 +195,22 @@ struct ConvLayer {
     size_t w_off = 0, b_off = 0; // offsets into the blob
     CUtensorMap map_w;
     CUtensorMap map_w_mc; // box = 1 / conv_cluster of the weight tile (multicast slices)
+    // ConvStage layers only
+    int cin_off = 0, tap_mask = 0x1ff;
+    int in_buf = 0, out_buf = 0, res_buf = -2; // activation buffer indices of the stage; -1 = the stage's input rows, -2 = none
+};
+
+// A run of 3x3 conv layers at one resolution executed as ONE launch of the fused tower kernel: the Atari representation network
+// changes resolution three times (muzero_atari_network.py:7-40), each resolution is a stage with its own geometry and buffers.
+struct ConvStage {
+    int n = 0, slots = 0, rows_alloc = 0, rows_ext = 0, cout = 0, cin_in = 0, cin_max = 0, stages = 8;
+    __half* in = nullptr; // [rows_alloc][cin_in] rows written by the kernel before the stage, or null when the input is act[0]
+    __half* act[3] = {nullptr, nullptr, nullptr};
+    CUtensorMap map_in_ext, map_act_ext[3];
+    std::vector<ConvLayer> convs;
+    mznn::TowerParams* params = nullptr;
+    int* d_done = nullptr;
+    int out_buf = 0;
 };
 
 // one residual tower: AlphaZero's, or MuZero's representation (0) / dynamics (1) network
@@ -181,6 +223,7 @@ struct NetTower {
     mznn::TowerParams* params = nullptr; // host copy of the fused-tower launch parameters (conv_mode 3)
     int* d_done = nullptr;
     int out_buf = 0;                     // index of the activation buffer holding its output
+    bool has_stem = true;                // false: the tower starts with a residual block on act[0] (last stage of the Atari representation network)
 };
 
 struct Blob {
@@ -243,6 +286,19 @@ struct mz_engine {
     int cin_max = 0;
     int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148, krot = 0, conv_cluster = 1, conv_pdl = 0, tower_sms = 148, tower_stages = 8, tower_pdl = 0;
     encode_tiled_fn encode = nullptr;
+
+    // Atari MuZero (MZ_GAME_ATARI)
+    bool atari = false;
+    ConvStage ast[3];              // representation stages at 48 x 48, 24 x 24, 12 x 12 (the 6 x 6 stage is tw[0], the dynamics network tw[1])
+    int at_c1 = 0;                 // padded channels of the first stage (num_hidden_channels / 2)
+    size_t off_dhead[3][6] = {{0}}; // value / reward heads: conv w, conv b, fc1 w^T, fc1 b, fc2 w^T, fc2 b; [2] = policy: conv w, conv b, fc w^T, fc b
+    int dh_planes = 0;             // planes of a discrete head: ceil(discrete_value_size / 36)
+    uint8_t* d_at_frames_in = nullptr; // [B][3][96][96] staging of mz_atari_observe
+    float* d_root_reward = nullptr;    // [B][A]
+    int32_t* d_bound_size = nullptr;
+    float *d_bound_lo = nullptr, *d_bound_hi = nullptr;
+    float* d_planes_f32 = nullptr;     // [B][32][96][96] parity hooks (allocated on first use)
+    int64_t memsets = 0;               // memset nodes issued (graph accounting)
 
     // graphs keyed by (num_evals, noise, rotations)
     std::map<int, SearchGraph> graphs;
@@ -401,6 +457,66 @@ int launch_heads(mz_engine* e, const __half* act, int* clear = nullptr, int clea
 }
 
 int launch_tower(mz_engine* e, int which, bool clear_counters = true, bool pdl = false);
+int launch_tower_params(mz_engine* e, mznn::TowerParams* params, int* d_done, int cout, int cin_max, int rows_ext, int stages, bool clear_counters, bool pdl);
+
+int launch_discrete_head(mz_engine* e, const __half* act, int head, bool with_policy, float* out)
+{
+    mzat::DiscreteHeadParams p;
+    auto f = [&](int h, int i) { return reinterpret_cast<const float*>(e->d_blob + e->off_dhead[h][i]); };
+    p.act = act, p.c = e->cpad, p.n = e->d.N, p.slots = e->d.slots, p.batch = e->d.B;
+    p.do_policy = (with_policy ? 1 : 0);
+    p.w_pc = f(2, 0), p.b_pc = f(2, 1), p.w_pf = f(2, 2), p.b_pf = f(2, 3), p.pol_ch = e->pol_ch, p.actions = e->d.A;
+    p.policy = e->s.policy, p.logits = e->s.logits;
+    p.w_dc = f(head, 0), p.b_dc = f(head, 1), p.w_d1 = f(head, 2), p.b_d1 = f(head, 3), p.w_d2 = f(head, 4), p.b_d2 = f(head, 5);
+    p.hc = e->dh_planes, p.vh = (head == 0 ? e->nd.num_value_hidden_channels : e->nd.num_hidden_channels), p.dv = e->nd.discrete_value_size;
+    p.out = out;
+    constexpr int BPC = 4, threads = 512;
+    const int hw = p.n * p.n, np = (with_policy ? p.pol_ch : 0) + p.hc;
+    const int parts = std::max(1, threads / p.vh);
+    const size_t smem = sizeof(float) * (static_cast<size_t>(np) * p.c + BPC * np * hw + BPC * p.vh + BPC * std::max(p.dv, p.actions) + static_cast<size_t>(parts) * BPC * p.vh);
+    if (smem > 96 * 1024) { return fail(MZ_ERR_ARG, "discrete head does not fit its shared-memory budget"); }
+    mzat::discrete_head_kernel<BPC><<<(e->d.B + BPC - 1) / BPC, threads, smem, e->stream>>>(p);
+    e->launches++;
+    return MZ_OK;
+}
+
+int launch_stage(mz_engine* e, ConvStage& st)
+{
+    return launch_tower_params(e, st.params, st.d_done, st.cout, st.cin_max, st.rows_ext, st.stages, true, false);
+}
+
+// MuZeroAtariNetwork (network/py/muzero_atari_network.py:157-183). which == 0: initial_inference on the space-to-depth planes already
+// in the first stage's input rows; which == 1: recurrent_inference on the rows in dyn_in. The reward head reads the dynamics output
+// before it is scaled (:53-54), the prediction heads the scaled hidden state.
+int forward_atari(mz_engine* e, int which)
+{
+    int rc;
+    const int B = e->d.B, grid = 4 * e->num_sms;
+    NetTower& T = e->tw[which];
+    if (which == 0) {
+        ConvStage &A = e->ast[0], &Bs = e->ast[1], &Cs = e->ast[2];
+        if ((rc = launch_stage(e, A))) { return rc; }
+        mzat::space_to_depth_kernel<<<grid, 256, 0, e->stream>>>(A.act[A.out_buf], Bs.in, B, A.n, A.cout);
+        e->launches++;
+        if ((rc = launch_stage(e, Bs))) { return rc; }
+        mzat::avgpool_kernel<<<grid, 256, 0, e->stream>>>(Bs.act[Bs.out_buf], Cs.act[0], B, Bs.n, Bs.cout);
+        e->launches++;
+        if ((rc = launch_stage(e, Cs))) { return rc; }
+        mzat::avgpool_kernel<<<grid, 256, 0, e->stream>>>(Cs.act[Cs.out_buf], e->act[0], B, Cs.n, Cs.cout);
+        e->launches++;
+    }
+    if ((rc = launch_tower(e, which, true, false))) { return rc; }
+    __half* out = e->act[T.out_buf];
+    if (which == 1) {
+        if ((rc = launch_discrete_head(e, out, 1, false, e->s.nn_reward))) { return rc; }
+    } else {
+        CUDA_OK(cudaMemsetAsync(e->s.nn_reward, 0, sizeof(float) * B, e->stream)); // initial_inference has no reward output: reward_ stays 0 (muzero_network.h:25)
+        e->memsets++;
+    }
+    mznn::scale_hidden_kernel<<<B, 256, 0, e->stream>>>(out, reinterpret_cast<__half*>(e->s.hid), e->s.eval_slot, e->d.N, e->d.slots, e->cpad, e->nd.num_hidden_channels, e->d.S + 1);
+    e->launches++;
+    return launch_discrete_head(e, out, 0, true, e->s.nn_value);
+}
 
 // AlphaZeroNetwork.forward (network/py/alphazero_network.py:90-113) on the rows already in nn_in; for a MuZero network
 // `which` selects initial_inference (0: representation, rows in nn_in) or recurrent_inference (1: dynamics, rows in dyn_in),
@@ -408,6 +524,7 @@ int launch_tower(mz_engine* e, int which, bool clear_counters = true, bool pdl =
 int forward(mz_engine* e, int which = 0, bool after_tree_step = false)
 {
     if (!e->net_ready) { return fail(MZ_ERR_STATE, "network not finalized"); }
+    if (e->atari) { return forward_atari(e, which); }
     NetTower& T = e->tw[which];
     int rc;
     if (e->conv_mode == 3) {
@@ -432,38 +549,44 @@ int forward(mz_engine* e, int which = 0, bool after_tree_step = false)
     return launch_heads(e, out);
 }
 
+// one launch of the fused tower kernel over `params` (a NetTower or a ConvStage)
+int launch_tower_params(mz_engine* e, mznn::TowerParams* params, int* d_done, int cout, int cin_max, int rows_ext, int stages, bool clear_counters, bool pdl)
+{
+    const int num_groups = (params->num_mtiles + 1) / 2;
+    if (clear_counters) {
+        CUDA_OK(cudaMemsetAsync(d_done, 0, sizeof(int) * params->num_layers * num_groups, e->stream));
+        e->memsets++;
+    }
+    const int units = num_groups * (cout / 128);
+    int clusters = e->tower_sms / 2;
+    if (units < clusters) { clusters = units; }
+    const size_t smem = 2 * static_cast<size_t>(cin_max / mznn::BK) * rows_ext * 128 + static_cast<size_t>(stages) * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * 2), cfg.blockDim = dim3(mznn::TOWER_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = e->stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    params->pdl = (pdl ? 1 : 0);
+    cfg.attrs = attr, cfg.numAttrs = (pdl ? 2 : 1);
+    if (params->dbg && stages == 8) {
+        CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8, true>, *params));
+    } else if (stages == 4) { // 185 KB of shared memory: a tree-step block (30 KB) of another engine fits on the same SM
+        CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 4, false>, *params));
+    } else if (stages == 5) {
+        CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 5, false>, *params));
+    } else {
+        CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8, false>, *params));
+    }
+    e->launches++;
+    return MZ_OK;
+}
+
 int launch_tower(mz_engine* e, int which, bool clear_counters, bool pdl)
 {
-    {
-        NetTower& T = e->tw[which];
-        const int num_groups = (T.params->num_mtiles + 1) / 2;
-        if (clear_counters) { CUDA_OK(cudaMemsetAsync(T.d_done, 0, sizeof(int) * T.params->num_layers * num_groups, e->stream)); }
-        const int units = num_groups * (e->cpad / 128);
-        int clusters = e->tower_sms / 2;
-        if (units < clusters) { clusters = units; }
-        const int stages = e->tower_stages;
-        const size_t smem = 2 * static_cast<size_t>(e->cin_max / mznn::BK) * e->rows_ext * 128 + static_cast<size_t>(stages) * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(clusters * 2), cfg.blockDim = dim3(mznn::TOWER_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = e->stream;
-        cudaLaunchAttribute attr[2];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[1].val.programmaticStreamSerializationAllowed = 1;
-        T.params->pdl = (pdl ? 1 : 0);
-        cfg.attrs = attr, cfg.numAttrs = (pdl ? 2 : 1);
-        if (T.params->dbg && stages == 8) {
-            CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8, true>, *T.params));
-        } else if (stages == 4) { // 185 KB of shared memory: a tree-step block (30 KB) of another engine fits on the same SM
-            CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 4, false>, *T.params));
-        } else if (stages == 5) {
-            CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 5, false>, *T.params));
-        } else {
-            CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8, false>, *T.params));
-        }
-        e->launches++;
-    }
-    return MZ_OK;
+    NetTower& T = e->tw[which];
+    return launch_tower_params(e, T.params, T.d_done, e->cpad, e->cin_max, e->rows_ext, e->tower_stages, clear_counters, pdl);
 }
 
 size_t step_smem_bytes(const mz_dims& d)
@@ -510,11 +633,75 @@ std::vector<float> fold_conv(const mz_engine* e, const std::string& conv, const 
     return out;
 }
 
+// Atari representation stages (muzero_atari_network.py:7-40) and the discrete heads. "stride 2": a 3x3 / stride-2 / pad-1
+// convolution is a stride-1 convolution over the space-to-depth(2) input: output cell (X, Y) reads pixels 2Y-1 .. 2Y+1, i.e. cell
+// row Y-1 (its lower pixel row, dy = 1) and cell row Y (both pixel rows), so only the taps that reach up / left exist:
+//   (tap row ty, sub-row dy) -> kernel row ky:  (0, 1) -> 0,  (1, 0) -> 1,  (1, 1) -> 2,  (0, 0) -> none      (columns alike).
+// conv1 (32 planes) runs as ONE layer over all four sub-positions (4 * 32 = 128 input channels, taps {0, 1, 3, 4}); conv2 (C/2
+// channels) as FOUR chained layers, one per sub-position, each reading its 128-channel slice of the space-to-depth rows with
+// exactly the taps that exist for it (1 + 2 + 2 + 4 = 9 tap-slices: the algorithmic FLOPs, nothing wasted) and adding the
+// previous partial sum through the residual path; bias, BatchNorm shift and ReLU belong to the last one.
+int stride2_tap_mask(int dy, int dx)
+{
+    int mask = 0;
+    for (int ty = (dy ? 0 : 1); ty <= 1; ++ty) {
+        for (int tx = (dx ? 0 : 1); tx <= 1; ++tx) { mask |= 1 << (ty * 3 + tx); }
+    }
+    return mask;
+}
+int stride2_kernel_index(int t, int d) { return t == 0 ? (d == 1 ? 0 : -1) : (d == 0 ? 1 : 2); }
+
+int plan_blob_atari(mz_engine* e)
+{
+    const mz_net_dims& nd = e->nd;
+    const int C = e->cpad, C1 = ((nd.num_hidden_channels / 2 + 127) / 128) * 128;
+    e->at_c1 = C1;
+    auto add = [&](ConvStage& st, int cin, int cout, int cin_off, int taps, int relu, int in_buf, int out_buf, int res_buf) {
+        ConvLayer L;
+        L.cin = cin, L.cout = cout, L.relu = relu, L.cin_off = cin_off, L.tap_mask = taps, L.in_buf = in_buf, L.out_buf = out_buf, L.res_buf = res_buf;
+        L.w_off = e->blob.take(sizeof(__half) * 9 * static_cast<size_t>(cout) * cin);
+        L.b_off = e->blob.take(sizeof(float) * cout);
+        st.convs.push_back(L);
+    };
+    ConvStage &A = e->ast[0], &B = e->ast[1], &Cs = e->ast[2];
+    A = ConvStage(), B = ConvStage(), Cs = ConvStage();
+    A.n = mzat::RES / 2, A.cin_in = 4 * mzat::PLANES, A.cout = C1; // conv1 + residual_blocks1
+    add(A, A.cin_in, C1, 0, 0x01b, 1, -1, 0, -2);
+    add(A, C1, C1, 0, 0x1ff, 1, 0, 1, -2);
+    add(A, C1, C1, 0, 0x1ff, 1, 1, 2, 0);
+    A.out_buf = 2;
+    B.n = mzat::RES / 4, B.cin_in = 4 * C1, B.cout = C; // conv2 (four sub-position layers) + residual_blocks2
+    for (int q = 0; q < 4; ++q) { add(B, C1, C, q * C1, stride2_tap_mask(q >> 1, q & 1), q == 3 ? 1 : 0, -1, q & 1, q == 0 ? -2 : ((q - 1) & 1)); }
+    add(B, C, C, 0, 0x1ff, 1, 1, 2, -2);
+    add(B, C, C, 0, 0x1ff, 1, 2, 0, 1);
+    B.out_buf = 0;
+    Cs.n = mzat::RES / 8, Cs.cin_in = 0, Cs.cout = C; // avg_pooling1 writes act[0]; residual_blocks3
+    add(Cs, C, C, 0, 0x1ff, 1, 0, 1, -2);
+    add(Cs, C, C, 0, 0x1ff, 1, 1, 2, 0);
+    Cs.out_buf = 2;
+    // heads (network_unit.py:26-42,68-87), fp32: policy conv [pol_ch][C], b, fc^T [pol_ch * 36][A], b; value / reward: conv [hc][C], b,
+    // fc1^T [hc * 36][vh], b, fc2^T [vh][dv], b
+    const int hw = e->d.N * e->d.N, dv = nd.discrete_value_size, vh = nd.num_value_hidden_channels;
+    e->dh_planes = (dv + hw - 1) / hw;
+    const int hc = e->dh_planes;
+    for (int h = 0; h < 2; ++h) {
+        const int fc1_out = (h == 0 ? vh : nd.num_hidden_channels); // the reward head's hidden width is num_channels (muzero_atari_network.py:50)
+        const size_t sizes[6] = {static_cast<size_t>(hc) * C, static_cast<size_t>(hc), static_cast<size_t>(hc) * hw * fc1_out, static_cast<size_t>(fc1_out),
+                                 static_cast<size_t>(fc1_out) * dv, static_cast<size_t>(dv)};
+        for (int i = 0; i < 6; ++i) { e->off_dhead[h][i] = e->blob.take(sizeof(float) * sizes[i]); }
+    }
+    const size_t psizes[4] = {static_cast<size_t>(e->pol_ch) * C, static_cast<size_t>(e->pol_ch), static_cast<size_t>(e->pol_ch) * hw * nd.action_size, static_cast<size_t>(nd.action_size)};
+    for (int i = 0; i < 4; ++i) { e->off_dhead[2][i] = e->blob.take(sizeof(float) * psizes[i]); }
+    return MZ_OK;
+}
+
 int plan_blob(mz_engine* e)
 {
     const mz_net_dims& nd = e->nd;
     e->cpad = ((nd.num_hidden_channels + 63) / 64) * 64;
-    e->pol_ch = (nd.action_size + nd.input_height * nd.input_width - 1) / (nd.input_height * nd.input_width);
+    if (e->atari) { e->cpad = ((nd.num_hidden_channels + 127) / 128) * 128; } // every stage of the Atari network runs through the fused tower (128-wide tiles)
+    const int head_hw = (e->atari ? e->d.N * e->d.N : nd.input_height * nd.input_width); // heads work on the hidden state's cells
+    e->pol_ch = (nd.action_size + head_hw - 1) / head_hw;
     // output-channel tile of the conv kernel: 128 keeps two CTAs resident per SM (epilogue of one overlaps the
     // main loop of the other) and gives 2x the tiles for wave balance; MZ_CONV_BN overrides for experiments
     e->bn_tile = (e->cpad % 128 == 0 ? 128 : 64);
@@ -528,24 +715,75 @@ int plan_blob(mz_engine* e)
     e->tw[0].cin0_real = nd.num_input_channels, e->tw[0].cin0 = MZ_NN_CPAD;
     e->tw[1].prefix = "dynamics_network.";
     e->tw[1].cin0_real = nd.num_hidden_channels + nd.num_action_feature_channels; // torch.cat((hidden_state, action_plane), dim=1), muzero_network.py:31
-    e->tw[1].cin0 = ((e->tw[1].cin0_real + 63) / 64) * 64;
+    e->tw[1].cin0 = ((std::max(e->tw[1].cin0_real, e->cpad) + 63) / 64) * 64; // the gather copies whole (padded) hidden rows, then the action planes over columns Ch ..
     e->cin_max = e->cpad;
     for (int t = 0; t < e->num_towers; ++t) {
         NetTower& T = e->tw[t];
-        T.convs.assign(1 + 2 * nd.num_blocks, ConvLayer());
-        if (T.cin0 > e->cin_max) { e->cin_max = T.cin0; }
+        T.has_stem = !(e->atari && t == 0); // the 6 x 6 stage of the Atari representation network is residual blocks only
+        T.convs.assign((T.has_stem ? 1 : 0) + 2 * nd.num_blocks, ConvLayer());
+        if (T.has_stem && T.cin0 > e->cin_max) { e->cin_max = T.cin0; }
         for (size_t i = 0; i < T.convs.size(); ++i) {
             ConvLayer& L = T.convs[i];
-            L.cin = (i == 0 ? T.cin0 : e->cpad), L.cout = e->cpad, L.relu = 1;
+            L.cin = (i == 0 && T.has_stem ? T.cin0 : e->cpad), L.cout = e->cpad, L.relu = 1;
             L.w_off = e->blob.take(sizeof(__half) * 9 * static_cast<size_t>(L.cout) * L.cin);
             L.b_off = e->blob.take(sizeof(float) * L.cout);
         }
     }
+    if (e->atari) { return plan_blob_atari(e); }
     const int hw = nd.input_height * nd.input_width;
     const size_t head_sizes[10] = {static_cast<size_t>(e->pol_ch) * e->cpad, static_cast<size_t>(e->pol_ch), static_cast<size_t>(nd.action_size) * e->pol_ch * hw,
                                    static_cast<size_t>(nd.action_size), static_cast<size_t>(e->cpad), 1, static_cast<size_t>(nd.num_value_hidden_channels) * hw,
                                    static_cast<size_t>(nd.num_value_hidden_channels), static_cast<size_t>(nd.num_value_hidden_channels), 1};
     for (int i = 0; i < 10; ++i) { e->off_head[i] = e->blob.take(sizeof(float) * head_sizes[i]); }
+    return MZ_OK;
+}
+
+// buffers, tensor maps and launch parameters of the three representation stages
+int alloc_atari(mz_engine* e)
+{
+    int rc;
+    for (int si = 0; si < 3; ++si) {
+        ConvStage& st = e->ast[si];
+        st.slots = (st.n + 1) * (st.n + 1);
+        st.rows_alloc = static_cast<int>((static_cast<size_t>(e->d.B) * st.slots + mznn::BM - 1) / mznn::BM * mznn::BM);
+        st.rows_ext = (mznn::BM + 2 * (st.n + 2) + 7) / 8 * 8;
+        st.cin_max = 0;
+        for (const ConvLayer& L : st.convs) { st.cin_max = std::max(st.cin_max, L.cin); }
+        st.stages = 0;
+        for (int cand : {8, 5, 4}) {
+            const size_t need = 2 * static_cast<size_t>(st.cin_max / mznn::BK) * st.rows_ext * 128 + static_cast<size_t>(cand) * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
+            if (st.stages == 0 && need <= 227 * 1024) { st.stages = cand; }
+        }
+        if (st.stages == 0 || st.rows_ext > 256) { return fail(MZ_ERR_ARG, "an Atari representation stage does not fit the tower kernel's shared memory"); }
+        const size_t rows = st.rows_alloc;
+        if (st.cin_in > 0) {
+            if ((rc = e->dalloc(&st.in, rows * st.cin_in))) { return rc; }
+            if ((rc = make_map_2d(e, &st.map_in_ext, st.in, st.cin_in, rows, mznn::BK, st.rows_ext))) { return rc; }
+        }
+        for (int i = 0; i < 3; ++i) {
+            if ((rc = e->dalloc(&st.act[i], rows * st.cout))) { return rc; }
+            if ((rc = make_map_2d(e, &st.map_act_ext[i], st.act[i], st.cout, rows, mznn::BK, st.rows_ext))) { return rc; }
+        }
+        st.params = new mznn::TowerParams();
+        mznn::TowerParams& T = *st.params;
+        T.num_layers = static_cast<int>(st.convs.size());
+        T.rows_valid = e->d.B * st.slots, T.n1 = st.n + 1, T.slots = st.slots, T.cout = st.cout, T.rows_ext = st.rows_ext, T.halo = st.n + 2;
+        T.num_mtiles = st.rows_alloc / mznn::BM, T.cin_max = st.cin_max;
+        T.rotate = 22, T.shift = 0, T.zigzag = 0, T.strided = 1, T.pdl = 0, T.dbg = nullptr;
+        for (int li = 0; li < T.num_layers; ++li) {
+            ConvLayer& L = st.convs[li];
+            if ((rc = make_map_2d(e, &L.map_w_mc, e->d_blob + L.w_off, L.cin, 9ull * L.cout, mznn::BK, 64))) { return rc; }
+            mznn::TowerLayer& TL = T.layer[li];
+            TL.map_in = (L.in_buf < 0 ? st.map_in_ext : st.map_act_ext[L.in_buf]), TL.map_w = L.map_w_mc;
+            TL.out = st.act[L.out_buf], TL.residual = (L.res_buf == -2 ? nullptr : (L.res_buf < 0 ? st.in : st.act[L.res_buf]));
+            TL.bias = reinterpret_cast<const float*>(e->d_blob + L.b_off), TL.cin = L.cin, TL.relu = L.relu, TL.cin_off = L.cin_off, TL.tap_mask = L.tap_mask;
+        }
+        const int num_groups = (T.num_mtiles + 1) / 2;
+        if ((rc = e->dalloc(&st.d_done, static_cast<size_t>(T.num_layers) * num_groups))) { return rc; }
+        T.done = st.d_done;
+    }
+    const int heads_smem = 96 * 1024;
+    CUDA_OK(cudaFuncSetAttribute(mzat::discrete_head_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, heads_smem));
     return MZ_OK;
 }
 
@@ -618,7 +856,8 @@ int alloc_net(mz_engine* e)
         const int v = std::atoi(env);
         if (v >= 2 && v <= e->num_sms) { e->tower_sms = v & ~1; }
     }
-    const bool tower_ok = (want_tower && e->conv_mode == 2 && 1 + 2 * e->nd.num_blocks <= mznn::TOWER_MAX_LAYERS);
+    const bool tower_ok = (want_tower && e->conv_mode == 2 && 1 + 2 * e->nd.num_blocks <= mznn::TOWER_MAX_LAYERS && (!e->atari || e->nd.num_blocks > 0));
+    if (e->atari && !tower_ok) { return fail(MZ_ERR_ARG, "the Atari network needs the fused tower (1 <= num_blocks <= 23)"); }
     for (int t = 0; t < e->num_towers; ++t) {
         NetTower& NT = e->tw[t];
         if ((rc = make_map_2d(e, &NT.map_in, NT.in, NT.cin0, rows, mznn::BK, mznn::BM))) { return rc; }
@@ -645,13 +884,15 @@ int alloc_net(mz_engine* e)
             mznn::TowerLayer& L = T.layer[li];
             L.map_in = in, L.map_w = NT.convs[li].map_w_mc, L.out = out, L.residual = residual;
             L.bias = reinterpret_cast<const float*>(e->d_blob + NT.convs[li].b_off), L.cin = NT.convs[li].cin, L.relu = NT.convs[li].relu;
+            L.cin_off = 0, L.tap_mask = 0x1ff;
         };
-        set(0, NT.map_in_ext, e->act[0], nullptr);
+        const int base = (NT.has_stem ? 1 : 0);
+        if (NT.has_stem) { set(0, NT.map_in_ext, e->act[0], nullptr); }
         int cur = 0;
         for (int b = 0; b < e->nd.num_blocks; ++b) {
             const int tt = (cur + 1) % 3, o = (cur + 2) % 3;
-            set(1 + 2 * b, e->map_act_ext[cur], e->act[tt], nullptr);
-            set(2 + 2 * b, e->map_act_ext[tt], e->act[o], e->act[cur]);
+            set(base + 2 * b, e->map_act_ext[cur], e->act[tt], nullptr);
+            set(base + 1 + 2 * b, e->map_act_ext[tt], e->act[o], e->act[cur]);
             cur = o;
         }
         const int num_groups = (T.num_mtiles + 1) / 2;
@@ -667,6 +908,121 @@ int alloc_net(mz_engine* e)
         }
     }
     if (tower_ok) { e->conv_mode = 3; }
+    if (e->atari) { return alloc_atari(e); }
+    return MZ_OK;
+}
+
+// weights of the Atari representation stages and of the discrete heads into the host copy of the blob
+int pack_atari_weights(mz_engine* e, std::vector<uint8_t>& host)
+{
+    const mz_net_dims& nd = e->nd;
+    const int Ch = nd.num_hidden_channels, Ch1 = Ch / 2, C1 = e->at_c1, hw = e->d.N * e->d.N;
+    std::string err;
+    const std::string rp = "representation_network.";
+    // a plain 3x3 layer: [tap][cout_pad][cin_pad] fp16
+    auto plain = [&](const ConvLayer& L, const std::string& cname, const std::string& bname, int cout_real, int cin_real) -> int {
+        std::vector<float> bias, w = fold_conv(e, cname, bname, cout_real, cin_real, 3, bias, err);
+        if (w.empty()) { return fail(MZ_ERR_ARG, err); }
+        __half* wd = reinterpret_cast<__half*>(host.data() + L.w_off);
+        float* bd = reinterpret_cast<float*>(host.data() + L.b_off);
+        for (int co = 0; co < cout_real; ++co) {
+            bd[co] = bias[co];
+            for (int ci = 0; ci < cin_real; ++ci) {
+                for (int tap = 0; tap < 9; ++tap) { wd[(static_cast<size_t>(tap) * L.cout + co) * L.cin + ci] = __float2half_rn(w[(static_cast<size_t>(co) * cin_real + ci) * 9 + tap]); }
+            }
+        }
+        return MZ_OK;
+    };
+    int rc;
+    ConvStage &A = e->ast[0], &B = e->ast[1], &Cs = e->ast[2];
+    { // conv1: stride 2 over the 32 planes, all four sub-positions in one layer (see plan_blob_atari)
+        const ConvLayer& L = A.convs[0];
+        std::vector<float> bias, w = fold_conv(e, rp + "conv1", rp + "bn1", Ch1, nd.num_input_channels, 3, bias, err);
+        if (w.empty()) { return fail(MZ_ERR_ARG, err); }
+        __half* wd = reinterpret_cast<__half*>(host.data() + L.w_off);
+        float* bd = reinterpret_cast<float*>(host.data() + L.b_off);
+        const int cin_real = nd.num_input_channels;
+        for (int co = 0; co < Ch1; ++co) {
+            bd[co] = bias[co];
+            for (int ty = 0; ty < 2; ++ty) {
+                for (int tx = 0; tx < 2; ++tx) {
+                    for (int sub = 0; sub < 4; ++sub) {
+                        const int ky = stride2_kernel_index(ty, sub >> 1), kx = stride2_kernel_index(tx, sub & 1);
+                        if (ky < 0 || kx < 0) { continue; }
+                        for (int c = 0; c < cin_real; ++c) {
+                            wd[(static_cast<size_t>(ty * 3 + tx) * L.cout + co) * L.cin + sub * mzat::PLANES + c] = __float2half_rn(w[(static_cast<size_t>(co) * cin_real + c) * 9 + ky * 3 + kx]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if ((rc = plain(A.convs[1], rp + "residual_blocks1.0.conv1", rp + "residual_blocks1.0.bn1", Ch1, Ch1))) { return rc; }
+    if ((rc = plain(A.convs[2], rp + "residual_blocks1.0.conv2", rp + "residual_blocks1.0.bn2", Ch1, Ch1))) { return rc; }
+    { // conv2: stride 2 over Ch / 2 channels, one layer per sub-position; the folded bias rides on the first
+        std::vector<float> bias, w = fold_conv(e, rp + "conv2", rp + "bn2", Ch, Ch1, 3, bias, err);
+        if (w.empty()) { return fail(MZ_ERR_ARG, err); }
+        for (int sub = 0; sub < 4; ++sub) {
+            const ConvLayer& L = B.convs[sub];
+            __half* wd = reinterpret_cast<__half*>(host.data() + L.w_off);
+            float* bd = reinterpret_cast<float*>(host.data() + L.b_off);
+            for (int co = 0; co < Ch; ++co) {
+                if (sub == 0) { bd[co] = bias[co]; }
+                for (int ty = 0; ty < 2; ++ty) {
+                    for (int tx = 0; tx < 2; ++tx) {
+                        const int ky = stride2_kernel_index(ty, sub >> 1), kx = stride2_kernel_index(tx, sub & 1);
+                        if (ky < 0 || kx < 0) { continue; }
+                        for (int c = 0; c < Ch1; ++c) {
+                            wd[(static_cast<size_t>(ty * 3 + tx) * L.cout + co) * L.cin + c] = __float2half_rn(w[(static_cast<size_t>(co) * Ch1 + c) * 9 + ky * 3 + kx]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if ((rc = plain(B.convs[4], rp + "residual_blocks2.0.conv1", rp + "residual_blocks2.0.bn1", Ch, Ch))) { return rc; }
+    if ((rc = plain(B.convs[5], rp + "residual_blocks2.0.conv2", rp + "residual_blocks2.0.bn2", Ch, Ch))) { return rc; }
+    if ((rc = plain(Cs.convs[0], rp + "residual_blocks3.0.conv1", rp + "residual_blocks3.0.bn1", Ch, Ch))) { return rc; }
+    if ((rc = plain(Cs.convs[1], rp + "residual_blocks3.0.conv2", rp + "residual_blocks3.0.bn2", Ch, Ch))) { return rc; }
+    // heads
+    auto raw = [&](const std::string& name, size_t n) -> const float* {
+        auto it = e->tensors.find(name);
+        if (it == e->tensors.end() || it->second.size() != n) {
+            err = "missing or mis-sized tensor " + name;
+            return nullptr;
+        }
+        return it->second.data();
+    };
+    auto conv1x1 = [&](const std::string& name, int planes, size_t w_off, size_t b_off) -> int {
+        std::vector<float> bias, w = fold_conv(e, name + ".conv", name + ".bn", planes, Ch, 1, bias, err);
+        if (w.empty()) { return fail(MZ_ERR_ARG, err); }
+        float* wd = reinterpret_cast<float*>(host.data() + w_off);
+        for (int o = 0; o < planes; ++o) {
+            for (int c = 0; c < Ch; ++c) { wd[static_cast<size_t>(o) * e->cpad + c] = w[static_cast<size_t>(o) * Ch + c]; }
+        }
+        std::memcpy(host.data() + b_off, bias.data(), sizeof(float) * planes);
+        return MZ_OK;
+    };
+    auto fc_t = [&](const std::string& name, int nout, int nin, size_t w_off, size_t b_off) -> int { // torch [out][in] -> [in][out]
+        const float *w = raw(name + ".weight", static_cast<size_t>(nout) * nin), *b = raw(name + ".bias", nout);
+        if (!w || !b) { return fail(MZ_ERR_ARG, err); }
+        float* wd = reinterpret_cast<float*>(host.data() + w_off);
+        for (int o = 0; o < nout; ++o) {
+            for (int i = 0; i < nin; ++i) { wd[static_cast<size_t>(i) * nout + o] = w[static_cast<size_t>(o) * nin + i]; }
+        }
+        std::memcpy(host.data() + b_off, b, sizeof(float) * nout);
+        return MZ_OK;
+    };
+    const int hc = e->dh_planes, dv = nd.discrete_value_size;
+    const std::string names[2] = {"prediction_network.value", "dynamics_network.reward_network"};
+    for (int h = 0; h < 2; ++h) {
+        const int fc1_out = (h == 0 ? nd.num_value_hidden_channels : Ch);
+        if ((rc = conv1x1(names[h], hc, e->off_dhead[h][0], e->off_dhead[h][1]))) { return rc; }
+        if ((rc = fc_t(names[h] + ".fc1", fc1_out, hc * hw, e->off_dhead[h][2], e->off_dhead[h][3]))) { return rc; }
+        if ((rc = fc_t(names[h] + ".fc2", dv, fc1_out, e->off_dhead[h][4], e->off_dhead[h][5]))) { return rc; }
+    }
+    if ((rc = conv1x1("prediction_network.policy", e->pol_ch, e->off_dhead[2][0], e->off_dhead[2][1]))) { return rc; }
+    if ((rc = fc_t("prediction_network.policy.fc", nd.action_size, e->pol_ch * hw, e->off_dhead[2][2], e->off_dhead[2][3]))) { return rc; }
     return MZ_OK;
 }
 
@@ -680,10 +1036,14 @@ int mz_create(const mz_config* cfg, mz_engine** out)
 {
     if (!cfg || !out) { return fail(MZ_ERR_ARG, "null argument"); }
     *out = nullptr;
-    if (cfg->game != MZ_GAME_GO && cfg->game != MZ_GAME_TICTACTOE && cfg->game != MZ_GAME_OTHELLO && cfg->game != MZ_GAME_NOGO && cfg->game != MZ_GAME_GOMOKU && cfg->game != MZ_GAME_HEX) {
+    if (cfg->game != MZ_GAME_GO && cfg->game != MZ_GAME_TICTACTOE && cfg->game != MZ_GAME_OTHELLO && cfg->game != MZ_GAME_NOGO && cfg->game != MZ_GAME_GOMOKU && cfg->game != MZ_GAME_HEX &&
+        cfg->game != MZ_GAME_ATARI) {
         return fail(MZ_ERR_ARG, "unsupported game");
     }
-    const int N = (cfg->game == MZ_GAME_TICTACTOE ? 3 : cfg->board_size);
+    const bool atari = (cfg->game == MZ_GAME_ATARI);
+    if (atari && !cfg->muzero) { return fail(MZ_ERR_ARG, "Atari is searched with a MuZero network only (the emulator cannot be copied into the tree)"); }
+    if (atari && (cfg->atari_legal_mask == 0 || (cfg->atari_legal_mask >> 18) != 0)) { return fail(MZ_ERR_ARG, "atari_legal_mask must name at least one of the 18 actions"); }
+    const int N = (cfg->game == MZ_GAME_TICTACTOE ? 3 : (atari ? 6 : cfg->board_size)); // Atari: side of the hidden state (atari.h:25-26)
     if (N < 2 || N > MZ_MAXN) { return fail(MZ_ERR_ARG, "board_size must be in [2, 19]"); }
     if (cfg->game == MZ_GAME_OTHELLO && (N < 4 || N > 16 || (N & 1))) { return fail(MZ_ERR_ARG, "othello board_size must be even and in [4, 16]"); }
     if (cfg->use_gumbel && cfg->gumbel_sample_size < 2) { return fail(MZ_ERR_ARG, "actor_gumbel_sample_size must be at least 2"); }
@@ -701,6 +1061,11 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     mz_dims& d = e->d;
     d.game = cfg->game, d.N = N, d.A = (cfg->game == MZ_GAME_TICTACTOE ? 9 : ((cfg->game == MZ_GAME_GOMOKU || cfg->game == MZ_GAME_HEX) ? N * N : N * N + 1)), d.C = (MZ_GO_FAMILY(cfg->game) ? 18 : 4);
     d.hex_swap_rule = (cfg->hex_swap_rule != 0);
+    d.num_players = 2, d.act_planes = 1, d.value_rescale = (cfg->value_rescale != 0);
+    e->atari = atari;
+    if (atari) { // atari.h:18-26, mcts.cpp:211-213
+        d.A = 18, d.C = mzat::PLANES, d.num_players = 1, d.atari_init_q = 1, d.has_reward = 1, d.act_planes = 18, d.legal_mask = cfg->atari_legal_mask;
+    }
     d.gomoku_exactly_five = (cfg->gomoku_exactly_five != 0), d.gomoku_outer_open = (cfg->gomoku_outer_open != 0);
     d.muzero = (cfg->muzero != 0), d.gumbel = (cfg->use_gumbel != 0), d.gumbel_noise = (cfg->gumbel_noise != 0), d.gumbel_m = cfg->gumbel_sample_size;
     d.sigma_visit_c = cfg->gumbel_sigma_visit_c, d.sigma_scale_c = cfg->gumbel_sigma_scale_c;
@@ -715,6 +1080,7 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     }
     d.S = cfg->num_simulation, d.B = cfg->num_games;
     d.NP = 1 + (d.S + 1) * d.A; // actor_group.cpp:183, tree.h:66
+    d.vb_cap = d.S + 2;
     if (d.NP >= (1 << MZ_LINK_SHIFT)) {
         delete e;
         return fail(MZ_ERR_ARG, "node pool per game exceeds 2^20 nodes");
@@ -775,6 +1141,14 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     guard(e->dalloc(&e->d_root_info, B * 4)), guard(e->dalloc(&e->d_root_action, BA));
     for (int i = 0; i < 6; ++i) { guard(e->dalloc(&e->d_root_f[i], BA)); }
     guard(e->dalloc(&e->d_feat_f32, B * d.C * N * N));
+    if (d.has_reward) { guard(e->dalloc(&s.reward, np)); }
+    guard(e->dalloc(&s.nn_reward, B));
+    if (d.value_rescale) { guard(e->dalloc(&s.vb_key, B * d.vb_cap)), guard(e->dalloc(&s.vb_cnt, B * d.vb_cap)), guard(e->dalloc(&s.vb_n, B)); }
+    guard(e->dalloc(&e->d_root_reward, BA)), guard(e->dalloc(&e->d_bound_size, B)), guard(e->dalloc(&e->d_bound_lo, B)), guard(e->dalloc(&e->d_bound_hi, B));
+    if (atari) {
+        guard(e->dalloc(&s.at_frames, B * MZ_HIST * MZ_ATARI_FRAME)), guard(e->dalloc(&s.at_meta, B * 16));
+        guard(e->dalloc(&e->d_at_frames_in, B * MZ_ATARI_FRAME));
+    }
     if (const char* env = knob("MZ_DEBUG_TREE")) {
         if (std::atoi(env) != 0) { guard(e->dalloc(&s.dbg, B * 16)); }
     }
@@ -842,6 +1216,7 @@ void mz_destroy(mz_engine* e)
     for (void* p : e->allocs) { cudaFree(p); }
     delete e->tw[0].params;
     delete e->tw[1].params;
+    for (ConvStage& st : e->ast) { delete st.params; }
     if (e->ev0) { cudaEventDestroy(e->ev0); }
     if (e->ev1) { cudaEventDestroy(e->ev1); }
     if (e->ev2) { cudaEventDestroy(e->ev2); }
@@ -851,23 +1226,31 @@ void mz_destroy(mz_engine* e)
 }
 
 int mz_action_size(const mz_engine* e) { return e ? e->d.A : MZ_ERR_ARG; }
-int mz_num_features(const mz_engine* e) { return e ? e->d.C * e->d.N * e->d.N : MZ_ERR_ARG; }
+int mz_num_features(const mz_engine* e) { return e ? (e->atari ? mzat::PLANES * mzat::RES * mzat::RES : e->d.C * e->d.N * e->d.N) : MZ_ERR_ARG; }
 int64_t mz_launch_count(const mz_engine* e) { return e ? e->launches : 0; }
 int mz_conv_layers_per_launch(const mz_engine* e) { return (e && e->net_ready) ? (e->conv_mode == 3 ? static_cast<int>(e->tw[0].convs.size()) : 1) : MZ_ERR_STATE; }
 
 int mz_net_configure(mz_engine* e, const mz_net_dims* dims)
 {
     if (!e || !dims) { return fail(MZ_ERR_ARG, "null argument"); }
-    if (dims->discrete_value_size != 1) { return fail(MZ_ERR_ARG, "discrete value heads are not implemented in this engine yet"); }
+    if (e->atari) { // muzero_atari: 32 x 96 x 96 planes, discrete heads, 18 action planes (atari.h:19-27,68-76)
+        if (dims->num_input_channels != mzat::PLANES || dims->input_height != mzat::RES || dims->input_width != mzat::RES || dims->action_size != e->d.A ||
+            dims->num_action_feature_channels != 18 || dims->discrete_value_size < 3 || !dims->is_muzero) {
+            return fail(MZ_ERR_ARG, "network dimensions do not match the Atari game (muzero_atari network expected)");
+        }
+        if (dims->num_hidden_channels % 16 != 0) { return fail(MZ_ERR_ARG, "Atari networks need num_hidden_channels divisible by 16"); }
+    } else {
+    if (dims->discrete_value_size != 1) { return fail(MZ_ERR_ARG, "discrete value heads exist for the Atari (muzero_atari) network only"); }
     if (dims->num_input_channels != e->d.C || dims->input_height != e->d.N || dims->input_width != e->d.N || dims->action_size != e->d.A) {
         return fail(MZ_ERR_ARG, "network dimensions do not match the game");
     }
     if ((dims->action_size + dims->input_height * dims->input_width - 1) / (dims->input_height * dims->input_width) > 3) {
         return fail(MZ_ERR_ARG, "policy head with more than 3 planes is not supported");
     }
-    if (dims->num_input_channels > MZ_NN_CPAD || dims->num_hidden_channels < 1 || dims->num_blocks < 0) { return fail(MZ_ERR_ARG, "unsupported network size"); }
+    }
+    if ((!e->atari && dims->num_input_channels > MZ_NN_CPAD) || dims->num_hidden_channels < 1 || dims->num_blocks < 0) { return fail(MZ_ERR_ARG, "unsupported network size"); }
     if ((dims->is_muzero != 0) != (e->cfg.muzero != 0)) { return fail(MZ_ERR_ARG, "network type (alphazero / muzero) does not match the engine's nn_type_name"); }
-    if (dims->is_muzero && dims->num_action_feature_channels != 1) { return fail(MZ_ERR_ARG, "only board-game MuZero networks (one action plane) are supported"); }
+    if (!e->atari && dims->is_muzero && dims->num_action_feature_channels != 1) { return fail(MZ_ERR_ARG, "board-game MuZero networks have one action plane"); }
     if (e->d_blob && std::memcmp(&e->nd, dims, sizeof(*dims)) != 0) {
         return fail(MZ_ERR_STATE, "a network of a different shape is already allocated for this engine");
     }
@@ -917,10 +1300,11 @@ int mz_net_finalize(mz_engine* e)
         const ConvLayer& L = T.convs[li];
         std::string cname, bname;
         int cin_real;
-        if (li == 0) {
+        if (li == 0 && T.has_stem) {
             cname = T.prefix + "conv", bname = T.prefix + "bn", cin_real = T.cin0_real;
         } else {
-            const int blk = static_cast<int>(li - 1) / 2, which = static_cast<int>(li - 1) % 2 + 1;
+            const int lb = static_cast<int>(li) - (T.has_stem ? 1 : 0);
+            const int blk = lb / 2, which = lb % 2 + 1;
             cname = T.prefix + "residual_blocks." + std::to_string(blk) + ".conv" + std::to_string(which);
             bname = T.prefix + "residual_blocks." + std::to_string(blk) + ".bn" + std::to_string(which);
             cin_real = Ch;
@@ -941,6 +1325,17 @@ int mz_net_finalize(mz_engine* e)
     }
     }
     const std::string hp = (e->cfg.muzero ? "prediction_network." : ""); // muzero_network.py:44-45
+    if (e->atari) {
+        int rc = pack_atari_weights(e, host);
+        if (rc) { return rc; }
+        rc = alloc_net(e);
+        if (rc) { return rc; }
+        CUDA_OK(cudaMemcpyAsync(e->d_blob, host.data(), host.size(), cudaMemcpyHostToDevice, e->stream));
+        CUDA_OK(cudaStreamSynchronize(e->stream));
+        e->tensors.clear();
+        e->net_ready = true;
+        return MZ_OK;
+    }
     // heads, fp32
     auto put = [&](int idx, const std::vector<float>& v) { std::memcpy(host.data() + e->off_head[idx], v.data(), v.size() * sizeof(float)); };
     auto raw = [&](const std::string& name, size_t n, std::vector<float>& out) -> bool {
@@ -1043,11 +1438,22 @@ int mz_eval_initial(mz_engine* e, const float* features, int32_t n, float* polic
     if (hidden_out && !e->cfg.muzero) { return fail(MZ_ERR_STATE, "hidden states exist only for a muzero network"); }
     CUDA_OK(cudaSetDevice(e->cfg.device));
     const mz_dims& d = e->d;
+    if (e->atari) { // planes [n][32][96][96] -> space-to-depth rows of the first representation stage
+        const size_t F = static_cast<size_t>(mzat::PLANES) * mzat::RES * mzat::RES;
+        if (!e->d_planes_f32) {
+            int rc0 = e->dalloc(&e->d_planes_f32, static_cast<size_t>(d.B) * F);
+            if (rc0) { return rc0; }
+        }
+        CUDA_OK(cudaMemcpyAsync(e->d_planes_f32, features, n * F * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        mzat::pack_input_kernel<true><<<4 * e->num_sms, 256, 0, e->stream>>>(nullptr, nullptr, e->d_planes_f32, e->ast[0].in, n);
+        e->launches++;
+    } else {
     const size_t F = static_cast<size_t>(d.C) * d.N * d.N;
     CUDA_OK(cudaMemcpyAsync(e->d_feat_f32, features, n * F * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     CUDA_OK(cudaMemsetAsync(e->s.nn_in, 0, static_cast<size_t>(e->rows_alloc) * MZ_NN_CPAD * sizeof(uint16_t), e->stream));
     mznn::pack_features_kernel<<<148, 256, 0, e->stream>>>(e->d_feat_f32, reinterpret_cast<__half*>(e->s.nn_in), n, d.C, d.N, d.slots, MZ_NN_CPAD);
     e->launches++;
+    }
     if (e->cfg.muzero) { CUDA_OK(cudaMemsetAsync(e->s.eval_slot, 0, sizeof(int32_t) * d.B, e->stream)); } // the hooks keep their hidden states in slot 0
     int rc = forward(e, 0);
     if (rc) { return rc; }
@@ -1070,12 +1476,52 @@ int mz_eval_recurrent(mz_engine* e, const float* hidden, const int32_t* actions,
     CUDA_OK(cudaMemcpyAsync(e->d_hidden_f32, hidden, sizeof(float) * n * ch * d.N * d.N, cudaMemcpyHostToDevice, e->stream));
     CUDA_OK(cudaMemcpyAsync(e->d_actions, actions, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
     CUDA_OK(cudaMemsetAsync(e->s.dyn_in, 0, static_cast<size_t>(e->rows_alloc) * d.dyn_c * sizeof(uint16_t), e->stream));
-    mznn::pack_hidden_kernel<<<148, 256, 0, e->stream>>>(e->d_hidden_f32, e->d_actions, reinterpret_cast<__half*>(e->s.dyn_in), n, ch, d.N, d.slots, d.dyn_c, d.act_col);
+    mznn::pack_hidden_kernel<<<148, 256, 0, e->stream>>>(e->d_hidden_f32, e->d_actions, reinterpret_cast<__half*>(e->s.dyn_in), n, ch, d.N, d.slots, d.dyn_c, d.act_col, d.act_planes);
     e->launches++;
     CUDA_OK(cudaMemsetAsync(e->s.eval_slot, 0, sizeof(int32_t) * d.B, e->stream));
     int rc = forward(e, 1);
     if (rc) { return rc; }
     return read_outputs(e, n, policy, logits, value, hidden_out);
+}
+
+int mz_eval_rewards(mz_engine* e, int32_t n, float* reward)
+{
+    if (!e || !reward || n < 1 || n > e->d.B) { return fail(MZ_ERR_ARG, "bad argument"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    CUDA_OK(cudaMemcpyAsync(reward, e->s.nn_reward, sizeof(float) * n, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    return MZ_OK;
+}
+
+int mz_atari_observe(mz_engine* e, const int32_t* actions, const uint8_t* frames)
+{
+    if (!e || !actions || !frames) { return fail(MZ_ERR_ARG, "null argument"); }
+    if (!e->atari) { return fail(MZ_ERR_STATE, "not an Atari engine"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    const int B = e->d.B;
+    CUDA_OK(cudaMemcpyAsync(e->d_actions, actions, sizeof(int32_t) * B, cudaMemcpyHostToDevice, e->stream));
+    CUDA_OK(cudaMemcpyAsync(e->d_at_frames_in, frames, static_cast<size_t>(B) * MZ_ATARI_FRAME, cudaMemcpyHostToDevice, e->stream));
+    k_atari_observe<<<B, 256, 0, e->stream>>>(e->d, e->s, e->d_actions, e->d_at_frames_in);
+    e->launches++;
+    CUDA_OK(cudaStreamSynchronize(e->stream)); // the caller's buffers are free again
+    CUDA_OK(cudaGetLastError());
+    return MZ_OK;
+}
+
+int mz_get_root_rewards(mz_engine* e, float* reward, int32_t* bound_size, float* bound_lo, float* bound_hi)
+{
+    if (!e) { return fail(MZ_ERR_ARG, "null argument"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    const int B = e->d.B;
+    k_gather_root_rewards<<<B, 32, 0, e->stream>>>(e->d, e->s, e->d_root_reward, e->d_bound_size, e->d_bound_lo, e->d_bound_hi);
+    e->launches++;
+    if (reward) { CUDA_OK(cudaMemcpyAsync(reward, e->d_root_reward, sizeof(float) * B * e->d.A, cudaMemcpyDeviceToHost, e->stream)); }
+    if (bound_size) { CUDA_OK(cudaMemcpyAsync(bound_size, e->d_bound_size, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, e->stream)); }
+    if (bound_lo) { CUDA_OK(cudaMemcpyAsync(bound_lo, e->d_bound_lo, sizeof(float) * B, cudaMemcpyDeviceToHost, e->stream)); }
+    if (bound_hi) { CUDA_OK(cudaMemcpyAsync(bound_hi, e->d_bound_hi, sizeof(float) * B, cudaMemcpyDeviceToHost, e->stream)); }
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    CUDA_OK(cudaGetLastError());
+    return MZ_OK;
 }
 
 int mz_search_leaf(mz_engine* e, int32_t* parent_slot, int32_t* leaf_action, int32_t* path_actions)
@@ -1231,7 +1677,16 @@ int mz_search_select(mz_engine* e, const uint8_t* rotations, float* features_out
     const mz_dims& d = e->d;
     if (rotations) { CUDA_OK(cudaMemcpyAsync(e->d_rot_all, rotations, d.B, cudaMemcpyHostToDevice, e->stream)); }
     step(e, STEP_BEFORE, rotations ? e->d_rot_all : nullptr);
-    if (features_out) {
+    if (features_out && e->atari) { // AtariEnv::getFeatures of every root's observation history (atari.cpp:106-116)
+        const size_t F = static_cast<size_t>(mzat::PLANES) * mzat::RES * mzat::RES;
+        if (!e->d_planes_f32) {
+            int rc0 = e->dalloc(&e->d_planes_f32, static_cast<size_t>(d.B) * F);
+            if (rc0) { return rc0; }
+        }
+        mzat::planes_f32_kernel<<<4 * e->num_sms, 256, 0, e->stream>>>(e->s.at_frames, e->s.at_meta, e->d_planes_f32, d.B);
+        e->launches++;
+        CUDA_OK(cudaMemcpyAsync(features_out, e->d_planes_f32, sizeof(float) * d.B * F, cudaMemcpyDeviceToHost, e->stream));
+    } else if (features_out) {
         const size_t F = static_cast<size_t>(d.C) * d.N * d.N;
         mznn::unpack_features_kernel<<<148, 256, 0, e->stream>>>(reinterpret_cast<const __half*>(e->s.nn_in), e->d_feat_f32, d.B, d.C, d.N, d.slots, MZ_NN_CPAD);
         e->launches++;
@@ -1245,10 +1700,20 @@ int mz_search_select(mz_engine* e, const uint8_t* rotations, float* features_out
 
 int mz_search_apply(mz_engine* e, const float* policy, const float* logits, const float* value, const float* noise)
 {
+    return mz_search_apply_reward(e, policy, logits, value, nullptr, noise);
+}
+
+int mz_search_apply_reward(mz_engine* e, const float* policy, const float* logits, const float* value, const float* reward, const float* noise)
+{
     if (!e || !policy || !logits || !value) { return fail(MZ_ERR_ARG, "null argument"); }
     CUDA_OK(cudaSetDevice(e->cfg.device));
     const mz_dims& d = e->d;
     const size_t BA = static_cast<size_t>(d.B) * d.A;
+    if (reward) {
+        CUDA_OK(cudaMemcpyAsync(e->s.nn_reward, reward, sizeof(float) * d.B, cudaMemcpyHostToDevice, e->stream));
+    } else {
+        CUDA_OK(cudaMemsetAsync(e->s.nn_reward, 0, sizeof(float) * d.B, e->stream));
+    }
     CUDA_OK(cudaMemcpyAsync(e->s.policy, policy, sizeof(float) * BA, cudaMemcpyHostToDevice, e->stream));
     CUDA_OK(cudaMemcpyAsync(e->s.logits, logits, sizeof(float) * BA, cudaMemcpyHostToDevice, e->stream));
     CUDA_OK(cudaMemcpyAsync(e->s.nn_value, value, sizeof(float) * d.B, cudaMemcpyHostToDevice, e->stream));
@@ -1288,11 +1753,15 @@ int mz_search_run(mz_engine* e, int32_t num_evals, float* device_ms)
     if (it == e->graphs.end()) {
         // capture the whole search: before | (NN, after+before) x (n-1) | NN, after
         cudaGraph_t graph = nullptr;
-        const int64_t launches_before = e->launches;
+        const int64_t launches_before = e->launches, memsets_before = e->memsets;
         CUDA_OK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
         int rc = MZ_OK;
         for (int c = 0; c < num_evals && !rc; ++c) {
             step(e, (c > 0 ? STEP_AFTER : 0) | STEP_BEFORE, e->rot_enabled ? e->d_rot_all + static_cast<size_t>(c) * d.B : nullptr);
+            if (e->atari && c == 0) { // the root's planes: observation history -> space-to-depth rows of the first representation stage
+                mzat::pack_input_kernel<false><<<4 * e->num_sms, 256, 0, e->stream>>>(e->s.at_frames, e->s.at_meta, nullptr, e->ast[0].in, d.B);
+                e->launches++;
+            }
             rc = forward(e, (e->cfg.muzero && c > 0) ? 1 : 0, true); // MuZero: initial inference for the root, recurrent below
         }
         step(e, STEP_AFTER, nullptr);
@@ -1305,7 +1774,7 @@ int mz_search_run(mz_engine* e, int32_t num_evals, float* device_ms)
         }
         size_t num_nodes = 0;
         cudaGraphGetNodes(graph, nullptr, &num_nodes);
-        if (static_cast<int64_t>(num_nodes) != captured) { // the graph holds kernel nodes only; a mismatch means a launch site does not count itself
+        if (static_cast<int64_t>(num_nodes) != captured + (e->memsets - memsets_before)) { // kernel + memset nodes; a mismatch means a launch site does not count itself
             cudaGraphDestroy(graph);
             return fail(MZ_ERR_STATE, "captured graph has " + std::to_string(num_nodes) + " nodes but " + std::to_string(captured) + " launches were counted");
         }

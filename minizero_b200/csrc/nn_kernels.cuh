@@ -839,6 +839,10 @@ struct alignas(64) TowerLayer {
     const float* bias;
     int cin;
     int relu;
+    int cin_off;  // first input channel of this layer within the rows of map_in (a layer may read a channel slice: the four
+                  // sub-position layers of a stride-2 convolution share one space-to-depth input)
+    int tap_mask; // bit t set: tap t = (ky * 3 + kx) takes part (0x1ff = a full 3x3; a stride-2 3x3 convolution over a
+                  // space-to-depth input only has taps that reach up / left: see engine.cu, "stride 2")
 };
 
 struct TowerParams {
@@ -968,6 +972,7 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                 const int half = u % nh;
                 int wrow = half * BN + crank * (BN / 2);
                 for (int tap = 0; tap < 9; ++tap, wrow += tp.cout) {
+                    if (!((L.tap_mask >> tap) & 1)) { continue; }
                     for (int kc = 0; kc < L.cin; kc += BK) {
                         const long long te = (DBG ? clock64() : 0ll);
                         mbar_wait_u32(empty0 + s * 8, ph);
@@ -1024,7 +1029,7 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                     if (leader) { mbar_arrive_expect_tx(&a_full[buf], 2 * a_kb * a_kb_bytes); }
                     const uint32_t bar = smem_u32(&a_full[buf]) & kPeerMask;
                     const uint64_t map_in_ptr = reinterpret_cast<uint64_t>(&L.map_in);
-                    for (int kb = 0; kb < a_kb; ++kb) { tma_load_2d_2sm(a_dst0 + buf * a_bytes_max + kb * a_kb_bytes, map_in_ptr, bar, kb * BK, (g * 2 + crank) * BM - tp.halo); }
+                    for (int kb = 0; kb < a_kb; ++kb) { tma_load_2d_2sm(a_dst0 + buf * a_bytes_max + kb * a_kb_bytes, map_in_ptr, bar, L.cin_off + kb * BK, (g * 2 + crank) * BM - tp.halo); }
                 }
                 __syncwarp();
                 ++gcount;
@@ -1042,7 +1047,7 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
             long long t_afull = 0, t_acc = 0, t_bfull = 0;
             const long long t_start = (DBG ? clock64() : 0ll);
             for (int l = 0; l < tp.num_layers; ++l) {
-                const int cin = tp.layer[l].cin;
+                const int cin = tp.layer[l].cin, tap_mask = tp.layer[l].tap_mask;
                 int ub, ue;
                 range(l, ub, ue);
                 for (int q = ub; q < ue; ++q) {
@@ -1071,6 +1076,7 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                     int row0 = tp.halo - tp.n1 - 1;
                     for (int ty = 0; ty < 3; ++ty, row0 += tp.n1 - 3) {
                         for (int tx = 0; tx < 3; ++tx, ++row0) {
+                            if (!((tap_mask >> (ty * 3 + tx)) & 1)) { continue; }
                             uint32_t a_lo = a_lo0 + static_cast<uint32_t>(abuf) * a_buf_step + static_cast<uint32_t>(row0) * 8u;
                             for (int kc = 0; kc < cin; kc += BK, a_lo += a_kb_step) {
                                 const long long tf = (DBG ? clock64() : 0ll);
@@ -1397,7 +1403,7 @@ __global__ void __launch_bounds__(256) scale_hidden_kernel(__half* __restrict__ 
 // MuZeroNetwork::pushBackRecurrentData layout (network/muzero_network.h:78-93) -> rows of the dynamics network's input:
 // hidden [n][c_real][H][W] fp32 + action ids -> [rows][dyn_c] fp16 with the one-hot action plane at column act_col (parity hook)
 __global__ void pack_hidden_kernel(const float* __restrict__ hidden, const int32_t* __restrict__ actions, __half* __restrict__ rows, int batch, int c_real, int n,
-                                   int slots, int dyn_c, int act_col)
+                                   int slots, int dyn_c, int act_col, int act_planes)
 {
     const int hw = n * n, total = batch * hw * dyn_c;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -1405,8 +1411,10 @@ __global__ void pack_hidden_kernel(const float* __restrict__ hidden, const int32
         float v = 0.0f;
         if (ch < c_real) {
             v = hidden[(static_cast<size_t>(g) * c_real + ch) * hw + cell];
-        } else if (ch == act_col) {
+        } else if (act_planes == 1 && ch == act_col) {
             v = (actions[g] == cell ? 1.0f : 0.0f);
+        } else if (act_planes > 1 && ch >= act_col && ch < act_col + act_planes) { // Atari: plane `action` of the block is all ones (atari.cpp:124-130)
+            v = (actions[g] == ch - act_col ? 1.0f : 0.0f);
         }
         rows[(static_cast<size_t>(g) * slots + (cell / n + 1) * (n + 1) + cell % n) * dyn_c + ch] = __float2half_rn(v);
     }

@@ -1608,6 +1608,7 @@ MZ_DEV void mz_before_nn_muzero(const mz_dims& d, const mz_state& s, int g, mz_s
                 const int cell = i / per_cell, k = i - cell * per_cell;
                 *reinterpret_cast<uint4*>(dst + (size_t)((cell / N + 1) * (N + 1) + cell % N) * d.dyn_c + k * 8) = src[i];
             }
+            mz_block_sync(); // the action planes may overwrite padded (zero) hidden columns copied above
             if (d.act_planes > 1) { // Atari: plane `a` of the 18 action planes is all ones (atari.cpp:124-130)
                 for (int i = tid; i < N * N * d.act_planes; i += nthreads) {
                     const int cell = i / d.act_planes, k = i - cell * d.act_planes;

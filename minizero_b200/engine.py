@@ -13,7 +13,8 @@ import subprocess
 
 import numpy as np
 
-GAME_TICTACTOE, GAME_GO, GAME_OTHELLO, GAME_NOGO, GAME_GOMOKU, GAME_HEX = 0, 1, 2, 3, 4, 5
+GAME_TICTACTOE, GAME_GO, GAME_OTHELLO, GAME_NOGO, GAME_GOMOKU, GAME_HEX, GAME_ATARI = 0, 1, 2, 3, 4, 5, 6
+ATARI_FRAME = 3 * 96 * 96  # one screen: RGB bytes, channel-major, 96 x 96 (environment/atari/atari.h:24)
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -26,7 +27,8 @@ class _Config(C.Structure):
                 ("puct_base", C.c_float), ("puct_init", C.c_float), ("reward_discount", C.c_float), ("komi", C.c_float), ("ko_situational", C.c_int32),
                 ("dirichlet_epsilon", C.c_float), ("muzero", C.c_int32), ("use_gumbel", C.c_int32), ("gumbel_noise", C.c_int32),
                 ("gumbel_sample_size", C.c_int32), ("gumbel_sigma_visit_c", C.c_float), ("gumbel_sigma_scale_c", C.c_float),
-                ("gomoku_exactly_five", C.c_int32), ("gomoku_outer_open", C.c_int32), ("hex_swap_rule", C.c_int32)]
+                ("gomoku_exactly_five", C.c_int32), ("gomoku_outer_open", C.c_int32), ("hex_swap_rule", C.c_int32), ("value_rescale", C.c_int32),
+                ("atari_legal_mask", C.c_uint32)]
 
 
 class _NetDims(C.Structure):
@@ -91,6 +93,10 @@ def _load():
     lib.mz_eval_initial.argtypes = [vp, f32p, i32, f32p, f32p, f32p, f32p]
     lib.mz_eval_recurrent.argtypes = [vp, f32p, i32p, i32, f32p, f32p, f32p, f32p]
     lib.mz_search_leaf.argtypes = [vp, i32p, i32p, i32p]
+    lib.mz_eval_rewards.argtypes = [vp, i32, f32p]
+    lib.mz_atari_observe.argtypes = [vp, i32p, u8p]
+    lib.mz_get_root_rewards.argtypes = [vp, f32p, i32p, f32p, f32p]
+    lib.mz_search_apply_reward.argtypes = [vp, f32p, f32p, f32p, f32p, f32p]
     lib.mz_gumbel_best_actions.argtypes = [vp, i32p]
     lib.mz_reset_game.argtypes = [vp, i32]
     lib.mz_play.argtypes = [vp, i32p, C.POINTER(_PlayResult)]
@@ -116,7 +122,8 @@ def _load():
 EXPORTS = ["mz_create", "mz_destroy", "mz_last_error", "mz_action_size", "mz_num_features", "mz_net_configure", "mz_net_set_tensor", "mz_net_finalize",
            "mz_net_blob", "mz_net_finalize_empty", "mz_eval_batch", "mz_reset_game", "mz_play", "mz_get_roots", "mz_search_select", "mz_search_apply",
            "mz_search_set_inputs", "mz_search_run", "mz_profile_kernels", "mz_launch_count", "mz_play_max_count", "mz_sync", "mz_timer_begin", "mz_timer_end", "mz_debug_tree_timing", "mz_debug_tower_timing", "mz_conv_layers_per_launch",
-           "mz_eval_initial", "mz_eval_recurrent", "mz_search_leaf", "mz_gumbel_best_actions"]
+           "mz_eval_initial", "mz_eval_recurrent", "mz_search_leaf", "mz_gumbel_best_actions", "mz_eval_rewards", "mz_atari_observe", "mz_get_root_rewards",
+           "mz_search_apply_reward"]
 
 
 def _fp(a):
@@ -136,12 +143,14 @@ class Engine:
 
     def __init__(self, game, board_size, num_games, num_simulation, device=0, puct_base=19652.0, puct_init=1.25, reward_discount=1.0, komi=7.5,
                  ko_situational=False, dirichlet_epsilon=0.25, muzero=0, use_gumbel=0, gumbel_noise=0, gumbel_sample_size=16, gumbel_sigma_visit_c=50.0,
-                 gumbel_sigma_scale_c=1.0, gomoku_exactly_five=True, gomoku_outer_open=False, hex_swap_rule=True):
+                 gumbel_sigma_scale_c=1.0, gomoku_exactly_five=True, gomoku_outer_open=False, hex_swap_rule=True, value_rescale=0,
+                 atari_legal_mask=0b1111111101):
         self.lib = _load()
         cfg = _Config(device, game, board_size, num_games, num_simulation, puct_base, puct_init, reward_discount, komi, int(ko_situational), dirichlet_epsilon,
                       int(muzero), int(use_gumbel), int(gumbel_noise), int(gumbel_sample_size), gumbel_sigma_visit_c, gumbel_sigma_scale_c,
-                      int(gomoku_exactly_five), int(gomoku_outer_open), int(hex_swap_rule))
+                      int(gomoku_exactly_five), int(gomoku_outer_open), int(hex_swap_rule), int(value_rescale), int(atari_legal_mask))
         self.muzero = bool(muzero)
+        self.atari = (game == GAME_ATARI)
         h = C.c_void_p()
         self.h = None
         self._check(self.lib.mz_create(C.byref(cfg), C.byref(h)))
@@ -174,7 +183,7 @@ class Engine:
             dims = dict(num_input_channels=m.get_num_input_channels(), input_height=m.get_input_channel_height(), input_width=m.get_input_channel_width(),
                         num_hidden_channels=m.get_num_hidden_channels(), num_blocks=m.get_num_blocks(), action_size=m.get_action_size(),
                         num_value_hidden_channels=m.get_num_value_hidden_channels(), discrete_value_size=m.get_discrete_value_size())
-            if m.get_type_name() == "muzero":  # network/muzero_network.h:46-52
+            if m.get_type_name() in ("muzero", "muzero_atari"):  # network/muzero_network.h:46-52
                 dims.update(num_action_feature_channels=m.get_num_action_feature_channels(), is_muzero=1)
             state = {k: v.detach().float().contiguous().numpy() for k, v in m.state_dict().items() if not k.endswith("num_batches_tracked")}
         else:
@@ -209,7 +218,7 @@ class Engine:
         """MuZeroNetwork initial inference: policy, logits, value, scaled hidden state [n][Ch*H*W]"""
         f = np.ascontiguousarray(features, np.float32).reshape(-1, self.F)
         n = f.shape[0]
-        hsz = int(self.net_dims["num_hidden_channels"]) * int(self.net_dims["input_height"]) * int(self.net_dims["input_width"])
+        hsz = int(self.net_dims["num_hidden_channels"]) * (36 if self.atari else int(self.net_dims["input_height"]) * int(self.net_dims["input_width"]))
         pol, lg, val, hid = np.zeros((n, self.A), np.float32), np.zeros((n, self.A), np.float32), np.zeros(n, np.float32), np.zeros((n, hsz), np.float32)
         self._check(self.lib.mz_eval_initial(self.h, _fp(f), n, _fp(pol), _fp(lg), _fp(val), _fp(hid)))
         return pol, lg, val, hid
@@ -222,6 +231,28 @@ class Engine:
         pol, lg, val, hid = np.zeros((n, self.A), np.float32), np.zeros((n, self.A), np.float32), np.zeros(n, np.float32), np.zeros_like(h)
         self._check(self.lib.mz_eval_recurrent(self.h, _fp(h), _i32(a), n, _fp(pol), _fp(lg), _fp(val), _fp(hid)))
         return pol, lg, val, hid
+
+    def eval_rewards(self, n):
+        """reward head output of the last eval_recurrent (muzero_atari; after the expectation over the bins and invertValue)"""
+        r = np.zeros(n, np.float32)
+        self._check(self.lib.mz_eval_rewards(self.h, n, _fp(r)))
+        return r
+
+    # ---- Atari: the emulator stays with the caller --------------------------------------------------
+    def observe_all(self, actions, frames):
+        """actions [B]: >= 0 the action the emulator just executed, -1 the first screen after a reset, -2 nothing for this game;
+        frames uint8 [B][3][96][96]"""
+        a = np.ascontiguousarray(actions, np.int32)
+        f = np.ascontiguousarray(frames, np.uint8).reshape(self.B, ATARI_FRAME)
+        self._check(self.lib.mz_atari_observe(self.h, _i32(a), _u8(f)))
+
+    def observe(self, g, action, frame, terminal=False):
+        a = np.full(self.B, -2, np.int32)
+        a[g] = action
+        f = np.zeros((self.B, ATARI_FRAME), np.uint8)
+        f[g] = np.ascontiguousarray(frame, np.uint8).reshape(-1)
+        self.observe_all(a, f)
+        self.terminal[g] = bool(terminal)
 
     # ---- per-phase hooks (per-phase parity hooks) ------------------------
     def select(self, rotations=None, want_features=True):
@@ -261,10 +292,11 @@ class Engine:
         self._check(self.lib.mz_gumbel_best_actions(self.h, _i32(out)))
         return out
 
-    def apply(self, policy, logits, value, noise=None):
+    def apply(self, policy, logits, value, noise=None, reward=None):
         p, l, v = (np.ascontiguousarray(x, np.float32) for x in (policy, logits, value))
         nz = None if noise is None else np.ascontiguousarray(noise, np.float32)
-        self._check(self.lib.mz_search_apply(self.h, _fp(p), _fp(l), _fp(v), _fp(nz)))
+        rw = None if reward is None else np.ascontiguousarray(reward, np.float32)
+        self._check(self.lib.mz_search_apply_reward(self.h, _fp(p), _fp(l), _fp(v), _fp(rw), _fp(nz)))
         self._roots = None
 
     def path_len(self, g):
@@ -281,6 +313,9 @@ class Engine:
         out["root_count"] = np.array([info[g].count for g in range(B)], np.float32)
         out["root_mean"] = np.array([info[g].mean for g in range(B)], np.float32)
         out["root_value"] = np.array([info[g].value for g in range(B)], np.float32)
+        out["reward"], out["bound_size"] = np.zeros((B, A), np.float32), np.zeros(B, np.int32)
+        out["bound_lo"], out["bound_hi"] = np.zeros(B, np.float32), np.zeros(B, np.float32)
+        self._check(self.lib.mz_get_root_rewards(self.h, _fp(out["reward"]), _i32(out["bound_size"]), _fp(out["bound_lo"]), _fp(out["bound_hi"])))
         return out
 
     def _cached_roots(self):
@@ -294,8 +329,9 @@ class Engine:
     def root(self, g):
         r = self._cached_roots()
         d = dict(num_children=int(r["num_children"][g]), root_count=float(r["root_count"][g]), root_mean=float(r["root_mean"][g]), root_value=float(r["root_value"][g]))
-        for n in ("action", "count", "mean", "policy", "logit", "noise", "value"):
+        for n in ("action", "count", "mean", "policy", "logit", "noise", "value", "reward"):
             d[n] = r[n][g]
+        d.update(bound_size=int(r["bound_size"][g]), bound_lo=float(r["bound_lo"][g]), bound_hi=float(r["bound_hi"][g]))
         return d
 
     # ---- games ----------------------------------------------------------------------------------
