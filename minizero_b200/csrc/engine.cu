@@ -1855,9 +1855,10 @@ int mz_profile_kernels(mz_engine* e, int32_t iters, float* conv_ms, float* tree_
         *conv_ms = ms / iters;
     }
     if (heads_ms) {
-        for (int i = 0; i < 3; ++i) { launch_heads(e, e->act[0]); }
+        auto heads = [&]() { return e->atari ? launch_discrete_head(e, e->act[0], 0, true, e->s.nn_value) : launch_heads(e, e->act[0]); };
+        for (int i = 0; i < 3; ++i) { heads(); }
         CUDA_OK(cudaEventRecord(e->ev0, e->stream));
-        for (int i = 0; i < iters; ++i) { launch_heads(e, e->act[0]); }
+        for (int i = 0; i < iters; ++i) { heads(); }
         CUDA_OK(cudaEventRecord(e->ev1, e->stream));
         CUDA_OK(cudaStreamSynchronize(e->stream));
         CUDA_OK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
