@@ -85,8 +85,12 @@ int recordTest()
                     v[i] = hexFloat(part);
                 }
             }
-            m.policy = mzhost::gumbelPolicy(acts.data(), f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), k, hexFloat(value_hex), m.player, 1.0f, sims,
-                                            visit_c, scale_c);
+            const int player = m.player;
+            m.policy = mzhost::gumbelPolicy(acts.data(), f[0].data(), f[2].data(), f[3].data(), f[4].data(), k, hexFloat(value_hex), m.player, sims, visit_c, scale_c, [&](int i) {
+                float value = 0.0f + 1.0f * f[1][i]; // board games: reward 0, discount 1, no rescale (mcts.cpp:40-53)
+                value = (player == 2 ? -value : value);
+                return (value * f[0][i] - 0.0f) / (f[0][i] + 0.0f);
+            });
             m.value = std::to_string(hexFloat(mean_hex));
             m.reward = "0";
             moves.push_back(m);
@@ -130,10 +134,6 @@ int main(int argc, char** argv)
     }
     if (cfg.getString("nn_type_name") != "alphazero" && cfg.getString("nn_type_name") != "muzero") {
         std::cerr << "this worker implements the alphazero and (board-game) muzero self-play paths" << std::endl;
-        return -1;
-    }
-    if (cfg.getBool("actor_mcts_value_rescale")) { // MCTS::updateTreeValueBound / min-max Q rescaling (mcts.cpp:43-49,219-228): Atari setting, not built
-        std::cerr << "actor_mcts_value_rescale=true is not implemented by this worker" << std::endl;
         return -1;
     }
     if (mode == "rng_test") { // CPU only: prints the host's draw sequence for root tables given on stdin

@@ -13,8 +13,32 @@
 #include <unordered_map>
 #include <utility>
 #include <vector>
+#include <zlib.h>
 
 namespace mzhost {
+
+// utils::compressString (utils/utils.h:34-47,49-57,84-87): gzip, then lower-case hex. The reference compresses through
+// boost::iostreams::gzip_compressor (default level, 15-bit window); the deflate stream here is the same zlib call, the 10-byte gzip
+// header is zlib's own (OS byte 3) where Boost writes its own (OS byte 255) — every gzip reader, the reference's included, accepts both.
+inline std::string compressToHex(const std::string& in)
+{
+    if (in.empty()) { return in; }
+    z_stream zs{};
+    if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) { return std::string(); }
+    std::string out(deflateBound(&zs, in.size()) + 32, '\0');
+    zs.next_in = reinterpret_cast<Bytef*>(const_cast<char*>(in.data())), zs.avail_in = static_cast<uInt>(in.size());
+    zs.next_out = reinterpret_cast<Bytef*>(&out[0]), zs.avail_out = static_cast<uInt>(out.size());
+    deflate(&zs, Z_FINISH);
+    out.resize(zs.total_out);
+    deflateEnd(&zs);
+    static const char* digits = "0123456789abcdef";
+    std::string hex(out.size() * 2, '0');
+    for (size_t i = 0; i < out.size(); ++i) {
+        const unsigned char c = static_cast<unsigned char>(out[i]);
+        hex[2 * i] = digits[c >> 4], hex[2 * i + 1] = digits[c & 15];
+    }
+    return hex;
+}
 
 struct MoveRecord {
     int action = 0;
@@ -76,15 +100,12 @@ inline std::string searchDistribution(const int* actions, const float* counts, i
 
 // GumbelZero::getMCTSPolicy (actor/gumbel_zero.cpp:9-59) from the root child table: softmax of the completed-Q logits,
 // entries below -38 dropped, printed in the iteration order of the same std::unordered_map<int, float> the reference fills
-// (same libstdc++, same insertion sequence => same order). Board games: no value rescale. child_player = side to move.
-inline std::string gumbelPolicy(const int* actions, const float* counts, const float* means, const float* policy, const float* logit, const float* noise,
-                                int num_children, float root_value, int child_player, float discount, int num_simulation, float sigma_visit_c, float sigma_scale_c)
+// (same libstdc++, same insertion sequence => same order). child_player = side to move.
+// `normalized(i)` = MCTSNode::getNormalizedMean of root child i (mcts.cpp:40-53; the caller knows about rewards and value bounds).
+template <class NormalizedMean>
+inline std::string gumbelPolicy(const int* actions, const float* counts, const float* policy, const float* logit, const float* noise, int num_children, float root_value,
+                                int child_player, int num_simulation, float sigma_visit_c, float sigma_scale_c, NormalizedMean normalized)
 {
-    auto normalized = [&](int i) { // MCTSNode::getNormalizedMean, mcts.cpp:40-53 (reward 0, no rescale, no virtual loss)
-        float value = 0.0f + discount * means[i];
-        value = (child_player == 2 ? -value : value);
-        return (value * counts[i] - 0.0f) / (counts[i] + 0.0f);
-    };
     float pi_sum = 0.0f, q_sum = 0.0f;
     for (int i = 0; i < num_children; ++i) {
         if (counts[i] == 0) { continue; }
@@ -123,17 +144,34 @@ struct GameHeader {
     std::string model_file; // config::nn_file_name
 };
 
+// what an Atari record carries beside the moves (AtariEnvLoader::loadFromEnvironment, atari.cpp:174-185; base_env.h:215-219)
+struct AtariRecord {
+    const std::vector<std::string>* observations = nullptr; // AtariEnv::observations_: one 3 x 96 x 96 byte screen per position, old ones emptied (atari.cpp:72-79)
+    const std::vector<int>* lives_history = nullptr;        // lives before every action (+ the current ones)
+    int seed = 0;                                           // SD tag
+    float total_reward = 0.0f;                              // AtariEnv::getEvalScore
+};
+
 // eval_score: Environment::getEvalScore(false) of the final position; terminal: Environment::isTerminal().
 // When the game is not terminal (resign) the side to move loses (base_actor.cpp:48-54, go.cpp:262-263).
 inline std::string selfPlayLine(const GameHeader& h, const std::vector<MoveRecord>& moves, bool terminal, float eval_score, int turn_to_move,
-                                const SequenceConfig& seq = SequenceConfig())
+                                const SequenceConfig& seq = SequenceConfig(), const AtariRecord* atari = nullptr)
 {
-    const float resign_score = (turn_to_move == 1 ? -1.0f : 1.0f); // the next player of `turn` wins
+    // a game that is not over counts as resigned by the side to move (base_actor.cpp:48-54); Atari's score is the total reward either way (atari.h:59)
+    const float resign_score = (atari ? atari->total_reward : (turn_to_move == 1 ? -1.0f : 1.0f));
+    if (atari) { eval_score = atari->total_reward; }
     std::vector<std::pair<std::string, std::string>> tags;
     tags.push_back({"GM", h.game_name});
     tags.push_back({"RE", std::to_string(eval_score)}); // loadFromEnvironment: std::to_string(env.getEvalScore())
-    tags.push_back({"OBS", ""});
-    tags.push_back({"SZ", std::to_string(h.board_size)});
+    if (atari) {
+        std::string all;
+        for (const std::string& o : *atari->observations) { all += o; }
+        tags.push_back({"OBS", compressToHex(all)});                  // base_env.h:215-219
+        tags.push_back({"SD", std::to_string(atari->seed)});          // atari.cpp:177
+    } else {
+        tags.push_back({"OBS", ""});
+        tags.push_back({"SZ", std::to_string(h.board_size)});
+    }
     if (h.has_komi) { tags.push_back({"KM", std::to_string(h.komi)}); }
     tags.push_back({"EV", h.model_file.substr(h.model_file.find_last_of('/') + 1)});
     if (!terminal) {
@@ -147,10 +185,12 @@ inline std::string selfPlayLine(const GameHeader& h, const std::vector<MoveRecor
     std::ostringstream rec;
     rec << "(;";
     for (const auto& t : tags) { rec << t.first << "[" << escapeSGF(t.second) << "]"; }
-    for (const MoveRecord& m : moves) {
+    for (size_t i = 0; i < moves.size(); ++i) {
+        const MoveRecord& m = moves[i];
         rec << ";" << playerToChar(m.player) << "[" << m.action << "]";
-        if (m.cleared) { continue; }
-        rec << "P[" << escapeSGF(m.policy) << "]V[" << escapeSGF(m.value) << "]R[" << escapeSGF(m.reward) << "]";
+        if (!m.cleared) { rec << "P[" << escapeSGF(m.policy) << "]V[" << escapeSGF(m.value) << "]R[" << escapeSGF(m.reward) << "]"; }
+        // life lost since the position before (atari.cpp:178-184): added at record time, so it survives the clearing of sent action info
+        if (atari && i > 0 && (*atari->lives_history)[i] < (*atari->lives_history)[i - 1]) { rec << "L[" << (*atari->lives_history)[i] << "]"; }
     }
     rec << ")";
     std::ostringstream oss;

@@ -28,11 +28,11 @@ bool Worker::initialize()
         std::cerr << "Failed to load model \"" << model << "\": " << err << std::endl;
         return false;
     }
-    if (net_.type_name != "alphazero" && net_.type_name != "muzero") {
-        std::cerr << "nn_type_name \"" << net_.type_name << "\" is not implemented by this worker (alphazero and board-game muzero)" << std::endl;
+    if (net_.type_name != "alphazero" && net_.type_name != "muzero" && net_.type_name != "muzero_atari") {
+        std::cerr << "nn_type_name \"" << net_.type_name << "\" is not implemented by this worker" << std::endl;
         return false;
     }
-    muzero_ = (net_.type_name == "muzero"); // the actor follows the loaded network's type (zero_actor.cpp:100-114)
+    muzero_ = (net_.type_name != "alphazero"); // the actor follows the loaded network's type (zero_actor.cpp:100-114)
     gumbel_ = cfg_.getBool("actor_use_gumbel");
     // the reference binary is compiled per game (environment/environment.h:5-110); here the model names its game
     if (net_.game_name == "tictactoe") {
@@ -51,6 +51,9 @@ bool Worker::initialize()
         game_type_ = MZ_GAME_NOGO, board_ = net_.dims.input_height;
     } else if (net_.game_name.rfind("othello_", 0) == 0) {
         game_type_ = MZ_GAME_OTHELLO, board_ = net_.dims.input_height;
+    } else if (net_.game_name.rfind("atari_", 0) == 0 && net_.type_name == "muzero_atari") {
+        // the emulator is a host-side plug-in; this image has no ALE, so the deterministic synthetic frame source stands in (synth_atari.h)
+        game_type_ = MZ_GAME_ATARI, board_ = 6, atari_ = true;
     } else {
         std::cerr << "game \"" << net_.game_name << "\" is not implemented by this worker" << std::endl;
         return false;
@@ -76,6 +79,10 @@ bool Worker::initialize()
         c.reward_discount = cfg_.getFloat("actor_mcts_reward_discount"), c.komi = cfg_.getFloat("env_go_komi");
         c.ko_situational = (cfg_.getString("env_go_ko_rule") == "situational"), c.dirichlet_epsilon = cfg_.getFloat("actor_dirichlet_noise_epsilon");
         c.muzero = muzero_, c.use_gumbel = gumbel_;
+        c.value_rescale = cfg_.getBool("actor_mcts_value_rescale");
+        if (atari_) {
+            for (int a : SynthAtari::minimalActionSet()) { c.atari_legal_mask |= 1u << a; }
+        }
         c.hex_swap_rule = cfg_.getBool("env_hex_use_swap_rule");
         c.gomoku_exactly_five = cfg_.getBool("env_gomoku_exactly_five_stones"), c.gomoku_outer_open = (cfg_.getString("env_gomoku_rule") == "outer_open");
         c.gumbel_noise = (!cfg_.getBool("actor_use_dirichlet_noise") && cfg_.getBool("actor_use_gumbel_noise")); // zero_actor.cpp:197,205
@@ -113,7 +120,23 @@ void Worker::startGames()
     // createActors: ZeroActor::reset draws the resign switch of every game on the main thread's generator,
     // seeded with program_seed (console/mode_handler.cpp:62, create_actor.h:12-14, zero_actor.cpp:23-27)
     games_.assign(num_games_, Game());
-    for (int g = 0; g < num_games_; ++g) { resetGameHost(g); }
+    next_seed_.assign(num_games_, 0);
+    for (int g = 0; g < num_games_; ++g) {
+        if (atari_) { (void)rng_.randInt(); } // the actor's AtariEnv member resets itself when it is constructed (atari.h:45-49): one seed drawn and dropped
+        resetGameHost(g);
+    }
+    if (atari_) { // the first screens
+        const int ne0 = static_cast<int>(engine_games_.size());
+        for (int e = 0; e < ne0; ++e) {
+            std::vector<int32_t> acts(engine_games_[e], -1);
+            std::vector<uint8_t> frames(static_cast<size_t>(engine_games_[e]) * 3 * 96 * 96);
+            for (int slot = 0; slot < engine_games_[e]; ++slot) {
+                const std::string& obs = games_[slot * ne0 + e].observations.back();
+                std::copy(obs.begin(), obs.end(), frames.begin() + static_cast<size_t>(slot) * obs.size());
+            }
+            if (!engines_.empty() && mz_atari_observe(engines_[e], acts.data(), frames.data()) != MZ_OK) { std::cerr << "mz_atari_observe failed: " << mz_last_error() << std::endl; }
+        }
+    }
     // slave thread 0 re-seeds: program_seed + thread id, or a random device (actor_group.cpp:66-70)
     rng_.seed(cfg_.getBool("program_auto_seed") ? static_cast<int>(std::random_device()()) : cfg_.getInt("program_seed") + 0);
     // first beforeNNEvaluation of every game: rotation draw of cycle 0 (zero_actor.cpp:56)
@@ -133,8 +156,49 @@ void Worker::resetGameHost(int g)
     game.num_legal = initialNumLegal();
     std::fill(game.ttt, game.ttt + 9, 0);
     game.stones.assign((game_type_ == MZ_GAME_NOGO || game_type_ == MZ_GAME_GOMOKU || game_type_ == MZ_GAME_HEX) ? board_ * board_ : 0, 0);
+    if (atari_) { atariReset(game, rng_.randInt()); } // BaseActor::reset -> AtariEnv::reset() draws the emulator seed (atari.h:54) before the resign switch
     game.enable_resign = (rng_.randReal() < cfg_.getFloat("zero_disable_resign_ratio") ? false : true);
 }
+
+namespace {
+std::string atariObservation(const SynthAtari& emu) // AtariEnv::getObservationString (atari.cpp:162-172): the 96 x 96 screen, channel-major bytes
+{
+    std::vector<uint8_t> rgb(3 * 96 * 96);
+    emu.screenRGB(rgb.data());
+    std::string obs(rgb.size(), '\0');
+    for (int c = 0; c < 3; ++c) {
+        for (int j = 0; j < 96 * 96; ++j) { obs[static_cast<size_t>(c) * 96 * 96 + j] = static_cast<char>(rgb[static_cast<size_t>(j) * 3 + c]); }
+    }
+    return obs;
+}
+} // namespace
+
+void Worker::atariReset(Game& game, int seed)
+{
+    game.seed = seed, game.reward = 0.0f, game.total_reward = 0.0f;
+    game.emu.reset(seed);
+    game.lives_history.assign(1, game.emu.lives());
+    game.observations.assign(1, atariObservation(game.emu));
+}
+
+void Worker::atariAct(Game& game, int action)
+{
+    game.reward = 0.0f;
+    for (int i = 0; i < 4; ++i) { game.reward += static_cast<float>(game.emu.act(action)); } // kAtariFrameSkip, atari.cpp:68
+    game.total_reward += game.reward;
+    game.lives_history.push_back(game.emu.lives());
+    game.observations.push_back(atariObservation(game.emu));
+    // "only keep the most recent N observations" (atari.cpp:72-79)
+    const int seq = cfg_.getInt("zero_actor_intermediate_sequence_length");
+    const size_t recent = (seq == 0 ? 108000 : seq + 8 + cfg_.getInt("learner_n_step_return") + cfg_.getInt("learner_muzero_unrolling_step")) + 1;
+    if (game.observations.size() > recent) {
+        std::string& old = game.observations[game.observations.size() - recent];
+        old.clear();
+        old.shrink_to_fit();
+    }
+}
+
+bool Worker::atariTerminal(const Game& game) const { return static_cast<int>(game.moves.size()) * 4 >= 108000 || game.emu.gameOver(); }
 
 bool Worker::loadModel(const std::string& path)
 {
@@ -243,21 +307,29 @@ void Worker::handleCommands()
 }
 
 // ---- move decision (zero_actor.cpp:178-192, mcts.cpp:84-124) -----------------------------------------------------
-namespace {
-// MCTSNode::getNormalizedMean for board games (mcts.cpp:40-53): reward 0, no rescale, no virtual loss
-float normalizedMean(float mean, float count, int player, float discount)
+// MCTSNode::getNormalizedMean (mcts.cpp:40-53) of a root child, or of the root itself (child < 0; its reward is 0): reward + discount *
+// mean, min-max rescaled with the tree's value bounds under actor_mcts_value_rescale, negated for White's nodes; no virtual loss
+float Worker::normalizedMean(const RootView& r, int child, int player) const
 {
-    float value = 0.0f + discount * mean;
+    const float discount = cfg_.getFloat("actor_mcts_reward_discount");
+    const float mean = (child < 0 ? r.root_mean : r.mean[child]), count = (child < 0 ? static_cast<float>(sims_ + 1) : r.cnt[child]);
+    float value = (child >= 0 && r.reward ? r.reward[child] : 0.0f) + discount * mean;
+    if (cfg_.getBool("actor_mcts_value_rescale")) {
+        if (r.bound_size < 2) { return 1.0f; }
+        value = (value - r.bound_lo) / (r.bound_hi - r.bound_lo);
+        value = fmin(1, fmax(-1, 2 * value - 1));
+    }
     value = (player == 2 ? -value : value);
     value = (value * count - 0.0f) / (count + 0.0f);
     return value;
 }
-} // namespace
 
-int Worker::decideAction(int g, const int* actions, const float* counts, const float* means, int num_children, float root_mean, bool& resign, int& child_index)
+int Worker::decideAction(int g, const RootView& r, bool& resign, int& child_index)
 {
     const Game& game = games_[g];
-    const float discount = cfg_.getFloat("actor_mcts_reward_discount");
+    const int* actions = r.acts;
+    const float* counts = r.cnt;
+    const int num_children = r.num_children;
     const int child_player = game.turn; // children of the root carry the side to move (zero_actor.cpp:33,217)
     // selectChildByMaxCount (mcts.cpp:91-104)
     int best = -1;
@@ -271,12 +343,12 @@ int Worker::decideAction(int g, const int* actions, const float* counts, const f
     if (!cfg_.getBool("actor_select_action_by_count") && cfg_.getBool("actor_select_action_by_softmax_count")) {
         // selectChildBySoftmaxCount (mcts.cpp:106-124)
         const float temperature = cfg_.getFloat("actor_select_action_softmax_temperature"), value_threshold = 0.1f;
-        const float best_mean = normalizedMean(means[best], counts[best], child_player, discount);
+        const float best_mean = normalizedMean(r, best, child_player);
         float sum = 0.0f;
         selected = -1;
         for (int i = 0; i < num_children; ++i) {
             float count = std::pow(counts[i], 1 / temperature);
-            float mean = (counts[i] == 0 ? 0.0f / 0.0f : normalizedMean(means[i], counts[i], child_player, discount));
+            float mean = (counts[i] == 0 ? 0.0f / 0.0f : normalizedMean(r, i, child_player));
             if (count == 0 || (mean < best_mean - value_threshold)) { continue; }
             sum += count;
             float rand = rng_.randReal(sum);
@@ -284,10 +356,9 @@ int Worker::decideAction(int g, const int* actions, const float* counts, const f
         }
     }
     child_index = selected;
-    // isResign (zero_actor.h:42, mcts.cpp:84-89); the root's action player is the previous player (zero_actor.cpp:33)
-    const float root_count = static_cast<float>(sims_ + 1);
-    const float root_win_rate = normalizedMean(root_mean, root_count, 3 - game.turn, discount);
-    const float action_win_rate = normalizedMean(means[selected], counts[selected], child_player, discount);
+    // isResign (zero_actor.h:42, mcts.cpp:84-89); the root's action player is the previous player (zero_actor.cpp:33; player 1 in a one-player game)
+    const float root_win_rate = normalizedMean(r, -1, atari_ ? 1 : 3 - game.turn);
+    const float action_win_rate = normalizedMean(r, selected, child_player);
     const float threshold = cfg_.getFloat("actor_resign_threshold");
     resign = game.enable_resign && (-root_win_rate < threshold && action_win_rate < threshold);
     return actions[selected];
@@ -401,7 +472,9 @@ bool Worker::nogoHasLegalMove(const Game& game) const
 
 void Worker::emitGame(int g, bool terminal, float eval_score)
 {
-    const std::string line = selfPlayLine(header_, games_[g].moves, terminal, eval_score, games_[g].turn, sequenceConfig());
+    AtariRecord at;
+    if (atari_) { at.observations = &games_[g].observations, at.lives_history = &games_[g].lives_history, at.seed = games_[g].seed, at.total_reward = games_[g].total_reward; }
+    const std::string line = selfPlayLine(header_, games_[g].moves, terminal, eval_score, games_[g].turn, sequenceConfig(), atari_ ? &at : nullptr);
     const std::string out = line + "\n"; // the only thing this process ever writes to the server (zero_server.cpp:111-139)
     size_t done = 0;
     while (done < out.size()) {
@@ -446,15 +519,15 @@ int Worker::advanceGame(int g, const RootView& r, bool& resign, bool& end)
     Game& game = games_[g];
     resign = false;
     int child = -1;
-    int action = decideAction(g, r.acts, r.cnt, r.mean, r.num_children, r.root_mean, resign, child);
+    int action = decideAction(g, r, resign, child);
     if (gumbel_ && cfg_.getBool("actor_select_action_by_count")) { // GumbelZero::decideActionNode: best-scoring candidate (gumbel_zero.cpp:61-66)
         action = r.gumbel_best;
         for (int i = 0; i < r.num_children; ++i) {
             if (r.acts[i] == action) { child = i; }
         }
-        const float discount = cfg_.getFloat("actor_mcts_reward_discount"), threshold = cfg_.getFloat("actor_resign_threshold");
-        const float root_win_rate = normalizedMean(r.root_mean, static_cast<float>(sims_ + 1), 3 - game.turn, discount);
-        const float action_win_rate = normalizedMean(r.mean[child], r.cnt[child], game.turn, discount);
+        const float threshold = cfg_.getFloat("actor_resign_threshold");
+        const float root_win_rate = normalizedMean(r, -1, atari_ ? 1 : 3 - game.turn);
+        const float action_win_rate = normalizedMean(r, child, game.turn);
         resign = game.enable_resign && (-root_win_rate < threshold && action_win_rate < threshold); // mcts.cpp:84-89
     }
     end = resign;
@@ -462,11 +535,26 @@ int Worker::advanceGame(int g, const RootView& r, bool& resign, bool& end)
     if (!resign) { // BaseActor::act + getActionInfo (base_actor.cpp:22-30,59-66)
         MoveRecord m;
         m.action = action, m.player = game.turn;
-        m.policy = (gumbel_ ? gumbelPolicy(r.acts, r.cnt, r.mean, r.policy, r.logit, r.noise, r.num_children, r.root_value, game.turn, cfg_.getFloat("actor_mcts_reward_discount"),
-                                           sims_, cfg_.getFloat("actor_gumbel_sigma_visit_c"), cfg_.getFloat("actor_gumbel_sigma_scale_c"))
+        float value_pi = r.root_value; // gumbel_zero.cpp:20-31: the root's own value goes through the same min-max rescaling
+        if (cfg_.getBool("actor_mcts_value_rescale")) {
+            if (r.bound_size < 2) {
+                value_pi = 1.0f;
+            } else {
+                value_pi = (value_pi - r.bound_lo) / (r.bound_hi - r.bound_lo);
+                value_pi = fmin(1, fmax(-1, 2 * value_pi - 1));
+            }
+        }
+        m.policy = (gumbel_ ? gumbelPolicy(r.acts, r.cnt, r.policy, r.logit, r.noise, r.num_children, value_pi, game.turn, sims_, cfg_.getFloat("actor_gumbel_sigma_visit_c"),
+                                           cfg_.getFloat("actor_gumbel_sigma_scale_c"), [&](int i) { return normalizedMean(r, i, game.turn); })
                             : searchDistribution(r.acts, r.cnt, r.num_children)); // zero_actor.h:48
         m.value = std::to_string(r.root_mean); // zero_actor.h:49
         m.reward = "0";                        // operator<< of Environment::getReward() == 0.0f (go.h:50, tictactoe.h:25)
+        if (atari_) { // the emulator answers: reward of the four frames (atari.cpp:66-70), streamed with operator<< (zero_actor.cpp:122-127)
+            atariAct(game, action);
+            std::ostringstream oss;
+            oss << game.reward;
+            m.reward = oss.str();
+        }
         game.moves.push_back(m);
         if (game_type_ == MZ_GAME_TICTACTOE && action >= 0 && action < 9) { game.ttt[action] = static_cast<uint8_t>(game.turn); }
         if ((game_type_ == MZ_GAME_NOGO || game_type_ == MZ_GAME_GOMOKU) && action >= 0 && action < board_ * board_) {
@@ -480,16 +568,19 @@ int Worker::advanceGame(int g, const RootView& r, bool& resign, bool& end)
             }
             game.stones[id] = static_cast<uint8_t>(game.turn);
         }
-        game.turn = 3 - game.turn;
+        if (!atari_) { game.turn = 3 - game.turn; } // a one-player game stays with player 1 (atari.h:18)
         play = action;
-        end = hostTerminal(game);
+        end = (atari_ ? atariTerminal(game) : hostTerminal(game));
     }
     if (g == 0 && !cfg_.getBool("program_quiet")) {
         std::cerr << "[actor 0] move " << game.moves.size() << " action " << action << (resign ? " (resign)" : "") << " root mean " << r.root_mean << std::endl;
     }
     // actor->reset() draws the resign switch of the next game (zero_actor.cpp:26); the deferred state reset must not consume
     // randomness, so only the draw happens here, in order
-    if (end) { game.enable_resign = (rng_.randReal() < cfg_.getFloat("zero_disable_resign_ratio") ? false : true); }
+    if (end) {
+        if (atari_) { next_seed_[g] = rng_.randInt(); } // AtariEnv::reset() of the next game (atari.h:54), before the resign switch
+        game.enable_resign = (rng_.randReal() < cfg_.getFloat("zero_disable_resign_ratio") ? false : true);
+    }
     rotations_[e][slot] = (random_rotation ? static_cast<uint8_t>(rng_.randInt() % 8) : 0); // cycle 0 of the next search
     return play;
 }
@@ -503,6 +594,7 @@ void Worker::restartGameHost(int g)
     game.num_legal = initialNumLegal();
     std::fill(game.ttt, game.ttt + 9, 0);
     std::fill(game.stones.begin(), game.stones.end(), 0);
+    if (atari_) { atariReset(game, next_seed_[g]); } // the seed was drawn in order when the game ended
 }
 
 // ---- one move for every game ------------------------------------------------------------------------------------------
@@ -527,9 +619,10 @@ bool Worker::playOneMove()
     struct Roots {
         std::vector<mz_root_info> info;
         std::vector<int32_t> action;
-        std::vector<float> count, mean, policy, logit, noise;
-        std::vector<int32_t> gumbel_best;
+        std::vector<float> count, mean, policy, logit, noise, reward, bound_lo, bound_hi;
+        std::vector<int32_t> gumbel_best, bound_size;
     };
+    const bool rescale = cfg_.getBool("actor_mcts_value_rescale");
     std::vector<Roots> roots(ne);
     for (int e = 0; e < ne; ++e) {
         const size_t n = engine_games_[e];
@@ -539,6 +632,13 @@ bool Worker::playOneMove()
                          gumbel_ ? roots[e].logit.data() : nullptr, gumbel_ ? roots[e].noise.data() : nullptr, nullptr) != MZ_OK) {
             std::cerr << "mz_get_roots failed: " << mz_last_error() << std::endl;
             return false;
+        }
+        if (atari_ || rescale) { // rewards of the root children and the value bounds: what getNormalizedMean reads beside count / mean (mcts.cpp:40-53)
+            roots[e].reward.resize(n * A), roots[e].bound_size.resize(n), roots[e].bound_lo.resize(n), roots[e].bound_hi.resize(n);
+            if (mz_get_root_rewards(engines_[e], roots[e].reward.data(), roots[e].bound_size.data(), roots[e].bound_lo.data(), roots[e].bound_hi.data()) != MZ_OK) {
+                std::cerr << "mz_get_root_rewards failed: " << mz_last_error() << std::endl;
+                return false;
+            }
         }
         if (gumbel_ && mz_gumbel_best_actions(engines_[e], roots[e].gumbel_best.data()) != MZ_OK) {
             std::cerr << "mz_gumbel_best_actions failed: " << mz_last_error() << std::endl;
@@ -561,6 +661,10 @@ bool Worker::playOneMove()
         if (gumbel_) {
             r.policy = roots[e].policy.data() + static_cast<size_t>(slot) * A, r.logit = roots[e].logit.data() + static_cast<size_t>(slot) * A;
             r.noise = roots[e].noise.data() + static_cast<size_t>(slot) * A, r.gumbel_best = roots[e].gumbel_best[slot];
+        }
+        if (!roots[e].reward.empty()) {
+            r.reward = roots[e].reward.data() + static_cast<size_t>(slot) * A;
+            r.bound_size = roots[e].bound_size[slot], r.bound_lo = roots[e].bound_lo[slot], r.bound_hi = roots[e].bound_hi[slot];
         }
         bool resign = false, end = false;
         play[e][slot] = advanceGame(g, r, resign, end);
@@ -589,6 +693,23 @@ bool Worker::playOneMove()
             games_[g].num_legal = res[e][slot].num_legal;
         }
     }
+    if (atari_) { // the emulator's answers join the observation histories on the devices (AtariEnv::act's history update)
+        for (int e = 0; e < ne; ++e) {
+            std::vector<int32_t> acts(engine_games_[e], -2);
+            std::vector<uint8_t> frames(static_cast<size_t>(engine_games_[e]) * 3 * 96 * 96);
+            for (int slot = 0; slot < engine_games_[e]; ++slot) {
+                const int g = slot * ne + e;
+                if (play[e][slot] < 0 || std::find(ended.begin(), ended.end(), g) != ended.end()) { continue; }
+                acts[slot] = play[e][slot];
+                const std::string& obs = games_[g].observations.back();
+                std::copy(obs.begin(), obs.end(), frames.begin() + static_cast<size_t>(slot) * obs.size());
+            }
+            if (mz_atari_observe(engines_[e], acts.data(), frames.data()) != MZ_OK) {
+                std::cerr << "mz_atari_observe failed: " << mz_last_error() << std::endl;
+                return false;
+            }
+        }
+    }
     const double t4 = now();
     // games that go on: an intermediate sequence may be due (actor_group.cpp:126-132)
     {
@@ -605,7 +726,7 @@ bool Worker::playOneMove()
     for (int g : ended) {
         const int e = g % ne, slot = g / ne;
         const bool terminal = !ended_by_resign[g];
-        if (terminal && !res[e][slot].terminal) {
+        if (terminal && !atari_ && !res[e][slot].terminal) { // (the end of an Atari episode is the emulator's word alone)
             std::cerr << "host / device disagree on the end of game " << g << std::endl;
             return false;
         }
@@ -614,6 +735,24 @@ bool Worker::playOneMove()
         mz_reset_game(engines_[e], slot);
         restartGameHost(g);
         games_[g].enable_resign = keep_resign;
+    }
+    if (atari_ && !ended.empty()) { // first screens of the restarted episodes
+        for (int e = 0; e < ne; ++e) {
+            std::vector<int32_t> acts(engine_games_[e], -2);
+            std::vector<uint8_t> frames(static_cast<size_t>(engine_games_[e]) * 3 * 96 * 96);
+            bool any = false;
+            for (int g : ended) {
+                if (g % ne != e) { continue; }
+                const int slot = g / ne;
+                acts[slot] = -1, any = true;
+                const std::string& obs = games_[g].observations.back();
+                std::copy(obs.begin(), obs.end(), frames.begin() + static_cast<size_t>(slot) * obs.size());
+            }
+            if (any && mz_atari_observe(engines_[e], acts.data(), frames.data()) != MZ_OK) {
+                std::cerr << "mz_atari_observe failed: " << mz_last_error() << std::endl;
+                return false;
+            }
+        }
     }
     ++moves_played_;
     t_draw_ += t1 - t0, t_search_ += t2 - t1, t_decide_ += t3 - t2, t_play_ += t4 - t3, t_emit_ += now() - t4;
@@ -636,6 +775,8 @@ int Worker::rngTest(std::istream& in)
     in >> word >> game_type_ >> board_ >> actions_;
     sims_ = cfg_.getInt("actor_num_simulation"), num_games_ = cfg_.getInt("zero_num_parallel_games");
     muzero_ = (cfg_.getString("nn_type_name") == "muzero"), gumbel_ = cfg_.getBool("actor_use_gumbel");
+    atari_ = (game_type_ == MZ_GAME_ATARI);
+    if (atari_) { header_.game_name = "atari_" + cfg_.getString("env_atari_name"), header_.model_file = cfg_.getString("nn_file_name"); }
     engine_games_.assign(1, num_games_);
     rotations_.assign(1, std::vector<uint8_t>(static_cast<size_t>(sims_ + 1) * num_games_, 0));
     noise_.assign(1, std::vector<float>(static_cast<size_t>(num_games_) * actions_, 0.0f));
@@ -644,18 +785,25 @@ int Worker::rngTest(std::istream& in)
     const int A = actions_;
     long cycle = 0;
     std::vector<std::vector<int32_t>> acts(num_games_);
-    std::vector<std::vector<float>> cnt(num_games_), mean(num_games_), pol(num_games_), lgt(num_games_), nse(num_games_);
+    std::vector<std::vector<float>> cnt(num_games_), mean(num_games_), pol(num_games_), lgt(num_games_), nse(num_games_), rwd(num_games_);
     std::vector<RootView> views(num_games_);
     for (;;) {
         bool ok = true;
         for (int i = 0; i < num_games_ && ok; ++i) {
             int g, k;
             std::string mean_hex, value_hex;
-            if (!(in >> word >> g >> k >> mean_hex >> value_hex)) {
+            if (!(in >> word)) {
                 ok = false;
                 break;
             }
-            acts[g].assign(A, -1), cnt[g].assign(A, 0.0f), mean[g].assign(A, 0.0f), pol[g].assign(A, 0.0f), lgt[g].assign(A, 0.0f), nse[g].assign(A, 0.0f);
+            int bsize = 0;
+            std::string blo = "0", bhi = "0";
+            if (word == "bounds") { in >> bsize >> blo >> bhi >> word; } // "bounds <size> <lo_hex> <hi_hex>" precedes the root line of a rescaled search
+            if (!(in >> g >> k >> mean_hex >> value_hex)) {
+                ok = false;
+                break;
+            }
+            acts[g].assign(A, -1), cnt[g].assign(A, 0.0f), mean[g].assign(A, 0.0f), pol[g].assign(A, 0.0f), lgt[g].assign(A, 0.0f), nse[g].assign(A, 0.0f), rwd[g].assign(A, 0.0f);
             for (int j = 0; j < k; ++j) {
                 std::string tok, part;
                 in >> tok;
@@ -669,11 +817,13 @@ int Worker::rngTest(std::istream& in)
                 if (std::getline(ts, part, ':')) { pol[g][j] = hexf(part); } // optional: policy, logit, noise (Gumbel records)
                 if (std::getline(ts, part, ':')) { lgt[g][j] = hexf(part); }
                 if (std::getline(ts, part, ':')) { nse[g][j] = hexf(part); }
+                if (std::getline(ts, part, ':')) { rwd[g][j] = hexf(part); }
             }
             RootView& r = views[g];
             r.num_children = k, r.root_mean = hexf(mean_hex), r.root_value = hexf(value_hex);
             r.acts = acts[g].data(), r.cnt = cnt[g].data(), r.mean = mean[g].data();
             r.policy = pol[g].data(), r.logit = lgt[g].data(), r.noise = nse[g].data();
+            r.reward = rwd[g].data(), r.bound_size = bsize, r.bound_lo = hexf(blo), r.bound_hi = hexf(bhi);
             games_[g].num_legal = k; // the root's children are its legal actions (Dirichlet / Gumbel draws, zero_actor.cpp:197,206)
         }
         if (!ok) { break; }
@@ -696,6 +846,17 @@ int Worker::rngTest(std::istream& in)
             bool resign = false, end = false;
             const int action = advanceGame(g, views[g], resign, end);
             std::cout << "act " << g << " " << action << " " << (resign ? 1 : 0) << " " << (end ? 1 : 0) << "\n";
+            if (atari_) { // the emulator lives on the host: whole records can be checked without a device
+                AtariRecord at;
+                at.observations = &games_[g].observations, at.lives_history = &games_[g].lives_history, at.seed = games_[g].seed, at.total_reward = games_[g].total_reward;
+                const SequenceConfig seq = sequenceConfig();
+                if (end) {
+                    std::cout << "line " << selfPlayLine(header_, games_[g].moves, !resign, 0.0f, 1, seq, &at) << "\n";
+                } else if (intermediateSequenceDue(static_cast<int>(games_[g].moves.size()), seq)) {
+                    std::cout << "line " << selfPlayLine(header_, games_[g].moves, false, 0.0f, 1, seq, &at) << "\n";
+                    clearSentActionInfo(games_[g].moves, false, seq);
+                }
+            }
             if (end) {
                 const bool keep = games_[g].enable_resign;
                 restartGameHost(g);

@@ -8,6 +8,7 @@
 #include "net_loader.h"
 #include "record.h"
 #include "rng.h"
+#include "synth_atari.h"
 #include <deque>
 #include <istream>
 #include <mutex>
@@ -24,6 +25,12 @@ struct Game {                    // what BaseActor / ZeroActor keep per game on 
     int num_legal = 0;             // root children of the next search (= Dirichlet draws)
     uint8_t ttt[9] = {0};          // tictactoe board, only to know the end of the game in RNG order
     std::vector<uint8_t> stones;   // NoGo board (stones are never removed), for the same purpose
+    // Atari (environment/atari/atari.{h,cpp}): the emulator and what AtariEnv keeps beside it
+    SynthAtari emu;
+    int seed = 0;                          // AtariEnv::seed_ (SD tag)
+    float reward = 0.0f, total_reward = 0.0f;
+    std::vector<int> lives_history;        // lives before every action, then the current ones
+    std::vector<std::string> observations; // one screen per position (3 x 96 x 96 bytes, channel-major); old ones emptied (atari.cpp:72-79)
 };
 
 struct RootView { // one game's root child table, children in stored order (what MCTS hands to the move decision and the record)
@@ -31,6 +38,9 @@ struct RootView { // one game's root child table, children in stored order (what
     float root_mean = 0.0f, root_value = 0.0f;
     const int32_t* acts = nullptr;
     const float *cnt = nullptr, *mean = nullptr, *policy = nullptr, *logit = nullptr, *noise = nullptr;
+    const float* reward = nullptr; // MCTSNode::getReward of the children (null: all zero)
+    int bound_size = 0;            // MCTS::getTreeValueBound: number of distinct values, smallest, largest (actor_mcts_value_rescale)
+    float bound_lo = 0.0f, bound_hi = 0.0f;
     int gumbel_best = -1;
 };
 
@@ -51,7 +61,11 @@ private:
     void drawSearchRandomness();             // root noise + rotations of cycles 1 .. S of one search
     int advanceGame(int g, const RootView& r, bool& resign, bool& end); // decide / act / end / next-game draws of one actor
     void restartGameHost(int g);
-    int decideAction(int g, const int* actions, const float* counts, const float* means, int num_children, float root_mean, bool& resign, int& child_index);
+    int decideAction(int g, const RootView& r, bool& resign, int& child_index);
+    float normalizedMean(const RootView& r, int child, int player) const; // MCTSNode::getNormalizedMean of a root child (child < 0: the root)
+    void atariReset(Game& game, int seed);          // AtariEnv::reset(seed), atari.cpp:36-59
+    void atariAct(Game& game, int action);          // AtariEnv::act, atari.cpp:61-92
+    bool atariTerminal(const Game& game) const;     // AtariEnv::isTerminal, atari.h:58
     bool hostTerminal(const Game& game) const;
     bool nogoHasLegalMove(const Game& game) const; // NoGoEnv::isTerminal needs the legal set (environment/nogo/nogo.h:27-68)
     void emitGame(int g, bool terminal, float eval_score);
@@ -63,7 +77,7 @@ private:
     NetInfo net_;
     GameHeader header_;
     int game_type_ = MZ_GAME_GO, board_ = 9, actions_ = 82, sims_ = 0, num_games_ = 0;
-    bool muzero_ = false, gumbel_ = false;
+    bool muzero_ = false, gumbel_ = false, atari_ = false;
     SequenceConfig sequenceConfig() const
     {
         SequenceConfig c;
@@ -78,11 +92,13 @@ private:
             const int inner = (board_ > 4 ? board_ - 4 : 0);
             return cfg_.getString("env_gomoku_rule") == "outer_open" ? board_ * board_ - inner * inner : board_ * board_;
         }
+        if (game_type_ == MZ_GAME_ATARI) { return static_cast<int>(SynthAtari::minimalActionSet().size()); }
         return game_type_ == MZ_GAME_GO ? board_ * board_ + 1 : (game_type_ == MZ_GAME_NOGO ? board_ * board_ : (game_type_ == MZ_GAME_OTHELLO ? 4 : 9));
     }
     std::vector<mz_engine*> engines_;  // one per visible GPU (actor_group.cpp:168-177)
     std::vector<int> engine_games_;    // games handled by each engine: game g -> engine g % n, slot g / n (actor_group.cpp:184-186)
     std::vector<Game> games_;
+    std::vector<int> next_seed_;                  // Atari: emulator seed of every game's NEXT episode, drawn in order when the current one ends
     std::vector<std::vector<uint8_t>> rotations_; // per engine [(S+1)][games]
     std::vector<std::vector<float>> noise_;       // per engine [games][A]
     void* nccl_comms_ = nullptr;

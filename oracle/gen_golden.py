@@ -60,6 +60,9 @@ CASES = {
     "atari_mz_s18_gumbel_b2": ("atari", "atari_mz_1bx32", ATARI + "actor_num_simulation=18:zero_num_parallel_games=2:"
                                "actor_use_gumbel=true:actor_use_gumbel_noise=true:actor_gumbel_sample_size=8:actor_gumbel_sigma_visit_c=50:actor_gumbel_sigma_scale_c=0.1:"
                                "actor_use_dirichlet_noise=false:" + COMMON_MZ % 7, 40),
+    # intermediate sequences of Atari records (zero_actor_intermediate_sequence_length, 200 by default: atari.h:90): OBS windows, L tags of sent moves
+    "atari_mz_seq_s8_b2": ("atari", "atari_mz_1bx32", ATARI + "actor_num_simulation=8:zero_num_parallel_games=2:zero_actor_intermediate_sequence_length=8:"
+                           "learner_n_step_return=3:learner_muzero_unrolling_step=2:" + COMMON_MZ % 8, 70),
     "go9_s400_b2": ("go", "go9_az_6bx256", "env_board_size=9:actor_num_simulation=400:zero_num_parallel_games=2:" + COMMON % 81, 6),
     "go19_s800_b2": ("go", "go19_az_1bx16", "env_board_size=19:actor_num_simulation=800:zero_num_parallel_games=2:" + COMMON % 82, 2),
 }

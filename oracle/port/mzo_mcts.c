@@ -334,6 +334,14 @@ int mzo_gumbel_policy(const mzo_batch* b, int g, int32_t* actions, float* probs)
         q_sum += t->policy[c] * value;
     }
     float value_pi = t->value[0];
+    if (b->cfg.value_rescale) { /* gumbel_zero.cpp:21-30 */
+        if (t->vb_n < 2) {
+            value_pi = 1.0f;
+        } else {
+            value_pi = (value_pi - t->vb_key[0]) / (t->vb_key[t->vb_n - 1] - t->vb_key[0]);
+            value_pi = (float)fmin(1, fmax(-1, 2 * value_pi - 1));
+        }
+    }
     value_pi = (t->player[fc] == 2 ? -value_pi : value_pi);
     const int S = b->cfg.num_simulation;
     float non_visited = (float)(1.0 / (1 + S) * (value_pi + (S / pi_sum) * q_sum));

@@ -79,3 +79,35 @@ def test_worker_reloads_model_and_updates_config():
     out, err = p.communicate(timeout=120)
     assert first.startswith("SelfPlay ") and p.returncode == 0, err[-400:]
     assert "[ignored command] reset_actors" in err  # zero_actor_ignored_command default (configuration.cpp:47)
+
+
+def test_worker_atari_mode_end_to_end():
+    """BASELINE configs[4] through the executable: Atari MuZero with value rescaling on the synthetic frame source; every line must
+    carry an OBS tag that gunzips to whole 96 x 96 x 3 screens covering the sequence's window, an SD seed, rewards summing to the return"""
+    import gzip
+    import re
+    model = os.path.join(NETS, "atari_mz_1bx32.pt")
+    if not (os.path.exists(BIN) and os.path.exists(model)):
+        pytest.skip("worker binary / nets not built")
+    conf = ("env_atari_name=ms_pacman:actor_mcts_value_rescale=true:actor_mcts_reward_discount=0.997:actor_num_simulation=20:zero_num_parallel_games=16:"
+            f"nn_type_name=muzero:zero_actor_intermediate_sequence_length=8:learner_n_step_return=3:learner_muzero_unrolling_step=2:nn_file_name={model}:"
+            "program_seed=3:program_auto_seed=false:program_quiet=true:zero_num_threads=1")
+    lines, err, rc = run_worker(conf, want_lines=24)
+    assert rc == 0, err[-500:]
+    assert len(lines) >= 24 and all(l.startswith("SelfPlay ") and l.endswith(" #") for l in lines)
+    terminal_seen = False
+    for l in lines:
+        f = l.split(" ")
+        terminal, data_len, game_len, ret = f[1] == "true", int(f[2]), int(f[3]), float(f[4])
+        rec = f[5]
+        assert rec.startswith("(;GM[atari_ms_pacman]RE[") and "EV[atari_mz_1bx32.pt]" in rec and re.search(r"SD\[\d+\]", rec)
+        obs = gzip.decompress(bytes.fromhex(re.search(r"OBS\[([0-9a-f]*)\]", rec).group(1)))
+        assert len(obs) % (3 * 96 * 96) == 0 and len(obs) // (3 * 96 * 96) == min(game_len + 1, 8 + 8 + 3 + 2 + 1)
+        moves = re.findall(r";B\[(\d+)\]([^;)]*)", rec)
+        assert len(moves) == game_len and 1 <= data_len <= game_len
+        assert all(int(a) in (0, 2, 3, 4, 5, 6, 7, 8, 9) for a, _ in moves)  # the minimal action set of the synthetic game
+        rewards = [float(re.search(r"R\[([^\]]*)\]", info).group(1)) for _, info in moves if "R[" in info]
+        if len(rewards) == game_len:  # no action info dropped yet: the rewards add up to the return
+            assert sum(rewards) == ret
+        terminal_seen |= terminal
+    assert terminal_seen
