@@ -131,130 +131,201 @@ __device__ __forceinline__ float invert_value(float value)
 // ---------------------------------------------------------------------------------------------
 // Heads of the Atari network. PolicyNetwork (network_unit.py:26-42): conv1x1-BN-ReLU-fc, softmax. DiscreteValueNetwork
 // (network_unit.py:68-87): conv1x1-BN-ReLU-fc1-ReLU-fc2 -> 601 logits; MuZeroNetwork::forward (muzero_network.h:157-171) takes the
-// softmax, the expectation sum_i p_i * (i - 300) and utils::invertValue: all fused here, only the scalar leaves the kernel.
-// One launch computes one discrete head (the value head together with the policy head on the scaled hidden state; the reward head
-// on the dynamics output BEFORE scaling, muzero_atari_network.py:53-54,176-178). BPC boards per CTA share every weight they read.
+// softmax, the expectation sum_i p_i * (i - 300) and utils::invertValue. The value and policy heads read the SCALED hidden state,
+// the reward head the dynamics output before scaling (muzero_atari_network.py:53-54,176-178). Four launches per evaluation:
+//   hidden_planes_kernel   per board: min / max scaling of the hidden state (scale_hidden_state, :185-193) into the node's hidden
+//                          slot, and the 1x1 convolutions of all three heads (fp32) -> fp16 rows of the FC inputs
+//   fc_gemm_kernel x 2     fc1 (+ ReLU) and fc2 of the value and reward heads as batched GEMMs over the boards on tensor cores
+//                          (mma.sync m16n8k16, fp16 in / fp32 accumulate; M = boards: far too small for a tcgen05 pipeline)
+//   discrete_finalize_kernel  per board: softmax + expectation + invertValue of both heads, policy fc + softmax
 // ---------------------------------------------------------------------------------------------
-struct DiscreteHeadParams {
-    const __half* act; // [batch * slots][c] rows of an n x n map
-    int c, n, slots, batch;
-    int do_policy;
-    const float* w_pc; // [pol_ch][c] policy conv (BN folded)      b_pc [pol_ch]
-    const float* b_pc;
-    const float* w_pf; // [pol_ch * hw][actions] transposed          b_pf [actions]
-    const float* b_pf;
-    int pol_ch, actions;
-    float* policy;     // [batch][actions]
-    float* logits;     // [batch][actions]
-    const float* w_dc; // [hc][c] conv of the discrete head (BN folded)   b_dc [hc]
-    const float* b_dc;
-    const float* w_d1; // [hc * hw][vh] transposed                        b_d1 [vh]
-    const float* b_d1;
-    const float* w_d2; // [vh][dv] transposed                             b_d2 [dv]
-    const float* b_d2;
-    int hc, vh, dv;
-    float* out;        // [batch] invertValue(expectation)
+struct PlanesParams {
+    const __half* act;   // [batch * slots][c] tower output rows (unscaled)
+    __half* hid;         // [batch][num_slots][hw][c] hidden states of the search
+    const int32_t* slot; // [batch] slot of this evaluation
+    int n, slots, c, c_real, num_slots;
+    const float *w_pol, *b_pol; // [pol_ch][c], [pol_ch]
+    const float *w_val, *b_val; // [hc][c], [hc]
+    const float *w_rew, *b_rew; // [hc][c], [hc]; null for the initial inference (no reward output)
+    int pol_ch, hc;
+    __half* a_val;       // [m_pad][k_pad] flattened value planes (plane-major, as x.view(-1, hw * hc) of an NCHW tensor)
+    __half* a_rew;
+    float* pol_planes;   // [batch][pol_ch * hw]
+    int k_pad;
 };
 
-template <int BPC>
-__global__ void __launch_bounds__(512) discrete_head_kernel(const DiscreteHeadParams p)
+__global__ void __launch_bounds__(256) hidden_planes_kernel(const PlanesParams p)
 {
-    extern __shared__ float sm[];
-    const int hw = p.n * p.n, n1 = p.n + 1;
-    const int np = (p.do_policy ? p.pol_ch : 0) + p.hc; // planes per board: policy planes first
-    float* wc = sm;                         // [np][c]
-    float* planes = wc + np * p.c;          // [BPC][np * hw]
-    float* hid = planes + BPC * np * hw;    // [BPC][vh]
-    float* lg = hid + BPC * p.vh;           // [BPC][max(dv, actions)]
-    float* partial = lg + BPC * (p.dv > p.actions ? p.dv : p.actions); // [parts][BPC][vh]
-    const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
-    const int g0 = blockIdx.x * BPC;
-    const int pol_planes = (p.do_policy ? p.pol_ch : 0);
-    for (int i = tid; i < np * p.c; i += nthr) { wc[i] = (i < pol_planes * p.c ? p.w_pc[i] : p.w_dc[i - pol_planes * p.c]); }
+    extern __shared__ float xs[]; // [hw][c_real] the board's hidden state, unscaled
+    __shared__ float red_mn[8], red_mx[8];
+    const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, hw = p.n * p.n, n1 = p.n + 1;
+    const __half* rows = p.act + static_cast<size_t>(g) * p.slots * p.c;
+    float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
+    for (int i = tid; i < hw * (p.c_real / 2); i += blockDim.x) {
+        const int cell = i / (p.c_real / 2), k = i - cell * (p.c_real / 2);
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(rows + static_cast<size_t>((cell / p.n + 1) * n1 + cell % p.n) * p.c + 2 * k));
+        xs[cell * p.c_real + 2 * k] = f.x, xs[cell * p.c_real + 2 * k + 1] = f.y;
+        mn = fminf(mn, fminf(f.x, f.y)), mx = fmaxf(mx, fmaxf(f.x, f.y));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)), mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    if (lane == 0) { red_mn[warp] = mn, red_mx[warp] = mx; }
     __syncthreads();
-    // 1x1 convolutions: one warp per (board, cell); lane l owns channel pairs {2l + 64i}; output planes in groups of 6
-    const int npair = p.c / 64;
-    for (int bc = warp; bc < BPC * hw; bc += nwarp) {
-        const int b = bc / hw, cell = bc - b * hw;
-        if (g0 + b >= p.batch) { continue; }
-        const __half2* row = reinterpret_cast<const __half2*>(p.act + (static_cast<size_t>(g0 + b) * p.slots + (cell / p.n + 1) * n1 + cell % p.n) * p.c);
-        for (int o0 = 0; o0 < np; o0 += 6) {
-            float acc[6];
+    mn = red_mn[0], mx = red_mx[0];
+    for (int i = 1; i < (blockDim.x >> 5); ++i) { mn = fminf(mn, red_mn[i]), mx = fmaxf(mx, red_mx[i]); }
+    float scale = mx - mn;
+    if (scale < 1e-5f) { scale += 1e-5f; }
+    // the scaled state -> the node's hidden slot (fp16, padded channels zero): what the next recurrent inference gathers
+    __half* dst = p.hid + (static_cast<size_t>(g) * p.num_slots + p.slot[g]) * hw * p.c;
+    for (int i = tid; i < hw * (p.c / 2); i += blockDim.x) {
+        const int cell = i / (p.c / 2), k = i - cell * (p.c / 2);
+        float a = 0.0f, b = 0.0f;
+        if (2 * k < p.c_real) { a = (xs[cell * p.c_real + 2 * k] - mn) / scale, b = (xs[cell * p.c_real + 2 * k + 1] - mn) / scale; }
+        *reinterpret_cast<__half2*>(dst + static_cast<size_t>(cell) * p.c + 2 * k) = __floats2half2_rn(a, b);
+    }
+    // 1x1 convolutions + folded BN + ReLU: one warp per plane (its weights stay in registers), lanes over the channels, cells in turn
+    __syncthreads();
+    const int n_rew = (p.w_rew ? p.hc : 0), planes = p.pol_ch + p.hc + n_rew;
+    const float inv_scale = 1.0f / scale;
+    for (int plane = warp; plane < planes; plane += (blockDim.x >> 5)) {
+        const float* w;
+        float bias;
+        bool scaled = true;
+        if (plane < p.pol_ch) {
+            w = p.w_pol + static_cast<size_t>(plane) * p.c, bias = p.b_pol[plane];
+        } else if (plane < p.pol_ch + p.hc) {
+            w = p.w_val + static_cast<size_t>(plane - p.pol_ch) * p.c, bias = p.b_val[plane - p.pol_ch];
+        } else {
+            w = p.w_rew + static_cast<size_t>(plane - p.pol_ch - p.hc) * p.c, bias = p.b_rew[plane - p.pol_ch - p.hc], scaled = false;
+        }
+        float wr[16]; // c_real <= 512
 #pragma unroll
-            for (int o = 0; o < 6; ++o) { acc[o] = 0.0f; }
-            for (int i = 0; i < npair; ++i) {
-                const float2 a = __half22float2(row[lane + 32 * i]);
-                const float* wp = wc + 2 * lane + 64 * i;
+        for (int i = 0; i < 16; ++i) {
+            wr[i] = (lane + 32 * i < p.c_real ? __ldg(w + lane + 32 * i) : 0.0f);
+        }
+        for (int cell = 0; cell < hw; ++cell) {
+            const float* x = xs + cell * p.c_real;
+            float acc = 0.0f;
 #pragma unroll
-                for (int o = 0; o < 6; ++o) {
-                    if (o0 + o < np) {
-                        const float2 wv = *reinterpret_cast<const float2*>(wp + (o0 + o) * p.c);
-                        acc[o] = fmaf(a.x, wv.x, fmaf(a.y, wv.y, acc[o]));
-                    }
-                }
+            for (int i = 0; i < 16; ++i) {
+                if (lane + 32 * i < p.c_real) { acc = fmaf(scaled ? (x[lane + 32 * i] - mn) * inv_scale : x[lane + 32 * i], wr[i], acc); }
             }
 #pragma unroll
-            for (int o = 0; o < 6; ++o) {
-                float v = acc[o];
-#pragma unroll
-                for (int sft = 16; sft > 0; sft >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, sft); }
-                if (lane == 0 && o0 + o < np) {
-                    const int pl = o0 + o;
-                    const float bias = (pl < pol_planes ? p.b_pc[pl] : p.b_dc[pl - pol_planes]);
-                    planes[(b * np + pl) * hw + cell] = fmaxf(v + bias, 0.0f);
+            for (int sft = 16; sft > 0; sft >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, sft); }
+            if (lane == 0) {
+                const float v = fmaxf(acc + bias, 0.0f);
+                if (plane < p.pol_ch) {
+                    p.pol_planes[static_cast<size_t>(g) * p.pol_ch * hw + plane * hw + cell] = v;
+                } else if (plane < p.pol_ch + p.hc) {
+                    p.a_val[static_cast<size_t>(g) * p.k_pad + (plane - p.pol_ch) * hw + cell] = __float2half_rn(v);
+                } else {
+                    p.a_rew[static_cast<size_t>(g) * p.k_pad + (plane - p.pol_ch - p.hc) * hw + cell] = __float2half_rn(v);
                 }
             }
         }
     }
-    __syncthreads();
-    // fc1 of the discrete head: vh outputs over hc * hw inputs (transposed weights, coalesced across threads), the input range split
-    // over `parts` thread groups; every weight feeds BPC boards
-    const int nin = p.hc * hw;
-    const int parts = (nthr / p.vh > 0 ? nthr / p.vh : 1);
-    for (int t = tid; t < parts * p.vh; t += nthr) {
-        const int part = t / p.vh, o = t - part * p.vh;
-        const int i0 = (nin * part) / parts, i1 = (nin * (part + 1)) / parts;
-        float acc[BPC];
+}
+
+// out[m][n] = act(sum_k a[m][k] * w[n][k] + bias[n]) for up to two independent problems (blockIdx.z): torch's Linear with its
+// weight in its own [out][in] layout. 64 x 64 tile per CTA of 4 warps (16 rows each), K in steps of 64 through a two-stage
+// cp.async pipeline, mma.sync.m16n8k16 fp16 -> fp32. m, n, k are padded to multiples of 64 by the caller (zero weights / rows).
+struct FcGemmParams {
+    const __half* a[2];
+    const __half* w[2];
+    const float* bias[2];
+    void* out[2];
+    int n[2], k[2], lda[2], ldw[2], ldc[2];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(mznn::smem_u32(smem)), "l"(gmem) : "memory");
+}
+
+template <bool HALF_RELU_OUT>
+__global__ void __launch_bounds__(128) fc_gemm_kernel(const FcGemmParams p)
+{
+    constexpr int T = 64, LD = T + 8; // +8 halves: rows 144 bytes apart, fragment loads hit distinct banks
+    __shared__ __align__(16) __half As[2][T][LD];
+    __shared__ __align__(16) __half Ws[2][T][LD];
+    const int h = blockIdx.z, n0 = blockIdx.x * T, m0 = blockIdx.y * T;
+    if (n0 >= p.n[h]) { return; }
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const __half* a = p.a[h] + static_cast<size_t>(m0) * p.lda[h];
+    const __half* w = p.w[h] + static_cast<size_t>(n0) * p.ldw[h];
+    auto load_tile = [&](int buf, int k0) {
 #pragma unroll
-        for (int b = 0; b < BPC; ++b) { acc[b] = 0.0f; }
-        const float* wp = p.w_d1 + o;
-#pragma unroll 8
-        for (int i = i0; i < i1; ++i) {
-            const float w = __ldg(wp + static_cast<size_t>(i) * p.vh);
-#pragma unroll
-            for (int b = 0; b < BPC; ++b) { acc[b] = fmaf(planes[(b * np + pol_planes) * hw + i], w, acc[b]); }
+        for (int i = 0; i < 4; ++i) {
+            const int chunk = tid + i * 128, row = chunk >> 3, col = (chunk & 7) * 8;
+            cp_async16(&As[buf][row][col], a + static_cast<size_t>(row) * p.lda[h] + k0 + col);
+            cp_async16(&Ws[buf][row][col], w + static_cast<size_t>(row) * p.ldw[h] + k0 + col);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    float acc[8][4];
 #pragma unroll
-        for (int b = 0; b < BPC; ++b) { partial[(part * BPC + b) * p.vh + o] = acc[b]; }
-    }
-    __syncthreads();
-    for (int t = tid; t < BPC * p.vh; t += nthr) {
-        const int b = t / p.vh, o = t - b * p.vh;
-        float acc = p.b_d1[o];
-        for (int q = 0; q < parts; ++q) { acc += partial[(q * BPC + b) * p.vh + o]; }
-        hid[b * p.vh + o] = fmaxf(acc, 0.0f);
-    }
-    __syncthreads();
-    // fc2: dv logits over vh inputs
-    for (int o = tid; o < p.dv; o += nthr) {
-        float acc[BPC];
-#pragma unroll
-        for (int b = 0; b < BPC; ++b) { acc[b] = 0.0f; }
-        const float* wp = p.w_d2 + o;
-#pragma unroll 8
-        for (int i = 0; i < p.vh; ++i) {
-            const float w = __ldg(wp + static_cast<size_t>(i) * p.dv);
-#pragma unroll
-            for (int b = 0; b < BPC; ++b) { acc[b] = fmaf(hid[b * p.vh + i], w, acc[b]); }
+    for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f; }
+    const int kt = p.k[h] / T;
+    load_tile(0, 0);
+    for (int it = 0; it < kt; ++it) {
+        const int buf = it & 1;
+        if (it + 1 < kt) {
+            load_tile(buf ^ 1, (it + 1) * T);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        const float bias = p.b_d2[o];
+        __syncthreads();
 #pragma unroll
-        for (int b = 0; b < BPC; ++b) { lg[b * p.dv + o] = acc[b] + bias; }
+        for (int kk = 0; kk < T; kk += 16) {
+            const int r = warp * 16 + g;
+            const uint32_t a0 = *reinterpret_cast<const uint32_t*>(&As[buf][r][kk + 2 * t]), a1 = *reinterpret_cast<const uint32_t*>(&As[buf][r + 8][kk + 2 * t]);
+            const uint32_t a2 = *reinterpret_cast<const uint32_t*>(&As[buf][r][kk + 2 * t + 8]), a3 = *reinterpret_cast<const uint32_t*>(&As[buf][r + 8][kk + 2 * t + 8]);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ws[buf][nt * 8 + g][kk + 2 * t]), b1 = *reinterpret_cast<const uint32_t*>(&Ws[buf][nt * 8 + g][kk + 2 * t + 8]);
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                             : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                             : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    // softmax, expectation over the bins (i - dv / 2), invertValue: one warp per board
-    if (warp < BPC && g0 + warp < p.batch) {
-        const float* l = lg + warp * p.dv;
+    const int row = m0 + warp * 16 + g;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int col = n0 + nt * 8 + 2 * t;
+        const float b0 = p.bias[h][col], b1 = p.bias[h][col + 1];
+        if (HALF_RELU_OUT) {
+            __half* o = static_cast<__half*>(p.out[h]);
+            *reinterpret_cast<__half2*>(o + static_cast<size_t>(row) * p.ldc[h] + col) = __floats2half2_rn(fmaxf(acc[nt][0] + b0, 0.0f), fmaxf(acc[nt][1] + b1, 0.0f));
+            *reinterpret_cast<__half2*>(o + static_cast<size_t>(row + 8) * p.ldc[h] + col) = __floats2half2_rn(fmaxf(acc[nt][2] + b0, 0.0f), fmaxf(acc[nt][3] + b1, 0.0f));
+        } else {
+            float* o = static_cast<float*>(p.out[h]);
+            *reinterpret_cast<float2*>(o + static_cast<size_t>(row) * p.ldc[h] + col) = make_float2(acc[nt][0] + b0, acc[nt][1] + b1);
+            *reinterpret_cast<float2*>(o + static_cast<size_t>(row + 8) * p.ldc[h] + col) = make_float2(acc[nt][2] + b0, acc[nt][3] + b1);
+        }
+    }
+}
+
+struct FinalizeParams {
+    const float* lg_val; // [m_pad][ld] logits of the value head's 601 bins
+    const float* lg_rew; // or null
+    int ld, dv;
+    const float* pol_planes; // [batch][pol_ch * hw]
+    const float *w_pf, *b_pf; // [pol_ch * hw][actions] transposed, [actions]
+    int pol_in, actions;
+    float *value, *reward, *policy, *logits;
+};
+
+// warp 0: value, warp 1: reward (softmax over the bins, expectation of (i - dv / 2), invertValue); warps 2-3: policy fc + softmax
+__global__ void __launch_bounds__(128) discrete_finalize_kernel(const FinalizeParams p)
+{
+    const int g = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < 2) {
+        const float* l = (warp == 0 ? p.lg_val : p.lg_rew);
+        if (!l) { return; }
+        l += static_cast<size_t>(g) * p.ld;
         float mx = -3.402823466e+38f;
         for (int i = lane; i < p.dv; i += 32) { mx = fmaxf(mx, l[i]); }
 #pragma unroll
@@ -267,32 +338,25 @@ __global__ void __launch_bounds__(512) discrete_head_kernel(const DiscreteHeadPa
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o), ex += __shfl_xor_sync(0xffffffffu, ex, o); }
-        if (lane == 0) { p.out[g0 + warp] = invert_value(ex / sum); }
+        if (lane == 0) { (warp == 0 ? p.value : p.reward)[g] = invert_value(ex / sum); }
+        return;
     }
-    if (!p.do_policy) { return; }
-    __syncthreads();
-    // policy fc + softmax (tiny: pol_ch * hw inputs, `actions` outputs)
-    for (int t = tid; t < BPC * p.actions; t += nthr) {
-        const int b = t / p.actions, o = t - b * p.actions;
-        float acc = p.b_pf[o];
-        for (int i = 0; i < p.pol_ch * hw; ++i) { acc = fmaf(planes[b * np * hw + i], __ldg(p.w_pf + static_cast<size_t>(i) * p.actions + o), acc); }
-        lg[b * p.actions + o] = acc;
-    }
-    __syncthreads();
-    if (warp < BPC && g0 + warp < p.batch) {
-        const float* l = lg + warp * p.actions;
-        float mx = -3.402823466e+38f;
-        for (int a = lane; a < p.actions; a += 32) { mx = fmaxf(mx, l[a]); }
+    if (warp == 2) { // (actions <= 32 for every Atari game: 18)
+        float acc = -3.402823466e+38f;
+        if (lane < p.actions) {
+            acc = p.b_pf[lane];
+            for (int i = 0; i < p.pol_in; ++i) { acc = fmaf(p.pol_planes[static_cast<size_t>(g) * p.pol_in + i], __ldg(p.w_pf + static_cast<size_t>(i) * p.actions + lane), acc); }
+        }
+        float mx = acc;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
-        float sum = 0.0f;
-        for (int a = lane; a < p.actions; a += 32) { sum += expf(l[a] - mx); }
+        const float e = (lane < p.actions ? expf(acc - mx) : 0.0f);
+        float sum = e;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); }
-        const float inv = 1.0f / sum;
-        for (int a = lane; a < p.actions; a += 32) {
-            p.logits[static_cast<size_t>(g0 + warp) * p.actions + a] = l[a];
-            p.policy[static_cast<size_t>(g0 + warp) * p.actions + a] = expf(l[a] - mx) * inv;
+        if (lane < p.actions) {
+            p.logits[static_cast<size_t>(g) * p.actions + lane] = acc;
+            p.policy[static_cast<size_t>(g) * p.actions + lane] = e / sum;
         }
     }
 }

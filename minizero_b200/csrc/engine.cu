@@ -291,8 +291,12 @@ struct mz_engine {
     bool atari = false;
     ConvStage ast[3];              // representation stages at 48 x 48, 24 x 24, 12 x 12 (the 6 x 6 stage is tw[0], the dynamics network tw[1])
     int at_c1 = 0;                 // padded channels of the first stage (num_hidden_channels / 2)
-    size_t off_dhead[3][6] = {{0}}; // value / reward heads: conv w, conv b, fc1 w^T, fc1 b, fc2 w^T, fc2 b; [2] = policy: conv w, conv b, fc w^T, fc b
+    size_t off_dhead[3][6] = {{0}}; // value / reward heads: conv w (fp32), conv b, fc1 w (fp16 [out_pad][in_pad]), fc1 b, fc2 w (fp16), fc2 b; [2] = policy: conv w, conv b, fc w^T, fc b (fp32)
     int dh_planes = 0;             // planes of a discrete head: ceil(discrete_value_size / 36)
+    int dh_k1 = 0, dh_n1[2] = {0, 0}, dh_n2 = 0, dh_mpad = 0; // padded GEMM sizes of the heads' FC layers: fc1 in, fc1 out (value / reward), fc2 out, boards
+    __half *d_a_head[2] = {nullptr, nullptr}, *d_h_head[2] = {nullptr, nullptr}; // FC inputs / hidden activations [mpad][k]
+    float* d_l_head[2] = {nullptr, nullptr};                                       // bin logits [mpad][n2]
+    float* d_pol_planes = nullptr;
     uint8_t* d_at_frames_in = nullptr; // [B][3][96][96] staging of mz_atari_observe
     float* d_root_reward = nullptr;    // [B][A]
     int32_t* d_bound_size = nullptr;
@@ -427,7 +431,7 @@ int conv(mz_engine* e, const CUtensorMap& in, const CUtensorMap& in_ext, const C
     }
 }
 
-int launch_heads(mz_engine* e, const __half* act, int* clear = nullptr, int clear_count = 0)
+int launch_heads(mz_engine* e, const __half* act, int* clear = nullptr, int clear_count = 0, bool scale_hidden = false)
 {
     mznn::HeadParams p;
     p.clear = clear, p.clear_count = clear_count;
@@ -438,6 +442,8 @@ int launch_heads(mz_engine* e, const __half* act, int* clear = nullptr, int clea
     p.c = e->cpad, p.n = e->d.N, p.slots = e->d.slots, p.pol_ch = e->pol_ch, p.actions = e->d.A, p.vh = e->nd.num_value_hidden_channels;
     const int hw = e->d.N * e->d.N, np1 = p.pol_ch + 1;
     p.batch = e->d.B, p.fc_in_smem = 0;
+    p.hid = nullptr, p.hid_slot = nullptr, p.c_real = e->nd.num_hidden_channels, p.num_slots = e->d.S + 1;
+    if (scale_hidden) { p.hid = reinterpret_cast<__half*>(e->s.hid), p.hid_slot = e->s.eval_slot; }
     const size_t smem = sizeof(float) * (np1 * p.c + np1 * hw + p.vh + p.actions + 32 + hw + 4 * (p.actions + p.vh));
     static const int threads_env = [] {
         const char* env = knob("MZ_HEADS_THREADS");
@@ -459,23 +465,39 @@ int launch_heads(mz_engine* e, const __half* act, int* clear = nullptr, int clea
 int launch_tower(mz_engine* e, int which, bool clear_counters = true, bool pdl = false);
 int launch_tower_params(mz_engine* e, mznn::TowerParams* params, int* d_done, int cout, int cin_max, int rows_ext, int stages, bool clear_counters, bool pdl);
 
-int launch_discrete_head(mz_engine* e, const __half* act, int head, bool with_policy, float* out)
+// hidden-state scaling + the three heads of the Atari network on the tower output `act` (see atari_kernels.cuh): 4 launches
+int launch_atari_heads(mz_engine* e, const __half* act, bool with_reward)
 {
-    mzat::DiscreteHeadParams p;
-    auto f = [&](int h, int i) { return reinterpret_cast<const float*>(e->d_blob + e->off_dhead[h][i]); };
-    p.act = act, p.c = e->cpad, p.n = e->d.N, p.slots = e->d.slots, p.batch = e->d.B;
-    p.do_policy = (with_policy ? 1 : 0);
-    p.w_pc = f(2, 0), p.b_pc = f(2, 1), p.w_pf = f(2, 2), p.b_pf = f(2, 3), p.pol_ch = e->pol_ch, p.actions = e->d.A;
-    p.policy = e->s.policy, p.logits = e->s.logits;
-    p.w_dc = f(head, 0), p.b_dc = f(head, 1), p.w_d1 = f(head, 2), p.b_d1 = f(head, 3), p.w_d2 = f(head, 4), p.b_d2 = f(head, 5);
-    p.hc = e->dh_planes, p.vh = (head == 0 ? e->nd.num_value_hidden_channels : e->nd.num_hidden_channels), p.dv = e->nd.discrete_value_size;
-    p.out = out;
-    constexpr int BPC = 4, threads = 512;
-    const int hw = p.n * p.n, np = (with_policy ? p.pol_ch : 0) + p.hc;
-    const int parts = std::max(1, threads / p.vh);
-    const size_t smem = sizeof(float) * (static_cast<size_t>(np) * p.c + BPC * np * hw + BPC * p.vh + BPC * std::max(p.dv, p.actions) + static_cast<size_t>(parts) * BPC * p.vh);
-    if (smem > 96 * 1024) { return fail(MZ_ERR_ARG, "discrete head does not fit its shared-memory budget"); }
-    mzat::discrete_head_kernel<BPC><<<(e->d.B + BPC - 1) / BPC, threads, smem, e->stream>>>(p);
+    auto f = [&](int h, int i) { return e->d_blob + e->off_dhead[h][i]; };
+    const int hw = e->d.N * e->d.N, Ch = e->nd.num_hidden_channels;
+    if (Ch > 512 || e->d.A > 32) { return fail(MZ_ERR_ARG, "Atari heads support up to 512 hidden channels and 32 actions"); }
+    mzat::PlanesParams pp;
+    pp.act = act, pp.hid = reinterpret_cast<__half*>(e->s.hid), pp.slot = e->s.eval_slot, pp.n = e->d.N, pp.slots = e->d.slots, pp.c = e->cpad, pp.c_real = Ch, pp.num_slots = e->d.S + 1;
+    pp.w_pol = reinterpret_cast<const float*>(f(2, 0)), pp.b_pol = reinterpret_cast<const float*>(f(2, 1));
+    pp.w_val = reinterpret_cast<const float*>(f(0, 0)), pp.b_val = reinterpret_cast<const float*>(f(0, 1));
+    pp.w_rew = (with_reward ? reinterpret_cast<const float*>(f(1, 0)) : nullptr), pp.b_rew = (with_reward ? reinterpret_cast<const float*>(f(1, 1)) : nullptr);
+    pp.pol_ch = e->pol_ch, pp.hc = e->dh_planes, pp.a_val = e->d_a_head[0], pp.a_rew = e->d_a_head[1], pp.pol_planes = e->d_pol_planes, pp.k_pad = e->dh_k1;
+    mzat::hidden_planes_kernel<<<e->d.B, 256, sizeof(float) * hw * Ch, e->stream>>>(pp);
+    e->launches++;
+    const int nh = (with_reward ? 2 : 1);
+    mzat::FcGemmParams g1{}, g2{};
+    int n1max = 0;
+    for (int h = 0; h < nh; ++h) {
+        g1.a[h] = e->d_a_head[h], g1.w[h] = reinterpret_cast<const __half*>(f(h, 2)), g1.bias[h] = reinterpret_cast<const float*>(f(h, 3)), g1.out[h] = e->d_h_head[h];
+        g1.n[h] = e->dh_n1[h], g1.k[h] = e->dh_k1, g1.lda[h] = e->dh_k1, g1.ldw[h] = e->dh_k1, g1.ldc[h] = e->dh_n1[h];
+        g2.a[h] = e->d_h_head[h], g2.w[h] = reinterpret_cast<const __half*>(f(h, 4)), g2.bias[h] = reinterpret_cast<const float*>(f(h, 5)), g2.out[h] = e->d_l_head[h];
+        g2.n[h] = e->dh_n2, g2.k[h] = e->dh_n1[h], g2.lda[h] = e->dh_n1[h], g2.ldw[h] = e->dh_n1[h], g2.ldc[h] = e->dh_n2;
+        n1max = std::max(n1max, e->dh_n1[h]);
+    }
+    mzat::fc_gemm_kernel<true><<<dim3(n1max / 64, e->dh_mpad / 64, nh), 128, 0, e->stream>>>(g1);
+    e->launches++;
+    mzat::fc_gemm_kernel<false><<<dim3(e->dh_n2 / 64, e->dh_mpad / 64, nh), 128, 0, e->stream>>>(g2);
+    e->launches++;
+    mzat::FinalizeParams fp;
+    fp.lg_val = e->d_l_head[0], fp.lg_rew = (with_reward ? e->d_l_head[1] : nullptr), fp.ld = e->dh_n2, fp.dv = e->nd.discrete_value_size;
+    fp.pol_planes = e->d_pol_planes, fp.w_pf = reinterpret_cast<const float*>(f(2, 2)), fp.b_pf = reinterpret_cast<const float*>(f(2, 3)), fp.pol_in = e->pol_ch * hw, fp.actions = e->d.A;
+    fp.value = e->s.nn_value, fp.reward = e->s.nn_reward, fp.policy = e->s.policy, fp.logits = e->s.logits;
+    mzat::discrete_finalize_kernel<<<e->d.B, 128, 0, e->stream>>>(fp);
     e->launches++;
     return MZ_OK;
 }
@@ -507,15 +529,11 @@ int forward_atari(mz_engine* e, int which)
     }
     if ((rc = launch_tower(e, which, true, false))) { return rc; }
     __half* out = e->act[T.out_buf];
-    if (which == 1) {
-        if ((rc = launch_discrete_head(e, out, 1, false, e->s.nn_reward))) { return rc; }
-    } else {
+    if (which == 0) {
         CUDA_OK(cudaMemsetAsync(e->s.nn_reward, 0, sizeof(float) * B, e->stream)); // initial_inference has no reward output: reward_ stays 0 (muzero_network.h:25)
         e->memsets++;
     }
-    mznn::scale_hidden_kernel<<<B, 256, 0, e->stream>>>(out, reinterpret_cast<__half*>(e->s.hid), e->s.eval_slot, e->d.N, e->d.slots, e->cpad, e->nd.num_hidden_channels, e->d.S + 1);
-    e->launches++;
-    return launch_discrete_head(e, out, 0, true, e->s.nn_value);
+    return launch_atari_heads(e, out, which == 1);
 }
 
 // AlphaZeroNetwork.forward (network/py/alphazero_network.py:90-113) on the rows already in nn_in; for a MuZero network
@@ -540,13 +558,15 @@ int forward(mz_engine* e, int which = 0, bool after_tree_step = false)
         }
     }
     __half* out = e->act[T.out_buf];
-    if (e->cfg.muzero) {
+    // MuZero: scale_hidden_state is part of the heads kernel when the hidden width is even (it reads channel pairs); else its own kernel first
+    const bool fused_scale = (e->cfg.muzero && e->nd.num_hidden_channels % 2 == 0);
+    if (e->cfg.muzero && !fused_scale) {
         mznn::scale_hidden_kernel<<<e->d.B, 256, 0, e->stream>>>(out, reinterpret_cast<__half*>(e->s.hid), e->s.eval_slot, e->d.N, e->d.slots, e->cpad,
                                                                   e->nd.num_hidden_channels, e->d.S + 1);
         e->launches++;
     }
-    if (e->conv_mode == 3) { return launch_heads(e, out, T.d_done, T.params->num_layers * ((T.params->num_mtiles + 1) / 2)); }
-    return launch_heads(e, out);
+    if (e->conv_mode == 3) { return launch_heads(e, out, T.d_done, T.params->num_layers * ((T.params->num_mtiles + 1) / 2), fused_scale); }
+    return launch_heads(e, out, nullptr, 0, fused_scale);
 }
 
 // one launch of the fused tower kernel over `params` (a NetTower or a ConvStage)
@@ -684,11 +704,14 @@ int plan_blob_atari(mz_engine* e)
     const int hw = e->d.N * e->d.N, dv = nd.discrete_value_size, vh = nd.num_value_hidden_channels;
     e->dh_planes = (dv + hw - 1) / hw;
     const int hc = e->dh_planes;
+    auto pad64 = [](int v) { return (v + 63) / 64 * 64; };
+    e->dh_k1 = pad64(hc * hw), e->dh_n2 = pad64(dv), e->dh_mpad = pad64(e->d.B);
     for (int h = 0; h < 2; ++h) {
         const int fc1_out = (h == 0 ? vh : nd.num_hidden_channels); // the reward head's hidden width is num_channels (muzero_atari_network.py:50)
-        const size_t sizes[6] = {static_cast<size_t>(hc) * C, static_cast<size_t>(hc), static_cast<size_t>(hc) * hw * fc1_out, static_cast<size_t>(fc1_out),
-                                 static_cast<size_t>(fc1_out) * dv, static_cast<size_t>(dv)};
-        for (int i = 0; i < 6; ++i) { e->off_dhead[h][i] = e->blob.take(sizeof(float) * sizes[i]); }
+        e->dh_n1[h] = pad64(fc1_out);
+        const size_t sizes[6] = {sizeof(float) * hc * C, sizeof(float) * hc, sizeof(__half) * e->dh_n1[h] * e->dh_k1, sizeof(float) * e->dh_n1[h],
+                                 sizeof(__half) * e->dh_n2 * e->dh_n1[h], sizeof(float) * e->dh_n2};
+        for (int i = 0; i < 6; ++i) { e->off_dhead[h][i] = e->blob.take(sizes[i]); }
     }
     const size_t psizes[4] = {static_cast<size_t>(e->pol_ch) * C, static_cast<size_t>(e->pol_ch), static_cast<size_t>(e->pol_ch) * hw * nd.action_size, static_cast<size_t>(nd.action_size)};
     for (int i = 0; i < 4; ++i) { e->off_dhead[2][i] = e->blob.take(sizeof(float) * psizes[i]); }
@@ -782,8 +805,13 @@ int alloc_atari(mz_engine* e)
         if ((rc = e->dalloc(&st.d_done, static_cast<size_t>(T.num_layers) * num_groups))) { return rc; }
         T.done = st.d_done;
     }
-    const int heads_smem = 96 * 1024;
-    CUDA_OK(cudaFuncSetAttribute(mzat::discrete_head_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, heads_smem));
+    for (int h = 0; h < 2; ++h) {
+        if ((rc = e->dalloc(&e->d_a_head[h], static_cast<size_t>(e->dh_mpad) * e->dh_k1))) { return rc; }
+        if ((rc = e->dalloc(&e->d_h_head[h], static_cast<size_t>(e->dh_mpad) * e->dh_n1[h]))) { return rc; }
+        if ((rc = e->dalloc(&e->d_l_head[h], static_cast<size_t>(e->dh_mpad) * e->dh_n2))) { return rc; }
+    }
+    if ((rc = e->dalloc(&e->d_pol_planes, static_cast<size_t>(e->d.B) * e->pol_ch * e->d.N * e->d.N))) { return rc; }
+    CUDA_OK(cudaFuncSetAttribute(mzat::hidden_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     return MZ_OK;
 }
 
@@ -916,7 +944,7 @@ int alloc_net(mz_engine* e)
 int pack_atari_weights(mz_engine* e, std::vector<uint8_t>& host)
 {
     const mz_net_dims& nd = e->nd;
-    const int Ch = nd.num_hidden_channels, Ch1 = Ch / 2, C1 = e->at_c1, hw = e->d.N * e->d.N;
+    const int Ch = nd.num_hidden_channels, Ch1 = Ch / 2, hw = e->d.N * e->d.N;
     std::string err;
     const std::string rp = "representation_network.";
     // a plain 3x3 layer: [tap][cout_pad][cin_pad] fp16
@@ -1003,6 +1031,16 @@ int pack_atari_weights(mz_engine* e, std::vector<uint8_t>& host)
         std::memcpy(host.data() + b_off, bias.data(), sizeof(float) * planes);
         return MZ_OK;
     };
+    auto fc_half = [&](const std::string& name, int nout, int nin, int nin_pad, size_t w_off, size_t b_off) -> int { // torch [out][in] -> fp16 [out_pad][in_pad]
+        const float *w = raw(name + ".weight", static_cast<size_t>(nout) * nin), *b = raw(name + ".bias", nout);
+        if (!w || !b) { return fail(MZ_ERR_ARG, err); }
+        __half* wd = reinterpret_cast<__half*>(host.data() + w_off);
+        for (int o = 0; o < nout; ++o) {
+            for (int i = 0; i < nin; ++i) { wd[static_cast<size_t>(o) * nin_pad + i] = __float2half_rn(w[static_cast<size_t>(o) * nin + i]); }
+        }
+        std::memcpy(host.data() + b_off, b, sizeof(float) * nout);
+        return MZ_OK;
+    };
     auto fc_t = [&](const std::string& name, int nout, int nin, size_t w_off, size_t b_off) -> int { // torch [out][in] -> [in][out]
         const float *w = raw(name + ".weight", static_cast<size_t>(nout) * nin), *b = raw(name + ".bias", nout);
         if (!w || !b) { return fail(MZ_ERR_ARG, err); }
@@ -1018,8 +1056,8 @@ int pack_atari_weights(mz_engine* e, std::vector<uint8_t>& host)
     for (int h = 0; h < 2; ++h) {
         const int fc1_out = (h == 0 ? nd.num_value_hidden_channels : Ch);
         if ((rc = conv1x1(names[h], hc, e->off_dhead[h][0], e->off_dhead[h][1]))) { return rc; }
-        if ((rc = fc_t(names[h] + ".fc1", fc1_out, hc * hw, e->off_dhead[h][2], e->off_dhead[h][3]))) { return rc; }
-        if ((rc = fc_t(names[h] + ".fc2", dv, fc1_out, e->off_dhead[h][4], e->off_dhead[h][5]))) { return rc; }
+        if ((rc = fc_half(names[h] + ".fc1", fc1_out, hc * hw, e->dh_k1, e->off_dhead[h][2], e->off_dhead[h][3]))) { return rc; }
+        if ((rc = fc_half(names[h] + ".fc2", dv, fc1_out, e->dh_n1[h], e->off_dhead[h][4], e->off_dhead[h][5]))) { return rc; }
     }
     if ((rc = conv1x1("prediction_network.policy", e->pol_ch, e->off_dhead[2][0], e->off_dhead[2][1]))) { return rc; }
     if ((rc = fc_t("prediction_network.policy.fc", nd.action_size, e->pol_ch * hw, e->off_dhead[2][2], e->off_dhead[2][3]))) { return rc; }
@@ -1855,7 +1893,7 @@ int mz_profile_kernels(mz_engine* e, int32_t iters, float* conv_ms, float* tree_
         *conv_ms = ms / iters;
     }
     if (heads_ms) {
-        auto heads = [&]() { return e->atari ? launch_discrete_head(e, e->act[0], 0, true, e->s.nn_value) : launch_heads(e, e->act[0]); };
+        auto heads = [&]() { return e->atari ? launch_atari_heads(e, e->act[0], true) : launch_heads(e, e->act[0]); };
         for (int i = 0; i < 3; ++i) { heads(); }
         CUDA_OK(cudaEventRecord(e->ev0, e->stream));
         for (int i = 0; i < iters; ++i) { heads(); }

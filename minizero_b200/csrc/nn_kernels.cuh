@@ -1212,6 +1212,11 @@ struct HeadParams {
     int fc_in_smem;     // 1: the transposed FC weights are staged in shared memory once per CTA
     int* clear;         // completion counters of the tower launch that produced `act` (or null): zeroed here for its next launch,
     int clear_count;    // which saves a memset node between every two kernels of the search graph
+    // MuZero: MuZeroNetwork.scale_hidden_state (network/py/muzero_network.py:150-160) fused in: `act` is the unscaled tower output, the
+    // heads read (x - min) / scale on the fly, and the scaled state goes to the evaluated node's hidden slot (null: no scaling)
+    __half* hid;              // [batch][num_slots][hw][c]
+    const int32_t* hid_slot;  // [batch]
+    int c_real, num_slots;
 };
 
 template <int NP1> // NP1 = policy planes + 1 value plane, a compile-time constant so that the plane loops carry no predicates
@@ -1235,6 +1240,41 @@ __global__ void __launch_bounds__(1024) heads_kernel(const HeadParams p)
     for (int i = tid; i < NP1 * p.c; i += nthr) { wc[i] = (i < p.pol_ch * p.c ? p.w_pc[i] : p.w_vc[i - p.pol_ch * p.c]); }
     for (int cell = tid; cell < hw; cell += nthr) { rowoff[cell] = ((cell / p.n + 1) * n1 + cell % p.n) * p.c; }
     __syncthreads();
+    float h_mn = 0.0f, h_scale = 1.0f;
+    if (p.hid) { // per-board min / max over the real channels of every cell, then the scaled state -> hidden slot (fp16, padded channels zero)
+        float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
+        const int half_real = p.c_real / 2, half_c = p.c / 2;
+        for (int i = tid; i < hw * half_real; i += nthr) {
+            const int cell = i / half_real, k = i - cell * half_real;
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(act + rowoff[cell] + 2 * k));
+            mn = fminf(mn, fminf(f.x, f.y)), mx = fmaxf(mx, fmaxf(f.x, f.y));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)), mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+        if (lane == 0) { red[warp] = mn; }
+        __syncthreads();
+        mn = red[0];
+        for (int i = 1; i < nwarp; ++i) { mn = fminf(mn, red[i]); }
+        __syncthreads();
+        if (lane == 0) { red[warp] = mx; }
+        __syncthreads();
+        mx = red[0];
+        for (int i = 1; i < nwarp; ++i) { mx = fmaxf(mx, red[i]); }
+        __syncthreads();
+        h_mn = mn, h_scale = mx - mn;
+        if (h_scale < 1e-5f) { h_scale += 1e-5f; }
+        __half* dst = p.hid + (static_cast<size_t>(g) * p.num_slots + p.hid_slot[g]) * hw * p.c;
+        for (int i = tid; i < hw * half_c; i += nthr) {
+            const int cell = i / half_c, k = i - cell * half_c;
+            __half2 o = __floats2half2_rn(0.0f, 0.0f);
+            if (k < half_real) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(act + rowoff[cell] + 2 * k));
+                o = __floats2half2_rn((f.x - h_mn) / h_scale, (f.y - h_mn) / h_scale);
+            }
+            *reinterpret_cast<__half2*>(dst + static_cast<size_t>(cell) * p.c + 2 * k) = o;
+        }
+    }
+    const bool scaling = (p.hid != nullptr);
     // 1x1 convolutions: one warp per cell; lane l owns channel pairs {2l + 64i}: every load instruction is one contiguous
     // 128-byte row segment and the weight reads from shared memory are conflict-free
     const int npair = p.c / 64;
@@ -1244,7 +1284,9 @@ __global__ void __launch_bounds__(1024) heads_kernel(const HeadParams p)
 #pragma unroll
         for (int o = 0; o < NP1; ++o) { acc[o] = 0.0f; }
         for (int i = 0; i < npair; ++i) {
-            const float2 a = __half22float2(row[lane + 32 * i]);
+            float2 a = __half22float2(row[lane + 32 * i]);
+            // the heads see the hidden state as the next inference will: scaled and rounded to fp16 (padded channels carry zero weights)
+            if (scaling) { a = __half22float2(__floats2half2_rn((a.x - h_mn) / h_scale, (a.y - h_mn) / h_scale)); }
             const float* wp = wc + 2 * lane + 64 * i;
 #pragma unroll
             for (int o = 0; o < NP1; ++o) {
