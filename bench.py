@@ -179,7 +179,7 @@ def port_baseline(w, budget_evals):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=None, help="default: 6 (configs 2 and 4: a step is 0.15 s / 1.9 s), 300 (config 3) or 60 (config 5): about a second of timed region")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS))
@@ -187,6 +187,8 @@ def main():
     ap.add_argument("--no-gpu-reference", action="store_true")
     args = ap.parse_args()
     w = WORKLOADS[args.config]
+    if args.steps is None:
+        args.steps = {3: 300, 5: 60}.get(args.config, 6)
     GAMES, SIMS = w["games"], w["sims"]
     S1 = SIMS + 1
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))

@@ -132,40 +132,49 @@ __device__ __forceinline__ float invert_value(float value)
 // Heads of the Atari network. PolicyNetwork (network_unit.py:26-42): conv1x1-BN-ReLU-fc, softmax. DiscreteValueNetwork
 // (network_unit.py:68-87): conv1x1-BN-ReLU-fc1-ReLU-fc2 -> 601 logits; MuZeroNetwork::forward (muzero_network.h:157-171) takes the
 // softmax, the expectation sum_i p_i * (i - 300) and utils::invertValue. The value and policy heads read the SCALED hidden state,
-// the reward head the dynamics output before scaling (muzero_atari_network.py:53-54,176-178). Four launches per evaluation:
+// the reward head the dynamics output before scaling (muzero_atari_network.py:53-54,176-178). Five launches per evaluation:
+//   fc_gemm_kernel         the 1x1 convolutions of all three heads as ONE GEMM over the tower's output rows (unscaled)
 //   hidden_planes_kernel   per board: min / max scaling of the hidden state (scale_hidden_state, :185-193) into the node's hidden
-//                          slot, and the 1x1 convolutions of all three heads (fp32) -> fp16 rows of the FC inputs
+//                          slot; bias + ReLU on the convolutions (rescaled by linearity for the value / policy planes) -> FC inputs
 //   fc_gemm_kernel x 2     fc1 (+ ReLU) and fc2 of the value and reward heads as batched GEMMs over the boards on tensor cores
 //                          (mma.sync m16n8k16, fp16 in / fp32 accumulate; M = boards: far too small for a tcgen05 pipeline)
 //   discrete_finalize_kernel  per board: softmax + expectation + invertValue of both heads, policy fc + softmax
 // ---------------------------------------------------------------------------------------------
 struct PlanesParams {
     const __half* act;   // [batch * slots][c] tower output rows (unscaled)
+    const float* raw;    // [batch * slots][ld_raw] 1x1 convolutions of all heads on the UNSCALED rows (fc_gemm_kernel): policy planes, value planes, reward planes
+    int ld_raw;
     __half* hid;         // [batch][num_slots][hw][c] hidden states of the search
     const int32_t* slot; // [batch] slot of this evaluation
     int n, slots, c, c_real, num_slots;
-    const float *w_pol, *b_pol; // [pol_ch][c], [pol_ch]
-    const float *w_val, *b_val; // [hc][c], [hc]
-    const float *w_rew, *b_rew; // [hc][c], [hc]; null for the initial inference (no reward output)
-    int pol_ch, hc;
+    const float* bias;   // [planes] folded BatchNorm shifts of the 1x1 convolutions, in plane order
+    const float* wsum;   // [planes] sum over the channels of every plane's (fp16-rounded) weights
+    int pol_ch, hc, with_reward;
     __half* a_val;       // [m_pad][k_pad] flattened value planes (plane-major, as x.view(-1, hw * hc) of an NCHW tensor)
     __half* a_rew;
     float* pol_planes;   // [batch][pol_ch * hw]
     int k_pad;
 };
 
+// per board: min / max of the hidden state, the scaled state into the node's hidden slot, and the heads' planes from the raw 1x1
+// convolutions: a convolution is linear, so conv((x - min) / scale) = (conv(x) - min * sum(w)) / scale for the value and policy
+// planes (which read the scaled state); the reward planes read the unscaled one
 __global__ void __launch_bounds__(256) hidden_planes_kernel(const PlanesParams p)
 {
-    extern __shared__ float xs[]; // [hw][c_real] the board's hidden state, unscaled
     __shared__ float red_mn[8], red_mx[8];
     const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, hw = p.n * p.n, n1 = p.n + 1;
     const __half* rows = p.act + static_cast<size_t>(g) * p.slots * p.c;
+    const int per_cell = p.c / 8, real_per_cell = p.c_real / 8; // 16-byte chunks (c_real is a multiple of 16)
     float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
-    for (int i = tid; i < hw * (p.c_real / 2); i += blockDim.x) {
-        const int cell = i / (p.c_real / 2), k = i - cell * (p.c_real / 2);
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(rows + static_cast<size_t>((cell / p.n + 1) * n1 + cell % p.n) * p.c + 2 * k));
-        xs[cell * p.c_real + 2 * k] = f.x, xs[cell * p.c_real + 2 * k + 1] = f.y;
-        mn = fminf(mn, fminf(f.x, f.y)), mx = fmaxf(mx, fmaxf(f.x, f.y));
+    for (int i = tid; i < hw * real_per_cell; i += blockDim.x) {
+        const int cell = i / real_per_cell, k = i - cell * real_per_cell;
+        const uint4 v = *reinterpret_cast<const uint4*>(rows + static_cast<size_t>((cell / p.n + 1) * n1 + cell % p.n) * p.c + 8 * k);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            mn = fminf(mn, fminf(f.x, f.y)), mx = fmaxf(mx, fmaxf(f.x, f.y));
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)), mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
@@ -177,51 +186,34 @@ __global__ void __launch_bounds__(256) hidden_planes_kernel(const PlanesParams p
     if (scale < 1e-5f) { scale += 1e-5f; }
     // the scaled state -> the node's hidden slot (fp16, padded channels zero): what the next recurrent inference gathers
     __half* dst = p.hid + (static_cast<size_t>(g) * p.num_slots + p.slot[g]) * hw * p.c;
-    for (int i = tid; i < hw * (p.c / 2); i += blockDim.x) {
-        const int cell = i / (p.c / 2), k = i - cell * (p.c / 2);
-        float a = 0.0f, b = 0.0f;
-        if (2 * k < p.c_real) { a = (xs[cell * p.c_real + 2 * k] - mn) / scale, b = (xs[cell * p.c_real + 2 * k + 1] - mn) / scale; }
-        *reinterpret_cast<__half2*>(dst + static_cast<size_t>(cell) * p.c + 2 * k) = __floats2half2_rn(a, b);
+    for (int i = tid; i < hw * per_cell; i += blockDim.x) {
+        const int cell = i / per_cell, k = i - cell * per_cell;
+        uint4 out = make_uint4(0u, 0u, 0u, 0u);
+        if (k < real_per_cell) {
+            const uint4 v = *reinterpret_cast<const uint4*>(rows + static_cast<size_t>((cell / p.n + 1) * n1 + cell % p.n) * p.c + 8 * k);
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
+            __half2* o = reinterpret_cast<__half2*>(&out);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h[j]);
+                o[j] = __floats2half2_rn((f.x - mn) / scale, (f.y - mn) / scale);
+            }
+        }
+        *reinterpret_cast<uint4*>(dst + static_cast<size_t>(i) * 8) = out;
     }
-    // 1x1 convolutions + folded BN + ReLU: one warp per plane (its weights stay in registers), lanes over the channels, cells in turn
-    __syncthreads();
-    const int n_rew = (p.w_rew ? p.hc : 0), planes = p.pol_ch + p.hc + n_rew;
-    const float inv_scale = 1.0f / scale;
-    for (int plane = warp; plane < planes; plane += (blockDim.x >> 5)) {
-        const float* w;
-        float bias;
-        bool scaled = true;
+    // planes: folded-BN bias + ReLU on the (rescaled) raw convolutions
+    const int planes = p.pol_ch + p.hc + (p.with_reward ? p.hc : 0);
+    for (int o = tid; o < planes * hw; o += blockDim.x) {
+        const int plane = o / hw, cell = o - plane * hw;
+        float v = p.raw[(static_cast<size_t>(g) * p.slots + (cell / p.n + 1) * n1 + cell % p.n) * p.ld_raw + plane];
+        if (plane < p.pol_ch + p.hc) { v = (v - mn * p.wsum[plane]) / scale; }
+        v = fmaxf(v + p.bias[plane], 0.0f);
         if (plane < p.pol_ch) {
-            w = p.w_pol + static_cast<size_t>(plane) * p.c, bias = p.b_pol[plane];
+            p.pol_planes[static_cast<size_t>(g) * p.pol_ch * hw + o] = v;
         } else if (plane < p.pol_ch + p.hc) {
-            w = p.w_val + static_cast<size_t>(plane - p.pol_ch) * p.c, bias = p.b_val[plane - p.pol_ch];
+            p.a_val[static_cast<size_t>(g) * p.k_pad + (o - p.pol_ch * hw)] = __float2half_rn(v);
         } else {
-            w = p.w_rew + static_cast<size_t>(plane - p.pol_ch - p.hc) * p.c, bias = p.b_rew[plane - p.pol_ch - p.hc], scaled = false;
-        }
-        float wr[16]; // c_real <= 512
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            wr[i] = (lane + 32 * i < p.c_real ? __ldg(w + lane + 32 * i) : 0.0f);
-        }
-        for (int cell = 0; cell < hw; ++cell) {
-            const float* x = xs + cell * p.c_real;
-            float acc = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if (lane + 32 * i < p.c_real) { acc = fmaf(scaled ? (x[lane + 32 * i] - mn) * inv_scale : x[lane + 32 * i], wr[i], acc); }
-            }
-#pragma unroll
-            for (int sft = 16; sft > 0; sft >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, sft); }
-            if (lane == 0) {
-                const float v = fmaxf(acc + bias, 0.0f);
-                if (plane < p.pol_ch) {
-                    p.pol_planes[static_cast<size_t>(g) * p.pol_ch * hw + plane * hw + cell] = v;
-                } else if (plane < p.pol_ch + p.hc) {
-                    p.a_val[static_cast<size_t>(g) * p.k_pad + (plane - p.pol_ch) * hw + cell] = __float2half_rn(v);
-                } else {
-                    p.a_rew[static_cast<size_t>(g) * p.k_pad + (plane - p.pol_ch - p.hc) * hw + cell] = __float2half_rn(v);
-                }
-            }
+            p.a_rew[static_cast<size_t>(g) * p.k_pad + (o - (p.pol_ch + p.hc) * hw)] = __float2half_rn(v);
         }
     }
 }
@@ -242,40 +234,45 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(mznn::smem_u32(smem)), "l"(gmem) : "memory");
 }
 
+constexpr int FC_TILE = 64, FC_LD = FC_TILE + 8, FC_STAGES = 4; // +8 halves: rows 144 bytes apart, fragment loads hit distinct banks
+constexpr int FC_SMEM = FC_STAGES * 2 * FC_TILE * FC_LD * 2;   // bytes of dynamic shared memory
+
 template <bool HALF_RELU_OUT>
 __global__ void __launch_bounds__(128) fc_gemm_kernel(const FcGemmParams p)
 {
-    constexpr int T = 64, LD = T + 8; // +8 halves: rows 144 bytes apart, fragment loads hit distinct banks
-    __shared__ __align__(16) __half As[2][T][LD];
-    __shared__ __align__(16) __half Ws[2][T][LD];
+    constexpr int T = FC_TILE, LD = FC_LD;
+    extern __shared__ __align__(16) uint8_t fc_smem[];
+    typedef __half Tile[T][LD];
+    Tile* As = reinterpret_cast<Tile*>(fc_smem);
+    Tile* Ws = As + FC_STAGES;
     const int h = blockIdx.z, n0 = blockIdx.x * T, m0 = blockIdx.y * T;
     if (n0 >= p.n[h]) { return; }
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const __half* a = p.a[h] + static_cast<size_t>(m0) * p.lda[h];
     const __half* w = p.w[h] + static_cast<size_t>(n0) * p.ldw[h];
-    auto load_tile = [&](int buf, int k0) {
+    const int kt = p.k[h] / T;
+    auto load_tile = [&](int it) { // always commits a group, so that the group count tracks the tile count
+        if (it < kt) {
+            const int buf = it % FC_STAGES, k0 = it * T;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int chunk = tid + i * 128, row = chunk >> 3, col = (chunk & 7) * 8;
-            cp_async16(&As[buf][row][col], a + static_cast<size_t>(row) * p.lda[h] + k0 + col);
-            cp_async16(&Ws[buf][row][col], w + static_cast<size_t>(row) * p.ldw[h] + k0 + col);
+            for (int i = 0; i < 4; ++i) {
+                const int chunk = tid + i * 128, row = chunk >> 3, col = (chunk & 7) * 8;
+                cp_async16(&As[buf][row][col], a + static_cast<size_t>(row) * p.lda[h] + k0 + col);
+                cp_async16(&Ws[buf][row][col], w + static_cast<size_t>(row) * p.ldw[h] + k0 + col);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     float acc[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f; }
-    const int kt = p.k[h] / T;
-    load_tile(0, 0);
+#pragma unroll
+    for (int i = 0; i < FC_STAGES - 1; ++i) { load_tile(i); }
     for (int it = 0; it < kt; ++it) {
-        const int buf = it & 1;
-        if (it + 1 < kt) {
-            load_tile(buf ^ 1, (it + 1) * T);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
+        const int buf = it % FC_STAGES;
+        asm volatile("cp.async.wait_group %0;" ::"n"(FC_STAGES - 2) : "memory"); // tile `it` has landed
+        __syncthreads();                                                         // ... for everybody, and tile it - 1 is no longer being read
+        load_tile(it + FC_STAGES - 1);                                           // into the buffer tile it - 1 used
 #pragma unroll
         for (int kk = 0; kk < T; kk += 16) {
             const int r = warp * 16 + g;
@@ -289,13 +286,12 @@ __global__ void __launch_bounds__(128) fc_gemm_kernel(const FcGemmParams p)
                              : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
             }
         }
-        __syncthreads();
     }
     const int row = m0 + warp * 16 + g;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
         const int col = n0 + nt * 8 + 2 * t;
-        const float b0 = p.bias[h][col], b1 = p.bias[h][col + 1];
+        const float b0 = (p.bias[h] ? p.bias[h][col] : 0.0f), b1 = (p.bias[h] ? p.bias[h][col + 1] : 0.0f);
         if (HALF_RELU_OUT) {
             __half* o = static_cast<__half*>(p.out[h]);
             *reinterpret_cast<__half2*>(o + static_cast<size_t>(row) * p.ldc[h] + col) = __floats2half2_rn(fmaxf(acc[nt][0] + b0, 0.0f), fmaxf(acc[nt][1] + b1, 0.0f));

@@ -297,6 +297,8 @@ struct mz_engine {
     __half *d_a_head[2] = {nullptr, nullptr}, *d_h_head[2] = {nullptr, nullptr}; // FC inputs / hidden activations [mpad][k]
     float* d_l_head[2] = {nullptr, nullptr};                                       // bin logits [mpad][n2]
     float* d_pol_planes = nullptr;
+    float* d_planes_raw = nullptr;         // [rows_alloc][64] 1x1 convolutions of the three heads on the unscaled tower output
+    size_t off_planes[3] = {0, 0, 0};      // combined 1x1 conv weights fp16 [64][cpad] (policy, value, reward planes), folded biases [64], channel sums of the weights [64]
     uint8_t* d_at_frames_in = nullptr; // [B][3][96][96] staging of mz_atari_observe
     float* d_root_reward = nullptr;    // [B][A]
     int32_t* d_bound_size = nullptr;
@@ -471,13 +473,18 @@ int launch_atari_heads(mz_engine* e, const __half* act, bool with_reward)
     auto f = [&](int h, int i) { return e->d_blob + e->off_dhead[h][i]; };
     const int hw = e->d.N * e->d.N, Ch = e->nd.num_hidden_channels;
     if (Ch > 512 || e->d.A > 32) { return fail(MZ_ERR_ARG, "Atari heads support up to 512 hidden channels and 32 actions"); }
+    mzat::FcGemmParams g0{};
+    g0.a[0] = act, g0.w[0] = reinterpret_cast<const __half*>(e->d_blob + e->off_planes[0]), g0.bias[0] = nullptr, g0.out[0] = e->d_planes_raw;
+    g0.n[0] = 64, g0.k[0] = e->cpad, g0.lda[0] = e->cpad, g0.ldw[0] = e->cpad, g0.ldc[0] = 64;
+    mzat::fc_gemm_kernel<false><<<dim3(1, e->rows_alloc / 64, 1), 128, mzat::FC_SMEM, e->stream>>>(g0);
+    e->launches++;
     mzat::PlanesParams pp;
-    pp.act = act, pp.hid = reinterpret_cast<__half*>(e->s.hid), pp.slot = e->s.eval_slot, pp.n = e->d.N, pp.slots = e->d.slots, pp.c = e->cpad, pp.c_real = Ch, pp.num_slots = e->d.S + 1;
-    pp.w_pol = reinterpret_cast<const float*>(f(2, 0)), pp.b_pol = reinterpret_cast<const float*>(f(2, 1));
-    pp.w_val = reinterpret_cast<const float*>(f(0, 0)), pp.b_val = reinterpret_cast<const float*>(f(0, 1));
-    pp.w_rew = (with_reward ? reinterpret_cast<const float*>(f(1, 0)) : nullptr), pp.b_rew = (with_reward ? reinterpret_cast<const float*>(f(1, 1)) : nullptr);
-    pp.pol_ch = e->pol_ch, pp.hc = e->dh_planes, pp.a_val = e->d_a_head[0], pp.a_rew = e->d_a_head[1], pp.pol_planes = e->d_pol_planes, pp.k_pad = e->dh_k1;
-    mzat::hidden_planes_kernel<<<e->d.B, 256, sizeof(float) * hw * Ch, e->stream>>>(pp);
+    pp.act = act, pp.raw = e->d_planes_raw, pp.ld_raw = 64, pp.hid = reinterpret_cast<__half*>(e->s.hid), pp.slot = e->s.eval_slot;
+    pp.n = e->d.N, pp.slots = e->d.slots, pp.c = e->cpad, pp.c_real = Ch, pp.num_slots = e->d.S + 1;
+    pp.bias = reinterpret_cast<const float*>(e->d_blob + e->off_planes[1]), pp.wsum = reinterpret_cast<const float*>(e->d_blob + e->off_planes[2]);
+    pp.pol_ch = e->pol_ch, pp.hc = e->dh_planes, pp.with_reward = (with_reward ? 1 : 0);
+    pp.a_val = e->d_a_head[0], pp.a_rew = e->d_a_head[1], pp.pol_planes = e->d_pol_planes, pp.k_pad = e->dh_k1;
+    mzat::hidden_planes_kernel<<<e->d.B, 256, 0, e->stream>>>(pp);
     e->launches++;
     const int nh = (with_reward ? 2 : 1);
     mzat::FcGemmParams g1{}, g2{};
@@ -489,9 +496,9 @@ int launch_atari_heads(mz_engine* e, const __half* act, bool with_reward)
         g2.n[h] = e->dh_n2, g2.k[h] = e->dh_n1[h], g2.lda[h] = e->dh_n1[h], g2.ldw[h] = e->dh_n1[h], g2.ldc[h] = e->dh_n2;
         n1max = std::max(n1max, e->dh_n1[h]);
     }
-    mzat::fc_gemm_kernel<true><<<dim3(n1max / 64, e->dh_mpad / 64, nh), 128, 0, e->stream>>>(g1);
+    mzat::fc_gemm_kernel<true><<<dim3(n1max / 64, e->dh_mpad / 64, nh), 128, mzat::FC_SMEM, e->stream>>>(g1);
     e->launches++;
-    mzat::fc_gemm_kernel<false><<<dim3(e->dh_n2 / 64, e->dh_mpad / 64, nh), 128, 0, e->stream>>>(g2);
+    mzat::fc_gemm_kernel<false><<<dim3(e->dh_n2 / 64, e->dh_mpad / 64, nh), 128, mzat::FC_SMEM, e->stream>>>(g2);
     e->launches++;
     mzat::FinalizeParams fp;
     fp.lg_val = e->d_l_head[0], fp.lg_rew = (with_reward ? e->d_l_head[1] : nullptr), fp.ld = e->dh_n2, fp.dv = e->nd.discrete_value_size;
@@ -713,6 +720,8 @@ int plan_blob_atari(mz_engine* e)
                                  sizeof(__half) * e->dh_n2 * e->dh_n1[h], sizeof(float) * e->dh_n2};
         for (int i = 0; i < 6; ++i) { e->off_dhead[h][i] = e->blob.take(sizes[i]); }
     }
+    if (e->pol_ch + 2 * hc > 64) { return fail(MZ_ERR_ARG, "the heads' 1x1 convolutions have more than 64 planes"); }
+    e->off_planes[0] = e->blob.take(sizeof(__half) * 64 * C), e->off_planes[1] = e->blob.take(sizeof(float) * 64), e->off_planes[2] = e->blob.take(sizeof(float) * 64);
     const size_t psizes[4] = {static_cast<size_t>(e->pol_ch) * C, static_cast<size_t>(e->pol_ch), static_cast<size_t>(e->pol_ch) * hw * nd.action_size, static_cast<size_t>(nd.action_size)};
     for (int i = 0; i < 4; ++i) { e->off_dhead[2][i] = e->blob.take(sizeof(float) * psizes[i]); }
     return MZ_OK;
@@ -811,7 +820,9 @@ int alloc_atari(mz_engine* e)
         if ((rc = e->dalloc(&e->d_l_head[h], static_cast<size_t>(e->dh_mpad) * e->dh_n2))) { return rc; }
     }
     if ((rc = e->dalloc(&e->d_pol_planes, static_cast<size_t>(e->d.B) * e->pol_ch * e->d.N * e->d.N))) { return rc; }
-    CUDA_OK(cudaFuncSetAttribute(mzat::hidden_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    if ((rc = e->dalloc(&e->d_planes_raw, static_cast<size_t>(e->rows_alloc) * 64))) { return rc; }
+    CUDA_OK(cudaFuncSetAttribute(mzat::fc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mzat::FC_SMEM));
+    CUDA_OK(cudaFuncSetAttribute(mzat::fc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mzat::FC_SMEM));
     return MZ_OK;
 }
 
@@ -1060,6 +1071,25 @@ int pack_atari_weights(mz_engine* e, std::vector<uint8_t>& host)
         if ((rc = fc_half(names[h] + ".fc2", dv, fc1_out, e->dh_n1[h], e->off_dhead[h][4], e->off_dhead[h][5]))) { return rc; }
     }
     if ((rc = conv1x1("prediction_network.policy", e->pol_ch, e->off_dhead[2][0], e->off_dhead[2][1]))) { return rc; }
+    { // the three 1x1 convolutions as one fp16 weight matrix [plane][channel] for the planes GEMM, with their folded biases and channel sums
+        __half* wd = reinterpret_cast<__half*>(host.data() + e->off_planes[0]);
+        float *bd = reinterpret_cast<float*>(host.data() + e->off_planes[1]), *sd = reinterpret_cast<float*>(host.data() + e->off_planes[2]);
+        const int src[3] = {2, 0, 1}, cnt[3] = {e->pol_ch, hc, hc}; // plane order: policy, value, reward
+        int plane = 0;
+        for (int k = 0; k < 3; ++k) {
+            const float* w = reinterpret_cast<const float*>(host.data() + e->off_dhead[src[k]][0]);
+            const float* b = reinterpret_cast<const float*>(host.data() + e->off_dhead[src[k]][1]);
+            for (int o = 0; o < cnt[k]; ++o, ++plane) {
+                float sum = 0.0f;
+                for (int c = 0; c < Ch; ++c) {
+                    const __half hv = __float2half_rn(w[static_cast<size_t>(o) * e->cpad + c]);
+                    wd[static_cast<size_t>(plane) * e->cpad + c] = hv;
+                    sum += __half2float(hv);
+                }
+                bd[plane] = b[o], sd[plane] = sum;
+            }
+        }
+    }
     if ((rc = fc_t("prediction_network.policy.fc", nd.action_size, e->pol_ch * hw, e->off_dhead[2][2], e->off_dhead[2][3]))) { return rc; }
     return MZ_OK;
 }

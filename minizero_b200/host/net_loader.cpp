@@ -18,7 +18,7 @@ bool fill(torch::jit::script::Module& m, NetInfo& info)
     info.dims.action_size = geti("get_action_size");
     info.dims.num_value_hidden_channels = geti("get_num_value_hidden_channels");
     info.dims.discrete_value_size = geti("get_discrete_value_size");
-    info.dims.is_muzero = (info.type_name == "muzero");
+    info.dims.is_muzero = (info.type_name == "muzero" || info.type_name == "muzero_atari");
     info.dims.num_action_feature_channels = (info.dims.is_muzero ? geti("get_num_action_feature_channels") : 0); // network/muzero_network.h:51
     return true;
 }
@@ -42,7 +42,7 @@ bool loadNetwork(const std::string& path, mz_engine* engine, std::string& error)
         m.eval();
         NetInfo info;
         fill(m, info);
-        if (info.type_name != "alphazero" && info.type_name != "muzero") {
+        if (info.type_name != "alphazero" && info.type_name != "muzero" && info.type_name != "muzero_atari") {
             error = "network type '" + info.type_name + "' is not supported by this engine";
             return false;
         }
