@@ -145,6 +145,14 @@ int mz_get_root_rewards(mz_engine* e, float* reward, int32_t* bound_size, float*
 int mz_get_roots(mz_engine* e, mz_root_info* info, int32_t* action, float* count, float* mean, float* policy, float* logit, float* noise,
                  float* value);
 
+/* ---- learner data path -------------------------------------------------------------- */
+/* BaseEnvLoader::getFeatures (environment/base/base_env.h:235-241; called per training sample by
+ * learner/data_loader.cpp:134-200): for n <= num_games samples, replay the first positions[i] actions of record i (actions
+ * [n][max_len], -1 padded, players alternate from the first player as Environment::act applies them) from the initial position and
+ * return the feature planes of the position reached under rotations[i] (NULL = none): features_out [n][C*H*W]. Board games only:
+ * Atari records carry their observations. The engine's search state is not touched (its network input rows are). */
+int mz_replay_features(mz_engine* e, const int32_t* actions, int32_t max_len, const int32_t* positions, const uint8_t* rotations, int32_t n, float* features_out);
+
 /* ---- search, one phase at a time (parity hooks; NN outputs supplied by the caller) ------------------ */
 /* ZeroActor::beforeNNEvaluation for every game (actor/zero_actor.cpp:51-58). rotations [B] or NULL;
  * features_out [B][C*H*W] or NULL; path_len_out [B] or NULL */

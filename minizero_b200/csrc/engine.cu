@@ -169,6 +169,25 @@ __global__ void __launch_bounds__(256) k_atari_observe(const mz_dims d, const mz
     for (int i = threadIdx.x; i < MZ_ATARI_FRAME / 16; i += blockDim.x) { dst[i] = src[i]; }
 }
 
+// BaseEnvLoader::getFeatures (environment/base/base_env.h:235-241), the learner's feature reconstruction: sample g replays the first
+// positions[g] actions of its record from the initial position and emits the planes of the position reached, rotated. One warp per
+// sample; the planes land in the network-input rows of "game" g (the caller unpacks them).
+__global__ void __launch_bounds__(32) k_replay_features(const mz_dims d, const mz_state s, const int32_t* __restrict__ actions, int max_len, const int32_t* __restrict__ positions,
+                                                        const uint8_t* __restrict__ rotations, int n)
+{
+    __shared__ mz_scratch w;
+    const int g = blockIdx.x, lane = threadIdx.x;
+    if (g >= n) { return; }
+    mz_env_reset(d, &w, lane);
+    const int upto = (positions[g] < max_len ? positions[g] : max_len);
+    for (int i = 0; i < upto; ++i) {
+        const int a = actions[(size_t)g * max_len + i];
+        if (a < 0) { break; } // record shorter than the position asked for: the final position (base_env.h:239)
+        mz_env_act(d, s, &w, a, w.turn, lane);
+    }
+    mz_env_features(d, s, g, &w, rotations ? rotations[g] : 0, lane, 32);
+}
+
 // action ids along the selected path of every game (-1 padded): parity hook for the MuZero / Gumbel selection
 __global__ void k_path_actions(const mz_dims d, const mz_state s, int32_t* __restrict__ out)
 {
@@ -195,6 +214,7 @@ struct ConvLayer {
     size_t w_off = 0, b_off = 0; // offsets into the blob
     CUtensorMap map_w;
     CUtensorMap map_w_mc; // box = 1 / conv_cluster of the weight tile (multicast slices)
+    CUtensorMap map_w_tower; // box = half of the fused tower's output-channel tile (tower_bn / 2 rows)
     // ConvStage layers only
     int cin_off = 0, tap_mask = 0x1ff;
     int in_buf = 0, out_buf = 0, res_buf = -2; // activation buffer indices of the stage; -1 = the stage's input rows, -2 = none
@@ -284,6 +304,7 @@ struct mz_engine {
     float* d_hidden_f32 = nullptr;   // [B][Ch * H * W] staging of the parity hooks
     int32_t* d_path_actions = nullptr; // [B][S + 2]
     int cin_max = 0;
+    int tower_bn = 128;
     int conv_mode = 1, rows_ext = 0, base_off_mode = 0, num_sms = 148, krot = 0, conv_cluster = 1, conv_pdl = 0, tower_sms = 148, tower_stages = 8, tower_pdl = 0;
     encode_tiled_fn encode = nullptr;
 
@@ -414,6 +435,8 @@ int configure_conv_kernels()
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<256, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<256, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return MZ_OK;
 }
 
@@ -433,7 +456,7 @@ int conv(mz_engine* e, const CUtensorMap& in, const CUtensorMap& in_ext, const C
     }
 }
 
-int launch_heads(mz_engine* e, const __half* act, int* clear = nullptr, int clear_count = 0, bool scale_hidden = false)
+int launch_heads(mz_engine* e, const __half* act, int* clear = nullptr, int clear_count = 0)
 {
     mznn::HeadParams p;
     p.clear = clear, p.clear_count = clear_count;
@@ -444,8 +467,6 @@ int launch_heads(mz_engine* e, const __half* act, int* clear = nullptr, int clea
     p.c = e->cpad, p.n = e->d.N, p.slots = e->d.slots, p.pol_ch = e->pol_ch, p.actions = e->d.A, p.vh = e->nd.num_value_hidden_channels;
     const int hw = e->d.N * e->d.N, np1 = p.pol_ch + 1;
     p.batch = e->d.B, p.fc_in_smem = 0;
-    p.hid = nullptr, p.hid_slot = nullptr, p.c_real = e->nd.num_hidden_channels, p.num_slots = e->d.S + 1;
-    if (scale_hidden) { p.hid = reinterpret_cast<__half*>(e->s.hid), p.hid_slot = e->s.eval_slot; }
     const size_t smem = sizeof(float) * (np1 * p.c + np1 * hw + p.vh + p.actions + 32 + hw + 4 * (p.actions + p.vh));
     static const int threads_env = [] {
         const char* env = knob("MZ_HEADS_THREADS");
@@ -465,7 +486,7 @@ int launch_heads(mz_engine* e, const __half* act, int* clear = nullptr, int clea
 }
 
 int launch_tower(mz_engine* e, int which, bool clear_counters = true, bool pdl = false);
-int launch_tower_params(mz_engine* e, mznn::TowerParams* params, int* d_done, int cout, int cin_max, int rows_ext, int stages, bool clear_counters, bool pdl);
+int launch_tower_params(mz_engine* e, mznn::TowerParams* params, int* d_done, int cout, int cin_max, int rows_ext, int stages, bool clear_counters, bool pdl, int bn = 128);
 
 // hidden-state scaling + the three heads of the Atari network on the tower output `act` (see atari_kernels.cuh): 4 launches
 int launch_atari_heads(mz_engine* e, const __half* act, bool with_reward)
@@ -565,29 +586,27 @@ int forward(mz_engine* e, int which = 0, bool after_tree_step = false)
         }
     }
     __half* out = e->act[T.out_buf];
-    // MuZero: scale_hidden_state is part of the heads kernel when the hidden width is even (it reads channel pairs); else its own kernel first
-    const bool fused_scale = (e->cfg.muzero && e->nd.num_hidden_channels % 2 == 0);
-    if (e->cfg.muzero && !fused_scale) {
+    if (e->cfg.muzero) {
         mznn::scale_hidden_kernel<<<e->d.B, 256, 0, e->stream>>>(out, reinterpret_cast<__half*>(e->s.hid), e->s.eval_slot, e->d.N, e->d.slots, e->cpad,
                                                                   e->nd.num_hidden_channels, e->d.S + 1);
         e->launches++;
     }
-    if (e->conv_mode == 3) { return launch_heads(e, out, T.d_done, T.params->num_layers * ((T.params->num_mtiles + 1) / 2), fused_scale); }
-    return launch_heads(e, out, nullptr, 0, fused_scale);
+    if (e->conv_mode == 3) { return launch_heads(e, out, T.d_done, T.params->num_layers * ((T.params->num_mtiles + 1) / 2)); }
+    return launch_heads(e, out);
 }
 
 // one launch of the fused tower kernel over `params` (a NetTower or a ConvStage)
-int launch_tower_params(mz_engine* e, mznn::TowerParams* params, int* d_done, int cout, int cin_max, int rows_ext, int stages, bool clear_counters, bool pdl)
+int launch_tower_params(mz_engine* e, mznn::TowerParams* params, int* d_done, int cout, int cin_max, int rows_ext, int stages, bool clear_counters, bool pdl, int bn)
 {
     const int num_groups = (params->num_mtiles + 1) / 2;
     if (clear_counters) {
         CUDA_OK(cudaMemsetAsync(d_done, 0, sizeof(int) * params->num_layers * num_groups, e->stream));
         e->memsets++;
     }
-    const int units = num_groups * (cout / 128);
+    const int units = num_groups * (cout / bn);
     int clusters = e->tower_sms / 2;
     if (units < clusters) { clusters = units; }
-    const size_t smem = 2 * static_cast<size_t>(cin_max / mznn::BK) * rows_ext * 128 + static_cast<size_t>(stages) * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
+    const size_t smem = 2 * static_cast<size_t>(cin_max / mznn::BK) * rows_ext * 128 + static_cast<size_t>(stages) * (bn / 2) * mznn::BK * 2 + 24 * 8 + 16 + 1024;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * 2), cfg.blockDim = dim3(mznn::TOWER_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = e->stream;
     cudaLaunchAttribute attr[2];
@@ -597,7 +616,13 @@ int launch_tower_params(mz_engine* e, mznn::TowerParams* params, int* d_done, in
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     params->pdl = (pdl ? 1 : 0);
     cfg.attrs = attr, cfg.numAttrs = (pdl ? 2 : 1);
-    if (params->dbg && stages == 8) {
+    if (bn == 256) { // output-channel tile of 256: half the input-block reads per FLOP (see DESIGN.md "What bounds the tower")
+        if (stages == 4) {
+            CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<256, 4, false>, *params));
+        } else {
+            CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<256, 2, false>, *params));
+        }
+    } else if (params->dbg && stages == 8) {
         CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8, true>, *params));
     } else if (stages == 4) { // 185 KB of shared memory: a tree-step block (30 KB) of another engine fits on the same SM
         CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 4, false>, *params));
@@ -613,7 +638,7 @@ int launch_tower_params(mz_engine* e, mznn::TowerParams* params, int* d_done, in
 int launch_tower(mz_engine* e, int which, bool clear_counters, bool pdl)
 {
     NetTower& T = e->tw[which];
-    return launch_tower_params(e, T.params, T.d_done, e->cpad, e->cin_max, e->rows_ext, e->tower_stages, clear_counters, pdl);
+    return launch_tower_params(e, T.params, T.d_done, e->cpad, e->cin_max, e->rows_ext, e->tower_stages, clear_counters, pdl, e->tower_bn);
 }
 
 size_t step_smem_bytes(const mz_dims& d)
@@ -801,7 +826,7 @@ int alloc_atari(mz_engine* e)
         T.num_layers = static_cast<int>(st.convs.size());
         T.rows_valid = e->d.B * st.slots, T.n1 = st.n + 1, T.slots = st.slots, T.cout = st.cout, T.rows_ext = st.rows_ext, T.halo = st.n + 2;
         T.num_mtiles = st.rows_alloc / mznn::BM, T.cin_max = st.cin_max;
-        T.rotate = 22, T.shift = 0, T.zigzag = 0, T.strided = 1, T.pdl = 0, T.dbg = nullptr;
+        T.rotate = 22, T.shift = 0, T.zigzag = 0, T.strided = 1, T.tap_rot = 0, T.fence_mode = 0, T.pdl = 0, T.dbg = nullptr;
         for (int li = 0; li < T.num_layers; ++li) {
             ConvLayer& L = st.convs[li];
             if ((rc = make_map_2d(e, &L.map_w_mc, e->d_blob + L.w_off, L.cin, 9ull * L.cout, mznn::BK, 64))) { return rc; }
@@ -865,6 +890,13 @@ int alloc_net(mz_engine* e)
         if (e->bn_tile == 128 && stages != 0) {
             e->conv_cluster = 2;
             if (!knob("MZ_TOWER_STAGES")) { e->tower_stages = stages; }
+            if (const char* env = knob("MZ_TOWER_BN")) { // 256-wide output tiles (experiment): stages of 16 KB per CTA, 4 or 2 of them
+                if (std::atoi(env) == 256 && want_tower && e->cpad % 256 == 0 && !e->atari) {
+                    auto need256 = [&](int st) { return 2 * static_cast<size_t>(e->cin_max / mznn::BK) * e->rows_ext * 128 + static_cast<size_t>(st) * 128 * mznn::BK * 2 + 24 * 8 + 16 + 1024; };
+                    const int st = (need256(4) <= 227 * 1024 ? 4 : (need256(2) <= 227 * 1024 ? 2 : 0));
+                    if (st) { e->tower_bn = 256, e->tower_stages = st; }
+                }
+            }
         } else {
             e->conv_mode = 1;
         }
@@ -904,6 +936,7 @@ int alloc_net(mz_engine* e)
         for (ConvLayer& L : NT.convs) {
             if ((rc = make_map_2d(e, &L.map_w, e->d_blob + L.w_off, L.cin, 9ull * L.cout, mznn::BK, e->bn_tile))) { return rc; }
             if ((rc = make_map_2d(e, &L.map_w_mc, e->d_blob + L.w_off, L.cin, 9ull * L.cout, mznn::BK, e->bn_tile / e->conv_cluster))) { return rc; }
+            if ((rc = make_map_2d(e, &L.map_w_tower, e->d_blob + L.w_off, L.cin, 9ull * L.cout, mznn::BK, e->tower_bn / 2))) { return rc; }
         }
         NT.out_buf = (2 * e->nd.num_blocks) % 3; // forward()'s buffer rotation: cur -> t -> o per residual block, o = cur + 2
         if (!tower_ok) { continue; }
@@ -914,14 +947,16 @@ int alloc_net(mz_engine* e)
         T.rows_valid = e->d.B * e->d.slots, T.n1 = e->d.N + 1, T.slots = e->d.slots, T.cout = e->cpad, T.rows_ext = e->rows_ext, T.halo = e->d.N + 2;
         T.num_mtiles = e->rows_alloc / mznn::BM;
         T.cin_max = e->cin_max;
-        T.rotate = 22, T.shift = 0, T.zigzag = 0, T.strided = 1;
+        T.rotate = 22, T.shift = 0, T.zigzag = 0, T.strided = 1, T.tap_rot = 0, T.fence_mode = 0;
+        if (const char* env = knob("MZ_TOWER_TAPROT")) { T.tap_rot = std::atoi(env); }
+        if (const char* env = knob("MZ_TOWER_FENCE")) { T.fence_mode = std::atoi(env); }
         if (const char* env = knob("MZ_TOWER_STRIDED")) { T.strided = std::atoi(env); }
         if (const char* env = knob("MZ_TOWER_ZIGZAG")) { T.zigzag = std::atoi(env); }
         if (const char* env = knob("MZ_TOWER_ROT")) { T.rotate = std::atoi(env); }
         if (const char* env = knob("MZ_TOWER_SHIFT")) { T.shift = std::atoi(env); }
         auto set = [&](int li, const CUtensorMap& in, __half* out, const __half* residual) {
             mznn::TowerLayer& L = T.layer[li];
-            L.map_in = in, L.map_w = NT.convs[li].map_w_mc, L.out = out, L.residual = residual;
+            L.map_in = in, L.map_w = NT.convs[li].map_w_tower, L.out = out, L.residual = residual;
             L.bias = reinterpret_cast<const float*>(e->d_blob + NT.convs[li].b_off), L.cin = NT.convs[li].cin, L.relu = NT.convs[li].relu;
             L.cin_off = 0, L.tap_mask = 0x1ff;
         };
@@ -1587,6 +1622,34 @@ int mz_get_root_rewards(mz_engine* e, float* reward, int32_t* bound_size, float*
     if (bound_size) { CUDA_OK(cudaMemcpyAsync(bound_size, e->d_bound_size, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, e->stream)); }
     if (bound_lo) { CUDA_OK(cudaMemcpyAsync(bound_lo, e->d_bound_lo, sizeof(float) * B, cudaMemcpyDeviceToHost, e->stream)); }
     if (bound_hi) { CUDA_OK(cudaMemcpyAsync(bound_hi, e->d_bound_hi, sizeof(float) * B, cudaMemcpyDeviceToHost, e->stream)); }
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    CUDA_OK(cudaGetLastError());
+    return MZ_OK;
+}
+
+int mz_replay_features(mz_engine* e, const int32_t* actions, int32_t max_len, const int32_t* positions, const uint8_t* rotations, int32_t n, float* features_out)
+{
+    if (!e || !actions || !positions || !features_out || n < 1 || n > e->d.B || max_len < 1) { return fail(MZ_ERR_ARG, "bad argument"); }
+    if (e->atari) { return fail(MZ_ERR_STATE, "Atari records carry their observations (OBS tag): there is nothing to replay on the device"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    const mz_dims& d = e->d;
+    int32_t *d_act = nullptr, *d_pos = nullptr;
+    uint8_t* d_rot = nullptr;
+    CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&d_act), sizeof(int32_t) * n * max_len, e->stream));
+    CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&d_pos), sizeof(int32_t) * n, e->stream));
+    CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&d_rot), n, e->stream));
+    CUDA_OK(cudaMemcpyAsync(d_act, actions, sizeof(int32_t) * n * max_len, cudaMemcpyHostToDevice, e->stream));
+    CUDA_OK(cudaMemcpyAsync(d_pos, positions, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    if (rotations) { CUDA_OK(cudaMemcpyAsync(d_rot, rotations, n, cudaMemcpyHostToDevice, e->stream)); }
+    k_replay_features<<<n, 32, 0, e->stream>>>(d, e->s, d_act, max_len, d_pos, rotations ? d_rot : nullptr, n);
+    e->launches++;
+    const size_t F = static_cast<size_t>(d.C) * d.N * d.N;
+    mznn::unpack_features_kernel<<<148, 256, 0, e->stream>>>(reinterpret_cast<const __half*>(e->s.nn_in), e->d_feat_f32, n, d.C, d.N, d.slots, MZ_NN_CPAD);
+    e->launches++;
+    CUDA_OK(cudaMemcpyAsync(features_out, e->d_feat_f32, sizeof(float) * n * F, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaFreeAsync(d_act, e->stream));
+    CUDA_OK(cudaFreeAsync(d_pos, e->stream));
+    CUDA_OK(cudaFreeAsync(d_rot, e->stream));
     CUDA_OK(cudaStreamSynchronize(e->stream));
     CUDA_OK(cudaGetLastError());
     return MZ_OK;

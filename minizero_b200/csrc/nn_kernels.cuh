@@ -854,6 +854,10 @@ struct TowerParams {
     int shift;    // unit offset per layer: position q of layer l is unit (q + l * shift) mod units
     int zigzag;   // odd layers process the cluster's range in reverse order
     int strided;  // units dealt round-robin to the clusters instead of in contiguous ranges
+    int tap_rot;  // 1: a unit starts its tap loop at tap (row group % 9) instead of tap 0, so that the CTA pairs working on the same (layer,
+                  // channel half) do not all ask the L2 for the same weight tile at the same moment. The order is a function of the row
+                  // group alone, never of the grid: a position's result does not depend on the batch it is evaluated in
+    int fence_mode; // how an epilogue warp publishes its rows: 0 = __threadfence by every lane, then one atomicAdd; 1 = __syncwarp, then one red.release.gpu
     int pdl;      // launched with programmatic stream serialization: the grid may start while the tree step before it is still running;
                   // only the first layer's input rows depend on that kernel, and the input producer waits for it (griddepcontrol.wait)
     int* done;    // [num_layers][num_groups] completion counters, zeroed before every launch
@@ -970,8 +974,9 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
             for (int q = ub; q < ue; ++q) {
                 const int u = unit_of(l, q);
                 const int half = u % nh;
-                int wrow = half * BN + crank * (BN / 2);
-                for (int tap = 0; tap < 9; ++tap, wrow += tp.cout) {
+                const int wrow0 = half * BN + crank * (BN / 2), tap0 = (tp.tap_rot ? (u / nh) % 9 : 0);
+                for (int t9 = 0; t9 < 9; ++t9) {
+                    const int tap = (t9 + tap0 >= 9 ? t9 + tap0 - 9 : t9 + tap0), wrow = wrow0 + tap * tp.cout;
                     if (!((L.tap_mask >> tap) & 1)) { continue; }
                     for (int kc = 0; kc < L.cin; kc += BK) {
                         const long long te = (DBG ? clock64() : 0ll);
@@ -1073,10 +1078,12 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                     tcgen05_fence_after();
                     const uint32_t tmem_d = tmem_base + buf * BN;
                     uint32_t accumulate = 0;
-                    int row0 = tp.halo - tp.n1 - 1;
-                    for (int ty = 0; ty < 3; ++ty, row0 += tp.n1 - 3) {
-                        for (int tx = 0; tx < 3; ++tx, ++row0) {
-                            if (!((tap_mask >> (ty * 3 + tx)) & 1)) { continue; }
+                    const int tap0 = (tp.tap_rot ? grp % 9 : 0);
+                    {
+                        for (int t9 = 0; t9 < 9; ++t9) {
+                            const int tap = (t9 + tap0 >= 9 ? t9 + tap0 - 9 : t9 + tap0), ty = tap / 3, tx = tap - 3 * ty;
+                            const int row0 = tp.halo - tp.n1 - 1 + ty * tp.n1 + tx;
+                            if (!((tap_mask >> tap) & 1)) { continue; }
                             uint32_t a_lo = a_lo0 + static_cast<uint32_t>(abuf) * a_buf_step + static_cast<uint32_t>(row0) * 8u;
                             for (int kc = 0; kc < cin; kc += BK, a_lo += a_kb_step) {
                                 const long long tf = (DBG ? clock64() : 0ll);
@@ -1169,11 +1176,19 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                     for (int q = 0; q < 4; ++q) { *reinterpret_cast<uint4*>(out_row + c + q * 8) = packed[q]; }
                 }
                 tcgen05_fence_before();
-                __threadfence(); // this warp's rows of (layer l, group grp) are visible device-wide before the counter moves
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u);
-                    atomicAdd(tp.done + l * num_groups + grp, 1);
+                if (tp.fence_mode == 0) {
+                    __threadfence(); // this warp's rows of (layer l, group grp) are visible device-wide before the counter moves
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u);
+                        atomicAdd(tp.done + l * num_groups + grp, 1);
+                    }
+                } else {
+                    __syncwarp(); // orders the lanes' row stores before lane 0's release (cumulativity carries them along)
+                    if (lane == 0) {
+                        mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u);
+                        asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(tp.done + l * num_groups + grp), "r"(1) : "memory");
+                    }
                 }
                 t_epi_work += (DBG ? clock64() : 0ll) - tw;
             }
@@ -1212,11 +1227,6 @@ struct HeadParams {
     int fc_in_smem;     // 1: the transposed FC weights are staged in shared memory once per CTA
     int* clear;         // completion counters of the tower launch that produced `act` (or null): zeroed here for its next launch,
     int clear_count;    // which saves a memset node between every two kernels of the search graph
-    // MuZero: MuZeroNetwork.scale_hidden_state (network/py/muzero_network.py:150-160) fused in: `act` is the unscaled tower output, the
-    // heads read (x - min) / scale on the fly, and the scaled state goes to the evaluated node's hidden slot (null: no scaling)
-    __half* hid;              // [batch][num_slots][hw][c]
-    const int32_t* hid_slot;  // [batch]
-    int c_real, num_slots;
 };
 
 template <int NP1> // NP1 = policy planes + 1 value plane, a compile-time constant so that the plane loops carry no predicates
@@ -1240,41 +1250,6 @@ __global__ void __launch_bounds__(1024) heads_kernel(const HeadParams p)
     for (int i = tid; i < NP1 * p.c; i += nthr) { wc[i] = (i < p.pol_ch * p.c ? p.w_pc[i] : p.w_vc[i - p.pol_ch * p.c]); }
     for (int cell = tid; cell < hw; cell += nthr) { rowoff[cell] = ((cell / p.n + 1) * n1 + cell % p.n) * p.c; }
     __syncthreads();
-    float h_mn = 0.0f, h_scale = 1.0f;
-    if (p.hid) { // per-board min / max over the real channels of every cell, then the scaled state -> hidden slot (fp16, padded channels zero)
-        float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
-        const int half_real = p.c_real / 2, half_c = p.c / 2;
-        for (int i = tid; i < hw * half_real; i += nthr) {
-            const int cell = i / half_real, k = i - cell * half_real;
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(act + rowoff[cell] + 2 * k));
-            mn = fminf(mn, fminf(f.x, f.y)), mx = fmaxf(mx, fmaxf(f.x, f.y));
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)), mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
-        if (lane == 0) { red[warp] = mn; }
-        __syncthreads();
-        mn = red[0];
-        for (int i = 1; i < nwarp; ++i) { mn = fminf(mn, red[i]); }
-        __syncthreads();
-        if (lane == 0) { red[warp] = mx; }
-        __syncthreads();
-        mx = red[0];
-        for (int i = 1; i < nwarp; ++i) { mx = fmaxf(mx, red[i]); }
-        __syncthreads();
-        h_mn = mn, h_scale = mx - mn;
-        if (h_scale < 1e-5f) { h_scale += 1e-5f; }
-        __half* dst = p.hid + (static_cast<size_t>(g) * p.num_slots + p.hid_slot[g]) * hw * p.c;
-        for (int i = tid; i < hw * half_c; i += nthr) {
-            const int cell = i / half_c, k = i - cell * half_c;
-            __half2 o = __floats2half2_rn(0.0f, 0.0f);
-            if (k < half_real) {
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(act + rowoff[cell] + 2 * k));
-                o = __floats2half2_rn((f.x - h_mn) / h_scale, (f.y - h_mn) / h_scale);
-            }
-            *reinterpret_cast<__half2*>(dst + static_cast<size_t>(cell) * p.c + 2 * k) = o;
-        }
-    }
-    const bool scaling = (p.hid != nullptr);
     // 1x1 convolutions: one warp per cell; lane l owns channel pairs {2l + 64i}: every load instruction is one contiguous
     // 128-byte row segment and the weight reads from shared memory are conflict-free
     const int npair = p.c / 64;
@@ -1284,9 +1259,7 @@ __global__ void __launch_bounds__(1024) heads_kernel(const HeadParams p)
 #pragma unroll
         for (int o = 0; o < NP1; ++o) { acc[o] = 0.0f; }
         for (int i = 0; i < npair; ++i) {
-            float2 a = __half22float2(row[lane + 32 * i]);
-            // the heads see the hidden state as the next inference will: scaled and rounded to fp16 (padded channels carry zero weights)
-            if (scaling) { a = __half22float2(__floats2half2_rn((a.x - h_mn) / h_scale, (a.y - h_mn) / h_scale)); }
+            const float2 a = __half22float2(row[lane + 32 * i]);
             const float* wp = wc + 2 * lane + 64 * i;
 #pragma unroll
             for (int o = 0; o < NP1; ++o) {

@@ -94,6 +94,7 @@ def _load():
     lib.mz_eval_recurrent.argtypes = [vp, f32p, i32p, i32, f32p, f32p, f32p, f32p]
     lib.mz_search_leaf.argtypes = [vp, i32p, i32p, i32p]
     lib.mz_eval_rewards.argtypes = [vp, i32, f32p]
+    lib.mz_replay_features.argtypes = [vp, i32p, i32, i32p, u8p, i32, f32p]
     lib.mz_atari_observe.argtypes = [vp, i32p, u8p]
     lib.mz_get_root_rewards.argtypes = [vp, f32p, i32p, f32p, f32p]
     lib.mz_search_apply_reward.argtypes = [vp, f32p, f32p, f32p, f32p, f32p]
@@ -123,7 +124,7 @@ EXPORTS = ["mz_create", "mz_destroy", "mz_last_error", "mz_action_size", "mz_num
            "mz_net_blob", "mz_net_finalize_empty", "mz_eval_batch", "mz_reset_game", "mz_play", "mz_get_roots", "mz_search_select", "mz_search_apply",
            "mz_search_set_inputs", "mz_search_run", "mz_profile_kernels", "mz_launch_count", "mz_play_max_count", "mz_sync", "mz_timer_begin", "mz_timer_end", "mz_debug_tree_timing", "mz_debug_tower_timing", "mz_conv_layers_per_launch",
            "mz_eval_initial", "mz_eval_recurrent", "mz_search_leaf", "mz_gumbel_best_actions", "mz_eval_rewards", "mz_atari_observe", "mz_get_root_rewards",
-           "mz_search_apply_reward"]
+           "mz_search_apply_reward", "mz_replay_features"]
 
 
 def _fp(a):
@@ -237,6 +238,17 @@ class Engine:
         r = np.zeros(n, np.float32)
         self._check(self.lib.mz_eval_rewards(self.h, n, _fp(r)))
         return r
+
+    # ---- learner data path --------------------------------------------------------------------------------
+    def replay_features(self, actions, positions, rotations=None):
+        """BaseEnvLoader::getFeatures for a batch of (record, position, rotation) samples: actions [n][max_len] (-1 padded)"""
+        a = np.ascontiguousarray(actions, np.int32)
+        n, max_len = a.shape
+        pos = np.ascontiguousarray(positions, np.int32)
+        rot = None if rotations is None else np.ascontiguousarray(rotations, np.uint8)
+        out = np.zeros((n, self.F), np.float32)
+        self._check(self.lib.mz_replay_features(self.h, _i32(a), max_len, _i32(pos), _u8(rot), n, _fp(out)))
+        return out
 
     # ---- Atari: the emulator stays with the caller --------------------------------------------------
     def observe_all(self, actions, frames):

@@ -1,4 +1,5 @@
-"""Prints the CUDA-event time of the conv / tree / heads kernels on BASELINE configs[1] state (env MZ_CONV_* select the variant)."""
+"""Prints the CUDA-event time of the conv / tree / heads kernels on the state of a BASELINE configuration (KT_CONFIG = bench.py's --config
+numbering, default 2). The MZ_* experiment switches need a library built with MZ_BUILD_EXPERIMENT=1."""
 import os
 import sys
 
@@ -9,16 +10,23 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 import minizero_b200  # noqa: E402
 
-eng = minizero_b200.Engine(minizero_b200.GAME_GO, bench.BOARD, bench.GAMES, bench.SIMS)
-eng.load_network(bench.NET)
+w = bench.WORKLOADS[int(os.environ.get("KT_CONFIG", "2"))]
+GAMES, SIMS = w["games"], w["sims"]
+eng = minizero_b200.Engine(minizero_b200.GAME_GO, w["board"], GAMES, SIMS)
+path = os.path.join(bench.NETS, w["net"] + ".pt")
+if os.path.exists(path):
+    eng.load_network(path)
+else:
+    import __graft_entry__ as ge
+    eng.load_network((w["dims"], ge.make_random_state(w["dims"], np.random.default_rng(0))))
 rng = np.random.default_rng(0)
-rot = rng.integers(0, 8, size=(bench.SIMS + 1, bench.GAMES)).astype(np.uint8)
-noise = rng.dirichlet([0.03] * bench.ACTIONS, size=bench.GAMES).astype(np.float32)
+rot = rng.integers(0, 8, size=(SIMS + 1, GAMES)).astype(np.uint8)
+noise = rng.dirichlet([0.03] * eng.A, size=GAMES).astype(np.float32)
 eng.set_search_inputs(rot, noise)
 ms = eng.search()
 p = eng.profile_kernels(100)
-tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("MZ_"))
-print(f"[{tag}] search {ms:.1f} ms ({bench.GAMES * (bench.SIMS + 1) / ms * 1e3:.0f} evals/s)  conv {p['conv_ms'] * 1e3:.1f} us  tree {p['tree_ms'] * 1e3:.1f} us  heads {p['heads_ms'] * 1e3:.1f} us")
+tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("MZ_") or k.startswith("KT_"))
+print(f"[{tag}] search {ms:.1f} ms ({GAMES * (SIMS + 1) / ms * 1e3:.0f} evals/s)  conv {p['conv_ms'] * 1e3:.1f} us  tree {p['tree_ms'] * 1e3:.1f} us  heads {p['heads_ms'] * 1e3:.1f} us")
 
 
 if os.environ.get("MZ_DEBUG_TREE"):
