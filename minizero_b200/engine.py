@@ -152,6 +152,7 @@ class Engine:
                       int(gomoku_exactly_five), int(gomoku_outer_open), int(hex_swap_rule), int(value_rescale), int(atari_legal_mask))
         self.muzero = bool(muzero)
         self.atari = (game == GAME_ATARI)
+        self.game, self.board_size = game, (3 if game == GAME_TICTACTOE else (6 if game == GAME_ATARI else board_size))
         h = C.c_void_p()
         self.h = None
         self._check(self.lib.mz_create(C.byref(cfg), C.byref(h)))
