@@ -240,6 +240,8 @@ struct NetTower {
     int cin0_real = 0, cin0 = 0;         // real / padded input channels of its first conv
     void* in = nullptr;                  // fp16 input rows [rows_alloc][cin0]
     CUtensorMap map_in, map_in_ext;      // box = one row tile / the resident block
+    CUtensorMap map_in_wide;             // box = half of the wide tower's input block (rows_ext_wide / 2 rows)
+    int done_count = 0;                  // completion counters of one launch (layers x row groups of the kernel variant in use)
     mznn::TowerParams* params = nullptr; // host copy of the fused-tower launch parameters (conv_mode 3)
     int* d_done = nullptr;
     int out_buf = 0;                     // index of the activation buffer holding its output
@@ -300,6 +302,10 @@ struct mz_engine {
     __half* act[3] = {nullptr, nullptr, nullptr};
     CUtensorMap map_act[3];
     CUtensorMap map_act_ext[3]; // same buffers, box = the resident block of conv3x3_resident_kernel
+    CUtensorMap map_act_wide[3]; // same buffers, box = half of the wide tower's input block
+    int tower_rot_override = -1; // MZ_TOWER_ROT (experiment builds)
+    bool tower_wide = false;    // conv_tower_wide_kernel (two row tiles per CTA) instead of conv_tower_kernel
+    int rows_ext_wide = 0, tower_wide_stages = 8;
     // MuZero
     float* d_hidden_f32 = nullptr;   // [B][Ch * H * W] staging of the parity hooks
     int32_t* d_path_actions = nullptr; // [B][S + 2]
@@ -437,6 +443,9 @@ int configure_conv_kernels()
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<256, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<256, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_wide_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_wide_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_wide_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return MZ_OK;
 }
 
@@ -591,8 +600,20 @@ int forward(mz_engine* e, int which = 0, bool after_tree_step = false)
                                                                   e->nd.num_hidden_channels, e->d.S + 1);
         e->launches++;
     }
-    if (e->conv_mode == 3) { return launch_heads(e, out, T.d_done, T.params->num_layers * ((T.params->num_mtiles + 1) / 2)); }
+    if (e->conv_mode == 3) { return launch_heads(e, out, T.d_done, T.done_count); }
     return launch_heads(e, out);
+}
+
+// Ownership rotation of the tower's units: pair c owns units c', c' + nc, ... of layer l with c' = (c + l * rotate) mod nc. A layer of `units`
+// units ends with a short pass of units mod nc units; the pairs that have no unit in it go on to the next layer at once, and with
+// rotate = nc - units mod nc they find there exactly the units whose 3x3 halo lies in the part of this layer that is already complete
+// (full passes), while the pairs still busy with the short pass later take the units next to it. With any other rotation a layer's short
+// pass acts as a barrier: measured at config 2, 100 units of the wide kernel on 74 pairs, rotation 22 (the narrow kernel's 200 units): the
+// MMA issuer waits for input blocks 39 % of its time.
+int tower_rotation(const mz_engine* e, int units, int clusters)
+{
+    if (e->tower_rot_override >= 0) { return e->tower_rot_override; }
+    return (clusters - units % clusters) % clusters;
 }
 
 // one launch of the fused tower kernel over `params` (a NetTower or a ConvStage)
@@ -606,6 +627,7 @@ int launch_tower_params(mz_engine* e, mznn::TowerParams* params, int* d_done, in
     const int units = num_groups * (cout / bn);
     int clusters = e->tower_sms / 2;
     if (units < clusters) { clusters = units; }
+    params->rotate = tower_rotation(e, units, clusters);
     const size_t smem = 2 * static_cast<size_t>(cin_max / mznn::BK) * rows_ext * 128 + static_cast<size_t>(stages) * (bn / 2) * mznn::BK * 2 + 24 * 8 + 16 + 1024;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * 2), cfg.blockDim = dim3(mznn::TOWER_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = e->stream;
@@ -635,9 +657,44 @@ int launch_tower_params(mz_engine* e, mznn::TowerParams* params, int* d_done, in
     return MZ_OK;
 }
 
+// the wide variant (two row tiles per CTA): see conv_tower_wide_kernel
+int launch_tower_wide(mz_engine* e, NetTower& T, bool clear_counters, bool pdl)
+{
+    mznn::TowerParams* params = T.params;
+    if (clear_counters) {
+        CUDA_OK(cudaMemsetAsync(T.d_done, 0, sizeof(int) * T.done_count, e->stream));
+        e->memsets++;
+    }
+    const int units = ((params->num_mtiles + 3) / 4) * (e->cpad / 128);
+    int clusters = e->tower_sms / 2;
+    if (units < clusters) { clusters = units; }
+    params->rotate = tower_rotation(e, units, clusters);
+    const int stages = e->tower_wide_stages;
+    const size_t smem = static_cast<size_t>(mznn::WIDE_AK) * e->rows_ext_wide * 128 + static_cast<size_t>(stages) * 64 * mznn::BK * 2 + (2 * stages + 2 * mznn::WIDE_AK + 4) * 8 + 16 + 1024;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * 2), cfg.blockDim = dim3(mznn::WIDE_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = e->stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    params->pdl = (pdl ? 1 : 0);
+    cfg.attrs = attr, cfg.numAttrs = (pdl ? 2 : 1);
+    if (params->dbg && stages == 8) {
+        CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_wide_kernel<8, true>, *params));
+    } else if (stages == 8) {
+        CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_wide_kernel<8, false>, *params));
+    } else {
+        CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_wide_kernel<6, false>, *params));
+    }
+    e->launches++;
+    return MZ_OK;
+}
+
 int launch_tower(mz_engine* e, int which, bool clear_counters, bool pdl)
 {
     NetTower& T = e->tw[which];
+    if (e->tower_wide) { return launch_tower_wide(e, T, clear_counters, pdl); }
     return launch_tower_params(e, T.params, T.d_done, e->cpad, e->cin_max, e->rows_ext, e->tower_stages, clear_counters, pdl, e->tower_bn);
 }
 
@@ -928,11 +985,36 @@ int alloc_net(mz_engine* e)
         if (v >= 2 && v <= e->num_sms) { e->tower_sms = v & ~1; }
     }
     const bool tower_ok = (want_tower && e->conv_mode == 2 && 1 + 2 * e->nd.num_blocks <= mznn::TOWER_MAX_LAYERS && (!e->atari || e->nd.num_blocks > 0));
+    // two row tiles per CTA (half the weight traffic per FLOP) where a layer still has a unit for every CTA pair
+    e->rows_ext_wide = (2 * mznn::BM + 2 * (e->d.N + 2) + 15) / 16 * 16;
+    {
+        auto wide_need = [&](int stages) {
+            return static_cast<size_t>(mznn::WIDE_AK) * e->rows_ext_wide * 128 + static_cast<size_t>(stages) * 64 * mznn::BK * 2 + (2 * stages + 2 * mznn::WIDE_AK + 4) * 8 + 16 + 1024;
+        };
+        e->tower_wide_stages = (wide_need(8) <= 227 * 1024 ? 8 : 6);
+        const int wide_units = ((e->rows_alloc / mznn::BM + 3) / 4) * (e->cpad / 128);
+        e->tower_wide = (tower_ok && !e->atari && e->tower_bn == 128 && e->cpad % 128 == 0 && wide_need(e->tower_wide_stages) <= 227 * 1024 && e->rows_ext_wide / 2 <= 256 &&
+                         wide_units >= e->tower_sms);
+        // (>= two wide units per pair and layer. Measured: config 4, 200 units on 74 pairs: 1727 us against the narrow kernel's 2038 us, the issuer's wait for
+        //  weights falls from 19 % to 10 %. Config 2, 100 units: 302 us against 264 us — weights 19 % -> 6 %, but with 1.35 units per pair and layer almost every
+        //  unit's halo was finished only just before it, and epilogue -> counter -> TMA sits on the critical path of every pass: the issuer waits 39 % for input.)
+        if (const char* env = knob("MZ_TOWER_WIDE")) {
+            const int v = std::atoi(env);
+            if (v == 0) { e->tower_wide = false; }
+            if (v == 1 && wide_units >= e->tower_sms / 2 && tower_ok && !e->atari && e->tower_bn == 128) { e->tower_wide = true; }
+        }
+    }
+    if (e->tower_wide) {
+        for (int i = 0; i < 3; ++i) {
+            if ((rc = make_map_2d(e, &e->map_act_wide[i], e->act[i], e->cpad, rows, mznn::BK, e->rows_ext_wide / 2))) { return rc; }
+        }
+    }
     if (e->atari && !tower_ok) { return fail(MZ_ERR_ARG, "the Atari network needs the fused tower (1 <= num_blocks <= 23)"); }
     for (int t = 0; t < e->num_towers; ++t) {
         NetTower& NT = e->tw[t];
         if ((rc = make_map_2d(e, &NT.map_in, NT.in, NT.cin0, rows, mznn::BK, mznn::BM))) { return rc; }
         if ((rc = make_map_2d(e, &NT.map_in_ext, NT.in, NT.cin0, rows, mznn::BK, e->rows_ext))) { return rc; }
+        if (e->tower_wide && (rc = make_map_2d(e, &NT.map_in_wide, NT.in, NT.cin0, rows, mznn::BK, e->rows_ext_wide / 2))) { return rc; }
         for (ConvLayer& L : NT.convs) {
             if ((rc = make_map_2d(e, &L.map_w, e->d_blob + L.w_off, L.cin, 9ull * L.cout, mznn::BK, e->bn_tile))) { return rc; }
             if ((rc = make_map_2d(e, &L.map_w_mc, e->d_blob + L.w_off, L.cin, 9ull * L.cout, mznn::BK, e->bn_tile / e->conv_cluster))) { return rc; }
@@ -944,7 +1026,7 @@ int alloc_net(mz_engine* e)
         NT.params = new mznn::TowerParams();
         mznn::TowerParams& T = *NT.params;
         T.num_layers = static_cast<int>(NT.convs.size());
-        T.rows_valid = e->d.B * e->d.slots, T.n1 = e->d.N + 1, T.slots = e->d.slots, T.cout = e->cpad, T.rows_ext = e->rows_ext, T.halo = e->d.N + 2;
+        T.rows_valid = e->d.B * e->d.slots, T.n1 = e->d.N + 1, T.slots = e->d.slots, T.cout = e->cpad, T.rows_ext = (e->tower_wide ? e->rows_ext_wide : e->rows_ext), T.halo = e->d.N + 2;
         T.num_mtiles = e->rows_alloc / mznn::BM;
         T.cin_max = e->cin_max;
         T.rotate = 22, T.shift = 0, T.zigzag = 0, T.strided = 1, T.tap_rot = 0, T.fence_mode = 0;
@@ -952,7 +1034,7 @@ int alloc_net(mz_engine* e)
         if (const char* env = knob("MZ_TOWER_FENCE")) { T.fence_mode = std::atoi(env); }
         if (const char* env = knob("MZ_TOWER_STRIDED")) { T.strided = std::atoi(env); }
         if (const char* env = knob("MZ_TOWER_ZIGZAG")) { T.zigzag = std::atoi(env); }
-        if (const char* env = knob("MZ_TOWER_ROT")) { T.rotate = std::atoi(env); }
+        if (const char* env = knob("MZ_TOWER_ROT")) { e->tower_rot_override = std::atoi(env); }
         if (const char* env = knob("MZ_TOWER_SHIFT")) { T.shift = std::atoi(env); }
         auto set = [&](int li, const CUtensorMap& in, __half* out, const __half* residual) {
             mznn::TowerLayer& L = T.layer[li];
@@ -961,15 +1043,17 @@ int alloc_net(mz_engine* e)
             L.cin_off = 0, L.tap_mask = 0x1ff;
         };
         const int base = (NT.has_stem ? 1 : 0);
-        if (NT.has_stem) { set(0, NT.map_in_ext, e->act[0], nullptr); }
+        const CUtensorMap* act_maps = (e->tower_wide ? e->map_act_wide : e->map_act_ext);
+        if (NT.has_stem) { set(0, e->tower_wide ? NT.map_in_wide : NT.map_in_ext, e->act[0], nullptr); }
         int cur = 0;
         for (int b = 0; b < e->nd.num_blocks; ++b) {
             const int tt = (cur + 1) % 3, o = (cur + 2) % 3;
-            set(base + 2 * b, e->map_act_ext[cur], e->act[tt], nullptr);
-            set(base + 1 + 2 * b, e->map_act_ext[tt], e->act[o], e->act[cur]);
+            set(base + 2 * b, act_maps[cur], e->act[tt], nullptr);
+            set(base + 1 + 2 * b, act_maps[tt], e->act[o], e->act[cur]);
             cur = o;
         }
-        const int num_groups = (T.num_mtiles + 1) / 2;
+        const int num_groups = (e->tower_wide ? 2 * ((T.num_mtiles + 3) / 4) : (T.num_mtiles + 1) / 2); // wide: 256-row subgroups incl. the phantom one of an odd tail
+        NT.done_count = T.num_layers * num_groups;
         if ((rc = e->dalloc(&NT.d_done, static_cast<size_t>(T.num_layers) * num_groups))) { return rc; }
         T.done = NT.d_done;
         T.dbg = nullptr;
@@ -1970,7 +2054,7 @@ int mz_profile_kernels(mz_engine* e, int32_t iters, float* conv_ms, float* tree_
         CUDA_OK(cudaEventRecord(e->ev1, e->stream));
         {   // leave the completion counters as a network forward expects them (zero; normally the heads kernel re-zeroes them)
             const NetTower& T = e->tw[which];
-            CUDA_OK(cudaMemsetAsync(T.d_done, 0, sizeof(int) * T.params->num_layers * ((T.params->num_mtiles + 1) / 2), e->stream));
+            CUDA_OK(cudaMemsetAsync(T.d_done, 0, sizeof(int) * T.done_count, e->stream));
         }
         CUDA_OK(cudaStreamSynchronize(e->stream));
         CUDA_OK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));

@@ -975,10 +975,12 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                 const int u = unit_of(l, q);
                 const int half = u % nh;
                 const int wrow0 = half * BN + crank * (BN / 2), tap0 = (tp.tap_rot ? (u / nh) % 9 : 0);
-                for (int t9 = 0; t9 < 9; ++t9) {
-                    const int tap = (t9 + tap0 >= 9 ? t9 + tap0 - 9 : t9 + tap0), wrow = wrow0 + tap * tp.cout;
-                    if (!((L.tap_mask >> tap) & 1)) { continue; }
-                    for (int kc = 0; kc < L.cin; kc += BK) {
+                // K-block outer, tap inner: the same accumulation order as conv_tower_wide_kernel, so that a position's result does not
+                // depend on which of the two kernels (i.e. which batch size) evaluates it
+                for (int kc = 0; kc < L.cin; kc += BK) {
+                    for (int t9 = 0; t9 < 9; ++t9) {
+                        const int tap = (t9 + tap0 >= 9 ? t9 + tap0 - 9 : t9 + tap0), wrow = wrow0 + tap * tp.cout;
+                        if (!((L.tap_mask >> tap) & 1)) { continue; }
                         const long long te = (DBG ? clock64() : 0ll);
                         mbar_wait_u32(empty0 + s * 8, ph);
                         t_bempty += (DBG ? clock64() : 0ll) - te;
@@ -1080,12 +1082,13 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                     uint32_t accumulate = 0;
                     const int tap0 = (tp.tap_rot ? grp % 9 : 0);
                     {
-                        for (int t9 = 0; t9 < 9; ++t9) {
-                            const int tap = (t9 + tap0 >= 9 ? t9 + tap0 - 9 : t9 + tap0), ty = tap / 3, tx = tap - 3 * ty;
-                            const int row0 = tp.halo - tp.n1 - 1 + ty * tp.n1 + tx;
-                            if (!((tap_mask >> tap) & 1)) { continue; }
-                            uint32_t a_lo = a_lo0 + static_cast<uint32_t>(abuf) * a_buf_step + static_cast<uint32_t>(row0) * 8u;
-                            for (int kc = 0; kc < cin; kc += BK, a_lo += a_kb_step) {
+                        uint32_t a_blk = a_lo0 + static_cast<uint32_t>(abuf) * a_buf_step;
+                        for (int kc = 0; kc < cin; kc += BK, a_blk += a_kb_step) {
+                            for (int t9 = 0; t9 < 9; ++t9) {
+                                const int tap = (t9 + tap0 >= 9 ? t9 + tap0 - 9 : t9 + tap0), ty = tap / 3, tx = tap - 3 * ty;
+                                const int row0 = tp.halo - tp.n1 - 1 + ty * tp.n1 + tx;
+                                if (!((tap_mask >> tap) & 1)) { continue; }
+                                const uint32_t a_lo = a_blk + static_cast<uint32_t>(row0) * 8u;
                                 const long long tf = (DBG ? clock64() : 0ll);
                                 mbar_wait_u32(full0 + s * 8, ph);
                                 t_bfull += (DBG ? clock64() : 0ll) - tf;
@@ -1200,6 +1203,330 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Wide variant of the tower: every CTA owns TWO row tiles (256 rows, 512 per pair) per unit, so that each weight stage that
+// arrives in shared memory feeds twice as many MMAs. Why: the narrow kernel streams a layer's full weights (1.18 MB at 256
+// channels) through every CTA pair once per 256 rows, 1.5 GB of L2 -> shared-memory traffic per launch at config 2; with the
+// MMAs running at their full rate that is ~39 B / clock / SM, ~5.8 KB / clock chip-wide — the L2's delivery limit — and the
+// issuer waits for weights 19 % of its time (DESIGN.md "What bounds the tower"). Here the same weights serve 512 rows: half
+// the weight traffic per FLOP. What changes with it:
+//   * accumulators: 2 tiles x 128 columns per unit, double-buffered = all 512 TMEM columns;
+//   * the input block of a unit (256 + 2 * halo rows x cin per CTA) no longer fits twice, so it is streamed as a ring of
+//     WIDE_AK K-blocks (64 input channels each) and the loop order becomes K-block outer, tap inner: the K-block of the
+//     NEXT unit loads while the current unit works on its later K-blocks;
+//   * 8 epilogue warps (two per TMEM lane quarter, each draining half of the columns of both tiles), the residual rows of the
+//     next chunk requested before the current chunk is converted;
+//   * completion counters per 256-row subgroup (one CTA's rows), as fine as the narrow kernel's.
+// Units are dealt round-robin to the pairs (the narrow kernel's "strided" order). Same arithmetic per output element as the
+// narrow kernel up to the order of the fp32 accumulation over (tap, K-block), which the tensor core does not expose anyway.
+// ---------------------------------------------------------------------------------------------
+constexpr int WIDE_THREADS = 384; // warp 0: weight TMA, warp 1: MMA issuer + TMEM owner, warp 2: input K-block TMA + dependency waits, warp 3: idle, warps 4-11: epilogue
+constexpr int WIDE_AK = 4;        // ring slots of input K-blocks
+
+template <int STAGES, bool DBG>
+__global__ void __launch_bounds__(WIDE_THREADS, 1)
+conv_tower_wide_kernel(const __grid_constant__ TowerParams tp)
+{
+    constexpr int BN = 128;
+    constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
+    constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const int a_kb_bytes = tp.rows_ext * 128; // rows_ext: 256 + 2 * halo rounded up to 16 (two TMA boxes of rows_ext / 2 rows)
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + WIDE_AK * a_kb_bytes;
+    uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_HALF_BYTES);
+    uint64_t* b_empty = b_full + STAGES;
+    uint64_t* a_full = b_empty + STAGES;   // [WIDE_AK]
+    uint64_t* a_empty = a_full + WIDE_AK;  // [WIDE_AK]
+    uint64_t* acc_full = a_empty + WIDE_AK; // [2]
+    uint64_t* acc_empty = acc_full + 2;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nh = tp.cout / BN;
+    const int crank = static_cast<int>(cluster_ctarank());
+    const bool leader = (crank == 0);
+    const int cid = blockIdx.x / 2, nc = gridDim.x / 2;
+    const int num_groups = (tp.num_mtiles + 3) / 4; // groups of 512 rows: two tiles per CTA of the pair
+    const int num_sg = 2 * num_groups;              // subgroups of 256 rows: the rows one CTA writes
+    const int units = num_groups * nh;
+    const int need = 8 * nh; // arrivals per (layer, subgroup): 8 epilogue warps x nh channel halves
+
+    if (warp == 0 && lane == 0) {
+        for (int l = 0; l < tp.num_layers; ++l) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tp.layer[l].map_in)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tp.layer[l].map_w)) : "memory");
+        }
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        for (int i = 0; i < WIDE_AK; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 16);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t full0 = smem_u32(b_full), empty0 = smem_u32(b_empty);
+    const uint32_t afull0 = smem_u32(a_full), aempty0 = smem_u32(a_empty);
+
+    // pair c owns units c', c' + nc, c' + 2 nc, ... of layer l with c' = (c + l * rotate) mod nc (the rotation lets the pairs take turns at the short lists)
+    auto first_unit = [&](int l) { return (cid + l * tp.rotate) % nc; };
+
+    if (warp == 0) {
+        // ===== weight producer (both CTAs): this CTA's half of every weight tile; waits for nothing but a free stage =====
+        int s = 0;
+        uint32_t ph = 1;
+        long long t_bempty = 0;
+        const long long t_start = (DBG ? clock64() : 0ll);
+        const uint32_t b_dst0 = smem_u32(smem_b);
+        for (int l = 0; l < tp.num_layers; ++l) {
+            const TowerLayer& L = tp.layer[l];
+            const uint64_t map_w_ptr = reinterpret_cast<uint64_t>(&L.map_w);
+            for (int u = first_unit(l); u < units; u += nc) {
+                const int wrow0 = (u % nh) * BN + crank * (BN / 2);
+                for (int kc = 0; kc < L.cin; kc += BK) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (!((L.tap_mask >> tap) & 1)) { continue; }
+                        const long long te = (DBG ? clock64() : 0ll);
+                        mbar_wait_u32(empty0 + s * 8, ph);
+                        t_bempty += (DBG ? clock64() : 0ll) - te;
+                        if (elect_one_sync()) {
+                            if (leader) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + s * 8), "r"(2 * B_HALF_BYTES) : "memory"); }
+                            tma_load_2d_2sm(b_dst0 + s * B_HALF_BYTES, map_w_ptr, (full0 + s * 8) & kPeerMask, kc, wrow0 + tap * tp.cout);
+                        }
+                        __syncwarp();
+                        if (++s == STAGES) { s = 0, ph ^= 1; }
+                    }
+                }
+            }
+        }
+        if (DBG && tp.dbg && lane == 0) {
+            tp.dbg[blockIdx.x * 8 + 0] = (DBG ? clock64() : 0ll) - t_start;
+            tp.dbg[blockIdx.x * 8 + 2] = t_bempty;
+        }
+    } else if (warp == 2) {
+        // ===== input producer (both CTAs): the K-blocks of every unit's 256 + 2 * halo rows through the ring; it alone waits for the
+        //       previous layer's completion counters =====
+        int slot = 0;
+        uint32_t ph = 1;
+        long long t_dep = 0;
+        const uint32_t a_dst0 = smem_u32(smem_a);
+        const int box_rows = tp.rows_ext / 2;
+        bool first = true;
+        for (int l = 0; l < tp.num_layers; ++l) {
+            const TowerLayer& L = tp.layer[l];
+            const uint64_t map_in_ptr = reinterpret_cast<uint64_t>(&L.map_in);
+            const int a_kb = L.cin / BK;
+            for (int u = first_unit(l); u < units; u += nc) {
+                const int sg = 2 * (u / nh) + crank;
+                if (first && tp.pdl) { // everything before this point (barriers, TMEM, weight prefetch) overlapped the previous kernel
+                    asm volatile("griddepcontrol.wait;" ::: "memory");
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
+                first = false;
+                if (l > 0) { // the 3x3 halo reaches into the neighbouring subgroups of the previous layer
+                    const long long td = (DBG ? clock64() : 0ll);
+                    if (lane == 0) {
+                        const int* d = tp.done + (l - 1) * num_sg;
+                        const int g0 = (sg > 0 ? sg - 1 : 0), g1 = (sg + 1 < num_sg ? sg + 1 : num_sg - 1);
+                        for (int gg = g0; gg <= g1; ++gg) {
+                            while (ld_acquire_gpu(d + gg) < need) { __nanosleep(32); }
+                        }
+                    }
+                    __syncwarp();
+                    asm volatile("fence.proxy.async;" ::: "memory"); // generic-proxy writes of other SMs -> this warp's TMA (async proxy) reads
+                    t_dep += (DBG ? clock64() : 0ll) - td;
+                }
+                const int row0 = sg * 2 * BM - tp.halo;
+                for (int kb = 0; kb < a_kb; ++kb) {
+                    mbar_wait_u32(aempty0 + slot * 8, ph); // the MMAs that read this slot WIDE_AK K-blocks ago are done
+                    if (elect_one_sync()) {
+                        if (leader) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(afull0 + slot * 8), "r"(2 * a_kb_bytes) : "memory"); }
+                        const uint32_t bar = (afull0 + slot * 8) & kPeerMask;
+                        const uint32_t dst = a_dst0 + slot * a_kb_bytes;
+                        tma_load_2d_2sm(dst, map_in_ptr, bar, L.cin_off + kb * BK, row0);
+                        tma_load_2d_2sm(dst + box_rows * 128, map_in_ptr, bar, L.cin_off + kb * BK, row0 + box_rows);
+                    }
+                    __syncwarp();
+                    if (++slot == WIDE_AK) { slot = 0, ph ^= 1; }
+                }
+            }
+        }
+        if (DBG && tp.dbg && lane == 0) { tp.dbg[blockIdx.x * 8 + 1] = t_dep; }
+    } else if (warp == 1) {
+        if (leader) { // ===== MMA issuer =====
+            constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN);
+            constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFFu) >> 4) | (1u << 16), b_lo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t a_slot_step = static_cast<uint32_t>(a_kb_bytes) >> 4;
+            constexpr uint32_t a_tile_step = (BM * 128) >> 4; // the CTA's second tile starts 128 rows further down the block
+            int s = 0, slot = 0, buf = 0;
+            uint32_t ph = 0, aph = 0, acc_ph0 = 1, acc_ph1 = 1;
+            long long t_afull = 0, t_acc = 0, t_bfull = 0;
+            const long long t_start = (DBG ? clock64() : 0ll);
+            for (int l = 0; l < tp.num_layers; ++l) {
+                const int a_kb = tp.layer[l].cin / BK, tap_mask = tp.layer[l].tap_mask;
+                for (int u = first_unit(l); u < units; u += nc) {
+                    const long long tc = (DBG ? clock64() : 0ll);
+                    if (buf == 0) {
+                        mbar_wait_u32(smem_u32(&acc_empty[0]), acc_ph0);
+                        acc_ph0 ^= 1;
+                    } else {
+                        mbar_wait_u32(smem_u32(&acc_empty[1]), acc_ph1);
+                        acc_ph1 ^= 1;
+                    }
+                    t_acc += (DBG ? clock64() : 0ll) - tc;
+                    tcgen05_fence_after();
+                    const uint32_t tmem_d = tmem_base + buf * (2 * BN);
+                    uint32_t accumulate = 0;
+                    for (int kb = 0; kb < a_kb; ++kb) {
+                        const long long ta = (DBG ? clock64() : 0ll);
+                        mbar_wait_u32(afull0 + slot * 8, aph);
+                        t_afull += (DBG ? clock64() : 0ll) - ta;
+                        tcgen05_fence_after();
+                        const uint32_t a_blk = a_lo0 + static_cast<uint32_t>(slot) * a_slot_step;
+                        for (int tap = 0; tap < 9; ++tap) {
+                            if (!((tap_mask >> tap) & 1)) { continue; }
+                            const int ty = tap / 3, tx = tap - 3 * ty;
+                            const uint32_t a_lo = a_blk + static_cast<uint32_t>(tp.halo - tp.n1 - 1 + ty * tp.n1 + tx) * 8u;
+                            const long long tf = (DBG ? clock64() : 0ll);
+                            mbar_wait_u32(full0 + s * 8, ph);
+                            t_bfull += (DBG ? clock64() : 0ll) - tf;
+                            tcgen05_fence_after();
+                            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(s) * (B_HALF_BYTES >> 4);
+                            if (elect_one_sync()) {
+                                umma_f16_lohi_2sm(tmem_d, a_lo, b_lo, desc_hi, idesc, accumulate);
+                                umma_f16_lohi_2sm(tmem_d, a_lo + 2, b_lo + 2, desc_hi, idesc, 1u);
+                                umma_f16_lohi_2sm(tmem_d, a_lo + 4, b_lo + 4, desc_hi, idesc, 1u);
+                                umma_f16_lohi_2sm(tmem_d, a_lo + 6, b_lo + 6, desc_hi, idesc, 1u);
+                                umma_f16_lohi_2sm(tmem_d + BN, a_lo + a_tile_step, b_lo, desc_hi, idesc, accumulate);
+                                umma_f16_lohi_2sm(tmem_d + BN, a_lo + a_tile_step + 2, b_lo + 2, desc_hi, idesc, 1u);
+                                umma_f16_lohi_2sm(tmem_d + BN, a_lo + a_tile_step + 4, b_lo + 4, desc_hi, idesc, 1u);
+                                umma_f16_lohi_2sm(tmem_d + BN, a_lo + a_tile_step + 6, b_lo + 6, desc_hi, idesc, 1u);
+                                tcgen05_commit_2sm_u32(empty0 + s * 8);
+                            }
+                            __syncwarp();
+                            accumulate = 1u;
+                            if (++s == STAGES) { s = 0, ph ^= 1; }
+                        }
+                        if (elect_one_sync()) { tcgen05_commit_2sm_u32(aempty0 + slot * 8); }
+                        __syncwarp();
+                        if (++slot == WIDE_AK) { slot = 0, aph ^= 1; }
+                    }
+                    if (elect_one_sync()) { tcgen05_commit_2sm_u32(smem_u32(&acc_full[buf])); }
+                    __syncwarp();
+                    buf ^= 1;
+                }
+            }
+            if (DBG && tp.dbg && lane == 0) {
+                tp.dbg[blockIdx.x * 8 + 3] = (DBG ? clock64() : 0ll) - t_start;
+                tp.dbg[blockIdx.x * 8 + 4] = t_afull;
+                tp.dbg[blockIdx.x * 8 + 5] = t_acc;
+                tp.dbg[blockIdx.x * 8 + 6] = t_bfull;
+            }
+        }
+    } else if (warp >= 4) { // ===== epilogue (both CTAs): warp & 3 = TMEM lane quarter, (warp - 4) / 4 = which 64 of a tile's 128 columns =====
+        const int quarter = warp & 3, chalf = (warp - 4) >> 2;
+        int ucount = 0;
+        long long t_epi_work = 0;
+        for (int l = 0; l < tp.num_layers; ++l) {
+            const TowerLayer& L = tp.layer[l];
+            for (int u = first_unit(l); u < units; u += nc, ++ucount) {
+                const int grp = u / nh, half = u - grp * nh, buf = ucount & 1;
+                const int mt0 = grp * 4 + crank * 2;
+                const int n0 = half * BN + chalf * 64;
+                int r[2];
+                bool live[2], in_range[2];
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    r[t] = (mt0 + t) * BM + quarter * 32 + lane;
+                    const int rr = r[t] % tp.slots;
+                    live[t] = (r[t] < tp.rows_valid) && (rr / tp.n1 != 0) && (rr % tp.n1 != tp.n1 - 1);
+                    in_range[t] = (mt0 + t < tp.num_mtiles);
+                }
+                mbar_wait(&acc_full[buf], (ucount >> 1) & 1);
+                const long long tw = (DBG ? clock64() : 0ll);
+                tcgen05_fence_after();
+                // chunk i = (tile i >> 1, columns n0 + (i & 1) * 32 .. + 32); the residual rows of chunk i + 1 are requested before chunk i is converted
+                uint4 res[2][4];
+                auto load_res = [&](int i, uint4* dst) {
+                    const int t = i >> 1;
+                    if (L.residual && live[t] && in_range[t]) { // written by other SMs earlier in this launch: read through L2, never through this SM's L1
+                        const __half* res_row = L.residual + static_cast<size_t>(r[t]) * tp.cout + n0 + (i & 1) * 32;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { dst[q] = __ldcg(reinterpret_cast<const uint4*>(res_row) + q); }
+                    }
+                };
+                load_res(0, res[0]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int t = i >> 1, c = (i & 1) * 32;
+                    if (!in_range[t]) { continue; } // warp-uniform
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * (2 * BN) + t * BN + chalf * 64 + c, v);
+                    if (i + 1 < 4) { load_res(i + 1, res[(i + 1) & 1]); }
+                    float4 bias4[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { bias4[q] = __ldg(reinterpret_cast<const float4*>(L.bias + n0 + c) + q); }
+                    const float* bias = reinterpret_cast<const float*>(bias4);
+                    tmem_ld_wait();
+                    uint4 packed[4];
+                    uint32_t* pk = reinterpret_cast<uint32_t*>(packed);
+                    const __half2* rh = reinterpret_cast<const __half2*>(res[i & 1]);
+                    const bool add_res = (L.residual != nullptr) && live[t];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float x0 = __uint_as_float(v[2 * j]) + bias[2 * j];
+                        float x1 = __uint_as_float(v[2 * j + 1]) + bias[2 * j + 1];
+                        if (add_res) {
+                            const float2 rf = __half22float2(rh[j]);
+                            x0 += rf.x, x1 += rf.y;
+                        }
+                        x0 = fminf(fmaxf(x0, L.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX), x1 = fminf(fmaxf(x1, L.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX); // ReLU + saturation at the fp16 range
+                        if (!live[t]) { x0 = 0.0f, x1 = 0.0f; }
+                        const __half2 h = __floats2half2_rn(x0, x1);
+                        pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    __half* out_row = L.out + static_cast<size_t>(r[t]) * tp.cout + n0 + c;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { *(reinterpret_cast<uint4*>(out_row) + q) = packed[q]; }
+                }
+                tcgen05_fence_before();
+                __threadfence(); // this warp's rows of (layer l, subgroup) are visible device-wide before the counter moves
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u);
+                    atomicAdd(tp.done + l * num_sg + 2 * grp + crank, 1);
+                }
+                t_epi_work += (DBG ? clock64() : 0ll) - tw;
+            }
+        }
+        if (DBG && tp.dbg && warp == 4 && lane == 0) { tp.dbg[blockIdx.x * 8 + 7] = t_epi_work; }
+    }
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
