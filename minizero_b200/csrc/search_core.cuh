@@ -221,6 +221,7 @@ struct mz_dims {
     int act_planes;     // action planes of the dynamics input: 1 (one-hot cell) or 18 (one-hot channel block, atari.cpp:124-130)
     uint32_t legal_mask; // Atari: minimal action set of the game (the root's legal actions, atari.h:57)
     int vb_cap;         // capacity of the value-bound table per game    // floor(S / (log2(m) * (m >> level) / 2)) in double, gumbel_zero.cpp:109
+    int think_k;        // actor_mcts_think_batch_size when > 1 (console think(), zero_actor.cpp:129-157): leaves selected per tree and network forward
 };
 
 struct mz_state {
@@ -280,7 +281,27 @@ struct mz_state {
     // Atari root environment: the last 8 screens and the actions that led to them (atari.cpp:47-93); ring, oldest entry at at_head
     uint8_t* at_frames;  // [B][8][3][96][96]
     int32_t* at_meta;    // [B][16]: [0] head, [1..8] action id per ring slot (-1: zero plane), [9] bit mask of slots holding a screen
+    // console think() with actor_mcts_think_batch_size = K > 1 (zero_actor.cpp:129-157): K leaves of ONE tree are selected one after the other, each
+    // selection leaving a virtual loss on its path; the K positions are evaluated together; the results are applied in selection order. A step runs as
+    // K "before" passes and K "after" passes over a VIEW of this struct per lane: the per-leaf arrays (path, path_len, leaf_*, nn_in, policy, logits,
+    // nn_value, rotations) are offset to the lane's section, everything belonging to the tree is shared.
+    float* vloss;           // [B][NP] MCTSNode::virtual_loss_ (null unless think_k > 1)
+    int32_t* think_pending; // [B] leaves of the current step that will be evaluated so far: their slots follow the finished simulations
+    int think_lane;         // lane of this view, 0 .. K-1
 };
+
+// view of the state for lane k of a batched think() step over `trees` trees: the per-leaf arrays point at the lane's section
+// (lane-major: index k * trees + tree), the tree's own arrays are shared by all lanes
+static inline mz_state mz_lane_view(const mz_dims& d, const mz_state& s, int k, int trees)
+{
+    mz_state v = s;
+    const size_t o = (size_t)k * trees;
+    v.path += o * (d.S + 2), v.path_len += o, v.leaf_legal += o * MZ_LEGAL_WORDS, v.leaf_meta += o * 4, v.leaf_score += o;
+    v.nn_in += o * d.slots * MZ_NN_CPAD, v.policy += o * d.A, v.logits += o * d.A, v.nn_value += o;
+    if (v.rotations) { v.rotations += o; }
+    v.think_lane = k;
+    return v;
+}
 
 // value bounds of the tree being searched + the game's reward column: what MCTSNode::getNormalizedMean reads beside the node
 struct mz_qb {
@@ -899,7 +920,7 @@ MZ_DEV void mz_env_features(const mz_dims& d, const mz_state& s, int g, const mz
 
 // MCTSNode::getNormalizedMean (mcts.cpp:40-53), no virtual loss: reward + discount * mean, min-max rescaled by the tree's value
 // bounds when actor_mcts_value_rescale (Atari), negated for White's nodes
-MZ_DEV float mz_normalized_mean(const mz_dims& d, const mz_qb& qb, int node, float mean, float count, int player)
+MZ_DEV float mz_normalized_mean(const mz_dims& d, const mz_qb& qb, int node, float mean, float count, int player, float vloss = 0.0f)
 {
     float v = mz_fadd(qb.reward ? qb.reward[node] : 0.0f, mz_fmul(d.discount, mean));
     if (d.value_rescale) {
@@ -909,7 +930,7 @@ MZ_DEV float mz_normalized_mean(const mz_dims& d, const mz_qb& qb, int node, flo
         v = (v < -1.0f ? -1.0f : v), v = (v > 1.0f ? 1.0f : v); // fmin(1, fmax(-1, x)) on a non-NaN x
     }
     if (player == 2) { v = -v; } // actor_mcts_value_flipping_player == 'W'
-    return mz_fdiv(mz_fsub(mz_fmul(v, count), 0.0f), mz_fadd(count, 0.0f));
+    return mz_fdiv(mz_fsub(mz_fmul(v, count), vloss), mz_fadd(count, vloss)); // value with virtual loss (0 outside think(), mcts.cpp:51)
 }
 
 // MCTS::calculateInitQValue (mcts.cpp:200-217) from the ordered sum over the visited children
@@ -1423,6 +1444,79 @@ MZ_DEV int mz_select(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, 
     return len;
 }
 
+// ---- console think() (zero_actor.cpp:129-157): selection under virtual loss ----
+// MCTS::selectChildByPUCTScore with virtual losses (mcts.cpp:181-217, 40-61): a child counts as visited when count + virtual loss != 0, its Q is
+// (q * count - vloss) / (count + vloss), the exploration term divides by 1 + count + vloss and the parent's total is count + vloss - 1. Every child
+// is scored (a virtual loss breaks the "unvisited children share one score" shortcut of mz_select_level); ordered f32 sum for init-Q as there.
+#define MZ_Q_NONE 3.0e38f
+MZ_DEV int mz_select_level_think(const mz_dims& d, const mz_state& s, const mz_qb& qb, const mz_hot* hot, const float* vl, int node, const mz_hot& h, int child_player,
+                                 float* q, int lane)
+{
+    const int nc = (int)(h.link >> MZ_LINK_SHIFT), fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
+    const int total = (int)mz_fsub(mz_fadd(h.count, vl[node]), 1.0f); // getCountWithVirtualLoss() - 1, mcts.cpp:185
+    const float bias = s.puct_bias[total];
+    const double sqrt_n = s.sqrt_table[total];
+    for (int i = lane; i < nc; i += MZ_W) {
+        const mz_hot c = mz_load_hot(hot + fc + i);
+        const float v = vl[fc + i];
+        q[i] = (mz_fadd(c.count, v) != 0.0f ? mz_normalized_mean(d, qb, fc + i, c.mean, c.count, child_player, v) : MZ_Q_NONE);
+    }
+    mz_sync();
+    float sum_win = 0.0f, sum_n = 0.0f;
+    for (int i = 0; i < nc; ++i) { // every lane folds the same ordered sum
+        const float x = q[i];
+        if (x != MZ_Q_NONE) { sum_win = mz_fadd(sum_win, x), sum_n = mz_fadd(sum_n, 1.0f); }
+    }
+    const float init_q = mz_init_q(d, sum_win, sum_n);
+    float best_s = 0.0f, best_p = 0.0f;
+    int best_i = -1;
+    for (int i = lane; i < nc; i += MZ_W) {
+        const mz_hot c = mz_load_hot(hot + fc + i);
+        const float cv = mz_fadd(c.count, vl[fc + i]);
+        const float u = (float)mz_ddiv(mz_dmul((double)mz_fmul(bias, c.policy), sqrt_n), (double)mz_fadd(1.0f, cv));
+        const float score = mz_fadd(u, (cv == 0.0f ? init_q : q[i]));
+        if (best_i < 0 || score > best_s || (score == best_s && c.policy > best_p)) { best_s = score, best_p = c.policy, best_i = i; }
+    }
+#if MZ_W > 1
+    {   // lexicographic arg-max (score desc, prior desc, index asc) over the lanes' candidates (mcts.cpp:187-194)
+        const int mine = best_i;
+        const uint32_t ks = (mine >= 0 ? mz_sortable(best_s) : 0u);
+        const uint32_t top_s = mz_redux_max(ks);
+        const bool in_s = (mine >= 0 && ks == top_s);
+        const uint32_t kp = (in_s ? mz_sortable(best_p) : 0u);
+        const uint32_t top_p = mz_redux_max(kp);
+        const bool in_p = (in_s && kp == top_p);
+        best_i = (int)mz_redux_min(in_p ? (uint32_t)mine : 0xffffffffu);
+    }
+#endif
+    mz_sync();
+    return best_i;
+}
+
+// MCTS::select (mcts.cpp:139-148) under virtual loss, one warp, level by level; returns the path length, path[] in s.path
+MZ_DEV int mz_select_think(const mz_dims& d, const mz_state& s, int g, mz_scratch* w, int root_turn, int lane)
+{
+    const mz_hot* hot = s.hot + (size_t)g * d.NP;
+    const float* vl = s.vloss + (size_t)g * d.NP;
+    int32_t* path = s.path + (size_t)g * (d.S + 2);
+    {
+        const mz_qb qb = mz_vb_bounds(d, s, g, lane);
+        if (lane == 0) { w->qb = qb, path[0] = 0; }
+    }
+    mz_sync();
+    int level = 0, node = 0;
+    mz_hot h = mz_load_hot(hot);
+    while ((h.link >> MZ_LINK_SHIFT) != 0) {
+        const int fc = (int)(h.link & ((1u << MZ_LINK_SHIFT) - 1u));
+        node = fc + mz_select_level_think(d, s, w->qb, hot, vl, node, h, mz_child_player(d, root_turn, level), w->q_warp, lane);
+        h = mz_load_hot(hot + node);
+        ++level;
+        if (lane == 0) { path[level] = node; }
+        mz_sync();
+    }
+    return level + 1;
+}
+
 MZ_DEV void mz_slot_store(const mz_dims& d, const mz_state& s, int g, int slot, const mz_scratch* w, int lane)
 {
     const size_t e = (size_t)g * (d.S + 1) + slot;
@@ -1656,7 +1750,32 @@ MZ_DEV void mz_before_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch*
     const int N = d.N, tid = wid * MZ_W + lane, nthreads = nw * MZ_W;
     const int root_turn = s.root_meta[g * 4 + 0], root_moves = s.root_meta[g * 4 + 1];
     const long long t0 = mz_clock();
-    {
+    if (s.vloss) { // one lane of a batched think() step (zero_actor.cpp:129-145)
+        const int done = (int)mz_load_hot(s.hot + (size_t)g * d.NP).count;
+        if (s.think_lane >= d.S + 1 - done) { // batch_size = min(K, simulations left), :133-135
+            if (tid == 0) { s.path_len[g] = 0; }
+            return;
+        }
+        if (wid == 0) {
+            const int len0 = mz_select_think(d, s, g, w, root_turn, lane);
+            float* vl = s.vloss + (size_t)g * d.NP;
+            const int32_t* sel = s.path + (size_t)g * (d.S + 2);
+            // a leaf that already carries a virtual loss was selected earlier in this step: it is evaluated once (:140-142) ...
+            const int dup = (vl[sel[len0 - 1]] != 0.0f);
+            mz_sync();
+            for (int i = lane; i < len0; i += MZ_W) { vl[sel[i]] = mz_fadd(vl[sel[i]], 1.0f); } // ... but every selection leaves its virtual loss (:143)
+            if (lane == 0) {
+                w->shared_len = (dup ? -len0 : len0);
+                w->shared_count = done + s.think_pending[g]; // slot of this evaluation: finished simulations + leaves queued before it in this step
+                if (!dup) { s.think_pending[g] += 1; }
+            }
+        }
+        mz_block_sync();
+        if (w->shared_len < 0) { // duplicate: nothing to evaluate, the lane reports -length
+            if (tid == 0) { s.path_len[g] = w->shared_len; }
+            return;
+        }
+    } else {
         const int len0 = mz_select(d, s, g, w, root_turn, lane, wid, nw);
         if (wid == 0 && lane == 0) {
             w->shared_len = len0;
@@ -2042,6 +2161,13 @@ MZ_DEV void mz_after_nn(const mz_dims& d, const mz_state& s, int g, mz_scratch* 
         mz_vis_insert(s, (size_t)g * d.NP, parent, leaf - (int)(ph.link & ((1u << MZ_LINK_SHIFT) - 1u)), (int)(ph.link >> MZ_LINK_SHIFT));
     }
     if (d.gumbel) { mz_gumbel_halving(d, s, g, s.root_meta[g * 4 + 0], tid, nthreads); } // zero_actor.cpp:97
+    if (s.vloss) { // think(): the leaf's virtual loss — how often this step selected it — comes off every node of its path (zero_actor.cpp:153-154)
+        float* vl = s.vloss + (size_t)g * d.NP;
+        mz_block_sync();
+        const float x = vl[leaf];
+        mz_block_sync();
+        for (int i = tid; i < len; i += nthreads) { vl[path[i]] = mz_fsub(vl[path[i]], x); }
+    }
     if (tid == 0) { s.path_len[g] = 0; }
 }
 

@@ -139,6 +139,13 @@ float mzo_root_normalized_mean(const mzo_batch* b, int g, int i);
 /* AtariEnv: reset() (action < 0: the initial screen) or act() (atari.cpp:47-93): frame = resized screen, RGB bytes [3][96][96] */
 void mzo_atari_observe(mzo_batch* b, int g, int action, const uint8_t* frame_chw, int terminal);
 
+/* ---- console think() with actor_mcts_think_batch_size = K > 1 (zero_actor.cpp:36-49,129-157; AlphaZero networks) ----
+ * One ZeroActor::step per call pair. mzo_think_select: min(K, simulations left) selections per tree under virtual loss; lane-major arrays:
+ * rotations [K][B], features [K][B][C*H*W] (every selection's position, used or not), path_len [K][B] (> 0: leaf to evaluate, < 0: duplicate
+ * of an earlier lane, 0: lane unused). mzo_think_apply: the evaluated lanes in selection order; policy / logits [K][B][A], value [K][B]. */
+void mzo_think_select(mzo_batch* b, int K, const uint8_t* rotations, float* features, int32_t* path_len);
+void mzo_think_apply(mzo_batch* b, const float* policy, const float* logits, const float* value, const float* noise);
+
 /* std::sort(candidates, policy descending) exactly as libstdc++ orders them, ties included (mzo_sort.c) */
 void mzo_std_sort_candidates(int n, int32_t* action, float* policy, float* logit);
 

@@ -38,6 +38,7 @@ typedef struct {
     int16_t* action;
     uint8_t* player;
     float *count, *mean, *policy, *logit, *noise, *value, *reward;
+    float* vloss; /* MCTSNode::virtual_loss_ (mcts.h:59): non-zero only inside a batched think() step */
     int16_t* slot; /* MuZero: simulation index that evaluated the node = index of its hidden state (tree.h hidden_state_data_index_) */
     /* GumbelZero state (gumbel_zero.h:20-23) */
     int32_t cand[MZO_MAX_ACTIONS];
@@ -66,6 +67,12 @@ struct mzo_batch {
     int32_t* path_len; /* [B] */
     uint8_t* rotation; /* [B] */
     atari_env* atari;  /* [B] when cfg.game == MZO_GAME_ATARI */
+    /* batched think() step (zero_actor.cpp:129-157): the lanes of mzo_think_select, lane-major [K][B] */
+    int think_k;
+    int32_t* t_path;     /* [K][B][S+2] */
+    int32_t* t_len;      /* [K][B]: > 0 evaluate, < 0 duplicate leaf (-length), 0 lane unused */
+    uint8_t* t_rot;      /* [K][B] */
+    mzo_env* t_env;      /* [K][B] leaf environments */
 };
 
 static int other(int p) { return p == 1 ? 2 : 1; }
@@ -74,7 +81,7 @@ static void node_reset(tree* t, int i)
 {
     t->num_children[i] = 0;
     t->first_child[i] = -1;
-    t->mean[i] = t->count[i] = t->policy[i] = t->logit[i] = t->noise[i] = t->value[i] = t->reward[i] = 0.0f;
+    t->mean[i] = t->count[i] = t->policy[i] = t->logit[i] = t->noise[i] = t->value[i] = t->reward[i] = t->vloss[i] = 0.0f;
     t->slot[i] = -1;
 }
 
@@ -120,6 +127,7 @@ mzo_batch* mzo_create(const mzo_config* cfg)
         t->noise = (float*)malloc(n * 4);
         t->value = (float*)malloc(n * 4);
         t->reward = (float*)malloc(n * 4);
+        t->vloss = (float*)malloc(n * 4);
         t->slot = (int16_t*)malloc(n * 2);
         t->vb_key = (float*)malloc(sizeof(float) * (size_t)(2 * cfg->num_simulation + 8));
         t->vb_cnt = (int32_t*)malloc(sizeof(int32_t) * (size_t)(2 * cfg->num_simulation + 8));
@@ -134,10 +142,11 @@ void mzo_destroy(mzo_batch* b)
     for (int g = 0; g < b->cfg.num_games; ++g) {
         tree* t = &b->trees[g];
         free(t->first_child), free(t->num_children), free(t->action), free(t->player);
-        free(t->count), free(t->mean), free(t->policy), free(t->logit), free(t->noise), free(t->value), free(t->reward), free(t->slot);
+        free(t->count), free(t->mean), free(t->policy), free(t->logit), free(t->noise), free(t->value), free(t->reward), free(t->slot), free(t->vloss);
         free(t->vb_key), free(t->vb_cnt);
     }
     free(b->atari);
+    free(b->t_path), free(b->t_len), free(b->t_rot), free(b->t_env);
     free(b->root_env), free(b->leaf_env), free(b->trees), free(b->path), free(b->path_len), free(b->rotation);
     free(b);
 }
@@ -164,7 +173,7 @@ void mzo_reset_game(mzo_batch* b, int g)
     mzo_reset_search(b, g);
 }
 
-/* mcts.cpp:40-53 with virtual_loss_ == 0 kept as an explicit term (self-play never sets it) */
+/* mcts.cpp:40-53; virtual_loss_ is 0 outside a batched think() step and stays in the formula as an explicit term */
 static float normalized_mean(const mzo_batch* b, const tree* t, int i)
 {
     float value = t->reward[i] + b->cfg.reward_discount * t->mean[i];
@@ -175,7 +184,7 @@ static float normalized_mean(const mzo_batch* b, const tree* t, int i)
         value = (float)fmin(1, fmax(-1, 2 * value - 1)); /* the double overloads of fmin / fmax, as compiled (SURVEY a-3) */
     }
     if (t->player[i] == 2) { value = -value; } /* actor_mcts_value_flipping_player == 'W' */
-    const float vloss = 0.0f;
+    const float vloss = t->vloss[i];
     value = (value * t->count[i] - vloss) / (t->count[i] + vloss);
     return value;
 }
@@ -212,8 +221,9 @@ static float puct_score(const mzo_batch* b, const tree* t, int i, int total_simu
     tt = tt / b->cfg.puct_base;
     float puct_bias = (float)((double)b->cfg.puct_init + log((double)tt));
     float bp = puct_bias * t->policy[i];
-    float value_u = (float)(((double)bp * sqrt((double)total_simulation)) / (double)(1.0f + t->count[i]));
-    float value_q = (t->count[i] == 0.0f ? init_q_value : normalized_mean(b, t, i));
+    const float count_vl = t->count[i] + t->vloss[i]; /* getCountWithVirtualLoss, mcts.h:47 */
+    float value_u = (float)(((double)bp * sqrt((double)total_simulation)) / (double)(1.0f + count_vl));
+    float value_q = (count_vl == 0.0f ? init_q_value : normalized_mean(b, t, i));
     return value_u + value_q;
 }
 
@@ -223,7 +233,7 @@ static float init_q(const mzo_batch* b, const tree* t, int node)
     float sum_of_win = 0.0f, sum = 0.0f;
     for (int k = 0; k < t->num_children[node]; ++k) {
         int c = t->first_child[node] + k;
-        if (t->count[c] == 0.0f) { continue; }
+        if (t->count[c] + t->vloss[c] == 0.0f) { continue; }
         sum_of_win += normalized_mean(b, t, c);
         sum += 1;
     }
@@ -234,7 +244,7 @@ static float init_q(const mzo_batch* b, const tree* t, int node)
 /* mcts.cpp:181-198 */
 static int select_child(const mzo_batch* b, const tree* t, int node)
 {
-    int total_simulation = (int)(t->count[node] - 1);
+    int total_simulation = (int)(t->count[node] + t->vloss[node] - 1);
     float iq = init_q(b, t, node);
     float best_score = -3.402823466e+38f, best_policy = -3.402823466e+38f;
     int selected = -1;
@@ -456,15 +466,23 @@ void mzo_apply(mzo_batch* b, const float* policy, const float* logits, const flo
     mzo_apply_mz(b, policy, logits, value, NULL, noise);
 }
 
-/* ZeroActor::afterNNEvaluation, zero_actor.cpp:74-98 */
+static void apply_game(mzo_batch* b, int g, const float* policy, const float* logits, const float* value, const float* reward, const float* noise);
+
+/* ZeroActor::afterNNEvaluation for every game */
 void mzo_apply_mz(mzo_batch* b, const float* policy, const float* logits, const float* value, const float* reward, const float* noise)
 {
+    for (int g = 0; g < b->cfg.num_games; ++g) { apply_game(b, g, policy, logits, value, reward, noise); }
+}
+
+/* ZeroActor::afterNNEvaluation, zero_actor.cpp:74-98, for game g: the network outputs are indexed [g] like the batch they came from */
+static void apply_game(mzo_batch* b, int g, const float* policy, const float* logits, const float* value, const float* reward, const float* noise)
+{
     int S2 = b->cfg.num_simulation + 2, A = b->A;
-    for (int g = 0; g < b->cfg.num_games; ++g) {
+    {
         tree* t = &b->trees[g];
         const int32_t* path = b->path + (size_t)g * S2;
         int len = b->path_len[g];
-        if (len == 0) { continue; }
+        if (len == 0) { return; }
         int leaf = path[len - 1];
         const mzo_env* e = &b->leaf_env[g];
         float v;
@@ -550,6 +568,72 @@ void mzo_apply_mz(mzo_batch* b, const float* policy, const float* logits, const 
         }
         if (b->cfg.use_gumbel) { sequential_halving(b, t); } /* zero_actor.cpp:97 */
         b->path_len[g] = 0;
+    }
+}
+
+/* ---- console think() with actor_mcts_think_batch_size = K (zero_actor.cpp:36-49,129-157), AlphaZero networks ----
+ * ZeroActor::step's first loop for every game: batch_size = min(K, simulations left) selections, one after the other; a leaf whose virtual
+ * loss is still 0 joins the batch (:140-142), every selection adds a virtual loss to its path (:143). Arrays are lane-major [K][B]. */
+void mzo_think_select(mzo_batch* b, int K, const uint8_t* rotations, float* features, int32_t* path_len)
+{
+    const int B = b->cfg.num_games, S2 = b->cfg.num_simulation + 2;
+    if (b->think_k != K) {
+        free(b->t_path), free(b->t_len), free(b->t_rot), free(b->t_env);
+        b->think_k = K;
+        b->t_path = (int32_t*)calloc((size_t)K * B * S2, sizeof(int32_t));
+        b->t_len = (int32_t*)calloc((size_t)K * B, sizeof(int32_t));
+        b->t_rot = (uint8_t*)calloc((size_t)K * B, 1);
+        b->t_env = (mzo_env*)calloc((size_t)K * B, sizeof(mzo_env));
+    }
+    for (int g = 0; g < B; ++g) {
+        tree* t = &b->trees[g];
+        const int left = b->cfg.num_simulation + 1 - (int)t->count[0];
+        const int batch = (K < left ? K : left); /* zero_actor.cpp:133-135 (an AlphaZero network also batches the root's first evaluation) */
+        for (int k = 0; k < K; ++k) {
+            const size_t l = (size_t)k * B + g;
+            b->t_len[l] = 0;
+            if (path_len) { path_len[l] = 0; }
+            if (k >= batch) { continue; }
+            int32_t* path = b->t_path + l * S2;
+            int len = 0, node = 0;
+            path[len++] = 0;
+            while (t->num_children[node] > 0) { /* mcts.cpp:139-148 */
+                node = select_child(b, t, node);
+                path[len++] = node;
+            }
+            const int fresh = (t->vloss[node] == 0.0f);
+            /* beforeNNEvaluation pushes the position whether or not it will be used (zero_actor.cpp:54-57) */
+            mzo_env* e = &b->t_env[l];
+            *e = b->root_env[g];
+            for (int i = 1; i < len; ++i) { mzo_env_act(e, t->action[path[i]], t->player[path[i]]); }
+            b->t_rot[l] = (rotations ? rotations[l] : 0);
+            if (features) { mzo_env_features(e, b->t_rot[l], features + l * (size_t)b->F); }
+            for (int i = 0; i < len; ++i) { t->vloss[path[i]] += 1.0f; }
+            b->t_len[l] = (fresh ? len : -len);
+            if (path_len) { path_len[l] = b->t_len[l]; }
+        }
+    }
+}
+
+/* ZeroActor::step's second loop (zero_actor.cpp:147-156): afterNNEvaluation for the queried lanes in selection order, then the leaf's virtual loss
+ * comes off every node of the path. policy / logits [K][B][A], value [K][B]; noise [B][A] by root child index (NULL = none) */
+void mzo_think_apply(mzo_batch* b, const float* policy, const float* logits, const float* value, const float* noise)
+{
+    const int B = b->cfg.num_games, S2 = b->cfg.num_simulation + 2, K = b->think_k;
+    for (int g = 0; g < B; ++g) {
+        tree* t = &b->trees[g];
+        for (int k = 0; k < K; ++k) {
+            const size_t l = (size_t)k * B + g;
+            const int len = b->t_len[l];
+            if (len <= 0) { continue; }
+            const int32_t* path = b->t_path + l * S2;
+            memcpy(b->path + (size_t)g * S2, path, sizeof(int32_t) * (size_t)len);
+            b->path_len[g] = len, b->leaf_env[g] = b->t_env[l], b->rotation[g] = b->t_rot[l];
+            /* apply_game reads the outputs at index g of the arrays it is given: hand it the lane's section */
+            apply_game(b, g, policy + (size_t)k * B * b->A, logits + (size_t)k * B * b->A, value + (size_t)k * B, NULL, noise);
+            const float vl = t->vloss[path[len - 1]];
+            for (int i = 0; i < len; ++i) { t->vloss[path[i]] -= vl; }
+        }
     }
 }
 

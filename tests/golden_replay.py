@@ -163,3 +163,51 @@ def replay_atari(engine, case, check_features=True):
                 assert action == case["move_action"][m]
                 engine.observe(g, action, frame)
     return checked
+
+
+def replay_think(engine, case, features_of_duplicates=True):
+    """Console-search recordings (oracle/gen_think_golden.py; one tree, actor_mcts_think_batch_size = K): every batched step's selections must agree
+    (which lanes exist, path lengths, which leaves are duplicates, the planes), the recorded network outputs are applied, and every search must end
+    with the recorded root child table. `engine` exposes think_select / think_apply / root / play / sims_done with lane-major arrays [K][1]."""
+    A, F, S, K = (int(case[k]) for k in "AFSK")
+    searches = int(case["move_action"].size)
+    checked = 0
+    for m in range(searches):
+        steps = np.unique(case["sel_step"][case["sel_search"] == m])
+        use_noise = bool(np.any(case["child_noise"][m] != 0))
+        for st in steps:
+            idx = np.nonzero(case["sel_step"] == st)[0]
+            n = idx.size
+            assert np.array_equal(case["sel_lane"][idx], np.arange(n))
+            rot = np.zeros((K, 1), np.uint8)
+            rot[:n, 0] = case["sel_rotation"][idx]
+            first = (engine.sims_done(0) == 0)
+            feats, plen = engine.think_select(K, rot)
+            want_len = np.zeros(K, np.int64)
+            want_len[:n] = np.where(case["sel_leaf_vloss"][idx] == 0, case["sel_path_len"][idx], -case["sel_path_len"][idx])
+            assert np.array_equal(plen[:, 0], want_len), (m, st, plen[:, 0], want_len)
+            want = np.unpackbits(case["sel_features"][idx], axis=1)[:, :F].astype(np.float32)
+            for k in range(n):
+                if want_len[k] > 0 or features_of_duplicates:
+                    assert np.array_equal(feats[k, 0], want[k]), f"planes differ: search {m} step {st} lane {k}"
+            pol, lg, val = np.zeros((K, 1, A), np.float32), np.zeros((K, 1, A), np.float32), np.zeros((K, 1), np.float32)
+            oidx = np.nonzero(case["out_step"] == st)[0]
+            assert np.array_equal(case["out_lane"][oidx], np.nonzero(want_len > 0)[0])
+            for o in oidx:
+                k = int(case["out_lane"][o])
+                pol[k, 0], lg[k, 0], val[k, 0] = case["out_policy"][o], case["out_logits"][o], case["out_value"][o]
+            noise = case["child_noise"][m][None, :].astype(np.float32) if (use_noise and first) else None
+            engine.think_apply(pol, lg, val, noise)
+        assert engine.sims_done(0) == S + 1
+        r = engine.root(0)
+        k = int(case["move_num_children"][m])
+        assert r["num_children"] == k
+        assert r["root_count"] == case["root_count"][m] and r["root_mean"] == case["root_mean"][m] and r["root_value"] == case["root_value"][m]
+        assert np.array_equal(r["action"][:k], case["child_action"][m, :k])
+        for name in ("count", "mean", "policy", "logit", "noise", "value"):
+            got, want = r[name][:k], case["child_" + name][m, :k]
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"root child {name} differs after search {m}"
+        assert np.all(case["child_vloss"][m] == 0)
+        checked += 1
+        assert engine.play(0, int(case["move_action"][m])) == 1
+    return checked

@@ -30,6 +30,8 @@ extern "C" {
 static int g_opt_i[4] = {0, 0, 0, 16};
 static float g_opt_f[2] = {50.0f, 1.0f};
 static int g_opt_atari[2] = {0, 0}; // value_rescale, legal mask (Atari MuZero)
+static int g_think_k = 0; // actor_mcts_think_batch_size of the next hs_create (console think(), zero_actor.cpp:129-157); 0 / 1: off
+void hs_set_think(int k) { g_think_k = k; }
 void hs_set_atari_options(int value_rescale, int legal_mask) { g_opt_atari[0] = value_rescale, g_opt_atari[1] = legal_mask; }
 void hs_set_options(int muzero, int use_gumbel, int gumbel_noise, int m, float visit_c, float scale_c)
 {
@@ -62,6 +64,8 @@ sim* hs_create(int game, int N, int B, int S, float puct_base, float puct_init, 
         }
     }
     d.NP = 1 + (S + 1) * d.A;
+    d.think_k = (g_think_k > 1 ? g_think_k : 0);
+    const int K = (d.think_k ? d.think_k : 1); // lanes: sections of the per-leaf arrays
     d.slots = (N + 1) * (N + 1);
     d.max_hashes = 2 * N * N + 4;
     d.puct_init = puct_init, d.puct_base = puct_base, d.discount = discount, d.komi = komi, d.eps = eps, d.turn_key = 0;
@@ -76,7 +80,8 @@ sim* hs_create(int game, int N, int B, int S, float puct_base, float puct_init, 
     h->w.sel = zalloc<int32_t>(S + 2);
     h->w.lvl_h = zalloc<mz_hot>(S + 2);
     h->w.lvl_v = zalloc<mz_vis>(S + 2);
-    if (!getenv("HS_NO_VIS")) { s.vis = zalloc<mz_vis>(np); }
+    if (!getenv("HS_NO_VIS") && !d.think_k) { s.vis = zalloc<mz_vis>(np); }
+    if (d.think_k) { s.vloss = zalloc<float>(np), s.think_pending = zalloc<int32_t>(B); }
     h->w.q_warp = zalloc<float>(MZ_MAXA);
     s.spec_len = zalloc<int32_t>(B);
     s.gum_cand = zalloc<int32_t>((size_t)B * d.A), s.gum_meta = zalloc<int32_t>((size_t)B * 4);
@@ -84,17 +89,18 @@ sim* hs_create(int game, int N, int B, int S, float puct_base, float puct_init, 
     if (d.has_reward) { s.reward = zalloc<float>(np), s.nn_reward = zalloc<float>(B); }
     if (d.value_rescale) { s.vb_key = zalloc<float>((size_t)B * d.vb_cap), s.vb_cnt = zalloc<int32_t>((size_t)B * d.vb_cap), s.vb_n = zalloc<int32_t>(B); }
     if (game == MZ_GAME_ATARI) { s.at_meta = zalloc<int32_t>((size_t)B * 16); }
-    h->sqrt_table.resize(S + 2);
-    for (int n = 0; n < S + 2; ++n) { h->sqrt_table[n] = sqrt((double)n); }
+    h->sqrt_table.resize(S + 2 + K);
+    for (int n = 0; n < S + 2 + K; ++n) { h->sqrt_table[n] = sqrt((double)n); }
     s.sqrt_table = h->sqrt_table.data();
     s.root_st = zalloc<uint32_t>((size_t)B * 2 * MZ_ROWS), s.root_hist = zalloc<uint32_t>((size_t)B * MZ_HIST * 2 * MZ_ROWS);
     s.root_hash = zalloc<uint64_t>(B), s.root_meta = zalloc<int32_t>((size_t)B * 4), s.hashes = zalloc<uint64_t>((size_t)B * d.max_hashes);
-    s.path = zalloc<int32_t>((size_t)B * (S + 2)), s.path_len = zalloc<int32_t>(B), s.leaf_legal = zalloc<uint32_t>((size_t)B * MZ_LEGAL_WORDS);
-    s.leaf_meta = zalloc<int32_t>((size_t)B * 4), s.leaf_score = zalloc<float>(B);
-    s.nn_in = zalloc<uint16_t>((size_t)B * d.slots * MZ_NN_CPAD);
-    s.policy = zalloc<float>((size_t)B * d.A), s.logits = zalloc<float>((size_t)B * d.A), s.nn_value = zalloc<float>(B);
-    h->bias.resize(S + 2);
-    for (int n = 0; n < S + 2; ++n) {
+    const size_t KB = (size_t)K * B;
+    s.path = zalloc<int32_t>(KB * (S + 2)), s.path_len = zalloc<int32_t>(KB), s.leaf_legal = zalloc<uint32_t>(KB * MZ_LEGAL_WORDS);
+    s.leaf_meta = zalloc<int32_t>(KB * 4), s.leaf_score = zalloc<float>(KB);
+    s.nn_in = zalloc<uint16_t>(KB * d.slots * MZ_NN_CPAD);
+    s.policy = zalloc<float>(KB * d.A), s.logits = zalloc<float>(KB * d.A), s.nn_value = zalloc<float>(KB);
+    h->bias.resize(S + 2 + K); // a node's total under virtual loss reaches S + K
+    for (int n = 0; n < S + 2 + K; ++n) {
         float t = (float)(1 + n) + puct_base;
         t = t / puct_base;
         h->bias[n] = (float)((double)puct_init + log((double)t));
@@ -108,7 +114,7 @@ sim* hs_create(int game, int N, int B, int S, float puct_base, float puct_init, 
         h->keys[1 * 361 + pos] = gen();
     }
     s.puct_bias = h->bias.data(), s.keys = h->keys.data();
-    h->rot.assign(B, 0), h->noise.assign((size_t)B * d.A, 0.0f);
+    h->rot.assign(KB, 0), h->noise.assign((size_t)B * d.A, 0.0f);
     s.rotations = h->rot.data(), s.noise_in = nullptr;
     for (int g = 0; g < B; ++g) { mz_game_reset(d, s, g, &h->w, 0); }
     return h;
@@ -147,6 +153,47 @@ void hs_apply_mz(sim* h, const float* policy, const float* logits, const float* 
     if (noise) { memcpy(h->noise.data(), noise, sizeof(float) * (size_t)d.B * d.A); }
     h->s.noise_in = (noise ? h->noise.data() : nullptr);
     for (int g = 0; g < d.B; ++g) { mz_after_nn(d, h->s, g, &h->w, 0, 1); }
+}
+
+// one batched think() step (zero_actor.cpp:129-157), "before" half: K selections per tree, one after the other. rotations / features / path_len
+// are lane-major [K][B]; path_len: > 0 leaf to evaluate, < 0 duplicate of an earlier lane (-length), 0 lane beyond the simulations left
+void hs_think_select(sim* h, const uint8_t* rotations, float* features, int32_t* path_len)
+{
+    const mz_dims& d = h->d;
+    const int K = d.think_k, N = d.N;
+    for (int i = 0; i < K * d.B; ++i) { h->rot[i] = (rotations ? rotations[i] : 0); }
+    for (int g = 0; g < d.B; ++g) { h->s.think_pending[g] = 0; }
+    for (int k = 0; k < K; ++k) {
+        const mz_state v = mz_lane_view(d, h->s, k, d.B);
+        for (int g = 0; g < d.B; ++g) { mz_before_nn(d, v, g, &h->w, 0, 0, 1); }
+        for (int g = 0; g < d.B; ++g) {
+            const size_t l = (size_t)k * d.B + g;
+            path_len[l] = v.path_len[g];
+            if (!features || v.path_len[g] <= 0) { continue; }
+            for (int c = 0; c < d.C; ++c) {
+                for (int pos = 0; pos < N * N; ++pos) {
+                    uint16_t x = v.nn_in[((size_t)g * d.slots + (pos / N + 1) * (N + 1) + pos % N) * MZ_NN_CPAD + c];
+                    features[(l * d.C + c) * N * N + pos] = (x == MZ_HALF_ONE ? 1.0f : 0.0f);
+                }
+            }
+        }
+    }
+}
+
+// "after" half: the evaluated lanes' results are applied in selection order; policy / logits [K][B][A], value [K][B], noise [B][A] by root child index
+void hs_think_apply(sim* h, const float* policy, const float* logits, const float* value, const float* noise)
+{
+    const mz_dims& d = h->d;
+    const size_t KB = (size_t)d.think_k * d.B;
+    memcpy(h->s.policy, policy, sizeof(float) * KB * d.A);
+    memcpy(h->s.logits, logits, sizeof(float) * KB * d.A);
+    memcpy(h->s.nn_value, value, sizeof(float) * KB);
+    if (noise) { memcpy(h->noise.data(), noise, sizeof(float) * (size_t)d.B * d.A); }
+    h->s.noise_in = (noise ? h->noise.data() : nullptr);
+    for (int k = 0; k < d.think_k; ++k) {
+        const mz_state v = mz_lane_view(d, h->s, k, d.B);
+        for (int g = 0; g < d.B; ++g) { mz_after_nn(d, v, g, &h->w, 0, 1); }
+    }
 }
 
 int hs_path_len(sim* h, int g) { return h->s.path_len[g]; }

@@ -31,6 +31,9 @@ def load():
     lib.hs_set_options.argtypes = [i32, i32, i32, i32, f32, f32]
     lib.hs_set_atari_options.argtypes = [i32, i32]
     lib.hs_apply_mz.argtypes = [vp, f32p, f32p, f32p, f32p, f32p]
+    lib.hs_set_think.argtypes = [i32]
+    lib.hs_think_select.argtypes = [vp, u8p, f32p, i32p]
+    lib.hs_think_apply.argtypes = [vp, f32p, f32p, f32p, f32p]
     lib.hs_atari_observe.argtypes = [vp, i32, i32]
     lib.hs_root_extra.argtypes = [vp, i32, f32p, i32p]
     for fn in ("hs_leaf_action", "hs_leaf_parent_slot", "hs_path_hash", "hs_gumbel_best_action"):
@@ -48,7 +51,7 @@ def root_dict(A, out_i, out_f):
 
 class HostSimSearch:
     def __init__(self, lib, game, board_size, num_games, num_simulation, muzero=0, use_gumbel=0, gumbel_noise=0, gumbel_sample_size=16,
-                 gumbel_sigma_visit_c=50.0, gumbel_sigma_scale_c=1.0, value_rescale=0, reward_discount=1.0, atari_legal_mask=0b1111111101):
+                 gumbel_sigma_visit_c=50.0, gumbel_sigma_scale_c=1.0, value_rescale=0, reward_discount=1.0, atari_legal_mask=0b1111111101, think_k=0):
         self.lib = lib
         n = 3 if game == 0 else board_size
         self.A = 9 if game == 0 else (n * n if game in (4, 5) else n * n + 1)
@@ -58,6 +61,8 @@ class HostSimSearch:
         self.B, self.S = num_games, num_simulation
         lib.hs_set_options(muzero, use_gumbel, gumbel_noise, gumbel_sample_size, gumbel_sigma_visit_c, gumbel_sigma_scale_c)
         lib.hs_set_atari_options(value_rescale, atari_legal_mask)
+        lib.hs_set_think(think_k)
+        self.K = think_k
         self.h = lib.hs_create(game, n, num_games, num_simulation, 19652.0, 1.25, reward_discount, 7.5, 0.25)
         self.terminal = [False] * num_games
 
@@ -73,6 +78,21 @@ class HostSimSearch:
         nz = None if noise is None else np.ascontiguousarray(noise, np.float32)
         rw = None if reward is None else np.ascontiguousarray(reward, np.float32)
         self.lib.hs_apply_mz(self.h, fp(p), fp(l), fp(v), None if rw is None else fp(rw), None if nz is None else fp(nz))
+
+    def think_select(self, K, rotations=None):
+        assert K == self.K
+        feats = np.zeros((K, self.B, self.F), np.float32)
+        plen = np.zeros((K, self.B), np.int32)
+        rot = None if rotations is None else np.ascontiguousarray(rotations, np.uint8)
+        self.lib.hs_think_select(self.h, None if rot is None else rot.ctypes.data_as(C.POINTER(C.c_uint8)), feats.ctypes.data_as(C.POINTER(C.c_float)),
+                                 plen.ctypes.data_as(C.POINTER(C.c_int32)))
+        return feats, plen
+
+    def think_apply(self, policy, logits, value, noise=None):
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+        p, l, v = (np.ascontiguousarray(x, np.float32) for x in (policy, logits, value))
+        nz = None if noise is None else np.ascontiguousarray(noise, np.float32)
+        self.lib.hs_think_apply(self.h, fp(p), fp(l), fp(v), None if nz is None else fp(nz))
 
     def observe(self, g, action, frame, terminal=False):
         self.lib.hs_atari_observe(self.h, g, int(action))

@@ -69,6 +69,8 @@ def load():
     lib.mzo_env_eval_score.restype = C.c_float
     lib.mzo_env_eval_score.argtypes = [vp, i32]
     lib.mzo_apply_mz.argtypes = [vp, f32p, f32p, f32p, f32p, f32p]
+    lib.mzo_think_select.argtypes = [vp, i32, u8p, f32p, C.POINTER(C.c_int32)]
+    lib.mzo_think_apply.argtypes = [vp, f32p, f32p, f32p, f32p]
     lib.mzo_root_extra.argtypes = [vp, i32, f32p, C.POINTER(C.c_int32), f32p, f32p]
     lib.mzo_root_normalized_mean.restype = C.c_float
     lib.mzo_root_normalized_mean.argtypes = [vp, i32, i32]
@@ -123,6 +125,19 @@ class OracleSearch:
         nz = None if noise is None else np.ascontiguousarray(noise, np.float32)
         rw = None if reward is None else np.ascontiguousarray(reward, np.float32)
         self.lib.mzo_apply_mz(self.h, fptr(p), fptr(l), fptr(v), None if rw is None else fptr(rw), None if nz is None else fptr(nz))
+
+    def think_select(self, K, rotations=None):
+        """one batched think() step, selection half: lane-major (features [K][B][F], path_len [K][B])"""
+        feats = np.zeros((K, self.B, self.F), np.float32)
+        plen = np.zeros((K, self.B), np.int32)
+        rot = None if rotations is None else np.ascontiguousarray(rotations, np.uint8)
+        self.lib.mzo_think_select(self.h, K, None if rot is None else u8ptr(rot), fptr(feats), plen.ctypes.data_as(C.POINTER(C.c_int32)))
+        return feats, plen
+
+    def think_apply(self, policy, logits, value, noise=None):
+        p, l, v = (np.ascontiguousarray(x, np.float32) for x in (policy, logits, value))
+        nz = None if noise is None else np.ascontiguousarray(noise, np.float32)
+        self.lib.mzo_think_apply(self.h, fptr(p), fptr(l), fptr(v), None if nz is None else fptr(nz))
 
     def observe(self, g, action, frame, terminal=False):
         """Atari: the emulator's answer to `action` (action < 0: the initial screen after a reset), frame = uint8 [3][96][96]"""

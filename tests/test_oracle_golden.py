@@ -133,3 +133,16 @@ def test_oracle_env_matches_reference_playouts(oracle, name):
             eng.reset_game(0)
         assert eng.play(0, int(case["action"][i])) == 1
         assert score(eng) == case["score_after"][i], i
+
+
+THINK_CASES = {"think_ttt_s50_k4": (oracle_lib.GAME_TICTACTOE, 3), "think_go5_s60_k8": (oracle_lib.GAME_GO, 5), "think_go9_s100_k16_det": (oracle_lib.GAME_GO, 9),
+               "think_go5_s23_k5": (oracle_lib.GAME_GO, 5)}
+
+
+@pytest.mark.parametrize("name", list(THINK_CASES))
+def test_oracle_think_matches_reference_recording(oracle, name):
+    """console search (ZeroActor::think, actor_mcts_think_batch_size > 1): selection under virtual loss, duplicate leaves, short last batch"""
+    game, n = THINK_CASES[name]
+    case = golden_replay.load_case(name)
+    eng = oracle_lib.OracleSearch(oracle, game, n, 1, int(case["S"]), **oracle_lib.conf_overrides(case["conf"]))
+    assert golden_replay.replay_think(eng, case) == case["move_action"].size

@@ -79,3 +79,15 @@ def test_search_core_env_matches_reference_playouts(name, game, n):
     case = env_replay.load(name)
     eng = hostsim_lib.HostSimSearch(hostsim_lib.load(), game, n, 1, 1)
     assert env_replay.replay(eng, case, check_score=lambda e: e.last_score) == case["game"].size
+
+
+THINK_CASES = {"think_ttt_s50_k4": (0, 3), "think_go5_s60_k8": (1, 5), "think_go9_s100_k16_det": (1, 9), "think_go5_s23_k5": (1, 5)}
+
+
+@pytest.mark.parametrize("name", list(THINK_CASES))
+def test_search_core_think_matches_reference_recording(name):
+    """console search (ZeroActor::think with a selection batch): the lane views, virtual loss in selection, duplicates, slot bookkeeping"""
+    game, n = THINK_CASES[name]
+    case = golden_replay.load_case(name)
+    eng = hostsim_lib.HostSimSearch(hostsim_lib.load(), game, n, 1, int(case["S"]), think_k=int(case["K"]), **oracle_lib.conf_overrides(case["conf"]))
+    assert golden_replay.replay_think(eng, case, features_of_duplicates=False) == case["move_action"].size
