@@ -61,6 +61,12 @@ typedef struct {
     int32_t hex_swap_rule;       /* env_hex_use_swap_rule (reference default: true) */
     int32_t value_rescale;       /* actor_mcts_value_rescale: min-max normalised Q from the tree's value bounds (actor/mcts.cpp:43-49,219-228) */
     uint32_t atari_legal_mask;   /* MZ_GAME_ATARI: the game's minimal action set as a bit mask over the 18 actions (AtariEnv::isLegalAction, atari.h:57) */
+    int32_t think_batch_size;    /* actor_mcts_think_batch_size (config/configuration.cpp:106; 0 or 1: off). K > 1 is the console search, ZeroActor::think /
+                                  * ZeroActor::step (actor/zero_actor.cpp:36-49,129-157): every step selects K leaves of ONE tree one after the other under
+                                  * virtual loss (actor/mcts.h:33-34, mcts.cpp:51-61,185), evaluates the distinct ones together and applies them in selection
+                                  * order. num_games is then the number of trees; every per-game array of this API has num_games * K entries, lane-major
+                                  * (index lane * num_games + tree): rotations, features, path lengths and network outputs per lane, while roots / moves /
+                                  * noise use the first num_games entries (one per tree). AlphaZero networks with PUCT selection only. */
 } mz_config;
 
 /* Hyper-parameters the reference reads from the TorchScript module (network/network.cpp:30-41). */
@@ -157,6 +163,8 @@ int mz_replay_features(mz_engine* e, const int32_t* actions, int32_t max_len, co
 /* ZeroActor::beforeNNEvaluation for every game (actor/zero_actor.cpp:51-58). rotations [B] or NULL;
  * features_out [B][C*H*W] or NULL; path_len_out [B] or NULL */
 int mz_search_select(mz_engine* e, const uint8_t* rotations, float* features_out, int32_t* path_len_out);
+/* think mode: path_len_out per lane is > 0 for a leaf to evaluate, < 0 (-length) for a leaf an earlier lane of this step already selected
+ * (zero_actor.cpp:140-142: it is not evaluated again, its planes are not produced), 0 for a lane beyond the simulations left (:133-135) */
 /* ZeroActor::afterNNEvaluation for every game (actor/zero_actor.cpp:74-98). policy/logits [B][A], value [B],
  * noise [B][A] by root child index or NULL (Dirichlet values drawn by the host, utils/random.h:15-24) */
 int mz_search_apply(mz_engine* e, const float* policy, const float* logits, const float* value, const float* noise);
@@ -203,6 +211,8 @@ int mz_debug_tower_timing(mz_engine* e, uint64_t* out, int32_t max_ctas);
 int mz_conv_layers_per_launch(const mz_engine* e);
 /* kernels launched by this engine so far */
 int64_t mz_launch_count(const mz_engine* e);
+/* think mode: batched steps (network forwards) the last mz_search_run took to bring every tree to S + 1 simulations (zero_actor.cpp:39-44) */
+int mz_think_steps(const mz_engine* e);
 
 #ifdef __cplusplus
 }

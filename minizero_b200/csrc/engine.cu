@@ -304,6 +304,8 @@ struct mz_engine {
     CUtensorMap map_act_ext[3]; // same buffers, box = the resident block of conv3x3_resident_kernel
     CUtensorMap map_act_wide[3]; // same buffers, box = half of the wide tower's input block
     int tower_rot_override = -1; // MZ_TOWER_ROT (experiment builds)
+    int think_steps = 0;         // batched steps the last think() search took
+    int think_trees = 0;         // think mode (mz_config.think_batch_size > 1): number of trees; d.B = think_trees * d.think_k lanes
     bool tower_wide = false;    // conv_tower_wide_kernel (two row tiles per CTA) instead of conv_tower_kernel
     int rows_ext_wide = 0, tower_wide_stages = 8;
     // MuZero
@@ -708,6 +710,25 @@ int step(mz_engine* e, int flags, const uint8_t* rotations)
     mz_state s = e->s;
     s.rotations = rotations;
     s.noise_in = (e->noise_enabled ? e->d_noise : nullptr);
+    if (e->d.think_k) {
+        // one batched think() step (zero_actor.cpp:129-157): the lanes' results are applied in selection order, then K selections per tree are made
+        // one after the other (each leaves its virtual loss for the next); a pass is one launch over the trees with the lane's view of the state
+        const int trees = e->think_trees;
+        for (int phase = 0; phase < 2; ++phase) {
+            const int f = (phase == 0 ? STEP_AFTER : STEP_BEFORE);
+            if (!(flags & f)) { continue; }
+            if (phase == 1) {
+                CUDA_OK(cudaMemsetAsync(e->s.think_pending, 0, sizeof(int32_t) * trees, e->stream));
+                e->memsets++;
+            }
+            for (int k = 0; k < e->d.think_k; ++k) {
+                const mz_state v = mz_lane_view(e->d, s, k, trees);
+                k_step<<<trees, 32 * STEP_WARPS, step_smem_bytes(e->d), e->stream>>>(e->d, v, f);
+                e->launches++;
+            }
+        }
+        return MZ_OK;
+    }
     k_step<<<e->d.B, 32 * STEP_WARPS, step_smem_bytes(e->d), e->stream>>>(e->d, s, flags);
     e->launches++;
     return MZ_OK;
@@ -1266,6 +1287,16 @@ int mz_create(const mz_config* cfg, mz_engine** out)
         }
     }
     d.S = cfg->num_simulation, d.B = cfg->num_games;
+    // console think() with a selection batch (zero_actor.cpp:129-157): K lanes per tree. Every array is sized for trees x K "games"; the trees use the
+    // first `trees` entries of the per-tree arrays, the lanes the sections of the per-leaf arrays (mz_lane_view), the network sees trees x K positions
+    const int think_k = (cfg->think_batch_size > 1 ? cfg->think_batch_size : 0);
+    if (think_k) {
+        if (cfg->muzero || cfg->use_gumbel || atari || cfg->value_rescale) {
+            delete e;
+            return fail(MZ_ERR_ARG, "think_batch_size > 1 is built for AlphaZero networks with PUCT selection (no MuZero / Gumbel / value rescale)");
+        }
+        d.think_k = think_k, e->think_trees = cfg->num_games, d.B = cfg->num_games * think_k;
+    }
     d.NP = 1 + (d.S + 1) * d.A; // actor_group.cpp:183, tree.h:66
     d.vb_cap = d.S + 2;
     if (d.NP >= (1 << MZ_LINK_SHIFT)) {
@@ -1287,8 +1318,8 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     }
     d.turn_key = (cfg->ko_situational ? turn_key : 0);
     // puct_bias[n] = (float)(init + log((1 + n + base) / base)) with the reference's float / double mix (mcts.cpp:57)
-    std::vector<float> bias(d.S + 2);
-    for (int n = 0; n < d.S + 2; ++n) {
+    std::vector<float> bias(d.S + 2 + think_k); // under virtual loss a node's total reaches S + K
+    for (int n = 0; n < d.S + 2 + think_k; ++n) {
         float t = static_cast<float>(1 + n) + cfg->puct_base;
         t = t / cfg->puct_base;
         bias[n] = static_cast<float>(static_cast<double>(cfg->puct_init) + std::log(static_cast<double>(t)));
@@ -1309,7 +1340,8 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     guard(e->dalloc(&s.hot, np)), guard(e->dalloc(&s.action, np)), guard(e->dalloc(&s.logit, np)), guard(e->dalloc(&s.value, np));
     guard(e->dalloc(&s.root_noise, BA)), guard(e->dalloc(&s.cursor, B));
     guard(e->dalloc(&s.last_child, np));
-    if (!knob("MZ_NO_VIS")) { guard(e->dalloc(&s.vis, np)); } // MZ_NO_VIS=1: selection always scans (A/B timing of the visited lists)
+    if (!knob("MZ_NO_VIS") && !think_k) { guard(e->dalloc(&s.vis, np)); } // MZ_NO_VIS=1: selection always scans (A/B timing of the visited lists)
+    if (think_k) { guard(e->dalloc(&s.vloss, np)), guard(e->dalloc(&s.think_pending, B)); }
     guard(e->dalloc(&s.node_slot, np)), guard(e->dalloc(&s.slot_st, B * (d.S + 1) * 2 * N)), guard(e->dalloc(&s.slot_hash, B * (d.S + 1)));
     guard(e->dalloc(&s.slot_meta, B * (d.S + 1) * 4));
     guard(e->dalloc(&s.root_st, B * 2 * MZ_ROWS)), guard(e->dalloc(&s.root_hist, B * MZ_HIST * 2 * MZ_ROWS)), guard(e->dalloc(&s.root_hash, B));
@@ -1415,6 +1447,7 @@ void mz_destroy(mz_engine* e)
 int mz_action_size(const mz_engine* e) { return e ? e->d.A : MZ_ERR_ARG; }
 int mz_num_features(const mz_engine* e) { return e ? (e->atari ? mzat::PLANES * mzat::RES * mzat::RES : e->d.C * e->d.N * e->d.N) : MZ_ERR_ARG; }
 int64_t mz_launch_count(const mz_engine* e) { return e ? e->launches : 0; }
+int mz_think_steps(const mz_engine* e) { return e ? e->think_steps : MZ_ERR_ARG; }
 int mz_conv_layers_per_launch(const mz_engine* e) { return (e && e->net_ready) ? (e->conv_mode == 3 ? static_cast<int>(e->tw[0].convs.size()) : 1) : MZ_ERR_STATE; }
 
 int mz_net_configure(mz_engine* e, const mz_net_dims* dims)
@@ -1963,6 +1996,33 @@ int mz_search_run(mz_engine* e, int32_t num_evals, float* device_ms)
     if (num_evals <= 0) { num_evals = d.S + 1; }
     if (num_evals > d.S + 1) { return fail(MZ_ERR_ARG, "num_evals exceeds actor_num_simulation + 1"); }
     if (e->cfg.muzero && num_evals != d.S + 1) { return fail(MZ_ERR_ARG, "a muzero search runs whole (the first evaluation is the initial inference): num_evals must be 0 or S + 1"); }
+    if (d.think_k) {
+        // ZeroActor::think (zero_actor.cpp:36-49): batched steps until every tree holds S + 1 simulations. How many steps that takes depends on how many
+        // selections of a step hit the same leaf, so the loop is driven from the host (the console path: one tree, a handful of steps per second of
+        // thinking time) instead of being captured whole; a step evaluates at least one new leaf per unfinished tree, so S + 1 steps always suffice
+        if (num_evals != d.S + 1) { return fail(MZ_ERR_ARG, "a think() search runs whole: num_evals must be 0 or S + 1"); }
+        const int trees = e->think_trees;
+        std::vector<float> counts(trees);
+        CUDA_OK(cudaEventRecord(e->ev0, e->stream));
+        e->think_steps = 0;
+        for (int c = 0; c <= d.S; ++c) {
+            int rc = step(e, STEP_BEFORE, e->rot_enabled ? e->d_rot_all + static_cast<size_t>(c) * d.B : nullptr);
+            if (!rc) { rc = forward(e, 0, true); }
+            if (!rc) { rc = step(e, STEP_AFTER, nullptr); }
+            if (rc) { return rc; }
+            ++e->think_steps;
+            CUDA_OK(cudaMemcpy2DAsync(counts.data(), sizeof(float), e->s.hot, sizeof(mz_hot) * d.NP, sizeof(float), trees, cudaMemcpyDeviceToHost, e->stream));
+            CUDA_OK(cudaStreamSynchronize(e->stream));
+            bool all_done = true;
+            for (int g = 0; g < trees; ++g) { all_done = all_done && (counts[g] >= static_cast<float>(d.S + 1)); }
+            if (all_done) { break; }
+        }
+        CUDA_OK(cudaEventRecord(e->ev1, e->stream));
+        CUDA_OK(cudaStreamSynchronize(e->stream));
+        CUDA_OK(cudaGetLastError());
+        if (device_ms) { CUDA_OK(cudaEventElapsedTime(device_ms, e->ev0, e->ev1)); }
+        return MZ_OK;
+    }
     const int key = num_evals * 4 + (e->noise_enabled ? 2 : 0) + (e->rot_enabled ? 1 : 0);
     auto it = e->graphs.find(key);
     if (it == e->graphs.end()) {

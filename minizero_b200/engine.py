@@ -28,7 +28,7 @@ class _Config(C.Structure):
                 ("dirichlet_epsilon", C.c_float), ("muzero", C.c_int32), ("use_gumbel", C.c_int32), ("gumbel_noise", C.c_int32),
                 ("gumbel_sample_size", C.c_int32), ("gumbel_sigma_visit_c", C.c_float), ("gumbel_sigma_scale_c", C.c_float),
                 ("gomoku_exactly_five", C.c_int32), ("gomoku_outer_open", C.c_int32), ("hex_swap_rule", C.c_int32), ("value_rescale", C.c_int32),
-                ("atari_legal_mask", C.c_uint32)]
+                ("atari_legal_mask", C.c_uint32), ("think_batch_size", C.c_int32)]
 
 
 class _NetDims(C.Structure):
@@ -114,6 +114,7 @@ def _load():
     lib.mz_debug_tree_timing.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.mz_debug_tower_timing.argtypes = [vp, C.POINTER(C.c_uint64), i32]
     lib.mz_conv_layers_per_launch.argtypes = [vp]
+    lib.mz_think_steps.argtypes = [vp]
     lib.mz_launch_count.argtypes = [vp]
     lib.mz_launch_count.restype = C.c_int64
     _lib = lib
@@ -124,7 +125,7 @@ EXPORTS = ["mz_create", "mz_destroy", "mz_last_error", "mz_action_size", "mz_num
            "mz_net_blob", "mz_net_finalize_empty", "mz_eval_batch", "mz_reset_game", "mz_play", "mz_get_roots", "mz_search_select", "mz_search_apply",
            "mz_search_set_inputs", "mz_search_run", "mz_profile_kernels", "mz_launch_count", "mz_play_max_count", "mz_sync", "mz_timer_begin", "mz_timer_end", "mz_debug_tree_timing", "mz_debug_tower_timing", "mz_conv_layers_per_launch",
            "mz_eval_initial", "mz_eval_recurrent", "mz_search_leaf", "mz_gumbel_best_actions", "mz_eval_rewards", "mz_atari_observe", "mz_get_root_rewards",
-           "mz_search_apply_reward", "mz_replay_features"]
+           "mz_search_apply_reward", "mz_replay_features", "mz_think_steps"]
 
 
 def _fp(a):
@@ -145,11 +146,11 @@ class Engine:
     def __init__(self, game, board_size, num_games, num_simulation, device=0, puct_base=19652.0, puct_init=1.25, reward_discount=1.0, komi=7.5,
                  ko_situational=False, dirichlet_epsilon=0.25, muzero=0, use_gumbel=0, gumbel_noise=0, gumbel_sample_size=16, gumbel_sigma_visit_c=50.0,
                  gumbel_sigma_scale_c=1.0, gomoku_exactly_five=True, gomoku_outer_open=False, hex_swap_rule=True, value_rescale=0,
-                 atari_legal_mask=0b1111111101):
+                 atari_legal_mask=0b1111111101, think_batch_size=0):
         self.lib = _load()
         cfg = _Config(device, game, board_size, num_games, num_simulation, puct_base, puct_init, reward_discount, komi, int(ko_situational), dirichlet_epsilon,
                       int(muzero), int(use_gumbel), int(gumbel_noise), int(gumbel_sample_size), gumbel_sigma_visit_c, gumbel_sigma_scale_c,
-                      int(gomoku_exactly_five), int(gomoku_outer_open), int(hex_swap_rule), int(value_rescale), int(atari_legal_mask))
+                      int(gomoku_exactly_five), int(gomoku_outer_open), int(hex_swap_rule), int(value_rescale), int(atari_legal_mask), int(think_batch_size))
         self.muzero = bool(muzero)
         self.atari = (game == GAME_ATARI)
         self.game, self.board_size = game, (3 if game == GAME_TICTACTOE else (6 if game == GAME_ATARI else board_size))
@@ -157,7 +158,10 @@ class Engine:
         self.h = None
         self._check(self.lib.mz_create(C.byref(cfg), C.byref(h)))
         self.h = h
-        self.B, self.S = num_games, num_simulation
+        # console think() (think_batch_size = K > 1): num_games trees, K lanes each; every per-game array of the C ABI has trees * K entries, lane-major
+        self.K = int(think_batch_size) if think_batch_size > 1 else 0
+        self.trees = num_games
+        self.B, self.S = num_games * max(1, self.K), num_simulation
         self.A = self.lib.mz_action_size(self.h)
         self.F = self.lib.mz_num_features(self.h)
         self.terminal = [False] * num_games
@@ -276,6 +280,22 @@ class Engine:
         self._roots = None
         self._leaf = None
         return feats
+
+    def think_select(self, K, rotations=None):
+        """selection half of one batched think() step: (planes [K][trees][F], path_len [K][trees]); path_len > 0: evaluate, < 0: duplicate leaf, 0: unused lane"""
+        assert K == self.K
+        feats = self.select(rotations)
+        return feats.reshape(K, self.trees, self.F), self._path_len.reshape(K, self.trees).copy()
+
+    def think_apply(self, policy, logits, value, noise=None):
+        nz = None
+        if noise is not None:
+            nz = np.zeros((self.B, self.A), np.float32)
+            nz[:self.trees] = noise
+        self.apply(np.asarray(policy).reshape(self.B, self.A), np.asarray(logits).reshape(self.B, self.A), np.asarray(value).reshape(self.B), nz)
+
+    def think_steps(self):
+        return int(self.lib.mz_think_steps(self.h))
 
     def _leaf_info(self):
         if getattr(self, "_leaf", None) is None:
