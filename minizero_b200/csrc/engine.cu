@@ -78,8 +78,7 @@ __global__ void __launch_bounds__(32 * STEP_WARPS, 2) k_step(const mz_dims d, co
 __global__ void __launch_bounds__(32) k_reset(const mz_dims d, const mz_state s, const int only_game)
 {
     __shared__ mz_scratch w;
-    const int g = blockIdx.x, lane = threadIdx.x;
-    if (only_game >= 0 && g != only_game) { return; }
+    const int g = (only_game >= 0 ? only_game : static_cast<int>(blockIdx.x)), lane = threadIdx.x; // one game: a grid of one block
     mz_game_reset(d, s, g, &w, lane);
 }
 
@@ -1810,9 +1809,9 @@ int mz_reset_game(mz_engine* e, int32_t g)
 {
     if (!e || g >= e->d.B) { return fail(MZ_ERR_ARG, "bad argument"); }
     CUDA_OK(cudaSetDevice(e->cfg.device));
-    k_reset<<<e->d.B, 32, 0, e->stream>>>(e->d, e->s, g);
+    // stream-ordered like everything else of the engine: several games ending on the same move cost one small launch each and no host round trip
+    k_reset<<<(g >= 0 ? 1 : e->d.B), 32, 0, e->stream>>>(e->d, e->s, g);
     e->launches++;
-    CUDA_OK(cudaStreamSynchronize(e->stream));
     CUDA_OK(cudaGetLastError());
     return MZ_OK;
 }

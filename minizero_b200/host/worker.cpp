@@ -1,6 +1,7 @@
 #include "worker.h"
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
@@ -20,6 +21,8 @@ Worker::~Worker()
 }
 
 // ---- start-up: createNeuralNetworks + createActors (actor_group.cpp:150-187) ---------------------------------
+thread_local Random* Worker::tl_rng_ = nullptr;
+
 bool Worker::initialize()
 {
     const std::string model = cfg_.getString("nn_file_name");
@@ -122,7 +125,7 @@ void Worker::startGames()
     games_.assign(num_games_, Game());
     next_seed_.assign(num_games_, 0);
     for (int g = 0; g < num_games_; ++g) {
-        if (atari_) { (void)rng_.randInt(); } // the actor's AtariEnv member resets itself when it is constructed (atari.h:45-49): one seed drawn and dropped
+        if (atari_) { (void)rng().randInt(); } // the actor's AtariEnv member resets itself when it is constructed (atari.h:45-49): one seed drawn and dropped
         resetGameHost(g);
     }
     if (atari_) { // the first screens
@@ -138,13 +141,13 @@ void Worker::startGames()
         }
     }
     // slave thread 0 re-seeds: program_seed + thread id, or a random device (actor_group.cpp:66-70)
-    rng_.seed(cfg_.getBool("program_auto_seed") ? static_cast<int>(std::random_device()()) : cfg_.getInt("program_seed") + 0);
+    rng().seed(cfg_.getBool("program_auto_seed") ? static_cast<int>(std::random_device()()) : cfg_.getInt("program_seed") + 0);
     // first beforeNNEvaluation of every game: rotation draw of cycle 0 (zero_actor.cpp:56)
     const bool random_rotation = cfg_.getBool("actor_use_random_rotation_features") && !muzero_; // only the AlphaZero branch draws one (zero_actor.cpp:54-57)
     const int ne = static_cast<int>(engine_games_.size());
     for (int g = 0; g < num_games_; ++g) {
         const int e = g % ne, slot = g / ne;
-        rotations_[e][slot] = (random_rotation ? static_cast<uint8_t>(rng_.randInt() % 8) : 0);
+        rotations_[e][slot] = (random_rotation ? static_cast<uint8_t>(rng().randInt() % 8) : 0);
     }
 }
 
@@ -156,8 +159,8 @@ void Worker::resetGameHost(int g)
     game.num_legal = initialNumLegal();
     std::fill(game.ttt, game.ttt + 9, 0);
     game.stones.assign((game_type_ == MZ_GAME_NOGO || game_type_ == MZ_GAME_GOMOKU || game_type_ == MZ_GAME_HEX) ? board_ * board_ : 0, 0);
-    if (atari_) { atariReset(game, rng_.randInt()); } // BaseActor::reset -> AtariEnv::reset() draws the emulator seed (atari.h:54) before the resign switch
-    game.enable_resign = (rng_.randReal() < cfg_.getFloat("zero_disable_resign_ratio") ? false : true);
+    if (atari_) { atariReset(game, rng().randInt()); } // BaseActor::reset -> AtariEnv::reset() draws the emulator seed (atari.h:54) before the resign switch
+    game.enable_resign = (rng().randReal() < cfg_.getFloat("zero_disable_resign_ratio") ? false : true);
 }
 
 namespace {
@@ -271,6 +274,12 @@ void Worker::handleCommands()
             std::cerr << "[command] " << command << std::endl;
             for (int g = 0; g < num_games_; ++g) { resetGameHost(g); }
             for (mz_engine* e : engines_) { mz_reset_game(e, -1); }
+            {   // every actor's next beforeNNEvaluation draws the rotation of cycle 0 afresh (zero_actor.cpp:56), in actor order. (The reference draws
+                // the resign switches above on its main-thread generator and these on the slave threads'; here both come from the calling thread's.)
+                const bool random_rotation = cfg_.getBool("actor_use_random_rotation_features") && !muzero_;
+                const int ne = static_cast<int>(engine_games_.size());
+                for (int g = 0; g < num_games_; ++g) { rotations_[g % ne][g / ne] = (random_rotation ? static_cast<uint8_t>(rng().randInt() % 8) : 0); }
+            }
         } else if (prefix == "load_model") {
             std::cerr << "[command] " << command << std::endl;
             if (command.find(" ") != std::string::npos && !loadModel(command.substr(command.find(" ") + 1))) { std::exit(0); }
@@ -283,9 +292,17 @@ void Worker::handleCommands()
                                                 "env_go_komi", "env_go_ko_rule", "env_gomoku_rule", "env_gomoku_exactly_five_stones", "env_hex_use_swap_rule"};
             std::vector<std::string> before;
             for (const char* k : fixed) { before.push_back(cfg_.getString(k)); }
+            // the engines were told at start-up whether root noise goes to the logits (Gumbel) or to the priors (Dirichlet): with Gumbel noise
+            // configured, the Dirichlet switch decides that and is fixed too
+            const bool noise_kind_fixed = cfg_.getBool("actor_use_gumbel_noise");
+            const std::string dirichlet_before = cfg_.getString("actor_use_dirichlet_noise");
             if (command.find(" ") == std::string::npos || !cfg_.loadFromString(command.substr(command.find(" ") + 1))) {
                 std::cerr << "Failed to load configuration string." << std::endl;
                 std::exit(0);
+            }
+            if (noise_kind_fixed && cfg_.getString("actor_use_dirichlet_noise") != dirichlet_before) {
+                std::cerr << "[warning] actor_use_dirichlet_noise is fixed when the worker starts with actor_use_gumbel_noise; the running engines keep " << dirichlet_before << std::endl;
+                cfg_.set("actor_use_dirichlet_noise", dirichlet_before);
             }
             for (size_t i = 0; i < before.size(); ++i) {
                 if (cfg_.getString(fixed[i]) != before[i]) {
@@ -351,7 +368,7 @@ int Worker::decideAction(int g, const RootView& r, bool& resign, int& child_inde
             float mean = (counts[i] == 0 ? 0.0f / 0.0f : normalizedMean(r, i, child_player));
             if (count == 0 || (mean < best_mean - value_threshold)) { continue; }
             sum += count;
-            float rand = rng_.randReal(sum);
+            float rand = rng().randReal(sum);
             if (selected == -1 || rand < count) { selected = i; }
         }
     }
@@ -476,6 +493,7 @@ void Worker::emitGame(int g, bool terminal, float eval_score)
     if (atari_) { at.observations = &games_[g].observations, at.lives_history = &games_[g].lives_history, at.seed = games_[g].seed, at.total_reward = games_[g].total_reward; }
     const std::string line = selfPlayLine(header_, games_[g].moves, terminal, eval_score, games_[g].turn, sequenceConfig(), atari_ ? &at : nullptr);
     const std::string out = line + "\n"; // the only thing this process ever writes to the server (zero_server.cpp:111-139)
+    std::lock_guard<std::mutex> lock(emit_mutex_); // engine threads share the wire
     size_t done = 0;
     while (done < out.size()) {
         const ssize_t n = write(wire_fd_, out.data() + done, out.size() - done);
@@ -490,7 +508,7 @@ void Worker::emitGame(int g, bool terminal, float eval_score)
 
 // (1) randomness of cycles 1 .. S of one search in the reference's per-cycle, per-actor order: in cycle 1
 //     every actor first receives its root noise (afterNNEvaluation of the root) and then draws the rotation of its next leaf
-void Worker::drawSearchRandomness()
+void Worker::drawSearchRandomness(int e0, int e1)
 {
     const int ne = static_cast<int>(engine_games_.size()), S1 = sims_ + 1, A = actions_;
     const bool use_dirichlet = cfg_.getBool("actor_use_dirichlet_noise"), use_gumbel_noise = (!use_dirichlet && cfg_.getBool("actor_use_gumbel_noise"));
@@ -499,13 +517,14 @@ void Worker::drawSearchRandomness()
     for (int c = 1; c < S1; ++c) {
         for (int g = 0; g < num_games_; ++g) {
             const int e = g % ne, slot = g / ne;
+            if (e < e0 || e >= e1) { continue; }
             if (c == 1 && use_noise) {
-                std::vector<float> dir = (use_dirichlet ? rng_.randDirichlet(alpha, games_[g].num_legal) : rng_.randGumbel(games_[g].num_legal)); // zero_actor.cpp:194-213
+                std::vector<float> dir = (use_dirichlet ? rng().randDirichlet(alpha, games_[g].num_legal) : rng().randGumbel(games_[g].num_legal)); // zero_actor.cpp:194-213
                 float* dst = noise_[e].data() + static_cast<size_t>(slot) * A;
                 std::fill(dst, dst + A, 0.0f);
                 std::copy(dir.begin(), dir.end(), dst);
             }
-            rotations_[e][static_cast<size_t>(c) * engine_games_[e] + slot] = (random_rotation ? static_cast<uint8_t>(rng_.randInt() % 8) : 0);
+            rotations_[e][static_cast<size_t>(c) * engine_games_[e] + slot] = (random_rotation ? static_cast<uint8_t>(rng().randInt() % 8) : 0);
         }
     }
 }
@@ -578,10 +597,10 @@ int Worker::advanceGame(int g, const RootView& r, bool& resign, bool& end)
     // actor->reset() draws the resign switch of the next game (zero_actor.cpp:26); the deferred state reset must not consume
     // randomness, so only the draw happens here, in order
     if (end) {
-        if (atari_) { next_seed_[g] = rng_.randInt(); } // AtariEnv::reset() of the next game (atari.h:54), before the resign switch
-        game.enable_resign = (rng_.randReal() < cfg_.getFloat("zero_disable_resign_ratio") ? false : true);
+        if (atari_) { next_seed_[g] = rng().randInt(); } // AtariEnv::reset() of the next game (atari.h:54), before the resign switch
+        game.enable_resign = (rng().randReal() < cfg_.getFloat("zero_disable_resign_ratio") ? false : true);
     }
-    rotations_[e][slot] = (random_rotation ? static_cast<uint8_t>(rng_.randInt() % 8) : 0); // cycle 0 of the next search
+    rotations_[e][slot] = (random_rotation ? static_cast<uint8_t>(rng().randInt() % 8) : 0); // cycle 0 of the next search
     return play;
 }
 
@@ -598,17 +617,19 @@ void Worker::restartGameHost(int g)
 }
 
 // ---- one move for every game ------------------------------------------------------------------------------------------
-bool Worker::playOneMove()
+// engines e0 .. e1-1 and their games: the whole worker from the main thread (zero_num_threads = 1: the reference's single-thread draw order, seed-exact),
+// or one engine from its own host thread (run(): the engines then never wait for each other or for another engine's host work)
+bool Worker::playOneMove(int e0, int e1)
 {
     const int ne = static_cast<int>(engines_.size()), A = actions_;
     const bool use_dirichlet = cfg_.getBool("actor_use_dirichlet_noise"), use_gumbel_noise = (!use_dirichlet && cfg_.getBool("actor_use_gumbel_noise"));
     const bool use_noise = use_dirichlet || use_gumbel_noise, random_rotation = cfg_.getBool("actor_use_random_rotation_features") && !muzero_;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
-    drawSearchRandomness(); // (1)
+    drawSearchRandomness(e0, e1); // (1)
     const double t1 = now();
     // (2) the whole search on the devices, all engines in flight together
-    for (int e = 0; e < ne; ++e) {
+    for (int e = e0; e < e1; ++e) {
         if (mz_search_set_inputs(engines_[e], random_rotation ? rotations_[e].data() : nullptr, use_noise ? noise_[e].data() : nullptr) != MZ_OK ||
             mz_search_run(engines_[e], 0, nullptr) != MZ_OK) {
             std::cerr << "search failed: " << mz_last_error() << std::endl;
@@ -624,7 +645,7 @@ bool Worker::playOneMove()
     };
     const bool rescale = cfg_.getBool("actor_mcts_value_rescale");
     std::vector<Roots> roots(ne);
-    for (int e = 0; e < ne; ++e) {
+    for (int e = e0; e < e1; ++e) {
         const size_t n = engine_games_[e];
         roots[e].info.resize(n), roots[e].action.resize(n * A), roots[e].count.resize(n * A), roots[e].mean.resize(n * A);
         if (gumbel_) { roots[e].policy.resize(n * A), roots[e].logit.resize(n * A), roots[e].noise.resize(n * A), roots[e].gumbel_best.resize(n); }
@@ -648,11 +669,12 @@ bool Worker::playOneMove()
     const double t2 = now();
     // (4) per actor, in order: decide, act or resign, restart finished games, draw the first rotation of the next search
     std::vector<std::vector<int32_t>> play(ne);
-    for (int e = 0; e < ne; ++e) { play[e].assign(engine_games_[e], -1); }
+    for (int e = e0; e < e1; ++e) { play[e].assign(engine_games_[e], -1); }
     std::vector<int> ended; // games to emit after the devices have applied the moves (the final score comes from there)
     std::vector<char> ended_by_resign(num_games_, 0);
     for (int g = 0; g < num_games_; ++g) {
         const int e = g % ne, slot = g / ne;
+        if (e < e0 || e >= e1) { continue; }
         const mz_root_info& ri = roots[e].info[slot];
         RootView r;
         r.num_children = ri.num_children, r.root_mean = ri.mean, r.root_value = ri.value;
@@ -676,7 +698,7 @@ bool Worker::playOneMove()
     const double t3 = now();
     // (5) apply the moves on the devices; finished games are emitted with the device's score and restarted
     std::vector<std::vector<mz_play_result>> res(ne);
-    for (int e = 0; e < ne; ++e) {
+    for (int e = e0; e < e1; ++e) {
         res[e].resize(engine_games_[e]);
         if (mz_play(engines_[e], play[e].data(), res[e].data()) != MZ_OK) {
             std::cerr << "mz_play failed: " << mz_last_error() << std::endl;
@@ -685,6 +707,7 @@ bool Worker::playOneMove()
     }
     for (int g = 0; g < num_games_; ++g) {
         const int e = g % ne, slot = g / ne;
+        if (e < e0 || e >= e1) { continue; }
         if (play[e][slot] >= 0) {
             if (!res[e][slot].applied) {
                 std::cerr << "device rejected action " << play[e][slot] << " of game " << g << std::endl;
@@ -694,7 +717,7 @@ bool Worker::playOneMove()
         }
     }
     if (atari_) { // the emulator's answers join the observation histories on the devices (AtariEnv::act's history update)
-        for (int e = 0; e < ne; ++e) {
+        for (int e = e0; e < e1; ++e) {
             std::vector<int32_t> acts(engine_games_[e], -2);
             std::vector<uint8_t> frames(static_cast<size_t>(engine_games_[e]) * 3 * 96 * 96);
             for (int slot = 0; slot < engine_games_[e]; ++slot) {
@@ -716,10 +739,14 @@ bool Worker::playOneMove()
         const SequenceConfig seq = sequenceConfig();
         for (int g = 0; g < num_games_ && seq.sequence_length > 0; ++g) {
             const int e = g % ne, slot = g / ne;
+            if (e < e0 || e >= e1) { continue; }
             if (play[e][slot] < 0 || std::find(ended.begin(), ended.end(), g) != ended.end()) { continue; }
             if (!intermediateSequenceDue(static_cast<int>(games_[g].moves.size()), seq)) { continue; }
             emitGame(g, false, 0.0f);
-            --games_finished_;
+            {
+                std::lock_guard<std::mutex> lock(emit_mutex_);
+                --games_finished_;
+            }
             clearSentActionInfo(games_[g].moves, false, seq);
         }
     }
@@ -737,7 +764,7 @@ bool Worker::playOneMove()
         games_[g].enable_resign = keep_resign;
     }
     if (atari_ && !ended.empty()) { // first screens of the restarted episodes
-        for (int e = 0; e < ne; ++e) {
+        for (int e = e0; e < e1; ++e) {
             std::vector<int32_t> acts(engine_games_[e], -2);
             std::vector<uint8_t> frames(static_cast<size_t>(engine_games_[e]) * 3 * 96 * 96);
             bool any = false;
@@ -754,8 +781,11 @@ bool Worker::playOneMove()
             }
         }
     }
-    ++moves_played_;
-    t_draw_ += t1 - t0, t_search_ += t2 - t1, t_decide_ += t3 - t2, t_play_ += t4 - t3, t_emit_ += now() - t4;
+    {
+        std::lock_guard<std::mutex> lock(stat_mutex_);
+        moves_played_ += e1 - e0; // engine moves: one search of one engine's games
+        t_draw_ += t1 - t0, t_search_ += t2 - t1, t_decide_ += t3 - t2, t_play_ += t4 - t3, t_emit_ += now() - t4;
+    }
     return true;
 }
 
@@ -780,7 +810,7 @@ int Worker::rngTest(std::istream& in)
     engine_games_.assign(1, num_games_);
     rotations_.assign(1, std::vector<uint8_t>(static_cast<size_t>(sims_ + 1) * num_games_, 0));
     noise_.assign(1, std::vector<float>(static_cast<size_t>(num_games_) * actions_, 0.0f));
-    rng_.seed(cfg_.getInt("program_seed")); // main thread generator (console/mode_handler.cpp:62)
+    rng().seed(cfg_.getInt("program_seed")); // main thread generator (console/mode_handler.cpp:62)
     startGames();
     const int A = actions_;
     long cycle = 0;
@@ -828,7 +858,7 @@ int Worker::rngTest(std::istream& in)
         }
         if (!ok) { break; }
         for (int g = 0; g < num_games_; ++g) { std::cout << "rot " << cycle << " " << g << " " << static_cast<int>(rotations_[0][g]) << "\n"; }
-        drawSearchRandomness();
+        drawSearchRandomness(0, static_cast<int>(engine_games_.size()));
         for (int c = 1; c <= sims_; ++c) {
             for (int g = 0; g < num_games_; ++g) { std::cout << "rot " << cycle + c << " " << g << " " << static_cast<int>(rotations_[0][static_cast<size_t>(c) * num_games_ + g]) << "\n"; }
         }
@@ -871,8 +901,10 @@ int Worker::rngTest(std::istream& in)
 int Worker::run()
 {
     // main thread generator: program_seed (console/mode_handler.cpp:62)
-    rng_.seed(cfg_.getInt("program_seed"));
+    rng().seed(cfg_.getInt("program_seed"));
     if (!initialize()) { return -1; }
+    const int ne = static_cast<int>(engines_.size());
+    if (ne > 1 && cfg_.getInt("zero_num_threads") > 1) { return runThreaded(); }
     while (!quit_) {
         handleCommands();
         if (quit_) { break; }
@@ -880,14 +912,92 @@ int Worker::run()
             std::this_thread::sleep_for(std::chrono::milliseconds(1));
             continue;
         }
-        if (!playOneMove()) { return -1; }
+        if (!playOneMove(0, ne)) { return -1; }
     }
-    if (moves_played_ > 0) {
+    reportTiming();
+    return 0;
+}
+
+// One host thread per engine (GPU), like the reference's slave threads (actor_group.cpp:66-70,81-134): each draws from its own generator seeded
+// with program_seed + thread id, searches, decides and records its own games, and shares nothing with the others but the wire. The reference hands
+// actors to its threads through a shared counter, so its draw order is not reproducible with more than one thread either; seed-exact runs use
+// zero_num_threads = 1 (the loop in run()). Commands are executed by the main thread while every engine thread is parked between two moves.
+int Worker::runThreaded()
+{
+    const int ne = static_cast<int>(engines_.size());
+    engine_rng_.assign(ne, Random());
+    for (int e = 0; e < ne; ++e) { engine_rng_[e].seed(cfg_.getBool("program_auto_seed") ? static_cast<int>(std::random_device()()) : cfg_.getInt("program_seed") + e); }
+    std::mutex ctl;
+    std::condition_variable cv;
+    int parked = 0;
+    bool pause = true, failed = false;
+    std::vector<std::thread> threads;
+    for (int e = 0; e < ne; ++e) {
+        threads.emplace_back([&, e] {
+            tl_rng_ = &engine_rng_[e];
+            for (;;) {
+                {
+                    std::unique_lock<std::mutex> lock(ctl);
+                    ++parked;
+                    cv.notify_all();
+                    cv.wait(lock, [&] { return quit_ || failed || (running_ && !pause); });
+                    --parked;
+                    if (quit_ || failed) { return; }
+                }
+                for (;;) {
+                    {
+                        std::lock_guard<std::mutex> lock(ctl);
+                        if (quit_ || failed || pause || !running_) { break; }
+                    }
+                    if (!playOneMove(e, e + 1)) {
+                        std::lock_guard<std::mutex> lock(ctl);
+                        failed = true;
+                        cv.notify_all();
+                        break;
+                    }
+                }
+            }
+        });
+    }
+    for (;;) {
+        bool pending;
+        {
+            std::lock_guard<std::mutex> lock(mutex_);
+            pending = !commands_.empty();
+        }
+        {
+            std::unique_lock<std::mutex> lock(ctl);
+            if (failed) { break; }
+            if (pending) {
+                pause = true;
+                cv.wait(lock, [&] { return parked == ne || failed; }); // every engine thread is between two moves
+                lock.unlock();
+                handleCommands(); // running_ / quit_ change here, under no lock the threads could be reading them through: they are parked
+                lock.lock();
+                pause = false;
+                cv.notify_all();
+                if (quit_) { break; }
+            }
+        }
+        std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    }
+    {
+        std::lock_guard<std::mutex> lock(ctl);
+        quit_ = true;
+        cv.notify_all();
+    }
+    for (std::thread& t : threads) { t.join(); }
+    reportTiming();
+    return failed ? -1 : 0;
+}
+
+void Worker::reportTiming()
+{
+    if (moves_played_ > 0) { // a "move" is one engine's move (one search of its games); the milliseconds are host wall time of the thread that drove it
         const double k = 1e3 / static_cast<double>(moves_played_);
         std::cerr << "[timing] " << moves_played_ << " moves, " << games_finished_ << " games; ms per move: draw " << t_draw_ * k << ", search + root tables " << t_search_ * k
                   << ", decide + records " << t_decide_ * k << ", play " << t_play_ * k << ", emit + restart " << t_emit_ * k << std::endl;
     }
-    return 0;
 }
 
 } // namespace mzhost

@@ -9,6 +9,7 @@
 #include "record.h"
 #include "rng.h"
 #include "synth_atari.h"
+#include <atomic>
 #include <deque>
 #include <istream>
 #include <mutex>
@@ -56,9 +57,11 @@ private:
     bool loadModel(const std::string& path); // load_model command (actor_group.cpp:227-232): rank-0 GPU reads, NCCL broadcast
     void handleIO();                         // actor_group.cpp:189-198
     void handleCommands();                   // actor_group.cpp:200-252
-    bool playOneMove();                      // S + 1 cycles of actor_group.cpp:81-134 for every game
+    bool playOneMove(int e0, int e1);        // S + 1 cycles of actor_group.cpp:81-134 for every game of engines e0 .. e1-1
+    int runThreaded();                       // one host thread per engine (zero_num_threads > 1 and more than one GPU)
+    void reportTiming();
     void startGames();                       // createActors + first rotation draws, in the reference's draw order
-    void drawSearchRandomness();             // root noise + rotations of cycles 1 .. S of one search
+    void drawSearchRandomness(int e0, int e1); // root noise + rotations of cycles 1 .. S of one search
     int advanceGame(int g, const RootView& r, bool& resign, bool& end); // decide / act / end / next-game draws of one actor
     void restartGameHost(int g);
     int decideAction(int g, const RootView& r, bool& resign, int& child_index);
@@ -73,7 +76,11 @@ private:
 
     Config& cfg_;
     int wire_fd_; // the zero server's end of the pipe (the process's original stdout)
-    Random rng_;
+    Random rng_;                            // the main thread's generator
+    std::vector<Random> engine_rng_;        // runThreaded: one per engine thread (program_seed + thread id, actor_group.cpp:66-70)
+    static thread_local Random* tl_rng_;    // generator of the calling thread (null: the main thread's)
+    Random& rng() { return tl_rng_ ? *tl_rng_ : rng_; }
+    std::mutex emit_mutex_, stat_mutex_;    // the wire + games_finished_; the timing sums
     NetInfo net_;
     GameHeader header_;
     int game_type_ = MZ_GAME_GO, board_ = 9, actions_ = 82, sims_ = 0, num_games_ = 0;
@@ -102,7 +109,7 @@ private:
     std::vector<std::vector<uint8_t>> rotations_; // per engine [(S+1)][games]
     std::vector<std::vector<float>> noise_;       // per engine [games][A]
     void* nccl_comms_ = nullptr;
-    bool running_ = false, quit_ = false;
+    std::atomic<bool> running_{false}, quit_{false};
     std::deque<std::string> commands_;
     std::mutex mutex_;
     std::thread io_thread_;

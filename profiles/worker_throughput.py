@@ -55,6 +55,11 @@ def main():
            "games_per_sec_first_to_last_line": (len(got) - 1) / span if len(got) > 1 else None,
            "leaf_evals_per_sec_from_finished_games": moves * 401 / (t1 - t0), "all_lines_are_selfplay": len(got) == len(lines),
            "worker_timing": next((e.strip() for e in errs if e.startswith("[timing]")), None)}
+    # every engine move is one whole search of that engine's 256 games (the [timing] line counts them): the steady-state rate of the executable
+    m = re.search(r"\[timing\] (\d+) moves", out["worker_timing"] or "")
+    if m:
+        out["engine_moves"] = int(m.group(1))
+        out["leaf_evals_per_sec"] = int(m.group(1)) * 256 * 401 / (t1 - t0)
     print(json.dumps(out))
 
 

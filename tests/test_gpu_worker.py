@@ -111,3 +111,23 @@ def test_worker_atari_mode_end_to_end():
             assert sum(rewards) == ret
         terminal_seen |= terminal
     assert terminal_seen
+
+
+def test_worker_on_all_visible_gpus_one_host_thread_per_engine():
+    """more than one GPU: the engines are driven by their own host threads (zero_num_threads > 1, Worker::runThreaded), the weights reach every
+    GPU through the NCCL broadcast, and every record of every engine is accepted by the reference's loader and rules"""
+    torch = pytest.importorskip("torch")
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    checker = os.path.join(ROOT, "oracle", "_ref", "ref_record_check_go")
+    model = os.path.join(NETS, "go9_az_2bx64.pt")
+    if not (os.path.exists(BIN) and os.path.exists(checker) and os.path.exists(model)):
+        pytest.skip("worker binary / oracle/_ref not built")
+    conf = (f"env_board_size=9:actor_num_simulation=32:zero_num_parallel_games={16 * n}:nn_file_name={model}:program_seed=3:program_auto_seed=false:"
+            "program_quiet=true:zero_num_threads=4")
+    lines, err, rc = run_worker(conf, want_lines=16 * n + 8)
+    assert rc == 0, err[-500:]
+    assert len(lines) >= 16 * n + 8 and all(l.startswith("SelfPlay ") and l.endswith(" #") for l in lines)
+    r = subprocess.run([checker, "env_board_size=9"], input="\n".join(lines) + "\n", capture_output=True, text=True)
+    assert r.stdout.strip() == f"RECORDS_OK {len(lines)}", r.stdout + r.stderr[-300:]
