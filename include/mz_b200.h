@@ -213,6 +213,10 @@ int mz_conv_layers_per_launch(const mz_engine* e);
 int64_t mz_launch_count(const mz_engine* e);
 /* think mode: batched steps (network forwards) the last mz_search_run took to bring every tree to S + 1 simulations (zero_actor.cpp:39-44) */
 int mz_think_steps(const mz_engine* e);
+/* 1 when the fused conv tower of this engine is launched cooperatively (its CTAs wait for each other through completion counters, so the whole grid
+ * must be resident: the driver guarantees it for a cooperative launch; probed when the network is allocated), 0 when the device refused and the
+ * engine fell back to an ordinary cluster launch on an otherwise idle device */
+int mz_tower_is_cooperative(const mz_engine* e);
 
 #ifdef __cplusplus
 }

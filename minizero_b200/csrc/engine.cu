@@ -5,6 +5,7 @@
 #include "atari_kernels.cuh"
 #include "search_core.cuh"
 
+#include <nvtx3/nvToolsExt.h> // header-only; ranges cost nothing unless a profiler injects its library
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -43,6 +44,12 @@ int fail(int code, const std::string& msg)
 // ---------------------------------------------------------------------------------------------------
 // kernels around search_core.cuh: one block per game (16 warps for the per-cycle tree step, one warp for the per-move kernels)
 // ---------------------------------------------------------------------------------------------------
+// NVTX range for the duration of a C-ABI call: a timeline (nsys / ncu --nvtx) shows search, move and model-load phases per engine
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 constexpr int STEP_AFTER = 1, STEP_BEFORE = 2;
 
 constexpr int STEP_WARPS = 16; // warps per game in k_step: the previous path is re-evaluated level-parallel (search_core.cuh, mz_select)
@@ -303,6 +310,7 @@ struct mz_engine {
     CUtensorMap map_act_ext[3]; // same buffers, box = the resident block of conv3x3_resident_kernel
     CUtensorMap map_act_wide[3]; // same buffers, box = half of the wide tower's input block
     int tower_rot_override = -1; // MZ_TOWER_ROT (experiment builds)
+    bool tower_coop = true;      // the fused tower is launched cooperatively (probed once per engine: alloc_net)
     int think_steps = 0;         // batched steps the last think() search took
     int think_trees = 0;         // think mode (mz_config.think_batch_size > 1): number of trees; d.B = think_trees * d.think_k lanes
     bool tower_wide = false;    // conv_tower_wide_kernel (two row tiles per CTA) instead of conv_tower_kernel
@@ -635,10 +643,17 @@ int launch_tower_params(mz_engine* e, mznn::TowerParams* params, int* d_done, in
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
     params->pdl = (pdl ? 1 : 0);
-    cfg.attrs = attr, cfg.numAttrs = (pdl ? 2 : 1);
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    if (pdl) {
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.numAttrs = 2;
+    } else if (e->tower_coop) { // the CTAs wait for each other: a cooperative launch makes the driver guarantee that the whole grid is resident
+        attr[1].id = cudaLaunchAttributeCooperative;
+        attr[1].val.cooperative = 1;
+        cfg.numAttrs = 2;
+    }
     if (bn == 256) { // output-channel tile of 256: half the input-block reads per FLOP (see DESIGN.md "What bounds the tower")
         if (stages == 4) {
             CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<256, 4, false>, *params));
@@ -677,10 +692,17 @@ int launch_tower_wide(mz_engine* e, NetTower& T, bool clear_counters, bool pdl)
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
     params->pdl = (pdl ? 1 : 0);
-    cfg.attrs = attr, cfg.numAttrs = (pdl ? 2 : 1);
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    if (pdl) {
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.numAttrs = 2;
+    } else if (e->tower_coop) { // the CTAs wait for each other: a cooperative launch makes the driver guarantee that the whole grid is resident
+        attr[1].id = cudaLaunchAttributeCooperative;
+        attr[1].val.cooperative = 1;
+        cfg.numAttrs = 2;
+    }
     if (params->dbg && stages == 8) {
         CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_wide_kernel<8, true>, *params));
     } else if (stages == 8) {
@@ -1086,7 +1108,30 @@ int alloc_net(mz_engine* e)
         }
     }
     if (tower_ok) { e->conv_mode = 3; }
-    if (e->atari) { return alloc_atari(e); }
+    if (e->atari && (rc = alloc_atari(e))) { return rc; }
+    if (const char* env = knob("MZ_TOWER_COOP")) {
+        if (std::atoi(env) == 0) { e->tower_coop = false; }
+    }
+    if (tower_ok) {
+        // one launch of every tower on the zeroed buffers, outside any capture: proves that the grid fits the device as a whole (an SM-restricted
+        // context, MPS with a thread percentage ...) and that this driver accepts a cooperative cluster launch; if it does not, the towers fall back
+        // to an ordinary launch (co-residency then rests on one CTA per SM of an otherwise idle device, as in round 1)
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            cudaError_t err = cudaSuccess;
+            for (int t = 0; t < e->num_towers && err == cudaSuccess; ++t) {
+                if (launch_tower(e, t, true, false) != MZ_OK) {
+                    err = cudaErrorUnknown;
+                    (void)cudaGetLastError();
+                }
+            }
+            if (err == cudaSuccess) { err = cudaStreamSynchronize(e->stream); }
+            if (err == cudaSuccess) { break; }
+            (void)cudaGetLastError();
+            if (attempt == 1 || !e->tower_coop) { return fail(MZ_ERR_CUDA, std::string("the fused tower cannot be launched on this device: ") + cudaGetErrorString(err)); }
+            e->tower_coop = false;
+        }
+        for (int t = 0; t < e->num_towers; ++t) { CUDA_OK(cudaMemsetAsync(e->tw[t].d_done, 0, sizeof(int) * e->tw[t].done_count, e->stream)); }
+    }
     return MZ_OK;
 }
 
@@ -1447,6 +1492,7 @@ int mz_action_size(const mz_engine* e) { return e ? e->d.A : MZ_ERR_ARG; }
 int mz_num_features(const mz_engine* e) { return e ? (e->atari ? mzat::PLANES * mzat::RES * mzat::RES : e->d.C * e->d.N * e->d.N) : MZ_ERR_ARG; }
 int64_t mz_launch_count(const mz_engine* e) { return e ? e->launches : 0; }
 int mz_think_steps(const mz_engine* e) { return e ? e->think_steps : MZ_ERR_ARG; }
+int mz_tower_is_cooperative(const mz_engine* e) { return (e && e->net_ready) ? ((e->conv_mode == 3 && e->tower_coop) ? 1 : 0) : MZ_ERR_STATE; }
 int mz_conv_layers_per_launch(const mz_engine* e) { return (e && e->net_ready) ? (e->conv_mode == 3 ? static_cast<int>(e->tw[0].convs.size()) : 1) : MZ_ERR_STATE; }
 
 int mz_net_configure(mz_engine* e, const mz_net_dims* dims)
@@ -1506,6 +1552,7 @@ int mz_net_finalize_empty(mz_engine* e)
 
 int mz_net_finalize(mz_engine* e)
 {
+    NvtxRange nvtx_range("mz_net_finalize");
     if (!e || !e->dims_set) { return fail(MZ_ERR_STATE, "mz_net_configure first"); }
     CUDA_OK(cudaSetDevice(e->cfg.device));
     const mz_net_dims& nd = e->nd;
@@ -1818,6 +1865,7 @@ int mz_reset_game(mz_engine* e, int32_t g)
 
 int mz_play(mz_engine* e, const int32_t* actions, mz_play_result* results)
 {
+    NvtxRange nvtx_range("mz_play");
     if (!e || !actions || !results) { return fail(MZ_ERR_ARG, "null argument"); }
     CUDA_OK(cudaSetDevice(e->cfg.device));
     const int B = e->d.B;
@@ -1839,6 +1887,7 @@ int mz_play(mz_engine* e, const int32_t* actions, mz_play_result* results)
 
 int mz_play_max_count(mz_engine* e, int32_t auto_reset, int32_t* actions_out, mz_play_result* results)
 {
+    NvtxRange nvtx_range("mz_play_max_count");
     if (!e) { return fail(MZ_ERR_ARG, "null argument"); }
     CUDA_OK(cudaSetDevice(e->cfg.device));
     const int B = e->d.B;
@@ -1891,6 +1940,7 @@ int mz_timer_end(mz_engine* e, float* device_ms)
 
 int mz_get_roots(mz_engine* e, mz_root_info* info, int32_t* action, float* count, float* mean, float* policy, float* logit, float* noise, float* value)
 {
+    NvtxRange nvtx_range("mz_get_roots");
     if (!e) { return fail(MZ_ERR_ARG, "null argument"); }
     CUDA_OK(cudaSetDevice(e->cfg.device));
     const int B = e->d.B;
@@ -1976,6 +2026,7 @@ int mz_search_apply_reward(mz_engine* e, const float* policy, const float* logit
 
 int mz_search_set_inputs(mz_engine* e, const uint8_t* rotations, const float* noise)
 {
+    NvtxRange nvtx_range("mz_search_set_inputs");
     if (!e) { return fail(MZ_ERR_ARG, "null argument"); }
     CUDA_OK(cudaSetDevice(e->cfg.device));
     const mz_dims& d = e->d;
@@ -1988,6 +2039,7 @@ int mz_search_set_inputs(mz_engine* e, const uint8_t* rotations, const float* no
 
 int mz_search_run(mz_engine* e, int32_t num_evals, float* device_ms)
 {
+    NvtxRange nvtx_range("mz_search_run");
     if (!e) { return fail(MZ_ERR_ARG, "null argument"); }
     if (!e->net_ready) { return fail(MZ_ERR_STATE, "network not finalized"); }
     CUDA_OK(cudaSetDevice(e->cfg.device));

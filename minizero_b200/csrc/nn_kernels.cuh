@@ -871,6 +871,27 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p)
     return v;
 }
 
+// Wait until a completion counter of the previous layer reaches `need`. The tower relies on every CTA of the grid being resident (it is launched
+// cooperatively, so the driver guarantees that); should a counter nevertheless stay short for 10 seconds of wall time — a launch that lost its
+// co-residency, counters that were not cleared — the kernel traps: the stream reports an error instead of spinning for ever.
+__device__ __forceinline__ void wait_counter(const int* p, int need)
+{
+    unsigned spins = 0;
+    unsigned long long t_first = 0;
+    while (ld_acquire_gpu(p) < need) {
+        __nanosleep(32);
+        if ((++spins & 0x3FFFFu) == 0u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t_first == 0) {
+                t_first = now;
+            } else if (now - t_first > 10000000000ull) {
+                __trap();
+            }
+        }
+    }
+}
+
 template <int BN, int STAGES, bool DBG>
 __global__ void __launch_bounds__(TOWER_THREADS, 1)
 conv_tower_kernel(const __grid_constant__ TowerParams tp)
@@ -1025,7 +1046,7 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                         const int* d = tp.done + (l - 1) * num_groups;
                         const int g0 = (g > 0 ? g - 1 : 0), g1 = (g + 1 < num_groups ? g + 1 : num_groups - 1);
                         for (int gg = g0; gg <= g1; ++gg) {
-                            while (ld_acquire_gpu(d + gg) < need) { __nanosleep(32); }
+                            wait_counter(d + gg, need);
                         }
                     }
                     __syncwarp();
@@ -1349,7 +1370,7 @@ conv_tower_wide_kernel(const __grid_constant__ TowerParams tp)
                         const int* d = tp.done + (l - 1) * num_sg;
                         const int g0 = (sg > 0 ? sg - 1 : 0), g1 = (sg + 1 < num_sg ? sg + 1 : num_sg - 1);
                         for (int gg = g0; gg <= g1; ++gg) {
-                            while (ld_acquire_gpu(d + gg) < need) { __nanosleep(32); }
+                            wait_counter(d + gg, need);
                         }
                     }
                     __syncwarp();

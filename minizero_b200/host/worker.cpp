@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <iostream>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 #include <random>
 #include <sstream>
 #include <unistd.h>
@@ -626,7 +627,11 @@ bool Worker::playOneMove(int e0, int e1)
     const bool use_noise = use_dirichlet || use_gumbel_noise, random_rotation = cfg_.getBool("actor_use_random_rotation_features") && !muzero_;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
+    nvtxRangePushA("move"); // phases of a move on the host timeline: draw, search, decide, play, emit
+    struct PopAtExit { ~PopAtExit() { nvtxRangePop(); } } pop_move;
+    nvtxRangePushA("draw");
     drawSearchRandomness(e0, e1); // (1)
+    nvtxRangePop();
     const double t1 = now();
     // (2) the whole search on the devices, all engines in flight together
     for (int e = e0; e < e1; ++e) {
@@ -667,6 +672,7 @@ bool Worker::playOneMove(int e0, int e1)
         }
     }
     const double t2 = now();
+    nvtxMarkA("decide + records");
     // (4) per actor, in order: decide, act or resign, restart finished games, draw the first rotation of the next search
     std::vector<std::vector<int32_t>> play(ne);
     for (int e = e0; e < e1; ++e) { play[e].assign(engine_games_[e], -1); }

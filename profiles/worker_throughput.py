@@ -59,7 +59,11 @@ def main():
     m = re.search(r"\[timing\] (\d+) moves", out["worker_timing"] or "")
     if m:
         out["engine_moves"] = int(m.group(1))
-        out["leaf_evals_per_sec"] = int(m.group(1)) * 256 * 401 / (t1 - t0)
+        out["leaf_evals_per_sec_wall_incl_startup"] = int(m.group(1)) * 256 * 401 / (t1 - t0)  # model load, NCCL set-up and graph capture are inside the wall time
+        # steady state from the worker's own clock: the phases of a move add up to the host thread's time per engine move, every engine runs its own loop
+        ms = sum(float(x) for x in re.findall(r"(?:draw|tables|records|play|restart) ([0-9.]+)", out["worker_timing"]))
+        out["ms_per_engine_move"] = ms
+        out["leaf_evals_per_sec_steady"] = gpus * 256 * 401 / ms * 1e3
     print(json.dumps(out))
 
 

@@ -34,7 +34,7 @@ def test_network_20bx256_19x19_matches_torchscript_fp32():
     batch, n = 128, 19
     eng = engine(1, n, batch, 4)
     eng.load_network(path)
-    assert eng.conv_layers_per_launch() == 41
+    assert eng.conv_layers_per_launch() == 41 and eng.tower_is_cooperative() == 1  # one cooperative launch for the whole tower
     rng = np.random.default_rng(23)
     feats = (rng.random((batch, 18, n, n)) < 0.25).astype(np.float32)
     feats[0] = 0.0
