@@ -131,3 +131,38 @@ def test_worker_on_all_visible_gpus_one_host_thread_per_engine():
     assert len(lines) >= 16 * n + 8 and all(l.startswith("SelfPlay ") and l.endswith(" #") for l in lines)
     r = subprocess.run([checker, "env_board_size=9"], input="\n".join(lines) + "\n", capture_output=True, text=True)
     assert r.stdout.strip() == f"RECORDS_OK {len(lines)}", r.stdout + r.stderr[-300:]
+
+
+@pytest.mark.parametrize("game,net,conf,checker_conf", [
+    ("go", "go9_az_2bx64", "env_board_size=9:actor_num_simulation=32:zero_num_parallel_games=32", "env_board_size=9"),
+    ("tictactoe", "ttt_az_2bx32", "actor_num_simulation=50:zero_num_parallel_games=16", ""),
+    ("othello", "othello_mz_1bx32", "actor_num_simulation=24:zero_num_parallel_games=16:nn_type_name=muzero", ""),
+])
+def test_reference_actor_group_bound_to_the_library(game, net, conf, checker_conf):
+    """integration/b200_actor_group.cpp: the REFERENCE's ActorGroup, actors, move decision and record writer (compiled from the unmodified sources)
+    with every search run by libmzb200 through the C ABI; driven over the wire protocol, records checked by the reference's loader"""
+    binding = os.path.join(ROOT, "oracle", "_ref", "b200_actor_group_" + game)
+    checker = os.path.join(ROOT, "oracle", "_ref", "ref_record_check_" + game)
+    model = os.path.join(NETS, net + ".pt")
+    if not (os.path.exists(binding) and os.path.exists(checker) and os.path.exists(model)):
+        pytest.skip("binding / oracle/_ref not built (needs the reference checkout)")
+    conf = conf + f":nn_file_name={model}:program_seed=5:program_auto_seed=false:program_quiet=true:zero_num_threads=2"
+    p = subprocess.Popen([binding, conf], stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    p.stdin.write("start\n")
+    p.stdin.flush()
+    lines, t0 = [], time.time()
+    while len(lines) < 20 and time.time() - t0 < 240:
+        line = p.stdout.readline()
+        if not line:
+            break
+        lines.append(line.rstrip("\n"))
+    p.stdin.write("quit\n")
+    p.stdin.flush()
+    try:
+        p.communicate(timeout=30)
+    except subprocess.TimeoutExpired:  # the reference's quit is exit(0) from the command thread: some builds linger in thread teardown
+        p.kill()
+    assert len(lines) >= 20 and all(l.startswith("SelfPlay ") and l.endswith(" #") for l in lines)
+    r = subprocess.run([checker, checker_conf], input="\n".join(lines) + "\n", capture_output=True, text=True)
+    assert r.stdout.strip() == f"RECORDS_OK {len(lines)}", r.stdout + r.stderr[-300:]
+    assert f"EV[{net}.pt]" in lines[0]
