@@ -34,8 +34,8 @@ KEEP = [
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3}
 
 
-def launches(tag):
-    path = os.path.join(OUT, "launches.csv")
+def launches(tag, src="launches.csv", suffix=""):
+    path = os.path.join(OUT, src)
     if not os.path.exists(path):
         return None
     text = [ln for ln in open(path) if ln.startswith('"')]
@@ -52,7 +52,7 @@ def launches(tag):
         a[2] = min(a[2], v)
         a[3] = max(a[3], v)
     total = sum(a[1] for a in agg.values())
-    out = os.path.join(ROOT, "profiles", f"{tag}_launches_by_kernel.csv")
+    out = os.path.join(ROOT, "profiles", f"{tag}_launches_by_kernel{suffix}.csv")
     with open(out, "w", newline="") as f:
         w = csv.writer(f)
         w.writerow(["kernel", "grid", "block", "launches", "total_us", "mean_us", "min_us", "max_us", "share_of_window"])
@@ -63,7 +63,7 @@ def launches(tag):
 
 def full(tag):
     res = OrderedDict()
-    for name in ("tower", "kstep", "heads"):
+    for name in ("tower", "kstep", "heads", "tower_cfg3", "tower_cfg4", "tower_cfg5"):
         rep = os.path.join(OUT, f"{name}_full.ncu-rep")
         if not os.path.exists(rep):
             continue
@@ -95,4 +95,6 @@ def full(tag):
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     print(launches(tag))
+    for cfg in (3, 4, 5):
+        print(launches(tag, f"launches_cfg{cfg}.csv", f"_cfg{cfg}"))
     print(full(tag))
