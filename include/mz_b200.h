@@ -213,10 +213,15 @@ int mz_conv_layers_per_launch(const mz_engine* e);
 int64_t mz_launch_count(const mz_engine* e);
 /* think mode: batched steps (network forwards) the last mz_search_run took to bring every tree to S + 1 simulations (zero_actor.cpp:39-44) */
 int mz_think_steps(const mz_engine* e);
-/* 1 when the fused conv tower of this engine is launched cooperatively (its CTAs wait for each other through completion counters, so the whole grid
- * must be resident: the driver guarantees it for a cooperative launch; probed when the network is allocated), 0 when the device refused and the
- * engine fell back to an ordinary cluster launch on an otherwise idle device */
+/* The fused conv tower's CTAs wait for each other through completion counters, so its whole grid must be resident. By default it is an ordinary
+ * cluster launch: mz_net_finalize checks (cudaOccupancyMaxActiveClusters) that the device / context can hold the grid, the engine's kernels are
+ * stream-ordered, and a wait that never ends traps after 10 s instead of hanging. Where OTHER work may compete for the SMs (a second engine on the
+ * same device, another process under MPS) switch the cooperative launch on: the driver then guarantees co-residency or refuses the launch. It is
+ * not the default because Nsight Compute fails every cooperative cluster launch of this kernel (LaunchFailed under ncu 2025.2 on B200, also for a
+ * 2-CTA grid), which would make the library unprofilable. Results do not depend on the mode; captured search graphs are rebuilt.
+ * mz_tower_is_cooperative: 1 / 0. mz_set_tower_cooperative(e, 1) probes with one launch and fails (leaving the mode off) if the device refuses. */
 int mz_tower_is_cooperative(const mz_engine* e);
+int mz_set_tower_cooperative(mz_engine* e, int32_t on);
 
 #ifdef __cplusplus
 }

@@ -310,7 +310,7 @@ struct mz_engine {
     CUtensorMap map_act_ext[3]; // same buffers, box = the resident block of conv3x3_resident_kernel
     CUtensorMap map_act_wide[3]; // same buffers, box = half of the wide tower's input block
     int tower_rot_override = -1; // MZ_TOWER_ROT (experiment builds)
-    bool tower_coop = true;      // the fused tower is launched cooperatively (probed once per engine: alloc_net)
+    bool tower_coop = false;     // the fused tower is launched cooperatively (opt-in: mz_set_tower_cooperative)
     int think_steps = 0;         // batched steps the last think() search took
     int think_trees = 0;         // think mode (mz_config.think_batch_size > 1): number of trees; d.B = think_trees * d.think_k lanes
     bool tower_wide = false;    // conv_tower_wide_kernel (two row tiles per CTA) instead of conv_tower_kernel
@@ -1109,28 +1109,42 @@ int alloc_net(mz_engine* e)
     }
     if (tower_ok) { e->conv_mode = 3; }
     if (e->atari && (rc = alloc_atari(e))) { return rc; }
-    if (const char* env = knob("MZ_TOWER_COOP")) {
-        if (std::atoi(env) == 0) { e->tower_coop = false; }
-    }
     if (tower_ok) {
-        // one launch of every tower on the zeroed buffers, outside any capture: proves that the grid fits the device as a whole (an SM-restricted
-        // context, MPS with a thread percentage ...) and that this driver accepts a cooperative cluster launch; if it does not, the towers fall back
-        // to an ordinary launch (co-residency then rests on one CTA per SM of an otherwise idle device, as in round 1)
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            cudaError_t err = cudaSuccess;
-            for (int t = 0; t < e->num_towers && err == cudaSuccess; ++t) {
-                if (launch_tower(e, t, true, false) != MZ_OK) {
-                    err = cudaErrorUnknown;
-                    (void)cudaGetLastError();
-                }
+        // the tower's CTAs wait for each other: the whole grid must be able to be resident at once on this device / context (SM-restricted contexts,
+        // MPS thread percentages ...). Checked here once; a second kernel competing for the SMs at run time is what the cooperative mode is for
+        for (int t = 0; t < e->num_towers; ++t) {
+            const mznn::TowerParams& T = *e->tw[t].params;
+            const int units = (e->tower_wide ? ((T.num_mtiles + 3) / 4) : ((T.num_mtiles + 1) / 2)) * (e->cpad / e->tower_bn);
+            const int clusters = std::min(units, e->tower_sms / 2);
+            cudaLaunchConfig_t cfg{};
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+            cfg.gridDim = dim3(clusters * 2), cfg.attrs = attr, cfg.numAttrs = 1;
+            int max_clusters = 0;
+            cudaError_t err;
+            if (e->tower_wide) {
+                cfg.blockDim = dim3(mznn::WIDE_THREADS);
+                cfg.dynamicSmemBytes = static_cast<size_t>(mznn::WIDE_AK) * e->rows_ext_wide * 128 + static_cast<size_t>(e->tower_wide_stages) * 64 * mznn::BK * 2 +
+                                       (2 * e->tower_wide_stages + 2 * mznn::WIDE_AK + 4) * 8 + 16 + 1024;
+                err = (e->tower_wide_stages == 8 ? cudaOccupancyMaxActiveClusters(&max_clusters, mznn::conv_tower_wide_kernel<8, false>, &cfg)
+                                                 : cudaOccupancyMaxActiveClusters(&max_clusters, mznn::conv_tower_wide_kernel<6, false>, &cfg));
+            } else {
+                cfg.blockDim = dim3(mznn::TOWER_THREADS);
+                cfg.dynamicSmemBytes = 2 * static_cast<size_t>(e->cin_max / mznn::BK) * e->rows_ext * 128 + static_cast<size_t>(e->tower_stages) * (e->tower_bn / 2) * mznn::BK * 2 + 24 * 8 + 16 + 1024;
+                err = (e->tower_bn == 256 ? cudaOccupancyMaxActiveClusters(&max_clusters, mznn::conv_tower_kernel<256, 4, false>, &cfg)
+                       : e->tower_stages == 4 ? cudaOccupancyMaxActiveClusters(&max_clusters, mznn::conv_tower_kernel<128, 4, false>, &cfg)
+                       : e->tower_stages == 5 ? cudaOccupancyMaxActiveClusters(&max_clusters, mznn::conv_tower_kernel<128, 5, false>, &cfg)
+                                              : cudaOccupancyMaxActiveClusters(&max_clusters, mznn::conv_tower_kernel<128, 8, false>, &cfg));
             }
-            if (err == cudaSuccess) { err = cudaStreamSynchronize(e->stream); }
-            if (err == cudaSuccess) { break; }
-            (void)cudaGetLastError();
-            if (attempt == 1 || !e->tower_coop) { return fail(MZ_ERR_CUDA, std::string("the fused tower cannot be launched on this device: ") + cudaGetErrorString(err)); }
-            e->tower_coop = false;
+            if (err != cudaSuccess) {
+                (void)cudaGetLastError();
+                return fail(MZ_ERR_CUDA, std::string("cudaOccupancyMaxActiveClusters: ") + cudaGetErrorString(err));
+            }
+            if (max_clusters < clusters) {
+                return fail(MZ_ERR_CUDA, "the fused tower needs " + std::to_string(clusters) + " co-resident CTA pairs, this device / context can hold " + std::to_string(max_clusters));
+            }
         }
-        for (int t = 0; t < e->num_towers; ++t) { CUDA_OK(cudaMemsetAsync(e->tw[t].d_done, 0, sizeof(int) * e->tw[t].done_count, e->stream)); }
     }
     return MZ_OK;
 }
@@ -1492,6 +1506,33 @@ int mz_action_size(const mz_engine* e) { return e ? e->d.A : MZ_ERR_ARG; }
 int mz_num_features(const mz_engine* e) { return e ? (e->atari ? mzat::PLANES * mzat::RES * mzat::RES : e->d.C * e->d.N * e->d.N) : MZ_ERR_ARG; }
 int64_t mz_launch_count(const mz_engine* e) { return e ? e->launches : 0; }
 int mz_think_steps(const mz_engine* e) { return e ? e->think_steps : MZ_ERR_ARG; }
+int mz_set_tower_cooperative(mz_engine* e, int32_t on)
+{
+    if (!e || !e->net_ready) { return fail(MZ_ERR_STATE, "network not finalized"); }
+    if (e->conv_mode != 3) { return fail(MZ_ERR_STATE, "this network does not run through the fused tower"); }
+    CUDA_OK(cudaSetDevice(e->cfg.device));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    for (auto& kv : e->graphs) { cudaGraphExecDestroy(kv.second.exec); } // the launch attribute is part of the captured kernel nodes
+    e->graphs.clear();
+    e->tower_coop = (on != 0);
+    if (!e->tower_coop) { return MZ_OK; }
+    // one launch of every tower, outside any capture: does this driver / context accept a cooperative cluster launch of that grid?
+    cudaError_t err = cudaSuccess;
+    for (int t = 0; t < e->num_towers && err == cudaSuccess; ++t) {
+        if (launch_tower(e, t, true, false) != MZ_OK) {
+            err = cudaErrorUnknown;
+            (void)cudaGetLastError();
+        }
+    }
+    if (err == cudaSuccess) { err = cudaStreamSynchronize(e->stream); }
+    for (int t = 0; t < e->num_towers; ++t) { cudaMemsetAsync(e->tw[t].d_done, 0, sizeof(int) * e->tw[t].done_count, e->stream); }
+    if (err != cudaSuccess) {
+        (void)cudaGetLastError();
+        e->tower_coop = false;
+        return fail(MZ_ERR_CUDA, std::string("cooperative launch of the tower refused: ") + cudaGetErrorString(err));
+    }
+    return MZ_OK;
+}
 int mz_tower_is_cooperative(const mz_engine* e) { return (e && e->net_ready) ? ((e->conv_mode == 3 && e->tower_coop) ? 1 : 0) : MZ_ERR_STATE; }
 int mz_conv_layers_per_launch(const mz_engine* e) { return (e && e->net_ready) ? (e->conv_mode == 3 ? static_cast<int>(e->tw[0].convs.size()) : 1) : MZ_ERR_STATE; }
 

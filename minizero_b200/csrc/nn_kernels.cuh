@@ -1705,6 +1705,58 @@ __global__ void __launch_bounds__(256) scale_hidden_kernel(__half* __restrict__ 
     const bool vec = (c_real % 8 == 0); // 16-byte accesses: 8 channels per thread and step
     const int per_cell = c / 8, real_per_cell = c_real / 8;
     float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
+    if (vec && c == c_real && hw * per_cell <= 4 * static_cast<int>(blockDim.x)) {
+        // the common shape (no padded channels, at most 4 x 16 bytes per thread: 8 x 8 cells x 128 channels at 256 threads): the board is read ONCE, all loads
+        // in flight together, kept in registers across the reduction, and leaves as two coalesced stores — one round trip to L2 instead of two
+        const int items = hw * per_cell;
+        uint4 v[4];
+        __half* src[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = tid + u * blockDim.x;
+            src[u] = nullptr;
+            if (i < items) {
+                const int cell = i / per_cell, k = i - cell * per_cell;
+                src[u] = rows + static_cast<size_t>((cell / n + 1) * n1 + cell % n) * c + 8 * k;
+                v[u] = *reinterpret_cast<const uint4*>(src[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (src[u]) {
+                const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h[j]);
+                    mn = fminf(mn, fminf(f.x, f.y)), mx = fmaxf(mx, fmaxf(f.x, f.y));
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)), mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+        if ((tid & 31) == 0) { red_mn[tid >> 5] = mn, red_mx[tid >> 5] = mx; }
+        __syncthreads();
+        mn = red_mn[0], mx = red_mx[0];
+        for (int i = 1; i < (blockDim.x >> 5); ++i) { mn = fminf(mn, red_mn[i]), mx = fmaxf(mx, red_mx[i]); }
+        float scale = mx - mn;
+        if (scale < 1e-5f) { scale += 1e-5f; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (src[u]) {
+                uint4 out;
+                const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+                __half2* o = reinterpret_cast<__half2*>(&out);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h[j]);
+                    o[j] = __floats2half2_rn((f.x - mn) / scale, (f.y - mn) / scale); // same operations as the general path below
+                }
+                *reinterpret_cast<uint4*>(src[u]) = out;
+                *reinterpret_cast<uint4*>(dst + static_cast<size_t>(tid + u * blockDim.x) * 8) = out;
+            }
+        }
+        return;
+    }
     if (vec) {
         for (int i = tid; i < hw * real_per_cell; i += blockDim.x) {
             const int cell = i / real_per_cell, k = i - cell * real_per_cell;

@@ -34,7 +34,7 @@ def test_network_20bx256_19x19_matches_torchscript_fp32():
     batch, n = 128, 19
     eng = engine(1, n, batch, 4)
     eng.load_network(path)
-    assert eng.conv_layers_per_launch() == 41 and eng.tower_is_cooperative() == 1  # one cooperative launch for the whole tower
+    assert eng.conv_layers_per_launch() == 41  # one launch for the whole tower
     rng = np.random.default_rng(23)
     feats = (rng.random((batch, 18, n, n)) < 0.25).astype(np.float32)
     feats[0] = 0.0
@@ -269,3 +269,28 @@ def test_config3_full_batch_sampled_games_match_oracle():
                 orc.reset_game(int(g))
     eng.close()
     ev.close()
+
+
+def test_cooperative_tower_launch_gives_the_same_search():
+    """mz_set_tower_cooperative: the tower launched with the cooperative attribute (co-residency guaranteed by the driver) inside the captured
+    search graph; the root tables must be bit-identical to the plain cluster launch's"""
+    torch, m, path = torchscript("go9_az_6bx256")
+    rng = np.random.default_rng(5)
+    B, S = 256, 40
+    rot = rng.integers(0, 8, size=(S + 1, B)).astype(np.uint8)
+    noise = rng.dirichlet([0.03] * 82, size=B).astype(np.float32)
+    tables = []
+    for coop in (0, 1):
+        eng = engine(1, 9, B, S)
+        eng.load_network(path)
+        assert eng.tower_is_cooperative() == 0
+        if coop:
+            eng.set_tower_cooperative(True)
+            assert eng.tower_is_cooperative() == 1
+        eng.set_search_inputs(rot, noise)
+        eng.search()
+        r = eng.get_roots()
+        tables.append((r["count"].copy(), r["mean"].copy(), r["policy"].copy()))
+        eng.close()
+    for a, b in zip(*tables):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
