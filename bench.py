@@ -269,29 +269,34 @@ def main():
 
     rng = np.random.default_rng(1234 + rank)
     use_rot = not w["muzero"]
-    rot = torch.empty((S1, GAMES), dtype=torch.uint8).pin_memory() if use_rot else None
-    noise = torch.empty((GAMES, A), dtype=torch.float32).pin_memory()
+    # two sets of pinned input buffers: the randomness of search k + 1 is drawn on the host while search k runs on the device
+    rots = [torch.empty((S1, GAMES), dtype=torch.uint8).pin_memory() if use_rot else None for _ in range(2)]
+    noises = [torch.empty((GAMES, A), dtype=torch.float32).pin_memory() for _ in range(2)]
+    rot, noise = rots[0], noises[0]
     frames = torch.empty((GAMES, 3, 96, 96), dtype=torch.uint8).pin_memory() if atari else None
     frame_pool = rng.integers(0, 256, size=(4, GAMES, 3, 96, 96), dtype=np.uint8) if atari else None
 
-    def draw_inputs():
+    def draw_inputs(i=0):
         # training-default stochasticity: random rotation per evaluation and Dirichlet(0.03) root noise (AlphaZero),
         # Gumbel root noise (config 3), Dirichlet(0.25) over the 9 legal actions (Atari; quick-run's MuZero Atari settings)
         if use_rot:
-            rot.numpy()[...] = rng.integers(0, 8, size=(S1, GAMES), dtype=np.uint8)
+            rots[i].numpy()[...] = rng.integers(0, 8, size=(S1, GAMES), dtype=np.uint8)
         if gumbel:
-            noise.numpy()[...] = rng.gumbel(size=(GAMES, A)).astype(np.float32)
+            noises[i].numpy()[...] = rng.gumbel(size=(GAMES, A)).astype(np.float32)
         else:
-            noise.numpy()[...] = rng.dirichlet([0.25 if atari else 0.03] * A, size=GAMES).astype(np.float32)
+            noises[i].numpy()[...] = rng.dirichlet([0.25 if atari else 0.03] * A, size=GAMES).astype(np.float32)
 
     step_no = [0]
+    cur = [0]
 
     def e2e_step():
         """public-API step with host buffers: draw + upload the search's randomness (Atari: and the emulator's new screens), search, read
         the root tables back, choose the moves on the host (softmax-count, T=1; Gumbel: the best candidate), play them, restart finished games."""
-        draw_inputs()
-        eng.set_search_inputs(rot.numpy() if use_rot else None, noise.numpy())
+        i = cur[0]
+        eng.set_search_inputs(rots[i].numpy() if use_rot else None, noises[i].numpy())  # host -> device, every step
         eng.search(wait=False)
+        draw_inputs(1 - i)  # the next search's randomness, drawn while this one runs
+        cur[0] = 1 - i
         r = eng.get_roots()
         if gumbel:
             actions = eng.gumbel_best_actions().astype(np.int32)
@@ -315,6 +320,7 @@ def main():
     if atari:
         eng.observe_all(np.full(GAMES, -1, np.int32), frame_pool[0])
     # ---- warm-up (also instantiates the CUDA graph) -------------------------------------------------
+    draw_inputs(0)
     for _ in range(max(3, args.warmup)):
         e2e_step()
     draw_inputs()

@@ -44,6 +44,11 @@ class _RootInfo(C.Structure):
     _fields_ = [("num_children", C.c_int32), ("count", C.c_float), ("mean", C.c_float), ("value", C.c_float)]
 
 
+_ROOT_INFO_DTYPE = np.dtype([("num_children", np.int32), ("count", np.float32), ("mean", np.float32), ("value", np.float32)])
+_PLAY_RESULT_DTYPE = np.dtype([("applied", np.int32), ("terminal", np.int32), ("num_legal", np.int32), ("turn", np.int32), ("eval_score", np.float32)])
+assert _ROOT_INFO_DTYPE.itemsize == C.sizeof(_RootInfo) and _PLAY_RESULT_DTYPE.itemsize == C.sizeof(_PlayResult)
+
+
 def library_path():
     return os.path.join(_ROOT, "minizero_b200", "lib", "libmzb200.so")
 
@@ -339,15 +344,13 @@ class Engine:
 
     def get_roots(self):
         B, A = self.B, self.A
-        info = (_RootInfo * B)()
-        out = dict(action=np.zeros((B, A), np.int32))
+        info = np.zeros(B, _ROOT_INFO_DTYPE)  # mz_root_info[B] without a Python loop per game
+        out = dict(action=np.empty((B, A), np.int32))
         for n in ("count", "mean", "policy", "logit", "noise", "value"):
-            out[n] = np.zeros((B, A), np.float32)
-        self._check(self.lib.mz_get_roots(self.h, info, _i32(out["action"]), *[_fp(out[n]) for n in ("count", "mean", "policy", "logit", "noise", "value")]))
-        out["num_children"] = np.array([info[g].num_children for g in range(B)], np.int32)
-        out["root_count"] = np.array([info[g].count for g in range(B)], np.float32)
-        out["root_mean"] = np.array([info[g].mean for g in range(B)], np.float32)
-        out["root_value"] = np.array([info[g].value for g in range(B)], np.float32)
+            out[n] = np.empty((B, A), np.float32)
+        self._check(self.lib.mz_get_roots(self.h, info.ctypes.data_as(C.POINTER(_RootInfo)), _i32(out["action"]),
+                                          *[_fp(out[n]) for n in ("count", "mean", "policy", "logit", "noise", "value")]))
+        out["num_children"], out["root_count"], out["root_mean"], out["root_value"] = info["num_children"], info["count"], info["mean"], info["value"]
         out["reward"], out["bound_size"] = np.zeros((B, A), np.float32), np.zeros(B, np.int32)
         out["bound_lo"], out["bound_hi"] = np.zeros(B, np.float32), np.zeros(B, np.float32)
         self._check(self.lib.mz_get_root_rewards(self.h, _fp(out["reward"]), _i32(out["bound_size"]), _fp(out["bound_lo"]), _fp(out["bound_hi"])))
@@ -372,15 +375,12 @@ class Engine:
     # ---- games ----------------------------------------------------------------------------------
     def play_all(self, actions):
         a = np.ascontiguousarray(actions, np.int32)
-        res = (_PlayResult * self.B)()
-        self._check(self.lib.mz_play(self.h, _i32(a), res))
+        res = np.zeros(self.B, _PLAY_RESULT_DTYPE)
+        self._check(self.lib.mz_play(self.h, _i32(a), res.ctypes.data_as(C.POINTER(_PlayResult))))
         self._roots = None
-        out = dict(applied=np.array([r.applied for r in res], np.int32), terminal=np.array([r.terminal for r in res], np.int32),
-                   num_legal=np.array([r.num_legal for r in res], np.int32), turn=np.array([r.turn for r in res], np.int32),
-                   eval_score=np.array([r.eval_score for r in res], np.float32))
-        for g in range(self.B):
-            if a[g] >= 0:
-                self.terminal[g] = bool(out["terminal"][g])
+        out = {k: res[k] for k in ("applied", "terminal", "num_legal", "turn", "eval_score")}
+        for g in np.nonzero(a >= 0)[0]:
+            self.terminal[g] = bool(out["terminal"][g])
         self.last_play = out
         return out
 
