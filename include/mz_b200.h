@@ -33,6 +33,8 @@ extern "C" {
 #define MZ_GAME_GOMOKU 4    /* environment/gomoku (N x N, no pass, five in a row through the last move) */
 #define MZ_GAME_HEX 5       /* environment/hex (N x N, no pass, swap rule, connect the two own edges; features and policy are never rotated) */
 
+#define MZ_GAME_KILLALLGO 7 /* environment/killallgo: GoEnv on 7 x 7; Black opens with two stones, wins when the whole board is unconditionally his (Benson), White wins
+                             * with any unconditionally alive group or by surviving (killallgo.cpp:27-48; env_killallgo_use_seki = false, the default). AlphaZero only */
 #define MZ_GAME_ATARI 6     /* environment/atari: one player, 18 actions, 32 x 96 x 96 planes; the emulator stays with the host (mz_atari_observe); MuZero only */
 
 typedef struct mz_engine mz_engine;

@@ -1303,9 +1303,11 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     if (!cfg || !out) { return fail(MZ_ERR_ARG, "null argument"); }
     *out = nullptr;
     if (cfg->game != MZ_GAME_GO && cfg->game != MZ_GAME_TICTACTOE && cfg->game != MZ_GAME_OTHELLO && cfg->game != MZ_GAME_NOGO && cfg->game != MZ_GAME_GOMOKU && cfg->game != MZ_GAME_HEX &&
-        cfg->game != MZ_GAME_ATARI) {
+        cfg->game != MZ_GAME_ATARI && cfg->game != MZ_GAME_KILLALLGO) {
         return fail(MZ_ERR_ARG, "unsupported game");
     }
+    if (cfg->game == MZ_GAME_KILLALLGO && cfg->board_size != 7) { return fail(MZ_ERR_ARG, "KillAllGo is played on 7 x 7 (killallgo.h:12,23)"); }
+    if (cfg->game == MZ_GAME_KILLALLGO && cfg->muzero) { return fail(MZ_ERR_ARG, "KillAllGo is built for AlphaZero networks (its terminal test needs the position)"); }
     const bool atari = (cfg->game == MZ_GAME_ATARI);
     if (atari && !cfg->muzero) { return fail(MZ_ERR_ARG, "Atari is searched with a MuZero network only (the emulator cannot be copied into the tree)"); }
     if (atari && (cfg->atari_legal_mask == 0 || (cfg->atari_legal_mask >> 18) != 0)) { return fail(MZ_ERR_ARG, "atari_legal_mask must name at least one of the 18 actions"); }
@@ -1325,7 +1327,7 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     mz_engine* e = new mz_engine();
     e->cfg = *cfg;
     mz_dims& d = e->d;
-    d.game = cfg->game, d.N = N, d.A = (cfg->game == MZ_GAME_TICTACTOE ? 9 : ((cfg->game == MZ_GAME_GOMOKU || cfg->game == MZ_GAME_HEX) ? N * N : N * N + 1)), d.C = (MZ_GO_FAMILY(cfg->game) ? 18 : 4);
+    d.game = (cfg->game == MZ_GAME_KILLALLGO ? MZ_GAME_GO : cfg->game), d.killall = (cfg->game == MZ_GAME_KILLALLGO ? 1 : 0), d.N = N, d.A = (cfg->game == MZ_GAME_TICTACTOE ? 9 : ((cfg->game == MZ_GAME_GOMOKU || cfg->game == MZ_GAME_HEX) ? N * N : N * N + 1)), d.C = ((MZ_GO_FAMILY(cfg->game) || cfg->game == MZ_GAME_KILLALLGO) ? 18 : 4);
     d.hex_swap_rule = (cfg->hex_swap_rule != 0);
     d.num_players = 2, d.act_planes = 1, d.value_rescale = (cfg->value_rescale != 0);
     e->atari = atari;

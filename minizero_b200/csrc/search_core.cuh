@@ -174,6 +174,8 @@ static inline mz_vis mz_load_vis(const mz_vis* p) { return *p; }
 static inline void mz_store_vis(mz_vis* p, const mz_vis& v) { *p = v; }
 #endif
 
+#include "killallgo_rules.h"
+
 #define MZ_GAME_TICTACTOE 0
 #define MZ_GAME_GO 1
 #define MZ_GAME_OTHELLO 2
@@ -181,6 +183,8 @@ static inline void mz_store_vis(mz_vis* p, const mz_vis& v) { *p = v; }
 #define MZ_GAME_GOMOKU 4     // environment/gomoku: N x N, no pass, five in a row through the last move
 #define MZ_GAME_HEX 5        // environment/hex: N x N, no pass, swap rule, connect the two own edges; never rotated
 #define MZ_GAME_ATARI 6      // environment/atari: one player, 18 actions, the emulator is the host's; MuZero only (hidden state 6 x 6)
+#define MZ_GAME_KILLALLGO 7  // environment/killallgo: GoEnv on 7 x 7 (mz_dims.game is MZ_GAME_GO with mz_dims.killall set: every Go rule applies) + its own opening
+                             // legality, terminal test (Benson's unconditional life) and result
 #define MZ_ATARI_RES 96      // kAtariResolution, atari.h:24
 #define MZ_ATARI_FRAME (3 * MZ_ATARI_RES * MZ_ATARI_RES)
 #define MZ_GO_FAMILY(game) ((game) == MZ_GAME_GO || (game) == MZ_GAME_NOGO)
@@ -221,6 +225,7 @@ struct mz_dims {
     int act_planes;     // action planes of the dynamics input: 1 (one-hot cell) or 18 (one-hot channel block, atari.cpp:124-130)
     uint32_t legal_mask; // Atari: minimal action set of the game (the root's legal actions, atari.h:57)
     int vb_cap;         // capacity of the value-bound table per game    // floor(S / (log2(m) * (m >> level) / 2)) in double, gumbel_zero.cpp:109
+    int killall;        // KillAllGo on top of the Go rules (game == MZ_GAME_GO, N == 7): killallgo.cpp:27-48 with env_killallgo_use_seki = false
     int think_k;        // actor_mcts_think_batch_size when > 1 (console think(), zero_actor.cpp:129-157): leaves selected per tree and network forward
 };
 
@@ -644,6 +649,14 @@ MZ_DEV int mz_gomoku_winner(const mz_dims& d, const mz_scratch* w)
     return 0;
 }
 
+// ---- KillAllGo (environment/killallgo/killallgo.cpp:27-48) on top of the Go rules; Benson's unconditional life lives in killallgo_rules.h ----
+MZ_DEV uint64_t mz_ka_board(const mz_scratch* w, int colour) // row bitboards -> one 64-bit board (bit y * 8 + x)
+{
+    uint64_t b = 0;
+    for (int y = 0; y < 7; ++y) { b |= (uint64_t)(w->st[colour][y] & 0x7fu) << (8 * y); }
+    return b;
+}
+
 MZ_DEV int mz_env_is_terminal(const mz_dims& d, const mz_scratch* w)
 {
     const int N = d.N;
@@ -656,6 +669,7 @@ MZ_DEV int mz_env_is_terminal(const mz_dims& d, const mz_scratch* w)
         return 1;
     }
     if (d.game == MZ_GAME_GO) {
+        if (d.killall && mz_ka_terminal(mz_ka_board(w, 0), mz_ka_board(w, 1))) { return 1; } // killallgo.cpp:34-40
         if (w->num_moves >= 2 && w->last == N * N && w->last2 == N * N) { return 1; } // go.cpp:249-251
         return w->num_moves > 2 * N * N;                                              // go.cpp:254
     }
@@ -679,6 +693,8 @@ MZ_DEV float mz_env_eval_score(const mz_dims& d, mz_scratch* w, int lane)
         winner = mz_gomoku_winner(d, w);
     } else if (d.game == MZ_GAME_HEX) { // hex.cpp:101-111
         winner = mz_hex_winner(d, w);
+    } else if (d.game == MZ_GAME_GO && d.killall) { // killallgo.cpp:42-48: Black wins when no White stone is left or the whole board is unconditionally Black's
+        winner = mz_ka_winner(mz_ka_board(w, 0), mz_ka_board(w, 1));
     } else if (d.game == MZ_GAME_GO) {
         int cnt_b = 0, cnt_w = 0;
         for (int i = lane; i < N; i += MZ_W) {
@@ -881,6 +897,17 @@ MZ_DEV int mz_env_legal_block(const mz_dims& d, const mz_state& s, mz_scratch* w
     mz_block_sync();
     if (tid == 0 && d.game == MZ_GAME_GO) { w->legal[NN >> 5] |= (1u << (NN & 31)); } // pass, go.cpp:213 (never legal in NoGo, nogo.h:32)
     mz_block_sync();
+    if (d.killall && w->num_moves < 3) { // KillAllGoEnv::isLegalAction, killallgo.cpp:27-32: Black opens with two stones, White's first move is the pass
+        if (tid == 0) {
+            if (w->num_moves == 1) {
+                for (int i = 0; i < MZ_LEGAL_WORDS; ++i) { w->legal[i] = 0u; }
+                w->legal[NN >> 5] = (1u << (NN & 31));
+            } else {
+                w->legal[NN >> 5] &= ~(1u << (NN & 31));
+            }
+        }
+        mz_block_sync();
+    }
     int n = 0;
     for (int i = 0; i < MZ_LEGAL_WORDS; ++i) { n += mz_popc(w->legal[i]); }
     return n;

@@ -13,7 +13,7 @@ import subprocess
 
 import numpy as np
 
-GAME_TICTACTOE, GAME_GO, GAME_OTHELLO, GAME_NOGO, GAME_GOMOKU, GAME_HEX, GAME_ATARI = 0, 1, 2, 3, 4, 5, 6
+GAME_TICTACTOE, GAME_GO, GAME_OTHELLO, GAME_NOGO, GAME_GOMOKU, GAME_HEX, GAME_ATARI, GAME_KILLALLGO = 0, 1, 2, 3, 4, 5, 6, 7
 ATARI_FRAME = 3 * 96 * 96  # one screen: RGB bytes, channel-major, 96 x 96 (environment/atari/atari.h:24)
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

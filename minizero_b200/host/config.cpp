@@ -35,7 +35,7 @@ const Def kDefs[] = {
     {"nn_type_name", 's', "alphazero"},
     {"env_board_size", 'i', "0"}, {"env_atari_rom_dir", 's', "/opt/atari57/"}, {"env_atari_name", 's', "ms_pacman"}, {"env_conhex_use_swap_rule", 'b', "true"},
     {"env_go_komi", 'f', "7.5"}, {"env_go_ko_rule", 's', "positional"}, {"env_gomoku_rule", 's', "standard"}, {"env_gomoku_exactly_five_stones", 'b', "true"},
-    {"env_havannah_use_swap_rule", 'b', "true"}, {"env_hex_use_swap_rule", 'b', "true"}, {"env_killallgo_ko_rule", 's', "situational"},
+    {"env_havannah_use_swap_rule", 'b', "true"}, {"env_hex_use_swap_rule", 'b', "true"}, {"env_killallgo_ko_rule", 's', "positional"},
     {"env_killallgo_use_seki", 'b', "false"}, {"env_rubiks_scramble_rotate", 'i', "5"}, {"env_surakarta_no_capture_plies", 'i', "50"},
     {"env_tetris_block_puzzle_num_holding_block", 'i', "3"}, {"env_tetris_block_puzzle_num_preview_holding_block", 'i', "0"},
 };

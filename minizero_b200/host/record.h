@@ -155,10 +155,11 @@ struct AtariRecord {
 // eval_score: Environment::getEvalScore(false) of the final position; terminal: Environment::isTerminal().
 // When the game is not terminal (resign) the side to move loses (base_actor.cpp:48-54, go.cpp:262-263).
 inline std::string selfPlayLine(const GameHeader& h, const std::vector<MoveRecord>& moves, bool terminal, float eval_score, int turn_to_move,
-                                const SequenceConfig& seq = SequenceConfig(), const AtariRecord* atari = nullptr)
+                                const SequenceConfig& seq = SequenceConfig(), const AtariRecord* atari = nullptr, const float* unfinished_score = nullptr)
 {
-    // a game that is not over counts as resigned by the side to move (base_actor.cpp:48-54); Atari's score is the total reward either way (atari.h:59)
-    const float resign_score = (atari ? atari->total_reward : (turn_to_move == 1 ? -1.0f : 1.0f));
+    // a game that is not over counts as resigned by the side to move (base_actor.cpp:48-54: getEvalScore(true)); Atari's score is the total reward either
+    // way (atari.h:59); KillAllGo's getEvalScore ignores the resign flag and reads the position (killallgo.cpp:42-48): the caller passes it
+    const float resign_score = (atari ? atari->total_reward : (unfinished_score ? *unfinished_score : (turn_to_move == 1 ? -1.0f : 1.0f)));
     if (atari) { eval_score = atari->total_reward; }
     std::vector<std::pair<std::string, std::string>> tags;
     tags.push_back({"GM", h.game_name});

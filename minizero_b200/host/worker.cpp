@@ -47,6 +47,12 @@ bool Worker::initialize()
             std::cerr << "env_board_size does not match the model's board" << std::endl;
             return false;
         }
+    } else if (net_.game_name.rfind("killallgo_", 0) == 0) { // environment/killallgo: 7 x 7 only (killallgo.h:12,23)
+        game_type_ = MZ_GAME_KILLALLGO, board_ = net_.dims.input_height;
+        if (board_ != 7 || muzero_ || cfg_.getBool("env_killallgo_use_seki")) {
+            std::cerr << "KillAllGo is built for 7x7 AlphaZero networks without the seki table (env_killallgo_use_seki=false)" << std::endl;
+            return false;
+        }
     } else if (net_.game_name.rfind("hex_", 0) == 0) {
         game_type_ = MZ_GAME_HEX, board_ = net_.dims.input_height;
     } else if (net_.game_name.rfind("gomoku_", 0) == 0) { // "gomoku_15x15" or, with env_gomoku_rule=outer_open, "gomoku_oo_15x15" (gomoku.h:36)
@@ -65,7 +71,7 @@ bool Worker::initialize()
     actions_ = net_.dims.action_size;
     sims_ = cfg_.getInt("actor_num_simulation");
     num_games_ = cfg_.getInt("zero_num_parallel_games");
-    header_.game_name = net_.game_name, header_.board_size = board_, header_.has_komi = (game_type_ == MZ_GAME_GO || game_type_ == MZ_GAME_NOGO), header_.komi = cfg_.getFloat("env_go_komi");
+    header_.game_name = net_.game_name, header_.board_size = board_, header_.has_komi = (game_type_ == MZ_GAME_GO || game_type_ == MZ_GAME_NOGO || game_type_ == MZ_GAME_KILLALLGO), header_.komi = cfg_.getFloat("env_go_komi");
     header_.model_file = model;
 
     int ndev = 0;
@@ -81,7 +87,9 @@ bool Worker::initialize()
         c.device = dev, c.game = game_type_, c.board_size = board_, c.num_games = engine_games_[dev], c.num_simulation = sims_;
         c.puct_base = cfg_.getFloat("actor_mcts_puct_base"), c.puct_init = cfg_.getFloat("actor_mcts_puct_init");
         c.reward_discount = cfg_.getFloat("actor_mcts_reward_discount"), c.komi = cfg_.getFloat("env_go_komi");
-        c.ko_situational = (cfg_.getString("env_go_ko_rule") == "situational"), c.dirichlet_epsilon = cfg_.getFloat("actor_dirichlet_noise_epsilon");
+        // env_killallgo_ko_rule is a second name of the same setting in the reference (configuration.cpp:178,187: both bind env_go_ko_rule)
+        c.ko_situational = (cfg_.getString("env_go_ko_rule") == "situational" || (game_type_ == MZ_GAME_KILLALLGO && cfg_.getString("env_killallgo_ko_rule") == "situational"));
+        c.dirichlet_epsilon = cfg_.getFloat("actor_dirichlet_noise_epsilon");
         c.muzero = muzero_, c.use_gumbel = gumbel_;
         c.value_rescale = cfg_.getBool("actor_mcts_value_rescale");
         if (atari_) {
@@ -159,6 +167,7 @@ void Worker::resetGameHost(int g)
     game.turn = 1;
     game.num_legal = initialNumLegal();
     std::fill(game.ttt, game.ttt + 9, 0);
+    game.ka[0] = game.ka[1] = 0;
     game.stones.assign((game_type_ == MZ_GAME_NOGO || game_type_ == MZ_GAME_GOMOKU || game_type_ == MZ_GAME_HEX) ? board_ * board_ : 0, 0);
     if (atari_) { atariReset(game, rng().randInt()); } // BaseActor::reset -> AtariEnv::reset() draws the emulator seed (atari.h:54) before the resign switch
     game.enable_resign = (rng().randReal() < cfg_.getFloat("zero_disable_resign_ratio") ? false : true);
@@ -390,6 +399,12 @@ bool Worker::hostTerminal(const Game& game) const
         if (n >= 2 && game.moves[n - 1].action == pass && game.moves[n - 2].action == pass) { return true; } // go.cpp:249-251
         return n > 2 * board_ * board_;                                                                        // go.cpp:254
     }
+    if (game_type_ == MZ_GAME_KILLALLGO) { // killallgo.cpp:34-40, then GoEnv::isTerminal
+        if (mz_ka_terminal(game.ka[0], game.ka[1])) { return true; }
+        const int pass = board_ * board_;
+        if (n >= 2 && game.moves[n - 1].action == pass && game.moves[n - 2].action == pass) { return true; }
+        return n > 2 * board_ * board_;
+    }
     if (game_type_ == MZ_GAME_NOGO) { return !nogoHasLegalMove(game); } // nogo.h:61-68
     if (game_type_ == MZ_GAME_HEX) { // hex.cpp:96-99: a player connects its two edges (Black columns 0 / N-1, White rows 0 / N-1; hex.cpp:47-58,305-347)
         const int N = board_;
@@ -492,7 +507,9 @@ void Worker::emitGame(int g, bool terminal, float eval_score)
 {
     AtariRecord at;
     if (atari_) { at.observations = &games_[g].observations, at.lives_history = &games_[g].lives_history, at.seed = games_[g].seed, at.total_reward = games_[g].total_reward; }
-    const std::string line = selfPlayLine(header_, games_[g].moves, terminal, eval_score, games_[g].turn, sequenceConfig(), atari_ ? &at : nullptr);
+    const float ka_score = (game_type_ == MZ_GAME_KILLALLGO ? (mz_ka_winner(games_[g].ka[0], games_[g].ka[1]) == 1 ? 1.0f : -1.0f) : 0.0f);
+    const std::string line = selfPlayLine(header_, games_[g].moves, terminal, eval_score, games_[g].turn, sequenceConfig(), atari_ ? &at : nullptr,
+                                          game_type_ == MZ_GAME_KILLALLGO ? &ka_score : nullptr);
     const std::string out = line + "\n"; // the only thing this process ever writes to the server (zero_server.cpp:111-139)
     std::lock_guard<std::mutex> lock(emit_mutex_); // engine threads share the wire
     size_t done = 0;
@@ -580,6 +597,9 @@ int Worker::advanceGame(int g, const RootView& r, bool& resign, bool& end)
         if ((game_type_ == MZ_GAME_NOGO || game_type_ == MZ_GAME_GOMOKU) && action >= 0 && action < board_ * board_) {
             game.stones[action] = static_cast<uint8_t>(game.turn);
         }
+        if (game_type_ == MZ_GAME_KILLALLGO && action >= 0 && action < board_ * board_) { // GoEnv::act with captures (go.cpp:150-178)
+            mz_ka_place(game.ka[game.turn - 1], game.ka[2 - game.turn], (action / board_) * 8 + action % board_);
+        }
         if (game_type_ == MZ_GAME_HEX && action >= 0 && action < board_ * board_) { // hex.cpp:21-66 (game.moves already holds this move)
             int id = action;
             if (cfg_.getBool("env_hex_use_swap_rule") && game.moves.size() == 2 && action == game.moves[0].action) { // swap: mirrored, first stone removed
@@ -614,6 +634,7 @@ void Worker::restartGameHost(int g)
     game.num_legal = initialNumLegal();
     std::fill(game.ttt, game.ttt + 9, 0);
     std::fill(game.stones.begin(), game.stones.end(), 0);
+    game.ka[0] = game.ka[1] = 0;
     if (atari_) { atariReset(game, next_seed_[g]); } // the seed was drawn in order when the game ended
 }
 

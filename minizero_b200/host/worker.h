@@ -9,6 +9,7 @@
 #include "record.h"
 #include "rng.h"
 #include "synth_atari.h"
+#include "../csrc/killallgo_rules.h"
 #include <atomic>
 #include <deque>
 #include <istream>
@@ -26,6 +27,7 @@ struct Game {                    // what BaseActor / ZeroActor keep per game on 
     int num_legal = 0;             // root children of the next search (= Dirichlet draws)
     uint8_t ttt[9] = {0};          // tictactoe board, only to know the end of the game in RNG order
     std::vector<uint8_t> stones;   // NoGo board (stones are never removed), for the same purpose
+    uint64_t ka[2] = {0, 0};       // KillAllGo: Black / White stones as 64-bit boards (csrc/killallgo_rules.h), captures applied: the game ends by Benson
     // Atari (environment/atari/atari.{h,cpp}): the emulator and what AtariEnv keeps beside it
     SynthAtari emu;
     int seed = 0;                          // AtariEnv::seed_ (SD tag)
@@ -100,6 +102,7 @@ private:
             return cfg_.getString("env_gomoku_rule") == "outer_open" ? board_ * board_ - inner * inner : board_ * board_;
         }
         if (game_type_ == MZ_GAME_ATARI) { return static_cast<int>(SynthAtari::minimalActionSet().size()); }
+        if (game_type_ == MZ_GAME_KILLALLGO) { return board_ * board_; } // Black's first move must be a stone (killallgo.cpp:29-31)
         return game_type_ == MZ_GAME_GO ? board_ * board_ + 1 : (game_type_ == MZ_GAME_NOGO ? board_ * board_ : (game_type_ == MZ_GAME_OTHELLO ? 4 : 9));
     }
     std::vector<mz_engine*> engines_;  // one per visible GPU (actor_group.cpp:168-177)

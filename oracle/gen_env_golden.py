@@ -23,6 +23,8 @@ CASES = {
     "env_hex11": ("hex", "program_quiet=true", 10, 10, 130),
     "env_hex11_noswap": ("hex", "env_hex_use_swap_rule=false:program_quiet=true", 11, 4, 130),
     "env_othello8": ("othello", "program_quiet=true", 6, 8, 200),
+    # KillAllGo 7x7 (seki table off, the default): the opening rule, Benson's unconditional life as the terminal test, the result
+    "env_killallgo7": ("killallgo", "program_quiet=true", 13, 60, 120),
 }
 
 
@@ -31,8 +33,12 @@ def main(names):
         binary, conf, seed, games, max_moves = CASES[name]
         with tempfile.TemporaryDirectory() as d:
             path = os.path.join(d, "p.bin")
+            # KillAllGo's set-up loads 7x7_seki.db from the working directory and otherwise GENERATES it with a search of its own (killallgo.cpp:10-25):
+            # an empty table (a zero entry count) stands in; env_killallgo_use_seki is false, the table is never consulted
+            with open(os.path.join(d, "7x7_seki.db"), "wb") as f:
+                f.write((0).to_bytes(8, "little"))
             res = subprocess.run([os.path.join(HERE, "_ref", "ref_env_playout_" + binary), conf, str(seed), str(games), str(max_moves), path], check=True,
-                                 capture_output=True, text=True)
+                                 capture_output=True, text=True, cwd=d)
             tok = res.stdout.split()
             A, F = int(tok[1]), int(tok[3])
             raw = np.fromfile(path, dtype=np.uint8).reshape(-1, 28 + A + F)

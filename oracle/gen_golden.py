@@ -41,6 +41,8 @@ CASES = {
     "gomoku15_s8_b2": ("gomoku", "gomoku15_az_1bx16", "actor_num_simulation=8:zero_num_parallel_games=2:" + COMMON % 51, 80),
     # Hex 11x11 (environment/hex): swap rule, connect the two own edges; features / policy are not rotated although a rotation is drawn
     "hex11_s8_b2": ("hex", "hex11_az_1bx16", "actor_num_simulation=8:zero_num_parallel_games=2:" + COMMON % 61, 110),
+    # KillAllGo 7x7 (environment/killallgo, seki table off): Black's two-stone opening, Benson's unconditional life ends the game inside the tree and at the root
+    "killallgo7_s16_b2": ("killallgo", "killallgo7_az_1bx16", "actor_num_simulation=16:zero_num_parallel_games=2:" + COMMON % 95, 120),
     # Othello 8x8 MuZero: Gumbel (configs[2] settings: n=16, m=16), Gumbel with real halving (n=32, m=8), plain PUCT MuZero with Dirichlet noise
     "othello_gmz_s16_b2": ("othello", "othello_mz_1bx32", "actor_num_simulation=16:zero_num_parallel_games=2:" + GUMBEL % 16 + COMMON_MZ % 7, 130),
     "othello_gmz_s32_m8_b2": ("othello", "othello_mz_1bx32", "actor_num_simulation=32:zero_num_parallel_games=2:" + GUMBEL % 8 + COMMON_MZ % 8, 70),
@@ -142,7 +144,9 @@ def main(names):
         binary, net, conf, max_moves = CASES[name]
         with tempfile.TemporaryDirectory() as d:
             conf_full = conf + ":nn_file_name=" + os.path.join(HERE, "_ref", "nets", net + ".pt")
-            res = subprocess.run([os.path.join(HERE, "_ref", "ref_stepper_" + binary), conf_full, d, str(max_moves)], check=True, capture_output=True, text=True)
+            with open(os.path.join(d, "7x7_seki.db"), "wb") as f:  # KillAllGo's set-up wants its seki table in the working directory: an empty one (see gen_env_golden.py)
+                f.write((0).to_bytes(8, "little"))
+            res = subprocess.run([os.path.join(HERE, "_ref", "ref_stepper_" + binary), conf_full, d, str(max_moves)], check=True, capture_output=True, text=True, cwd=d)
             meta = dict(line.split() for line in open(os.path.join(d, "meta.txt")))
             if meta["type"] == "muzero_atari":
                 data = read_case_atari(d, int(meta["A"]), int(meta["F"]))

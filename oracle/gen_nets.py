@@ -22,6 +22,7 @@ NETS = {
     "nogo9_az_1bx16": ("nogo_9x9", 18, 9, 9, 16, 9, 9, 1, 1, 82, 64, 1, "alphazero"),
     "gomoku15_az_1bx16": ("gomoku_15x15", 4, 15, 15, 16, 15, 15, 1, 1, 225, 64, 1, "alphazero"),
     "hex11_az_1bx16": ("hex_11x11", 4, 11, 11, 16, 11, 11, 1, 1, 121, 64, 1, "alphazero"),
+    "killallgo7_az_1bx16": ("killallgo_7x7", 18, 7, 7, 16, 7, 7, 1, 1, 50, 64, 1, "alphazero"),
     "go9_az_2bx64": ("go_9x9", 18, 9, 9, 64, 9, 9, 1, 2, 82, 256, 1, "alphazero"),
     "go9_az_6bx256": ("go_9x9", 18, 9, 9, 256, 9, 9, 1, 6, 82, 256, 1, "alphazero"),
     "go19_az_2bx128": ("go_19x19", 18, 19, 19, 128, 19, 19, 1, 2, 362, 64, 1, "alphazero"),     # smallest 19x19 net the fused tower takes

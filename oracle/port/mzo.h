@@ -25,6 +25,7 @@ extern "C" {
 #define MZO_GAME_GOMOKU 4
 #define MZO_GAME_HEX 5
 #define MZO_GAME_ATARI 6 /* environment/atari: one player, 18 actions, host-side emulator; MuZero only (6 x 6 hidden state) */
+#define MZO_GAME_KILLALLGO 7 /* environment/killallgo: GoEnv on 7 x 7 with its own legality in the opening, terminal test (Benson) and result */
 #define MZO_ATARI_RES 96
 #define MZO_ATARI_HIST 8
 #define MZO_HEX_SWAP_RULE 4       /* env_hex_use_swap_rule (default true); shares the flags word with the Gomoku options */

@@ -133,7 +133,7 @@ int mzo_env_num_actions(const mzo_env* e)
     if (e->game == MZO_GAME_TICTACTOE) { return 9; }
     return (e->game == MZO_GAME_GOMOKU || e->game == MZO_GAME_HEX) ? e->n * e->n : e->n * e->n + 1; /* gomoku.h:32, hex.h:56: no pass */
 }
-int mzo_env_input_channels(const mzo_env* e) { return (e->game == MZO_GAME_GO || e->game == MZO_GAME_NOGO) ? 18 : 4; }
+int mzo_env_input_channels(const mzo_env* e) { return (e->game == MZO_GAME_GO || e->game == MZO_GAME_NOGO || e->game == MZO_GAME_KILLALLGO) ? 18 : 4; }
 
 /* neighbour order of go_grid.h:43-54: up(+n), right(+1), down(-n), left(-1) */
 static int neighbours(int n, int pos, int* out)
@@ -251,9 +251,12 @@ static void push_history(mzo_env* e)
     e->hashes[e->num_moves] = e->hash;
 }
 
+static int killallgo_is_legal(const mzo_env* e, int action, int player);
+
 static int go_act(mzo_env* e, int action, int player)
 {
-    if (!(e->game == MZO_GAME_NOGO ? nogo_is_legal(e, action, player) : go_is_legal(e, action, player))) { return 0; } /* go.cpp:134 (virtual call) */
+    if (!(e->game == MZO_GAME_NOGO ? nogo_is_legal(e, action, player)
+                                   : (e->game == MZO_GAME_KILLALLGO ? killallgo_is_legal(e, action, player) : go_is_legal(e, action, player)))) { return 0; } /* go.cpp:134 (virtual call) */
     int n = e->n;
     e->turn = other(player);   /* go.cpp:140 */
     e->hash ^= e->turn_key;    /* go.cpp:141 */
@@ -286,6 +289,96 @@ static int go_is_terminal(const mzo_env* e)
     int n2 = e->n * e->n, m = e->num_moves;
     if (m >= 2 && e->actions[m - 1] == n2 && e->actions[m - 2] == n2) { return 1; } /* go.cpp:249-251 */
     return m > 2 * n2;                                                                /* go.cpp:254 */
+}
+
+/* ---- KillAllGo (environment/killallgo/killallgo.cpp:27-48; env_killallgo_use_seki = false, the default) ----
+ * Unconditional life (Benson) of `player`'s stones, GoEnv::findBensonBitboard (go.cpp:614-676) evaluated on the whole position: the reference keeps
+ * its area / Benson bitboards incrementally (go.cpp:464-612) and re-evaluates them only where a move can change them; the restatement recomputes
+ * them from the position after every move (pinned against playouts of the reference's own environment, tests/golden/env_killallgo7*).
+ * Blocks = connected groups of the player's stones; areas = connected regions of everything else (empty points and opposing stones, go.cpp:573-589);
+ * an area is vital to a neighbouring block when every EMPTY point of it is a liberty of that block (go.cpp:627-633). Returns the number of points
+ * of the Benson bitboard (surviving blocks and their surviving areas). */
+static int benson_count(const mzo_env* e, int player)
+{
+    const int n = e->n, n2 = n * n;
+    int block_of[MZO_MAX_CELLS], area_of[MZO_MAX_CELLS], stack[MZO_MAX_CELLS];
+    int nblocks = 0, nareas = 0;
+    for (int i = 0; i < n2; ++i) { block_of[i] = area_of[i] = -1; }
+    for (int s0 = 0; s0 < n2; ++s0) {
+        const int own = (e->board[s0] == player);
+        int* lab = own ? block_of : area_of;
+        if (lab[s0] >= 0) { continue; }
+        const int id = own ? nblocks++ : nareas++;
+        int top = 0;
+        stack[top++] = s0, lab[s0] = id;
+        while (top > 0) {
+            int p = stack[--top], nb[4], k = neighbours(n, p, nb);
+            for (int j = 0; j < k; ++j) {
+                int q = nb[j];
+                if ((e->board[q] == player) == own && lab[q] < 0) { lab[q] = id, stack[top++] = q; }
+            }
+        }
+    }
+    if (nblocks == 0) { return 0; }
+    /* adjacency and vitality */
+    static uint8_t adj[MZO_MAX_CELLS][MZO_MAX_CELLS], vital[MZO_MAX_CELLS][MZO_MAX_CELLS]; /* [block][area] */
+    for (int b = 0; b < nblocks; ++b) {
+        memset(adj[b], 0, (size_t)nareas), memset(vital[b], 0, (size_t)nareas);
+    }
+    for (int p = 0; p < n2; ++p) {
+        if (block_of[p] < 0) { continue; }
+        int nb[4], k = neighbours(n, p, nb);
+        for (int j = 0; j < k; ++j) {
+            if (area_of[nb[j]] >= 0) { adj[block_of[p]][area_of[nb[j]]] = 1; }
+        }
+    }
+    for (int b = 0; b < nblocks; ++b) {
+        for (int a = 0; a < nareas; ++a) {
+            if (!adj[b][a]) { continue; }
+            int ok = 1;
+            for (int p = 0; p < n2 && ok; ++p) {
+                if (area_of[p] != a || e->board[p] != 0) { continue; }
+                int nb[4], k = neighbours(n, p, nb), lib = 0;
+                for (int j = 0; j < k; ++j) { lib |= (block_of[nb[j]] == b); }
+                ok = lib;
+            }
+            vital[b][a] = (uint8_t)ok;
+        }
+    }
+    uint8_t in_b[MZO_MAX_CELLS], in_a[MZO_MAX_CELLS];
+    memset(in_b, 0, sizeof(in_b)), memset(in_a, 0, sizeof(in_a));
+    for (int b = 0; b < nblocks; ++b) {
+        for (int a = 0; a < nareas; ++a) {
+            if (vital[b][a]) { in_b[b] = 1, in_a[a] = 1; } /* go.cpp:630-632 */
+        }
+    }
+    for (int changed = 1; changed;) { /* go.cpp:638-671 */
+        changed = 0;
+        for (int b = 0; b < nblocks; ++b) {
+            if (!in_b[b]) { continue; }
+            int cnt = 0;
+            for (int a = 0; a < nareas; ++a) { cnt += (vital[b][a] && in_a[a]); }
+            if (cnt < 2) { in_b[b] = 0, changed = 1; }
+        }
+        for (int a = 0; a < nareas; ++a) {
+            if (!in_a[a]) { continue; }
+            for (int b = 0; b < nblocks; ++b) {
+                if (adj[b][a] && !in_b[b]) { in_a[a] = 0, changed = 1; }
+            }
+        }
+    }
+    int count = 0;
+    for (int p = 0; p < n2; ++p) { count += (block_of[p] >= 0 ? in_b[block_of[p]] : in_a[area_of[p]]); }
+    return count;
+}
+
+/* KillAllGoEnv::isLegalAction, killallgo.cpp:27-32: Black opens with two stones (move 0 and 2 must be stones, move 1 must be the pass) */
+static int killallgo_is_legal(const mzo_env* e, int action, int player)
+{
+    const int pass = e->n * e->n;
+    if (e->num_moves == 1) { return action == pass; }
+    if (e->num_moves < 3) { return action != pass && go_is_legal(e, action, player); }
+    return go_is_legal(e, action, player);
 }
 
 /* go.cpp:703-723 */
@@ -570,6 +663,7 @@ static int ttt_eval(const mzo_env* e)
 int mzo_env_is_legal(const mzo_env* e, int action, int player)
 {
     if (e->game == MZO_GAME_GO) { return go_is_legal(e, action, player); }
+    if (e->game == MZO_GAME_KILLALLGO) { return killallgo_is_legal(e, action, player); }
     if (e->game == MZO_GAME_NOGO) { return nogo_is_legal(e, action, player); }
     if (e->game == MZO_GAME_GOMOKU) { return gomoku_is_legal(e, action, player); }
     if (e->game == MZO_GAME_HEX) { return hex_is_legal(e, action, player); }
@@ -579,7 +673,7 @@ int mzo_env_is_legal(const mzo_env* e, int action, int player)
 
 int mzo_env_act(mzo_env* e, int action, int player)
 {
-    if (e->game == MZO_GAME_GO || e->game == MZO_GAME_NOGO) { return go_act(e, action, player); }
+    if (e->game == MZO_GAME_GO || e->game == MZO_GAME_NOGO || e->game == MZO_GAME_KILLALLGO) { return go_act(e, action, player); }
     if (e->game == MZO_GAME_OTHELLO) { return othello_act(e, action, player); }
     if (e->game == MZO_GAME_HEX) { return hex_act(e, action, player); }
     if (e->game == MZO_GAME_GOMOKU) { /* gomoku.cpp:23-31 */
@@ -599,6 +693,10 @@ int mzo_env_act(mzo_env* e, int action, int player)
 int mzo_env_is_terminal(const mzo_env* e)
 {
     if (e->game == MZO_GAME_GO) { return go_is_terminal(e); }
+    if (e->game == MZO_GAME_KILLALLGO) { /* killallgo.cpp:34-40: all of the board unconditionally Black's, or any unconditionally alive White group */
+        if (benson_count(e, 1) == e->n * e->n || benson_count(e, 2) > 0) { return 1; }
+        return go_is_terminal(e);
+    }
     if (e->game == MZO_GAME_NOGO) { /* nogo.h:61-68 */
         for (int pos = 0; pos < e->n * e->n; ++pos) {
             if (nogo_is_legal(e, pos, e->turn)) { return 0; }
@@ -624,6 +722,11 @@ int mzo_env_is_terminal(const mzo_env* e)
 float mzo_env_eval_score(const mzo_env* e, int is_resign)
 {
     if (e->game == MZO_GAME_GO) { return go_eval_score(e, is_resign); }
+    if (e->game == MZO_GAME_KILLALLGO) { /* killallgo.cpp:42-48 (is_resign is not consulted) */
+        int white = 0;
+        for (int p = 0; p < e->n * e->n; ++p) { white += (e->board[p] == 2); }
+        return (white == 0 || benson_count(e, 1) == e->n * e->n) ? 1.0f : -1.0f;
+    }
     if (e->game == MZO_GAME_NOGO) { return other(e->turn) == 1 ? 1.0f : -1.0f; } /* nogo.h:70-78: whoever is to move has lost */
     if (e->game == MZO_GAME_OTHELLO) { return othello_eval_score(e, is_resign); }
     if (e->game == MZO_GAME_HEX) { /* hex.cpp:101-111 */
@@ -640,7 +743,7 @@ float mzo_env_eval_score(const mzo_env* e, int is_resign)
 
 void mzo_env_features(const mzo_env* e, int rotation, float* out)
 {
-    if (e->game == MZO_GAME_GO || e->game == MZO_GAME_NOGO) {
+    if (e->game == MZO_GAME_GO || e->game == MZO_GAME_NOGO || e->game == MZO_GAME_KILLALLGO) {
         go_features(e, rotation, out);
         return;
     }

@@ -46,6 +46,7 @@ sim* hs_create(int game, int N, int B, int S, float puct_base, float puct_init, 
     memset(&d, 0, sizeof(d));
     memset(&h->s, 0, sizeof(h->s));
     d.game = game, d.N = N, d.A = (game == MZ_GAME_TICTACTOE ? 9 : ((game == MZ_GAME_GOMOKU || game == MZ_GAME_HEX) ? N * N : N * N + 1)), d.C = (MZ_GO_FAMILY(game) ? 18 : 4), d.S = S, d.B = B;
+    if (game == MZ_GAME_KILLALLGO) { d.game = MZ_GAME_GO, d.killall = 1, d.C = 18; } // every Go rule + killallgo.cpp:27-48 (engine.cu maps it the same way)
     d.gomoku_exactly_five = 1, d.gomoku_outer_open = 0, d.hex_swap_rule = 1; // reference defaults (configuration.cpp:82-85)
     d.num_players = 2, d.act_planes = 1;
     if (game == MZ_GAME_ATARI) { // atari.h:18-26

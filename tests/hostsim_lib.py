@@ -55,7 +55,7 @@ class HostSimSearch:
         self.lib = lib
         n = 3 if game == 0 else board_size
         self.A = 9 if game == 0 else (n * n if game in (4, 5) else n * n + 1)
-        self.F = (18 if game in (1, 3) else 4) * n * n
+        self.F = (18 if game in (1, 3, 7) else 4) * n * n
         if game == 6:  # Atari MuZero: 18 actions, planes from the device's screen ring (not produced by the host build)
             self.A, self.F = 18, 0
         self.B, self.S = num_games, num_simulation

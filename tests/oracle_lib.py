@@ -7,7 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MAX_ACTIONS = 19 * 19 + 1
-GAME_TICTACTOE, GAME_GO, GAME_OTHELLO, GAME_NOGO, GAME_GOMOKU, GAME_HEX, GAME_ATARI = 0, 1, 2, 3, 4, 5, 6
+GAME_TICTACTOE, GAME_GO, GAME_OTHELLO, GAME_NOGO, GAME_GOMOKU, GAME_HEX, GAME_ATARI, GAME_KILLALLGO = 0, 1, 2, 3, 4, 5, 6, 7
 ATARI_LEGAL_MASK = 0b1111111101  # ms_pacman's minimal action set: NOOP, UP, RIGHT, LEFT, DOWN and the four diagonals (ALE ids 0, 2..9)
 
 
@@ -102,7 +102,7 @@ class OracleSearch:
         self.h = lib.mzo_create(C.byref(self.cfg))
         n = 3 if game == GAME_TICTACTOE else board_size
         self.A = 9 if game == GAME_TICTACTOE else (n * n if game in (GAME_GOMOKU, GAME_HEX) else n * n + 1)
-        self.F = (18 if game in (GAME_GO, GAME_NOGO) else 4) * n * n
+        self.F = (18 if game in (GAME_GO, GAME_NOGO, GAME_KILLALLGO) else 4) * n * n
         self.atari = (game == GAME_ATARI)
         if self.atari:
             self.A, self.F = 18, 32 * 96 * 96

@@ -4,6 +4,7 @@ loader and rules (oracle/_ref/ref_record_check_*), which must parse it, replay e
 lengths and return."""
 import os
 import subprocess
+import tempfile
 import time
 
 import pytest
@@ -49,6 +50,8 @@ def run_worker(conf, want_lines, timeout=240):
     ("nogo", "nogo9_az_1bx16", "actor_num_simulation=16:zero_num_parallel_games=16", ""),
     ("gomoku", "gomoku15_az_1bx16", "actor_num_simulation=8:zero_num_parallel_games=24", ""),
     ("hex", "hex11_az_1bx16", "actor_num_simulation=8:zero_num_parallel_games=24", ""),
+    # KillAllGo 7x7: the worker ends games by Benson's unconditional life on its own copy of the position, in the reference's draw order
+    ("killallgo", "killallgo7_az_1bx16", "actor_num_simulation=16:zero_num_parallel_games=16", ""),
 ])
 def test_worker_speaks_the_wire_protocol_and_reference_accepts_its_records(game, net, conf, checker_conf):
     checker = os.path.join(ROOT, "oracle", "_ref", "ref_record_check_" + game)
@@ -60,7 +63,10 @@ def test_worker_speaks_the_wire_protocol_and_reference_accepts_its_records(game,
     assert rc == 0, err[-500:]
     assert len(lines) >= 24, err[-500:]
     assert all(l.startswith("SelfPlay ") and l.endswith(" #") for l in lines), "stdout must carry nothing but SelfPlay lines (zero_server.cpp:130-139)"
-    r = subprocess.run([checker, checker_conf], input="\n".join(lines) + "\n", capture_output=True, text=True)
+    with tempfile.TemporaryDirectory() as d:  # the KillAllGo build of the reference wants its seki table in the working directory: an empty one (unused)
+        with open(os.path.join(d, "7x7_seki.db"), "wb") as f:
+            f.write((0).to_bytes(8, "little"))
+        r = subprocess.run([checker, checker_conf], input="\n".join(lines) + "\n", capture_output=True, text=True, cwd=d)
     assert r.stdout.strip() == f"RECORDS_OK {len(lines)}", r.stdout + r.stderr[-300:]
     assert f"EV[{net}.pt]" in lines[0]
 

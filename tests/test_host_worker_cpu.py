@@ -139,7 +139,7 @@ def test_intermediate_sequence_lines_match_reference_bytes(worker_binary):
 
 
 @pytest.mark.parametrize("name,game_type,board", [("go5_s24_b2", 1, 5), ("ttt_s50_b2", 0, 3), ("go9_s32_b2", 1, 9), ("othello_gmz_s16_b2", 2, 8),
-                                                  ("othello_mz_s24_b2", 2, 8), ("nogo9_s8_b2", 3, 9), ("gomoku15_s8_b2", 4, 15), ("hex11_s8_b2", 5, 11)])
+                                                  ("othello_mz_s24_b2", 2, 8), ("nogo9_s8_b2", 3, 9), ("gomoku15_s8_b2", 4, 15), ("hex11_s8_b2", 5, 11), ("killallgo7_s16_b2", 7, 7)])
 def test_host_draw_sequence_matches_reference_seed(worker_binary, name, game_type, board):
     """Seed-exact randomness: fed with the root tables the reference saw, the worker's host logic — the same
     member functions the GPU path uses, libstdc++'s mt19937 and distributions in the reference's order — reproduces every rotation

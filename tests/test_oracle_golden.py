@@ -14,6 +14,7 @@ CASES = {
     "nogo9_s8_b2": (oracle_lib.GAME_NOGO, 9),
     "gomoku15_s8_b2": (oracle_lib.GAME_GOMOKU, 15),
     "hex11_s8_b2": (oracle_lib.GAME_HEX, 11),
+    "killallgo7_s16_b2": (oracle_lib.GAME_KILLALLGO, 7),
     "go5_mz_s16_b2": (oracle_lib.GAME_GO, 5),
     "ttt_gmz_s16_b2": (oracle_lib.GAME_TICTACTOE, 3),
     "othello_gmz_s16_b2": (oracle_lib.GAME_OTHELLO, 8),
@@ -107,7 +108,7 @@ def test_oracle_gumbel_policy_matches_reference_records(oracle):
 ENV_CASES = {"env_ttt": (oracle_lib.GAME_TICTACTOE, 3), "env_go5": (oracle_lib.GAME_GO, 5), "env_go9": (oracle_lib.GAME_GO, 9),
              "env_go9_situational": (oracle_lib.GAME_GO, 9), "env_go19": (oracle_lib.GAME_GO, 19), "env_othello8": (oracle_lib.GAME_OTHELLO, 8), "env_nogo9": (oracle_lib.GAME_NOGO, 9),
              "env_gomoku15": (oracle_lib.GAME_GOMOKU, 15), "env_gomoku15_freestyle": (oracle_lib.GAME_GOMOKU, 15),
-             "env_hex11": (oracle_lib.GAME_HEX, 11), "env_hex11_noswap": (oracle_lib.GAME_HEX, 11)}
+             "env_hex11": (oracle_lib.GAME_HEX, 11), "env_hex11_noswap": (oracle_lib.GAME_HEX, 11), "env_killallgo7": (oracle_lib.GAME_KILLALLGO, 7)}
 
 
 @pytest.mark.parametrize("name", list(ENV_CASES))

@@ -8,7 +8,7 @@ import hostsim_lib
 
 import oracle_lib
 
-CASES = {"ttt_s50_b2": (0, 3), "ttt_s50_b1_det": (0, 3), "go5_s24_b2": (1, 5), "go9_s32_b2": (1, 9), "go19_s8_b2": (1, 19), "nogo9_s8_b2": (3, 9), "gomoku15_s8_b2": (4, 15), "hex11_s8_b2": (5, 11),
+CASES = {"ttt_s50_b2": (0, 3), "ttt_s50_b1_det": (0, 3), "go5_s24_b2": (1, 5), "go9_s32_b2": (1, 9), "go19_s8_b2": (1, 19), "nogo9_s8_b2": (3, 9), "gomoku15_s8_b2": (4, 15), "hex11_s8_b2": (5, 11), "killallgo7_s16_b2": (7, 7),
          "go5_mz_s16_b2": (1, 5), "ttt_gmz_s16_b2": (0, 3), "othello_gmz_s16_b2": (2, 8), "othello_gmz_s32_m8_b2": (2, 8), "othello_mz_s24_b2": (2, 8),
          # odd Gumbel sample sizes and BASELINE search lengths: 400 simulations with the 6b x 256 net, 19x19 with 800 simulations
          "go5_gmz_s64_m12_b2": (1, 5), "go5_gmz_s100_m14_b2": (1, 5), "go9_s400_b2": (1, 9), "go19_s800_b2": (1, 19)}
@@ -73,7 +73,7 @@ def test_candidate_sort_is_libstdcxx_std_sort():
         assert np.array_equal(a, order[:n]), (n, pol[:20])
 
 
-@pytest.mark.parametrize("name,game,n", [("env_ttt", 0, 3), ("env_go5", 1, 5), ("env_go9", 1, 9), ("env_go19", 1, 19), ("env_othello8", 2, 8), ("env_nogo9", 3, 9), ("env_gomoku15", 4, 15), ("env_hex11", 5, 11)])
+@pytest.mark.parametrize("name,game,n", [("env_ttt", 0, 3), ("env_go5", 1, 5), ("env_go9", 1, 9), ("env_go19", 1, 19), ("env_othello8", 2, 8), ("env_nogo9", 3, 9), ("env_gomoku15", 4, 15), ("env_hex11", 5, 11), ("env_killallgo7", 7, 7)])
 def test_search_core_env_matches_reference_playouts(name, game, n):
     import env_replay
     case = env_replay.load(name)
