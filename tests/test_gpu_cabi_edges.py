@@ -25,7 +25,8 @@ def net(name):
 
 
 @pytest.mark.parametrize("kw,needle", [
-    (dict(game=7, board_size=9), "unsupported game"),
+    (dict(game=8, board_size=9), "unsupported game"),
+    (dict(game=7, board_size=9), "7 x 7"),
     (dict(game=1, board_size=1), "board_size"),
     (dict(game=1, board_size=20), "board_size"),
     (dict(game=2, board_size=7), "othello"),
