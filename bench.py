@@ -367,6 +367,11 @@ def main():
     evals = world * GAMES * S1 * args.steps
     value = evals / (dev_ms * 1e-3)
     e2e_value = world * GAMES * S1 * args.steps / e2e_s
+    # the engine runs the wide tower (two row tiles per CTA) when a layer holds at least two wide units per CTA pair (engine.cu alloc_net); 148 SMs on a B200
+    n1 = (6 if atari else w["board"]) + 1
+    hidden = int(eng.net_dims["num_hidden_channels"])
+    wide_units = -(-(-(-GAMES * n1 * n1 // 128)) // 4) * max(1, hidden // 128)
+    tower_kernel = "conv_tower_wide_kernel" if (not atari and hidden % 128 == 0 and wide_units >= 148) else "conv_tower_kernel"
     layers = eng.conv_layers_per_launch()
     flops_per_launch = w["tower_flops"](GAMES)
     conv_tflops = flops_per_launch / (prof["conv_ms"] * 1e-3) / 1e12
@@ -382,7 +387,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "leaf-evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": f"conv_tower_kernel ({w['tower']}; {GAMES} positions, one launch covering {layers} layers)", "flops_per_launch": flops_per_launch, "bound": "tensor",
+        "roofline": {"kernel": f"{tower_kernel} ({w['tower']}; {GAMES} positions, one launch covering {layers} layers)", "flops_per_launch": flops_per_launch, "bound": "tensor",
                      "achieved": conv_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": conv_tflops / pk["bf16_tflops"], "traffic": traffic,
                      "traffic_source": traffic_src, "peak_source": pk["source"] + " burst (kernel timed alone, 50 launches)", "launch_ms": prof["conv_ms"]},
         "kernels_ms": {"conv_tower": prof["conv_ms"], "tree_select_transition": prof["tree_ms"], "heads": prof["heads_ms"]},
