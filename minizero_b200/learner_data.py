@@ -9,6 +9,7 @@ Reference interfaces mirrored (paths relative to /root/reference/minizero):
   environment/go/go.h:137, othello.h:79 getValue = the game's return        -> Record.value
   utils/rotation.h:51-93                getPositionByRotating               -> rotate_action
   learner/data_loader.cpp:134-157       setAlphaZeroTrainingData            -> alphazero_batch
+  learner/data_loader.cpp:159-200       setMuZeroTrainingData               -> muzero_batch (board games: go.cpp:725-736, othello.cpp:264-275 action planes)
 """
 import re
 
@@ -66,6 +67,26 @@ class Record:
         """GoEnvLoader / OthelloEnvLoader / ... ::getValue: the game's return (RE tag)"""
         return np.float32(float(self.tags["RE"]))
 
+    def reward(self, pos):
+        """BaseEnvLoader::getReward (base_env.h:279): the move's R tag, 0 past the end of the game"""
+        return np.float32(float(self.infos[pos]["R"])) if pos < len(self.actions) else np.float32(0.0)
+
+    def action_plane(self, pos, rotation, board_size, rand_int, rotates=True):
+        """GoEnvLoader / OthelloEnvLoader::getActionFeatures (go.cpp:725-736, othello.cpp:264-275): one-hot cell of the rotated move (a pass is the empty
+        plane); past the end of the game a random action id drawn with the learner's generator (rand_int() = Random::randInt()), set only when it is
+        smaller than the game's length — the reference's own condition, kept as it is"""
+        n2 = board_size * board_size
+        out = np.zeros(n2, np.float32)
+        if pos < len(self.actions):
+            a = self.actions[pos]
+            if a != n2:
+                out[rotate_action(a, rotation, board_size) if rotates else a] = 1.0
+        else:
+            a = rand_int() % (n2 + 1)
+            if a < len(self.actions) and a < n2:  # (the reference writes index n2 of an n2-element vector when the draw is n2 and the game is longer: skipped here)
+                out[a] = 1.0
+        return out
+
 
 _TAG = re.compile(r"([A-Z]+)\[((?:\\.|[^\]\\])*)\]")
 
@@ -105,3 +126,27 @@ def alphazero_batch(engine, records, picks):
     policy = np.stack([records[r].policy(p, q, engine.A, engine.board_size, rotates) for r, p, q in picks])
     value = np.array([records[r].value(p) for r, p, _ in picks], np.float32)
     return feats, policy, value
+
+
+def muzero_batch(engine, records, picks, unrolling_step, rand_int):
+    """DataLoaderThread::setMuZeroTrainingData (data_loader.cpp:159-200) for board games: the root planes of every pick rebuilt on the device, then per
+    unroll step the action plane, policy target, value (the game's return) and reward. Returns features [n][C*H*W], action_features [n][K][N*N],
+    policy [n][K + 1][A], value [n][K + 1], reward [n][K]."""
+    from .engine import GAME_HEX
+    rotates = (engine.game != GAME_HEX)
+    n, K, N = len(picks), int(unrolling_step), engine.board_size
+    feats, _, _ = alphazero_batch(engine, records, picks)
+    act = np.zeros((n, K, N * N), np.float32)
+    policy = np.zeros((n, K + 1, engine.A), np.float32)
+    value = np.zeros((n, K + 1), np.float32)
+    reward = np.zeros((n, K), np.float32)
+    for j, (r, p, q) in enumerate(picks):
+        rec = records[r]
+        for step in range(K + 1):  # the reference's order of calls per step: action plane, policy, value, reward (the random draws follow it)
+            if step < K:
+                act[j, step] = rec.action_plane(p + step, q, N, rand_int, rotates)
+            policy[j, step] = rec.policy(p + step, q, engine.A, N, rotates)
+            value[j, step] = rec.value(p + step)
+            if step < K:
+                reward[j, step] = rec.reward(p + step)
+    return feats, act, policy, value, reward
