@@ -68,7 +68,8 @@ typedef struct {
                                   * virtual loss (actor/mcts.h:33-34, mcts.cpp:51-61,185), evaluates the distinct ones together and applies them in selection
                                   * order. num_games is then the number of trees; every per-game array of this API has num_games * K entries, lane-major
                                   * (index lane * num_games + tree): rotations, features, path lengths and network outputs per lane, while roots / moves /
-                                  * noise use the first num_games entries (one per tree). AlphaZero networks with PUCT selection only. */
+                                  * noise use the first num_games entries (one per tree). PUCT selection on the board games, AlphaZero and MuZero networks (a MuZero root's
+                                  * initial inference is a batch of one lane, zero_actor.cpp:134-135); Gumbel, Atari and value rescaling are refused. */
 } mz_config;
 
 /* Hyper-parameters the reference reads from the TorchScript module (network/network.cpp:30-41). */

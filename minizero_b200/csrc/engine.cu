@@ -587,6 +587,7 @@ int forward_atari(mz_engine* e, int which)
 // each followed by scale_hidden_state and the prediction heads (network/py/muzero_network.py:136-160)
 int forward(mz_engine* e, int which = 0, bool after_tree_step = false)
 {
+    const bool in_search = after_tree_step; // think(): only a search step knows which lanes hold a leaf (the evaluation hooks fill every board)
     if (!e->net_ready) { return fail(MZ_ERR_STATE, "network not finalized"); }
     if (e->atari) { return forward_atari(e, which); }
     NetTower& T = e->tw[which];
@@ -606,7 +607,8 @@ int forward(mz_engine* e, int which = 0, bool after_tree_step = false)
     __half* out = e->act[T.out_buf];
     if (e->cfg.muzero) {
         mznn::scale_hidden_kernel<<<e->d.B, 256, 0, e->stream>>>(out, reinterpret_cast<__half*>(e->s.hid), e->s.eval_slot, e->d.N, e->d.slots, e->cpad,
-                                                                  e->nd.num_hidden_channels, e->d.S + 1);
+                                                                  e->nd.num_hidden_channels, e->d.S + 1, e->d.think_k ? e->think_trees : 0,
+                                                                  (e->d.think_k && in_search) ? e->s.path_len : nullptr);
         e->launches++;
     }
     if (e->conv_mode == 3) { return launch_heads(e, out, T.d_done, T.done_count); }
@@ -1351,9 +1353,9 @@ int mz_create(const mz_config* cfg, mz_engine** out)
     // first `trees` entries of the per-tree arrays, the lanes the sections of the per-leaf arrays (mz_lane_view), the network sees trees x K positions
     const int think_k = (cfg->think_batch_size > 1 ? cfg->think_batch_size : 0);
     if (think_k) {
-        if (cfg->muzero || cfg->use_gumbel || atari || cfg->value_rescale) {
+        if (cfg->use_gumbel || atari || cfg->value_rescale) {
             delete e;
-            return fail(MZ_ERR_ARG, "think_batch_size > 1 is built for AlphaZero networks with PUCT selection (no MuZero / Gumbel / value rescale)");
+            return fail(MZ_ERR_ARG, "think_batch_size > 1 is built for PUCT selection on the board games (no Gumbel / Atari / value rescale)");
         }
         d.think_k = think_k, e->think_trees = cfg->num_games, d.B = cfg->num_games * think_k;
     }
@@ -2101,7 +2103,7 @@ int mz_search_run(mz_engine* e, int32_t num_evals, float* device_ms)
         e->think_steps = 0;
         for (int c = 0; c <= d.S; ++c) {
             int rc = step(e, STEP_BEFORE, e->rot_enabled ? e->d_rot_all + static_cast<size_t>(c) * d.B : nullptr);
-            if (!rc) { rc = forward(e, 0, true); }
+            if (!rc) { rc = forward(e, (e->cfg.muzero && c > 0) ? 1 : 0, true); } // MuZero: the root's initial inference (a batch of one lane), recurrent below
             if (!rc) { rc = step(e, STEP_AFTER, nullptr); }
             if (rc) { return rc; }
             ++e->think_steps;

@@ -1695,13 +1695,16 @@ __global__ void __launch_bounds__(1024) heads_kernel(const HeadParams p)
 // below 1e-5). The scaled state is written back in place (the prediction heads read it there) and into the hidden-state
 // slot of the node being evaluated (hid[g][slot[g]], compact [cell][c] rows; padded channels stay zero).
 // ---------------------------------------------------------------------------------------------
+// think() lanes (trees > 0): board g = lane * trees + tree stores into ITS TREE's slots, and only when the lane holds a leaf to evaluate (path_len > 0;
+// a duplicate or unused lane carries stale rows and a stale slot index)
 __global__ void __launch_bounds__(256) scale_hidden_kernel(__half* __restrict__ act, __half* __restrict__ hid, const int32_t* __restrict__ slot, int n, int slots, int c,
-                                                          int c_real, int num_slots)
+                                                          int c_real, int num_slots, int trees, const int32_t* __restrict__ path_len)
 {
     __shared__ float red_mn[8], red_mx[8];
     const int g = blockIdx.x, tid = threadIdx.x, hw = n * n, n1 = n + 1;
+    if (path_len && path_len[g] <= 0) { return; } // uniform for the block
     __half* rows = act + static_cast<size_t>(g) * slots * c;
-    __half* dst = hid + (static_cast<size_t>(g) * num_slots + slot[g]) * hw * c;
+    __half* dst = hid + (static_cast<size_t>(trees > 0 ? g % trees : g) * num_slots + slot[g]) * hw * c;
     const bool vec = (c_real % 8 == 0); // 16-byte accesses: 8 channels per thread and step
     const int per_cell = c / 8, real_per_cell = c_real / 8;
     float mn = 3.402823466e+38f, mx = -3.402823466e+38f;

@@ -303,6 +303,9 @@ static inline mz_state mz_lane_view(const mz_dims& d, const mz_state& s, int k, 
     const size_t o = (size_t)k * trees;
     v.path += o * (d.S + 2), v.path_len += o, v.leaf_legal += o * MZ_LEGAL_WORDS, v.leaf_meta += o * 4, v.leaf_score += o;
     v.nn_in += o * d.slots * MZ_NN_CPAD, v.policy += o * d.A, v.logits += o * d.A, v.nn_value += o;
+    if (v.dyn_in) { v.dyn_in += o * d.slots * d.dyn_c; } // MuZero: the lane's dynamics input rows, evaluation slot and parity-hook record;
+    if (v.eval_slot) { v.eval_slot += o; }               // the hidden states themselves (hid) belong to the tree
+    if (v.leaf_parent) { v.leaf_parent += o * 2; }
     if (v.rotations) { v.rotations += o; }
     v.think_lane = k;
     return v;
@@ -1674,7 +1677,31 @@ MZ_DEV void mz_before_nn_muzero(const mz_dims& d, const mz_state& s, int g, mz_s
     const mz_hot* hot = s.hot + (size_t)g * d.NP;
     int32_t* path = s.path + (size_t)g * (d.S + 2);
     const int sims = (int)mz_load_hot(hot).count; // MCTS::getNumSimulation, mcts.h:100
-    if (d.gumbel && sims > 0) {
+    int slot_of_eval = sims; // hidden states are stored in evaluation order (zero_actor.cpp:90)
+    if (s.vloss) { // one lane of a batched think() step (zero_actor.cpp:129-145); the root's initial inference is a batch of one (:134-135)
+        if (s.think_lane >= (sims == 0 ? 1 : d.S + 1 - sims)) {
+            if (tid == 0) { s.path_len[g] = 0; }
+            return;
+        }
+        if (wid == 0) {
+            const int len0 = mz_select_think(d, s, g, w, root_turn, lane);
+            float* vl = s.vloss + (size_t)g * d.NP;
+            const int dup = (vl[path[len0 - 1]] != 0.0f); // selected earlier in this step: evaluated once (:140-142)
+            mz_sync();
+            for (int i = lane; i < len0; i += MZ_W) { vl[path[i]] = mz_fadd(vl[path[i]], 1.0f); }
+            if (lane == 0) {
+                w->shared_len = (dup ? -len0 : len0);
+                w->shared_count = sims + s.think_pending[g];
+                if (!dup) { s.think_pending[g] += 1; }
+            }
+        }
+        mz_block_sync();
+        if (w->shared_len < 0) {
+            if (tid == 0) { s.path_len[g] = w->shared_len; }
+            return;
+        }
+        slot_of_eval = w->shared_count;
+    } else if (d.gumbel && sims > 0) {
         if (wid == 0) {
             int level = 1;
             const mz_qb qb = mz_vb_bounds(d, s, g, lane);
@@ -1747,8 +1774,8 @@ MZ_DEV void mz_before_nn_muzero(const mz_dims& d, const mz_state& s, int g, mz_s
     mz_block_sync();
     for (int i = tid; i < MZ_LEGAL_WORDS; i += nthreads) { s.leaf_legal[g * MZ_LEGAL_WORDS + i] = w->legal[i]; }
     if (tid == 0) {
-        s.node_slot[(size_t)g * d.NP + leaf] = (int16_t)sims; // hidden states are stored in evaluation order (zero_actor.cpp:90)
-        if (s.eval_slot) { s.eval_slot[g] = sims; }
+        s.node_slot[(size_t)g * d.NP + leaf] = (int16_t)slot_of_eval;
+        if (s.eval_slot) { s.eval_slot[g] = slot_of_eval; }
         if (L == 0 && s.leaf_parent) { s.leaf_parent[g * 2 + 0] = -1, s.leaf_parent[g * 2 + 1] = -1; }
         s.path_len[g] = len;
         s.spec_len[g] = (d.gumbel ? 0 : len);

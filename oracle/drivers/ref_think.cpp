@@ -35,22 +35,34 @@ public:
         ZeroActor::beforeNNEvaluation();
         const auto& path = mcts_search_data_.node_path_;
         // record kind 0: batch id, rotation, path length, virtual loss of the leaf BEFORE this selection's own is added (0: it joins the batch)
-        put_i32(f_ev, 0), put_i32(f_ev, nn_evaluation_batch_id_), put_i32(f_ev, static_cast<int>(feature_rotation_)), put_i32(f_ev, static_cast<int>(path.size()));
+        put_i32(f_ev, 0), put_i32(f_ev, nn_evaluation_batch_id_), put_i32(f_ev, alphazero_network_ ? static_cast<int>(feature_rotation_) : 0), put_i32(f_ev, static_cast<int>(path.size()));
         put_f32(f_ev, path.back()->getVirtualLoss());
-        Environment t = getEnvironmentTransition(path);
-        std::vector<float> feats = t.getFeatures(feature_rotation_);
-        std::vector<uint8_t> fb(g_F);
-        for (int k = 0; k < g_F; ++k) { fb[k] = (feats[k] != 0.0f); }
+        std::vector<uint8_t> fb(g_F, 0);
+        if (alphazero_network_) {
+            Environment t = getEnvironmentTransition(path);
+            std::vector<float> feats = t.getFeatures(feature_rotation_);
+            for (int k = 0; k < g_F; ++k) { fb[k] = (feats[k] != 0.0f); }
+        } else if (path.size() == 1) { // MuZero: only the root's initial inference consumes planes (zero_actor.cpp:59-61)
+            std::vector<float> feats = env_.getFeatures();
+            for (int k = 0; k < g_F; ++k) { fb[k] = (feats[k] != 0.0f); }
+        }
         fwrite(fb.data(), 1, g_F, f_ev);
     }
     void afterNNEvaluation(const std::shared_ptr<NetworkOutput>& out) override
     {
-        auto o = std::static_pointer_cast<AlphaZeroNetworkOutput>(out);
         // record kind 1: batch id, policy, logits, value
         put_i32(f_ev, 1), put_i32(f_ev, nn_evaluation_batch_id_);
-        fwrite(o->policy_.data(), 4, g_A, f_ev);
-        fwrite(o->policy_logits_.data(), 4, g_A, f_ev);
-        put_f32(f_ev, o->value_);
+        if (alphazero_network_) {
+            auto o = std::static_pointer_cast<AlphaZeroNetworkOutput>(out);
+            fwrite(o->policy_.data(), 4, g_A, f_ev);
+            fwrite(o->policy_logits_.data(), 4, g_A, f_ev);
+            put_f32(f_ev, o->value_);
+        } else {
+            auto o = std::static_pointer_cast<MuZeroNetworkOutput>(out);
+            fwrite(o->policy_.data(), 4, g_A, f_ev);
+            fwrite(o->policy_logits_.data(), 4, g_A, f_ev);
+            put_f32(f_ev, o->value_);
+        }
         ZeroActor::afterNNEvaluation(out);
     }
 };
@@ -69,7 +81,7 @@ int main(int argc, char** argv)
     if (!cl.loadFromString(argv[1])) { return 1; }
     utils::Random::seed(config::program_seed);
     std::shared_ptr<Network> network = createNetwork(config::nn_file_name, -1);
-    if (network->getNetworkTypeName() != "alphazero") { return 3; }
+    if (network->getNetworkTypeName() != "alphazero" && network->getNetworkTypeName() != "muzero") { return 3; }
     g_A = network->getActionSize();
     g_F = network->getNumInputChannels() * network->getInputChannelHeight() * network->getInputChannelWidth();
     const uint64_t tree_node_size = static_cast<uint64_t>(config::actor_num_simulation + 1) * g_A;

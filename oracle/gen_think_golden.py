@@ -21,6 +21,9 @@ CASES = {
                                "actor_use_random_rotation_features=false:" + COMMON % 93, 4),
     # a batch that does not divide the simulations: the last step is short (batch_size = min(K, simulations left))
     "think_go5_s23_k5": ("go", "go5_az_1bx16", "env_board_size=5:actor_num_simulation=23:actor_mcts_think_batch_size=5:" + COMMON % 94, 30),
+    # MuZero: the root's initial inference is a batch of one, the recurrent steps select K leaves (zero_actor.cpp:134-135); hidden-state slots in evaluation order
+    "think_othello_mz_s30_k6": ("othello", "othello_mz_1bx32", "actor_num_simulation=30:actor_mcts_think_batch_size=6:" + (COMMON % 96).replace("nn_type_name=alphazero", "nn_type_name=muzero"), 14),
+    "think_go5_mz_s20_k4": ("go", "go5_mz_1bx16", "env_board_size=5:actor_num_simulation=20:actor_mcts_think_batch_size=4:" + (COMMON % 97).replace("nn_type_name=alphazero", "nn_type_name=muzero"), 16),
 }
 
 

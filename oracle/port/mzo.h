@@ -146,6 +146,7 @@ void mzo_atari_observe(mzo_batch* b, int g, int action, const uint8_t* frame_chw
  * of an earlier lane, 0: lane unused). mzo_think_apply: the evaluated lanes in selection order; policy / logits [K][B][A], value [K][B]. */
 void mzo_think_select(mzo_batch* b, int K, const uint8_t* rotations, float* features, int32_t* path_len);
 void mzo_think_apply(mzo_batch* b, const float* policy, const float* logits, const float* value, const float* noise);
+void mzo_think_leaf(const mzo_batch* b, int k, int g, int32_t* parent_slot, int32_t* action);
 
 /* std::sort(candidates, policy descending) exactly as libstdc++ orders them, ties included (mzo_sort.c) */
 void mzo_std_sort_candidates(int n, int32_t* action, float* policy, float* logit);

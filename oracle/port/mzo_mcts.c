@@ -588,7 +588,8 @@ void mzo_think_select(mzo_batch* b, int K, const uint8_t* rotations, float* feat
     for (int g = 0; g < B; ++g) {
         tree* t = &b->trees[g];
         const int left = b->cfg.num_simulation + 1 - (int)t->count[0];
-        const int batch = (K < left ? K : left); /* zero_actor.cpp:133-135 (an AlphaZero network also batches the root's first evaluation) */
+        /* zero_actor.cpp:133-135: an AlphaZero network also batches the root's first evaluation, a MuZero network's initial inference is a batch of one */
+        const int batch = ((b->cfg.muzero && t->count[0] == 0.0f) ? 1 : (K < left ? K : left));
         for (int k = 0; k < K; ++k) {
             const size_t l = (size_t)k * B + g;
             b->t_len[l] = 0;
@@ -602,12 +603,23 @@ void mzo_think_select(mzo_batch* b, int K, const uint8_t* rotations, float* feat
                 path[len++] = node;
             }
             const int fresh = (t->vloss[node] == 0.0f);
-            /* beforeNNEvaluation pushes the position whether or not it will be used (zero_actor.cpp:54-57) */
-            mzo_env* e = &b->t_env[l];
-            *e = b->root_env[g];
-            for (int i = 1; i < len; ++i) { mzo_env_act(e, t->action[path[i]], t->player[path[i]]); }
-            b->t_rot[l] = (rotations ? rotations[l] : 0);
-            if (features) { mzo_env_features(e, b->t_rot[l], features + l * (size_t)b->F); }
+            if (b->cfg.muzero) { /* zero_actor.cpp:59-67: root planes for the initial inference; below the root the network consumes (hidden state, action) */
+                b->t_rot[l] = 0;
+                if (features) {
+                    if (len == 1) {
+                        mzo_env_features(&b->root_env[g], 0, features + l * (size_t)b->F);
+                    } else {
+                        memset(features + l * (size_t)b->F, 0, sizeof(float) * (size_t)b->F);
+                    }
+                }
+            } else {
+                /* beforeNNEvaluation pushes the position whether or not it will be used (zero_actor.cpp:54-57) */
+                mzo_env* e = &b->t_env[l];
+                *e = b->root_env[g];
+                for (int i = 1; i < len; ++i) { mzo_env_act(e, t->action[path[i]], t->player[path[i]]); }
+                b->t_rot[l] = (rotations ? rotations[l] : 0);
+                if (features) { mzo_env_features(e, b->t_rot[l], features + l * (size_t)b->F); }
+            }
             for (int i = 0; i < len; ++i) { t->vloss[path[i]] += 1.0f; }
             b->t_len[l] = (fresh ? len : -len);
             if (path_len) { path_len[l] = b->t_len[l]; }
@@ -628,13 +640,24 @@ void mzo_think_apply(mzo_batch* b, const float* policy, const float* logits, con
             if (len <= 0) { continue; }
             const int32_t* path = b->t_path + l * S2;
             memcpy(b->path + (size_t)g * S2, path, sizeof(int32_t) * (size_t)len);
-            b->path_len[g] = len, b->leaf_env[g] = b->t_env[l], b->rotation[g] = b->t_rot[l];
+            b->path_len[g] = len, b->rotation[g] = b->t_rot[l];
+            if (!b->cfg.muzero) { b->leaf_env[g] = b->t_env[l]; }
             /* apply_game reads the outputs at index g of the arrays it is given: hand it the lane's section */
             apply_game(b, g, policy + (size_t)k * B * b->A, logits + (size_t)k * B * b->A, value + (size_t)k * B, NULL, noise);
             const float vl = t->vloss[path[len - 1]];
             for (int i = 0; i < len; ++i) { t->vloss[path[i]] -= vl; }
         }
     }
+}
+
+/* MuZero think(): what lane k of tree g hands to the recurrent inference — the evaluation slot of the leaf's parent and the leaf's action (-1, -1: the root) */
+void mzo_think_leaf(const mzo_batch* b, int k, int g, int32_t* parent_slot, int32_t* action)
+{
+    const size_t l = (size_t)k * b->cfg.num_games + g;
+    const int len = b->t_len[l] < 0 ? -b->t_len[l] : b->t_len[l];
+    const int32_t* path = b->t_path + l * (size_t)(b->cfg.num_simulation + 2);
+    *parent_slot = (len > 1 ? b->trees[g].slot[path[len - 2]] : -1);
+    *action = (len > 1 ? b->trees[g].action[path[len - 1]] : -1);
 }
 
 int mzo_num_simulation_done(const mzo_batch* b, int g) { return (int)b->trees[g].count[0]; }

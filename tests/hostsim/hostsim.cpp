@@ -86,7 +86,7 @@ sim* hs_create(int game, int N, int B, int S, float puct_base, float puct_init, 
     h->w.q_warp = zalloc<float>(MZ_MAXA);
     s.spec_len = zalloc<int32_t>(B);
     s.gum_cand = zalloc<int32_t>((size_t)B * d.A), s.gum_meta = zalloc<int32_t>((size_t)B * 4);
-    s.leaf_parent = zalloc<int32_t>((size_t)B * 2);
+    s.leaf_parent = zalloc<int32_t>((size_t)K * B * 2); // per-leaf array: one section per think() lane
     if (d.has_reward) { s.reward = zalloc<float>(np), s.nn_reward = zalloc<float>(B); }
     if (d.value_rescale) { s.vb_key = zalloc<float>((size_t)B * d.vb_cap), s.vb_cnt = zalloc<int32_t>((size_t)B * d.vb_cap), s.vb_n = zalloc<int32_t>(B); }
     if (game == MZ_GAME_ATARI) { s.at_meta = zalloc<int32_t>((size_t)B * 16); }

@@ -71,6 +71,7 @@ def load():
     lib.mzo_apply_mz.argtypes = [vp, f32p, f32p, f32p, f32p, f32p]
     lib.mzo_think_select.argtypes = [vp, i32, u8p, f32p, C.POINTER(C.c_int32)]
     lib.mzo_think_apply.argtypes = [vp, f32p, f32p, f32p, f32p]
+    lib.mzo_think_leaf.argtypes = [vp, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.mzo_root_extra.argtypes = [vp, i32, f32p, C.POINTER(C.c_int32), f32p, f32p]
     lib.mzo_root_normalized_mean.restype = C.c_float
     lib.mzo_root_normalized_mean.argtypes = [vp, i32, i32]
@@ -133,6 +134,12 @@ class OracleSearch:
         rot = None if rotations is None else np.ascontiguousarray(rotations, np.uint8)
         self.lib.mzo_think_select(self.h, K, None if rot is None else u8ptr(rot), fptr(feats), plen.ctypes.data_as(C.POINTER(C.c_int32)))
         return feats, plen
+
+    def think_leaf(self, k, g):
+        """MuZero: (evaluation slot of the leaf's parent, leaf action) of lane k of tree g; (-1, -1) for the root"""
+        ps, a = C.c_int32(0), C.c_int32(0)
+        self.lib.mzo_think_leaf(self.h, k, g, C.byref(ps), C.byref(a))
+        return ps.value, a.value
 
     def think_apply(self, policy, logits, value, noise=None):
         p, l, v = (np.ascontiguousarray(x, np.float32) for x in (policy, logits, value))

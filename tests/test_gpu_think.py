@@ -11,7 +11,8 @@ import oracle_lib
 pytestmark = pytest.mark.gpu
 
 NETS = os.path.join(oracle_lib.ROOT, "oracle", "_ref", "nets")
-CASES = {"think_ttt_s50_k4": (0, 3), "think_go5_s60_k8": (1, 5), "think_go9_s100_k16_det": (1, 9), "think_go5_s23_k5": (1, 5)}
+CASES = {"think_ttt_s50_k4": (0, 3), "think_go5_s60_k8": (1, 5), "think_go9_s100_k16_det": (1, 9), "think_go5_s23_k5": (1, 5),
+         "think_othello_mz_s30_k6": (2, 8), "think_go5_mz_s20_k4": (1, 5)}
 
 
 def engine(*args, **kw):
@@ -83,6 +84,70 @@ def test_on_device_think_search_matches_oracle(net, game, n, trees, S, K, moves)
 def test_think_mode_refuses_what_is_not_built():
     import minizero_b200
     with pytest.raises(minizero_b200.EngineError):
-        engine(2, 8, 1, 16, think_batch_size=4, muzero=1)
+        engine(6, 6, 1, 16, think_batch_size=4, muzero=1, value_rescale=1)
     with pytest.raises(minizero_b200.EngineError):
         engine(1, 9, 1, 16, think_batch_size=4, use_gumbel=1)
+
+
+@pytest.mark.parametrize("net,game,n,trees,S,K,moves", [("othello_mz_1bx32", 2, 8, 3, 40, 6, 4), ("go5_mz_1bx16", 1, 5, 2, 25, 4, 5)])
+def test_on_device_muzero_think_search_matches_oracle(net, game, n, trees, S, K, moves):
+    """MuZero think(): the root's initial inference as a batch of one lane, then K selections per step whose (parent hidden state, action) pairs go
+    through the dynamics network together; hidden states live in their TREE's slots in evaluation order. Oracle fed by a network-only engine."""
+    path = os.path.join(NETS, net + ".pt")
+    if not os.path.exists(path):
+        pytest.skip("net fixture missing")
+    lib = oracle_lib.load()
+    eng = engine(game, n, trees, S, think_batch_size=K, muzero=1)
+    eng.load_network(path)
+    ev = engine(game, n, trees * K, 2, muzero=1)
+    ev.load_network(path)
+    orc = oracle_lib.OracleSearch(lib, game, n, trees, S, muzero=1)
+    rng = np.random.default_rng(11)
+    A = eng.A
+    for move in range(moves):
+        noise = rng.dirichlet([0.3] * A, size=trees).astype(np.float32)
+        full_noise = np.zeros((eng.B, A), np.float32)
+        full_noise[:trees] = noise
+        eng.set_search_inputs(None, full_noise)
+        eng.search()
+        store = [dict() for _ in range(trees)]  # tree -> evaluation slot -> hidden state
+        steps = 0
+        while any(orc.sims_done(g) < S + 1 for g in range(trees)):
+            before = [orc.sims_done(g) for g in range(trees)]
+            feats, plen = orc.think_select(K, None)
+            pol, lg, val = np.zeros((K, trees, A), np.float32), np.zeros((K, trees, A), np.float32), np.zeros((K, trees), np.float32)
+            lanes = [(k, g) for g in range(trees) for k in range(K) if plen[k, g] > 0]
+            if steps == 0:
+                assert all(k == 0 for k, _ in lanes) and len(lanes) == trees
+                p, l, v, h = ev.eval_initial(np.stack([feats[0, g] for _, g in lanes]))
+            else:
+                leaves = [orc.think_leaf(k, g) for k, g in lanes]
+                hidden = np.stack([store[g][ps] for (k, g), (ps, _) in zip(lanes, leaves)])
+                p, l, v, h = ev.eval_recurrent(hidden, np.array([a for _, a in leaves], np.int32))
+            queued = [0] * trees
+            for j, (k, g) in enumerate(lanes):  # lanes are listed per tree in selection order: slots follow the finished simulations
+                pol[k, g], lg[k, g], val[k, g] = p[j], l[j], v[j]
+                store[g][before[g] + queued[g]] = h[j]
+                queued[g] += 1
+            orc.think_apply(pol, lg, val, noise)
+            steps += 1
+        assert eng.think_steps() == steps
+        r = eng.get_roots()
+        for g in range(trees):
+            b = orc.root(g)
+            k = b["num_children"]
+            assert r["root_count"][g] == S + 1 and r["num_children"][g] == k, (move, g)
+            assert np.array_equal(r["action"][g, :k], b["action"][:k]), (move, g)
+            assert np.array_equal(r["count"][g, :k], b["count"][:k]), (move, g, r["count"][g, :k], b["count"][:k])
+            assert np.array_equal(r["mean"][g, :k].view(np.uint32), b["mean"][:k].view(np.uint32)), (move, g)
+        acts = np.full(eng.B, -1, np.int32)
+        for g in range(trees):
+            acts[g] = r["action"][g, int(r["count"][g].argmax())]
+        res = eng.play_all(acts)
+        for g in range(trees):
+            assert res["applied"][g] == 1 and orc.play(g, int(acts[g])) == 1
+            if res["terminal"][g]:
+                eng.reset_game(g)
+                orc.reset_game(g)
+    eng.close()
+    ev.close()

@@ -137,7 +137,7 @@ def test_oracle_env_matches_reference_playouts(oracle, name):
 
 
 THINK_CASES = {"think_ttt_s50_k4": (oracle_lib.GAME_TICTACTOE, 3), "think_go5_s60_k8": (oracle_lib.GAME_GO, 5), "think_go9_s100_k16_det": (oracle_lib.GAME_GO, 9),
-               "think_go5_s23_k5": (oracle_lib.GAME_GO, 5)}
+               "think_go5_s23_k5": (oracle_lib.GAME_GO, 5), "think_othello_mz_s30_k6": (oracle_lib.GAME_OTHELLO, 8), "think_go5_mz_s20_k4": (oracle_lib.GAME_GO, 5)}
 
 
 @pytest.mark.parametrize("name", list(THINK_CASES))

@@ -81,7 +81,8 @@ def test_search_core_env_matches_reference_playouts(name, game, n):
     assert env_replay.replay(eng, case, check_score=lambda e: e.last_score) == case["game"].size
 
 
-THINK_CASES = {"think_ttt_s50_k4": (0, 3), "think_go5_s60_k8": (1, 5), "think_go9_s100_k16_det": (1, 9), "think_go5_s23_k5": (1, 5)}
+THINK_CASES = {"think_ttt_s50_k4": (0, 3), "think_go5_s60_k8": (1, 5), "think_go9_s100_k16_det": (1, 9), "think_go5_s23_k5": (1, 5),
+               "think_othello_mz_s30_k6": (2, 8), "think_go5_mz_s20_k4": (1, 5)}
 
 
 @pytest.mark.parametrize("name", list(THINK_CASES))
