@@ -294,3 +294,48 @@ def test_cooperative_tower_launch_gives_the_same_search():
         eng.close()
     for a, b in zip(*tables):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_two_engines_on_one_device_with_cooperative_towers():
+    """Two engines whose towers each need every SM, searching concurrently on ONE device from two host threads: with the cooperative launch the
+    driver never lets the two grids share the SMs half and half (the case an ordinary cluster launch of a spin-waiting kernel can deadlock in — it
+    would trap after 10 s). Runs in a subprocess under a timeout; both engines must finish and agree with a single-engine run bit for bit."""
+    import subprocess
+    import sys
+    torch, m, path = torchscript("go9_az_6bx256")
+    code = f'''
+import sys, threading
+import numpy as np
+sys.path.insert(0, {oracle_lib.ROOT!r})
+import minizero_b200 as mz
+B, S = 256, 30
+rng = np.random.default_rng(9)
+rot = rng.integers(0, 8, size=(S + 1, B)).astype(np.uint8)
+noise = rng.dirichlet([0.03] * 82, size=B).astype(np.float32)
+def make(coop):
+    e = mz.Engine(mz.GAME_GO, 9, B, S)
+    e.load_network({path!r})
+    if coop:
+        e.set_tower_cooperative(True)
+    return e
+ref = make(False)
+ref.set_search_inputs(rot, noise)
+ref.search()
+want = ref.get_roots()["count"].copy()
+ref.close()
+engines = [make(True), make(True)]
+out = [None, None]
+def run(i):
+    for _ in range(6):
+        engines[i].reset_game(-1)
+        engines[i].set_search_inputs(rot, noise)
+        engines[i].search()
+    out[i] = engines[i].get_roots()["count"].copy()
+threads = [threading.Thread(target=run, args=(i,)) for i in range(2)]
+[t.start() for t in threads]
+[t.join() for t in threads]
+assert np.array_equal(out[0], want) and np.array_equal(out[1], want)
+print("TWO_ENGINES_OK")
+'''
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "TWO_ENGINES_OK" in r.stdout, r.stdout[-300:] + r.stderr[-800:]
