@@ -367,11 +367,7 @@ def main():
     evals = world * GAMES * S1 * args.steps
     value = evals / (dev_ms * 1e-3)
     e2e_value = world * GAMES * S1 * args.steps / e2e_s
-    # the engine runs the wide tower (two row tiles per CTA) when a layer holds at least two wide units per CTA pair (engine.cu alloc_net); 148 SMs on a B200
-    n1 = (6 if atari else w["board"]) + 1
-    hidden = int(eng.net_dims["num_hidden_channels"])
-    wide_units = -(-(-(-GAMES * n1 * n1 // 128)) // 4) * max(1, hidden // 128)
-    tower_kernel = "conv_tower_wide_kernel" if (not atari and hidden % 128 == 0 and wide_units >= 148) else "conv_tower_kernel"
+    tower_kernel = "conv_tower_wide_kernel" if eng.tower_is_wide() == 1 else "conv_tower_kernel"
     layers = eng.conv_layers_per_launch()
     flops_per_launch = w["tower_flops"](GAMES)
     conv_tflops = flops_per_launch / (prof["conv_ms"] * 1e-3) / 1e12

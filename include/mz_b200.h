@@ -224,6 +224,9 @@ int mz_think_steps(const mz_engine* e);
  * 2-CTA grid), which would make the library unprofilable. Results do not depend on the mode; captured search graphs are rebuilt.
  * mz_tower_is_cooperative: 1 / 0. mz_set_tower_cooperative(e, 1) probes with one launch and fails (leaving the mode off) if the device refuses. */
 int mz_tower_is_cooperative(const mz_engine* e);
+/* 1 when this engine's network runs through conv_tower_wide_kernel (two row tiles per CTA: chosen when a layer holds at least two such units per CTA pair,
+ * e.g. 19x19 x 128 boards x 256 channels), 0 for conv_tower_kernel; a position's outputs are bit-identical either way */
+int mz_tower_is_wide(const mz_engine* e);
 int mz_set_tower_cooperative(mz_engine* e, int32_t on);
 
 #ifdef __cplusplus

@@ -1537,6 +1537,7 @@ int mz_set_tower_cooperative(mz_engine* e, int32_t on)
     }
     return MZ_OK;
 }
+int mz_tower_is_wide(const mz_engine* e) { return (e && e->net_ready) ? ((e->conv_mode == 3 && e->tower_wide) ? 1 : 0) : MZ_ERR_STATE; }
 int mz_tower_is_cooperative(const mz_engine* e) { return (e && e->net_ready) ? ((e->conv_mode == 3 && e->tower_coop) ? 1 : 0) : MZ_ERR_STATE; }
 int mz_conv_layers_per_launch(const mz_engine* e) { return (e && e->net_ready) ? (e->conv_mode == 3 ? static_cast<int>(e->tw[0].convs.size()) : 1) : MZ_ERR_STATE; }
 

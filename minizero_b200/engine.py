@@ -121,6 +121,7 @@ def _load():
     lib.mz_conv_layers_per_launch.argtypes = [vp]
     lib.mz_think_steps.argtypes = [vp]
     lib.mz_tower_is_cooperative.argtypes = [vp]
+    lib.mz_tower_is_wide.argtypes = [vp]
     lib.mz_set_tower_cooperative.argtypes = [vp, i32]
     lib.mz_launch_count.argtypes = [vp]
     lib.mz_launch_count.restype = C.c_int64
@@ -132,7 +133,7 @@ EXPORTS = ["mz_create", "mz_destroy", "mz_last_error", "mz_action_size", "mz_num
            "mz_net_blob", "mz_net_finalize_empty", "mz_eval_batch", "mz_reset_game", "mz_play", "mz_get_roots", "mz_search_select", "mz_search_apply",
            "mz_search_set_inputs", "mz_search_run", "mz_profile_kernels", "mz_launch_count", "mz_play_max_count", "mz_sync", "mz_timer_begin", "mz_timer_end", "mz_debug_tree_timing", "mz_debug_tower_timing", "mz_conv_layers_per_launch",
            "mz_eval_initial", "mz_eval_recurrent", "mz_search_leaf", "mz_gumbel_best_actions", "mz_eval_rewards", "mz_atari_observe", "mz_get_root_rewards",
-           "mz_search_apply_reward", "mz_replay_features", "mz_think_steps", "mz_tower_is_cooperative", "mz_set_tower_cooperative"]
+           "mz_search_apply_reward", "mz_replay_features", "mz_think_steps", "mz_tower_is_cooperative", "mz_set_tower_cooperative", "mz_tower_is_wide"]
 
 
 def _fp(a):
@@ -456,6 +457,9 @@ class Engine:
     def set_tower_cooperative(self, on):
         """profiler runs switch the cooperative launch off (see include/mz_b200.h); results do not depend on it"""
         self._check(self.lib.mz_set_tower_cooperative(self.h, int(on)))
+
+    def tower_is_wide(self):
+        return int(self.lib.mz_tower_is_wide(self.h))
 
     def tower_is_cooperative(self):
         return int(self.lib.mz_tower_is_cooperative(self.h))

@@ -339,3 +339,29 @@ print("TWO_ENGINES_OK")
 '''
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert "TWO_ENGINES_OK" in r.stdout, r.stdout[-300:] + r.stderr[-800:]
+
+
+def test_wide_and_narrow_towers_agree_bit_for_bit():
+    """conv_tower_wide_kernel (two row tiles per CTA, chosen when a layer holds two wide units per CTA pair: here 19x19 x 192 boards x 128 channels = 150
+    units) against conv_tower_kernel (the same network in an engine of 48 boards): both accumulate K-block outer / tap inner, so every logit and value
+    of a position must be identical whichever kernel — whichever batch — evaluated it"""
+    import __graft_entry__ as ge
+    rng = np.random.default_rng(17)
+    dims = dict(num_input_channels=18, input_height=19, input_width=19, num_hidden_channels=128, num_blocks=3, action_size=362, num_value_hidden_channels=64,
+                discrete_value_size=1)
+    st = ge.make_random_state(dims, rng)
+    feats = (rng.random((192, 18 * 361)) < 0.25).astype(np.float32)
+    wide = engine(1, 19, 192, 2)
+    wide.load_network((dims, st))
+    assert wide.tower_is_wide() == 1
+    pol_w, lg_w, val_w = wide.eval_batch(feats)
+    wide.close()
+    narrow = engine(1, 19, 48, 2)
+    narrow.load_network((dims, st))
+    assert narrow.tower_is_wide() == 0
+    for lo in range(0, 192, 48):
+        pol_n, lg_n, val_n = narrow.eval_batch(feats[lo:lo + 48])
+        assert np.array_equal(lg_n.view(np.uint32), lg_w[lo:lo + 48].view(np.uint32)), lo
+        assert np.array_equal(val_n.view(np.uint32), val_w[lo:lo + 48].view(np.uint32)), lo
+        assert np.array_equal(pol_n.view(np.uint32), pol_w[lo:lo + 48].view(np.uint32)), lo
+    narrow.close()
