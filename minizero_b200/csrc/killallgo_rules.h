@@ -11,8 +11,11 @@
 
 #if defined(__CUDACC__)
 #define MZ_KA_FN __host__ __device__ inline
+#define MZ_KA_COLD __host__ __device__ __noinline__ // Benson's algorithm keeps ~700 bytes of block / area tables: a real call, so that the tree-step kernel's
+                                                    // own frame and register allocation do not carry them for the games that never use it
 #else
 #define MZ_KA_FN static inline
+#define MZ_KA_COLD static
 #endif
 
 #define MZ_KA_BOARD 0x007f7f7f7f7f7f7full
@@ -33,7 +36,7 @@ MZ_KA_FN uint64_t mz_ka_flood(uint64_t seed, uint64_t mask)
         f = g;
     }
 }
-MZ_KA_FN uint64_t mz_ka_benson(uint64_t own, uint64_t opp)
+MZ_KA_COLD uint64_t mz_ka_benson(uint64_t own, uint64_t opp)
 {
     uint64_t blk[28], area[28];
     uint32_t adj[28], vital[28];
