@@ -52,7 +52,9 @@ struct NvtxRange {
 
 constexpr int STEP_AFTER = 1, STEP_BEFORE = 2;
 
-constexpr int STEP_WARPS = 16; // warps per game in k_step: the previous path is re-evaluated level-parallel (search_core.cuh, mz_select)
+constexpr int STEP_WARPS = 12; // warps per game in k_step: the previous path is re-evaluated level-parallel (search_core.cuh, mz_select). 12 warps at two blocks per
+                               // SM leave 80 registers per thread (16 warps: 64, and 380 bytes of spill loads on the serial paths): tree step 37.0 -> 34.3 us at
+                               // config 2, 73.3 -> 69.7 us at config 4 (profiles/r2_stepwarps_ab.log); 8 warps (114 registers, no spills) measure the same as 12
 
 __global__ void __launch_bounds__(32 * STEP_WARPS, 2) k_step(const mz_dims d, const mz_state s, const int flags)
 {
