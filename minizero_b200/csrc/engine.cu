@@ -311,12 +311,13 @@ struct mz_engine {
     CUtensorMap map_act[3];
     CUtensorMap map_act_ext[3]; // same buffers, box = the resident block of conv3x3_resident_kernel
     CUtensorMap map_act_wide[3]; // same buffers, box = half of the wide tower's input block
+    CUtensorMap map_act_store[3]; // same buffers as the targets of the towers' epilogues (TMA stores): box = 32 channels x 32 rows, 64-byte swizzle
     int tower_rot_override = -1; // MZ_TOWER_ROT (experiment builds)
     bool tower_coop = false;     // the fused tower is launched cooperatively (opt-in: mz_set_tower_cooperative)
     int think_steps = 0;         // batched steps the last think() search took
     int think_trees = 0;         // think mode (mz_config.think_batch_size > 1): number of trees; d.B = think_trees * d.think_k lanes
     bool tower_wide = false;    // conv_tower_wide_kernel (two row tiles per CTA) instead of conv_tower_kernel
-    int rows_ext_wide = 0, tower_wide_stages = 8;
+    int rows_ext_wide = 0, tower_wide_stages = 8, tower_epi_bufs = 2;
     // MuZero
     float* d_hidden_f32 = nullptr;   // [B][Ch * H * W] staging of the parity hooks
     int32_t* d_path_actions = nullptr; // [B][S + 2]
@@ -359,13 +360,13 @@ struct mz_engine {
 
 namespace {
 
-int make_map_2d(mz_engine* e, CUtensorMap* map, void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows)
+int make_map_2d(mz_engine* e, CUtensorMap* map, void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B)
 {
     const cuuint64_t dims[2] = {inner, rows};
     const cuuint64_t strides[1] = {inner * sizeof(__half)};
     const cuuint32_t box[2] = {box_inner, box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult r = e->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    CUresult r = e->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { return fail(MZ_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r))); }
     return MZ_OK;
@@ -450,13 +451,16 @@ int configure_conv_kernels()
     CUDA_OK(cudaFuncSetAttribute(mznn::conv3x3_pair_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<256, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<256, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_wide_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_wide_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_wide_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_wide_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_wide_kernel<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_wide_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_wide_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return MZ_OK;
 }
 
@@ -641,7 +645,7 @@ int launch_tower_params(mz_engine* e, mznn::TowerParams* params, int* d_done, in
     int clusters = e->tower_sms / 2;
     if (units < clusters) { clusters = units; }
     params->rotate = tower_rotation(e, units, clusters);
-    const size_t smem = 2 * static_cast<size_t>(cin_max / mznn::BK) * rows_ext * 128 + static_cast<size_t>(stages) * (bn / 2) * mznn::BK * 2 + 24 * 8 + 16 + 1024;
+    const size_t smem = mznn::tower_smem_bytes(cin_max, rows_ext, stages, bn, params->epi_bufs);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * 2), cfg.blockDim = dim3(mznn::TOWER_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = e->stream;
     cudaLaunchAttribute attr[2];
@@ -668,6 +672,10 @@ int launch_tower_params(mz_engine* e, mznn::TowerParams* params, int* d_done, in
         CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8, true>, *params));
     } else if (stages == 4) { // 185 KB of shared memory: a tree-step block (30 KB) of another engine fits on the same SM
         CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 4, false>, *params));
+    } else if (stages == 3) {
+        CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 3, false>, *params));
+    } else if (params->dbg && stages == 5) {
+        CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 5, true>, *params));
     } else if (stages == 5) {
         CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 5, false>, *params));
     } else {
@@ -690,7 +698,7 @@ int launch_tower_wide(mz_engine* e, NetTower& T, bool clear_counters, bool pdl)
     if (units < clusters) { clusters = units; }
     params->rotate = tower_rotation(e, units, clusters);
     const int stages = e->tower_wide_stages;
-    const size_t smem = static_cast<size_t>(mznn::WIDE_AK) * e->rows_ext_wide * 128 + static_cast<size_t>(stages) * 64 * mznn::BK * 2 + (2 * stages + 2 * mznn::WIDE_AK + 4) * 8 + 16 + 1024;
+    const size_t smem = mznn::wide_smem_bytes(e->rows_ext_wide, stages);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * 2), cfg.blockDim = dim3(mznn::WIDE_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = e->stream;
     cudaLaunchAttribute attr[2];
@@ -707,12 +715,18 @@ int launch_tower_wide(mz_engine* e, NetTower& T, bool clear_counters, bool pdl)
         attr[1].val.cooperative = 1;
         cfg.numAttrs = 2;
     }
-    if (params->dbg && stages == 8) {
-        CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_wide_kernel<8, true>, *params));
-    } else if (stages == 8) {
-        CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_wide_kernel<8, false>, *params));
+    if (stages == 10) {
+        if (params->dbg) {
+            CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_wide_kernel<10, true>, *params));
+        } else {
+            CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_wide_kernel<10, false>, *params));
+        }
     } else {
-        CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_wide_kernel<6, false>, *params));
+        if (params->dbg) {
+            CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_wide_kernel<9, true>, *params));
+        } else {
+            CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_wide_kernel<9, false>, *params));
+        }
     }
     e->launches++;
     return MZ_OK;
@@ -910,9 +924,11 @@ int alloc_atari(mz_engine* e)
         st.cin_max = 0;
         for (const ConvLayer& L : st.convs) { st.cin_max = std::max(st.cin_max, L.cin); }
         st.stages = 0;
-        for (int cand : {8, 5, 4}) {
-            const size_t need = 2 * static_cast<size_t>(st.cin_max / mznn::BK) * st.rows_ext * 128 + static_cast<size_t>(cand) * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
-            if (st.stages == 0 && need <= 227 * 1024) { st.stages = cand; }
+        int st_bufs = 2;
+        for (int bufs : {2, 1}) {
+            for (int cand : {8, 5, 4, 3}) { // (3 stages: the 24 x 24 stage of a 256-channel network, which runs once per move)
+                if (st.stages == 0 && mznn::tower_smem_bytes(st.cin_max, st.rows_ext, cand, 128, bufs) <= 227 * 1024) { st.stages = cand, st_bufs = bufs; }
+            }
         }
         if (st.stages == 0 || st.rows_ext > 256) { return fail(MZ_ERR_ARG, "an Atari representation stage does not fit the tower kernel's shared memory"); }
         const size_t rows = st.rows_alloc;
@@ -929,7 +945,7 @@ int alloc_atari(mz_engine* e)
         T.num_layers = static_cast<int>(st.convs.size());
         T.rows_valid = e->d.B * st.slots, T.n1 = st.n + 1, T.slots = st.slots, T.cout = st.cout, T.rows_ext = st.rows_ext, T.halo = st.n + 2;
         T.num_mtiles = st.rows_alloc / mznn::BM, T.cin_max = st.cin_max;
-        T.rotate = 22, T.shift = 0, T.zigzag = 0, T.strided = 1, T.tap_rot = 0, T.fence_mode = 0, T.pdl = 0, T.dbg = nullptr;
+        T.rotate = 22, T.shift = 0, T.zigzag = 0, T.strided = 1, T.tap_rot = 0, T.fence_mode = 0, T.pdl = 0, T.dbg = nullptr, T.epi_bufs = st_bufs;
         for (int li = 0; li < T.num_layers; ++li) {
             ConvLayer& L = st.convs[li];
             if ((rc = make_map_2d(e, &L.map_w_mc, e->d_blob + L.w_off, L.cin, 9ull * L.cout, mznn::BK, 64))) { return rc; }
@@ -937,6 +953,12 @@ int alloc_atari(mz_engine* e)
             TL.map_in = (L.in_buf < 0 ? st.map_in_ext : st.map_act_ext[L.in_buf]), TL.map_w = L.map_w_mc;
             TL.out = st.act[L.out_buf], TL.residual = (L.res_buf == -2 ? nullptr : (L.res_buf < 0 ? st.in : st.act[L.res_buf]));
             TL.bias = reinterpret_cast<const float*>(e->d_blob + L.b_off), TL.cin = L.cin, TL.relu = L.relu, TL.cin_off = L.cin_off, TL.tap_mask = L.tap_mask;
+            // the epilogue stores through TMA; residual rows: the stage's input was written before the launch, an activation buffer by some earlier
+            // layer of this launch (-2: the epilogue reads it after the accumulator barrier, which orders it behind that layer like every input row)
+            TL.out_map = L.out_buf, TL.res_layer = (L.res_buf == -2 || L.res_buf < 0 ? -1 : -2);
+        }
+        for (int i = 0; i < 3; ++i) {
+            if ((rc = make_map_2d(e, &T.map_out[i], st.act[i], st.cout, rows, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) { return rc; }
         }
         const int num_groups = (T.num_mtiles + 1) / 2;
         if ((rc = e->dalloc(&st.d_done, static_cast<size_t>(T.num_layers) * num_groups))) { return rc; }
@@ -983,19 +1005,19 @@ int alloc_net(mz_engine* e)
     if (e->conv_mode == 2) { // CTA pairs: needs the 128-wide tile and half-tile weight boxes
         // the fused tower runs as fast with 4 or 5 weight stages as with 8 (measured), so a larger resident block (19x19: 176 rows)
         // simply takes fewer stages; the per-layer pair kernel is instantiated for 8 only
-        auto pair_need = [&](int stages) {
-            return 2 * static_cast<size_t>(e->cin_max / mznn::BK) * e->rows_ext * 128 + static_cast<size_t>(stages) * 64 * mznn::BK * 2 + 24 * 8 + 16 + 1024;
-        };
+        auto pair_need = [&](int stages, int bufs) { return mznn::tower_smem_bytes(e->cin_max, e->rows_ext, stages, 128, bufs); };
         int stages = 0;
-        for (int cand : {8, 5, 4}) {
-            if (stages == 0 && pair_need(cand) <= 227 * 1024 && (want_tower || cand == 8)) { stages = cand; }
+        for (int bufs : {2, 1}) { // staging tiles per epilogue warp: two where they fit
+            for (int cand : {8, 5, 4}) {
+                if (stages == 0 && pair_need(cand, bufs) <= 227 * 1024 && (want_tower || cand == 8)) { stages = cand, e->tower_epi_bufs = bufs; }
+            }
         }
         if (e->bn_tile == 128 && stages != 0) {
             e->conv_cluster = 2;
             if (!knob("MZ_TOWER_STAGES")) { e->tower_stages = stages; }
             if (const char* env = knob("MZ_TOWER_BN")) { // 256-wide output tiles (experiment): stages of 16 KB per CTA, 4 or 2 of them
                 if (std::atoi(env) == 256 && want_tower && e->cpad % 256 == 0 && !e->atari) {
-                    auto need256 = [&](int st) { return 2 * static_cast<size_t>(e->cin_max / mznn::BK) * e->rows_ext * 128 + static_cast<size_t>(st) * 128 * mznn::BK * 2 + 24 * 8 + 16 + 1024; };
+                    auto need256 = [&](int st) { return mznn::tower_smem_bytes(e->cin_max, e->rows_ext, st, 256, 2); };
                     const int st = (need256(4) <= 227 * 1024 ? 4 : (need256(2) <= 227 * 1024 ? 2 : 0));
                     if (st) { e->tower_bn = 256, e->tower_stages = st; }
                 }
@@ -1010,6 +1032,7 @@ int alloc_net(mz_engine* e)
         if ((rc = e->dalloc(&e->act[i], rows * e->cpad))) { return rc; }
         if ((rc = make_map_2d(e, &e->map_act[i], e->act[i], e->cpad, rows, mznn::BK, mznn::BM))) { return rc; }
         if ((rc = make_map_2d(e, &e->map_act_ext[i], e->act[i], e->cpad, rows, mznn::BK, e->rows_ext))) { return rc; }
+        if (e->cpad % 32 == 0 && (rc = make_map_2d(e, &e->map_act_store[i], e->act[i], e->cpad, rows, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) { return rc; }
     }
     if (e->cfg.muzero) {
         // hidden states of the evaluated nodes (slot = simulation index) and the dynamics network's input rows
@@ -1034,16 +1057,16 @@ int alloc_net(mz_engine* e)
     // two row tiles per CTA (half the weight traffic per FLOP) where a layer still has a unit for every CTA pair
     e->rows_ext_wide = (2 * mznn::BM + 2 * (e->d.N + 2) + 15) / 16 * 16;
     {
-        auto wide_need = [&](int stages) {
-            return static_cast<size_t>(mznn::WIDE_AK) * e->rows_ext_wide * 128 + static_cast<size_t>(stages) * 64 * mznn::BK * 2 + (2 * stages + 2 * mznn::WIDE_AK + 4) * 8 + 16 + 1024;
-        };
-        e->tower_wide_stages = (wide_need(8) <= 227 * 1024 ? 8 : 6);
+        auto wide_need = [&](int stages) { return mznn::wide_smem_bytes(e->rows_ext_wide, stages); };
+        e->tower_wide_stages = (wide_need(10) <= 227 * 1024 ? 10 : 9); // weight stages beside the input ring and the epilogue's staging tiles: at least the nine taps of a K-block
         const int wide_units = ((e->rows_alloc / mznn::BM + 3) / 4) * (e->cpad / 128);
         e->tower_wide = (tower_ok && !e->atari && e->tower_bn == 128 && e->cpad % 128 == 0 && wide_need(e->tower_wide_stages) <= 227 * 1024 && e->rows_ext_wide / 2 <= 256 &&
-                         wide_units >= e->tower_sms);
-        // (>= two wide units per pair and layer. Measured: config 4, 200 units on 74 pairs: 1727 us against the narrow kernel's 2038 us, the issuer's wait for
-        //  weights falls from 19 % to 10 %. Config 2, 100 units: 302 us against 264 us — weights 19 % -> 6 %, but with 1.35 units per pair and layer almost every
-        //  unit's halo was finished only just before it, and epilogue -> counter -> TMA sits on the critical path of every pass: the issuer waits 39 % for input.)
+                         wide_units >= e->tower_sms / 2);
+        // (>= one wide unit per pair and layer. A layer's critical path is one unit's MMAs + the hand-off to the next layer (epilogue -> counter -> poll -> TMA
+        //  of the first K-block), and a layer holds units / pairs unit-times of work: the wide kernel wins where its halved weight traffic outweighs the longer
+        //  unit. Measured after the epilogue went to TMA stores (profiles/r2_epi_ab.log), wide vs narrow: config 4 (200 units on 74 pairs) 1640 vs 2000 us,
+        //  config 2 (100 units) 241-246 vs 263-271 us, config 3 (81 units, dynamics tower) 95.7 vs 102.9 us. Before that the hand-off cost 12 k cycles per
+        //  unit in the epilogue alone and config 2 lost: 302 vs 264 us, the issuer waiting 39 % of its time for input.)
         if (const char* env = knob("MZ_TOWER_WIDE")) {
             const int v = std::atoi(env);
             if (v == 0) { e->tower_wide = false; }
@@ -1075,18 +1098,25 @@ int alloc_net(mz_engine* e)
         T.rows_valid = e->d.B * e->d.slots, T.n1 = e->d.N + 1, T.slots = e->d.slots, T.cout = e->cpad, T.rows_ext = (e->tower_wide ? e->rows_ext_wide : e->rows_ext), T.halo = e->d.N + 2;
         T.num_mtiles = e->rows_alloc / mznn::BM;
         T.cin_max = e->cin_max;
-        T.rotate = 22, T.shift = 0, T.zigzag = 0, T.strided = 1, T.tap_rot = 0, T.fence_mode = 0;
+        T.rotate = 22, T.shift = 0, T.zigzag = 0, T.strided = 1, T.tap_rot = 0, T.fence_mode = 0, T.epi_bufs = e->tower_epi_bufs;
         if (const char* env = knob("MZ_TOWER_TAPROT")) { T.tap_rot = std::atoi(env); }
         if (const char* env = knob("MZ_TOWER_FENCE")) { T.fence_mode = std::atoi(env); }
         if (const char* env = knob("MZ_TOWER_STRIDED")) { T.strided = std::atoi(env); }
         if (const char* env = knob("MZ_TOWER_ZIGZAG")) { T.zigzag = std::atoi(env); }
         if (const char* env = knob("MZ_TOWER_ROT")) { e->tower_rot_override = std::atoi(env); }
         if (const char* env = knob("MZ_TOWER_SHIFT")) { T.shift = std::atoi(env); }
+        for (int i = 0; i < 3; ++i) { T.map_out[i] = e->map_act_store[i]; }
         auto set = [&](int li, const CUtensorMap& in, __half* out, const __half* residual) {
             mznn::TowerLayer& L = T.layer[li];
             L.map_in = in, L.map_w = NT.convs[li].map_w_tower, L.out = out, L.residual = residual;
             L.bias = reinterpret_cast<const float*>(e->d_blob + NT.convs[li].b_off), L.cin = NT.convs[li].cin, L.relu = NT.convs[li].relu;
             L.cin_off = 0, L.tap_mask = 0x1ff;
+            L.out_map = 0, L.res_layer = -1;
+            for (int i = 0; i < 3; ++i) {
+                if (out == e->act[i]) { L.out_map = i; }
+            }
+            // the residual of a block's second convolution is the block's input: the output of layer li - 2, or the tower's input rows (written before the launch)
+            if (residual != nullptr && li >= 2) { L.res_layer = li - 2; }
         };
         const int base = (NT.has_stem ? 1 : 0);
         const CUtensorMap* act_maps = (e->tower_wide ? e->map_act_wide : e->map_act_ext);
@@ -1129,13 +1159,12 @@ int alloc_net(mz_engine* e)
             cudaError_t err;
             if (e->tower_wide) {
                 cfg.blockDim = dim3(mznn::WIDE_THREADS);
-                cfg.dynamicSmemBytes = static_cast<size_t>(mznn::WIDE_AK) * e->rows_ext_wide * 128 + static_cast<size_t>(e->tower_wide_stages) * 64 * mznn::BK * 2 +
-                                       (2 * e->tower_wide_stages + 2 * mznn::WIDE_AK + 4) * 8 + 16 + 1024;
-                err = (e->tower_wide_stages == 8 ? cudaOccupancyMaxActiveClusters(&max_clusters, mznn::conv_tower_wide_kernel<8, false>, &cfg)
-                                                 : cudaOccupancyMaxActiveClusters(&max_clusters, mznn::conv_tower_wide_kernel<6, false>, &cfg));
+                cfg.dynamicSmemBytes = mznn::wide_smem_bytes(e->rows_ext_wide, e->tower_wide_stages);
+                err = (e->tower_wide_stages == 10 ? cudaOccupancyMaxActiveClusters(&max_clusters, mznn::conv_tower_wide_kernel<10, false>, &cfg)
+                                                 : cudaOccupancyMaxActiveClusters(&max_clusters, mznn::conv_tower_wide_kernel<9, false>, &cfg));
             } else {
                 cfg.blockDim = dim3(mznn::TOWER_THREADS);
-                cfg.dynamicSmemBytes = 2 * static_cast<size_t>(e->cin_max / mznn::BK) * e->rows_ext * 128 + static_cast<size_t>(e->tower_stages) * (e->tower_bn / 2) * mznn::BK * 2 + 24 * 8 + 16 + 1024;
+                cfg.dynamicSmemBytes = mznn::tower_smem_bytes(e->cin_max, e->rows_ext, e->tower_stages, e->tower_bn, e->tower_epi_bufs);
                 err = (e->tower_bn == 256 ? cudaOccupancyMaxActiveClusters(&max_clusters, mznn::conv_tower_kernel<256, 4, false>, &cfg)
                        : e->tower_stages == 4 ? cudaOccupancyMaxActiveClusters(&max_clusters, mznn::conv_tower_kernel<128, 4, false>, &cfg)
                        : e->tower_stages == 5 ? cudaOccupancyMaxActiveClusters(&max_clusters, mznn::conv_tower_kernel<128, 5, false>, &cfg)

@@ -109,6 +109,19 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// fp32 -> two fp16 activations: round to nearest even, saturate at +-65504 (activations are stored as fp16: the epilogues saturate
+// instead of producing inf), ReLU if asked for — one F2FP.SATFINITE(.RELU).F16.F32.PACK_AB. x0 goes to the low half.
+__device__ __forceinline__ uint32_t pack_act_f16x2(float x0, float x1, int relu)
+{
+    uint32_t r;
+    if (relu) {
+        asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+    } else {
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+    }
+    return r;
+}
+
 struct ConvParams {
     __half* out;            // [rows_alloc][cout]
     const __half* residual; // [rows_alloc][cout] or null
@@ -231,10 +244,8 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_
                     const float2 rf = __half22float2(rh[j]);
                     x0 += rf.x, x1 += rf.y;
                 }
-                x0 = fminf(fmaxf(x0, p.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX), x1 = fminf(fmaxf(x1, p.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX); // ReLU + saturation at the fp16 range
                 if (!live) { x0 = 0.0f, x1 = 0.0f; }
-                const __half2 h = __floats2half2_rn(x0, x1);
-                pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+                pk[j] = pack_act_f16x2(x0, x1, p.relu); // ReLU + saturation at the fp16 range + rounding in one F2FP
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) { *reinterpret_cast<uint4*>(out_row + c + q * 8) = packed[q]; }
@@ -537,10 +548,8 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap map_in, const __grid
                         const float2 rf = __half22float2(rh[j]);
                         x0 += rf.x, x1 += rf.y;
                     }
-                    x0 = fminf(fmaxf(x0, p.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX), x1 = fminf(fmaxf(x1, p.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX); // ReLU + saturation at the fp16 range
                     if (!live) { x0 = 0.0f, x1 = 0.0f; }
-                    const __half2 h = __floats2half2_rn(x0, x1);
-                    pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    pk[j] = pack_act_f16x2(x0, x1, p.relu); // ReLU + saturation at the fp16 range + rounding in one F2FP
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) { *reinterpret_cast<uint4*>(out_row + c + q * 8) = packed[q]; }
@@ -796,10 +805,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
                         const float2 rf = __half22float2(rh[j]);
                         x0 += rf.x, x1 += rf.y;
                     }
-                    x0 = fminf(fmaxf(x0, p.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX), x1 = fminf(fmaxf(x1, p.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX); // ReLU + saturation at the fp16 range
                     if (!live) { x0 = 0.0f, x1 = 0.0f; }
-                    const __half2 h = __floats2half2_rn(x0, x1);
-                    pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    pk[j] = pack_act_f16x2(x0, x1, p.relu); // ReLU + saturation at the fp16 range + rounding in one F2FP
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) { *reinterpret_cast<uint4*>(out_row + c + q * 8) = packed[q]; }
@@ -843,6 +850,9 @@ struct alignas(64) TowerLayer {
                   // sub-position layers of a stride-2 convolution share one space-to-depth input)
     int tap_mask; // bit t set: tap t = (ky * 3 + kx) takes part (0x1ff = a full 3x3; a stride-2 3x3 convolution over a
                   // space-to-depth input only has taps that reach up / left: see engine.cu, "stride 2")
+    int out_map;  // wide tower: which of TowerParams::map_out covers `out` (its epilogue stores through TMA)
+    int res_layer; // wide tower: the layer whose output `residual` is (its completion counters let the epilogue fetch the residual
+                   // rows before the accumulators are ready), or -1 when `residual` was written before the launch
 };
 
 struct TowerParams {
@@ -862,6 +872,9 @@ struct TowerParams {
                   // only the first layer's input rows depend on that kernel, and the input producer waits for it (griddepcontrol.wait)
     int* done;    // [num_layers][num_groups] completion counters, zeroed before every launch
     unsigned long long* dbg; // optional [grid][8] cycle counters (profiling)
+    int epi_bufs;   // narrow tower: staging tiles per epilogue warp (1 or 2), see tower_smem_bytes
+    CUtensorMap map_out[3]; // wide tower: the three activation buffers as TMA store targets, box = 32 channels x 32 rows (one TMEM load of an
+                            // epilogue warp), 64-byte swizzle
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p)
@@ -878,8 +891,7 @@ __device__ __forceinline__ void wait_counter(const int* p, int need)
 {
     unsigned spins = 0;
     unsigned long long t_first = 0;
-    while (ld_acquire_gpu(p) < need) {
-        __nanosleep(32);
+    while (ld_acquire_gpu(p) < need) { // every poll is an L2 round trip: no back-off needed between them
         if ((++spins & 0x3FFFFu) == 0u) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -892,6 +904,34 @@ __device__ __forceinline__ void wait_counter(const int* p, int need)
     }
 }
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int32_t c0, int32_t c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// explicit shared-space accesses (through a generic pointer the compiler emits LD / ST, which wait on the long scoreboard like a global access)
+__device__ __forceinline__ float4 lds_f4(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, const uint4& v) { asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+__device__ __forceinline__ void sts_f2(uint32_t addr, const float2& v) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory"); }
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); } // every store has read its source tile
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); } // all but the newest store have read their source tiles
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }       // the stores are complete (visible)
+// shared memory of a narrow tower CTA (the 1024 bytes at the end pay for aligning the base). epi_bufs: staging tiles per epilogue warp (32 rows x 32 fp16
+// channels, 64-byte swizzle, 2 KB each): 2 where they fit, 1 where the input blocks leave no room (Atari dynamics: 320 input channels)
+__host__ __device__ constexpr size_t tower_smem_bytes(int cin_max, int rows_ext, int stages, int bn, int epi_bufs)
+{
+    return static_cast<size_t>(bn == 128 ? 4 * epi_bufs * 2048 + 4 * bn * 4 : 0) + 2 * static_cast<size_t>(cin_max / BK) * rows_ext * 128 +
+           static_cast<size_t>(stages) * (bn / 2) * BK * 2 + 24 * 8 + 16 + 1024;
+}
+
+__device__ __forceinline__ void sts_f4(uint32_t addr, const float4& v) { asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory"); }
+
 template <int BN, int STAGES, bool DBG>
 __global__ void __launch_bounds__(TOWER_THREADS, 1)
 conv_tower_kernel(const __grid_constant__ TowerParams tp)
@@ -902,8 +942,11 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     const int a_kb_bytes = tp.rows_ext * 128;
     const int a_bytes_max = (tp.cin_max / BK) * a_kb_bytes; // hidden layers have cin == cout; an AlphaZero stem is narrower, a MuZero dynamics stem wider
-    uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + 2 * a_bytes_max;
+    const int epi_bytes = (BN == 128 ? 4 * tp.epi_bufs * 2048 + 4 * BN * 4 : 0); // staging tiles + per-warp bias rows of the epilogue (128-wide tiles)
+    uint8_t* smem_epi = smem;
+    float* smem_bias = reinterpret_cast<float*>(smem + 4 * tp.epi_bufs * 2048);
+    uint8_t* smem_a = smem + epi_bytes;
+    uint8_t* smem_b = smem_a + 2 * a_bytes_max;
     uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_HALF_BYTES);
     uint64_t* b_empty = b_full + STAGES;
     uint64_t* a_full = b_empty + STAGES; // [2]
@@ -1042,12 +1085,9 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
                 }
                 if (l > 0) { // the 3x3 halo reaches into the neighbouring groups of the previous layer
                     const long long td = (DBG ? clock64() : 0ll);
-                    if (lane == 0) {
-                        const int* d = tp.done + (l - 1) * num_groups;
-                        const int g0 = (g > 0 ? g - 1 : 0), g1 = (g + 1 < num_groups ? g + 1 : num_groups - 1);
-                        for (int gg = g0; gg <= g1; ++gg) {
-                            wait_counter(d + gg, need);
-                        }
+                    if (lane < 3) { // three lanes, three counters: one L2 round trip when the rows are long complete, not three
+                        const int gg = g - 1 + lane;
+                        if (gg >= 0 && gg < num_groups) { wait_counter(tp.done + (l - 1) * num_groups + gg, need); }
                     }
                     __syncwarp();
                     asm volatile("fence.proxy.async;" ::: "memory"); // generic-proxy writes of other SMs -> this warp's TMA (async proxy) reads
@@ -1148,73 +1188,177 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
         const int quarter = warp & 3;
         int ucount = 0;
         long long t_epi_work = 0;
-        for (int l = 0; l < tp.num_layers; ++l) {
-            const TowerLayer& L = tp.layer[l];
-            int ub, ue;
-            range(l, ub, ue);
-            for (int q = ub; q < ue; ++q, ++ucount) {
-                const int u = unit_of(l, q);
-                const int grp = u / nh, half = u - grp * nh, buf = ucount & 1;
-                const int mt = grp * 2 + crank;
-                const int n0 = half * BN;
-                const int r = mt * BM + quarter * 32 + lane;
-                const int rr = r % tp.slots;
-                const bool live = (r < tp.rows_valid) && (rr / tp.n1 != 0) && (rr % tp.n1 != tp.n1 - 1);
-                const bool in_range = (mt < tp.num_mtiles);
-                mbar_wait(&acc_full[buf], (ucount >> 1) & 1);
-                const long long tw = (DBG ? clock64() : 0ll);
-                tcgen05_fence_after();
-                __half* out_row = L.out + static_cast<size_t>(r) * tp.cout + n0;
-                const __half* res_row = (L.residual ? L.residual + static_cast<size_t>(r) * tp.cout + n0 : nullptr);
-#pragma unroll 1
-                for (int c = 0; c < BN && in_range; c += 32) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + c, v);
-                    uint4 res[4];
-                    if (res_row && live) { // written by other SMs earlier in this launch: read through L2, never through this SM's L1
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) { res[q] = __ldcg(reinterpret_cast<const uint4*>(res_row + c + q * 8)); }
-                    }
-                    float4 bias4[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) { bias4[q] = __ldg(reinterpret_cast<const float4*>(L.bias + n0 + c) + q); }
-                    const float* bias = reinterpret_cast<const float*>(bias4);
-                    tmem_ld_wait();
-                    uint4 packed[4];
-                    uint32_t* pk = reinterpret_cast<uint32_t*>(packed);
-                    const __half2* rh = reinterpret_cast<const __half2*>(res);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float x0 = __uint_as_float(v[2 * j]) + bias[2 * j];
-                        float x1 = __uint_as_float(v[2 * j + 1]) + bias[2 * j + 1];
-                        if (res_row && live) {
-                            const float2 rf = __half22float2(rh[j]);
-                            x0 += rf.x, x1 += rf.y;
-                        }
-                        x0 = fminf(fmaxf(x0, L.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX), x1 = fminf(fmaxf(x1, L.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX); // ReLU + saturation at the fp16 range
-                        if (!live) { x0 = 0.0f, x1 = 0.0f; }
-                        const __half2 h = __floats2half2_rn(x0, x1);
-                        pk[j] = *reinterpret_cast<const uint32_t*>(&h);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) { *reinterpret_cast<uint4*>(out_row + c + q * 8) = packed[q]; }
-                }
-                tcgen05_fence_before();
-                if (tp.fence_mode == 0) {
-                    __threadfence(); // this warp's rows of (layer l, group grp) are visible device-wide before the counter moves
+        if constexpr (BN == 128) {
+            // Everything that does not need the accumulators happens before they are ready (the bias row in shared memory; the residual rows in
+            // registers where the layer that wrote them is known: one acquire of its counter orders the loads); afterwards the warp converts
+            // TMEM -> registers -> fp16 rows in a 64-byte-swizzled staging tile -> one TMA store per 32 channels, and publishes with one
+            // red.release after the bulk stores have completed. (A lane-per-row st.global touches 32 cache lines per instruction, and a
+            // __threadfence by every lane costs a MEMBAR.SC + an L1 invalidate: see conv_tower_wide_kernel.)
+            const int ew = warp - 2;
+            const uint32_t stage_u32 = smem_u32(smem_epi + ew * tp.epi_bufs * 2048), bias_u32 = smem_u32(smem_bias + ew * BN);
+            const int buf_mask = tp.epi_bufs - 1;
+            for (int l = 0; l < tp.num_layers; ++l) {
+                const TowerLayer& L = tp.layer[l];
+                const CUtensorMap* map_out = &tp.map_out[L.out_map];
+                int ub, ue;
+                range(l, ub, ue);
+                for (int q = ub; q < ue; ++q, ++ucount) {
+                    const int u = unit_of(l, q);
+                    const int grp = u / nh, half = u - grp * nh, buf = ucount & 1;
+                    const int mt = grp * 2 + crank;
+                    const int n0 = half * BN;
+                    const int r = mt * BM + quarter * 32 + lane;
+                    const int rr = r % tp.slots;
+                    const bool live = (r < tp.rows_valid) && (rr / tp.n1 != 0) && (rr % tp.n1 != tp.n1 - 1);
+                    const bool in_range = (mt < tp.num_mtiles);
+                    const bool add_res = (L.residual != nullptr) && live && in_range;
                     __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u);
-                        atomicAdd(tp.done + l * num_groups + grp, 1);
+                    sts_f4(bias_u32 + 16 * lane, __ldg(reinterpret_cast<const float4*>(L.bias + n0) + lane));
+                    uint4 res[16];
+                    const uint4* res_row = reinterpret_cast<const uint4*>(L.residual + static_cast<size_t>(r) * tp.cout + n0);
+                    const bool res_early = (L.residual != nullptr) && (L.res_layer != -2);
+                    if (res_early) {
+                        if (L.res_layer >= 0) { // rows written by other SMs earlier in this launch: complete long ago, but this warp has not synchronised with them yet
+                            if (lane == 0) { wait_counter(tp.done + L.res_layer * num_groups + grp, need); }
+                            __syncwarp();
+                        }
+                        if (add_res) { // read through L2, never through this SM's L1
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) { res[i] = __ldcg(res_row + i); }
+                        }
                     }
-                } else {
-                    __syncwarp(); // orders the lanes' row stores before lane 0's release (cumulativity carries them along)
-                    if (lane == 0) {
-                        mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u);
-                        asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(tp.done + l * num_groups + grp), "r"(1) : "memory");
+                    __syncwarp();
+                    mbar_wait(&acc_full[buf], (ucount >> 1) & 1);
+                    const long long tw = (DBG ? clock64() : 0ll);
+                    tcgen05_fence_after();
+                    if (add_res && !res_early) { // a layer wiring this kernel has no counter for: ordered by the accumulator barrier, as before
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { res[i] = __ldcg(res_row + i); }
                     }
+                    if (in_range) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            uint32_t v[32];
+                            tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + c * 32, v);
+                            float4 b0 = lds_f4(bias_u32 + c * 128), b1 = lds_f4(bias_u32 + c * 128 + 16);
+                            tmem_ld_wait();
+                            if (lane == 0) { // the staging tile is free again once the store that used it last has read it
+                                if (buf_mask) {
+                                    tma_store_wait_read1();
+                                } else {
+                                    tma_store_wait_read0();
+                                }
+                            }
+                            __syncwarp();
+                            const __half2* rh = reinterpret_cast<const __half2*>(&res[c * 4]);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                uint4 pk4;
+                                uint32_t* pk = reinterpret_cast<uint32_t*>(&pk4);
+                                const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                                if (k < 3) { b0 = lds_f4(bias_u32 + c * 128 + (k + 1) * 32), b1 = lds_f4(bias_u32 + c * 128 + (k + 1) * 32 + 16); }
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float x0 = __uint_as_float(v[k * 8 + 2 * j]) + bias[2 * j];
+                                    float x1 = __uint_as_float(v[k * 8 + 2 * j + 1]) + bias[2 * j + 1];
+                                    if (add_res) {
+                                        const float2 rf = __half22float2(rh[k * 4 + j]);
+                                        x0 += rf.x, x1 += rf.y;
+                                    }
+                                    if (!live) { x0 = 0.0f, x1 = 0.0f; }
+                                    pk[j] = pack_act_f16x2(x0, x1, L.relu); // ReLU + saturation at the fp16 range + rounding in one F2FP
+                                }
+                                sts_u4(stage_u32 + (c & buf_mask) * 2048 + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4), pk4);
+                            }
+                            if (c == 3) { // the accumulators of this unit have been read: the issuer may reuse them
+                                tcgen05_fence_before();
+                                __syncwarp();
+                                if (lane == 0) { mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u); }
+                            }
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // this lane's row in shared memory -> the TMA engine
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_2d(map_out, stage_u32 + (c & buf_mask) * 2048, n0 + c * 32, mt * BM + quarter * 32);
+                                tma_store_commit();
+                            }
+                        }
+                    } else if (lane == 0) { // a phantom tile behind the last row tile: nothing to read
+                        mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u);
+                    }
+                    if (lane == 0) {
+                        tma_store_wait_all(); // this warp's rows of (layer l, group grp) are written ...
+                        asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(tp.done + l * num_groups + grp), "r"(1) : "memory"); // ... before the counter moves
+                    }
+                    t_epi_work += (DBG ? clock64() : 0ll) - tw;
                 }
-                t_epi_work += (DBG ? clock64() : 0ll) - tw;
+            }
+        } else {
+            for (int l = 0; l < tp.num_layers; ++l) {
+                const TowerLayer& L = tp.layer[l];
+                int ub, ue;
+                range(l, ub, ue);
+                for (int q = ub; q < ue; ++q, ++ucount) {
+                    const int u = unit_of(l, q);
+                    const int grp = u / nh, half = u - grp * nh, buf = ucount & 1;
+                    const int mt = grp * 2 + crank;
+                    const int n0 = half * BN;
+                    const int r = mt * BM + quarter * 32 + lane;
+                    const int rr = r % tp.slots;
+                    const bool live = (r < tp.rows_valid) && (rr / tp.n1 != 0) && (rr % tp.n1 != tp.n1 - 1);
+                    const bool in_range = (mt < tp.num_mtiles);
+                    mbar_wait(&acc_full[buf], (ucount >> 1) & 1);
+                    const long long tw = (DBG ? clock64() : 0ll);
+                    tcgen05_fence_after();
+                    __half* out_row = L.out + static_cast<size_t>(r) * tp.cout + n0;
+                    const __half* res_row = (L.residual ? L.residual + static_cast<size_t>(r) * tp.cout + n0 : nullptr);
+    #pragma unroll 1
+                    for (int c = 0; c < BN && in_range; c += 32) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + c, v);
+                        uint4 res[4];
+                        if (res_row && live) { // written by other SMs earlier in this launch: read through L2, never through this SM's L1
+    #pragma unroll
+                            for (int q = 0; q < 4; ++q) { res[q] = __ldcg(reinterpret_cast<const uint4*>(res_row + c + q * 8)); }
+                        }
+                        float4 bias4[8];
+    #pragma unroll
+                        for (int q = 0; q < 8; ++q) { bias4[q] = __ldg(reinterpret_cast<const float4*>(L.bias + n0 + c) + q); }
+                        const float* bias = reinterpret_cast<const float*>(bias4);
+                        tmem_ld_wait();
+                        uint4 packed[4];
+                        uint32_t* pk = reinterpret_cast<uint32_t*>(packed);
+                        const __half2* rh = reinterpret_cast<const __half2*>(res);
+    #pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float x0 = __uint_as_float(v[2 * j]) + bias[2 * j];
+                            float x1 = __uint_as_float(v[2 * j + 1]) + bias[2 * j + 1];
+                            if (res_row && live) {
+                                const float2 rf = __half22float2(rh[j]);
+                                x0 += rf.x, x1 += rf.y;
+                            }
+                            if (!live) { x0 = 0.0f, x1 = 0.0f; }
+                            pk[j] = pack_act_f16x2(x0, x1, L.relu); // ReLU + saturation at the fp16 range + rounding in one F2FP
+                        }
+    #pragma unroll
+                        for (int q = 0; q < 4; ++q) { *reinterpret_cast<uint4*>(out_row + c + q * 8) = packed[q]; }
+                    }
+                    tcgen05_fence_before();
+                    if (tp.fence_mode == 0) {
+                        __threadfence(); // this warp's rows of (layer l, group grp) are visible device-wide before the counter moves
+                        __syncwarp();
+                        if (lane == 0) {
+                            mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u);
+                            atomicAdd(tp.done + l * num_groups + grp, 1);
+                        }
+                    } else {
+                        __syncwarp(); // orders the lanes' row stores before lane 0's release (cumulativity carries them along)
+                        if (lane == 0) {
+                            mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u);
+                            asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(tp.done + l * num_groups + grp), "r"(1) : "memory");
+                        }
+                    }
+                    t_epi_work += (DBG ? clock64() : 0ll) - tw;
+                }
             }
         }
         if (DBG && tp.dbg && warp == 2 && lane == 0) { tp.dbg[blockIdx.x * 8 + 7] = t_epi_work; }
@@ -1245,26 +1389,40 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
 // narrow kernel up to the order of the fp32 accumulation over (tap, K-block), which the tensor core does not expose anyway.
 // ---------------------------------------------------------------------------------------------
 constexpr int WIDE_THREADS = 384; // warp 0: weight TMA, warp 1: MMA issuer + TMEM owner, warp 2: input K-block TMA + dependency waits, warp 3: idle, warps 4-11: epilogue
-constexpr int WIDE_AK = 4;        // ring slots of input K-blocks
+constexpr int WIDE_AK = 3;        // ring slots of input K-blocks (64 input channels each): the producer runs up to three K-blocks = 0.75 units ahead of the MMAs,
+                                  // far more than a TMA round trip; a fourth slot bought nothing and costs four weight stages
+constexpr int WIDE_EPI_BYTES = 8 * 2 * 32 * 64; // epilogue staging: per warp two tiles of 32 rows x 32 fp16 channels, 64-byte swizzled like the TMA box that stores them
+constexpr int WIDE_BIAS_BYTES = 8 * 64 * 4;
+
+// shared memory of a wide tower CTA (the 1024 bytes at the end pay for aligning the base)
+__host__ __device__ constexpr size_t wide_smem_bytes(int rows_ext, int stages)
+{
+    return static_cast<size_t>(WIDE_EPI_BYTES) + WIDE_BIAS_BYTES + static_cast<size_t>(WIDE_AK) * rows_ext * 128 + static_cast<size_t>(stages) * 64 * BK * 2 +
+           (2 * stages + 2 * WIDE_AK + 6) * 8 + 16 + 1024;
+}
+
 
 template <int STAGES, bool DBG>
 __global__ void __launch_bounds__(WIDE_THREADS, 1)
 conv_tower_wide_kernel(const __grid_constant__ TowerParams tp)
 {
+    static_assert(STAGES >= 9, "a K-block's nine weight stages stay resident while both row tiles use them");
     constexpr int BN = 128;
     constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
     constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     const int a_kb_bytes = tp.rows_ext * 128; // rows_ext: 256 + 2 * halo rounded up to 16 (two TMA boxes of rows_ext / 2 rows)
-    uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + WIDE_AK * a_kb_bytes;
+    uint8_t* smem_epi = smem;                                   // 8 epilogue warps x 2 x 2 KB: fp16 rows of (32 rows, 32 channels) on their way to a TMA store
+    float* smem_bias = reinterpret_cast<float*>(smem + WIDE_EPI_BYTES); // 8 epilogue warps x 64 floats: the bias of the warp's 64 channels
+    uint8_t* smem_a = smem + WIDE_EPI_BYTES + WIDE_BIAS_BYTES;
+    uint8_t* smem_b = smem_a + WIDE_AK * a_kb_bytes;
     uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_HALF_BYTES);
     uint64_t* b_empty = b_full + STAGES;
     uint64_t* a_full = b_empty + STAGES;   // [WIDE_AK]
     uint64_t* a_empty = a_full + WIDE_AK;  // [WIDE_AK]
-    uint64_t* acc_full = a_empty + WIDE_AK; // [2]
-    uint64_t* acc_empty = acc_full + 2;    // [2]
+    uint64_t* acc_full = a_empty + WIDE_AK; // [2 accumulator buffers][2 row tiles]
+    uint64_t* acc_empty = acc_full + 4;    // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1290,10 +1448,8 @@ conv_tower_wide_kernel(const __grid_constant__ TowerParams tp)
             mbar_init(&a_full[i], 1);
             mbar_init(&a_empty[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 16);
-        }
+        for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_empty[i], 16); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -1366,15 +1522,12 @@ conv_tower_wide_kernel(const __grid_constant__ TowerParams tp)
                 first = false;
                 if (l > 0) { // the 3x3 halo reaches into the neighbouring subgroups of the previous layer
                     const long long td = (DBG ? clock64() : 0ll);
-                    if (lane == 0) {
-                        const int* d = tp.done + (l - 1) * num_sg;
-                        const int g0 = (sg > 0 ? sg - 1 : 0), g1 = (sg + 1 < num_sg ? sg + 1 : num_sg - 1);
-                        for (int gg = g0; gg <= g1; ++gg) {
-                            wait_counter(d + gg, need);
-                        }
+                    if (lane < 3) { // three lanes, three counters: one L2 round trip when the rows are long complete, not three
+                        const int gg = sg - 1 + lane;
+                        if (gg >= 0 && gg < num_sg) { wait_counter(tp.done + (l - 1) * num_sg + gg, need); }
                     }
                     __syncwarp();
-                    asm volatile("fence.proxy.async;" ::: "memory"); // generic-proxy writes of other SMs -> this warp's TMA (async proxy) reads
+                    asm volatile("fence.proxy.async;" ::: "memory"); // writes of other SMs (TMA stores, ordered by their release) -> this warp's TMA (async proxy) reads
                     t_dep += (DBG ? clock64() : 0ll) - td;
                 }
                 const int row0 = sg * 2 * BM - tp.halo;
@@ -1418,43 +1571,69 @@ conv_tower_wide_kernel(const __grid_constant__ TowerParams tp)
                     t_acc += (DBG ? clock64() : 0ll) - tc;
                     tcgen05_fence_after();
                     const uint32_t tmem_d = tmem_base + buf * (2 * BN);
-                    uint32_t accumulate = 0;
+                    // K-block outer, row tile middle, tap inner: a K-block's weight stages (one per tap) serve tile 0, then tile 1, and are released by
+                    // tile 1 — the weights still stream once per 512 rows, but tile 0's accumulators are complete nine taps (36 MMAs, ~2.3 k cycles)
+                    // before tile 1's, so half of the unit's epilogue runs under the last MMAs instead of after them. (Needs STAGES >= 9.)
                     for (int kb = 0; kb < a_kb; ++kb) {
                         const long long ta = (DBG ? clock64() : 0ll);
                         mbar_wait_u32(afull0 + slot * 8, aph);
                         t_afull += (DBG ? clock64() : 0ll) - ta;
                         tcgen05_fence_after();
                         const uint32_t a_blk = a_lo0 + static_cast<uint32_t>(slot) * a_slot_step;
-                        for (int tap = 0; tap < 9; ++tap) {
-                            if (!((tap_mask >> tap) & 1)) { continue; }
-                            const int ty = tap / 3, tx = tap - 3 * ty;
-                            const uint32_t a_lo = a_blk + static_cast<uint32_t>(tp.halo - tp.n1 - 1 + ty * tp.n1 + tx) * 8u;
-                            const long long tf = (DBG ? clock64() : 0ll);
-                            mbar_wait_u32(full0 + s * 8, ph);
-                            t_bfull += (DBG ? clock64() : 0ll) - tf;
-                            tcgen05_fence_after();
-                            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(s) * (B_HALF_BYTES >> 4);
-                            if (elect_one_sync()) {
-                                umma_f16_lohi_2sm(tmem_d, a_lo, b_lo, desc_hi, idesc, accumulate);
-                                umma_f16_lohi_2sm(tmem_d, a_lo + 2, b_lo + 2, desc_hi, idesc, 1u);
-                                umma_f16_lohi_2sm(tmem_d, a_lo + 4, b_lo + 4, desc_hi, idesc, 1u);
-                                umma_f16_lohi_2sm(tmem_d, a_lo + 6, b_lo + 6, desc_hi, idesc, 1u);
-                                umma_f16_lohi_2sm(tmem_d + BN, a_lo + a_tile_step, b_lo, desc_hi, idesc, accumulate);
-                                umma_f16_lohi_2sm(tmem_d + BN, a_lo + a_tile_step + 2, b_lo + 2, desc_hi, idesc, 1u);
-                                umma_f16_lohi_2sm(tmem_d + BN, a_lo + a_tile_step + 4, b_lo + 4, desc_hi, idesc, 1u);
-                                umma_f16_lohi_2sm(tmem_d + BN, a_lo + a_tile_step + 6, b_lo + 6, desc_hi, idesc, 1u);
-                                tcgen05_commit_2sm_u32(empty0 + s * 8);
+                        const int s_kb = s;
+                        const bool last_kb = (kb + 1 == a_kb);
+                        const uint32_t acc0 = (kb > 0 ? 1u : 0u); // a unit's first MMA into a tile overwrites it
+                        const uint32_t tap_row0 = static_cast<uint32_t>(tp.halo - tp.n1 - 1);
+                        { // ---- tile 0: waits for the weight stages as they arrive
+                            uint32_t accumulate = acc0;
+                            for (int tap = 0; tap < 9; ++tap) {
+                                if (!((tap_mask >> tap) & 1)) { continue; }
+                                const int ty = tap / 3, tx = tap - 3 * ty;
+                                const uint32_t a_lo = a_blk + (tap_row0 + static_cast<uint32_t>(ty * tp.n1 + tx)) * 8u;
+                                const long long tf = (DBG ? clock64() : 0ll);
+                                mbar_wait_u32(full0 + s * 8, ph);
+                                t_bfull += (DBG ? clock64() : 0ll) - tf;
+                                tcgen05_fence_after();
+                                const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(s) * (B_HALF_BYTES >> 4);
+                                if (elect_one_sync()) {
+                                    umma_f16_lohi_2sm(tmem_d, a_lo, b_lo, desc_hi, idesc, accumulate);
+                                    umma_f16_lohi_2sm(tmem_d, a_lo + 2, b_lo + 2, desc_hi, idesc, 1u);
+                                    umma_f16_lohi_2sm(tmem_d, a_lo + 4, b_lo + 4, desc_hi, idesc, 1u);
+                                    umma_f16_lohi_2sm(tmem_d, a_lo + 6, b_lo + 6, desc_hi, idesc, 1u);
+                                }
+                                __syncwarp();
+                                accumulate = 1u;
+                                if (++s == STAGES) { s = 0, ph ^= 1; }
                             }
-                            __syncwarp();
-                            accumulate = 1u;
-                            if (++s == STAGES) { s = 0, ph ^= 1; }
                         }
+                        // ---- tile 1: every stage of the K-block is in place — one thread issues the whole pass (no per-tap election or barrier
+                        //      traffic: with four MMAs per tap the issue loop must stay well under their 256 tensor cycles) and releases the stages
+                        if (elect_one_sync()) {
+                            if (last_kb) { tcgen05_commit_2sm_u32(smem_u32(&acc_full[buf * 2 + 0])); } // tile 0's accumulators are complete
+                            uint32_t accumulate = acc0;
+                            int s1 = s_kb;
+                            const uint32_t a_t1 = a_blk + a_tile_step;
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                if (!((tap_mask >> tap) & 1)) { continue; }
+                                const int ty = tap / 3, tx = tap - 3 * ty;
+                                const uint32_t a_lo = a_t1 + (tap_row0 + static_cast<uint32_t>(ty * tp.n1 + tx)) * 8u;
+                                const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(s1) * (B_HALF_BYTES >> 4);
+                                umma_f16_lohi_2sm(tmem_d + BN, a_lo, b_lo, desc_hi, idesc, accumulate);
+                                umma_f16_lohi_2sm(tmem_d + BN, a_lo + 2, b_lo + 2, desc_hi, idesc, 1u);
+                                umma_f16_lohi_2sm(tmem_d + BN, a_lo + 4, b_lo + 4, desc_hi, idesc, 1u);
+                                umma_f16_lohi_2sm(tmem_d + BN, a_lo + 6, b_lo + 6, desc_hi, idesc, 1u);
+                                tcgen05_commit_2sm_u32(empty0 + s1 * 8);
+                                accumulate = 1u;
+                                if (++s1 == STAGES) { s1 = 0; }
+                            }
+                            if (last_kb) { tcgen05_commit_2sm_u32(smem_u32(&acc_full[buf * 2 + 1])); }
+                        }
+                        __syncwarp();
                         if (elect_one_sync()) { tcgen05_commit_2sm_u32(aempty0 + slot * 8); }
                         __syncwarp();
                         if (++slot == WIDE_AK) { slot = 0, aph ^= 1; }
                     }
-                    if (elect_one_sync()) { tcgen05_commit_2sm_u32(smem_u32(&acc_full[buf])); }
-                    __syncwarp();
                     buf ^= 1;
                 }
             }
@@ -1466,11 +1645,21 @@ conv_tower_wide_kernel(const __grid_constant__ TowerParams tp)
             }
         }
     } else if (warp >= 4) { // ===== epilogue (both CTAs): warp & 3 = TMEM lane quarter, (warp - 4) / 4 = which 64 of a tile's 128 columns =====
-        const int quarter = warp & 3, chalf = (warp - 4) >> 2;
+        // The time from a unit's last MMA to its rows being published is on the critical path of every unit of the next layer that needs them
+        // (at config 2 a layer holds 1.35 units per pair: most units wait for rows finished just before). So everything that does not need the
+        // accumulators happens BEFORE they are ready — the bias of the warp's 64 channels goes to shared memory, the residual rows (complete
+        // since layer l - 2; checked with one acquire of that layer's counter) into registers — and afterwards the warp only converts: TMEM ->
+        // registers -> fp16 rows in a 128-byte-swizzled staging tile -> ONE TMA store per (row tile, 64 channels). A lane-per-row st.global
+        // touches 32 cache lines per instruction (measured: 12 k cycles per unit in the epilogue, a third of them in __threadfence's
+        // MEMBAR.SC + L1 invalidate); the TMA store leaves the LSU out of it, and publishing is: wait for the bulk stores, one red.release.
+        const int quarter = warp & 3, chalf = (warp - 4) >> 2, ew = warp - 4;
+        const uint32_t stage_u32 = smem_u32(smem_epi + ew * 4096); // two tiles of 2 KB, used alternately
+        const uint32_t bias_u32 = smem_u32(smem_bias + ew * 64);
         int ucount = 0;
         long long t_epi_work = 0;
         for (int l = 0; l < tp.num_layers; ++l) {
             const TowerLayer& L = tp.layer[l];
+            const CUtensorMap* map_out = &tp.map_out[L.out_map];
             for (int u = first_unit(l); u < units; u += nc, ++ucount) {
                 const int grp = u / nh, half = u - grp * nh, buf = ucount & 1;
                 const int mt0 = grp * 4 + crank * 2;
@@ -1484,59 +1673,83 @@ conv_tower_wide_kernel(const __grid_constant__ TowerParams tp)
                     live[t] = (r[t] < tp.rows_valid) && (rr / tp.n1 != 0) && (rr % tp.n1 != tp.n1 - 1);
                     in_range[t] = (mt0 + t < tp.num_mtiles);
                 }
-                mbar_wait(&acc_full[buf], (ucount >> 1) & 1);
-                const long long tw = (DBG ? clock64() : 0ll);
-                tcgen05_fence_after();
-                // chunk i = (tile i >> 1, columns n0 + (i & 1) * 32 .. + 32); the residual rows of chunk i + 1 are requested before chunk i is converted
-                uint4 res[2][4];
-                auto load_res = [&](int i, uint4* dst) {
-                    const int t = i >> 1;
-                    if (L.residual && live[t] && in_range[t]) { // written by other SMs earlier in this launch: read through L2, never through this SM's L1
-                        const __half* res_row = L.residual + static_cast<size_t>(r[t]) * tp.cout + n0 + (i & 1) * 32;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) { dst[q] = __ldcg(reinterpret_cast<const uint4*>(res_row) + q); }
+                // ---- before the accumulators are ready: bias slice and residual rows
+                __syncwarp();
+                sts_f2(bias_u32 + 8 * lane, __ldg(reinterpret_cast<const float2*>(L.bias + n0) + lane));
+                uint4 res[2][8];
+                if (L.residual) {
+                    if (L.res_layer >= 0) { // rows of an earlier layer of this launch, written by other SMs: complete long ago, but this warp has not synchronised with them yet
+                        if (lane == 0) { wait_counter(tp.done + L.res_layer * num_sg + 2 * grp + crank, need); }
+                        __syncwarp();
                     }
-                };
-                load_res(0, res[0]);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int t = i >> 1, c = (i & 1) * 32;
+                    for (int t = 0; t < 2; ++t) {
+                        if (live[t] && in_range[t]) { // read through L2, never through this SM's L1
+                            const uint4* res_row = reinterpret_cast<const uint4*>(L.residual + static_cast<size_t>(r[t]) * tp.cout + n0);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) { res[t][q] = __ldcg(res_row + q); }
+                        }
+                    }
+                }
+                __syncwarp();
+                long long tw = 0;
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
                     if (!in_range[t]) { continue; } // warp-uniform
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * (2 * BN) + t * BN + chalf * 64 + c, v);
-                    if (i + 1 < 4) { load_res(i + 1, res[(i + 1) & 1]); }
-                    float4 bias4[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) { bias4[q] = __ldg(reinterpret_cast<const float4*>(L.bias + n0 + c) + q); }
-                    const float* bias = reinterpret_cast<const float*>(bias4);
-                    tmem_ld_wait();
-                    uint4 packed[4];
-                    uint32_t* pk = reinterpret_cast<uint32_t*>(packed);
-                    const __half2* rh = reinterpret_cast<const __half2*>(res[i & 1]);
+                    mbar_wait(&acc_full[buf * 2 + t], (ucount >> 1) & 1); // tile 0 is complete nine taps before tile 1: its rows are converted under the last MMAs
+                    if (t == 1 || !in_range[1]) { tw = (DBG ? clock64() : 0ll); }
+                    tcgen05_fence_after();
                     const bool add_res = (L.residual != nullptr) && live[t];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float x0 = __uint_as_float(v[2 * j]) + bias[2 * j];
-                        float x1 = __uint_as_float(v[2 * j + 1]) + bias[2 * j + 1];
-                        if (add_res) {
-                            const float2 rf = __half22float2(rh[j]);
-                            x0 += rf.x, x1 += rf.y;
-                        }
-                        x0 = fminf(fmaxf(x0, L.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX), x1 = fminf(fmaxf(x1, L.relu ? 0.0f : -MZ_HALF_MAX), MZ_HALF_MAX); // ReLU + saturation at the fp16 range
-                        if (!live[t]) { x0 = 0.0f, x1 = 0.0f; }
-                        const __half2 h = __floats2half2_rn(x0, x1);
-                        pk[j] = *reinterpret_cast<const uint32_t*>(&h);
-                    }
-                    __half* out_row = L.out + static_cast<size_t>(r[t]) * tp.cout + n0 + c;
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * (2 * BN) + t * BN + chalf * 64 + c * 32, v);
+                        float4 b0 = lds_f4(bias_u32 + c * 128), b1 = lds_f4(bias_u32 + c * 128 + 16);
+                        tmem_ld_wait();
+                        if (lane == 0) { tma_store_wait_read1(); } // staging tile c is free again once the store before the last one has read it
+                        __syncwarp();
+                        const __half2* rh = reinterpret_cast<const __half2*>(&res[t][c * 4]);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { *(reinterpret_cast<uint4*>(out_row) + q) = packed[q]; }
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 pk4;
+                            uint32_t* pk = reinterpret_cast<uint32_t*>(&pk4);
+                            const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                            if (q < 3) { b0 = lds_f4(bias_u32 + c * 128 + (q + 1) * 32), b1 = lds_f4(bias_u32 + c * 128 + (q + 1) * 32 + 16); } // the next eight, under this chunk's arithmetic
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float x0 = __uint_as_float(v[q * 8 + 2 * j]) + bias[2 * j];
+                                float x1 = __uint_as_float(v[q * 8 + 2 * j + 1]) + bias[2 * j + 1];
+                                if (add_res) {
+                                    const float2 rf = __half22float2(rh[q * 4 + j]);
+                                    x0 += rf.x, x1 += rf.y;
+                                }
+                                if (!live[t]) { x0 = 0.0f, x1 = 0.0f; }
+                                pk[j] = pack_act_f16x2(x0, x1, L.relu); // ReLU + saturation at the fp16 range + rounding in one F2FP
+                            }
+                            // row `lane` of staging tile c, 16-byte chunk q, at the position the 64-byte swizzle gives it (conflict-free: 8 lanes cover 8 chunk columns)
+                            sts_u4(stage_u32 + c * 2048 + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4), pk4);
+                        }
+                        if (c == 1 && (t == 1 || !in_range[1])) { // the accumulators of this unit have been read: the issuer may reuse them
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) { mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u); }
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // this lane's row in shared memory -> the TMA engine
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(map_out, stage_u32 + c * 2048, n0 + c * 32, (mt0 + t) * BM + quarter * 32);
+                            tma_store_commit();
+                        }
+                    }
                 }
-                tcgen05_fence_before();
-                __threadfence(); // this warp's rows of (layer l, subgroup) are visible device-wide before the counter moves
-                __syncwarp();
+                if (!in_range[0] && lane == 0) { mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u); } // a phantom unit behind the last row tile: nothing to read
                 if (lane == 0) {
-                    mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u);
-                    atomicAdd(tp.done + l * num_sg + 2 * grp + crank, 1);
+                    tma_store_wait_all(); // this warp's rows of (layer l, subgroup) are written ...
+                    if (tp.fence_mode == 2) { // experiment: the stores are complete (acknowledged by L2) — count without a fence
+                        asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(tp.done + l * num_sg + 2 * grp + crank), "r"(1) : "memory");
+                    } else {
+                        asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(tp.done + l * num_sg + 2 * grp + crank), "r"(1) : "memory"); // ... before the counter moves
+                    }
                 }
                 t_epi_work += (DBG ? clock64() : 0ll) - tw;
             }

@@ -342,7 +342,7 @@ print("TWO_ENGINES_OK")
 
 
 def test_wide_and_narrow_towers_agree_bit_for_bit():
-    """conv_tower_wide_kernel (two row tiles per CTA, chosen when a layer holds two wide units per CTA pair: here 19x19 x 192 boards x 128 channels = 150
+    """conv_tower_wide_kernel (two row tiles per CTA, chosen when a layer holds at least one wide unit per CTA pair: here 19x19 x 192 boards x 128 channels = 150
     units) against conv_tower_kernel (the same network in an engine of 48 boards): both accumulate K-block outer / tap inner, so every logit and value
     of a position must be identical whichever kernel — whichever batch — evaluated it"""
     import __graft_entry__ as ge
