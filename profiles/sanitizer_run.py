@@ -58,6 +58,19 @@ if os.environ.get("SAN_WIDE", "1") == "1":
     assert np.all(np.isfinite(lg)) and np.all(np.isfinite(val))
     eng.close()
 
+# the narrow tower (conv_tower_kernel: TMA-store epilogue, residual prefetch behind one counter acquire): 9x9 boards, a 2-block x 128-channel net, a whole search
+if os.environ.get("SAN_NARROW", "1") == "1":
+    import __graft_entry__ as ge  # noqa: E402
+    dims = dict(num_input_channels=18, input_height=9, input_width=9, num_hidden_channels=128, num_blocks=2, action_size=82, num_value_hidden_channels=64,
+                discrete_value_size=1)
+    eng = mz.Engine(mz.GAME_GO, 9, 8, 12)
+    eng.load_network((dims, ge.make_random_state(dims, rng)))
+    assert eng.tower_is_wide() == 0 and eng.conv_layers_per_launch() == 5
+    eng.set_search_inputs(rng.integers(0, 8, size=(13, 8)).astype(np.uint8), rng.dirichlet([0.3] * 82, size=8).astype(np.float32))
+    eng.search()
+    assert np.all(eng.get_roots()["root_count"] == 13)
+    eng.close()
+
 import golden_replay  # noqa: E402
 case = golden_replay.load_case("ttt_s50_b2")
 eng = mz.Engine(mz.GAME_TICTACTOE, 3, 2, 50)
