@@ -1128,7 +1128,9 @@ int alloc_net(mz_engine* e)
             set(base + 1 + 2 * b, act_maps[tt], e->act[o], e->act[cur]);
             cur = o;
         }
-        const int num_groups = (e->tower_wide ? 2 * ((T.num_mtiles + 3) / 4) : (T.num_mtiles + 1) / 2); // wide: 256-row subgroups incl. the phantom one of an odd tail
+        // completion counters: narrow tower one per (layer, 256-row group); wide tower one per (layer, 256-row subgroup incl. the phantom one of an odd tail,
+        // block of 64 output channels)
+        const int num_groups = (e->tower_wide ? 2 * ((T.num_mtiles + 3) / 4) * (e->cpad / 64) : (T.num_mtiles + 1) / 2);
         NT.done_count = T.num_layers * num_groups;
         if ((rc = e->dalloc(&NT.d_done, static_cast<size_t>(T.num_layers) * num_groups))) { return rc; }
         T.done = NT.d_done;

@@ -917,6 +917,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr)
     return v;
 }
 __device__ __forceinline__ void sts_u4(uint32_t addr, const uint4& v) { asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+__device__ __forceinline__ void sts_f1(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts_f2(uint32_t addr, const float2& v) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory"); }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); } // every store has read its source tile
@@ -1433,7 +1434,8 @@ conv_tower_wide_kernel(const __grid_constant__ TowerParams tp)
     const int num_groups = (tp.num_mtiles + 3) / 4; // groups of 512 rows: two tiles per CTA of the pair
     const int num_sg = 2 * num_groups;              // subgroups of 256 rows: the rows one CTA writes
     const int units = num_groups * nh;
-    const int need = 8 * nh; // arrivals per (layer, subgroup): 8 epilogue warps x nh channel halves
+    const int nkbo = tp.cout / 64; // completion counters per (layer, subgroup): one per block of 64 output channels = per K-block of the next layer's input
+    constexpr int need = 8;        // arrivals per counter: the CTA's 8 epilogue warps (each converts 32 of the 64 channels, for both row tiles)
 
     if (warp == 0 && lane == 0) {
         for (int l = 0; l < tp.num_layers; ++l) {
@@ -1520,18 +1522,20 @@ conv_tower_wide_kernel(const __grid_constant__ TowerParams tp)
                     asm volatile("fence.proxy.async;" ::: "memory");
                 }
                 first = false;
-                if (l > 0) { // the 3x3 halo reaches into the neighbouring subgroups of the previous layer
-                    const long long td = (DBG ? clock64() : 0ll);
-                    if (lane < 3) { // three lanes, three counters: one L2 round trip when the rows are long complete, not three
-                        const int gg = sg - 1 + lane;
-                        if (gg >= 0 && gg < num_sg) { wait_counter(tp.done + (l - 1) * num_sg + gg, need); }
-                    }
-                    __syncwarp();
-                    asm volatile("fence.proxy.async;" ::: "memory"); // writes of other SMs (TMA stores, ordered by their release) -> this warp's TMA (async proxy) reads
-                    t_dep += (DBG ? clock64() : 0ll) - td;
-                }
                 const int row0 = sg * 2 * BM - tp.halo;
                 for (int kb = 0; kb < a_kb; ++kb) {
+                    if (l > 0) { // K-block kb = 64 channels of the previous layer's output, rows of this subgroup and (3x3 halo) of its two neighbours: their
+                                 // counters for THAT channel block only — a unit starts when the first 64 channels of its rows exist, the later blocks are
+                                 // waited for as the ring gets to them (a quarter of a unit later each)
+                        const long long td = (DBG ? clock64() : 0ll);
+                        if (lane < 3) { // three lanes, three counters: one L2 round trip when the rows are long complete, not three
+                            const int gg = sg - 1 + lane;
+                            if (gg >= 0 && gg < num_sg) { wait_counter(tp.done + (static_cast<size_t>(l - 1) * num_sg + gg) * nkbo + (kb < nkbo ? kb : nkbo - 1), need); }
+                        }
+                        __syncwarp();
+                        asm volatile("fence.proxy.async;" ::: "memory"); // writes of other SMs (TMA stores, ordered by their release) -> this warp's TMA (async proxy) reads
+                        t_dep += (DBG ? clock64() : 0ll) - td;
+                    }
                     mbar_wait_u32(aempty0 + slot * 8, ph); // the MMAs that read this slot WIDE_AK K-blocks ago are done
                     if (elect_one_sync()) {
                         if (leader) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(afull0 + slot * 8), "r"(2 * a_kb_bytes) : "memory"); }
@@ -1652,8 +1656,8 @@ conv_tower_wide_kernel(const __grid_constant__ TowerParams tp)
         // registers -> fp16 rows in a 128-byte-swizzled staging tile -> ONE TMA store per (row tile, 64 channels). A lane-per-row st.global
         // touches 32 cache lines per instruction (measured: 12 k cycles per unit in the epilogue, a third of them in __threadfence's
         // MEMBAR.SC + L1 invalidate); the TMA store leaves the LSU out of it, and publishing is: wait for the bulk stores, one red.release.
-        const int quarter = warp & 3, chalf = (warp - 4) >> 2, ew = warp - 4;
-        const uint32_t stage_u32 = smem_u32(smem_epi + ew * 4096); // two tiles of 2 KB, used alternately
+        const int quarter = warp & 3, x = (warp - 4) >> 2, ew = warp - 4; // x: which 32 of every 64-channel block this warp converts
+        const uint32_t stage_u32 = smem_u32(smem_epi + ew * 4096); // two tiles of 2 KB: piece 0 / piece 1
         const uint32_t bias_u32 = smem_u32(smem_bias + ew * 64);
         int ucount = 0;
         long long t_epi_work = 0;
@@ -1662,8 +1666,8 @@ conv_tower_wide_kernel(const __grid_constant__ TowerParams tp)
             const CUtensorMap* map_out = &tp.map_out[L.out_map];
             for (int u = first_unit(l); u < units; u += nc, ++ucount) {
                 const int grp = u / nh, half = u - grp * nh, buf = ucount & 1;
-                const int mt0 = grp * 4 + crank * 2;
-                const int n0 = half * BN + chalf * 64;
+                const int mt0 = grp * 4 + crank * 2, sg = 2 * grp + crank;
+                const int n0 = half * BN + x * 32; // this warp's channels: n0 .. n0 + 32 (piece 0, channel block 2 * half) and n0 + 64 .. n0 + 96 (piece 1, block 2 * half + 1)
                 int r[2];
                 bool live[2], in_range[2];
 #pragma unroll
@@ -1675,11 +1679,11 @@ conv_tower_wide_kernel(const __grid_constant__ TowerParams tp)
                 }
                 // ---- before the accumulators are ready: bias slice and residual rows
                 __syncwarp();
-                sts_f2(bias_u32 + 8 * lane, __ldg(reinterpret_cast<const float2*>(L.bias + n0) + lane));
+                sts_f1(bias_u32 + 4 * lane, __ldg(L.bias + n0 + lane)), sts_f1(bias_u32 + 128 + 4 * lane, __ldg(L.bias + n0 + 64 + lane)); // piece p, channel j: float 32 p + j
                 uint4 res[2][8];
                 if (L.residual) {
                     if (L.res_layer >= 0) { // rows of an earlier layer of this launch, written by other SMs: complete long ago, but this warp has not synchronised with them yet
-                        if (lane == 0) { wait_counter(tp.done + L.res_layer * num_sg + 2 * grp + crank, need); }
+                        if (lane < 2) { wait_counter(tp.done + (static_cast<size_t>(L.res_layer) * num_sg + sg) * nkbo + 2 * half + lane, need); }
                         __syncwarp();
                     }
 #pragma unroll
@@ -1687,7 +1691,7 @@ conv_tower_wide_kernel(const __grid_constant__ TowerParams tp)
                         if (live[t] && in_range[t]) { // read through L2, never through this SM's L1
                             const uint4* res_row = reinterpret_cast<const uint4*>(L.residual + static_cast<size_t>(r[t]) * tp.cout + n0);
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) { res[t][q] = __ldcg(res_row + q); }
+                            for (int q = 0; q < 4; ++q) { res[t][q] = __ldcg(res_row + q), res[t][4 + q] = __ldcg(res_row + 8 + q); }
                         }
                     }
                 }
@@ -1697,15 +1701,22 @@ conv_tower_wide_kernel(const __grid_constant__ TowerParams tp)
                 for (int t = 0; t < 2; ++t) {
                     if (!in_range[t]) { continue; } // warp-uniform
                     mbar_wait(&acc_full[buf * 2 + t], (ucount >> 1) & 1); // tile 0 is complete nine taps before tile 1: its rows are converted under the last MMAs
-                    if (t == 1 || !in_range[1]) { tw = (DBG ? clock64() : 0ll); }
+                    const bool last_tile = (t == 1 || !in_range[1]);
+                    if (last_tile) { tw = (DBG ? clock64() : 0ll); }
                     tcgen05_fence_after();
                     const bool add_res = (L.residual != nullptr) && live[t];
+                    uint32_t vv[2][32]; // both pieces of the tile at once: one TMEM round trip, and the accumulators are free before the first store
+                    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * (2 * BN) + t * BN + x * 32, vv[0]);
+                    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * (2 * BN) + t * BN + 64 + x * 32, vv[1]);
+                    tmem_ld_wait();
+                    if (last_tile) { // the accumulators of this unit have been read: the issuer may reuse them
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u); }
+                    }
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t v[32];
-                        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * (2 * BN) + t * BN + chalf * 64 + c * 32, v);
-                        float4 b0 = lds_f4(bias_u32 + c * 128), b1 = lds_f4(bias_u32 + c * 128 + 16);
-                        tmem_ld_wait();
+                    for (int c = 0; c < 2; ++c) { // piece c: channels n0 + 64 c .. + 32
+                        const uint32_t* v = vv[c];
                         if (lane == 0) { tma_store_wait_read1(); } // staging tile c is free again once the store before the last one has read it
                         __syncwarp();
                         const __half2* rh = reinterpret_cast<const __half2*>(&res[t][c * 4]);
@@ -1713,8 +1724,8 @@ conv_tower_wide_kernel(const __grid_constant__ TowerParams tp)
                         for (int q = 0; q < 4; ++q) {
                             uint4 pk4;
                             uint32_t* pk = reinterpret_cast<uint32_t*>(&pk4);
+                            const float4 b0 = lds_f4(bias_u32 + c * 128 + q * 32), b1 = lds_f4(bias_u32 + c * 128 + q * 32 + 16);
                             const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                            if (q < 3) { b0 = lds_f4(bias_u32 + c * 128 + (q + 1) * 32), b1 = lds_f4(bias_u32 + c * 128 + (q + 1) * 32 + 16); } // the next eight, under this chunk's arithmetic
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 float x0 = __uint_as_float(v[q * 8 + 2 * j]) + bias[2 * j];
@@ -1729,27 +1740,24 @@ conv_tower_wide_kernel(const __grid_constant__ TowerParams tp)
                             // row `lane` of staging tile c, 16-byte chunk q, at the position the 64-byte swizzle gives it (conflict-free: 8 lanes cover 8 chunk columns)
                             sts_u4(stage_u32 + c * 2048 + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4), pk4);
                         }
-                        if (c == 1 && (t == 1 || !in_range[1])) { // the accumulators of this unit have been read: the issuer may reuse them
-                            tcgen05_fence_before();
-                            __syncwarp();
-                            if (lane == 0) { mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u); }
-                        }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // this lane's row in shared memory -> the TMA engine
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_2d(map_out, stage_u32 + c * 2048, n0 + c * 32, (mt0 + t) * BM + quarter * 32);
+                            tma_store_2d(map_out, stage_u32 + c * 2048, n0 + c * 64, (mt0 + t) * BM + quarter * 32);
                             tma_store_commit();
+                            if (last_tile) { // channel block 2 * half + c of this subgroup: both tiles' rows of this warp are on their way — publish it on its own,
+                                             // the next layer's K-block 2 * half + c waits for nothing else
+                                tma_store_wait_all(); // ... written ...
+                                asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(tp.done + (static_cast<size_t>(l) * num_sg + sg) * nkbo + 2 * half + c), "r"(1)
+                                             : "memory"); // ... before the counter moves
+                            }
                         }
                     }
                 }
-                if (!in_range[0] && lane == 0) { mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u); } // a phantom unit behind the last row tile: nothing to read
-                if (lane == 0) {
-                    tma_store_wait_all(); // this warp's rows of (layer l, subgroup) are written ...
-                    if (tp.fence_mode == 2) { // experiment: the stores are complete (acknowledged by L2) — count without a fence
-                        asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(tp.done + l * num_sg + 2 * grp + crank), "r"(1) : "memory");
-                    } else {
-                        asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(tp.done + l * num_sg + 2 * grp + crank), "r"(1) : "memory"); // ... before the counter moves
-                    }
+                if (!in_range[0] && lane == 0) { // a phantom unit behind the last row tile: nothing to read, but the counters are waited for
+                    mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0u);
+                    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(tp.done + (static_cast<size_t>(l) * num_sg + sg) * nkbo + 2 * half), "r"(1) : "memory");
+                    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(tp.done + (static_cast<size_t>(l) * num_sg + sg) * nkbo + 2 * half + 1), "r"(1) : "memory");
                 }
                 t_epi_work += (DBG ? clock64() : 0ll) - tw;
             }
