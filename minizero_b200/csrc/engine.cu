@@ -452,7 +452,6 @@ int configure_conv_kernels()
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<128, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(mznn::conv_tower_kernel<256, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -672,8 +671,6 @@ int launch_tower_params(mz_engine* e, mznn::TowerParams* params, int* d_done, in
         CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 8, true>, *params));
     } else if (stages == 4) { // 185 KB of shared memory: a tree-step block (30 KB) of another engine fits on the same SM
         CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 4, false>, *params));
-    } else if (stages == 3) {
-        CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 3, false>, *params));
     } else if (params->dbg && stages == 5) {
         CUDA_OK(cudaLaunchKernelEx(&cfg, mznn::conv_tower_kernel<128, 5, true>, *params));
     } else if (stages == 5) {
@@ -925,8 +922,12 @@ int alloc_atari(mz_engine* e)
         for (const ConvLayer& L : st.convs) { st.cin_max = std::max(st.cin_max, L.cin); }
         st.stages = 0;
         int st_bufs = 2;
-        for (int bufs : {2, 1}) {
-            for (int cand : {8, 5, 4, 3}) { // (3 stages: the 24 x 24 stage of a 256-channel network, which runs once per move)
+        // the TMA-store epilogue shortens the hand-off between layers; a stage with many units per CTA pair and layer is bound by the epilogue's throughput instead
+        const int st_units = (st.rows_alloc / mznn::BM + 1) / 2 * (st.cout / 128);
+        const bool st_chain_bound = (st_units <= 4 * (e->num_sms / 2));
+        for (int bufs : {2, 1, 0}) { // (0 is also the fall-back where the input blocks leave no room for staging tiles: the 24 x 24 stage of a 256-channel network)
+            if (bufs != 0 && !st_chain_bound) { continue; }
+            for (int cand : {8, 5, 4}) {
                 if (st.stages == 0 && mznn::tower_smem_bytes(st.cin_max, st.rows_ext, cand, 128, bufs) <= 227 * 1024) { st.stages = cand, st_bufs = bufs; }
             }
         }
@@ -1007,7 +1008,10 @@ int alloc_net(mz_engine* e)
         // simply takes fewer stages; the per-layer pair kernel is instantiated for 8 only
         auto pair_need = [&](int stages, int bufs) { return mznn::tower_smem_bytes(e->cin_max, e->rows_ext, stages, 128, bufs); };
         int stages = 0;
-        for (int bufs : {2, 1}) { // staging tiles per epilogue warp: two where they fit
+        const int narrow_units = (e->rows_alloc / mznn::BM + 1) / 2 * (e->cpad / 128);
+        const bool chain_bound = (narrow_units <= 4 * (e->num_sms / 2)); // else: many units per CTA pair and layer, the epilogue's throughput counts (see tower_smem_bytes)
+        for (int bufs : {2, 1, 0}) { // staging tiles per epilogue warp: two where they fit
+            if (bufs != 0 && !chain_bound) { continue; }
             for (int cand : {8, 5, 4}) {
                 if (stages == 0 && pair_need(cand, bufs) <= 227 * 1024 && (want_tower || cand == 8)) { stages = cand, e->tower_epi_bufs = bufs; }
             }

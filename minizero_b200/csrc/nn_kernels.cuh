@@ -872,7 +872,7 @@ struct TowerParams {
                   // only the first layer's input rows depend on that kernel, and the input producer waits for it (griddepcontrol.wait)
     int* done;    // [num_layers][num_groups] completion counters, zeroed before every launch
     unsigned long long* dbg; // optional [grid][8] cycle counters (profiling)
-    int epi_bufs;   // narrow tower: staging tiles per epilogue warp (1 or 2), see tower_smem_bytes
+    int epi_bufs;   // narrow tower: staging tiles per epilogue warp (1 or 2; 0 = lane-per-row stores), see tower_smem_bytes
     CUtensorMap map_out[3]; // wide tower: the three activation buffers as TMA store targets, box = 32 channels x 32 rows (one TMEM load of an
                             // epilogue warp), 64-byte swizzle
 };
@@ -924,10 +924,12 @@ __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); } // all but the newest store have read their source tiles
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }       // the stores are complete (visible)
 // shared memory of a narrow tower CTA (the 1024 bytes at the end pay for aligning the base). epi_bufs: staging tiles per epilogue warp (32 rows x 32 fp16
-// channels, 64-byte swizzle, 2 KB each): 2 where they fit, 1 where the input blocks leave no room (Atari dynamics: 320 input channels)
+// channels, 64-byte swizzle, 2 KB each): 2 where they fit, 1 where the input blocks leave no room (Atari dynamics: 320 input channels), 0 = the
+// lane-per-row st.global epilogue (towers with many units per CTA pair and layer: nothing waits for a single unit's rows, and with 128 input
+// channels a unit's MMAs are shorter than four staged chunks + a release — measured on the 48 x 48 Atari stage: 517 us against 603 us)
 __host__ __device__ constexpr size_t tower_smem_bytes(int cin_max, int rows_ext, int stages, int bn, int epi_bufs)
 {
-    return static_cast<size_t>(bn == 128 ? 4 * epi_bufs * 2048 + 4 * bn * 4 : 0) + 2 * static_cast<size_t>(cin_max / BK) * rows_ext * 128 +
+    return static_cast<size_t>(bn == 128 && epi_bufs > 0 ? 4 * epi_bufs * 2048 + 4 * bn * 4 : 0) + 2 * static_cast<size_t>(cin_max / BK) * rows_ext * 128 +
            static_cast<size_t>(stages) * (bn / 2) * BK * 2 + 24 * 8 + 16 + 1024;
 }
 
@@ -943,7 +945,7 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     const int a_kb_bytes = tp.rows_ext * 128;
     const int a_bytes_max = (tp.cin_max / BK) * a_kb_bytes; // hidden layers have cin == cout; an AlphaZero stem is narrower, a MuZero dynamics stem wider
-    const int epi_bytes = (BN == 128 ? 4 * tp.epi_bufs * 2048 + 4 * BN * 4 : 0); // staging tiles + per-warp bias rows of the epilogue (128-wide tiles)
+    const int epi_bytes = (BN == 128 && tp.epi_bufs > 0 ? 4 * tp.epi_bufs * 2048 + 4 * BN * 4 : 0); // staging tiles + per-warp bias rows of the epilogue
     uint8_t* smem_epi = smem;
     float* smem_bias = reinterpret_cast<float*>(smem + 4 * tp.epi_bufs * 2048);
     uint8_t* smem_a = smem + epi_bytes;
@@ -1189,7 +1191,7 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
         const int quarter = warp & 3;
         int ucount = 0;
         long long t_epi_work = 0;
-        if constexpr (BN == 128) {
+        if (BN == 128 && tp.epi_bufs > 0) {
             // Everything that does not need the accumulators happens before they are ready (the bias row in shared memory; the residual rows in
             // registers where the layer that wrote them is known: one acquire of its counter orders the loads); afterwards the warp converts
             // TMEM -> registers -> fp16 rows in a 64-byte-swizzled staging tile -> one TMA store per 32 channels, and publishes with one
