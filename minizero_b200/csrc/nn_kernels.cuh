@@ -1383,13 +1383,16 @@ conv_tower_kernel(const __grid_constant__ TowerParams tp)
 // the weight traffic per FLOP. What changes with it:
 //   * accumulators: 2 tiles x 128 columns per unit, double-buffered = all 512 TMEM columns;
 //   * the input block of a unit (256 + 2 * halo rows x cin per CTA) no longer fits twice, so it is streamed as a ring of
-//     WIDE_AK K-blocks (64 input channels each) and the loop order becomes K-block outer, tap inner: the K-block of the
-//     NEXT unit loads while the current unit works on its later K-blocks;
-//   * 8 epilogue warps (two per TMEM lane quarter, each draining half of the columns of both tiles), the residual rows of the
-//     next chunk requested before the current chunk is converted;
-//   * completion counters per 256-row subgroup (one CTA's rows), as fine as the narrow kernel's.
+//     WIDE_AK K-blocks (64 input channels each) and the loop order becomes K-block outer, row tile middle, tap inner: the
+//     K-block of the NEXT unit loads while the current unit works on its later K-blocks, a K-block's nine weight stages
+//     serve tile 0 and then tile 1 (STAGES >= 9), and tile 0's accumulators are complete 36 MMAs before tile 1's;
+//   * 8 epilogue warps (two per TMEM lane quarter; each converts 32 of every 64 output channels, for both tiles): bias and
+//     residual rows are fetched before the accumulators are ready, the fp16 rows leave through swizzled staging tiles and TMA
+//     stores (DESIGN.md "The hand-off between layers");
+//   * completion counters per (256-row subgroup = one CTA's rows, block of 64 output channels = one K-block of the next
+//     layer), published as soon as both tiles of the block are stored; the consumer waits K-block by K-block.
 // Units are dealt round-robin to the pairs (the narrow kernel's "strided" order). Same arithmetic per output element as the
-// narrow kernel up to the order of the fp32 accumulation over (tap, K-block), which the tensor core does not expose anyway.
+// narrow kernel: both accumulate K-block outer / tap inner, so a position's result does not depend on which kernel ran it.
 // ---------------------------------------------------------------------------------------------
 constexpr int WIDE_THREADS = 384; // warp 0: weight TMA, warp 1: MMA issuer + TMEM owner, warp 2: input K-block TMA + dependency waits, warp 3: idle, warps 4-11: epilogue
 constexpr int WIDE_AK = 3;        // ring slots of input K-blocks (64 input channels each): the producer runs up to three K-blocks = 0.75 units ahead of the MMAs,

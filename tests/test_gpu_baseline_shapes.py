@@ -152,7 +152,7 @@ def test_network_saturates_instead_of_overflowing():
     eng.close()
 
 
-def sampled_search_vs_oracle(game, n, B, S, net_path, moves, seed, sample, dirichlet_alpha=0.03):
+def sampled_search_vs_oracle(game, n, B, S, net_path, moves, seed, sample, dirichlet_alpha=0.03, expect_wide=None):
     """The engine searches ALL B games (full BASELINE batch, one CUDA graph per move); the oracle re-runs the first `sample` games
     with the same rotations and noise, fed by a second, network-only engine (a position's network outputs do not depend on what
     else is in the batch: every row tile of the implicit GEMM accumulates its own rows in the same order). Root tables of the
@@ -162,6 +162,8 @@ def sampled_search_vs_oracle(game, n, B, S, net_path, moves, seed, sample, diric
     eng.load_network(net_path)
     ev = engine(game, n, sample, 2)
     ev.load_network(net_path)
+    if expect_wide is not None:  # the full batch runs conv_tower_wide_kernel, the sampled games' evaluations conv_tower_kernel: two kernels, one result
+        assert eng.tower_is_wide() == expect_wide and ev.tower_is_wide() == 0
     orc = oracle_lib.OracleSearch(lib, game, n, sample, S)
     rng = np.random.default_rng(seed)
     A = eng.A
@@ -202,7 +204,7 @@ def sampled_search_vs_oracle(game, n, B, S, net_path, moves, seed, sample, diric
 def test_config2_full_batch_sampled_games_match_oracle():
     """BASELINE configs[1]: 256 games x 400 simulations x 6b x 256, Dirichlet(0.03) + random rotations; 16 sampled games bit-exact"""
     torch, m, path = torchscript("go9_az_6bx256")
-    sampled_search_vs_oracle(1, 9, 256, 400, path, moves=2, seed=41, sample=16)
+    sampled_search_vs_oracle(1, 9, 256, 400, path, moves=2, seed=41, sample=16, expect_wide=1)
 
 
 def test_19x19_search_through_fused_tower_matches_oracle():
