@@ -831,7 +831,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
 // the per-layer unit ranges rotate over the clusters so that nobody is systematically short of work, and a cluster moves on
 // to the next layer as soon as ITS inputs are complete: a unit (layer l, row-tile group g) only needs groups g-1, g, g+1 of
 // layer l-1 (the 3x3 halo), which it learns from per-(layer, group) completion counters in global memory
-// (release: epilogue stores -> __threadfence -> atomicAdd; acquire: producer polls with ld.acquire.gpu, then a
+// (release: the epilogue's TMA stores -> cp.async.bulk.wait_group 0 -> one red.release.gpu per warp [lane-per-row epilogue of
+// the many-unit Atari stages: st.global -> __threadfence -> atomicAdd]; acquire: producer polls with ld.acquire.gpu, then a
 // generic->async proxy fence before the TMA loads). All CTAs are co-resident (one per SM), and every wait points at a
 // strictly earlier layer, so the waits cannot cycle.
 // ---------------------------------------------------------------------------------------------
@@ -867,7 +868,7 @@ struct TowerParams {
     int tap_rot;  // 1: a unit starts its tap loop at tap (row group % 9) instead of tap 0, so that the CTA pairs working on the same (layer,
                   // channel half) do not all ask the L2 for the same weight tile at the same moment. The order is a function of the row
                   // group alone, never of the grid: a position's result does not depend on the batch it is evaluated in
-    int fence_mode; // how an epilogue warp publishes its rows: 0 = __threadfence by every lane, then one atomicAdd; 1 = __syncwarp, then one red.release.gpu
+    int fence_mode; // lane-per-row epilogue (epi_bufs == 0) only: how a warp publishes its rows: 0 = __threadfence by every lane, then one atomicAdd; 1 = __syncwarp, then one red.release.gpu
     int pdl;      // launched with programmatic stream serialization: the grid may start while the tree step before it is still running;
                   // only the first layer's input rows depend on that kernel, and the input producer waits for it (griddepcontrol.wait)
     int* done;    // [num_layers][num_groups] completion counters, zeroed before every launch
